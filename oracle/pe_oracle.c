@@ -1,0 +1,778 @@
+/* pe_oracle.c -- CPU restatement of the LiVES per-frame pixel path (plain C).
+ *
+ * TEST INFRASTRUCTURE ONLY -- see pe_oracle.h.  Each function cites the
+ * reference file:line it follows; deviations from the reference are listed in
+ * DESIGN.md ("quirk table") and are limited to undefined / thread-count
+ * dependent behaviour.
+ */
+#include "pe_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- scalar helpers ------------------------------------------------------ */
+
+/* src/maths.h:118 */
+static int or_myround(double n) { return n >= 0. ? (int)(n + 0.5) : (int)(n - 0.5); }
+
+/* src/maths.h:88 */
+static uint8_t or_clamp0255f(double a) { /* macro in the reference: evaluated in the argument's own type */
+  return a >= 254.5 ? (uint8_t)255 : a < -0.5 ? (uint8_t)0 : (uint8_t)(a + .5);
+}
+
+/* src/colourspace.h:19-23 written as plain range clamps */
+static int or_clamp16_240(int n) { return n < 16 ? 16 : n > 240 ? 240 : n; }
+static int or_clamp0_255(int n) { return n < 0 ? 0 : n > 255 ? 255 : n; }
+
+/* src/colourspace.c:832-835 */
+static int32_t or_spc_rnd(int32_t val, int quality) {
+  if (quality != OR_QUALITY_HIGH) return val >> 16;
+  return (int32_t)((float)val / 65536.);
+}
+
+#define OR_SF 65793. /* SCALE_FACTOR src/colourspace.h:60 */
+
+/* ---- conversion tables  src/colourspace.c:851-1105 ------------------------ */
+
+typedef struct {
+  int32_t t[14][256];
+  int min_y, max_y, min_uv, max_uv;
+} or_conv_t;
+
+static void or_build_conv(int clamping, int subspace, or_conv_t *c) {
+  const int bt709 = (subspace == OR_SUBSPACE_BT709);
+  const double kr = bt709 ? 0.2126 : 0.299, kb = bt709 ? 0.0722 : 0.114; /* colourspace.h:84-91 */
+  const double cfy = (235. - 16.) / 255., cfuv = (240. - 16.) / 255.;     /* colourspace.h:120-121 */
+  int i;
+  if (clamping == OR_CLAMPED) {
+    /* colourspace.c:878-894 / :919-947 */
+    for (i = 0; i < 256; i++) {
+      double fac;
+      c->t[0][i] = or_myround(kr * (double)i * cfy * OR_SF);
+      c->t[1][i] = or_myround((1. - kr - kb) * (double)i * cfy * OR_SF);
+      c->t[2][i] = or_myround((kb * (double)i * cfy + 16.) * OR_SF);
+      fac = .5 / (1. - kb);
+      c->t[3][i] = or_myround(-fac * kr * (double)i * cfuv * OR_SF);
+      c->t[4][i] = or_myround(-fac * (1. - kb - kr) * (double)i * cfuv * OR_SF);
+      c->t[5][i] = or_myround((0.5 * (double)i * cfuv + 128.) * OR_SF);
+      fac = .5 / (1. - kr);
+      c->t[6][i] = or_myround((0.5 * (double)i * cfuv + 128.) * OR_SF);
+      c->t[7][i] = or_myround(-fac * (1. - kb - kr) * (double)i * cfuv * OR_SF);
+      c->t[8][i] = or_myround(-fac * kb * (double)i * cfuv * OR_SF);
+    }
+    c->min_y = c->min_uv = 16; c->max_y = 235; c->max_uv = 240; /* :362-366 */
+  } else {
+    /* colourspace.c:896-912 / :949-977 */
+    for (i = 0; i < 256; i++) {
+      double fac;
+      c->t[0][i] = or_myround(kr * (double)i * OR_SF);
+      c->t[1][i] = or_myround((1. - kr - kb) * (double)i * OR_SF);
+      c->t[2][i] = or_myround(kb * (double)i * OR_SF);
+      fac = .5 / (1. - kb);
+      c->t[3][i] = or_myround(-fac * kr * (double)i * OR_SF);
+      c->t[4][i] = or_myround(-fac * (1. - kb - kr) * (double)i * OR_SF);
+      c->t[5][i] = or_myround((0.5 * (double)i + 128.) * OR_SF);
+      fac = .5 / (1. - kr);
+      c->t[6][i] = or_myround((0.5 * (double)i + 128.) * OR_SF);
+      c->t[7][i] = or_myround(-fac * (1. - kb - kr) * (double)i * OR_SF);
+      c->t[8][i] = or_myround(-fac * kb * (double)i * OR_SF);
+    }
+    c->min_y = c->min_uv = 0; c->max_y = c->max_uv = 255; /* :367-370 */
+  }
+  /* YUV -> RGB, colourspace.c:984-1105.  G_Cb uses -.5/(1+Kb+Kr) for YCbCr (:1005) and
+   * -.5/(1+Kb+Kb) for BT.709 (:1062) -- replicated as written. */
+  {
+    const double gcb = bt709 ? -.5 / (1. + kb + kb) : -.5 / (1. + kb + kr);
+    if (clamping == OR_CLAMPED) {
+      for (i = 0; i <= 16; i++) c->t[9][i] = 0;
+      for (; i < 235; i++) c->t[9][i] = or_myround(((double)i - 16.) / (235. - 16.) * 255. * OR_SF);
+      for (; i < 256; i++) c->t[9][i] = (int)(255 * OR_SF);
+      for (i = 0; i <= 16; i++) c->t[10][i] = c->t[11][i] = c->t[12][i] = c->t[13][i] = 0;
+      for (; i < 240; i++) {
+        double cc = (((double)i - 16.) / (240. - 16.) * 255.) - 128.;
+        c->t[10][i] = or_myround(2. * (1. - kr) * cc * OR_SF);
+        c->t[11][i] = or_myround(gcb * cc * OR_SF);
+        c->t[12][i] = or_myround(-.5 / (1. - kr) * cc * OR_SF);
+        c->t[13][i] = or_myround(2. * (1. - kb) * cc * OR_SF);
+      }
+      for (; i < 256; i++) {
+        /* saturating value: YCbCr uses c(240) (:1015-1024), BT.709 uses 255-128 (:1078-1081) */
+        double cc = bt709 ? (255. - 128.) : (((240. - 16.) / (240. - 16.) * 255.) - 128.);
+        c->t[10][i] = or_myround(2. * (1. - kr) * cc * OR_SF);
+        c->t[11][i] = or_myround(gcb * cc * OR_SF);
+        c->t[12][i] = or_myround(-.5 / (1. - kr) * cc * OR_SF);
+        c->t[13][i] = or_myround(2. * (1. - kb) * cc * OR_SF);
+      }
+    } else {
+      for (i = 0; i < 256; i++) {
+        double cc = (double)i - 128.;
+        c->t[9][i] = (int)(i * OR_SF);
+        c->t[10][i] = or_myround(2. * (1. - kr) * cc * OR_SF);
+        c->t[11][i] = or_myround(gcb * cc * OR_SF);
+        c->t[12][i] = or_myround(-.5 / (1. - kr) * cc * OR_SF);
+        c->t[13][i] = or_myround(2. * (1. - kb) * cc * OR_SF);
+      }
+    }
+  }
+}
+
+/* cache of the four (clamping, subspace) variants */
+static or_conv_t or_cache[2][2];
+static int or_cache_ok[2][2];
+static const or_conv_t *or_conv(int clamping, int subspace) {
+  int a = clamping == OR_CLAMPED ? 0 : 1, b = subspace == OR_SUBSPACE_BT709 ? 1 : 0;
+  if (!or_cache_ok[a][b]) { or_build_conv(clamping, subspace, &or_cache[a][b]); or_cache_ok[a][b] = 1; }
+  return &or_cache[a][b];
+}
+
+void pe_or_conv_table(int clamping, int subspace, int which, int32_t out[256]) {
+  memcpy(out, or_conv(clamping, subspace)->t[which], 256 * sizeof(int32_t));
+}
+
+/* ---- premultiply tables  src/colourspace.c:1141-1160 ---------------------- */
+
+void pe_or_premult_table(int which, int32_t out[65536]) {
+  for (int i = 0; i < 256; i++) {
+    float alpha = (float)255. / (float)i;
+    for (int j = 0; j < 256; j++) {
+      int32_t v;
+      switch (which) {
+      case 0: v = or_clamp0255f((float)j / alpha); break;
+      case 1: v = or_clamp0255f((float)j * alpha); break;
+      case 2: v = (int)((float)j / alpha + .5) > (235. - 16.) ? 235
+                  : (int)((float)(j - 16.) / alpha + 16. + .5); break;
+      case 3: v = (int)((float)j / alpha + .5) > (240. - 16.) ? 240
+                  : (int)((float)(j - 16.) / alpha + 16. + .5); break;
+      case 4: v = or_clamp0255f((float)(j - 16.) * alpha + 16.); break;
+      default: v = or_clamp0255f((float)(j - 128.) * alpha + 128.); break;
+      }
+      out[i * 256 + j] = v;
+    }
+  }
+}
+
+/* ---- gamma LUTs  src/colourspace.c:655-819, colourspace.h:152-185 ---------- */
+
+typedef struct { float offs, lin, thresh, pf; } or_gamma_const;
+
+static void or_gamma_consts(or_gamma_const g[2]) {
+  /* INIT_GAMMA colourspace.h:157-161; sRGB (12.92, 0.04045, 2.4), BT709 (4.5, 0.018, 1/.45) :168-169 */
+  g[0].offs = 0.; g[0].lin = 12.92; g[0].thresh = 0.04045; g[0].pf = 2.4;
+  g[1].offs = 0.; g[1].lin = 4.5; g[1].thresh = 0.018; g[1].pf = 1. / .45;
+  for (int k = 0; k < 2; k++) {
+    g[k].offs = (powf((g[k].thresh / g[k].lin), (1. / g[k].pf)) - g[k].thresh)
+                / (1. - (powf((g[k].thresh / g[k].lin), (1. / g[k].pf))));
+  }
+}
+
+static int or_gamma_idx(int gamma_type) { return gamma_type == OR_GAMMA_BT709 ? 1 : 0; } /* :625-628 */
+
+/* one LUT entry; *gamma_from is mutated across calls exactly as the by-value parameter is
+ * mutated across loop iterations in the reference (:697-713) */
+static float or_gamma_entry(float a0, double fileg, int *gamma_from, int gamma_to, double screen_gamma,
+                            float inv_gamma, const or_gamma_const g[2]) {
+  float a = a0, x = a0;
+  int idx;
+  if (fileg != 1.0) x = powf(a, fileg);
+  if (*gamma_from == OR_GAMMA_MONITOR) {
+    x = powf(a, screen_gamma);
+    *gamma_from = OR_GAMMA_SRGB;
+  }
+  if (*gamma_from != OR_GAMMA_LINEAR && !(*gamma_from == OR_GAMMA_SRGB && gamma_to == OR_GAMMA_MONITOR)) {
+    idx = or_gamma_idx(*gamma_from);
+    a = (a < g[idx].thresh) ? a / g[idx].lin : powf((a + g[idx].offs) / (1. + g[idx].offs), g[idx].pf);
+    *gamma_from = OR_GAMMA_LINEAR;
+  }
+  if (gamma_to != OR_GAMMA_LINEAR) {
+    idx = (gamma_to == OR_GAMMA_MONITOR) ? or_gamma_idx(OR_GAMMA_SRGB) : or_gamma_idx(gamma_to);
+    x = (a < (g[idx].thresh) / g[idx].lin) ? a * g[idx].lin
+        : powf((1. + g[idx].offs) * a, 1. / g[idx].pf) - g[idx].offs;
+  }
+  if (gamma_to == OR_GAMMA_MONITOR) x = powf(a, inv_gamma);
+  return x;
+}
+
+int pe_or_gamma_lut8(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint8_t out[256]) {
+  or_gamma_const g[2];
+  float inv_gamma = 0.;
+  if (fileg == 1.0 && (gamma_to == gamma_from || gamma_to == OR_GAMMA_UNKNOWN || gamma_from == OR_GAMMA_UNKNOWN))
+    return -1; /* :662-663 returns NULL */
+  or_gamma_consts(g);
+  if (gamma_to == OR_GAMMA_MONITOR) inv_gamma = 1. / (float)screen_gamma;
+  out[0] = 0;
+  for (int i = 1; i < 256; ++i) {
+    float x = or_gamma_entry((float)i / 255., fileg, &gamma_from, gamma_to, screen_gamma, inv_gamma, g);
+    out[i] = (uint8_t)or_clamp0_255((int)(x * 255.)); /* CLAMP0_255i :716 */
+  }
+  return 0;
+}
+
+int pe_or_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint16_t out[65536]) {
+  or_gamma_const g[2];
+  float inv_gamma = 0.;
+  if (fileg == 1.0 && (gamma_to == gamma_from || gamma_to == OR_GAMMA_UNKNOWN || gamma_from == OR_GAMMA_UNKNOWN))
+    return -1;
+  or_gamma_consts(g);
+  if (gamma_to == OR_GAMMA_MONITOR) inv_gamma = 1. / (float)screen_gamma;
+  out[0] = 0;
+  for (int i = 1; i < 65536; ++i) {
+    float x = or_gamma_entry((float)i / 65536., fileg, &gamma_from, gamma_to, screen_gamma, inv_gamma, g);
+    /* CLAMP16bit colourspace.h:16 */
+    out[i] = (x) >= 0.99999 ? 65535 : x < 0.00001 ? 0 : (uint16_t)(x * 65535.9999);
+  }
+  return 0;
+}
+
+/* ---- per-pixel kernels  src/colourspace.c:2119-2127, :2345-2356 ------------ */
+
+static inline void or_px_rgb2yuv(const or_conv_t *c, int q, uint8_t r, uint8_t g, uint8_t b, uint8_t *y, uint8_t *u,
+                                 uint8_t *v) {
+  short a;
+  if ((a = or_spc_rnd(c->t[0][r] + c->t[1][g] + c->t[2][b], q)) > c->max_y) *y = c->max_y;
+  else *y = a < c->min_y ? c->min_y : a;
+  if ((a = or_spc_rnd(c->t[3][r] + c->t[4][g] + c->t[5][b], q)) > c->max_uv) *u = c->max_uv;
+  else *u = a < c->min_uv ? c->min_uv : a;
+  if ((a = or_spc_rnd(c->t[6][r] + c->t[7][g] + c->t[8][b], q)) > c->max_uv) *v = c->max_uv;
+  else *v = a < c->min_uv ? c->min_uv : a;
+}
+
+static inline void or_px_yuv2rgb(const or_conv_t *c, int q, const uint16_t *lut16, uint8_t y, uint8_t u, uint8_t v,
+                                 uint8_t *r, uint8_t *g, uint8_t *b) {
+  int yy = c->t[9][y];
+  if (!lut16) {
+    *r = or_clamp0255f(or_spc_rnd(yy + c->t[10][v], q));
+    *g = or_clamp0255f(or_spc_rnd(yy + c->t[11][u] + c->t[12][v], q));
+    *b = or_clamp0255f(or_spc_rnd(yy + c->t[13][u], q));
+  } else {
+    /* xyuv2rgb_with_gamma :2386-2390 */
+    int t;
+    t = (yy + c->t[10][v]) >> 8; t = t > 65535 ? 65535 : t < 0 ? 0 : t; *r = lut16[t] >> 8;
+    t = (yy + c->t[11][u] + c->t[12][v]) >> 8; t = t > 65535 ? 65535 : t < 0 ? 0 : t; *g = lut16[t] >> 8;
+    t = (yy + c->t[13][u]) >> 8; t = t > 65535 ? 65535 : t < 0 ? 0 : t; *b = lut16[t] >> 8;
+  }
+}
+
+void pe_or_rgb2yuv(int clamping, int subspace, int quality, const uint8_t *rgb, uint8_t *yuv, long n) {
+  const or_conv_t *c = or_conv(clamping, subspace);
+  for (long i = 0; i < n; i++)
+    or_px_rgb2yuv(c, quality, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], &yuv[3 * i], &yuv[3 * i + 1], &yuv[3 * i + 2]);
+}
+
+void pe_or_yuv2rgb(int clamping, int subspace, int quality, const uint8_t *yuv, uint8_t *rgb, long n) {
+  const or_conv_t *c = or_conv(clamping, subspace);
+  for (long i = 0; i < n; i++)
+    or_px_yuv2rgb(c, quality, NULL, yuv[3 * i], yuv[3 * i + 1], yuv[3 * i + 2], &rgb[3 * i], &rgb[3 * i + 1], &rgb[3 * i + 2]);
+}
+
+/* byte offsets of R,G,B,(A) inside an output pixel for each order */
+static void or_order_offsets(int order, int add_alpha, int *ro, int *go, int *bo, int *ao, int *psize) {
+  if (order == OR_ORDER_ARGB) { *ao = 0; *ro = 1; *go = 2; *bo = 3; *psize = 4; return; }
+  *psize = add_alpha ? 4 : 3; *ao = add_alpha ? 3 : -1; *go = 1;
+  if (order == OR_ORDER_RGB) { *ro = 0; *bo = 2; } else { *ro = 2; *bo = 0; }
+}
+
+/* ---- planar 4:2:0 / 4:2:2 -> RGB  src/colourspace.c:3260-3904 --------------- */
+
+/* chroma sample one past the end of a chroma row: the reference reads plane[stride*r + cw]
+ * (:3508-3512, :3613).  That byte is row padding, or the first sample of row r+1; only on the
+ * last chroma row of a plane whose stride equals its width does it lie outside the plane, and
+ * there we define it as the replicated edge sample. */
+static inline int or_chroma_at(const uint8_t *p, int stride, int r, int c, int cw, int ch) {
+  if (c < cw) return p[(long)stride * r + c];
+  if (cw < stride || r + 1 < ch) return p[(long)stride * r + cw];
+  return p[(long)stride * r + cw - 1];
+}
+
+void pe_or_yuv420p_to_rgb(const uint8_t *const src[3], const int istrides[3], int width, int height,
+                          uint8_t *dest, int orowstride, int order, int add_alpha, int is_422,
+                          int clamping, int subspace, int quality, int quirks, const uint16_t *lut16) {
+  const or_conv_t *c = or_conv(clamping, subspace);
+  const uint8_t *s_y = src[0], *s_u = src[1], *s_v = src[2];
+  const int cw = width >> 1, ch = is_422 ? height : (height + 1) >> 1;
+  int ro, go, bo, ao, ps;
+  int (*clampf)(int) = clamping == OR_CLAMPED ? or_clamp16_240 : or_clamp0_255;
+  or_order_offsets(order, add_alpha, &ro, &go, &bo, &ao, &ps);
+
+#define OR_EMIT(row, col, yv, uv, vv) do { \
+    uint8_t *d_ = dest + (long)orowstride * (row) + (long)(col) * ps; \
+    or_px_yuv2rgb(c, quality, lut16, (yv), (uint8_t)(uv), (uint8_t)(vv), &d_[ro], &d_[go], &d_[bo]); \
+    if (ao >= 0) d_[ao] = 255; } while (0)
+
+  if (is_422) {
+    /* :3598-3642.  quirk (R): the running "last/this" pair is seeded from chroma row i>>1 */
+    for (int i = 0; i < height; i++) {
+      int seed_row = quirks ? (i >> 1) : i;
+      int last_u = s_u[(long)istrides[1] * seed_row], last_v = s_v[(long)istrides[2] * seed_row];
+      int this_u = last_u, this_v = last_v;
+      for (int j = 0; j < width; j += 2) {
+        int jc = j >> 1;
+        int u1 = clampf((this_u + last_u) >> 1), v1 = clampf((this_v + last_v) >> 1);
+        int next_u = or_chroma_at(s_u, istrides[1], i, jc + 1, cw, ch);
+        int next_v = or_chroma_at(s_v, istrides[2], i, jc + 1, cw, ch);
+        int u2 = clampf((this_u + next_u) >> 1), v2 = clampf((this_v + next_v) >> 1);
+        last_u = this_u; last_v = this_v; this_u = next_u; this_v = next_v;
+        OR_EMIT(i, j, s_y[(long)istrides[0] * i + j], u1, v1);
+        OR_EMIT(i, j + 1, s_y[(long)istrides[0] * i + j + 1], u2, v2);
+      }
+    }
+    return;
+  }
+
+  /* rows 0 and (even height) height-1: single chroma row, horizontal average only.
+   * X rows: the reference indexes the tables with an unshifted sum (:3421-3428) and reads
+   * luma row 0 / writes row 0 for the last row (:3561,:3584); we define the evident intent. */
+  for (int pass = 0; pass < 2; pass++) {
+    int i = pass == 0 ? 0 : height - 1;
+    if (pass == 1 && (height < 2 || (height & 1))) break;
+    int r2 = i >> 1;
+    int last_u = s_u[(long)istrides[1] * r2], last_v = s_v[(long)istrides[2] * r2];
+    int this_u = last_u, this_v = last_v;
+    for (int j = 0; j < width; j += 2) {
+      int jc = j >> 1;
+      int u1 = clampf((this_u + last_u) >> 1), v1 = clampf((this_v + last_v) >> 1);
+      int next_u = or_chroma_at(s_u, istrides[1], r2, jc + 1, cw, ch);
+      int next_v = or_chroma_at(s_v, istrides[2], r2, jc + 1, cw, ch);
+      int u2 = clampf((this_u + next_u) >> 1), v2 = clampf((this_v + next_v) >> 1);
+      OR_EMIT(i, j, s_y[(long)istrides[0] * i + j], u1, v1);
+      OR_EMIT(i, j + 1, s_y[(long)istrides[0] * i + j + 1], u2, v2);
+      last_u = this_u; last_v = this_v; this_u = next_u; this_v = next_v;
+    }
+  }
+
+  /* interior row pairs (i, i+1), i odd: chroma rows r2 = i>>1 and r2+1, weights 2/3-1/3 (:3440-3549) */
+  for (int i = 1; i < height - 1; i += 2) {
+    int r2 = i >> 1;
+    int last_u1 = s_u[(long)istrides[1] * r2], last_v1 = s_v[(long)istrides[2] * r2];
+    int last_u2 = s_u[(long)istrides[1] * (r2 + 1)], last_v2 = s_v[(long)istrides[2] * (r2 + 1)];
+    int this_u1 = last_u1, this_v1 = last_v1, this_u2 = last_u2, this_v2 = last_v2;
+    for (int j = 0; j < width; j += 2) {
+      int jc = j >> 1, u1, u2, v1, v2, u3, u4, v3, v4;
+      int next_u1, next_v1, next_u2, next_v2;
+      /* left pixel */
+      u1 = this_u1 + last_u1;
+      v1 = this_v1 + last_v1;
+      u2 = quirks ? this_u1 + last_u1 : this_u2 + last_u2; /* :3461 */
+      v2 = this_v2 + last_v2;
+      if (quality != OR_QUALITY_LOW || order != OR_ORDER_RGB) { /* bgr/argb variants have no LOW branch (:4090) */
+        u3 = clampf((int)((u1 + (u2 >> 1)) / 3. + .5));
+        u4 = clampf((int)(((u1 >> 1) + u2) / 3. + .5));
+        v3 = clampf((int)((v1 + (v2 >> 1)) / 3. + .5));
+        v4 = clampf((int)(((v1 >> 1) + v2) / 3. + .5));
+      } else {
+        u3 = clampf(u1 >> 1); u4 = clampf(u2 >> 1); v3 = clampf(v1 >> 1); v4 = clampf(v2 >> 1);
+      }
+      OR_EMIT(i, j, s_y[(long)istrides[0] * i + j], u3, v3);
+      OR_EMIT(i + 1, j, s_y[(long)istrides[0] * (i + 1) + j], u4, v4);
+      /* right pixel */
+      next_u1 = or_chroma_at(s_u, istrides[1], r2, jc + 1, cw, ch);
+      next_v1 = or_chroma_at(s_v, istrides[2], r2, jc + 1, cw, ch);
+      next_u2 = or_chroma_at(s_u, istrides[1], r2 + 1, jc + 1, cw, ch);
+      next_v2 = or_chroma_at(s_v, istrides[2], r2 + 1, jc + 1, cw, ch);
+      u1 = this_u1 + next_u1; v1 = this_v1 + next_v1;
+      u2 = this_u2 + next_u2; v2 = this_v2 + next_v2;
+      if (quality != OR_QUALITY_LOW || order != OR_ORDER_RGB) {
+        u3 = clampf((int)((u1 + (u2 >> 1)) / 3. + .5));
+        u4 = clampf((int)(((u1 >> 1) + u2) / 3. + .5));
+        v3 = clampf((int)((v1 + (v2 >> 1)) / 3. + .5));
+        v4 = clampf((int)(((v1 >> 1) + v2) / 3. + .5));
+      } else {
+        u3 = clampf(u1 >> 1); u4 = clampf(u2 >> 1); v3 = clampf(v1 >> 1); v4 = clampf(v2 >> 1);
+      }
+      OR_EMIT(i, j + 1, s_y[(long)istrides[0] * i + j + 1], u3, v3);
+      OR_EMIT(i + 1, j + 1, s_y[(long)istrides[0] * (i + 1) + j + 1], u4, v4);
+      /* :3538-3546 -- with quirks, last_v1 takes this_v2 and last_v2 is never advanced */
+      last_u1 = this_u1; this_u1 = next_u1;
+      last_u2 = this_u2; this_u2 = next_u2;
+      if (quirks) { last_v1 = this_v2; }
+      else { last_v1 = this_v1; last_v2 = this_v2; }
+      this_v1 = next_v1; this_v2 = next_v2;
+    }
+  }
+#undef OR_EMIT
+}
+
+/* ---- packed 4:2:2 -> RGB  src/colourspace.c:6616-7103, uyvy2rgb :2410 ------- */
+
+void pe_or_packed422_to_rgb(int fmt, const uint8_t *src, int irow, int width_mpx, int height,
+                            uint8_t *dest, int orowstride, int order, int add_alpha, int clamping, int subspace,
+                            int quality) {
+  /* only convert_uyvy_to_rgb_frame honours the subspace (:6624); the other five select YCbCr */
+  const or_conv_t *c = or_conv(clamping, (fmt == 0 && order == OR_ORDER_RGB) ? subspace : OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ps;
+  or_order_offsets(order, add_alpha, &ro, &go, &bo, &ao, &ps);
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orowstride * i;
+    for (int j = 0; j < width_mpx; j++, s += 4, d += 2 * ps) {
+      uint8_t y0, y1, u, v;
+      if (fmt == 0) { u = s[0]; y0 = s[1]; v = s[2]; y1 = s[3]; }
+      else { y0 = s[0]; u = s[1]; y1 = s[2]; v = s[3]; }
+      or_px_yuv2rgb(c, quality, NULL, y0, u, v, &d[ro], &d[go], &d[bo]);
+      or_px_yuv2rgb(c, quality, NULL, y1, u, v, &d[ps + ro], &d[ps + go], &d[ps + bo]);
+      if (ao >= 0) d[ao] = d[ps + ao] = 255;
+    }
+  }
+}
+
+/* ---- packed 4:4:4  src/colourspace.c:2750-3258 / :5700-6239 ---------------- */
+
+void pe_or_yuv888_to_rgb(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow,
+                         int order, int in_alpha, int out_alpha, int clamping, int subspace, int quality) {
+  const or_conv_t *c = or_conv(clamping, subspace);
+  int ro, go, bo, ao, ps, ips = in_alpha ? 4 : 3;
+  or_order_offsets(order, out_alpha, &ro, &go, &bo, &ao, &ps);
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < width; j++, s += ips, d += ps) {
+      or_px_yuv2rgb(c, quality, NULL, s[0], s[1], s[2], &d[ro], &d[go], &d[bo]);
+      if (ao >= 0) d[ao] = in_alpha ? s[3] : 255;
+    }
+  }
+}
+
+void pe_or_rgb_to_yuv888(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow,
+                         int order, int in_alpha, int out_alpha, int clamping, int quality) {
+  /* always YCbCr tables (:5710); width is rounded down to even (:5750) */
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ips, ops = out_alpha ? 4 : 3;
+  or_order_offsets(order, in_alpha, &ro, &go, &bo, &ao, &ips);
+  width = (width >> 1) << 1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < width; j++, s += ips, d += ops) {
+      if (out_alpha) d[3] = ao >= 0 ? s[ao] : 255;
+      or_px_rgb2yuv(c, quality, s[ro], s[go], s[bo], &d[0], &d[1], &d[2]);
+    }
+  }
+}
+
+/* ---- RGB <-> RGB  src/colourspace.c:12370-12556 dispatch, loops :9259-10515 -- */
+
+static int or_rgb_layout(int pal, int *ro, int *go, int *bo, int *ao, int *ps) {
+  switch (pal) {
+  case OR_PAL_RGB24: *ro = 0; *go = 1; *bo = 2; *ao = -1; *ps = 3; return 0;
+  case OR_PAL_BGR24: *ro = 2; *go = 1; *bo = 0; *ao = -1; *ps = 3; return 0;
+  case OR_PAL_RGBA32: *ro = 0; *go = 1; *bo = 2; *ao = 3; *ps = 4; return 0;
+  case OR_PAL_BGRA32: *ro = 2; *go = 1; *bo = 0; *ao = 3; *ps = 4; return 0;
+  case OR_PAL_ARGB32: *ro = 1; *go = 2; *bo = 3; *ao = 0; *ps = 4; return 0;
+  }
+  return -1;
+}
+
+int pe_or_rgb_to_rgb(int inpal, int outpal, const uint8_t *src, int irow, int width, int height,
+                     uint8_t *dest, int orow, const uint8_t *lut8) {
+  int iro, igo, ibo, iao, ips, oro, ogo, obo, oao, ops;
+  if (or_rgb_layout(inpal, &iro, &igo, &ibo, &iao, &ips) || or_rgb_layout(outpal, &oro, &ogo, &obo, &oao, &ops)) return -1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < width; j++, s += ips, d += ops) {
+      uint8_t r = s[iro], g = s[igo], b = s[ibo], a = iao >= 0 ? s[iao] : 255;
+      if (lut8) { r = lut8[r]; g = lut8[g]; b = lut8[b]; }
+      d[oro] = r; d[ogo] = g; d[obo] = b;
+      if (oao >= 0) d[oao] = a;
+    }
+  }
+  return 0;
+}
+
+/* ---- gamma apply  src/colourspace.c:14034-14062 ---------------------------- */
+
+void pe_or_gamma_apply(uint8_t *pixels, int rowstride, int palette, int x, int y, int width, int height,
+                       const uint8_t lut8[256]) {
+  int ro, go, bo, ao, ps;
+  if (or_rgb_layout(palette, &ro, &go, &bo, &ao, &ps)) return;
+  {
+    const int px = ps < 3 ? ps : 3;
+    const int start = x * ps + (palette == OR_PAL_ARGB32 ? 1 : 0);
+    const int end = start + width * ps;
+    for (int i = 0; i < height; i++) {
+      uint8_t *row = pixels + (long)rowstride * (y + i);
+      for (int j = start; j < end; j += ps)
+        for (int k = 0; k < px; k++) row[j + k] = lut8[row[j + k]];
+    }
+  }
+}
+
+/* ---- alpha premultiply  src/colourspace.c:11968-12106 ---------------------- */
+
+void pe_or_alpha_premult(uint8_t *pixels, int rowstride, int palette, int clamping, int width, int height,
+                         int direction) {
+  static int32_t *tabs[6];
+  int psize = 4, psizel, coffs, aoffs;
+  if (!tabs[0]) for (int k = 0; k < 6; k++) { tabs[k] = (int32_t *)malloc(65536 * sizeof(int32_t)); pe_or_premult_table(k, tabs[k]); }
+  switch (palette) {
+  case OR_PAL_RGBA32: case OR_PAL_BGRA32: case OR_PAL_YUVA8888: psizel = 3; coffs = 0; aoffs = 3; break;
+  case OR_PAL_ARGB32: psizel = 4; coffs = 1; aoffs = 0; break;
+  default: return;
+  }
+  if (palette != OR_PAL_YUVA8888 || clamping != OR_CLAMPED) {
+    /* REVERSE indexes unal, FORWARD indexes al (:12058-12074) */
+    const int32_t *t = direction < 0 ? tabs[0] : tabs[1];
+    for (int i = 0; i < height; i++) {
+      uint8_t *ptr = pixels + (long)i * rowstride;
+      for (int j = 0; j < width * psize; j += psize) {
+        int alpha = ptr[j + aoffs];
+        for (int p = coffs; p < psizel; p++) ptr[j + p] = (uint8_t)t[alpha * 256 + ptr[j + p]];
+      }
+    }
+  } else {
+    /* clamped YUVA8888 (:12076-12098); forward path reads ptr[j] for U and V as written (:12093-12094) */
+    for (int i = 0; i < height; i++) {
+      uint8_t *ptr = pixels + (long)i * rowstride;
+      for (int j = 0; j < width * psize; j += psize) {
+        int alpha = ptr[j + 3];
+        if (direction < 0) {
+          ptr[j] = (uint8_t)tabs[2][alpha * 256 + ptr[j]];
+          ptr[j + 1] = (uint8_t)tabs[4][alpha * 256 + ptr[j + 1]];
+          ptr[j + 2] = (uint8_t)tabs[4][alpha * 256 + ptr[j + 2]];
+        } else {
+          ptr[j] = (uint8_t)tabs[3][alpha * 256 + ptr[j]];
+          ptr[j + 1] = (uint8_t)tabs[5][alpha * 256 + ptr[j]];
+          ptr[j + 2] = (uint8_t)tabs[5][alpha * 256 + ptr[j]];
+        }
+      }
+    }
+  }
+}
+
+/* ---- effects --------------------------------------------------------------- */
+
+/* calc_luma libweed/weed-plugin-utils.c:924-934 with its own 16.16 tables (:881-886, SCALE_FACTOR 65536) */
+static int32_t or_lY_R[256], or_lY_G[256], or_lY_B[256];
+static int or_luma_ok;
+static uint8_t or_calc_luma(const uint8_t *px, int palette) {
+  if (!or_luma_ok) {
+    for (int i = 0; i < 256; i++) {
+      or_lY_R[i] = or_myround(0.299 * (double)i * 65536.);
+      or_lY_G[i] = or_myround((1. - 0.299 - 0.114) * (double)i * 65536.);
+      or_lY_B[i] = or_myround(0.114 * (double)i * 65536.);
+    }
+    or_luma_ok = 1;
+  }
+  switch (palette) {
+  case OR_PAL_RGB24: case OR_PAL_RGBA32: return (or_lY_R[px[0]] + or_lY_G[px[1]] + or_lY_B[px[2]]) >> 16;
+  case OR_PAL_BGR24: case OR_PAL_BGRA32: return (or_lY_R[px[2]] + or_lY_G[px[1]] + or_lY_B[px[0]]) >> 16;
+  case OR_PAL_ARGB32: return (or_lY_R[px[1]] + or_lY_G[px[2]] + or_lY_B[px[3]]) >> 16;
+  }
+  return 0;
+}
+
+/* simple_blend.c:58-200.  src2_bytes bounds the ARGB "next pixel alpha" read (:130, start = 1) */
+void pe_or_simple_blend(int type, int palette, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2,
+                        uint8_t *dst, int orow, int width, int height, int bf, long src2_bytes) {
+  const int psize = (palette == OR_PAL_RGB24 || palette == OR_PAL_BGR24) ? 3 : 4;
+  const int widthx = width * psize;
+  const int start = palette == OR_PAL_ARGB32 ? 1 : 0;
+  const uint8_t blend_factor = (uint8_t)bf, blendneg = 0xFF - blend_factor;
+  const int inplace = (src1 == dst);
+  if (type == 0) {
+#define OR_BL(i_, j_) ((uint8_t)((blend_factor * (i_) + blendneg * (j_)) >> 8)) /* make_blend_table :31-35 */
+    for (int i = 0; i < height; i++) {
+      const long o = (long)orow * i, r1 = (long)irow1 * i, r2 = (long)irow2 * i;
+      if (psize == 3) {
+        for (int j = start; j < widthx; j++) dst[o + j] = OR_BL(src2[r2 + j], src1[r1 + j]);
+      } else {
+        for (int j = start; j < widthx; j += 4) {
+          /* with start == 1 (ARGB) byte j+3 is the alpha of the NEXT pixel; past the end of the
+           * buffer we take 255 (the reference reads out of bounds there) */
+          int a2 = (r2 + j + 3 < src2_bytes) ? src2[r2 + j + 3] : 255;
+          if (a2 == 255) {
+            for (int k = 0; k < 3; k++) dst[o + j + k] = OR_BL(src2[r2 + j + k], src1[r1 + j + k]);
+          } else {
+            const float alpha = (float)a2 / 255., inv_alpha = 1. - alpha;
+            for (int k = 0; k < 3; k++)
+              dst[o + j + k] = OR_BL((uint8_t)((float)src2[r2 + j + k] * alpha), (uint8_t)((float)src1[r1 + j + k] * inv_alpha));
+          }
+        }
+      }
+    }
+#undef OR_BL
+    return;
+  }
+  /* luma overlay / underlay / negative overlay :153-197 (type 4 "averaged" not restated) */
+  for (int i = 0; i < height; i++) {
+    const long o = (long)orow * i, r1 = (long)irow1 * i, r2 = (long)irow2 * i;
+    for (int j = start; j < widthx; j += psize) {
+      int take2;
+      if (type == 1) take2 = or_calc_luma(&src1[r1 + j], palette) < blend_factor;
+      else if (type == 2) take2 = or_calc_luma(&src2[r2 + j], palette) > blendneg;
+      else take2 = or_calc_luma(&src1[r1 + j], palette) > blendneg;
+      if (take2) memcpy(&dst[o + j], &src2[r2 + j], 3);
+      else if (!inplace) memcpy(&dst[o + j], &src1[r1 + j], 3);
+    }
+  }
+}
+
+/* multi_blends.c:26-165; RGB24/BGR24 only (width*3 at :33) */
+void pe_or_multi_blend(int type, int palette, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2,
+                       uint8_t *dst, int orow, int width, int height, int bf) {
+  const uint8_t blend_factor = (uint8_t)bf;
+  const uint8_t blend1 = blend_factor * 2, blendneg1 = 255 - blend_factor * 2;
+  const uint8_t blend2 = (255 - blend_factor) * 2, blendneg2 = (blend_factor - 128) * 2;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s1 = src1 + (long)irow1 * i, *s2 = src2 + (long)irow2 * i;
+    uint8_t *d = dst + (long)orow * i;
+    for (int j = 0; j < width * 3; j += 3) {
+      uint8_t pixel[3];
+      int intval, k, mpy = 0, scr = 0;
+      uint8_t luma1, luma2;
+      switch (type) {
+      case 0: mpy = 1; break;
+      case 1: scr = 1; break;
+      case 2:
+        luma1 = or_calc_luma(&s1[j], palette); luma2 = or_calc_luma(&s2[j], palette);
+        memcpy(pixel, luma1 <= luma2 ? &s1[j] : &s2[j], 3); break;
+      case 3:
+        luma1 = or_calc_luma(&s1[j], palette); luma2 = or_calc_luma(&s2[j], palette);
+        memcpy(pixel, luma1 >= luma2 ? &s1[j] : &s2[j], 3); break;
+      case 4:
+        luma1 = or_calc_luma(&s1[j], palette);
+        if (luma1 < 128) mpy = 1; else scr = 1;
+        break;
+      case 5:
+        for (k = 0; k < 3; k++) {
+          if (s2[j + k] == 255) pixel[k] = 255;
+          else { intval = ((int)(s1[j + k]) << 8) / (int)(255 - s2[j + k]); pixel[k] = intval > 255 ? 255 : (uint8_t)intval; }
+        }
+        break;
+      default:
+        for (k = 0; k < 3; k++) {
+          if (s2[j + k] == 0) pixel[k] = 0;
+          else { intval = 255 - (255 - ((int)(s1[j + k]) << 8)) / (int)(s2[j + k]); pixel[k] = intval < 0 ? 0 : (uint8_t)intval; }
+        }
+        break;
+      }
+      if (mpy) for (k = 0; k < 3; k++) pixel[k] = (uint8_t)((s2[j + k] * s1[j + k]) >> 8);
+      if (scr) for (k = 0; k < 3; k++) pixel[k] = (uint8_t)(255 - (((255 - s2[j + k]) * (255 - s1[j + k])) >> 8));
+      if (blend_factor < 128) for (k = 0; k < 3; k++) d[j + k] = (blend1 * pixel[k] + blendneg1 * s1[j + k]) >> 8;
+      else for (k = 0; k < 3; k++) d[j + k] = (blend2 * pixel[k] + blendneg2 * s2[j + k]) >> 8;
+    }
+  }
+}
+
+/* gdk/compositor.c paint_pixel :120-125 (double arithmetic, truncation on store) */
+void pe_or_alpha_over(uint8_t *dst, int orow, const uint8_t *src, int irow, int palette, int width, int height,
+                      double alpha) {
+  const int psize = (palette == OR_PAL_RGB24 || palette == OR_PAL_BGR24) ? 3 : 4;
+  for (int y = 0; y < height; y++) {
+    uint8_t *d = dst + (long)orow * y;
+    const uint8_t *s = src + (long)irow * y;
+    for (int x = 0; x < width; x++, d += psize, s += psize) {
+      double invalpha = 1. - alpha;
+      d[0] = d[0] * invalpha + s[0] * alpha;
+      d[1] = d[1] * invalpha + s[1] * alpha;
+      d[2] = d[2] * invalpha + s[2] * alpha;
+    }
+  }
+}
+
+/* gdk/compositor.c:172-186 */
+void pe_or_fill(uint8_t *dst, int orow, int palette, int width, int height, int r, int g, int b) {
+  const int psize = (palette == OR_PAL_RGB24 || palette == OR_PAL_BGR24) ? 3 : 4;
+  const int swap = (palette == OR_PAL_BGR24 || palette == OR_PAL_BGRA32);
+  for (int y = 0; y < height; y++) {
+    uint8_t *d = dst + (long)orow * y;
+    for (int x = 0; x < width; x++, d += psize) {
+      d[0] = swap ? b : r; d[1] = g; d[2] = swap ? r : b;
+      if (psize == 4) d[3] = 0xFF;
+    }
+  }
+}
+
+/* ---- resize: OUR contract (reference = libswscale, unavailable) ------------- */
+/* Separable, swscale-shaped data path:
+ *   per axis a filter bank of `taps` coefficients per output sample, centre aligned:
+ *     centre(i) = (i + 0.5) * src_n / dst_n - 0.5
+ *     scale >= 1 (upscale or equal): 2 taps, triangle of half-width 1
+ *     scale <  1 (downscale): triangle of half-width 1/scale, taps = ceil(2/scale) + 1
+ *   weights are computed in double, normalised so they sum to exactly 1 << shift_bits
+ *   (residual added to the largest tap), source indices clamped to the edge;
+ *   horizontal pass: shift_bits = 14, tmp = min(sum(coef * pix) >> 7, 32767)      (15-bit)
+ *   vertical pass:   shift_bits = 12, out = clip_u8((sum(coef * tmp) + (1 << 18)) >> 19)
+ * At scale 1 both passes are exact identities. */
+int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+  const double ratio = (double)src_n / (double)dst_n; /* source samples per destination sample */
+  const double support = ratio > 1. ? ratio : 1.;
+  int taps = ratio > 1. ? (int)ceil(2. * ratio) + 1 : 2;
+  const int one = 1 << shift_bits;
+  if (taps > max_taps) return -1;
+  for (int i = 0; i < dst_n; i++) {
+    const double centre = ((double)i + 0.5) * ratio - 0.5;
+    int left = (int)floor(centre - support) + 1;
+    double w[64], sum = 0.;
+    int acc = 0, big = 0;
+    if (ratio <= 1.) left = (int)floor(centre);
+    for (int k = 0; k < taps; k++) {
+      double d = fabs((double)(left + k) - centre) / support;
+      w[k] = d < 1. ? 1. - d : 0.;
+      sum += w[k];
+    }
+    for (int k = 0; k < taps; k++) {
+      int q = (int)floor(w[k] / sum * one + 0.5);
+      coefs[(long)i * max_taps + k] = (int16_t)q;
+      acc += q;
+      if (w[k] > w[big]) big = k;
+    }
+    coefs[(long)i * max_taps + big] += (int16_t)(one - acc);
+    for (int k = taps; k < max_taps; k++) coefs[(long)i * max_taps + k] = 0;
+    first[i] = left;
+  }
+  return taps;
+}
+
+void pe_or_resize_packed(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh,
+                         int psize) {
+  enum { MT = 64 };
+  int32_t *fx = (int32_t *)malloc(sizeof(int32_t) * dw), *fy = (int32_t *)malloc(sizeof(int32_t) * dh);
+  int16_t *cx = (int16_t *)malloc(sizeof(int16_t) * MT * dw), *cy = (int16_t *)malloc(sizeof(int16_t) * MT * dh);
+  int tx = pe_or_resize_filter(sw, dw, 14, fx, cx, MT), ty = pe_or_resize_filter(sh, dh, 12, fy, cy, MT);
+  int16_t *tmp = (int16_t *)malloc(sizeof(int16_t) * (size_t)sh * dw * psize);
+  if (tx > 0 && ty > 0) {
+    for (int y = 0; y < sh; y++) {
+      const uint8_t *s = src + (long)irow * y;
+      for (int x = 0; x < dw; x++)
+        for (int ch = 0; ch < psize; ch++) {
+          int acc = 0;
+          for (int k = 0; k < tx; k++) {
+            int sx = fx[x] + k; sx = sx < 0 ? 0 : sx >= sw ? sw - 1 : sx;
+            acc += cx[(long)x * MT + k] * s[sx * psize + ch];
+          }
+          acc >>= 7;
+          tmp[((long)y * dw + x) * psize + ch] = (int16_t)(acc > 32767 ? 32767 : acc);
+        }
+    }
+    for (int y = 0; y < dh; y++) {
+      uint8_t *d = dst + (long)orow * y;
+      for (int x = 0; x < dw * psize; x++) {
+        int acc = 1 << 18;
+        for (int k = 0; k < ty; k++) {
+          int sy = fy[y] + k; sy = sy < 0 ? 0 : sy >= sh ? sh - 1 : sy;
+          acc += cy[(long)y * MT + k] * tmp[(long)sy * dw * psize + x];
+        }
+        acc >>= 19;
+        d[x] = (uint8_t)(acc < 0 ? 0 : acc > 255 ? 255 : acc);
+      }
+    }
+  }
+  free(fx); free(fy); free(cx); free(cy); free(tmp);
+}
+
+/* letterbox_layer src/colourspace.c:15343: offsets ((outer - inner + 1) >> 1) (:15522-15523),
+ * border = black with opaque alpha (blank_pixel via :15489) */
+void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint8_t *outer, int orow, int ow, int oh,
+                            int palette) {
+  int ro, go, bo, ao, ps;
+  if (or_rgb_layout(palette, &ro, &go, &bo, &ao, &ps)) return;
+  {
+    const int ox = (ow - iw + 1) >> 1, oy = (oh - ih + 1) >> 1;
+    for (int y = 0; y < oh; y++) {
+      uint8_t *d = outer + (long)orow * y;
+      for (int x = 0; x < ow; x++, d += ps) { d[ro] = d[go] = d[bo] = 0; if (ao >= 0) d[ao] = 255; }
+    }
+    for (int y = 0; y < ih; y++)
+      memcpy(outer + (long)orow * (y + oy) + (long)ox * ps, inner + (long)irow * y, (size_t)iw * ps);
+  }
+}

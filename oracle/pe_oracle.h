@@ -1,0 +1,98 @@
+/* pe_oracle.h -- CPU restatement of the LiVES per-frame pixel path.
+ *
+ * TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product
+ * (lives_b200/) never links, imports or calls it.
+ *
+ * PARITY STATUS: the reference holds no golden vectors for this path
+ * (SURVEY.md section 4), so the oracle is pinned against the reference itself:
+ * tests/test_oracle_vs_reference.py compares every function below with
+ * oracle/_ref/libref_oracle.so / simple_blend.so / ref_paint_pixel.so, which
+ * oracle/build_ref.py compiles from the reference sources where they lie, and
+ * tests/golden/ freezes the outputs of that compiled reference.
+ * Resize (pe_or_resize_*) is "parity unpinned": the reference delegates it to
+ * libswscale, which is neither in the tree nor installed.
+ *
+ * All citations are file:line in /root/reference.
+ */
+#ifndef PE_ORACLE_H
+#define PE_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* palette / enum values: libweed/weed-palettes.h:43-183 */
+enum {
+  OR_PAL_RGB24 = 1, OR_PAL_BGR24 = 2, OR_PAL_RGBA32 = 3, OR_PAL_BGRA32 = 4, OR_PAL_ARGB32 = 5,
+  OR_PAL_YUV420P = 512, OR_PAL_YVU420P = 513, OR_PAL_YUV422P = 522, OR_PAL_YUV444P = 544,
+  OR_PAL_YUVA4444P = 545, OR_PAL_UYVY = 564, OR_PAL_YUYV = 565, OR_PAL_YUV888 = 588, OR_PAL_YUVA8888 = 589
+};
+enum { OR_CLAMPED = 0, OR_UNCLAMPED = 1 };
+enum { OR_SUBSPACE_YUV = 0, OR_SUBSPACE_YCBCR = 1, OR_SUBSPACE_BT709 = 2 };
+enum { OR_GAMMA_UNKNOWN = 0, OR_GAMMA_LINEAR = -1, OR_GAMMA_SRGB = 1, OR_GAMMA_BT709 = 2, OR_GAMMA_MONITOR = 1024 };
+enum { OR_QUALITY_LOW = 1, OR_QUALITY_MED = 2, OR_QUALITY_HIGH = 3 };
+enum { OR_ORDER_RGB = 0, OR_ORDER_BGR = 1, OR_ORDER_ARGB = 2 };
+
+/* which: 0..8 Y_R Y_G Y_B Cb_R Cb_G Cb_B Cr_R Cr_G Cr_B, 9..13 RGB_Y R_Cr G_Cb G_Cr B_Cb */
+void pe_or_conv_table(int clamping, int subspace, int which, int32_t out[256]);
+/* which: 0 unal 1 al 2 unalcy 3 alcy 4 unalcuv 5 alcuv (colourspace.c:1141) */
+void pe_or_premult_table(int which, int32_t out[65536]);
+int pe_or_gamma_lut8(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint8_t out[256]);
+int pe_or_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint16_t out[65536]);
+
+void pe_or_rgb2yuv(int clamping, int subspace, int quality, const uint8_t *rgb, uint8_t *yuv, long n);
+void pe_or_yuv2rgb(int clamping, int subspace, int quality, const uint8_t *yuv, uint8_t *rgb, long n);
+
+/* planar 4:2:0 / 4:2:2 -> packed RGB(A); quirks != 0 replicates the deterministic
+ * copy-paste slips of colourspace.c:3461,3544,3600; plane_sizes bound the
+ * one-past-row chroma read (see DESIGN.md "edge read"). lut16 may be NULL. */
+void pe_or_yuv420p_to_rgb(const uint8_t *const src[3], const int istrides[3], int width, int height,
+                          uint8_t *dest, int orowstride, int order, int add_alpha, int is_422,
+                          int clamping, int subspace, int quality, int quirks, const uint16_t *lut16);
+/* fmt 0 UYVY, 1 YUYV; width in macropixels (colourspace.c:6616,6862) */
+void pe_or_packed422_to_rgb(int fmt, const uint8_t *src, int irow, int width_mpx, int height,
+                            uint8_t *dest, int orowstride, int order, int add_alpha, int clamping, int subspace,
+                            int quality);
+void pe_or_yuv888_to_rgb(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow,
+                         int order, int in_alpha, int out_alpha, int clamping, int subspace, int quality);
+void pe_or_rgb_to_yuv888(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow,
+                         int order, int in_alpha, int out_alpha, int clamping, int quality);
+
+/* RGB<->RGB: any of the 5 RGB palettes to any other, optional lut8 on colour bytes
+ * (colourspace.c:12370-12556 + :9259-10515, intended whole-row semantics) */
+int pe_or_rgb_to_rgb(int inpal, int outpal, const uint8_t *src, int irow, int width, int height,
+                     uint8_t *dest, int orow, const uint8_t *lut8);
+
+/* gamma_convert_layer_thread colourspace.c:14034 on an explicit rectangle */
+void pe_or_gamma_apply(uint8_t *pixels, int rowstride, int palette, int x, int y, int width, int height,
+                       const uint8_t lut8[256]);
+/* alpha_premult colourspace.c:11968 for the packed 4-byte palettes; direction +1 forward, -1 reverse */
+void pe_or_alpha_premult(uint8_t *pixels, int rowstride, int palette, int clamping, int width, int height,
+                         int direction);
+
+/* simple_blend.c common_process :58.  type 0 chroma blend, 1 luma overlay, 2 luma underlay, 3 neg luma overlay */
+void pe_or_simple_blend(int type, int palette, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2,
+                        uint8_t *dst, int orow, int width, int height, int bf, long src2_bytes);
+/* multi_blends.c common_process :26. type 0 multiply 1 screen 2 darken 3 lighten 4 overlay 5 dodge 6 burn */
+void pe_or_multi_blend(int type, int palette, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2,
+                       uint8_t *dst, int orow, int width, int height, int bf);
+/* compositor.c paint_pixel :120 over a same-size layer at offset 0, scalar alpha */
+void pe_or_alpha_over(uint8_t *dst, int orow, const uint8_t *src, int irow, int palette, int width, int height,
+                      double alpha);
+/* compositor.c:178-186 background fill */
+void pe_or_fill(uint8_t *dst, int orow, int palette, int width, int height, int r, int g, int b);
+
+/* bilinear / triangle resize on packed 3- or 4-byte pixels -- OUR published contract
+ * (parity unpinned, see header comment and DESIGN.md) */
+void pe_or_resize_packed(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh,
+                         int psize);
+int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
+/* letterbox_layer colourspace.c:15343: centre an inner packed frame in a black outer one */
+void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint8_t *outer, int orow, int ow, int oh,
+                            int palette);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

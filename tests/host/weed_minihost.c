@@ -1,0 +1,143 @@
+/* weed_minihost.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A minimal libweed *host*, linked against the reference's own libweed
+ * (oracle/_ref/libweed*.so, compiled unchanged by oracle/build_ref.py).
+ * It loads ANY weed effect plugin exactly the way LiVES does
+ * (src/effects-weed.c:4468-4568: dlopen RTLD_NOW|RTLD_LOCAL, dlsym "weed_setup",
+ * setup_fn(weed_bootstrap)), builds channel / parameter / instance plants and
+ * calls init_func / process_func on caller-supplied frames.
+ *
+ * The parity tests use it twice with identical inputs: once on the reference's
+ * simple_blend.so / multi_blends.so and once on our CUDA plugin
+ * (lives_b200/csrc/libpe_weed_plugin.so) -- the drop-in check for boundary B1.
+ *
+ * Exported flat API (ctypes):
+ *   int  mh_open(const char *plugin_path);              -> handle >= 0
+ *   int  mh_num_filters(int h);
+ *   int  mh_filter_name(int h, int idx, char *buf, int len);
+ *   int  mh_filter_flags(int h, int idx);
+ *   int  mh_run2(int h, int filter_idx, int palette, int width, int height,
+ *                void *src1, int rs1, void *src2, int rs2, void *dst, int rsd,
+ *                int int_param0, int nframes);
+ *        two in channels, one out channel, one integer in-parameter; dst may
+ *        equal src1 (in-place, as LiVES does for CAN_DO_INPLACE channels);
+ *        calls init once, process nframes times, deinit once.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <dlfcn.h>
+
+#include <weed/weed-host.h>
+#include <weed/weed.h>
+#include <weed/weed-effects.h>
+#include <weed/weed-palettes.h>
+#include <weed/weed-utils.h>
+#include <weed/weed-host-utils.h>
+
+#define MH_MAX 16
+
+typedef struct {
+  void *dl;
+  weed_plant_t *plugin_info;
+  weed_plant_t **filters;
+  int nfilters;
+} mh_plugin;
+
+static mh_plugin mh_tab[MH_MAX];
+static int mh_inited = 0;
+
+static void mh_init_once(void) {
+  if (mh_inited) return;
+  libweed_init(WEED_ABI_VERSION, 0);
+  mh_inited = 1;
+}
+
+int mh_open(const char *path) {
+  int h;
+  weed_setup_f setup_fn;
+  mh_init_once();
+  for (h = 0; h < MH_MAX; h++) if (!mh_tab[h].dl) break;
+  if (h == MH_MAX) return -1;
+  mh_tab[h].dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!mh_tab[h].dl) { fprintf(stderr, "minihost: dlopen %s: %s\n", path, dlerror()); return -2; }
+  setup_fn = (weed_setup_f)dlsym(mh_tab[h].dl, "weed_setup");
+  if (!setup_fn) { dlclose(mh_tab[h].dl); mh_tab[h].dl = NULL; return -3; }
+  mh_tab[h].plugin_info = (*setup_fn)(weed_bootstrap);
+  if (!mh_tab[h].plugin_info) { dlclose(mh_tab[h].dl); mh_tab[h].dl = NULL; return -4; }
+  mh_tab[h].filters = weed_get_plantptr_array_counted(mh_tab[h].plugin_info, WEED_LEAF_FILTERS, &mh_tab[h].nfilters);
+  return h;
+}
+
+int mh_num_filters(int h) { return (h < 0 || h >= MH_MAX || !mh_tab[h].dl) ? -1 : mh_tab[h].nfilters; }
+
+int mh_filter_name(int h, int idx, char *buf, int len) {
+  char *name;
+  if (mh_num_filters(h) <= idx || idx < 0) return -1;
+  name = weed_get_string_value(mh_tab[h].filters[idx], WEED_LEAF_NAME, NULL);
+  if (!name) return -2;
+  strncpy(buf, name, len - 1); buf[len - 1] = 0;
+  free(name);
+  return 0;
+}
+
+int mh_filter_flags(int h, int idx) {
+  if (mh_num_filters(h) <= idx || idx < 0) return -1;
+  return weed_get_int_value(mh_tab[h].filters[idx], WEED_LEAF_FLAGS, NULL);
+}
+
+static weed_plant_t *mh_channel(weed_plant_t *tmpl, int palette, int width, int height, void *pixels, int rowstride) {
+  weed_plant_t *ch = weed_plant_new(WEED_PLANT_CHANNEL);
+  weed_set_plantptr_value(ch, WEED_LEAF_TEMPLATE, tmpl);
+  weed_set_int_value(ch, WEED_LEAF_WIDTH, width); /* macropixels == pixels for the RGB palettes */
+  weed_set_int_value(ch, WEED_LEAF_HEIGHT, height);
+  weed_set_int_value(ch, WEED_LEAF_CURRENT_PALETTE, palette);
+  weed_set_int_value(ch, WEED_LEAF_ROWSTRIDES, rowstride);
+  weed_set_voidptr_value(ch, WEED_LEAF_PIXEL_DATA, pixels);
+  return ch;
+}
+
+int mh_run2(int h, int fidx, int palette, int width, int height, void *src1, int rs1, void *src2, int rs2,
+            void *dst, int rsd, int int_param0, int nframes) {
+  weed_plant_t *filter, *inst, *in_ch[2], *out_ch, *param;
+  weed_plant_t **ictm, **octm, **iptm;
+  weed_init_f init_fn;
+  weed_process_f process_fn;
+  weed_deinit_f deinit_fn;
+  weed_error_t err = WEED_SUCCESS;
+  int n;
+  if (mh_num_filters(h) <= fidx || fidx < 0) return -1;
+  filter = mh_tab[h].filters[fidx];
+  ictm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_CHANNEL_TEMPLATES, &n);
+  if (n < 2) return -2;
+  octm = weed_get_plantptr_array_counted(filter, WEED_LEAF_OUT_CHANNEL_TEMPLATES, &n);
+  if (n < 1) return -3;
+  iptm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_PARAMETER_TEMPLATES, &n);
+  if (n < 1) return -4;
+
+  in_ch[0] = mh_channel(ictm[0], palette, width, height, src1, rs1);
+  in_ch[1] = mh_channel(ictm[1], palette, width, height, src2, rs2);
+  out_ch = mh_channel(octm[0], palette, width, height, dst, rsd);
+  param = weed_plant_new(WEED_PLANT_PARAMETER);
+  weed_set_plantptr_value(param, WEED_LEAF_TEMPLATE, iptm[0]);
+  weed_set_int_value(param, WEED_LEAF_VALUE, int_param0);
+
+  inst = weed_plant_new(WEED_PLANT_FILTER_INSTANCE);
+  weed_set_plantptr_value(inst, WEED_LEAF_FILTER_CLASS, filter);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_CHANNELS, 2, in_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_OUT_CHANNELS, 1, &out_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_PARAMETERS, 1, &param);
+
+  init_fn = (weed_init_f)weed_get_funcptr_value(filter, WEED_LEAF_INIT_FUNC, NULL);
+  process_fn = (weed_process_f)weed_get_funcptr_value(filter, WEED_LEAF_PROCESS_FUNC, NULL);
+  deinit_fn = (weed_deinit_f)weed_get_funcptr_value(filter, WEED_LEAF_DEINIT_FUNC, NULL);
+  if (!process_fn) return -5;
+  if (init_fn) err = (*init_fn)(inst);
+  for (int f = 0; f < nframes && err == WEED_SUCCESS; f++) err = (*process_fn)(inst, (weed_timecode_t)f);
+  if (deinit_fn) (*deinit_fn)(inst);
+
+  weed_plant_free(inst); weed_plant_free(param);
+  weed_plant_free(in_ch[0]); weed_plant_free(in_ch[1]); weed_plant_free(out_ch);
+  free(ictm); free(octm); free(iptm);
+  return (int)err;
+}

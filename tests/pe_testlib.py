@@ -1,0 +1,190 @@
+"""ctypes loaders + frame helpers shared by the tests.
+
+The oracle (oracle/libpe_oracle.so) and the compiled reference (oracle/_ref/*.so)
+are CHECKERS: they are loaded only here, never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(REPO, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+PAL = dict(RGB24=1, BGR24=2, RGBA32=3, BGRA32=4, ARGB32=5, YUV420P=512, YVU420P=513, YUV422P=522,
+           YUV444P=544, YUVA4444P=545, UYVY=564, YUYV=565, YUV888=588, YUVA8888=589)
+CLAMPED, UNCLAMPED = 0, 1
+SUB_YUV, SUB_YCBCR, SUB_BT709 = 0, 1, 2
+G_UNKNOWN, G_LINEAR, G_SRGB, G_BT709, G_MONITOR = 0, -1, 1, 2, 1024
+Q_LOW, Q_MED, Q_HIGH = 1, 2, 3
+
+u8p = C.POINTER(C.c_uint8)
+
+
+def p8(a):
+    return a.ctypes.data_as(u8p)
+
+
+def align_ceil(a, b):
+    return ((a + b - 1) // b) * b
+
+
+def rowstride(width, psize):
+    """colourspace.c:11299-11342 default rowstride = ALIGN_CEIL(width*psize, 32)"""
+    return align_ceil(width * psize, 32)
+
+
+def psize_of(pal):
+    return {1: 3, 2: 3, 3: 4, 4: 4, 5: 4, 588: 3, 589: 4, 564: 4, 565: 4}.get(pal, 1)
+
+
+I, L, D, VP = C.c_int, C.c_long, C.c_double, C.c_void_p
+
+_ORACLE_PROTOS = {
+    "pe_or_conv_table": [I, I, I, VP],
+    "pe_or_premult_table": [I, VP],
+    "pe_or_gamma_lut8": [D, I, I, D, VP],
+    "pe_or_gamma_lut16": [D, I, I, D, VP],
+    "pe_or_rgb2yuv": [I, I, I, VP, VP, L],
+    "pe_or_yuv2rgb": [I, I, I, VP, VP, L],
+    "pe_or_yuv420p_to_rgb": [VP, VP, I, I, VP, I, I, I, I, I, I, I, I, VP],
+    "pe_or_packed422_to_rgb": [I, VP, I, I, I, VP, I, I, I, I, I, I],
+    "pe_or_yuv888_to_rgb": [VP, I, I, I, VP, I, I, I, I, I, I, I],
+    "pe_or_rgb_to_yuv888": [VP, I, I, I, VP, I, I, I, I, I, I],
+    "pe_or_rgb_to_rgb": [I, I, VP, I, I, I, VP, I, VP],
+    "pe_or_gamma_apply": [VP, I, I, I, I, I, I, VP],
+    "pe_or_alpha_premult": [VP, I, I, I, I, I, I],
+    "pe_or_simple_blend": [I, I, VP, I, VP, I, VP, I, I, I, I, L],
+    "pe_or_multi_blend": [I, I, VP, I, VP, I, VP, I, I, I, I],
+    "pe_or_alpha_over": [VP, I, VP, I, I, I, I, D],
+    "pe_or_fill": [VP, I, I, I, I, I, I, I],
+    "pe_or_resize_packed": [VP, I, I, I, VP, I, I, I, I],
+    "pe_or_resize_filter": [I, I, I, VP, VP, I],
+    "pe_or_letterbox_packed": [VP, I, I, I, VP, I, I, I, I],
+}
+
+_REF_PROTOS = {
+    "ref_init": [],
+    "ref_set_prefs": [I, I, D],
+    "ref_get_conv_table": [I, I, I, VP],
+    "ref_get_premult_table": [I, VP],
+    "ref_get_avg_table": [I, VP],
+    "ref_get_yy_table": [I, VP],
+    "ref_gamma_lut8": [D, I, I, VP],
+    "ref_gamma_lut16": [D, I, I, VP],
+    "ref_gamma_consts": [VP],
+    "ref_rgb2yuv_bulk": [I, I, VP, VP, L],
+    "ref_yuv2rgb_bulk": [I, I, VP, VP, L],
+    "ref_yuv420p_to_rgb": [VP, I, I, VP, I, VP, I, I, I, I, I, I, I, I],
+    "ref_packed422_to_rgb": [I, VP, I, I, I, I, VP, I, I, I, I],
+    "ref_yuv888_to_rgb": [VP, I, I, I, I, VP, I, I, I, I, I],
+    "ref_yuv444p_to_rgb": [VP, I, I, I, I, VP, I, I, I, I],
+    "ref_rgb_permute": [I, VP, I, I, I, I, VP, VP, I, I],
+    "ref_rgb_to_yuv888": [VP, I, I, I, I, VP, I, I, I, I],
+    "ref_rgb_to_yuv444p": [VP, I, I, I, I, VP, I, I, I, I],
+    "ref_rgb_to_yuv420": [VP, I, I, I, VP, VP, I, I, I, I, I],
+    "ref_alpha_premult": [VP, I, I, I, I, I, I, VP],
+    "ref_gamma_apply": [VP, I, I, I, I, I, I, VP],
+}
+
+
+def _bind(lib, protos):
+    for name, args in protos.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    return lib
+
+
+def ptr(a):
+    """raw address of a numpy array (or None)"""
+    return None if a is None else a.ctypes.data
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        so = os.path.join(ORACLE_DIR, "libpe_oracle.so")
+        src = os.path.join(ORACLE_DIR, "pe_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "libpe_oracle.so"], stdout=subprocess.DEVNULL)
+        _oracle = _bind(C.CDLL(so), _ORACLE_PROTOS)
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "libref_oracle.so"))
+
+
+_ref = None
+
+
+def ref():
+    """compiled reference slices (oracle/_ref/libref_oracle.so)"""
+    global _ref
+    if _ref is None:
+        _ref = _bind(C.CDLL(os.path.join(REF_DIR, "libref_oracle.so")), _REF_PROTOS)
+        _ref.ref_init()
+    return _ref
+
+
+_paint = None
+
+
+def ref_paint():
+    global _paint
+    if _paint is None:
+        _paint = C.CDLL(os.path.join(REF_DIR, "ref_paint_pixel.so"))
+        _paint.ref_paint_rows.argtypes = [VP, VP, L, I, D]
+    return _paint
+
+
+# ---------------------------------------------------------------- frame makers
+
+def make_packed(rng, width, height, psize, stride=None, lo=0, hi=256):
+    stride = stride or rowstride(width, psize)
+    a = np.zeros((height, stride), np.uint8)
+    a[:, :width * psize] = rng.integers(lo, hi, (height, width * psize), dtype=np.uint8)
+    return a
+
+
+def _plane(rng, rows, cols, stride, lo, hi):
+    """one plane + a guard byte right after it holding the replicated edge sample, so that the
+    reference's one-past-row chroma read (colourspace.c:3508) sees what our contract defines"""
+    buf = np.zeros(rows * stride + 16, np.uint8)
+    pl = buf[:rows * stride].reshape(rows, stride)
+    pl[:, :cols] = rng.integers(lo, hi, (rows, cols), dtype=np.uint8)
+    if stride == cols:
+        buf[rows * stride] = pl[rows - 1, cols - 1]
+    return pl
+
+
+def make_yuv_planar(rng, width, height, is_422=False, clamped=True):
+    """Planar frame with the reference strides (colourspace.c:11344-11357)."""
+    ys = rowstride(width, 1)
+    cs = ys >> 1
+    cw, ch = width >> 1, (height if is_422 else (height + 1) >> 1)
+    if clamped:
+        y = _plane(rng, height, width, ys, 16, 236)
+        u = _plane(rng, ch, cw, cs, 16, 241)
+        v = _plane(rng, ch, cw, cs, 16, 241)
+    else:
+        y = _plane(rng, height, width, ys, 0, 256)
+        u = _plane(rng, ch, cw, cs, 0, 256)
+        v = _plane(rng, ch, cw, cs, 0, 256)
+    return y, u, v
+
+
+def planes_arg(*planes):
+    """uint8_t *planes[n] (keeps nothing alive: callers hold the arrays)"""
+    return (C.c_void_p * len(planes))(*[p.ctypes.data for p in planes])
+
+
+def strides_arg(*planes):
+    return (C.c_int * len(planes))(*[p.strides[0] for p in planes])
