@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the LiVES per-frame pixel path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            our arm  (torchrun for N > 1, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's CPU loops on this box's host cores
+
+Workload (N = 1 and every N: weak scaling, frames are independent -- SURVEY.md 8e): the north-star headline row,
+    3840x2160 YUV420P fg -> RGBA32 (reference converter arithmetic), letterboxed to a 3840x1608 inner rectangle in
+    a 3840x2160 frame (vertical bilinear squeeze), scalar alpha-over (0.5) a 3840x2160 RGBA32 bg, gamma LUT8
+    (linear -> sRGB) -- ONE fused kernel per batch of frames.
+A "step" is one pass over a batch of --batch independent frames per GPU (all distinct, resident in HBM: the batch
+is far larger than the 126 MB L2, so nothing is served from cache between steps).
+  value     frames/s over all ranks, inputs resident in HBM, CUDA-event timed on the engine's stream (max over ranks)
+  e2e       the same chain through the host-buffer C-ABI call (pe_host_fused_convert_letterbox_over_gamma): pinned host
+            frames in, pinned host frame out, H2D + kernel + D2H all inside the timed region
+  roofline  algorithmic bytes (78 796 800 B / frame: fg planes + bg read once, out written once) / kernel time,
+            against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference CPU chain on a bounded sample of the same workload (rank 0, N = 1 only)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "frames/sec 4K RGBA convert+resize+composite @1/2/4/8 B200; % HBM roofline"
+FW, FH = 3840, 2160          # fg (YUV420P) and bg / out (RGBA32) size
+IW, IH = 3840, 1608          # letterbox inner rectangle
+ALPHA = 0.5
+G_LINEAR, G_SRGB = -1, 1
+FG_BYTES = FW * FH + 2 * (FW // 2) * (FH // 2)      # 12 441 600
+RGBA_BYTES = FW * FH * 4                            # 33 177 600
+ALGO_BYTES_PER_FRAME = FG_BYTES + 2 * RGBA_BYTES    # 78 796 800
+WORKLOAD = "headline: 3840x2160 YUV420P fg -> RGBA32 + letterbox(3840x1608 in 3840x2160, bilinear) + alpha-over(0.5) RGBA32 bg + gamma LUT8, fused"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference chain
+
+class CpuChain:
+    """The reference's CPU implementation of the workload, one frame per call (test infrastructure: oracle/).
+
+    convert   compiled reference convert_yuv420p_to_rgb_frame (oracle/_ref/libref_oracle.so), pb_quality HIGH
+    resize    oracle port of our published filter (the reference calls libswscale, absent from its tree and this image)
+    letterbox oracle port of letterbox_layer's centred row copies
+    over      compiled reference compositor.c paint_pixel (oracle/_ref/ref_paint_pixel.so)
+    gamma     compiled reference gamma_convert_layer_thread with the LUT of create_gamma_lut8
+    Falls back to the oracle port for every stage (kind "port") when oracle/_ref is absent.
+    """
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import pe_testlib as T
+        self.T = T
+        self.o = T.oracle()
+        self.kind = "reference" if T.have_ref() else "port"
+        if self.kind == "reference":
+            self.r = T.ref()
+            self.r.ref_set_prefs(1, T.Q_HIGH, 1.4)  # frames are spread over the cores, one band per frame
+            self.p = T.ref_paint()
+        self.lut = np.zeros(256, np.uint8)
+        assert self.o.pe_or_gamma_lut8(1.0, G_LINEAR, G_SRGB, 1.4, T.ptr(self.lut)) == 0
+        self.tls = threading.local()
+
+    def _bufs(self):
+        t = self.tls
+        if not hasattr(t, "rgba"):
+            t.rgba_full = np.zeros((FH + 16, FW * 4), np.uint8)  # slack rows: the reference has stray writes (:3584)
+            t.rgba = t.rgba_full[8:8 + FH]
+            t.inner = np.zeros((IH, IW * 4), np.uint8)
+            t.boxed = np.zeros((FH, FW * 4), np.uint8)
+        return t
+
+    def frame(self, y, u, v, bg, out):
+        T, t = self.T, self._bufs()
+        pl, st = T.planes_arg(y, u, v), T.strides_arg(y, u, v)
+        if self.kind == "reference":
+            self.r.ref_yuv420p_to_rgb(pl, FW, FH, st, FW * 4, T.ptr(t.rgba), 0, 1, 0, 0, 0, 1, 0, 0)
+        else:
+            self.o.pe_or_yuv420p_to_rgb(pl, st, FW, FH, T.ptr(t.rgba), FW * 4, 0, 1, 0, 0, 1, T.Q_HIGH, 1, None)
+        self.o.pe_or_resize_packed(T.ptr(t.rgba), FW * 4, FW, FH, T.ptr(t.inner), IW * 4, IW, IH, 4)
+        self.o.pe_or_letterbox_packed(T.ptr(t.inner), IW * 4, IW, IH, T.ptr(t.boxed), FW * 4, FW, FH, 3)
+        np.copyto(out, bg)
+        if self.kind == "reference":
+            self.p.ref_paint_rows(T.ptr(out), T.ptr(t.boxed), FW * FH, 4, ALPHA)
+            out[:, 3::4] = 255
+            self.r.ref_gamma_apply(T.ptr(out), FW * 4, 4, 0, FW, FH, 0, T.ptr(self.lut))
+        else:
+            self.o.pe_or_alpha_over(T.ptr(out), FW * 4, T.ptr(t.boxed), FW * 4, 3, FW, FH, ALPHA)
+            out[:, 3::4] = 255
+            self.o.pe_or_gamma_apply(T.ptr(out), FW * 4, 3, 0, 0, FW, FH, T.ptr(self.lut))
+
+
+def host_frames(n, seed0=20):
+    """synthetic frames exactly as SURVEY.md 8d: Y in [16,235], U,V in [16,240], bg uniform u8"""
+    frames = []
+
+    def plane(rng, rows, cols, lo, hi):
+        # + guard bytes: the reference converter reads one byte past the last chroma row (colourspace.c:3508)
+        buf = np.zeros(rows * cols + 16, np.uint8)
+        pl = buf[:rows * cols].reshape(rows, cols)
+        pl[...] = rng.integers(lo, hi, (rows, cols), dtype=np.uint8)
+        buf[rows * cols] = pl[-1, -1]
+        return pl
+
+    for i in range(n):
+        rng = np.random.default_rng(seed0 + 2 * i)
+        y = plane(rng, FH, FW, 16, 236)
+        u = plane(rng, FH // 2, FW // 2, 16, 241)
+        v = plane(rng, FH // 2, FW // 2, 16, 241)
+        bg = np.random.default_rng(seed0 + 2 * i + 1).integers(0, 256, (FH, FW * 4), dtype=np.uint8)
+        frames.append((y, u, v, bg))
+    return frames
+
+
+class CpuBench:
+    """n_frames independent frames of the CPU chain spread over `cores` threads (ctypes drops the GIL)"""
+
+    def __init__(self, n_frames, cores):
+        from concurrent.futures import ThreadPoolExecutor
+        self.chain = CpuChain()
+        self.n, self.cores = n_frames, cores
+        self.distinct = host_frames(2)
+        self.outs = [np.zeros((FH, FW * 4), np.uint8) for _ in range(min(cores, n_frames))]
+        self.ex = ThreadPoolExecutor(max_workers=cores)
+        list(self.ex.map(self._work, range(min(cores, n_frames))))  # warm-up: page in buffers, build tables
+
+    def _work(self, i):
+        y, u, v, bg = self.distinct[i % len(self.distinct)]
+        self.chain.frame(y, u, v, bg, self.outs[i % len(self.outs)])
+
+    def step(self):
+        t0 = time.perf_counter()
+        list(self.ex.map(self._work, range(self.n)))
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.ex.shutdown()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------ arms
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = host_cores()
+    n_frames = cores  # one frame per host thread and step: about one chain latency (~1 s) per step
+    cb = CpuBench(n_frames, cores)
+    kind = cb.chain.kind
+    fps_steps = []
+    for s in range(args.warmup + args.steps):
+        dt = cb.step()
+        if s >= args.warmup:
+            fps_steps.append((n_frames / dt, dt))
+    cb.close()
+    total_frames = n_frames * len(fps_steps)
+    total_t = sum(dt for _, dt in fps_steps)
+    value = total_frames / total_t
+    sample = ("%d frames/step of the headline workload over %d host threads (one frame per thread); convert / alpha-over / gamma = "
+              "compiled reference loops, resize + letterbox = oracle port (libswscale absent)" % (n_frames, cores)) if kind == "reference" \
+        else "%d frames/step over %d host threads, oracle port for every stage" % (n_frames, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total_t / max(len(fps_steps), 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": n_frames},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import lives_b200 as lb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the pixel engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = lb.Engine(device=local_rank)
+    B = args.batch
+    g = torch.Generator(device=dev)
+    g.manual_seed(20 + rank)
+    keep, fgs, bgs, outs = [], [], [], []
+    for i in range(B):
+        y = torch.randint(16, 236, (FH, FW), dtype=torch.uint8, device=dev, generator=g)
+        u = torch.randint(16, 241, (FH // 2, FW // 2), dtype=torch.uint8, device=dev, generator=g)
+        v = torch.randint(16, 241, (FH // 2, FW // 2), dtype=torch.uint8, device=dev, generator=g)
+        bg = torch.randint(0, 256, (FH, FW * 4), dtype=torch.uint8, device=dev, generator=g)
+        out = torch.empty((FH, FW * 4), dtype=torch.uint8, device=dev)
+        keep += [y, u, v, bg, out]
+        fgs.append(lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV420P, FW, FH, [y.data_ptr(), u.data_ptr(), v.data_ptr()],
+                                        [FW, FW // 2, FW // 2], yuv_clamping=0, yuv_subspace=1))
+        bgs.append(lb.Layer.wrap_device(eng, lb.WEED_PALETTE_RGBA32, FW, FH, [bg.data_ptr()], [FW * 4], gamma_type=G_LINEAR))
+        outs.append(lb.Layer.wrap_device(eng, lb.WEED_PALETTE_RGBA32, FW, FH, [out.data_ptr()], [FW * 4]))
+    torch.cuda.synchronize()
+
+    def step():
+        lb.fused_convert_letterbox_over_gamma_batch(fgs, bgs, outs, IW, IH, ALPHA, G_LINEAR, G_SRGB)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count
+    barrier()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = eng.timer_stop_ms()
+    barrier()
+    launches = eng.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames_total = B * args.steps * world
+    value = frames_total / (ms / 1000.0)
+    kernel_ms = ms / max(launches, 1) if launches else ms / args.steps
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES_PER_FRAME * B / (kernel_ms / 1000.0) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI drop-in, H2D + kernel + D2H timed (per rank, frames independent)
+    hframes = host_frames(2, seed0=20 + 100 * rank)
+    pinned = []
+    for (y, u, v, bg) in hframes:
+        bufs = []
+        for a in (y, u, v, bg, np.zeros((FH, FW * 4), np.uint8)):
+            p = lb._capi.lib().pe_host_alloc(a.nbytes)
+            if not p:
+                raise SystemExit("pinned host allocation failed")
+            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(a.nbytes,)).reshape(a.shape)
+            arr[...] = a
+            bufs.append(arr)
+        pinned.append(bufs)
+    hl = [(lb.HostLayer(lb.WEED_PALETTE_YUV420P, FW, FH, b[:3], yuv_subspace=1),
+           lb.HostLayer(lb.WEED_PALETTE_RGBA32, FW, FH, [b[3]], gamma_type=G_LINEAR),
+           lb.HostLayer(lb.WEED_PALETTE_RGBA32, FW, FH, [b[4]])) for b in pinned]
+    e2e_frames = args.e2e_frames
+
+    def e2e_pass(n):
+        for i in range(n):
+            f, b_, o = hl[i % len(hl)]
+            lb.host_fused_convert_letterbox_over_gamma(eng, f, b_, o, IW, IH, ALPHA, G_LINEAR, G_SRGB)
+
+    e2e_pass(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(e2e_frames)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = e2e_frames * world / e2e_s
+    checksum = int(pinned[0][4][::97, ::101].astype(np.uint64).sum())  # the D2H result is really read
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        cb = CpuBench(cores, cores)
+        kind, n, dt = cb.chain.kind, 0, 0.0
+        while dt < 10.0 and n < 64 * cores:  # bounded sample: >= 10 s of wall clock over all host threads
+            dt += cb.step()
+            n += cores
+        cb.close()
+        fps = n / dt
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": "%d frames of the same workload over %d host threads in %.1f s; convert / alpha-over / gamma = compiled "
+                         "reference loops, resize + letterbox = oracle port (libswscale absent)" % (n, cores, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": "frames sharded, no collective",
+                           "l2": "inputs larger than L2: %.0f MB touched per step vs 126 MB L2" % (ALGO_BYTES_PER_FRAME * B / 1e6)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "k_fused", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": FG_BYTES + RGBA_BYTES,
+                        "d2h_bytes_per_step": RGBA_BYTES, "frames": e2e_frames, "step": "one frame per call",
+                        "api": "pe_host_fused_convert_letterbox_over_gamma (pinned host in / out)", "checksum": checksum},
+                "gpu_launches": int(launches), "clocks": clk}
+        prof = os.path.join(REPO, "profiles", "traffic_r01.json")
+        if os.path.exists(prof):
+            try:
+                line["roofline"]["traffic"] = json.load(open(prof)).get("k_fused_bytes_per_launch_batch%d" % B)
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    for b in pinned:
+        for a in b:
+            lb._capi.lib().pe_host_free(a.ctypes.data)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="independent frames per step per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it, as the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
+               "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+/* pixel_engine.h -- C ABI of the B200 per-frame pixel engine (libpe_b200.so).
+ *
+ * Drop-in boundary for the LiVES hot path
+ *     palette conversion -> resize / letterbox -> effect blend / composite -> gamma
+ * Plain C: opaque handles, raw pointers, ints and doubles only.  Every entry point cites the
+ * reference interface it replaces (file:line in the LiVES tree).  INTEGRATION.md shows the
+ * reference-side bindings (the weed_layer_t shim of include/pe_weed.h and the dlopen'd effect
+ * plugin libpe_weed_plugin.so).
+ *
+ * Conventions (same as the reference):
+ *   - "boolean" results are int PE_TRUE / PE_FALSE; a frame is MUTATED IN PLACE by the layer ops
+ *     (palette, size, rowstrides, plane pointers, gamma / clamping fields are rewritten) and is
+ *     left untouched when PE_FALSE is returned (colourspace.c:13906-13927).
+ *   - widths are in PIXELS everywhere in this header (the weed shim converts macropixels).
+ *   - rowstride rule: ALIGN_CEIL(width * bytes_per_pixel, 32); chroma planes of 4:2:0 / 4:2:2
+ *     use rowstride[0] >> 1 (colourspace.c:11299-11357).
+ *   - all work is enqueued on the engine's CUDA stream; device-frame calls return without
+ *     synchronising, host-frame calls (pe_host_*) synchronise before returning.
+ *   - the library FAILS LOUDLY (PE_ERR_CUDA / PE_FALSE + pe_last_error) when no CUDA device is
+ *     usable; there is no CPU fallback.
+ */
+#ifndef PIXEL_ENGINE_H
+#define PIXEL_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_ABI_VERSION 1
+#define PE_TRUE 1
+#define PE_FALSE 0
+#define PE_MAXPLANES 4 /* WEED_MAXPPLANES */
+
+/* error codes of the int-returning calls (0 = ok) */
+enum {
+  PE_OK = 0,
+  PE_ERR_CUDA = 1,      /* CUDA runtime / driver failure (see pe_last_error) */
+  PE_ERR_ARG = 2,       /* NULL / out-of-range argument */
+  PE_ERR_PALETTE = 3,   /* palette (pair) not handled by this build */
+  PE_ERR_MEMORY = 4,    /* device allocation failed -> WEED_ERROR_MEMORY_ALLOCATION */
+  PE_ERR_SIZE = 5       /* frame sizes do not match */
+};
+
+/* palettes, clamping, subspace, gamma: numeric values of libweed/weed-palettes.h:43-183 */
+enum {
+  PE_PALETTE_NONE = 0,
+  PE_PALETTE_RGB24 = 1, PE_PALETTE_BGR24 = 2, PE_PALETTE_RGBA32 = 3, PE_PALETTE_BGRA32 = 4, PE_PALETTE_ARGB32 = 5,
+  PE_PALETTE_YUV420P = 512, PE_PALETTE_YVU420P = 513, PE_PALETTE_YUV422P = 522, PE_PALETTE_YUV444P = 544,
+  PE_PALETTE_YUVA4444P = 545, PE_PALETTE_UYVY = 564, PE_PALETTE_YUYV = 565, PE_PALETTE_YUV888 = 588,
+  PE_PALETTE_YUVA8888 = 589
+};
+enum { PE_YUV_CLAMPING_CLAMPED = 0, PE_YUV_CLAMPING_UNCLAMPED = 1 };
+enum { PE_YUV_SAMPLING_DEFAULT = 0, PE_YUV_SAMPLING_JPEG = 0, PE_YUV_SAMPLING_MPEG = 1 };
+enum { PE_YUV_SUBSPACE_YUV = 0, PE_YUV_SUBSPACE_YCBCR = 1, PE_YUV_SUBSPACE_BT709 = 2 };
+enum { PE_GAMMA_UNKNOWN = 0, PE_GAMMA_LINEAR = -1, PE_GAMMA_SRGB = 1, PE_GAMMA_BT709 = 2,
+       PE_GAMMA_MONITOR = 1024, PE_GAMMA_FILE = 1025, PE_GAMMA_VARIANT = 2048 }; /* colourspace.h:28-30 */
+enum { PE_QUALITY_LOW = 1, PE_QUALITY_MED = 2, PE_QUALITY_HIGH = 3 };             /* preferences.h:100-104 */
+enum { PE_INTERP_FAST = 0, PE_INTERP_NORMAL = 1, PE_INTERP_BEST = 2 };             /* LiVESInterpType */
+enum { PE_DIRECTION_REVERSE = -1, PE_DIRECTION_FORWARD = 1 };                      /* defs.h:427-442 */
+#define PE_LAYER_ALPHA_PREMULT 1                                                    /* colourspace.h:26 */
+
+typedef struct pe_engine pe_engine_t; /* one per (process, GPU): stream, tables and LUT cache in HBM */
+typedef struct pe_frame pe_frame_t;   /* a device-resident frame (the weed_layer_t of src/layers.c) */
+
+/* the `prefs` fields that change pixel results */
+typedef struct pe_config {
+  int device;          /* CUDA ordinal */
+  int pb_quality;      /* prefs->pb_quality; render/transcode force HIGH (colourspace.c:2103-2114) */
+  double screen_gamma; /* prefs->screen_gamma (colourspace.c:677) */
+  int apply_gamma;     /* prefs->apply_gamma (colourspace.c:12311) */
+  int alpha_post;      /* prefs->alpha_post (colourspace.c:12290) */
+  int ref_quirks;      /* 1: reproduce the deterministic slips of colourspace.c:3461,3544,3600 (parity default) */
+  void *stream;        /* optional cudaStream_t to run on (e.g. the caller's); NULL -> engine-owned stream */
+} pe_config_t;
+
+/* frame descriptor: the leaves of a layer that the path reads (libweed/weed-effects.h:269-277,350-375) */
+typedef struct pe_frame_desc {
+  int palette;
+  int width;  /* pixels */
+  int height;
+  int nplanes;
+  int rowstrides[PE_MAXPLANES];
+  void *planes[PE_MAXPLANES]; /* device pointers (pe_frame_t) or host pointers (pe_host_*) */
+  int yuv_clamping, yuv_sampling, yuv_subspace;
+  int gamma_type;
+  int flags; /* PE_LAYER_ALPHA_PREMULT */
+} pe_frame_desc_t;
+
+/* ---- engine ------------------------------------------------------------------------------ */
+
+void pe_config_default(pe_config_t *cfg);
+/* init_colour_engine (colourspace.c:1973): builds every table on the host and uploads it */
+int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out);
+void pe_engine_destroy(pe_engine_t *e);
+int pe_engine_sync(pe_engine_t *e);
+void *pe_engine_stream(pe_engine_t *e); /* cudaStream_t */
+const char *pe_last_error(void);
+/* kernels launched by this engine since creation (bench.py "gpu_launches") */
+long pe_engine_launch_count(pe_engine_t *e);
+/* CUDA-event timing on the engine stream (torch.cuda.Event only sees torch's stream) */
+int pe_timer_start(pe_engine_t *e);
+int pe_timer_stop_ms(pe_engine_t *e, float *ms); /* synchronises on the stop event */
+int pe_sm_count(pe_engine_t *e);
+
+/* ---- frames (create_empty_pixel_data colourspace.c:11434, weed_layer_* src/layers.c) ------- */
+
+/* plane geometry for a palette: fills nplanes / rowstrides / plane heights; returns total bytes when the
+ * planes are laid out contiguously (what pe_frame_create allocates) */
+size_t pe_frame_layout(int palette, int width, int height, int *nplanes, int rowstrides[PE_MAXPLANES],
+                       int plane_heights[PE_MAXPLANES]);
+int pe_frame_create(pe_engine_t *e, int palette, int width, int height, int yuv_clamping, int yuv_sampling,
+                    int yuv_subspace, int gamma_type, int black_fill, pe_frame_t **out);
+/* wrap caller-owned DEVICE memory (e.g. a torch tensor); never freed by the engine */
+int pe_frame_wrap(pe_engine_t *e, const pe_frame_desc_t *desc, pe_frame_t **out);
+void pe_frame_destroy(pe_frame_t *f);
+int pe_frame_get_desc(const pe_frame_t *f, pe_frame_desc_t *out);
+int pe_frame_set_gamma(pe_frame_t *f, int gamma_type);
+int pe_frame_set_flags(pe_frame_t *f, int flags);
+/* host <-> device (pinned host memory recommended); rowstrides may differ from the device ones */
+int pe_frame_upload(pe_engine_t *e, pe_frame_t *f, const void *const host_planes[PE_MAXPLANES],
+                    const int host_rowstrides[PE_MAXPLANES]);
+int pe_frame_download(pe_engine_t *e, const pe_frame_t *f, void *const host_planes[PE_MAXPLANES],
+                      const int host_rowstrides[PE_MAXPLANES]);
+/* weed_layer_copy (src/layers.c:840) deep copy on the device */
+int pe_frame_copy(pe_engine_t *e, const pe_frame_t *src, pe_frame_t **out);
+/* pinned host buffers for callers without their own allocator */
+void *pe_host_alloc(size_t bytes);
+void pe_host_free(void *p);
+
+/* ---- boundary B2: frame ops (same argument meaning as the reference functions) -------------- */
+
+/* boolean convert_layer_palette_full(weed_layer_t *, int outpl, int oclamping, int osampling,
+ *                                    int osubspace, int tgt_gamma)            colourspace.h:395, .c:12190 */
+int pe_convert_layer_palette_full(pe_engine_t *e, pe_frame_t *layer, int outpl, int oclamping, int osampling,
+                                  int osubspace, int tgt_gamma);
+/* boolean convert_layer_palette(weed_layer_t *, int outpl, int op_clamping)   colourspace.h:393, .c:13931 */
+int pe_convert_layer_palette(pe_engine_t *e, pe_frame_t *layer, int outpl, int op_clamping);
+/* boolean resize_layer_full(weed_layer_t *, int width, int height, LiVESInterpType interp, int opal_hint,
+ *                           int oclamp_hint, int osamp_hint, int osubs_hint, int tgt_gamma)
+ *                                                                             colourspace.h:409, .c:14759 */
+int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
+                         int oclamp_hint, int osamp_hint, int osubs_hint, int tgt_gamma);
+/* boolean resize_layer(weed_layer_t *, int w, int h, LiVESInterpType, int opal, int oclamp)
+ *                                                                             colourspace.h:413, .c:15331 */
+int pe_resize_layer(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
+                    int oclamp_hint);
+/* boolean letterbox_layer(weed_layer_t *, int nwidth, int nheight, int width, int height, LiVESInterpType,
+ *                         int tpal, int tclamp)                               colourspace.h:415, .c:15343 */
+int pe_letterbox_layer(pe_engine_t *e, pe_frame_t *layer, int nwidth, int nheight, int width, int height,
+                       int interp, int tpal, int tclamp);
+/* boolean gamma_convert_layer(int gamma_type, weed_layer_t *)                 colourspace.h:389, .c:14146 */
+int pe_gamma_convert_layer(pe_engine_t *e, int gamma_type, pe_frame_t *layer);
+/* boolean gamma_convert_sub_layer(int gamma_type, double fileg, weed_layer_t *, int x, int y, int width,
+ *                                 int height, boolean may_thread)             colourspace.h:391, .c:14069 */
+int pe_gamma_convert_sub_layer(pe_engine_t *e, int gamma_type, double fileg, pe_frame_t *layer, int x, int y,
+                               int width, int height, int may_thread);
+/* void alpha_premult(weed_layer_t *, int direction)                           colourspace.h:387, .c:11968 */
+void pe_alpha_premult(pe_engine_t *e, pe_frame_t *layer, int direction);
+/* uint8_t *create_gamma_lut8(double fileg, int gamma_from, int gamma_to)      colourspace.c:655 (host copy) */
+int pe_gamma_lut8(pe_engine_t *e, double fileg, int gamma_from, int gamma_to, uint8_t out[256]);
+
+/* ---- boundary B1 arithmetic: effect process functions on device frames ---------------------- */
+
+/* simple_blend.c common_process :58.  type 0 "chroma blend", 1 "luma overlay", 2 "luma underlay",
+ * 3 "negative luma overlay".  out may be in1 (in-place, effects-weed.c:2304-2314). */
+int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
+                       int blend_factor);
+/* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
+int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
+                      int blend_factor);
+/* gdk/compositor.c compositor_process :127 at scale 1 / offset 0: out = bgcol, then paint_pixel(:120) of every
+ * layer, last first (revz == WEED_FALSE, :189-197); alpha[i] is the scalar per-layer alpha */
+int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
+                     int nlayers, const int bgcol[3]);
+/* batches of independent frames (render-to-disk / multitrack): one launch, frames spread over the SMs */
+int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const pe_frame_t *const *in1,
+                             const pe_frame_t *const *in2, pe_frame_t *const *out, int blend_factor);
+
+/* ---- fused chain ---------------------------------------------------------------------------- */
+
+/* One kernel for: convert_layer_palette(fg -> RGBA32) ; letterbox_layer(fg, outer = bg size, inner = inner_w x
+ * inner_h, bilinear) ; compositor over bg with scalar alpha (paint_pixel) ; gamma_convert_layer(out, gamma_to).
+ * fg: YUV420P / YUV422P, bg and out: RGBA32 of the same size.  Bit-identical to calling the four ops above. */
+int pe_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_t *fg, const pe_frame_t *bg,
+                                          pe_frame_t *out, int inner_w, int inner_h, double alpha,
+                                          int gamma_from, int gamma_to);
+int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_t *const *fg,
+                                                const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
+                                                int inner_h, double alpha, int gamma_from, int gamma_to);
+
+/* ---- per-frame diagnostics (is_all_black_ish colourspace.c:2554, hash_cmp_layer :16044) ------ */
+
+typedef struct pe_frame_stats {
+  uint8_t min[4], max[4]; /* per byte position of a packed pixel (plane 0 for planar) */
+  uint32_t hist[256];     /* histogram of byte position 0..2 (colour bytes) of plane 0 */
+  uint64_t sum;           /* sum of all payload bytes of plane 0 */
+  int all_black_ish;      /* every colour byte < 20 (colourspace.c:2554-2594, exact == 0 mode) */
+} pe_frame_stats_t;
+int pe_frame_stats(pe_engine_t *e, const pe_frame_t *f, pe_frame_stats_t *out);
+
+/* ---- host-frame drop-ins: H2D -> device op -> D2H around the calls above --------------------- */
+
+/* allocator the caller wants new pixel buffers to come from (LiVES: create_empty_pixel_data / bigblocks) */
+typedef void *(*pe_host_alloc_f)(size_t bytes, void *user);
+typedef void (*pe_host_free_f)(void *ptr, void *user);
+typedef struct pe_host_allocator { pe_host_alloc_f alloc; pe_host_free_f free; void *user; } pe_host_allocator_t;
+
+/* layer->planes are HOST pointers; on success they are replaced (old ones released with the allocator) when the
+ * byte size changes, exactly where the reference swaps pixel_data (colourspace.c:13859-13900) */
+int pe_host_convert_layer_palette_full(pe_engine_t *e, pe_frame_desc_t *layer, int outpl, int oclamping,
+                                       int osampling, int osubspace, int tgt_gamma,
+                                       const pe_host_allocator_t *alloc);
+int pe_host_resize_layer(pe_engine_t *e, pe_frame_desc_t *layer, int width, int height, int interp, int opal_hint,
+                         int oclamp_hint, const pe_host_allocator_t *alloc);
+int pe_host_letterbox_layer(pe_engine_t *e, pe_frame_desc_t *layer, int nwidth, int nheight, int width, int height,
+                            int interp, int tpal, int tclamp, const pe_host_allocator_t *alloc);
+int pe_host_gamma_convert_layer(pe_engine_t *e, int gamma_type, pe_frame_desc_t *layer);
+/* the weed process_func body: host channels in, host channel out (what libpe_weed_plugin.so calls) */
+int pe_host_simple_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
+                         pe_frame_desc_t *out, int blend_factor);
+int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
+                        pe_frame_desc_t *out, int blend_factor);
+int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_desc_t *fg, const pe_frame_desc_t *bg,
+                                               pe_frame_desc_t *out, int inner_w, int inner_h, double alpha,
+                                               int gamma_from, int gamma_to);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXEL_ENGINE_H */

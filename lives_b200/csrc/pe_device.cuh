@@ -1,0 +1,50 @@
+// pe_device.cuh -- device-side helpers shared by the kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pe {
+
+// ---- vector loads / stores with streaming hints (data is touched once: keep it out of L1) ----
+
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+// plain (coherent) variants for in-place kernels, where .nc would be illegal
+__device__ __forceinline__ uint4 ld_u4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void st_stream_u4(void *p, const uint4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(void *p, const uint2 &v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// ---- byte helpers --------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+__device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// (int)(n / 3. + .5) for the chroma weights of colourspace.c:3465; n = u1 + (u2 >> 1) <= 765.
+// (2n + 3) / 6 with the division as a multiply-shift (exact for n < 21845, tests/test_host_logic.py)
+__device__ __forceinline__ int third_round(int n) { return ((2 * n + 3) * 43691) >> 18; }
+
+// grid-stride helpers
+__device__ __forceinline__ long long global_tid() { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ long long global_threads() { return (long long)gridDim.x * blockDim.x; }
+
+}  // namespace pe

@@ -1,0 +1,1442 @@
+// pe_engine.cu -- the C ABI of include/pixel_engine.h: engine, device frames, and the host-side logic of the
+// reference's layer ops (which converter runs, which tables / LUT it gets, how the layer's metadata changes),
+// restated from src/colourspace.c with file:line citations.  All pixel arithmetic lives in pe_kernels_*.cu.
+//
+// There is deliberately NO CPU fallback: every op either launches a kernel on the engine's stream or fails with
+// PE_FALSE / PE_ERR_* and a message in pe_last_error().
+#include "pe_engine.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+using namespace pe;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PE_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess)                                                                      \
+      return set_err(PE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+// for the boolean-returning layer ops
+#define PE_CUDA_B(call)                                                                            \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess) {                                                                    \
+      set_err(PE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return PE_FALSE;                                                                             \
+    }                                                                                              \
+  } while (0)
+
+extern "C" const char *pe_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------------------
+// palettes (libweed/weed-palettes.h, weed_palette_* helpers of libweed/weed-utils.c)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+inline bool pal_is_rgb(int p) { return p >= PE_PALETTE_RGB24 && p <= PE_PALETTE_ARGB32; }
+inline bool pal_is_yuv(int p) { return p >= 512 && p < 1024; }
+inline bool pal_has_alpha(int p) {
+  return p == PE_PALETTE_RGBA32 || p == PE_PALETTE_BGRA32 || p == PE_PALETTE_ARGB32 || p == PE_PALETTE_YUVA8888 ||
+         p == PE_PALETTE_YUVA4444P;
+}
+inline bool pal_known(int p) {
+  switch (p) {
+  case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_ARGB32:
+  case PE_PALETTE_YUV420P: case PE_PALETTE_YVU420P: case PE_PALETTE_YUV422P: case PE_PALETTE_YUV444P:
+  case PE_PALETTE_YUVA4444P: case PE_PALETTE_UYVY: case PE_PALETTE_YUYV: case PE_PALETTE_YUV888: case PE_PALETTE_YUVA8888:
+    return true;
+  }
+  return false;
+}
+inline int pal_nplanes(int p) {
+  switch (p) {
+  case PE_PALETTE_YUV420P: case PE_PALETTE_YVU420P: case PE_PALETTE_YUV422P: case PE_PALETTE_YUV444P: return 3;
+  case PE_PALETTE_YUVA4444P: return 4;
+  default: return 1;
+  }
+}
+inline bool pal_is_planar(int p) { return pal_nplanes(p) > 1; }
+// bytes per macropixel of plane 0
+inline int pal_psize(int p) {
+  switch (p) {
+  case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: case PE_PALETTE_YUV888: return 3;
+  case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_ARGB32: case PE_PALETTE_YUVA8888:
+  case PE_PALETTE_UYVY: case PE_PALETTE_YUYV: return 4;
+  default: return 1;
+  }
+}
+inline int pal_ppmp(int p) { return (p == PE_PALETTE_UYVY || p == PE_PALETTE_YUYV) ? 2 : 1; }
+
+inline RgbLayout rgb_layout(int p) {
+  switch (p) {
+  case PE_PALETTE_RGB24: return {0, 1, 2, -1, 3};
+  case PE_PALETTE_BGR24: return {2, 1, 0, -1, 3};
+  case PE_PALETTE_RGBA32: return {0, 1, 2, 3, 4};
+  case PE_PALETTE_BGRA32: return {2, 1, 0, 3, 4};
+  default: return {1, 2, 3, 0, 4};  // ARGB32
+  }
+}
+
+inline int align_ceil(int a, int b) { return (a + b - 1) / b * b; }
+
+// can_inline_gamma colourspace.c:12128
+bool can_inline_gamma(int inpl, int opal) {
+  if (pal_is_rgb(inpl) && pal_is_rgb(opal)) return true;
+  if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P || inpl == PE_PALETTE_YUV422P || inpl == PE_PALETTE_YUV444P) &&
+      pal_is_rgb(opal))
+    return true;
+  if (pal_is_rgb(opal)) return true;
+  if (opal == PE_PALETTE_UYVY || opal == PE_PALETTE_YUYV) {
+    if (pal_is_rgb(inpl) || inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// device block pool
+// ---------------------------------------------------------------------------------------------------------
+
+void *DevPool::get(size_t bytes, size_t *granted) {
+  const size_t kClass = 64 * 1024;
+  const size_t want = (bytes + kClass - 1) / kClass * kClass;
+  auto it = free_.find(want);
+  if (it != free_.end()) {
+    void *p = it->second;
+    free_.erase(it);
+    held_ -= want;
+    *granted = want;
+    return p;
+  }
+  void *p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    release_all();  // give cached blocks back to the driver and retry once
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  *granted = want;
+  return p;
+}
+
+void DevPool::put(void *p, size_t granted) {
+  if (!p) return;
+  const size_t kMaxHeld = (size_t)8 << 30;  // 8 GiB of recycled blocks at most (HBM is 180 GB)
+  if (held_ + granted > kMaxHeld) {
+    cudaFree(p);
+    return;
+  }
+  free_.emplace(granted, p);
+  held_ += granted;
+}
+
+void DevPool::release_all() {
+  for (auto &kv : free_) cudaFree(kv.second);
+  free_.clear();
+  held_ = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------
+
+extern "C" void pe_config_default(pe_config_t *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0;
+  cfg->pb_quality = PE_QUALITY_HIGH;  // render / transcode force HIGH (colourspace.c:2103-2114)
+  cfg->screen_gamma = 1.4;            // DEF_SCREEN_GAMMA
+  cfg->apply_gamma = 1;
+  cfg->alpha_post = 0;
+  cfg->ref_quirks = 1;
+  cfg->stream = nullptr;
+}
+
+extern "C" int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out) {
+  if (!out) return set_err(PE_ERR_ARG, "pe_engine_create: out is NULL");
+  *out = nullptr;
+  pe_config_t c;
+  if (cfg) c = *cfg; else pe_config_default(&c);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return set_err(PE_ERR_CUDA, "no usable CUDA device (%s); the pixel engine has no CPU fallback",
+                   ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+  }
+  if (c.device < 0 || c.device >= ndev) return set_err(PE_ERR_ARG, "device %d out of range (0..%d)", c.device, ndev - 1);
+  PE_CUDA(cudaSetDevice(c.device));
+  pe_engine *e = new pe_engine();
+  e->cfg = c;
+  e->device = c.device;
+  cudaDeviceProp prop;
+  PE_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  e->sm_count = prop.multiProcessorCount;
+  if (c.stream) {
+    e->stream = (cudaStream_t)c.stream;
+  } else {
+    PE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+  }
+  PE_CUDA(cudaEventCreate(&e->ev0));
+  PE_CUDA(cudaEventCreate(&e->ev1));
+  PE_CUDA(cudaEventCreateWithFlags(&e->args_ev, cudaEventDisableTiming));
+  // init_colour_engine (colourspace.c:1973): every (clamping, subspace) variant up front
+  for (int cl = 0; cl < 2; cl++) {
+    for (int hd = 0; hd < 2; hd++) {
+      build_conv_tables(cl == 0 ? PE_YUV_CLAMPING_CLAMPED : PE_YUV_CLAMPING_UNCLAMPED,
+                        hd ? PE_YUV_SUBSPACE_BT709 : PE_YUV_SUBSPACE_YCBCR, &e->conv_host[cl][hd]);
+      PE_CUDA(cudaMalloc(&e->conv_dev[cl][hd], sizeof(int32_t) * N_CONVTAB * 256));
+      PE_CUDA(cudaMemcpyAsync(e->conv_dev[cl][hd], e->conv_host[cl][hd].t, sizeof(int32_t) * N_CONVTAB * 256,
+                              cudaMemcpyHostToDevice, e->stream));
+    }
+  }
+  {
+    int32_t luma[3][256];
+    build_plugin_luma_tables(luma[0], luma[1], luma[2]);
+    PE_CUDA(cudaMalloc(&e->luma_dev, sizeof(luma)));
+    PE_CUDA(cudaMemcpyAsync(e->luma_dev, luma, sizeof(luma), cudaMemcpyHostToDevice, e->stream));
+    PE_CUDA(cudaStreamSynchronize(e->stream));  // `luma` is a stack buffer
+  }
+  PE_CUDA(cudaMalloc(&e->stats_dev, sizeof(DevStats)));
+  *out = e;
+  return PE_OK;
+}
+
+extern "C" void pe_engine_destroy(pe_engine_t *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (int cl = 0; cl < 2; cl++)
+    for (int hd = 0; hd < 2; hd++) cudaFree(e->conv_dev[cl][hd]);
+  for (int k = 0; k < 6; k++) cudaFree(e->premult_dev[k]);
+  cudaFree(e->luma_dev);
+  for (auto &kv : e->lut8) cudaFree(kv.second.dev);
+  for (auto &kv : e->lut16) cudaFree(kv.second);
+  for (auto &kv : e->over) cudaFree(kv.second);
+  for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); }
+  e->pool.release_all();
+  cudaFree(e->stats_dev);
+  cudaFree(e->args_dev);
+  if (e->args_pinned) cudaFreeHost(e->args_pinned);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaEventDestroy(e->args_ev);
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int pe_engine_sync(pe_engine_t *e) {
+  if (!e) return set_err(PE_ERR_ARG, "engine is NULL");
+  PE_CUDA(cudaStreamSynchronize(e->stream));
+  return PE_OK;
+}
+
+extern "C" void *pe_engine_stream(pe_engine_t *e) { return e ? (void *)e->stream : nullptr; }
+extern "C" long pe_engine_launch_count(pe_engine_t *e) { return e ? e->launches : 0; }
+extern "C" int pe_sm_count(pe_engine_t *e) { return e ? e->sm_count : 0; }
+
+extern "C" int pe_timer_start(pe_engine_t *e) {
+  if (!e) return set_err(PE_ERR_ARG, "engine is NULL");
+  PE_CUDA(cudaEventRecord(e->ev0, e->stream));
+  return PE_OK;
+}
+
+extern "C" int pe_timer_stop_ms(pe_engine_t *e, float *ms) {
+  if (!e || !ms) return set_err(PE_ERR_ARG, "NULL argument");
+  PE_CUDA(cudaEventRecord(e->ev1, e->stream));
+  PE_CUDA(cudaEventSynchronize(e->ev1));
+  PE_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return PE_OK;
+}
+
+// ---- engine-internal helpers ----------------------------------------------------------------------------
+
+namespace {
+
+inline const ConvTables &conv_host(pe_engine *e, int clamping, int subspace) {
+  return e->conv_host[clamping == PE_YUV_CLAMPING_CLAMPED ? 0 : 1][subspace == PE_YUV_SUBSPACE_BT709 ? 1 : 0];
+}
+inline DevConv dev_conv(pe_engine *e, int clamping, int subspace) {
+  const int cl = clamping == PE_YUV_CLAMPING_CLAMPED ? 0 : 1, hd = subspace == PE_YUV_SUBSPACE_BT709 ? 1 : 0;
+  const ConvTables &h = e->conv_host[cl][hd];
+  return DevConv{e->conv_dev[cl][hd], h.min_y, h.max_y, h.min_uv, h.max_uv};
+}
+
+// create_gamma_lut8 (colourspace.c:655).  Our cache is keyed by the ARGUMENTS; the reference keys its process-wide
+// cache by a value it mutates while building (:701,:721-733) which makes its result depend on call history --
+// DESIGN.md quirk table, X.
+Lut8Entry *get_lut8(pe_engine *e, double fileg, int from, int to) {
+  GammaKey k{fileg, from, to};
+  auto it = e->lut8.find(k);
+  if (it != e->lut8.end()) return &it->second;
+  Lut8Entry ent;
+  if (!build_gamma_lut8(fileg, from, to, e->cfg.screen_gamma, ent.host)) return nullptr;
+  if (cudaMalloc(&ent.dev, 256) != cudaSuccess) return nullptr;
+  auto ins = e->lut8.emplace(k, ent).first;
+  // source is the map node (stable address), so the async copy may outlive this call
+  if (cudaMemcpyAsync(ins->second.dev, ins->second.host, 256, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return nullptr;
+  return &ins->second;
+}
+
+uint16_t *get_lut16(pe_engine *e, double fileg, int from, int to) {
+  GammaKey k{fileg, from, to};
+  auto it = e->lut16.find(k);
+  if (it != e->lut16.end()) return it->second;
+  std::vector<uint16_t> host(65536);
+  if (!build_gamma_lut16(fileg, from, to, e->cfg.screen_gamma, host.data())) return nullptr;
+  uint16_t *dev = nullptr;
+  if (cudaMalloc(&dev, 65536 * 2) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(dev, host.data(), 65536 * 2, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  e->lut16.emplace(k, dev);
+  return dev;
+}
+
+uint8_t *get_premult(pe_engine *e, int which) {
+  if (e->premult_dev[which]) return e->premult_dev[which];
+  std::vector<uint8_t> host(65536);
+  build_premult_table(which, host.data());
+  uint8_t *dev = nullptr;
+  if (cudaMalloc(&dev, 65536) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(dev, host.data(), 65536, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  e->premult_dev[which] = dev;
+  return dev;
+}
+
+// 64 KB [bg][fg] table of paint_pixel (compositor.c:120) for one scalar alpha, optionally composed with a gamma LUT
+uint8_t *get_over_table(pe_engine *e, double alpha, const uint8_t *lut_dev) {
+  OverKey k{alpha, lut_dev};
+  auto it = e->over.find(k);
+  if (it != e->over.end()) return it->second;
+  uint8_t *dev = nullptr;
+  if (cudaMalloc(&dev, 65536) != cudaSuccess) return nullptr;
+  if (launch_over_table(e->L(), alpha, lut_dev, dev) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  e->over.emplace(k, dev);
+  return dev;
+}
+
+DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
+  FilterKey k{src_n, dst_n, bits};
+  auto it = e->filters.find(k);
+  if (it != e->filters.end()) return &it->second;
+  DevFilterEntry ent;
+  if (!build_resize_filter(src_n, dst_n, bits, &ent.host)) return nullptr;
+  int32_t *first = nullptr;
+  int16_t *coef = nullptr;
+  if (cudaMalloc(&first, sizeof(int32_t) * dst_n) != cudaSuccess) return nullptr;
+  if (cudaMalloc(&coef, sizeof(int16_t) * (size_t)dst_n * ent.host.taps) != cudaSuccess) { cudaFree(first); return nullptr; }
+  auto ins = e->filters.emplace(k, std::move(ent)).first;
+  DevFilterEntry &r = ins->second;
+  r.dev = DevFilter{first, coef, r.host.taps};
+  if (cudaMemcpyAsync(first, r.host.first.data(), sizeof(int32_t) * dst_n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaMemcpyAsync(coef, r.host.coef.data(), sizeof(int16_t) * (size_t)dst_n * r.host.taps, cudaMemcpyHostToDevice,
+                      e->stream) != cudaSuccess)
+    return nullptr;
+  return &r;
+}
+
+// upload a small per-launch argument array (BlendFrame[] / FusedArgs[]) through a pinned staging buffer
+void *upload_args(pe_engine *e, const void *src, size_t bytes) {
+  if (bytes > e->args_cap) {
+    if (e->args_dev) { cudaStreamSynchronize(e->stream); cudaFree(e->args_dev); }
+    size_t cap = bytes < 4096 ? 4096 : bytes * 2;
+    if (cudaMalloc(&e->args_dev, cap) != cudaSuccess) { e->args_dev = nullptr; e->args_cap = 0; return nullptr; }
+    e->args_cap = cap;
+  }
+  if (bytes > e->args_pinned_cap) {
+    if (e->args_pinned) { cudaEventSynchronize(e->args_ev); cudaFreeHost(e->args_pinned); }
+    size_t cap = bytes < 4096 ? 4096 : bytes * 2;
+    if (cudaMallocHost(&e->args_pinned, cap) != cudaSuccess) { e->args_pinned = nullptr; e->args_pinned_cap = 0; return nullptr; }
+    e->args_pinned_cap = cap;
+  } else {
+    cudaEventSynchronize(e->args_ev);  // previous upload out of the staging buffer has finished
+  }
+  memcpy(e->args_pinned, src, bytes);
+  // kernels of earlier launches that read args_dev are ordered before this copy on the same stream
+  if (cudaMemcpyAsync(e->args_dev, e->args_pinned, bytes, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return nullptr;
+  cudaEventRecord(e->args_ev, e->stream);
+  return e->args_dev;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// frames
+// ---------------------------------------------------------------------------------------------------------
+
+// calc_rowstrides colourspace.c:11252-11365 with RS_ALIGN_DEF = 32 (colourspace.h:45)
+extern "C" size_t pe_frame_layout(int palette, int width, int height, int *nplanes, int rowstrides[PE_MAXPLANES],
+                                  int plane_heights[PE_MAXPLANES]) {
+  if (!pal_known(palette) || width <= 0 || height <= 0) return 0;
+  const int np = pal_nplanes(palette);
+  int rs[PE_MAXPLANES] = {0, 0, 0, 0}, ph[PE_MAXPLANES] = {0, 0, 0, 0};
+  rs[0] = align_ceil((width / pal_ppmp(palette)) * pal_psize(palette), 32);
+  ph[0] = height;
+  switch (palette) {
+  case PE_PALETTE_YUV420P: case PE_PALETTE_YVU420P:
+    rs[1] = rs[2] = rs[0] >> 1; ph[1] = ph[2] = (height + 1) >> 1; break;
+  case PE_PALETTE_YUV422P:
+    rs[1] = rs[2] = rs[0] >> 1; ph[1] = ph[2] = height; break;
+  case PE_PALETTE_YUV444P:
+    rs[1] = rs[2] = rs[0]; ph[1] = ph[2] = height; break;
+  case PE_PALETTE_YUVA4444P:
+    rs[1] = rs[2] = rs[3] = rs[0]; ph[1] = ph[2] = ph[3] = height; break;
+  default: break;
+  }
+  size_t total = 0;
+  for (int p = 0; p < np; p++) total += ((size_t)rs[p] * ph[p] + 255) / 256 * 256;  // planes start 256-byte aligned
+  if (nplanes) *nplanes = np;
+  for (int p = 0; p < PE_MAXPLANES; p++) {
+    if (rowstrides) rowstrides[p] = rs[p];
+    if (plane_heights) plane_heights[p] = ph[p];
+  }
+  return total;
+}
+
+namespace {
+
+// allocate pixel memory for f->d.{palette,width,height}; fills nplanes / rowstrides / planes
+int frame_alloc(pe_engine *e, pe_frame *f) {
+  int np = 0;
+  const size_t bytes = pe_frame_layout(f->d.palette, f->d.width, f->d.height, &np, f->d.rowstrides, f->plane_heights);
+  if (!bytes) return set_err(PE_ERR_ARG, "bad frame geometry: palette %d, %d x %d", f->d.palette, f->d.width, f->d.height);
+  // + 16 guard bytes: vector tails and the one-past-row chroma read of the last plane stay inside the block
+  f->base = e->pool.get(bytes + 16, &f->granted);
+  if (!f->base) return set_err(PE_ERR_MEMORY, "device allocation of %zu bytes failed", bytes);
+  f->d.nplanes = np;
+  size_t off = 0;
+  for (int p = 0; p < PE_MAXPLANES; p++) {
+    if (p < np) {
+      f->d.planes[p] = (uint8_t *)f->base + off;
+      off += ((size_t)f->d.rowstrides[p] * f->plane_heights[p] + 255) / 256 * 256;
+    } else {
+      f->d.planes[p] = nullptr;
+    }
+  }
+  return PE_OK;
+}
+
+void frame_release_pixels(pe_frame *f) {
+  if (f->base) f->e->pool.put(f->base, f->granted);
+  f->base = nullptr;
+  f->granted = 0;
+  for (int p = 0; p < PE_MAXPLANES; p++) f->d.planes[p] = nullptr;
+}
+
+// black per create_empty_pixel_data (colourspace.c:11448-11449, :11213 blank_frame): RGB 0 with opaque alpha,
+// YUV 16 (clamped) or 0 / 128 / 128
+int frame_fill_black(pe_engine *e, pe_frame *f) {
+  const int pal = f->d.palette;
+  const uint8_t y0 = (pal_is_yuv(pal) && f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED) ? 16 : 0;
+  if (pal_is_planar(pal)) {
+    for (int p = 0; p < f->d.nplanes; p++) {
+      const uint8_t v = p == 0 ? y0 : p == 3 ? 255 : 128;
+      PE_CUDA(cudaMemsetAsync(f->d.planes[p], v, (size_t)f->d.rowstrides[p] * f->plane_heights[p], e->stream));
+    }
+    return PE_OK;
+  }
+  uint32_t px;
+  switch (pal) {
+  case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: px = 0; break;
+  case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: px = 0xFF000000u; break;
+  case PE_PALETTE_ARGB32: px = 0x000000FFu; break;
+  case PE_PALETTE_YUV888: px = y0 | (128u << 8) | (128u << 16); break;
+  case PE_PALETTE_YUVA8888: px = y0 | (128u << 8) | (128u << 16) | 0xFF000000u; break;
+  case PE_PALETTE_UYVY: px = 128u | ((uint32_t)y0 << 8) | (128u << 16) | ((uint32_t)y0 << 24); break;
+  default: px = y0 | (128u << 8) | ((uint32_t)y0 << 16) | (128u << 24); break;  // YUYV
+  }
+  PE_CUDA(launch_fill(e->L(), Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, f->d.width / pal_ppmp(pal), f->d.height,
+                      pal_psize(pal), px));
+  return PE_OK;
+}
+
+inline int chroma_height(const pe_frame *f) { return f->plane_heights[1]; }
+
+// replace the pixel memory and geometry of `f` by those of `n` (which is consumed)
+void frame_take(pe_frame *f, pe_frame *n) {
+  frame_release_pixels(f);
+  f->base = n->base;
+  f->granted = n->granted;
+  f->d.palette = n->d.palette;
+  f->d.width = n->d.width;
+  f->d.height = n->d.height;
+  f->d.nplanes = n->d.nplanes;
+  for (int p = 0; p < PE_MAXPLANES; p++) {
+    f->d.rowstrides[p] = n->d.rowstrides[p];
+    f->d.planes[p] = n->d.planes[p];
+    f->plane_heights[p] = n->plane_heights[p];
+  }
+  n->base = nullptr;
+}
+
+}  // namespace
+
+// fill: 0 leave the block as it is (internal: every payload byte is about to be overwritten), 1 zero, 2 black
+static int frame_create_impl(pe_engine_t *e, int palette, int width, int height, int yuv_clamping, int yuv_sampling,
+                             int yuv_subspace, int gamma_type, int fill, pe_frame_t **out) {
+  if (!e || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (!pal_known(palette)) return set_err(PE_ERR_PALETTE, "palette %d is not handled by this build", palette);
+  if (palette == PE_PALETTE_YUV420P || palette == PE_PALETTE_YVU420P) {  // colourspace.c:11603-11604
+    width = (width >> 1) << 1;
+    height = (height >> 1) << 1;
+  }
+  if (width <= 0 || height <= 0) return set_err(PE_ERR_ARG, "bad size %d x %d", width, height);
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  pe_frame *f = new pe_frame();
+  f->e = e;
+  f->d.palette = palette; f->d.width = width; f->d.height = height;
+  f->d.yuv_clamping = yuv_clamping; f->d.yuv_sampling = yuv_sampling; f->d.yuv_subspace = yuv_subspace;
+  f->d.gamma_type = gamma_type; f->d.flags = 0;
+  int rc = frame_alloc(e, f);
+  if (rc != PE_OK) { delete f; return rc; }
+  if (fill == 2) rc = frame_fill_black(e, f);
+  else if (fill == 1 && cudaMemsetAsync(f->base, 0, f->granted, e->stream) != cudaSuccess) rc = set_err(PE_ERR_CUDA, "memset failed");
+  if (rc != PE_OK) { frame_release_pixels(f); delete f; return rc; }
+  *out = f;
+  return PE_OK;
+}
+
+extern "C" int pe_frame_create(pe_engine_t *e, int palette, int width, int height, int yuv_clamping, int yuv_sampling,
+                               int yuv_subspace, int gamma_type, int black_fill, pe_frame_t **out) {
+  return frame_create_impl(e, palette, width, height, yuv_clamping, yuv_sampling, yuv_subspace, gamma_type, black_fill ? 2 : 1, out);
+}
+
+extern "C" int pe_frame_wrap(pe_engine_t *e, const pe_frame_desc_t *desc, pe_frame_t **out) {
+  if (!e || !desc || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (!pal_known(desc->palette)) return set_err(PE_ERR_PALETTE, "palette %d is not handled by this build", desc->palette);
+  if (desc->width <= 0 || desc->height <= 0) return set_err(PE_ERR_ARG, "bad size %d x %d", desc->width, desc->height);
+  const int np = pal_nplanes(desc->palette);
+  for (int p = 0; p < np; p++)
+    if (!desc->planes[p] || desc->rowstrides[p] <= 0) return set_err(PE_ERR_ARG, "plane %d missing", p);
+  pe_frame *f = new pe_frame();
+  f->e = e;
+  f->d = *desc;
+  f->d.nplanes = np;
+  int rs[PE_MAXPLANES];
+  pe_frame_layout(desc->palette, desc->width, desc->height, nullptr, rs, f->plane_heights);
+  *out = f;
+  return PE_OK;
+}
+
+extern "C" void pe_frame_destroy(pe_frame_t *f) {
+  if (!f) return;
+  if (f->e) {
+    std::lock_guard<std::mutex> lk(f->e->mu);
+    frame_release_pixels(f);
+  }
+  delete f;
+}
+
+extern "C" int pe_frame_get_desc(const pe_frame_t *f, pe_frame_desc_t *out) {
+  if (!f || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  *out = f->d;
+  return PE_OK;
+}
+
+extern "C" int pe_frame_set_gamma(pe_frame_t *f, int gamma_type) {
+  if (!f) return set_err(PE_ERR_ARG, "NULL argument");
+  f->d.gamma_type = gamma_type;
+  return PE_OK;
+}
+
+extern "C" int pe_frame_set_flags(pe_frame_t *f, int flags) {
+  if (!f) return set_err(PE_ERR_ARG, "NULL argument");
+  f->d.flags = flags;
+  return PE_OK;
+}
+
+namespace {
+// payload bytes of one row of plane p
+inline int plane_row_bytes(const pe_frame_desc_t &d, int p) {
+  if (p == 0) return (d.width / pal_ppmp(d.palette)) * pal_psize(d.palette);
+  switch (d.palette) {
+  case PE_PALETTE_YUV420P: case PE_PALETTE_YVU420P: case PE_PALETTE_YUV422P: return d.width >> 1;
+  default: return d.width;
+  }
+}
+}  // namespace
+
+extern "C" int pe_frame_upload(pe_engine_t *e, pe_frame_t *f, const void *const host_planes[PE_MAXPLANES],
+                               const int host_rowstrides[PE_MAXPLANES]) {
+  if (!e || !f || !host_planes) return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  for (int p = 0; p < f->d.nplanes; p++) {
+    if (!host_planes[p]) return set_err(PE_ERR_ARG, "host plane %d is NULL", p);
+    const int hrs = host_rowstrides ? host_rowstrides[p] : f->d.rowstrides[p];
+    // whole strides when they agree (row padding travels too: the reference's 4:2:x converters read one byte
+    // past the chroma row, colourspace.c:3508), else the payload bytes
+    int wbytes = plane_row_bytes(f->d, p);
+    if (hrs == f->d.rowstrides[p]) wbytes = hrs;
+    PE_CUDA(cudaMemcpy2DAsync(f->d.planes[p], f->d.rowstrides[p], host_planes[p], hrs, wbytes, f->plane_heights[p],
+                              cudaMemcpyHostToDevice, e->stream));
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_frame_download(pe_engine_t *e, const pe_frame_t *f, void *const host_planes[PE_MAXPLANES],
+                                 const int host_rowstrides[PE_MAXPLANES]) {
+  if (!e || !f || !host_planes) return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  for (int p = 0; p < f->d.nplanes; p++) {
+    if (!host_planes[p]) return set_err(PE_ERR_ARG, "host plane %d is NULL", p);
+    const int hrs = host_rowstrides ? host_rowstrides[p] : f->d.rowstrides[p];
+    PE_CUDA(cudaMemcpy2DAsync(host_planes[p], hrs, f->d.planes[p], f->d.rowstrides[p], plane_row_bytes(f->d, p),
+                              f->plane_heights[p], cudaMemcpyDeviceToHost, e->stream));
+  }
+  PE_CUDA(cudaStreamSynchronize(e->stream));
+  return PE_OK;
+}
+
+extern "C" int pe_frame_copy(pe_engine_t *e, const pe_frame_t *src, pe_frame_t **out) {
+  if (!e || !src || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  pe_frame *f = new pe_frame();
+  f->e = e;
+  f->d = src->d;
+  int rc = frame_alloc(e, f);
+  if (rc != PE_OK) { delete f; return rc; }
+  for (int p = 0; p < f->d.nplanes; p++) {
+    const int rb = src->d.rowstrides[p] < f->d.rowstrides[p] ? src->d.rowstrides[p] : f->d.rowstrides[p];
+    cudaError_t ce = launch_copy2d(e->L(), (const uint8_t *)src->d.planes[p], src->d.rowstrides[p], (uint8_t *)f->d.planes[p],
+                                   f->d.rowstrides[p], rb, f->plane_heights[p], 0, 0);
+    if (ce != cudaSuccess) { frame_release_pixels(f); delete f; return set_err(PE_ERR_CUDA, "copy failed: %s", cudaGetErrorString(ce)); }
+  }
+  *out = f;
+  return PE_OK;
+}
+
+extern "C" void *pe_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void pe_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------------------
+// gamma (colourspace.c:14034-14160)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+int gamma_convert_sub_layer_locked(pe_engine *e, int gamma_type, double fileg, pe_frame *f, int x, int y, int width, int height) {
+  if (!e->cfg.apply_gamma) return PE_TRUE;                      // :14071
+  if (!pal_is_rgb(f->d.palette)) return PE_FALSE;               // :14076 "dont know how to convert in yuv space"
+  const int lgamma = f->d.gamma_type;
+  if (gamma_type == lgamma && fileg == 1.0) return PE_TRUE;     // :14080
+  Lut8Entry *lut = gamma_type == PE_GAMMA_VARIANT ? get_lut8(e, fileg, lgamma, gamma_type) : get_lut8(e, 1.0, lgamma, gamma_type);
+  if (!lut) return PE_TRUE;                                     // :14103 (no-op pairs return NULL)
+  // the rectangle: the reference's band arithmetic (:14096-14124) is thread-count dependent; contract = whole rect
+  if (x < 0 || y < 0 || width <= 0 || height <= 0 || x + width > f->d.width || y + height > f->d.height) {
+    set_err(PE_ERR_ARG, "gamma rectangle %d,%d %dx%d outside the %dx%d frame", x, y, width, height, f->d.width, f->d.height);
+    return PE_FALSE;
+  }
+  PE_CUDA_B(launch_lut8_rect(e->L(), Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, rgb_layout(f->d.palette), x, y, width,
+                             height, lut->dev));
+  if (gamma_type != PE_GAMMA_VARIANT) f->d.gamma_type = gamma_type;  // :14139
+  return PE_TRUE;
+}
+
+int gamma_convert_layer_locked(pe_engine *e, int gamma_type, pe_frame *f) {
+  if (!f || !f->d.planes[0] || !f->d.width || !f->d.height) return PE_FALSE;  // :14146-14156
+  return gamma_convert_sub_layer_locked(e, gamma_type, 1.0, f, 0, 0, f->d.width, f->d.height);
+}
+
+}  // namespace
+
+extern "C" int pe_gamma_convert_sub_layer(pe_engine_t *e, int gamma_type, double fileg, pe_frame_t *layer, int x, int y,
+                                          int width, int height, int may_thread) {
+  (void)may_thread;  // row bands are the CUDA grid's business
+  if (!e || !layer) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA_B(cudaSetDevice(e->device));
+  return gamma_convert_sub_layer_locked(e, gamma_type, fileg, layer, x, y, width, height);
+}
+
+extern "C" int pe_gamma_convert_layer(pe_engine_t *e, int gamma_type, pe_frame_t *layer) {
+  if (!e || !layer) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA_B(cudaSetDevice(e->device));
+  return gamma_convert_layer_locked(e, gamma_type, layer);
+}
+
+extern "C" int pe_gamma_lut8(pe_engine_t *e, double fileg, int gamma_from, int gamma_to, uint8_t out[256]) {
+  if (!e || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  if (!build_gamma_lut8(fileg, gamma_from, gamma_to, e->cfg.screen_gamma, out))
+    return set_err(PE_ERR_ARG, "no LUT for this pair (create_gamma_lut8 returns NULL, colourspace.c:662)");
+  return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// alpha premultiply (colourspace.c:11968-12106)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+void alpha_premult_locked(pe_engine *e, pe_frame *f, int direction) {
+  const int pal = f->d.palette;
+  int coffs, aoffs;
+  switch (pal) {
+  case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_YUVA8888: coffs = 0; aoffs = 3; break;
+  case PE_PALETTE_ARGB32: coffs = 1; aoffs = 0; break;
+  default: return;  // YUVA4444P: not handled by this build (planar alpha); other palettes: no-op as in the reference
+  }
+  const bool clamped_yuva = (pal == PE_PALETTE_YUVA8888 && f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED);
+  const uint8_t *t0, *t1, *t2;
+  int quirk = 0;
+  if (!clamped_yuva) {
+    t0 = t1 = t2 = get_premult(e, direction == PE_DIRECTION_REVERSE ? 0 : 1);  // REVERSE -> unal, FORWARD -> al (:12058-12074)
+  } else if (direction == PE_DIRECTION_REVERSE) {
+    t0 = get_premult(e, 2); t1 = t2 = get_premult(e, 4);  // unalcy / unalcuv
+  } else {
+    t0 = get_premult(e, 3); t1 = t2 = get_premult(e, 5);  // alcy / alcuv
+    quirk = 1;  // U and V are looked up with the (already rewritten) Y byte, :12093-12094
+  }
+  if (!t0 || !t1) { set_err(PE_ERR_MEMORY, "premultiply tables could not be built"); return; }
+  cudaError_t ce = launch_premult(e->L(), Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, f->d.width, f->d.height, coffs, 3,
+                                  aoffs, t0, t1, t2, quirk);
+  if (ce != cudaSuccess) { set_err(PE_ERR_CUDA, "premult launch failed: %s", cudaGetErrorString(ce)); return; }
+  if (direction == PE_DIRECTION_FORWARD) f->d.flags |= PE_LAYER_ALPHA_PREMULT;  // :12100-12104
+  else f->d.flags &= ~PE_LAYER_ALPHA_PREMULT;
+}
+
+}  // namespace
+
+extern "C" void pe_alpha_premult(pe_engine_t *e, pe_frame_t *layer, int direction) {
+  if (!e || !layer || !layer->d.planes[0]) return;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) return;
+  alpha_premult_locked(e, layer, direction);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// convert_layer_palette_full (colourspace.c:12190-13928)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osampling, int osubspace, int tgt_gamma);
+
+inline int convert_simple_locked(pe_engine *e, pe_frame *f, int outpl, int op_clamping) {  // convert_layer_palette :13931
+  return convert_locked(e, f, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN);
+}
+
+Planes planes_of(const pe_frame *f, bool swap_uv) {
+  Planes P;
+  P.y = (const uint8_t *)f->d.planes[0];
+  P.u = (const uint8_t *)f->d.planes[swap_uv ? 2 : 1];
+  P.v = (const uint8_t *)f->d.planes[swap_uv ? 1 : 2];
+  P.rs_y = f->d.rowstrides[0];
+  P.rs_u = f->d.rowstrides[swap_uv ? 2 : 1];
+  P.rs_v = f->d.rowstrides[swap_uv ? 1 : 2];
+  P.cw = f->d.width >> 1;
+  P.ch = f->plane_heights[1];
+  return P;
+}
+
+int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osampling, int osubspace, int tgt_gamma) {
+  if (!f || !f->d.planes[0]) return PE_FALSE;  // :12206
+  if (!pal_known(outpl)) { set_err(PE_ERR_PALETTE, "output palette %d is not handled by this build", outpl); return PE_FALSE; }
+  int inpl = f->d.palette;
+  int isampling = f->d.yuv_sampling, iclamping = f->d.yuv_clamping, isubspace = f->d.yuv_subspace;
+
+  if (pal_is_yuv(inpl) && pal_is_yuv(outpl) && (iclamping != oclamping || isubspace != osubspace)) {  // :12241
+    if (isubspace == osubspace) {
+      set_err(PE_ERR_PALETTE, "YUV clamping switch (switch_yuv_clamping_and_subspace, colourspace.c:10929) is not in this build");
+      return PE_FALSE;
+    }
+    // different subspace: go through RGB(A) first (:12249-12262)
+    if (!convert_simple_locked(e, f, pal_has_alpha(inpl) ? PE_PALETTE_RGBA32 : PE_PALETTE_RGB24, 0)) return PE_FALSE;
+    inpl = f->d.palette;
+    isubspace = osubspace; isampling = osampling; iclamping = oclamping;
+  }
+  if (inpl == outpl) return PE_TRUE;  // :12265-12288 (sampling switches "not yet written" in the reference either)
+
+  // premultiplied-alpha bookkeeping (:12290-12306)
+  int flags = f->d.flags;
+  if (e->cfg.alpha_post) {
+    if ((flags & PE_LAYER_ALPHA_PREMULT) && pal_has_alpha(inpl) && !pal_has_alpha(outpl)) {
+      alpha_premult_locked(e, f, PE_DIRECTION_REVERSE);
+      flags = f->d.flags;
+    }
+  } else if (!pal_has_alpha(inpl) && pal_has_alpha(outpl)) {
+    flags |= PE_LAYER_ALPHA_PREMULT;
+  }
+  if (pal_has_alpha(inpl) && !pal_has_alpha(outpl) && (flags & PE_LAYER_ALPHA_PREMULT)) flags &= ~PE_LAYER_ALPHA_PREMULT;
+  f->d.flags = flags;
+
+  // gamma decision (:12311-12332)
+  int gamma_type = PE_GAMMA_UNKNOWN, new_gamma_type = PE_GAMMA_UNKNOWN;
+  if (e->cfg.apply_gamma) {
+    gamma_type = f->d.gamma_type;
+    if (gamma_type != PE_GAMMA_UNKNOWN) {
+      if (tgt_gamma != PE_GAMMA_UNKNOWN) new_gamma_type = tgt_gamma;
+      else if (pal_is_rgb(inpl) && !pal_is_rgb(outpl))
+        new_gamma_type = osubspace == PE_YUV_SUBSPACE_BT709 ? PE_GAMMA_BT709 : PE_GAMMA_SRGB;
+      else new_gamma_type = gamma_type;
+      if (pal_is_rgb(inpl) && !pal_is_rgb(outpl) && !can_inline_gamma(inpl, outpl)) {
+        gamma_convert_layer_locked(e, new_gamma_type, f);
+        gamma_type = new_gamma_type = f->d.gamma_type;
+      }
+    }
+  }
+
+  const int width = f->d.width, height = f->d.height;
+  const Launch L = e->L();
+
+  // destination frame
+  pe_frame n;
+  n.e = e;
+  n.d.palette = outpl; n.d.width = width; n.d.height = height;
+  bool inplace = false;
+  cudaError_t ce = cudaSuccess;
+
+  if (pal_is_rgb(inpl) && pal_is_rgb(outpl)) {
+    // all RGB <-> RGB conversions (:12370-12556): byte permutation + alpha add / drop, optional LUT8
+    const uint8_t *lut = nullptr;
+    if (gamma_type != new_gamma_type) {
+      Lut8Entry *le = get_lut8(e, 1.0, gamma_type, new_gamma_type);
+      lut = le ? le->dev : nullptr;
+    }
+    const RgbLayout li = rgb_layout(inpl), lo = rgb_layout(outpl);
+    inplace = (li.psize == lo.psize);  // pconv_can_inplace :12148
+    if (!inplace && frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    Img dst = inplace ? Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]} : Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]};
+    ce = launch_rgb_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, dst, width, height, li, lo, lut);
+  } else if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P || inpl == PE_PALETTE_YUV422P) && pal_is_rgb(outpl)) {
+    // convert_yuv420p_to_{rgb,bgr,argb}_frame (:13521-13560, :13648-13685)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    YuvToRgbArgs A;
+    A.src = planes_of(f, inpl == PE_PALETTE_YVU420P);  // swap_chroma_planes :12354
+    A.dst = Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]};
+    A.width = width; A.height = height;
+    A.out = rgb_layout(outpl);
+    A.is_422 = inpl == PE_PALETTE_YUV422P;
+    A.clamped = iclamping == PE_YUV_CLAMPING_CLAMPED;
+    // only the RGB-order converter has the PB_QUALITY_LOW chroma shortcut (:3470; none at :4090, :4700)
+    A.low_quality = (e->cfg.pb_quality == PE_QUALITY_LOW && (outpl == PE_PALETTE_RGB24 || outpl == PE_PALETTE_RGBA32));
+    A.quirks = e->cfg.ref_quirks;
+    A.conv = dev_conv(e, iclamping, isubspace);
+    A.lut16 = nullptr;
+    if (new_gamma_type != PE_GAMMA_UNKNOWN) A.lut16 = get_lut16(e, 1.0, gamma_type, new_gamma_type);  // `if (tgt_gamma)` :3273
+    ce = launch_yuv_planar_to_rgb(L, A);
+  } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) && pal_is_rgb(outpl)) {
+    // convert_{uyvy,yuyv}_to_*_frame (:13147-13190, :13244-13290).  Table choice as the reference makes it:
+    // uyvy->RGB24 passes the layer's subspace, uyvy->RGBA32 passes its SAMPLING in that slot (:13160), every other
+    // variant selects YCbCr itself.
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    int sub = PE_YUV_SUBSPACE_YCBCR;
+    if (inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_RGB24) sub = isubspace;
+    else if (inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_RGBA32) sub = isampling;
+    ce = launch_packed422_to_rgb(L, inpl == PE_PALETTE_UYVY ? 0 : 1, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
+                                 Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width >> 1, height, rgb_layout(outpl),
+                                 dev_conv(e, iclamping, sub));
+  } else if ((inpl == PE_PALETTE_YUV888 || inpl == PE_PALETTE_YUVA8888) && pal_is_rgb(outpl)) {
+    // convert_yuv888_to_*_frame / convert_yuva8888_to_*_frame: the dispatcher passes isampling where the converter
+    // expects the subspace (:13359-13385, :13453-13478) -- replicated
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    ce = launch_yuv888_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
+                              Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height, inpl == PE_PALETTE_YUVA8888,
+                              rgb_layout(outpl), dev_conv(e, iclamping, isampling));
+  } else if (pal_is_rgb(inpl) && (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888)) {
+    // convert_{rgb,bgr,argb}_to_yuv_frame: always the YCbCr tables (:5710), clamping = oclamping
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    if (width & 1) {  // the converter drops an odd last column (:5750): leave it defined (black)
+      n.d.yuv_clamping = oclamping;
+      if (frame_fill_black(e, &n) != PE_OK) { frame_release_pixels(&n); return PE_FALSE; }
+    }
+    ce = launch_rgb_to_yuv888(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
+                              Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height, rgb_layout(inpl),
+                              outpl == PE_PALETTE_YUVA8888, dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
+  } else {
+    set_err(PE_ERR_PALETTE, "palette conversion %d -> %d is not handled by this build", inpl, outpl);
+    return PE_FALSE;  // memfail: the layer is left as it was
+  }
+  if (ce != cudaSuccess) {
+    set_err(PE_ERR_CUDA, "conversion kernel launch failed: %s", cudaGetErrorString(ce));
+    if (!inplace) frame_release_pixels(&n);
+    return PE_FALSE;
+  }
+  if (inplace) f->d.palette = outpl;
+  else frame_take(f, &n);
+
+  // conv_done (:13859-13900)
+  if (new_gamma_type != PE_GAMMA_UNKNOWN && can_inline_gamma(inpl, outpl)) {
+    f->d.gamma_type = new_gamma_type;
+    gamma_type = new_gamma_type;
+  }
+  if (pal_is_rgb(outpl)) {
+    f->d.yuv_clamping = 0; f->d.yuv_subspace = 0; f->d.yuv_sampling = 0;  // leaves deleted
+  } else {
+    f->d.yuv_clamping = oclamping;
+    if (pal_is_rgb(inpl)) f->d.yuv_subspace = gamma_type == PE_GAMMA_BT709 ? PE_YUV_SUBSPACE_BT709 : PE_YUV_SUBSPACE_YCBCR;
+  }
+  return PE_TRUE;
+}
+
+}  // namespace
+
+extern "C" int pe_convert_layer_palette_full(pe_engine_t *e, pe_frame_t *layer, int outpl, int oclamping, int osampling,
+                                             int osubspace, int tgt_gamma) {
+  if (!e || !layer) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA_B(cudaSetDevice(e->device));
+  return convert_locked(e, layer, outpl, oclamping, osampling, osubspace, tgt_gamma);
+}
+
+extern "C" int pe_convert_layer_palette(pe_engine_t *e, pe_frame_t *layer, int outpl, int op_clamping) {
+  return pe_convert_layer_palette_full(e, layer, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV,
+                                       PE_GAMMA_UNKNOWN);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// resize_layer_full (colourspace.c:14759) / letterbox_layer (:15343)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+// one plane (or packed image) src -> dst through the separable filter bank
+int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint8_t *dst, int drs, int dw, int dh, int psize) {
+  DevFilterEntry *fx = get_filter(e, sw, dw, 14), *fy = get_filter(e, sh, dh, 12);
+  if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range (%dx%d -> %dx%d; at most 31x down)", sw, sh, dw, dh);
+  size_t granted = 0;
+  const size_t tmp_bytes = sizeof(int16_t) * (size_t)sh * dw * psize;
+  int16_t *tmp = (int16_t *)e->pool.get(tmp_bytes, &granted);
+  if (!tmp) return set_err(PE_ERR_MEMORY, "device allocation of %zu bytes failed", tmp_bytes);
+  cudaError_t ce = launch_resize_h(e->L(), CImg{src, srs}, sw, sh, tmp, dw, psize, fx->dev);
+  if (ce == cudaSuccess) ce = launch_resize_v(e->L(), tmp, sh, Img{dst, drs}, dw, dh, psize, fy->dev);
+  e->pool.put(tmp, granted);  // stream ordered: the next user is enqueued behind the two kernels
+  if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "resize launch failed: %s", cudaGetErrorString(ce));
+  return PE_OK;
+}
+
+int resize_locked(pe_engine *e, pe_frame *f, int width, int height, int interp, int opal_hint, int oclamp_hint, int osamp_hint,
+                  int osubs_hint, int tgt_gamma) {
+  (void)interp;  // NORMAL / FAST / BEST all map to the one published filter of this build (DESIGN.md "resize")
+  int palette = f->d.palette;
+  if (opal_hint == PE_PALETTE_NONE) opal_hint = palette;  // WEED_PALETTE_ANY: keep
+  if (!f->d.planes[0]) {  // :14820-14832
+    f->d.width = width; f->d.height = height;
+    if (pal_known(opal_hint)) f->d.palette = opal_hint;
+    f->d.yuv_clamping = oclamp_hint;
+    return PE_FALSE;
+  }
+  if (width <= 0 || height <= 0) return PE_FALSE;  // :14834
+  int iwidth = (f->d.width >> 1) << 1, iheight = (f->d.height >> 1) << 1;  // :14850-14851
+  if (width < 4) width = 4;
+  if (height < 4) height = 4;
+  if (iwidth != width || iheight != height) height = (height >> 1) << 1;  // :14856-14859
+  if (iwidth == width && iheight == height) return PE_TRUE;
+
+  // tgt_gamma resolution (:14884-14893)
+  if (tgt_gamma == PE_GAMMA_UNKNOWN && pal_is_yuv(opal_hint) && osubs_hint == PE_YUV_SUBSPACE_BT709) tgt_gamma = PE_GAMMA_BT709;
+  if (tgt_gamma == PE_GAMMA_UNKNOWN) tgt_gamma = f->d.gamma_type;
+  if (tgt_gamma == PE_GAMMA_BT709 && pal_is_yuv(opal_hint)) osubs_hint = PE_YUV_SUBSPACE_BT709;
+
+  // get_resizable (:14577): what gets scaled.  Packed 3/4-byte palettes and planar YUV scale as they are; packed
+  // 4:2:2 is converted first.  A YUV source with an RGB target is converted BEFORE scaling, with the reference's own
+  // converter arithmetic (the reference lets swscale do both at once, :14601-14620 -- see DESIGN.md "resize").
+  int resolved = palette;
+  if (pal_is_yuv(palette) && pal_is_rgb(opal_hint)) resolved = opal_hint;
+  else if (palette == PE_PALETTE_UYVY || palette == PE_PALETTE_YUYV) resolved = pal_is_rgb(opal_hint) ? opal_hint : PE_PALETTE_RGB24;
+  if (resolved != palette) {
+    if (!convert_locked(e, f, resolved, oclamp_hint, osamp_hint, osubs_hint, tgt_gamma)) return PE_FALSE;
+    if (f->d.palette != resolved) return PE_FALSE;
+    palette = resolved;
+    iwidth = (f->d.width >> 1) << 1; iheight = (f->d.height >> 1) << 1;
+    if (iwidth == width && iheight == height) return PE_TRUE;
+  }
+
+  pe_frame n;
+  n.e = e;
+  n.d.palette = palette; n.d.width = width; n.d.height = height;
+  if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+  int rc = PE_OK;
+  if (!pal_is_planar(palette)) {
+    rc = resize_plane(e, (const uint8_t *)f->d.planes[0], f->d.rowstrides[0], f->d.width, f->d.height, (uint8_t *)n.d.planes[0],
+                      n.d.rowstrides[0], width, height, pal_psize(palette));
+  } else {
+    for (int p = 0; p < n.d.nplanes && rc == PE_OK; p++) {
+      const bool sub_h = p > 0 && p < 3 && palette != PE_PALETTE_YUV444P && palette != PE_PALETTE_YUVA4444P;
+      const int sw = sub_h ? f->d.width >> 1 : f->d.width, dw = sub_h ? width >> 1 : width;
+      rc = resize_plane(e, (const uint8_t *)f->d.planes[p], f->d.rowstrides[p], sw, f->plane_heights[p], (uint8_t *)n.d.planes[p],
+                        n.d.rowstrides[p], dw, n.plane_heights[p], 1);
+    }
+  }
+  if (rc != PE_OK) { frame_release_pixels(&n); return PE_FALSE; }
+  frame_take(f, &n);
+  if (opal_hint != palette && pal_known(opal_hint)) {
+    if (!convert_locked(e, f, opal_hint, oclamp_hint, osamp_hint, osubs_hint, tgt_gamma)) return PE_FALSE;
+  }
+  return PE_TRUE;
+}
+
+int letterbox_locked(pe_engine *e, pe_frame *f, int nwidth, int nheight, int width, int height, int interp, int tpal, int tclamp) {
+  if (!width || !height || !nwidth || !nheight) return PE_TRUE;  // :15375
+  if (nwidth < width) nwidth = width;
+  if (nheight < height) nheight = height;
+  if (nheight == height && nwidth == width) {  // :15380-15383
+    resize_locked(e, f, width, height, interp, tpal, tclamp, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN);
+    return PE_TRUE;
+  }
+  if (f->d.width != width || f->d.height != height) {  // :15388-15393
+    if (!resize_locked(e, f, width, height, interp, tpal, tclamp, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN))
+      return PE_FALSE;
+  }
+  width = f->d.width; height = f->d.height;
+  const int pal = f->d.palette;
+  pe_frame n;
+  n.e = e;
+  n.d = f->d;
+  n.d.width = nwidth; n.d.height = nheight;
+  if (pal == PE_PALETTE_YUV420P || pal == PE_PALETTE_YVU420P) { n.d.width &= ~1; n.d.height &= ~1; }
+  if (n.d.width < width || n.d.height < height) return PE_FALSE;  // :15503
+  if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+  nwidth = n.d.width; nheight = n.d.height;
+  const int offs_x = (nwidth - width + 1) >> 1, offs_y = (nheight - height + 1) >> 1;  // :15522-15523
+  cudaError_t ce = cudaSuccess;
+  if (!pal_is_planar(pal) && pal_ppmp(pal) == 1) {
+    uint32_t black;
+    const uint32_t y0 = (pal_is_yuv(pal) && f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED) ? 16 : 0;
+    switch (pal) {
+    case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: black = 0; break;
+    case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: black = 0xFF000000u; break;
+    case PE_PALETTE_ARGB32: black = 0x000000FFu; break;
+    case PE_PALETTE_YUV888: black = y0 | (128u << 8) | (128u << 16); break;
+    default: black = y0 | (128u << 8) | (128u << 16) | 0xFF000000u; break;
+    }
+    ce = launch_letterbox(e->L(), CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, width, height,
+                          Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, nwidth, nheight, pal_psize(pal), black);
+  } else {
+    // planar / macropixel palettes: black frame, then one 2-D copy per plane with the offsets scaled by the plane's
+    // subsampling ratios (:15538-15549)
+    if (frame_fill_black(e, &n) != PE_OK) { frame_release_pixels(&n); return PE_FALSE; }
+    for (int p = 0; p < n.d.nplanes && ce == cudaSuccess; p++) {
+      const int rb = plane_row_bytes(f->d, p);
+      const int hr = p == 0 ? 1 : f->d.width / (rb ? rb : 1);                     // horizontal ratio denominator
+      const int vr = p == 0 ? 1 : f->d.height / (f->plane_heights[p] ? f->plane_heights[p] : 1);
+      const int xo = p == 0 ? (offs_x / pal_ppmp(pal)) * pal_psize(pal) : offs_x / (hr ? hr : 1);
+      const int yo = offs_y / (vr ? vr : 1);
+      ce = launch_copy2d(e->L(), (const uint8_t *)f->d.planes[p], f->d.rowstrides[p],
+                         (uint8_t *)n.d.planes[p] + (size_t)yo * n.d.rowstrides[p] + xo, n.d.rowstrides[p], rb,
+                         f->plane_heights[p], 0, 0);
+    }
+  }
+  if (ce != cudaSuccess) {
+    set_err(PE_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(ce));
+    frame_release_pixels(&n);
+    return PE_FALSE;
+  }
+  frame_take(f, &n);
+  return PE_TRUE;
+}
+
+}  // namespace
+
+extern "C" int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
+                                    int oclamp_hint, int osamp_hint, int osubs_hint, int tgt_gamma) {
+  if (!e || !layer) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA_B(cudaSetDevice(e->device));
+  return resize_locked(e, layer, width, height, interp, opal_hint, oclamp_hint, osamp_hint, osubs_hint, tgt_gamma);
+}
+
+extern "C" int pe_resize_layer(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
+                               int oclamp_hint) {  // :15331
+  return pe_resize_layer_full(e, layer, width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT,
+                              PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN);
+}
+
+extern "C" int pe_letterbox_layer(pe_engine_t *e, pe_frame_t *layer, int nwidth, int nheight, int width, int height,
+                                  int interp, int tpal, int tclamp) {
+  if (!e || !layer) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA_B(cudaSetDevice(e->device));
+  return letterbox_locked(e, layer, nwidth, nheight, width, height, interp, tpal, tclamp);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// effects (boundary B1 arithmetic)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+int check_blend_frames(const pe_frame *in1, const pe_frame *in2, const pe_frame *out, bool rgb24_only) {
+  if (!in1 || !in2 || !out || !in1->d.planes[0] || !in2->d.planes[0] || !out->d.planes[0])
+    return set_err(PE_ERR_ARG, "NULL frame");
+  const int pal = in1->d.palette;
+  if (!pal_is_rgb(pal) || (rgb24_only && pal_psize(pal) != 3))
+    return set_err(PE_ERR_PALETTE, "palette %d is not in this filter's palette list", pal);
+  if (in2->d.palette != pal || out->d.palette != pal) return set_err(PE_ERR_PALETTE, "channel palettes differ");
+  if (in2->d.width != in1->d.width || in2->d.height != in1->d.height || out->d.width != in1->d.width ||
+      out->d.height != in1->d.height)
+    return set_err(PE_ERR_SIZE, "channel sizes differ");
+  return PE_OK;
+}
+
+inline BlendFrame blend_frame(const pe_frame *in1, const pe_frame *in2, const pe_frame *out) {
+  BlendFrame b;
+  b.s1 = (const uint8_t *)in1->d.planes[0]; b.s2 = (const uint8_t *)in2->d.planes[0]; b.d = (uint8_t *)out->d.planes[0];
+  b.rs1 = in1->d.rowstrides[0]; b.rs2 = in2->d.rowstrides[0]; b.rsd = out->d.rowstrides[0];
+  b.s2_bytes = (long long)in2->d.rowstrides[0] * (in2->d.height - 1) + (long long)in2->d.width * pal_psize(in2->d.palette);
+  return b;
+}
+
+}  // namespace
+
+extern "C" int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const pe_frame_t *const *in1,
+                                        const pe_frame_t *const *in2, pe_frame_t *const *out, int blend_factor) {
+  if (!e || n <= 0 || !in1 || !in2 || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  if (type < 0 || type > 3) return set_err(PE_ERR_ARG, "simple_blend type %d out of range", type);
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  std::vector<BlendFrame> frames(n);
+  for (int i = 0; i < n; i++) {
+    int rc = check_blend_frames(in1[i], in2[i], out[i], false);
+    if (rc != PE_OK) return rc;
+    if (in1[i]->d.palette != in1[0]->d.palette || in1[i]->d.width != in1[0]->d.width || in1[i]->d.height != in1[0]->d.height)
+      return set_err(PE_ERR_SIZE, "frames of a batch must share palette and size");
+    frames[i] = blend_frame(in1[i], in2[i], out[i]);
+  }
+  const BlendFrame *dev = (const BlendFrame *)upload_args(e, frames.data(), sizeof(BlendFrame) * n);
+  if (!dev) return set_err(PE_ERR_CUDA, "argument upload failed");
+  PE_CUDA(launch_simple_blend(e->L(), type, dev, n, in1[0]->d.width, in1[0]->d.height, rgb_layout(in1[0]->d.palette), blend_factor,
+                              e->luma_dev));
+  return PE_OK;
+}
+
+extern "C" int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
+                                  int blend_factor) {
+  const pe_frame_t *a[1] = {in1}, *b[1] = {in2};
+  pe_frame_t *o[1] = {out};
+  return pe_fx_simple_blend_batch(e, type, 1, a, b, o, blend_factor);
+}
+
+extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
+                                 int blend_factor) {
+  if (!e) return set_err(PE_ERR_ARG, "NULL engine");
+  if (type < 0 || type > 6) return set_err(PE_ERR_ARG, "multi_blend type %d out of range", type);
+  int rc = check_blend_frames(in1, in2, out, true);
+  if (rc != PE_OK) return rc;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  PE_CUDA(launch_multi_blend(e->L(), type, blend_frame(in1, in2, out), in1->d.width, in1->d.height,
+                             in1->d.palette == PE_PALETTE_BGR24, blend_factor, e->luma_dev));
+  return PE_OK;
+}
+
+extern "C" int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
+                                int nlayers, const int bgcol[3]) {
+  if (!e || !out || !out->d.planes[0] || nlayers < 0 || (nlayers > 0 && (!layers || !alpha)))
+    return set_err(PE_ERR_ARG, "NULL argument");
+  const int pal = out->d.palette;
+  if (!pal_is_rgb(pal) || pal == PE_PALETTE_ARGB32) return set_err(PE_ERR_PALETTE, "compositor palettes: RGB24 BGR24 RGBA32 BGRA32");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  const int psize = pal_psize(pal);
+  const Img dst{(uint8_t *)out->d.planes[0], out->d.rowstrides[0]};
+  // background fill (compositor.c:172-186); alpha byte 0xFF
+  const int r = bgcol ? bgcol[0] : 0, g = bgcol ? bgcol[1] : 0, b = bgcol ? bgcol[2] : 0;
+  const bool swap = (pal == PE_PALETTE_BGR24 || pal == PE_PALETTE_BGRA32);
+  const uint32_t px = (uint32_t)((swap ? b : r) & 255) | ((uint32_t)(g & 255) << 8) | ((uint32_t)((swap ? r : b) & 255) << 16) | 0xFF000000u;
+  PE_CUDA(launch_fill(e->L(), dst, out->d.width, out->d.height, psize, px));
+  // layers painted last first (revz == WEED_FALSE, :189-197); a layer with alpha 0 is skipped (:232)
+  for (int z = nlayers - 1; z >= 0; z--) {
+    const pe_frame *l = layers[z];
+    if (!l || !l->d.planes[0]) continue;
+    if (l->d.palette != pal) return set_err(PE_ERR_PALETTE, "layer %d palette differs from the output's", z);
+    if (l->d.width != out->d.width || l->d.height != out->d.height)
+      return set_err(PE_ERR_SIZE, "layer %d: only scale 1 / offset 0 layers are handled by this build", z);
+    if (alpha[z] <= 0.) continue;
+    uint8_t *tab = get_over_table(e, alpha[z], nullptr);
+    if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
+    PE_CUDA(launch_alpha_over(e->L(), CImg{dst.p, dst.rs}, CImg{(const uint8_t *)l->d.planes[0], l->d.rowstrides[0]}, dst,
+                              out->d.width, out->d.height, psize, tab, 1));
+  }
+  return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused chain
+// ---------------------------------------------------------------------------------------------------------
+
+extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_t *const *fg,
+                                                           const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
+                                                           int inner_h, double alpha, int gamma_from, int gamma_to) {
+  if (!e || n <= 0 || !fg || !bg || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  const pe_frame *f0 = fg[0], *b0 = bg[0];
+  if (!f0 || !b0) return set_err(PE_ERR_ARG, "NULL frame");
+  const int ow = b0->d.width, oh = b0->d.height;
+  if (inner_w <= 0 || inner_h <= 0 || inner_w > ow || inner_h > oh) return set_err(PE_ERR_SIZE, "inner rectangle does not fit");
+  // gamma LUT folded into the [bg][fg] table
+  const uint8_t *lut = nullptr;
+  if (e->cfg.apply_gamma) {
+    Lut8Entry *le = get_lut8(e, 1.0, gamma_from, gamma_to);
+    lut = le ? le->dev : nullptr;
+  }
+  uint8_t *tab = get_over_table(e, alpha, lut);
+  if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
+  DevFilterEntry *fx = get_filter(e, f0->d.width, inner_w, 14), *fy = get_filter(e, f0->d.height, inner_h, 12);
+  if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range");
+  // source extent one output tile can touch
+  const int tw = fused_tile_w(), th = fused_tile_h();
+  auto span = [](const ResizeFilter &F, int dst_n, int src_n, int tile) {
+    int worst = 1;
+    for (int i0 = 0; i0 < dst_n; i0 += 1) {
+      const int i1 = i0 + tile - 1 < dst_n - 1 ? i0 + tile - 1 : dst_n - 1;
+      int lo = F.first[i0], hi = F.first[i1] + F.taps - 1;
+      lo = lo < 0 ? 0 : lo; hi = hi > src_n - 1 ? src_n - 1 : hi;
+      if (hi - lo + 1 > worst) worst = hi - lo + 1;
+    }
+    return worst;
+  };
+  const int max_cols = span(fx->host, inner_w, f0->d.width, tw), max_rows = span(fy->host, inner_h, f0->d.height, th);
+  std::vector<FusedArgs> args(n);
+  for (int i = 0; i < n; i++) {
+    const pe_frame *f = fg[i], *b = bg[i];
+    pe_frame *o = out[i];
+    if (!f || !b || !o || !f->d.planes[0] || !b->d.planes[0] || !o->d.planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
+    if (f->d.palette != PE_PALETTE_YUV420P && f->d.palette != PE_PALETTE_YVU420P && f->d.palette != PE_PALETTE_YUV422P)
+      return set_err(PE_ERR_PALETTE, "fused chain: fg must be YUV420P / YVU420P / YUV422P");
+    if (b->d.palette != PE_PALETTE_RGBA32 || o->d.palette != PE_PALETTE_RGBA32)
+      return set_err(PE_ERR_PALETTE, "fused chain: bg and out must be RGBA32");
+    if (b->d.width != ow || b->d.height != oh || o->d.width != ow || o->d.height != oh || f->d.width != f0->d.width ||
+        f->d.height != f0->d.height)
+      return set_err(PE_ERR_SIZE, "frames of a batch must share sizes");
+    FusedArgs &A = args[i];
+    A.fg = planes_of(f, f->d.palette == PE_PALETTE_YVU420P);
+    A.fw = f->d.width; A.fh = f->d.height;
+    A.is_422 = f->d.palette == PE_PALETTE_YUV422P;
+    A.clamped = f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED;
+    A.low_quality = e->cfg.pb_quality == PE_QUALITY_LOW;
+    A.quirks = e->cfg.ref_quirks;
+    A.conv = dev_conv(e, f->d.yuv_clamping, f->d.yuv_subspace);
+    A.bg = CImg{(const uint8_t *)b->d.planes[0], b->d.rowstrides[0]};
+    A.out = Img{(uint8_t *)o->d.planes[0], o->d.rowstrides[0]};
+    A.ow = ow; A.oh = oh; A.iw = inner_w; A.ih = inner_h;
+    A.ox = (ow - inner_w + 1) >> 1; A.oy = (oh - inner_h + 1) >> 1;
+    A.fx = fx->dev; A.fy = fy->dev;
+    A.over_table = tab;
+  }
+  const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);
+  if (!dev) return set_err(PE_ERR_CUDA, "argument upload failed");
+  PE_CUDA(launch_fused_dev(e->L(), dev, n, ow, oh, max_rows, max_cols));
+  for (int i = 0; i < n; i++) {
+    out[i]->d.gamma_type = (lut ? gamma_to : gamma_from);
+    out[i]->d.flags = bg[i]->d.flags;
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_t *fg, const pe_frame_t *bg,
+                                                     pe_frame_t *out, int inner_w, int inner_h, double alpha, int gamma_from,
+                                                     int gamma_to) {
+  const pe_frame_t *f[1] = {fg}, *b[1] = {bg};
+  pe_frame_t *o[1] = {out};
+  return pe_fused_convert_letterbox_over_gamma_batch(e, 1, f, b, o, inner_w, inner_h, alpha, gamma_from, gamma_to);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------------------
+
+extern "C" int pe_frame_stats(pe_engine_t *e, const pe_frame_t *f, pe_frame_stats_t *out) {
+  if (!e || !f || !out || !f->d.planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  DevStats init;
+  memset(&init, 0, sizeof(init));
+  for (int k = 0; k < 4; k++) { init.minv[k] = 255; init.maxv[k] = 0; }
+  PE_CUDA(cudaMemcpyAsync(e->stats_dev, &init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
+  const int pal = f->d.palette;
+  const int psize = pal_is_planar(pal) ? 1 : pal_psize(pal);
+  int a_off = -1;
+  if (pal == PE_PALETTE_RGBA32 || pal == PE_PALETTE_BGRA32 || pal == PE_PALETTE_YUVA8888) a_off = 3;
+  else if (pal == PE_PALETTE_ARGB32) a_off = 0;
+  PE_CUDA(launch_stats(e->L(), CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, f->d.width / pal_ppmp(pal), f->d.height,
+                       psize, a_off, e->stats_dev));
+  DevStats res;
+  PE_CUDA(cudaMemcpyAsync(&res, e->stats_dev, sizeof(res), cudaMemcpyDeviceToHost, e->stream));
+  PE_CUDA(cudaStreamSynchronize(e->stream));
+  for (int k = 0; k < 4; k++) { out->min[k] = (uint8_t)res.minv[k]; out->max[k] = (uint8_t)res.maxv[k]; }
+  memcpy(out->hist, res.hist, sizeof(out->hist));
+  out->sum = res.sum;
+  out->all_black_ish = res.not_black ? 0 : 1;
+  return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-frame drop-ins: H2D -> device op -> D2H
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct HostFrame {
+  pe_engine *e;
+  pe_frame *f = nullptr;
+  explicit HostFrame(pe_engine *eng) : e(eng) {}
+  ~HostFrame() { if (f) pe_frame_destroy(f); }
+  int upload(const pe_frame_desc_t *d) {
+    int rc = frame_create_impl(e, d->palette, d->width, d->height, d->yuv_clamping, d->yuv_sampling, d->yuv_subspace,
+                               d->gamma_type, 0, &f);
+    if (rc != PE_OK) return rc;
+    f->d.flags = d->flags;
+    return pe_frame_upload(e, f, (const void *const *)d->planes, d->rowstrides);
+  }
+  int create_like(const pe_frame_desc_t *d) {
+    return frame_create_impl(e, d->palette, d->width, d->height, d->yuv_clamping, d->yuv_sampling, d->yuv_subspace, d->gamma_type,
+                             0, &f);
+  }
+};
+
+void *default_alloc(size_t bytes, void *) { return malloc(bytes); }
+void default_free(void *p, void *) { free(p); }
+
+// write the device frame back into the host layer: same geometry -> into the existing buffers, otherwise new
+// buffers from the caller's allocator (planes laid out contiguously, as create_empty_pixel_data does with may_contig)
+int download_into(pe_engine *e, pe_frame *f, pe_frame_desc_t *layer, const pe_host_allocator_t *alloc) {
+  pe_frame_desc_t d = f->d;
+  bool same = layer->palette == d.palette && layer->width == d.width && layer->height == d.height && layer->planes[0];
+  if (same) {
+    int rc = pe_frame_download(e, f, layer->planes, layer->rowstrides);
+    if (rc != PE_OK) return rc;
+  } else {
+    pe_host_allocator_t a = alloc && alloc->alloc && alloc->free ? *alloc : pe_host_allocator_t{default_alloc, default_free, nullptr};
+    int np, rs[PE_MAXPLANES], ph[PE_MAXPLANES];
+    pe_frame_layout(d.palette, d.width, d.height, &np, rs, ph);
+    size_t total = 0;
+    for (int p = 0; p < np; p++) total += (size_t)rs[p] * ph[p];
+    uint8_t *blk = (uint8_t *)a.alloc(total + 64, a.user);
+    if (!blk) return set_err(PE_ERR_MEMORY, "host allocator returned NULL for %zu bytes", total);
+    void *planes[PE_MAXPLANES] = {nullptr, nullptr, nullptr, nullptr};
+    size_t off = 0;
+    for (int p = 0; p < np; p++) { planes[p] = blk + off; off += (size_t)rs[p] * ph[p]; }
+    int rc = pe_frame_download(e, f, planes, rs);
+    if (rc != PE_OK) { a.free(blk, a.user); return rc; }
+    if (layer->planes[0]) a.free(layer->planes[0], a.user);  // the old contiguous block
+    for (int p = 0; p < PE_MAXPLANES; p++) { layer->planes[p] = planes[p]; layer->rowstrides[p] = p < np ? rs[p] : 0; }
+    layer->nplanes = np;
+  }
+  layer->palette = d.palette; layer->width = d.width; layer->height = d.height;
+  layer->yuv_clamping = d.yuv_clamping; layer->yuv_sampling = d.yuv_sampling; layer->yuv_subspace = d.yuv_subspace;
+  layer->gamma_type = d.gamma_type; layer->flags = d.flags;
+  return PE_OK;
+}
+
+}  // namespace
+
+extern "C" int pe_host_convert_layer_palette_full(pe_engine_t *e, pe_frame_desc_t *layer, int outpl, int oclamping, int osampling,
+                                                  int osubspace, int tgt_gamma, const pe_host_allocator_t *alloc) {
+  if (!e || !layer || !layer->planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  HostFrame h(e);
+  if (h.upload(layer) != PE_OK) return PE_FALSE;
+  if (!pe_convert_layer_palette_full(e, h.f, outpl, oclamping, osampling, osubspace, tgt_gamma)) return PE_FALSE;
+  return download_into(e, h.f, layer, alloc) == PE_OK ? PE_TRUE : PE_FALSE;
+}
+
+extern "C" int pe_host_resize_layer(pe_engine_t *e, pe_frame_desc_t *layer, int width, int height, int interp, int opal_hint,
+                                    int oclamp_hint, const pe_host_allocator_t *alloc) {
+  if (!e || !layer || !layer->planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  HostFrame h(e);
+  if (h.upload(layer) != PE_OK) return PE_FALSE;
+  if (!pe_resize_layer(e, h.f, width, height, interp, opal_hint, oclamp_hint)) return PE_FALSE;
+  return download_into(e, h.f, layer, alloc) == PE_OK ? PE_TRUE : PE_FALSE;
+}
+
+extern "C" int pe_host_letterbox_layer(pe_engine_t *e, pe_frame_desc_t *layer, int nwidth, int nheight, int width, int height,
+                                       int interp, int tpal, int tclamp, const pe_host_allocator_t *alloc) {
+  if (!e || !layer || !layer->planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  HostFrame h(e);
+  if (h.upload(layer) != PE_OK) return PE_FALSE;
+  if (!pe_letterbox_layer(e, h.f, nwidth, nheight, width, height, interp, tpal, tclamp)) return PE_FALSE;
+  return download_into(e, h.f, layer, alloc) == PE_OK ? PE_TRUE : PE_FALSE;
+}
+
+extern "C" int pe_host_gamma_convert_layer(pe_engine_t *e, int gamma_type, pe_frame_desc_t *layer) {
+  if (!e || !layer || !layer->planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  HostFrame h(e);
+  if (h.upload(layer) != PE_OK) return PE_FALSE;
+  if (!pe_gamma_convert_layer(e, gamma_type, h.f)) return PE_FALSE;
+  return download_into(e, h.f, layer, nullptr) == PE_OK ? PE_TRUE : PE_FALSE;
+}
+
+namespace {
+int host_blend(pe_engine_t *e, int which, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out,
+               int bf) {
+  if (!e || !in1 || !in2 || !out || !in1->planes[0] || !in2->planes[0] || !out->planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  HostFrame a(e), b(e), o(e);
+  int rc;
+  if ((rc = a.upload(in1)) != PE_OK || (rc = b.upload(in2)) != PE_OK) return rc;
+  const bool inplace = out->planes[0] == in1->planes[0];  // effects-weed.c:2304-2314
+  // the 4-byte chroma blend never writes the alpha byte: a separate out channel keeps what it held
+  if (!inplace && (rc = (pal_psize(out->palette) == 4 ? o.upload(out) : o.create_like(out))) != PE_OK) return rc;
+  pe_frame *of = inplace ? a.f : o.f;
+  rc = which == 0 ? pe_fx_simple_blend(e, type, a.f, b.f, of, bf) : pe_fx_multi_blend(e, type, a.f, b.f, of, bf);
+  if (rc != PE_OK) return rc;
+  return pe_frame_download(e, of, out->planes, out->rowstrides);
+}
+}  // namespace
+
+extern "C" int pe_host_simple_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
+                                    pe_frame_desc_t *out, int blend_factor) {
+  return host_blend(e, 0, type, in1, in2, out, blend_factor);
+}
+
+extern "C" int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
+                                   pe_frame_desc_t *out, int blend_factor) {
+  return host_blend(e, 1, type, in1, in2, out, blend_factor);
+}
+
+extern "C" int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_desc_t *fg, const pe_frame_desc_t *bg,
+                                                          pe_frame_desc_t *out, int inner_w, int inner_h, double alpha,
+                                                          int gamma_from, int gamma_to) {
+  if (!e || !fg || !bg || !out || !fg->planes[0] || !bg->planes[0] || !out->planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  HostFrame a(e), b(e), o(e);
+  int rc;
+  if ((rc = a.upload(fg)) != PE_OK || (rc = b.upload(bg)) != PE_OK || (rc = o.create_like(out)) != PE_OK) return rc;
+  rc = pe_fused_convert_letterbox_over_gamma(e, a.f, b.f, o.f, inner_w, inner_h, alpha, gamma_from, gamma_to);
+  if (rc != PE_OK) return rc;
+  rc = pe_frame_download(e, o.f, out->planes, out->rowstrides);
+  if (rc == PE_OK) { out->gamma_type = o.f->d.gamma_type; out->flags = o.f->d.flags; }
+  return rc;
+}

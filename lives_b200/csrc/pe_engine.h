@@ -1,0 +1,94 @@
+// pe_engine.h -- internal state behind the opaque handles of include/pixel_engine.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/pixel_engine.h"
+#include "pe_kernels.h"
+#include "pe_tables.h"
+
+namespace pe {
+
+// Device block pool (the role of LiVES' bigblock allocator, src/memory.c:37-47): frames are replaced on every
+// palette conversion / resize, so blocks are recycled by size class instead of going through cudaMalloc / cudaFree
+// (both synchronise the device).  Stream-ordered: a recycled block is only ever reused on the engine's own stream.
+class DevPool {
+ public:
+  void *get(size_t bytes, size_t *granted);
+  void put(void *p, size_t granted);
+  void release_all();
+  size_t bytes_held() const { return held_; }
+
+ private:
+  std::multimap<size_t, void *> free_;
+  size_t held_ = 0;
+};
+
+struct GammaKey {
+  double fileg;
+  int from, to;
+  bool operator<(const GammaKey &o) const { return std::tie(fileg, from, to) < std::tie(o.fileg, o.from, o.to); }
+};
+struct OverKey {
+  double alpha;
+  const uint8_t *lut;
+  bool operator<(const OverKey &o) const { return std::tie(alpha, lut) < std::tie(o.alpha, o.lut); }
+};
+struct FilterKey {
+  int src_n, dst_n, bits;
+  bool operator<(const FilterKey &o) const { return std::tie(src_n, dst_n, bits) < std::tie(o.src_n, o.dst_n, o.bits); }
+};
+struct DevFilterEntry {
+  DevFilter dev;
+  ResizeFilter host;
+};
+struct Lut8Entry {
+  uint8_t host[256];
+  uint8_t *dev;
+};
+
+}  // namespace pe
+
+struct pe_engine {
+  pe_config_t cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;  // the reference calls these entry points from several proc-threads (different layers)
+
+  pe::ConvTables conv_host[2][2];    // [clamping][bt709]
+  int32_t *conv_dev[2][2] = {};      // 14 x 256 int32 each
+  uint8_t *premult_dev[6] = {};      // built on first use (init_unal is lazy in the reference too, :11985)
+  int32_t *luma_dev = nullptr;       // plugin-side calc_luma tables [3][256]
+  std::map<pe::GammaKey, pe::Lut8Entry> lut8;
+  std::map<pe::GammaKey, uint16_t *> lut16;
+  std::map<pe::OverKey, uint8_t *> over;
+  std::map<pe::FilterKey, pe::DevFilterEntry> filters;
+  pe::DevPool pool;
+  pe::DevStats *stats_dev = nullptr;
+  // small device scratch for per-launch argument arrays (BlendFrame / FusedArgs), grown on demand
+  void *args_dev = nullptr;
+  size_t args_cap = 0;
+  void *args_pinned = nullptr;
+  size_t args_pinned_cap = 0;
+  cudaEvent_t args_ev = nullptr;  // args_pinned may be rewritten once the previous upload has completed
+
+  pe::Launch L() { return pe::Launch{stream, sm_count, &launches}; }
+};
+
+struct pe_frame {
+  pe_engine *e = nullptr;
+  pe_frame_desc_t d{};
+  void *base = nullptr;  // pool block holding all planes (nullptr for wrapped frames)
+  size_t granted = 0;
+  int plane_heights[PE_MAXPLANES] = {};
+};

@@ -1,0 +1,129 @@
+// pe_kernels.h -- launchers of the sm_100a kernels (definitions in pe_kernels_*.cu).
+// Plain structs only; no CUDA types leak past this header except cudaStream_t.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pe {
+
+struct Launch {
+  cudaStream_t stream;
+  int sm_count;
+  long *launch_counter;  // host counter, incremented once per kernel launch
+};
+
+// packed image view
+struct Img {
+  uint8_t *p;
+  int rs;  // rowstride in bytes
+};
+struct CImg {
+  const uint8_t *p;
+  int rs;
+};
+// planar YUV view
+struct Planes {
+  const uint8_t *y, *u, *v;
+  int rs_y, rs_u, rs_v;
+  int cw, ch;  // chroma plane width / height in samples
+};
+
+// device-resident tables of one (clamping, subspace) variant: 14 x int[256] (ConvTab order)
+struct DevConv {
+  const int32_t *t;  // [14][256]
+  int min_y, max_y, min_uv, max_uv;
+};
+
+// byte order of an RGB palette: offsets of R,G,B,A inside a pixel (A = -1 when absent)
+struct RgbLayout {
+  int r, g, b, a, psize;
+};
+
+// ---- RGB <-> RGB (colourspace.c:9259-10515) ---------------------------------------------------
+cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in, RgbLayout out,
+                              const uint8_t *lut8_dev);
+// ---- gamma LUT on a rectangle (colourspace.c:14034) ---------------------------------------------
+cudaError_t launch_lut8_rect(const Launch &L, Img img, RgbLayout lay, int x, int y, int width, int height,
+                             const uint8_t *lut8_dev);
+// ---- premultiply (colourspace.c:11968) ------------------------------------------------------------
+cudaError_t launch_premult(const Launch &L, Img img, int width, int height, int coffs, int ncol, int aoffs,
+                           const uint8_t *tab0, const uint8_t *tab1, const uint8_t *tab2, int yuva_fwd_quirk);
+// ---- planar 4:2:0 / 4:2:2 -> RGB (colourspace.c:3260-5127) -----------------------------------------
+struct YuvToRgbArgs {
+  Planes src;
+  Img dst;
+  int width, height;
+  RgbLayout out;      // out.a >= 0 -> alpha byte written as 255
+  int is_422;
+  int clamped;        // chroma clamp range 16..240 vs 0..255
+  int low_quality;    // PB_QUALITY_LOW chroma shortcut (RGB order only, colourspace.c:3470)
+  int quirks;         // replicate colourspace.c:3461,3544,3600
+  DevConv conv;
+  const uint16_t *lut16;  // optional inline gamma (xyuv2rgb_with_gamma :2386)
+};
+cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a);
+// ---- packed 4:2:2 / 4:4:4 (colourspace.c:6616-7103, :2750-3258, :5700-6239) ---------------------------
+cudaError_t launch_packed422_to_rgb(const Launch &L, int fmt, CImg src, Img dst, int width_mpx, int height,
+                                    RgbLayout out, DevConv conv);
+cudaError_t launch_yuv888_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, int in_alpha,
+                                 RgbLayout out, DevConv conv);
+cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in,
+                                 int out_alpha, DevConv conv);
+// ---- effects ---------------------------------------------------------------------------------------
+struct BlendFrame {
+  const uint8_t *s1, *s2;
+  uint8_t *d;
+  int rs1, rs2, rsd;
+  long long s2_bytes;  // size of the src2 buffer (bounds the ARGB next-pixel alpha read, simple_blend.c:130)
+};
+cudaError_t launch_simple_blend(const Launch &L, int type, const BlendFrame *frames_dev, int nframes, int width,
+                                int height, RgbLayout lay, int bf, const int32_t *luma_tabs_dev);
+cudaError_t launch_multi_blend(const Launch &L, int type, BlendFrame f, int width, int height, int bgr, int bf,
+                               const int32_t *luma_tabs_dev);
+// dst = trunc(bg * (1 - alpha) + fg * alpha) in double (compositor.c:120), optional lut8 afterwards:
+// launch_over_table builds the 64 KB [bg][fg] result table for one (alpha, lut8), launch_alpha_over applies it
+cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev);
+cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize,
+                              const uint8_t *over_table_dev, int force_opaque);
+cudaError_t launch_fill(const Launch &L, Img dst, int width, int height, int psize, uint32_t pixel);
+// ---- resize (our contract) + letterbox (colourspace.c:15343) -------------------------------------------
+struct DevFilter {
+  const int32_t *first;
+  const int16_t *coef;
+  int taps;
+};
+cudaError_t launch_resize_h(const Launch &L, CImg src, int sw, int sh, int16_t *tmp, int dw, int psize, DevFilter fx);
+cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst, int dw, int dh, int psize, DevFilter fy);
+cudaError_t launch_letterbox(const Launch &L, CImg inner, int iw, int ih, Img outer, int ow, int oh, int psize,
+                             uint32_t black_pixel);
+cudaError_t launch_copy2d(const Launch &L, const uint8_t *src, int srs, uint8_t *dst, int drs, int row_bytes, int rows,
+                          int fill, uint8_t fill_value);
+// ---- fused chain -----------------------------------------------------------------------------------------
+struct FusedArgs {
+  Planes fg;
+  int fw, fh;           // fg luma size
+  int is_422, clamped, low_quality, quirks;
+  DevConv conv;
+  CImg bg;
+  Img out;
+  int ow, oh;           // outer (= bg = out) size
+  int iw, ih, ox, oy;   // inner rect of the letterbox
+  DevFilter fx, fy;     // fw -> iw (14 bit), fh -> ih (12 bit)
+  const uint8_t *over_table;  // 64 KB [bg][fg] -> composited (+ gamma) byte, see launch_over_table
+};
+// frames_dev: FusedArgs[nframes] in DEVICE memory; max_src_rows / max_src_cols: the largest source extent one output tile
+// touches (computed by the engine from the host copy of the filter banks)
+cudaError_t launch_fused_dev(const Launch &L, const FusedArgs *frames_dev, int nframes, int ow, int oh, int max_src_rows,
+                             int max_src_cols);
+int fused_tile_w();
+int fused_tile_h();
+// ---- diagnostics -------------------------------------------------------------------------------------------
+struct DevStats {
+  unsigned int minv[4], maxv[4];
+  unsigned int hist[256];
+  unsigned long long sum;
+  unsigned int not_black;
+};
+cudaError_t launch_stats(const Launch &L, CImg img, int width, int height, int psize, int a_off, DevStats *out_dev);
+
+}  // namespace pe

@@ -1,0 +1,289 @@
+// pe_kernels_fused.cu -- resize kernels and the fused convert -> letterbox/resize -> alpha-over -> gamma kernel.
+//
+// Resize arithmetic is OUR contract (the reference hands resizing to libswscale, which is not in its tree):
+// separable, swscale-shaped data path
+//     horizontal: tmp = min((sum_k coef14[k] * pix[first + k]) >> 7, 32767)            (15-bit intermediate)
+//     vertical  : out = clip_u8((sum_k coef12[k] * tmp[first + k] + (1 << 18)) >> 19)
+// with source indices clamped to the frame; see pe_tables.cpp build_resize_filter and DESIGN.md.
+//
+// k_fused computes, per 64 x 16 output tile held by one CTA:
+//   1. the source pixels the tile needs, converted YUV4:2:x planar -> RGBA once each into shared memory
+//      (same arithmetic as k_yuv_planar_to_rgb),
+//   2. the horizontally scaled 15-bit rows in shared memory,
+//   3. vertical scale, letterbox placement (black opaque border), alpha-over against the background through
+//      the 64 KB [bg][fg] table (which already contains the gamma LUT) and a 128-bit store.
+// HBM traffic is therefore the algorithmic minimum: fg planes + bg read once, out written once.
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+
+namespace pe {
+
+namespace {
+
+constexpr int kBlock = 256;
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+inline int grid_for(const Launch &L, long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kBlock - 1) / kBlock;
+  long long cap = (long long)L.sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__global__ void __launch_bounds__(kBlock) k_resize_h(const uint8_t *__restrict__ src, int srs, int sw, int sh, int16_t *__restrict__ tmp,
+                                                     int dw, int psize, DevFilter fx) {
+  const long long total = (long long)dw * sh;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int y = (int)(it / dw), x = (int)(it - (long long)y * dw);
+    const uint8_t *row = src + (long long)srs * y;
+    const int first = fx.first[x];
+    int acc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < fx.taps; k++) {
+      const int sx = min(max(first + k, 0), sw - 1);
+      const int c = fx.coef[(long long)x * fx.taps + k];
+      for (int ch = 0; ch < psize; ch++) acc[ch] += c * row[sx * psize + ch];
+    }
+    for (int ch = 0; ch < psize; ch++) tmp[((long long)y * dw + x) * psize + ch] = (int16_t)min(acc[ch] >> 7, 32767);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_resize_v(const int16_t *__restrict__ tmp, int sh, uint8_t *__restrict__ dst, int drs, int dw,
+                                                     int dh, int psize, DevFilter fy) {
+  const int rowlen = dw * psize;
+  const long long total = (long long)rowlen * dh;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int y = (int)(it / rowlen), x = (int)(it - (long long)y * rowlen);
+    const int first = fy.first[y];
+    int acc = 1 << 18;
+    for (int k = 0; k < fy.taps; k++) {
+      const int sy = min(max(first + k, 0), sh - 1);
+      acc += fy.coef[(long long)y * fy.taps + k] * tmp[(long long)sy * rowlen + x];
+    }
+    dst[(long long)drs * y + x] = (uint8_t)min(max(acc >> 19, 0), 255);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused kernel
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kTileW = 64, kTileH = 16;
+
+struct FusedSmem {
+  // carved from dynamic shared memory: [over table 64 KB][yuv tables 5 KB][rgba tile][hscaled tile]
+  uint8_t *over;
+  int32_t *tabs;   // [5][256]
+  uint32_t *rgba;  // [src_rows][src_cols]
+  uint2 *hs;       // [src_rows][kTileW]  4 x int16 per pixel
+};
+
+__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+
+__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, int stride, int r, int c, int cw, int ch) {
+  if (c >= cw) c = (cw < stride || r + 1 < ch) ? cw : cw - 1;
+  return __ldg(p + (long long)stride * r + c);
+}
+
+// (u, v) of source pixel (sx, sy): the per-pixel form of the row / row-pair loops of colourspace.c:3391-3642,
+// identical to k_yuv_planar_to_rgb
+__device__ __forceinline__ void chroma_for_pixel(const FusedArgs &A, int sx, int sy, int &u, int &v) {
+  const Planes &S = A.fg;
+  const int cw = S.cw, ch = S.ch, h = A.fh;
+  const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
+  const int jc = sx >> 1, right = sx & 1;
+  bool pair = false;
+  int cr_a, cr_b = 0, upper = 0;
+  if (A.is_422) cr_a = sy;
+  else if (sy == 0) cr_a = 0;
+  else if (!(h & 1) && sy == h - 1) cr_a = ch - 1;
+  else { pair = true; const int k = (sy + 1) >> 1; cr_a = k - 1; cr_b = k; upper = sy & 1; }
+  if (!pair) {
+    const int seed_row = (A.is_422 && A.quirks) ? (sy >> 1) : cr_a;
+    // column <= 0 is the seed sample
+    const int ca = jc, cb = right ? jc + 1 : jc - 1;
+    const int ua = ca <= 0 ? __ldg(S.u + (long long)S.rs_u * seed_row) : chroma_at(S.u, S.rs_u, cr_a, ca, cw, ch);
+    const int va = ca <= 0 ? __ldg(S.v + (long long)S.rs_v * seed_row) : chroma_at(S.v, S.rs_v, cr_a, ca, cw, ch);
+    const int ub = cb <= 0 ? __ldg(S.u + (long long)S.rs_u * seed_row) : chroma_at(S.u, S.rs_u, cr_a, cb, cw, ch);
+    const int vb = cb <= 0 ? __ldg(S.v + (long long)S.rs_v * seed_row) : chroma_at(S.v, S.rs_v, cr_a, cb, cw, ch);
+    u = clamp_i((ua + ub) >> 1, lo, hi);
+    v = clamp_i((va + vb) >> 1, lo, hi);
+    return;
+  }
+  const int cn = right ? jc + 1 : max(jc - 1, 0);  // neighbour column
+  const int u1t = chroma_at(S.u, S.rs_u, cr_a, jc, cw, ch), u1n = chroma_at(S.u, S.rs_u, cr_a, cn, cw, ch);
+  const int u2t = chroma_at(S.u, S.rs_u, cr_b, jc, cw, ch), u2n = chroma_at(S.u, S.rs_u, cr_b, cn, cw, ch);
+  const int v1t = chroma_at(S.v, S.rs_v, cr_a, jc, cw, ch), v1n = chroma_at(S.v, S.rs_v, cr_a, cn, cw, ch);
+  const int v2t = chroma_at(S.v, S.rs_v, cr_b, jc, cw, ch), v2n = chroma_at(S.v, S.rs_v, cr_b, cn, cw, ch);
+  int u1 = u1t + u1n, u2 = u2t + u2n, v1 = v1t + v1n, v2 = v2t + v2n;
+  if (!right && A.quirks) {
+    u2 = u1;                                                           // colourspace.c:3461
+    if (jc > 0) v1 = v1t + v2n;                                        // :3544
+    v2 = v2t + __ldg(S.v + (long long)S.rs_v * cr_b);                  // last_v2 never advanced
+  }
+  if (!A.low_quality) {
+    u = upper ? third_round(u1 + (u2 >> 1)) : third_round((u1 >> 1) + u2);
+    v = upper ? third_round(v1 + (v2 >> 1)) : third_round((v1 >> 1) + v2);
+  } else {
+    u = upper ? (u1 >> 1) : (u2 >> 1);
+    v = upper ? (v1 >> 1) : (v2 >> 1);
+  }
+  u = clamp_i(u, lo, hi);
+  v = clamp_i(v, lo, hi);
+}
+
+__global__ void __launch_bounds__(kBlock) k_fused(const FusedArgs *__restrict__ frames, int nframes, int tiles_x, int tiles_y,
+                                                  int max_src_rows, int max_src_cols) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  FusedSmem sm;
+  sm.over = smem_raw;
+  sm.tabs = (int32_t *)(smem_raw + 65536);
+  sm.rgba = (uint32_t *)(smem_raw + 65536 + 5 * 1024);
+  sm.hs = (uint2 *)(smem_raw + 65536 + 5 * 1024 + (size_t)max_src_rows * max_src_cols * 4);
+
+  const uint8_t *cur_over = nullptr;
+  const int32_t *cur_conv = nullptr;
+  const long long tiles_per_frame = (long long)tiles_x * tiles_y, total_tiles = tiles_per_frame * nframes;
+
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int f = (int)(tile / tiles_per_frame);
+    const int t = (int)(tile - (long long)f * tiles_per_frame);
+    const FusedArgs A = frames[f];
+    __syncthreads();  // previous tile done with shared memory
+    if (A.over_table != cur_over) {
+      for (int i = threadIdx.x; i < 4096; i += blockDim.x) ((uint4 *)sm.over)[i] = ((const uint4 *)A.over_table)[i];
+      cur_over = A.over_table;
+    }
+    if (A.conv.t != cur_conv) {
+      for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) sm.tabs[i] = A.conv.t[9 * 256 + i];
+      cur_conv = A.conv.t;
+    }
+    const int tx = t % tiles_x, ty = t / tiles_x;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int x1 = min(x0 + kTileW, A.ow), y1 = min(y0 + kTileH, A.oh);
+    // intersection with the inner rectangle, in inner coordinates
+    const int ix0 = max(x0 - A.ox, 0), ix1 = min(x1 - A.ox, A.iw);
+    const int iy0 = max(y0 - A.oy, 0), iy1 = min(y1 - A.oy, A.ih);
+    const bool has_inner = ix0 < ix1 && iy0 < iy1;
+    int sr0 = 0, sr1 = -1, sc0 = 0, sc1 = -1;
+    if (has_inner) {
+      sr0 = min(max(A.fy.first[iy0], 0), A.fh - 1);
+      sr1 = min(max(A.fy.first[iy1 - 1] + A.fy.taps - 1, 0), A.fh - 1);
+      sc0 = min(max(A.fx.first[ix0], 0), A.fw - 1);
+      sc1 = min(max(A.fx.first[ix1 - 1] + A.fx.taps - 1, 0), A.fw - 1);
+    }
+    const int nsr = sr1 - sr0 + 1, nsc = sc1 - sc0 + 1;
+    __syncthreads();
+    // ---- stage 1: convert the needed source pixels once
+    for (int i = threadIdx.x; i < nsr * nsc; i += blockDim.x) {
+      const int r = i / nsc, c = i - r * nsc;
+      const int sy = sr0 + r, sx = sc0 + c;
+      int u, v;
+      chroma_for_pixel(A, sx, sy, u, v);
+      const int y = __ldg(A.fg.y + (long long)A.fg.rs_y * sy + sx);
+      const int yy = sm.tabs[y];
+      const int rr = sat8((yy + sm.tabs[256 + v]) >> 16);
+      const int gg = sat8((yy + sm.tabs[512 + u] + sm.tabs[768 + v]) >> 16);
+      const int bb = sat8((yy + sm.tabs[1024 + u]) >> 16);
+      sm.rgba[r * max_src_cols + c] = (uint32_t)rr | ((uint32_t)gg << 8) | ((uint32_t)bb << 16) | 0xFF000000u;
+    }
+    __syncthreads();
+    // ---- stage 2: horizontal scale of every needed source row, for the tile's inner columns
+    const int niw = ix1 - ix0;
+    for (int i = threadIdx.x; i < nsr * niw; i += blockDim.x) {
+      const int r = i / niw, xi = ix0 + (i - r * niw);
+      const int first = A.fx.first[xi];
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int k = 0; k < A.fx.taps; k++) {
+        const int sx = min(max(first + k, 0), A.fw - 1) - sc0;
+        const int c = A.fx.coef[(long long)xi * A.fx.taps + k];
+        const uint32_t p = sm.rgba[r * max_src_cols + sx];
+        a0 += c * (int)(p & 0xFF); a1 += c * (int)((p >> 8) & 0xFF); a2 += c * (int)((p >> 16) & 0xFF); a3 += c * (int)(p >> 24);
+      }
+      a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
+      sm.hs[r * kTileW + (xi - ix0)] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
+    }
+    __syncthreads();
+    // ---- stage 3: vertical scale, letterbox, alpha-over (+ gamma) and store; one thread = 4 output pixels
+    const int gw = kTileW / 4;
+    for (int i = threadIdx.x; i < gw * (y1 - y0); i += blockDim.x) {
+      const int ry = i / gw, gx = i - ry * gw;
+      const int oy_ = y0 + ry, ox_ = x0 + gx * 4;
+      if (ox_ >= A.ow) continue;
+      const int npx = min(4, A.ow - ox_);
+      const uint8_t *bgp = A.bg.p + (long long)A.bg.rs * oy_ + (long long)ox_ * 4;
+      uint8_t *dp = A.out.p + (long long)A.out.rs * oy_ + (long long)ox_ * 4;
+      const bool vec = npx == 4 && ((((uintptr_t)bgp | (uintptr_t)dp) & 15) == 0);
+      uint32_t bgw[4], outw[4];
+      if (vec) { const uint4 b = ld_stream_u4(bgp); bgw[0] = b.x; bgw[1] = b.y; bgw[2] = b.z; bgw[3] = b.w; }
+      else for (int k = 0; k < npx; k++) bgw[k] = *(const uint32_t *)(bgp + 4 * k);
+      const int iy = oy_ - A.oy;
+      const bool row_in = iy >= iy0 && iy < iy1;
+      int vfirst = 0;
+      if (row_in) vfirst = A.fy.first[iy];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k >= npx) break;
+        const int ix = ox_ + k - A.ox;
+        uint32_t fgp = 0xFF000000u;  // letterbox border: black, opaque (blank_pixel, colourspace.c:11169)
+        if (row_in && ix >= ix0 && ix < ix1) {
+          int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
+          for (int t2 = 0; t2 < A.fy.taps; t2++) {
+            const int sy = min(max(vfirst + t2, 0), A.fh - 1) - sr0;
+            const int c = A.fy.coef[(long long)iy * A.fy.taps + t2];
+            const uint2 hv = sm.hs[sy * kTileW + (ix - ix0)];
+            a0 += c * (int)(hv.x & 0xFFFF); a1 += c * (int)(hv.x >> 16);
+            a2 += c * (int)(hv.y & 0xFFFF); a3 += c * (int)(hv.y >> 16);
+          }
+          fgp = (uint32_t)sat8(a0 >> 19) | ((uint32_t)sat8(a1 >> 19) << 8) | ((uint32_t)sat8(a2 >> 19) << 16) |
+                ((uint32_t)sat8(a3 >> 19) << 24);
+        }
+        const uint32_t b = bgw[k];
+        outw[k] = (uint32_t)sm.over[((b & 0xFF) << 8) | (fgp & 0xFF)] |
+                  ((uint32_t)sm.over[(((b >> 8) & 0xFF) << 8) | ((fgp >> 8) & 0xFF)] << 8) |
+                  ((uint32_t)sm.over[(((b >> 16) & 0xFF) << 8) | ((fgp >> 16) & 0xFF)] << 16) | 0xFF000000u;
+      }
+      if (vec) st_stream_u4(dp, make_uint4(outw[0], outw[1], outw[2], outw[3]));
+      else for (int k = 0; k < npx; k++) *(uint32_t *)(dp + 4 * k) = outw[k];
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_resize_h(const Launch &L, CImg src, int sw, int sh, int16_t *tmp, int dw, int psize, DevFilter fx) {
+  k_resize_h<<<grid_for(L, (long long)dw * sh), kBlock, 0, L.stream>>>(src.p, src.rs, sw, sh, tmp, dw, psize, fx);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst, int dw, int dh, int psize, DevFilter fy) {
+  k_resize_v<<<grid_for(L, (long long)dw * psize * dh), kBlock, 0, L.stream>>>(tmp, sh, dst.p, dst.rs, dw, dh, psize, fy);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// frames_dev: FusedArgs array in DEVICE memory; src extents computed by the caller (engine) from the filter banks
+cudaError_t launch_fused_dev(const Launch &L, const FusedArgs *frames_dev, int nframes, int ow, int oh, int max_src_rows,
+                             int max_src_cols) {
+  const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
+  const size_t smem = 65536 + 5 * 1024 + (size_t)max_src_rows * max_src_cols * 4 + (size_t)max_src_rows * kTileW * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = smem;
+  }
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  long long total = (long long)tiles_x * tiles_y * nframes;
+  int grid = (int)(total < (long long)L.sm_count * per_sm ? total : (long long)L.sm_count * per_sm);
+  k_fused<<<grid, kBlock, smem, L.stream>>>(frames_dev, nframes, tiles_x, tiles_y, max_src_rows, max_src_cols);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+int fused_tile_w() { return kTileW; }
+int fused_tile_h() { return kTileH; }
+
+}  // namespace pe

@@ -1,0 +1,689 @@
+// pe_kernels_rgb.cu -- packed-RGB kernels: palette permutation, gamma LUT, premultiply, letterbox,
+// effect blends, alpha-over, frame statistics.  sm_100a.
+//
+// All of these are HBM-bound byte streams (<= ~20 integer ops per byte): the design rules are
+// 128-bit coalesced accesses, L1-bypassing streaming loads/stores, grids sized as a multiple of the
+// SM count with grid-stride loops, and look-up tables staged in shared memory.
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+
+namespace pe {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(const Launch &L, long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kBlock - 1) / kBlock;
+  long long cap = (long long)L.sm_count * per_sm;  // a whole number of waves of resident CTAs
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+// =====================================================================================================
+// RGB <-> RGB.  One thread = 4 pixels.  3-byte pixels travel as 3 x u32, 4-byte pixels as one uint4.
+// Replaces convert_swap3 / swap4 / addpost / addpre / delpost / delpre / swap3* / swapprepost
+// (colourspace.c:9259-10515) as dispatched by convert_layer_palette_full (:12370-12556).
+// =====================================================================================================
+
+struct PermuteParams {
+  const uint8_t *src;
+  uint8_t *dst;
+  int irow, orow, width, height;
+  int in_r, in_g, in_b, in_a;      // byte offsets inside an input pixel (in_a = -1: none)
+  int out_r, out_g, out_b, out_a;  // byte offsets inside an output pixel
+  uint32_t sel;                    // PRMT selector building an output pixel from (in_pixel, 0xFFFFFFFF)
+  const uint8_t *lut;              // device LUT or nullptr
+  int vec_ok;                      // rows are 4-byte (3 bpp) / 16-byte (4 bpp) aligned on both sides
+};
+
+template <bool HAS_LUT>
+__device__ __forceinline__ uint32_t permute_pixel(uint32_t pix, const PermuteParams &P, const uint8_t *s_lut) {
+  if (!HAS_LUT) return __byte_perm(pix, 0xFFFFFFFFu, P.sel);
+  uint32_t r = s_lut[byte_of(pix, P.in_r)], g = s_lut[byte_of(pix, P.in_g)], b = s_lut[byte_of(pix, P.in_b)];
+  uint32_t o = (r << (8 * P.out_r)) | (g << (8 * P.out_g)) | (b << (8 * P.out_b));
+  if (P.out_a >= 0) o |= (P.in_a >= 0 ? byte_of(pix, P.in_a) : 255u) << (8 * P.out_a);
+  return o;
+}
+
+template <int IPS, int OPS, bool HAS_LUT>
+__global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P) {
+  __shared__ uint8_t s_lut[256];
+  if (HAS_LUT) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
+    __syncthreads();
+  }
+  const int groups = (P.width + 3) >> 2;
+  const long long total = (long long)groups * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const uint8_t *s = P.src + (long long)row * P.irow + (long long)g * 4 * IPS;
+    uint8_t *d = P.dst + (long long)row * P.orow + (long long)g * 4 * OPS;
+    const int npx = min(4, P.width - g * 4);
+    uint32_t pix[4];
+    if (P.vec_ok && npx == 4) {
+      if (IPS == 4) {
+        const uint4 v = ld_u4(s);  // may be in place: plain load
+        pix[0] = v.x; pix[1] = v.y; pix[2] = v.z; pix[3] = v.w;
+      } else {
+        const uint32_t w0 = *(const uint32_t *)(s), w1 = *(const uint32_t *)(s + 4), w2 = *(const uint32_t *)(s + 8);
+        pix[0] = w0;
+        pix[1] = __byte_perm(w0, w1, 0x0543);
+        pix[2] = __byte_perm(w1, w2, 0x0432);
+        pix[3] = w2 >> 8;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) pix[k] = permute_pixel<HAS_LUT>(pix[k], P, s_lut);
+      if (OPS == 4) {
+        *(uint4 *)d = make_uint4(pix[0], pix[1], pix[2], pix[3]);
+      } else {
+        *(uint32_t *)(d) = __byte_perm(pix[0], pix[1], 0x4210);
+        *(uint32_t *)(d + 4) = __byte_perm(pix[1], pix[2], 0x5421);
+        *(uint32_t *)(d + 8) = __byte_perm(pix[2], pix[3], 0x6542);
+      }
+    } else {
+      // ragged tail / unaligned frame: byte path
+      for (int k = 0; k < npx; k++) {
+        uint32_t p = 0;
+        for (int b = 0; b < IPS; b++) p |= (uint32_t)s[k * IPS + b] << (8 * b);
+        p = permute_pixel<HAS_LUT>(p, P, s_lut);
+        for (int b = 0; b < OPS; b++) d[k * OPS + b] = (uint8_t)(p >> (8 * b));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in, RgbLayout out,
+                              const uint8_t *lut8_dev) {
+  PermuteParams P;
+  P.src = src.p; P.dst = dst.p; P.irow = src.rs; P.orow = dst.rs; P.width = width; P.height = height;
+  P.in_r = in.r; P.in_g = in.g; P.in_b = in.b; P.in_a = in.a;
+  P.out_r = out.r; P.out_g = out.g; P.out_b = out.b; P.out_a = out.a;
+  P.lut = lut8_dev;
+  // selector nibble per output byte: index of the source byte, or 4 (= a byte of 0xFFFFFFFF) for opaque alpha
+  uint32_t nib[4] = {0, 0, 0, 0};
+  nib[out.r] = in.r; nib[out.g] = in.g; nib[out.b] = in.b;
+  if (out.a >= 0) nib[out.a] = in.a >= 0 ? in.a : 4;
+  P.sel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+  const int ia = in.psize == 4 ? 16 : 4, oa = out.psize == 4 ? 16 : 4;
+  P.vec_ok = ((uintptr_t)src.p % ia == 0) && (src.rs % ia == 0) && ((uintptr_t)dst.p % oa == 0) && (dst.rs % oa == 0);
+  const long long work = (long long)((width + 3) >> 2) * height;
+  const int grid = grid_for(L, work);
+#define PE_PERM(I, O) \
+  do { if (lut8_dev) k_rgb_to_rgb<I, O, true><<<grid, kBlock, 0, L.stream>>>(P); \
+       else k_rgb_to_rgb<I, O, false><<<grid, kBlock, 0, L.stream>>>(P); } while (0)
+  if (in.psize == 3 && out.psize == 3) PE_PERM(3, 3);
+  else if (in.psize == 3 && out.psize == 4) PE_PERM(3, 4);
+  else if (in.psize == 4 && out.psize == 3) PE_PERM(4, 3);
+  else PE_PERM(4, 4);
+#undef PE_PERM
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// 8-bit gamma LUT over a rectangle, in place (gamma_convert_layer_thread colourspace.c:14034-14062):
+// the first min(3, psize) bytes of every pixel, starting one byte later for ARGB.
+// =====================================================================================================
+
+namespace {
+
+struct LutRectParams {
+  uint8_t *p;
+  int rs, psize, x, y, width, height;
+  uint32_t keep_mask;  // 4-byte palettes: byte lanes that are NOT transformed (the alpha byte)
+  const uint8_t *lut;
+};
+
+__device__ __forceinline__ uint32_t lut_word(uint32_t w, const uint8_t *s_lut, uint32_t keep_mask) {
+  uint32_t o = pack4(s_lut[byte_of(w, 0)], s_lut[byte_of(w, 1)], s_lut[byte_of(w, 2)], s_lut[byte_of(w, 3)]);
+  return (o & ~keep_mask) | (w & keep_mask);
+}
+
+__global__ void __launch_bounds__(kBlock) k_lut8_rect(const LutRectParams P) {
+  __shared__ uint8_t s_lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
+  __syncthreads();
+  // byte span of the rectangle inside a row
+  const int b0 = P.x * P.psize, b1 = (P.x + P.width) * P.psize;
+  // 16-byte chunks; for 3-byte pixels every byte is colour so chunks need no pixel alignment, for 4-byte pixels
+  // a 16-byte aligned chunk always holds 4 whole pixels (rows are 16-byte aligned when vec is used)
+  const bool vec = ((uintptr_t)P.p % 16 == 0) && (P.rs % 16 == 0);
+  const int c0 = vec ? (b0 & ~15) : b0, nchunks = vec ? ((b1 - c0 + 15) >> 4) : 0;
+  if (vec) {
+    const long long total = (long long)nchunks * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / nchunks), c = (int)(it - (long long)row * nchunks);
+      uint8_t *q = P.p + (long long)(P.y + row) * P.rs + c0 + c * 16;
+      const int lo = c0 + c * 16;
+      if (lo >= b0 && lo + 16 <= b1) {
+        uint4 v = *(uint4 *)q;
+        v.x = lut_word(v.x, s_lut, P.keep_mask); v.y = lut_word(v.y, s_lut, P.keep_mask);
+        v.z = lut_word(v.z, s_lut, P.keep_mask); v.w = lut_word(v.w, s_lut, P.keep_mask);
+        *(uint4 *)q = v;
+      } else {
+        for (int b = max(lo, b0); b < min(lo + 16, b1); b++) {
+          if (P.psize == 4 && ((P.keep_mask >> (8 * (b & 3))) & 0xFF)) continue;
+          q[b - lo] = s_lut[q[b - lo]];
+        }
+      }
+    }
+  } else {
+    const long long total = (long long)(b1 - b0) * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / (b1 - b0)), b = b0 + (int)(it - (long long)row * (b1 - b0));
+      if (P.psize == 4 && ((P.keep_mask >> (8 * (b & 3))) & 0xFF)) continue;
+      uint8_t *q = P.p + (long long)(P.y + row) * P.rs + b;
+      *q = s_lut[*q];
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_lut8_rect(const Launch &L, Img img, RgbLayout lay, int x, int y, int width, int height,
+                             const uint8_t *lut8_dev) {
+  LutRectParams P;
+  P.p = img.p; P.rs = img.rs; P.psize = lay.psize; P.x = x; P.y = y; P.width = width; P.height = height;
+  P.keep_mask = lay.a >= 0 ? (0xFFu << (8 * lay.a)) : 0u;
+  P.lut = lut8_dev;
+  const long long work = ((long long)width * lay.psize + 15) / 16 * height;
+  k_lut8_rect<<<grid_for(L, work), kBlock, 0, L.stream>>>(P);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// alpha premultiply / un-premultiply, in place (alpha_premult colourspace.c:11968-12106).
+// tab0/1/2: the 64 KB [alpha][value] table for colour byte 0/1/2 of the pixel (RGB: all the same table;
+// clamped YUVA8888: Y table + UV table twice).  yuva_fwd_quirk: index the U and V tables with the pixel's
+// Y byte, as colourspace.c:12093-12094 does.
+// =====================================================================================================
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_premult(uint8_t *p, int rs, int width, int height, int coffs, int aoffs,
+                                                    const uint8_t *__restrict__ t0, const uint8_t *__restrict__ t1,
+                                                    const uint8_t *__restrict__ t2, int quirk) {
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    uint32_t *q = (uint32_t *)(p + (long long)row * rs) + x;
+    const uint32_t w = *q;
+    const uint32_t a = byte_of(w, aoffs);
+    const uint32_t c0 = byte_of(w, coffs), c1 = byte_of(w, coffs + 1), c2 = byte_of(w, coffs + 2);
+    const uint32_t n0 = __ldg(t0 + a * 256 + c0);
+    // quirk: U and V are looked up with the Y byte AFTER it was rewritten (colourspace.c:12092-12094)
+    const uint32_t n1 = __ldg(t1 + a * 256 + (quirk ? n0 : c1));
+    const uint32_t n2 = __ldg(t2 + a * 256 + (quirk ? n0 : c2));
+    *q = (a << (8 * aoffs)) | (n0 << (8 * coffs)) | (n1 << (8 * (coffs + 1))) | (n2 << (8 * (coffs + 2)));
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_premult(const Launch &L, Img img, int width, int height, int coffs, int ncol, int aoffs,
+                           const uint8_t *tab0, const uint8_t *tab1, const uint8_t *tab2, int yuva_fwd_quirk) {
+  (void)ncol;
+  k_premult<<<grid_for(L, (long long)width * height), kBlock, 0, L.stream>>>(img.p, img.rs, width, height, coffs, aoffs,
+                                                                           tab0, tab1, tab2, yuva_fwd_quirk);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// fill / 2-D copy / letterbox (blank_frame colourspace.c:11213, letterbox_layer :15343-15567)
+// =====================================================================================================
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_fill(uint8_t *p, int rs, int width, int height, int psize, uint32_t pixel) {
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    uint8_t *q = p + (long long)row * rs + (long long)x * psize;
+    if (psize == 4) *(uint32_t *)q = pixel;
+    else { q[0] = (uint8_t)pixel; q[1] = (uint8_t)(pixel >> 8); q[2] = (uint8_t)(pixel >> 16); }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_copy2d(const uint8_t *__restrict__ src, int srs, uint8_t *__restrict__ dst,
+                                                   int drs, int row_bytes, int rows, int fill, uint8_t fv) {
+  const bool vec = ((uintptr_t)dst % 16 == 0) && (drs % 16 == 0) && (fill || (((uintptr_t)src % 16 == 0) && (srs % 16 == 0)));
+  if (vec) {
+    const int chunks = (row_bytes + 15) >> 4;
+    const long long total = (long long)chunks * rows;
+    const uint32_t f4 = fv * 0x01010101u;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / chunks), c = (int)(it - (long long)row * chunks);
+      uint8_t *d = dst + (long long)row * drs + c * 16;
+      if (c * 16 + 16 <= row_bytes) {
+        st_stream_u4(d, fill ? make_uint4(f4, f4, f4, f4) : ld_stream_u4(src + (long long)row * srs + c * 16));
+      } else {
+        for (int b = c * 16; b < row_bytes; b++) dst[(long long)row * drs + b] = fill ? fv : src[(long long)row * srs + b];
+      }
+    }
+  } else {
+    const long long total = (long long)row_bytes * rows;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / row_bytes), b = (int)(it - (long long)row * row_bytes);
+      dst[(long long)row * drs + b] = fill ? fv : src[(long long)row * srs + b];
+    }
+  }
+}
+
+// every outer pixel is written exactly once: inner pixel or black border
+__global__ void __launch_bounds__(kBlock) k_letterbox(const uint8_t *__restrict__ inner, int irs, int iw, int ih,
+                                                      uint8_t *__restrict__ outer, int ors, int ow, int oh, int psize,
+                                                      int ox, int oy, uint32_t black) {
+  const long long total = (long long)ow * oh;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / ow), x = (int)(it - (long long)row * ow);
+    const int ix = x - ox, iy = row - oy;
+    const bool in = ix >= 0 && ix < iw && iy >= 0 && iy < ih;
+    uint8_t *d = outer + (long long)row * ors + (long long)x * psize;
+    if (psize == 4) {
+      *(uint32_t *)d = in ? *(const uint32_t *)(inner + (long long)iy * irs + (long long)ix * 4) : black;
+    } else {
+      const uint8_t *s = inner + (long long)iy * irs + (long long)ix * 3;
+      d[0] = in ? s[0] : (uint8_t)black; d[1] = in ? s[1] : (uint8_t)(black >> 8); d[2] = in ? s[2] : (uint8_t)(black >> 16);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fill(const Launch &L, Img dst, int width, int height, int psize, uint32_t pixel) {
+  k_fill<<<grid_for(L, (long long)width * height), kBlock, 0, L.stream>>>(dst.p, dst.rs, width, height, psize, pixel);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy2d(const Launch &L, const uint8_t *src, int srs, uint8_t *dst, int drs, int row_bytes, int rows,
+                          int fill, uint8_t fill_value) {
+  if (rows <= 0 || row_bytes <= 0) return cudaSuccess;
+  k_copy2d<<<grid_for(L, (long long)((row_bytes + 15) >> 4) * rows), kBlock, 0, L.stream>>>(src, srs, dst, drs, row_bytes,
+                                                                                          rows, fill, fill_value);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_letterbox(const Launch &L, CImg inner, int iw, int ih, Img outer, int ow, int oh, int psize,
+                             uint32_t black_pixel) {
+  const int ox = (ow - iw + 1) >> 1, oy = (oh - ih + 1) >> 1;  // colourspace.c:15522-15523
+  k_letterbox<<<grid_for(L, (long long)ow * oh), kBlock, 0, L.stream>>>(inner.p, inner.rs, iw, ih, outer.p, outer.rs, ow, oh,
+                                                                       psize, ox, oy, black_pixel);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// simple_blend.c (chroma blend + luma overlays).  A batch of frames shares one launch: blockIdx.y = frame.
+// =====================================================================================================
+
+namespace {
+
+// (bf * a + bfn * b) >> 8 on the four bytes of a word, two 16-bit lanes at a time.
+// bf + bfn == 255, so every lane stays below 65536 and nothing carries between lanes.
+__device__ __forceinline__ uint32_t blend4(uint32_t a, uint32_t b, uint32_t bf, uint32_t bfn) {
+  const uint32_t lo = (a & 0x00FF00FFu) * bf + (b & 0x00FF00FFu) * bfn;
+  const uint32_t hi = ((a >> 8) & 0x00FF00FFu) * bf + ((b >> 8) & 0x00FF00FFu) * bfn;
+  return ((lo >> 8) & 0x00FF00FFu) | (hi & 0xFF00FF00u);
+}
+
+struct BlendParams {
+  const BlendFrame *frames;
+  int width, height, psize, bf, type;
+  int r_off, g_off, b_off, a_off;  // a_off: 3 (RGBA/BGRA), 0 (ARGB), -1
+  const int32_t *luma;             // [3][256] plugin-side 16.16 luma tables
+};
+
+// chroma blend on 3-byte pixels: a pure byte stream (simple_blend.c:117-125)
+__global__ void __launch_bounds__(kBlock) k_chroma_blend3(const BlendParams P) {
+  const BlendFrame F = P.frames[blockIdx.y];
+  const uint32_t bf = (uint8_t)P.bf, bfn = 0xFFu - bf;
+  const int row_bytes = P.width * 3;
+  const bool vec = (((uintptr_t)F.s1 | (uintptr_t)F.s2 | (uintptr_t)F.d) % 16 == 0) && ((F.rs1 | F.rs2 | F.rsd) % 16 == 0);
+  if (vec) {
+    const int chunks = (row_bytes + 15) >> 4;
+    const long long total = (long long)chunks * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / chunks), c = (int)(it - (long long)row * chunks);
+      const long long o1 = (long long)row * F.rs1 + c * 16, o2 = (long long)row * F.rs2 + c * 16,
+                      od = (long long)row * F.rsd + c * 16;
+      if (c * 16 + 16 <= row_bytes) {
+        const uint4 a = ld_u4(F.s2 + o2), b = ld_u4(F.s1 + o1);
+        uint4 r;
+        r.x = blend4(a.x, b.x, bf, bfn); r.y = blend4(a.y, b.y, bf, bfn);
+        r.z = blend4(a.z, b.z, bf, bfn); r.w = blend4(a.w, b.w, bf, bfn);
+        *(uint4 *)(F.d + od) = r;
+      } else {
+        for (int k = 0; k < row_bytes - c * 16; k++)
+          F.d[od + k] = (uint8_t)((bf * F.s2[o2 + k] + bfn * F.s1[o1 + k]) >> 8);
+      }
+    }
+  } else {
+    const long long total = (long long)row_bytes * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / row_bytes), k = (int)(it - (long long)row * row_bytes);
+      F.d[(long long)row * F.rsd + k] =
+          (uint8_t)((bf * F.s2[(long long)row * F.rs2 + k] + bfn * F.s1[(long long)row * F.rs1 + k]) >> 8);
+    }
+  }
+}
+
+// chroma blend on 4-byte pixels (simple_blend.c:127-148): opaque src2 pixels blend bytewise, others scale both
+// operands by alpha in float32 first; the alpha byte of dst is never written.  For ARGB the plugin starts at
+// byte 1 (start = 1, :80) so the "alpha" it tests is byte 0 of the NEXT pixel: replicated via a_next.
+__global__ void __launch_bounds__(kBlock) k_chroma_blend4(const BlendParams P) {
+  const BlendFrame F = P.frames[blockIdx.y];
+  const uint32_t bf = (uint8_t)P.bf, bfn = 0xFFu - bf;
+  const bool argb = (P.a_off == 0);
+  const long long total = (long long)P.width * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / P.width), x = (int)(it - (long long)row * P.width);
+    const long long o1 = (long long)row * F.rs1 + x * 4, o2 = (long long)row * F.rs2 + x * 4, od = (long long)row * F.rsd + x * 4;
+    const uint32_t p1 = *(const uint32_t *)(F.s1 + o1), p2 = *(const uint32_t *)(F.s2 + o2);
+    uint32_t a2;
+    if (!argb) a2 = p2 >> 24;
+    else a2 = (o2 + 4 < F.s2_bytes) ? F.s2[o2 + 4] : 255u;
+    const uint32_t cmask = argb ? 0xFFFFFF00u : 0x00FFFFFFu;
+    uint32_t res;
+    if (a2 == 255u) {
+      res = blend4(p2, p1, bf, bfn);
+    } else {
+      const float alpha = (float)((double)(float)a2 / 255.), inv_alpha = (float)(1. - (double)alpha);
+      uint32_t q2 = 0, q1 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        q2 |= ((uint32_t)(uint8_t)__fmul_rn((float)byte_of(p2, k), alpha)) << (8 * k);
+        q1 |= ((uint32_t)(uint8_t)__fmul_rn((float)byte_of(p1, k), inv_alpha)) << (8 * k);
+      }
+      res = blend4(q2, q1, bf, bfn);
+    }
+    // bytes outside the colour mask keep whatever dst holds (in place: src1's alpha)
+    const uint32_t keep = (F.d == F.s1) ? p1 : *(const uint32_t *)(F.d + od);
+    *(uint32_t *)(F.d + od) = (res & cmask) | (keep & ~cmask);
+  }
+}
+
+__device__ __forceinline__ uint32_t plugin_luma(const int32_t *luma, uint32_t r, uint32_t g, uint32_t b) {
+  return (uint32_t)((luma[r] + luma[256 + g] + luma[512 + b]) >> 16) & 0xFFu;  // calc_luma returns uint8_t
+}
+
+// luma overlay / underlay / negative overlay (simple_blend.c:153-197): whole-pixel select
+__global__ void __launch_bounds__(kBlock) k_luma_select(const BlendParams P) {
+  __shared__ int32_t s_luma[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_luma[i] = P.luma[i];
+  __syncthreads();
+  const BlendFrame F = P.frames[blockIdx.y];
+  const uint32_t bf = (uint8_t)P.bf, bfn = 0xFFu - bf;
+  const int start = (P.a_off == 0) ? 1 : 0;  // ARGB
+  const long long total = (long long)P.width * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / P.width), x = (int)(it - (long long)row * P.width);
+    const uint8_t *s1 = F.s1 + (long long)row * F.rs1 + x * P.psize + start;
+    const uint8_t *s2 = F.s2 + (long long)row * F.rs2 + x * P.psize + start;
+    uint8_t *d = F.d + (long long)row * F.rsd + x * P.psize + start;
+    // colour bytes relative to `start`
+    const int ro = P.r_off - start, go = P.g_off - start, bo = P.b_off - start;
+    bool take2;
+    if (P.type == 1) take2 = plugin_luma(s_luma, s1[ro], s1[go], s1[bo]) < bf;
+    else if (P.type == 2) take2 = plugin_luma(s_luma, s2[ro], s2[go], s2[bo]) > bfn;
+    else take2 = plugin_luma(s_luma, s1[ro], s1[go], s1[bo]) > bfn;
+    const uint8_t *s = take2 ? s2 : s1;
+    if (take2 || F.d != F.s1) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_simple_blend(const Launch &L, int type, const BlendFrame *frames_dev, int nframes, int width,
+                                int height, RgbLayout lay, int bf, const int32_t *luma_tabs_dev) {
+  BlendParams P;
+  P.frames = frames_dev; P.width = width; P.height = height; P.psize = lay.psize; P.bf = bf; P.type = type;
+  P.r_off = lay.r; P.g_off = lay.g; P.b_off = lay.b; P.a_off = lay.a; P.luma = luma_tabs_dev;
+  const long long per_frame = type == 0 && lay.psize == 3 ? (long long)((width * 3 + 15) >> 4) * height
+                                                          : (long long)width * height;
+  // split the SMs between the frames of the batch
+  int gx = grid_for(L, per_frame, 8);
+  if (nframes > 1) gx = max(1, min(gx, (L.sm_count * 8 + nframes - 1) / nframes));
+  dim3 grid(gx, nframes);
+  if (type == 0 && lay.psize == 3) k_chroma_blend3<<<grid, kBlock, 0, L.stream>>>(P);
+  else if (type == 0) k_chroma_blend4<<<grid, kBlock, 0, L.stream>>>(P);
+  else k_luma_select<<<grid, kBlock, 0, L.stream>>>(P);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// multi_blends.c (multiply, screen, darken, lighten, overlay, dodge, burn), RGB24 / BGR24
+// =====================================================================================================
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_multi_blend(int type, BlendFrame F, int width, int height, int bgr, int bf,
+                                                        const int32_t *__restrict__ luma) {
+  __shared__ int32_t s_luma[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_luma[i] = luma[i];
+  __syncthreads();
+  const uint8_t blend_factor = (uint8_t)bf;
+  // unsigned char arithmetic of multi_blends.c:56-60 (wraps modulo 256)
+  const uint32_t blend1 = (uint8_t)(blend_factor * 2), blendneg1 = (uint8_t)(255 - blend_factor * 2);
+  const uint32_t blend2 = (uint8_t)((255 - blend_factor) * 2), blendneg2 = (uint8_t)((blend_factor - 128) * 2);
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    const uint8_t *s1 = F.s1 + (long long)row * F.rs1 + x * 3, *s2 = F.s2 + (long long)row * F.rs2 + x * 3;
+    uint8_t *d = F.d + (long long)row * F.rsd + x * 3;
+    int a[3] = {s1[0], s1[1], s1[2]}, b[3] = {s2[0], s2[1], s2[2]}, px[3];
+    const int r1 = bgr ? a[2] : a[0], bl1 = bgr ? a[0] : a[2], r2 = bgr ? b[2] : b[0], bl2 = bgr ? b[0] : b[2];
+    bool mpy = false, scr = false;
+    switch (type) {
+    case 0: mpy = true; break;
+    case 1: scr = true; break;
+    case 2: case 3: {
+      const uint32_t l1 = plugin_luma(s_luma, r1, a[1], bl1), l2 = plugin_luma(s_luma, r2, b[1], bl2);
+      const bool first = type == 2 ? (l1 <= l2) : (l1 >= l2);
+#pragma unroll
+      for (int k = 0; k < 3; k++) px[k] = first ? a[k] : b[k];
+      break;
+    }
+    case 4: if (plugin_luma(s_luma, r1, a[1], bl1) < 128) mpy = true; else scr = true; break;
+    case 5:
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (b[k] == 255) px[k] = 255;
+        else { const int v = (a[k] << 8) / (255 - b[k]); px[k] = v > 255 ? 255 : (v & 0xFF); }
+      }
+      break;
+    default:
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (b[k] == 0) px[k] = 0;
+        else { const int v = 255 - (255 - (a[k] << 8)) / b[k]; px[k] = v < 0 ? 0 : (v & 0xFF); }
+      }
+      break;
+    }
+    if (mpy) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) px[k] = (b[k] * a[k]) >> 8;
+    }
+    if (scr) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) px[k] = (255 - (((255 - b[k]) * (255 - a[k])) >> 8)) & 0xFF;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      d[k] = blend_factor < 128 ? (uint8_t)((blend1 * px[k] + blendneg1 * a[k]) >> 8)
+                                : (uint8_t)((blend2 * px[k] + blendneg2 * b[k]) >> 8);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_multi_blend(const Launch &L, int type, BlendFrame f, int width, int height, int bgr, int bf,
+                               const int32_t *luma_tabs_dev) {
+  k_multi_blend<<<grid_for(L, (long long)width * height), kBlock, 0, L.stream>>>(type, f, width, height, bgr, bf, luma_tabs_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// alpha-over: dst = (u8)(bg * (1 - alpha) + fg * alpha) in double, truncating store
+// (gdk/compositor.c paint_pixel :120-125), optionally followed by the 8-bit gamma LUT in the same pass.
+//
+// The scalar alpha makes the result a pure function of the (bg, fg) byte pair.  k_over_table evaluates the
+// reference's double expression (no FMA contraction: __dmul_rn / __dadd_rn) once for all 65536 pairs --
+// composed with the gamma LUT when there is one -- into a 64 KB table in HBM (cached by the engine per
+// (alpha, LUT)); k_alpha_over stages that table in shared memory and the per-pixel work becomes one gather
+// per colour byte, with 128-bit loads / stores of 4 pixels per thread.
+// =====================================================================================================
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_over_table(double alpha, const uint8_t *__restrict__ lut, uint8_t *__restrict__ tab) {
+  const double invalpha = 1. - alpha;
+  for (int i = (int)global_tid(); i < 65536; i += (int)global_threads()) {
+    const double v = __dadd_rn(__dmul_rn((double)(i >> 8), invalpha), __dmul_rn((double)(i & 255), alpha));
+    uint8_t r = (uint8_t)(int)v;  // C conversion double -> unsigned char: truncation
+    if (lut) r = lut[r];
+    tab[i] = r;  // [bg][fg]
+  }
+}
+
+struct OverParams {
+  const uint8_t *bg, *fg;
+  uint8_t *dst;
+  int rs_bg, rs_fg, rs_d, width, height, psize;
+  const uint8_t *tab;
+  int force_opaque;  // compositor fills alpha with 0xFF (compositor.c:184) and never paints it
+  int a_off;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_alpha_over(const OverParams P) {
+  extern __shared__ __align__(16) uint8_t s_tab[];  // [bg][fg]
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) ((uint4 *)s_tab)[i] = ((const uint4 *)P.tab)[i];
+  __syncthreads();
+  if (P.psize == 4) {
+    const uint32_t amask = 0xFFu << (8 * P.a_off);
+    const bool vec = (((uintptr_t)P.bg | (uintptr_t)P.fg | (uintptr_t)P.dst) % 16 == 0) && ((P.rs_bg | P.rs_fg | P.rs_d) % 16 == 0);
+    const int groups = (P.width + 3) >> 2;
+    const long long total = (long long)groups * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+      const int npx = min(4, P.width - g * 4);
+      const uint8_t *b = P.bg + (long long)row * P.rs_bg + g * 16, *f = P.fg + (long long)row * P.rs_fg + g * 16;
+      uint8_t *d = P.dst + (long long)row * P.rs_d + g * 16;
+      uint32_t bw[4], fw[4], ow[4];
+      if (vec && npx == 4) {
+        const uint4 vb = ld_u4(b), vf = ld_u4(f);
+        bw[0] = vb.x; bw[1] = vb.y; bw[2] = vb.z; bw[3] = vb.w;
+        fw[0] = vf.x; fw[1] = vf.y; fw[2] = vf.z; fw[3] = vf.w;
+      } else {
+        for (int k = 0; k < npx; k++) { bw[k] = *(const uint32_t *)(b + 4 * k); fw[k] = *(const uint32_t *)(f + 4 * k); }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < npx) {
+          uint32_t o = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) o |= (uint32_t)s_tab[(byte_of(bw[k], c) << 8) | byte_of(fw[k], c)] << (8 * c);
+          ow[k] = (o & ~amask) | (P.force_opaque ? amask : (bw[k] & amask));
+        }
+      }
+      if (vec && npx == 4) *(uint4 *)d = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      else for (int k = 0; k < npx; k++) *(uint32_t *)(d + 4 * k) = ow[k];
+    }
+  } else {
+    const int row_bytes = P.width * 3;
+    const long long total = (long long)row_bytes * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / row_bytes), k = (int)(it - (long long)row * row_bytes);
+      P.dst[(long long)row * P.rs_d + k] = s_tab[((uint32_t)P.bg[(long long)row * P.rs_bg + k] << 8) | P.fg[(long long)row * P.rs_fg + k]];
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev) {
+  k_over_table<<<64, kBlock, 0, L.stream>>>(alpha, lut8_dev, table_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize,
+                              const uint8_t *over_table_dev, int force_opaque) {
+  OverParams P;
+  P.bg = bg.p; P.fg = fg.p; P.dst = dst.p; P.rs_bg = bg.rs; P.rs_fg = fg.rs; P.rs_d = dst.rs;
+  P.width = width; P.height = height; P.psize = psize; P.tab = over_table_dev;
+  P.force_opaque = force_opaque; P.a_off = 3;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_alpha_over, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_alpha_over<<<L.sm_count, 1024, 65536, L.stream>>>(P);  // persistent: one CTA per SM (64 KB table each)
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// per-frame diagnostics: min / max per byte position, histogram of the colour bytes, byte sum, black test.
+// Warp-shuffle reductions, one atomic per warp (per CTA for the histogram).
+// =====================================================================================================
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_stats(const uint8_t *__restrict__ p, int rs, int width, int height, int psize,
+                                                  int a_off, DevStats *out) {
+  __shared__ unsigned int s_hist[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  unsigned int mn[4] = {255, 255, 255, 255}, mx[4] = {0, 0, 0, 0}, notblack = 0;
+  unsigned long long sum = 0;
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    const uint8_t *q = p + (long long)row * rs + (long long)x * psize;
+    for (int k = 0; k < psize; k++) {
+      const unsigned int v = q[k];
+      mn[k] = min(mn[k], v); mx[k] = max(mx[k], v); sum += v;
+      if (k != a_off) { atomicAdd(&s_hist[v], 1u); notblack |= (v != 0); }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+      mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    notblack |= __shfl_xor_sync(0xffffffffu, notblack, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 4; k++) { atomicMin(&out->minv[k], mn[k]); atomicMax(&out->maxv[k], mx[k]); }
+    atomicAdd(&out->sum, sum);
+    if (notblack) atomicOr(&out->not_black, 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (s_hist[i]) atomicAdd(&out->hist[i], s_hist[i]);
+}
+
+}  // namespace
+
+cudaError_t launch_stats(const Launch &L, CImg img, int width, int height, int psize, int a_off, DevStats *out_dev) {
+  k_stats<<<grid_for(L, (long long)width * height, 4), kBlock, 0, L.stream>>>(img.p, img.rs, width, height, psize, a_off, out_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+}  // namespace pe

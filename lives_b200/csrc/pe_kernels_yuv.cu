@@ -1,0 +1,315 @@
+// pe_kernels_yuv.cu -- YUV <-> RGB conversion kernels (sm_100a).
+//
+//   k_yuv_planar_to_rgb   convert_yuv420p_to_{rgb,bgr,argb}_frame  colourspace.c:3260 / 3927 / 4527
+//                         (4:2:0 and 4:2:2 planar, chroma super-sampling, optional inline 16-bit gamma LUT)
+//   k_packed422_to_rgb    convert_{uyvy,yuyv}_to_*_frame            colourspace.c:6616-7103
+//   k_yuv888_to_rgb       convert_yuv888 / yuva8888_to_*_frame      colourspace.c:2750-3258
+//   k_rgb_to_yuv888       convert_{rgb,bgr,argb}_to_yuv_frame       colourspace.c:5700-6239
+//
+// Arithmetic contract (bit exact with the reference):
+//   R = clamp((RGB_Y[y] + R_Cr[v]) >> 16, 0, 255) etc. -- the reference's float32 spc_rnd(HIGH) and
+//   CLAMP0255f are byte-identical to this integer form for all 2^24 inputs (tests/test_oracle_vs_reference.py),
+//   chroma weights (int)(n / 3. + .5) == (2n + 3) / 6.
+// The five 256-entry int tables live in shared memory.
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+
+namespace pe {
+
+namespace {
+
+constexpr int kBlock = 256;
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+inline int grid_for(const Launch &L, long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kBlock - 1) / kBlock;
+  long long cap = (long long)L.sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// shared-memory copy of the YUV->RGB tables: [0] RGB_Y [1] R_Cr [2] G_Cb [3] G_Cr [4] B_Cb
+struct SmemYuvTabs {
+  int32_t t[5][256];
+};
+
+__device__ __forceinline__ void load_yuv_tabs(SmemYuvTabs &s, const int32_t *conv_t) {
+  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) s.t[i >> 8][i & 255] = conv_t[(9 + (i >> 8)) * 256 + (i & 255)];
+}
+
+__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+
+// yuv2rgb_int colourspace.c:2345 / xyuv2rgb :2351 (+ xyuv2rgb_with_gamma :2386 when lut16 != nullptr)
+__device__ __forceinline__ void yuv_px(const SmemYuvTabs &s, const uint16_t *lut16, int y, int u, int v, int &r, int &g,
+                                       int &b) {
+  const int yy = s.t[0][y];
+  const int rr = yy + s.t[1][v], gg = yy + s.t[2][u] + s.t[3][v], bb = yy + s.t[4][u];
+  if (!lut16) {
+    r = sat8(rr >> 16); g = sat8(gg >> 16); b = sat8(bb >> 16);
+  } else {
+    r = __ldg(lut16 + min(max(rr >> 8, 0), 65535)) >> 8;
+    g = __ldg(lut16 + min(max(gg >> 8, 0), 65535)) >> 8;
+    b = __ldg(lut16 + min(max(bb >> 8, 0), 65535)) >> 8;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_px(const RgbLayout &o, int r, int g, int b) {
+  uint32_t w = ((uint32_t)r << (8 * o.r)) | ((uint32_t)g << (8 * o.g)) | ((uint32_t)b << (8 * o.b));
+  if (o.a >= 0) w |= 0xFFu << (8 * o.a);
+  return w;
+}
+
+// store 4 pixels (already packed, one per word) as 16 or 12 bytes
+__device__ __forceinline__ void store_px4(uint8_t *d, int psize, const uint32_t px[4], bool vec) {
+  if (psize == 4) {
+    if (vec) st_stream_u4(d, make_uint4(px[0], px[1], px[2], px[3]));
+    else for (int k = 0; k < 4; k++) *(uint32_t *)(d + 4 * k) = px[k];
+  } else {
+    const uint32_t w0 = __byte_perm(px[0], px[1], 0x4210), w1 = __byte_perm(px[1], px[2], 0x5421),
+                   w2 = __byte_perm(px[2], px[3], 0x6542);
+    if (vec) { st_stream_u32(d, w0); st_stream_u32(d + 4, w1); st_stream_u32(d + 8, w2); }
+    else for (int k = 0; k < 12; k++) d[k] = (uint8_t)((k < 4 ? w0 : k < 8 ? w1 : w2) >> (8 * (k & 3)));
+  }
+}
+
+__device__ __forceinline__ void store_px_n(uint8_t *d, int psize, const uint32_t *px, int n) {
+  for (int k = 0; k < n; k++)
+    for (int b = 0; b < psize; b++) d[k * psize + b] = (uint8_t)(px[k] >> (8 * b));
+}
+
+// chroma sample with the reference's one-past-row read (colourspace.c:3508-3512, :3613): column == cw reads the
+// byte at plane[stride * r + cw] -- padding or the first sample of row r+1 -- except on the last chroma row of a
+// plane whose stride equals its width, where it is defined as the replicated edge sample (DESIGN.md "edge read").
+__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, int stride, int r, int c, int cw, int ch) {
+  if (c >= cw) c = (cw < stride || r + 1 < ch) ? cw : cw - 1;
+  return __ldg(p + (long long)stride * r + c);
+}
+
+// One thread = 4 luma columns (two chroma columns) of one "job":
+//   4:2:0  job 0           : luma row 0      with chroma row 0              (single-row average)
+//          job k, 1..ch-1  : luma rows 2k-1, 2k with chroma rows k-1, k     (2/3 - 1/3 vertical weights)
+//          job ch (h even) : luma row h-1    with chroma row ch-1           (single-row average)
+//   4:2:2  job i           : luma row i      with chroma row i
+__global__ void __launch_bounds__(kBlock) k_yuv_planar_to_rgb(const YuvToRgbArgs A) {
+  __shared__ SmemYuvTabs s;
+  load_yuv_tabs(s, A.conv.t);
+  __syncthreads();
+  const Planes &S = A.src;
+  const int w = A.width, h = A.height, cw = S.cw, ch = S.ch;
+  const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
+  const int groups = (w + 3) >> 2;
+  const int njobs = A.is_422 ? h : (h >= 2 && !(h & 1) ? ch + 1 : ch);
+  const bool vec = ((uintptr_t)A.dst.p % 16 == 0) && (A.dst.rs % 16 == 0);
+  const bool yvec = ((uintptr_t)S.y % 4 == 0) && (S.rs_y % 4 == 0);
+  const long long total = (long long)groups * njobs;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int job = (int)(it / groups), g = (int)(it - (long long)job * groups);
+    const int x0 = g * 4, npx = min(4, w - x0), jc0 = g * 2;
+    int row_a, row_b = -1, cr_a, cr_b = -1;  // luma rows / chroma rows
+    bool pair = false;
+    if (A.is_422) { row_a = job; cr_a = job; }
+    else if (job == 0) { row_a = 0; cr_a = 0; }
+    else if (job < ch) { pair = true; row_a = 2 * job - 1; row_b = 2 * job; cr_a = job - 1; cr_b = job; }
+    else { row_a = h - 1; cr_a = ch - 1; }
+
+    // luma
+    uint32_t ya, yb = 0;
+    {
+      const uint8_t *py = S.y + (long long)S.rs_y * row_a + x0;
+      if (yvec && npx == 4) ya = ld_stream_u32(py);
+      else { ya = 0; for (int k = 0; k < npx; k++) ya |= (uint32_t)py[k] << (8 * k); }
+      if (pair) {
+        py = S.y + (long long)S.rs_y * row_b + x0;
+        if (yvec && npx == 4) yb = ld_stream_u32(py);
+        else for (int k = 0; k < npx; k++) yb |= (uint32_t)py[k] << (8 * k);
+      }
+    }
+
+    uint32_t out_a[4], out_b[4];
+    if (!pair) {
+      // horizontal average only (:3394-3438 row 0, :3551-3596 last row -- X rows: intended arithmetic -- and the
+      // whole 4:2:2 branch :3598-3642).  4:2:2 quirk: the running pair is seeded from chroma row (i >> 1) (:3600)
+      const int seed_row = (A.is_422 && A.quirks) ? (row_a >> 1) : cr_a;
+      int uc[4], vc[4];  // chroma columns jc0-1 .. jc0+2
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = jc0 - 1 + k;
+        if (c <= 0) {  // column 0 is replaced by the seed sample (last = this = seed at the start of a row)
+          uc[k] = __ldg(S.u + (long long)S.rs_u * seed_row);
+          vc[k] = __ldg(S.v + (long long)S.rs_v * seed_row);
+        } else {
+          uc[k] = chroma_at(S.u, S.rs_u, cr_a, c, cw, ch);
+          vc[k] = chroma_at(S.v, S.rs_v, cr_a, c, cw, ch);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        // pixel x0+k: pair index p = k>>1 (chroma column jc0+p = uc[p+1]); left pixel averages with the previous
+        // column, right pixel with the next one
+        const int p = k >> 1;
+        const int ua = uc[p + 1], va = vc[p + 1];
+        const int ub = (k & 1) ? uc[p + 2] : uc[p], vb = (k & 1) ? vc[p + 2] : vc[p];
+        const int u = clamp_i((ua + ub) >> 1, lo, hi), v = clamp_i((va + vb) >> 1, lo, hi);
+        int r, gg, b;
+        yuv_px(s, A.lut16, byte_of(ya, k), u, v, r, gg, b);
+        out_a[k] = pack_px(A.out, r, gg, b);
+      }
+    } else {
+      // interior row pair (:3440-3549)
+      int u1c[4], u2c[4], v1c[4], v2c[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = max(jc0 - 1 + k, 0);  // column -1 replicates column 0 (last = this at the start of a row)
+        u1c[k] = chroma_at(S.u, S.rs_u, cr_a, c, cw, ch);
+        u2c[k] = chroma_at(S.u, S.rs_u, cr_b, c, cw, ch);
+        v1c[k] = chroma_at(S.v, S.rs_v, cr_a, c, cw, ch);
+        v2c[k] = chroma_at(S.v, S.rs_v, cr_b, c, cw, ch);
+      }
+      const int v2_first = A.quirks ? __ldg(S.v + (long long)S.rs_v * cr_b) : 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int p = k >> 1, jc = jc0 + p;
+        int u1, u2, v1, v2;
+        if (k & 1) {  // right pixel: this + next
+          u1 = u1c[p + 1] + u1c[p + 2]; u2 = u2c[p + 1] + u2c[p + 2];
+          v1 = v1c[p + 1] + v1c[p + 2]; v2 = v2c[p + 1] + v2c[p + 2];
+        } else {      // left pixel: this + last
+          u1 = u1c[p + 1] + u1c[p];
+          v2 = v2c[p + 1] + v2c[p];
+          u2 = u2c[p + 1] + u2c[p];
+          v1 = v1c[p + 1] + v1c[p];
+          if (A.quirks) {
+            u2 = u1;                                        // `u2 = this_u1 + last_u1`          (:3461)
+            if (jc > 0) v1 = v1c[p + 1] + v2c[p];           // `last_v1 = this_v2`               (:3544)
+            v2 = v2c[p + 1] + v2_first;                     // last_v2 is never advanced         (:3543-3546)
+          }
+        }
+        int u3, u4, v3, v4;
+        if (!A.low_quality) {
+          u3 = clamp_i(third_round(u1 + (u2 >> 1)), lo, hi); u4 = clamp_i(third_round((u1 >> 1) + u2), lo, hi);
+          v3 = clamp_i(third_round(v1 + (v2 >> 1)), lo, hi); v4 = clamp_i(third_round((v1 >> 1) + v2), lo, hi);
+        } else {
+          u3 = clamp_i(u1 >> 1, lo, hi); u4 = clamp_i(u2 >> 1, lo, hi);
+          v3 = clamp_i(v1 >> 1, lo, hi); v4 = clamp_i(v2 >> 1, lo, hi);
+        }
+        int r, gg, b;
+        yuv_px(s, A.lut16, byte_of(ya, k), u3, v3, r, gg, b);
+        out_a[k] = pack_px(A.out, r, gg, b);
+        yuv_px(s, A.lut16, byte_of(yb, k), u4, v4, r, gg, b);
+        out_b[k] = pack_px(A.out, r, gg, b);
+      }
+    }
+    uint8_t *da = A.dst.p + (long long)A.dst.rs * row_a + (long long)x0 * A.out.psize;
+    if (npx == 4) store_px4(da, A.out.psize, out_a, vec); else store_px_n(da, A.out.psize, out_a, npx);
+    if (pair) {
+      uint8_t *db = A.dst.p + (long long)A.dst.rs * row_b + (long long)x0 * A.out.psize;
+      if (npx == 4) store_px4(db, A.out.psize, out_b, vec); else store_px_n(db, A.out.psize, out_b, npx);
+    }
+  }
+}
+
+// packed 4:2:2: both pixels of a macropixel share u0, v0 (uyvy2rgb colourspace.c:2410-2415). One thread = 2
+// macropixels = 4 output pixels.
+__global__ void __launch_bounds__(kBlock) k_packed422_to_rgb(int fmt, const uint8_t *__restrict__ src, int irow, uint8_t *dst,
+                                                             int orow, int width_mpx, int height, RgbLayout out, DevConv conv) {
+  __shared__ SmemYuvTabs s;
+  load_yuv_tabs(s, conv.t);
+  __syncthreads();
+  const int groups = (width_mpx + 1) >> 1;
+  const bool vec = ((uintptr_t)dst % 16 == 0) && (orow % 16 == 0);
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int nm = min(2, width_mpx - g * 2);
+    uint32_t px[4];
+    for (int m = 0; m < nm; m++) {
+      const uint32_t mp = *(const uint32_t *)(src + (long long)irow * row + (long long)(g * 2 + m) * 4);
+      int y0, y1, u, v, r, gg, b;
+      if (fmt == 0) { u = byte_of(mp, 0); y0 = byte_of(mp, 1); v = byte_of(mp, 2); y1 = byte_of(mp, 3); }
+      else { y0 = byte_of(mp, 0); u = byte_of(mp, 1); y1 = byte_of(mp, 2); v = byte_of(mp, 3); }
+      yuv_px(s, nullptr, y0, u, v, r, gg, b); px[2 * m] = pack_px(out, r, gg, b);
+      yuv_px(s, nullptr, y1, u, v, r, gg, b); px[2 * m + 1] = pack_px(out, r, gg, b);
+    }
+    uint8_t *d = dst + (long long)orow * row + (long long)g * 4 * out.psize;
+    if (nm == 2) store_px4(d, out.psize, px, vec); else store_px_n(d, out.psize, px, 2 * nm);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_yuv888_to_rgb(const uint8_t *__restrict__ src, int irow, uint8_t *dst, int orow,
+                                                          int width, int height, int in_alpha, RgbLayout out, DevConv conv) {
+  __shared__ SmemYuvTabs s;
+  load_yuv_tabs(s, conv.t);
+  __syncthreads();
+  const int ips = in_alpha ? 4 : 3;
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    const uint8_t *q = src + (long long)irow * row + (long long)x * ips;
+    int r, g, b;
+    yuv_px(s, nullptr, q[0], q[1], q[2], r, g, b);
+    uint32_t w = ((uint32_t)r << (8 * out.r)) | ((uint32_t)g << (8 * out.g)) | ((uint32_t)b << (8 * out.b));
+    if (out.a >= 0) w |= (in_alpha ? (uint32_t)q[3] : 255u) << (8 * out.a);
+    uint8_t *d = dst + (long long)orow * row + (long long)x * out.psize;
+    for (int k = 0; k < out.psize; k++) d[k] = (uint8_t)(w >> (8 * k));
+  }
+}
+
+// rgb2yuv colourspace.c:2119-2127: always the YCbCr tables (:5710); the reference rounds the width down to even (:5750)
+__global__ void __launch_bounds__(kBlock) k_rgb_to_yuv888(const uint8_t *__restrict__ src, int irow, uint8_t *dst, int orow,
+                                                          int width, int height, RgbLayout in, int out_alpha, DevConv conv) {
+  __shared__ int32_t t[9][256];
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[i];
+  __syncthreads();
+  const int ops = out_alpha ? 4 : 3;
+  const long long total = (long long)width * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
+    const uint8_t *q = src + (long long)irow * row + (long long)x * in.psize;
+    const int r = q[in.r], g = q[in.g], b = q[in.b];
+    // the reference stores the rounded sum in a short before comparing (:2120); sums are < 2^15 so no wrap
+    const int y = clamp_i((t[0][r] + t[1][g] + t[2][b]) >> 16, conv.min_y, conv.max_y);
+    const int u = clamp_i((t[3][r] + t[4][g] + t[5][b]) >> 16, conv.min_uv, conv.max_uv);
+    const int v = clamp_i((t[6][r] + t[7][g] + t[8][b]) >> 16, conv.min_uv, conv.max_uv);
+    uint8_t *d = dst + (long long)orow * row + (long long)x * ops;
+    d[0] = (uint8_t)y; d[1] = (uint8_t)u; d[2] = (uint8_t)v;
+    if (out_alpha) d[3] = in.a >= 0 ? q[in.a] : 255;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a) {
+  const int groups = (a.width + 3) >> 2;
+  const int njobs = a.is_422 ? a.height : a.src.ch + 1;
+  k_yuv_planar_to_rgb<<<grid_for(L, (long long)groups * njobs), kBlock, 0, L.stream>>>(a);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_packed422_to_rgb(const Launch &L, int fmt, CImg src, Img dst, int width_mpx, int height,
+                                    RgbLayout out, DevConv conv) {
+  k_packed422_to_rgb<<<grid_for(L, (long long)((width_mpx + 1) >> 1) * height), kBlock, 0, L.stream>>>(
+      fmt, src.p, src.rs, dst.p, dst.rs, width_mpx, height, out, conv);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_yuv888_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, int in_alpha,
+                                 RgbLayout out, DevConv conv) {
+  k_yuv888_to_rgb<<<grid_for(L, (long long)width * height), kBlock, 0, L.stream>>>(src.p, src.rs, dst.p, dst.rs, width, height,
+                                                                                 in_alpha, out, conv);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in,
+                                 int out_alpha, DevConv conv) {
+  width = (width >> 1) << 1;
+  k_rgb_to_yuv888<<<grid_for(L, (long long)width * height), kBlock, 0, L.stream>>>(src.p, src.rs, dst.p, dst.rs, width, height, in,
+                                                                                 out_alpha, conv);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+}  // namespace pe

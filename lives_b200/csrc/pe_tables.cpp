@@ -1,0 +1,259 @@
+// pe_tables.cpp -- host-side table construction (see pe_tables.h).
+//
+// Bit-parity notes
+//  * colour matrices are evaluated in double with the reference's operand order
+//    (a * i * clamp_factor * SCALE_FACTOR, left to right) and rounded half away from zero
+//    (myround, src/maths.h:118); SCALE_FACTOR is 65793 = 0xFFFFFF / 0xFF (colourspace.h:60).
+//  * the BT.709 green/Cb coefficient uses 1 + Kb + Kb and the YCbCr one 1 + Kb + Kr exactly as the
+//    reference spells them (colourspace.c:1005,1062) -- they are table constants, not "fixed" here.
+//  * gamma LUTs go through float32 / powf and reproduce the reference's loop-carried overwrite of
+//    gamma_from (colourspace.c:701): after the first entry the source is treated as linear.
+#include "pe_tables.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/pixel_engine.h"
+
+namespace pe {
+
+namespace {
+
+inline int round_half_away(double n) { return n >= 0. ? (int)(n + 0.5) : (int)(n - 0.5); }
+
+constexpr double kScale = 65793.;  // SCALE_FACTOR with USE_EXTEND (colourspace.h:13,60)
+
+struct Primaries { double kr, kb; };
+inline Primaries primaries_for(int subspace) {
+  // colourspace.h:84-91; WEED_YUV_SUBSPACE_YUV is treated as YCbCr (colourspace.c:226)
+  if (subspace == PE_YUV_SUBSPACE_BT709) return {0.2126, 0.0722};
+  return {0.299, 0.114};
+}
+
+}  // namespace
+
+void build_conv_tables(int clamping, int subspace, ConvTables *out) {
+  const Primaries p = primaries_for(subspace);
+  const bool clamped = (clamping == PE_YUV_CLAMPING_CLAMPED);
+  const bool hd = (subspace == PE_YUV_SUBSPACE_BT709);
+  const double kg = 1. - p.kr - p.kb;          // written (1. - KR - KB) in the luma rows
+  const double kg_c = 1. - p.kb - p.kr;        // written (1. - KB - KR) in the chroma rows
+  const double fy = (235. - 16.) / 255.;       // CLAMP_FACTOR_Y  colourspace.h:120
+  const double fuv = (240. - 16.) / 255.;      // CLAMP_FACTOR_UV colourspace.h:121
+  const double fac_b = .5 / (1. - p.kb), fac_r = .5 / (1. - p.kr);
+
+  // ---- RGB -> YUV (init_RGB_to_YUV_tables, colourspace.c:851-981)
+  for (int i = 0; i < 256; i++) {
+    const double d = (double)i;
+    if (clamped) {
+      out->t[Y_R][i] = round_half_away(p.kr * d * fy * kScale);
+      out->t[Y_G][i] = round_half_away(kg * d * fy * kScale);
+      out->t[Y_B][i] = round_half_away((p.kb * d * fy + 16.) * kScale);
+      out->t[CB_R][i] = round_half_away(-fac_b * p.kr * d * fuv * kScale);
+      out->t[CB_G][i] = round_half_away(-fac_b * kg_c * d * fuv * kScale);
+      out->t[CB_B][i] = round_half_away((0.5 * d * fuv + 128.) * kScale);
+      out->t[CR_R][i] = round_half_away((0.5 * d * fuv + 128.) * kScale);
+      out->t[CR_G][i] = round_half_away(-fac_r * kg_c * d * fuv * kScale);
+      out->t[CR_B][i] = round_half_away(-fac_r * p.kb * d * fuv * kScale);
+    } else {
+      out->t[Y_R][i] = round_half_away(p.kr * d * kScale);
+      out->t[Y_G][i] = round_half_away(kg * d * kScale);
+      out->t[Y_B][i] = round_half_away(p.kb * d * kScale);
+      out->t[CB_R][i] = round_half_away(-fac_b * p.kr * d * kScale);
+      out->t[CB_G][i] = round_half_away(-fac_b * kg_c * d * kScale);
+      out->t[CB_B][i] = round_half_away((0.5 * d + 128.) * kScale);
+      out->t[CR_R][i] = round_half_away((0.5 * d + 128.) * kScale);
+      out->t[CR_G][i] = round_half_away(-fac_r * kg_c * d * kScale);
+      out->t[CR_B][i] = round_half_away(-fac_r * p.kb * d * kScale);
+    }
+  }
+  if (clamped) { out->min_y = out->min_uv = 16; out->max_y = 235; out->max_uv = 240; }
+  else { out->min_y = out->min_uv = 0; out->max_y = out->max_uv = 255; }
+
+  // ---- YUV -> RGB (init_YUV_to_RGB_tables, colourspace.c:984-1105)
+  const double c_rcr = 2. * (1. - p.kr);
+  const double c_gcb = hd ? -.5 / (1. + p.kb + p.kb) : -.5 / (1. + p.kb + p.kr);
+  const double c_gcr = -.5 / (1. - p.kr);
+  const double c_bcb = 2. * (1. - p.kb);
+  auto chroma_row = [&](int i, double centred) {
+    out->t[R_CR][i] = round_half_away(c_rcr * centred * kScale);
+    out->t[G_CB][i] = round_half_away(c_gcb * centred * kScale);
+    out->t[G_CR][i] = round_half_away(c_gcr * centred * kScale);
+    out->t[B_CB][i] = round_half_away(c_bcb * centred * kScale);
+  };
+  if (clamped) {
+    for (int i = 0; i < 256; i++) {
+      if (i <= 16) out->t[RGB_Y][i] = 0;
+      else if (i < 235) out->t[RGB_Y][i] = round_half_away(((double)i - 16.) / (235. - 16.) * 255. * kScale);
+      else out->t[RGB_Y][i] = (int)(255 * kScale);
+      if (i <= 16) {
+        out->t[R_CR][i] = out->t[G_CB][i] = out->t[G_CR][i] = out->t[B_CB][i] = 0;
+      } else if (i < 240) {
+        chroma_row(i, (((double)i - 16.) / (240. - 16.) * 255.) - 128.);
+      } else {
+        // above 240: YCbCr saturates at the value for 240 (:1015-1024), BT.709 at 255 - 128 (:1078-1081)
+        chroma_row(i, hd ? (255. - 128.) : (((240. - 16.) / (240. - 16.) * 255.) - 128.));
+      }
+    }
+  } else {
+    for (int i = 0; i < 256; i++) {
+      out->t[RGB_Y][i] = (int)(i * kScale);
+      chroma_row(i, (double)i - 128.);
+    }
+  }
+}
+
+// ---- gamma ------------------------------------------------------------------------------------
+
+namespace {
+
+struct GammaTx { float offs, lin, thresh, pf; };
+
+// INIT_GAMMA (colourspace.h:157-161) for sRGB and BT.709 (colourspace.h:168-169)
+void gamma_tx_table(GammaTx tx[2]) {
+  tx[0] = {0.f, 12.92f, 0.04045f, 2.4f};
+  tx[1] = {0.f, 4.5f, 0.018f, (float)(1. / .45)};
+  for (int k = 0; k < 2; k++) {
+    const float knee = powf((tx[k].thresh / tx[k].lin), (1. / tx[k].pf));
+    tx[k].offs = (knee - tx[k].thresh) / (1. - knee);
+  }
+}
+
+inline int tx_index(int gamma_type) { return gamma_type == PE_GAMMA_BT709 ? 1 : 0; }  // get_gamma_idx :625
+
+struct GammaWalk {
+  // state carried from one LUT entry to the next, as the reference's parameter is (colourspace.c:697-713)
+  int from;
+  const int to;
+  const double fileg, screen_gamma;
+  float inv_gamma;
+  GammaTx tx[2];
+
+  GammaWalk(double fg, int f, int t, double sg) : from(f), to(t), fileg(fg), screen_gamma(sg), inv_gamma(0.f) {
+    gamma_tx_table(tx);
+    if (to == PE_GAMMA_MONITOR) inv_gamma = 1. / (float)screen_gamma;
+  }
+
+  float step(float a) {
+    float x = a;
+    if (fileg != 1.0) x = powf(a, fileg);
+    if (from == PE_GAMMA_MONITOR) {
+      x = powf(a, screen_gamma);
+      from = PE_GAMMA_SRGB;
+    }
+    if (from != PE_GAMMA_LINEAR && !(from == PE_GAMMA_SRGB && to == PE_GAMMA_MONITOR)) {
+      const GammaTx &g = tx[tx_index(from)];
+      a = (a < g.thresh) ? a / g.lin : powf((a + g.offs) / (1. + g.offs), g.pf);
+      from = PE_GAMMA_LINEAR;
+    }
+    if (to != PE_GAMMA_LINEAR) {
+      const GammaTx &g = tx[to == PE_GAMMA_MONITOR ? 0 : tx_index(to)];
+      x = (a < (g.thresh) / g.lin) ? a * g.lin : powf((1. + g.offs) * a, 1. / g.pf) - g.offs;
+    }
+    if (to == PE_GAMMA_MONITOR) x = powf(a, inv_gamma);
+    return x;
+  }
+};
+
+inline bool gamma_is_noop(double fileg, int from, int to) {
+  return fileg == 1.0 && (to == from || to == PE_GAMMA_UNKNOWN || from == PE_GAMMA_UNKNOWN);  // :662-663
+}
+
+}  // namespace
+
+bool build_gamma_lut8(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint8_t out[256]) {
+  if (gamma_is_noop(fileg, gamma_from, gamma_to)) return false;
+  GammaWalk w(fileg, gamma_from, gamma_to, screen_gamma);
+  out[0] = 0;
+  for (int i = 1; i < 256; ++i) {
+    const float x = w.step((float)i / 255.);
+    const int v = (int)(x * 255.);  // CLAMP0_255i, colourspace.h:22-23
+    out[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+  }
+  return true;
+}
+
+bool build_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint16_t *out) {
+  if (gamma_is_noop(fileg, gamma_from, gamma_to)) return false;
+  GammaWalk w(fileg, gamma_from, gamma_to, screen_gamma);
+  out[0] = 0;
+  for (int i = 1; i < 65536; ++i) {
+    const float x = w.step((float)i / 65536.);
+    out[i] = x >= 0.99999 ? 65535 : x < 0.00001 ? 0 : (uint16_t)(x * 65535.9999);  // CLAMP16bit colourspace.h:16
+  }
+  return true;
+}
+
+// ---- premultiply (init_unal, colourspace.c:1141-1160) ------------------------------------------
+
+namespace {
+// CLAMP0255f (src/maths.h:88) evaluated in the type of the expression handed to it
+template <typename T>
+inline uint8_t clamp_round_u8(T a) { return a >= 254.5 ? (uint8_t)255 : a < -0.5 ? (uint8_t)0 : (uint8_t)(a + .5); }
+}  // namespace
+
+void build_premult_table(int which, uint8_t *out) {
+  for (int a = 0; a < 256; a++) {
+    const float alpha = (float)255. / (float)a;
+    for (int v = 0; v < 256; v++) {
+      int r;
+      switch (which) {
+      case 0: r = clamp_round_u8((float)v / alpha); break;                               // unal
+      case 1: r = clamp_round_u8((float)v * alpha); break;                               // al
+      case 2: r = (int)((float)v / alpha + .5) > (235. - 16.) ? 235                      // unalcy
+                  : (int)((float)(v - 16.) / alpha + 16. + .5); break;
+      case 3: r = (int)((float)v / alpha + .5) > (240. - 16.) ? 240                      // alcy
+                  : (int)((float)(v - 16.) / alpha + 16. + .5); break;
+      case 4: r = clamp_round_u8((float)(v - 16.) * alpha + 16.); break;                 // unalcuv
+      default: r = clamp_round_u8((float)(v - 128.) * alpha + 128.); break;              // alcuv
+      }
+      out[a * 256 + v] = (uint8_t)r;  // the int tables are only ever stored into bytes (:12061,12071)
+    }
+  }
+}
+
+void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]) {
+  for (int i = 0; i < 256; i++) {
+    yr[i] = round_half_away(0.299 * (double)i * 65536.);
+    yg[i] = round_half_away((1. - 0.299 - 0.114) * (double)i * 65536.);
+    yb[i] = round_half_away(0.114 * (double)i * 65536.);
+  }
+}
+
+// ---- resize filter bank (our contract; the reference delegates to libswscale) --------------------
+
+bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out) {
+  if (src_n <= 0 || dst_n <= 0) return false;
+  const double ratio = (double)src_n / (double)dst_n;
+  const bool down = ratio > 1.;
+  const double support = down ? ratio : 1.;
+  const int taps = down ? (int)std::ceil(2. * ratio) + 1 : 2;
+  if (taps > 64) return false;
+  const int one = 1 << shift_bits;
+  out->taps = taps;
+  out->first.assign(dst_n, 0);
+  out->coef.assign((size_t)dst_n * taps, 0);
+  std::vector<double> w(taps);
+  for (int i = 0; i < dst_n; i++) {
+    const double centre = ((double)i + 0.5) * ratio - 0.5;
+    const int left = down ? (int)std::floor(centre - support) + 1 : (int)std::floor(centre);
+    double sum = 0.;
+    for (int k = 0; k < taps; k++) {
+      const double d = std::fabs((double)(left + k) - centre) / support;
+      w[k] = d < 1. ? 1. - d : 0.;
+      sum += w[k];
+    }
+    int acc = 0, big = 0;
+    for (int k = 0; k < taps; k++) {
+      const int q = (int)std::floor(w[k] / sum * one + 0.5);
+      out->coef[(size_t)i * taps + k] = (int16_t)q;
+      acc += q;
+      if (w[k] > w[big]) big = k;
+    }
+    out->coef[(size_t)i * taps + big] += (int16_t)(one - acc);
+    out->first[i] = left;
+  }
+  return true;
+}
+
+}  // namespace pe

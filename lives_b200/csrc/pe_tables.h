@@ -1,0 +1,40 @@
+// pe_tables.h -- host-side construction of every lookup table the kernels use.
+// Product code (no oracle involvement): the formulas follow the reference's table builders
+// (file:line cited per function in pe_tables.cpp) and are evaluated in the same C types
+// (double for the colour matrices, float32 + powf for gamma) so that the tables are bit-identical.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace pe {
+
+// index of the 14 conversion tables, the order struct _conv_array lists them (colourspace.h:65-82)
+enum ConvTab { Y_R = 0, Y_G, Y_B, CB_R, CB_G, CB_B, CR_R, CR_G, CR_B, RGB_Y, R_CR, G_CB, G_CR, B_CB, N_CONVTAB };
+
+struct ConvTables {
+  int32_t t[N_CONVTAB][256];
+  int min_y, max_y, min_uv, max_uv;
+};
+
+void build_conv_tables(int clamping, int subspace, ConvTables *out);
+
+// create_gamma_lut8 / create_gamma_lut (colourspace.c:655 / :738); return false when the reference returns NULL
+bool build_gamma_lut8(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint8_t out[256]);
+bool build_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint16_t *out /*65536*/);
+
+// init_unal (colourspace.c:1141): which = 0 unal 1 al 2 unalcy 3 alcy 4 unalcuv 5 alcuv, as uint8
+void build_premult_table(int which, uint8_t *out /*65536*/);
+
+// calc_luma tables of libweed/weed-plugin-utils.c:881-886 (16.16, SCALE_FACTOR 65536)
+void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]);
+
+// Resize filter bank (our published contract, DESIGN.md "resize"): taps per output sample, first source
+// index and fixed-point coefficients summing to 1 << shift_bits.
+struct ResizeFilter {
+  int taps = 0;
+  std::vector<int32_t> first;  // [dst_n]
+  std::vector<int16_t> coef;   // [dst_n * taps]
+};
+bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out);
+
+}  // namespace pe

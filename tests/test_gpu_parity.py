@@ -1,0 +1,611 @@
+"""GPU parity: the CUDA path, called through the C ABI (lives_b200 -> libpe_b200.so), against the CPU oracle
+(oracle/libpe_oracle.so, itself pinned to the compiled reference by tests/test_oracle_vs_reference.py).
+
+Bit-exact everywhere (integer / byte work).  Run on the B200 box: pytest -m gpu.
+"""
+import ctypes as C
+import itertools
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import pe_testlib as T  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+lb = pytest.importorskip("lives_b200")
+
+RGB_PALS = (1, 2, 3, 4, 5)
+ORDER_OF = {1: (0, 0), 2: (1, 0), 3: (0, 1), 4: (1, 1), 5: (2, 1)}  # palette -> (oracle order, add_alpha)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = lb.Engine()
+    yield e
+    e.close()
+
+
+def packed_layer(eng, pal, w, h, arr, **kw):
+    return lb.Layer.from_host(eng, pal, w, h, [arr], **kw)
+
+
+def payload(arr, w, ps):
+    return arr[:, :w * ps]
+
+
+# ------------------------------------------------------------------------------------------------ RGB <-> RGB
+
+@pytest.mark.parametrize("size", [(640, 480), (37, 11), (1, 1), (1921, 7)])
+def test_config1_rgb24_to_bgr24_and_all_rgb_pairs(eng, size):
+    """BASELINE config 1 (640x480 RGB24 -> BGR24 convert_layer_palette) + every pair of the 5 RGB palettes"""
+    o = T.oracle()
+    rng = np.random.default_rng(1)
+    w, h = size
+    for ipal, opal in itertools.product(RGB_PALS, RGB_PALS):
+        if ipal == opal:
+            continue
+        ips, ops = T.psize_of(ipal), T.psize_of(opal)
+        src = T.make_packed(rng, w, h, ips)
+        exp = np.zeros((h, T.rowstride(w, ops)), np.uint8)
+        assert o.pe_or_rgb_to_rgb(ipal, opal, T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], None) == 0
+        lay = packed_layer(eng, ipal, w, h, src)
+        assert lb.convert_layer_palette(lay, opal, 0)
+        assert lay.palette == opal and lay.width == w and lay.height == h
+        got = lay.to_host()[0]
+        assert got.shape == exp.shape
+        assert (payload(got, w, ops) == payload(exp, w, ops)).all(), (ipal, opal)
+        lay.free()
+
+
+def test_rgb_to_rgb_with_gamma_lut(eng):
+    """gamma_lut8 inside the permutation (colourspace.c:12372), tgt_gamma given"""
+    o = T.oracle()
+    rng = np.random.default_rng(2)
+    w, h = 123, 17
+    for (gf, gt), (ipal, opal) in itertools.product(((T.G_SRGB, T.G_LINEAR), (T.G_LINEAR, T.G_SRGB), (T.G_SRGB, T.G_BT709),
+                                                     (T.G_LINEAR, T.G_MONITOR)), ((1, 2), (1, 3), (3, 1), (4, 5), (5, 3))):
+        ips, ops = T.psize_of(ipal), T.psize_of(opal)
+        src = T.make_packed(rng, w, h, ips)
+        lut = np.zeros(256, np.uint8)
+        assert o.pe_or_gamma_lut8(1.0, gf, gt, 1.4, T.ptr(lut)) == 0
+        exp = np.zeros((h, T.rowstride(w, ops)), np.uint8)
+        o.pe_or_rgb_to_rgb(ipal, opal, T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], T.ptr(lut))
+        lay = packed_layer(eng, ipal, w, h, src, gamma_type=gf)
+        assert lb.convert_layer_palette_full(lay, opal, 0, 0, 0, gt)
+        assert lay.gamma_type == gt
+        got = lay.to_host()[0]
+        assert (payload(got, w, ops) == payload(exp, w, ops)).all(), (gf, gt, ipal, opal)
+        assert (eng.gamma_lut8(1.0, gf, gt) == lut).all()
+
+
+def test_rgb_roundtrip_4k_property(eng):
+    """size-independent property at 4K: RGB24 -> BGRA32 -> ARGB32 -> RGB24 is the identity"""
+    rng = np.random.default_rng(3)
+    w, h = 3840, 2160
+    src = T.make_packed(rng, w, h, 3)
+    lay = packed_layer(eng, 1, w, h, src)
+    for pal in (4, 5, 2, 3, 1):
+        assert lb.convert_layer_palette(lay, pal, 0)
+    got = lay.to_host()[0]
+    assert (payload(got, w, 3) == payload(src, w, 3)).all()
+
+
+# ------------------------------------------------------------------------------------------------ planar YUV -> RGB
+
+def _oracle_planar(o, y, u, v, w, h, opal, is422, cl, sub, q, quirks=1, lut16=None):
+    order, add_alpha = ORDER_OF[opal]
+    ps = T.psize_of(opal)
+    exp = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+    o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(exp), exp.strides[0], order, add_alpha,
+                           is422, cl, sub, q, quirks, T.ptr(lut16))
+    return exp
+
+
+@pytest.mark.parametrize("size", [(64, 48), (130, 34), (2, 2), (6, 4), (642, 362)])
+@pytest.mark.parametrize("is422", [0, 1])
+def test_planar_yuv_to_rgb(eng, size, is422):
+    """convert_yuv420p_to_{rgb,bgr,argb}_frame (colourspace.c:3260,3927,4527) through convert_layer_palette_full"""
+    o = T.oracle()
+    rng = np.random.default_rng(4)
+    w, h = size
+    inpal = T.PAL["YUV422P"] if is422 else T.PAL["YUV420P"]
+    for opal, cl, sub in itertools.product(RGB_PALS, (0, 1), (1, 2)):
+        y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), cl == 0)
+        exp = _oracle_planar(o, y, u, v, w, h, opal, is422, cl, sub, T.Q_HIGH)
+        lay = lb.Layer.from_host(eng, inpal, w, h, [y, u, v], yuv_clamping=cl, yuv_subspace=sub)
+        assert lb.convert_layer_palette_full(lay, opal, cl, 0, sub, 0)
+        got = lay.to_host()[0]
+        ps = T.psize_of(opal)
+        assert (payload(got, w, ps) == payload(exp, w, ps)).all(), (opal, cl, sub)
+        assert lay.yuv_clamping == 0 and lay.yuv_subspace == 0
+        lay.free()
+
+
+def test_planar_yuv_quality_quirks_and_yvu(eng):
+    """PB_QUALITY_LOW chroma shortcut (RGB order only, :3470), ref_quirks off, YVU420P plane swap (:12354)"""
+    o = T.oracle()
+    rng = np.random.default_rng(5)
+    w, h = 98, 50
+    y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+    e_low = lb.Engine(pb_quality=lb.PB_QUALITY_LOW)
+    for opal in RGB_PALS:
+        exp = _oracle_planar(o, y, u, v, w, h, opal, 0, 0, 1, T.Q_LOW)
+        lay = lb.Layer.from_host(e_low, 512, w, h, [y, u, v], yuv_subspace=1)
+        assert lb.convert_layer_palette(lay, opal, 0)
+        ps = T.psize_of(opal)
+        assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), opal
+    e_low.close()
+    e_nq = lb.Engine(ref_quirks=False)
+    for is422 in (0, 1):
+        yy, uu, vv = T.make_yuv_planar(rng, w, h, bool(is422), True)
+        exp = _oracle_planar(o, yy, uu, vv, w, h, 3, is422, 0, 1, T.Q_HIGH, quirks=0)
+        lay = lb.Layer.from_host(e_nq, 522 if is422 else 512, w, h, [yy, uu, vv], yuv_subspace=1)
+        assert lb.convert_layer_palette(lay, 3, 0)
+        assert (payload(lay.to_host()[0], w, 4) == payload(exp, w, 4)).all()
+    e_nq.close()
+    exp = _oracle_planar(o, y, u, v, w, h, 1, 0, 0, 1, T.Q_HIGH)
+    lay = lb.Layer.from_host(eng, 513, w, h, [y, v, u], yuv_subspace=1)  # YVU: V plane first
+    assert lb.convert_layer_palette(lay, 1, 0)
+    assert (payload(lay.to_host()[0], w, 3) == payload(exp, w, 3)).all()
+
+
+def test_planar_yuv_inline_gamma(eng):
+    """xyuv2rgb_with_gamma (colourspace.c:2386): 16-bit LUT inside the converter when the layer has a gamma type"""
+    o = T.oracle()
+    rng = np.random.default_rng(6)
+    w, h = 64, 48
+    for gf, gt, opal in ((T.G_SRGB, T.G_LINEAR, 3), (T.G_SRGB, T.G_BT709, 1), (T.G_LINEAR, T.G_SRGB, 2), (T.G_BT709, T.G_SRGB, 5)):
+        y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+        lut = np.zeros(65536, np.uint16)
+        assert o.pe_or_gamma_lut16(1.0, gf, gt, 1.4, T.ptr(lut)) == 0
+        exp = _oracle_planar(o, y, u, v, w, h, opal, 0, 0, 1, T.Q_HIGH, lut16=lut)
+        lay = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_subspace=1, gamma_type=gf)
+        assert lb.convert_layer_palette_full(lay, opal, 0, 0, 1, gt)
+        assert lay.gamma_type == gt
+        ps = T.psize_of(opal)
+        assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), (gf, gt, opal)
+
+
+def test_config2_1080p_yuv420p_to_rgba_resize_720p(eng):
+    """BASELINE config 2: 1920x1080 YUV420P (clamped, BT.601) -> RGBA32 -> bilinear 1280x720.  Conversion is
+    bit-exact with the reference arithmetic; the resize follows OUR published filter (parity unpinned: libswscale)."""
+    o = T.oracle()
+    rng = np.random.default_rng(2)
+    w, h, dw, dh = 1920, 1080, 1280, 720
+    y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+    rgba = _oracle_planar(o, y, u, v, w, h, 3, 0, 0, 1, T.Q_HIGH)
+    exp = np.zeros((dh, T.rowstride(dw, 4)), np.uint8)
+    o.pe_or_resize_packed(T.ptr(rgba), rgba.strides[0], w, h, T.ptr(exp), exp.strides[0], dw, dh, 4)
+    lay = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_clamping=0, yuv_subspace=1)
+    assert lb.resize_layer(lay, dw, dh, lb.LIVES_INTERP_NORMAL, lb.WEED_PALETTE_RGBA32, 0)
+    assert (lay.palette, lay.width, lay.height) == (3, dw, dh)
+    got = lay.to_host()[0]
+    assert (payload(got, dw, 4) == payload(exp, dw, 4)).all()
+    # sanity against an independent area-average (float) of the converted frame: mean abs diff well below 1 LSB
+    ref = rgba[:, :w * 4].reshape(h, w, 4).astype(np.float64)
+    blk = ref.reshape(dh, 3, w, 4)  # 1.5x down is not integer: compare only the global mean
+    assert abs(float(got[:, :dw * 4].mean()) - float(ref.mean())) < 0.5
+    del blk
+
+
+# ------------------------------------------------------------------------------------------------ packed YUV
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_packed422_to_rgb(eng, fmt):
+    o = T.oracle()
+    rng = np.random.default_rng(7)
+    wm, h = 49, 21
+    inpal = 564 if fmt == 0 else 565
+    for opal, cl, sub in itertools.product(RGB_PALS, (0, 1), (1, 2)):
+        order, add_alpha = ORDER_OF[opal]
+        ps = T.psize_of(opal)
+        src = T.make_packed(rng, wm, h, 4)
+        exp = np.zeros((h, T.rowstride(wm * 2, ps)), np.uint8)
+        # table choice of the dispatcher: uyvy->RGB24 honours the subspace, uyvy->RGBA32 gets the SAMPLING (0 here)
+        osub = sub if (fmt == 0 and opal == 1) else 1
+        o.pe_or_packed422_to_rgb(fmt, T.ptr(src), src.strides[0], wm, h, T.ptr(exp), exp.strides[0], order, add_alpha, cl,
+                                 osub, T.Q_HIGH)
+        lay = lb.Layer.from_host(eng, inpal, wm * 2, h, [src], yuv_clamping=cl, yuv_subspace=sub)
+        assert lb.convert_layer_palette_full(lay, opal, cl, 0, sub, 0)
+        assert lay.width == wm * 2
+        assert (payload(lay.to_host()[0], wm * 2, ps) == payload(exp, wm * 2, ps)).all(), (opal, cl, sub)
+
+
+def test_yuv888_both_directions(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(8)
+    w, h = 50, 13
+    for inpal, opal, cl in itertools.product((588, 589), RGB_PALS, (0, 1)):
+        order, out_alpha = ORDER_OF[opal]
+        ips, ops = T.psize_of(inpal), T.psize_of(opal)
+        src = T.make_packed(rng, w, h, ips)
+        exp = np.zeros((h, T.rowstride(w, ops)), np.uint8)
+        o.pe_or_yuv888_to_rgb(T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], order, int(inpal == 589), out_alpha,
+                              cl, 1, T.Q_HIGH)
+        lay = lb.Layer.from_host(eng, inpal, w, h, [src], yuv_clamping=cl, yuv_subspace=1)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        assert (payload(lay.to_host()[0], w, ops) == payload(exp, w, ops)).all(), (inpal, opal, cl)
+    for ipal, opal, cl in itertools.product(RGB_PALS, (588, 589), (0, 1)):
+        order, in_alpha = ORDER_OF[ipal]
+        ips, ops = T.psize_of(ipal), T.psize_of(opal)
+        src = T.make_packed(rng, w, h, ips)
+        exp = np.zeros((h, T.rowstride(w, ops)), np.uint8)
+        o.pe_or_rgb_to_yuv888(T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], order, in_alpha, int(opal == 589),
+                              cl, T.Q_HIGH)
+        lay = packed_layer(eng, ipal, w, h, src)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        assert lay.yuv_clamping == cl and lay.yuv_subspace == 1
+        assert (payload(lay.to_host()[0], w, ops) == payload(exp, w, ops)).all(), (ipal, opal, cl)
+
+
+def test_unhandled_conversion_fails_and_leaves_layer(eng):
+    rng = np.random.default_rng(9)
+    src = T.make_packed(rng, 32, 8, 3)
+    lay = packed_layer(eng, 1, 32, 8, src)
+    assert not lb.convert_layer_palette(lay, lb.WEED_PALETTE_YUV420P, 0)
+    assert "not handled" in lb._capi.last_error()
+    assert lay.palette == 1
+    assert (lay.to_host()[0] == src).all()
+
+
+# ------------------------------------------------------------------------------------------------ gamma / premult
+
+def test_gamma_convert_layer_and_sub_layer(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(10)
+    w, h = 67, 19
+    lut = np.zeros(256, np.uint8)
+    o.pe_or_gamma_lut8(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut))
+    for pal in RGB_PALS:
+        ps = T.psize_of(pal)
+        src = T.make_packed(rng, w, h, ps)
+        exp = src.copy()
+        o.pe_or_gamma_apply(T.ptr(exp), exp.strides[0], pal, 0, 0, w, h, T.ptr(lut))
+        lay = packed_layer(eng, pal, w, h, src, gamma_type=T.G_LINEAR)
+        assert lb.gamma_convert_layer(T.G_SRGB, lay)
+        assert lay.gamma_type == T.G_SRGB
+        assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), pal
+        # sub rectangle
+        exp = src.copy()
+        o.pe_or_gamma_apply(T.ptr(exp), exp.strides[0], pal, 5, 3, 41, 11, T.ptr(lut))
+        lay = packed_layer(eng, pal, w, h, src, gamma_type=T.G_LINEAR)
+        assert lb.gamma_convert_sub_layer(T.G_SRGB, 1.0, lay, 5, 3, 41, 11)
+        assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), pal
+    # same gamma -> untouched TRUE; YUV -> FALSE (colourspace.c:14076-14080)
+    lay = packed_layer(eng, 1, w, h, T.make_packed(rng, w, h, 3), gamma_type=T.G_SRGB)
+    assert lb.gamma_convert_layer(T.G_SRGB, lay)
+    ylay = packed_layer(eng, 588, w, h, T.make_packed(rng, w, h, 3), gamma_type=T.G_SRGB)
+    assert not lb.gamma_convert_layer(T.G_LINEAR, ylay)
+
+
+def test_alpha_premult(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(11)
+    w, h = 45, 9
+    for pal, cl, direction in itertools.product((3, 4, 5, 589), (0, 1), (1, -1)):
+        src = T.make_packed(rng, w, h, 4)
+        exp = src.copy()
+        o.pe_or_alpha_premult(T.ptr(exp), exp.strides[0], pal, cl, w, h, direction)
+        lay = packed_layer(eng, pal, w, h, src, yuv_clamping=cl, flags=(1 if direction == -1 else 0))
+        lb.alpha_premult(lay, direction)
+        assert (payload(lay.to_host()[0], w, 4) == payload(exp, w, 4)).all(), (pal, cl, direction)
+        assert lay.flags == (1 if direction == 1 else 0)
+
+
+# ------------------------------------------------------------------------------------------------ effects
+
+@pytest.mark.parametrize("size", [(64, 32), (61, 7), (1920, 1080)])
+def test_simple_blend_all_filters(eng, size):
+    """simple_blend.c: chroma blend + luma overlays on the 5 RGB palettes, separate output and in place"""
+    o = T.oracle()
+    rng = np.random.default_rng(12)
+    w, h = size
+    bfs = (0, 1, 100, 128, 255) if w < 1000 else (100,)
+    for pal, bf in itertools.product(RGB_PALS, bfs):
+        ps = T.psize_of(pal)
+        s1 = T.make_packed(rng, w, h, ps)
+        s2 = T.make_packed(rng, w, h, ps)
+        if ps == 4:
+            al = s2[:, 3::4] if pal != 5 else s2[:, 0::4]
+            al[rng.random(al.shape) < 0.4] = 255
+        l1, l2 = packed_layer(eng, pal, w, h, s1), packed_layer(eng, pal, w, h, s2)
+        for typ in (0, 1, 2, 3):
+            d0 = np.full_like(s1, 9)
+            exp = d0.copy()
+            o.pe_or_simple_blend(typ, pal, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0], w, h,
+                                 bf, s2.strides[0] * (h - 1) + w * ps)
+            lo = packed_layer(eng, pal, w, h, d0)
+            lb.simple_blend(typ, l1, l2, lo, bf)
+            assert (payload(lo.to_host()[0], w, ps) == payload(exp, w, ps)).all(), (pal, bf, typ)
+            lo.free()
+        exp = s1.copy()
+        o.pe_or_simple_blend(0, pal, T.ptr(exp), exp.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0], w, h, bf,
+                             s2.strides[0] * (h - 1) + w * ps)
+        lb.simple_blend("chroma blend", l1, l2, l1, bf)  # in place (effects-weed.c:2304-2314)
+        assert (payload(l1.to_host()[0], w, ps) == payload(exp, w, ps)).all(), (pal, bf, "inplace")
+        l1.free()
+        l2.free()
+
+
+def test_config4_chroma_blend_batch_chain(eng):
+    """BASELINE config 4 (reduced batch for the oracle): 1080p RGB24 'chroma blend' bf=100, chain of 3 (64/128/192),
+    a batch of independent frames in ONE launch"""
+    o = T.oracle()
+    n, w, h = 6, 1920, 1080
+    ins1, ins2, outs, exps = [], [], [], []
+    for i in range(n):
+        rng = np.random.default_rng(5 + i)
+        s1, s2 = T.make_packed(rng, w, h, 3), T.make_packed(rng, w, h, 3)
+        exp = s1.copy()
+        for bf in (100, 64, 128, 192):
+            o.pe_or_simple_blend(0, 1, T.ptr(exp), exp.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0], w, h, bf,
+                                 s2.size)
+        exps.append(exp)
+        ins1.append(packed_layer(eng, 1, w, h, s1))
+        ins2.append(packed_layer(eng, 1, w, h, s2))
+    before = eng.launch_count
+    for bf in (100, 64, 128, 192):
+        lb.simple_blend_batch(0, ins1, ins2, ins1, bf)
+    assert eng.launch_count - before == 4
+    for i in range(n):
+        assert (payload(ins1[i].to_host()[0], w, 3) == payload(exps[i], w, 3)).all(), i
+
+
+def test_multi_blends(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(13)
+    w, h = 53, 12
+    for pal, bf, typ in itertools.product((1, 2), (0, 17, 127, 128, 200, 255), range(7)):
+        s1, s2 = T.make_packed(rng, w, h, 3), T.make_packed(rng, w, h, 3)
+        exp = np.full_like(s1, 9)
+        o.pe_or_multi_blend(typ, pal, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0], w, h, bf)
+        l1, l2, lo = packed_layer(eng, pal, w, h, s1), packed_layer(eng, pal, w, h, s2), packed_layer(eng, pal, w, h, np.full_like(s1, 9))
+        lb.multi_blend(typ, l1, l2, lo, bf)
+        assert (payload(lo.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (pal, bf, typ)
+
+
+def _oracle_compositor(o, pal, w, h, layers, alphas, bg):
+    ps = T.psize_of(pal)
+    out = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+    o.pe_or_fill(T.ptr(out), out.strides[0], pal, w, h, *bg)
+    for z in range(len(layers) - 1, -1, -1):
+        if alphas[z] > 0:
+            o.pe_or_alpha_over(T.ptr(out), out.strides[0], T.ptr(layers[z]), layers[z].strides[0], pal, w, h, alphas[z])
+    return out
+
+
+def test_compositor_alpha_over(eng):
+    """compositor.c: bg fill + paint_pixel (double, truncation) per layer, last layer first"""
+    o = T.oracle()
+    rng = np.random.default_rng(14)
+    w, h = 75, 21
+    for pal in (1, 2, 3, 4):
+        ps = T.psize_of(pal)
+        srcs = [T.make_packed(rng, w, h, ps) for _ in range(3)]
+        alphas = [0.5, 1.0 / 3.0, 0.9]
+        exp = _oracle_compositor(o, pal, w, h, srcs, alphas, (10, 20, 30))
+        out = lb.Layer.create(eng, pal, w, h)
+        lb.compositor(out, [packed_layer(eng, pal, w, h, s) for s in srcs], alphas, (10, 20, 30))
+        assert (payload(out.to_host()[0], w, ps) == payload(exp, w, ps)).all(), pal
+
+
+def test_config3_4k_alpha_over_gamma(eng):
+    """BASELINE config 3: two 3840x2160 RGBA32 layers, scalar alpha 0.5 alpha-over, then gamma (LUT8 on RGB)"""
+    o = T.oracle()
+    w, h = 3840, 2160
+    bg = T.make_packed(np.random.default_rng(3), w, h, 4)
+    fg = T.make_packed(np.random.default_rng(4), w, h, 4)
+    exp = _oracle_compositor(o, 3, w, h, [fg, bg], [0.5, 1.0], (0, 0, 0))
+    lut = np.zeros(256, np.uint8)
+    o.pe_or_gamma_lut8(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut))
+    o.pe_or_gamma_apply(T.ptr(exp), exp.strides[0], 3, 0, 0, w, h, T.ptr(lut))
+    out = lb.Layer.create(eng, 3, w, h, gamma_type=T.G_LINEAR)
+    lb.compositor(out, [packed_layer(eng, 3, w, h, fg), packed_layer(eng, 3, w, h, bg)], [0.5, 1.0])
+    assert lb.gamma_convert_layer(T.G_SRGB, out)
+    got = out.to_host()[0]
+    assert (got == exp).all()
+    # the north-star's sRGB -> linear LUT is the identity table in the reference: gamma is then a no-op
+    assert (eng.gamma_lut8(1.0, T.G_SRGB, T.G_LINEAR) == np.arange(256)).all()
+
+
+# ------------------------------------------------------------------------------------------------ resize / letterbox
+
+@pytest.mark.parametrize("case", [(64, 48, 32, 24, 3), (64, 48, 96, 72, 4), (130, 50, 77, 34, 4), (1920, 1080, 1280, 720, 3),
+                                  (640, 360, 3840, 2160, 4), (100, 100, 100, 50, 3)])
+def test_resize_packed_matches_contract(eng, case):
+    o = T.oracle()
+    rng = np.random.default_rng(15)
+    sw, sh, dw, dh, ps = case
+    pal = 1 if ps == 3 else 3
+    src = T.make_packed(rng, sw, sh, ps)
+    exp = np.zeros((dh, T.rowstride(dw, ps)), np.uint8)
+    o.pe_or_resize_packed(T.ptr(src), src.strides[0], sw, sh, T.ptr(exp), exp.strides[0], dw, dh, ps)
+    lay = packed_layer(eng, pal, sw, sh, src)
+    assert lb.resize_layer(lay, dw, dh, lb.LIVES_INTERP_NORMAL, pal, 0)
+    assert (lay.width, lay.height) == (dw, dh)
+    assert (payload(lay.to_host()[0], dw, ps) == payload(exp, dw, ps)).all()
+
+
+def test_resize_planar_and_noop(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(16)
+    w, h, dw, dh = 128, 96, 64, 48
+    y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+    lay = lb.Layer.from_host(eng, 512, w, h, [y, u, v])
+    assert lb.resize_layer(lay, dw, dh, 1, lb.WEED_PALETTE_NONE, 0)
+    got = lay.to_host()
+    for src, g, (pw, ph, qw, qh) in zip((y, u, v), got, ((w, h, dw, dh), (w // 2, h // 2, dw // 2, dh // 2), (w // 2, h // 2, dw // 2, dh // 2))):
+        exp = np.zeros((qh, g.shape[1]), np.uint8)
+        o.pe_or_resize_packed(T.ptr(src), src.strides[0], pw, ph, T.ptr(exp), exp.strides[0], qw, qh, 1)
+        assert (g[:, :qw] == exp[:, :qw]).all()
+    # same size -> TRUE, nothing changes (colourspace.c:14860)
+    src = T.make_packed(rng, 64, 48, 3)
+    lay = packed_layer(eng, 1, 64, 48, src)
+    before = eng.launch_count
+    assert lb.resize_layer(lay, 64, 48, 1, 1, 0)
+    assert eng.launch_count == before
+
+
+def test_letterbox_packed_and_planar(eng):
+    o = T.oracle()
+    rng = np.random.default_rng(17)
+    for pal in (1, 3, 5):
+        ps = T.psize_of(pal)
+        iw, ih, ow, oh = 64, 36, 64, 48
+        src = T.make_packed(rng, iw, ih, ps)
+        exp = np.zeros((oh, T.rowstride(ow, ps)), np.uint8)
+        o.pe_or_letterbox_packed(T.ptr(src), src.strides[0], iw, ih, T.ptr(exp), exp.strides[0], ow, oh, pal)
+        lay = packed_layer(eng, pal, iw, ih, src)
+        assert lb.letterbox_layer(lay, ow, oh, iw, ih, 1, pal, 0)
+        assert (lay.width, lay.height) == (ow, oh)
+        assert (payload(lay.to_host()[0], ow, ps) == payload(exp, ow, ps)).all(), pal
+    # resize + letterbox (pillarbox): inner 48x48 from 64x36, centred in 80x48
+    src = T.make_packed(rng, 64, 36, 4)
+    inner = np.zeros((48, T.rowstride(48, 4)), np.uint8)
+    o.pe_or_resize_packed(T.ptr(src), src.strides[0], 64, 36, T.ptr(inner), inner.strides[0], 48, 48, 4)
+    exp = np.zeros((48, T.rowstride(81, 4)), np.uint8)
+    o.pe_or_letterbox_packed(T.ptr(inner), inner.strides[0], 48, 48, T.ptr(exp), exp.strides[0], 81, 48, 3)
+    lay = packed_layer(eng, 3, 64, 36, src)
+    assert lb.letterbox_layer(lay, 81, 48, 48, 48, 1, 3, 0)
+    assert (payload(lay.to_host()[0], 81, 4) == payload(exp, 81, 4)).all()
+    # planar: Y black = 16 (clamped), chroma 128, offsets halved on the chroma planes (:15538-15549)
+    y, u, v = T.make_yuv_planar(rng, 64, 32, False, True)
+    lay = lb.Layer.from_host(eng, 512, 64, 32, [y, u, v], yuv_clamping=0)
+    assert lb.letterbox_layer(lay, 64, 48, 64, 32, 1, 512, 0)
+    gy, gu, gv = lay.to_host()
+    assert (gy[8:40, :64] == y[:, :64]).all() and (gy[:8, :64] == 16).all() and (gy[40:, :64] == 16).all()
+    assert (gu[4:20, :32] == u[:, :32]).all() and (gu[:4, :32] == 128).all() and (gv[20:, :32] == 128).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused chain
+
+def _oracle_chain(o, y, u, v, fw, fh, is422, bg, ow, oh, iw, ih, alpha, lut8, quirks=1):
+    rgba = _oracle_planar(o, y, u, v, fw, fh, 3, is422, 0, 1, T.Q_HIGH, quirks=quirks)
+    if (iw, ih) != (fw, fh):
+        inner = np.zeros((ih, T.rowstride(iw, 4)), np.uint8)
+        o.pe_or_resize_packed(T.ptr(rgba), rgba.strides[0], fw, fh, T.ptr(inner), inner.strides[0], iw, ih, 4)
+    else:
+        inner = rgba
+    boxed = np.zeros((oh, T.rowstride(ow, 4)), np.uint8)
+    o.pe_or_letterbox_packed(T.ptr(inner), inner.strides[0], iw, ih, T.ptr(boxed), boxed.strides[0], ow, oh, 3)
+    out = bg.copy()
+    o.pe_or_alpha_over(T.ptr(out), out.strides[0], T.ptr(boxed), boxed.strides[0], 3, ow, oh, alpha)
+    out[:, 3:ow * 4:4] = 255  # compositor forces the alpha byte (compositor.c:184)
+    if lut8 is not None:
+        o.pe_or_gamma_apply(T.ptr(out), out.strides[0], 3, 0, 0, ow, oh, T.ptr(lut8))
+    return out
+
+
+@pytest.mark.parametrize("case", [
+    # fw, fh, is422, ow, oh, iw, ih
+    (64, 48, 0, 64, 48, 64, 48), (64, 48, 0, 128, 96, 128, 72), (128, 96, 0, 64, 64, 64, 48), (130, 34, 1, 200, 80, 150, 40),
+    (640, 360, 0, 1280, 720, 1280, 536), (1920, 1080, 0, 1280, 720, 1280, 720),
+])
+def test_fused_chain_equals_unfused_oracle(eng, case):
+    """the fused kernel == convert_layer_palette -> resize -> letterbox -> alpha-over -> gamma run one by one"""
+    o = T.oracle()
+    rng = np.random.default_rng(18)
+    fw, fh, is422, ow, oh, iw, ih = case
+    y, u, v = T.make_yuv_planar(rng, fw, fh, bool(is422), True)
+    bg = T.make_packed(rng, ow, oh, 4)
+    lut = np.zeros(256, np.uint8)
+    o.pe_or_gamma_lut8(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut))
+    exp = _oracle_chain(o, y, u, v, fw, fh, is422, bg, ow, oh, iw, ih, 0.5, lut)
+    fg_l = lb.Layer.from_host(eng, 522 if is422 else 512, fw, fh, [y, u, v], yuv_subspace=1)
+    bg_l = packed_layer(eng, 3, ow, oh, bg, gamma_type=T.G_LINEAR)
+    out_l = lb.Layer.create(eng, 3, ow, oh)
+    before = eng.launch_count
+    lb.fused_convert_letterbox_over_gamma(fg_l, bg_l, out_l, iw, ih, 0.5, T.G_LINEAR, T.G_SRGB)
+    got = out_l.to_host()[0]
+    assert (payload(got, ow, 4) == payload(exp, ow, 4)).all()
+    assert out_l.gamma_type == T.G_SRGB
+    # ... and == the engine's own unfused ops
+    lay = lb.Layer.from_host(eng, 522 if is422 else 512, fw, fh, [y, u, v], yuv_subspace=1)
+    assert lb.convert_layer_palette(lay, 3, 0)
+    assert lb.letterbox_layer(lay, ow, oh, iw, ih, 1, 3, 0)
+    out2 = lb.Layer.create(eng, 3, ow, oh, gamma_type=T.G_LINEAR)
+    lb.compositor(out2, [lay, bg_l], [0.5, 1.0])
+    assert lb.gamma_convert_layer(T.G_SRGB, out2)
+    assert (payload(out2.to_host()[0], ow, 4) == payload(exp, ow, 4)).all()
+    del before
+
+
+def test_fused_headline_4k(eng):
+    """north-star headline: 3840x2160 YUV420P fg -> RGBA, letterboxed 3840x1608 inner in a 4K frame, alpha-over a 4K
+    RGBA bg, gamma; batch of 2 in one launch"""
+    o = T.oracle()
+    fw, fh, ow, oh, iw, ih = 3840, 2160, 3840, 2160, 3840, 1608
+    lut = np.zeros(256, np.uint8)
+    o.pe_or_gamma_lut8(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut))
+    fgs, bgs, outs, exps = [], [], [], []
+    for i in range(2):
+        y, u, v = T.make_yuv_planar(np.random.default_rng(20 + 2 * i), fw, fh, False, True)
+        bg = T.make_packed(np.random.default_rng(21 + 2 * i), ow, oh, 4)
+        exps.append(_oracle_chain(o, y, u, v, fw, fh, 0, bg, ow, oh, iw, ih, 0.5, lut))
+        fgs.append(lb.Layer.from_host(eng, 512, fw, fh, [y, u, v], yuv_subspace=1))
+        bgs.append(packed_layer(eng, 3, ow, oh, bg, gamma_type=T.G_LINEAR))
+        outs.append(lb.Layer.create(eng, 3, ow, oh))
+    before = eng.launch_count
+    lb.fused_convert_letterbox_over_gamma_batch(fgs, bgs, outs, iw, ih, 0.5, T.G_LINEAR, T.G_SRGB)
+    assert eng.launch_count - before <= 2  # the fused kernel (+ the one-off [bg][fg] table build)
+    for i in range(2):
+        assert (outs[i].to_host()[0] == exps[i]).all(), i
+
+
+# ------------------------------------------------------------------------------------------------ diagnostics / host path
+
+def test_frame_stats(eng):
+    rng = np.random.default_rng(19)
+    w, h = 333, 77
+    for pal in (1, 3, 5):
+        ps = T.psize_of(pal)
+        src = T.make_packed(rng, w, h, ps, lo=3, hi=250)
+        st = packed_layer(eng, pal, w, h, src).stats()
+        px = src[:, :w * ps].reshape(h, w, ps)
+        a_off = {1: -1, 3: 3, 5: 0}[pal]
+        for k in range(ps):
+            assert st["min"][k] == px[..., k].min() and st["max"][k] == px[..., k].max()
+        col = [k for k in range(ps) if k != a_off]
+        assert (st["hist"] == np.bincount(px[..., col].reshape(-1), minlength=256)).all()
+        assert st["sum"] == int(px.astype(np.uint64).sum())
+        assert not st["all_black_ish"]
+    blk = lb.Layer.create(eng, 3, 64, 64, black_fill=True)
+    assert blk.stats()["all_black_ish"]
+
+
+def test_host_dropins(eng):
+    """pe_host_*: host buffers in, host buffers out (H2D and D2H inside the call)"""
+    o = T.oracle()
+    rng = np.random.default_rng(20)
+    w, h = 96, 40
+    y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+    exp = _oracle_planar(o, y, u, v, w, h, 3, 0, 0, 1, T.Q_HIGH)
+    hl = lb.HostLayer(512, w, h, [y.copy(), u.copy(), v.copy()], yuv_subspace=1)
+    assert lb.host_convert_layer_palette_full(eng, hl, 3, 0, 0, 1, 0)
+    assert hl.d.palette == 3 and hl.d.rowstrides[0] == T.rowstride(w, 4)
+    assert (payload(hl.planes[0], w, 4) == payload(exp, w, 4)).all()
+    # RGB24 -> BGR24: same byte size, new palette
+    src = T.make_packed(rng, w, h, 3)
+    hl = lb.HostLayer(1, w, h, [src.copy()])
+    assert lb.host_convert_layer_palette_full(eng, hl, 2, 0, 0, 0, 0)
+    assert (hl.planes[0][:, 0:w * 3:3] == src[:, 2:w * 3:3]).all()
+    # blend
+    s1, s2 = T.make_packed(rng, w, h, 3), T.make_packed(rng, w, h, 3)
+    exp = np.zeros_like(s1)
+    o.pe_or_simple_blend(0, 1, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0], w, h, 100, s2.size)
+    d = np.zeros_like(s1)
+    lb.host_simple_blend(eng, 0, lb.HostLayer(1, w, h, [s1]), lb.HostLayer(1, w, h, [s2]), lb.HostLayer(1, w, h, [d]), 100)
+    assert (payload(d, w, 3) == payload(exp, w, 3)).all()
+    # resize + letterbox
+    hl = lb.HostLayer(1, w, h, [s1.copy()])
+    assert lb.host_letterbox_layer(eng, hl, 128, 64, 128, 52, 1, 1, 0)
+    assert (hl.d.width, hl.d.height) == (128, 64)
+    inner = np.zeros((52, T.rowstride(128, 3)), np.uint8)
+    o.pe_or_resize_packed(T.ptr(s1), s1.strides[0], w, h, T.ptr(inner), inner.strides[0], 128, 52, 3)
+    box = np.zeros((64, T.rowstride(128, 3)), np.uint8)
+    o.pe_or_letterbox_packed(T.ptr(inner), inner.strides[0], 128, 52, T.ptr(box), box.strides[0], 128, 64, 1)
+    assert (payload(hl.planes[0], 128, 3) == payload(box, 128, 3)).all()
