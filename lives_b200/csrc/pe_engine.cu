@@ -367,25 +367,39 @@ DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
   return &r;
 }
 
-// upload a small per-launch argument array (BlendFrame[] / FusedArgs[]) through a pinned staging buffer
+// upload a small per-launch argument array (BlendFrame / FusedArgs) through a pinned staging buffer; on failure the
+// reason is left in pe_last_error()
 void *upload_args(pe_engine *e, const void *src, size_t bytes) {
+  cudaError_t ce;
   if (bytes > e->args_cap) {
     if (e->args_dev) { cudaStreamSynchronize(e->stream); cudaFree(e->args_dev); }
     size_t cap = bytes < 4096 ? 4096 : bytes * 2;
-    if (cudaMalloc(&e->args_dev, cap) != cudaSuccess) { e->args_dev = nullptr; e->args_cap = 0; return nullptr; }
+    if ((ce = cudaMalloc(&e->args_dev, cap)) != cudaSuccess) {
+      set_err(PE_ERR_CUDA, "argument buffer cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(ce));
+      e->args_dev = nullptr; e->args_cap = 0;
+      return nullptr;
+    }
     e->args_cap = cap;
   }
   if (bytes > e->args_pinned_cap) {
     if (e->args_pinned) { cudaEventSynchronize(e->args_ev); cudaFreeHost(e->args_pinned); }
     size_t cap = bytes < 4096 ? 4096 : bytes * 2;
-    if (cudaMallocHost(&e->args_pinned, cap) != cudaSuccess) { e->args_pinned = nullptr; e->args_pinned_cap = 0; return nullptr; }
+    if ((ce = cudaMallocHost(&e->args_pinned, cap)) != cudaSuccess) {
+      set_err(PE_ERR_CUDA, "argument staging cudaMallocHost(%zu) failed: %s", cap, cudaGetErrorString(ce));
+      e->args_pinned = nullptr; e->args_pinned_cap = 0;
+      return nullptr;
+    }
     e->args_pinned_cap = cap;
-  } else {
-    cudaEventSynchronize(e->args_ev);  // previous upload out of the staging buffer has finished
+  } else if ((ce = cudaEventSynchronize(e->args_ev)) != cudaSuccess) {  // previous upload out of the staging buffer is done
+    set_err(PE_ERR_CUDA, "an earlier kernel on the engine stream failed: %s", cudaGetErrorString(ce));
+    return nullptr;
   }
   memcpy(e->args_pinned, src, bytes);
   // kernels of earlier launches that read args_dev are ordered before this copy on the same stream
-  if (cudaMemcpyAsync(e->args_dev, e->args_pinned, bytes, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return nullptr;
+  if ((ce = cudaMemcpyAsync(e->args_dev, e->args_pinned, bytes, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) {
+    set_err(PE_ERR_CUDA, "argument upload failed: %s", cudaGetErrorString(ce));
+    return nullptr;
+  }
   cudaEventRecord(e->args_ev, e->stream);
   return e->args_dev;
 }
@@ -1137,7 +1151,7 @@ extern "C" int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const p
     frames[i] = blend_frame(in1[i], in2[i], out[i]);
   }
   const BlendFrame *dev = (const BlendFrame *)upload_args(e, frames.data(), sizeof(BlendFrame) * n);
-  if (!dev) return set_err(PE_ERR_CUDA, "argument upload failed");
+  if (!dev) return PE_ERR_CUDA;
   PE_CUDA(launch_simple_blend(e->L(), type, dev, n, in1[0]->d.width, in1[0]->d.height, rgb_layout(in1[0]->d.palette), blend_factor,
                               e->luma_dev));
   return PE_OK;
@@ -1259,7 +1273,7 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
     A.over_table = tab;
   }
   const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);
-  if (!dev) return set_err(PE_ERR_CUDA, "argument upload failed");
+  if (!dev) return PE_ERR_CUDA;
   PE_CUDA(launch_fused_dev(e->L(), dev, n, ow, oh, max_rows, max_cols));
   for (int i = 0; i < n; i++) {
     out[i]->d.gamma_type = (lut ? gamma_to : gamma_from);

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const FusedArgs *__restrict__ 
   sm.over = smem_raw;
   sm.tabs = (int32_t *)(smem_raw + 65536);
   sm.rgba = (uint32_t *)(smem_raw + 65536 + 5 * 1024);
-  sm.hs = (uint2 *)(smem_raw + 65536 + 5 * 1024 + (size_t)max_src_rows * max_src_cols * 4);
+  sm.hs = (uint2 *)(smem_raw + 65536 + 5 * 1024 + (((size_t)max_src_rows * max_src_cols * 4 + 15) & ~(size_t)15));
 
   const uint8_t *cur_over = nullptr;
   const int32_t *cur_conv = nullptr;
@@ -267,7 +267,7 @@ cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst
 cudaError_t launch_fused_dev(const Launch &L, const FusedArgs *frames_dev, int nframes, int ow, int oh, int max_src_rows,
                              int max_src_cols) {
   const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
-  const size_t smem = 65536 + 5 * 1024 + (size_t)max_src_rows * max_src_cols * 4 + (size_t)max_src_rows * kTileW * 8;
+  const size_t smem = 65536 + 5 * 1024 + (((size_t)max_src_rows * max_src_cols * 4 + 15) & ~(size_t)15) + (size_t)max_src_rows * kTileW * 8;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static size_t attr_set = 0;
   if (smem > attr_set) {

@@ -416,26 +416,34 @@ __device__ __forceinline__ uint32_t plugin_luma(const int32_t *luma, uint32_t r,
   return (uint32_t)((luma[r] + luma[256 + g] + luma[512 + b]) >> 16) & 0xFFu;  // calc_luma returns uint8_t
 }
 
-// luma overlay / underlay / negative overlay (simple_blend.c:153-197): whole-pixel select
+// luma overlay / underlay / negative overlay (simple_blend.c:153-197): whole-pixel select.
+// ARGB: the plugin walks the row from byte 1 (start = 1, :80) and hands calc_luma that pointer, so the luma it
+// compares is lumaR[G] + lumaG[B] + lumaB[alpha byte of the NEXT pixel] -- replicated; past the end of the buffer
+// that byte is taken as 255 (s2_bytes; both inputs share src2's geometry).
 __global__ void __launch_bounds__(kBlock) k_luma_select(const BlendParams P) {
   __shared__ int32_t s_luma[768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_luma[i] = P.luma[i];
   __syncthreads();
   const BlendFrame F = P.frames[blockIdx.y];
   const uint32_t bf = (uint8_t)P.bf, bfn = 0xFFu - bf;
-  const int start = (P.a_off == 0) ? 1 : 0;  // ARGB
+  const bool argb = (P.a_off == 0);
+  const int start = argb ? 1 : 0;
   const long long total = (long long)P.width * P.height;
   for (long long it = global_tid(); it < total; it += global_threads()) {
     const int row = (int)(it / P.width), x = (int)(it - (long long)row * P.width);
-    const uint8_t *s1 = F.s1 + (long long)row * F.rs1 + x * P.psize + start;
-    const uint8_t *s2 = F.s2 + (long long)row * F.rs2 + x * P.psize + start;
+    const long long o1 = (long long)row * F.rs1 + x * P.psize + start, o2 = (long long)row * F.rs2 + x * P.psize + start;
+    const uint8_t *s1 = F.s1 + o1, *s2 = F.s2 + o2;
     uint8_t *d = F.d + (long long)row * F.rsd + x * P.psize + start;
-    // colour bytes relative to `start`
-    const int ro = P.r_off - start, go = P.g_off - start, bo = P.b_off - start;
-    bool take2;
-    if (P.type == 1) take2 = plugin_luma(s_luma, s1[ro], s1[go], s1[bo]) < bf;
-    else if (P.type == 2) take2 = plugin_luma(s_luma, s2[ro], s2[go], s2[bo]) > bfn;
-    else take2 = plugin_luma(s_luma, s1[ro], s1[go], s1[bo]) > bfn;
+    const uint8_t *sl = (P.type == 2) ? s2 : s1;  // the input whose luma is tested
+    uint32_t l;
+    if (!argb) {
+      l = plugin_luma(s_luma, sl[P.r_off], sl[P.g_off], sl[P.b_off]);
+    } else {
+      const long long o3 = ((P.type == 2) ? o2 : o1) + 3;
+      const uint32_t nxt = o3 < F.s2_bytes ? sl[3] : 255u;
+      l = plugin_luma(s_luma, sl[1], sl[2], nxt);
+    }
+    const bool take2 = (P.type == 1) ? (l < bf) : (l > bfn);
     const uint8_t *s = take2 ? s2 : s1;
     if (take2 || F.d != F.s1) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
   }

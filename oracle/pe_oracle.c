@@ -592,14 +592,22 @@ void pe_or_simple_blend(int type, int palette, const uint8_t *src1, int irow1, c
 #undef OR_BL
     return;
   }
-  /* luma overlay / underlay / negative overlay :153-197 (type 4 "averaged" not restated) */
+  /* luma overlay / underlay / negative overlay :153-197 (type 4 "averaged" not restated).
+   * ARGB (start == 1): calc_luma is handed the pixel pointer + 1, so it weighs G, B and the NEXT pixel's alpha byte
+   * (libweed/weed-plugin-utils.c:924-934 reads px[1..3]) -- replicated.  For the last pixel of the buffer that byte
+   * lies outside it (the reference reads out of bounds); there we take 255, as for the chroma blend above.  Both
+   * inputs are assumed to have src2's geometry. */
   for (int i = 0; i < height; i++) {
     const long o = (long)orow * i, r1 = (long)irow1 * i, r2 = (long)irow2 * i;
     for (int j = start; j < widthx; j += psize) {
       int take2;
-      if (type == 1) take2 = or_calc_luma(&src1[r1 + j], palette) < blend_factor;
-      else if (type == 2) take2 = or_calc_luma(&src2[r2 + j], palette) > blendneg;
-      else take2 = or_calc_luma(&src1[r1 + j], palette) > blendneg;
+      uint8_t p1[4], p2[4];
+      memcpy(p1, &src1[r1 + j], 3); memcpy(p2, &src2[r2 + j], 3);
+      p1[3] = (psize == 4 && r1 + j + 3 < src2_bytes) ? src1[r1 + j + 3] : 255;
+      p2[3] = (psize == 4 && r2 + j + 3 < src2_bytes) ? src2[r2 + j + 3] : 255;
+      if (type == 1) take2 = or_calc_luma(p1, palette) < blend_factor;
+      else if (type == 2) take2 = or_calc_luma(p2, palette) > blendneg;
+      else take2 = or_calc_luma(p1, palette) > blendneg;
       if (take2) memcpy(&dst[o + j], &src2[r2 + j], 3);
       else if (!inplace) memcpy(&dst[o + j], &src1[r1 + j], 3);
     }
