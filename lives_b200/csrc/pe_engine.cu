@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 using namespace pe;
@@ -1274,7 +1275,31 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
   }
   const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);
   if (!dev) return PE_ERR_CUDA;
-  PE_CUDA(launch_fused_dev(e->L(), dev, n, ow, oh, max_rows, max_cols));
+  // fast path: no horizontal scaling, <= 4 vertical taps, aligned planes (pe_kernels_fused2.cu)
+  bool fast = getenv("PE_FUSED_GENERIC") == nullptr;
+  for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.taps, 0);
+  int tile_h = 0;
+  if (fast) {
+    // tallest tile whose virtual source rows (first .. first + 3 of its last row) fit the shared-memory tile
+    const ResizeFilter &F = fy->host;
+    for (tile_h = fused2_max_tile_h(); tile_h >= 4; tile_h -= 4) {
+      int worst = 0;
+      for (int i0 = 0; i0 < inner_h; i0++) {
+        const int i1 = i0 + tile_h - 1 < inner_h - 1 ? i0 + tile_h - 1 : inner_h - 1;
+        const int spanr = F.first[i1] + 3 - F.first[i0] + 1;
+        if (spanr > worst) worst = spanr;
+      }
+      if (worst <= fused2_max_virtual_rows()) break;
+    }
+    if (tile_h < 4) fast = false;
+  }
+  if (fast) {
+    const double k256 = alpha * 256.;
+    const bool dyadic = k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256;
+    PE_CUDA(launch_fused2_dev(e->L(), dev, n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
+  } else {
+    PE_CUDA(launch_fused_dev(e->L(), dev, n, ow, oh, max_rows, max_cols));
+  }
   for (int i = 0; i < n; i++) {
     out[i]->d.gamma_type = (lut ? gamma_to : gamma_from);
     out[i]->d.flags = bg[i]->d.flags;

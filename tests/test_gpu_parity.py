@@ -532,6 +532,57 @@ def test_fused_chain_equals_unfused_oracle(eng, case):
     del before
 
 
+@pytest.mark.parametrize("case", [
+    # fw, fh, is422, ow, oh, ih, alpha, gamma(from, to) or None   -- inner width == fw: the fast kernel (pe_kernels_fused2.cu)
+    (64, 48, 0, 64, 48, 48, 0.5, (-1, 1)),          # no scaling at all
+    (128, 96, 0, 128, 96, 72, 0.5, (-1, 1)),        # vertical squeeze 4:3, letterboxed
+    (256, 270, 0, 256, 270, 202, 0.25, None),       # ratio 1.337 (the headline's), no gamma, alpha 1/4
+    (128, 64, 0, 140, 100, 100, 0.75, (-1, 1)),     # vertical stretch + pillarbox offset 6 (not a multiple of 4)
+    (132, 50, 1, 150, 90, 75, 0.5, (1, 2)),         # 4:2:2, stretch, offset 9
+    (64, 34, 0, 64, 40, 30, 1.0, (-1, 1)),          # alpha 1
+    (644, 362, 0, 700, 400, 300, 0.1, (-1, 1)),     # non-dyadic alpha: table blend
+    (640, 360, 1, 640, 360, 240, 1.0 / 3.0, None),  # 4:2:2, ratio 1.5, table blend, no gamma
+    (128, 400, 0, 128, 220, 200, 0.5, (-1, 1)),     # ratio 2: five taps -> generic kernel
+])
+@pytest.mark.parametrize("variant", ["clamped", "unclamped_noquirks"])
+def test_fused_fast_path_cases(case, variant):
+    o = T.oracle()
+    rng = np.random.default_rng(23)
+    fw, fh, is422, ow, oh, ih, alpha, gam = case
+    cl = 0 if variant == "clamped" else 1
+    quirks = variant == "clamped"
+    e = lb.Engine(ref_quirks=quirks)
+    y, u, v = T.make_yuv_planar(rng, fw, fh, bool(is422), cl == 0)
+    bg = T.make_packed(rng, ow, oh, 4)
+    lut = None
+    if gam:
+        lut = np.zeros(256, np.uint8)
+        assert o.pe_or_gamma_lut8(1.0, gam[0], gam[1], 1.4, T.ptr(lut)) == 0
+    # oracle chain with this variant's clamping / quirks
+    order, add_alpha = ORDER_OF[3]
+    rgba = np.zeros((fh, T.rowstride(fw, 4)), np.uint8)
+    o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), fw, fh, T.ptr(rgba), rgba.strides[0], order, add_alpha,
+                           is422, cl, 1, T.Q_HIGH, int(quirks), None)
+    inner = np.zeros((ih, T.rowstride(fw, 4)), np.uint8)
+    o.pe_or_resize_packed(T.ptr(rgba), rgba.strides[0], fw, fh, T.ptr(inner), inner.strides[0], fw, ih, 4)
+    boxed = np.zeros((oh, T.rowstride(ow, 4)), np.uint8)
+    o.pe_or_letterbox_packed(T.ptr(inner), inner.strides[0], fw, ih, T.ptr(boxed), boxed.strides[0], ow, oh, 3)
+    exp = bg.copy()
+    o.pe_or_alpha_over(T.ptr(exp), exp.strides[0], T.ptr(boxed), boxed.strides[0], 3, ow, oh, alpha)
+    exp[:, 3:ow * 4:4] = 255
+    if lut is not None:
+        o.pe_or_gamma_apply(T.ptr(exp), exp.strides[0], 3, 0, 0, ow, oh, T.ptr(lut))
+    fg_l = lb.Layer.from_host(e, 522 if is422 else 512, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
+    gf, gt = gam if gam else (0, 0)
+    bg_l = packed_layer(e, 3, ow, oh, bg, gamma_type=gf)
+    out_l = lb.Layer.create(e, 3, ow, oh)
+    lb.fused_convert_letterbox_over_gamma(fg_l, bg_l, out_l, fw, ih, alpha, gf, gt)
+    got = out_l.to_host()[0]
+    bad = np.argwhere(payload(got, ow, 4) != payload(exp, ow, 4))
+    assert len(bad) == 0, (len(bad), bad[:5])
+    e.close()
+
+
 def test_fused_headline_4k(eng):
     """north-star headline: 3840x2160 YUV420P fg -> RGBA, letterboxed 3840x1608 inner in a 4K frame, alpha-over a 4K
     RGBA bg, gamma; batch of 2 in one launch"""
