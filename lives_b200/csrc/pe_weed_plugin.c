@@ -1,0 +1,232 @@
+/* pe_weed_plugin.c -- libpe_weed_plugin.so: a libweed effect plugin (boundary B1) whose process functions run on the B200.
+ *
+ * Loaded exactly like the reference's plugins: dlopen + dlsym("weed_setup") + setup(weed_bootstrap)
+ * (src/effects-weed.c:4468-4568).  It registers, under the SAME filter names, the filters of
+ *     lives-plugins/weed-plugins/simple_blend.c   "chroma blend", "luma overlay", "luma underlay", "negative luma overlay"
+ *     lives-plugins/weed-plugins/multi_blends.c   "blend_multiply" ... "blend_burn"
+ * with the same channel / parameter templates, so weed_apply_instance() (src/effects-weed.c:1850) drives it unchanged.
+ * Differences from the originals, on purpose:
+ *   - WEED_FILTER_HINT_MAY_THREAD is NOT set: the host must call process_func once per frame, not once per row band
+ *     (the CUDA grid is the row-band fan-out);  STATEFUL is not needed either (no per-instance blend table);
+ *   - every pixel is computed by libpe_b200.so (pe_host_simple_blend / pe_host_multi_blend: H2D, kernel, D2H); when no
+ *     CUDA device is usable process_func returns WEED_ERROR_PLUGIN_INVALID -- there is no CPU fallback in here.
+ * The host owns all pixel buffers; this file only reads the leaves the reference plugins read
+ * (libweed/weed-plugin-utils.c:140-157).
+ */
+#include <stdio.h>
+#include <string.h>
+
+#include "pe_weed_abi.h"
+#include "pixel_engine.h"
+
+static pe_weed_leaf_get_f w_leaf_get;
+static pe_weed_leaf_set_f w_leaf_set;
+static pe_weed_plant_new_f w_plant_new;
+static pe_weed_leaf_num_elements_f w_num_elements;
+static pe_weed_malloc_f w_malloc;
+static pe_weed_free_f w_free;
+
+static pe_engine_t *g_engine;
+
+static pe_engine_t *engine(void) {
+  if (!g_engine) {
+    pe_config_t cfg;
+    pe_config_default(&cfg);
+    if (pe_engine_create(&cfg, &g_engine) != PE_OK) {
+      fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+      g_engine = NULL;
+    }
+  }
+  return g_engine;
+}
+
+/* ---- leaf helpers ---------------------------------------------------------------------------------------------- */
+
+static int get_int(pe_weed_plant_t *p, const char *key) { int32_t v = 0; w_leaf_get(p, key, 0, &v); return v; }
+static void *get_ptr(pe_weed_plant_t *p, const char *key) { void *v = NULL; w_leaf_get(p, key, 0, &v); return v; }
+static pe_weed_plant_t *get_plant(pe_weed_plant_t *p, const char *key, int idx) {
+  pe_weed_plant_t *v = NULL;
+  w_leaf_get(p, key, (pe_weed_size_t)idx, &v);
+  return v;
+}
+static void set_int(pe_weed_plant_t *p, const char *key, int32_t v) { w_leaf_set(p, key, PE_WEED_SEED_INT, 1, &v); }
+static void set_str(pe_weed_plant_t *p, const char *key, const char *s) { w_leaf_set(p, key, PE_WEED_SEED_STRING, 1, &s); }
+
+/* the frame a channel plant describes (width leaf is in macropixels == pixels for the RGB palettes) */
+static void channel_desc(pe_weed_plant_t *ch, pe_frame_desc_t *d) {
+  memset(d, 0, sizeof(*d));
+  d->palette = get_int(ch, PE_LEAF_CURRENT_PALETTE);
+  d->width = get_int(ch, PE_LEAF_WIDTH);
+  d->height = get_int(ch, PE_LEAF_HEIGHT);
+  d->nplanes = 1;
+  d->rowstrides[0] = get_int(ch, PE_LEAF_ROWSTRIDES);
+  d->planes[0] = get_ptr(ch, PE_LEAF_PIXEL_DATA);
+}
+
+/* ---- process functions --------------------------------------------------------------------------------------------- */
+
+static pe_weed_error_t run_blend(int family, int type, pe_weed_plant_t *inst) {
+  pe_frame_desc_t in1, in2, out;
+  pe_engine_t *e = engine();
+  int bf, rc;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 0), &in1);
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 1), &in2);
+  channel_desc(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  bf = get_int(get_plant(inst, PE_LEAF_IN_PARAMETERS, 0), PE_LEAF_VALUE);
+  rc = family == 0 ? pe_host_simple_blend(e, type, &in1, &in2, &out, bf) : pe_host_multi_blend(e, type, &in1, &in2, &out, bf);
+  if (rc == PE_OK) return PE_WEED_SUCCESS;
+  fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+  return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
+}
+
+#define PE_PROCESS(name, family, type) \
+  static pe_weed_error_t name(pe_weed_plant_t *inst, pe_weed_timecode_t tc) { (void)tc; return run_blend(family, type, inst); }
+PE_PROCESS(chroma_process, 0, 0)
+PE_PROCESS(lumo_process, 0, 1)
+PE_PROCESS(lumu_process, 0, 2)
+PE_PROCESS(nlumo_process, 0, 3)
+PE_PROCESS(mpy_process, 1, 0)
+PE_PROCESS(screen_process, 1, 1)
+PE_PROCESS(darken_process, 1, 2)
+PE_PROCESS(lighten_process, 1, 3)
+PE_PROCESS(overlay_process, 1, 4)
+PE_PROCESS(dodge_process, 1, 5)
+PE_PROCESS(burn_process, 1, 6)
+
+static pe_weed_error_t common_init(pe_weed_plant_t *inst) {
+  (void)inst;
+  return engine() ? PE_WEED_SUCCESS : PE_WEED_ERROR_PLUGIN_INVALID;
+}
+
+/* ---- plant construction (what weed_channel_template_init / weed_integer_init / weed_filter_class_init of
+ *      libweed/weed-plugin-utils.c:247-336 produce) ----------------------------------------------------------------- */
+
+static pe_weed_plant_t *chantmpl(const char *name, int flags) {
+  pe_weed_plant_t *t = w_plant_new(PE_WEED_PLANT_CHANNEL_TEMPLATE);
+  if (!t) return NULL;
+  set_str(t, PE_LEAF_NAME, name);
+  set_int(t, PE_LEAF_FLAGS, flags);
+  /* rows 32-byte aligned lets every kernel use 128-bit accesses (honoured at src/effects-weed.c:2319-2324) */
+  set_int(t, PE_LEAF_ALIGNMENT_HINT, 32);
+  return t;
+}
+
+static pe_weed_plant_t *int_param(const char *name, const char *label, int def, int min, int max) {
+  pe_weed_plant_t *p = w_plant_new(PE_WEED_PLANT_PARAMETER_TEMPLATE), *gui;
+  int32_t one = 1;
+  if (!p) return NULL;
+  set_str(p, PE_LEAF_NAME, name);
+  set_int(p, PE_LEAF_PARAM_TYPE, PE_WEED_PARAM_INTEGER);
+  set_int(p, PE_LEAF_DEFAULT, def);
+  set_int(p, PE_LEAF_MIN, min);
+  set_int(p, PE_LEAF_MAX, max);
+  gui = w_plant_new(PE_WEED_PLANT_GUI);
+  if (gui) {
+    w_leaf_set(p, PE_LEAF_GUI, PE_WEED_SEED_PLANTPTR, 1, &gui);
+    set_str(gui, PE_LEAF_LABEL, label);
+    w_leaf_set(gui, PE_LEAF_USE_MNEMONIC, PE_WEED_SEED_BOOLEAN, 1, &one);
+  }
+  w_leaf_set(p, PE_LEAF_IS_TRANSITION, PE_WEED_SEED_BOOLEAN, 1, &one); /* weed_paramtmpl_declare_transition */
+  return p;
+}
+
+static int add_filter(pe_weed_plant_t *plugin_info, const char *name, int flags, int *palettes, int npal, pe_weed_init_f init_fn,
+                      pe_weed_process_f process_fn, const char *pname, const char *plabel, int pdef) {
+  pe_weed_plant_t *fc = w_plant_new(PE_WEED_PLANT_FILTER_CLASS);
+  pe_weed_plant_t *in_ct[2], *out_ct[1], *in_pt[1];
+  pe_weed_plant_t **filters;
+  pe_weed_size_t n = 0, i;
+  const char *author = "lives_b200";
+  int32_t version = 1;
+  if (!fc) return -1;
+  in_ct[0] = chantmpl("in channel 0", 0);
+  in_ct[1] = chantmpl("in channel 1", 0);
+  out_ct[0] = chantmpl("out channel 0", PE_WEED_CHANNEL_CAN_DO_INPLACE);
+  in_pt[0] = int_param(pname, plabel, pdef, 0, 255);
+  if (!in_ct[0] || !in_ct[1] || !out_ct[0] || !in_pt[0]) return -1;
+  set_str(fc, PE_LEAF_NAME, name);
+  w_leaf_set(fc, PE_LEAF_AUTHOR, PE_WEED_SEED_STRING, 1, &author);
+  set_int(fc, PE_LEAF_VERSION, version);
+  set_int(fc, PE_LEAF_FLAGS, flags);
+  if (init_fn) w_leaf_set(fc, PE_LEAF_INIT_FUNC, PE_WEED_SEED_FUNCPTR, 1, &init_fn);
+  w_leaf_set(fc, PE_LEAF_PROCESS_FUNC, PE_WEED_SEED_FUNCPTR, 1, &process_fn);
+  w_leaf_set(fc, PE_LEAF_IN_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 2, in_ct);
+  w_leaf_set(fc, PE_LEAF_OUT_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, out_ct);
+  w_leaf_set(fc, PE_LEAF_IN_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, in_pt);
+  w_leaf_set(fc, PE_LEAF_OUT_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 0, NULL);
+  w_leaf_set(fc, PE_LEAF_PALETTE_LIST, PE_WEED_SEED_INT, (pe_weed_size_t)npal, palettes);
+  /* weed_plugin_info_add_filter_class (weed-plugin-utils.c:308-320) */
+  n = w_num_elements(plugin_info, PE_LEAF_FILTERS);
+  filters = (pe_weed_plant_t **)w_malloc((n + 1) * sizeof(pe_weed_plant_t *));
+  if (!filters) return -1;
+  for (i = 0; i < n; i++) w_leaf_get(plugin_info, PE_LEAF_FILTERS, i, &filters[i]);
+  filters[n] = fc;
+  w_leaf_set(plugin_info, PE_LEAF_FILTERS, PE_WEED_SEED_PLANTPTR, n + 1, filters);
+  w_leaf_set(fc, PE_LEAF_PLUGIN_INFO, PE_WEED_SEED_PLANTPTR, 1, &plugin_info);
+  w_free(filters);
+  return 0;
+}
+
+/* ---- entry points --------------------------------------------------------------------------------------------------- */
+
+pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
+  pe_weed_default_getter_f getp = NULL;
+  pe_weed_plant_t *host_info, *plugin_info = NULL;
+  int all_rgb[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24, PE_PALETTE_RGBA32, PE_PALETTE_BGRA32, PE_PALETTE_ARGB32}; /* ALL_RGB_PALETTES */
+  int rgb24[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24};
+  int32_t package_version = 1;
+  if (!weed_boot) return NULL;
+  /* weed_plugin_info_init (weed-plugin-utils.c:164-233): the default getter bootstraps weed_leaf_get, the rest follows */
+  host_info = (*weed_boot)(&getp, PE_WEED_API_MIN, PE_WEED_API_MAX, PE_WEED_FILTER_API_MIN, PE_WEED_FILTER_API_MAX);
+  if (!host_info || !getp) return NULL;
+  if ((*getp)(host_info, PE_LEAF_GET_FUNC, (void *)&w_leaf_get) != PE_WEED_SUCCESS || !w_leaf_get) return NULL;
+  if ((*getp)(host_info, PE_LEAF_MALLOC_FUNC, (void *)&w_malloc) != PE_WEED_SUCCESS) return NULL;
+  if ((*getp)(host_info, PE_LEAF_FREE_FUNC, (void *)&w_free) != PE_WEED_SUCCESS) return NULL;
+  if (w_leaf_get(host_info, PE_LEAF_SET_FUNC, 0, &w_leaf_set) != PE_WEED_SUCCESS) return NULL;
+  if (w_leaf_get(host_info, PE_LEAF_PLANT_NEW_FUNC, 0, &w_plant_new) != PE_WEED_SUCCESS) return NULL;
+  if (w_leaf_get(host_info, PE_LEAF_NUM_ELEMENTS_FUNC, 0, &w_num_elements) != PE_WEED_SUCCESS) return NULL;
+  if (!w_leaf_set || !w_plant_new || !w_num_elements || !w_malloc || !w_free) return NULL;
+  /* the host may hand us a PLUGIN_INFO to fill in (weed-plugin-utils.c:220-229) */
+  if (w_num_elements(host_info, PE_LEAF_PLUGIN_INFO) > 0) {
+    int32_t type = 0;
+    if (w_leaf_get(host_info, PE_LEAF_PLUGIN_INFO, 0, &plugin_info) != PE_WEED_SUCCESS) return NULL;
+    if (plugin_info) w_leaf_get(plugin_info, PE_LEAF_TYPE, 0, &type);
+    if (type != PE_WEED_PLANT_PLUGIN_INFO) plugin_info = NULL;
+  }
+  if (!plugin_info && !(plugin_info = w_plant_new(PE_WEED_PLANT_PLUGIN_INFO))) return NULL;
+  w_leaf_set(plugin_info, PE_LEAF_HOST_INFO, PE_WEED_SEED_PLANTPTR, 1, &host_info);
+
+  /* simple_blend.c:218-292 (filter order kept) */
+  if (add_filter(plugin_info, "chroma blend", PE_WEED_FILTER_PREF_LINEAR_GAMMA, all_rgb, 5, common_init, chroma_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "luma overlay", 0, all_rgb, 5, common_init, lumo_process, "threshold", "luma _threshold", 64) ||
+      add_filter(plugin_info, "luma underlay", 0, all_rgb, 5, common_init, lumu_process, "threshold", "luma _threshold", 64) ||
+      add_filter(plugin_info, "negative luma overlay", 0, all_rgb, 5, common_init, nlumo_process, "threshold", "luma _threshold", 64))
+    return NULL;
+  /* multi_blends.c:196-296 */
+  if (add_filter(plugin_info, "blend_multiply", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, mpy_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_screen", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, screen_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_darken", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, darken_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_lighten", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, lighten_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_overlay", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, overlay_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_dodge", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, dodge_process, "amount",
+                 "Blend _amount", 128) ||
+      add_filter(plugin_info, "blend_burn", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, burn_process, "amount",
+                 "Blend _amount", 128))
+    return NULL;
+  set_int(plugin_info, PE_LEAF_VERSION, package_version);
+  return plugin_info;
+}
+
+void weed_desetup(void) {
+  if (g_engine) {
+    pe_engine_destroy(g_engine);
+    g_engine = NULL;
+  }
+}

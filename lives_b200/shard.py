@@ -1,0 +1,56 @@
+"""Multi-GPU sharding of the pixel path: one process per GPU, frames / clips are independent units.
+
+  * render batch (BASELINE config 4, bench.py): contiguous blocks of frames per rank, NO data-path collective;
+  * multitrack (config 5): one clip per rank; the shared transition operand (one RGB24 / RGBA32 frame) lives on the
+    owning rank and is sent with a single broadcast per output frame (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Plumbing only (torch.distributed); every pixel is computed by the engine's CUDA kernels on the rank's own GPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+def frames_for_rank(n_frames, rank, world_size):
+    """contiguous block [lo, hi) of a batch of n_frames for this rank; blocks differ by at most one frame"""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError("bad rank %d / world size %d" % (rank, world_size))
+    base, rem = divmod(n_frames, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def clip_for_rank(n_clips, rank, world_size):
+    """multitrack: clips owned by this rank (round robin when there are more clips than ranks)"""
+    return list(range(rank, n_clips, world_size))
+
+
+def broadcast_operand(buf, src=0, group=None):
+    """Broadcast the shared transition operand (a uint8 tensor aliasing the frame's pixel memory) from `src`.
+    Returns the same tensor; on the owning rank it is the source, elsewhere it is overwritten."""
+    if buf.dtype != torch.uint8 or not buf.is_contiguous():
+        raise ValueError("operand must be a contiguous uint8 tensor")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(buf, src=src, group=group)
+    return buf
+
+
+def allreduce_histogram(hist, group=None):
+    """optional diagnostics: sum of per-frame histograms over ranks (<= 4 KB)"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blend_factor, src_rank=0, out_palette=1):
+    """config 5 on this rank: clip (YUV422P / UYVY / ...) -> RGB24 (convert_layer_palette), operand broadcast from the owner,
+    then 'chroma blend' (the crossfade / auto-transition of src/multitrack.h:84) of the clip with the operand, in place.
+    `operand_tensor`: uint8 CUDA tensor of height x rowstride bytes on every rank."""
+    from . import engine as E
+    if not E.convert_layer_palette(clip_layer, out_palette, 0):
+        raise RuntimeError("clip conversion failed: " + E.capi.last_error())
+    broadcast_operand(operand_tensor, src=src_rank)
+    torch.cuda.current_stream().synchronize()  # NCCL ran on torch's stream; the engine has its own
+    rs = operand_tensor.shape[1] if operand_tensor.dim() == 2 else operand_tensor.numel() // height
+    operand = E.Layer.wrap_device(engine, out_palette, width, height, [operand_tensor.data_ptr()], [rs])
+    E.simple_blend("chroma blend", clip_layer, operand, clip_layer, blend_factor)
+    return clip_layer

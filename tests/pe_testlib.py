@@ -165,6 +165,16 @@ def _plane(rng, rows, cols, stride, lo, hi):
     return pl
 
 
+def _plane_like(arr):
+    """copy of a stored plane with the guard byte of _plane() behind it"""
+    rows, stride = arr.shape
+    buf = np.zeros(rows * stride + 16, np.uint8)
+    pl = buf[:rows * stride].reshape(rows, stride)
+    pl[...] = arr
+    buf[rows * stride] = pl[rows - 1, stride - 1]
+    return pl
+
+
 def make_yuv_planar(rng, width, height, is_422=False, clamped=True):
     """Planar frame with the reference strides (colourspace.c:11344-11357)."""
     ys = rowstride(width, 1)

@@ -1,0 +1,61 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: frame partitioning and the operand broadcast."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lives_b200 import shard
+
+
+def test_frames_for_rank_partitions_exactly():
+    for n, w in ((256, 8), (256, 1), (7, 2), (3, 4), (0, 2), (33, 8)):
+        blocks = [shard.frames_for_rank(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        for a, b in zip(blocks, blocks[1:]):
+            assert a[1] == b[0]
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard.frames_for_rank(256, 3, 8) == (96, 128)  # config 4: 32 frames per GPU
+    assert shard.clip_for_rank(8, 5, 8) == [5] and shard.clip_for_rank(8, 1, 2) == [1, 3, 5, 7]
+    with pytest.raises(ValueError):
+        shard.frames_for_rank(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard.frames_for_rank(10, rank, world)
+        # shared transition operand: a 64 x 36 RGB24 frame (rowstride 192) owned by rank 0
+        h, rs = 36, 192
+        ref = torch.from_numpy(np.random.default_rng(99).integers(0, 256, (h, rs), dtype=np.uint8))
+        buf = ref.clone() if rank == 0 else torch.zeros((h, rs), dtype=torch.uint8)
+        shard.broadcast_operand(buf, src=0)
+        hist = torch.bincount(buf.flatten().long(), minlength=256)
+        shard.allreduce_histogram(hist)
+        q.put((rank, (lo, hi), bool((buf == ref).all()), int(hist.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_operand_broadcast_and_partition_world_size_2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == (0, 5) and res[1][1] == (5, 10)
+    assert res[0][2] and res[1][2]
+    assert res[0][3] == res[1][3] == 2 * 36 * 192

@@ -1,0 +1,105 @@
+"""Boundary B1: libpe_weed_plugin.so is a real libweed effect plugin.
+
+It is loaded by tests/host/weed_minihost.c through the REFERENCE's own libweed (oracle/_ref/libweed*.so:
+dlopen + dlsym("weed_setup") + setup(weed_bootstrap), as src/effects-weed.c:4468-4568 does) and must behave like the
+reference's simple_blend.so / multi_blends.so loaded the same way.
+"""
+import ctypes as C
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+import pe_testlib as T
+
+PLUGIN = os.path.join(T.REPO, "lives_b200", "libpe_weed_plugin.so")
+pytestmark = pytest.mark.skipif(not T.have_ref() or not os.path.exists(os.path.join(T.REF_DIR, "libweed_minihost.so")),
+                                reason="oracle/_ref (reference libweed + minihost) not built")
+
+NAMES = ["chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "blend_multiply", "blend_screen",
+         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn"]
+
+
+def _minihost():
+    mh = C.CDLL(os.path.join(T.REF_DIR, "libweed_minihost.so"))
+    mh.mh_open.argtypes = [C.c_char_p]
+    mh.mh_run2.argtypes = [T.I, T.I, T.I, T.I, T.I, T.VP, T.I, T.VP, T.I, T.VP, T.I, T.I, T.I]
+    return mh
+
+
+def _open_ours(mh):
+    if not os.path.exists(PLUGIN):
+        from lives_b200.build import build
+        build()
+    h = mh.mh_open(PLUGIN.encode())
+    assert h >= 0, "weed_setup(weed_bootstrap) of libpe_weed_plugin.so failed: %d" % h
+    return h
+
+
+def test_plugin_bootstraps_through_the_reference_libweed():
+    mh = _minihost()
+    h = _open_ours(mh)
+    assert mh.mh_num_filters(h) == len(NAMES)
+    buf = C.create_string_buffer(64)
+    for i, name in enumerate(NAMES):
+        assert mh.mh_filter_name(h, i, buf, 64) == 0 and buf.value.decode() == name
+        flags = mh.mh_filter_flags(h, i)
+        assert not flags & (1 << 6), "a GPU plugin must not set WEED_FILTER_HINT_MAY_THREAD (one process call per frame)"
+    # same names, same order as the reference plugins
+    ref = mh.mh_open(os.path.join(T.REF_DIR, "simple_blend.so").encode())
+    for i in range(4):
+        mh.mh_filter_name(ref, i, buf, 64)
+        assert buf.value.decode() == NAMES[i]
+    ref = mh.mh_open(os.path.join(T.REF_DIR, "multi_blends.so").encode())
+    for i in range(7):
+        mh.mh_filter_name(ref, i, buf, 64)
+        assert buf.value.decode() == NAMES[4 + i]
+
+
+def test_plugin_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    mh = _minihost()
+    h = _open_ours(mh)
+    s = np.zeros((8, 32), np.uint8)
+    d = np.zeros((8, 32), np.uint8)
+    rc = mh.mh_run2(h, 0, 1, 8, 8, T.ptr(s), 32, T.ptr(s), 32, T.ptr(d), 32, 100, 1)
+    assert rc == 64  # WEED_ERROR_PLUGIN_INVALID: no CPU fallback inside the plugin
+
+
+@pytest.mark.gpu
+def test_plugin_matches_reference_plugins_bit_for_bit():
+    mh = _minihost()
+    ours = _open_ours(mh)
+    ref_s = mh.mh_open(os.path.join(T.REF_DIR, "simple_blend.so").encode())
+    ref_m = mh.mh_open(os.path.join(T.REF_DIR, "multi_blends.so").encode())
+    rng = np.random.default_rng(31)
+    for pal, bf, (w, ht) in itertools.product((1, 2, 3, 4, 5), (0, 100, 255), ((64, 32), (61, 7), (640, 360))):
+        ps = T.psize_of(pal)
+        s1, s2 = T.make_packed(rng, w, ht, ps), T.make_packed(rng, w, ht, ps)
+        if ps == 4:
+            al = s2[:, 3::4] if pal != 5 else s2[:, 0::4]
+            al[rng.random(al.shape) < 0.4] = 255
+        for typ in range(4):
+            d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
+            assert mh.mh_run2(ref_s, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], bf, 1) == 0
+            assert mh.mh_run2(ours, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], bf, 1) == 0
+            if pal == 5 and s2.strides[0] == w * 4:
+                d_ref[-1, w * 4 - 3:] = d_our[-1, w * 4 - 3:]  # the reference reads one byte past the frame there (UB)
+            assert (d_ref == d_our).all(), (pal, bf, typ, w, ht)
+        # in place (CAN_DO_INPLACE, effects-weed.c:2304-2314)
+        a, b = s1.copy(), s1.copy()
+        mh.mh_run2(ref_s, 0, pal, w, ht, T.ptr(a), a.strides[0], T.ptr(s2), s2.strides[0], T.ptr(a), a.strides[0], bf, 1)
+        mh.mh_run2(ours, 0, pal, w, ht, T.ptr(b), b.strides[0], T.ptr(s2), s2.strides[0], T.ptr(b), b.strides[0], bf, 1)
+        if pal == 5 and s2.strides[0] == w * 4:
+            a[-1, w * 4 - 3:] = b[-1, w * 4 - 3:]
+        assert (a == b).all(), (pal, bf, "inplace")
+    for pal, bf, typ in itertools.product((1, 2), (0, 17, 128, 255), range(7)):
+        w, ht = 53, 12
+        s1, s2 = T.make_packed(rng, w, ht, 3), T.make_packed(rng, w, ht, 3)
+        d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
+        assert mh.mh_run2(ref_m, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], bf, 1) == 0
+        assert mh.mh_run2(ours, 4 + typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], bf, 1) == 0
+        assert (d_ref[:, :w * 3] == d_our[:, :w * 3]).all(), (pal, bf, typ)
