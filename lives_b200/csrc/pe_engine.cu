@@ -1277,7 +1277,7 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
   if (!dev) return PE_ERR_CUDA;
   // fast path: no horizontal scaling, <= 4 vertical taps, aligned planes (pe_kernels_fused2.cu)
   bool fast = getenv("PE_FUSED_GENERIC") == nullptr;
-  for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.taps, 0);
+  for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.taps, 0) && args[i].is_422 == args[0].is_422;
   int tile_h = 0;
   if (fast) {
     // tallest tile whose virtual source rows (first .. first + 3 of its last row) fit the shared-memory tile
@@ -1289,7 +1289,7 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
         const int spanr = F.first[i1] + 3 - F.first[i0] + 1;
         if (spanr > worst) worst = spanr;
       }
-      if (worst <= fused2_max_virtual_rows()) break;
+      if (worst <= fused2_max_virtual_rows(args[0].is_422)) break;
     }
     if (tile_h < 4) fast = false;
   }

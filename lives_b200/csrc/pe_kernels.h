@@ -119,7 +119,7 @@ int fused_tile_w();
 int fused_tile_h();
 // fast path (pe_kernels_fused2.cu): no horizontal scaling, <= 4 vertical taps, 4-byte aligned planes
 bool fused2_supported(const FusedArgs &a, int fy_taps, int unused);
-int fused2_max_virtual_rows();
+int fused2_max_virtual_rows(int is422);
 int fused2_max_tile_h();
 // blend_a in 0..256: integer blend (alpha = blend_a / 256) + optional lut8; blend_a < 0: FusedArgs::over_table
 cudaError_t launch_fused2_dev(const Launch &L, const FusedArgs *frames_dev, int nframes, int ow, int oh, int tile_h, int blend_a,

@@ -27,26 +27,33 @@ namespace {
 
 constexpr int F2_NT = 128;
 constexpr int F2_TW = 128;                 // output tile width
-constexpr int F2_MAXVR = 60;               // max virtual source rows (first .. first + 3 of the last row) per tile
+constexpr int F2_MAXVR = 60;               // max virtual source rows (first .. first + 3 of the last row) per 4:2:0 tile
+constexpr int F2_MAXVR_422 = 28;           // ... per 4:2:2 tile (one chroma row per luma row: bounded by F2_CROWS)
 constexpr int F2_CW = 17;                  // words per column of the converted tile (68 rows)
 constexpr int F2_CCOLS = F2_TW + 4;        // columns of the converted tile (alignment slack of one quad)
-constexpr int F2_YROWS = 72;               // raw luma rows
+constexpr int F2_YROWS = 68;               // raw luma rows
 constexpr int F2_YRS = 136;                // raw luma row stride in bytes (34 words, == 2 mod 8)
-constexpr int F2_CROWS = 72;               // raw chroma rows (4:2:2: one per luma row)
+constexpr int F2_CROWS = 36;               // raw chroma rows
 constexpr int F2_CRS = 72;                 // raw chroma row stride in bytes: [1] left halo, [2 ..] interior, then right halo
 constexpr int F2_MAXTH = 48;               // max output rows per tile
+constexpr int F2_NEXT = 768;               // entries of an extended chroma table (index n = u1 + (u2 >> 1) <= 765)
 
-constexpr int OFF_TAB = 0;                                   // int32 [5][256]
-constexpr int OFF_LUT = OFF_TAB + 5 * 1024;                  // u8 [256]
+// Shared-memory tables: RGB_Y[256], then four chroma tables indexed by the UN-divided chroma sum n:
+//   ext[t][n] = table_t[clamp(third_round(n), lo, hi)]        (third_round(n) = (int)(n / 3. + .5), colourspace.c:3465)
+// which folds the divide-by-3 rounding and CLAMP16_240 / CLAMP0_255 of the reference into the lookup.  A plain chroma
+// sample m (single rows, PB_QUALITY_LOW) is looked up at n = 3 * m (third_round(3 m) == m).
+constexpr int OFF_TAB = 0;                                   // int32 [256 + 4 * F2_NEXT]
+constexpr int OFF_LUT = OFF_TAB + (256 + 4 * F2_NEXT) * 4;   // u8 [256]
 constexpr int OFF_ROW = OFF_LUT + 256;                       // int32 [F2_MAXTH][4]: pos, a0, a1, -
 constexpr int OFF_VF = OFF_ROW + F2_MAXTH * 16;              // u8 [F2_CROWS] true column 0 of V per chroma row (+ pad)
-constexpr int OFF_Y = OFF_VF + 80;
+constexpr int OFF_Y = OFF_VF + 48;
 constexpr int OFF_U = OFF_Y + F2_YROWS * F2_YRS;
 constexpr int OFF_V = OFF_U + F2_CROWS * F2_CRS;
 constexpr int OFF_C = OFF_V + F2_CROWS * F2_CRS;             // u32 [3][F2_CCOLS][F2_CW]
 constexpr int OFF_OVER = OFF_C + 3 * F2_CCOLS * F2_CW * 4;   // u8 [65536] (table blend only)
 constexpr int F2_SMEM_ARITH = OFF_OVER;
 constexpr int F2_SMEM_TABLE = OFF_OVER + 65536;
+static_assert(OFF_ROW % 16 == 0 && OFF_Y % 16 == 0 && OFF_C % 16 == 0 && OFF_OVER % 16 == 0, "alignment");
 
 struct Fused2Params {
   const FusedArgs *frames;
@@ -78,12 +85,20 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
 __device__ __forceinline__ int quad_of(int row, int is422) { return is422 ? (row >> 2) : ((row + 3) >> 2); }
 __device__ __forceinline__ int quad_first_row(int g, int is422) { return is422 ? 4 * g : 4 * g - 3; }
 
-// yuv2rgb_int / xyuv2rgb (colourspace.c:2345-2356) through the shared-memory tables; byte results
-__device__ __forceinline__ void px_rgb(const int32_t *__restrict__ t, int y, int u, int v, uint32_t &r, uint32_t &g, uint32_t &b) {
+// d = (c[15:0] << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// yuv2rgb_int / xyuv2rgb (colourspace.c:2345-2356) through the shared-memory tables.  nu / nv index the extended chroma
+// tables; results are the UNSATURATED (sum >> 16) values, saturated when they are packed (pack_sat).
+__device__ __forceinline__ void px_rgb(const int32_t *__restrict__ t, int y, int nu, int nv, int &r, int &g, int &b) {
   const int yy = t[y];
-  r = (uint32_t)sat8((yy + t[256 + v]) >> 16);
-  g = (uint32_t)sat8((yy + t[512 + u] + t[768 + v]) >> 16);
-  b = (uint32_t)sat8((yy + t[1024 + u]) >> 16);
+  r = (yy + t[256 + nv]) >> 16;
+  g = (yy + t[256 + F2_NEXT + nu] + t[256 + 2 * F2_NEXT + nv]) >> 16;
+  b = (yy + t[256 + 3 * F2_NEXT + nu]) >> 16;
 }
 
 template <int MODE>  // 0: arithmetic blend (alpha = k / 256), 1: [bg][fg] table blend
@@ -91,7 +106,7 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
   extern __shared__ __align__(16) uint8_t smem[];
   int32_t *s_tab = reinterpret_cast<int32_t *>(smem + OFF_TAB);
   uint8_t *s_lut = smem + OFF_LUT;
-  int32_t *s_row = reinterpret_cast<int32_t *>(smem + OFF_ROW);
+  int4 *s_row = reinterpret_cast<int4 *>(smem + OFF_ROW);
   uint8_t *s_vf = smem + OFF_VF;
   uint8_t *s_y = smem + OFF_Y;
   uint8_t *s_u = smem + OFF_U;
@@ -101,17 +116,19 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int32_t *cur_conv = nullptr;
+  int cur_clamped = -1;
   const uint8_t *cur_over = nullptr;
   const bool has_lut = P.lut8 != nullptr;
   if (has_lut) for (int i = tid; i < 256; i += F2_NT) s_lut[i] = P.lut8[i];
 
-  const long long tiles_per_frame = (long long)P.tiles_x * P.tiles_y, total_tiles = tiles_per_frame * P.nframes;
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+  const long long total_tiles = (long long)tiles_per_frame * P.nframes;
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int f = (int)(tile / tiles_per_frame);
     const int t = (int)(tile - (long long)f * tiles_per_frame);
     const FusedArgs &A = P.frames[f];
-    const int is422 = A.is_422, fw = A.fw, fh = A.fh;
-    const int tx = t % P.tiles_x, ty = t / P.tiles_x;
+    const int is422 = A.is_422, fh = A.fh;
+    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
     const int x0 = tx * F2_TW, y0 = ty * P.tile_h;
     const int x1 = min(x0 + F2_TW, A.ow), y1 = min(y0 + P.tile_h, A.oh);
     // intersection with the inner rectangle, in inner (= source column) coordinates
@@ -120,9 +137,17 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
     const bool has_inner = ix0 < ix1 && iy0 < iy1;
 
     __syncthreads();  // the previous tile is done with shared memory
-    if (A.conv.t != cur_conv) {
-      for (int i = tid; i < 5 * 256; i += F2_NT) s_tab[i] = A.conv.t[9 * 256 + i];
+    if (A.conv.t != cur_conv || A.clamped != cur_clamped) {
+      const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
+      const int32_t *ct = A.conv.t + 9 * 256;  // RGB_Y, R_Cr, G_Cb, G_Cr, B_Cb
+      for (int i = tid; i < 256; i += F2_NT) s_tab[i] = ct[i];
+      for (int i = tid; i < F2_NEXT; i += F2_NT) {
+        const int c = clamp_i(third_round(i), lo, hi);
+#pragma unroll
+        for (int k = 0; k < 4; k++) s_tab[256 + k * F2_NEXT + i] = ct[(1 + k) * 256 + c];
+      }
       cur_conv = A.conv.t;
+      cur_clamped = A.clamped;
     }
     if (MODE == 1 && A.over_table != cur_over) {
       for (int i = tid; i < 4096; i += F2_NT) reinterpret_cast<uint4 *>(s_over)[i] = reinterpret_cast<const uint4 *>(A.over_table)[i];
@@ -133,7 +158,7 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
     if (has_inner) {
       const int vr0 = A.fy.first[iy0], vr1 = A.fy.first[iy1 - 1] + 3;     // virtual source rows of the tile
       const int ar0 = min(max(vr0, 0), fh - 1), ar1 = min(max(vr1, 0), fh - 1);
-      base_g = quad_of(vr0, is422);                                       // (vr0 >= -3 always: first >= -support)
+      base_g = quad_of(vr0, is422);
       const int ga = quad_of(ar0, is422), gb = quad_of(ar1, is422);       // quads that hold real rows
       cq0 = ix0 >> 2;
       const int cq1 = (ix1 - 1) >> 2, ncq = cq1 - cq0 + 1;
@@ -146,64 +171,54 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
       // ---- per-row filter data: window position inside the converted tile, coefficient pairs
       for (int i = tid; i < iy1 - iy0; i += F2_NT) {
         const int iy = iy0 + i;
-        const int first = A.fy.first[iy];
-        const int16_t *c = A.fy.coef + (long long)iy * A.fy.taps;
-        uint32_t cc[4] = {0, 0, 0, 0};
-        for (int k = 0; k < A.fy.taps; k++) cc[k] = (uint16_t)c[k];
-        s_row[4 * i + 0] = first + (is422 ? 0 : 3) - 4 * base_g;
-        s_row[4 * i + 1] = (int)(cc[0] | (cc[1] << 16));
-        s_row[4 * i + 2] = (int)(cc[2] | (cc[3] << 16));
+        const int16_t *c = A.fy.coef + iy * A.fy.taps;
+        const int nt = A.fy.taps;
+        const uint32_t c0 = (uint16_t)c[0], c1 = nt > 1 ? (uint16_t)c[1] : 0u, c2 = nt > 2 ? (uint16_t)c[2] : 0u,
+                       c3 = nt > 3 ? (uint16_t)c[3] : 0u;
+        s_row[i] = make_int4(A.fy.first[iy] + (is422 ? 0 : 3) - 4 * base_g, (int)(c0 | (c1 << 16)), (int)(c2 | (c3 << 16)), 0);
       }
-      // ---- stage raw luma: rows yrow0..yrow1, 32-bit words cq0..cq1
+      // ---- stage raw luma: rows yrow0..yrow1, 32-bit words cq0..cq1 (one row per warp pass, one word per lane)
       {
-        const int nw = ncq;
-        for (int i = tid; i < nyr * nw; i += F2_NT) {
-          const int r = i / nw, w = i - r * nw;
-          const uint32_t v = ld_stream_u32(A.fg.y + (long long)A.fg.rs_y * (yrow0 + r) + 4 * (cq0 + w));
-          *reinterpret_cast<uint32_t *>(s_y + r * F2_YRS + 4 * w) = v;
-        }
+        const uint8_t *src = A.fg.y + (size_t)A.fg.rs_y * yrow0 + 4 * cq0;
+        for (int w = lane; w < ncq; w += 32)  // (33 words when the inner rectangle is not quad aligned)
+          for (int r = warp; r < nyr; r += F2_NT / 32)
+            *reinterpret_cast<uint32_t *>(s_y + r * F2_YRS + 4 * w) = ld_stream_u32(src + (size_t)A.fg.rs_y * r + 4 * w);
       }
-      // ---- stage raw chroma: interior columns 2*cq0 .. 2*cq1+1 as 16-bit pairs, the two halo columns with the reference's
-      //      edge rules: column -1 replicates column 0 (last = this at the start of a row); column >= cw reads the byte at
-      //      plane[stride * r + cw] -- padding or the first sample of the next row -- except on the last chroma row of a
-      //      plane without padding, where it is the replicated edge sample (colourspace.c:3508-3512, DESIGN.md "edge read");
+      // ---- stage raw chroma: interior columns 2*cq0 .. 2*cq1+1 as 16-bit pairs (lane = pair), the two halo columns with the
+      //      reference's edge rules: column -1 replicates column 0 (last = this at the start of a row); column >= cw reads the
+      //      byte at plane[stride * r + cw] -- padding or the first sample of the next row -- except on the last chroma row of
+      //      a plane without padding, where it is the replicated edge sample (colourspace.c:3508-3512, DESIGN.md "edge read");
       //      4:2:2 with ref_quirks: columns <= 0 take column 0 of chroma row (r >> 1) (the seed slip, :3600)
       {
-        const int npair = ncq;  // 16-bit pairs per row
-        const int per_row = npair + 2;
-        for (int i = tid; i < ncr * per_row * 2; i += F2_NT) {
-          const int plane = i / (ncr * per_row);
-          const int j = i - plane * (ncr * per_row);
-          const int r = j / per_row, e = j - r * per_row;
+        const bool seed = is422 && A.quirks;
+        for (int rr = warp; rr < 2 * ncr; rr += F2_NT / 32) {
+          const int plane = rr >= ncr, r = plane ? rr - ncr : rr;
           const int cr = crow0 + r;
-          const uint8_t *src = plane ? A.fg.v : A.fg.u;
+          const uint8_t *srow = (plane ? A.fg.v : A.fg.u) + (size_t)(plane ? A.fg.rs_v : A.fg.rs_u) * cr;
           const int rs = plane ? A.fg.rs_v : A.fg.rs_u;
           uint8_t *dst = (plane ? s_v : s_u) + r * F2_CRS;
-          const bool seed = is422 && A.quirks;
-          if (e < npair) {
-            const int c = 2 * (cq0 + e);  // even column; c + 1 <= cw may be the one-past column
+          const uint8_t *seedp = (plane ? A.fg.v : A.fg.u) + (size_t)rs * (cr >> 1);
+          for (int w = lane; w < ncq; w += 32) {
+            const int c = 2 * (cq0 + w);  // even column; c + 1 <= cw may be the one-past column
             uint32_t b0, b1;
             if (c + 1 < cw) {
-              const uint32_t v = *reinterpret_cast<const uint16_t *>(src + (long long)rs * cr + c);
+              const uint32_t v = *reinterpret_cast<const uint16_t *>(srow + c);
               b0 = v & 0xFFu; b1 = v >> 8;
             } else {
-              b0 = chroma_edge(src, rs, cr, c, cw, ch);
-              b1 = chroma_edge(src, rs, cr, c + 1, cw, ch);
+              b0 = chroma_edge(srow - (size_t)rs * cr, rs, cr, c, cw, ch);
+              b1 = chroma_edge(srow - (size_t)rs * cr, rs, cr, c + 1, cw, ch);
             }
-            if (seed && c == 0) b0 = src[(long long)rs * (cr >> 1)];
-            *reinterpret_cast<uint16_t *>(dst + 2 + 2 * e) = (uint16_t)(b0 | (b1 << 8));
-          } else if (e == npair) {  // left halo
+            if (seed && c == 0) b0 = seedp[0];
+            *reinterpret_cast<uint16_t *>(dst + 2 + 2 * w) = (uint16_t)(b0 | (b1 << 8));
+          }
+          if (lane == 0) {        // left halo
             const int c = 2 * cq0 - 1;
-            uint32_t b;
-            if (c < 0) b = seed ? src[(long long)rs * (cr >> 1)] : src[(long long)rs * cr];
-            else b = src[(long long)rs * cr + c];
-            dst[1] = (uint8_t)b;
-          } else {                  // right halo
-            const int c = 2 * cq1 + 2;
-            dst[2 + 2 * npair] = (uint8_t)chroma_edge(src, rs, cr, c, cw, ch);
+            dst[1] = c < 0 ? (seed ? seedp[0] : srow[0]) : srow[c];
+            if (plane) s_vf[r] = srow[0];
+          } else if (lane == 1) { // right halo
+            dst[2 + 2 * ncq] = (uint8_t)chroma_edge(srow - (size_t)rs * cr, rs, cr, 2 * cq1 + 2, cw, ch);
           }
         }
-        for (int r = tid; r < ncr; r += F2_NT) s_vf[r] = A.fg.v[(long long)A.fg.rs_v * (crow0 + r)];
       }
       __syncthreads();
 
@@ -211,98 +226,159 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
       {
         const int ngr = gb - ga + 1;
         const int cq_groups = (ncq + 7) >> 3, rq_groups = (ngr + 3) >> 2;
-        const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
-        for (int wt = warp; wt < cq_groups * rq_groups; wt += F2_NT / 32) {
-          const int cg = wt % cq_groups, rg = wt / cq_groups;
-          const int q = cg * 8 + (lane & 7), gl = rg * 4 + (lane >> 3);
-          if (q >= ncq || gl >= ngr) continue;
-          const int g = ga + gl;
-          const int jc0 = 2 * (cq0 + q);  // absolute chroma column of the unit's first pair
-          uint32_t acc[4][3];
+        const int quirks = A.quirks;
+        for (int rg = 0; rg < rq_groups; rg++) {
+          for (int cg = warp; cg < cq_groups; cg += F2_NT / 32) {
+            const int q = cg * 8 + (lane & 7), gl = rg * 4 + (lane >> 3);
+            if (q >= ncq || gl >= ngr) continue;
+            const int g = ga + gl;
+            const int jc0 = 2 * (cq0 + q);  // absolute chroma column of the unit's first pair
+            uint32_t *dst = s_c + (4 * q) * F2_CW + (g - base_g);
+            // chroma words: columns jc0-1 .. jc0+2 of one staged chroma row
+            const int cidx = 2 * q + 1;  // byte index of column jc0 - 1 in a staged row
+            auto cword = [&](const uint8_t *pl, int cr) -> uint32_t {
+              const uint8_t *rowp = pl + (cr - crow0) * F2_CRS + (cidx & ~3);
+              return __funnelshift_r(*reinterpret_cast<const uint32_t *>(rowp), *reinterpret_cast<const uint32_t *>(rowp + 4),
+                                     8 * (cidx & 3));
+            };
+            const uint8_t *yp = s_y + 4 * q;
+            const int row0 = quad_first_row(g, is422);
+            const bool full420 = !is422 && !A.low_quality && row0 >= 1 && row0 + 3 <= fh - 1 - ((fh & 1) ? 0 : 1);
+            if (full420) {
+              // ===== fast path: both row pairs of the quad are interior pairs (colourspace.c:3440-3549)
+              const int cA = 2 * g - 2 - crow0;  // staged chroma rows cA, cA + 1, cA + 2
+              const uint32_t uw[3] = {cword(s_u, crow0 + cA), cword(s_u, crow0 + cA + 1), cword(s_u, crow0 + cA + 2)};
+              const uint32_t vw[3] = {cword(s_v, crow0 + cA), cword(s_v, crow0 + cA + 1), cword(s_v, crow0 + cA + 2)};
+              const int vf1 = s_vf[cA + 1], vf2 = s_vf[cA + 2];
+              uint32_t yw[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0;
-          // chroma words: columns jc0-1 .. jc0+2 of one staged chroma row
-          auto cword = [&](const uint8_t *pl, int cr) -> uint32_t {
-            const uint8_t *rowp = pl + (cr - crow0) * F2_CRS;
-            const int idx = 2 * q + 1;  // byte index of column jc0 - 1
-            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(rowp + (idx & ~3));
-            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(rowp + (idx & ~3) + 4);
-            return __funnelshift_r(w0, w1, 8 * (idx & 3));
-          };
-          auto yword = [&](int row) -> uint32_t { return *reinterpret_cast<const uint32_t *>(s_y + (row - yrow0) * F2_YRS + 4 * q); };
-          // a single row: horizontal average only (row 0, an even frame's last row, every 4:2:2 row)
-          auto do_single = [&](int row, int cr, int bytepos) {
-            const uint32_t yw = yword(row), uw = cword(s_u, cr), vw = cword(s_v, cr);
+              for (int r = 0; r < 4; r++) yw[r] = *reinterpret_cast<const uint32_t *>(yp + (row0 + r - yrow0) * F2_YRS);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int p = k >> 1;
-              const int ua = byte_of(uw, p + 1), va = byte_of(vw, p + 1);
-              const int ub = (k & 1) ? byte_of(uw, p + 2) : byte_of(uw, p), vb = (k & 1) ? byte_of(vw, p + 2) : byte_of(vw, p);
-              const int u = clamp_i((ua + ub) >> 1, lo, hi), v = clamp_i((va + vb) >> 1, lo, hi);
-              uint32_t r, gg, b;
-              px_rgb(s_tab, byte_of(yw, k), u, v, r, gg, b);
-              acc[k][0] |= r << (8 * bytepos); acc[k][1] |= gg << (8 * bytepos); acc[k][2] |= b << (8 * bytepos);
-            }
-          };
-          // an interior row pair (colourspace.c:3440-3549)
-          auto do_pair = [&](int row_a, int cr_a, int bytepos) {
-            const int cr_b = cr_a + 1;
-            const uint32_t ya = yword(row_a), yb = yword(row_a + 1);
-            const uint32_t u1w = cword(s_u, cr_a), u2w = cword(s_u, cr_b), v1w = cword(s_v, cr_a), v2w = cword(s_v, cr_b);
-            const int v2_first = s_vf[cr_b - crow0];
+              for (int p = 0; p < 2; p++) {
+                // chroma samples of columns jc0+p-1, jc0+p, jc0+p+1 in the three rows
+                int U[3][3], V[3][3];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int p = k >> 1;
-              int u1, u2, v1, v2;
-              if (k & 1) {
-                u1 = byte_of(u1w, p + 1) + byte_of(u1w, p + 2); u2 = byte_of(u2w, p + 1) + byte_of(u2w, p + 2);
-                v1 = byte_of(v1w, p + 1) + byte_of(v1w, p + 2); v2 = byte_of(v2w, p + 1) + byte_of(v2w, p + 2);
-              } else {
-                u1 = byte_of(u1w, p + 1) + byte_of(u1w, p); u2 = byte_of(u2w, p + 1) + byte_of(u2w, p);
-                v1 = byte_of(v1w, p + 1) + byte_of(v1w, p); v2 = byte_of(v2w, p + 1) + byte_of(v2w, p);
-                if (A.quirks) {
-                  u2 = u1;                                                          // colourspace.c:3461
-                  if (jc0 + p > 0) v1 = byte_of(v1w, p + 1) + byte_of(v2w, p);      // :3544
-                  v2 = byte_of(v2w, p + 1) + v2_first;                              // last_v2 never advanced
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                  for (int c = 0; c < 3; c++) { U[r][c] = byte_of(uw[r], p + c); V[r][c] = byte_of(vw[r], p + c); }
+                // n indices (u1 + (u2 >> 1) upper, (u1 >> 1) + u2 lower) for the left / right pixel of both pairs
+                int nu[2][4], nv[2][4];  // [left/right][row in quad]
+#pragma unroll
+                for (int pr = 0; pr < 2; pr++) {  // pair: chroma rows (pr, pr + 1)
+                  // right pixel: this + next
+                  {
+                    const int u1 = U[pr][1] + U[pr][2], u2 = U[pr + 1][1] + U[pr + 1][2];
+                    const int v1 = V[pr][1] + V[pr][2], v2 = V[pr + 1][1] + V[pr + 1][2];
+                    nu[1][2 * pr] = u1 + (u2 >> 1); nu[1][2 * pr + 1] = (u1 >> 1) + u2;
+                    nv[1][2 * pr] = v1 + (v2 >> 1); nv[1][2 * pr + 1] = (v1 >> 1) + v2;
+                  }
+                  // left pixel: this + last, with the reference's slips under `quirks`
+                  {
+                    const int u1 = U[pr][1] + U[pr][0];
+                    int u2 = U[pr + 1][1] + U[pr + 1][0];
+                    int v1 = V[pr][1] + V[pr][0], v2 = V[pr + 1][1] + V[pr + 1][0];
+                    if (quirks) {
+                      u2 = u1;                                            // colourspace.c:3461
+                      if (jc0 + p > 0) v1 = V[pr][1] + V[pr + 1][0];      // :3544
+                      v2 = V[pr + 1][1] + (pr ? vf2 : vf1);               // last_v2 never advanced
+                    }
+                    nu[0][2 * pr] = u1 + (u2 >> 1); nu[0][2 * pr + 1] = (u1 >> 1) + u2;
+                    nv[0][2 * pr] = v1 + (v2 >> 1); nv[0][2 * pr + 1] = (v1 >> 1) + v2;
+                  }
+                }
+#pragma unroll
+                for (int lr = 0; lr < 2; lr++) {
+                  const int k = 2 * p + lr;
+                  int r[4], gg[4], b[4];
+#pragma unroll
+                  for (int rw = 0; rw < 4; rw++) px_rgb(s_tab, byte_of(yw[rw], k), nu[lr][rw], nv[lr][rw], r[rw], gg[rw], b[rw]);
+                  dst[k * F2_CW] = pack_sat(r[1], r[0], pack_sat(r[3], r[2], 0u));
+                  dst[F2_CCOLS * F2_CW + k * F2_CW] = pack_sat(gg[1], gg[0], pack_sat(gg[3], gg[2], 0u));
+                  dst[2 * F2_CCOLS * F2_CW + k * F2_CW] = pack_sat(b[1], b[0], pack_sat(b[3], b[2], 0u));
                 }
               }
-              int u3, u4, v3, v4;
-              if (!A.low_quality) {
-                u3 = third_round(u1 + (u2 >> 1)); u4 = third_round((u1 >> 1) + u2);
-                v3 = third_round(v1 + (v2 >> 1)); v4 = third_round((v1 >> 1) + v2);
-              } else {
-                u3 = u1 >> 1; u4 = u2 >> 1; v3 = v1 >> 1; v4 = v2 >> 1;
+              continue;
+            }
+            // ===== general path: 4:2:2, PB_QUALITY_LOW, and the quads that hold row 0 / the last rows of the frame
+            uint32_t acc[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0;
+            auto put = [&](int k, int bytepos, int r, int gg, int b) {
+              acc[k][0] |= (uint32_t)sat8(r) << (8 * bytepos);
+              acc[k][1] |= (uint32_t)sat8(gg) << (8 * bytepos);
+              acc[k][2] |= (uint32_t)sat8(b) << (8 * bytepos);
+            };
+            // a single row: horizontal average only (row 0, an even frame's last row, every 4:2:2 row)
+            auto do_single = [&](int row, int cr, int bytepos) {
+              const uint32_t yw = *reinterpret_cast<const uint32_t *>(yp + (row - yrow0) * F2_YRS);
+              const uint32_t uw = cword(s_u, cr), vw = cword(s_v, cr);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int p = k >> 1;
+                const int ua = byte_of(uw, p + 1), va = byte_of(vw, p + 1);
+                const int ub = (k & 1) ? byte_of(uw, p + 2) : byte_of(uw, p), vb = (k & 1) ? byte_of(vw, p + 2) : byte_of(vw, p);
+                int r, gg, b;
+                px_rgb(s_tab, byte_of(yw, k), 3 * ((ua + ub) >> 1), 3 * ((va + vb) >> 1), r, gg, b);
+                put(k, bytepos, r, gg, b);
               }
-              u3 = clamp_i(u3, lo, hi); u4 = clamp_i(u4, lo, hi); v3 = clamp_i(v3, lo, hi); v4 = clamp_i(v4, lo, hi);
-              uint32_t r, gg, b;
-              px_rgb(s_tab, byte_of(ya, k), u3, v3, r, gg, b);
-              acc[k][0] |= r << (8 * bytepos); acc[k][1] |= gg << (8 * bytepos); acc[k][2] |= b << (8 * bytepos);
-              px_rgb(s_tab, byte_of(yb, k), u4, v4, r, gg, b);
-              acc[k][0] |= r << (8 * bytepos + 8); acc[k][1] |= gg << (8 * bytepos + 8); acc[k][2] |= b << (8 * bytepos + 8);
-            }
-          };
-          if (is422) {
+            };
+            auto do_pair = [&](int row_a, int cr_a, int bytepos) {
+              const int cr_b = cr_a + 1;
+              const uint32_t ya = *reinterpret_cast<const uint32_t *>(yp + (row_a - yrow0) * F2_YRS);
+              const uint32_t yb = *reinterpret_cast<const uint32_t *>(yp + (row_a + 1 - yrow0) * F2_YRS);
+              const uint32_t u1w = cword(s_u, cr_a), u2w = cword(s_u, cr_b), v1w = cword(s_v, cr_a), v2w = cword(s_v, cr_b);
+              const int v2_first = s_vf[cr_b - crow0];
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-              const int row = 4 * g + rr;
-              if (row < fh) do_single(row, row, rr);
-            }
-          } else {
-            // quad g holds rows 4g-3 .. 4g: pairs (4g-3, 4g-2) and (4g-1, 4g); chroma rows (2g-2, 2g-1) and (2g-1, 2g)
+              for (int k = 0; k < 4; k++) {
+                const int p = k >> 1;
+                int u1, u2, v1, v2;
+                if (k & 1) {
+                  u1 = byte_of(u1w, p + 1) + byte_of(u1w, p + 2); u2 = byte_of(u2w, p + 1) + byte_of(u2w, p + 2);
+                  v1 = byte_of(v1w, p + 1) + byte_of(v1w, p + 2); v2 = byte_of(v2w, p + 1) + byte_of(v2w, p + 2);
+                } else {
+                  u1 = byte_of(u1w, p + 1) + byte_of(u1w, p); u2 = byte_of(u2w, p + 1) + byte_of(u2w, p);
+                  v1 = byte_of(v1w, p + 1) + byte_of(v1w, p); v2 = byte_of(v2w, p + 1) + byte_of(v2w, p);
+                  if (quirks) {
+                    u2 = u1;
+                    if (jc0 + p > 0) v1 = byte_of(v1w, p + 1) + byte_of(v2w, p);
+                    v2 = byte_of(v2w, p + 1) + v2_first;
+                  }
+                }
+                int n3u, n4u, n3v, n4v;
+                if (!A.low_quality) {
+                  n3u = u1 + (u2 >> 1); n4u = (u1 >> 1) + u2; n3v = v1 + (v2 >> 1); n4v = (v1 >> 1) + v2;
+                } else {  // PB_QUALITY_LOW: u3 = u1 >> 1, u4 = u2 >> 1 (:3470-3474)
+                  n3u = 3 * (u1 >> 1); n4u = 3 * (u2 >> 1); n3v = 3 * (v1 >> 1); n4v = 3 * (v2 >> 1);
+                }
+                int r, gg, b;
+                px_rgb(s_tab, byte_of(ya, k), n3u, n3v, r, gg, b);
+                put(k, bytepos, r, gg, b);
+                px_rgb(s_tab, byte_of(yb, k), n4u, n4v, r, gg, b);
+                put(k, bytepos + 1, r, gg, b);
+              }
+            };
+            if (is422) {
 #pragma unroll
-            for (int pp = 0; pp < 2; pp++) {
-              const int row_a = 4 * g - 3 + 2 * pp, cr_a = 2 * g - 2 + pp;
-              if (row_a + 1 == 0) do_single(0, 0, 2 * pp + 1);                       // row 0 (lower half of the "pair" -1, 0)
-              else if (row_a >= 0 && row_a + 1 < fh) do_pair(row_a, cr_a, 2 * pp);
-              else if (row_a == fh - 1 && row_a >= 0) do_single(row_a, ch - 1, 2 * pp);  // even height: last row alone
-            }
-          }
-          uint32_t *dst = s_c + (4 * q) * F2_CW + (g - base_g);
+              for (int rr = 0; rr < 4; rr++) {
+                const int row = 4 * g + rr;
+                if (row < fh) do_single(row, row, rr);
+              }
+            } else {
+              // quad g holds rows 4g-3 .. 4g: pairs (4g-3, 4g-2) and (4g-1, 4g); chroma rows (2g-2, 2g-1) and (2g-1, 2g)
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            dst[k * F2_CW] = acc[k][0];
-            dst[F2_CCOLS * F2_CW + k * F2_CW] = acc[k][1];
-            dst[2 * F2_CCOLS * F2_CW + k * F2_CW] = acc[k][2];
+              for (int pp = 0; pp < 2; pp++) {
+                const int row_a = 4 * g - 3 + 2 * pp, cr_a = 2 * g - 2 + pp;
+                if (row_a + 1 == 0) do_single(0, 0, 2 * pp + 1);                       // row 0 (lower half of the "pair" -1, 0)
+                else if (row_a >= 0 && row_a + 1 < fh) do_pair(row_a, cr_a, 2 * pp);
+                else if (row_a == fh - 1 && row_a >= 0) do_single(row_a, ch - 1, 2 * pp);  // even height: last row alone
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              dst[k * F2_CW] = acc[k][0];
+              dst[F2_CCOLS * F2_CW + k * F2_CW] = acc[k][1];
+              dst[2 * F2_CCOLS * F2_CW + k * F2_CW] = acc[k][2];
+            }
           }
         }
       }
@@ -312,16 +388,17 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
         const int shift = is422 ? 0 : 3;
         const int ncols = 4 * ncq;
         uint8_t *cb = reinterpret_cast<uint8_t *>(s_c);
-        for (int i = tid; i < 3 * ncols; i += F2_NT) {
-          const int chn = i / ncols, col = i - chn * ncols;
-          uint8_t *colp = cb + ((chn * F2_CCOLS + col) * F2_CW) * 4;
-          if (vr0 < 0) {
-            const uint8_t v = colp[0 + shift - 4 * base_g];
-            for (int r = vr0; r < 0; r++) colp[r + shift - 4 * base_g] = v;
-          }
-          if (vr1 > fh - 1) {
-            const uint8_t v = colp[fh - 1 + shift - 4 * base_g];
-            for (int r = fh; r <= vr1; r++) colp[r + shift - 4 * base_g] = v;
+        for (int chn = 0; chn < 3; chn++) {
+          for (int col = tid; col < ncols; col += F2_NT) {
+            uint8_t *colp = cb + ((chn * F2_CCOLS + col) * F2_CW) * 4;
+            if (vr0 < 0) {
+              const uint8_t v = colp[0 + shift - 4 * base_g];
+              for (int r = vr0; r < 0; r++) colp[r + shift - 4 * base_g] = v;
+            }
+            if (vr1 > fh - 1) {
+              const uint8_t v = colp[fh - 1 + shift - 4 * base_g];
+              for (int r = fh; r <= vr1; r++) colp[r + shift - 4 * base_g] = v;
+            }
           }
         }
         __syncthreads();
@@ -332,61 +409,62 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 4 : 2) k_fused2(const Fused
     {
       const int th = y1 - y0;
       const int nquads = (th + 3) >> 2;
-      for (int task = warp; task < nquads * (F2_TW / 32); task += F2_NT / 32) {
-        const int qd = task / (F2_TW / 32), cwp = task - qd * (F2_TW / 32);
+      const uint32_t ka = (uint32_t)P.blend_a, kia = (uint32_t)P.blend_ia;
+#pragma unroll 1
+      for (int cwp = 0; cwp < F2_TW / 32; cwp++) {
         const int x = x0 + cwp * 32 + lane;
         if (x >= A.ow) continue;
         const int ix = x - A.ox;
         const bool col_in = has_inner && ix >= ix0 && ix < ix1;
-        const int lcol = ix - 4 * cq0;
-        uint32_t bgw[4];
+        const uint32_t *colp = s_c + (col_in ? ix - 4 * cq0 : 0) * F2_CW;
+#pragma unroll 1
+        for (int qd = warp; qd < nquads; qd += F2_NT / 32) {
+          const int oy0 = y0 + qd * 4;
+          const int nrow = min(4, y1 - oy0);
+          const uint8_t *bgp = A.bg.p + (size_t)A.bg.rs * oy0 + 4 * (size_t)x;
+          uint8_t *outp = A.out.p + (size_t)A.out.rs * oy0 + 4 * (size_t)x;
+          uint32_t bgw[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int oy = y0 + qd * 4 + r;
-          bgw[r] = oy < y1 ? ld_stream_u32(A.bg.p + (long long)A.bg.rs * oy + 4ll * x) : 0u;
-        }
-        // cached words of the converted column (per channel): positions wi, wi + 1
-        uint32_t wl[3] = {0, 0, 0}, wh[3] = {0, 0, 0};
-        int cur = -100;
+          for (int r = 0; r < 4; r++) bgw[r] = r < nrow ? ld_stream_u32(bgp + (size_t)A.bg.rs * r) : 0u;
+          // cached words of the converted column (per channel): positions cur, cur + 1
+          uint32_t wl[3] = {0, 0, 0}, wh[3] = {0, 0, 0};
+          int cur = -100;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int oy = y0 + qd * 4 + r;
-          if (oy >= y1) break;
-          const int iy = oy - A.oy;
-          uint32_t fr = 0, fg_ = 0, fb = 0;  // letterbox border: black (blank_pixel, colourspace.c:11169)
-          if (col_in && iy >= iy0 && iy < iy1) {
-            const int pos = s_row[4 * (iy - iy0)];
-            const uint32_t a0 = (uint32_t)s_row[4 * (iy - iy0) + 1], a1 = (uint32_t)s_row[4 * (iy - iy0) + 2];
-            const int wi = pos >> 2, sh = 8 * (pos & 3);
-            if (wi != cur) {  // warp-uniform
+          for (int r = 0; r < 4; r++) {
+            if (r >= nrow) break;
+            const int iyl = oy0 + r - A.oy - iy0;  // row inside the tile's inner range
+            uint32_t fr = 0, fg_ = 0, fb = 0;  // letterbox border: black (blank_pixel, colourspace.c:11169)
+            if (col_in && iyl >= 0 && iyl < iy1 - iy0) {
+              const int4 ri = s_row[iyl];
+              const int wi = ri.x >> 2, sh = 8 * (ri.x & 3);
+              if (wi != cur) {  // warp-uniform
 #pragma unroll
-              for (int c = 0; c < 3; c++) {
-                const uint32_t *colp = s_c + (c * F2_CCOLS + lcol) * F2_CW;
-                wl[c] = (wi == cur + 1) ? wh[c] : colp[wi];
-                wh[c] = colp[wi + 1];
+                for (int c = 0; c < 3; c++) {
+                  wl[c] = (wi == cur + 1) ? wh[c] : colp[c * F2_CCOLS * F2_CW + wi];
+                  wh[c] = colp[c * F2_CCOLS * F2_CW + wi + 1];
+                }
+                cur = wi;
               }
-              cur = wi;
+              const uint32_t b0 = __funnelshift_r(wl[0], wh[0], sh), b1 = __funnelshift_r(wl[1], wh[1], sh),
+                             b2 = __funnelshift_r(wl[2], wh[2], sh);
+              fr = dp2a_hi((uint32_t)ri.z, b0, dp2a_lo((uint32_t)ri.y, b0, 2048u)) >> 12;
+              fg_ = dp2a_hi((uint32_t)ri.z, b1, dp2a_lo((uint32_t)ri.y, b1, 2048u)) >> 12;
+              fb = dp2a_hi((uint32_t)ri.z, b2, dp2a_lo((uint32_t)ri.y, b2, 2048u)) >> 12;
             }
-            const uint32_t b0 = __funnelshift_r(wl[0], wh[0], sh), b1 = __funnelshift_r(wl[1], wh[1], sh),
-                           b2 = __funnelshift_r(wl[2], wh[2], sh);
-            fr = dp2a_hi(a1, b0, dp2a_lo(a0, b0, 2048u)) >> 12;
-            fg_ = dp2a_hi(a1, b1, dp2a_lo(a0, b1, 2048u)) >> 12;
-            fb = dp2a_hi(a1, b2, dp2a_lo(a0, b2, 2048u)) >> 12;
+            const uint32_t b = bgw[r];
+            uint32_t o0, o1, o2;
+            if (MODE == 0) {
+              o0 = ((b & 0xFFu) * kia + fr * ka) >> 8;
+              o1 = (((b >> 8) & 0xFFu) * kia + fg_ * ka) >> 8;
+              o2 = (((b >> 16) & 0xFFu) * kia + fb * ka) >> 8;
+              if (has_lut) { o0 = s_lut[o0]; o1 = s_lut[o1]; o2 = s_lut[o2]; }
+            } else {  // the table already contains the gamma LUT (launch_over_table)
+              o0 = s_over[((b & 0xFFu) << 8) | fr];
+              o1 = s_over[(((b >> 8) & 0xFFu) << 8) | fg_];
+              o2 = s_over[(((b >> 16) & 0xFFu) << 8) | fb];
+            }
+            st_stream_u32(outp + (size_t)A.out.rs * r, o0 | (o1 << 8) | (o2 << 16) | 0xFF000000u);
           }
-          const uint32_t b = bgw[r];
-          uint32_t o0, o1, o2;
-          if (MODE == 0) {
-            const uint32_t ka = (uint32_t)P.blend_a, kia = (uint32_t)P.blend_ia;
-            o0 = ((b & 0xFFu) * kia + fr * ka) >> 8;
-            o1 = (((b >> 8) & 0xFFu) * kia + fg_ * ka) >> 8;
-            o2 = (((b >> 16) & 0xFFu) * kia + fb * ka) >> 8;
-            if (has_lut) { o0 = s_lut[o0]; o1 = s_lut[o1]; o2 = s_lut[o2]; }
-          } else {  // the table already contains the gamma LUT (launch_over_table)
-            o0 = s_over[((b & 0xFFu) << 8) | fr];
-            o1 = s_over[(((b >> 8) & 0xFFu) << 8) | fg_];
-            o2 = s_over[(((b >> 16) & 0xFFu) << 8) | fb];
-          }
-          st_stream_u32(A.out.p + (long long)A.out.rs * oy + 4ll * x, o0 | (o1 << 8) | (o2 << 16) | 0xFF000000u);
         }
       }
     }
@@ -408,7 +486,7 @@ bool fused2_supported(const FusedArgs &a, int fy_taps, int max_virtual_rows_per_
   return true;
 }
 
-int fused2_max_virtual_rows() { return F2_MAXVR; }
+int fused2_max_virtual_rows(int is422) { return is422 ? F2_MAXVR_422 : F2_MAXVR; }
 int fused2_max_tile_h() { return F2_MAXTH; }
 
 // blend_a < 0: table blend (FusedArgs::over_table, gamma folded in); else arithmetic blend with weights blend_a / 256 - blend_a
