@@ -1273,8 +1273,6 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
     A.fx = fx->dev; A.fy = fy->dev;
     A.over_table = tab;
   }
-  const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);
-  if (!dev) return PE_ERR_CUDA;
   // fast path: no horizontal scaling, <= 4 vertical taps, aligned planes (pe_kernels_fused2.cu)
   bool fast = getenv("PE_FUSED_GENERIC") == nullptr;
   for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.taps, 0) && args[i].is_422 == args[0].is_422;
@@ -1296,8 +1294,10 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
   if (fast) {
     const double k256 = alpha * 256.;
     const bool dyadic = k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256;
-    PE_CUDA(launch_fused2_dev(e->L(), dev, n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
+    PE_CUDA(launch_fused2(e->L(), args.data(), n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
   } else {
+    const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);
+    if (!dev) return PE_ERR_CUDA;
     PE_CUDA(launch_fused_dev(e->L(), dev, n, ow, oh, max_rows, max_cols));
   }
   for (int i = 0; i < n; i++) {

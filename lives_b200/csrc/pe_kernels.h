@@ -121,9 +121,10 @@ int fused_tile_h();
 bool fused2_supported(const FusedArgs &a, int fy_taps, int unused);
 int fused2_max_virtual_rows(int is422);
 int fused2_max_tile_h();
+// frames_host: FusedArgs[nframes] in HOST memory (they travel as kernel parameters).
 // blend_a in 0..256: integer blend (alpha = blend_a / 256) + optional lut8; blend_a < 0: FusedArgs::over_table
-cudaError_t launch_fused2_dev(const Launch &L, const FusedArgs *frames_dev, int nframes, int ow, int oh, int tile_h, int blend_a,
-                              const uint8_t *lut8_dev);
+cudaError_t launch_fused2(const Launch &L, const FusedArgs *frames_host, int nframes, int ow, int oh, int tile_h, int blend_a,
+                          const uint8_t *lut8_dev);
 // ---- diagnostics -------------------------------------------------------------------------------------------
 struct DevStats {
   unsigned int minv[4], maxv[4];
