@@ -387,6 +387,84 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """Kernel-level numbers of the other BASELINE configs (N = 1, inputs resident; not the driver's headline line)."""
+    import torch
+    import lives_b200 as lb
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    eng = lb.Engine(device=0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    keep = []
+
+    def rnd(h, nbytes, lo=0, hi=256):
+        t = torch.randint(lo, hi, (h, nbytes), dtype=torch.uint8, device=dev, generator=g)
+        keep.append(t)
+        return t
+
+    def wrap(pal, w, h, tensors, **kw):
+        return lb.Layer.wrap_device(eng, pal, w, h, [t.data_ptr() for t in tensors], [t.shape[1] for t in tensors], **kw)
+
+    wl = args.workload
+    if wl == "cfg4":    # batch of 1080p RGB24 chroma blends, one launch
+        W, H, n = 1920, 1080, 64
+        a = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
+        b = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
+        o = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
+        step = lambda: lb.simple_blend_batch("chroma blend", a, b, o, 100)
+        frames, algo, name = n, 3 * W * H * 3, "cfg4: %d x 1080p RGB24 chroma blend bf=100, one launch" % n
+    elif wl == "cfg3":  # 4K RGBA alpha-over + gamma (unfused ops: fill + 2 x alpha_over + lut)
+        W, H, n = 3840, 2160, 8
+        bg = [wrap(3, W, H, [rnd(H, W * 4)]) for _ in range(n)]
+        fg = [wrap(3, W, H, [rnd(H, W * 4)]) for _ in range(n)]
+        out = [wrap(3, W, H, [rnd(H, W * 4)], gamma_type=G_LINEAR) for _ in range(n)]
+
+        def step():
+            for i in range(n):
+                out[i].gamma_type = G_LINEAR
+                lb.compositor(out[i], [fg[i], bg[i]], [0.5, 1.0])
+                lb.gamma_convert_layer(G_SRGB, out[i])
+        frames, algo, name = n, 3 * W * H * 4, "cfg3: %d x 4K RGBA32 alpha-over(0.5) + gamma, unfused ops (4 kernels / frame)" % n
+    elif wl == "cfg2":  # 1080p YUV420P -> RGBA32 -> 1280x720 (unfused convert + resize)
+        W, H, n = 1920, 1080, 16
+        src = [(rnd(H, W, 16, 236), rnd(H // 2, W // 2, 16, 241), rnd(H // 2, W // 2, 16, 241)) for _ in range(n)]
+
+        def step():
+            for y, u, v in src:
+                lay = wrap(512, W, H, [y, u, v], yuv_subspace=1)
+                lb.resize_layer(lay, 1280, 720, 1, 3, 0)
+                lay.free()
+        frames, algo, name = n, W * H * 3 // 2 + 1280 * 720 * 4, "cfg2: %d x 1080p YUV420P -> RGBA32 -> 1280x720, unfused (3 kernels / frame)" % n
+    elif wl == "cfg1":  # 640x480 RGB24 -> BGR24 in place
+        W, H, n = 640, 480, 256
+        lay = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
+
+        def step():
+            for i, l in enumerate(lay):
+                lb.convert_layer_palette(l, 2 if l.palette == 1 else 1, 0)
+        frames, algo, name = n, 2 * W * H * 3, "cfg1: %d x 640x480 RGB24 <-> BGR24 in place (one launch per frame)" % n
+    else:
+        raise SystemExit("unknown workload " + wl)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    eng.sync()
+    l0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = eng.timer_stop_ms()
+    launches = eng.launch_count - l0
+    peak, peak_src = measured_peak()
+    fps = frames * args.steps / (ms / 1e3)
+    achieved = algo * frames * args.steps / (ms / 1e3) / 1e9
+    print(json.dumps({"metric": "frames/s (secondary workload)", "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+                      "ms_per_step": ms / args.steps, "config": {"workload": name},
+                      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                   "algorithmic_bytes_per_frame": algo, "peak_source": peak_src},
+                      "gpu_launches": int(launches)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,12 +474,17 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="independent frames per step per GPU")
     ap.add_argument("--e2e-frames", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="headline", help="headline (the driver's line) | cfg1 | cfg2 | cfg3 | cfg4: kernel-level "
+                    "numbers of the other BASELINE configs, N = 1 only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "headline":
+        run_secondary(args)
         return
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under it, as the driver would

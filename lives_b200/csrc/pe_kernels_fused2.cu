@@ -518,18 +518,21 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
       }
     }
 
-    // ---- stage 3: vertical filter + letterbox + alpha-over (+ gamma), one thread = one column x 4 consecutive rows
+    // ---- stage 3: vertical filter + letterbox + alpha-over (+ gamma), one thread = one column x 4 consecutive rows.
+    //      The four bg words of the NEXT task are loaded before the current one is computed (register double buffer).
     {
       const int x0 = G.x0, y0 = G.y0, y1 = G.y1;
       const int nquads = (y1 - y0 + 3) >> 2;
+      const int ntasks = nquads * (F2_TW / 32);
       const int niy = iy1 - iy0;
       const uint32_t ka = (uint32_t)P.blend_a, kia = (uint32_t)P.blend_ia;
       auto blend_store = [&](uint8_t *outp, uint32_t b, uint32_t fr, uint32_t fg_, uint32_t fb) {
         uint32_t o0, o1, o2;
         if (MODE == 0) {
-          o0 = ((b & 0xFFu) * kia + fr * ka) >> 8;
-          o1 = (((b >> 8) & 0xFFu) * kia + fg_ * ka) >> 8;
-          o2 = (((b >> 16) & 0xFFu) * kia + fb * ka) >> 8;
+          // two channels per multiply: (bg * kia + fg * ka) for R | B in the 16-bit halves, G alone
+          const uint32_t rb = (b & 0x00FF00FFu) * kia + (fr | (fb << 16)) * ka;
+          const uint32_t gg = ((b >> 8) & 0xFFu) * kia + fg_ * ka;
+          o0 = (rb >> 8) & 0xFFu; o1 = gg >> 8; o2 = rb >> 24;
           if (has_lut) { o0 = s_lut[o0]; o1 = s_lut[o1]; o2 = s_lut[o2]; }
         } else {  // the table already contains the gamma LUT (launch_over_table)
           o0 = s_over[((b & 0xFFu) << 8) | fr];
@@ -538,55 +541,74 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
         }
         st_stream_u32(outp, o0 | (o1 << 8) | (o2 << 16) | 0xFF000000u);
       };
-      for (int task = warp; task < nquads * (F2_TW / 32); task += F2_NW) {
+      // row pointers advance by 32-bit strides (frames are far below 4 GB): no 64-bit multiplies per row
+      const uint32_t bg_rs32 = (uint32_t)A.bg.rs, out_rs32 = (uint32_t)A.out.rs;
+      auto load_bg = [&](int task, uint32_t w[4]) {
         const int qd = task >> 2, cwp = task & 3;
         const int x = x0 + cwp * 32 + lane;
-        if (x >= A.ow) continue;
-        const int ix = x - A.ox;
-        const bool col_in = G.has_inner && ix >= G.ix0 && ix < G.ix1;
-        const uint32_t *colp = s_c + (col_in ? ix - 4 * cq0 : 0) * F2_CW;
         const int oy0 = y0 + qd * 4;
-        const int nrow = min(4, y1 - oy0);
-        const size_t bg_rs = (size_t)A.bg.rs, out_rs = (size_t)A.out.rs;
-        const uint8_t *bgp = A.bg.p + bg_rs * oy0 + 4 * (size_t)x;
-        uint8_t *outp = A.out.p + out_rs * oy0 + 4 * (size_t)x;
-        const int iyl0 = oy0 - A.oy - iy0;  // first row of the quad inside the tile's inner rows
-        if (nrow == 4 && col_in && iyl0 >= 0 && iyl0 + 3 < niy) {
-          // ===== fast path: four inner rows
-          const uint32_t bgw[4] = {ld_stream_u32(bgp), ld_stream_u32(bgp + bg_rs), ld_stream_u32(bgp + 2 * bg_rs),
-                                   ld_stream_u32(bgp + 3 * bg_rs)};
+        const int nrow = (task < ntasks && x < A.ow) ? y1 - oy0 : 0;
+        const uint8_t *p0 = A.bg.p + (bg_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
+        const uint8_t *p1 = p0 + bg_rs32, *p2 = p1 + bg_rs32, *p3 = p2 + bg_rs32;
+        w[0] = nrow > 0 ? ld_stream_u32(p0) : 0u;
+        w[1] = nrow > 1 ? ld_stream_u32(p1) : 0u;
+        w[2] = nrow > 2 ? ld_stream_u32(p2) : 0u;
+        w[3] = nrow > 3 ? ld_stream_u32(p3) : 0u;
+      };
+      uint32_t bgw[4], bgn[4];
+      load_bg(warp, bgw);
+      for (int task = warp; task < ntasks; task += F2_NW) {
+        load_bg(task + F2_NW, bgn);
+        const int qd = task >> 2, cwp = task & 3;
+        const int x = x0 + cwp * 32 + lane;
+        if (x < A.ow) {
+          const int ix = x - A.ox;
+          const bool col_in = G.has_inner && ix >= G.ix0 && ix < G.ix1;
+          const uint32_t *colp = s_c + (col_in ? ix - 4 * cq0 : 0) * F2_CW;
+          const int oy0 = y0 + qd * 4;
+          const int nrow = min(4, y1 - oy0);
+          uint8_t *outp = A.out.p + (out_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
+          const int iyl0 = oy0 - A.oy - iy0;  // first row of the quad inside the tile's inner rows
+          if (nrow == 4 && col_in && iyl0 >= 0 && iyl0 + 3 < niy) {
+            // ===== fast path: four inner rows
 #pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int4 ri = s_row[iyl0 + r];
-            const uint32_t *wp = colp + (ri.x >> 2);
-            const int sh = 8 * (ri.x & 3);
-            const uint32_t b0 = __funnelshift_r(wp[0], wp[1], sh);
-            const uint32_t b1 = __funnelshift_r(wp[F2_CCOLS * F2_CW], wp[F2_CCOLS * F2_CW + 1], sh);
-            const uint32_t b2 = __funnelshift_r(wp[2 * F2_CCOLS * F2_CW], wp[2 * F2_CCOLS * F2_CW + 1], sh);
-            const uint32_t fr = dp2a_hi((uint32_t)ri.z, b0, dp2a_lo((uint32_t)ri.y, b0, 2048u)) >> 12;
-            const uint32_t fg_ = dp2a_hi((uint32_t)ri.z, b1, dp2a_lo((uint32_t)ri.y, b1, 2048u)) >> 12;
-            const uint32_t fb = dp2a_hi((uint32_t)ri.z, b2, dp2a_lo((uint32_t)ri.y, b2, 2048u)) >> 12;
-            blend_store(outp + out_rs * r, bgw[r], fr, fg_, fb);
+            for (int r = 0; r < 4; r++) {
+              const int4 ri = s_row[iyl0 + r];
+              const uint32_t *wp = colp + (ri.x >> 2);
+              const int sh = 8 * (ri.x & 3);
+              const uint32_t b0 = __funnelshift_r(wp[0], wp[1], sh);
+              const uint32_t b1 = __funnelshift_r(wp[F2_CCOLS * F2_CW], wp[F2_CCOLS * F2_CW + 1], sh);
+              const uint32_t b2 = __funnelshift_r(wp[2 * F2_CCOLS * F2_CW], wp[2 * F2_CCOLS * F2_CW + 1], sh);
+              const uint32_t fr = dp2a_hi((uint32_t)ri.z, b0, dp2a_lo((uint32_t)ri.y, b0, 2048u)) >> 12;
+              const uint32_t fg_ = dp2a_hi((uint32_t)ri.z, b1, dp2a_lo((uint32_t)ri.y, b1, 2048u)) >> 12;
+              const uint32_t fb = dp2a_hi((uint32_t)ri.z, b2, dp2a_lo((uint32_t)ri.y, b2, 2048u)) >> 12;
+              blend_store(outp + out_rs32 * (uint32_t)r, bgw[r], fr, fg_, fb);
+            }
+          } else {
+            // ===== general path: tile borders, letterbox border rows / columns
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              if (r < nrow) {
+                const int iyl = iyl0 + r;
+                uint32_t fr = 0, fg_ = 0, fb = 0;  // letterbox border: black (blank_pixel, colourspace.c:11169)
+                if (col_in && iyl >= 0 && iyl < niy) {
+                  const int4 ri = s_row[iyl];
+                  const uint32_t *wp = colp + (ri.x >> 2);
+                  const int sh = 8 * (ri.x & 3);
+                  const uint32_t b0 = __funnelshift_r(wp[0], wp[1], sh);
+                  const uint32_t b1 = __funnelshift_r(wp[F2_CCOLS * F2_CW], wp[F2_CCOLS * F2_CW + 1], sh);
+                  const uint32_t b2 = __funnelshift_r(wp[2 * F2_CCOLS * F2_CW], wp[2 * F2_CCOLS * F2_CW + 1], sh);
+                  fr = dp2a_hi((uint32_t)ri.z, b0, dp2a_lo((uint32_t)ri.y, b0, 2048u)) >> 12;
+                  fg_ = dp2a_hi((uint32_t)ri.z, b1, dp2a_lo((uint32_t)ri.y, b1, 2048u)) >> 12;
+                  fb = dp2a_hi((uint32_t)ri.z, b2, dp2a_lo((uint32_t)ri.y, b2, 2048u)) >> 12;
+                }
+                blend_store(outp + out_rs32 * (uint32_t)r, bgw[r], fr, fg_, fb);
+              }
+            }
           }
-          continue;
         }
-        // ===== general path: tile borders, letterbox border rows / columns
-        for (int r = 0; r < nrow; r++) {
-          const int iyl = iyl0 + r;
-          uint32_t fr = 0, fg_ = 0, fb = 0;  // letterbox border: black (blank_pixel, colourspace.c:11169)
-          if (col_in && iyl >= 0 && iyl < niy) {
-            const int4 ri = s_row[iyl];
-            const uint32_t *wp = colp + (ri.x >> 2);
-            const int sh = 8 * (ri.x & 3);
-            const uint32_t b0 = __funnelshift_r(wp[0], wp[1], sh);
-            const uint32_t b1 = __funnelshift_r(wp[F2_CCOLS * F2_CW], wp[F2_CCOLS * F2_CW + 1], sh);
-            const uint32_t b2 = __funnelshift_r(wp[2 * F2_CCOLS * F2_CW], wp[2 * F2_CCOLS * F2_CW + 1], sh);
-            fr = dp2a_hi((uint32_t)ri.z, b0, dp2a_lo((uint32_t)ri.y, b0, 2048u)) >> 12;
-            fg_ = dp2a_hi((uint32_t)ri.z, b1, dp2a_lo((uint32_t)ri.y, b1, 2048u)) >> 12;
-            fb = dp2a_hi((uint32_t)ri.z, b2, dp2a_lo((uint32_t)ri.y, b2, 2048u)) >> 12;
-          }
-          blend_store(outp + out_rs * r, ld_stream_u32(bgp + bg_rs * r), fr, fg_, fb);
-        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) bgw[r] = bgn[r];
       }
     }
     __syncthreads();  // everyone is done with this tile's buffers, tables and s_c

@@ -26,7 +26,7 @@ def main():
         if m:
             cur = (m.group(1).split("/")[-1], int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             lines.append(cur)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
