@@ -423,9 +423,8 @@ def run_secondary(args):
         def step():
             for i in range(n):
                 out[i].gamma_type = G_LINEAR
-                lb.compositor(out[i], [fg[i], bg[i]], [0.5, 1.0])
-                lb.gamma_convert_layer(G_SRGB, out[i])
-        frames, algo, name = n, 3 * W * H * 4, "cfg3: %d x 4K RGBA32 alpha-over(0.5) + gamma, unfused ops (4 kernels / frame)" % n
+                lb.compositor_gamma(out[i], [fg[i], bg[i]], [0.5, 1.0], G_SRGB)
+        frames, algo, name = n, 3 * W * H * 4, "cfg3: %d x 4K RGBA32 alpha-over(0.5) + gamma LUT8 (pe_fx_compositor_gamma, one kernel / frame)" % n
     elif wl == "cfg2":  # 1080p YUV420P -> RGBA32 -> 1280x720 (unfused convert + resize)
         W, H, n = 1920, 1080, 16
         src = [(rnd(H, W, 16, 236), rnd(H // 2, W // 2, 16, 241), rnd(H // 2, W // 2, 16, 241)) for _ in range(n)]

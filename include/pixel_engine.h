@@ -175,6 +175,10 @@ int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_
  * layer, last first (revz == WEED_FALSE, :189-197); alpha[i] is the scalar per-layer alpha */
 int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
                      int nlayers, const int bgcol[3]);
+/* compositor_process followed by gamma_convert_layer(gamma_to, out) (colourspace.c:14146; the APPLY_INST + gamma substeps of
+ * src/nodemodel.c:1119-1333) with the LUT folded into the last paint: same bytes, one pass less over the frame */
+int pe_fx_compositor_gamma(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
+                           int nlayers, const int bgcol[3], int gamma_to);
 /* batches of independent frames (render-to-disk / multitrack): one launch, frames spread over the SMs */
 int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const pe_frame_t *const *in1,
                              const pe_frame_t *const *in2, pe_frame_t *const *out, int blend_factor);

@@ -952,6 +952,12 @@ namespace {
 int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint8_t *dst, int drs, int dw, int dh, int psize) {
   DevFilterEntry *fx = get_filter(e, sw, dw, 14), *fy = get_filter(e, sh, dh, 12);
   if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range (%dx%d -> %dx%d; at most 31x down)", sw, sh, dw, dh);
+  // one tiled kernel (15-bit intermediate stays in shared memory) ...
+  cudaError_t te = launch_resize_tile(e->L(), CImg{src, srs}, sw, sh, Img{dst, drs}, dw, dh, psize, fx->dev, fy->dev,
+                                      fx->host.first.data(), fy->host.first.data());
+  if (te == cudaSuccess) return PE_OK;
+  if (te != cudaErrorInvalidConfiguration) return set_err(PE_ERR_CUDA, "resize launch failed: %s", cudaGetErrorString(te));
+  // ... or, for scale factors whose source rectangle does not fit there, the two-kernel path through an HBM intermediate
   size_t granted = 0;
   const size_t tmp_bytes = sizeof(int16_t) * (size_t)sh * dw * psize;
   int16_t *tmp = (int16_t *)e->pool.get(tmp_bytes, &granted);
@@ -1178,35 +1184,106 @@ extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1
   return PE_OK;
 }
 
-extern "C" int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
-                                int nlayers, const int bgcol[3]) {
-  if (!e || !out || !out->d.planes[0] || nlayers < 0 || (nlayers > 0 && (!layers || !alpha)))
-    return set_err(PE_ERR_ARG, "NULL argument");
+namespace {
+
+// compositor_process (gdk/compositor.c:127) at scale 1 / offset 0, optionally followed by gamma_convert_layer(gamma_to, out)
+// folded into the last paint.  Work avoided without changing a byte of the result:
+//   * the background fill is skipped when an opaque (alpha == 1) layer covers it -- the fill is dead;
+//   * painting that opaque layer is not a pass of its own: the next paint reads it as its background;
+//   * alpha = k / 256 uses the integer blend (exact, see k_alpha_over_arith), other alphas the 64 KB [bg][fg] table.
+int compositor_locked(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha, int nlayers,
+                      const int bgcol[3], int gamma_to) {
   const int pal = out->d.palette;
   if (!pal_is_rgb(pal) || pal == PE_PALETTE_ARGB32) return set_err(PE_ERR_PALETTE, "compositor palettes: RGB24 BGR24 RGBA32 BGRA32");
-  std::lock_guard<std::mutex> lk(e->mu);
-  PE_CUDA(cudaSetDevice(e->device));
-  const int psize = pal_psize(pal);
+  const int psize = pal_psize(pal), w = out->d.width, h = out->d.height;
   const Img dst{(uint8_t *)out->d.planes[0], out->d.rowstrides[0]};
-  // background fill (compositor.c:172-186); alpha byte 0xFF
-  const int r = bgcol ? bgcol[0] : 0, g = bgcol ? bgcol[1] : 0, b = bgcol ? bgcol[2] : 0;
-  const bool swap = (pal == PE_PALETTE_BGR24 || pal == PE_PALETTE_BGRA32);
-  const uint32_t px = (uint32_t)((swap ? b : r) & 255) | ((uint32_t)(g & 255) << 8) | ((uint32_t)((swap ? r : b) & 255) << 16) | 0xFF000000u;
-  PE_CUDA(launch_fill(e->L(), dst, out->d.width, out->d.height, psize, px));
+  // the gamma step that follows (gamma_convert_sub_layer :14069): which LUT, if any
+  const uint8_t *lut = nullptr;
+  bool set_gamma = false;
+  if (gamma_to != PE_GAMMA_UNKNOWN && e->cfg.apply_gamma && !(gamma_to == out->d.gamma_type)) {
+    Lut8Entry *le = get_lut8(e, 1.0, out->d.gamma_type, gamma_to);
+    lut = le ? le->dev : nullptr;
+    set_gamma = le != nullptr;
+  }
   // layers painted last first (revz == WEED_FALSE, :189-197); a layer with alpha 0 is skipped (:232)
+  std::vector<int> order;
   for (int z = nlayers - 1; z >= 0; z--) {
     const pe_frame *l = layers[z];
     if (!l || !l->d.planes[0]) continue;
     if (l->d.palette != pal) return set_err(PE_ERR_PALETTE, "layer %d palette differs from the output's", z);
-    if (l->d.width != out->d.width || l->d.height != out->d.height)
+    if (l->d.width != w || l->d.height != h)
       return set_err(PE_ERR_SIZE, "layer %d: only scale 1 / offset 0 layers are handled by this build", z);
     if (alpha[z] <= 0.) continue;
-    uint8_t *tab = get_over_table(e, alpha[z], nullptr);
-    if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
-    PE_CUDA(launch_alpha_over(e->L(), CImg{dst.p, dst.rs}, CImg{(const uint8_t *)l->d.planes[0], l->d.rowstrides[0]}, dst,
-                              out->d.width, out->d.height, psize, tab, 1));
+    order.push_back(z);
   }
+  // everything below the last fully opaque layer is dead
+  size_t first = 0;
+  for (size_t i = 0; i < order.size(); i++)
+    if (alpha[order[i]] >= 1.0) first = i;
+  const bool opaque_base = !order.empty() && alpha[order[first]] >= 1.0;
+  CImg cur{dst.p, dst.rs};  // what the next paint reads as background
+  if (opaque_base) {
+    const pe_frame *l = layers[order[first]];
+    cur = CImg{(const uint8_t *)l->d.planes[0], l->d.rowstrides[0]};
+    first++;
+  } else {
+    // background fill (compositor.c:172-186); alpha byte 0xFF
+    const int r = bgcol ? bgcol[0] : 0, g = bgcol ? bgcol[1] : 0, b = bgcol ? bgcol[2] : 0;
+    const bool swap = (pal == PE_PALETTE_BGR24 || pal == PE_PALETTE_BGRA32);
+    const uint32_t px = (uint32_t)((swap ? b : r) & 255) | ((uint32_t)(g & 255) << 8) | ((uint32_t)((swap ? r : b) & 255) << 16) | 0xFF000000u;
+    PE_CUDA(launch_fill(e->L(), dst, w, h, psize, px));
+    first = 0;
+  }
+  bool lut_done = lut == nullptr;
+  auto paint = [&](CImg bg, CImg fg, double a, const uint8_t *l8) -> int {
+    const double k256 = a * 256.;
+    if (k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256) {
+      PE_CUDA(launch_alpha_over_arith(e->L(), bg, fg, dst, w, h, psize, (int)k256, l8, 1));
+    } else {
+      uint8_t *tab = get_over_table(e, a, l8);
+      if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
+      PE_CUDA(launch_alpha_over(e->L(), bg, fg, dst, w, h, psize, tab, 1));
+    }
+    return PE_OK;
+  };
+  for (size_t i = first; i < order.size(); i++) {
+    const pe_frame *l = layers[order[i]];
+    const bool last = i + 1 == order.size();
+    int rc = paint(cur, CImg{(const uint8_t *)l->d.planes[0], l->d.rowstrides[0]}, alpha[order[i]], last ? lut : nullptr);
+    if (rc != PE_OK) return rc;
+    if (last) lut_done = true;
+    cur = CImg{dst.p, dst.rs};
+  }
+  if (cur.p != dst.p) {
+    // only the opaque base was painted: out = that layer with the alpha byte forced to 0xFF (+ the LUT)
+    int rc = paint(cur, cur, 1.0, lut);
+    if (rc != PE_OK) return rc;
+    lut_done = true;
+  }
+  if (!lut_done)  // nothing was painted after the fill: plain gamma pass over the background colour
+    PE_CUDA(launch_lut8_rect(e->L(), dst, rgb_layout(pal), 0, 0, w, h, lut));
+  if (set_gamma && gamma_to != PE_GAMMA_VARIANT) out->d.gamma_type = gamma_to;
   return PE_OK;
+}
+
+}  // namespace
+
+extern "C" int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
+                                int nlayers, const int bgcol[3]) {
+  if (!e || !out || !out->d.planes[0] || nlayers < 0 || (nlayers > 0 && (!layers || !alpha)))
+    return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  return compositor_locked(e, out, layers, alpha, nlayers, bgcol, PE_GAMMA_UNKNOWN);
+}
+
+extern "C" int pe_fx_compositor_gamma(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
+                                      int nlayers, const int bgcol[3], int gamma_to) {
+  if (!e || !out || !out->d.planes[0] || nlayers < 0 || (nlayers > 0 && (!layers || !alpha)))
+    return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  return compositor_locked(e, out, layers, alpha, nlayers, bgcol, gamma_to);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -85,6 +85,9 @@ cudaError_t launch_multi_blend(const Launch &L, int type, BlendFrame f, int widt
 cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev);
 cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize,
                               const uint8_t *over_table_dev, int force_opaque);
+// alpha = k256 / 256 exactly: integer blend, no table; optional gamma LUT applied to the result
+cudaError_t launch_alpha_over_arith(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize, int k256,
+                                    const uint8_t *lut8_dev, int force_opaque);
 cudaError_t launch_fill(const Launch &L, Img dst, int width, int height, int psize, uint32_t pixel);
 // ---- resize (our contract) + letterbox (colourspace.c:15343) -------------------------------------------
 struct DevFilter {
@@ -94,6 +97,9 @@ struct DevFilter {
 };
 cudaError_t launch_resize_h(const Launch &L, CImg src, int sw, int sh, int16_t *tmp, int dw, int psize, DevFilter fx);
 cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst, int dw, int dh, int psize, DevFilter fy);
+// both passes in one kernel (intermediate in shared memory); cudaErrorInvalidConfiguration when the scale factor is too large
+cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
+                               DevFilter fy, const int32_t *hx_first, const int32_t *hy_first);
 cudaError_t launch_letterbox(const Launch &L, CImg inner, int iw, int ih, Img outer, int ow, int oh, int psize,
                              uint32_t black_pixel);
 cudaError_t launch_copy2d(const Launch &L, const uint8_t *src, int srs, uint8_t *dst, int drs, int row_bytes, int rows,

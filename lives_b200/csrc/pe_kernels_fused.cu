@@ -65,6 +65,109 @@ __global__ void __launch_bounds__(kBlock) k_resize_v(const int16_t *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_resize_tile: both passes of the contract in one kernel.  One CTA = one output tile (tw x th):
+//   1. the source rectangle the tile needs is staged in shared memory (source indices clamped to the frame),
+//   2. horizontal pass into a 15-bit shared-memory intermediate (4 x int16 per pixel),
+//   3. vertical pass, 8-bit store.
+// Same arithmetic as k_resize_h + k_resize_v (which remain the fallback for scale factors whose source rectangle
+// does not fit in shared memory); the intermediate never touches HBM.
+// ------------------------------------------------------------------------------------------------------
+
+struct ResizeTileParams {
+  const uint8_t *src;
+  uint8_t *dst;
+  int srs, drs, sw, sh, dw, dh;
+  int tw, th;                 // output tile
+  int max_rows, max_cols;     // largest source extent of a tile
+  DevFilter fx, fy;
+};
+
+template <int PS>
+__global__ void __launch_bounds__(kBlock) k_resize_tile(const ResizeTileParams P) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  const int raw_stride = (P.max_cols * PS + 3) & ~3;
+  uint8_t *s_raw = rsm;                                                    // [max_rows][raw_stride]
+  uint2 *s_tmp = reinterpret_cast<uint2 *>(rsm + (((size_t)P.max_rows * raw_stride + 15) & ~(size_t)15));  // [max_rows][tw]
+  const int tiles_x = (P.dw + P.tw - 1) / P.tw;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int x0 = tx * P.tw, y0 = ty * P.th;
+  const int x1 = min(x0 + P.tw, P.dw), y1 = min(y0 + P.th, P.dh);
+  const int ncol = x1 - x0, nrow = y1 - y0;
+  const int sr0 = min(max(P.fy.first[y0], 0), P.sh - 1), sr1 = min(max(P.fy.first[y1 - 1] + P.fy.taps - 1, 0), P.sh - 1);
+  const int sc0 = min(max(P.fx.first[x0], 0), P.sw - 1), sc1 = min(max(P.fx.first[x1 - 1] + P.fx.taps - 1, 0), P.sw - 1);
+  const int nsr = sr1 - sr0 + 1, nsb = (sc1 - sc0 + 1) * PS;
+  // ---- 1. stage the source rectangle (bytes sc0*PS .. of rows sr0..sr1)
+  {
+    const uint8_t *base = P.src + (size_t)P.srs * sr0 + (size_t)sc0 * PS;
+    const bool w4 = (((uintptr_t)base | (uintptr_t)P.srs) & 3) == 0;
+    if (w4) {
+      const int nw = nsb >> 2;
+      for (int r = threadIdx.x >> 5; r < nsr; r += kBlock / 32) {
+        const uint8_t *rp = base + (size_t)P.srs * r;
+        for (int w = threadIdx.x & 31; w < nw; w += 32)
+          *reinterpret_cast<uint32_t *>(s_raw + r * raw_stride + 4 * w) = ld_stream_u32(rp + 4 * w);
+        for (int b = (nw << 2) + (threadIdx.x & 31); b < nsb; b += 32) s_raw[r * raw_stride + b] = rp[b];
+      }
+    } else {
+      for (int r = threadIdx.x >> 5; r < nsr; r += kBlock / 32)
+        for (int b = threadIdx.x & 31; b < nsb; b += 32) s_raw[r * raw_stride + b] = P.src[(size_t)P.srs * (sr0 + r) + (size_t)sc0 * PS + b];
+    }
+  }
+  __syncthreads();
+  // ---- 2. horizontal pass: tmp = min((sum c14 * pix) >> 7, 32767)
+  for (int i = threadIdx.x; i < nsr * ncol; i += kBlock) {
+    const int r = i / ncol, xo = i - r * ncol;
+    const int x = x0 + xo;
+    const int first = P.fx.first[x];
+    const int16_t *cf = P.fx.coef + (size_t)x * P.fx.taps;
+    const uint8_t *row = s_raw + r * raw_stride;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int k = 0; k < P.fx.taps; k++) {
+      const int sx = min(max(first + k, 0), P.sw - 1) - sc0;
+      const int c = cf[k];
+      if (PS == 4) {
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(row + 4 * sx);
+        a0 += c * (int)(p & 0xFF); a1 += c * (int)((p >> 8) & 0xFF); a2 += c * (int)((p >> 16) & 0xFF); a3 += c * (int)(p >> 24);
+      } else if (PS == 3) {
+        a0 += c * row[3 * sx]; a1 += c * row[3 * sx + 1]; a2 += c * row[3 * sx + 2];
+      } else {
+        a0 += c * row[sx];
+      }
+    }
+    a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
+    s_tmp[r * P.tw + xo] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
+  }
+  __syncthreads();
+  // ---- 3. vertical pass: out = clip_u8((sum c12 * tmp + 2^18) >> 19)
+  for (int i = threadIdx.x; i < nrow * ncol; i += kBlock) {
+    const int yo = i / ncol, xo = i - yo * ncol;
+    const int y = y0 + yo;
+    const int first = P.fy.first[y];
+    const int16_t *cf = P.fy.coef + (size_t)y * P.fy.taps;
+    int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
+    for (int k = 0; k < P.fy.taps; k++) {
+      const int sy = min(max(first + k, 0), P.sh - 1) - sr0;
+      const int c = cf[k];
+      const uint2 hv = s_tmp[sy * P.tw + xo];
+      a0 += c * (int)(hv.x & 0xFFFF);
+      if (PS > 1) { a1 += c * (int)(hv.x >> 16); a2 += c * (int)(hv.y & 0xFFFF); }
+      if (PS == 4) a3 += c * (int)(hv.y >> 16);
+    }
+    uint8_t *d = P.dst + (size_t)P.drs * y + (size_t)(x0 + xo) * PS;
+    const uint32_t o0 = (uint32_t)min(max(a0 >> 19, 0), 255), o1 = (uint32_t)min(max(a1 >> 19, 0), 255),
+                   o2 = (uint32_t)min(max(a2 >> 19, 0), 255), o3 = (uint32_t)min(max(a3 >> 19, 0), 255);
+    if (PS == 4) {
+      if (((uintptr_t)d & 3) == 0) *reinterpret_cast<uint32_t *>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+      else { d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2; d[3] = (uint8_t)o3; }
+    } else if (PS == 3) {
+      d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2;
+    } else {
+      d[0] = (uint8_t)o0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------------
 
@@ -259,6 +362,52 @@ cudaError_t launch_resize_h(const Launch &L, CImg src, int sw, int sh, int16_t *
 
 cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst, int dw, int dh, int psize, DevFilter fy) {
   k_resize_v<<<grid_for(L, (long long)dw * psize * dh), kBlock, 0, L.stream>>>(tmp, sh, dst.p, dst.rs, dw, dh, psize, fy);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// hx / hy: host copies of the filter banks (to size the tile).  Returns cudaErrorInvalidConfiguration when no tile fits in
+// shared memory (the caller then runs the two-kernel path).
+cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
+                               DevFilter fy, const int32_t *hx_first, const int32_t *hy_first) {
+  auto span = [](const int32_t *first, int taps, int dst_n, int src_n, int tile) {
+    int worst = 1;
+    for (int i0 = 0; i0 < dst_n; i0 += tile) {
+      const int i1 = i0 + tile - 1 < dst_n - 1 ? i0 + tile - 1 : dst_n - 1;
+      int lo = first[i0], hi = first[i1] + taps - 1;
+      lo = lo < 0 ? 0 : (lo > src_n - 1 ? src_n - 1 : lo);
+      hi = hi > src_n - 1 ? src_n - 1 : (hi < 0 ? 0 : hi);
+      if (hi - lo + 1 > worst) worst = hi - lo + 1;
+    }
+    return worst;
+  };
+  ResizeTileParams P;
+  P.src = src.p; P.dst = dst.p; P.srs = src.rs; P.drs = dst.rs; P.sw = sw; P.sh = sh; P.dw = dw; P.dh = dh; P.fx = fx; P.fy = fy;
+  size_t smem = 0;
+  bool ok = false;
+  for (int tw = 64, th = 32; tw >= 8 && !ok; tw >>= 1, th = th > 8 ? th >> 1 : th) {
+    P.tw = tw; P.th = th;
+    P.max_cols = span(hx_first, fx.taps, dw, sw, tw);
+    P.max_rows = span(hy_first, fy.taps, dh, sh, th);
+    const size_t raw = (((size_t)P.max_rows * ((P.max_cols * psize + 3) & ~3)) + 15) & ~(size_t)15;
+    smem = raw + (size_t)P.max_rows * tw * 8;
+    ok = smem <= 96 * 1024;
+  }
+  if (!ok) return cudaErrorInvalidConfiguration;
+  const int tiles = ((dw + P.tw - 1) / P.tw) * ((dh + P.th - 1) / P.th);
+  static size_t attr[5] = {0, 0, 0, 0, 0};
+  cudaError_t e = cudaSuccess;
+  if (smem > attr[psize]) {
+    if (psize == 4) e = cudaFuncSetAttribute(k_resize_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    else if (psize == 3) e = cudaFuncSetAttribute(k_resize_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    else e = cudaFuncSetAttribute(k_resize_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    attr[psize] = 96 * 1024;
+  }
+  if (psize == 4) k_resize_tile<4><<<tiles, kBlock, smem, L.stream>>>(P);
+  else if (psize == 3) k_resize_tile<3><<<tiles, kBlock, smem, L.stream>>>(P);
+  else if (psize == 1) k_resize_tile<1><<<tiles, kBlock, smem, L.stream>>>(P);
+  else return cudaErrorInvalidValue;
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

@@ -620,6 +620,85 @@ __global__ void __launch_bounds__(1024, 1) k_alpha_over(const OverParams P) {
 
 }  // namespace
 
+namespace {
+
+// alpha = k / 256: (bg * (256 - k) + fg * k) >> 8 is exactly trunc(bg * (1 - a) + fg * a) in double (all terms exact), so the
+// table is not needed: two channels per multiply, 4 pixels (128 bits) per thread, optional 8-bit gamma LUT afterwards.
+struct OverArithParams {
+  const uint8_t *bg, *fg;
+  uint8_t *dst;
+  int rs_bg, rs_fg, rs_d, width, height, psize;
+  uint32_t ka, kia;
+  const uint8_t *lut;  // nullptr: none
+  int force_opaque;
+};
+
+__device__ __forceinline__ uint32_t over_px4(uint32_t b, uint32_t f, uint32_t ka, uint32_t kia, const uint8_t *s_lut, bool has_lut,
+                                             bool force_opaque) {
+  const uint32_t rb = (b & 0x00FF00FFu) * kia + (f & 0x00FF00FFu) * ka;          // R | B, 16 bits each, no carry: kia + ka = 256
+  const uint32_t g = ((b >> 8) & 0xFFu) * kia + ((f >> 8) & 0xFFu) * ka;
+  uint32_t o0 = (rb >> 8) & 0xFFu, o1 = g >> 8, o2 = rb >> 24;
+  if (has_lut) { o0 = s_lut[o0]; o1 = s_lut[o1]; o2 = s_lut[o2]; }
+  return o0 | (o1 << 8) | (o2 << 16) | (force_opaque ? 0xFF000000u : (b & 0xFF000000u));
+}
+
+__global__ void __launch_bounds__(kBlock) k_alpha_over_arith(const OverArithParams P) {
+  __shared__ uint8_t s_lut[256];
+  const bool has_lut = P.lut != nullptr;
+  if (has_lut) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
+    __syncthreads();
+  }
+  if (P.psize == 4) {
+    const bool vec = (((uintptr_t)P.bg | (uintptr_t)P.fg | (uintptr_t)P.dst) % 16 == 0) && ((P.rs_bg | P.rs_fg | P.rs_d) % 16 == 0);
+    const int groups = (P.width + 3) >> 2;
+    const long long total = (long long)groups * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+      const int npx = min(4, P.width - g * 4);
+      const uint8_t *b = P.bg + (size_t)row * P.rs_bg + g * 16, *f = P.fg + (size_t)row * P.rs_fg + g * 16;
+      uint8_t *d = P.dst + (size_t)row * P.rs_d + g * 16;
+      if (vec && npx == 4) {
+        const uint4 vb = ld_u4(b), vf = ld_u4(f);  // dst may alias bg: plain loads
+        uint4 o;
+        o.x = over_px4(vb.x, vf.x, P.ka, P.kia, s_lut, has_lut, P.force_opaque);
+        o.y = over_px4(vb.y, vf.y, P.ka, P.kia, s_lut, has_lut, P.force_opaque);
+        o.z = over_px4(vb.z, vf.z, P.ka, P.kia, s_lut, has_lut, P.force_opaque);
+        o.w = over_px4(vb.w, vf.w, P.ka, P.kia, s_lut, has_lut, P.force_opaque);
+        *reinterpret_cast<uint4 *>(d) = o;
+      } else {
+        for (int k = 0; k < npx; k++)
+          *reinterpret_cast<uint32_t *>(d + 4 * k) = over_px4(*reinterpret_cast<const uint32_t *>(b + 4 * k),
+                                                               *reinterpret_cast<const uint32_t *>(f + 4 * k), P.ka, P.kia, s_lut,
+                                                               has_lut, P.force_opaque);
+      }
+    }
+  } else {
+    const int row_bytes = P.width * 3;
+    const long long total = (long long)row_bytes * P.height;
+    for (long long it = global_tid(); it < total; it += global_threads()) {
+      const int row = (int)(it / row_bytes), k = (int)(it - (long long)row * row_bytes);
+      uint32_t o = ((uint32_t)P.bg[(size_t)row * P.rs_bg + k] * P.kia + (uint32_t)P.fg[(size_t)row * P.rs_fg + k] * P.ka) >> 8;
+      if (has_lut) o = s_lut[o];
+      P.dst[(size_t)row * P.rs_d + k] = (uint8_t)o;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_alpha_over_arith(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize, int k256,
+                                    const uint8_t *lut8_dev, int force_opaque) {
+  OverArithParams P;
+  P.bg = bg.p; P.fg = fg.p; P.dst = dst.p; P.rs_bg = bg.rs; P.rs_fg = fg.rs; P.rs_d = dst.rs;
+  P.width = width; P.height = height; P.psize = psize; P.ka = (uint32_t)k256; P.kia = 256u - (uint32_t)k256;
+  P.lut = lut8_dev; P.force_opaque = force_opaque;
+  const long long work = psize == 4 ? (long long)((width + 3) >> 2) * height : (long long)width * 3 * height;
+  k_alpha_over_arith<<<grid_for(L, work, 8), kBlock, 0, L.stream>>>(P);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev) {
   k_over_table<<<64, kBlock, 0, L.stream>>>(alpha, lut8_dev, table_dev);
   PE_COUNT_LAUNCH(L);

@@ -328,6 +328,14 @@ def compositor(out, layers, alphas, bgcol=(0, 0, 0)):
     capi.check(e._lib.pe_fx_compositor(e._h, out._h, _arr(layers), al, len(layers), bg))
 
 
+def compositor_gamma(out, layers, alphas, gamma_to, bgcol=(0, 0, 0)):
+    """compositor() followed by gamma_convert_layer(gamma_to, out), the LUT folded into the last paint"""
+    e = out.engine
+    al = (C.c_double * max(len(alphas), 1))(*alphas)
+    bg = (C.c_int * 3)(*bgcol)
+    capi.check(e._lib.pe_fx_compositor_gamma(e._h, out._h, _arr(layers), al, len(layers), bg, gamma_to))
+
+
 def fused_convert_letterbox_over_gamma(fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):
     """convert_layer_palette(fg -> RGBA32); letterbox_layer; compositor over bg; gamma_convert_layer -- one kernel"""
     e = fg.engine

@@ -406,6 +406,16 @@ def test_config3_4k_alpha_over_gamma(eng):
     assert lb.gamma_convert_layer(T.G_SRGB, out)
     got = out.to_host()[0]
     assert (got == exp).all()
+    # ... and fused: compositor + gamma in one pass (pe_fx_compositor_gamma), dyadic and non-dyadic alpha
+    for alpha in (0.5, 0.3):
+        exp2 = _oracle_compositor(o, 3, w, h, [fg, bg], [alpha, 1.0], (0, 0, 0))
+        o.pe_or_gamma_apply(T.ptr(exp2), exp2.strides[0], 3, 0, 0, w, h, T.ptr(lut))
+        out2 = lb.Layer.create(eng, 3, w, h, gamma_type=T.G_LINEAR)
+        before = eng.launch_count
+        lb.compositor_gamma(out2, [packed_layer(eng, 3, w, h, fg), packed_layer(eng, 3, w, h, bg)], [alpha, 1.0], T.G_SRGB)
+        assert eng.launch_count - before <= 2  # one paint (+ the one-off table build for alpha 0.3)
+        assert out2.gamma_type == T.G_SRGB
+        assert (out2.to_host()[0] == exp2).all(), alpha
     # the north-star's sRGB -> linear LUT is the identity table in the reference: gamma is then a no-op
     assert (eng.gamma_lut8(1.0, T.G_SRGB, T.G_LINEAR) == np.arange(256)).all()
 
