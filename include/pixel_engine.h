@@ -231,6 +231,12 @@ int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_de
                                                pe_frame_desc_t *out, int inner_w, int inner_h, double alpha,
                                                int gamma_from, int gamma_to);
 
+/* a batch of independent host frames (render-to-disk) through the fused chain: uploads, kernels and downloads of
+ * consecutive frames overlap on three streams; host buffers should be pinned (pe_host_alloc) */
+int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_desc_t *const *fg,
+                                                     const pe_frame_desc_t *const *bg, pe_frame_desc_t *const *out,
+                                                     int inner_w, int inner_h, double alpha, int gamma_from, int gamma_to);
+
 #ifdef __cplusplus
 }
 #endif

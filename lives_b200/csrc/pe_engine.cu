@@ -208,9 +208,23 @@ extern "C" int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out) {
     for (int hd = 0; hd < 2; hd++) {
       build_conv_tables(cl == 0 ? PE_YUV_CLAMPING_CLAMPED : PE_YUV_CLAMPING_UNCLAMPED,
                         hd ? PE_YUV_SUBSPACE_BT709 : PE_YUV_SUBSPACE_YCBCR, &e->conv_host[cl][hd]);
-      PE_CUDA(cudaMalloc(&e->conv_dev[cl][hd], sizeof(int32_t) * N_CONVTAB * 256));
-      PE_CUDA(cudaMemcpyAsync(e->conv_dev[cl][hd], e->conv_host[cl][hd].t, sizeof(int32_t) * N_CONVTAB * 256,
-                              cudaMemcpyHostToDevice, e->stream));
+      // [14][256] as the reference has them + the extended planar YUV -> RGB tables (DevConv::ext, pe_kernels.h)
+      std::vector<int32_t> host(N_CONVTAB * 256 + 256 + 4 * kExtN);
+      const ConvTables &ct = e->conv_host[cl][hd];
+      memcpy(host.data(), ct.t, sizeof(int32_t) * N_CONVTAB * 256);
+      int32_t *ext = host.data() + N_CONVTAB * 256;
+      memcpy(ext, ct.t[RGB_Y], sizeof(int32_t) * 256);
+      const int lo = cl == 0 ? 16 : 0, hi = cl == 0 ? 240 : 255;
+      for (int n = 0; n < kExtN; n++) {
+        int c = (2 * n + 3) / 6;  // (int)(n / 3. + .5)
+        c = c < lo ? lo : c > hi ? hi : c;
+        ext[256 + 0 * kExtN + n] = ct.t[R_CR][c];
+        ext[256 + 1 * kExtN + n] = ct.t[G_CB][c];
+        ext[256 + 2 * kExtN + n] = ct.t[G_CR][c];
+        ext[256 + 3 * kExtN + n] = ct.t[B_CB][c];
+      }
+      PE_CUDA(cudaMalloc(&e->conv_dev[cl][hd], sizeof(int32_t) * host.size()));
+      PE_CUDA(cudaMemcpy(e->conv_dev[cl][hd], host.data(), sizeof(int32_t) * host.size(), cudaMemcpyHostToDevice));
     }
   }
   {
@@ -244,6 +258,11 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
   cudaEventDestroy(e->args_ev);
+  if (e->h2d_stream) {
+    cudaStreamDestroy(e->h2d_stream);
+    cudaStreamDestroy(e->d2h_stream);
+    for (int k = 0; k < 3; k++) { cudaEventDestroy(e->pipe_up[k]); cudaEventDestroy(e->pipe_comp[k]); cudaEventDestroy(e->pipe_free[k]); }
+  }
   if (e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -282,7 +301,7 @@ inline const ConvTables &conv_host(pe_engine *e, int clamping, int subspace) {
 inline DevConv dev_conv(pe_engine *e, int clamping, int subspace) {
   const int cl = clamping == PE_YUV_CLAMPING_CLAMPED ? 0 : 1, hd = subspace == PE_YUV_SUBSPACE_BT709 ? 1 : 0;
   const ConvTables &h = e->conv_host[cl][hd];
-  return DevConv{e->conv_dev[cl][hd], h.min_y, h.max_y, h.min_uv, h.max_uv};
+  return DevConv{e->conv_dev[cl][hd], h.min_y, h.max_y, h.min_uv, h.max_uv, e->conv_dev[cl][hd] + N_CONVTAB * 256};
 }
 
 // create_gamma_lut8 (colourspace.c:655).  Our cache is keyed by the ARGUMENTS; the reference keys its process-wide
@@ -1290,12 +1309,8 @@ extern "C" int pe_fx_compositor_gamma(pe_engine_t *e, pe_frame_t *out, const pe_
 // fused chain
 // ---------------------------------------------------------------------------------------------------------
 
-extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_t *const *fg,
-                                                           const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
-                                                           int inner_h, double alpha, int gamma_from, int gamma_to) {
-  if (!e || n <= 0 || !fg || !bg || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
-  std::lock_guard<std::mutex> lk(e->mu);
-  PE_CUDA(cudaSetDevice(e->device));
+static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, const pe_frame_t *const *bg, pe_frame_t *const *out,
+                        int inner_w, int inner_h, double alpha, int gamma_from, int gamma_to) {
   const pe_frame *f0 = fg[0], *b0 = bg[0];
   if (!f0 || !b0) return set_err(PE_ERR_ARG, "NULL frame");
   const int ow = b0->d.width, oh = b0->d.height;
@@ -1382,6 +1397,15 @@ extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n
     out[i]->d.flags = bg[i]->d.flags;
   }
   return PE_OK;
+}
+
+extern "C" int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_t *const *fg,
+                                                           const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
+                                                           int inner_h, double alpha, int gamma_from, int gamma_to) {
+  if (!e || n <= 0 || !fg || !bg || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  return fused_locked(e, n, fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to);
 }
 
 extern "C" int pe_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_t *fg, const pe_frame_t *bg,
@@ -1541,6 +1565,98 @@ extern "C" int pe_host_simple_blend(pe_engine_t *e, int type, const pe_frame_des
 extern "C" int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
                                    pe_frame_desc_t *out, int blend_factor) {
   return host_blend(e, 1, type, in1, in2, out, blend_factor);
+}
+
+// A batch of host frames through the fused chain with the PCIe copies overlapped: three device slots rotate through
+// upload (h2d stream) -> kernel (engine stream) -> download (d2h stream), chained by events, so that frame i+1 travels to the
+// device and frame i-1 travels back while frame i is computed.  Host buffers should be pinned (pe_host_alloc) for the copies to
+// be asynchronous; pageable memory still gives correct results.
+extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_frame_desc_t *const *fg,
+                                                                const pe_frame_desc_t *const *bg, pe_frame_desc_t *const *out,
+                                                                int inner_w, int inner_h, double alpha, int gamma_from,
+                                                                int gamma_to) {
+  if (!e || n <= 0 || !fg || !bg || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  for (int i = 0; i < n; i++)
+    if (!fg[i] || !bg[i] || !out[i] || !fg[i]->planes[0] || !bg[i]->planes[0] || !out[i]->planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  constexpr int NS = 3;
+  if (!e->h2d_stream) {
+    PE_CUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    PE_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < NS; k++) {
+      PE_CUDA(cudaEventCreateWithFlags(&e->pipe_up[k], cudaEventDisableTiming));
+      PE_CUDA(cudaEventCreateWithFlags(&e->pipe_comp[k], cudaEventDisableTiming));
+      PE_CUDA(cudaEventCreateWithFlags(&e->pipe_free[k], cudaEventDisableTiming));
+    }
+  }
+  // device slots
+  pe_frame slots[NS][3];
+  const int ns = n < NS ? n : NS;
+  int rc = PE_OK;
+  auto release = [&]() { for (int k = 0; k < ns; k++) for (int j = 0; j < 3; j++) frame_release_pixels(&slots[k][j]); };
+  for (int k = 0; k < ns && rc == PE_OK; k++) {
+    const pe_frame_desc_t *d3[3] = {fg[0], bg[0], out[0]};
+    for (int j = 0; j < 3 && rc == PE_OK; j++) {
+      slots[k][j].e = e;
+      slots[k][j].d = *d3[j];
+      rc = frame_alloc(e, &slots[k][j]);
+    }
+  }
+  if (rc != PE_OK) { release(); return rc; }
+  // blocks from the pool may still be in use by earlier work on the engine stream
+  PE_CUDA(cudaEventRecord(e->pipe_free[0], e->stream));
+  PE_CUDA(cudaStreamWaitEvent(e->h2d_stream, e->pipe_free[0], 0));
+  auto copy_planes = [&](cudaStream_t st, pe_frame &dev, const pe_frame_desc_t &host, bool to_device) -> cudaError_t {
+    for (int p = 0; p < dev.d.nplanes; p++) {
+      const int wbytes = plane_row_bytes(dev.d, p);
+      cudaError_t ce = to_device ? cudaMemcpy2DAsync(dev.d.planes[p], dev.d.rowstrides[p], host.planes[p], host.rowstrides[p], wbytes,
+                                                     dev.plane_heights[p], cudaMemcpyHostToDevice, st)
+                                 : cudaMemcpy2DAsync(host.planes[p], host.rowstrides[p], dev.d.planes[p], dev.d.rowstrides[p], wbytes,
+                                                     dev.plane_heights[p], cudaMemcpyDeviceToHost, st);
+      if (ce != cudaSuccess) return ce;
+    }
+    return cudaSuccess;
+  };
+  for (int i = 0; i < n; i++) {
+    const int k = i % NS;
+    if (fg[i]->palette != fg[0]->palette || fg[i]->width != fg[0]->width || fg[i]->height != fg[0]->height ||
+        bg[i]->width != bg[0]->width || bg[i]->height != bg[0]->height || bg[i]->palette != bg[0]->palette ||
+        out[i]->width != out[0]->width || out[i]->height != out[0]->height || out[i]->palette != out[0]->palette) {
+      rc = set_err(PE_ERR_SIZE, "frames of a batch must share palette and size");
+      break;
+    }
+    cudaError_t ce = cudaSuccess;
+    // upload into slot k once its previous occupant has been downloaded
+    if (i >= NS) ce = cudaStreamWaitEvent(e->h2d_stream, e->pipe_free[k], 0);
+    slots[k][0].d.yuv_clamping = fg[i]->yuv_clamping; slots[k][0].d.yuv_subspace = fg[i]->yuv_subspace;
+    slots[k][1].d.gamma_type = bg[i]->gamma_type; slots[k][1].d.flags = bg[i]->flags;
+    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][0], *fg[i], true);
+    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][1], *bg[i], true);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->pipe_up[k], e->h2d_stream);
+    // compute
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->pipe_up[k], 0);
+    if (ce != cudaSuccess) { rc = set_err(PE_ERR_CUDA, "pipeline upload failed: %s", cudaGetErrorString(ce)); break; }
+    const pe_frame_t *f1[1] = {&slots[k][0]}, *b1[1] = {&slots[k][1]};
+    pe_frame_t *o1[1] = {&slots[k][2]};
+    rc = fused_locked(e, 1, f1, b1, o1, inner_w, inner_h, alpha, gamma_from, gamma_to);
+    if (rc != PE_OK) break;
+    ce = cudaEventRecord(e->pipe_comp[k], e->stream);
+    // download
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->d2h_stream, e->pipe_comp[k], 0);
+    if (ce == cudaSuccess) ce = copy_planes(e->d2h_stream, slots[k][2], *out[i], false);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->pipe_free[k], e->d2h_stream);
+    if (ce != cudaSuccess) { rc = set_err(PE_ERR_CUDA, "pipeline download failed: %s", cudaGetErrorString(ce)); break; }
+    out[i]->gamma_type = slots[k][2].d.gamma_type;
+    out[i]->flags = slots[k][2].d.flags;
+  }
+  cudaError_t ce = cudaStreamSynchronize(e->d2h_stream);
+  cudaError_t ce2 = cudaStreamSynchronize(e->h2d_stream);
+  cudaError_t ce3 = cudaStreamSynchronize(e->stream);
+  release();
+  if (rc == PE_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))
+    rc = set_err(PE_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2 != cudaSuccess ? ce2 : ce3));
+  return rc;
 }
 
 extern "C" int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_desc_t *fg, const pe_frame_desc_t *bg,

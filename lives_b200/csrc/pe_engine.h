@@ -63,10 +63,13 @@ struct pe_engine {
   int sm_count = 0;
   long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t pipe_up[3] = {}, pipe_comp[3] = {}, pipe_free[3] = {};
   std::mutex mu;  // the reference calls these entry points from several proc-threads (different layers)
 
   pe::ConvTables conv_host[2][2];    // [clamping][bt709]
-  int32_t *conv_dev[2][2] = {};      // 14 x 256 int32 each
+  int32_t *conv_dev[2][2] = {};      // 14 x 256 int32 each, followed by the extended planar tables (DevConv::ext)
   uint8_t *premult_dev[6] = {};      // built on first use (init_unal is lazy in the reference too, :11985)
   int32_t *luma_dev = nullptr;       // plugin-side calc_luma tables [3][256]
   std::map<pe::GammaKey, pe::Lut8Entry> lut8;

@@ -30,9 +30,15 @@ struct Planes {
 
 // device-resident tables of one (clamping, subspace) variant: 14 x int[256] (ConvTab order)
 struct DevConv {
-  const int32_t *t;  // [14][256]
+  const int32_t *t;    // [14][256]
   int min_y, max_y, min_uv, max_uv;
+  // YUV -> RGB tables for the planar converters: RGB_Y[256] then R_Cr, G_Cb, G_Cr, B_Cb indexed by the UN-divided chroma
+  // sum n = u1 + (u2 >> 1) <= 765 (kExtN entries each):  ext[t][n] = table_t[clamp(third_round(n), lo, hi)], which folds the
+  // (int)(n / 3. + .5) rounding and CLAMP16_240 / CLAMP0_255 of colourspace.c:3465-3469 into the lookup.  A plain chroma
+  // sample m is looked up at n = 3 * m.
+  const int32_t *ext;  // [256 + 4 * kExtN]
 };
+constexpr int kExtN = 768;
 
 // byte order of an RGB palette: offsets of R,G,B,A inside a pixel (A = -1 when absent)
 struct RgbLayout {

@@ -82,87 +82,114 @@ struct ResizeTileParams {
   DevFilter fx, fy;
 };
 
+// Shared memory: [raw source rectangle, edge-replicated][tmp: 4 x int16 per (row, out column)][x taps][y taps]
+//   * the staged rectangle covers the UNCLAMPED tap range of the tile (virtual rows / columns outside the frame hold the
+//     replicated edge pixel), so the two passes below index it without clamping;
+//   * the coefficients of the tile's columns / rows are staged once per tile (int16, taps padded to even).
 template <int PS>
 __global__ void __launch_bounds__(kBlock) k_resize_tile(const ResizeTileParams P) {
   extern __shared__ __align__(16) uint8_t rsm[];
   const int raw_stride = (P.max_cols * PS + 3) & ~3;
+  const int tx_taps = P.fx.taps, ty_taps = P.fy.taps;
   uint8_t *s_raw = rsm;                                                    // [max_rows][raw_stride]
-  uint2 *s_tmp = reinterpret_cast<uint2 *>(rsm + (((size_t)P.max_rows * raw_stride + 15) & ~(size_t)15));  // [max_rows][tw]
+  size_t off = ((size_t)P.max_rows * raw_stride + 15) & ~(size_t)15;
+  uint2 *s_tmp = reinterpret_cast<uint2 *>(rsm + off);                     // [max_rows][tw]
+  off += (size_t)P.max_rows * P.tw * 8;
+  int16_t *s_cx = reinterpret_cast<int16_t *>(rsm + off);                  // [tw][tx_taps]
+  off += ((size_t)P.tw * tx_taps * 2 + 15) & ~(size_t)15;
+  int16_t *s_cy = reinterpret_cast<int16_t *>(rsm + off);                  // [th][ty_taps]
+  off += ((size_t)P.th * ty_taps * 2 + 15) & ~(size_t)15;
+  int *s_fx = reinterpret_cast<int *>(rsm + off);                          // [tw] first - vc0
+  int *s_fy = s_fx + P.tw;                                                 // [th] first - vr0
+
   const int tiles_x = (P.dw + P.tw - 1) / P.tw;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
   const int x0 = tx * P.tw, y0 = ty * P.th;
   const int x1 = min(x0 + P.tw, P.dw), y1 = min(y0 + P.th, P.dh);
   const int ncol = x1 - x0, nrow = y1 - y0;
-  const int sr0 = min(max(P.fy.first[y0], 0), P.sh - 1), sr1 = min(max(P.fy.first[y1 - 1] + P.fy.taps - 1, 0), P.sh - 1);
-  const int sc0 = min(max(P.fx.first[x0], 0), P.sw - 1), sc1 = min(max(P.fx.first[x1 - 1] + P.fx.taps - 1, 0), P.sw - 1);
-  const int nsr = sr1 - sr0 + 1, nsb = (sc1 - sc0 + 1) * PS;
-  // ---- 1. stage the source rectangle (bytes sc0*PS .. of rows sr0..sr1)
+  // virtual (unclamped) source range of the tile
+  const int vr0 = P.fy.first[y0], vr1 = P.fy.first[y1 - 1] + ty_taps - 1;
+  const int vc0 = P.fx.first[x0], vc1 = P.fx.first[x1 - 1] + tx_taps - 1;
+  const int nvr = vr1 - vr0 + 1, nvc = vc1 - vc0 + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- 0. filter data of the tile
+  for (int i = threadIdx.x; i < ncol * tx_taps; i += kBlock) s_cx[i] = P.fx.coef[(size_t)x0 * tx_taps + i];
+  for (int i = threadIdx.x; i < nrow * ty_taps; i += kBlock) s_cy[i] = P.fy.coef[(size_t)y0 * ty_taps + i];
+  for (int i = threadIdx.x; i < ncol; i += kBlock) s_fx[i] = P.fx.first[x0 + i] - vc0;
+  for (int i = threadIdx.x; i < nrow; i += kBlock) s_fy[i] = P.fy.first[y0 + i] - vr0;
+  // ---- 1. stage the source rectangle, replicating the frame edges
   {
-    const uint8_t *base = P.src + (size_t)P.srs * sr0 + (size_t)sc0 * PS;
-    const bool w4 = (((uintptr_t)base | (uintptr_t)P.srs) & 3) == 0;
-    if (w4) {
-      const int nw = nsb >> 2;
-      for (int r = threadIdx.x >> 5; r < nsr; r += kBlock / 32) {
-        const uint8_t *rp = base + (size_t)P.srs * r;
-        for (int w = threadIdx.x & 31; w < nw; w += 32)
-          *reinterpret_cast<uint32_t *>(s_raw + r * raw_stride + 4 * w) = ld_stream_u32(rp + 4 * w);
-        for (int b = (nw << 2) + (threadIdx.x & 31); b < nsb; b += 32) s_raw[r * raw_stride + b] = rp[b];
-      }
-    } else {
-      for (int r = threadIdx.x >> 5; r < nsr; r += kBlock / 32)
-        for (int b = threadIdx.x & 31; b < nsb; b += 32) s_raw[r * raw_stride + b] = P.src[(size_t)P.srs * (sr0 + r) + (size_t)sc0 * PS + b];
-    }
-  }
-  __syncthreads();
-  // ---- 2. horizontal pass: tmp = min((sum c14 * pix) >> 7, 32767)
-  for (int i = threadIdx.x; i < nsr * ncol; i += kBlock) {
-    const int r = i / ncol, xo = i - r * ncol;
-    const int x = x0 + xo;
-    const int first = P.fx.first[x];
-    const int16_t *cf = P.fx.coef + (size_t)x * P.fx.taps;
-    const uint8_t *row = s_raw + r * raw_stride;
-    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int k = 0; k < P.fx.taps; k++) {
-      const int sx = min(max(first + k, 0), P.sw - 1) - sc0;
-      const int c = cf[k];
-      if (PS == 4) {
-        const uint32_t p = *reinterpret_cast<const uint32_t *>(row + 4 * sx);
-        a0 += c * (int)(p & 0xFF); a1 += c * (int)((p >> 8) & 0xFF); a2 += c * (int)((p >> 16) & 0xFF); a3 += c * (int)(p >> 24);
-      } else if (PS == 3) {
-        a0 += c * row[3 * sx]; a1 += c * row[3 * sx + 1]; a2 += c * row[3 * sx + 2];
+    const int cin0 = max(vc0, 0), cin1 = min(vc1, P.sw - 1);       // columns that exist
+    const int lead = cin0 - vc0;                                   // replicated columns on the left
+    for (int r = warp; r < nvr; r += kBlock / 32) {
+      const int sy = min(max(vr0 + r, 0), P.sh - 1);
+      const uint8_t *rp = P.src + (size_t)P.srs * sy;
+      uint8_t *dp = s_raw + r * raw_stride;
+      if (PS == 4 && (((uintptr_t)rp) & 3) == 0) {
+        for (int c = lane; c < nvc; c += 32) {
+          const int sx = min(max(vc0 + c, 0), P.sw - 1);
+          reinterpret_cast<uint32_t *>(dp)[c] = ld_stream_u32(rp + 4 * sx);
+        }
       } else {
-        a0 += c * row[sx];
+        for (int b = lane; b < nvc * PS; b += 32) {
+          const int c = b / PS, k = b - c * PS;
+          const int sx = min(max(vc0 + c, 0), P.sw - 1);
+          dp[b] = rp[sx * PS + k];
+        }
       }
     }
-    a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
-    s_tmp[r * P.tw + xo] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
+    (void)cin1; (void)lead;
   }
   __syncthreads();
-  // ---- 3. vertical pass: out = clip_u8((sum c12 * tmp + 2^18) >> 19)
-  for (int i = threadIdx.x; i < nrow * ncol; i += kBlock) {
-    const int yo = i / ncol, xo = i - yo * ncol;
-    const int y = y0 + yo;
-    const int first = P.fy.first[y];
-    const int16_t *cf = P.fy.coef + (size_t)y * P.fy.taps;
-    int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
-    for (int k = 0; k < P.fy.taps; k++) {
-      const int sy = min(max(first + k, 0), P.sh - 1) - sr0;
-      const int c = cf[k];
-      const uint2 hv = s_tmp[sy * P.tw + xo];
-      a0 += c * (int)(hv.x & 0xFFFF);
-      if (PS > 1) { a1 += c * (int)(hv.x >> 16); a2 += c * (int)(hv.y & 0xFFFF); }
-      if (PS == 4) a3 += c * (int)(hv.y >> 16);
+  // ---- 2. horizontal pass: tmp = min((sum c14 * pix) >> 7, 32767); lanes walk the output columns of one source row
+  for (int r = warp; r < nvr; r += kBlock / 32) {
+    const uint8_t *row = s_raw + r * raw_stride;
+    for (int xo = lane; xo < ncol; xo += 32) {
+      const int16_t *cf = s_cx + xo * tx_taps;
+      const int f0 = s_fx[xo];
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int k = 0; k < tx_taps; k++) {
+        const int c = cf[k];
+        if (PS == 4) {
+          const uint32_t p = reinterpret_cast<const uint32_t *>(row)[f0 + k];
+          a0 += c * (int)(p & 0xFF); a1 += c * (int)((p >> 8) & 0xFF); a2 += c * (int)((p >> 16) & 0xFF); a3 += c * (int)(p >> 24);
+        } else if (PS == 3) {
+          const uint8_t *q = row + 3 * (f0 + k);
+          a0 += c * q[0]; a1 += c * q[1]; a2 += c * q[2];
+        } else {
+          a0 += c * row[f0 + k];
+        }
+      }
+      a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
+      s_tmp[r * P.tw + xo] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
     }
-    uint8_t *d = P.dst + (size_t)P.drs * y + (size_t)(x0 + xo) * PS;
-    const uint32_t o0 = (uint32_t)min(max(a0 >> 19, 0), 255), o1 = (uint32_t)min(max(a1 >> 19, 0), 255),
-                   o2 = (uint32_t)min(max(a2 >> 19, 0), 255), o3 = (uint32_t)min(max(a3 >> 19, 0), 255);
-    if (PS == 4) {
-      if (((uintptr_t)d & 3) == 0) *reinterpret_cast<uint32_t *>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
-      else { d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2; d[3] = (uint8_t)o3; }
-    } else if (PS == 3) {
-      d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2;
-    } else {
-      d[0] = (uint8_t)o0;
+  }
+  __syncthreads();
+  // ---- 3. vertical pass: out = clip_u8((sum c12 * tmp + 2^18) >> 19); lanes walk the columns of one output row
+  for (int yo = warp; yo < nrow; yo += kBlock / 32) {
+    const int16_t *cf = s_cy + yo * ty_taps;
+    const int f0 = s_fy[yo];
+    uint8_t *drow = P.dst + (size_t)P.drs * (y0 + yo) + (size_t)x0 * PS;
+    for (int xo = lane; xo < ncol; xo += 32) {
+      int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
+      for (int k = 0; k < ty_taps; k++) {
+        const int c = cf[k];
+        const uint2 hv = s_tmp[(f0 + k) * P.tw + xo];
+        a0 += c * (int)(hv.x & 0xFFFF);
+        if (PS > 1) { a1 += c * (int)(hv.x >> 16); a2 += c * (int)(hv.y & 0xFFFF); }
+        if (PS == 4) a3 += c * (int)(hv.y >> 16);
+      }
+      const uint32_t o0 = (uint32_t)min(max(a0 >> 19, 0), 255), o1 = (uint32_t)min(max(a1 >> 19, 0), 255),
+                     o2 = (uint32_t)min(max(a2 >> 19, 0), 255), o3 = (uint32_t)min(max(a3 >> 19, 0), 255);
+      uint8_t *d = drow + xo * PS;
+      if (PS == 4) {
+        if (((uintptr_t)d & 3) == 0) *reinterpret_cast<uint32_t *>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        else { d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2; d[3] = (uint8_t)o3; }
+      } else if (PS == 3) {
+        d[0] = (uint8_t)o0; d[1] = (uint8_t)o1; d[2] = (uint8_t)o2;
+      } else {
+        d[0] = (uint8_t)o0;
+      }
     }
   }
 }
@@ -370,14 +397,12 @@ cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst
 // shared memory (the caller then runs the two-kernel path).
 cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
                                DevFilter fy, const int32_t *hx_first, const int32_t *hy_first) {
-  auto span = [](const int32_t *first, int taps, int dst_n, int src_n, int tile) {
+  auto span = [](const int32_t *first, int taps, int dst_n, int tile) {  // unclamped tap range of the widest tile
     int worst = 1;
     for (int i0 = 0; i0 < dst_n; i0 += tile) {
       const int i1 = i0 + tile - 1 < dst_n - 1 ? i0 + tile - 1 : dst_n - 1;
-      int lo = first[i0], hi = first[i1] + taps - 1;
-      lo = lo < 0 ? 0 : (lo > src_n - 1 ? src_n - 1 : lo);
-      hi = hi > src_n - 1 ? src_n - 1 : (hi < 0 ? 0 : hi);
-      if (hi - lo + 1 > worst) worst = hi - lo + 1;
+      const int n = first[i1] + taps - 1 - first[i0] + 1;
+      if (n > worst) worst = n;
     }
     return worst;
   };
@@ -387,10 +412,11 @@ cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img ds
   bool ok = false;
   for (int tw = 64, th = 32; tw >= 8 && !ok; tw >>= 1, th = th > 8 ? th >> 1 : th) {
     P.tw = tw; P.th = th;
-    P.max_cols = span(hx_first, fx.taps, dw, sw, tw);
-    P.max_rows = span(hy_first, fy.taps, dh, sh, th);
+    P.max_cols = span(hx_first, fx.taps, dw, tw);
+    P.max_rows = span(hy_first, fy.taps, dh, th);
     const size_t raw = (((size_t)P.max_rows * ((P.max_cols * psize + 3) & ~3)) + 15) & ~(size_t)15;
-    smem = raw + (size_t)P.max_rows * tw * 8;
+    smem = raw + (size_t)P.max_rows * tw * 8 + (((size_t)tw * fx.taps * 2 + 15) & ~(size_t)15) +
+           (((size_t)th * fy.taps * 2 + 15) & ~(size_t)15) + (size_t)(tw + th) * 4;
     ok = smem <= 96 * 1024;
   }
   if (!ok) return cudaErrorInvalidConfiguration;

@@ -241,14 +241,8 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
     bool rebuilt = false;
     if (A.conv.t != cur_conv || A.clamped != cur_clamped) {
       rebuilt = true;
-      const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
-      const int32_t *ct = A.conv.t + 9 * 256;  // RGB_Y, R_Cr, G_Cb, G_Cr, B_Cb
-      for (int i = tid; i < 256; i += F2_NT) s_tab[i] = ct[i];
-      for (int i = tid; i < F2_NEXT; i += F2_NT) {
-        const int c = clamp_i(third_round(i), lo, hi);
-#pragma unroll
-        for (int k = 0; k < 4; k++) s_tab[256 + k * F2_NEXT + i] = ct[(1 + k) * 256 + c];
-      }
+      static_assert(F2_NEXT == kExtN, "extended table size");
+      for (int i = tid; i < 256 + 4 * F2_NEXT; i += F2_NT) s_tab[i] = A.conv.ext[i];
       cur_conv = A.conv.t;
       cur_clamped = A.clamped;
     }

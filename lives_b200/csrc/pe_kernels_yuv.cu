@@ -86,22 +86,67 @@ __device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ p, int stri
   return __ldg(p + (long long)stride * r + c);
 }
 
+// d = (c[15:0] << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // One thread = 4 luma columns (two chroma columns) of one "job":
 //   4:2:0  job 0           : luma row 0      with chroma row 0              (single-row average)
 //          job k, 1..ch-1  : luma rows 2k-1, 2k with chroma rows k-1, k     (2/3 - 1/3 vertical weights)
 //          job ch (h even) : luma row h-1    with chroma row ch-1           (single-row average)
 //   4:2:2  job i           : luma row i      with chroma row i
+// The chroma tables in shared memory are the extended ones (DevConv::ext): indexed by the un-divided chroma sum, they
+// already contain the (int)(n / 3. + .5) rounding and the CLAMP16_240 / CLAMP0_255 of colourspace.c:3465-3469.
+// Interior threads fetch the 4 chroma samples they need (columns jc0-1 .. jc0+2) with two aligned 32-bit loads and a funnel
+// shift; threads at the left / right frame edge take the byte path with the reference's edge rules (chroma_at).
 __global__ void __launch_bounds__(kBlock) k_yuv_planar_to_rgb(const YuvToRgbArgs A) {
-  __shared__ SmemYuvTabs s;
-  load_yuv_tabs(s, A.conv.t);
+  __shared__ int32_t s_t[256 + 4 * kExtN];
+  for (int i = threadIdx.x; i < 256 + 4 * kExtN; i += kBlock) s_t[i] = A.conv.ext[i];
   __syncthreads();
   const Planes &S = A.src;
   const int w = A.width, h = A.height, cw = S.cw, ch = S.ch;
-  const int lo = A.clamped ? 16 : 0, hi = A.clamped ? 240 : 255;
   const int groups = (w + 3) >> 2;
   const int njobs = A.is_422 ? h : (h >= 2 && !(h & 1) ? ch + 1 : ch);
   const bool vec = ((uintptr_t)A.dst.p % 16 == 0) && (A.dst.rs % 16 == 0);
   const bool yvec = ((uintptr_t)S.y % 4 == 0) && (S.rs_y % 4 == 0);
+  const bool cvec = ((((uintptr_t)S.u | (uintptr_t)S.v) & 3) == 0) && (((S.rs_u | S.rs_v) & 3) == 0);
+  // canonical pixel word = [r, g, b, 255]; sel moves its bytes to the palette's order
+  uint32_t sel = 0;
+  {
+    uint32_t nib[4] = {3, 3, 3, 3};
+    nib[A.out.r] = 0; nib[A.out.g] = 1; nib[A.out.b] = 2;
+    if (A.out.a >= 0) nib[A.out.a] = 3;
+    sel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+  }
+  const uint16_t *lut16 = A.lut16;
+  auto emit = [&](int y, int nu, int nv) -> uint32_t {
+    const int yy = s_t[y];
+    const int rr = yy + s_t[256 + nv], gg = yy + s_t[256 + kExtN + nu] + s_t[256 + 2 * kExtN + nv], bb = yy + s_t[256 + 3 * kExtN + nu];
+    uint32_t px;
+    if (!lut16) {
+      px = pack_sat(gg >> 16, rr >> 16, pack_sat(255, bb >> 16, 0u));
+    } else {  // xyuv2rgb_with_gamma colourspace.c:2386
+      const uint32_t r = __ldg(lut16 + min(max(rr >> 8, 0), 65535)) >> 8, g = __ldg(lut16 + min(max(gg >> 8, 0), 65535)) >> 8,
+                     b = __ldg(lut16 + min(max(bb >> 8, 0), 65535)) >> 8;
+      px = r | (g << 8) | (b << 16) | 0xFF000000u;
+    }
+    return __byte_perm(px, 0u, sel);
+  };
+  // chroma samples of columns jc0-1 .. jc0+2 of row r as one word
+  auto cword = [&](const uint8_t *__restrict__ p, int stride, int r, int jc0, bool interior) -> uint32_t {
+    if (interior) {
+      const uint8_t *q = p + (size_t)stride * r + ((jc0 - 1) & ~3);
+      return __funnelshift_r(__ldg(reinterpret_cast<const uint32_t *>(q)), __ldg(reinterpret_cast<const uint32_t *>(q + 4)),
+                             8 * ((jc0 - 1) & 3));
+    }
+    uint32_t wv = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) wv |= (uint32_t)chroma_at(p, stride, r, max(jc0 - 1 + k, 0), cw, ch) << (8 * k);
+    return wv;
+  };
   const long long total = (long long)groups * njobs;
   for (long long it = global_tid(); it < total; it += global_threads()) {
     const int job = (int)(it / groups), g = (int)(it - (long long)job * groups);
@@ -112,15 +157,17 @@ __global__ void __launch_bounds__(kBlock) k_yuv_planar_to_rgb(const YuvToRgbArgs
     else if (job == 0) { row_a = 0; cr_a = 0; }
     else if (job < ch) { pair = true; row_a = 2 * job - 1; row_b = 2 * job; cr_a = job - 1; cr_b = job; }
     else { row_a = h - 1; cr_a = ch - 1; }
+    // columns jc0-1 .. jc0+2 all inside the plane, and the two aligned words inside the row
+    const bool interior = cvec && jc0 >= 1 && jc0 + 2 < cw && (((jc0 - 1) & ~3) + 8 <= min(S.rs_u, S.rs_v));
 
     // luma
     uint32_t ya, yb = 0;
     {
-      const uint8_t *py = S.y + (long long)S.rs_y * row_a + x0;
+      const uint8_t *py = S.y + (size_t)S.rs_y * row_a + x0;
       if (yvec && npx == 4) ya = ld_stream_u32(py);
       else { ya = 0; for (int k = 0; k < npx; k++) ya |= (uint32_t)py[k] << (8 * k); }
       if (pair) {
-        py = S.y + (long long)S.rs_y * row_b + x0;
+        py = S.y + (size_t)S.rs_y * row_b + x0;
         if (yvec && npx == 4) yb = ld_stream_u32(py);
         else for (int k = 0; k < npx; k++) yb |= (uint32_t)py[k] << (8 * k);
       }
@@ -131,79 +178,61 @@ __global__ void __launch_bounds__(kBlock) k_yuv_planar_to_rgb(const YuvToRgbArgs
       // horizontal average only (:3394-3438 row 0, :3551-3596 last row -- X rows: intended arithmetic -- and the
       // whole 4:2:2 branch :3598-3642).  4:2:2 quirk: the running pair is seeded from chroma row (i >> 1) (:3600)
       const int seed_row = (A.is_422 && A.quirks) ? (row_a >> 1) : cr_a;
-      int uc[4], vc[4];  // chroma columns jc0-1 .. jc0+2
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int c = jc0 - 1 + k;
-        if (c <= 0) {  // column 0 is replaced by the seed sample (last = this = seed at the start of a row)
-          uc[k] = __ldg(S.u + (long long)S.rs_u * seed_row);
-          vc[k] = __ldg(S.v + (long long)S.rs_v * seed_row);
-        } else {
-          uc[k] = chroma_at(S.u, S.rs_u, cr_a, c, cw, ch);
-          vc[k] = chroma_at(S.v, S.rs_v, cr_a, c, cw, ch);
-        }
+      uint32_t uw = cword(S.u, S.rs_u, cr_a, jc0, interior), vw = cword(S.v, S.rs_v, cr_a, jc0, interior);
+      if (jc0 == 0) {  // columns <= 0 are the seed sample (last = this = seed at the start of a row)
+        const uint32_t su = __ldg(S.u + (size_t)S.rs_u * seed_row), sv = __ldg(S.v + (size_t)S.rs_v * seed_row);
+        uw = (uw & 0xFFFF0000u) | su | (su << 8);
+        vw = (vw & 0xFFFF0000u) | sv | (sv << 8);
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        // pixel x0+k: pair index p = k>>1 (chroma column jc0+p = uc[p+1]); left pixel averages with the previous
+        // pixel x0+k: pair index p = k>>1 (chroma column jc0+p = byte p+1); left pixel averages with the previous
         // column, right pixel with the next one
         const int p = k >> 1;
-        const int ua = uc[p + 1], va = vc[p + 1];
-        const int ub = (k & 1) ? uc[p + 2] : uc[p], vb = (k & 1) ? vc[p + 2] : vc[p];
-        const int u = clamp_i((ua + ub) >> 1, lo, hi), v = clamp_i((va + vb) >> 1, lo, hi);
-        int r, gg, b;
-        yuv_px(s, A.lut16, byte_of(ya, k), u, v, r, gg, b);
-        out_a[k] = pack_px(A.out, r, gg, b);
+        const int ua = byte_of(uw, p + 1), va = byte_of(vw, p + 1);
+        const int ub = (k & 1) ? byte_of(uw, p + 2) : byte_of(uw, p), vb = (k & 1) ? byte_of(vw, p + 2) : byte_of(vw, p);
+        out_a[k] = emit(byte_of(ya, k), 3 * ((ua + ub) >> 1), 3 * ((va + vb) >> 1));
       }
     } else {
       // interior row pair (:3440-3549)
-      int u1c[4], u2c[4], v1c[4], v2c[4];
+      const uint32_t u1w = cword(S.u, S.rs_u, cr_a, jc0, interior), u2w = cword(S.u, S.rs_u, cr_b, jc0, interior);
+      const uint32_t v1w = cword(S.v, S.rs_v, cr_a, jc0, interior), v2w = cword(S.v, S.rs_v, cr_b, jc0, interior);
+      const int v2_first = A.quirks ? __ldg(S.v + (size_t)S.rs_v * cr_b) : 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int c = max(jc0 - 1 + k, 0);  // column -1 replicates column 0 (last = this at the start of a row)
-        u1c[k] = chroma_at(S.u, S.rs_u, cr_a, c, cw, ch);
-        u2c[k] = chroma_at(S.u, S.rs_u, cr_b, c, cw, ch);
-        v1c[k] = chroma_at(S.v, S.rs_v, cr_a, c, cw, ch);
-        v2c[k] = chroma_at(S.v, S.rs_v, cr_b, c, cw, ch);
-      }
-      const int v2_first = A.quirks ? __ldg(S.v + (long long)S.rs_v * cr_b) : 0;
+      for (int p = 0; p < 2; p++) {
+        const int U1[3] = {(int)byte_of(u1w, p), (int)byte_of(u1w, p + 1), (int)byte_of(u1w, p + 2)};
+        const int U2[3] = {(int)byte_of(u2w, p), (int)byte_of(u2w, p + 1), (int)byte_of(u2w, p + 2)};
+        const int V1[3] = {(int)byte_of(v1w, p), (int)byte_of(v1w, p + 1), (int)byte_of(v1w, p + 2)};
+        const int V2[3] = {(int)byte_of(v2w, p), (int)byte_of(v2w, p + 1), (int)byte_of(v2w, p + 2)};
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int p = k >> 1, jc = jc0 + p;
-        int u1, u2, v1, v2;
-        if (k & 1) {  // right pixel: this + next
-          u1 = u1c[p + 1] + u1c[p + 2]; u2 = u2c[p + 1] + u2c[p + 2];
-          v1 = v1c[p + 1] + v1c[p + 2]; v2 = v2c[p + 1] + v2c[p + 2];
-        } else {      // left pixel: this + last
-          u1 = u1c[p + 1] + u1c[p];
-          v2 = v2c[p + 1] + v2c[p];
-          u2 = u2c[p + 1] + u2c[p];
-          v1 = v1c[p + 1] + v1c[p];
-          if (A.quirks) {
-            u2 = u1;                                        // `u2 = this_u1 + last_u1`          (:3461)
-            if (jc > 0) v1 = v1c[p + 1] + v2c[p];           // `last_v1 = this_v2`               (:3544)
-            v2 = v2c[p + 1] + v2_first;                     // last_v2 is never advanced         (:3543-3546)
+        for (int lr = 0; lr < 2; lr++) {
+          const int k = 2 * p + lr;
+          int u1, u2, v1, v2;
+          if (lr) {      // right pixel: this + next
+            u1 = U1[1] + U1[2]; u2 = U2[1] + U2[2]; v1 = V1[1] + V1[2]; v2 = V2[1] + V2[2];
+          } else {       // left pixel: this + last
+            u1 = U1[1] + U1[0]; u2 = U2[1] + U2[0]; v1 = V1[1] + V1[0]; v2 = V2[1] + V2[0];
+            if (A.quirks) {
+              u2 = u1;                                        // `u2 = this_u1 + last_u1`          (:3461)
+              if (jc0 + p > 0) v1 = V1[1] + V2[0];            // `last_v1 = this_v2`               (:3544)
+              v2 = V2[1] + v2_first;                          // last_v2 is never advanced         (:3543-3546)
+            }
           }
+          int n3u, n4u, n3v, n4v;
+          if (!A.low_quality) {
+            n3u = u1 + (u2 >> 1); n4u = (u1 >> 1) + u2; n3v = v1 + (v2 >> 1); n4v = (v1 >> 1) + v2;
+          } else {       // PB_QUALITY_LOW: u3 = u1 >> 1, u4 = u2 >> 1 (:3470-3474)
+            n3u = 3 * (u1 >> 1); n4u = 3 * (u2 >> 1); n3v = 3 * (v1 >> 1); n4v = 3 * (v2 >> 1);
+          }
+          out_a[k] = emit(byte_of(ya, k), n3u, n3v);
+          out_b[k] = emit(byte_of(yb, k), n4u, n4v);
         }
-        int u3, u4, v3, v4;
-        if (!A.low_quality) {
-          u3 = clamp_i(third_round(u1 + (u2 >> 1)), lo, hi); u4 = clamp_i(third_round((u1 >> 1) + u2), lo, hi);
-          v3 = clamp_i(third_round(v1 + (v2 >> 1)), lo, hi); v4 = clamp_i(third_round((v1 >> 1) + v2), lo, hi);
-        } else {
-          u3 = clamp_i(u1 >> 1, lo, hi); u4 = clamp_i(u2 >> 1, lo, hi);
-          v3 = clamp_i(v1 >> 1, lo, hi); v4 = clamp_i(v2 >> 1, lo, hi);
-        }
-        int r, gg, b;
-        yuv_px(s, A.lut16, byte_of(ya, k), u3, v3, r, gg, b);
-        out_a[k] = pack_px(A.out, r, gg, b);
-        yuv_px(s, A.lut16, byte_of(yb, k), u4, v4, r, gg, b);
-        out_b[k] = pack_px(A.out, r, gg, b);
       }
     }
-    uint8_t *da = A.dst.p + (long long)A.dst.rs * row_a + (long long)x0 * A.out.psize;
+    uint8_t *da = A.dst.p + (size_t)A.dst.rs * row_a + (size_t)x0 * A.out.psize;
     if (npx == 4) store_px4(da, A.out.psize, out_a, vec); else store_px_n(da, A.out.psize, out_a, npx);
     if (pair) {
-      uint8_t *db = A.dst.p + (long long)A.dst.rs * row_b + (long long)x0 * A.out.psize;
+      uint8_t *db = A.dst.p + (size_t)A.dst.rs * row_b + (size_t)x0 * A.out.psize;
       if (npx == 4) store_px4(db, A.out.psize, out_b, vec); else store_px_n(db, A.out.psize, out_b, npx);
     }
   }

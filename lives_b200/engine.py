@@ -450,3 +450,16 @@ def host_multi_blend(engine, filter_type, in1, in2, out, blend_factor):
 def host_fused_convert_letterbox_over_gamma(engine, fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):
     capi.check(engine._lib.pe_host_fused_convert_letterbox_over_gamma(engine._h, C.byref(fg.d), C.byref(bg.d), C.byref(out.d),
                                                                       inner_w, inner_h, alpha, gamma_from, gamma_to))
+
+
+def host_fused_convert_letterbox_over_gamma_batch(engine, fgs, bgs, outs, inner_w, inner_h, alpha, gamma_from, gamma_to):
+    """n independent host frames; H2D, kernel and D2H of consecutive frames overlap (three streams)"""
+    n = len(fgs)
+
+    def arr(ls):
+        a = (capi.PDESC * n)()
+        for i, l in enumerate(ls):
+            a[i] = C.pointer(l.d)
+        return a
+    capi.check(engine._lib.pe_host_fused_convert_letterbox_over_gamma_batch(engine._h, n, arr(fgs), arr(bgs), arr(outs), inner_w,
+                                                                            inner_h, alpha, gamma_from, gamma_to))

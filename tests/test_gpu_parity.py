@@ -668,3 +668,26 @@ def test_host_dropins(eng):
     box = np.zeros((64, T.rowstride(128, 3)), np.uint8)
     o.pe_or_letterbox_packed(T.ptr(inner), inner.strides[0], 128, 52, T.ptr(box), box.strides[0], 128, 64, 1)
     assert (payload(hl.planes[0], 128, 3) == payload(box, 128, 3)).all()
+
+
+def test_host_fused_batch_pipeline(eng):
+    """pe_host_fused_convert_letterbox_over_gamma_batch: 7 host frames through the 3-slot H2D / kernel / D2H pipeline ==
+    the same frames one by one"""
+    rng = np.random.default_rng(21)
+    fw, fh, ow, oh, ih = 128, 96, 128, 96, 72
+    fgs, bgs, outs, exps = [], [], [], []
+    for i in range(7):
+        y, u, v = T.make_yuv_planar(rng, fw, fh, False, True)
+        bg = T.make_packed(rng, ow, oh, 4)
+        f = lb.HostLayer(512, fw, fh, [y, u, v], yuv_subspace=1)
+        b = lb.HostLayer(3, ow, oh, [bg], gamma_type=T.G_LINEAR)
+        one = lb.HostLayer(3, ow, oh, [np.zeros_like(bg)])
+        lb.host_fused_convert_letterbox_over_gamma(eng, f, b, one, fw, ih, 0.5, T.G_LINEAR, T.G_SRGB)
+        exps.append(one.planes[0].copy())
+        fgs.append(f)
+        bgs.append(b)
+        outs.append(lb.HostLayer(3, ow, oh, [np.zeros_like(bg)]))
+    lb.host_fused_convert_letterbox_over_gamma_batch(eng, fgs, bgs, outs, fw, ih, 0.5, T.G_LINEAR, T.G_SRGB)
+    for i in range(7):
+        assert (outs[i].planes[0] == exps[i]).all(), i
+        assert outs[i].d.gamma_type == T.G_SRGB
