@@ -18,17 +18,19 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
+// (the streaming stores carry no "memory" clobber: they only ever write output pixels that the same kernel never reads,
+// and a clobber would force every loop to reload its constants and shared-memory values after each store)
 // plain (coherent) variants for in-place kernels, where .nc would be illegal
 __device__ __forceinline__ uint4 ld_u4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
 __device__ __forceinline__ void st_stream_u4(void *p, const uint4 &v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
-               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 __device__ __forceinline__ void st_stream_u2(void *p, const uint2 &v) {
-  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y));
 }
 __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
-  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v));
 }
 
 // ---- byte helpers --------------------------------------------------------------------------------

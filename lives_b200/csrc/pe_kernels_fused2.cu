@@ -126,13 +126,13 @@ struct TileGeo {
 };
 
 template <bool ASYNC>
-__device__ __forceinline__ TileGeo tile_geo(const Fused2Params &P, long long tile) {
+__device__ __forceinline__ TileGeo tile_geo(const Fused2Params &P, uint32_t tile) {
   TileGeo G;
-  const int tiles_per_frame = P.tiles_x * P.tiles_y;
-  G.f = (int)(tile / tiles_per_frame);
-  const int t = (int)(tile - (long long)G.f * tiles_per_frame);
+  const uint32_t tiles_per_frame = (uint32_t)(P.tiles_x * P.tiles_y);
+  const uint32_t fi = tile / tiles_per_frame, t = tile - fi * tiles_per_frame;  // 32-bit: a launch has far fewer than 2^31 tiles
+  G.f = (int)fi;
   const FusedArgs &A = P.fr[G.f];
-  const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+  const int ty = (int)(t / (uint32_t)P.tiles_x), tx = (int)t - ty * P.tiles_x;
   G.x0 = tx * F2_TW; G.y0 = ty * P.tile_h;
   G.x1 = min(G.x0 + F2_TW, A.ow); G.y1 = min(G.y0 + P.tile_h, A.oh);
   // intersection with the inner rectangle, in inner (= source column) coordinates
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
   const bool has_lut = P.lut8 != nullptr;
   if (has_lut) for (int i = tid; i < 256; i += F2_NT) s_lut[i] = P.lut8[i];
 
-  const long long total_tiles = (long long)P.tiles_x * P.tiles_y * P.nframes;
-  long long tile = blockIdx.x;
+  const uint32_t total_tiles = (uint32_t)(P.tiles_x * P.tiles_y * P.nframes);
+  uint32_t tile = blockIdx.x;
   if (tile >= total_tiles) return;
   TileGeo G = tile_geo<ASYNC>(P, tile);
   int buf = 0;
@@ -535,14 +535,19 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
         }
         st_stream_u32(outp, o0 | (o1 << 8) | (o2 << 16) | 0xFF000000u);
       };
-      // row pointers advance by 32-bit strides (frames are far below 4 GB): no 64-bit multiplies per row
+      // row pointers advance by 32-bit strides (frames are far below 4 GB): no 64-bit multiplies per row.
+      // Everything the task loop needs from the frame descriptor is pulled into registers once per tile.
       const uint32_t bg_rs32 = (uint32_t)A.bg.rs, out_rs32 = (uint32_t)A.out.rs;
+      const uint8_t *const bg_base = A.bg.p;
+      uint8_t *const out_base = A.out.p;
+      const int a_ow = A.ow, a_ox = A.ox, a_oy = A.oy;
+      const int g_ix0 = G.ix0, g_ix1 = G.has_inner ? G.ix1 : G.ix0;  // empty column range without inner rows
       auto load_bg = [&](int task, uint32_t w[4]) {
         const int qd = task >> 2, cwp = task & 3;
         const int x = x0 + cwp * 32 + lane;
         const int oy0 = y0 + qd * 4;
-        const int nrow = (task < ntasks && x < A.ow) ? y1 - oy0 : 0;
-        const uint8_t *p0 = A.bg.p + (bg_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
+        const int nrow = (task < ntasks && x < a_ow) ? y1 - oy0 : 0;
+        const uint8_t *p0 = bg_base + (bg_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
         const uint8_t *p1 = p0 + bg_rs32, *p2 = p1 + bg_rs32, *p3 = p2 + bg_rs32;
         w[0] = nrow > 0 ? ld_stream_u32(p0) : 0u;
         w[1] = nrow > 1 ? ld_stream_u32(p1) : 0u;
@@ -555,14 +560,14 @@ __global__ void __launch_bounds__(F2_NT, MODE == 0 ? 2 : 1) k_fused2(const __gri
         load_bg(task + F2_NW, bgn);
         const int qd = task >> 2, cwp = task & 3;
         const int x = x0 + cwp * 32 + lane;
-        if (x < A.ow) {
-          const int ix = x - A.ox;
-          const bool col_in = G.has_inner && ix >= G.ix0 && ix < G.ix1;
+        if (x < a_ow) {
+          const int ix = x - a_ox;
+          const bool col_in = ix >= g_ix0 && ix < g_ix1;
           const uint32_t *colp = s_c + (col_in ? ix - 4 * cq0 : 0) * F2_CW;
           const int oy0 = y0 + qd * 4;
           const int nrow = min(4, y1 - oy0);
-          uint8_t *outp = A.out.p + (out_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
-          const int iyl0 = oy0 - A.oy - iy0;  // first row of the quad inside the tile's inner rows
+          uint8_t *outp = out_base + (out_rs32 * (uint32_t)oy0 + 4u * (uint32_t)x);
+          const int iyl0 = oy0 - a_oy - iy0;  // first row of the quad inside the tile's inner rows
           if (nrow == 4 && col_in && iyl0 >= 0 && iyl0 + 3 < niy) {
             // ===== fast path: four inner rows
 #pragma unroll
