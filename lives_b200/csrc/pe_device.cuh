@@ -35,7 +35,8 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
 
 // ---- byte helpers --------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+// byte k of a word, zero extended: one PRMT (selector 0x444k: bytes 1..3 come from the zero operand)
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)k); }
 __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
   return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
 }

@@ -920,6 +920,27 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     ce = launch_rgb_to_yuv888(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
                               Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height, rgb_layout(inpl),
                               outpl == PE_PALETTE_YUVA8888, dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
+  } else if (pal_is_rgb(inpl) && (outpl == PE_PALETTE_UYVY || outpl == PE_PALETTE_YUYV)) {
+    // convert_{rgb,bgr,argb}_to_{uyvy,yuyv}_frame (:12562-12580 etc.): YCbCr tables, clamping = oclamping, the 16-bit gamma
+    // LUT inside the converter when the gamma changes; the layer gets width >> 1 macropixels (an odd last column is cut)
+    n.d.width = (width >> 1) << 1;
+    if (n.d.width < 2) { set_err(PE_ERR_SIZE, "frame too narrow for a 4:2:2 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint16_t *lut16 = gamma_type == new_gamma_type ? nullptr : get_lut16(e, 1.0, gamma_type, new_gamma_type);
+    ce = launch_rgb_to_packed422(L, outpl == PE_PALETTE_UYVY ? 0 : 1, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
+                                 Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height, rgb_layout(inpl),
+                                 dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR), lut16);
+  } else if (pal_is_rgb(inpl) && (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P)) {
+    // convert_{rgb,bgr,argb}_to_yuvp_frame (:12613-12626 etc.)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    if (width & 1) {  // the converter drops an odd last column: leave it defined (black)
+      n.d.yuv_clamping = oclamping;
+      if (frame_fill_black(e, &n) != PE_OK) { frame_release_pixels(&n); return PE_FALSE; }
+    }
+    uint8_t *pl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2],
+                      outpl == PE_PALETTE_YUVA4444P ? (uint8_t *)n.d.planes[3] : nullptr};
+    ce = launch_rgb_to_yuv444p(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides[0], width, height,
+                               rgb_layout(inpl), dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
   } else {
     set_err(PE_ERR_PALETTE, "palette conversion %d -> %d is not handled by this build", inpl, outpl);
     return PE_FALSE;  // memfail: the layer is left as it was

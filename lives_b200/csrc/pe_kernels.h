@@ -75,6 +75,12 @@ cudaError_t launch_yuv888_to_rgb(const Launch &L, CImg src, Img dst, int width, 
                                  RgbLayout out, DevConv conv);
 cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in,
                                  int out_alpha, DevConv conv);
+// RGB(A) -> UYVY (fmt 0) / YUYV (fmt 1), colourspace.c:5129-5700; width in pixels (odd last column dropped); lut16 optional
+cudaError_t launch_rgb_to_packed422(const Launch &L, int fmt, CImg src, Img dst, int width_px, int height, RgbLayout in, DevConv conv,
+                                    const uint16_t *lut16_dev);
+// RGB(A) -> YUV444P / YUVA4444P (planes[3] = alpha plane or nullptr), colourspace.c:5786-6240
+cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const planes[4], int orow, int width, int height, RgbLayout in,
+                                  DevConv conv);
 // ---- effects ---------------------------------------------------------------------------------------
 struct BlendFrame {
   const uint8_t *s1, *s2;

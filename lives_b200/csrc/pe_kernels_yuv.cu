@@ -11,6 +11,8 @@
 //   CLAMP0255f are byte-identical to this integer form for all 2^24 inputs (tests/test_oracle_vs_reference.py),
 //   chroma weights (int)(n / 3. + .5) == (2n + 3) / 6.
 // The five 256-entry int tables live in shared memory.
+#include <algorithm>
+
 #include "pe_device.cuh"
 #include "pe_kernels.h"
 
@@ -306,6 +308,77 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_yuv888(const uint8_t *__restr
   }
 }
 
+// RGB(A) -> UYVY / YUYV (convert_{rgb,bgr,argb}_to_{uyvy,yuyv}_frame colourspace.c:5129-5700): one thread = one macropixel.
+// Cb from the first pixel, Cr from the second, YCbCr tables; YUYV keeps the reference's missing `else` (no max clamp on U, V,
+// :2183-2190); optional 16-bit gamma LUT on the 16.8 sums (rgb2uyvy_with_gamma :2146).
+__global__ void __launch_bounds__(kBlock) k_rgb_to_packed422(int fmt, const uint8_t *__restrict__ src, int irow, uint8_t *dst, int orow,
+                                                             int width_mpx, int height, RgbLayout in, DevConv conv,
+                                                             const uint16_t *__restrict__ lut16) {
+  __shared__ int32_t t[9][256];
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[i];
+  __syncthreads();
+  const long long total = (long long)width_mpx * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width_mpx), m = (int)(it - (long long)row * width_mpx);
+    const uint8_t *q = src + (size_t)irow * row + (size_t)m * 2 * in.psize;
+    const int r0 = q[in.r], g0 = q[in.g], b0 = q[in.b], r1 = q[in.psize + in.r], g1 = q[in.psize + in.g], b1 = q[in.psize + in.b];
+    int au = t[3][r0] + t[4][g0] + t[5][b0], ay0 = t[0][r0] + t[1][g0] + t[2][b0];
+    int av = t[6][r1] + t[7][g1] + t[8][b1], ay1 = t[0][r1] + t[1][g1] + t[2][b1];
+    if (lut16) {
+      au = __ldg(lut16 + (au >> 8)) >> 8; ay0 = __ldg(lut16 + (ay0 >> 8)) >> 8;
+      av = __ldg(lut16 + (av >> 8)) >> 8; ay1 = __ldg(lut16 + (ay1 >> 8)) >> 8;
+    } else {
+      au >>= 16; ay0 >>= 16; av >>= 16; ay1 >>= 16;
+    }
+    const uint32_t y0 = (uint32_t)clamp_i(ay0, conv.min_y, conv.max_y), y1 = (uint32_t)clamp_i(ay1, conv.min_y, conv.max_y);
+    uint32_t w;
+    if (fmt == 0) {
+      const uint32_t u = (uint32_t)clamp_i(au, conv.min_uv, conv.max_uv), v = (uint32_t)clamp_i(av, conv.min_uv, conv.max_uv);
+      w = u | (y0 << 8) | (v << 16) | (y1 << 24);
+    } else {
+      const uint32_t u = au < conv.min_uv ? (uint32_t)conv.min_uv : ((uint32_t)au & 0xFFu);
+      const uint32_t v = av < conv.min_uv ? (uint32_t)conv.min_uv : ((uint32_t)av & 0xFFu);
+      w = y0 | (u << 8) | (y1 << 16) | (v << 24);
+    }
+    *reinterpret_cast<uint32_t *>(dst + (size_t)orow * row + 4 * (size_t)m) = w;
+  }
+}
+
+// RGB(A) -> planar 4:4:4 (+ alpha plane) (convert_{rgb,bgr,argb}_to_yuvp_frame colourspace.c:5786-6240): one thread = 4 pixels,
+// one 32-bit store per plane.
+__global__ void __launch_bounds__(kBlock) k_rgb_to_yuv444p(const uint8_t *__restrict__ src, int irow, uint8_t *py, uint8_t *pu, uint8_t *pv,
+                                                           uint8_t *pa, int orow, int width, int height, RgbLayout in, DevConv conv) {
+  __shared__ int32_t t[9][256];
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[i];
+  __syncthreads();
+  const int groups = (width + 3) >> 2;
+  const bool vec = (((uintptr_t)py | (uintptr_t)pu | (uintptr_t)pv | (uintptr_t)pa) & 3) == 0 && (orow & 3) == 0;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int npx = min(4, width - 4 * g);
+    const uint8_t *q = src + (size_t)irow * row + (size_t)g * 4 * in.psize;
+    uint32_t wy = 0, wu = 0, wv = 0, wa = 0;
+    for (int k = 0; k < npx; k++, q += in.psize) {
+      const int r = q[in.r], gg = q[in.g], b = q[in.b];
+      wy |= (uint32_t)clamp_i((t[0][r] + t[1][gg] + t[2][b]) >> 16, conv.min_y, conv.max_y) << (8 * k);
+      wu |= (uint32_t)clamp_i((t[3][r] + t[4][gg] + t[5][b]) >> 16, conv.min_uv, conv.max_uv) << (8 * k);
+      wv |= (uint32_t)clamp_i((t[6][r] + t[7][gg] + t[8][b]) >> 16, conv.min_uv, conv.max_uv) << (8 * k);
+      wa |= (in.a >= 0 ? (uint32_t)q[in.a] : 255u) << (8 * k);
+    }
+    const size_t o = (size_t)orow * row + 4 * (size_t)g;
+    if (vec && npx == 4) {
+      *reinterpret_cast<uint32_t *>(py + o) = wy; *reinterpret_cast<uint32_t *>(pu + o) = wu; *reinterpret_cast<uint32_t *>(pv + o) = wv;
+      if (pa) *reinterpret_cast<uint32_t *>(pa + o) = wa;
+    } else {
+      for (int k = 0; k < npx; k++) {
+        py[o + k] = (uint8_t)(wy >> (8 * k)); pu[o + k] = (uint8_t)(wu >> (8 * k)); pv[o + k] = (uint8_t)(wv >> (8 * k));
+        if (pa) pa[o + k] = (uint8_t)(wa >> (8 * k));
+      }
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a) {
@@ -341,4 +414,27 @@ cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, 
   return cudaGetLastError();
 }
 
+}  // namespace pe
+
+namespace pe {
+cudaError_t launch_rgb_to_packed422(const Launch &L, int fmt, CImg src, Img dst, int width_px, int height, RgbLayout in, DevConv conv,
+                                    const uint16_t *lut16_dev) {
+  const int mpx = width_px >> 1;
+  if (mpx <= 0 || height <= 0) return cudaSuccess;
+  k_rgb_to_packed422<<<(int)std::min<long long>(((long long)mpx * height + 255) / 256, (long long)L.sm_count * 8), 256, 0, L.stream>>>(
+      fmt, src.p, src.rs, dst.p, dst.rs, mpx, height, in, conv, lut16_dev);
+  if (L.launch_counter) ++*L.launch_counter;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const planes[4], int orow, int width, int height, RgbLayout in,
+                                  DevConv conv) {
+  width = (width >> 1) << 1;  // the reference drops an odd last column (colourspace.c:5866)
+  if (width <= 0 || height <= 0) return cudaSuccess;
+  const long long work = (long long)((width + 3) >> 2) * height;
+  k_rgb_to_yuv444p<<<(int)std::min<long long>((work + 255) / 256, (long long)L.sm_count * 8), 256, 0, L.stream>>>(
+      src.p, src.rs, planes[0], planes[1], planes[2], planes[3], orow, width, height, in, conv);
+  if (L.launch_counter) ++*L.launch_counter;
+  return cudaGetLastError();
+}
 }  // namespace pe

@@ -448,6 +448,69 @@ void pe_or_rgb_to_yuv888(const uint8_t *src, int irow, int width, int height, ui
   }
 }
 
+/* ---- RGB -> packed 4:2:2  src/colourspace.c:5129-5700 (rgb2uyvy :2162, rgb2yuyv :2176) ---------------------
+ * One macropixel from two pixels: Cb from the FIRST pixel, Cr from the SECOND (no chroma averaging), always the YCbCr tables
+ * (:5146).  YUYV: the max clamp of U and V is overwritten by the following statement (missing `else`, :2183-2184,2189-2190),
+ * so values above max_UV pass through -- replicated.  Rows are written with the output rowstride (the reference's own row
+ * advance `orowstride / 2 - hsize` in macropixel units only works for unpadded rows, :5206). */
+void pe_or_rgb_to_packed422(int fmt, const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order,
+                            int in_alpha, int clamping, int quality, const uint16_t *lut16) {
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ips;
+  or_order_offsets(order, in_alpha, &ro, &go, &bo, &ao, &ips);
+  width = (width >> 1) << 1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < width; j += 2, s += 2 * ips, d += 4) {
+      const uint8_t r0 = s[ro], g0 = s[go], b0 = s[bo], r1 = s[ips + ro], g1 = s[ips + go], b1 = s[ips + bo];
+      short au, ay0, av, ay1;
+      if (lut16) { /* rgb2uyvy_with_gamma :2146 */
+        au = lut16[(c->t[3][r0] + c->t[4][g0] + c->t[5][b0]) >> 8] >> 8;
+        ay0 = lut16[(c->t[0][r0] + c->t[1][g0] + c->t[2][b0]) >> 8] >> 8;
+        av = lut16[(c->t[6][r1] + c->t[7][g1] + c->t[8][b1]) >> 8] >> 8;
+        ay1 = lut16[(c->t[0][r1] + c->t[1][g1] + c->t[2][b1]) >> 8] >> 8;
+      } else {
+        au = or_spc_rnd(c->t[3][r0] + c->t[4][g0] + c->t[5][b0], quality);
+        ay0 = or_spc_rnd(c->t[0][r0] + c->t[1][g0] + c->t[2][b0], quality);
+        av = or_spc_rnd(c->t[6][r1] + c->t[7][g1] + c->t[8][b1], quality);
+        ay1 = or_spc_rnd(c->t[0][r1] + c->t[1][g1] + c->t[2][b1], quality);
+      }
+      {
+        const uint8_t y0 = ay0 > c->max_y ? c->max_y : ay0 < c->min_y ? c->min_y : ay0;
+        const uint8_t y1 = ay1 > c->max_y ? c->max_y : ay1 < c->min_y ? c->min_y : ay1;
+        uint8_t u, v;
+        if (fmt == 0) {
+          u = au > c->max_uv ? c->max_uv : au < c->min_uv ? c->min_uv : au;
+          v = av > c->max_uv ? c->max_uv : av < c->min_uv ? c->min_uv : av;
+          d[0] = u; d[1] = y0; d[2] = v; d[3] = y1;
+        } else {
+          u = au < c->min_uv ? c->min_uv : (uint8_t)au; /* missing else: no max clamp */
+          v = av < c->min_uv ? c->min_uv : (uint8_t)av;
+          d[0] = y0; d[1] = u; d[2] = y1; d[3] = v;
+        }
+      }
+    }
+  }
+}
+
+/* ---- RGB -> planar 4:4:4  src/colourspace.c:5786-5880 (rgb), :5971 (bgr), :6154 (argb) ----------------------- */
+void pe_or_rgb_to_yuv444p(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[4], int orow, int order,
+                          int in_alpha, int out_alpha, int clamping, int quality) {
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ips;
+  or_order_offsets(order, in_alpha, &ro, &go, &bo, &ao, &ips);
+  width = (width >> 1) << 1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    for (int j = 0; j < width; j++, s += ips) {
+      const long o = (long)orow * i + j;
+      if (out_alpha) dest[3][o] = ao >= 0 ? s[ao] : 255;
+      or_px_rgb2yuv(c, quality, s[ro], s[go], s[bo], &dest[0][o], &dest[1][o], &dest[2][o]);
+    }
+  }
+}
+
 /* ---- RGB <-> RGB  src/colourspace.c:12370-12556 dispatch, loops :9259-10515 -- */
 
 static int or_rgb_layout(int pal, int *ro, int *go, int *bo, int *ao, int *ps) {

@@ -59,6 +59,13 @@ void pe_or_yuv888_to_rgb(const uint8_t *src, int irow, int width, int height, ui
 void pe_or_rgb_to_yuv888(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow,
                          int order, int in_alpha, int out_alpha, int clamping, int quality);
 
+/* fmt 0 UYVY, 1 YUYV; width in PIXELS (rounded down to even); lut16 may be NULL (colourspace.c:5129-5700) */
+void pe_or_rgb_to_packed422(int fmt, const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order,
+                            int in_alpha, int clamping, int quality, const uint16_t *lut16);
+/* planar 4:4:4 (+ alpha plane), colourspace.c:5786,5971,6154 */
+void pe_or_rgb_to_yuv444p(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[4], int orow, int order,
+                          int in_alpha, int out_alpha, int clamping, int quality);
+
 /* RGB<->RGB: any of the 5 RGB palettes to any other, optional lut8 on colour bytes
  * (colourspace.c:12370-12556 + :9259-10515, intended whole-row semantics) */
 int pe_or_rgb_to_rgb(int inpal, int outpal, const uint8_t *src, int irow, int width, int height,

@@ -232,6 +232,22 @@ void ref_rgb_to_yuv420(uint8_t *rgb, int width, int height, int irow, int *ostri
   else convert_argb_to_yuv420_frame(rgb, width, height, irow, ostrides, dest, is_422, subspace, clamping);
 }
 
+/* fmt 0 uyvy 1 yuyv; order 0 rgb 1 bgr 2 argb; gamma LUT variant when gamma != tgt_gamma (both != 0) */
+void ref_rgb_to_packed422(int fmt, uint8_t *rgb, int width, int height, int irow, int orow, void *dest, int order, int has_alpha,
+                          int clamping, int gamma, int tgt_gamma) {
+  ref_init();
+  uint16_t *lut = (gamma != tgt_gamma) ? create_gamma_lut(1.0, gamma, tgt_gamma) : NULL;
+  if (fmt == 0) {
+    if (order == 0) convert_rgb_to_uyvy_frame(rgb, width, height, irow, orow, (uyvy_macropixel *)dest, has_alpha, clamping, lut, -USE_THREADS);
+    else if (order == 1) convert_bgr_to_uyvy_frame(rgb, width, height, irow, orow, (uyvy_macropixel *)dest, has_alpha, clamping, lut, -USE_THREADS);
+    else convert_argb_to_uyvy_frame(rgb, width, height, irow, orow, (uyvy_macropixel *)dest, clamping, lut, -USE_THREADS);
+  } else {
+    if (order == 0) convert_rgb_to_yuyv_frame(rgb, width, height, irow, orow, (yuyv_macropixel *)dest, has_alpha, clamping, lut, -USE_THREADS);
+    else if (order == 1) convert_bgr_to_yuyv_frame(rgb, width, height, irow, orow, (yuyv_macropixel *)dest, has_alpha, clamping, lut, -USE_THREADS);
+    else convert_argb_to_yuyv_frame(rgb, width, height, irow, orow, (yuyv_macropixel *)dest, clamping, lut, -USE_THREADS);
+  }
+}
+
 /* ---- in-place layer ops -------------------------------------------------- */
 
 void ref_alpha_premult(uint8_t *pixels, int width, int height, int rowstride, int palette, int clamping,

@@ -240,6 +240,47 @@ def test_yuv888_both_directions(eng):
         assert (payload(lay.to_host()[0], w, ops) == payload(exp, w, ops)).all(), (ipal, opal, cl)
 
 
+def test_rgb_to_packed422_and_planar444(eng):
+    """convert_{rgb,bgr,argb}_to_{uyvy,yuyv}_frame :5129-5700 and ..._to_yuvp_frame :5786-6240 through the dispatcher,
+    with and without the inline 16-bit gamma LUT"""
+    o = T.oracle()
+    rng = np.random.default_rng(24)
+    for (w, h), ipal, cl in itertools.product(((48, 10), (101, 7), (642, 33)), RGB_PALS, (0, 1)):
+        order, in_alpha = ORDER_OF[ipal]
+        ips = T.psize_of(ipal)
+        src = T.make_packed(rng, w, h, ips)
+        for opal, fmt in ((564, 0), (565, 1)):
+            we = (w >> 1) << 1
+            exp = np.zeros((h, T.rowstride(we // 2, 4)), np.uint8)
+            o.pe_or_rgb_to_packed422(fmt, T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], order, in_alpha, cl, T.Q_HIGH, None)
+            lay = packed_layer(eng, ipal, w, h, src)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.palette, lay.width, lay.height) == (opal, we, h) and lay.yuv_clamping == cl and lay.yuv_subspace == 1
+            assert (payload(lay.to_host()[0], we // 2, 4) == payload(exp, we // 2, 4)).all(), (w, ipal, cl, opal)
+        for opal in (544, 545):
+            we = (w >> 1) << 1
+            ors = T.rowstride(w, 1)
+            pl = [np.zeros((h, ors), np.uint8) for _ in range(4)]
+            o.pe_or_rgb_to_yuv444p(T.ptr(src), src.strides[0], w, h, T.planes_arg(*pl), ors, order, in_alpha, int(opal == 545), cl, T.Q_HIGH)
+            lay = packed_layer(eng, ipal, w, h, src)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            got = lay.to_host()
+            assert len(got) == (4 if opal == 545 else 3)
+            for k, g in enumerate(got):
+                assert (g[:, :we] == pl[k][:, :we]).all(), (w, ipal, cl, opal, k)
+    # gamma: a linear RGB layer to UYVY gets the LINEAR -> sRGB 16-bit LUT inside the converter (colourspace.c:12320-12322)
+    w, h = 64, 12
+    src = T.make_packed(rng, w, h, 3)
+    lut = np.zeros(65536, np.uint16)
+    assert o.pe_or_gamma_lut16(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut)) == 0
+    exp = np.zeros((h, T.rowstride(w // 2, 4)), np.uint8)
+    o.pe_or_rgb_to_packed422(0, T.ptr(src), src.strides[0], w, h, T.ptr(exp), exp.strides[0], 0, 0, 0, T.Q_HIGH, T.ptr(lut))
+    lay = packed_layer(eng, 1, w, h, src, gamma_type=T.G_LINEAR)
+    assert lb.convert_layer_palette_full(lay, 564, 0, 0, 1, 0)
+    assert lay.gamma_type == T.G_SRGB
+    assert (payload(lay.to_host()[0], w // 2, 4) == payload(exp, w // 2, 4)).all()
+
+
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
     src = T.make_packed(rng, 32, 8, 3)

@@ -415,3 +415,58 @@ def test_alpha_over_matches_paint_pixel():
         o.pe_or_alpha_over(T.ptr(a), n * 3, T.ptr(src), n * 3, 1, n, 1, alpha)
         p.ref_paint_rows(T.ptr(b), T.ptr(src), n, 3, alpha)
         assert (a == b).all(), alpha
+
+
+def test_rgb_to_packed422_and_planar444_match_reference():
+    """convert_{rgb,bgr,argb}_to_{uyvy,yuyv}_frame :5129-5700 (rows unpadded: the reference's row advance only works then)
+    and convert_{rgb,bgr,argb}_to_yuvp_frame :5786-6240"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(12)
+    w, h = 48, 10  # 48 px: 96-byte macropixel rows and 144 / 192-byte RGB rows are multiples of 32 -> no padding
+    r.ref_set_prefs(1, T.Q_HIGH, 1.4)
+    for fmt, order, in_alpha, cl in itertools.product((0, 1), (0, 1, 2), (0, 1), (0, 1)):
+        if order == 2 and not in_alpha:
+            continue
+        ips = 4 if in_alpha else 3
+        src = T.make_packed(rng, w, h, ips)
+        a = np.zeros((h, w * 2), np.uint8)
+        b = np.zeros((h, w * 2), np.uint8)
+        o.pe_or_rgb_to_packed422(fmt, T.ptr(src), src.strides[0], w, h, T.ptr(a), a.strides[0], order, in_alpha, cl, T.Q_HIGH, None)
+        r.ref_rgb_to_packed422(fmt, T.ptr(src), w, h, src.strides[0], b.strides[0], T.ptr(b), order, in_alpha, cl, 0, 0)
+        assert (a == b).all(), ("packed422", fmt, order, in_alpha, cl)
+    for order, in_alpha, out_alpha, cl in itertools.product((0, 1, 2), (0, 1), (0, 1), (0, 1)):
+        if order == 2 and not in_alpha:
+            continue
+        ips = 4 if in_alpha else 3
+        src = T.make_packed(rng, w, h, ips)
+        ors = T.rowstride(w, 1)
+        pa = [np.zeros((h, ors), np.uint8) for _ in range(4)]
+        pb = [np.zeros((h, ors), np.uint8) for _ in range(4)]
+        o.pe_or_rgb_to_yuv444p(T.ptr(src), src.strides[0], w, h, T.planes_arg(*pa), ors, order, in_alpha, out_alpha, cl, T.Q_HIGH)
+        r.ref_rgb_to_yuv444p(T.ptr(src), w, h, src.strides[0], ors, T.planes_arg(*pb), order, in_alpha, out_alpha, cl)
+        for k in range(4 if out_alpha else 3):
+            if k == 3 and order == 2:
+                continue  # the ARGB variant has no in_has_alpha argument and copies byte 3 (blue) as alpha (:6220): X
+            assert (pa[k] == pb[k]).all(), ("yuv444p", order, in_alpha, out_alpha, cl, k)
+
+
+def test_rgb_to_packed422_gamma_lut_variant():
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import pe_testlib as T
+o, r = T.oracle(), T.ref()
+rng = np.random.default_rng(13)
+w, h = 48, 6
+src = T.make_packed(rng, w, h, 3)
+lut = np.zeros(65536, np.uint16)
+assert o.pe_or_gamma_lut16(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut)) == 0
+for fmt in (0, 1):
+    a = np.zeros((h, w * 2), np.uint8); b = np.zeros((h, w * 2), np.uint8)
+    o.pe_or_rgb_to_packed422(fmt, T.ptr(src), src.strides[0], w, h, T.ptr(a), a.strides[0], 0, 0, 0, T.Q_HIGH, T.ptr(lut))
+    r.ref_rgb_to_packed422(fmt, T.ptr(src), w, h, src.strides[0], b.strides[0], T.ptr(b), 0, 0, 0, T.G_LINEAR, T.G_SRGB)
+    assert (a == b).all(), fmt
+print("OK")
+""" % os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr + out.stdout
