@@ -250,7 +250,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
   for (auto &kv : e->over) cudaFree(kv.second);
-  for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); }
+  for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); cudaFree(kv.second.rows4); }
   e->pool.release_all();
   cudaFree(e->stats_dev);
   cudaFree(e->args_dev);
@@ -1404,9 +1404,30 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
     }
     if (tile_h < 4) fast = false;
   }
-  if (fast) {
-    const double k256 = alpha * 256.;
-    const bool dyadic = k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256;
+  const double k256 = alpha * 256.;
+  const bool dyadic = k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256;
+  // register-resident path (pe_kernels_fused3.cu): 4:2:0, full-width letterbox, alpha = k / 256, one conversion variant
+  const bool regs = dyadic && getenv("PE_FUSED_GENERIC") == nullptr && getenv("PE_FUSED3_OFF") == nullptr &&
+                    fused3_supported(args.data(), n, fy->host.taps) &&
+                    fused3_tables_ok(conv_host(e, f0->d.yuv_clamping, f0->d.yuv_subspace));
+  if (regs) {
+    if (!fy->rows4) {
+      const ResizeFilter &F = fy->host;
+      std::vector<int32_t> r4((size_t)inner_h * 4);
+      for (int i = 0; i < inner_h; i++) {
+        uint32_t c[4] = {0, 0, 0, 0};
+        for (int t = 0; t < F.taps; t++) c[t] = (uint16_t)F.coef[(size_t)i * F.taps + t];
+        r4[4 * i] = F.first[i];
+        r4[4 * i + 1] = (int32_t)(c[3] | (c[2] << 16));
+        r4[4 * i + 2] = (int32_t)(c[1] | (c[0] << 16));
+        r4[4 * i + 3] = 0;
+      }
+      PE_CUDA(cudaMalloc(&fy->rows4, r4.size() * sizeof(int32_t)));
+      PE_CUDA(cudaMemcpyAsync(fy->rows4, r4.data(), r4.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+      PE_CUDA(cudaStreamSynchronize(e->stream));  // r4 is a local
+    }
+    PE_CUDA(launch_fused3(e->L(), args.data(), n, (int)k256, lut, fy->rows4));
+  } else if (fast) {
     PE_CUDA(launch_fused2(e->L(), args.data(), n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
   } else {
     const FusedArgs *dev = (const FusedArgs *)upload_args(e, args.data(), sizeof(FusedArgs) * n);

@@ -47,6 +47,7 @@ struct FilterKey {
 struct DevFilterEntry {
   DevFilter dev;
   ResizeFilter host;
+  void *rows4 = nullptr;  // int4 per output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}: k_fused3's view of a <= 4-tap bank
 };
 struct Lut8Entry {
   uint8_t host[256];

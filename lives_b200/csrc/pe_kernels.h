@@ -143,6 +143,13 @@ int fused2_max_tile_h();
 // blend_a in 0..256: integer blend (alpha = blend_a / 256) + optional lut8; blend_a < 0: FusedArgs::over_table
 cudaError_t launch_fused2(const Launch &L, const FusedArgs *frames_host, int nframes, int ow, int oh, int tile_h, int blend_a,
                           const uint8_t *lut8_dev);
+// register-resident path (pe_kernels_fused3.cu): 4:2:0, full-width letterbox, alpha = k / 256, one conversion variant per batch
+struct ConvTables;
+bool fused3_tables_ok(const ConvTables &t);
+bool fused3_supported(const FusedArgs *frames_host, int nframes, int fy_taps);
+// rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}
+cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
+                          const void *rows4_dev);
 // ---- diagnostics -------------------------------------------------------------------------------------------
 struct DevStats {
   unsigned int minv[4], maxv[4];

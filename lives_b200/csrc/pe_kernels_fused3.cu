@@ -1,0 +1,606 @@
+// pe_kernels_fused3.cu -- the register-resident fused chain (the kernel bench.py's headline runs):
+//     planar 4:2:0 fg -> RGBA  |  full-width letterbox (inner width == outer width == fg width), vertical filter of <= 4 taps
+//     |  scalar alpha-over (alpha = k / 256) a RGBA32 bg  |  optional 8-bit gamma LUT
+// Same arithmetic, bit for bit, as k_fused2 / k_fused and as the unfused ops (tests/test_gpu_parity.py); everything outside
+// this envelope runs k_fused2 (pe_kernels_fused2.cu).  What differs is where the data lives:
+//
+//   * NO shared-memory image tile and NO block barrier in the main loop.  A warp owns a strip of 128 columns (one lane =
+//     4 adjacent columns = one 32-bit luma word = one 16-byte bg / out vector) and marches down the source rows one
+//     reference row pair (colourspace.c:3440-3549) per step.  The converted pixels of the last steps live in REGISTERS,
+//     packed vertically: W = [row 2k, row 2k-1, row 2k-2, row 2k-3] per column and channel, pushed two rows at a time by
+//     the saturating pack (cvt.pack.sat) that the conversion needs anyway.  An output row is emitted as soon as its four
+//     source rows are in the window: the <= 4-tap vertical filter is two DP2A per channel on W (or on a byte-permute of
+//     W and the previous W), then letterbox / alpha-over / gamma / one 128-bit streaming store.
+//   * the raw luma / chroma words of step k+1 and the bg vector of the next output row are loaded into registers while step k
+//     is computed (ld.global.nc, L1 no-allocate): each byte of fg and bg crosses the memory system once, as whole sectors.
+//   * every table is REPLICATED ACROSS BANKS in shared memory so that a lookup never conflicts, whatever the pixel values:
+//       RGB_Y      [256][32 lanes]  u32        lane l reads bank l
+//       {R_Cr,G_Cr}[256][16]        2 x u32    64-bit loads, lane l reads bank pair l & 15
+//       {G_Cb,B_Cb}[256][16]        2 x u32
+//       gamma LUT  [256][32 lanes]  u32 = v * 0x010101 | 0xFF000000
+//     (128 KB per SM, one 512-thread CTA per SM).  The chroma tables are indexed by m = third_round(n) (the (int)(n / 3. + .5)
+//     of colourspace.c:3465); CLAMP16_240 / CLAMP0_255 are no-ops on these tables (flat outside the range; checked on the
+//     host by fused3_tables_ok) and third_round is one multiply-high on the PACKED pair of sums (see idx_hi / idx_lo).
+//   * chroma sums are computed two columns at a time in the 16-bit halves of a register (Q = 2 n + 3, <= 1533).
+//   * work is split by COST, not by tiles: the (frame, band, strip, row) sequence is cut into one contiguous share per warp
+//     (border rows are ~4x cheaper than inner rows), so all warps finish together; consecutive warps get neighbouring strips
+//     of the same band.
+// Rows that cannot take the fast step (row 0, the last row of an even frame, virtual rows beyond the frame, the last chroma
+// row of a plane without padding) go through slow_step(): scalar code with the reference's edge rules, a few steps per strip.
+#include <cstdlib>
+
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+#include "pe_tables.h"
+
+namespace pe {
+
+namespace {
+
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+constexpr int F3_NT = 512;
+constexpr int F3_NW = F3_NT / 32;
+constexpr int F3_MAXF = 16;               // frames per launch (their pointers travel as kernel parameters)
+constexpr int S3_TY = 0;                  // u32 [256][32]
+constexpr int S3_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
+constexpr int S3_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
+constexpr int S3_LUT = 98304;             // u32 [256][32]
+constexpr int S3_BYTES = 131072;           // + 16 bytes per inner output row (filter rows)
+constexpr int F3_BG_AHEAD = 6;            // bg rows prefetched into L2 ahead of the register load
+constexpr int F3_MAX_IH = 4096;
+
+struct Fused3Frame {
+  const uint8_t *y, *u, *v, *bg;
+  uint8_t *out;
+};
+
+struct Fused3Params {
+  Fused3Frame fr[F3_MAXF];
+  int nframes;
+  int fw, fh, cw, ch;                      // fg luma / chroma size
+  int rs_y, rs_u, rs_v, rs_bg, rs_out;     // shared by all frames of the launch
+  int oh, oy, ih;                          // outer height, first inner row, inner height
+  int nstrips, band_h;
+  int k_fast_max;                          // steps 1 .. k_fast_max take the fast path
+  int cost_b, cost_i;                      // cost of a border / an inner output row
+  long long frame_cost, total_cost;
+  uint32_t ka, kia;                        // blend weights of fg / bg, sum 256
+  const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0
+  const int32_t *conv;                     // [14][256] (ConvTab order)
+  const uint8_t *lut8;                     // optional
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// d = (c[15:0] << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+constexpr uint32_t MSK = 0xFFFEFFFEu;   // clears bit 0 of both halves: 2 * (s >> 1) = s & ~1
+constexpr uint32_t K3 = 0x00030003u;    // + 3 in both halves (Q = 2 n + 3)
+
+// m = third_round(n) = (2 n + 3) / 6 for the n in the HIGH / LOW half of a packed Q = 2 n + 3 (each half <= 1533).
+// 10923 / 65536 = 1 / 6 + 5e-6: the product is off by < 0.008 (plus < 0.004 from the low half leaking into the high one),
+// and (2 n + 3) / 6 is never closer than 1 / 6 to an integer, so the floor is exact.
+__device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u); }
+__device__ __forceinline__ uint32_t idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u); }
+
+// the three 'this / last / next' views of one chroma row for the lane's two chroma columns jc0, jc0 + 1, as 16-bit halves
+struct RowC {
+  uint32_t a, b, c;  // a = [c(jc0), c(jc0+1)], b = [c(jc0-1), c(jc0)], c = [c(jc0+1), c(jc0+2)]
+};
+__device__ __forceinline__ RowC unpack_row(uint32_t w0, uint32_t w1, uint32_t sel) {
+  const uint32_t cw4 = __byte_perm(w0, w1, sel);  // bytes: columns jc0-1, jc0, jc0+1, jc0+2
+  RowC r;
+  r.a = __byte_perm(cw4, 0u, 0x4241u);
+  r.b = __byte_perm(cw4, 0u, 0x4140u);
+  r.c = __byte_perm(cw4, 0u, 0x4342u);
+  return r;
+}
+
+// state carried from one row pair to the next: the sums of the previous chroma row
+struct Carry {
+  uint32_t DUr, MUr, DVr, MVr;   // right pixel (this + next): doubled / bit-0-cleared sums
+  uint32_t DUl, MUl, DVl, MVl;   // left pixel (this + last), intended stencil (no quirks)
+  uint32_t QUL, aV;              // quirks: Q of the left U (u2 = u1, colourspace.c:3461); 'this' V (:3544)
+};
+
+// raw words of one step, loaded one step ahead
+struct Pre {
+  uint32_t yA, yB, u0, u1, v0, v1, vf;
+};
+
+struct Lane {
+  // per-lane constants of the current segment
+  const uint8_t *yp, *up0, *up1, *vp0, *vp1, *vfp;
+  uint32_t sel, selB;
+  uint32_t tyl, tul, tvl, lutl;
+  int x;
+};
+
+// chroma sample with the reference's edge rules: column -1 replicates column 0; column cw reads the byte behind the row
+// (padding or the first sample of the next row, colourspace.c:3508) except on the last row of a plane without padding
+__device__ __forceinline__ uint32_t chroma_at(const uint8_t *__restrict__ p, int stride, int r, int c, int cw, int ch) {
+  if (c < 0) c = 0;
+  if (c >= cw) c = (cw < stride || r + 1 < ch) ? cw : cw - 1;
+  return p[(size_t)stride * r + c];
+}
+
+template <bool QUIRKS, bool HAS_LUT>
+__global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+
+  // ---- replicated tables
+  {
+    uint32_t *ty = reinterpret_cast<uint32_t *>(smem + S3_TY);
+    uint2 *tv = reinterpret_cast<uint2 *>(smem + S3_TV), *tu = reinterpret_cast<uint2 *>(smem + S3_TU);
+    uint32_t *tl = reinterpret_cast<uint32_t *>(smem + S3_LUT);
+    const int32_t *cv = P.conv;
+    for (int i = tid; i < 256 * 32; i += F3_NT) ty[i] = (uint32_t)cv[RGB_Y * 256 + (i >> 5)];
+    for (int i = tid; i < 256 * 16; i += F3_NT) {
+      const int m = i >> 4;
+      tv[i] = make_uint2((uint32_t)cv[R_CR * 256 + m], (uint32_t)cv[G_CR * 256 + m]);
+      tu[i] = make_uint2((uint32_t)cv[G_CB * 256 + m], (uint32_t)cv[B_CB * 256 + m]);
+    }
+    if (HAS_LUT)
+      for (int i = tid; i < 256 * 32; i += F3_NT) tl[i] = (uint32_t)P.lut8[i >> 5] * 0x010101u | 0xFF000000u;
+    int4 *sr = reinterpret_cast<int4 *>(smem + S3_BYTES);
+    for (int i = tid; i < P.ih; i += F3_NT) sr[i] = P.rows4[i];
+  }
+  const int4 *s_rows = reinterpret_cast<const int4 *>(smem + S3_BYTES);  // per inner output row: first, c3 | c2 << 16, c1 | c0 << 16
+  __syncthreads();  // the only barrier of the kernel
+
+  Lane L;
+  L.tyl = sbase + S3_TY + 4 * lane;
+  L.tul = sbase + S3_TU + 8 * (lane & 15);
+  L.tvl = sbase + S3_TV + 8 * (lane & 15);
+  L.lutl = sbase + S3_LUT + 4 * lane;
+
+  const int fw = P.fw, fh = P.fh, cw = P.cw, ch = P.ch;
+  const int oy = P.oy, ih = P.ih, oh = P.oh;
+  const uint32_t ka = P.ka, kia = P.kia;
+
+  // yuv2rgb_int (colourspace.c:2345-2356) through the replicated tables; results UNSATURATED (saturated by pack_sat)
+  auto rgb = [&](uint32_t y, uint32_t mu, uint32_t mv, int &r, int &g, int &b) {
+    const int yy = (int)lds32(L.tyl + y * 128u);
+    const uint2 tv = lds64(L.tvl + mv * 128u), tu = lds64(L.tul + mu * 128u);
+    r = (yy + (int)tv.x) >> 16;
+    g = (yy + (int)tu.x + (int)tv.y) >> 16;
+    b = (yy + (int)tu.y) >> 16;
+  };
+
+  // alpha-over (integer form of compositor.c:120 for alpha = ka / 256) + gamma LUT of one pixel
+  auto blend = [&](uint32_t bg, uint32_t fr, uint32_t fg_, uint32_t fb) -> uint32_t {
+    const uint32_t rb = (bg & 0x00FF00FFu) * kia + __byte_perm(fr, fb, 0x5410u) * ka;   // R | B in the 16-bit halves
+    const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia + fg_ * ka;
+    if (HAS_LUT) {
+      const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
+      const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
+      const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
+      return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
+    }
+    return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
+  };
+  auto blend_border = [&](uint32_t bg) -> uint32_t {  // letterbox border: fg = black (blank_pixel, colourspace.c:11169)
+    const uint32_t rb = (bg & 0x00FF00FFu) * kia;
+    const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia;
+    if (HAS_LUT) {
+      const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
+      const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
+      const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
+      return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
+    }
+    return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
+  };
+
+  // ---- the warp's share of the cost sequence (frame, band, strip, row)
+  const int cb = P.cost_b, ci = P.cost_i, Hb = P.band_h, nstrips = P.nstrips;
+  auto cost_upto = [&](int r) -> int {  // cost of the rows [0, r) of one strip
+    const int top = min(r, oy), mid = min(max(r - oy, 0), ih), bot = max(r - oy - ih, 0);
+    return cb * (top + bot) + ci * mid;
+  };
+  auto row_at = [&](int t) -> int {  // smallest r with cost_upto(r) >= t
+    if (t <= cb * oy) return (t + cb - 1) / cb;
+    t -= cb * oy;
+    if (t <= ci * ih) return oy + (t + ci - 1) / ci;
+    t -= ci * ih;
+    return oy + ih + (t + cb - 1) / cb;
+  };
+  const long long gw = (long long)blockIdx.x * F3_NW + warp, nwarps = (long long)gridDim.x * F3_NW;
+  long long pos = P.total_cost * gw / nwarps;
+  const long long pos_end = P.total_cost * (gw + 1) / nwarps;
+
+  while (pos < pos_end) {
+    // ---- locate the unit (frame, band, strip) that holds `pos` and the rows of it that belong to this warp
+    const int f = (int)(pos / P.frame_cost);
+    long long rem = pos - (long long)f * P.frame_cost;
+    int b = 0, bc = 0, base = 0;
+    for (;; b++) {
+      const int r0 = b * Hb, r1 = min(oh, r0 + Hb);
+      base = cost_upto(r0);
+      bc = cost_upto(r1) - base;
+      if (rem < (long long)bc * nstrips) break;
+      rem -= (long long)bc * nstrips;
+    }
+    const int s = (int)(rem / bc);
+    const int within = (int)(rem - (long long)s * bc);
+    const long long unit0 = pos - within;
+    const int hi = (int)min((long long)bc, pos_end - unit0);
+    const int ra = row_at(base + within), rb = row_at(base + hi);
+    pos = unit0 + bc;
+
+    const int x = 128 * s + 4 * lane;  // the lane's first column
+    if (x >= fw || ra >= rb) continue;
+    const Fused3Frame &F = P.fr[f];
+    const uint8_t *bgp = F.bg + 4 * (size_t)x;
+    uint8_t *outp = F.out + 4 * (size_t)x;
+    const uint32_t rs_bg = (uint32_t)P.rs_bg, rs_out = (uint32_t)P.rs_out;
+
+    // ---- border rows above / below the inner rectangle: bg * (1 - alpha) -> gamma
+    auto border_rows = [&](int r0, int r1) {
+      if (r0 >= r1) return;
+      // four rows per iteration, the next four in flight meanwhile (the loads of a row past r1 - 1 re-read row r1 - 1)
+      uint4 w[4], wn[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) w[j] = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)min(r0 + j, r1 - 1));
+      for (int r = r0; r < r1; r += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) wn[j] = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)min(r + 4 + j, r1 - 1));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (r + j < r1) {
+            uint4 o;
+            o.x = blend_border(w[j].x); o.y = blend_border(w[j].y); o.z = blend_border(w[j].z); o.w = blend_border(w[j].w);
+            st_stream_u4(outp + (size_t)rs_out * (uint32_t)(r + j), o);
+          }
+          w[j] = wn[j];
+        }
+      }
+    };
+    border_rows(ra, min(rb, oy));
+
+    const int ia = max(ra, oy) - oy, ib = min(rb, oy + ih) - oy;  // inner rows [ia, ib)
+    if (ia < ib) {
+      // ---- per-lane constants
+      const int jc0 = x >> 1;                 // first chroma column of the lane
+      const int o = jc0 - 1;                  // byte offset of chroma column jc0 - 1
+      const int off0 = x == 0 ? 0 : (o & ~3), off1 = x == 0 ? 0 : (o & ~3) + 4;
+      L.x = x;
+      L.yp = F.y + x;
+      L.up0 = F.u + off0; L.up1 = F.u + off1;
+      L.vp0 = F.v + off0; L.vp1 = F.v + off1;
+      L.vfp = F.v;
+      L.sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+      L.selB = x == 0 ? 0x3254u : 0x3210u;
+      const uint32_t rs_y = (uint32_t)P.rs_y, rs_u = (uint32_t)P.rs_u, rs_v = (uint32_t)P.rs_v;
+      const int k_fast_max = P.k_fast_max;
+
+      auto load_pre = [&](int k, Pre &p) {  // raw words of the fast step k: luma rows 2k-1, 2k, chroma row k
+        const uint8_t *yr = L.yp + (size_t)rs_y * (uint32_t)(2 * k - 1);
+        p.yA = ld_stream_u32(yr);
+        p.yB = ld_stream_u32(yr + rs_y);
+        const uint32_t uo = rs_u * (uint32_t)k, vo = rs_v * (uint32_t)k;
+        p.u0 = ld_stream_u32(L.up0 + uo); p.u1 = ld_stream_u32(L.up1 + uo);
+        p.v0 = ld_stream_u32(L.vp0 + vo); p.v1 = ld_stream_u32(L.vp1 + vo);
+        p.vf = ldg_u8(L.vfp + vo);
+      };
+      auto init_carry = [&](int r, Carry &c) {  // sums of chroma row r (0 <= r <= ch - 2), as a fast step leaves them
+        const uint32_t uo = rs_u * (uint32_t)r, vo = rs_v * (uint32_t)r;
+        const RowC U = unpack_row(ld_stream_u32(L.up0 + uo), ld_stream_u32(L.up1 + uo), L.sel);
+        const RowC V = unpack_row(ld_stream_u32(L.vp0 + vo), ld_stream_u32(L.vp1 + vo), L.sel);
+        const uint32_t RU = U.a + U.c, RV = V.a + V.c, LU = U.a + U.b, LV = V.a + V.b;
+        c.DUr = RU * 2u; c.MUr = RU & MSK; c.DVr = RV * 2u; c.MVr = RV & MSK;
+        c.DUl = LU * 2u; c.MUl = LU & MSK; c.DVl = LV * 2u; c.MVl = LV & MSK;
+        c.QUL = LU * 2u + (LU & MSK) + K3;
+        c.aV = V.a;
+      };
+
+      // ---- one step: rows A = 2k-1, B = 2k of the lane's 4 columns -> Wc = [B, A, Wp.byte0, Wp.byte1]
+      int iy = ia;
+      int4 ri = s_rows[iy];
+      int k = ((ri.x + 4) >> 1) - 2;
+      bool carry_ok = false;
+      Carry C;
+      Pre pre;
+      C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
+      pre.yA = pre.yB = pre.u0 = pre.u1 = pre.v0 = pre.v1 = pre.vf = 0u;
+      if (k >= 1 && k <= k_fast_max) {
+        load_pre(k, pre);
+        init_carry(k - 1, C);
+        carry_ok = true;
+      }
+      uint4 bgw = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)(oy + iy));
+
+      auto step = [&](int k, uint32_t(&Wc)[12], const uint32_t(&Wp)[12]) {
+        int rA[12], rB[12];
+        const bool fast = k >= 1 && k <= k_fast_max;
+        const bool next_fast = k + 1 >= 1 && k + 1 <= k_fast_max;
+        Pre nxt = pre;
+        if (next_fast) load_pre(k + 1, nxt);
+        if (fast) {
+          const RowC U = unpack_row(pre.u0, pre.u1, L.sel), V = unpack_row(pre.v0, pre.v1, L.sel);
+          // right pixel of both chroma columns: this + next
+          const uint32_t RU = U.a + U.c, RV = V.a + V.c;
+          const uint32_t DUn = RU * 2u, MUn = RU & MSK, DVn = RV * 2u, MVn = RV & MSK;
+          const uint32_t QUR_up = C.DUr + MUn + K3, QUR_lo = C.MUr + DUn + K3;
+          const uint32_t QVR_up = C.DVr + MVn + K3, QVR_lo = C.MVr + DVn + K3;
+          C.DUr = DUn; C.MUr = MUn; C.DVr = DVn; C.MVr = MVn;
+          // left pixel: this + last
+          uint32_t QUL_up, QUL_lo, QVL_up, QVL_lo;
+          const uint32_t LU = U.a + U.b;
+          if (QUIRKS) {
+            QUL_up = QUL_lo = C.QUL;                        // u2 = this_u1 + last_u1 (colourspace.c:3461)
+            C.QUL = LU * 2u + (LU & MSK) + K3;
+            const uint32_t bq = __byte_perm(V.b, C.aV, L.selB);   // last_v1 = this_v2 (:3544), except at column 0
+            const uint32_t v1 = C.aV + bq;
+            const uint32_t v2 = V.a + pre.vf * 0x10001u;    // last_v2 is never advanced: the row's first V sample
+            QVL_up = v1 * 2u + (v2 & MSK) + K3;
+            QVL_lo = (v1 & MSK) + v2 * 2u + K3;
+            C.aV = V.a;
+          } else {
+            const uint32_t LV = V.a + V.b;
+            const uint32_t DUn_l = LU * 2u, MUn_l = LU & MSK, DVn_l = LV * 2u, MVn_l = LV & MSK;
+            QUL_up = C.DUl + MUn_l + K3; QUL_lo = C.MUl + DUn_l + K3;
+            QVL_up = C.DVl + MVn_l + K3; QVL_lo = C.MVl + DVn_l + K3;
+            C.DUl = DUn_l; C.MUl = MUn_l; C.DVl = DVn_l; C.MVl = MVn_l;
+          }
+#pragma unroll
+          for (int col = 0; col < 4; col++) {
+            const bool hi_half = col >> 1, right = col & 1;
+            const uint32_t qu_up = right ? QUR_up : QUL_up, qu_lo = right ? QUR_lo : QUL_lo;
+            const uint32_t qv_up = right ? QVR_up : QVL_up, qv_lo = right ? QVR_lo : QVL_lo;
+            const uint32_t mu_up = hi_half ? idx_hi(qu_up) : idx_lo(qu_up), mv_up = hi_half ? idx_hi(qv_up) : idx_lo(qv_up);
+            const uint32_t mv_lo = hi_half ? idx_hi(qv_lo) : idx_lo(qv_lo);
+            const uint32_t mu_lo = (QUIRKS && !right) ? mu_up : (hi_half ? idx_hi(qu_lo) : idx_lo(qu_lo));
+            rgb(byte_of(pre.yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+            rgb(byte_of(pre.yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+          }
+        } else {
+          // ---- slow step: frame edges.  k <= 0: row 0 alone (horizontal average only, colourspace.c:3421-3428); the last row
+          //      of an even frame alone; rows beyond the frame replicate the last row (the filter clamps source indices);
+          //      the last chroma row of a plane without padding (one-past-row read, :3508)
+          const int x0 = L.x;
+          auto single = [&](int row, int cr) {
+            const uint32_t yw = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * row + x0);
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+              const uint32_t mu = (chroma_at(F.u, rs_u, cr, jc, cw, ch) + chroma_at(F.u, rs_u, cr, jo, cw, ch)) >> 1;
+              const uint32_t mv = (chroma_at(F.v, rs_v, cr, jc, cw, ch) + chroma_at(F.v, rs_v, cr, jo, cw, ch)) >> 1;
+              rgb(byte_of(yw, col), mu, mv, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rB[3 * col] = rA[3 * col]; rB[3 * col + 1] = rA[3 * col + 1]; rB[3 * col + 2] = rA[3 * col + 2];
+            }
+          };
+          if (k <= 0) {
+            single(0, 0);
+          } else if (2 * k <= fh - 1) {
+            const int ca = k - 1, cbr = k;
+            const uint32_t ya = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * (2 * k - 1) + x0);
+            const uint32_t yb = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * (2 * k) + x0);
+            const uint32_t vfirst = F.v[(size_t)rs_v * cbr];
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+              uint32_t u1 = chroma_at(F.u, rs_u, ca, jc, cw, ch) + chroma_at(F.u, rs_u, ca, jo, cw, ch);
+              uint32_t u2 = chroma_at(F.u, rs_u, cbr, jc, cw, ch) + chroma_at(F.u, rs_u, cbr, jo, cw, ch);
+              uint32_t v1 = chroma_at(F.v, rs_v, ca, jc, cw, ch) + chroma_at(F.v, rs_v, ca, jo, cw, ch);
+              uint32_t v2 = chroma_at(F.v, rs_v, cbr, jc, cw, ch) + chroma_at(F.v, rs_v, cbr, jo, cw, ch);
+              if (QUIRKS && !(col & 1)) {
+                u2 = u1;
+                if (jc > 0) v1 = chroma_at(F.v, rs_v, ca, jc, cw, ch) + chroma_at(F.v, rs_v, cbr, jo, cw, ch);
+                v2 = chroma_at(F.v, rs_v, cbr, jc, cw, ch) + vfirst;
+              }
+              const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
+              const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
+              rgb(byte_of(ya, col), mu3, mv3, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rgb(byte_of(yb, col), mu4, mv4, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+            }
+          } else if (2 * k - 1 == fh - 1) {
+            single(fh - 1, ch - 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) rA[i] = rB[i] = (int)(Wp[i] & 0xFFu);
+          }
+          carry_ok = false;
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) Wc[i] = pack_sat(rA[i], rB[i], Wp[i]);
+        if (next_fast && !carry_ok) {
+          init_carry(k, C);
+          carry_ok = true;
+        }
+        pre = nxt;
+      };
+
+      // ---- emit every output row whose window [first, first + 3] is complete after step k
+      auto emit = [&](int k, const uint32_t(&Wc)[12], const uint32_t(&Wp)[12]) {
+        while (iy < ib && ri.x + 3 <= 2 * k) {
+          const int j0 = 2 * k - ri.x - 3;  // 0: the window is Wc; 1: one row older
+          const uint32_t CA = (uint32_t)ri.y, CB = (uint32_t)ri.z;
+          const int iyn = min(iy + 1, ib - 1);
+          const uint4 bgn = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)(oy + iyn));
+          prefetch_l2(bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_BG_AHEAD, ib - 1)));
+          const int4 rin = s_rows[iyn];
+          const uint32_t bgv[4] = {bgw.x, bgw.y, bgw.z, bgw.w};
+          uint32_t ov[4];
+          if (j0 == 0) {
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              uint32_t fch[3];
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const uint32_t win = Wc[3 * col + c];
+                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
+              }
+              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
+            }
+          } else {
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              uint32_t fch[3];
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const uint32_t win = __byte_perm(Wc[3 * col + c], Wp[3 * col + c], 0x6321u);
+                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
+              }
+              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
+            }
+          }
+          st_stream_u4(outp + (size_t)rs_out * (uint32_t)(oy + iy), make_uint4(ov[0], ov[1], ov[2], ov[3]));
+          bgw = bgn;
+          ri = rin;
+          iy++;
+        }
+      };
+
+      uint32_t W0[12], W1[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) W0[i] = W1[i] = 0u;
+      for (;;) {
+        step(k, W0, W1);
+        emit(k, W0, W1);
+        if (iy >= ib) break;
+        k++;
+        step(k, W1, W0);
+        emit(k, W1, W0);
+        if (iy >= ib) break;
+        k++;
+      }
+    }
+    border_rows(max(ra, oy + ih), rb);
+  }
+}
+
+}  // namespace
+
+// CLAMP16_240 / CLAMP0_255 before the chroma lookups (colourspace.c:3465-3469) must be no-ops on the tables: flat below
+// min_uv and above max_uv.  True for all four variants the reference builds; checked because the kernel relies on it.
+bool fused3_tables_ok(const ConvTables &t) {
+  const int tabs[4] = {R_CR, G_CB, G_CR, B_CB};
+  for (int i = 0; i < 4; i++)
+    for (int m = 0; m < 256; m++) {
+      const int c = m < t.min_uv ? t.min_uv : (m > t.max_uv ? t.max_uv : m);
+      if (t.t[tabs[i]][m] != t.t[tabs[i]][c]) return false;
+    }
+  return true;
+}
+
+// Can the register-resident kernel take this batch?  (everything else: k_fused2 / k_fused)
+bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
+  if (n <= 0 || fy_taps > 4) return false;
+  const FusedArgs &f0 = a[0];
+  if (f0.is_422 || f0.low_quality) return false;
+  if (f0.iw != f0.fw || f0.ow != f0.fw || f0.ox != 0) return false;          // full-width letterbox, no horizontal scaling
+  if ((f0.fw & 3) || f0.fw < 4 || f0.fh < 4 || f0.ih > F3_MAX_IH) return false;
+  if (f0.fg.cw != f0.fw / 2 || f0.fg.ch != (f0.fh + 1) / 2) return false;
+  for (int i = 0; i < n; i++) {
+    const FusedArgs &f = a[i];
+    if (f.is_422 != f0.is_422 || f.low_quality != f0.low_quality || f.quirks != f0.quirks || f.conv.t != f0.conv.t) return false;
+    if (f.fw != f0.fw || f.fh != f0.fh || f.ow != f0.ow || f.oh != f0.oh || f.ih != f0.ih || f.oy != f0.oy) return false;
+    if (f.fg.rs_y != f0.fg.rs_y || f.fg.rs_u != f0.fg.rs_u || f.fg.rs_v != f0.fg.rs_v || f.bg.rs != f0.bg.rs || f.out.rs != f0.out.rs)
+      return false;
+    if (((uintptr_t)f.fg.y | (uintptr_t)f.fg.u | (uintptr_t)f.fg.v) & 3) return false;
+    if ((f.fg.rs_y | f.fg.rs_u | f.fg.rs_v) & 3) return false;
+    if (((uintptr_t)f.bg.p | (uintptr_t)f.out.p) & 15) return false;
+    if ((f.bg.rs | f.out.rs) & 15) return false;
+  }
+  return true;
+}
+
+// rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0} (built by the engine from the filter bank)
+cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
+                          const void *rows4_dev) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e;
+    const int mx = S3_BYTES + 16 * F3_MAX_IH;
+    if ((e = cudaFuncSetAttribute(k_fused3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_fused3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_fused3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_fused3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    attr_set = true;
+  }
+  static int cost_b = 0, cost_i = 0;
+  if (!cost_b) {
+    const char *eb = getenv("PE_F3_COST_B"), *ei = getenv("PE_F3_COST_I");
+    cost_b = eb ? atoi(eb) : 2;
+    cost_i = ei ? atoi(ei) : 9;
+    if (cost_b < 1) cost_b = 1;
+    if (cost_i < 1) cost_i = 1;
+  }
+  const FusedArgs &a0 = frames_host[0];
+  for (int base = 0; base < nframes; base += F3_MAXF) {
+    Fused3Params P;
+    P.nframes = nframes - base < F3_MAXF ? nframes - base : F3_MAXF;
+    for (int i = 0; i < F3_MAXF; i++) {
+      const FusedArgs &a = frames_host[base + (i < P.nframes ? i : 0)];
+      P.fr[i] = Fused3Frame{a.fg.y, a.fg.u, a.fg.v, a.bg.p, a.out.p};
+    }
+    P.fw = a0.fw; P.fh = a0.fh; P.cw = a0.fg.cw; P.ch = a0.fg.ch;
+    P.rs_y = a0.fg.rs_y; P.rs_u = a0.fg.rs_u; P.rs_v = a0.fg.rs_v; P.rs_bg = a0.bg.rs; P.rs_out = a0.out.rs;
+    P.oh = a0.oh; P.oy = a0.oy; P.ih = a0.ih;
+    P.nstrips = (a0.fw + 127) / 128;
+    // the fast step reads whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
+    const bool last_row_unsafe = a0.fg.rs_u < a0.fg.cw + 4 || a0.fg.rs_v < a0.fg.cw + 4;
+    P.k_fast_max = a0.fg.ch - 1 - (last_row_unsafe ? 1 : 0);
+    P.cost_b = cost_b; P.cost_i = cost_i;
+    const long long strip_cost = (long long)cost_b * (a0.oh - a0.ih) + (long long)cost_i * a0.ih;
+    P.frame_cost = strip_cost * P.nstrips;
+    P.total_cost = P.frame_cost * P.nframes;
+    const int grid = L.sm_count;
+    // band height: about one warp share of rows, so that consecutive warps work on neighbouring strips of the same band
+    const long long share = P.total_cost / ((long long)grid * F3_NW);
+    long long bh = share * a0.oh / (strip_cost > 0 ? strip_cost : 1);
+    if (bh < 16) bh = 16;
+    if (bh > a0.oh) bh = a0.oh;
+    P.band_h = (int)bh;
+    P.ka = (uint32_t)blend_a; P.kia = (uint32_t)(256 - blend_a);
+    P.rows4 = reinterpret_cast<const int4 *>(rows4_dev);
+    P.conv = a0.conv.t;
+    P.lut8 = lut8_dev;
+    const int smem_bytes = S3_BYTES + 16 * a0.ih;
+    if (a0.quirks) {
+      if (lut8_dev) k_fused3<true, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      else k_fused3<true, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+    } else {
+      if (lut8_dev) k_fused3<false, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      else k_fused3<false, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+    }
+    PE_COUNT_LAUNCH(L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace pe

@@ -594,6 +594,14 @@ def test_fused_chain_equals_unfused_oracle(eng, case):
     (644, 362, 0, 700, 400, 300, 0.1, (-1, 1)),     # non-dyadic alpha: table blend
     (640, 360, 1, 640, 360, 240, 1.0 / 3.0, None),  # 4:2:2, ratio 1.5, table blend, no gamma
     (128, 400, 0, 128, 220, 200, 0.5, (-1, 1)),     # ratio 2: five taps -> generic kernel
+    # the register-resident kernel's envelope (pe_kernels_fused3.cu): 4:2:0, inner width == outer width, alpha = k / 256
+    (132, 50, 0, 132, 60, 45, 0.5, (-1, 1)),        # partial strip, chroma rows with padding (4:2:0 frames are even, :11603)
+    (64, 30, 0, 64, 80, 72, 0.5, (-1, 1)),          # vertical stretch 2.4x: several output rows per step, 2 taps
+    (644, 362, 0, 644, 400, 300, 0.5, (-1, 1)),     # six strips, the last one partial; squeeze 1.207
+    (1920, 1080, 0, 1920, 1080, 804, 0.5, (-1, 1)), # the headline's ratio at 1080p; chroma stride == chroma width
+    (256, 96, 0, 256, 96, 64, 0.375, None),         # ratio 1.5 (four full taps), alpha 3/8, no gamma
+    (8, 6, 0, 8, 9, 7, 0.5, (-1, 1)),               # tiny frame: two lanes
+    (4, 4, 0, 4, 4, 4, 0.5, (-1, 1)),               # one lane, identity
 ])
 @pytest.mark.parametrize("variant", ["clamped", "unclamped_noquirks"])
 def test_fused_fast_path_cases(case, variant):
