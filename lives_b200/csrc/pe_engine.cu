@@ -254,6 +254,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   e->pool.release_all();
   cudaFree(e->stats_dev);
   cudaFree(e->args_dev);
+  cudaFree(e->f3_sched);
   if (e->args_pinned) cudaFreeHost(e->args_pinned);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -1426,7 +1427,11 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
       PE_CUDA(cudaMemcpyAsync(fy->rows4, r4.data(), r4.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
       PE_CUDA(cudaStreamSynchronize(e->stream));  // r4 is a local
     }
-    PE_CUDA(launch_fused3(e->L(), args.data(), n, (int)k256, lut, fy->rows4));
+    if (!e->f3_sched) {
+      PE_CUDA(cudaMalloc(&e->f3_sched, 2 * sizeof(unsigned int)));
+      PE_CUDA(cudaMemsetAsync(e->f3_sched, 0, 2 * sizeof(unsigned int), e->stream));
+    }
+    PE_CUDA(launch_fused3(e->L(), args.data(), n, (int)k256, lut, fy->rows4, e->f3_sched));
   } else if (fast) {
     PE_CUDA(launch_fused2(e->L(), args.data(), n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
   } else {

@@ -81,6 +81,7 @@ struct pe_engine {
   pe::DevStats *stats_dev = nullptr;
   // small device scratch for per-launch argument arrays (BlendFrame / FusedArgs), grown on demand
   void *args_dev = nullptr;
+  unsigned int *f3_sched = nullptr;  // k_fused3's two work counters (zero between launches)
   size_t args_cap = 0;
   void *args_pinned = nullptr;
   size_t args_pinned_cap = 0;

@@ -64,7 +64,8 @@ struct Fused3Params {
   int nstrips, band_h;
   int k_fast_max;                          // steps 1 .. k_fast_max take the fast path
   int cost_b, cost_i;                      // cost of a border / an inner output row
-  long long frame_cost, total_cost;
+  long long frame_cost, total_cost, static_cost, chunk_cost;
+  unsigned int *sched;                     // [2] device counters, zero between launches
   uint32_t ka, kia;                        // blend weights of fg / bg, sum 256
   const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0
   const int32_t *conv;                     // [14][256] (ConvTab order)
@@ -140,7 +141,7 @@ struct Pre {
 
 struct Lane {
   // per-lane constants of the current segment
-  const uint8_t *yp, *up0, *up1, *vp0, *vp1, *vfp;
+  const uint8_t *yp, *up0, *vp0, *vfp;
   uint32_t sel, selB;
   uint32_t tyl, tul, tvl, lutl;
   int x;
@@ -236,10 +237,13 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     t -= ci * ih;
     return oy + ih + (t + cb - 1) / cb;
   };
+  // static part: [0, static_cost) in equal shares; the rest is handed out in small chunks as warps run dry (P.sched: the
+  // chunk counter and the count of finished warps; the last warp to finish zeroes both for the next launch)
   const long long gw = (long long)blockIdx.x * F3_NW + warp, nwarps = (long long)gridDim.x * F3_NW;
-  long long pos = P.total_cost * gw / nwarps;
-  const long long pos_end = P.total_cost * (gw + 1) / nwarps;
+  long long pos = P.static_cost * gw / nwarps;
+  long long pos_end = P.static_cost * (gw + 1) / nwarps;
 
+  for (;;) {
   while (pos < pos_end) {
     // ---- locate the unit (frame, band, strip) that holds `pos` and the rows of it that belong to this warp
     const int f = (int)(pos / P.frame_cost);
@@ -294,11 +298,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       // ---- per-lane constants
       const int jc0 = x >> 1;                 // first chroma column of the lane
       const int o = jc0 - 1;                  // byte offset of chroma column jc0 - 1
-      const int off0 = x == 0 ? 0 : (o & ~3), off1 = x == 0 ? 0 : (o & ~3) + 4;
+      const int off0 = x == 0 ? 0 : (o & ~3);  // the second word is the next one (lane 0 of strip 0 only uses the first)
       L.x = x;
       L.yp = F.y + x;
-      L.up0 = F.u + off0; L.up1 = F.u + off1;
-      L.vp0 = F.v + off0; L.vp1 = F.v + off1;
+      L.up0 = F.u + off0;
+      L.vp0 = F.v + off0;
       L.vfp = F.v;
       L.sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
       L.selB = x == 0 ? 0x3254u : 0x3210u;
@@ -310,14 +314,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         p.yA = ld_stream_u32(yr);
         p.yB = ld_stream_u32(yr + rs_y);
         const uint32_t uo = rs_u * (uint32_t)k, vo = rs_v * (uint32_t)k;
-        p.u0 = ld_stream_u32(L.up0 + uo); p.u1 = ld_stream_u32(L.up1 + uo);
-        p.v0 = ld_stream_u32(L.vp0 + vo); p.v1 = ld_stream_u32(L.vp1 + vo);
+        p.u0 = ld_stream_u32(L.up0 + uo); p.u1 = ld_stream_u32(L.up0 + uo + 4);
+        p.v0 = ld_stream_u32(L.vp0 + vo); p.v1 = ld_stream_u32(L.vp0 + vo + 4);
         p.vf = ldg_u8(L.vfp + vo);
       };
       auto init_carry = [&](int r, Carry &c) {  // sums of chroma row r (0 <= r <= ch - 2), as a fast step leaves them
         const uint32_t uo = rs_u * (uint32_t)r, vo = rs_v * (uint32_t)r;
-        const RowC U = unpack_row(ld_stream_u32(L.up0 + uo), ld_stream_u32(L.up1 + uo), L.sel);
-        const RowC V = unpack_row(ld_stream_u32(L.vp0 + vo), ld_stream_u32(L.vp1 + vo), L.sel);
+        const RowC U = unpack_row(ld_stream_u32(L.up0 + uo), ld_stream_u32(L.up0 + uo + 4), L.sel);
+        const RowC V = unpack_row(ld_stream_u32(L.vp0 + vo), ld_stream_u32(L.vp0 + vo + 4), L.sel);
         const uint32_t RU = U.a + U.c, RV = V.a + V.c, LU = U.a + U.b, LV = V.a + V.b;
         c.DUr = RU * 2u; c.MUr = RU & MSK; c.DVr = RV * 2u; c.MVr = RV & MSK;
         c.DUl = LU * 2u; c.MUl = LU & MSK; c.DVl = LV * 2u; c.MVl = LV & MSK;
@@ -345,6 +349,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         int rA[12], rB[12];
         const bool fast = k >= 1 && k <= k_fast_max;
         const bool next_fast = k + 1 >= 1 && k + 1 <= k_fast_max;
+        // (the copy keeps the consumer of these loads at the END of the step: ptxas then waits for them there, one step after
+        // they were issued, instead of tying the next step's first instructions to the scoreboard of the loads just issued)
         Pre nxt = pre;
         if (next_fast) load_pre(k + 1, nxt);
         if (fast) {
@@ -499,6 +505,22 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     }
     border_rows(max(ra, oy + ih), rb);
   }
+    // ---- next chunk of the dynamic tail
+    __syncwarp();
+    long long t = 0;
+    if (lane == 0) t = (long long)atomicAdd(P.sched, 1u);
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    pos = P.static_cost + t * P.chunk_cost;
+    if (pos >= P.total_cost) break;
+    pos_end = min(pos + P.chunk_cost, P.total_cost);
+  }
+  if (lane == 0) {
+    const unsigned int done = atomicAdd(P.sched + 1, 1u);
+    if (done == (unsigned int)nwarps - 1u) {  // every warp has drawn its last (out of range) chunk: reset for the next launch
+      P.sched[0] = 0u;
+      P.sched[1] = 0u;
+    }
+  }
 }
 
 }  // namespace
@@ -539,7 +561,7 @@ bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
 
 // rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0} (built by the engine from the filter bank)
 cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
-                          const void *rows4_dev) {
+                          const void *rows4_dev, unsigned int *sched_dev) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e;
@@ -550,8 +572,12 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if ((e = cudaFuncSetAttribute(k_fused3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
     attr_set = true;
   }
-  static int cost_b = 0, cost_i = 0;
+  static int cost_b = 0, cost_i = 0, static_pct = 92, chunk_rows = 24;
   if (!cost_b) {
+    if (getenv("PE_F3_STATIC_PCT")) static_pct = atoi(getenv("PE_F3_STATIC_PCT"));
+    if (getenv("PE_F3_CHUNK_ROWS")) chunk_rows = atoi(getenv("PE_F3_CHUNK_ROWS"));
+    if (static_pct < 0 || static_pct > 100) static_pct = 100;
+    if (chunk_rows < 4) chunk_rows = 4;
     const char *eb = getenv("PE_F3_COST_B"), *ei = getenv("PE_F3_COST_I");
     cost_b = eb ? atoi(eb) : 2;
     cost_i = ei ? atoi(ei) : 9;
@@ -584,6 +610,11 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (bh < 16) bh = 16;
     if (bh > a0.oh) bh = a0.oh;
     P.band_h = (int)bh;
+    // the last part of the sequence is handed out dynamically, in chunks of about F3_CHUNK_ROWS inner rows
+    P.chunk_cost = (long long)cost_i * chunk_rows;
+    P.static_cost = P.total_cost * static_pct / 100;
+    if (P.total_cost - P.static_cost < P.chunk_cost * grid) P.static_cost = P.total_cost;  // small jobs: all static
+    P.sched = sched_dev;
     P.ka = (uint32_t)blend_a; P.kia = (uint32_t)(256 - blend_a);
     P.rows4 = reinterpret_cast<const int4 *>(rows4_dev);
     P.conv = a0.conv.t;

@@ -511,6 +511,76 @@ void pe_or_rgb_to_yuv444p(const uint8_t *src, int irow, int width, int height, u
   }
 }
 
+/* ---- chroma averaging tables  src/colourspace.c:190-217 (init_average, !MULT_AVG) ---------------------------
+ * which 0: cavgc (clamped: float maths, result clamped to 16..240)   1: cavgu (unclamped: ((x-128)+(y-128) >> 1) + 128) */
+void pe_or_avg_table(int which, uint8_t out[65536]) {
+  for (int x = 0; x < 256; x++) {
+    float fa = (float)(x - 128.) * 255. / 244.;
+    short sa = (short)(x - 128);
+    for (int y = 0; y < 256; y++) {
+      float fb = (float)(y - 128.) * 255. / 244.;
+      short sb = (short)(y - 128);
+      float fc = (fa + fb) * 224. / 512. + 128.;
+      short c = ((sa + sb) >> 1) + 128;
+      out[x * 256 + y] = which == 0 ? (uint8_t)(fc > 240. ? 240 : fc < 16. ? 16 : fc) : (uint8_t)(c > 255 ? 255 : c < 0 ? 0 : c);
+    }
+  }
+}
+
+/* ---- RGB -> planar 4:2:0 / 4:2:2  src/colourspace.c:6250-6320 (rgb), :6385-6440 (bgr) ---------------------------
+ * One rgb2uyvy macropixel (:2162) per pixel pair: Y of both pixels, Cb of the FIRST, Cr of the SECOND; tables of the
+ * (clamping, subspace) handed in -- the dispatcher passes osubspace for 4:2:0 and WEED_YUV_SAMPLING_DEFAULT (= YCbCr) in
+ * that slot for 4:2:2 (:12681-12690).  Width and height are cut to even.
+ * 4:2:0 chroma (the pointer dance of :6291-6306): luma row 0 writes chroma row 0, row 1 overwrites it; from then on every
+ * even row 2c+2 writes chroma row c+1 and folds itself into row c, avg_chroma(new, old); the following odd row overwrites
+ * row c+1.  Net effect:  C[c] = cavg[C(2c+2)][C(2c+1)] for c < h/2 - 1,  C[h/2 - 1] = C(h - 1)  (luma row 0 contributes
+ * nothing).  The reference advances its Y / Cb / Cr pointers densely, so it is only right for unpadded planes
+ * (ostride == width); this restatement uses the plane strides and equals it there.
+ * ARGB (:6323): reads G1 / B1 of the second pixel two / one bytes too far (:6357-6358, past the row on the last pair) -- X,
+ * not restated. */
+void pe_or_rgb_to_yuv420p(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[3], const int ostrides[3],
+                          int order, int in_alpha, int is_422, int clamping, int subspace, int quality) {
+  const or_conv_t *c = or_conv(clamping, subspace);
+  static uint8_t avg[2][65536];
+  static int avg_ok = 0;
+  int ro, go, bo, ao, ips;
+  if (!avg_ok) { pe_or_avg_table(0, avg[0]); pe_or_avg_table(1, avg[1]); avg_ok = 1; }
+  const uint8_t *cavg = avg[clamping == OR_CLAMPED ? 0 : 1];
+  or_order_offsets(order, in_alpha, &ro, &go, &bo, &ao, &ips);
+  width = (width >> 1) << 1;
+  height = (height >> 1) << 1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *y = dest[0] + (long)ostrides[0] * i;
+    /* chroma row this luma row lands in (rows 2c and 2c+1 both write row c, the odd one last), and whether it also folds
+     * into the row above */
+    const int crow = is_422 ? i : i >> 1;
+    const int fold = !is_422 && i > 0 && !(i & 1);           /* even rows > 0 average into row crow - 1 */
+    uint8_t *cb = dest[1] + (long)ostrides[1] * crow;
+    uint8_t *cr = dest[2] + (long)ostrides[2] * crow;
+    for (int j = 0; j < width; j += 2, s += 2 * ips) {
+      const uint8_t r0 = s[ro], g0 = s[go], b0 = s[bo], r1 = s[ips + ro], g1 = s[ips + go], b1 = s[ips + bo];
+      short a;
+      uint8_t u, v, y0, y1;
+      a = or_spc_rnd(c->t[3][r0] + c->t[4][g0] + c->t[5][b0], quality);
+      u = a > c->max_uv ? c->max_uv : a < c->min_uv ? c->min_uv : a;
+      a = or_spc_rnd(c->t[0][r0] + c->t[1][g0] + c->t[2][b0], quality);
+      y0 = a > c->max_y ? c->max_y : a < c->min_y ? c->min_y : a;
+      a = or_spc_rnd(c->t[6][r1] + c->t[7][g1] + c->t[8][b1], quality);
+      v = a > c->max_uv ? c->max_uv : a < c->min_uv ? c->min_uv : a;
+      a = or_spc_rnd(c->t[0][r1] + c->t[1][g1] + c->t[2][b1], quality);
+      y1 = a > c->max_y ? c->max_y : a < c->min_y ? c->min_y : a;
+      y[j] = y0; y[j + 1] = y1;
+      if (fold) {
+        uint8_t *pb = dest[1] + (long)ostrides[1] * (crow - 1) + (j >> 1), *pr = dest[2] + (long)ostrides[2] * (crow - 1) + (j >> 1);
+        *pb = cavg[((int)u << 8) + *pb];
+        *pr = cavg[((int)v << 8) + *pr];
+      }
+      cb[j >> 1] = u; cr[j >> 1] = v;
+    }
+  }
+}
+
 /* ---- RGB <-> RGB  src/colourspace.c:12370-12556 dispatch, loops :9259-10515 -- */
 
 static int or_rgb_layout(int pal, int *ro, int *go, int *bo, int *ao, int *ps) {

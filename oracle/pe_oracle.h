@@ -63,6 +63,10 @@ void pe_or_rgb_to_yuv888(const uint8_t *src, int irow, int width, int height, ui
 void pe_or_rgb_to_packed422(int fmt, const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order,
                             int in_alpha, int clamping, int quality, const uint16_t *lut16);
 /* planar 4:4:4 (+ alpha plane), colourspace.c:5786,5971,6154 */
+/* init_average :190 (which 0 cavgc, 1 cavgu) and convert_{rgb,bgr}_to_yuv420_frame :6250 / :6385 (4:2:0 and 4:2:2 planar) */
+void pe_or_avg_table(int which, uint8_t out[65536]);
+void pe_or_rgb_to_yuv420p(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[3], const int ostrides[3],
+                          int order, int in_alpha, int is_422, int clamping, int subspace, int quality);
 void pe_or_rgb_to_yuv444p(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[4], int orow, int order,
                           int in_alpha, int out_alpha, int clamping, int quality);
 

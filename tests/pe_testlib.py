@@ -57,6 +57,8 @@ _ORACLE_PROTOS = {
     "pe_or_rgb_to_rgb": [I, I, VP, I, I, I, VP, I, VP],
     "pe_or_rgb_to_packed422": [I, VP, I, I, I, VP, I, I, I, I, I, VP],
     "pe_or_rgb_to_yuv444p": [VP, I, I, I, VP, I, I, I, I, I, I],
+    "pe_or_rgb_to_yuv420p": [VP, I, I, I, VP, VP, I, I, I, I, I, I],
+    "pe_or_avg_table": [I, VP],
     "pe_or_gamma_apply": [VP, I, I, I, I, I, I, VP],
     "pe_or_alpha_premult": [VP, I, I, I, I, I, I],
     "pe_or_simple_blend": [I, I, VP, I, VP, I, VP, I, I, I, I, L],

@@ -470,3 +470,27 @@ print("OK")
 """ % os.path.dirname(os.path.abspath(__file__))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr + out.stdout
+
+
+def test_avg_tables_and_rgb_to_planar420_422_match_reference():
+    """init_average :190 (cavgc / cavgu) and convert_{rgb,bgr}_to_yuv420_frame :6250 / :6385, 4:2:0 and 4:2:2, on unpadded planes
+    (the reference advances its plane pointers densely)"""
+    o, r = T.oracle(), T.ref()
+    for which in (0, 1):
+        a, b = np.zeros(65536, np.uint8), np.zeros(65536, np.uint8)
+        o.pe_or_avg_table(which, T.ptr(a))
+        assert r.ref_get_avg_table(which, T.ptr(b)) == 0
+        assert (a == b).all(), which
+    rng = np.random.default_rng(14)
+    r.ref_set_prefs(1, T.Q_HIGH, 1.4)
+    for (w, h), order, in_alpha, is422, cl, sub in itertools.product(((64, 10), (32, 2), (96, 36)), (0, 1), (0, 1), (0, 1), (0, 1), (1, 2)):
+        ips = 4 if in_alpha else 3
+        src = T.make_packed(rng, w, h, ips)
+        ch = h if is422 else h // 2
+        pa = [np.full((h, w), 7, np.uint8), np.full((ch, w // 2), 7, np.uint8), np.full((ch, w // 2), 7, np.uint8)]
+        pb = [p.copy() for p in pa]
+        strides = (C.c_int * 3)(w, w // 2, w // 2)
+        o.pe_or_rgb_to_yuv420p(T.ptr(src), src.strides[0], w, h, T.planes_arg(*pa), strides, order, in_alpha, is422, cl, sub, T.Q_HIGH)
+        r.ref_rgb_to_yuv420(T.ptr(src), w, h, src.strides[0], strides, T.planes_arg(*pb), order, is422, in_alpha, sub, cl)
+        for k in range(3):
+            assert (pa[k] == pb[k]).all(), ("yuv420p", w, h, order, in_alpha, is422, cl, sub, k)
