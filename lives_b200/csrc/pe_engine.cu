@@ -246,6 +246,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   for (int cl = 0; cl < 2; cl++)
     for (int hd = 0; hd < 2; hd++) cudaFree(e->conv_dev[cl][hd]);
   for (int k = 0; k < 6; k++) cudaFree(e->premult_dev[k]);
+  for (int k = 0; k < 2; k++) cudaFree(e->cavg_dev[k]);
   cudaFree(e->luma_dev);
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
@@ -350,6 +351,22 @@ uint8_t *get_premult(pe_engine *e, int which) {
     return nullptr;
   }
   e->premult_dev[which] = dev;
+  return dev;
+}
+
+uint8_t *get_cavg(pe_engine *e, bool clamped) {
+  const int which = clamped ? 0 : 1;
+  if (e->cavg_dev[which]) return e->cavg_dev[which];
+  std::vector<uint8_t> host(65536);
+  build_avg_table(clamped, host.data());
+  uint8_t *dev = nullptr;
+  if (cudaMalloc(&dev, 65536) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(dev, host.data(), 65536, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  e->cavg_dev[which] = dev;
   return dev;
 }
 
@@ -942,6 +959,22 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                       outpl == PE_PALETTE_YUVA4444P ? (uint8_t *)n.d.planes[3] : nullptr};
     ce = launch_rgb_to_yuv444p(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides[0], width, height,
                                rgb_layout(inpl), dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
+  } else if (pal_is_rgb(inpl) && inpl != PE_PALETTE_ARGB32 &&
+             (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P)) {
+    // convert_{rgb,bgr}_to_yuv420_frame (:12681-12690, :12754-12763, :12600-12609, :12828-12837): width and height cut to even;
+    // 4:2:0 takes the tables of osubspace, 4:2:2 gets WEED_YUV_SAMPLING_DEFAULT in that slot (= YCbCr); the planes are
+    // written in layer order (YVU420P receives Cb in plane 1 exactly as the reference's dest[1]).  ARGB32 (:6323) reads
+    // past its pixels (:6357) and is not built.
+    n.d.width = width & ~1; n.d.height = height & ~1;
+    if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const bool is422 = outpl == PE_PALETTE_YUV422P;
+    const uint8_t *cavg = get_cavg(e, oclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    uint8_t *pl[3] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2]};
+    ce = launch_rgb_to_yuv420p(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides, n.d.width, n.d.height,
+                               rgb_layout(inpl), is422 ? 1 : 0, dev_conv(e, oclamping, is422 ? PE_YUV_SUBSPACE_YCBCR : osubspace), cavg);
+    n.d.yuv_sampling = PE_YUV_SAMPLING_DEFAULT;
   } else {
     set_err(PE_ERR_PALETTE, "palette conversion %d -> %d is not handled by this build", inpl, outpl);
     return PE_FALSE;  // memfail: the layer is left as it was

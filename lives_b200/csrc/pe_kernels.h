@@ -81,6 +81,9 @@ cudaError_t launch_rgb_to_packed422(const Launch &L, int fmt, CImg src, Img dst,
 // RGB(A) -> YUV444P / YUVA4444P (planes[3] = alpha plane or nullptr), colourspace.c:5786-6240
 cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const planes[4], int orow, int width, int height, RgbLayout in,
                                   DevConv conv);
+// RGB(A) -> YUV420P / YUV422P (colourspace.c:6250 / :6385); cavg_dev: the 64 KB averaging table of the output clamping
+cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const planes[3], const int rowstrides[3], int width, int height,
+                                  RgbLayout in, int is_422, DevConv conv, const uint8_t *cavg_dev);
 // ---- effects ---------------------------------------------------------------------------------------
 struct BlendFrame {
   const uint8_t *s1, *s2;

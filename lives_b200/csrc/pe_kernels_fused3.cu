@@ -46,9 +46,10 @@ constexpr int S3_TY = 0;                  // u32 [256][32]
 constexpr int S3_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
 constexpr int S3_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
 constexpr int S3_LUT = 98304;             // u32 [256][32]
-constexpr int S3_BYTES = 131072;           // + 16 bytes per inner output row (filter rows)
-constexpr int F3_BG_AHEAD = 6;            // bg rows prefetched into L2 ahead of the register load
-constexpr int F3_MAX_IH = 4096;
+constexpr int S3_RING = 131072;           // per warp: F3_RING bg rows of 512 bytes, filled by cp.async ahead of the emit
+constexpr int F3_RING = 4;
+constexpr int S3_BYTES = S3_RING + F3_NW * F3_RING * 512;   // + 16 bytes per inner output row (filter rows)
+constexpr int F3_MAX_IH = 3200;
 
 struct Fused3Frame {
   const uint8_t *y, *u, *v, *bg;
@@ -98,7 +99,17 @@ __device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
   asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
   uint32_t r;
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
@@ -343,7 +354,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         init_carry(k - 1, C);
         carry_ok = true;
       }
-      uint4 bgw = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)(oy + iy));
+      // bg rows travel through the warp's cp.async ring, F3_RING - 1 rows ahead of the emit: no registers are tied up and the
+      // emit never waits on a load it has just issued.  A lane only ever reads the 16 bytes it copied itself.
+      const uint32_t ring = sbase + S3_RING + (uint32_t)warp * (F3_RING * 512) + 16u * (uint32_t)lane;
+#pragma unroll
+      for (int j = 0; j < F3_RING - 1; j++) {
+        cp_async16(ring + (uint32_t)((iy + j) & (F3_RING - 1)) * 512u, bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + j, ib - 1)));
+        cp_async_commit();
+      }
 
       auto step = [&](int k, uint32_t(&Wc)[12], const uint32_t(&Wp)[12]) {
         int rA[12], rB[12];
@@ -454,8 +472,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           const int j0 = 2 * k - ri.x - 3;  // 0: the window is Wc; 1: one row older
           const uint32_t CA = (uint32_t)ri.y, CB = (uint32_t)ri.z;
           const int iyn = min(iy + 1, ib - 1);
-          const uint4 bgn = ld_stream_u4(bgp + (size_t)rs_bg * (uint32_t)(oy + iyn));
-          prefetch_l2(bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_BG_AHEAD, ib - 1)));
+          cp_async16(ring + (uint32_t)((iy + F3_RING - 1) & (F3_RING - 1)) * 512u,
+                     bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_RING - 1, ib - 1)));
+          cp_async_commit();
+          cp_async_wait<F3_RING - 1>();  // all but the newest F3_RING - 1 groups have landed: row iy is in its slot
+          const uint4 bgw = lds128(ring + (uint32_t)(iy & (F3_RING - 1)) * 512u);
           const int4 rin = s_rows[iyn];
           const uint32_t bgv[4] = {bgw.x, bgw.y, bgw.z, bgw.w};
           uint32_t ov[4];
@@ -483,7 +504,6 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
             }
           }
           st_stream_u4(outp + (size_t)rs_out * (uint32_t)(oy + iy), make_uint4(ov[0], ov[1], ov[2], ov[3]));
-          bgw = bgn;
           ri = rin;
           iy++;
         }
@@ -502,6 +522,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         if (iy >= ib) break;
         k++;
       }
+      cp_async_wait<0>();  // the ring is reused by the warp's next segment
     }
     border_rows(max(ra, oy + ih), rb);
   }

@@ -414,6 +414,71 @@ cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, 
   return cudaGetLastError();
 }
 
+// RGB(A) -> planar 4:2:0 / 4:2:2 (convert_{rgb,bgr}_to_yuv420_frame colourspace.c:6250 / :6385).  One rgb2uyvy macropixel
+// (:2162) per pixel pair: Y of both pixels, Cb of the first, Cr of the second.  4:2:0 chroma as the reference's pointer dance
+// leaves it (:6291-6306, oracle/pe_oracle.c pe_or_rgb_to_yuv420p):  C[c] = cavg[C(2c+2)][C(2c+1)],  last row C(h-1).
+// One thread = two macropixels (4 pixels) of the luma rows (2g-1, 2g) of row group g = 0 .. h/2 (4:2:0) or of one row (4:2:2):
+// one 32-bit luma store per row, one 16-bit store per chroma plane.
+__global__ void __launch_bounds__(kBlock) k_rgb_to_yuv420p(const uint8_t *__restrict__ src, int irow, uint8_t *py, uint8_t *pu, uint8_t *pv,
+                                                           int rs_y, int rs_u, int rs_v, int width, int height, RgbLayout in, int is_422,
+                                                           DevConv conv, const uint8_t *__restrict__ cavg) {
+  __shared__ int32_t t[9][256];
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[i];
+  __syncthreads();
+  const int quads = (width + 3) >> 2;                       // width is even: the last quad may hold one macropixel
+  const int groups = is_422 ? height : (height >> 1) + 1;
+  const long long total = (long long)quads * groups;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int g = (int)(it / quads), q = (int)(it - (long long)g * quads);
+    const int x = 4 * q, nm = min(2, (width - x) >> 1);     // macropixels of this thread
+    const int ra = is_422 ? g : 2 * g - 1, rb = is_422 ? -1 : 2 * g;
+    uint32_t cu[2][2], cv[2][2];                            // [row a / b][macropixel]
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const int row = rr ? rb : ra;
+      if (row < 0 || row >= height) continue;
+      const uint8_t *p = src + (size_t)irow * row + (size_t)x * in.psize;
+      uint32_t yw = 0;
+#pragma unroll
+      for (int m = 0; m < 2; m++) {
+        if (m < nm) {
+          const uint8_t *p0 = p + 2 * m * in.psize, *p1 = p0 + in.psize;
+          const int r0 = p0[in.r], g0 = p0[in.g], b0 = p0[in.b], r1 = p1[in.r], g1 = p1[in.g], b1 = p1[in.b];
+          const int y0 = clamp_i((t[0][r0] + t[1][g0] + t[2][b0]) >> 16, conv.min_y, conv.max_y);
+          const int y1 = clamp_i((t[0][r1] + t[1][g1] + t[2][b1]) >> 16, conv.min_y, conv.max_y);
+          cu[rr][m] = (uint32_t)clamp_i((t[3][r0] + t[4][g0] + t[5][b0]) >> 16, conv.min_uv, conv.max_uv);
+          cv[rr][m] = (uint32_t)clamp_i((t[6][r1] + t[7][g1] + t[8][b1]) >> 16, conv.min_uv, conv.max_uv);
+          yw |= ((uint32_t)y0 | ((uint32_t)y1 << 8)) << (16 * m);
+        }
+      }
+      uint8_t *yo = py + (size_t)rs_y * row + x;
+      if (nm == 2) *reinterpret_cast<uint32_t *>(yo) = yw;
+      else *reinterpret_cast<uint16_t *>(yo) = (uint16_t)yw;
+    }
+    // chroma row of this group
+    int crow;
+    bool have_a, have_b;
+    if (is_422) { crow = g; have_a = true; have_b = false; }
+    else { crow = g - 1; have_a = ra >= 0; have_b = rb < height; }
+    if (crow < 0 || !have_a) continue;
+    uint32_t uo = 0, vo = 0;
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      if (m < nm) {
+        uint32_t u = cu[0][m], v = cv[0][m];
+        if (have_b) {  // avg_chroma(new = row 2c+2, old = row 2c+1)
+          u = __ldg(cavg + ((cu[1][m] << 8) | u));
+          v = __ldg(cavg + ((cv[1][m] << 8) | v));
+        }
+        uo |= u << (8 * m); vo |= v << (8 * m);
+      }
+    }
+    uint8_t *uop = pu + (size_t)rs_u * crow + (x >> 1), *vop = pv + (size_t)rs_v * crow + (x >> 1);
+    if (nm == 2) { *reinterpret_cast<uint16_t *>(uop) = (uint16_t)uo; *reinterpret_cast<uint16_t *>(vop) = (uint16_t)vo; }
+    else { *uop = (uint8_t)uo; *vop = (uint8_t)vo; }
+  }
+}
+
 }  // namespace pe
 
 namespace pe {
@@ -437,4 +502,17 @@ cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const plan
   if (L.launch_counter) ++*L.launch_counter;
   return cudaGetLastError();
 }
+cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const planes[3], const int rowstrides[3], int width, int height,
+                                  RgbLayout in, int is_422, DevConv conv, const uint8_t *cavg_dev) {
+  width &= ~1; height &= ~1;
+  if (width <= 0 || height <= 0) return cudaSuccess;
+  const long long work = (long long)((width + 3) >> 2) * (is_422 ? height : (height >> 1) + 1);
+  k_rgb_to_yuv420p<<<(int)std::min<long long>((work + 255) / 256, (long long)L.sm_count * 8), 256, 0, L.stream>>>(
+      src.p, src.rs, planes[0], planes[1], planes[2], rowstrides[0], rowstrides[1], rowstrides[2], width, height, in, is_422, conv,
+      cavg_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
 }  // namespace pe
+

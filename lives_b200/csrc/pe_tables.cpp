@@ -212,6 +212,22 @@ void build_premult_table(int which, uint8_t *out) {
   }
 }
 
+// init_average (colourspace.c:190-217, !MULT_AVG): the chroma averaging tables behind avg_chroma().  clamped (cavgc): float
+// maths as the reference spells it, result clamped to 16..240; unclamped (cavgu): short arithmetic
+void build_avg_table(bool clamped, uint8_t *out) {
+  for (int x = 0; x < 256; x++) {
+    const float fa = (float)(x - 128.) * 255. / 244.;
+    const short sa = (short)(x - 128);
+    for (int y = 0; y < 256; y++) {
+      const float fb = (float)(y - 128.) * 255. / 244.;
+      const short sb = (short)(y - 128);
+      const float fc = (fa + fb) * 224. / 512. + 128.;
+      const short c = ((sa + sb) >> 1) + 128;
+      out[x * 256 + y] = clamped ? (uint8_t)(fc > 240. ? 240 : fc < 16. ? 16 : fc) : (uint8_t)(c > 255 ? 255 : c < 0 ? 0 : c);
+    }
+  }
+}
+
 void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]) {
   for (int i = 0; i < 256; i++) {
     yr[i] = round_half_away(0.299 * (double)i * 65536.);

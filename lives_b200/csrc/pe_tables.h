@@ -25,6 +25,9 @@ bool build_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen
 // init_unal (colourspace.c:1141): which = 0 unal 1 al 2 unalcy 3 alcy 4 unalcuv 5 alcuv, as uint8
 void build_premult_table(int which, uint8_t *out /*65536*/);
 
+// init_average (colourspace.c:190): cavgc (clamped) / cavgu, [x][y] as uint8
+void build_avg_table(bool clamped, uint8_t *out /*65536*/);
+
 // calc_luma tables of libweed/weed-plugin-utils.c:881-886 (16.16, SCALE_FACTOR 65536)
 void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]);
 

@@ -281,13 +281,42 @@ def test_rgb_to_packed422_and_planar444(eng):
     assert (payload(lay.to_host()[0], w // 2, 4) == payload(exp, w // 2, 4)).all()
 
 
+def test_rgb_to_planar420_and_422(eng):
+    """convert_{rgb,bgr}_to_yuv420_frame :6250 / :6385 through the dispatcher: 4:2:0 (tables of osubspace) and 4:2:2 (YCbCr),
+    padded planes, odd sizes cut to even; ARGB32 is not built and fails loudly"""
+    o = T.oracle()
+    rng = np.random.default_rng(26)
+    for (w, h), ipal, cl, sub in itertools.product(((48, 10), (101, 7), (642, 34), (6, 2)), (1, 2, 3, 4), (0, 1), (1, 2)):
+        order, in_alpha = ORDER_OF[ipal]
+        src = T.make_packed(rng, w, h, T.psize_of(ipal))
+        we, he = w & ~1, h & ~1
+        for opal, is422 in ((512, 0), (522, 1)):
+            rs = T.rowstride(we, 1)
+            ch = he if is422 else he // 2
+            pl = [np.zeros((he, rs), np.uint8), np.zeros((ch, rs // 2), np.uint8), np.zeros((ch, rs // 2), np.uint8)]
+            strides = (C.c_int * 3)(rs, rs // 2, rs // 2)
+            o.pe_or_rgb_to_yuv420p(T.ptr(src), src.strides[0], w, h, T.planes_arg(*pl), strides, order, in_alpha, is422, cl,
+                                   1 if is422 else sub, T.Q_HIGH)
+            lay = packed_layer(eng, ipal, w, h, src)
+            assert lb.convert_layer_palette_full(lay, opal, cl, 0, sub, 0)
+            assert (lay.palette, lay.width, lay.height, lay.yuv_clamping) == (opal, we, he, cl)
+            got = lay.to_host()
+            assert (got[0][:he, :we] == pl[0][:, :we]).all(), (w, h, ipal, cl, sub, opal, "Y")
+            assert (got[1][:ch, :we // 2] == pl[1][:, :we // 2]).all(), (w, h, ipal, cl, sub, opal, "U")
+            assert (got[2][:ch, :we // 2] == pl[2][:, :we // 2]).all(), (w, h, ipal, cl, sub, opal, "V")
+    src = T.make_packed(rng, 32, 8, 4)
+    lay = packed_layer(eng, 5, 32, 8, src)
+    assert not lb.convert_layer_palette(lay, 512, 0)
+    assert lay.palette == 5
+
+
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
-    src = T.make_packed(rng, 32, 8, 3)
-    lay = packed_layer(eng, 1, 32, 8, src)
+    src = T.make_packed(rng, 32, 8, 4)
+    lay = packed_layer(eng, 5, 32, 8, src)  # ARGB32 -> YUV420P: the reference loop reads past its pixels (:6357); not built
     assert not lb.convert_layer_palette(lay, lb.WEED_PALETTE_YUV420P, 0)
     assert "not handled" in lb._capi.last_error()
-    assert lay.palette == 1
+    assert lay.palette == 5
     assert (lay.to_host()[0] == src).all()
 
 

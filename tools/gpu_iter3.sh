@@ -2,7 +2,7 @@
 # one k_fused3 iteration on the GPU box: fused parity tests, bench line, optional ncu full profile, optional env sweeps
 TAG=${1:-it}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "fused or smoke or host" > gpurun_out/pytest_$TAG.log 2>&1; tail -15 gpurun_out/pytest_$TAG.log
+timeout 900 python -m pytest tests -m gpu -q -k "fused or smoke or host or planar420 or unhandled" > gpurun_out/pytest_$TAG.log 2>&1; tail -15 gpurun_out/pytest_$TAG.log
 B="python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-frames 2 --e2e-steps 1"
 timeout 300 $B > gpurun_out/bench_$TAG.log 2>&1; tail -1 gpurun_out/bench_$TAG.log | cut -c1-200
 if [ "$2" = "prof" ]; then
