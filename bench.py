@@ -369,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": "frames sharded, no collective",
                            "l2": "inputs larger than L2: %.0f MB touched per step vs 126 MB L2" % (ALGO_BYTES_PER_FRAME * B / 1e6)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "k_fused", "kernel_ms": kernel_ms,
+                             "traffic": None, "peak_source": peak_src, "kernel": "k_fused3", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (FG_BYTES + RGBA_BYTES) * e2e_frames,
@@ -380,7 +380,9 @@ def run_ours(args, rank, world, local_rank):
         prof = os.path.join(REPO, "profiles", "traffic_r01.json")
         if os.path.exists(prof):
             try:
-                line["roofline"]["traffic"] = json.load(open(prof)).get("k_fused_bytes_per_launch_batch%d" % B)
+                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per frame
+                per_frame = json.load(open(prof)).get("k_fused3_dram_bytes_per_frame")
+                line["roofline"]["traffic"] = per_frame * B if per_frame else None
             except Exception:
                 pass
         print(json.dumps(line), flush=True)
@@ -474,7 +476,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="independent frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="independent frames per step per GPU (one kernel launch)")
     ap.add_argument("--e2e-frames", type=int, default=16, help="host frames per e2e step (one batch call)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -41,7 +41,7 @@ namespace {
 
 constexpr int F3_NT = 512;
 constexpr int F3_NW = F3_NT / 32;
-constexpr int F3_MAXF = 16;               // frames per launch (their pointers travel as kernel parameters)
+constexpr int F3_MAXF = 32;               // frames per launch (their pointers travel as kernel parameters)
 constexpr int S3_TY = 0;                  // u32 [256][32]
 constexpr int S3_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
 constexpr int S3_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
@@ -122,8 +122,10 @@ constexpr uint32_t K3 = 0x00030003u;    // + 3 in both halves (Q = 2 n + 3)
 // m = third_round(n) = (2 n + 3) / 6 for the n in the HIGH / LOW half of a packed Q = 2 n + 3 (each half <= 1533).
 // 10923 / 65536 = 1 / 6 + 5e-6: the product is off by < 0.008 (plus < 0.004 from the low half leaking into the high one),
 // and (2 n + 3) / 6 is never closer than 1 / 6 to an integer, so the floor is exact.
-__device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u); }
-__device__ __forceinline__ uint32_t idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u); }
+// The kernel wants the table offset 128 * m: with the multiplier scaled by 128 the product is floor(128 * m_real), whose bits
+// 7.. are 128 * floor(m_real) (the bits below are masked off together with the OR of the lane's column offset).
+__device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u * 128u) & 0x7F80u; }
+__device__ __forceinline__ uint32_t idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u * 128u) & 0x7F80u; }
 
 // the three 'this / last / next' views of one chroma row for the lane's two chroma columns jc0, jc0 + 1, as 16-bit halves
 struct RowC {
@@ -203,9 +205,13 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   const uint32_t ka = P.ka, kia = P.kia;
 
   // yuv2rgb_int (colourspace.c:2345-2356) through the replicated tables; results UNSATURATED (saturated by pack_sat)
-  auto rgb = [&](uint32_t y, uint32_t mu, uint32_t mv, int &r, int &g, int &b) {
+  // (ou, ov = 128 * m: byte offsets of the chroma entries; plain shared-memory loads so that the table bases fold into the
+  // instructions' address immediates)
+  const uint32_t lane8 = 8u * (uint32_t)(lane & 15);
+  auto rgb = [&](uint32_t y, uint32_t ou, uint32_t ov, int &r, int &g, int &b) {
     const int yy = (int)lds32(L.tyl + y * 128u);
-    const uint2 tv = lds64(L.tvl + mv * 128u), tu = lds64(L.tul + mu * 128u);
+    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (ov | lane8));
+    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (ou | lane8));
     r = (yy + (int)tv.x) >> 16;
     g = (yy + (int)tu.x + (int)tv.y) >> 16;
     b = (yy + (int)tu.y) >> 16;
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
               const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
               const uint32_t mu = (chroma_at(F.u, rs_u, cr, jc, cw, ch) + chroma_at(F.u, rs_u, cr, jo, cw, ch)) >> 1;
               const uint32_t mv = (chroma_at(F.v, rs_v, cr, jc, cw, ch) + chroma_at(F.v, rs_v, cr, jo, cw, ch)) >> 1;
-              rgb(byte_of(yw, col), mu, mv, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rgb(byte_of(yw, col), mu * 128u, mv * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
               rB[3 * col] = rA[3 * col]; rB[3 * col + 1] = rA[3 * col + 1]; rB[3 * col + 2] = rA[3 * col + 2];
             }
           };
@@ -446,8 +452,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
               }
               const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
               const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
-              rgb(byte_of(ya, col), mu3, mv3, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-              rgb(byte_of(yb, col), mu4, mv4, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+              rgb(byte_of(ya, col), mu3 * 128u, mv3 * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rgb(byte_of(yb, col), mu4 * 128u, mv4 * 128u, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
             }
           } else if (2 * k - 1 == fh - 1) {
             single(fh - 1, ch - 1);

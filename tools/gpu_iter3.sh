@@ -18,3 +18,5 @@ for spec in "$@"; do
   done
 done > gpurun_out/sweep_$TAG.log 2>&1
 cat gpurun_out/sweep_$TAG.log
+for b in 32 64; do r=$(timeout 120 $B --batch $b 2>&1 | tail -1 | grep -o '"value": [0-9.]*' | head -1); echo "batch=$b $r"; done >> gpurun_out/sweep_$TAG.log 2>&1
+tail -2 gpurun_out/sweep_$TAG.log
