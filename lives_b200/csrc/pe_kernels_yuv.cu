@@ -416,7 +416,7 @@ cudaError_t launch_rgb_to_yuv888(const Launch &L, CImg src, Img dst, int width, 
 
 // RGB(A) -> planar 4:2:0 / 4:2:2 (convert_{rgb,bgr}_to_yuv420_frame colourspace.c:6250 / :6385).  One rgb2uyvy macropixel
 // (:2162) per pixel pair: Y of both pixels, Cb of the first, Cr of the second.  4:2:0 chroma as the reference's pointer dance
-// leaves it (:6291-6306, oracle/pe_oracle.c pe_or_rgb_to_yuv420p):  C[c] = cavg[C(2c+2)][C(2c+1)],  last row C(h-1).
+// leaves it (:6291-6306):  C[c] = cavg[C(2c+2)][C(2c+1)],  last row C(h-1).
 // One thread = two macropixels (4 pixels) of the luma rows (2g-1, 2g) of row group g = 0 .. h/2 (4:2:0) or of one row (4:2:2):
 // one 32-bit luma store per row, one 16-bit store per chroma plane.
 __global__ void __launch_bounds__(kBlock) k_rgb_to_yuv420p(const uint8_t *__restrict__ src, int irow, uint8_t *py, uint8_t *pu, uint8_t *pv,
