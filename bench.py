@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="independent frames per step per GPU (one kernel launch)")
-    ap.add_argument("--e2e-frames", type=int, default=16, help="host frames per e2e step (one batch call)")
+    ap.add_argument("--e2e-frames", type=int, default=48, help="host frames per e2e step (one batch call)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="headline", help="headline (the driver's line) | cfg1 | cfg2 | cfg3 | cfg4: kernel-level "
