@@ -35,7 +35,8 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pixel_engine.h")]
     deps = [d for d in deps if os.path.isfile(d)]
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        extra = ["-DPE_F3_NT=" + os.environ["PE_F3_NT"]] if os.environ.get("PE_F3_NT") else []  # tuning experiments only
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd, cwd=CSRC)

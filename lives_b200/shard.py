@@ -41,16 +41,35 @@ def allreduce_histogram(hist, group=None):
     return hist
 
 
+_ENGINE_STREAMS = {}
+
+
+def _engine_stream(engine):
+    """the engine's CUDA stream as a torch stream (for event ordering against NCCL, which runs on torch's stream)"""
+    key = id(engine)
+    if key not in _ENGINE_STREAMS:
+        _ENGINE_STREAMS[key] = torch.cuda.ExternalStream(engine.stream)
+    return _ENGINE_STREAMS[key]
+
+
 def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blend_factor, src_rank=0, out_palette=1):
     """config 5 on this rank: clip (YUV422P / UYVY / ...) -> RGB24 (convert_layer_palette), operand broadcast from the owner,
     then 'chroma blend' (the crossfade / auto-transition of src/multitrack.h:84) of the clip with the operand, in place.
-    `operand_tensor`: uint8 CUDA tensor of height x rowstride bytes on every rank."""
+    `operand_tensor`: uint8 CUDA tensor of height x rowstride bytes on every rank.
+    Stream ordered, no host synchronisation: the broadcast (torch's current stream) overlaps the conversion (engine stream);
+    the blend waits for the broadcast, and the next broadcast into the same tensor waits for the blend."""
     from . import engine as E
+    es, ts = _engine_stream(engine), torch.cuda.current_stream()
     if not E.convert_layer_palette(clip_layer, out_palette, 0):
         raise RuntimeError("clip conversion failed: " + E.capi.last_error())
     broadcast_operand(operand_tensor, src=src_rank)
-    torch.cuda.current_stream().synchronize()  # NCCL ran on torch's stream; the engine has its own
+    arrived = torch.cuda.Event()
+    arrived.record(ts)
+    es.wait_event(arrived)
     rs = operand_tensor.shape[1] if operand_tensor.dim() == 2 else operand_tensor.numel() // height
     operand = E.Layer.wrap_device(engine, out_palette, width, height, [operand_tensor.data_ptr()], [rs])
     E.simple_blend("chroma blend", clip_layer, operand, clip_layer, blend_factor)
+    consumed = torch.cuda.Event()
+    consumed.record(es)
+    ts.wait_event(consumed)
     return clip_layer

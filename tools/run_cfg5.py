@@ -54,8 +54,7 @@ def main():
     def frame():
         clip = lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2], yuv_subspace=1)
         shard.multitrack_crossfade(eng, clip, operand, W, H, 128)
-        eng.sync()
-        clip.free()
+        clip.free()  # stream ordered: the block returns to the pool behind the kernels that use it
 
     for _ in range(3):
         frame()
@@ -64,6 +63,7 @@ def main():
     ev0.record()
     for _ in range(steps):
         frame()
+    eng.sync()
     ev1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
