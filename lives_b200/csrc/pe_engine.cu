@@ -1448,18 +1448,13 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
     if (!fy->rows4) {
       const ResizeFilter &F = fy->host;
       std::vector<int32_t> r4((size_t)inner_h * 4);
-      // coefficients scaled by 16 (sum 65536) when every one of them still fits 16 bits, i.e. no row has the single tap 4096:
-      // the kernel then reads the filtered value as byte 2 of its accumulator instead of shifting by 12
-      int cmax = 0;
-      for (size_t i = 0; i < (size_t)inner_h * F.taps; i++) cmax = F.coef[i] > cmax ? F.coef[i] : cmax;
-      const uint32_t scale = cmax < 4096 ? 16u : 1u;
       for (int i = 0; i < inner_h; i++) {
         uint32_t c[4] = {0, 0, 0, 0};
-        for (int t = 0; t < F.taps; t++) c[t] = (uint32_t)(uint16_t)F.coef[(size_t)i * F.taps + t] * scale;
+        for (int t = 0; t < F.taps; t++) c[t] = (uint16_t)F.coef[(size_t)i * F.taps + t];
         r4[4 * i] = F.first[i];
         r4[4 * i + 1] = (int32_t)(c[3] | (c[2] << 16));
         r4[4 * i + 2] = (int32_t)(c[1] | (c[0] << 16));
-        r4[4 * i + 3] = scale == 16u ? 1 : 0;
+        r4[4 * i + 3] = 0;
       }
       PE_CUDA(cudaMalloc(&fy->rows4, r4.size() * sizeof(int32_t)));
       PE_CUDA(cudaMemcpyAsync(fy->rows4, r4.data(), r4.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));

