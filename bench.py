@@ -309,6 +309,16 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     achieved = ALGO_BYTES_PER_FRAME * B / (kernel_ms / 1000.0) / 1e9
 
+    # ---- single-frame latency: one frame per launch, device resident (SURVEY.md 8d asks for it beside the batch figure)
+    for _ in range(3):
+        lb.fused_convert_letterbox_over_gamma_batch(fgs[:1], bgs[:1], outs[:1], IW, IH, ALPHA, G_LINEAR, G_SRGB)
+    eng.sync()
+    eng.timer_start()
+    for i in range(20):
+        j = i % B
+        lb.fused_convert_letterbox_over_gamma_batch(fgs[j:j + 1], bgs[j:j + 1], outs[j:j + 1], IW, IH, ALPHA, G_LINEAR, G_SRGB)
+    single_frame_us = eng.timer_stop_ms() * 1000.0 / 20
+
     # ---- e2e: host buffers through the C-ABI drop-in, H2D + kernel + D2H timed (per rank, frames independent)
     hframes = host_frames(4, seed0=20 + 100 * rank)
     pinned = []
@@ -370,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "inputs larger than L2: %.0f MB touched per step vs 126 MB L2" % (ALGO_BYTES_PER_FRAME * B / 1e6)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "k_fused3", "kernel_ms": kernel_ms,
-                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B},
+                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "single_frame_launch_us": single_frame_us},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (FG_BYTES + RGBA_BYTES) * e2e_frames,
                         "d2h_bytes_per_step": RGBA_BYTES * e2e_frames, "frames_per_step": e2e_frames, "steps": args.e2e_steps,

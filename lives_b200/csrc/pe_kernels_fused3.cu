@@ -1,5 +1,6 @@
 // pe_kernels_fused3.cu -- the register-resident fused chain (the kernel bench.py's headline runs):
-//     planar 4:2:0 fg -> RGBA  |  full-width letterbox (inner width == outer width == fg width), vertical filter of <= 4 taps
+//     planar 4:2:0 fg -> RGBA  |  letter- / pillarbox without horizontal scaling (inner width == fg width, inner offset a
+//     multiple of 4), vertical filter of <= 4 taps
 //     |  scalar alpha-over (alpha = k / 256) a RGBA32 bg  |  optional 8-bit gamma LUT
 // Same arithmetic, bit for bit, as k_fused2 / k_fused and as the unfused ops (tests/test_gpu_parity.py); everything outside
 // this envelope runs k_fused2 (pe_kernels_fused2.cu).  What differs is where the data lives:
@@ -65,6 +66,7 @@ struct Fused3Params {
   int fw, fh, cw, ch;                      // fg luma / chroma size
   int rs_y, rs_u, rs_v, rs_bg, rs_out;     // shared by all frames of the launch
   int oh, oy, ih;                          // outer height, first inner row, inner height
+  int ow, ox;                              // outer width, first inner column (inner width == fw)
   int nstrips, band_h;
   int k_fast_max;                          // steps 1 .. k_fast_max take the fast path
   int cost_b, cost_i;                      // cost of a border / an inner output row
@@ -283,8 +285,9 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     const int ra = row_at(base + within), rb = row_at(base + hi);
     pos = unit0 + bc;
 
-    const int x = 128 * s + 4 * lane;  // the lane's first column
-    if (x >= fw || ra >= rb) continue;
+    const int x = 128 * s + 4 * lane;  // the lane's first output column
+    if (x >= P.ow || ra >= rb) continue;
+    const int xs = x - P.ox;           // ... and its first source column (pillarbox: the inner rectangle starts at ox)
     const Fused3Frame &F = P.fr[f];
     const uint8_t *bgp = F.bg + 4 * (size_t)x;
     uint8_t *outp = F.out + 4 * (size_t)x;
@@ -311,21 +314,25 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         }
       }
     };
+    if (xs < 0 || xs >= fw) {  // a lane left / right of the inner rectangle: border on every row
+      border_rows(ra, rb);
+      continue;
+    }
     border_rows(ra, min(rb, oy));
 
     const int ia = max(ra, oy) - oy, ib = min(rb, oy + ih) - oy;  // inner rows [ia, ib)
     if (ia < ib) {
       // ---- per-lane constants
-      const int jc0 = x >> 1;                 // first chroma column of the lane
+      const int jc0 = xs >> 1;                // first chroma column of the lane
       const int o = jc0 - 1;                  // byte offset of chroma column jc0 - 1
-      const int off0 = x == 0 ? 0 : (o & ~3);  // the second word is the next one (lane 0 of strip 0 only uses the first)
-      L.x = x;
-      L.yp = F.y + x;
+      const int off0 = xs == 0 ? 0 : (o & ~3);  // the second word is the next one (the lane of source column 0 only uses the first)
+      L.x = xs;
+      L.yp = F.y + xs;
       L.up0 = F.u + off0;
       L.vp0 = F.v + off0;
       L.vfp = F.v;
-      L.sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
-      L.selB = x == 0 ? 0x3254u : 0x3210u;
+      L.sel = xs == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+      L.selB = xs == 0 ? 0x3254u : 0x3210u;
       const uint32_t rs_y = (uint32_t)P.rs_y, rs_u = (uint32_t)P.rs_u, rs_v = (uint32_t)P.rs_v;
       const int k_fast_max = P.k_fast_max;
 
@@ -572,13 +579,13 @@ bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
   if (n <= 0 || fy_taps > 4) return false;
   const FusedArgs &f0 = a[0];
   if (f0.is_422 || f0.low_quality) return false;
-  if (f0.iw != f0.fw || f0.ow != f0.fw || f0.ox != 0) return false;          // full-width letterbox, no horizontal scaling
+  if (f0.iw != f0.fw || (f0.ox & 3) || (f0.ow & 3) || f0.ox + f0.iw > f0.ow) return false;   // no horizontal scaling; lanes = 4 px
   if ((f0.fw & 3) || f0.fw < 4 || f0.fh < 4 || f0.ih > F3_MAX_IH) return false;
   if (f0.fg.cw != f0.fw / 2 || f0.fg.ch != (f0.fh + 1) / 2) return false;
   for (int i = 0; i < n; i++) {
     const FusedArgs &f = a[i];
     if (f.is_422 != f0.is_422 || f.low_quality != f0.low_quality || f.quirks != f0.quirks || f.conv.t != f0.conv.t) return false;
-    if (f.fw != f0.fw || f.fh != f0.fh || f.ow != f0.ow || f.oh != f0.oh || f.ih != f0.ih || f.oy != f0.oy) return false;
+    if (f.fw != f0.fw || f.fh != f0.fh || f.ow != f0.ow || f.oh != f0.oh || f.ih != f0.ih || f.oy != f0.oy || f.ox != f0.ox) return false;
     if (f.fg.rs_y != f0.fg.rs_y || f.fg.rs_u != f0.fg.rs_u || f.fg.rs_v != f0.fg.rs_v || f.bg.rs != f0.bg.rs || f.out.rs != f0.out.rs)
       return false;
     if (((uintptr_t)f.fg.y | (uintptr_t)f.fg.u | (uintptr_t)f.fg.v) & 3) return false;
@@ -624,8 +631,8 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     }
     P.fw = a0.fw; P.fh = a0.fh; P.cw = a0.fg.cw; P.ch = a0.fg.ch;
     P.rs_y = a0.fg.rs_y; P.rs_u = a0.fg.rs_u; P.rs_v = a0.fg.rs_v; P.rs_bg = a0.bg.rs; P.rs_out = a0.out.rs;
-    P.oh = a0.oh; P.oy = a0.oy; P.ih = a0.ih;
-    P.nstrips = (a0.fw + 127) / 128;
+    P.oh = a0.oh; P.oy = a0.oy; P.ih = a0.ih; P.ow = a0.ow; P.ox = a0.ox;
+    P.nstrips = (a0.ow + 127) / 128;
     // the fast step reads whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
     const bool last_row_unsafe = a0.fg.rs_u < a0.fg.cw + 4 || a0.fg.rs_v < a0.fg.cw + 4;
     P.k_fast_max = a0.fg.ch - 1 - (last_row_unsafe ? 1 : 0);

@@ -631,6 +631,8 @@ def test_fused_chain_equals_unfused_oracle(eng, case):
     (256, 96, 0, 256, 96, 64, 0.375, None),         # ratio 1.5 (four full taps), alpha 3/8, no gamma
     (8, 6, 0, 8, 9, 7, 0.5, (-1, 1)),               # tiny frame: two lanes
     (4, 4, 0, 4, 4, 4, 0.5, (-1, 1)),               # one lane, identity
+    (128, 64, 0, 160, 100, 100, 0.5, (-1, 1)),      # pillarbox + letterbox: inner offset 16, border lanes inside inner rows
+    (640, 360, 0, 1000, 360, 360, 0.25, (-1, 1)),   # pure pillarbox (offset 180), strips left and right without inner lanes
 ])
 @pytest.mark.parametrize("variant", ["clamped", "unclamped_noquirks"])
 def test_fused_fast_path_cases(case, variant):
