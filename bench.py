@@ -451,6 +451,18 @@ def run_secondary(args):
                 lb.resize_layer(lay, 1280, 720, 1, 3, 0)
                 lay.free()
         frames, algo, name = n, W * H * 3 // 2 + 1280 * 720 * 4, "cfg2: %d x 1080p YUV420P -> RGBA32 -> 1280x720, unfused (3 kernels / frame)" % n
+    elif wl == "cfg5":  # per clip: 4K YUV422P -> RGB24 + crossfade (chroma blend bf=128) with the shared operand; no broadcast at N = 1
+        W, H, n = 3840, 2160, 8
+        src = [(rnd(H, W, 16, 236), rnd(H, W // 2, 16, 241), rnd(H, W // 2, 16, 241)) for _ in range(n)]
+        operand = wrap(1, W, H, [rnd(H, W * 3)])
+
+        def step():
+            for y, u, v in src:
+                lay = wrap(522, W, H, [y, u, v], yuv_subspace=1)
+                lb.convert_layer_palette(lay, 1, 0)
+                lb.simple_blend("chroma blend", lay, operand, lay, 128)
+                lay.free()
+        frames, algo, name = n, W * H * 2 + 2 * W * H * 3, "cfg5 (1 GPU, no broadcast): %d x 4K YUV422P -> RGB24 + chroma blend bf=128 with one operand (2 kernels / clip)" % n
     elif wl == "cfg1":  # 640x480 RGB24 -> BGR24 in place
         W, H, n = 640, 480, 256
         lay = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
@@ -490,7 +502,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=48, help="host frames per e2e step (one batch call)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="headline", help="headline (the driver's line) | cfg1 | cfg2 | cfg3 | cfg4: kernel-level "
+    ap.add_argument("--workload", default="headline", help="headline (the driver's line) | cfg1 | cfg2 | cfg3 | cfg4 | cfg5: kernel-level "
                     "numbers of the other BASELINE configs, N = 1 only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -648,7 +648,10 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (bh > a0.oh) bh = a0.oh;
     P.band_h = (int)bh;
     // the last part of the sequence is handed out dynamically, in chunks of about F3_CHUNK_ROWS inner rows
+    // (a chunk is at most a third of a warp's static share, so that a single-frame launch is not stretched by its last chunks)
     P.chunk_cost = (long long)cost_i * chunk_rows;
+    if (P.chunk_cost > share / 3) P.chunk_cost = share / 3;
+    if (P.chunk_cost < (long long)cost_i * 4) P.chunk_cost = (long long)cost_i * 4;
     P.static_cost = P.total_cost * static_pct / 100;
     if (P.total_cost - P.static_cost < P.chunk_cost * grid) P.static_cost = P.total_cost;  // small jobs: all static
     P.sched = sched_dev;

@@ -47,13 +47,16 @@ def main():
     yy = torch.randint(16, 236, (H, W), dtype=torch.uint8, device=dev, generator=g)
     uu = torch.randint(16, 241, (H, W // 2), dtype=torch.uint8, device=dev, generator=g)
     vv = torch.randint(16, 241, (H, W // 2), dtype=torch.uint8, device=dev, generator=g)
-    operand = torch.randint(0, 256, (H, W * 3), dtype=torch.uint8, device=dev, generator=g)
-    steps = 20
+    # two operand buffers: the broadcast of output frame t + 1 overlaps the conversion and the blend of frame t
+    operands = [torch.randint(0, 256, (H, W * 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    steps = 40
+    it = [0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def frame():
         clip = lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2], yuv_subspace=1)
-        shard.multitrack_crossfade(eng, clip, operand, W, H, 128)
+        shard.multitrack_crossfade(eng, clip, operands[it[0] & 1], W, H, 128)
+        it[0] += 1
         clip.free()  # stream ordered: the block returns to the pool behind the kernels that use it
 
     for _ in range(3):
