@@ -446,11 +446,11 @@ def run_secondary(args):
         src = [(rnd(H, W, 16, 236), rnd(H // 2, W // 2, 16, 241), rnd(H // 2, W // 2, 16, 241)) for _ in range(n)]
 
         def step():
-            for y, u, v in src:
-                lay = wrap(512, W, H, [y, u, v], yuv_subspace=1)
-                lb.resize_layer(lay, 1280, 720, 1, 3, 0)
+            lays = [wrap(512, W, H, [y, u, v], yuv_subspace=1) for y, u, v in src]
+            assert lb.resize_layer_batch(lays, 1280, 720, 1, 3, 0) == n
+            for lay in lays:
                 lay.free()
-        frames, algo, name = n, W * H * 3 // 2 + 1280 * 720 * 4, "cfg2: %d x 1080p YUV420P -> RGBA32 -> 1280x720, unfused (3 kernels / frame)" % n
+        frames, algo, name = n, W * H * 3 // 2 + 1280 * 720 * 4, "cfg2: %d x 1080p YUV420P -> RGBA32 -> 1280x720, pe_resize_layer_batch (convert + tiled resize per frame)" % n
     elif wl == "cfg5":  # per clip: 4K YUV422P -> RGB24 + crossfade (chroma blend bf=128) with the shared operand; no broadcast at N = 1
         W, H, n = 3840, 2160, 8
         src = [(rnd(H, W, 16, 236), rnd(H, W // 2, 16, 241), rnd(H, W // 2, 16, 241)) for _ in range(n)]
@@ -459,18 +459,16 @@ def run_secondary(args):
         def step():
             for y, u, v in src:
                 lay = wrap(522, W, H, [y, u, v], yuv_subspace=1)
-                lb.convert_layer_palette(lay, 1, 0)
-                lb.simple_blend("chroma blend", lay, operand, lay, 128)
+                lb.convert_crossfade(lay, operand, 1, 0, 128)
                 lay.free()
-        frames, algo, name = n, W * H * 2 + 2 * W * H * 3, "cfg5 (1 GPU, no broadcast): %d x 4K YUV422P -> RGB24 + chroma blend bf=128 with one operand (2 kernels / clip)" % n
+        frames, algo, name = n, W * H * 2 + 2 * W * H * 3, "cfg5 (1 GPU, no broadcast): %d x 4K YUV422P -> RGB24 + chroma blend bf=128 with one operand (pe_fx_convert_crossfade, 1 kernel / clip)" % n
     elif wl == "cfg1":  # 640x480 RGB24 -> BGR24 in place
         W, H, n = 640, 480, 256
         lay = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]
 
         def step():
-            for i, l in enumerate(lay):
-                lb.convert_layer_palette(l, 2 if l.palette == 1 else 1, 0)
-        frames, algo, name = n, 2 * W * H * 3, "cfg1: %d x 640x480 RGB24 <-> BGR24 in place (one launch per frame)" % n
+            assert lb.convert_layer_palette_batch(lay, 2 if lay[0].palette == 1 else 1, 0) == n
+        frames, algo, name = n, 2 * W * H * 3, "cfg1: %d x 640x480 RGB24 <-> BGR24 in place (pe_convert_layer_palette_batch, one launch per frame)" % n
     else:
         raise SystemExit("unknown workload " + wl)
     for _ in range(max(args.warmup, 3)):

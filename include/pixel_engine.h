@@ -147,6 +147,11 @@ int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width, int heigh
  *                                                                             colourspace.h:413, .c:15331 */
 int pe_resize_layer(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
                     int oclamp_hint);
+/* batches of independent layers (what the render-to-disk loop, src/events.c:4239-4253, issues one by one): one lock, the
+ * launches go out back to back.  Return the number of layers for which the per-layer call returned TRUE. */
+int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *layers, int width, int height, int interp, int opal_hint,
+                          int oclamp_hint);
+int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t *const *layers, int outpl, int op_clamping);
 /* boolean letterbox_layer(weed_layer_t *, int nwidth, int nheight, int width, int height, LiVESInterpType,
  *                         int tpal, int tclamp)                               colourspace.h:415, .c:15343 */
 int pe_letterbox_layer(pe_engine_t *e, pe_frame_t *layer, int nwidth, int nheight, int width, int height,
@@ -169,6 +174,11 @@ int pe_gamma_lut8(pe_engine_t *e, double fileg, int gamma_from, int gamma_to, ui
 int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                        int blend_factor);
 /* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
+/* convert_layer_palette(clip, outpl) (colourspace.c:13521-13685) + the 'chroma blend' of simple_blend.c:58 with in1 = the
+ * converted clip, in2 = operand, result in the clip: the multitrack crossfade (src/multitrack.h:84) as one kernel.
+ * clip: YUV420P / YVU420P / YUV422P, outpl = operand palette = RGB24 or BGR24. */
+int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const pe_frame_t *operand, int outpl, int op_clamping,
+                            int blend_factor);
 int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                       int blend_factor);
 /* gdk/compositor.c compositor_process :127 at scale 1 / offset 0: out = bgcol, then paint_pixel(:120) of every

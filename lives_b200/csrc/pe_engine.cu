@@ -909,6 +909,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     A.conv = dev_conv(e, iclamping, isubspace);
     A.lut16 = nullptr;
     if (new_gamma_type != PE_GAMMA_UNKNOWN) A.lut16 = get_lut16(e, 1.0, gamma_type, new_gamma_type);  // `if (tgt_gamma)` :3273
+    A.blend2 = e->fuse_blend2; A.blend2_rs = e->fuse_blend2_rs; A.blend_bf = e->fuse_blend_bf;
     ce = launch_yuv_planar_to_rgb(L, A);
   } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) && pal_is_rgb(outpl)) {
     // convert_{uyvy,yuyv}_to_*_frame (:13147-13190, :13244-13290).  Table choice as the reference makes it:
@@ -1174,6 +1175,34 @@ extern "C" int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width
   return resize_locked(e, layer, width, height, interp, opal_hint, oclamp_hint, osamp_hint, osubs_hint, tgt_gamma);
 }
 
+// A batch of independent layers through resize_layer_full (the render-to-disk loop of src/events.c:4239-4253 issues them one
+// by one): one lock, no host work between the launches.  Returns the number of layers that were resized (TRUE results).
+extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *layers, int width, int height, int interp,
+                                     int opal_hint, int oclamp_hint) {
+  if (!e || !layers || n <= 0) { set_err(PE_ERR_ARG, "NULL / empty argument"); return 0; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
+  int done = 0;
+  for (int i = 0; i < n; i++)
+    if (layers[i] && resize_locked(e, layers[i], width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT,
+                                   PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN) == PE_TRUE)
+      done++;
+  return done;
+}
+
+// ... and through convert_layer_palette
+extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t *const *layers, int outpl, int op_clamping) {
+  if (!e || !layers || n <= 0) { set_err(PE_ERR_ARG, "NULL / empty argument"); return 0; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
+  int done = 0;
+  for (int i = 0; i < n; i++)
+    if (layers[i] && convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV,
+                                    PE_GAMMA_UNKNOWN) == PE_TRUE)
+      done++;
+  return done;
+}
+
 extern "C" int pe_resize_layer(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
                                int oclamp_hint) {  // :15331
   return pe_resize_layer_full(e, layer, width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT,
@@ -1243,6 +1272,29 @@ extern "C" int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in
   const pe_frame_t *a[1] = {in1}, *b[1] = {in2};
   pe_frame_t *o[1] = {out};
   return pe_fx_simple_blend_batch(e, type, 1, a, b, o, blend_factor);
+}
+
+// convert_layer_palette(clip, outpl) followed by the 'chroma blend' of simple_blend.c with in1 = the converted clip and
+// in2 = operand, written back to the clip -- the multitrack crossfade of BASELINE config 5 -- in ONE kernel: the converted
+// frame never travels to HBM and back.  clip: YUV420P / YVU420P / YUV422P; outpl: RGB24 / BGR24 (= the operand's palette).
+extern "C" int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const pe_frame_t *operand, int outpl, int op_clamping,
+                                       int blend_factor) {
+  if (!e || !clip || !operand || !clip->d.planes[0] || !operand->d.planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  const int ip = clip->d.palette;
+  if (ip != PE_PALETTE_YUV420P && ip != PE_PALETTE_YVU420P && ip != PE_PALETTE_YUV422P)
+    return set_err(PE_ERR_PALETTE, "convert_crossfade: the clip must be YUV420P / YVU420P / YUV422P");
+  if ((outpl != PE_PALETTE_RGB24 && outpl != PE_PALETTE_BGR24) || operand->d.palette != outpl)
+    return set_err(PE_ERR_PALETTE, "convert_crossfade: output and operand must both be RGB24 or both BGR24");
+  if (operand->d.width != clip->d.width || operand->d.height != clip->d.height)
+    return set_err(PE_ERR_SIZE, "convert_crossfade: clip and operand differ in size");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  e->fuse_blend2 = (const uint8_t *)operand->d.planes[0];
+  e->fuse_blend2_rs = operand->d.rowstrides[0];
+  e->fuse_blend_bf = blend_factor;
+  const int ok = convert_locked(e, clip, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN);
+  e->fuse_blend2 = nullptr;
+  return ok == PE_TRUE ? PE_OK : PE_ERR_PALETTE;
 }
 
 extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,

@@ -82,6 +82,9 @@ struct pe_engine {
   pe::DevStats *stats_dev = nullptr;
   // small device scratch for per-launch argument arrays (BlendFrame / FusedArgs), grown on demand
   void *args_dev = nullptr;
+  // set around convert_locked by pe_fx_convert_crossfade: the planar YUV -> RGB converter blends with this frame on the fly
+  const uint8_t *fuse_blend2 = nullptr;
+  int fuse_blend2_rs = 0, fuse_blend_bf = 0;
   unsigned int *f3_sched = nullptr;  // k_fused3's two work counters (zero between launches)
   size_t args_cap = 0;
   void *args_pinned = nullptr;

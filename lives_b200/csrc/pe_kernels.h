@@ -66,6 +66,9 @@ struct YuvToRgbArgs {
   int quirks;         // replicate colourspace.c:3461,3544,3600
   DevConv conv;
   const uint16_t *lut16;  // optional inline gamma (xyuv2rgb_with_gamma :2386)
+  // optional fused crossfade (simple_blend.c 'chroma blend' with the converted frame as in1): 3-byte output palettes only
+  const uint8_t *blend2 = nullptr;  // in2 pixels (same palette and size as dst), nullptr: off
+  int blend2_rs = 0, blend_bf = 0;
 };
 cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a);
 // ---- packed 4:2:2 / 4:4:4 (colourspace.c:6616-7103, :2750-3258, :5700-6239) ---------------------------

@@ -231,6 +231,28 @@ __global__ void __launch_bounds__(kBlock) k_yuv_planar_to_rgb(const YuvToRgbArgs
         }
       }
     }
+    if (A.blend2) {
+      // fused crossfade: dst = (bf * in2 + (255 - bf) * converted) >> 8 per byte (make_blend_table, simple_blend.c:31-35)
+      const uint32_t bf = (uint32_t)A.blend_bf & 0xFFu, nb = 255u - bf;
+      auto xfade = [&](uint32_t *px, int row) {
+        const uint8_t *q = A.blend2 + (size_t)A.blend2_rs * row + (size_t)x0 * 3;
+        uint32_t o[4];
+        if (npx == 4 && (((uintptr_t)A.blend2 | (uint32_t)A.blend2_rs) & 3) == 0) {
+          const uint32_t w0 = ld_stream_u32(q), w1 = ld_stream_u32(q + 4), w2 = ld_stream_u32(q + 8);
+          o[0] = w0; o[1] = __byte_perm(w0, w1, 0x0543); o[2] = __byte_perm(w1, w2, 0x0432); o[3] = w2 >> 8;
+        } else {
+          for (int k = 0; k < 4; k++) o[k] = k < npx ? (uint32_t)q[3 * k] | ((uint32_t)q[3 * k + 1] << 8) | ((uint32_t)q[3 * k + 2] << 16) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t even = (((px[k] & 0x00FF00FFu) * nb + (o[k] & 0x00FF00FFu) * bf) >> 8) & 0x00FF00FFu;
+          const uint32_t mid = (((px[k] >> 8) & 0xFFu) * nb + ((o[k] >> 8) & 0xFFu) * bf) & 0xFF00u;
+          px[k] = even | mid;
+        }
+      };
+      xfade(out_a, row_a);
+      if (pair) xfade(out_b, row_b);
+    }
     uint8_t *da = A.dst.p + (size_t)A.dst.rs * row_a + (size_t)x0 * A.out.psize;
     if (npx == 4) store_px4(da, A.out.psize, out_a, vec); else store_px_n(da, A.out.psize, out_a, npx);
     if (pair) {

@@ -261,6 +261,19 @@ def resize_layer(layer, width, height, interp, opal_hint, oclamp_hint):
     return bool(e._lib.pe_resize_layer(e._h, layer._h, width, height, interp, opal_hint, oclamp_hint))
 
 
+def resize_layer_batch(layers, width, height, interp, opal_hint, oclamp_hint):
+    """resize_layer over a batch of independent layers (the render loop of src/events.c:4239-4253): one call, launches back to
+    back; returns how many layers were resized"""
+    e = layers[0].engine
+    return int(e._lib.pe_resize_layer_batch(e._h, len(layers), _arr(layers), width, height, interp, opal_hint, oclamp_hint))
+
+
+def convert_layer_palette_batch(layers, outpl, op_clamping):
+    """convert_layer_palette over a batch of independent layers; returns how many were converted"""
+    e = layers[0].engine
+    return int(e._lib.pe_convert_layer_palette_batch(e._h, len(layers), _arr(layers), outpl, op_clamping))
+
+
 def letterbox_layer(layer, nwidth, nheight, width, height, interp, tpal, tclamp):
     """colourspace.h:415 / colourspace.c:15343"""
     e = layer.engine
@@ -341,6 +354,12 @@ def fused_convert_letterbox_over_gamma(fg, bg, out, inner_w, inner_h, alpha, gam
     e = fg.engine
     capi.check(e._lib.pe_fused_convert_letterbox_over_gamma(e._h, fg._h, bg._h, out._h, inner_w, inner_h, alpha, gamma_from,
                                                             gamma_to))
+
+
+def convert_crossfade(clip, operand, outpl, op_clamping, blend_factor):
+    """convert_layer_palette(clip, outpl) + 'chroma blend' (in1 = converted clip, in2 = operand) -> clip, one kernel"""
+    e = clip.engine
+    capi.check(e._lib.pe_fx_convert_crossfade(e._h, clip._h, operand._h, outpl, op_clamping, blend_factor))
 
 
 def fused_convert_letterbox_over_gamma_batch(fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):

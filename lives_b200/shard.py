@@ -56,19 +56,23 @@ def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blen
     """config 5 on this rank: clip (YUV422P / UYVY / ...) -> RGB24 (convert_layer_palette), operand broadcast from the owner,
     then 'chroma blend' (the crossfade / auto-transition of src/multitrack.h:84) of the clip with the operand, in place.
     `operand_tensor`: uint8 CUDA tensor of height x rowstride bytes on every rank.
-    Stream ordered, no host synchronisation: the broadcast (torch's current stream) overlaps the conversion (engine stream);
-    the blend waits for the broadcast, and the next broadcast into the same tensor waits for the blend."""
+    Stream ordered, no host synchronisation: the fused convert + crossfade kernel (engine stream) waits for the broadcast
+    (torch's current stream), and the next broadcast into the same tensor waits for that kernel; with two operand buffers
+    the broadcast of output frame t + 1 overlaps the kernel of frame t."""
     from . import engine as E
     es, ts = _engine_stream(engine), torch.cuda.current_stream()
-    if not E.convert_layer_palette(clip_layer, out_palette, 0):
-        raise RuntimeError("clip conversion failed: " + E.capi.last_error())
     broadcast_operand(operand_tensor, src=src_rank)
     arrived = torch.cuda.Event()
     arrived.record(ts)
     es.wait_event(arrived)
     rs = operand_tensor.shape[1] if operand_tensor.dim() == 2 else operand_tensor.numel() // height
     operand = E.Layer.wrap_device(engine, out_palette, width, height, [operand_tensor.data_ptr()], [rs])
-    E.simple_blend("chroma blend", clip_layer, operand, clip_layer, blend_factor)
+    if out_palette in (E.WEED_PALETTE_RGB24, E.WEED_PALETTE_BGR24) and clip_layer.palette in (512, 513, 522):
+        E.convert_crossfade(clip_layer, operand, out_palette, 0, blend_factor)  # one kernel: convert + crossfade
+    else:
+        if not E.convert_layer_palette(clip_layer, out_palette, 0):
+            raise RuntimeError("clip conversion failed: " + E.capi.last_error())
+        E.simple_blend("chroma blend", clip_layer, operand, clip_layer, blend_factor)
     consumed = torch.cuda.Event()
     consumed.record(es)
     ts.wait_event(consumed)

@@ -188,6 +188,19 @@ def test_config2_1080p_yuv420p_to_rgba_resize_720p(eng):
     # sanity against an independent area-average (float) of the converted frame: mean abs diff well below 1 LSB
     ref = rgba[:, :w * 4].reshape(h, w, 4).astype(np.float64)
     assert abs(float(got[:, :dw * 4].mean()) - float(ref.mean())) < 0.5  # 1.5x down: compare the global mean
+    # the batch entry points give the same frames (a second, different frame rides along)
+    y2, u2, v2 = T.make_yuv_planar(rng, w, h, False, True)
+    rgba2 = _oracle_planar(o, y2, u2, v2, w, h, 3, 0, 0, 1, T.Q_HIGH)
+    exp2 = np.zeros_like(exp)
+    o.pe_or_resize_packed(T.ptr(rgba2), rgba2.strides[0], w, h, T.ptr(exp2), exp2.strides[0], dw, dh, 4)
+    lays = [lb.Layer.from_host(eng, 512, w, h, p, yuv_clamping=0, yuv_subspace=1) for p in ([y, u, v], [y2, u2, v2])]
+    assert lb.resize_layer_batch(lays, dw, dh, lb.LIVES_INTERP_NORMAL, lb.WEED_PALETTE_RGBA32, 0) == 2
+    for lay, e in zip(lays, (exp, exp2)):
+        assert (payload(lay.to_host()[0], dw, 4) == payload(e, dw, 4)).all()
+    lays = [lb.Layer.from_host(eng, 512, w, h, p, yuv_clamping=0, yuv_subspace=1) for p in ([y, u, v], [y2, u2, v2])]
+    assert lb.convert_layer_palette_batch(lays, 3, 0) == 2
+    for lay, e in zip(lays, (rgba, rgba2)):
+        assert (payload(lay.to_host()[0], w, 4) == payload(e, w, 4)).all()
 
 
 # ------------------------------------------------------------------------------------------------ packed YUV
@@ -308,6 +321,36 @@ def test_rgb_to_planar420_and_422(eng):
     lay = packed_layer(eng, 5, 32, 8, src)
     assert not lb.convert_layer_palette(lay, 512, 0)
     assert lay.palette == 5
+
+
+def test_convert_crossfade_fused(eng):
+    """BASELINE config 5 per clip as ONE kernel: planar YUV -> RGB24 / BGR24 + 'chroma blend' with the operand ==
+    convert_layer_palette followed by simple_blend (oracle), 4:2:2 and 4:2:0, aligned and ragged sizes"""
+    o = T.oracle()
+    rng = np.random.default_rng(31)
+    for (w, h), is422, opal, bf in itertools.product(((256, 64), (130, 34), (642, 362)), (1, 0), (1, 2), (128, 37)):
+        y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), True)
+        operand = T.make_packed(rng, w, h, 3)
+        order = 0 if opal == 1 else 1
+        exp = np.zeros((h, T.rowstride(w, 3)), np.uint8)
+        o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(exp), exp.strides[0], order, 0, is422, 0, 1,
+                               T.Q_HIGH, 1, None)
+        o.pe_or_simple_blend(0, opal, T.ptr(exp), exp.strides[0], T.ptr(operand), operand.strides[0], T.ptr(exp), exp.strides[0], w, h, bf,
+                             operand.size)
+        clip = lb.Layer.from_host(eng, 522 if is422 else 512, w, h, [y, u, v], yuv_subspace=1)
+        op_l = packed_layer(eng, opal, w, h, operand)
+        before = eng.launch_count
+        lb.convert_crossfade(clip, op_l, opal, 0, bf)
+        assert eng.launch_count - before == 1
+        assert (clip.palette, clip.width, clip.height) == (opal, w, h)
+        assert (payload(clip.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (w, h, is422, opal, bf)
+    # RGBA32 output is not a crossfade target (the alpha path of simple_blend.c:132 is a different formula): fails loudly
+    y, u, v = T.make_yuv_planar(rng, 64, 32, True, True)
+    clip = lb.Layer.from_host(eng, 522, 64, 32, [y, u, v], yuv_subspace=1)
+    op_l = packed_layer(eng, 3, 64, 32, T.make_packed(rng, 64, 32, 4))
+    with pytest.raises(Exception):
+        lb.convert_crossfade(clip, op_l, 3, 0, 128)
+    assert clip.palette == 522
 
 
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
