@@ -46,6 +46,26 @@ __device__ __forceinline__ int clamp_i(int v, int lo, int hi) { return min(max(v
 // (2n + 3) / 6 with the division as a multiply-shift (exact for n < 21845, tests/test_host_logic.py)
 __device__ __forceinline__ int third_round(int n) { return ((2 * n + 3) * 43691) >> 18; }
 
+// Bank-replicated YUV -> RGB tables in shared memory (k_fused3, k_yuv_planar_to_rgb_fast): RGB_Y as [256][32 lanes] u32,
+// {R_Cr, G_Cr} and {G_Cb, B_Cb} as [256][16] pairs.  cv = the 14 x 256 conversion tables in ConvTab order (RGB_Y = 9, R_CR = 10,
+// G_CB = 11, G_CR = 12, B_CB = 13).  Every table value is loaded ONCE and stored to all its copies with 128-bit stores
+// (a value-per-word loop is a chain of L2 round trips that costs several microseconds per launch).
+__device__ __forceinline__ void fill_replicated_yuv_tables(uint8_t *ty, uint8_t *tv, uint8_t *tu, const int32_t *__restrict__ cv,
+                                                           int tid, int nthreads) {
+  for (int m = tid; m < 256; m += nthreads) {
+    const uint32_t y = (uint32_t)cv[9 * 256 + m], rcr = (uint32_t)cv[10 * 256 + m], gcb = (uint32_t)cv[11 * 256 + m],
+                   gcr = (uint32_t)cv[12 * 256 + m], bcb = (uint32_t)cv[13 * 256 + m];
+    uint4 *py = reinterpret_cast<uint4 *>(ty + 128 * m), *pv = reinterpret_cast<uint4 *>(tv + 128 * m),
+          *pu = reinterpret_cast<uint4 *>(tu + 128 * m);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      py[j] = make_uint4(y, y, y, y);
+      pv[j] = make_uint4(rcr, gcr, rcr, gcr);
+      pu[j] = make_uint4(gcb, bcb, gcb, bcb);
+    }
+  }
+}
+
 // grid-stride helpers
 __device__ __forceinline__ long long global_tid() { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
 __device__ __forceinline__ long long global_threads() { return (long long)gridDim.x * blockDim.x; }

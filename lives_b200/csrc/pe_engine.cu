@@ -910,7 +910,10 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     A.lut16 = nullptr;
     if (new_gamma_type != PE_GAMMA_UNKNOWN) A.lut16 = get_lut16(e, 1.0, gamma_type, new_gamma_type);  // `if (tgt_gamma)` :3273
     A.blend2 = e->fuse_blend2; A.blend2_rs = e->fuse_blend2_rs; A.blend_bf = e->fuse_blend_bf;
-    ce = launch_yuv_planar_to_rgb(L, A);
+    if (getenv("PE_YUV_SLOW") == nullptr && yuv_planar_fast_ok(A, &conv_host(e, iclamping, isubspace)))
+      ce = launch_yuv_planar_to_rgb_fast(L, A);
+    else
+      ce = launch_yuv_planar_to_rgb(L, A);
   } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) && pal_is_rgb(outpl)) {
     // convert_{uyvy,yuyv}_to_*_frame (:13147-13190, :13244-13290).  Table choice as the reference makes it:
     // uyvy->RGB24 passes the layer's subspace, uyvy->RGBA32 passes its SAMPLING in that slot (:13160), every other

@@ -71,6 +71,11 @@ struct YuvToRgbArgs {
   int blend2_rs = 0, blend_bf = 0;
 };
 cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a);
+// the fast variant (pe_kernels_yuv2.cu: bank-replicated tables, packed chroma sums): width % 4 == 0, aligned planes, no
+// PB_QUALITY_LOW, no inline gamma LUT; host_tables = the ConvTables a.conv was uploaded from
+struct ConvTables;
+bool yuv_planar_fast_ok(const YuvToRgbArgs &a, const ConvTables *host_tables);
+cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a);
 // ---- packed 4:2:2 / 4:4:4 (colourspace.c:6616-7103, :2750-3258, :5700-6239) ---------------------------
 cudaError_t launch_packed422_to_rgb(const Launch &L, int fmt, CImg src, Img dst, int width_mpx, int height,
                                     RgbLayout out, DevConv conv);
@@ -150,7 +155,6 @@ int fused2_max_tile_h();
 cudaError_t launch_fused2(const Launch &L, const FusedArgs *frames_host, int nframes, int ow, int oh, int tile_h, int blend_a,
                           const uint8_t *lut8_dev);
 // register-resident path (pe_kernels_fused3.cu): 4:2:0, full-width letterbox, alpha = k / 256, one conversion variant per batch
-struct ConvTables;
 bool fused3_tables_ok(const ConvTables &t);
 bool fused3_supported(const FusedArgs *frames_host, int nframes, int fy_taps);
 // rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}

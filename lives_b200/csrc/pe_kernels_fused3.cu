@@ -181,18 +181,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 
   // ---- replicated tables
   {
-    uint32_t *ty = reinterpret_cast<uint32_t *>(smem + S3_TY);
-    uint2 *tv = reinterpret_cast<uint2 *>(smem + S3_TV), *tu = reinterpret_cast<uint2 *>(smem + S3_TU);
     uint32_t *tl = reinterpret_cast<uint32_t *>(smem + S3_LUT);
-    const int32_t *cv = P.conv;
-    for (int i = tid; i < 256 * 32; i += F3_NT) ty[i] = (uint32_t)cv[RGB_Y * 256 + (i >> 5)];
-    for (int i = tid; i < 256 * 16; i += F3_NT) {
-      const int m = i >> 4;
-      tv[i] = make_uint2((uint32_t)cv[R_CR * 256 + m], (uint32_t)cv[G_CR * 256 + m]);
-      tu[i] = make_uint2((uint32_t)cv[G_CB * 256 + m], (uint32_t)cv[B_CB * 256 + m]);
-    }
+    fill_replicated_yuv_tables(smem + S3_TY, smem + S3_TV, smem + S3_TU, P.conv, tid, F3_NT);
     if (HAS_LUT)
-      for (int i = tid; i < 256 * 32; i += F3_NT) tl[i] = (uint32_t)P.lut8[i >> 5] * 0x010101u | 0xFF000000u;
+      for (int m = tid; m < 256; m += F3_NT) {
+        const uint32_t e = (uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) reinterpret_cast<uint4 *>(tl + 32 * m)[j] = make_uint4(e, e, e, e);
+      }
     int4 *sr = reinterpret_cast<int4 *>(smem + S3_BYTES);
     for (int i = tid; i < P.ih; i += F3_NT) sr[i] = P.rows4[i];
   }

@@ -1,0 +1,365 @@
+// pe_kernels_yuv2.cu -- the fast planar 4:2:0 / 4:2:2 -> RGB converter (convert_yuv420p_to_{rgb,bgr,argb}_frame,
+// colourspace.c:3260-5127), built like the conversion stage of k_fused3 (pe_kernels_fused3.cu):
+//   * RGB_Y, {R_Cr, G_Cr} and {G_Cb, B_Cb} REPLICATED ACROSS BANKS in shared memory (96 KB, one 512-thread CTA per SM): a lane
+//     only touches its own bank (pair), so the five lookups of a pixel cost 1 + 2 + 2 wavefronts whatever the pixel values are
+//     (the old kernel, k_yuv_planar_to_rgb, paid ~16 on random data);
+//   * the chroma sums of colourspace.c:3440-3549 two columns at a time in the 16-bit halves of a register (Q = 2 n + 3), the
+//     (int)(n / 3. + .5) rounding as one multiply-high that directly yields the table offset;
+//   * one thread = 4 columns x one reference row pair (4:2:0) or one row (4:2:2); luma as one 32-bit word per row, chroma as
+//     two words per row and plane, 128-bit (RGBA) or 3 x 32-bit (RGB24) streaming stores;
+//   * optional fused crossfade with an operand frame (pe_fx_convert_crossfade, BASELINE config 5).
+// Same results, bit for bit, as k_yuv_planar_to_rgb (which keeps PB_QUALITY_LOW, the inline 16-bit gamma LUT, widths that are
+// not a multiple of 4 and unaligned planes).  Rows and columns at the frame edges follow the reference's edge rules through
+// the scalar slow path below (row 0, the last row of an even frame, the last chroma row of a plane without padding, the
+// 4:2:2 seed slip of column 0).
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+#include "pe_tables.h"
+
+namespace pe {
+
+namespace {
+
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+constexpr int Y2_NT = 512;
+constexpr int S2_TY = 0;                  // u32 [256][32]
+constexpr int S2_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
+constexpr int S2_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
+constexpr int S2_RING = 98304;            // u32 [Y2_DEPTH][Y2_WORDS][Y2_NT]: per-thread cp.async ring of raw input words
+constexpr int Y2_DEPTH = 3, Y2_WORDS = 17;  // 2 luma, 8 chroma, first V word, 2 x 3 operand words (crossfade)
+constexpr int S2_BYTES = S2_RING + Y2_DEPTH * Y2_WORDS * Y2_NT * 4;
+
+constexpr uint32_t MSK = 0xFFFEFFFEu;     // clears bit 0 of both halves
+constexpr uint32_t K3 = 0x00030003u;
+
+// d = (c[15:0] << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// 128 * third_round(n) for the n in the high / low half of a packed Q = 2 n + 3 (see pe_kernels_fused3.cu, tests/test_host_logic.py)
+__device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u * 128u) & 0x7F80u; }
+__device__ __forceinline__ uint32_t idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u * 128u) & 0x7F80u; }
+
+struct RowC {
+  uint32_t a, b, c;  // [c(jc0), c(jc0+1)], [c(jc0-1), c(jc0)], [c(jc0+1), c(jc0+2)] as 16-bit halves
+};
+__device__ __forceinline__ RowC unpack_row(uint32_t w0, uint32_t w1, uint32_t sel) {
+  const uint32_t cw4 = __byte_perm(w0, w1, sel);
+  RowC r;
+  r.a = __byte_perm(cw4, 0u, 0x4241u);
+  r.b = __byte_perm(cw4, 0u, 0x4140u);
+  r.c = __byte_perm(cw4, 0u, 0x4342u);
+  return r;
+}
+
+// chroma sample with the reference's edge rules (column -1 replicates column 0; column cw: the byte behind the row)
+__device__ __forceinline__ uint32_t chroma_at(const uint8_t *__restrict__ p, int stride, int r, int c, int cw, int ch) {
+  if (c < 0) c = 0;
+  if (c >= cw) c = (cw < stride || r + 1 < ch) ? cw : cw - 1;
+  return p[(size_t)stride * r + c];
+}
+
+template <bool QUIRKS>
+__global__ void __launch_bounds__(Y2_NT, 1) k_yuv_planar_to_rgb_fast(const __grid_constant__ YuvToRgbArgs A, int k_fast_max) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  fill_replicated_yuv_tables(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid, Y2_NT);
+  __syncthreads();
+
+  const Planes &S = A.src;
+  const int w = A.width, h = A.height, cw = S.cw, ch = S.ch;
+  const int is422 = A.is_422;
+  const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
+  // canonical pixel word = [r, g, b, 255]; sel moves its bytes to the palette's order
+  uint32_t osel;
+  {
+    uint32_t nib[4] = {3, 3, 3, 3};
+    nib[A.out.r] = 0; nib[A.out.g] = 1; nib[A.out.b] = 2;
+    if (A.out.a >= 0) nib[A.out.a] = 3;
+    osel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+  }
+  // one pixel: yuv2rgb_int (colourspace.c:2345-2356) through the replicated tables, packed in the palette's byte order
+  auto px = [&](uint32_t y, uint32_t ou, uint32_t ov) -> uint32_t {
+    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S2_TY + (y * 128u + lane4));
+    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S2_TV + (ov | lane8));
+    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S2_TU + (ou | lane8));
+    const int r = (yy + (int)tv.x) >> 16, g = (yy + (int)tu.x + (int)tv.y) >> 16, b = (yy + (int)tu.y) >> 16;
+    return __byte_perm(pack_sat(g, r, pack_sat(255, b, 0u)), 0u, osel);
+  };
+  const uint32_t bf = (uint32_t)A.blend_bf & 0xFFu, nb = 255u - bf;
+  const bool xf_vec = A.blend2 && ((((uintptr_t)A.blend2) | (uint32_t)A.blend2_rs) & 3) == 0;
+  // store 4 pixels of one row (after the optional crossfade with the operand)
+  auto store_row = [&](uint32_t *p4, int row, int x0, uint32_t opslot = 0u) {
+    if (A.blend2) {  // dst = (bf * in2 + (255 - bf) * converted) >> 8 per byte (make_blend_table, simple_blend.c:31-35)
+      const uint8_t *q = A.blend2 + (size_t)A.blend2_rs * row + (size_t)x0 * 3;
+      uint32_t o[4];
+      if (xf_vec) {
+        uint32_t w0, w1, w2;
+        if (opslot) { w0 = lds_u32(opslot); w1 = lds_u32(opslot + Y2_NT * 4); w2 = lds_u32(opslot + 2 * Y2_NT * 4); }  // prefetched
+        else { w0 = ld_stream_u32(q); w1 = ld_stream_u32(q + 4); w2 = ld_stream_u32(q + 8); }
+        o[0] = w0; o[1] = __byte_perm(w0, w1, 0x0543); o[2] = __byte_perm(w1, w2, 0x0432); o[3] = w2 >> 8;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = (uint32_t)q[3 * k] | ((uint32_t)q[3 * k + 1] << 8) | ((uint32_t)q[3 * k + 2] << 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t even = (((p4[k] & 0x00FF00FFu) * nb + (o[k] & 0x00FF00FFu) * bf) >> 8) & 0x00FF00FFu;
+        const uint32_t mid = (((p4[k] >> 8) & 0xFFu) * nb + ((o[k] >> 8) & 0xFFu) * bf) & 0xFF00u;
+        p4[k] = even | mid;
+      }
+    }
+    uint8_t *d = A.dst.p + (size_t)A.dst.rs * row + (size_t)x0 * A.out.psize;
+    if (A.out.psize == 4) {
+      st_stream_u4(d, make_uint4(p4[0], p4[1], p4[2], p4[3]));
+    } else {
+      st_stream_u32(d, __byte_perm(p4[0], p4[1], 0x4210));
+      st_stream_u32(d + 4, __byte_perm(p4[1], p4[2], 0x5421));
+      st_stream_u32(d + 8, __byte_perm(p4[2], p4[3], 0x6542));
+    }
+  };
+
+  const int quads = w >> 2;
+  const int njobs = is422 ? h : (!(h & 1) ? ch + 1 : ch);
+  const long long total = (long long)quads * njobs;
+  const uint32_t rs_y = (uint32_t)S.rs_y, rs_u = (uint32_t)S.rs_u, rs_v = (uint32_t)S.rs_v;
+  // The raw words of a job (2 luma, 8 chroma, the row's first V word) travel through a per-thread cp.async ring in shared
+  // memory, Y2_DEPTH - 1 grid strides ahead of their use: 16 warps per SM do not hide DRAM latency by themselves, and a register
+  // pipeline that deep would spill.  Slot layout [depth][word][thread]: conflict-free, and a thread only reads what it copied.
+  auto job_class = [&](int job, int x0) -> int {  // 0: 4:2:0 interior pair, 1: 4:2:2 row, 2: slow path
+    if (!is422) return (job >= 1 && job <= k_fast_max) ? 0 : 2;
+    return (!(QUIRKS && x0 == 0) && !(job == ch - 1 && k_fast_max < ch - 1)) ? 1 : 2;
+  };
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + S2_RING + 4u * (uint32_t)tid;
+  auto slot = [&](int d, int word) -> uint32_t { return ring + (uint32_t)((d * Y2_WORDS + word) * (Y2_NT * 4)); };
+  auto issue = [&](int job, int g, int d) {
+    const int x0 = 4 * g, o = 2 * g - 1;
+    const int cls = job_class(job, x0);
+    if (cls != 2) {
+      const size_t off0 = x0 == 0 ? 0 : (size_t)(o & ~3);
+      if (cls == 0) {
+        const uint8_t *yr = S.y + (size_t)rs_y * (uint32_t)(2 * job - 1) + x0;
+        cp_async4(slot(d, 0), yr); cp_async4(slot(d, 1), yr + rs_y);
+        const uint8_t *up = S.u + (size_t)rs_u * (uint32_t)(job - 1) + off0, *vp = S.v + (size_t)rs_v * (uint32_t)(job - 1) + off0;
+        cp_async4(slot(d, 2), up); cp_async4(slot(d, 3), up + 4); cp_async4(slot(d, 4), up + rs_u); cp_async4(slot(d, 5), up + rs_u + 4);
+        cp_async4(slot(d, 6), vp); cp_async4(slot(d, 7), vp + 4); cp_async4(slot(d, 8), vp + rs_v); cp_async4(slot(d, 9), vp + rs_v + 4);
+        if (QUIRKS) cp_async4(slot(d, 10), S.v + (size_t)rs_v * (uint32_t)job);
+      } else {
+        cp_async4(slot(d, 0), S.y + (size_t)rs_y * (uint32_t)job + x0);
+        const uint8_t *up = S.u + (size_t)rs_u * (uint32_t)job + off0, *vp = S.v + (size_t)rs_v * (uint32_t)job + off0;
+        cp_async4(slot(d, 2), up); cp_async4(slot(d, 3), up + 4);
+        cp_async4(slot(d, 6), vp); cp_async4(slot(d, 7), vp + 4);
+      }
+    }
+    if (xf_vec && cls != 2) {  // crossfade operand: the 12 bytes under the job's 4 pixels, per row
+      const int ra = cls == 0 ? 2 * job - 1 : job;
+      const uint8_t *q = A.blend2 + (size_t)A.blend2_rs * ra + (size_t)x0 * 3;
+      cp_async4(slot(d, 11), q); cp_async4(slot(d, 12), q + 4); cp_async4(slot(d, 13), q + 8);
+      if (cls == 0) {
+        q += A.blend2_rs;
+        cp_async4(slot(d, 14), q); cp_async4(slot(d, 15), q + 4); cp_async4(slot(d, 16), q + 8);
+      }
+    }
+    cp_async_commit();  // one group per job, empty for the slow class: the wait below counts groups
+  };
+  struct Raw {
+    uint32_t yA, yB, u00, u01, u10, u11, v00, v01, v10, v11, vf;
+  };
+  // (job, quad) advance by one grid stride without a division per job
+  const long long stride = global_threads();
+  const int d_job = (int)(stride / quads), d_g = (int)(stride - (long long)d_job * quads);
+  auto advance = [&](int &job, int &g) {
+    job += d_job; g += d_g;
+    if (g >= quads) { g -= quads; job++; }
+  };
+  long long it = global_tid();
+  int job = (int)(it / quads), g = (int)(it - (long long)job * quads);
+  int pj = job, pg = g;            // the job the next issue is for
+  long long pit = it;
+#pragma unroll
+  for (int d = 0; d < Y2_DEPTH - 1; d++) {
+    if (pit < total) issue(pj, pg, d); else cp_async_commit();
+    advance(pj, pg); pit += stride;
+  }
+  int d = 0;
+  for (; it < total; it += stride, d = d + 1 == Y2_DEPTH ? 0 : d + 1) {
+    if (pit < total) issue(pj, pg, d == 0 ? Y2_DEPTH - 1 : d - 1); else cp_async_commit();
+    advance(pj, pg); pit += stride;
+    cp_async_wait<Y2_DEPTH - 1>();  // all but the newest Y2_DEPTH - 1 groups have landed: this job's words are in slot d
+    Raw cur;
+    cur.yA = lds_u32(slot(d, 0)); cur.yB = lds_u32(slot(d, 1));
+    cur.u00 = lds_u32(slot(d, 2)); cur.u01 = lds_u32(slot(d, 3)); cur.u10 = lds_u32(slot(d, 4)); cur.u11 = lds_u32(slot(d, 5));
+    cur.v00 = lds_u32(slot(d, 6)); cur.v01 = lds_u32(slot(d, 7)); cur.v10 = lds_u32(slot(d, 8)); cur.v11 = lds_u32(slot(d, 9));
+    cur.vf = lds_u32(slot(d, 10)) & 0xFFu;
+    const int jobn = job + d_job + (g + d_g >= quads ? 1 : 0), gn = g + d_g >= quads ? g + d_g - quads : g + d_g;
+    const int x0 = 4 * g, jc0 = 2 * g;
+    const int cls = job_class(job, x0);
+    uint32_t pa[4], pb[4];
+    if (cls == 0) {
+      // ===== 4:2:0 interior row pair (colourspace.c:3440-3549): rows 2k-1, 2k with chroma rows k-1, k
+      const int k = job;
+      const int o = jc0 - 1;
+      const uint32_t sel = x0 == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+      const uint32_t yA = cur.yA, yB = cur.yB;
+      const RowC U0 = unpack_row(cur.u00, cur.u01, sel), U1 = unpack_row(cur.u10, cur.u11, sel);
+      const RowC V0 = unpack_row(cur.v00, cur.v01, sel), V1 = unpack_row(cur.v10, cur.v11, sel);
+      // right pixel of both chroma columns: this + next
+      const uint32_t RU0 = U0.a + U0.c, RU1 = U1.a + U1.c, RV0 = V0.a + V0.c, RV1 = V1.a + V1.c;
+      const uint32_t QUR_up = RU0 * 2u + (RU1 & MSK) + K3, QUR_lo = (RU0 & MSK) + RU1 * 2u + K3;
+      const uint32_t QVR_up = RV0 * 2u + (RV1 & MSK) + K3, QVR_lo = (RV0 & MSK) + RV1 * 2u + K3;
+      // left pixel: this + last, with the reference's slips under QUIRKS
+      uint32_t QUL_up, QUL_lo, QVL_up, QVL_lo;
+      const uint32_t LU0 = U0.a + U0.b;
+      if (QUIRKS) {
+        QUL_up = QUL_lo = LU0 * 2u + (LU0 & MSK) + K3;                              // u2 = this_u1 + last_u1 (:3461)
+        const uint32_t bq = x0 == 0 ? __byte_perm(V1.b, V0.a, 0x3254u) : V1.b;      // last_v1 = this_v2 (:3544), except at column 0
+        const uint32_t v1 = V0.a + bq;
+        const uint32_t v2 = V1.a + cur.vf * 0x10001u;                               // last_v2 never advanced: the row's first V sample
+        QVL_up = v1 * 2u + (v2 & MSK) + K3; QVL_lo = (v1 & MSK) + v2 * 2u + K3;
+      } else {
+        const uint32_t LU1 = U1.a + U1.b, LV0 = V0.a + V0.b, LV1 = V1.a + V1.b;
+        QUL_up = LU0 * 2u + (LU1 & MSK) + K3; QUL_lo = (LU0 & MSK) + LU1 * 2u + K3;
+        QVL_up = LV0 * 2u + (LV1 & MSK) + K3; QVL_lo = (LV0 & MSK) + LV1 * 2u + K3;
+      }
+#pragma unroll
+      for (int col = 0; col < 4; col++) {
+        const bool hi_half = col >> 1, right = col & 1;
+        const uint32_t qu_up = right ? QUR_up : QUL_up, qu_lo = right ? QUR_lo : QUL_lo;
+        const uint32_t qv_up = right ? QVR_up : QVL_up, qv_lo = right ? QVR_lo : QVL_lo;
+        const uint32_t ou_up = hi_half ? idx_hi(qu_up) : idx_lo(qu_up), ov_up = hi_half ? idx_hi(qv_up) : idx_lo(qv_up);
+        const uint32_t ov_lo = hi_half ? idx_hi(qv_lo) : idx_lo(qv_lo);
+        const uint32_t ou_lo = (QUIRKS && !right) ? ou_up : (hi_half ? idx_hi(qu_lo) : idx_lo(qu_lo));
+        pa[col] = px(byte_of(yA, col), ou_up, ov_up);
+        pb[col] = px(byte_of(yB, col), ou_lo, ov_lo);
+      }
+      store_row(pa, 2 * k - 1, x0, slot(d, 11));
+      store_row(pb, 2 * k, x0, slot(d, 14));
+      job = jobn; g = gn;
+      continue;
+    }
+    if (cls == 1) {
+      // ===== 4:2:2 row (:3598-3642): horizontal average only, m = (this + neighbour) >> 1
+      const int o = jc0 - 1;
+      const uint32_t sel = x0 == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+      const uint32_t yA = cur.yA;
+      const RowC U = unpack_row(cur.u00, cur.u01, sel), V = unpack_row(cur.v00, cur.v01, sel);
+      const uint32_t LU = U.a + U.b, RU = U.a + U.c, LV = V.a + V.b, RV = V.a + V.c;   // sums <= 510 per half
+#pragma unroll
+      for (int col = 0; col < 4; col++) {
+        const bool hi_half = col >> 1, right = col & 1;
+        const uint32_t su = right ? RU : LU, sv = right ? RV : LV;
+        // 128 * (s >> 1) = (s & ~1) << 6
+        const uint32_t ou = hi_half ? ((su >> 10) & 0x7F80u) : ((su << 6) & 0x7F80u);
+        const uint32_t ov = hi_half ? ((sv >> 10) & 0x7F80u) : ((sv << 6) & 0x7F80u);
+        pa[col] = px(byte_of(yA, col), ou, ov);
+      }
+      store_row(pa, job, x0, slot(d, 11));
+      job = jobn; g = gn;
+      continue;
+    }
+    // ===== slow path: scalar code with the reference's edge rules
+    {
+      auto single = [&](int row, int cr, int seed_row) {
+        const uint32_t yw = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * row + x0);
+#pragma unroll
+        for (int col = 0; col < 4; col++) {
+          const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+          uint32_t ua = chroma_at(S.u, rs_u, cr, jc, cw, ch), ub = chroma_at(S.u, rs_u, cr, jo, cw, ch);
+          uint32_t va = chroma_at(S.v, rs_v, cr, jc, cw, ch), vb = chroma_at(S.v, rs_v, cr, jo, cw, ch);
+          if (jc0 == 0 && seed_row != cr) {  // 4:2:2 seed slip (:3600): columns <= 0 are column 0 of chroma row (i >> 1)
+            const uint32_t su = S.u[(size_t)rs_u * seed_row], sv = S.v[(size_t)rs_v * seed_row];
+            if (jc == 0) { ua = su; va = sv; }
+            if (jo <= 0) { ub = su; vb = sv; }
+          }
+          pa[col] = px(byte_of(yw, col), ((ua + ub) >> 1) * 128u, ((va + vb) >> 1) * 128u);
+        }
+        store_row(pa, row, x0);
+      };
+      if (is422) {
+        single(job, job, QUIRKS ? (job >> 1) : job);
+      } else if (job == 0) {
+        single(0, 0, 0);
+      } else if (job < ch) {
+        const int k = job, ca = k - 1, cb = k;
+        const uint32_t ya = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * (2 * k - 1) + x0);
+        const uint32_t yb = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * (2 * k) + x0);
+        const uint32_t vfirst = S.v[(size_t)rs_v * cb];
+#pragma unroll
+        for (int col = 0; col < 4; col++) {
+          const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+          uint32_t u1 = chroma_at(S.u, rs_u, ca, jc, cw, ch) + chroma_at(S.u, rs_u, ca, jo, cw, ch);
+          uint32_t u2 = chroma_at(S.u, rs_u, cb, jc, cw, ch) + chroma_at(S.u, rs_u, cb, jo, cw, ch);
+          uint32_t v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, ca, jo, cw, ch);
+          uint32_t v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
+          if (QUIRKS && !(col & 1)) {
+            u2 = u1;
+            if (jc > 0) v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
+            v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + vfirst;
+          }
+          const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
+          const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
+          pa[col] = px(byte_of(ya, col), mu3 * 128u, mv3 * 128u);
+          pb[col] = px(byte_of(yb, col), mu4 * 128u, mv4 * 128u);
+        }
+        store_row(pa, 2 * k - 1, x0);
+        store_row(pb, 2 * k, x0);
+      } else {
+        single(h - 1, ch - 1, ch - 1);
+      }
+    }
+    job = jobn; g = gn;
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace
+
+// Can the fast converter take this frame?  (checked by launch_yuv_planar_to_rgb; everything else: k_yuv_planar_to_rgb)
+bool yuv_planar_fast_ok(const YuvToRgbArgs &a, const ConvTables *host_tables) {
+  if (a.low_quality || a.lut16) return false;
+  if ((a.width & 3) || a.width < 4 || a.height < 2) return false;
+  if (!a.is_422 && (a.height & 1)) return false;                         // 4:2:0 frames are even (colourspace.c:11603)
+  if (a.src.cw != a.width / 2 || a.src.ch != (a.is_422 ? a.height : (a.height + 1) / 2)) return false;
+  if (((uintptr_t)a.src.y | (uintptr_t)a.src.u | (uintptr_t)a.src.v) & 3) return false;
+  if ((a.src.rs_y | a.src.rs_u | a.src.rs_v) & 3) return false;
+  if (a.out.psize == 4 ? ((((uintptr_t)a.dst.p) | (uint32_t)a.dst.rs) & 15) != 0 : ((((uintptr_t)a.dst.p) | (uint32_t)a.dst.rs) & 3) != 0)
+    return false;
+  if (a.blend2 && a.out.psize != 3) return false;
+  return host_tables && fused3_tables_ok(*host_tables);
+}
+
+cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_yuv_planar_to_rgb_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_yuv_planar_to_rgb_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_BYTES)) != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // the fast paths read whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
+  const bool last_row_unsafe = a.src.rs_u < a.src.cw + 4 || a.src.rs_v < a.src.cw + 4;
+  const int k_fast_max = a.src.ch - 1 - (last_row_unsafe ? 1 : 0);
+  const long long work = (long long)(a.width >> 2) * (a.is_422 ? a.height : a.src.ch + 1);
+  long long blocks = (work + Y2_NT - 1) / Y2_NT;
+  if (blocks > L.sm_count) blocks = L.sm_count;
+  if (a.quirks) k_yuv_planar_to_rgb_fast<true><<<(int)blocks, Y2_NT, S2_BYTES, L.stream>>>(a, k_fast_max);
+  else k_yuv_planar_to_rgb_fast<false><<<(int)blocks, Y2_NT, S2_BYTES, L.stream>>>(a, k_fast_max);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+}  // namespace pe

@@ -105,7 +105,7 @@ def _oracle_planar(o, y, u, v, w, h, opal, is422, cl, sub, q, quirks=1, lut16=No
     return exp
 
 
-@pytest.mark.parametrize("size", [(64, 48), (130, 34), (2, 2), (6, 4), (642, 362)])
+@pytest.mark.parametrize("size", [(64, 48), (130, 34), (2, 2), (6, 4), (642, 362), (644, 362), (256, 34), (4, 2), (8, 4)])
 @pytest.mark.parametrize("is422", [0, 1])
 def test_planar_yuv_to_rgb(eng, size, is422):
     """convert_yuv420p_to_{rgb,bgr,argb}_frame (colourspace.c:3260,3927,4527) through convert_layer_palette_full"""
@@ -140,12 +140,12 @@ def test_planar_yuv_quality_quirks_and_yvu(eng):
         assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), opal
     e_low.close()
     e_nq = lb.Engine(ref_quirks=False)
-    for is422 in (0, 1):
-        yy, uu, vv = T.make_yuv_planar(rng, w, h, bool(is422), True)
-        exp = _oracle_planar(o, yy, uu, vv, w, h, 3, is422, 0, 1, T.Q_HIGH, quirks=0)
-        lay = lb.Layer.from_host(e_nq, 522 if is422 else 512, w, h, [yy, uu, vv], yuv_subspace=1)
+    for (w2, h2), is422 in itertools.product(((w, h), (132, 50), (320, 48)), (0, 1)):  # 98: the general kernel; 132, 320: the fast one
+        yy, uu, vv = T.make_yuv_planar(rng, w2, h2, bool(is422), True)
+        exp = _oracle_planar(o, yy, uu, vv, w2, h2, 3, is422, 0, 1, T.Q_HIGH, quirks=0)
+        lay = lb.Layer.from_host(e_nq, 522 if is422 else 512, w2, h2, [yy, uu, vv], yuv_subspace=1)
         assert lb.convert_layer_palette(lay, 3, 0)
-        assert (payload(lay.to_host()[0], w, 4) == payload(exp, w, 4)).all()
+        assert (payload(lay.to_host()[0], w2, 4) == payload(exp, w2, 4)).all(), (w2, h2, is422)
     e_nq.close()
     exp = _oracle_planar(o, y, u, v, w, h, 1, 0, 0, 1, T.Q_HIGH)
     lay = lb.Layer.from_host(eng, 513, w, h, [y, v, u], yuv_subspace=1)  # YVU: V plane first
