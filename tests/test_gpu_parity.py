@@ -716,6 +716,38 @@ def test_fused_fast_path_cases(case, variant):
     e.close()
 
 
+def test_fused_random_geometries_equal_unfused_ops(eng):
+    """40 random geometries inside k_fused3's envelope (and a few that fall out of it): the fused call == the engine's own
+    convert_layer_palette -> letterbox_layer -> compositor -> gamma_convert_layer, which the tests above pin to the oracle"""
+    rng = np.random.default_rng(77)
+    for it in range(40):
+        fw = int(rng.integers(1, 80)) * 4
+        fh = int(rng.integers(2, 120)) * 2
+        ih = max(4, int(fh * rng.uniform(0.67, 3.0)) & ~1)           # ratio <= 1.5 down (four taps) .. 3x up
+        oh = ih + 2 * int(rng.integers(0, 20))
+        ow = fw + 8 * int(rng.integers(0, 12)) if it % 3 else fw     # pillarbox offsets: multiples of 4
+        alpha = float(rng.choice([0.0, 0.25, 0.5, 0.75, 1.0, 37 / 256]))
+        cl = int(rng.integers(0, 2))
+        y, u, v = T.make_yuv_planar(rng, fw, fh, False, cl == 0)
+        bg = T.make_packed(rng, ow, oh, 4)
+        fg_l = lb.Layer.from_host(eng, 512, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
+        bg_l = packed_layer(eng, 3, ow, oh, bg, gamma_type=T.G_LINEAR)
+        out_l = lb.Layer.create(eng, 3, ow, oh)
+        lb.fused_convert_letterbox_over_gamma(fg_l, bg_l, out_l, fw, ih, alpha, T.G_LINEAR, T.G_SRGB)
+        got = out_l.to_host()[0]
+        lay = lb.Layer.from_host(eng, 512, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
+        assert lb.convert_layer_palette(lay, 3, 0)
+        assert lb.letterbox_layer(lay, ow, oh, fw, ih, 1, 3, 0)
+        out2 = lb.Layer.create(eng, 3, ow, oh, gamma_type=T.G_LINEAR)
+        lb.compositor(out2, [lay, bg_l], [alpha, 1.0])
+        assert lb.gamma_convert_layer(T.G_SRGB, out2)
+        exp = out2.to_host()[0]
+        bad = np.argwhere(payload(got, ow, 4) != payload(exp, ow, 4))
+        assert len(bad) == 0, (it, fw, fh, ih, ow, oh, alpha, cl, len(bad), bad[:4])
+        for l in (fg_l, bg_l, out_l, lay, out2):
+            l.free()
+
+
 def test_fused_headline_4k(eng):
     """north-star headline: 3840x2160 YUV420P fg -> RGBA, letterboxed 3840x1608 inner in a 4K frame, alpha-over a 4K
     RGBA bg, gamma; batch of 2 in one launch"""
