@@ -141,8 +141,15 @@ void *DevPool::get(size_t bytes, size_t *granted) {
   return p;
 }
 
+void DevPool::flush_deferred() {
+  std::vector<std::pair<void *, size_t>> d;
+  d.swap(deferred_);
+  for (auto &b : d) put(b.first, b.second);
+}
+
 void DevPool::put(void *p, size_t granted) {
   if (!p) return;
+  if (defer_) { deferred_.emplace_back(p, granted); return; }
   const size_t kMaxHeld = (size_t)8 << 30;  // 8 GiB of recycled blocks at most (HBM is 180 GB)
   if (held_ + granted > kMaxHeld) {
     cudaFree(p);
@@ -256,6 +263,8 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   cudaFree(e->stats_dev);
   cudaFree(e->args_dev);
   cudaFree(e->f3_sched);
+  for (int k = 0; k < 4; k++) { if (e->fan_stream[k]) cudaStreamDestroy(e->fan_stream[k]); if (e->fan_join[k]) cudaEventDestroy(e->fan_join[k]); }
+  if (e->fan_fork) cudaEventDestroy(e->fan_fork);
   if (e->args_pinned) cudaFreeHost(e->args_pinned);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
@@ -1178,6 +1187,53 @@ extern "C" int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width
   return resize_locked(e, layer, width, height, interp, opal_hint, oclamp_hint, osamp_hint, osubs_hint, tgt_gamma);
 }
 
+namespace {
+
+// Fan a batch of independent per-layer calls out over four side streams.  Layer 0 runs on the engine stream first (it
+// creates whatever cached tables the batch needs: filter banks, LUTs -- their uploads are ordered before the fork); the other
+// layers of the same geometry run on the side streams, so that the small kernels of different layers overlap instead of
+// queueing behind each other's tails; blocks freed meanwhile are parked until the streams have joined.
+struct FanOut {
+  pe_engine *e;
+  cudaStream_t main;
+  bool active = false;
+  explicit FanOut(pe_engine *e_) : e(e_), main(e_->stream) {}
+  bool begin() {
+    if (!e->fan_fork) {
+      if (cudaEventCreateWithFlags(&e->fan_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+      for (int k = 0; k < 4; k++)
+        if (cudaStreamCreateWithFlags(&e->fan_stream[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e->fan_join[k], cudaEventDisableTiming) != cudaSuccess)
+          return false;
+    }
+    if (cudaEventRecord(e->fan_fork, main) != cudaSuccess) return false;
+    for (int k = 0; k < 4; k++)
+      if (cudaStreamWaitEvent(e->fan_stream[k], e->fan_fork, 0) != cudaSuccess) return false;
+    e->pool.defer(true);
+    active = true;
+    return true;
+  }
+  void use(int i) { e->stream = active ? e->fan_stream[i & 3] : main; }
+  void use_main() { e->stream = main; }
+  ~FanOut() {
+    e->stream = main;
+    if (!active) return;
+    for (int k = 0; k < 4; k++) {
+      cudaEventRecord(e->fan_join[k], e->fan_stream[k]);
+      cudaStreamWaitEvent(main, e->fan_join[k], 0);
+    }
+    e->pool.defer(false);
+    e->pool.flush_deferred();
+  }
+};
+
+inline bool same_geometry(const pe_frame *a, const pe_frame *b) {
+  return a->d.palette == b->d.palette && a->d.width == b->d.width && a->d.height == b->d.height &&
+         a->d.yuv_clamping == b->d.yuv_clamping && a->d.yuv_subspace == b->d.yuv_subspace && a->d.gamma_type == b->d.gamma_type;
+}
+
+}  // namespace
+
 // A batch of independent layers through resize_layer_full (the render-to-disk loop of src/events.c:4239-4253 issues them one
 // by one): one lock, no host work between the launches.  Returns the number of layers that were resized (TRUE results).
 extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *layers, int width, int height, int interp,
@@ -1186,10 +1242,16 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   int done = 0;
-  for (int i = 0; i < n; i++)
-    if (layers[i] && resize_locked(e, layers[i], width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT,
-                                   PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN) == PE_TRUE)
+  const pe_frame ref0 = layers[0] ? *layers[0] : pe_frame();
+  FanOut fan(e);
+  for (int i = 0; i < n; i++) {
+    if (!layers[i]) continue;
+    if (i == 1 && n > 2 && layers[0]) fan.begin();
+    if (i >= 1 && same_geometry(&ref0, layers[i])) fan.use(i); else fan.use_main();
+    if (resize_locked(e, layers[i], width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR,
+                      PE_GAMMA_UNKNOWN) == PE_TRUE)
       done++;
+  }
   return done;
 }
 
@@ -1199,10 +1261,15 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   int done = 0;
-  for (int i = 0; i < n; i++)
-    if (layers[i] && convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV,
-                                    PE_GAMMA_UNKNOWN) == PE_TRUE)
+  const pe_frame ref0 = layers[0] ? *layers[0] : pe_frame();
+  FanOut fan(e);
+  for (int i = 0; i < n; i++) {
+    if (!layers[i]) continue;
+    if (i == 1 && n > 2 && layers[0]) fan.begin();
+    if (i >= 1 && same_geometry(&ref0, layers[i])) fan.use(i); else fan.use_main();
+    if (convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE)
       done++;
+  }
   return done;
 }
 

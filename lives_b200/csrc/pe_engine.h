@@ -24,9 +24,15 @@ class DevPool {
   void put(void *p, size_t granted);
   void release_all();
   size_t bytes_held() const { return held_; }
+  // While a batch call fans its layers out over side streams, freed blocks must not be handed out again before the streams
+  // have joined: put() parks them, flush_deferred() returns them to the free lists.
+  void defer(bool on) { defer_ = on; }
+  void flush_deferred();
 
  private:
   std::multimap<size_t, void *> free_;
+  std::vector<std::pair<void *, size_t>> deferred_;
+  bool defer_ = false;
   size_t held_ = 0;
 };
 
@@ -85,6 +91,9 @@ struct pe_engine {
   // set around convert_locked by pe_fx_convert_crossfade: the planar YUV -> RGB converter blends with this frame on the fly
   const uint8_t *fuse_blend2 = nullptr;
   int fuse_blend2_rs = 0, fuse_blend_bf = 0;
+  // batch calls: layers 1 .. n-1 run on four side streams (forked from / joined to the engine stream by events)
+  cudaStream_t fan_stream[4] = {};
+  cudaEvent_t fan_fork = nullptr, fan_join[4] = {};
   unsigned int *f3_sched = nullptr;  // k_fused3's two work counters (zero between launches)
   size_t args_cap = 0;
   void *args_pinned = nullptr;
