@@ -115,6 +115,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+// chroma words are read by the lanes of two neighbouring strips (one sector of overlap on each side): plain read-only loads,
+// so that L2 keeps the shared sectors until the neighbour has asked for them (the streaming hint marks them evict-first)
+__device__ __forceinline__ uint32_t ld_keep_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
   uint32_t r;
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
@@ -337,8 +344,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         p.yA = ld_stream_u32(yr);
         p.yB = ld_stream_u32(yr + rs_y);
         const uint32_t uo = rs_u * (uint32_t)k, vo = rs_v * (uint32_t)k;
-        p.u0 = ld_stream_u32(L.up0 + uo); p.u1 = ld_stream_u32(L.up0 + uo + 4);
-        p.v0 = ld_stream_u32(L.vp0 + vo); p.v1 = ld_stream_u32(L.vp0 + vo + 4);
+        p.u0 = ld_keep_u32(L.up0 + uo); p.u1 = ld_keep_u32(L.up0 + uo + 4);
+        p.v0 = ld_keep_u32(L.vp0 + vo); p.v1 = ld_keep_u32(L.vp0 + vo + 4);
         p.vf = ldg_u8(L.vfp + vo);
       };
       auto init_carry = [&](int r, Carry &c) {  // sums of chroma row r (0 <= r <= ch - 2), as a fast step leaves them
