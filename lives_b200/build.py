@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
     deps = [d for d in deps if os.path.isfile(d)]
     if force or _stale(LIB, deps):
         extra = ["-DPE_F3_NT=" + os.environ["PE_F3_NT"]] if os.environ.get("PE_F3_NT") else []  # tuning experiments only
+        extra += os.environ.get("PE_NVCC_EXTRA", "").split()
         cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
         if verbose:
             print(" ".join(cmd))

@@ -51,11 +51,11 @@ __device__ __forceinline__ int third_round(int n) { return ((2 * n + 3) * 43691)
 // G_CB = 11, G_CR = 12, B_CB = 13).  Every table value is loaded ONCE and stored to all its copies with 128-bit stores
 // (a value-per-word loop is a chain of L2 round trips that costs several microseconds per launch).
 __device__ __forceinline__ void fill_replicated_yuv_tables(uint8_t *ty, uint8_t *tv, uint8_t *tu, const int32_t *__restrict__ cv,
-                                                           int tid, int nthreads) {
+                                                           int tid, int nthreads, int ty_stride = 128) {
   for (int m = tid; m < 256; m += nthreads) {
     const uint32_t y = (uint32_t)cv[9 * 256 + m], rcr = (uint32_t)cv[10 * 256 + m], gcb = (uint32_t)cv[11 * 256 + m],
                    gcr = (uint32_t)cv[12 * 256 + m], bcb = (uint32_t)cv[13 * 256 + m];
-    uint4 *py = reinterpret_cast<uint4 *>(ty + 128 * m), *pv = reinterpret_cast<uint4 *>(tv + 128 * m),
+    uint4 *py = reinterpret_cast<uint4 *>(ty + ty_stride * m), *pv = reinterpret_cast<uint4 *>(tv + 128 * m),
           *pu = reinterpret_cast<uint4 *>(tu + 128 * m);
 #pragma unroll
     for (int j = 0; j < 8; j++) {

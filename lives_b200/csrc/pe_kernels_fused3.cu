@@ -15,10 +15,10 @@
 //   * the raw luma / chroma words of step k+1 and the bg vector of the next output row are loaded into registers while step k
 //     is computed (ld.global.nc, L1 no-allocate): each byte of fg and bg crosses the memory system once, as whole sectors.
 //   * every table is REPLICATED ACROSS BANKS in shared memory so that a lookup never conflicts, whatever the pixel values:
-//       RGB_Y      [256][32 lanes]  u32        lane l reads bank l
 //       {R_Cr,G_Cr}[256][16]        2 x u32    64-bit loads, lane l reads bank pair l & 15
 //       {G_Cb,B_Cb}[256][16]        2 x u32
-//       gamma LUT  [256][32 lanes]  u32 = v * 0x010101 | 0xFF000000
+//       gamma LUT  [256][32 lanes]  u32 = v * 0x010101 | 0xFF000000   } interleaved: one 256-byte entry per value, so that the
+//       RGB_Y      [256][32 lanes]  u32        lane l reads bank l     } offset of a lookup is (byte << 8) | 4 * lane
 //     (128 KB per SM, one 512-thread CTA per SM).  The chroma tables are indexed by m = third_round(n) (the (int)(n / 3. + .5)
 //     of colourspace.c:3465); CLAMP16_240 / CLAMP0_255 are no-ops on these tables (flat outside the range; checked on the
 //     host by fused3_tables_ok) and third_round is one multiply-high on the PACKED pair of sums (see idx_hi / idx_lo).
@@ -46,12 +46,30 @@ namespace {
 constexpr int F3_NT = PE_F3_NT;         // threads per CTA (one CTA per SM).  Measured: 512 (128 regs) 46.6k fps, 640 (96 regs) 42.7k, 768 (80 regs) 36.8k
 constexpr int F3_NW = F3_NT / 32;
 constexpr int F3_MAXF = 32;               // frames per launch (their pointers travel as kernel parameters)
+// RGB_Y and the gamma LUT share one [256][2][32] region (entry stride 256 bytes), so that a lookup offset is
+// (value << 8) | lane * 4 -- one LOP3 on the word that already holds the byte at bits 8..15, no PRMT + IMAD
+// (measured: 49.7k vs 49.0k fps with separate 128-byte-stride tables, -DPE_F3_SEPARATE_TABLES)
+#ifndef PE_F3_SEPARATE_TABLES
+#define PE_F3_INTERLEAVE 1
+#endif
+#ifdef PE_F3_INTERLEAVE
+constexpr int S3_TV = 0;                  // uint2 [256][16]: {R_Cr, G_Cr}
+constexpr int S3_TU = 32768;              // uint2 [256][16]: {G_Cb, B_Cb}
+constexpr int S3_LUT = 65536;             // u32 [256][64]: words 0..31 of an entry = the gamma LUT copies ...
+constexpr int S3_TY = 65536 + 128;        //                words 32..63 = the RGB_Y copies
+constexpr int S3_TYSTRIDE = 256;
+#else
 constexpr int S3_TY = 0;                  // u32 [256][32]
+constexpr int S3_TYSTRIDE = 128;
 constexpr int S3_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
 constexpr int S3_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
 constexpr int S3_LUT = 98304;             // u32 [256][32]
+#endif
 constexpr int S3_RING = 131072;           // per warp: F3_RING bg rows of 512 bytes, filled by cp.async ahead of the emit
-constexpr int F3_RING = 4;
+#ifndef PE_F3_RING
+#define PE_F3_RING 4
+#endif
+constexpr int F3_RING = PE_F3_RING;      // power of two
 constexpr int S3_BYTES = S3_RING + F3_NW * F3_RING * 512;   // + 16 bytes per inner output row (filter rows)
 constexpr int F3_MAX_IH = 3200;
 
@@ -128,6 +146,15 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
   return r;
 }
 
+// luma byte `col` of a word as the RGB_Y table index: the byte value, or (PE_F3_INTERLEAVE) the value already shifted to bits 8..15
+__device__ __forceinline__ uint32_t ysel(uint32_t w, int col) {
+#ifdef PE_F3_INTERLEAVE
+  return col == 0 ? (w << 8) & 0xFF00u : col == 1 ? w & 0xFF00u : col == 2 ? (w >> 8) & 0xFF00u : (w >> 16) & 0xFF00u;
+#else
+  return byte_of(w, col);
+#endif
+}
+
 constexpr uint32_t MSK = 0xFFFEFFFEu;   // clears bit 0 of both halves: 2 * (s >> 1) = s & ~1
 constexpr uint32_t K3 = 0x00030003u;    // + 3 in both halves (Q = 2 n + 3)
 
@@ -189,12 +216,12 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   // ---- replicated tables
   {
     uint32_t *tl = reinterpret_cast<uint32_t *>(smem + S3_LUT);
-    fill_replicated_yuv_tables(smem + S3_TY, smem + S3_TV, smem + S3_TU, P.conv, tid, F3_NT);
+    fill_replicated_yuv_tables(smem + S3_TY, smem + S3_TV, smem + S3_TU, P.conv, tid, F3_NT, S3_TYSTRIDE);
     if (HAS_LUT)
       for (int m = tid; m < 256; m += F3_NT) {
         const uint32_t e = (uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u;
 #pragma unroll
-        for (int j = 0; j < 8; j++) reinterpret_cast<uint4 *>(tl + 32 * m)[j] = make_uint4(e, e, e, e);
+        for (int j = 0; j < 8; j++) reinterpret_cast<uint4 *>(tl + (S3_TYSTRIDE / 4) * m)[j] = make_uint4(e, e, e, e);
       }
     int4 *sr = reinterpret_cast<int4 *>(smem + S3_BYTES);
     for (int i = tid; i < P.ih; i += F3_NT) sr[i] = P.rows4[i];
@@ -215,9 +242,13 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   // yuv2rgb_int (colourspace.c:2345-2356) through the replicated tables; results UNSATURATED (saturated by pack_sat)
   // (ou, ov = 128 * m: byte offsets of the chroma entries; plain shared-memory loads so that the table bases fold into the
   // instructions' address immediates)
-  const uint32_t lane8 = 8u * (uint32_t)(lane & 15);
+  const uint32_t lane8 = 8u * (uint32_t)(lane & 15), lane4 = 4u * (uint32_t)lane;
   auto rgb = [&](uint32_t y, uint32_t ou, uint32_t ov, int &r, int &g, int &b) {
+#ifdef PE_F3_INTERLEAVE
+    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S3_TY + (y | lane4));   // y = value << 8
+#else
     const int yy = (int)lds32(L.tyl + y * 128u);
+#endif
     const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (ov | lane8));
     const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (ou | lane8));
     r = (yy + (int)tv.x) >> 16;
@@ -230,9 +261,15 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     const uint32_t rb = (bg & 0x00FF00FFu) * kia + __byte_perm(fr, fb, 0x5410u) * ka;   // R | B in the 16-bit halves
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia + fg_ * ka;
     if (HAS_LUT) {
+#ifdef PE_F3_INTERLEAVE
+      const uint32_t e0 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((rb & 0xFF00u) | lane4));
+      const uint32_t e1 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((gg & 0xFF00u) | lane4));
+      const uint32_t e2 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + (((rb >> 16) & 0xFF00u) | lane4));
+#else
       const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
       const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
       const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
+#endif
       return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
     }
     return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
@@ -241,9 +278,15 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     const uint32_t rb = (bg & 0x00FF00FFu) * kia;
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia;
     if (HAS_LUT) {
+#ifdef PE_F3_INTERLEAVE
+      const uint32_t e0 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((rb & 0xFF00u) | lane4));
+      const uint32_t e1 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((gg & 0xFF00u) | lane4));
+      const uint32_t e2 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + (((rb >> 16) & 0xFF00u) | lane4));
+#else
       const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
       const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
       const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
+#endif
       return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
     }
     return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
@@ -341,8 +384,13 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 
       auto load_pre = [&](int k, Pre &p) {  // raw words of the fast step k: luma rows 2k-1, 2k, chroma row k
         const uint8_t *yr = L.yp + (size_t)rs_y * (uint32_t)(2 * k - 1);
+#ifdef PE_F3_LUMA_NC
+        p.yA = ld_keep_u32(yr);
+        p.yB = ld_keep_u32(yr + rs_y);
+#else
         p.yA = ld_stream_u32(yr);
         p.yB = ld_stream_u32(yr + rs_y);
+#endif
         const uint32_t uo = rs_u * (uint32_t)k, vo = rs_v * (uint32_t)k;
         p.u0 = ld_keep_u32(L.up0 + uo); p.u1 = ld_keep_u32(L.up0 + uo + 4);
         p.v0 = ld_keep_u32(L.vp0 + vo); p.v1 = ld_keep_u32(L.vp0 + vo + 4);
@@ -425,8 +473,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
             const uint32_t mu_up = hi_half ? idx_hi(qu_up) : idx_lo(qu_up), mv_up = hi_half ? idx_hi(qv_up) : idx_lo(qv_up);
             const uint32_t mv_lo = hi_half ? idx_hi(qv_lo) : idx_lo(qv_lo);
             const uint32_t mu_lo = (QUIRKS && !right) ? mu_up : (hi_half ? idx_hi(qu_lo) : idx_lo(qu_lo));
-            rgb(byte_of(pre.yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-            rgb(byte_of(pre.yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+            rgb(ysel(pre.yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+            rgb(ysel(pre.yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
           }
         } else {
           // ---- slow step: frame edges.  k <= 0: row 0 alone (horizontal average only, colourspace.c:3421-3428); the last row
@@ -440,7 +488,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
               const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
               const uint32_t mu = (chroma_at(F.u, rs_u, cr, jc, cw, ch) + chroma_at(F.u, rs_u, cr, jo, cw, ch)) >> 1;
               const uint32_t mv = (chroma_at(F.v, rs_v, cr, jc, cw, ch) + chroma_at(F.v, rs_v, cr, jo, cw, ch)) >> 1;
-              rgb(byte_of(yw, col), mu * 128u, mv * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rgb(ysel(yw, col), mu * 128u, mv * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
               rB[3 * col] = rA[3 * col]; rB[3 * col + 1] = rA[3 * col + 1]; rB[3 * col + 2] = rA[3 * col + 2];
             }
           };
@@ -465,8 +513,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
               }
               const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
               const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
-              rgb(byte_of(ya, col), mu3 * 128u, mv3 * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-              rgb(byte_of(yb, col), mu4 * 128u, mv4 * 128u, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+              rgb(ysel(ya, col), mu3 * 128u, mv3 * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+              rgb(ysel(yb, col), mu4 * 128u, mv4 * 128u, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
             }
           } else if (2 * k - 1 == fh - 1) {
             single(fh - 1, ch - 1);
@@ -620,7 +668,7 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (chunk_rows < 4) chunk_rows = 4;
     const char *eb = getenv("PE_F3_COST_B"), *ei = getenv("PE_F3_COST_I");
     cost_b = eb ? atoi(eb) : 2;
-    cost_i = ei ? atoi(ei) : 9;
+    cost_i = ei ? atoi(ei) : 7;
     if (cost_b < 1) cost_b = 1;
     if (cost_i < 1) cost_i = 1;
   }
