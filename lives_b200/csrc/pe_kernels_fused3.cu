@@ -155,6 +155,17 @@ __device__ __forceinline__ uint32_t ysel(uint32_t w, int col) {
 #endif
 }
 
+// acc >> 12 of the vertical filter.  PE_F3_SHR12_IMAD: as a multiply-high on the FMA-heavy pipe instead of a shift on the ALU pipe
+__device__ __forceinline__ uint32_t shr12(uint32_t x) {
+#ifdef PE_F3_SHR12_IMAD
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, 1048576;" : "=r"(d) : "r"(x));
+  return d;
+#else
+  return x >> 12;
+#endif
+}
+
 constexpr uint32_t MSK = 0xFFFEFFFEu;   // clears bit 0 of both halves: 2 * (s >> 1) = s & ~1
 constexpr uint32_t K3 = 0x00030003u;    // + 3 in both halves (Q = 2 n + 3)
 
@@ -554,7 +565,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 #pragma unroll
               for (int c = 0; c < 3; c++) {
                 const uint32_t win = Wc[3 * col + c];
-                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
+                fch[c] = shr12(dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)));
               }
               ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
             }
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 #pragma unroll
               for (int c = 0; c < 3; c++) {
                 const uint32_t win = __byte_perm(Wc[3 * col + c], Wp[3 * col + c], 0x6321u);
-                fch[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)) >> 12;
+                fch[c] = shr12(dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)));
               }
               ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
             }
