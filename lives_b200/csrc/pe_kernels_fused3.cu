@@ -263,7 +263,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (ov | lane8));
     const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (ou | lane8));
     r = (yy + (int)tv.x) >> 16;
+#ifdef PE_F3_SAR16_G_IMAD
+    asm("mul.hi.s32 %0, %1, 65536;" : "=r"(g) : "r"(yy + (int)tu.x + (int)tv.y));   // one of the three shifts on the FMA-heavy pipe
+#else
     g = (yy + (int)tu.x + (int)tv.y) >> 16;
+#endif
     b = (yy + (int)tu.y) >> 16;
   };
 

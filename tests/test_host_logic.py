@@ -1,5 +1,6 @@
 """CPU checks of the integer identities the CUDA kernels rely on (each one is a claim in a kernel comment / DESIGN.md):
-exhaustive over the value ranges that can occur, no GPU and no oracle needed."""
+exhaustive over the value ranges that can occur, no GPU needed; the last test checks the (unpinned) resize contract of the
+oracle against OpenCV."""
 import numpy as np
 
 
@@ -76,3 +77,25 @@ def test_window_push_and_tap_order():
         wcur, wprev = hist[0:4], [2 * (k - 1) - j for j in range(4)]
         win = wcur if j0 == 0 else [wcur[1], wcur[2], wcur[3], wprev[2]]   # PRMT 0x6321
         assert win == [f + 3, f + 2, f + 1, f]
+
+
+def test_resize_contract_tracks_independent_resamplers():
+    """The resize filter is OUR contract (the reference calls libswscale, which is neither in its tree nor in this image:
+    parity unpinned).  Sanity against an independent implementation (OpenCV): a smooth image resized by the
+    oracle's filter stays within a couple of LSB of cv2's INTER_AREA (downscale) / INTER_LINEAR (upscale) result."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pe_testlib as T
+    o = T.oracle()
+    yy, xx = np.mgrid[0:270, 0:480]
+    img = np.stack([(127 + 100 * np.sin(xx / 37.0) * np.cos(yy / 23.0)), (xx * 255 / 479), (yy * 255 / 269), np.full(xx.shape, 255)], -1)
+    src = np.ascontiguousarray(img.astype(np.uint8))
+    for (dw, dh), interp, tol_mean, tol_max in (((320, 180), cv2.INTER_AREA, 0.6, 4), ((720, 404), cv2.INTER_LINEAR, 0.6, 4),
+                                                ((480, 202), cv2.INTER_AREA, 0.6, 4)):
+        got = np.zeros((dh, dw * 4), np.uint8)
+        o.pe_or_resize_packed(T.ptr(src), 480 * 4, 480, 270, T.ptr(got), dw * 4, dw, dh, 4)
+        ref = cv2.resize(src, (dw, dh), interpolation=interp).reshape(dh, dw * 4)
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert d.mean() < tol_mean and d.max() <= tol_max, (dw, dh, float(d.mean()), int(d.max()))
