@@ -1570,9 +1570,15 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
     if (!fy->rows4) {
       const ResizeFilter &F = fy->host;
       std::vector<int32_t> r4((size_t)inner_h * 4);
+      // scaled by 16 (sum 65536) when every coefficient still fits 16 bits, i.e. no row has the single tap 4096: the kernel
+      // then reads the filtered value as byte 2 of its accumulator instead of shifting by 12 (PE_F3_NO_C16 turns it off)
+      int cmax = 0;
+      for (size_t i = 0; i < (size_t)inner_h * F.taps; i++) cmax = F.coef[i] > cmax ? F.coef[i] : cmax;
+      fy->rows4_x16 = cmax < 4096 && getenv("PE_F3_NO_C16") == nullptr;
+      const uint32_t scale = fy->rows4_x16 ? 16u : 1u;
       for (int i = 0; i < inner_h; i++) {
         uint32_t c[4] = {0, 0, 0, 0};
-        for (int t = 0; t < F.taps; t++) c[t] = (uint16_t)F.coef[(size_t)i * F.taps + t];
+        for (int t = 0; t < F.taps; t++) c[t] = (uint32_t)(uint16_t)F.coef[(size_t)i * F.taps + t] * scale;
         r4[4 * i] = F.first[i];
         r4[4 * i + 1] = (int32_t)(c[3] | (c[2] << 16));
         r4[4 * i + 2] = (int32_t)(c[1] | (c[0] << 16));
@@ -1586,7 +1592,7 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
       PE_CUDA(cudaMalloc(&e->f3_sched, 2 * sizeof(unsigned int)));
       PE_CUDA(cudaMemsetAsync(e->f3_sched, 0, 2 * sizeof(unsigned int), e->stream));
     }
-    PE_CUDA(launch_fused3(e->L(), args.data(), n, (int)k256, lut, fy->rows4, e->f3_sched));
+    PE_CUDA(launch_fused3(e->L(), args.data(), n, (int)k256, lut, fy->rows4, fy->rows4_x16, e->f3_sched));
   } else if (fast) {
     PE_CUDA(launch_fused2(e->L(), args.data(), n, ow, oh, tile_h, dyadic ? (int)k256 : -1, lut));
   } else {

@@ -54,6 +54,7 @@ struct DevFilterEntry {
   DevFilter dev;
   ResizeFilter host;
   void *rows4 = nullptr;  // int4 per output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}: k_fused3's view of a <= 4-tap bank
+  int rows4_x16 = 0;      // its coefficients are scaled by 16 (no tap of the bank is 4096)
 };
 struct Lut8Entry {
   uint8_t host[256];

@@ -157,9 +157,9 @@ cudaError_t launch_fused2(const Launch &L, const FusedArgs *frames_host, int nfr
 // register-resident path (pe_kernels_fused3.cu): 4:2:0, full-width letterbox, alpha = k / 256, one conversion variant per batch
 bool fused3_tables_ok(const ConvTables &t);
 bool fused3_supported(const FusedArgs *frames_host, int nframes, int fy_taps);
-// rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}
+// rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}; coef16: the coefficients in it are scaled by 16
 cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
-                          const void *rows4_dev, unsigned int *sched_dev /* [2], zero; reset by the kernel */);
+                          const void *rows4_dev, int coef16, unsigned int *sched_dev /* [2], zero; reset by the kernel */);
 // ---- diagnostics -------------------------------------------------------------------------------------------
 struct DevStats {
   unsigned int minv[4], maxv[4];

@@ -29,6 +29,7 @@
 // Rows that cannot take the fast step (row 0, the last row of an even frame, virtual rows beyond the frame, the last chroma
 // row of a plane without padding) go through slow_step(): scalar code with the reference's edge rules, a few steps per strip.
 #include <cstdlib>
+#include <type_traits>
 
 #include "pe_device.cuh"
 #include "pe_kernels.h"
@@ -91,7 +92,7 @@ struct Fused3Params {
   long long frame_cost, total_cost, static_cost, chunk_cost;
   unsigned int *sched;                     // [2] device counters, zero between launches
   uint32_t ka, kia;                        // blend weights of fg / bg, sum 256
-  const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0
+  const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0 (coefficients x 16 under C16)
   const int32_t *conv;                     // [14][256] (ConvTab order)
   const uint8_t *lut8;                     // optional
 };
@@ -218,7 +219,9 @@ __device__ __forceinline__ uint32_t chroma_at(const uint8_t *__restrict__ p, int
   return p[(size_t)stride * r + c];
 }
 
-template <bool QUIRKS, bool HAS_LUT>
+// C16: the filter coefficients arrive scaled by 16 (sum 65536; only banks without a 4096 tap): the filtered value is byte 2 of
+// the accumulator (byte 3 is zero), so R | B pack with one PRMT and two of the three shifts per pixel disappear
+template <bool QUIRKS, bool HAS_LUT, bool C16>
 __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -272,8 +275,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   };
 
   // alpha-over (integer form of compositor.c:120 for alpha = ka / 256) + gamma LUT of one pixel
-  auto blend = [&](uint32_t bg, uint32_t fr, uint32_t fg_, uint32_t fb) -> uint32_t {
-    const uint32_t rb = (bg & 0x00FF00FFu) * kia + __byte_perm(fr, fb, 0x5410u) * ka;   // R | B in the 16-bit halves
+  auto blend = [&](uint32_t bg, uint32_t frb, uint32_t fg_) -> uint32_t {   // frb = filtered R | B << 16
+    const uint32_t rb = (bg & 0x00FF00FFu) * kia + frb * ka;   // R | B in the 16-bit halves
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia + fg_ * ka;
     if (HAS_LUT) {
 #ifdef PE_F3_INTERLEAVE
@@ -565,24 +568,26 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           if (j0 == 0) {
 #pragma unroll
             for (int col = 0; col < 4; col++) {
-              uint32_t fch[3];
+              uint32_t acc[3];
 #pragma unroll
               for (int c = 0; c < 3; c++) {
                 const uint32_t win = Wc[3 * col + c];
-                fch[c] = shr12(dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)));
+                acc[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, C16 ? 32768u : 2048u));
               }
-              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
+              ov[col] = C16 ? blend(bgv[col], __byte_perm(acc[0], acc[2], 0x7632u), acc[1] >> 16)
+                            : blend(bgv[col], __byte_perm(shr12(acc[0]), shr12(acc[2]), 0x5410u), shr12(acc[1]));
             }
           } else {
 #pragma unroll
             for (int col = 0; col < 4; col++) {
-              uint32_t fch[3];
+              uint32_t acc[3];
 #pragma unroll
               for (int c = 0; c < 3; c++) {
                 const uint32_t win = __byte_perm(Wc[3 * col + c], Wp[3 * col + c], 0x6321u);
-                fch[c] = shr12(dp2a_hi(CB, win, dp2a_lo(CA, win, 2048u)));
+                acc[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, C16 ? 32768u : 2048u));
               }
-              ov[col] = blend(bgv[col], fch[0], fch[1], fch[2]);
+              ov[col] = C16 ? blend(bgv[col], __byte_perm(acc[0], acc[2], 0x7632u), acc[1] >> 16)
+                            : blend(bgv[col], __byte_perm(shr12(acc[0]), shr12(acc[2]), 0x5410u), shr12(acc[1]));
             }
           }
           st_stream_u4(outp + (size_t)rs_out * (uint32_t)(oy + iy), make_uint4(ov[0], ov[1], ov[2], ov[3]));
@@ -664,15 +669,17 @@ bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
 
 // rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0} (built by the engine from the filter bank)
 cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
-                          const void *rows4_dev, unsigned int *sched_dev) {
+                          const void *rows4_dev, int coef16, unsigned int *sched_dev) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e;
     const int mx = S3_BYTES + 16 * F3_MAX_IH;
-    if ((e = cudaFuncSetAttribute(k_fused3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_fused3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_fused3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_fused3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    const void *fns[8] = {(const void *)k_fused3<true, true, true>,   (const void *)k_fused3<true, true, false>,
+                          (const void *)k_fused3<true, false, true>,  (const void *)k_fused3<true, false, false>,
+                          (const void *)k_fused3<false, true, true>,  (const void *)k_fused3<false, true, false>,
+                          (const void *)k_fused3<false, false, true>, (const void *)k_fused3<false, false, false>};
+    for (int i = 0; i < 8; i++)
+      if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
     attr_set = true;
   }
   static int cost_b = 0, cost_i = 0, static_pct = 92, chunk_rows = 24;
@@ -726,13 +733,12 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     P.conv = a0.conv.t;
     P.lut8 = lut8_dev;
     const int smem_bytes = S3_BYTES + 16 * a0.ih;
-    if (a0.quirks) {
-      if (lut8_dev) k_fused3<true, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
-      else k_fused3<true, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
-    } else {
-      if (lut8_dev) k_fused3<false, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
-      else k_fused3<false, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
-    }
+    auto go = [&](auto q, auto l, auto c) {
+      k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+    };
+    auto pick_c = [&](auto q, auto l) { if (coef16) go(q, l, std::true_type()); else go(q, l, std::false_type()); };
+    auto pick_l = [&](auto q) { if (lut8_dev) pick_c(q, std::true_type()); else pick_c(q, std::false_type()); };
+    if (a0.quirks) pick_l(std::true_type()); else pick_l(std::false_type());
     PE_COUNT_LAUNCH(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
