@@ -12,6 +12,8 @@
 // not a multiple of 4 and unaligned planes).  Rows and columns at the frame edges follow the reference's edge rules through
 // the scalar slow path below (row 0, the last row of an even frame, the last chroma row of a plane without padding, the
 // 4:2:2 seed slip of column 0).
+#include <cstdlib>
+
 #include "pe_device.cuh"
 #include "pe_kernels.h"
 #include "pe_tables.h"
@@ -49,6 +51,16 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
+}
+__device__ __forceinline__ uint32_t ld_u32nc(const void *p) {  // chroma words are shared by neighbouring lanes / strips: keep them in L2
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_u8nc(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
 }
 // 128 * third_round(n) for the n in the high / low half of a packed Q = 2 n + 3 (see pe_kernels_fused3.cu, tests/test_host_logic.py)
 __device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u * 128u) & 0x7F80u; }
@@ -326,6 +338,278 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_planar_to_rgb_fast(const __gri
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// k_yuv_march: the same conversion, organised like k_fused3 (pe_kernels_fused3.cu) for frames tall enough to march through: a
+// warp owns a strip of 128 columns and walks down the rows one reference row pair per step.  What the job kernel above pays per
+// 4 x 2 pixels -- (job, quad) bookkeeping, 64-bit addresses of ten cp.async, both chroma rows of the pair unpacked -- is paid
+// once per strip here: addresses advance by the row strides, the sums of the previous chroma row are CARRIED from step to step
+// (4:2:0), and the raw words of step k + 1 are loaded into registers while step k is computed.
+// 4:2:2: a step is two independent rows (horizontal average only); the lane of column 0 takes the scalar path when the seed slip
+// (colourspace.c:3600) is on.
+struct MarchPre {
+  uint32_t yA, yB, u0, u1, v0, v1, u2, u3, v2, v3, vf;   // 4:2:0: chroma row k in u0 u1 v0 v1; 4:2:2: rows 2k-1 / 2k in (u0 u1 v0 v1) / (u2 u3 v2 v3)
+};
+struct MarchCarry {
+  uint32_t DUr, MUr, DVr, MVr, DUl, MUl, DVl, MVl, QUL, aV;
+};
+
+template <bool QUIRKS, bool IS422>
+__global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ YuvToRgbArgs A, int k_fast_max, int band_h) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  fill_replicated_yuv_tables(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid, Y2_NT);
+  __syncthreads();
+
+  const Planes &S = A.src;
+  const int w = A.width, h = A.height, cw = S.cw, ch = S.ch;
+  const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
+  uint32_t osel;
+  {
+    uint32_t nib[4] = {3, 3, 3, 3};
+    nib[A.out.r] = 0; nib[A.out.g] = 1; nib[A.out.b] = 2;
+    if (A.out.a >= 0) nib[A.out.a] = 3;
+    osel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
+  }
+  auto px = [&](uint32_t y, uint32_t ou, uint32_t ov) -> uint32_t {
+    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S2_TY + (y * 128u + lane4));
+    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S2_TV + (ov | lane8));
+    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S2_TU + (ou | lane8));
+    const int r = (yy + (int)tv.x) >> 16, g = (yy + (int)tu.x + (int)tv.y) >> 16, b = (yy + (int)tu.y) >> 16;
+    return __byte_perm(pack_sat(g, r, pack_sat(255, b, 0u)), 0u, osel);
+  };
+  const uint32_t bf = (uint32_t)A.blend_bf & 0xFFu, nb = 255u - bf;
+  const bool xf = A.blend2 != nullptr;
+  const uint32_t rs_y = (uint32_t)S.rs_y, rs_u = (uint32_t)S.rs_u, rs_v = (uint32_t)S.rs_v, rs_d = (uint32_t)A.dst.rs,
+                 rs_x = (uint32_t)A.blend2_rs;
+
+  // ---- the warp's share of the (band, strip, row) sequence: every row costs the same
+  const int nstrips = (w + 127) >> 7;
+  const long long total = (long long)nstrips * h;
+  const long long gw = (long long)blockIdx.x * (Y2_NT / 32) + warp, nwarps = (long long)gridDim.x * (Y2_NT / 32);
+  long long pos = total * gw / nwarps;
+  const long long pos_end = total * (gw + 1) / nwarps;
+  while (pos < pos_end) {
+    const long long band_units = (long long)band_h * nstrips;
+    const int b = (int)(pos / band_units);
+    const int r0 = b * band_h, bh = min(band_h, h - r0);
+    const long long rem = pos - (long long)b * band_units;
+    const int s = (int)(rem / bh), within = (int)(rem - (long long)s * bh);
+    const long long unit0 = pos - within;
+    const int hi = (int)min((long long)bh, pos_end - unit0);
+    const int ra = r0 + within, rb = r0 + hi;
+    pos = unit0 + bh;
+    const int x = 128 * s + 4 * lane;
+    if (x >= w || ra >= rb) continue;
+
+    const int jc0 = x >> 1, o = jc0 - 1;
+    const size_t off0 = x == 0 ? 0 : (size_t)(o & ~3);
+    const uint32_t sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+    const uint32_t selB = x == 0 ? 0x3254u : 0x3210u;
+    const uint8_t *yp = S.y + x, *up = S.u + off0, *vp = S.v + off0;
+    uint8_t *dp = A.dst.p + (size_t)x * A.out.psize;
+    const uint8_t *xp = xf ? A.blend2 + (size_t)x * 3 : nullptr;
+    const bool seed_lane = IS422 && QUIRKS && x == 0;
+
+    auto store_row = [&](uint32_t *p4, int row, const uint32_t *op) {
+      if (xf) {  // dst = (bf * in2 + (255 - bf) * converted) >> 8 per byte (make_blend_table, simple_blend.c:31-35)
+        const uint32_t o4[4] = {op[0], __byte_perm(op[0], op[1], 0x0543), __byte_perm(op[1], op[2], 0x0432), op[2] >> 8};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t even = (((p4[k] & 0x00FF00FFu) * nb + (o4[k] & 0x00FF00FFu) * bf) >> 8) & 0x00FF00FFu;
+          const uint32_t mid = (((p4[k] >> 8) & 0xFFu) * nb + ((o4[k] >> 8) & 0xFFu) * bf) & 0xFF00u;
+          p4[k] = even | mid;
+        }
+      }
+      uint8_t *d = dp + (size_t)rs_d * (uint32_t)row;
+      if (A.out.psize == 4) {
+        st_stream_u4(d, make_uint4(p4[0], p4[1], p4[2], p4[3]));
+      } else {
+        st_stream_u32(d, __byte_perm(p4[0], p4[1], 0x4210));
+        st_stream_u32(d + 4, __byte_perm(p4[1], p4[2], 0x5421));
+        st_stream_u32(d + 8, __byte_perm(p4[2], p4[3], 0x6542));
+      }
+    };
+    auto load_op = [&](int row, uint32_t *op) {   // crossfade operand: the 12 bytes under the lane's 4 pixels
+      if (!xf) return;
+      const uint8_t *q = xp + (size_t)rs_x * (uint32_t)row;
+      op[0] = ld_stream_u32(q); op[1] = ld_stream_u32(q + 4); op[2] = ld_stream_u32(q + 8);
+    };
+    // scalar single row with the reference's edge rules (row 0, the last row of an even 4:2:0 frame, unsafe rows, the 4:2:2 seed lane)
+    auto single = [&](int row, int cr, int seed_row, uint32_t *out4) {
+      const uint32_t yw = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * row + x);
+#pragma unroll
+      for (int col = 0; col < 4; col++) {
+        const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+        uint32_t ua = chroma_at(S.u, rs_u, cr, jc, cw, ch), ub = chroma_at(S.u, rs_u, cr, jo, cw, ch);
+        uint32_t va = chroma_at(S.v, rs_v, cr, jc, cw, ch), vb = chroma_at(S.v, rs_v, cr, jo, cw, ch);
+        if (jc0 == 0 && seed_row != cr) {  // 4:2:2 seed slip (:3600): columns <= 0 are column 0 of chroma row (i >> 1)
+          const uint32_t su = S.u[(size_t)rs_u * seed_row], sv = S.v[(size_t)rs_v * seed_row];
+          if (jc == 0) { ua = su; va = sv; }
+          if (jo <= 0) { ub = su; vb = sv; }
+        }
+        out4[col] = px(byte_of(yw, col), ((ua + ub) >> 1) * 128u, ((va + vb) >> 1) * 128u);
+      }
+    };
+    auto emit_single = [&](int row, int cr, int seed_row) {
+      uint32_t p4[4], op[3] = {0u, 0u, 0u};
+      load_op(row, op);
+      single(row, cr, seed_row, p4);
+      store_row(p4, row, op);
+    };
+
+    auto load_pre = [&](int k, MarchPre &p) {
+      const uint8_t *yr = yp + (size_t)rs_y * (uint32_t)(2 * k - 1);
+      p.yA = ld_stream_u32(yr); p.yB = ld_stream_u32(yr + rs_y);
+      if (IS422) {
+        const uint8_t *ur = up + (size_t)rs_u * (uint32_t)(2 * k - 1), *vr = vp + (size_t)rs_v * (uint32_t)(2 * k - 1);
+        p.u0 = ld_u32nc(ur); p.u1 = ld_u32nc(ur + 4); p.u2 = ld_u32nc(ur + rs_u); p.u3 = ld_u32nc(ur + rs_u + 4);
+        p.v0 = ld_u32nc(vr); p.v1 = ld_u32nc(vr + 4); p.v2 = ld_u32nc(vr + rs_v); p.v3 = ld_u32nc(vr + rs_v + 4);
+      } else {
+        const uint8_t *ur = up + (size_t)rs_u * (uint32_t)k, *vr = vp + (size_t)rs_v * (uint32_t)k;
+        p.u0 = ld_u32nc(ur); p.u1 = ld_u32nc(ur + 4);
+        p.v0 = ld_u32nc(vr); p.v1 = ld_u32nc(vr + 4);
+        if (QUIRKS) p.vf = ld_u8nc(S.v + (size_t)rs_v * (uint32_t)k);
+      }
+    };
+    auto init_carry = [&](int r, MarchCarry &c) {  // sums of chroma row r as a fast 4:2:0 step leaves them
+      const uint8_t *ur = up + (size_t)rs_u * (uint32_t)r, *vr = vp + (size_t)rs_v * (uint32_t)r;
+      const RowC U = unpack_row(ld_u32nc(ur), ld_u32nc(ur + 4), sel), V = unpack_row(ld_u32nc(vr), ld_u32nc(vr + 4), sel);
+      const uint32_t RU = U.a + U.c, RV = V.a + V.c, LU = U.a + U.b, LV = V.a + V.b;
+      c.DUr = RU * 2u; c.MUr = RU & MSK; c.DVr = RV * 2u; c.MVr = RV & MSK;
+      c.DUl = LU * 2u; c.MUl = LU & MSK; c.DVl = LV * 2u; c.MVl = LV & MSK;
+      c.QUL = LU * 2u + (LU & MSK) + K3;
+      c.aV = V.a;
+    };
+
+    const int k_first = (ra + 1) >> 1, k_last = rb >> 1;
+    MarchPre pre;
+    MarchCarry C;
+    pre.yA = pre.yB = pre.u0 = pre.u1 = pre.v0 = pre.v1 = pre.u2 = pre.u3 = pre.v2 = pre.v3 = pre.vf = 0u;
+    C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
+    bool carry_ok = false;
+    auto is_fast = [&](int k) { return k >= 1 && k <= k_fast_max; };
+    if (is_fast(k_first)) {
+      load_pre(k_first, pre);
+      if (!IS422) { init_carry(k_first - 1, C); carry_ok = true; }
+    }
+    for (int k = k_first; k <= k_last; k++) {
+      const int rowA = 2 * k - 1, rowB = 2 * k;
+      const bool stA = rowA >= ra && rowA < rb, stB = rowB >= ra && rowB < rb && rowB < h;
+      MarchPre nxt = pre;   // (consumed at the end of the step: see k_fused3)
+      const bool next_fast = k + 1 <= k_last && is_fast(k + 1);
+      if (next_fast) load_pre(k + 1, nxt);
+      if (is_fast(k)) {
+        uint32_t opA[3] = {0u, 0u, 0u}, opB[3] = {0u, 0u, 0u};
+        if (stA) load_op(rowA, opA);
+        if (stB) load_op(rowB, opB);
+        uint32_t pa[4], pb[4];
+        if (IS422) {
+          if (seed_lane) {
+            single(rowA, rowA, rowA >> 1, pa);
+            single(rowB, rowB, rowB >> 1, pb);
+          } else {
+            const RowC UA = unpack_row(pre.u0, pre.u1, sel), VA = unpack_row(pre.v0, pre.v1, sel);
+            const RowC UB = unpack_row(pre.u2, pre.u3, sel), VB = unpack_row(pre.v2, pre.v3, sel);
+            const uint32_t LUA = UA.a + UA.b, RUA = UA.a + UA.c, LVA = VA.a + VA.b, RVA = VA.a + VA.c;
+            const uint32_t LUB = UB.a + UB.b, RUB = UB.a + UB.c, LVB = VB.a + VB.b, RVB = VB.a + VB.c;
+#pragma unroll
+            for (int col = 0; col < 4; col++) {
+              const bool hi_half = col >> 1, right = col & 1;
+              const uint32_t sua = right ? RUA : LUA, sva = right ? RVA : LVA, sub = right ? RUB : LUB, svb = right ? RVB : LVB;
+              // 128 * (s >> 1) = (s & ~1) << 6
+              pa[col] = px(byte_of(pre.yA, col), hi_half ? ((sua >> 10) & 0x7F80u) : ((sua << 6) & 0x7F80u),
+                           hi_half ? ((sva >> 10) & 0x7F80u) : ((sva << 6) & 0x7F80u));
+              pb[col] = px(byte_of(pre.yB, col), hi_half ? ((sub >> 10) & 0x7F80u) : ((sub << 6) & 0x7F80u),
+                           hi_half ? ((svb >> 10) & 0x7F80u) : ((svb << 6) & 0x7F80u));
+            }
+          }
+        } else {
+          const RowC U = unpack_row(pre.u0, pre.u1, sel), V = unpack_row(pre.v0, pre.v1, sel);
+          const uint32_t RU = U.a + U.c, RV = V.a + V.c;
+          const uint32_t DUn = RU * 2u, MUn = RU & MSK, DVn = RV * 2u, MVn = RV & MSK;
+          const uint32_t QUR_up = C.DUr + MUn + K3, QUR_lo = C.MUr + DUn + K3;
+          const uint32_t QVR_up = C.DVr + MVn + K3, QVR_lo = C.MVr + DVn + K3;
+          C.DUr = DUn; C.MUr = MUn; C.DVr = DVn; C.MVr = MVn;
+          uint32_t QUL_up, QUL_lo, QVL_up, QVL_lo;
+          const uint32_t LU = U.a + U.b;
+          if (QUIRKS) {
+            QUL_up = QUL_lo = C.QUL;                                  // u2 = this_u1 + last_u1 (colourspace.c:3461)
+            C.QUL = LU * 2u + (LU & MSK) + K3;
+            const uint32_t bq = __byte_perm(V.b, C.aV, selB);         // last_v1 = this_v2 (:3544), except at column 0
+            const uint32_t v1 = C.aV + bq;
+            const uint32_t v2 = V.a + pre.vf * 0x10001u;              // last_v2 is never advanced
+            QVL_up = v1 * 2u + (v2 & MSK) + K3; QVL_lo = (v1 & MSK) + v2 * 2u + K3;
+            C.aV = V.a;
+          } else {
+            const uint32_t LV = V.a + V.b;
+            const uint32_t DUn_l = LU * 2u, MUn_l = LU & MSK, DVn_l = LV * 2u, MVn_l = LV & MSK;
+            QUL_up = C.DUl + MUn_l + K3; QUL_lo = C.MUl + DUn_l + K3;
+            QVL_up = C.DVl + MVn_l + K3; QVL_lo = C.MVl + DVn_l + K3;
+            C.DUl = DUn_l; C.MUl = MUn_l; C.DVl = DVn_l; C.MVl = MVn_l;
+          }
+#pragma unroll
+          for (int col = 0; col < 4; col++) {
+            const bool hi_half = col >> 1, right = col & 1;
+            const uint32_t qu_up = right ? QUR_up : QUL_up, qu_lo = right ? QUR_lo : QUL_lo;
+            const uint32_t qv_up = right ? QVR_up : QVL_up, qv_lo = right ? QVR_lo : QVL_lo;
+            const uint32_t ou_up = hi_half ? idx_hi(qu_up) : idx_lo(qu_up), ov_up = hi_half ? idx_hi(qv_up) : idx_lo(qv_up);
+            const uint32_t ov_lo = hi_half ? idx_hi(qv_lo) : idx_lo(qv_lo);
+            const uint32_t ou_lo = (QUIRKS && !right) ? ou_up : (hi_half ? idx_hi(qu_lo) : idx_lo(qu_lo));
+            pa[col] = px(byte_of(pre.yA, col), ou_up, ov_up);
+            pb[col] = px(byte_of(pre.yB, col), ou_lo, ov_lo);
+          }
+        }
+        if (stA) store_row(pa, rowA, opA);
+        if (stB) store_row(pb, rowB, opB);
+      } else {
+        // ---- slow step: frame edges
+        if (IS422) {
+          if (stA && rowA >= 0) emit_single(rowA, rowA, QUIRKS ? rowA >> 1 : rowA);
+          if (stB) emit_single(rowB, rowB, QUIRKS ? rowB >> 1 : rowB);
+        } else if (k <= 0) {
+          if (stB) emit_single(0, 0, 0);
+        } else if (2 * k <= h - 1) {
+          // the last chroma row of a plane without padding: scalar pair with the edge rules
+          const int ca = k - 1, cb = k;
+          const uint32_t ya = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * rowA + x);
+          const uint32_t yb = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * rowB + x);
+          const uint32_t vfirst = S.v[(size_t)rs_v * cb];
+          uint32_t pa[4], pb[4], opA[3] = {0u, 0u, 0u}, opB[3] = {0u, 0u, 0u};
+          if (stA) load_op(rowA, opA);
+          if (stB) load_op(rowB, opB);
+#pragma unroll
+          for (int col = 0; col < 4; col++) {
+            const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+            uint32_t u1 = chroma_at(S.u, rs_u, ca, jc, cw, ch) + chroma_at(S.u, rs_u, ca, jo, cw, ch);
+            uint32_t u2 = chroma_at(S.u, rs_u, cb, jc, cw, ch) + chroma_at(S.u, rs_u, cb, jo, cw, ch);
+            uint32_t v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, ca, jo, cw, ch);
+            uint32_t v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
+            if (QUIRKS && !(col & 1)) {
+              u2 = u1;
+              if (jc > 0) v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
+              v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + vfirst;
+            }
+            const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
+            const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
+            pa[col] = px(byte_of(ya, col), mu3 * 128u, mv3 * 128u);
+            pb[col] = px(byte_of(yb, col), mu4 * 128u, mv4 * 128u);
+          }
+          if (stA) store_row(pa, rowA, opA);
+          if (stB) store_row(pb, rowB, opB);
+        } else if (rowA == h - 1) {
+          if (stA) emit_single(h - 1, ch - 1, ch - 1);
+        }
+        carry_ok = false;
+      }
+      if (!IS422 && next_fast && !carry_ok) {
+        init_carry(k, C);
+        carry_ok = true;
+      }
+      pre = nxt;
+    }
+  }
+}
+
 }  // namespace
 
 // Can the fast converter take this frame?  (checked by launch_yuv_planar_to_rgb; everything else: k_yuv_planar_to_rgb)
@@ -353,6 +637,40 @@ cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a
   // the fast paths read whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
   const bool last_row_unsafe = a.src.rs_u < a.src.cw + 4 || a.src.rs_v < a.src.cw + 4;
   const int k_fast_max = a.src.ch - 1 - (last_row_unsafe ? 1 : 0);
+  // frames tall enough for every warp to march through a few dozen rows of a strip take k_yuv_march; small ones the job kernel.
+  // Measured on a single 4K 4:2:2 clip + crossfade (27 rows per warp): march 35.5 us and 15.5 M warp instructions, job kernel
+  // 34.6 us and 20.3 M -- at that size both are bounded by the per-launch overheads (table fill, first loads, tail), so the
+  // marching kernel only takes over where its lower instruction count can show
+  const int nstrips = (a.width + 127) / 128;
+  const long long rows_per_warp = (long long)nstrips * a.height / ((long long)L.sm_count * (Y2_NT / 32));
+  const bool blend_ok = !a.blend2 || ((((uintptr_t)a.blend2) | (uint32_t)a.blend2_rs) & 3) == 0;
+  const char *mr = getenv("PE_YUV_MARCH_MIN_ROWS");  // tests force the marching kernel onto small frames with 0
+  if (rows_per_warp >= (mr ? atoi(mr) : 48) && blend_ok && getenv("PE_YUV_NO_MARCH") == nullptr) {
+    static bool march_attr = false;
+    if (!march_attr) {
+      cudaError_t e;
+      if ((e = cudaFuncSetAttribute(k_yuv_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k_yuv_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k_yuv_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k_yuv_march<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+      march_attr = true;
+    }
+    // 4:2:2: a fast step reads chroma rows 2k - 1 and 2k; the last one needs 4 bytes of padding behind it
+    const int kmax = a.is_422 ? (a.height - 1 - (last_row_unsafe ? 1 : 0)) / 2 : k_fast_max;
+    int band_h = (int)rows_per_warp;
+    if (band_h < 8) band_h = 8;
+    if (band_h > a.height) band_h = a.height;
+    const int grid = L.sm_count;
+    if (a.quirks) {
+      if (a.is_422) k_yuv_march<true, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
+      else k_yuv_march<true, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
+    } else {
+      if (a.is_422) k_yuv_march<false, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
+      else k_yuv_march<false, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
+    }
+    PE_COUNT_LAUNCH(L);
+    return cudaGetLastError();
+  }
   const long long work = (long long)(a.width >> 2) * (a.is_422 ? a.height : a.src.ch + 1);
   long long blocks = (work + Y2_NT - 1) / Y2_NT;
   if (blocks > L.sm_count) blocks = L.sm_count;

@@ -125,6 +125,49 @@ def test_planar_yuv_to_rgb(eng, size, is422):
         lay.free()
 
 
+def test_planar_yuv_marching_kernel(eng, monkeypatch):
+    """k_yuv_march (the strip-marching converter that large frames take) forced onto small frames: every RGB palette, both
+    samplings, clamped / unclamped, quirks on / off, padded and unpadded chroma planes, with and without the fused crossfade;
+    then a 4K 4:2:2 clip"""
+    o = T.oracle()
+    rng = np.random.default_rng(41)
+    monkeypatch.setenv("PE_YUV_MARCH_MIN_ROWS", "0")
+    e_nq = lb.Engine(ref_quirks=False)
+    for (w, h), is422 in itertools.product(((64, 48), (644, 362), (256, 34), (8, 4), (132, 50), (4, 2)), (0, 1)):
+        inpal = 522 if is422 else 512
+        for opal, cl, sub, quirks in itertools.product(RGB_PALS, (0, 1), (1, 2), (1, 0)):
+            if (cl, sub, quirks) not in ((0, 1, 1), (1, 2, 1), (0, 2, 0), (1, 1, 0)) and (w, h) != (64, 48):
+                continue
+            e = eng if quirks else e_nq
+            y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), cl == 0)
+            exp = _oracle_planar(o, y, u, v, w, h, opal, is422, cl, sub, T.Q_HIGH, quirks=quirks)
+            lay = lb.Layer.from_host(e, inpal, w, h, [y, u, v], yuv_clamping=cl, yuv_subspace=sub)
+            assert lb.convert_layer_palette_full(lay, opal, cl, 0, sub, 0)
+            ps = T.psize_of(opal)
+            bad = np.argwhere(payload(lay.to_host()[0], w, ps) != payload(exp, w, ps))
+            assert len(bad) == 0, (w, h, is422, opal, cl, sub, quirks, len(bad), bad[:4])
+            lay.free()
+        # fused crossfade through the marching kernel
+        y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), True)
+        operand = T.make_packed(rng, w, h, 3)
+        exp = np.zeros((h, T.rowstride(w, 3)), np.uint8)
+        o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(exp), exp.strides[0], 0, 0, is422, 0, 1,
+                               T.Q_HIGH, 1, None)
+        o.pe_or_simple_blend(0, 1, T.ptr(exp), exp.strides[0], T.ptr(operand), operand.strides[0], T.ptr(exp), exp.strides[0], w, h, 77,
+                             operand.size)
+        clip = lb.Layer.from_host(eng, inpal, w, h, [y, u, v], yuv_subspace=1)
+        lb.convert_crossfade(clip, packed_layer(eng, 1, w, h, operand), 1, 0, 77)
+        assert (payload(clip.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (w, h, is422, "crossfade")
+    e_nq.close()
+    monkeypatch.setenv("PE_YUV_MARCH_MIN_ROWS", "12")
+    w, h = 3840, 2160
+    y, u, v = T.make_yuv_planar(rng, w, h, True, True)
+    exp = _oracle_planar(o, y, u, v, w, h, 1, 1, 0, 1, T.Q_HIGH)
+    lay = lb.Layer.from_host(eng, 522, w, h, [y, u, v], yuv_subspace=1)
+    assert lb.convert_layer_palette(lay, 1, 0)
+    assert (payload(lay.to_host()[0], w, 3) == payload(exp, w, 3)).all()
+
+
 def test_planar_yuv_quality_quirks_and_yvu(eng):
     """PB_QUALITY_LOW chroma shortcut (RGB order only, :3470), ref_quirks off, YVU420P plane swap (:12354)"""
     o = T.oracle()
