@@ -219,6 +219,68 @@ __device__ __forceinline__ uint32_t chroma_at(const uint8_t *__restrict__ p, int
   return p[(size_t)stride * r + c];
 }
 
+// ---- slow step, out of line (a few steps per strip; keeping it out of the marching loop keeps the loop's code small): rows
+//      A = 2k-1, B = 2k of the lane's 4 columns with the reference's edge rules, as (sat(A) << 8) | sat(B) per column-channel.
+//      k <= 0: row 0 alone (horizontal average only, colourspace.c:3421-3428); 2k-1 == fh-1: the last row of an even frame alone;
+//      otherwise an interior pair whose last chroma row has no padding behind it (one-past-row read, :3508).
+struct SlowRows {
+  uint32_t ab[12];
+};
+template <bool QUIRKS>
+__device__ __noinline__ SlowRows slow_rows(const uint8_t *smem, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, uint32_t rs_y,
+                                           uint32_t rs_u, uint32_t rs_v, int x0, int k, int fh, int cw, int ch, int lane) {
+  const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
+  int rA[12], rB[12];
+  auto rgb = [&](uint32_t y, uint32_t mu, uint32_t mv, int &r, int &g, int &b) {   // y: byte value, mu / mv: table indices
+    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S3_TY + (y * (uint32_t)S3_TYSTRIDE + lane4));
+    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (mv * 128u + lane8));
+    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (mu * 128u + lane8));
+    r = (yy + (int)tv.x) >> 16; g = (yy + (int)tu.x + (int)tv.y) >> 16; b = (yy + (int)tu.y) >> 16;
+  };
+  auto single = [&](int row, int cr) {
+    const uint32_t yw = *reinterpret_cast<const uint32_t *>(py + (size_t)rs_y * row + x0);
+#pragma unroll
+    for (int col = 0; col < 4; col++) {
+      const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+      const uint32_t mu = (chroma_at(pu, rs_u, cr, jc, cw, ch) + chroma_at(pu, rs_u, cr, jo, cw, ch)) >> 1;
+      const uint32_t mv = (chroma_at(pv, rs_v, cr, jc, cw, ch) + chroma_at(pv, rs_v, cr, jo, cw, ch)) >> 1;
+      rgb(byte_of(yw, col), mu, mv, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+      rB[3 * col] = rA[3 * col]; rB[3 * col + 1] = rA[3 * col + 1]; rB[3 * col + 2] = rA[3 * col + 2];
+    }
+  };
+  if (k <= 0) {
+    single(0, 0);
+  } else if (2 * k <= fh - 1) {
+    const int ca = k - 1, cbr = k;
+    const uint32_t ya = *reinterpret_cast<const uint32_t *>(py + (size_t)rs_y * (2 * k - 1) + x0);
+    const uint32_t yb = *reinterpret_cast<const uint32_t *>(py + (size_t)rs_y * (2 * k) + x0);
+    const uint32_t vfirst = pv[(size_t)rs_v * cbr];
+#pragma unroll
+    for (int col = 0; col < 4; col++) {
+      const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+      uint32_t u1 = chroma_at(pu, rs_u, ca, jc, cw, ch) + chroma_at(pu, rs_u, ca, jo, cw, ch);
+      uint32_t u2 = chroma_at(pu, rs_u, cbr, jc, cw, ch) + chroma_at(pu, rs_u, cbr, jo, cw, ch);
+      uint32_t v1 = chroma_at(pv, rs_v, ca, jc, cw, ch) + chroma_at(pv, rs_v, ca, jo, cw, ch);
+      uint32_t v2 = chroma_at(pv, rs_v, cbr, jc, cw, ch) + chroma_at(pv, rs_v, cbr, jo, cw, ch);
+      if (QUIRKS && !(col & 1)) {
+        u2 = u1;
+        if (jc > 0) v1 = chroma_at(pv, rs_v, ca, jc, cw, ch) + chroma_at(pv, rs_v, cbr, jo, cw, ch);
+        v2 = chroma_at(pv, rs_v, cbr, jc, cw, ch) + vfirst;
+      }
+      const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
+      const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
+      rgb(byte_of(ya, col), mu3, mv3, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+      rgb(byte_of(yb, col), mu4, mv4, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+    }
+  } else {
+    single(fh - 1, ch - 1);
+  }
+  SlowRows out;
+#pragma unroll
+  for (int i = 0; i < 12; i++) out.ab[i] = pack_sat(rA[i], rB[i], 0u);
+  return out;
+}
+
 // C16: the filter coefficients arrive scaled by 16 (sum 65536; only banks without a 4096 tap): the filtered value is byte 2 of
 // the accumulator (byte 3 is zero), so R | B pack with one PRMT and two of the three shifts per pixel disappear
 template <bool QUIRKS, bool HAS_LUT, bool C16>
@@ -494,56 +556,21 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
             rgb(ysel(pre.yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
             rgb(ysel(pre.yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
           }
+#pragma unroll
+          for (int i = 0; i < 12; i++) Wc[i] = pack_sat(rA[i], rB[i], Wp[i]);
         } else {
-          // ---- slow step: frame edges.  k <= 0: row 0 alone (horizontal average only, colourspace.c:3421-3428); the last row
-          //      of an even frame alone; rows beyond the frame replicate the last row (the filter clamps source indices);
-          //      the last chroma row of a plane without padding (one-past-row read, :3508)
-          const int x0 = L.x;
-          auto single = [&](int row, int cr) {
-            const uint32_t yw = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * row + x0);
+          // ---- slow step (frame edges): out of line; rows beyond the frame replicate the last row (the filter clamps its
+          //      source indices)
+          if (k <= 0 || 2 * k - 1 <= fh - 1) {
+            const SlowRows sr = slow_rows<QUIRKS>(smem, F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane);
 #pragma unroll
-            for (int col = 0; col < 4; col++) {
-              const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
-              const uint32_t mu = (chroma_at(F.u, rs_u, cr, jc, cw, ch) + chroma_at(F.u, rs_u, cr, jo, cw, ch)) >> 1;
-              const uint32_t mv = (chroma_at(F.v, rs_v, cr, jc, cw, ch) + chroma_at(F.v, rs_v, cr, jo, cw, ch)) >> 1;
-              rgb(ysel(yw, col), mu * 128u, mv * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-              rB[3 * col] = rA[3 * col]; rB[3 * col + 1] = rA[3 * col + 1]; rB[3 * col + 2] = rA[3 * col + 2];
-            }
-          };
-          if (k <= 0) {
-            single(0, 0);
-          } else if (2 * k <= fh - 1) {
-            const int ca = k - 1, cbr = k;
-            const uint32_t ya = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * (2 * k - 1) + x0);
-            const uint32_t yb = *reinterpret_cast<const uint32_t *>(F.y + (size_t)rs_y * (2 * k) + x0);
-            const uint32_t vfirst = F.v[(size_t)rs_v * cbr];
-#pragma unroll
-            for (int col = 0; col < 4; col++) {
-              const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
-              uint32_t u1 = chroma_at(F.u, rs_u, ca, jc, cw, ch) + chroma_at(F.u, rs_u, ca, jo, cw, ch);
-              uint32_t u2 = chroma_at(F.u, rs_u, cbr, jc, cw, ch) + chroma_at(F.u, rs_u, cbr, jo, cw, ch);
-              uint32_t v1 = chroma_at(F.v, rs_v, ca, jc, cw, ch) + chroma_at(F.v, rs_v, ca, jo, cw, ch);
-              uint32_t v2 = chroma_at(F.v, rs_v, cbr, jc, cw, ch) + chroma_at(F.v, rs_v, cbr, jo, cw, ch);
-              if (QUIRKS && !(col & 1)) {
-                u2 = u1;
-                if (jc > 0) v1 = chroma_at(F.v, rs_v, ca, jc, cw, ch) + chroma_at(F.v, rs_v, cbr, jo, cw, ch);
-                v2 = chroma_at(F.v, rs_v, cbr, jc, cw, ch) + vfirst;
-              }
-              const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
-              const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
-              rgb(ysel(ya, col), mu3 * 128u, mv3 * 128u, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-              rgb(ysel(yb, col), mu4 * 128u, mv4 * 128u, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
-            }
-          } else if (2 * k - 1 == fh - 1) {
-            single(fh - 1, ch - 1);
+            for (int i = 0; i < 12; i++) Wc[i] = __byte_perm(sr.ab[i], Wp[i], 0x5410u);
           } else {
 #pragma unroll
-            for (int i = 0; i < 12; i++) rA[i] = rB[i] = (int)(Wp[i] & 0xFFu);
+            for (int i = 0; i < 12; i++) Wc[i] = __byte_perm(Wp[i], 0u, 0x1000u);   // [b0, b0, b0, b1]: the newest row twice more
           }
           carry_ok = false;
         }
-#pragma unroll
-        for (int i = 0; i < 12; i++) Wc[i] = pack_sat(rA[i], rB[i], Wp[i]);
         if (next_fast && !carry_ok) {
           init_carry(k, C);
           carry_ok = true;
