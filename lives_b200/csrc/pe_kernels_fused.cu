@@ -196,6 +196,110 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile(const ResizeTileParams P
   }
 }
 
+// k_resize_tile4: the same tile kernel specialised for 4-byte pixels and <= 4 taps per axis (bilinear up to 1.5x down), where
+// the generic loops above spend ~350 instructions per output pixel.  Horizontal pass: the four tap pixels are byte-transposed
+// with 8 PRMT into one word per channel and filtered with two DP2A per channel (16-bit coefficient pairs x 4 bytes); vertical
+// pass: 4 x 64-bit tmp loads, unrolled multiply-adds, one saturating pack.  Coefficients are staged per tile as 16-bit pairs
+// padded to 4 taps.  Same arithmetic, bit for bit (tests/test_gpu_parity.py::test_resize_*).
+__device__ __forceinline__ uint32_t rz_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t rz_dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+__global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams P) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  const int raw_stride = P.max_cols * 4 + 16;                                // + 3 words of slack: the 4-word tap window of the last column
+  const int tx_taps = P.fx.taps, ty_taps = P.fy.taps;
+  uint8_t *s_raw = rsm;                                                    // [max_rows][raw_stride]
+  size_t off = ((size_t)P.max_rows * raw_stride + 15) & ~(size_t)15;
+  uint2 *s_tmp = reinterpret_cast<uint2 *>(rsm + off);                     // [max_rows + 3][tw]
+  off += (size_t)(P.max_rows + 3) * P.tw * 8;
+  uint2 *s_cx = reinterpret_cast<uint2 *>(rsm + off);                      // [tw]: c0 | c1 << 16, c2 | c3 << 16
+  off += (size_t)P.tw * 8;
+  int4 *s_cy = reinterpret_cast<int4 *>(rsm + off);                        // [th]: c0..c3
+  off += (size_t)P.th * 16;
+  int *s_fx = reinterpret_cast<int *>(rsm + off);                          // [tw] first - vc0
+  int *s_fy = s_fx + P.tw;                                                 // [th] first - vr0
+
+  const int tiles_x = (P.dw + P.tw - 1) / P.tw;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int x0 = tx * P.tw, y0 = ty * P.th;
+  const int x1 = min(x0 + P.tw, P.dw), y1 = min(y0 + P.th, P.dh);
+  const int ncol = x1 - x0, nrow = y1 - y0;
+  const int vr0 = P.fy.first[y0], vr1 = P.fy.first[y1 - 1] + ty_taps - 1;
+  const int vc0 = P.fx.first[x0], vc1 = P.fx.first[x1 - 1] + tx_taps - 1;
+  const int nvr = vr1 - vr0 + 1, nvc = vc1 - vc0 + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- 0. filter data of the tile, padded to 4 taps
+  for (int i = threadIdx.x; i < ncol; i += kBlock) {
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (int k = 0; k < tx_taps; k++) c[k] = (uint16_t)P.fx.coef[(size_t)(x0 + i) * tx_taps + k];
+    s_cx[i] = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
+    s_fx[i] = P.fx.first[x0 + i] - vc0;
+  }
+  for (int i = threadIdx.x; i < nrow; i += kBlock) {
+    int c[4] = {0, 0, 0, 0};
+    for (int k = 0; k < ty_taps; k++) c[k] = P.fy.coef[(size_t)(y0 + i) * ty_taps + k];
+    s_cy[i] = make_int4(c[0], c[1], c[2], c[3]);
+    s_fy[i] = P.fy.first[y0 + i] - vr0;
+  }
+  // ---- 1. stage the source rectangle, replicating the frame edges (+ 3 slack words per row so that a 4-word window never leaves it)
+  for (int r = warp; r < nvr; r += kBlock / 32) {
+    const int sy = min(max(vr0 + r, 0), P.sh - 1);
+    const uint8_t *rp = P.src + (size_t)P.srs * sy;
+    uint32_t *dp = reinterpret_cast<uint32_t *>(s_raw + r * raw_stride);
+    for (int c = lane; c < nvc + 3; c += 32) {
+      const int sx = min(max(vc0 + c, 0), P.sw - 1);
+      dp[c] = ld_stream_u32(rp + 4 * sx);
+    }
+  }
+  __syncthreads();
+  // ---- 2. horizontal pass: tmp = min((sum c14 * pix) >> 7, 32767)
+  for (int r = warp; r < nvr; r += kBlock / 32) {
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(s_raw + r * raw_stride);
+    for (int xo = lane; xo < ncol; xo += 32) {
+      const uint2 cf = s_cx[xo];
+      const uint32_t *q = row + s_fx[xo];
+      const uint32_t p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
+      // 4 x 4 byte transpose: one word per channel holding the four taps
+      const uint32_t a01 = __byte_perm(p0, p1, 0x5140), b01 = __byte_perm(p0, p1, 0x7362);
+      const uint32_t a23 = __byte_perm(p2, p3, 0x5140), b23 = __byte_perm(p2, p3, 0x7362);
+      const uint32_t c0 = __byte_perm(a01, a23, 0x5410), c1 = __byte_perm(a01, a23, 0x7632);
+      const uint32_t c2 = __byte_perm(b01, b23, 0x5410), c3 = __byte_perm(b01, b23, 0x7632);
+      const uint32_t t0 = min(rz_dp2a_hi(cf.y, c0, rz_dp2a_lo(cf.x, c0, 0u)) >> 7, 32767u);
+      const uint32_t t1 = min(rz_dp2a_hi(cf.y, c1, rz_dp2a_lo(cf.x, c1, 0u)) >> 7, 32767u);
+      const uint32_t t2 = min(rz_dp2a_hi(cf.y, c2, rz_dp2a_lo(cf.x, c2, 0u)) >> 7, 32767u);
+      const uint32_t t3 = min(rz_dp2a_hi(cf.y, c3, rz_dp2a_lo(cf.x, c3, 0u)) >> 7, 32767u);
+      s_tmp[r * P.tw + xo] = make_uint2(t0 | (t1 << 16), t2 | (t3 << 16));
+    }
+  }
+  __syncthreads();
+  // ---- 3. vertical pass: out = clip_u8((sum c12 * tmp + 2^18) >> 19)   (rows past nvr - 1 are only ever multiplied by the zero padding taps)
+  for (int yo = warp; yo < nrow; yo += kBlock / 32) {
+    const int4 cf = s_cy[yo];
+    const uint2 *t = s_tmp + s_fy[yo] * P.tw;
+    uint8_t *drow = P.dst + (size_t)P.drs * (y0 + yo) + (size_t)x0 * 4;
+    for (int xo = lane; xo < ncol; xo += 32) {
+      const uint2 h0 = t[xo], h1 = t[P.tw + xo], h2 = t[2 * P.tw + xo], h3 = t[3 * P.tw + xo];
+      int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
+      a0 += cf.x * (int)(h0.x & 0xFFFF) + cf.y * (int)(h1.x & 0xFFFF) + cf.z * (int)(h2.x & 0xFFFF) + cf.w * (int)(h3.x & 0xFFFF);
+      a1 += cf.x * (int)(h0.x >> 16) + cf.y * (int)(h1.x >> 16) + cf.z * (int)(h2.x >> 16) + cf.w * (int)(h3.x >> 16);
+      a2 += cf.x * (int)(h0.y & 0xFFFF) + cf.y * (int)(h1.y & 0xFFFF) + cf.z * (int)(h2.y & 0xFFFF) + cf.w * (int)(h3.y & 0xFFFF);
+      a3 += cf.x * (int)(h0.y >> 16) + cf.y * (int)(h1.y >> 16) + cf.z * (int)(h2.y >> 16) + cf.w * (int)(h3.y >> 16);
+      uint32_t lo, px;
+      asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(a1 >> 19), "r"(a0 >> 19), "r"(0u));
+      asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(a3 >> 19), "r"(a2 >> 19), "r"(0u));
+      *reinterpret_cast<uint32_t *>(drow + 4 * xo) = lo | (px << 16);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------------
@@ -438,6 +542,22 @@ cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img ds
     else e = cudaFuncSetAttribute(k_resize_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
     attr[psize] = 96 * 1024;
+  }
+  if (psize == 4 && fx.taps <= 4 && fy.taps <= 4 && ((((uintptr_t)dst.p | (uintptr_t)src.p) | (uint32_t)dst.rs | (uint32_t)src.rs) & 3) == 0 &&
+      getenv("PE_RESIZE_GENERIC") == nullptr) {
+    // the specialised kernel has its own (slightly larger) shared-memory layout
+    const size_t raw4 = (((size_t)P.max_rows * (P.max_cols * 4 + 16)) + 15) & ~(size_t)15;
+    const size_t smem4 = raw4 + (size_t)(P.max_rows + 3) * P.tw * 8 + (size_t)P.tw * 8 + (size_t)P.th * 16 + (size_t)(P.tw + P.th) * 4;
+    static bool attr4 = false;
+    if (smem4 <= 96 * 1024) {
+      if (!attr4) {
+        if ((e = cudaFuncSetAttribute(k_resize_tile4, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        attr4 = true;
+      }
+      k_resize_tile4<<<tiles, kBlock, smem4, L.stream>>>(P);
+      PE_COUNT_LAUNCH(L);
+      return cudaGetLastError();
+    }
   }
   if (psize == 4) k_resize_tile<4><<<tiles, kBlock, smem, L.stream>>>(P);
   else if (psize == 3) k_resize_tile<3><<<tiles, kBlock, smem, L.stream>>>(P);
