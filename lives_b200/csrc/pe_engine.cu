@@ -919,10 +919,12 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     A.lut16 = nullptr;
     if (new_gamma_type != PE_GAMMA_UNKNOWN) A.lut16 = get_lut16(e, 1.0, gamma_type, new_gamma_type);  // `if (tgt_gamma)` :3273
     A.blend2 = e->fuse_blend2; A.blend2_rs = e->fuse_blend2_rs; A.blend_bf = e->fuse_blend_bf;
-    if (getenv("PE_YUV_SLOW") == nullptr && yuv_planar_fast_ok(A, &conv_host(e, iclamping, isubspace)))
-      ce = launch_yuv_planar_to_rgb_fast(L, A);
-    else
+    if (getenv("PE_YUV_SLOW") == nullptr && yuv_planar_fast_ok(A, &conv_host(e, iclamping, isubspace))) {
+      if (e->yuv_defer && !A.blend2) e->yuv_pending.push_back(A);  // batch call: launched by flush_yuv_pending
+      else ce = launch_yuv_planar_to_rgb_fast(L, A);
+    } else {
       ce = launch_yuv_planar_to_rgb(L, A);
+    }
   } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) && pal_is_rgb(outpl)) {
     // convert_{uyvy,yuyv}_to_*_frame (:13147-13190, :13244-13290).  Table choice as the reference makes it:
     // uyvy->RGB24 passes the layer's subspace, uyvy->RGBA32 passes its SAMPLING in that slot (:13160), every other
@@ -1189,6 +1191,21 @@ extern "C" int pe_resize_layer_full(pe_engine_t *e, pe_frame_t *layer, int width
 
 namespace {
 
+// launch the planar YUV -> RGB conversions a batch call has queued: runs of same-shaped frames leave as one launch per 32
+int flush_yuv_pending(pe_engine *e) {
+  std::vector<YuvToRgbArgs> q;
+  q.swap(e->yuv_pending);
+  size_t i = 0;
+  while (i < q.size()) {
+    size_t j = i + 1;
+    while (j < q.size() && yuv_planar_same_shape(q[i], q[j])) j++;
+    cudaError_t ce = j - i == 1 ? launch_yuv_planar_to_rgb_fast(e->L(), q[i]) : launch_yuv_planar_to_rgb_batch(e->L(), &q[i], (int)(j - i));
+    if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "conversion kernel launch failed: %s", cudaGetErrorString(ce));
+    i = j;
+  }
+  return PE_OK;
+}
+
 // Fan a batch of independent per-layer calls out over four side streams.  Layer 0 runs on the engine stream first (it
 // creates whatever cached tables the batch needs: filter banks, LUTs -- their uploads are ordered before the fork); the other
 // layers of the same geometry run on the side streams, so that the small kernels of different layers overlap instead of
@@ -1242,6 +1259,31 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   int done = 0;
+  // phase 1: planar YUV layers with an RGB target are converted first (resize_layer_full converts before it scales, :14601);
+  // the conversions of the whole batch are queued and leave as one launch per 32 same-shaped frames
+  if (pal_is_rgb(opal_hint)) {
+    e->yuv_defer = true;
+    e->pool.defer(true);
+    for (int i = 0; i < n; i++) {
+      pe_frame *f = layers[i];
+      if (!f || !f->d.planes[0] || width <= 0 || height <= 0) continue;
+      const int pal = f->d.palette;
+      if (pal != PE_PALETTE_YUV420P && pal != PE_PALETTE_YVU420P && pal != PE_PALETTE_YUV422P) continue;
+      {  // resize_locked returns before converting when the (evened) sizes already match (:14850-14859)
+        const int iw = (f->d.width >> 1) << 1, ih = (f->d.height >> 1) << 1, w2 = width < 4 ? 4 : width;
+        int h2 = height < 4 ? 4 : height;
+        if (iw != w2 || ih != h2) h2 = (h2 >> 1) << 1;
+        if (iw == w2 && ih == h2) continue;
+      }
+      convert_locked(e, f, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN);
+    }
+    e->yuv_defer = false;
+    const int frc = flush_yuv_pending(e);
+    e->pool.defer(false);
+    e->pool.flush_deferred();
+    if (frc != PE_OK) return 0;
+  }
+  // phase 2: the resizes, fanned out over the side streams
   const pe_frame ref0 = layers[0] ? *layers[0] : pe_frame();
   FanOut fan(e);
   for (int i = 0; i < n; i++) {
@@ -1261,6 +1303,22 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   int done = 0;
+  bool all_planar = pal_is_rgb(outpl);
+  for (int i = 0; i < n && all_planar; i++)
+    all_planar = layers[i] && (layers[i]->d.palette == PE_PALETTE_YUV420P || layers[i]->d.palette == PE_PALETTE_YVU420P ||
+                               layers[i]->d.palette == PE_PALETTE_YUV422P);
+  if (all_planar) {
+    // planar YUV -> RGB: the conversions are queued and leave as one launch per 32 same-shaped frames
+    e->yuv_defer = true;
+    e->pool.defer(true);
+    for (int i = 0; i < n; i++)
+      if (convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
+    e->yuv_defer = false;
+    const int frc = flush_yuv_pending(e);
+    e->pool.defer(false);
+    e->pool.flush_deferred();
+    return frc == PE_OK ? done : 0;
+  }
   const pe_frame ref0 = layers[0] ? *layers[0] : pe_frame();
   FanOut fan(e);
   for (int i = 0; i < n; i++) {

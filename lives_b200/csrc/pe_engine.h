@@ -92,6 +92,9 @@ struct pe_engine {
   // set around convert_locked by pe_fx_convert_crossfade: the planar YUV -> RGB converter blends with this frame on the fly
   const uint8_t *fuse_blend2 = nullptr;
   int fuse_blend2_rs = 0, fuse_blend_bf = 0;
+  // batch calls: planar YUV -> RGB conversions are queued and leave as ONE launch per 32 same-shaped frames (flush_yuv_pending)
+  bool yuv_defer = false;
+  std::vector<pe::YuvToRgbArgs> yuv_pending;
   // batch calls: layers 1 .. n-1 run on four side streams (forked from / joined to the engine stream by events)
   cudaStream_t fan_stream[4] = {};
   cudaEvent_t fan_fork = nullptr, fan_join[4] = {};

@@ -76,6 +76,9 @@ cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a);
 struct ConvTables;
 bool yuv_planar_fast_ok(const YuvToRgbArgs &a, const ConvTables *host_tables);
 cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a);
+// n frames that differ only in their pointers (yuv_planar_same_shape), each passing yuv_planar_fast_ok: one launch per 32 frames
+bool yuv_planar_same_shape(const YuvToRgbArgs &a, const YuvToRgbArgs &b);
+cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *frames, int n);
 // ---- packed 4:2:2 / 4:4:4 (colourspace.c:6616-7103, :2750-3258, :5700-6239) ---------------------------
 cudaError_t launch_packed422_to_rgb(const Launch &L, int fmt, CImg src, Img dst, int width_mpx, int height,
                                     RgbLayout out, DevConv conv);

@@ -346,6 +346,13 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_planar_to_rgb_fast(const __gri
 // (4:2:0), and the raw words of step k + 1 are loaded into registers while step k is computed.
 // 4:2:2: a step is two independent rows (horizontal average only); the lane of column 0 takes the scalar path when the seed slip
 // (colourspace.c:3600) is on.
+// frames of one batched launch (same geometry, strides, palettes and tables: everything else comes from the common YuvToRgbArgs)
+struct YuvFrameList {
+  const uint8_t *y[32], *u[32], *v[32];
+  uint8_t *dst[32];
+  int n;
+};
+
 struct MarchPre {
   uint32_t yA, yB, u0, u1, v0, v1, u2, u3, v2, v3, vf;   // 4:2:0: chroma row k in u0 u1 v0 v1; 4:2:2: rows 2k-1 / 2k in (u0 u1 v0 v1) / (u2 u3 v2 v3)
 };
@@ -354,7 +361,7 @@ struct MarchCarry {
 };
 
 template <bool QUIRKS, bool IS422>
-__global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ YuvToRgbArgs A, int k_fast_max, int band_h) {
+__global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ YuvToRgbArgs A, const __grid_constant__ YuvFrameList FL, int k_fast_max, int band_h) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   fill_replicated_yuv_tables(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid, Y2_NT);
@@ -384,15 +391,18 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
 
   // ---- the warp's share of the (band, strip, row) sequence: every row costs the same
   const int nstrips = (w + 127) >> 7;
-  const long long total = (long long)nstrips * h;
+  const long long per_frame = (long long)nstrips * h;
+  const long long total = per_frame * FL.n;   // FL.n frames of the same geometry (a batch is one launch)
   const long long gw = (long long)blockIdx.x * (Y2_NT / 32) + warp, nwarps = (long long)gridDim.x * (Y2_NT / 32);
   long long pos = total * gw / nwarps;
   const long long pos_end = total * (gw + 1) / nwarps;
   while (pos < pos_end) {
+    const int fidx = (int)(pos / per_frame);
+    const long long fpos = pos - (long long)fidx * per_frame;
     const long long band_units = (long long)band_h * nstrips;
-    const int b = (int)(pos / band_units);
+    const int b = (int)(fpos / band_units);
     const int r0 = b * band_h, bh = min(band_h, h - r0);
-    const long long rem = pos - (long long)b * band_units;
+    const long long rem = fpos - (long long)b * band_units;
     const int s = (int)(rem / bh), within = (int)(rem - (long long)s * bh);
     const long long unit0 = pos - within;
     const int hi = (int)min((long long)bh, pos_end - unit0);
@@ -405,8 +415,9 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
     const size_t off0 = x == 0 ? 0 : (size_t)(o & ~3);
     const uint32_t sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
     const uint32_t selB = x == 0 ? 0x3254u : 0x3210u;
-    const uint8_t *yp = S.y + x, *up = S.u + off0, *vp = S.v + off0;
-    uint8_t *dp = A.dst.p + (size_t)x * A.out.psize;
+    const uint8_t *const Fy = FL.y[fidx], *const Fu = FL.u[fidx], *const Fv = FL.v[fidx];
+    const uint8_t *yp = Fy + x, *up = Fu + off0, *vp = Fv + off0;
+    uint8_t *dp = FL.dst[fidx] + (size_t)x * A.out.psize;
     const uint8_t *xp = xf ? A.blend2 + (size_t)x * 3 : nullptr;
     const bool seed_lane = IS422 && QUIRKS && x == 0;
 
@@ -436,14 +447,14 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
     };
     // scalar single row with the reference's edge rules (row 0, the last row of an even 4:2:0 frame, unsafe rows, the 4:2:2 seed lane)
     auto single = [&](int row, int cr, int seed_row, uint32_t *out4) {
-      const uint32_t yw = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * row + x);
+      const uint32_t yw = *reinterpret_cast<const uint32_t *>(Fy + (size_t)rs_y * row + x);
 #pragma unroll
       for (int col = 0; col < 4; col++) {
         const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
-        uint32_t ua = chroma_at(S.u, rs_u, cr, jc, cw, ch), ub = chroma_at(S.u, rs_u, cr, jo, cw, ch);
-        uint32_t va = chroma_at(S.v, rs_v, cr, jc, cw, ch), vb = chroma_at(S.v, rs_v, cr, jo, cw, ch);
+        uint32_t ua = chroma_at(Fu, rs_u, cr, jc, cw, ch), ub = chroma_at(Fu, rs_u, cr, jo, cw, ch);
+        uint32_t va = chroma_at(Fv, rs_v, cr, jc, cw, ch), vb = chroma_at(Fv, rs_v, cr, jo, cw, ch);
         if (jc0 == 0 && seed_row != cr) {  // 4:2:2 seed slip (:3600): columns <= 0 are column 0 of chroma row (i >> 1)
-          const uint32_t su = S.u[(size_t)rs_u * seed_row], sv = S.v[(size_t)rs_v * seed_row];
+          const uint32_t su = Fu[(size_t)rs_u * seed_row], sv = Fv[(size_t)rs_v * seed_row];
           if (jc == 0) { ua = su; va = sv; }
           if (jo <= 0) { ub = su; vb = sv; }
         }
@@ -468,7 +479,7 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
         const uint8_t *ur = up + (size_t)rs_u * (uint32_t)k, *vr = vp + (size_t)rs_v * (uint32_t)k;
         p.u0 = ld_u32nc(ur); p.u1 = ld_u32nc(ur + 4);
         p.v0 = ld_u32nc(vr); p.v1 = ld_u32nc(vr + 4);
-        if (QUIRKS) p.vf = ld_u8nc(S.v + (size_t)rs_v * (uint32_t)k);
+        if (QUIRKS) p.vf = ld_u8nc(Fv + (size_t)rs_v * (uint32_t)k);
       }
     };
     auto init_carry = [&](int r, MarchCarry &c) {  // sums of chroma row r as a fast 4:2:0 step leaves them
@@ -571,23 +582,23 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
         } else if (2 * k <= h - 1) {
           // the last chroma row of a plane without padding: scalar pair with the edge rules
           const int ca = k - 1, cb = k;
-          const uint32_t ya = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * rowA + x);
-          const uint32_t yb = *reinterpret_cast<const uint32_t *>(S.y + (size_t)rs_y * rowB + x);
-          const uint32_t vfirst = S.v[(size_t)rs_v * cb];
+          const uint32_t ya = *reinterpret_cast<const uint32_t *>(Fy + (size_t)rs_y * rowA + x);
+          const uint32_t yb = *reinterpret_cast<const uint32_t *>(Fy + (size_t)rs_y * rowB + x);
+          const uint32_t vfirst = Fv[(size_t)rs_v * cb];
           uint32_t pa[4], pb[4], opA[3] = {0u, 0u, 0u}, opB[3] = {0u, 0u, 0u};
           if (stA) load_op(rowA, opA);
           if (stB) load_op(rowB, opB);
 #pragma unroll
           for (int col = 0; col < 4; col++) {
             const int jc = jc0 + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
-            uint32_t u1 = chroma_at(S.u, rs_u, ca, jc, cw, ch) + chroma_at(S.u, rs_u, ca, jo, cw, ch);
-            uint32_t u2 = chroma_at(S.u, rs_u, cb, jc, cw, ch) + chroma_at(S.u, rs_u, cb, jo, cw, ch);
-            uint32_t v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, ca, jo, cw, ch);
-            uint32_t v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
+            uint32_t u1 = chroma_at(Fu, rs_u, ca, jc, cw, ch) + chroma_at(Fu, rs_u, ca, jo, cw, ch);
+            uint32_t u2 = chroma_at(Fu, rs_u, cb, jc, cw, ch) + chroma_at(Fu, rs_u, cb, jo, cw, ch);
+            uint32_t v1 = chroma_at(Fv, rs_v, ca, jc, cw, ch) + chroma_at(Fv, rs_v, ca, jo, cw, ch);
+            uint32_t v2 = chroma_at(Fv, rs_v, cb, jc, cw, ch) + chroma_at(Fv, rs_v, cb, jo, cw, ch);
             if (QUIRKS && !(col & 1)) {
               u2 = u1;
-              if (jc > 0) v1 = chroma_at(S.v, rs_v, ca, jc, cw, ch) + chroma_at(S.v, rs_v, cb, jo, cw, ch);
-              v2 = chroma_at(S.v, rs_v, cb, jc, cw, ch) + vfirst;
+              if (jc > 0) v1 = chroma_at(Fv, rs_v, ca, jc, cw, ch) + chroma_at(Fv, rs_v, cb, jo, cw, ch);
+              v2 = chroma_at(Fv, rs_v, cb, jc, cw, ch) + vfirst;
             }
             const uint32_t mu3 = (uint32_t)third_round((int)(u1 + (u2 >> 1))), mu4 = (uint32_t)third_round((int)((u1 >> 1) + u2));
             const uint32_t mv3 = (uint32_t)third_round((int)(v1 + (v2 >> 1))), mv4 = (uint32_t)third_round((int)((v1 >> 1) + v2));
@@ -626,6 +637,63 @@ bool yuv_planar_fast_ok(const YuvToRgbArgs &a, const ConvTables *host_tables) {
   return host_tables && fused3_tables_ok(*host_tables);
 }
 
+static void launch_march(const Launch &L, const YuvToRgbArgs &a, const YuvFrameList &fl, int kmax, int band_h) {
+  const int grid = L.sm_count;
+  if (a.quirks) {
+    if (a.is_422) k_yuv_march<true, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, fl, kmax, band_h);
+    else k_yuv_march<true, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, fl, kmax, band_h);
+  } else {
+    if (a.is_422) k_yuv_march<false, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, fl, kmax, band_h);
+    else k_yuv_march<false, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, fl, kmax, band_h);
+  }
+}
+
+static cudaError_t march_attrs() {
+  static bool march_attr = false;
+  if (!march_attr) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_yuv_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_yuv_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_yuv_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_yuv_march<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
+    march_attr = true;
+  }
+  return cudaSuccess;
+}
+
+// A batch of frames that share everything but their pointers (geometry, strides, palettes, tables, flags) in ONE launch of the
+// marching kernel: the per-launch costs (table fill, first loads, tail) are paid once, and the warps get shares long enough to
+// march.  frames[i] must all pass yuv_planar_fast_ok and compare equal under yuv_planar_same_shape; no crossfade operand.
+bool yuv_planar_same_shape(const YuvToRgbArgs &a, const YuvToRgbArgs &b) {
+  return a.width == b.width && a.height == b.height && a.is_422 == b.is_422 && a.clamped == b.clamped && a.low_quality == b.low_quality &&
+         a.quirks == b.quirks && a.conv.t == b.conv.t && a.lut16 == b.lut16 && a.src.rs_y == b.src.rs_y && a.src.rs_u == b.src.rs_u &&
+         a.src.rs_v == b.src.rs_v && a.src.cw == b.src.cw && a.src.ch == b.src.ch && a.dst.rs == b.dst.rs && a.out.r == b.out.r &&
+         a.out.g == b.out.g && a.out.b == b.out.b && a.out.a == b.out.a && a.out.psize == b.out.psize && !a.blend2 && !b.blend2;
+}
+cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *frames, int n) {
+  cudaError_t e = march_attrs();
+  if (e != cudaSuccess) return e;
+  const YuvToRgbArgs &a = frames[0];
+  const bool last_row_unsafe = a.src.rs_u < a.src.cw + 4 || a.src.rs_v < a.src.cw + 4;
+  const int kmax = a.is_422 ? (a.height - 1 - (last_row_unsafe ? 1 : 0)) / 2 : a.src.ch - 1 - (last_row_unsafe ? 1 : 0);
+  const int nstrips = (a.width + 127) / 128;
+  for (int base = 0; base < n; base += 32) {
+    YuvFrameList fl;
+    fl.n = n - base < 32 ? n - base : 32;
+    for (int i = 0; i < 32; i++) {
+      const YuvToRgbArgs &f = frames[base + (i < fl.n ? i : 0)];
+      fl.y[i] = f.src.y; fl.u[i] = f.src.u; fl.v[i] = f.src.v; fl.dst[i] = f.dst.p;
+    }
+    long long rows_per_warp = (long long)nstrips * a.height * fl.n / ((long long)L.sm_count * (Y2_NT / 32));
+    int band_h = (int)(rows_per_warp < 8 ? 8 : rows_per_warp);
+    if (band_h > a.height) band_h = a.height;
+    launch_march(L, a, fl, kmax, band_h);
+    PE_COUNT_LAUNCH(L);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -646,28 +714,16 @@ cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a
   const bool blend_ok = !a.blend2 || ((((uintptr_t)a.blend2) | (uint32_t)a.blend2_rs) & 3) == 0;
   const char *mr = getenv("PE_YUV_MARCH_MIN_ROWS");  // tests force the marching kernel onto small frames with 0
   if (rows_per_warp >= (mr ? atoi(mr) : 48) && blend_ok && getenv("PE_YUV_NO_MARCH") == nullptr) {
-    static bool march_attr = false;
-    if (!march_attr) {
-      cudaError_t e;
-      if ((e = cudaFuncSetAttribute(k_yuv_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(k_yuv_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(k_yuv_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(k_yuv_march<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
-      march_attr = true;
-    }
+    { cudaError_t e = march_attrs(); if (e != cudaSuccess) return e; }
     // 4:2:2: a fast step reads chroma rows 2k - 1 and 2k; the last one needs 4 bytes of padding behind it
     const int kmax = a.is_422 ? (a.height - 1 - (last_row_unsafe ? 1 : 0)) / 2 : k_fast_max;
     int band_h = (int)rows_per_warp;
     if (band_h < 8) band_h = 8;
     if (band_h > a.height) band_h = a.height;
-    const int grid = L.sm_count;
-    if (a.quirks) {
-      if (a.is_422) k_yuv_march<true, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
-      else k_yuv_march<true, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
-    } else {
-      if (a.is_422) k_yuv_march<false, true><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
-      else k_yuv_march<false, false><<<grid, Y2_NT, S2_RING, L.stream>>>(a, kmax, band_h);
-    }
+    YuvFrameList fl;
+    fl.n = 1; fl.y[0] = a.src.y; fl.u[0] = a.src.u; fl.v[0] = a.src.v; fl.dst[0] = a.dst.p;
+    for (int i = 1; i < 32; i++) { fl.y[i] = fl.y[0]; fl.u[i] = fl.u[0]; fl.v[i] = fl.v[0]; fl.dst[i] = fl.dst[0]; }
+    launch_march(L, a, fl, kmax, band_h);
     PE_COUNT_LAUNCH(L);
     return cudaGetLastError();
   }

@@ -244,6 +244,16 @@ def test_config2_1080p_yuv420p_to_rgba_resize_720p(eng):
     assert lb.convert_layer_palette_batch(lays, 3, 0) == 2
     for lay, e in zip(lays, (rgba, rgba2)):
         assert (payload(lay.to_host()[0], w, 4) == payload(e, w, 4)).all()
+    # a longer batch with a differently shaped layer in the middle: three launches (run of 3, the odd one, run of 2)
+    ys, us, vs = T.make_yuv_planar(rng, 320, 180, False, True)
+    rgba_s = _oracle_planar(o, ys, us, vs, 320, 180, 3, 0, 0, 1, T.Q_HIGH)
+    srcs = [(w, h, (y, u, v)), (w, h, (y2, u2, v2)), (w, h, (y, u, v)), (320, 180, (ys, us, vs)), (w, h, (y2, u2, v2)), (w, h, (y, u, v))]
+    lays = [lb.Layer.from_host(eng, 512, ww, hh, list(p), yuv_clamping=0, yuv_subspace=1) for ww, hh, p in srcs]
+    before = eng.launch_count
+    assert lb.convert_layer_palette_batch(lays, 3, 0) == 6
+    assert eng.launch_count - before == 3
+    for lay, e, ww in zip(lays, (rgba, rgba2, rgba, rgba_s, rgba2, rgba), (w, w, w, 320, w, w)):
+        assert (payload(lay.to_host()[0], ww, 4) == payload(e, ww, 4)).all()
 
 
 # ------------------------------------------------------------------------------------------------ packed YUV
