@@ -1041,6 +1041,10 @@ namespace {
 int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint8_t *dst, int drs, int dw, int dh, int psize) {
   DevFilterEntry *fx = get_filter(e, sw, dw, 14), *fy = get_filter(e, sh, dh, 12);
   if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range (%dx%d -> %dx%d; at most 31x down)", sw, sh, dw, dh);
+  if (e->rsz_defer && psize == 4 && fx->host.taps <= 4 && fy->host.taps <= 4) {  // batch call: launched by flush_rsz_pending
+    e->rsz_pending.push_back(pe_engine::RszJob{src, srs, sw, sh, dst, drs, dw, dh, psize});
+    return PE_OK;
+  }
   // one tiled kernel (15-bit intermediate stays in shared memory) ...
   cudaError_t te = launch_resize_tile(e->L(), CImg{src, srs}, sw, sh, Img{dst, drs}, dw, dh, psize, fx->dev, fy->dev,
                                       fx->host.first.data(), fy->host.first.data());
@@ -1206,6 +1210,40 @@ int flush_yuv_pending(pe_engine *e) {
   return PE_OK;
 }
 
+// launch the packed resizes a batch call has queued: runs of same-shaped frames leave as one launch per 32
+int flush_rsz_pending(pe_engine *e) {
+  std::vector<pe_engine::RszJob> q;
+  q.swap(e->rsz_pending);
+  e->rsz_defer = false;  // (resize_plane below must launch)
+  size_t i = 0;
+  int rc = PE_OK;
+  while (i < q.size() && rc == PE_OK) {
+    size_t j = i + 1;
+    auto same = [&](const pe_engine::RszJob &a, const pe_engine::RszJob &b) {
+      return a.srs == b.srs && a.sw == b.sw && a.sh == b.sh && a.drs == b.drs && a.dw == b.dw && a.dh == b.dh && a.psize == b.psize;
+    };
+    while (j < q.size() && same(q[i], q[j])) j++;
+    bool done = false;
+    if (j - i > 1) {
+      DevFilterEntry *fx = get_filter(e, q[i].sw, q[i].dw, 14), *fy = get_filter(e, q[i].sh, q[i].dh, 12);
+      if (fx && fy) {
+        std::vector<const uint8_t *> srcs;
+        std::vector<uint8_t *> dsts;
+        for (size_t k = i; k < j; k++) { srcs.push_back(q[k].src); dsts.push_back(q[k].dst); }
+        cudaError_t te = launch_resize_tile_batch(e->L(), srcs.data(), q[i].srs, q[i].sw, q[i].sh, dsts.data(), q[i].drs, q[i].dw, q[i].dh,
+                                                  q[i].psize, fx->dev, fy->dev, fx->host.first.data(), fy->host.first.data(), (int)(j - i));
+        if (te == cudaSuccess) done = true;
+        else if (te != cudaErrorInvalidConfiguration) rc = set_err(PE_ERR_CUDA, "resize launch failed: %s", cudaGetErrorString(te));
+      }
+    }
+    if (!done && rc == PE_OK)
+      for (size_t k = i; k < j && rc == PE_OK; k++)
+        rc = resize_plane(e, q[k].src, q[k].srs, q[k].sw, q[k].sh, q[k].dst, q[k].drs, q[k].dw, q[k].dh, q[k].psize);
+    i = j;
+  }
+  return rc;
+}
+
 // Fan a batch of independent per-layer calls out over four side streams.  Layer 0 runs on the engine stream first (it
 // creates whatever cached tables the batch needs: filter banks, LUTs -- their uploads are ordered before the fork); the other
 // layers of the same geometry run on the side streams, so that the small kernels of different layers overlap instead of
@@ -1283,7 +1321,26 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
     e->pool.flush_deferred();
     if (frc != PE_OK) return 0;
   }
-  // phase 2: the resizes, fanned out over the side streams
+  // phase 2: the resizes.  4-byte packed frames of one geometry are queued and leave as one launch per 32; anything else is
+  // fanned out over the side streams
+  {
+    bool uniform = n > 1 && layers[0] != nullptr;
+    for (int i = 0; i < n && uniform; i++)
+      uniform = layers[i] && layers[i]->d.planes[0] && pal_psize(layers[i]->d.palette) == 4 && !pal_is_planar(layers[i]->d.palette) &&
+                same_geometry(layers[0], layers[i]) && (opal_hint == PE_PALETTE_NONE || opal_hint == layers[i]->d.palette);
+    if (uniform) {
+      e->rsz_defer = true;
+      e->pool.defer(true);
+      for (int i = 0; i < n; i++)
+        if (resize_locked(e, layers[i], width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR,
+                          PE_GAMMA_UNKNOWN) == PE_TRUE)
+          done++;
+      const int frc = flush_rsz_pending(e);
+      e->pool.defer(false);
+      e->pool.flush_deferred();
+      return frc == PE_OK ? done : 0;
+    }
+  }
   const pe_frame ref0 = layers[0] ? *layers[0] : pe_frame();
   FanOut fan(e);
   for (int i = 0; i < n; i++) {

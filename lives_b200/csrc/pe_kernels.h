@@ -126,6 +126,10 @@ cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst
 // both passes in one kernel (intermediate in shared memory); cudaErrorInvalidConfiguration when the scale factor is too large
 cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
                                DevFilter fy, const int32_t *hx_first, const int32_t *hy_first);
+// n frames of the same geometry and strides in one launch per 32 (4-byte pixels, <= 4 taps); cudaErrorInvalidConfiguration otherwise
+cudaError_t launch_resize_tile_batch(const Launch &L, const uint8_t *const *srcs, int srs, int sw, int sh, uint8_t *const *dsts, int drs,
+                                     int dw, int dh, int psize, DevFilter fx, DevFilter fy, const int32_t *hx_first,
+                                     const int32_t *hy_first, int n);
 cudaError_t launch_letterbox(const Launch &L, CImg inner, int iw, int ih, Img outer, int ow, int oh, int psize,
                              uint32_t black_pixel);
 cudaError_t launch_copy2d(const Launch &L, const uint8_t *src, int srs, uint8_t *dst, int drs, int row_bytes, int rows,

@@ -212,7 +212,15 @@ __device__ __forceinline__ uint32_t rz_dp2a_hi(uint32_t a, uint32_t b, uint32_t 
   return d;
 }
 
-__global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams P) {
+// frames of one batched launch: same geometry and strides, blockIdx.y selects the frame
+struct ResizeFrameList {
+  const uint8_t *src[32];
+  uint8_t *dst[32];
+};
+
+__global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams P, const __grid_constant__ ResizeFrameList FL) {
+  const uint8_t *const f_src = FL.src[blockIdx.y];
+  uint8_t *const f_dst = FL.dst[blockIdx.y];
   extern __shared__ __align__(16) uint8_t rsm[];
   const int raw_stride = P.max_cols * 4 + 16;                                // + 3 words of slack: the 4-word tap window of the last column
   const int tx_taps = P.fx.taps, ty_taps = P.fy.taps;
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams 
   // ---- 1. stage the source rectangle, replicating the frame edges (+ 3 slack words per row so that a 4-word window never leaves it)
   for (int r = warp; r < nvr; r += kBlock / 32) {
     const int sy = min(max(vr0 + r, 0), P.sh - 1);
-    const uint8_t *rp = P.src + (size_t)P.srs * sy;
+    const uint8_t *rp = f_src + (size_t)P.srs * sy;
     uint32_t *dp = reinterpret_cast<uint32_t *>(s_raw + r * raw_stride);
     for (int c = lane; c < nvc + 3; c += 32) {
       const int sx = min(max(vc0 + c, 0), P.sw - 1);
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams 
   for (int yo = warp; yo < nrow; yo += kBlock / 32) {
     const int4 cf = s_cy[yo];
     const uint2 *t = s_tmp + s_fy[yo] * P.tw;
-    uint8_t *drow = P.dst + (size_t)P.drs * (y0 + yo) + (size_t)x0 * 4;
+    uint8_t *drow = f_dst + (size_t)P.drs * (y0 + yo) + (size_t)x0 * 4;
     for (int xo = lane; xo < ncol; xo += 32) {
       const uint2 h0 = t[xo], h1 = t[P.tw + xo], h2 = t[2 * P.tw + xo], h3 = t[3 * P.tw + xo];
       int a0 = 1 << 18, a1 = 1 << 18, a2 = 1 << 18, a3 = 1 << 18;
@@ -501,8 +509,24 @@ cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst
 
 // hx / hy: host copies of the filter banks (to size the tile).  Returns cudaErrorInvalidConfiguration when no tile fits in
 // shared memory (the caller then runs the two-kernel path).
+// nbatch > 0: srcs / dsts hold nbatch frames of the same geometry and strides (as src / dst describe frame 0): one launch per 32
+// frames of k_resize_tile4; cudaErrorInvalidConfiguration when the specialised kernel cannot take the job (the caller then
+// issues them one by one)
+static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
+                                           DevFilter fy, const int32_t *hx_first, const int32_t *hy_first, const uint8_t *const *srcs,
+                                           uint8_t *const *dsts, int nbatch);
 cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
                                DevFilter fy, const int32_t *hx_first, const int32_t *hy_first) {
+  return launch_resize_tile_impl(L, src, sw, sh, dst, dw, dh, psize, fx, fy, hx_first, hy_first, nullptr, nullptr, 0);
+}
+cudaError_t launch_resize_tile_batch(const Launch &L, const uint8_t *const *srcs, int srs, int sw, int sh, uint8_t *const *dsts, int drs,
+                                     int dw, int dh, int psize, DevFilter fx, DevFilter fy, const int32_t *hx_first,
+                                     const int32_t *hy_first, int n) {
+  return launch_resize_tile_impl(L, CImg{srcs[0], srs}, sw, sh, Img{dsts[0], drs}, dw, dh, psize, fx, fy, hx_first, hy_first, srcs, dsts, n);
+}
+static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, int sh, Img dst, int dw, int dh, int psize, DevFilter fx,
+                                           DevFilter fy, const int32_t *hx_first, const int32_t *hy_first, const uint8_t *const *srcs,
+                                           uint8_t *const *dsts, int nbatch) {
   auto span = [](const int32_t *first, int taps, int dst_n, int tile) {  // unclamped tap range of the widest tile
     int worst = 1;
     for (int i0 = 0; i0 < dst_n; i0 += tile) {
@@ -554,11 +578,23 @@ cudaError_t launch_resize_tile(const Launch &L, CImg src, int sw, int sh, Img ds
         if ((e = cudaFuncSetAttribute(k_resize_tile4, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
         attr4 = true;
       }
-      k_resize_tile4<<<tiles, kBlock, smem4, L.stream>>>(P);
-      PE_COUNT_LAUNCH(L);
-      return cudaGetLastError();
+      const int nf = nbatch > 0 ? nbatch : 1;
+      for (int base = 0; base < nf; base += 32) {
+        ResizeFrameList fl;
+        const int cnt = nf - base < 32 ? nf - base : 32;
+        for (int i = 0; i < 32; i++) {
+          const int k = base + (i < cnt ? i : 0);
+          fl.src[i] = nbatch > 0 ? srcs[k] : src.p;
+          fl.dst[i] = nbatch > 0 ? dsts[k] : dst.p;
+        }
+        k_resize_tile4<<<dim3(tiles, cnt), kBlock, smem4, L.stream>>>(P, fl);
+        PE_COUNT_LAUNCH(L);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      }
+      return cudaSuccess;
     }
   }
+  if (nbatch > 0) return cudaErrorInvalidConfiguration;  // only the specialised kernel takes frame lists
   if (psize == 4) k_resize_tile<4><<<tiles, kBlock, smem, L.stream>>>(P);
   else if (psize == 3) k_resize_tile<3><<<tiles, kBlock, smem, L.stream>>>(P);
   else if (psize == 1) k_resize_tile<1><<<tiles, kBlock, smem, L.stream>>>(P);
