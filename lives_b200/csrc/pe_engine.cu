@@ -901,7 +901,10 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     inplace = (li.psize == lo.psize);  // pconv_can_inplace :12148
     if (!inplace && frame_alloc(e, &n) != PE_OK) return PE_FALSE;
     Img dst = inplace ? Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]} : Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]};
-    ce = launch_rgb_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, dst, width, height, li, lo, lut);
+    if (e->rgb_defer)  // batch call: launched by flush_rgb_pending
+      e->rgb_pending.push_back(pe_engine::RgbJob{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0], dst.p, dst.rs, width, height, li, lo, lut});
+    else
+      ce = launch_rgb_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, dst, width, height, li, lo, lut);
   } else if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P || inpl == PE_PALETTE_YUV422P) && pal_is_rgb(outpl)) {
     // convert_yuv420p_to_{rgb,bgr,argb}_frame (:13521-13560, :13648-13685)
     if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
@@ -1210,6 +1213,29 @@ int flush_yuv_pending(pe_engine *e) {
   return PE_OK;
 }
 
+// launch the RGB <-> RGB permutations a batch call has queued: runs of same-shaped frames leave as one launch per 64
+int flush_rgb_pending(pe_engine *e) {
+  std::vector<pe_engine::RgbJob> q;
+  q.swap(e->rgb_pending);
+  e->rgb_defer = false;
+  auto same_lay = [](const RgbLayout &a, const RgbLayout &b) { return a.r == b.r && a.g == b.g && a.b == b.b && a.a == b.a && a.psize == b.psize; };
+  size_t i = 0;
+  while (i < q.size()) {
+    size_t j = i + 1;
+    while (j < q.size() && q[j].irow == q[i].irow && q[j].orow == q[i].orow && q[j].width == q[i].width && q[j].height == q[i].height &&
+           q[j].lut == q[i].lut && same_lay(q[j].in, q[i].in) && same_lay(q[j].out, q[i].out))
+      j++;
+    std::vector<const uint8_t *> srcs;
+    std::vector<uint8_t *> dsts;
+    for (size_t k = i; k < j; k++) { srcs.push_back(q[k].src); dsts.push_back(q[k].dst); }
+    cudaError_t ce = launch_rgb_to_rgb_batch(e->L(), srcs.data(), q[i].irow, dsts.data(), q[i].orow, (int)(j - i), q[i].width, q[i].height,
+                                             q[i].in, q[i].out, q[i].lut);
+    if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "conversion kernel launch failed: %s", cudaGetErrorString(ce));
+    i = j;
+  }
+  return PE_OK;
+}
+
 // launch the packed resizes a batch call has queued: runs of same-shaped frames leave as one launch per 32
 int flush_rsz_pending(pe_engine *e) {
   std::vector<pe_engine::RszJob> q;
@@ -1364,6 +1390,19 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
   for (int i = 0; i < n && all_planar; i++)
     all_planar = layers[i] && (layers[i]->d.palette == PE_PALETTE_YUV420P || layers[i]->d.palette == PE_PALETTE_YVU420P ||
                                layers[i]->d.palette == PE_PALETTE_YUV422P);
+  bool all_rgb = pal_is_rgb(outpl);
+  for (int i = 0; i < n && all_rgb; i++) all_rgb = layers[i] && pal_is_rgb(layers[i]->d.palette);
+  if (all_rgb) {
+    // RGB <-> RGB: the permutations are queued and leave as one launch per 64 same-shaped frames
+    e->rgb_defer = true;
+    e->pool.defer(true);
+    for (int i = 0; i < n; i++)
+      if (convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
+    const int frc = flush_rgb_pending(e);
+    e->pool.defer(false);
+    e->pool.flush_deferred();
+    return frc == PE_OK ? done : 0;
+  }
   if (all_planar) {
     // planar YUV -> RGB: the conversions are queued and leave as one launch per 32 same-shaped frames
     e->yuv_defer = true;

@@ -93,6 +93,9 @@ struct pe_engine {
   const uint8_t *fuse_blend2 = nullptr;
   int fuse_blend2_rs = 0, fuse_blend_bf = 0;
   // batch calls: planar YUV -> RGB conversions are queued and leave as ONE launch per 32 same-shaped frames (flush_yuv_pending)
+  struct RgbJob { const uint8_t *src; int irow; uint8_t *dst; int orow, width, height; pe::RgbLayout in, out; const uint8_t *lut; };
+  bool rgb_defer = false;            // ... and the RGB <-> RGB permutations (flush_rgb_pending)
+  std::vector<RgbJob> rgb_pending;
   struct RszJob { const uint8_t *src; int srs, sw, sh; uint8_t *dst; int drs, dw, dh, psize; };
   bool rsz_defer = false;            // ... and so are the resizes of 4-byte packed frames (flush_rsz_pending)
   std::vector<RszJob> rsz_pending;

@@ -48,6 +48,8 @@ struct RgbLayout {
 // ---- RGB <-> RGB (colourspace.c:9259-10515) ---------------------------------------------------
 cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in, RgbLayout out,
                               const uint8_t *lut8_dev);
+cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs, int irow, uint8_t *const *dsts, int orow, int n, int width,
+                                    int height, RgbLayout in, RgbLayout out, const uint8_t *lut8_dev);
 // ---- gamma LUT on a rectangle (colourspace.c:14034) ---------------------------------------------
 cudaError_t launch_lut8_rect(const Launch &L, Img img, RgbLayout lay, int x, int y, int width, int height,
                              const uint8_t *lut8_dev);

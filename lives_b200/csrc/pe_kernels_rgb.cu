@@ -49,9 +49,17 @@ __device__ __forceinline__ uint32_t permute_pixel(uint32_t pix, const PermutePar
   return o;
 }
 
+// frames of one batched launch (same geometry, strides and palettes): blockIdx.y selects the frame
+struct RgbFrameList {
+  const uint8_t *src[64];
+  uint8_t *dst[64];
+};
+
 template <int IPS, int OPS, bool HAS_LUT>
-__global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P) {
+__global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P, const __grid_constant__ RgbFrameList FL) {
   __shared__ uint8_t s_lut[256];
+  const uint8_t *const f_src = FL.src[blockIdx.y];
+  uint8_t *const f_dst = FL.dst[blockIdx.y];
   if (HAS_LUT) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
     __syncthreads();
@@ -60,8 +68,8 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P) {
   const long long total = (long long)groups * P.height;
   for (long long it = global_tid(); it < total; it += global_threads()) {
     const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
-    const uint8_t *s = P.src + (long long)row * P.irow + (long long)g * 4 * IPS;
-    uint8_t *d = P.dst + (long long)row * P.orow + (long long)g * 4 * OPS;
+    const uint8_t *s = f_src + (long long)row * P.irow + (long long)g * 4 * IPS;
+    uint8_t *d = f_dst + (long long)row * P.orow + (long long)g * 4 * OPS;
     const int npx = min(4, P.width - g * 4);
     uint32_t pix[4];
     if (P.vec_ok && npx == 4) {
@@ -98,10 +106,11 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P) {
 
 }  // namespace
 
-cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in, RgbLayout out,
-                              const uint8_t *lut8_dev) {
+// n frames of the same geometry, strides and palettes in one launch per 64 (srcs[i] may equal dsts[i]: in place)
+cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs, int irow, uint8_t *const *dsts, int orow, int n, int width,
+                                    int height, RgbLayout in, RgbLayout out, const uint8_t *lut8_dev) {
   PermuteParams P;
-  P.src = src.p; P.dst = dst.p; P.irow = src.rs; P.orow = dst.rs; P.width = width; P.height = height;
+  P.src = srcs[0]; P.dst = dsts[0]; P.irow = irow; P.orow = orow; P.width = width; P.height = height;
   P.in_r = in.r; P.in_g = in.g; P.in_b = in.b; P.in_a = in.a;
   P.out_r = out.r; P.out_g = out.g; P.out_b = out.b; P.out_a = out.a;
   P.lut = lut8_dev;
@@ -111,19 +120,39 @@ cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int
   if (out.a >= 0) nib[out.a] = in.a >= 0 ? in.a : 4;
   P.sel = nib[0] | (nib[1] << 4) | (nib[2] << 8) | (nib[3] << 12);
   const int ia = in.psize == 4 ? 16 : 4, oa = out.psize == 4 ? 16 : 4;
-  P.vec_ok = ((uintptr_t)src.p % ia == 0) && (src.rs % ia == 0) && ((uintptr_t)dst.p % oa == 0) && (dst.rs % oa == 0);
+  bool vec = (irow % ia == 0) && (orow % oa == 0);
+  for (int i = 0; i < n && vec; i++) vec = ((uintptr_t)srcs[i] % ia == 0) && ((uintptr_t)dsts[i] % oa == 0);
+  P.vec_ok = vec;
   const long long work = (long long)((width + 3) >> 2) * height;
-  const int grid = grid_for(L, work);
+  for (int base = 0; base < n; base += 64) {
+    RgbFrameList fl;
+    const int cnt = n - base < 64 ? n - base : 64;
+    for (int i = 0; i < 64; i++) { fl.src[i] = srcs[base + (i < cnt ? i : 0)]; fl.dst[i] = dsts[base + (i < cnt ? i : 0)]; }
+    // the frames of a launch share the grid: about 8 CTAs per SM over all of them
+    int gx = grid_for(L, work);
+    const int cap = (L.sm_count * 8 + cnt - 1) / cnt;
+    if (gx > cap) gx = cap < 1 ? 1 : cap;
+    const dim3 grid(gx, cnt);
 #define PE_PERM(I, O) \
-  do { if (lut8_dev) k_rgb_to_rgb<I, O, true><<<grid, kBlock, 0, L.stream>>>(P); \
-       else k_rgb_to_rgb<I, O, false><<<grid, kBlock, 0, L.stream>>>(P); } while (0)
-  if (in.psize == 3 && out.psize == 3) PE_PERM(3, 3);
-  else if (in.psize == 3 && out.psize == 4) PE_PERM(3, 4);
-  else if (in.psize == 4 && out.psize == 3) PE_PERM(4, 3);
-  else PE_PERM(4, 4);
+  do { if (lut8_dev) k_rgb_to_rgb<I, O, true><<<grid, kBlock, 0, L.stream>>>(P, fl); \
+       else k_rgb_to_rgb<I, O, false><<<grid, kBlock, 0, L.stream>>>(P, fl); } while (0)
+    if (in.psize == 3 && out.psize == 3) PE_PERM(3, 3);
+    else if (in.psize == 3 && out.psize == 4) PE_PERM(3, 4);
+    else if (in.psize == 4 && out.psize == 3) PE_PERM(4, 3);
+    else PE_PERM(4, 4);
 #undef PE_PERM
-  PE_COUNT_LAUNCH(L);
-  return cudaGetLastError();
+    PE_COUNT_LAUNCH(L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_rgb_to_rgb(const Launch &L, CImg src, Img dst, int width, int height, RgbLayout in, RgbLayout out,
+                              const uint8_t *lut8_dev) {
+  const uint8_t *s1[1] = {src.p};
+  uint8_t *d1[1] = {dst.p};
+  return launch_rgb_to_rgb_batch(L, s1, src.rs, d1, dst.rs, 1, width, height, in, out, lut8_dev);
 }
 
 // =====================================================================================================

@@ -61,6 +61,25 @@ def test_config1_rgb24_to_bgr24_and_all_rgb_pairs(eng, size):
         lay.free()
 
 
+def test_rgb_permutation_batch(eng):
+    """pe_convert_layer_palette_batch on RGB layers: runs of same-shaped layers leave as one launch, results as layer by layer"""
+    o = T.oracle()
+    rng = np.random.default_rng(3)
+    for ipal, opal in ((1, 2), (1, 3), (4, 1), (3, 5)):
+        ips, ops = T.psize_of(ipal), T.psize_of(opal)
+        shapes = [(640, 480), (640, 480), (640, 480), (37, 11), (640, 480), (640, 480)]
+        srcs = [T.make_packed(rng, w, h, ips) for w, h in shapes]
+        lays = [packed_layer(eng, ipal, w, h, s) for (w, h), s in zip(shapes, srcs)]
+        before = eng.launch_count
+        assert lb.convert_layer_palette_batch(lays, opal, 0) == len(lays)
+        assert eng.launch_count - before == 3  # runs of 3, 1 and 2 layers
+        for (w, h), s, lay in zip(shapes, srcs, lays):
+            exp = np.zeros((h, T.rowstride(w, ops)), np.uint8)
+            assert o.pe_or_rgb_to_rgb(ipal, opal, T.ptr(s), s.strides[0], w, h, T.ptr(exp), exp.strides[0], None) == 0
+            assert lay.palette == opal
+            assert (payload(lay.to_host()[0], w, ops) == payload(exp, w, ops)).all(), (ipal, opal, w, h)
+
+
 def test_rgb_to_rgb_with_gamma_lut(eng):
     """gamma_lut8 inside the permutation (colourspace.c:12372), tgt_gamma given"""
     o = T.oracle()
