@@ -89,6 +89,29 @@ def main():
     dst = np.zeros((12, T.rowstride(50, 3)), np.uint8)
     r.ref_yuv888_to_rgb(T.ptr(src), 50, 12, src.strides[0], dst.strides[0], T.ptr(dst), 0, 0, 0, 0, 1)
     out["yuv888_to_rgb_cl0"] = dst
+    # RGB -> packed 4:2:2 / planar 4:4:4 / planar 4:2:0 / 4:2:2 (unpadded planes: the reference advances its pointers densely)
+    src = T.make_packed(np.random.default_rng(2024), 64, 12, 3)  # (its own generator: the entries above and below keep their values)
+    out["rgb2_src"] = src
+    for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
+        dst = np.zeros((12, 128), np.uint8)
+        r.ref_rgb_to_packed422(fmt, T.ptr(src), 64, 12, src.strides[0], dst.strides[0], T.ptr(dst), 0, 0, 0, 0, 0)
+        out["rgb_to_%s_cl0" % nm] = dst
+    pl = [np.zeros((12, 64), np.uint8) for _ in range(4)]
+    r.ref_rgb_to_yuv444p(T.ptr(src), 64, 12, src.strides[0], 64, T.planes_arg(*pl), 0, 0, 0, 0)
+    for k, nm in enumerate("yuv"):
+        out["rgb_to_yuv444p_cl0_" + nm] = pl[k]
+    for is422, nm in ((0, "yuv420p"), (1, "yuv422p")):
+        ch = 12 if is422 else 6
+        pl = [np.zeros((12, 64), np.uint8), np.zeros((ch, 32), np.uint8), np.zeros((ch, 32), np.uint8)]
+        strides = (C.c_int * 3)(64, 32, 32)
+        r.ref_rgb_to_yuv420(T.ptr(src), 64, 12, src.strides[0], strides, T.planes_arg(*pl), 0, is422, 0, 1, 0)
+        for k, pn in enumerate("yuv"):
+            out["rgb_to_%s_cl0_%s" % (nm, pn)] = pl[k]
+    for which, nm in ((0, "cavgc"), (1, "cavgu")):
+        t = np.zeros(65536, np.uint8)
+        assert r.ref_get_avg_table(which, T.ptr(t)) == 0
+        out["avg_%s_sha256" % nm] = np.frombuffer(hashlib.sha256(t.tobytes()).digest(), np.uint8)
+        out["avg_%s_row200" % nm] = t[200 * 256:201 * 256].copy()
     # effect plugins through the real bootstrap
     mh = C.CDLL(os.path.join(T.REF_DIR, "libweed_minihost.so"))
     mh.mh_open.argtypes = [C.c_char_p]

@@ -6,6 +6,8 @@ GPU: the CUDA path reproduces them through the C ABI.
 import hashlib
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -83,6 +85,32 @@ def test_oracle_frames_match_golden():
     assert (got == G["yuv888_to_rgb_cl0"]).all()
 
 
+def test_oracle_rgb_to_yuv_match_golden():
+    """RGB -> UYVY / YUYV / YUV444P / YUV420P / YUV422P and the chroma averaging tables, frozen from the compiled reference"""
+    import hashlib
+    o = T.oracle()
+    src = np.ascontiguousarray(G["rgb2_src"])
+    for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
+        got = np.zeros_like(G["rgb_to_%s_cl0" % nm])
+        o.pe_or_rgb_to_packed422(fmt, T.ptr(src), src.strides[0], 64, 12, T.ptr(got), got.strides[0], 0, 0, 0, T.Q_HIGH, None)
+        assert (got == G["rgb_to_%s_cl0" % nm]).all(), nm
+    pl = [np.zeros((12, 64), np.uint8) for _ in range(4)]
+    o.pe_or_rgb_to_yuv444p(T.ptr(src), src.strides[0], 64, 12, T.planes_arg(*pl), 64, 0, 0, 0, 0, T.Q_HIGH)
+    for k, pn in enumerate("yuv"):
+        assert (pl[k] == G["rgb_to_yuv444p_cl0_" + pn]).all(), pn
+    for is422, nm in ((0, "yuv420p"), (1, "yuv422p")):
+        ch = 12 if is422 else 6
+        pl = [np.zeros((12, 64), np.uint8), np.zeros((ch, 32), np.uint8), np.zeros((ch, 32), np.uint8)]
+        o.pe_or_rgb_to_yuv420p(T.ptr(src), src.strides[0], 64, 12, T.planes_arg(*pl), (C.c_int * 3)(64, 32, 32), 0, 0, is422, 0, 1, T.Q_HIGH)
+        for k, pn in enumerate("yuv"):
+            assert (pl[k] == G["rgb_to_%s_cl0_%s" % (nm, pn)]).all(), (nm, pn)
+    for which, nm in ((0, "cavgc"), (1, "cavgu")):
+        t = np.zeros(65536, np.uint8)
+        o.pe_or_avg_table(which, T.ptr(t))
+        assert hashlib.sha256(t.tobytes()).digest() == G["avg_%s_sha256" % nm].tobytes(), nm
+        assert (t[200 * 256:201 * 256] == G["avg_%s_row200" % nm]).all()
+
+
 def test_oracle_effects_match_golden():
     o = T.oracle()
     s1, s2 = G["blend_s1"], G["blend_s2"]
@@ -138,6 +166,18 @@ def test_cuda_matches_golden():
     lay = lb.Layer.from_host(eng, 588, 50, 12, [src], yuv_clamping=0, yuv_subspace=1)
     assert lb.convert_layer_palette(lay, 1, 0)
     assert (lay.to_host()[0][:, :150] == G["yuv888_to_rgb_cl0"][:, :150]).all()
+    src = np.ascontiguousarray(G["rgb2_src"])
+    for pal, nm in ((564, "uyvy"), (565, "yuyv")):
+        lay = lb.Layer.from_host(eng, 1, 64, 12, [src])
+        assert lb.convert_layer_palette(lay, pal, 0)
+        assert (lay.to_host()[0][:, :128] == G["rgb_to_%s_cl0" % nm]).all(), nm
+    for pal, nm in ((544, "yuv444p"), (512, "yuv420p"), (522, "yuv422p")):
+        lay = lb.Layer.from_host(eng, 1, 64, 12, [src])
+        assert lb.convert_layer_palette_full(lay, pal, 0, 0, 1, 0)
+        got = lay.to_host()
+        for k, pn in enumerate("yuv"):
+            exp = G["rgb_to_%s_cl0_%s" % (nm, pn)]
+            assert (got[k][:exp.shape[0], :exp.shape[1]] == exp).all(), (nm, pn)
     s1, s2 = np.ascontiguousarray(G["blend_s1"]), np.ascontiguousarray(G["blend_s2"])
     l1, l2 = lb.Layer.from_host(eng, 1, 61, 9, [s1]), lb.Layer.from_host(eng, 1, 61, 9, [s2])
     for typ in range(4):
