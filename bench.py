@@ -467,12 +467,19 @@ def run_secondary(args):
         def prepare(nsteps):
             pool.extend(wrap(522, W, H, [y, u, v], yuv_subspace=1) for _ in range(nsteps) for (y, u, v) in src)
 
+        per_clip = os.environ.get("PE_CFG5_PER_CLIP") is not None  # the one-kernel-per-clip form (what one rank of the N-GPU run issues)
+
         def step():
-            for _ in range(n):
-                lay = pool.pop()
-                lb.convert_crossfade(lay, operand, 1, 0, 128)
+            lays = [pool.pop() for _ in range(n)]
+            if per_clip:
+                for lay in lays:
+                    lb.convert_crossfade(lay, operand, 1, 0, 128)
+            else:
+                assert lb.convert_crossfade_batch(lays, operand, 1, 0, 128) == n
+            for lay in lays:
                 lay.free()  # stream ordered: the converted frame goes back to the pool behind the kernel
-        frames, algo, name = n, W * H * 2 + 2 * W * H * 3, "cfg5 (1 GPU, no broadcast): %d x 4K YUV422P -> RGB24 + chroma blend bf=128 with one operand (pe_fx_convert_crossfade, 1 kernel / clip)" % n
+        frames, algo, name = n, W * H * 2 + 2 * W * H * 3, "cfg5 (1 GPU, no broadcast): %d x 4K YUV422P -> RGB24 + chroma blend bf=128 with one shared operand (%s)" % (
+            n, "pe_fx_convert_crossfade, 1 kernel / clip" if per_clip else "pe_fx_convert_crossfade_batch, 1 kernel / %d clips" % n)
     elif wl == "cfg1":  # 640x480 RGB24 -> BGR24 in place
         W, H, n = 640, 480, 256
         lay = [wrap(1, W, H, [rnd(H, W * 3)]) for _ in range(n)]

@@ -173,12 +173,17 @@ int pe_gamma_lut8(pe_engine_t *e, double fileg, int gamma_from, int gamma_to, ui
  * 3 "negative luma overlay".  out may be in1 (in-place, effects-weed.c:2304-2314). */
 int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                        int blend_factor);
-/* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
 /* convert_layer_palette(clip, outpl) (colourspace.c:13521-13685) + the 'chroma blend' of simple_blend.c:58 with in1 = the
  * converted clip, in2 = operand, result in the clip: the multitrack crossfade (src/multitrack.h:84) as one kernel.
  * clip: YUV420P / YVU420P / YUV422P, outpl = operand palette = RGB24 or BGR24. */
 int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const pe_frame_t *operand, int outpl, int op_clamping,
                             int blend_factor);
+/* the same for the n clips of a multitrack stack that fade against ONE shared operand (BASELINE config 5: the operand every
+ * rank receives by broadcast): same-shaped clips leave as one kernel launch per 32.  Returns the number of clips converted
+ * (clips that fail are left untouched, as convert_layer_palette leaves its layer, colourspace.c:13906-13927). */
+int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *operand, int outpl,
+                                  int op_clamping, int blend_factor);
+/* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
 int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                       int blend_factor);
 /* gdk/compositor.c compositor_process :127 at scale 1 / offset 0: out = bgcol, then paint_pixel(:120) of every

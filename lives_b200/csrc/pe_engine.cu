@@ -923,7 +923,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     if (new_gamma_type != PE_GAMMA_UNKNOWN) A.lut16 = get_lut16(e, 1.0, gamma_type, new_gamma_type);  // `if (tgt_gamma)` :3273
     A.blend2 = e->fuse_blend2; A.blend2_rs = e->fuse_blend2_rs; A.blend_bf = e->fuse_blend_bf;
     if (getenv("PE_YUV_SLOW") == nullptr && yuv_planar_fast_ok(A, &conv_host(e, iclamping, isubspace))) {
-      if (e->yuv_defer && !A.blend2) e->yuv_pending.push_back(A);  // batch call: launched by flush_yuv_pending
+      if (e->yuv_defer) e->yuv_pending.push_back(A);  // batch call: launched by flush_yuv_pending
       else ce = launch_yuv_planar_to_rgb_fast(L, A);
     } else {
       ce = launch_yuv_planar_to_rgb(L, A);
@@ -1519,6 +1519,44 @@ extern "C" int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const p
   const int ok = convert_locked(e, clip, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN);
   e->fuse_blend2 = nullptr;
   return ok == PE_TRUE ? PE_OK : PE_ERR_PALETTE;
+}
+
+extern "C" int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *operand, int outpl,
+                                             int op_clamping, int blend_factor) {
+  if (!e || !clips || n < 0 || !operand || !operand->d.planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return 0; }
+  if ((outpl != PE_PALETTE_RGB24 && outpl != PE_PALETTE_BGR24) || operand->d.palette != outpl) {
+    set_err(PE_ERR_PALETTE, "convert_crossfade: output and operand must both be RGB24 or both BGR24");
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
+  e->fuse_blend2 = (const uint8_t *)operand->d.planes[0];
+  e->fuse_blend2_rs = operand->d.rowstrides[0];
+  e->fuse_blend_bf = blend_factor;
+  // the conversions are queued and leave as one k_yuv_march launch per 32 same-shaped clips (flush_yuv_pending)
+  e->yuv_defer = true;
+  e->pool.defer(true);
+  int done = 0;
+  for (int i = 0; i < n; i++) {
+    pe_frame_t *c = clips[i];
+    if (!c || !c->d.planes[0]) continue;
+    const int ip = c->d.palette;
+    if (ip != PE_PALETTE_YUV420P && ip != PE_PALETTE_YVU420P && ip != PE_PALETTE_YUV422P) {
+      set_err(PE_ERR_PALETTE, "convert_crossfade: the clip must be YUV420P / YVU420P / YUV422P");
+      continue;
+    }
+    if (operand->d.width != c->d.width || operand->d.height != c->d.height) {
+      set_err(PE_ERR_SIZE, "convert_crossfade: clip and operand differ in size");
+      continue;
+    }
+    if (convert_locked(e, c, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
+  }
+  e->yuv_defer = false;
+  e->fuse_blend2 = nullptr;
+  const int frc = flush_yuv_pending(e);
+  e->pool.defer(false);
+  e->pool.flush_deferred();
+  return frc == PE_OK ? done : 0;
 }
 
 extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,

@@ -81,6 +81,7 @@ struct ResizeTileParams {
   int srs, drs, sw, sh, dw, dh;
   int tw, th;                 // output tile
   int max_rows, max_cols;     // largest source extent of a tile
+  int vec_src;                // k_resize_tile4: source rows are 16-byte aligned (128-bit staging loads)
   DevFilter fx, fy;
 };
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams 
   const uint8_t *const f_src = FL.src[blockIdx.y];
   uint8_t *const f_dst = FL.dst[blockIdx.y];
   extern __shared__ __align__(16) uint8_t rsm[];
-  const int raw_stride = P.max_cols * 4 + 16;                                // + 3 words of slack: the 4-word tap window of the last column
+  const int raw_stride = ((P.max_cols + 10) * 4 + 15) & ~15;                 // window start aligned down to 4 columns, + 3 words of slack for the 4-word tap window, rounded to whole 16-byte groups
   const int tx_taps = P.fx.taps, ty_taps = P.fy.taps;
   uint8_t *s_raw = rsm;                                                    // [max_rows][raw_stride]
   size_t off = ((size_t)P.max_rows * raw_stride + 15) & ~(size_t)15;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams 
     uint32_t c[4] = {0, 0, 0, 0};
     for (int k = 0; k < tx_taps; k++) c[k] = (uint16_t)P.fx.coef[(size_t)(x0 + i) * tx_taps + k];
     s_cx[i] = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
-    s_fx[i] = P.fx.first[x0 + i] - vc0;
+    s_fx[i] = P.fx.first[x0 + i] - (vc0 & ~3);
   }
   for (int i = threadIdx.x; i < nrow; i += kBlock) {
     int c[4] = {0, 0, 0, 0};
@@ -257,14 +258,30 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile4(const ResizeTileParams 
     s_cy[i] = make_int4(c[0], c[1], c[2], c[3]);
     s_fy[i] = P.fy.first[y0 + i] - vr0;
   }
-  // ---- 1. stage the source rectangle, replicating the frame edges (+ 3 slack words per row so that a 4-word window never leaves it)
-  for (int r = warp; r < nvr; r += kBlock / 32) {
-    const int sy = min(max(vr0 + r, 0), P.sh - 1);
-    const uint8_t *rp = f_src + (size_t)P.srs * sy;
-    uint32_t *dp = reinterpret_cast<uint32_t *>(s_raw + r * raw_stride);
-    for (int c = lane; c < nvc + 3; c += 32) {
-      const int sx = min(max(vc0 + c, 0), P.sw - 1);
-      dp[c] = ld_stream_u32(rp + 4 * sx);
+  // ---- 1. stage the source rectangle, replicating the frame edges: whole 16-byte groups of 4 pixels, starting at a column that
+  //         is a multiple of 4 (so that global and shared addresses are 16-byte aligned together) and reaching 3 pixels past
+  //         the last tap (the 4-word window of the last column); groups that touch a frame edge go pixel by pixel
+  {
+    const int vca = vc0 & ~3;
+    const int ngroups = (vc1 + 4 - vca + 3) >> 2;
+    const bool vec = P.vec_src != 0;
+    for (int r = warp; r < nvr; r += kBlock / 32) {
+      const int sy = min(max(vr0 + r, 0), P.sh - 1);
+      const uint8_t *rp = f_src + (size_t)P.srs * sy;
+      uint4 *dp = reinterpret_cast<uint4 *>(s_raw + r * raw_stride);
+      for (int g = lane; g < ngroups; g += 32) {
+        const int col = vca + 4 * g;
+        if (vec && col >= 0 && col + 3 <= P.sw - 1) {
+          dp[g] = ld_stream_u4(rp + 4 * col);
+        } else {
+          uint4 v;
+          v.x = ld_stream_u32(rp + 4 * min(max(col, 0), P.sw - 1));
+          v.y = ld_stream_u32(rp + 4 * min(max(col + 1, 0), P.sw - 1));
+          v.z = ld_stream_u32(rp + 4 * min(max(col + 2, 0), P.sw - 1));
+          v.w = ld_stream_u32(rp + 4 * min(max(col + 3, 0), P.sw - 1));
+          dp[g] = v;
+        }
+      }
     }
   }
   __syncthreads();
@@ -538,6 +555,7 @@ static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, in
   };
   ResizeTileParams P;
   P.src = src.p; P.dst = dst.p; P.srs = src.rs; P.drs = dst.rs; P.sw = sw; P.sh = sh; P.dw = dw; P.dh = dh; P.fx = fx; P.fy = fy;
+  P.vec_src = 0;
   size_t smem = 0;
   bool ok = false;
   static int tw0 = 0, th0 = 0;
@@ -570,7 +588,9 @@ static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, in
   if (psize == 4 && fx.taps <= 4 && fy.taps <= 4 && ((((uintptr_t)dst.p | (uintptr_t)src.p) | (uint32_t)dst.rs | (uint32_t)src.rs) & 3) == 0 &&
       getenv("PE_RESIZE_GENERIC") == nullptr) {
     // the specialised kernel has its own (slightly larger) shared-memory layout
-    const size_t raw4 = (((size_t)P.max_rows * (P.max_cols * 4 + 16)) + 15) & ~(size_t)15;
+    const size_t raw4 = (size_t)P.max_rows * ((((size_t)P.max_cols + 10) * 4 + 15) & ~(size_t)15);
+    P.vec_src = ((uint32_t)src.rs & 15) == 0 && getenv("PE_RESIZE_NOVEC") == nullptr;
+    for (int i = 0; i < (nbatch > 0 ? nbatch : 1) && P.vec_src; i++) P.vec_src = (((uintptr_t)(nbatch > 0 ? srcs[i] : src.p)) & 15) == 0;
     const size_t smem4 = raw4 + (size_t)(P.max_rows + 3) * P.tw * 8 + (size_t)P.tw * 8 + (size_t)P.th * 16 + (size_t)(P.tw + P.th) * 4;
     static bool attr4 = false;
     if (smem4 <= 96 * 1024) {

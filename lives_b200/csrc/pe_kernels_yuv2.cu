@@ -663,12 +663,16 @@ static cudaError_t march_attrs() {
 
 // A batch of frames that share everything but their pointers (geometry, strides, palettes, tables, flags) in ONE launch of the
 // marching kernel: the per-launch costs (table fill, first loads, tail) are paid once, and the warps get shares long enough to
-// march.  frames[i] must all pass yuv_planar_fast_ok and compare equal under yuv_planar_same_shape; no crossfade operand.
+// march.  frames[i] must all pass yuv_planar_fast_ok and compare equal under yuv_planar_same_shape (which admits ONE shared crossfade
+// operand for the whole run: pe_fx_convert_crossfade_batch).
 bool yuv_planar_same_shape(const YuvToRgbArgs &a, const YuvToRgbArgs &b) {
   return a.width == b.width && a.height == b.height && a.is_422 == b.is_422 && a.clamped == b.clamped && a.low_quality == b.low_quality &&
          a.quirks == b.quirks && a.conv.t == b.conv.t && a.lut16 == b.lut16 && a.src.rs_y == b.src.rs_y && a.src.rs_u == b.src.rs_u &&
          a.src.rs_v == b.src.rs_v && a.src.cw == b.src.cw && a.src.ch == b.src.ch && a.dst.rs == b.dst.rs && a.out.r == b.out.r &&
-         a.out.g == b.out.g && a.out.b == b.out.b && a.out.a == b.out.a && a.out.psize == b.out.psize && !a.blend2 && !b.blend2;
+         a.out.g == b.out.g && a.out.b == b.out.b && a.out.a == b.out.a && a.out.psize == b.out.psize &&
+         // a crossfade operand must be the SAME frame for the whole run (the shared transition operand of a multitrack stack), word aligned
+         a.blend2 == b.blend2 && a.blend2_rs == b.blend2_rs && a.blend_bf == b.blend_bf &&
+         (!a.blend2 || ((((uintptr_t)a.blend2) | (uint32_t)a.blend2_rs) & 3) == 0);
 }
 cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *frames, int n) {
   cudaError_t e = march_attrs();

@@ -362,6 +362,13 @@ def convert_crossfade(clip, operand, outpl, op_clamping, blend_factor):
     capi.check(e._lib.pe_fx_convert_crossfade(e._h, clip._h, operand._h, outpl, op_clamping, blend_factor))
 
 
+def convert_crossfade_batch(clips, operand, outpl, op_clamping, blend_factor):
+    """convert_crossfade for the clips of a multitrack stack that fade against ONE shared operand (BASELINE config 5): same-shaped
+    clips leave as one kernel launch per 32; returns how many clips were converted"""
+    e = operand.engine
+    return int(e._lib.pe_fx_convert_crossfade_batch(e._h, len(clips), _arr(clips), operand._h, outpl, op_clamping, blend_factor))
+
+
 def fused_convert_letterbox_over_gamma_batch(fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):
     e = fg[0].engine
     capi.check(e._lib.pe_fused_convert_letterbox_over_gamma_batch(e._h, len(fg), _arr(fg), _arr(bg), _arr(out), inner_w,

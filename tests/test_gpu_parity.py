@@ -425,6 +425,42 @@ def test_convert_crossfade_fused(eng):
     assert clip.palette == 522
 
 
+def test_convert_crossfade_batch_shared_operand(eng):
+    """The clips of a multitrack stack against ONE shared operand (BASELINE config 5): pe_fx_convert_crossfade_batch == the per-clip
+    call == convert_layer_palette + simple_blend of the oracle; same-shaped clips leave as one launch, odd ones on their own"""
+    o = T.oracle()
+    rng = np.random.default_rng(33)
+    for (w, h), is422, nclips in (((256, 64), 1, 5), ((640, 360), 0, 3), ((1920, 1080), 1, 4), ((132, 34), 1, 2)):
+        operand = T.make_packed(rng, w, h, 3)
+        op_l = packed_layer(eng, 1, w, h, operand)
+        clips, exps = [], []
+        for _ in range(nclips):
+            y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), True)
+            exp = np.zeros((h, T.rowstride(w, 3)), np.uint8)
+            o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(exp), exp.strides[0], 0, 0, is422, 0, 1,
+                                   T.Q_HIGH, 1, None)
+            o.pe_or_simple_blend(0, 1, T.ptr(exp), exp.strides[0], T.ptr(operand), operand.strides[0], T.ptr(exp), exp.strides[0], w, h,
+                                 128, operand.size)
+            clips.append(lb.Layer.from_host(eng, 522 if is422 else 512, w, h, [y, u, v], yuv_subspace=1))
+            exps.append(exp)
+        before = eng.launch_count
+        assert lb.convert_crossfade_batch(clips, op_l, 1, 0, 128) == nclips
+        assert eng.launch_count - before == 1, (w, h, eng.launch_count - before)
+        for c, exp in zip(clips, exps):
+            assert (c.palette, c.width, c.height) == (1, w, h)
+            assert (payload(c.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (w, h, is422)
+    # a clip of another size is refused and left alone; the others still convert
+    w, h = 128, 32
+    operand = T.make_packed(rng, w, h, 3)
+    op_l = packed_layer(eng, 1, w, h, operand)
+    y, u, v = T.make_yuv_planar(rng, w, h, True, True)
+    good = lb.Layer.from_host(eng, 522, w, h, [y, u, v], yuv_subspace=1)
+    y2, u2, v2 = T.make_yuv_planar(rng, 64, 32, True, True)
+    bad = lb.Layer.from_host(eng, 522, 64, 32, [y2, u2, v2], yuv_subspace=1)
+    assert lb.convert_crossfade_batch([good, bad], op_l, 1, 0, 128) == 1
+    assert (good.palette, bad.palette, bad.width) == (1, 522, 64)
+
+
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
     src = T.make_packed(rng, 32, 8, 4)
