@@ -254,6 +254,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
     for (int hd = 0; hd < 2; hd++) cudaFree(e->conv_dev[cl][hd]);
   for (int k = 0; k < 6; k++) cudaFree(e->premult_dev[k]);
   for (int k = 0; k < 2; k++) cudaFree(e->cavg_dev[k]);
+  cudaFree(e->yy_dev);
   cudaFree(e->luma_dev);
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
@@ -833,6 +834,49 @@ Planes planes_of(const pe_frame *f, bool swap_uv) {
   return P;
 }
 
+const uint8_t *get_yy(pe_engine *e) {
+  if (e->yy_dev) return e->yy_dev;
+  uint8_t host[4 * 256];
+  for (int k = 0; k < 4; k++) build_yy_table(k, host + 256 * k);
+  uint8_t *dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(host)) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(dev, host, sizeof(host), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    cudaFree(dev);
+    return nullptr;
+  }
+  e->yy_dev = dev;
+  return dev;
+}
+
+// switch_yuv_clamping_and_subspace (colourspace.c:10929): in place, all planes
+int switch_clamping_locked(pe_engine *e, pe_frame *f, int oclamping) {
+  const uint8_t *yy = get_yy(e);
+  if (!yy) return set_err(PE_ERR_MEMORY, "clamping tables could not be built");
+  const bool to_unclamped = f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED;  // :1177-1185: anything else is treated as unclamped input
+  const uint8_t *ty = yy + (to_unclamped ? 0 : 512), *tc = yy + (to_unclamped ? 256 : 768);
+  const int pal = f->d.palette;
+  cudaError_t ce = cudaSuccess;
+  for (int p = 0; p < f->d.nplanes && ce == cudaSuccess; p++) {
+    int kind;
+    switch (pal) {
+    case PE_PALETTE_YUV888: kind = 2; break;
+    case PE_PALETTE_YUVA8888: kind = 3; break;
+    case PE_PALETTE_UYVY: kind = 4; break;
+    case PE_PALETTE_YUYV: kind = 5; break;
+    default: kind = p == 0 ? 0 : 1; break;
+    }
+    if (p == 3) break;  // the alpha plane of YUVA4444P is not touched (:10971-10984)
+    // YUV888: the reference walks Y U V Y U V ... densely across the row padding (:10959-10969), so with a rowstride that is not
+    // a multiple of 3 the tables are misapplied from row 1 on -- replicated under ref_quirks, per-row phase without
+    ce = launch_clamp_lut(e->L(), (uint8_t *)f->d.planes[p], (long long)f->d.rowstrides[p] * f->plane_heights[p], kind,
+                          e->cfg.ref_quirks ? 0 : f->d.rowstrides[p], ty, tc);
+  }
+  if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "clamping switch launch failed: %s", cudaGetErrorString(ce));
+  f->d.yuv_clamping = oclamping;
+  return PE_OK;
+}
+
 int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osampling, int osubspace, int tgt_gamma) {
   if (!f || !f->d.planes[0]) return PE_FALSE;  // :12206
   if (!pal_known(outpl)) { set_err(PE_ERR_PALETTE, "output palette %d is not handled by this build", outpl); return PE_FALSE; }
@@ -841,13 +885,16 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
 
   if (pal_is_yuv(inpl) && pal_is_yuv(outpl) && (iclamping != oclamping || isubspace != osubspace)) {  // :12241
     if (isubspace == osubspace) {
-      set_err(PE_ERR_PALETTE, "YUV clamping switch (switch_yuv_clamping_and_subspace, colourspace.c:10929) is not in this build");
-      return PE_FALSE;
+      // switch_yuv_clamping_and_subspace (:10929-11092): every byte of every plane through Y_to_Y / U_to_U (= V_to_V), walked
+      // densely over height * rowstride bytes (row padding included); "currently subspace conversions are not performed"
+      if (switch_clamping_locked(e, f, oclamping) != PE_OK) return PE_FALSE;
+      iclamping = oclamping;
+    } else {
+      // different subspace: go through RGB(A) first (:12249-12262)
+      if (!convert_simple_locked(e, f, pal_has_alpha(inpl) ? PE_PALETTE_RGBA32 : PE_PALETTE_RGB24, 0)) return PE_FALSE;
+      inpl = f->d.palette;
+      isubspace = osubspace; isampling = osampling; iclamping = oclamping;
     }
-    // different subspace: go through RGB(A) first (:12249-12262)
-    if (!convert_simple_locked(e, f, pal_has_alpha(inpl) ? PE_PALETTE_RGBA32 : PE_PALETTE_RGB24, 0)) return PE_FALSE;
-    inpl = f->d.palette;
-    isubspace = osubspace; isampling = osampling; iclamping = oclamping;
   }
   if (inpl == outpl) return PE_TRUE;  // :12265-12288 (sampling switches "not yet written" in the reference either)
 
@@ -993,6 +1040,71 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     ce = launch_rgb_to_yuv420p(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides, n.d.width, n.d.height,
                                rgb_layout(inpl), is422 ? 1 : 0, dev_conv(e, oclamping, is422 ? PE_YUV_SUBSPACE_YCBCR : osubspace), cavg);
     n.d.yuv_sampling = PE_YUV_SAMPLING_DEFAULT;
+  } else if ((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && pal_is_rgb(outpl)) {
+    // convert_yuv_planar_to_{rgb,bgr,argb}_frame (:12950-12976, :13055-13080): YCbCr tables of the layer's clamping
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *pl[4] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2],
+                            inpl == PE_PALETTE_YUVA4444P ? (const uint8_t *)f->d.planes[3] : nullptr};
+    ce = launch_yuv444p_to_rgb(L, pl, f->d.rowstrides[0], Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height,
+                               inpl == PE_PALETTE_YUVA4444P, rgb_layout(outpl), dev_conv(e, iclamping, PE_YUV_SUBSPACE_YCBCR));
+  } else if ((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888)) {
+    // convert_combineplanes_frame (:12999-13009, :13098-13108)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *pl[4] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2],
+                            inpl == PE_PALETTE_YUVA4444P ? (const uint8_t *)f->d.planes[3] : nullptr};
+    ce = launch_combine_planes(L, pl, f->d.rowstrides[0], Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height,
+                               inpl == PE_PALETTE_YUVA4444P, outpl == PE_PALETTE_YUVA8888);
+  } else if ((inpl == PE_PALETTE_YUV888 || inpl == PE_PALETTE_YUVA8888) && (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P)) {
+    // convert_splitplanes_frame (:13346-13356, :13438-13448)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    uint8_t *pl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], (uint8_t *)n.d.planes[3]};
+    ce = launch_split_planes(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides, width, height,
+                             inpl == PE_PALETTE_YUVA8888, outpl == PE_PALETTE_YUVA4444P);
+  } else if ((inpl == PE_PALETTE_YUV444P && outpl == PE_PALETTE_YUVA4444P) || (inpl == PE_PALETTE_YUVA4444P && outpl == PE_PALETTE_YUV444P)) {
+    // convert_yuvp_to_yuvap_frame / convert_yuvap_to_yuvp_frame (:7643-7688): plane copies, alpha = 255 over the whole plane
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    for (int p = 0; p < 3 && ce == cudaSuccess; p++)
+      ce = launch_copy2d(L, (const uint8_t *)f->d.planes[p], f->d.rowstrides[p], (uint8_t *)n.d.planes[p], n.d.rowstrides[p], width, height, 0, 0);
+    if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)
+      ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
+  } else if ((inpl == PE_PALETTE_YUV420P && outpl == PE_PALETTE_YUV422P) || (inpl == PE_PALETTE_YUV422P && outpl == PE_PALETTE_YUV420P)) {
+    // 4:2:0 -> 4:2:2: luma copied, convert_double_chroma(width >> 1, height >> 1) (:13587-13597).
+    // 4:2:2 -> 4:2:0: luma copied, convert_halve_chroma (:13700-13710) -- the dispatcher passes height >> 1 where the function
+    // expects the SOURCE chroma height, so the reference fills only the top half of the 4:2:0 chroma planes (X); here the whole
+    // plane goes through the function's own arithmetic.
+    const bool dbl = outpl == PE_PALETTE_YUV422P;
+    if (!dbl) n.d.height = height & ~1;
+    n.d.width = width & ~1;
+    if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    ce = launch_copy2d(L, (const uint8_t *)f->d.planes[0], f->d.rowstrides[0], (uint8_t *)n.d.planes[0], n.d.rowstrides[0], n.d.width,
+                       n.d.height, 0, 0);
+    // source chroma rows that take part: 4:2:0 -> all (the result has 2 ch rows = the luma height rounded up to even is the
+    // caller's business: frames are even, :11603); 4:2:2 -> the first n.d.height rows
+    const int ch = dbl ? (n.plane_heights[1] >> 1) : n.d.height;
+    if (ce == cudaSuccess)
+      ce = launch_resample_chroma_v(L, dbl ? 1 : 0, (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2], f->d.rowstrides[1],
+                                    f->d.rowstrides[2], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1],
+                                    n.d.rowstrides[2], n.d.width >> 1, ch, cavg);
+  } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
+    // convert_swab_frame in place (:13138-13140, :13238-13240)
+    inplace = true;
+    ce = launch_swab(L, Img{(uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, width >> 1, height);
+  } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) &&
+             (outpl == PE_PALETTE_YUV422P || outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P || outpl == PE_PALETTE_YUV888 ||
+              outpl == PE_PALETTE_YUVA8888)) {
+    // convert_{uyvy,yuyv}_to_yuv422_frame (:13141-13146, :13241-13246; with ref_quirks the reference's never-advanced source
+    // pointer, :8103: the whole frame is its first macropixel), _to_yuvp_frame (:13189-13200), _to_yuv888_frame (:13203-13214)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const int mode = outpl == PE_PALETTE_YUV422P ? 0 : (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888) ? 2 : 1;
+    uint8_t *pl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], (uint8_t *)n.d.planes[3]};
+    ce = launch_packed422_unpack(L, inpl == PE_PALETTE_UYVY ? 0 : 1, mode, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl,
+                                 n.d.rowstrides, width >> 1, height, outpl == PE_PALETTE_YUVA4444P || outpl == PE_PALETTE_YUVA8888,
+                                 mode == 0 && e->cfg.ref_quirks);
+    if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)  // lives_memset(dest[3], 255, orow[3] * height): padding included
+      ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
   } else {
     set_err(PE_ERR_PALETTE, "palette conversion %d -> %d is not handled by this build", inpl, outpl);
     return PE_FALSE;  // memfail: the layer is left as it was
@@ -2007,9 +2119,17 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
   // blocks from the pool may still be in use by earlier work on the engine stream
   PE_CUDA(cudaEventRecord(e->pipe_free[0], e->stream));
   PE_CUDA(cudaStreamWaitEvent(e->h2d_stream, e->pipe_free[0], 0));
+  const bool copy2d_only = getenv("PE_HOST_COPY2D") != nullptr;  // A/B switch for the measurement only
   auto copy_planes = [&](cudaStream_t st, pe_frame &dev, const pe_frame_desc_t &host, bool to_device) -> cudaError_t {
     for (int p = 0; p < dev.d.nplanes; p++) {
       const int wbytes = plane_row_bytes(dev.d, p);
+      if (host.rowstrides[p] == dev.d.rowstrides[p] && dev.plane_heights[p] > 0 && !copy2d_only) {  // same pitch on both sides: one linear copy
+        const size_t nbytes = (size_t)dev.d.rowstrides[p] * (dev.plane_heights[p] - 1) + wbytes;
+        cudaError_t ce1 = to_device ? cudaMemcpyAsync(dev.d.planes[p], host.planes[p], nbytes, cudaMemcpyHostToDevice, st)
+                                    : cudaMemcpyAsync(host.planes[p], dev.d.planes[p], nbytes, cudaMemcpyDeviceToHost, st);
+        if (ce1 != cudaSuccess) return ce1;
+        continue;
+      }
       cudaError_t ce = to_device ? cudaMemcpy2DAsync(dev.d.planes[p], dev.d.rowstrides[p], host.planes[p], host.rowstrides[p], wbytes,
                                                      dev.plane_heights[p], cudaMemcpyHostToDevice, st)
                                  : cudaMemcpy2DAsync(host.planes[p], host.rowstrides[p], dev.d.planes[p], dev.d.rowstrides[p], wbytes,

@@ -98,6 +98,25 @@ cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const plan
 cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const planes[3], const int rowstrides[3], int width, int height,
                                   RgbLayout in, int is_422, DevConv conv, const uint8_t *cavg_dev);
 // ---- effects ---------------------------------------------------------------------------------------
+// ---- YUV <-> YUV family + planar 4:4:4 -> RGB (pe_kernels_yuv3.cu) ---------------------------------------
+cudaError_t launch_yuv444p_to_rgb(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,
+                                  RgbLayout out, DevConv conv);
+cudaError_t launch_combine_planes(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,
+                                  int out_alpha);
+cudaError_t launch_split_planes(const Launch &L, CImg src, uint8_t *const planes[4], const int orows[4], int width, int height,
+                                int src_alpha, int dest_alpha);
+// dbl 0: convert_halve_chroma (cw x ch source chroma -> (ch + 1) / 2 rows), 1: convert_double_chroma (-> 2 ch rows)
+cudaError_t launch_resample_chroma_v(const Launch &L, int dbl, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, uint8_t *du,
+                                     uint8_t *dv, int ors_u, int ors_v, int cw, int ch, const uint8_t *cavg_dev);
+// fmt 0 UYVY 1 YUYV; mode 0 -> planar 4:2:2, 1 -> planar 4:4:4 (+ alpha), 2 -> YUV888 / YUVA8888 (planes[0])
+cudaError_t launch_packed422_unpack(const Launch &L, int fmt, int mode, CImg src, uint8_t *const planes[4], const int orows[4], int width_mpx,
+                                    int height, int add_alpha, int first_only);
+cudaError_t launch_swab(const Launch &L, Img img, int width_mpx, int height);
+// kind 0 luma plane, 1 chroma plane, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; row_phase_stride (YUV888): 0 = the reference's dense
+// walk across the row padding, else the rowstride (the Y U V phase restarts with every row)
+cudaError_t launch_clamp_lut(const Launch &L, uint8_t *plane, long long nbytes, int kind, int row_phase_stride, const uint8_t *ty_dev,
+                             const uint8_t *tc_dev);
+
 struct BlendFrame {
   const uint8_t *s1, *s2;
   uint8_t *d;

@@ -1,0 +1,357 @@
+// pe_kernels_yuv3.cu -- the YUV <-> YUV family of convert_layer_palette_full and planar 4:4:4 -> RGB (sm_100a).
+//
+//   k_yuv444p_to_rgb      convert_yuv_planar_to_{rgb,bgr,argb}_frame     colourspace.c:7200 / 7304 / 7405
+//   k_combine_planes      convert_combineplanes_frame                    colourspace.c:7593   (4:4:4 planar -> YUV888 / YUVA8888)
+//   k_split_planes        convert_splitplanes_frame                      colourspace.c:9198   (the reverse)
+//   k_halve_chroma        convert_halve_chroma                           colourspace.c:10578  (4:2:2 -> 4:2:0 chroma planes)
+//   k_double_chroma       convert_double_chroma                          colourspace.c:10612  (4:2:0 -> 4:2:2 chroma planes)
+//   k_packed422_unpack    convert_{uyvy,yuyv}_to_{yuv422,yuvp,yuv888}_frame  colourspace.c:8093 / 7800 / 7845
+//   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
+//   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
+//
+// All of it is pure byte shuffling / table lookups at 1 load + 1 store per byte: HBM-bound.  One thread handles 4 pixels (one
+// 32-bit word per plane, a 128-bit / 3 x 32-bit packed vector); frames whose pointers or strides are not word aligned, and the
+// ragged last group of a row, go byte by byte through the same code.
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+
+namespace pe {
+
+namespace {
+
+constexpr int kBlock = 256;
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+inline int grid_for(const Launch &L, long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kBlock - 1) / kBlock;
+  long long cap = (long long)L.sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// up to 4 bytes of a plane row as one word (missing bytes read as 0)
+__device__ __forceinline__ uint32_t ld_px4(const uint8_t *p, int n, bool vec) {
+  if (vec && n == 4) return ld_stream_u32(p);
+  uint32_t w = 0;
+  for (int k = 0; k < n; k++) w |= (uint32_t)p[k] << (8 * k);
+  return w;
+}
+__device__ __forceinline__ void st_px4(uint8_t *p, uint32_t w, int n, bool vec) {
+  if (vec && n == 4) { st_stream_u32(p, w); return; }
+  for (int k = 0; k < n; k++) p[k] = (uint8_t)(w >> (8 * k));
+}
+// n (<= 4) packed pixels of psize 3 / 4, px[k] = the pixel's bytes in memory order
+__device__ __forceinline__ void st_packed4(uint8_t *d, const uint32_t px[4], int psize, int n, bool vec) {
+  if (vec && n == 4) {
+    if (psize == 4) { st_stream_u4(d, make_uint4(px[0], px[1], px[2], px[3])); return; }
+    st_stream_u32(d, __byte_perm(px[0], px[1], 0x4210));
+    st_stream_u32(d + 4, __byte_perm(px[1], px[2], 0x5421));
+    st_stream_u32(d + 8, __byte_perm(px[2], px[3], 0x6542));
+    return;
+  }
+  for (int k = 0; k < n; k++)
+    for (int b = 0; b < psize; b++) d[k * psize + b] = (uint8_t)(px[k] >> (8 * b));
+}
+__device__ __forceinline__ void ld_packed4(const uint8_t *s, uint32_t px[4], int psize, int n, bool vec) {
+  if (vec && n == 4) {
+    if (psize == 4) { const uint4 v = ld_stream_u4(s); px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w; return; }
+    const uint32_t a = ld_stream_u32(s), b = ld_stream_u32(s + 4), c = ld_stream_u32(s + 8);
+    px[0] = a; px[1] = __byte_perm(a, b, 0x0543); px[2] = __byte_perm(b, c, 0x0432); px[3] = c >> 8;
+    return;
+  }
+  for (int k = 0; k < 4; k++) {
+    px[k] = 0;
+    if (k < n) for (int b = 0; b < psize; b++) px[k] |= (uint32_t)s[k * psize + b] << (8 * b);
+  }
+}
+
+__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+
+struct Planes4 {
+  const uint8_t *p[4];
+  int rs;  // all planes of a 4:4:4 frame share one stride
+};
+struct OutPlanes4 {
+  uint8_t *p[4];
+  int rs[4];
+};
+
+__global__ void __launch_bounds__(kBlock) k_yuv444p_to_rgb(Planes4 S, uint8_t *dst, int orow, int width, int height, int in_alpha,
+                                                          RgbLayout out, DevConv conv, int vec) {
+  __shared__ int32_t t[5][256];  // RGB_Y R_Cr G_Cb G_Cr B_Cb
+  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[9 * 256 + i];
+  __syncthreads();
+  const int groups = (width + 3) >> 2;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, width - x);
+    const long long o = (long long)S.rs * row + x;
+    const uint32_t yw = ld_px4(S.p[0] + o, n, vec), uw = ld_px4(S.p[1] + o, n, vec), vw = ld_px4(S.p[2] + o, n, vec);
+    const uint32_t aw = (in_alpha && out.a >= 0) ? ld_px4(S.p[3] + o, n, vec) : 0xFFFFFFFFu;
+    uint32_t px[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int yy = t[0][byte_of(yw, k)], u = byte_of(uw, k), v = byte_of(vw, k);
+      const uint32_t r = sat8((yy + t[1][v]) >> 16), gg = sat8((yy + t[2][u] + t[3][v]) >> 16), b = sat8((yy + t[4][u]) >> 16);
+      uint32_t w = (r << (8 * out.r)) | (gg << (8 * out.g)) | (b << (8 * out.b));
+      if (out.a >= 0) w |= byte_of(aw, k) << (8 * out.a);
+      px[k] = w;
+    }
+    st_packed4(dst + (long long)orow * row + (long long)x * out.psize, px, out.psize, n, vec);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_combine_planes(Planes4 S, uint8_t *dst, int orow, int width, int height, int in_alpha,
+                                                          int out_alpha, int vec) {
+  const int groups = (width + 3) >> 2, ops = out_alpha ? 4 : 3;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, width - x);
+    const long long o = (long long)S.rs * row + x;
+    const uint32_t yw = ld_px4(S.p[0] + o, n, vec), uw = ld_px4(S.p[1] + o, n, vec), vw = ld_px4(S.p[2] + o, n, vec);
+    const uint32_t aw = (in_alpha && out_alpha) ? ld_px4(S.p[3] + o, n, vec) : 0xFFFFFFFFu;
+    // 4 x 4 byte transpose: px[k] = y_k | u_k << 8 | v_k << 16 | a_k << 24
+    const uint32_t yu_lo = __byte_perm(yw, uw, 0x5140), yu_hi = __byte_perm(yw, uw, 0x7362);
+    const uint32_t va_lo = __byte_perm(vw, aw, 0x5140), va_hi = __byte_perm(vw, aw, 0x7362);
+    const uint32_t px[4] = {__byte_perm(yu_lo, va_lo, 0x5410), __byte_perm(yu_lo, va_lo, 0x7632), __byte_perm(yu_hi, va_hi, 0x5410),
+                            __byte_perm(yu_hi, va_hi, 0x7632)};
+    st_packed4(dst + (long long)orow * row + (long long)x * ops, px, ops, n, vec);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_split_planes(const uint8_t *__restrict__ src, int irow, OutPlanes4 D, int width, int height,
+                                                        int src_alpha, int dest_alpha, int vec) {
+  const int groups = (width + 3) >> 2, ips = src_alpha ? 4 : 3;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, width - x);
+    uint32_t px[4];
+    ld_packed4(src + (long long)irow * row + (long long)x * ips, px, ips, n, vec);
+    const uint32_t a01 = __byte_perm(px[0], px[1], 0x5140), b01 = __byte_perm(px[0], px[1], 0x7362);
+    const uint32_t a23 = __byte_perm(px[2], px[3], 0x5140), b23 = __byte_perm(px[2], px[3], 0x7362);
+    st_px4(D.p[0] + (long long)D.rs[0] * row + x, __byte_perm(a01, a23, 0x5410), n, vec);
+    st_px4(D.p[1] + (long long)D.rs[1] * row + x, __byte_perm(a01, a23, 0x7632), n, vec);
+    st_px4(D.p[2] + (long long)D.rs[2] * row + x, __byte_perm(b01, b23, 0x5410), n, vec);
+    if (dest_alpha) st_px4(D.p[3] + (long long)D.rs[3] * row + x, src_alpha ? __byte_perm(b01, b23, 0x7632) : 0xFFFFFFFFu, n, vec);
+  }
+}
+
+// avg_chroma(x, y) = cavg[x][y] (colourspace.c:2079); the 64 KB table stays in L1 / L2
+__device__ __forceinline__ uint32_t avg4(const uint8_t *__restrict__ cavg, uint32_t a, uint32_t b) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) w |= (uint32_t)__ldg(cavg + ((byte_of(a, k) << 8) | byte_of(b, k))) << (8 * k);
+  return w;
+}
+
+// out row k = avg_chroma(src row 2k, src row 2k + 1); a trailing unpaired row is copied.  blockIdx.y = plane (U, V)
+__global__ void __launch_bounds__(kBlock) k_halve_chroma(const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, uint8_t *du, uint8_t *dv,
+                                                        int ors_u, int ors_v, int cw, int ch, const uint8_t *__restrict__ cavg, int vec) {
+  const uint8_t *s = blockIdx.y ? sv : su;
+  uint8_t *d = blockIdx.y ? dv : du;
+  const int irs = blockIdx.y ? irs_v : irs_u, ors = blockIdx.y ? ors_v : ors_u;
+  const int groups = (cw + 3) >> 2, orows = (ch + 1) >> 1;
+  const long long total = (long long)groups * orows;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, cw - x);
+    uint32_t w = ld_px4(s + (long long)irs * (2 * row) + x, n, vec);
+    if (2 * row + 1 < ch) w = avg4(cavg, w, ld_px4(s + (long long)irs * (2 * row + 1) + x, n, vec));
+    st_px4(d + (long long)ors * row + x, w, n, vec);
+  }
+}
+
+// out row 2k = src row k; out row 2k + 1 = avg_chroma(src row k, src row k + 1), the last one a copy of src row ch - 1
+__global__ void __launch_bounds__(kBlock) k_double_chroma(const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, uint8_t *du, uint8_t *dv,
+                                                         int ors_u, int ors_v, int cw, int ch, const uint8_t *__restrict__ cavg, int vec) {
+  const uint8_t *s = blockIdx.y ? sv : su;
+  uint8_t *d = blockIdx.y ? dv : du;
+  const int irs = blockIdx.y ? irs_v : irs_u, ors = blockIdx.y ? ors_v : ors_u;
+  const int groups = (cw + 3) >> 2;
+  const long long total = (long long)groups * ch;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, cw - x);
+    const uint32_t a = ld_px4(s + (long long)irs * row + x, n, vec);
+    uint32_t b = a;
+    if (row + 1 < ch) b = avg4(cavg, a, ld_px4(s + (long long)irs * (row + 1) + x, n, vec));
+    st_px4(d + (long long)ors * (2 * row) + x, a, n, vec);
+    st_px4(d + (long long)ors * (2 * row + 1) + x, b, n, vec);
+  }
+}
+
+// packed 4:2:2 -> planar 4:2:2 (mode 0), planar 4:4:4 (+ alpha) (mode 1), YUV888 / YUVA8888 (mode 2).  One thread = 2 macropixels
+// = 4 pixels.  fmt 0 UYVY, 1 YUYV.  first_only: the reference's never-advanced source pointer (colourspace.c:8103, mode 0 only).
+__global__ void __launch_bounds__(kBlock) k_packed422_unpack(int fmt, int mode, const uint8_t *__restrict__ src, int irow, OutPlanes4 D,
+                                                            int width_mpx, int height, int add_alpha, int first_only, int vec) {
+  const int groups = (width_mpx + 1) >> 1;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int m = 2 * g, nm = min(2, width_mpx - m);
+    const uint8_t *q = first_only ? src : src + (long long)irow * row + 4LL * m;
+    uint32_t m0, m1;
+    if (first_only) { m0 = m1 = ld_px4(q, 4, vec); }
+    else { m0 = ld_px4(q, 4, vec); m1 = nm == 2 ? ld_px4(q + 4, 4, vec) : 0u; }
+    if (fmt == 0) { m0 = __byte_perm(m0, 0u, 0x2301); m1 = __byte_perm(m1, 0u, 0x2301); }  // -> y0 u y1 v
+    const uint32_t yw = __byte_perm(m0, m1, 0x6420);                                       // y0 y1 y0' y1'
+    if (mode == 0) {
+      st_px4(D.p[0] + (long long)D.rs[0] * row + 2 * m, yw, 2 * nm, vec);
+      uint8_t *du = D.p[1] + (long long)D.rs[1] * row + m, *dv = D.p[2] + (long long)D.rs[2] * row + m;
+      du[0] = (uint8_t)(m0 >> 8); dv[0] = (uint8_t)(m0 >> 24);
+      if (nm == 2) { du[1] = (uint8_t)(m1 >> 8); dv[1] = (uint8_t)(m1 >> 24); }
+    } else if (mode == 1) {
+      const uint32_t uw = __byte_perm(m0, m1, 0x5511), vw = __byte_perm(m0, m1, 0x7733);
+      st_px4(D.p[0] + (long long)D.rs[0] * row + 2 * m, yw, 2 * nm, vec);
+      st_px4(D.p[1] + (long long)D.rs[1] * row + 2 * m, uw, 2 * nm, vec);
+      st_px4(D.p[2] + (long long)D.rs[2] * row + 2 * m, vw, 2 * nm, vec);
+      if (add_alpha) st_px4(D.p[3] + (long long)D.rs[3] * row + 2 * m, 0xFFFFFFFFu, 2 * nm, vec);
+    } else {
+      const int ps = add_alpha ? 4 : 3;
+      const uint32_t ff = 0xFF000000u;
+      const uint32_t px[4] = {__byte_perm(m0, ff, 0x7310), __byte_perm(m0, ff, 0x7312), __byte_perm(m1, ff, 0x7310),
+                              __byte_perm(m1, ff, 0x7312)};
+      st_packed4(D.p[0] + (long long)D.rs[0] * row + 2LL * m * ps, px, ps, 2 * nm, vec);
+    }
+  }
+}
+
+// UYVY <-> YUYV in place: swab() of every row
+__global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
+  const long long total = (long long)width_mpx * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / width_mpx), m = (int)(it - (long long)row * width_mpx);
+    uint8_t *p = pix + (long long)rs * row + 4LL * m;
+    if (vec) *reinterpret_cast<uint32_t *>(p) = __byte_perm(*reinterpret_cast<const uint32_t *>(p), 0u, 0x2301);
+    else { const uint8_t a = p[0], b = p[1], c = p[2], d = p[3]; p[0] = b; p[1] = a; p[2] = d; p[3] = c; }
+  }
+}
+
+// every byte of a plane, walked densely, through the luma or the chroma table.  kind 0 all luma, 1 all chroma, 2 YUV888 (byte i is
+// luma when i % 3 == 0), 3 YUVA8888 (i % 4: 0 luma, 1 2 chroma, 3 untouched), 4 UYVY (odd bytes luma), 5 YUYV (even bytes luma)
+// rs3 (kind 2 only): 0 = the reference's dense walk (the Y U V phase runs on across the row padding), else the rowstride: the phase
+// restarts with every row
+__global__ void __launch_bounds__(kBlock) k_clamp_lut(uint8_t *plane, long long nbytes, int kind, int rs3, const uint8_t *__restrict__ ty,
+                                                     const uint8_t *__restrict__ tc) {
+  __shared__ uint8_t sy[256], sc[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { sy[i] = ty[i]; sc[i] = tc[i]; }
+  __syncthreads();
+  const long long words = (nbytes + 3) >> 2;  // the plane starts word aligned (checked by the launcher)
+  for (long long it = global_tid(); it < words; it += global_threads()) {
+    const long long i0 = 4 * it;
+    const int n = (int)min(4LL, nbytes - i0);
+    uint32_t w = n == 4 ? *reinterpret_cast<const uint32_t *>(plane + i0) : 0u;
+    if (n < 4) for (int k = 0; k < n; k++) w |= (uint32_t)plane[i0 + k] << (8 * k);
+    const int ph3 = (int)((rs3 ? i0 % rs3 : i0) % 3);  // (rowstrides are multiples of 4: a word never straddles two rows)
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t b = byte_of(w, k);
+      int luma;  // 1 luma, 0 chroma, -1 untouched
+      switch (kind) {
+      case 0: luma = 1; break;
+      case 1: luma = 0; break;
+      case 2: luma = ((ph3 + k) % 3) == 0; break;
+      case 3: luma = k == 3 ? -1 : k == 0; break;
+      case 4: luma = k & 1; break;
+      default: luma = !(k & 1); break;
+      }
+      o |= (luma < 0 ? b : luma ? (uint32_t)sy[b] : (uint32_t)sc[b]) << (8 * k);
+    }
+    if (n == 4) *reinterpret_cast<uint32_t *>(plane + i0) = o;
+    else for (int k = 0; k < n; k++) plane[i0 + k] = (uint8_t)(o >> (8 * k));
+  }
+}
+
+inline bool aligned4(const void *p) { return (((uintptr_t)p) & 3) == 0; }
+inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+cudaError_t launch_yuv444p_to_rgb(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,
+                                  RgbLayout out, DevConv conv) {
+  Planes4 S;
+  for (int k = 0; k < 4; k++) S.p[k] = planes[k];
+  S.rs = irow;
+  bool vec = aligned4(planes[0]) && aligned4(planes[1]) && aligned4(planes[2]) && (!in_alpha || aligned4(planes[3])) && !(irow & 3);
+  vec = vec && (out.psize == 4 ? aligned16(dst.p) && !(dst.rs & 15) : aligned4(dst.p) && !(dst.rs & 3));
+  k_yuv444p_to_rgb<<<grid_for(L, (long long)((width + 3) / 4) * height), kBlock, 0, L.stream>>>(S, dst.p, dst.rs, width, height, in_alpha,
+                                                                                                out, conv, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_combine_planes(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,
+                                  int out_alpha) {
+  Planes4 S;
+  for (int k = 0; k < 4; k++) S.p[k] = planes[k];
+  S.rs = irow;
+  bool vec = aligned4(planes[0]) && aligned4(planes[1]) && aligned4(planes[2]) && (!in_alpha || aligned4(planes[3])) && !(irow & 3);
+  vec = vec && (out_alpha ? aligned16(dst.p) && !(dst.rs & 15) : aligned4(dst.p) && !(dst.rs & 3));
+  k_combine_planes<<<grid_for(L, (long long)((width + 3) / 4) * height), kBlock, 0, L.stream>>>(S, dst.p, dst.rs, width, height, in_alpha,
+                                                                                                out_alpha, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_planes(const Launch &L, CImg src, uint8_t *const planes[4], const int orows[4], int width, int height,
+                                int src_alpha, int dest_alpha) {
+  OutPlanes4 D;
+  bool vec = src_alpha ? aligned16(src.p) && !(src.rs & 15) : aligned4(src.p) && !(src.rs & 3);
+  for (int k = 0; k < 4; k++) {
+    D.p[k] = planes[k]; D.rs[k] = orows[k];
+    if (k < 3 || dest_alpha) vec = vec && aligned4(planes[k]) && !(orows[k] & 3);
+  }
+  k_split_planes<<<grid_for(L, (long long)((width + 3) / 4) * height), kBlock, 0, L.stream>>>(src.p, src.rs, D, width, height, src_alpha,
+                                                                                              dest_alpha, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_chroma_v(const Launch &L, int dbl, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, uint8_t *du,
+                                     uint8_t *dv, int ors_u, int ors_v, int cw, int ch, const uint8_t *cavg_dev) {
+  const bool vec = aligned4(su) && aligned4(sv) && aligned4(du) && aligned4(dv) && !((irs_u | irs_v | ors_u | ors_v) & 3);
+  const long long work = (long long)((cw + 3) / 4) * (dbl ? ch : (ch + 1) / 2);
+  const dim3 grid(grid_for(L, work), 2);
+  if (dbl) k_double_chroma<<<grid, kBlock, 0, L.stream>>>(su, sv, irs_u, irs_v, du, dv, ors_u, ors_v, cw, ch, cavg_dev, vec);
+  else k_halve_chroma<<<grid, kBlock, 0, L.stream>>>(su, sv, irs_u, irs_v, du, dv, ors_u, ors_v, cw, ch, cavg_dev, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_packed422_unpack(const Launch &L, int fmt, int mode, CImg src, uint8_t *const planes[4], const int orows[4], int width_mpx,
+                                    int height, int add_alpha, int first_only) {
+  OutPlanes4 D;
+  bool vec = aligned4(src.p) && !(src.rs & 3);
+  const int np = mode == 2 ? 1 : mode == 0 ? 3 : (add_alpha ? 4 : 3);
+  for (int k = 0; k < 4; k++) {
+    D.p[k] = k < np ? planes[k] : nullptr; D.rs[k] = k < np ? orows[k] : 0;
+    if (k < np && !(mode == 0 && k > 0)) vec = vec && (mode == 2 && add_alpha ? aligned16(planes[k]) && !(orows[k] & 15) : aligned4(planes[k]) && !(orows[k] & 3));
+  }
+  k_packed422_unpack<<<grid_for(L, (long long)((width_mpx + 1) / 2) * height), kBlock, 0, L.stream>>>(fmt, mode, src.p, src.rs, D, width_mpx,
+                                                                                                      height, add_alpha, first_only, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_swab(const Launch &L, Img img, int width_mpx, int height) {
+  const bool vec = aligned4(img.p) && !(img.rs & 3);
+  k_swab<<<grid_for(L, (long long)width_mpx * height), kBlock, 0, L.stream>>>(img.p, img.rs, width_mpx, height, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clamp_lut(const Launch &L, uint8_t *plane, long long nbytes, int kind, int row_phase_stride, const uint8_t *ty_dev,
+                             const uint8_t *tc_dev) {
+  if (!aligned4(plane) || (row_phase_stride & 3)) return cudaErrorMisalignedAddress;
+  if (nbytes <= 0) return cudaSuccess;
+  k_clamp_lut<<<grid_for(L, (nbytes + 3) / 4), kBlock, 0, L.stream>>>(plane, nbytes, kind, kind == 2 ? row_phase_stride : 0, ty_dev, tc_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+}  // namespace pe

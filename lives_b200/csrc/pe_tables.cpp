@@ -228,6 +228,32 @@ void build_avg_table(bool clamped, uint8_t *out) {
   }
 }
 
+// init_YUV_to_YUV_tables (colourspace.c:1108-1138): clamped <-> unclamped, same subspace.  Limits 16 / 235 / 240
+// (colourspace.h:96-109); the first luma loop runs to i <= 16, the first chroma loop to i < 16; rounding is myround
+// (maths.h:118: half away from zero, in double)
+void build_yy_table(int which, uint8_t out[256]) {
+  const double lo = 16., ymax = 235., cmax = 240.;
+  int i = 0;
+  switch (which) {
+  case 0:
+    for (; i <= 16; i++) out[i] = 0;
+    for (; i < 235; i++) out[i] = (uint8_t)round_half_away((i - lo) * 255. / (ymax - lo));
+    for (; i < 256; i++) out[i] = 255;
+    break;
+  case 1:
+    for (; i < 16; i++) out[i] = 0;
+    for (; i < 240; i++) out[i] = (uint8_t)round_half_away((i - lo) * 255. / (cmax - lo));
+    for (; i < 256; i++) out[i] = 255;
+    break;
+  case 2:
+    for (; i < 256; i++) out[i] = (uint8_t)round_half_away((i / 255.) * (ymax - lo) + lo);
+    break;
+  default:
+    for (; i < 256; i++) out[i] = (uint8_t)round_half_away((i / 255.) * (cmax - lo) + lo);
+    break;
+  }
+}
+
 void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]) {
   for (int i = 0; i < 256; i++) {
     yr[i] = round_half_away(0.299 * (double)i * 65536.);

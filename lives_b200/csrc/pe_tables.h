@@ -28,6 +28,10 @@ void build_premult_table(int which, uint8_t *out /*65536*/);
 // init_average (colourspace.c:190): cavgc (clamped) / cavgu, [x][y] as uint8
 void build_avg_table(bool clamped, uint8_t *out /*65536*/);
 
+// init_YUV_to_YUV_tables (colourspace.c:1108): which = 0 Yclamped_to_Yunclamped 1 UVclamped_to_UVunclamped 2 Yunclamped_to_Yclamped
+// 3 UVunclamped_to_UVclamped
+void build_yy_table(int which, uint8_t out[256]);
+
 // calc_luma tables of libweed/weed-plugin-utils.c:881-886 (16.16, SCALE_FACTOR 65536)
 void build_plugin_luma_tables(int32_t yr[256], int32_t yg[256], int32_t yb[256]);
 

@@ -917,3 +917,198 @@ void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint
       memcpy(outer + (long)orow * (y + oy) + (long)ox * ps, inner + (long)irow * y, (size_t)iw * ps);
   }
 }
+
+/* ==== YUV <-> YUV family ======================================================================================= */
+
+/* convert_yuv_planar_to_rgb_frame src/colourspace.c:7200-7290 (bgr :7304, argb :7405): yuv2rgb per sample, the YCbCr tables of
+ * the clamping (set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_YCBCR)), alpha from the 4th plane or 255.
+ * X: the BGR variant starts with opstep = 4 (:7313) and only ever sets it to 4, so BGR24 output walks 4 bytes per pixel and runs
+ * past its rows / buffer -- restated with the palette's own 3-byte step.  X: the ARGB variant subtracts the width from the output
+ * stride twice and never from the input stride (:7471-7472) and never selects its tables -- restated as the RGB variant with
+ * the alpha byte first. */
+void pe_or_yuv444p_to_rgb(const uint8_t *const src[4], int irow, int width, int height, uint8_t *dest, int orow, int order,
+                          int in_alpha, int out_alpha, int clamping, int quality) {
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ps;
+  or_order_offsets(order, out_alpha, &ro, &go, &bo, &ao, &ps);
+  for (int i = 0; i < height; i++) {
+    uint8_t *d = dest + (long)orow * i;
+    const long o = (long)irow * i;
+    for (int j = 0; j < width; j++, d += ps) {
+      or_px_yuv2rgb(c, quality, NULL, src[0][o + j], src[1][o + j], src[2][o + j], &d[ro], &d[go], &d[bo]);
+      if (ao >= 0) d[ao] = in_alpha ? src[3][o + j] : 255;
+    }
+  }
+}
+
+/* convert_combineplanes_frame :7593-7640.  X: on padded planes the reference's alpha pointer is never advanced by the row padding
+ * (:7625-7637); restated with the stride on all four planes. */
+void pe_or_combine_planes(const uint8_t *const src[4], int irow, int width, int height, uint8_t *dest, int orow, int in_alpha,
+                          int out_alpha) {
+  const int ops = out_alpha ? 4 : 3;
+  for (int k = 0; k < height; k++) {
+    uint8_t *d = dest + (long)orow * k;
+    const long o = (long)irow * k;
+    for (int x = 0; x < width; x++, d += ops) {
+      d[0] = src[0][o + x]; d[1] = src[1][o + x]; d[2] = src[2][o + x];
+      if (out_alpha) d[3] = in_alpha ? src[3][o + x] : 255;
+    }
+  }
+}
+
+/* convert_splitplanes_frame :9198-9252.  X: with a destination alpha plane the reference advances that plane by
+ * (stride - width * ipsize) per row (:9233-9236) and writes before its buffer; with a source alpha but no destination alpha the
+ * 4th source byte is never skipped (:9238-9246).  Restated as the evident intent (equal to the reference for 3 -> 3 planes). */
+void pe_or_split_planes(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[4], const int orows[4],
+                        int src_alpha, int dest_alpha) {
+  const int ips = src_alpha ? 4 : 3;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    for (int j = 0; j < width; j++, s += ips) {
+      dest[0][(long)orows[0] * i + j] = s[0];
+      dest[1][(long)orows[1] * i + j] = s[1];
+      dest[2][(long)orows[2] * i + j] = s[2];
+      if (dest_alpha) dest[3][(long)orows[3] * i + j] = src_alpha ? s[3] : 255;
+    }
+  }
+}
+
+static const uint8_t *or_avg(int clamping) { /* cavg = cavgc / cavgu, set_conversion_arrays :220-300 */
+  static uint8_t avg[2][65536];
+  static int ok = 0;
+  if (!ok) { pe_or_avg_table(0, avg[0]); pe_or_avg_table(1, avg[1]); ok = 1; }
+  return avg[clamping == OR_CLAMPED ? 0 : 1];
+}
+
+/* convert_halve_chroma :10578-10609: source chroma rows (2k, 2k+1) -> row k = avg_chroma(row 2k, row 2k+1) (the copy of the
+ * even row is the first operand, i.e. the table ROW); a trailing unpaired row is copied */
+void pe_or_halve_chroma(const uint8_t *const src[3], const int istrides[3], int cwidth, int cheight, uint8_t *const dest[3],
+                        const int ostrides[3], int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  for (int p = 1; p <= 2; p++)
+    for (int i = 0; i < cheight; i++) {
+      const uint8_t *s = src[p] + (long)istrides[p] * i;
+      uint8_t *d = dest[p] + (long)ostrides[p] * (i >> 1);
+      for (int j = 0; j < cwidth; j++) d[j] = (i & 1) ? avg[(d[j] << 8) + s[j]] : s[j];
+    }
+}
+
+/* convert_double_chroma :10612-10639: output rows 2k and 2k+1 are copies of source row k; then, when the copy of row k (k > 0)
+ * lands in output row 2k, output row 2k-1 becomes avg_chroma(row 2k-1, row 2k) = avg(src k-1, src k) */
+void pe_or_double_chroma(const uint8_t *const src[3], const int istrides[3], int cwidth, int cheight, uint8_t *const dest[3],
+                         const int ostrides[3], int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  for (int p = 1; p <= 2; p++)
+    for (int i = 0; i < 2 * cheight; i++) {
+      const uint8_t *s = src[p] + (long)istrides[p] * (i >> 1);
+      uint8_t *d = dest[p] + (long)ostrides[p] * i;
+      memcpy(d, s, (size_t)cwidth);
+      if (!(i & 1) && i > 0) {
+        uint8_t *pr = d - ostrides[p];
+        for (int j = 0; j < cwidth; j++) pr[j] = avg[(pr[j] << 8) + d[j]];
+      }
+    }
+}
+
+static inline void or_mpx(int fmt, const uint8_t *m, uint8_t *y0, uint8_t *u, uint8_t *y1, uint8_t *v) {
+  if (fmt == 0) { *u = m[0]; *y0 = m[1]; *v = m[2]; *y1 = m[3]; }  /* uyvy_macropixel colourspace.h:222-227 */
+  else { *y0 = m[0]; *u = m[1]; *y1 = m[2]; *v = m[3]; }            /* yuyv_macropixel :229-234 */
+}
+
+/* convert_{uyvy,yuyv}_to_yuv422_frame :8093-8127.  The reference walks source and planes densely (only right for unpadded rows;
+ * strides honoured here, equal there) and NEVER advances its source pointer (:8103,:8121): with quirks every sample of the frame
+ * is the first macropixel's; quirks == 0 is the evident intent. */
+void pe_or_packed422_to_yuv422p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[3],
+                                const int orows[3], int quirks) {
+  for (int k = 0; k < height; k++)
+    for (int x = 0; x < width_mpx; x++) {
+      const uint8_t *m = quirks ? src : src + (long)irow * k + 4L * x;
+      uint8_t y0, u, y1, v;
+      or_mpx(fmt, m, &y0, &u, &y1, &v);
+      dest[0][(long)orows[0] * k + 2 * x] = y0; dest[0][(long)orows[0] * k + 2 * x + 1] = y1;
+      dest[1][(long)orows[1] * k + x] = u; dest[2][(long)orows[2] * k + x] = v;
+    }
+}
+
+/* convert_{uyvy,yuyv}_to_yuvp_frame :7800-7842: chroma duplicated onto both pixels, no interpolation ("TODO - avg_chroma").
+ * The reference indexes the planes with mixed strides (y with orow[1] / orow[0], u with orow[0]); all planes of a 4:4:4 frame
+ * share one stride, where this restatement equals it. */
+void pe_or_packed422_to_yuv444p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[4],
+                                const int orows[4], int add_alpha) {
+  for (int k = 0; k < height; k++)
+    for (int x = 0; x < width_mpx; x++) {
+      uint8_t y0, u, y1, v;
+      or_mpx(fmt, src + (long)irow * k + 4L * x, &y0, &u, &y1, &v);
+      dest[0][(long)orows[0] * k + 2 * x] = y0; dest[0][(long)orows[0] * k + 2 * x + 1] = y1;
+      dest[1][(long)orows[1] * k + 2 * x] = dest[1][(long)orows[1] * k + 2 * x + 1] = u;
+      dest[2][(long)orows[2] * k + 2 * x] = dest[2][(long)orows[2] * k + 2 * x + 1] = v;
+    }
+  if (add_alpha) memset(dest[3], 255, (size_t)orows[3] * height);
+}
+
+/* convert_{uyvy,yuyv}_to_yuv888_frame :7845-7885 */
+void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *dest, int orow,
+                               int add_alpha) {
+  const int ps = add_alpha ? 4 : 3;
+  for (int k = 0; k < height; k++) {
+    uint8_t *d = dest + (long)orow * k;
+    for (int x = 0; x < width_mpx; x++, d += 2 * ps) {
+      uint8_t y0, u, y1, v;
+      or_mpx(fmt, src + (long)irow * k + 4L * x, &y0, &u, &y1, &v);
+      d[0] = y0; d[1] = u; d[2] = v; d[ps] = y1; d[ps + 1] = u; d[ps + 2] = v;
+      if (add_alpha) d[3] = d[ps + 3] = 255;
+    }
+  }
+}
+
+/* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
+void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
+  for (int k = 0; k < height; k++) {
+    uint8_t *r = pixels + (long)irow * k;
+    for (int x = 0; x < width_mpx * 2; x++) { const uint8_t t = r[2 * x]; r[2 * x] = r[2 * x + 1]; r[2 * x + 1] = t; }
+  }
+}
+
+/* init_YUV_to_YUV_tables :1108-1138 (YUV_CLAMP_MIN 16, Y_CLAMP_MAX 235, UV_CLAMP_MAX 240, colourspace.h:16-18; note `<=` in
+ * the first Y loop and `<` in the first UV loop) */
+void pe_or_yy_table(int which, uint8_t out[256]) {
+  int i;
+  switch (which) {
+  case 0:
+    for (i = 0; i <= 16; i++) out[i] = 0;
+    for (; i < 235; i++) out[i] = (uint8_t)or_myround((i - 16.) * 255. / (235. - 16.));
+    for (; i < 256; i++) out[i] = 255;
+    break;
+  case 1:
+    for (i = 0; i < 16; i++) out[i] = 0;
+    for (; i < 240; i++) out[i] = (uint8_t)or_myround((i - 16.) * 255. / (240. - 16.));
+    for (; i < 256; i++) out[i] = 255;
+    break;
+  case 2:
+    for (i = 0; i < 256; i++) out[i] = (uint8_t)or_myround((i / 255.) * (235. - 16.) + 16.);
+    break;
+  default:
+    for (i = 0; i < 256; i++) out[i] = (uint8_t)or_myround((i / 255.) * (240. - 16.) + 16.);
+    break;
+  }
+}
+
+/* switch_yuv_clamping_and_subspace :10929-11100: every byte of the plane through Y_to_Y / U_to_U (= V_to_V), walked densely
+ * from the plane start for height * rowstride bytes -- row padding included */
+void pe_or_switch_clamping_plane(uint8_t *plane, long nbytes, int kind, int to_unclamped) {
+  uint8_t ty[256], tc[256];
+  pe_or_yy_table(to_unclamped ? 0 : 2, ty);
+  pe_or_yy_table(to_unclamped ? 1 : 3, tc);
+  for (long i = 0; i < nbytes; i++) {
+    int luma;
+    switch (kind) {
+    case 0: luma = 1; break;
+    case 1: luma = 0; break;
+    case 2: luma = (i % 3) == 0; break;
+    case 3: if ((i & 3) == 3) continue; luma = (i & 3) == 0; break;
+    case 4: luma = (i & 1) == 1; break;
+    default: luma = (i & 1) == 0; break;
+    }
+    plane[i] = luma ? ty[plane[i]] : tc[plane[i]];
+  }
+}

@@ -103,6 +103,39 @@ int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, in
 void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint8_t *outer, int orow, int ow, int oh,
                             int palette);
 
+/* ---- YUV <-> YUV family --------------------------------------------------------------------------- */
+/* planar 4:4:4 (+ alpha plane) -> packed RGB(A), convert_yuv_planar_to_{rgb,bgr,argb}_frame colourspace.c:7200,7304,7405:
+ * always the YCbCr tables; order 0 RGB 1 BGR 2 ARGB */
+void pe_or_yuv444p_to_rgb(const uint8_t *const src[4], int irow, int width, int height, uint8_t *dest, int orow, int order,
+                          int in_alpha, int out_alpha, int clamping, int quality);
+/* convert_combineplanes_frame :7593 (4:4:4 planar -> YUV888 / YUVA8888) and convert_splitplanes_frame :9198 (the reverse) */
+void pe_or_combine_planes(const uint8_t *const src[4], int irow, int width, int height, uint8_t *dest, int orow, int in_alpha,
+                          int out_alpha);
+void pe_or_split_planes(const uint8_t *src, int irow, int width, int height, uint8_t *const dest[4], const int orows[4],
+                        int src_alpha, int dest_alpha);
+/* convert_halve_chroma :10578 (4:2:2 -> 4:2:0 chroma planes) / convert_double_chroma :10612 (4:2:0 -> 4:2:2); cwidth x cheight =
+ * the SOURCE chroma plane; planes 1 and 2 only (the caller copies luma, :13706,:13593) */
+void pe_or_halve_chroma(const uint8_t *const src[3], const int istrides[3], int cwidth, int cheight, uint8_t *const dest[3],
+                        const int ostrides[3], int clamping);
+void pe_or_double_chroma(const uint8_t *const src[3], const int istrides[3], int cwidth, int cheight, uint8_t *const dest[3],
+                         const int ostrides[3], int clamping);
+/* packed 4:2:2 (fmt 0 UYVY, 1 YUYV; width in macropixels) -> planar 4:2:2 (convert_{uyvy,yuyv}_to_yuv422_frame :8093,:8111;
+ * quirks != 0: the source pointer is never advanced, every sample is the frame's FIRST macropixel), planar 4:4:4 (+ alpha)
+ * (convert_{uyvy,yuyv}_to_yuvp_frame :7800,:7823) and YUV888 / YUVA8888 (convert_{uyvy,yuyv}_to_yuv888_frame :7845,:7866) */
+void pe_or_packed422_to_yuv422p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[3],
+                                const int orows[3], int quirks);
+void pe_or_packed422_to_yuv444p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[4],
+                                const int orows[4], int add_alpha);
+void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *dest, int orow,
+                               int add_alpha);
+/* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
+void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
+/* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */
+void pe_or_yy_table(int which, uint8_t out[256]);
+/* switch_yuv_clamping_and_subspace :10929 on one plane walked densely (padding included, as the reference walks it):
+ * kind 0 all luma, 1 all chroma, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; to_unclamped selects the table pair */
+void pe_or_switch_clamping_plane(uint8_t *plane, long nbytes, int kind, int to_unclamped);
+
 #ifdef __cplusplus
 }
 #endif

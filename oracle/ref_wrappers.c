@@ -273,3 +273,45 @@ void ref_gamma_apply(uint8_t *pixels, int rowstride, int psize, int x, int width
   cc.xoffset = (size_t)x * psize; cc.alpha_first = alpha_first; cc.lut8 = lut8;
   gamma_convert_layer_thread(&cc);
 }
+
+/* ---- YUV <-> YUV family -------------------------------------------------- */
+
+void ref_combineplanes(uint8_t **src, int width, int height, int irow, int orow, uint8_t *dest, int in_alpha, int out_alpha) {
+  convert_combineplanes_frame(src, width, height, irow, orow, dest, in_alpha, out_alpha);
+}
+
+void ref_splitplanes(uint8_t *src, int width, int height, int irow, int *orows, uint8_t **dest, int src_alpha, int dest_alpha) {
+  int o[4] = {orows[0], orows[1], orows[2], orows[3]}; /* the reference subtracts the width from its argument array */
+  convert_splitplanes_frame(src, width, height, irow, o, dest, src_alpha, dest_alpha);
+}
+
+/* cwidth x cheight = the SOURCE chroma plane */
+void ref_halve_chroma(uint8_t **src, int cwidth, int cheight, int *istrides, int *ostrides, uint8_t **dest, int clamping) {
+  ref_init();
+  convert_halve_chroma(src, cwidth, cheight, istrides, ostrides, dest, clamping);
+}
+
+void ref_double_chroma(uint8_t **src, int cwidth, int cheight, int *istrides, int *ostrides, uint8_t **dest, int clamping) {
+  ref_init();
+  convert_double_chroma(src, cwidth, cheight, istrides, ostrides, dest, clamping);
+}
+
+/* fmt 0 uyvy 1 yuyv; width in macropixels */
+void ref_packed422_to_yuv422p(int fmt, void *src, int width, int height, uint8_t **dest) {
+  if (fmt == 0) convert_uyvy_to_yuv422_frame((uyvy_macropixel *)src, width, height, dest);
+  else convert_yuyv_to_yuv422_frame((yuyv_macropixel *)src, width, height, dest);
+}
+
+void ref_packed422_to_yuv444p(int fmt, void *src, int width, int height, int irow, int *orows, uint8_t **dest, int add_alpha) {
+  if (fmt == 0) convert_uyvy_to_yuvp_frame((uyvy_macropixel *)src, width, height, irow, orows, dest, add_alpha);
+  else convert_yuyv_to_yuvp_frame((yuyv_macropixel *)src, width, height, irow, orows, dest, add_alpha);
+}
+
+void ref_packed422_to_yuv888(int fmt, void *src, int width, int height, int irow, int orow, uint8_t *dest, int add_alpha) {
+  if (fmt == 0) convert_uyvy_to_yuv888_frame((uyvy_macropixel *)src, width, height, irow, orow, dest, add_alpha);
+  else convert_yuyv_to_yuv888_frame((yuyv_macropixel *)src, width, height, irow, orow, dest, add_alpha);
+}
+
+void ref_swab(uint8_t *src, int width, int height, int irow) {
+  convert_swab_frame(src, width, height, irow, -USE_THREADS);
+}

@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_vectors_yuv.npz -- the YUV <-> YUV family -- from the COMPILED REFERENCE (oracle/_ref/libref_oracle.so,
+built by oracle/build_ref.py from /root/reference).  Run in the build container only; the GPU box consumes the committed .npz.
+
+Only reference behaviour that is defined goes in (see the X rows of DESIGN.md's quirk table): planar 4:4:4 -> RGB24 / RGBA32 /
+BGRA32, combineplanes without source alpha on padded planes, splitplanes 3 -> 3 planes, halve / double chroma, packed 4:2:2 ->
+planar 4:2:2 (dense buffers; the never-advanced source pointer included) / 4:4:4 / YUV888, swab, the four clamping tables.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import pe_testlib as T  # noqa: E402
+
+W, H = 48, 10
+
+
+def planes444(rng, n):
+    st = T.rowstride(W, 1)
+    out = []
+    for _ in range(n):
+        a = np.zeros((H, st), np.uint8)
+        a[:, :W] = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        out.append(a)
+    return out
+
+
+def main():
+    assert T.have_ref(), "build oracle/_ref first (python oracle/build_ref.py)"
+    r = T.ref()
+    r.ref_set_prefs(1, T.Q_HIGH, 1.4)
+    rng = np.random.default_rng(2026)
+    out = {}
+    for w in range(4):
+        t = np.zeros(256, np.uint8)
+        assert r.ref_get_yy_table(w, T.ptr(t)) == 0
+        out["yy%d" % w] = t
+    pl = planes444(rng, 4)
+    for k in range(4):
+        out["p444_%d" % k] = pl[k]
+    for cl in (0, 1):
+        for nm, order, ia, oa in (("rgb24", 0, 0, 0), ("rgba32", 0, 1, 1), ("bgra32", 1, 0, 1)):
+            ps = 4 if oa else 3
+            d = np.zeros((H, T.rowstride(W, ps)), np.uint8)
+            r.ref_yuv444p_to_rgb(T.planes_arg(*pl), W, H, pl[0].strides[0], d.strides[0], T.ptr(d), order, ia, oa, cl)
+            out["yuv444p_to_%s_cl%d" % (nm, cl)] = d
+    for oa in (0, 1):
+        ps = 4 if oa else 3
+        d = np.zeros((H, T.rowstride(W, ps)), np.uint8)
+        r.ref_combineplanes(T.planes_arg(*pl), W, H, pl[0].strides[0], d.strides[0], T.ptr(d), 0, oa)
+        out["combine_a%d" % oa] = d
+    src = T.make_packed(rng, W, H, 3)
+    out["yuv888_src"] = src
+    sp = [np.zeros((H, T.rowstride(W, 1)), np.uint8) for _ in range(4)]
+    r.ref_splitplanes(T.ptr(src), W, H, src.strides[0], T.strides_arg(*sp), T.planes_arg(*sp), 0, 0)
+    for k in range(3):
+        out["split_%d" % k] = sp[k]
+    # chroma planes 24 x 10 (4:2:2 source) / 24 x 5 (4:2:0 source)
+    cw, st = W // 2, T.rowstride(W, 1) // 2
+    c422 = [np.zeros((H, st), np.uint8) for _ in range(3)]
+    c420 = [np.zeros((H // 2, st), np.uint8) for _ in range(3)]
+    for p in c422[1:] + c420[1:]:
+        p[:, :cw] = rng.integers(0, 256, (p.shape[0], cw), dtype=np.uint8)
+    out["c422_u"], out["c422_v"], out["c420_u"], out["c420_v"] = c422[1], c422[2], c420[1], c420[2]
+    for cl in (0, 1):
+        d = [np.zeros((H // 2, st), np.uint8) for _ in range(3)]
+        r.ref_halve_chroma(T.planes_arg(*c422), cw, H, T.strides_arg(*c422), T.strides_arg(*d), T.planes_arg(*d), cl)
+        out["halve_cl%d_u" % cl], out["halve_cl%d_v" % cl] = d[1], d[2]
+        d = [np.zeros((H, st), np.uint8) for _ in range(3)]
+        r.ref_double_chroma(T.planes_arg(*c420), cw, H // 2, T.strides_arg(*c420), T.strides_arg(*d), T.planes_arg(*d), cl)
+        out["double_cl%d_u" % cl], out["double_cl%d_v" % cl] = d[1], d[2]
+    wm = W // 2
+    m = T.make_packed(rng, wm, H, 4)
+    out["mpx_src"] = m
+    dense = np.ascontiguousarray(m[:, :wm * 4])
+    for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
+        d = [np.zeros((H, W), np.uint8), np.zeros((H, wm), np.uint8), np.zeros((H, wm), np.uint8)]
+        r.ref_packed422_to_yuv422p(fmt, T.ptr(dense), wm, H, T.planes_arg(*d))
+        for k, pn in enumerate("yuv"):
+            out["%s_to_yuv422p_%s" % (nm, pn)] = d[k]
+        d = [np.zeros((H, T.rowstride(W, 1)), np.uint8) for _ in range(4)]
+        r.ref_packed422_to_yuv444p(fmt, T.ptr(m), wm, H, m.strides[0], T.strides_arg(*d), T.planes_arg(*d), 1)
+        for k, pn in enumerate("yuva"):
+            out["%s_to_yuva4444p_%s" % (nm, pn)] = d[k]
+        for aa in (0, 1):
+            d8 = np.zeros((H, T.rowstride(W, 4 if aa else 3)), np.uint8)
+            r.ref_packed422_to_yuv888(fmt, T.ptr(m), wm, H, m.strides[0], d8.strides[0], T.ptr(d8), aa)
+            out["%s_to_yuv888_a%d" % (nm, aa)] = d8
+    sw = m.copy()
+    r.ref_swab(T.ptr(sw), wm, H, sw.strides[0])
+    out["swab"] = sw
+    np.savez_compressed(os.path.join(HERE, "ref_vectors_yuv.npz"), **out)
+    print("wrote", os.path.join(HERE, "ref_vectors_yuv.npz"), len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

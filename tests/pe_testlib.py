@@ -68,6 +68,17 @@ _ORACLE_PROTOS = {
     "pe_or_resize_packed": [VP, I, I, I, VP, I, I, I, I],
     "pe_or_resize_filter": [I, I, I, VP, VP, I],
     "pe_or_letterbox_packed": [VP, I, I, I, VP, I, I, I, I],
+    "pe_or_yuv444p_to_rgb": [VP, I, I, I, VP, I, I, I, I, I, I],
+    "pe_or_combine_planes": [VP, I, I, I, VP, I, I, I],
+    "pe_or_split_planes": [VP, I, I, I, VP, VP, I, I],
+    "pe_or_halve_chroma": [VP, VP, I, I, VP, VP, I],
+    "pe_or_double_chroma": [VP, VP, I, I, VP, VP, I],
+    "pe_or_packed422_to_yuv422p": [I, VP, I, I, I, VP, VP, I],
+    "pe_or_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
+    "pe_or_packed422_to_yuv888": [I, VP, I, I, I, VP, I, I],
+    "pe_or_swab": [VP, I, I, I],
+    "pe_or_yy_table": [I, VP],
+    "pe_or_switch_clamping_plane": [VP, L, I, I],
 }
 
 _REF_PROTOS = {
@@ -93,6 +104,14 @@ _REF_PROTOS = {
     "ref_rgb_to_packed422": [I, VP, I, I, I, I, VP, I, I, I, I, I],
     "ref_alpha_premult": [VP, I, I, I, I, I, I, VP],
     "ref_gamma_apply": [VP, I, I, I, I, I, I, VP],
+    "ref_combineplanes": [VP, I, I, I, I, VP, I, I],
+    "ref_splitplanes": [VP, I, I, I, VP, VP, I, I],
+    "ref_halve_chroma": [VP, I, I, VP, VP, VP, I],
+    "ref_double_chroma": [VP, I, I, VP, VP, VP, I],
+    "ref_packed422_to_yuv422p": [I, VP, I, I, VP],
+    "ref_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
+    "ref_packed422_to_yuv888": [I, VP, I, I, I, I, VP, I],
+    "ref_swab": [VP, I, I, I],
 }
 
 

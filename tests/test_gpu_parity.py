@@ -461,6 +461,214 @@ def test_convert_crossfade_batch_shared_operand(eng):
     assert (good.palette, bad.palette, bad.width) == (1, 522, 64)
 
 
+# ------------------------------------------------------------------------------------------------ YUV <-> YUV family
+
+def _planes444(rng, w, h, n, lo=0, hi=256):
+    st = T.rowstride(w, 1)
+    out = []
+    for _ in range(n):
+        a = np.zeros((h, st), np.uint8)
+        a[:, :w] = rng.integers(lo, hi, (h, w), dtype=np.uint8)
+        out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("size", [(64, 12), (37, 5), (1920, 1080), (3, 2)])
+def test_yuv444p_to_rgb_and_packed_yuv(eng, size):
+    """YUV444P / YUVA4444P -> the five RGB palettes (convert_yuv_planar_to_*_frame), -> YUV888 / YUVA8888 (combineplanes) and back
+    (splitplanes), YUV444P <-> YUVA4444P.  The layers carry subspace YUV (0), what convert_layer_palette asks for: a layer
+    tagged YCbCr would be sent through RGB first (colourspace.c:12241-12262)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(80 + w)
+    for ipal, cl in itertools.product((544, 545), (0, 1)):
+        ia = int(ipal == 545)
+        pl = _planes444(rng, w, h, 4 if ia else 3)
+        pl4 = pl + ([np.zeros_like(pl[0])] if not ia else [])
+        for opal in (1, 2, 3, 4, 5):
+            order, oa = {1: (0, 0), 2: (1, 0), 3: (0, 1), 4: (1, 1), 5: (2, 1)}[opal]
+            ps = 4 if oa else 3
+            exp = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+            o.pe_or_yuv444p_to_rgb(T.planes_arg(*pl4), pl[0].strides[0], w, h, T.ptr(exp), exp.strides[0], order, ia, oa, cl, T.Q_HIGH)
+            lay = lb.Layer.from_host(eng, ipal, w, h, pl, yuv_clamping=cl, yuv_subspace=0)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.palette, lay.width, lay.height) == (opal, w, h)
+            assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), (w, h, ipal, cl, opal)
+        for opal in (588, 589):
+            oa = int(opal == 589)
+            ps = 4 if oa else 3
+            exp = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+            o.pe_or_combine_planes(T.planes_arg(*pl4), pl[0].strides[0], w, h, T.ptr(exp), exp.strides[0], ia, oa)
+            lay = lb.Layer.from_host(eng, ipal, w, h, pl, yuv_clamping=cl, yuv_subspace=0)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.palette, lay.yuv_clamping) == (opal, cl)
+            got = lay.to_host()[0]
+            assert (payload(got, w, ps) == payload(exp, w, ps)).all(), (w, h, ipal, cl, opal)
+            # and back into planes
+            for bpal in (544, 545):
+                ba = int(bpal == 545)
+                st = T.rowstride(w, 1)
+                ep = [np.zeros((h, st), np.uint8) for _ in range(4)]
+                o.pe_or_split_planes(T.ptr(exp), exp.strides[0], w, h, T.planes_arg(*ep), T.strides_arg(*ep), oa, ba)
+                lay2 = packed_layer(eng, opal, w, h, exp, yuv_clamping=cl, yuv_subspace=0)
+                assert lb.convert_layer_palette(lay2, bpal, cl)
+                g2 = lay2.to_host()
+                assert len(g2) == (4 if ba else 3)
+                for k, g in enumerate(g2):
+                    assert (g[:, :w] == ep[k][:, :w]).all(), (w, h, opal, bpal, k)
+        # YUV444P <-> YUVA4444P
+        opal = 544 if ia else 545
+        lay = lb.Layer.from_host(eng, ipal, w, h, pl, yuv_clamping=cl, yuv_subspace=0)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        got = lay.to_host()
+        assert len(got) == (3 if ia else 4)
+        for k in range(3):
+            assert (got[k][:, :w] == pl[k][:, :w]).all()
+        if not ia:
+            assert (got[3][:, :w] == 255).all()
+
+
+@pytest.mark.parametrize("size", [(64, 12), (38, 6), (1920, 1080), (2, 2)])
+def test_yuv420p_yuv422p_chroma_resampling(eng, size):
+    """YUV420P -> YUV422P (convert_double_chroma) and YUV422P -> YUV420P (convert_halve_chroma over the whole plane)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(90 + w)
+    for cl in (0, 1):
+        y, u, v = T.make_yuv_planar(rng, w, h, False, cl == 0)
+        st = T.rowstride(w, 1)
+        e = [np.zeros((h, st), np.uint8), np.zeros((h, st >> 1), np.uint8), np.zeros((h, st >> 1), np.uint8)]
+        o.pe_or_double_chroma(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w >> 1, h >> 1, T.planes_arg(*e), T.strides_arg(*e), cl)
+        lay = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_clamping=cl, yuv_subspace=0)
+        assert lb.convert_layer_palette(lay, 522, cl)
+        assert (lay.palette, lay.width, lay.height, lay.yuv_clamping) == (522, w, h, cl)
+        got = lay.to_host()
+        assert (got[0][:, :w] == y[:, :w]).all()
+        for k in (1, 2):
+            assert (got[k][:, :w >> 1] == e[k][:, :w >> 1]).all(), ("double", w, h, cl, k)
+        # and down again
+        y2, u2, v2 = T.make_yuv_planar(rng, w, h, True, cl == 0)
+        e = [np.zeros((h, st), np.uint8), np.zeros((h >> 1, st >> 1), np.uint8), np.zeros((h >> 1, st >> 1), np.uint8)]
+        o.pe_or_halve_chroma(T.planes_arg(y2, u2, v2), T.strides_arg(y2, u2, v2), w >> 1, h, T.planes_arg(*e), T.strides_arg(*e), cl)
+        lay = lb.Layer.from_host(eng, 522, w, h, [y2, u2, v2], yuv_clamping=cl, yuv_subspace=0)
+        assert lb.convert_layer_palette(lay, 512, cl)
+        assert (lay.palette, lay.width, lay.height) == (512, w, h)
+        got = lay.to_host()
+        assert (got[0][:, :w] == y2[:, :w]).all()
+        for k in (1, 2):
+            assert (got[k][:, :w >> 1] == e[k][:, :w >> 1]).all(), ("halve", w, h, cl, k)
+
+
+@pytest.mark.parametrize("size", [(64, 6), (34, 5), (1920, 1080), (2, 1)])
+def test_packed422_to_planar_packed444_and_swab(eng, size):
+    """UYVY / YUYV -> YUV422P (with and without the reference's never-advanced source pointer), -> YUV444P / YUVA4444P,
+    -> YUV888 / YUVA8888, UYVY <-> YUYV in place"""
+    o = T.oracle()
+    w, h = size
+    wm = w >> 1
+    rng = np.random.default_rng(100 + w)
+    e_nq = lb.Engine(ref_quirks=False)
+    for ipal in (564, 565):
+        fmt = ipal - 564
+        src = T.make_packed(rng, wm, h, 4)
+        for quirks, en in ((1, eng), (0, e_nq)):
+            st = T.rowstride(w, 1)
+            ep = [np.zeros((h, st), np.uint8), np.zeros((h, st >> 1), np.uint8), np.zeros((h, st >> 1), np.uint8)]
+            o.pe_or_packed422_to_yuv422p(fmt, T.ptr(src), src.strides[0], wm, h, T.planes_arg(*ep), T.strides_arg(*ep), quirks)
+            lay = packed_layer(en, ipal, w, h, src, yuv_subspace=0)
+            assert lb.convert_layer_palette(lay, 522, 0)
+            assert (lay.palette, lay.width, lay.height) == (522, w, h)
+            got = lay.to_host()
+            assert (got[0][:, :w] == ep[0][:, :w]).all(), ("422p y", w, h, ipal, quirks)
+            for k in (1, 2):
+                assert (got[k][:, :wm] == ep[k][:, :wm]).all(), ("422p", w, h, ipal, quirks, k)
+        for opal in (544, 545):
+            aa = int(opal == 545)
+            st = T.rowstride(w, 1)
+            ep = [np.zeros((h, st), np.uint8) for _ in range(4)]
+            o.pe_or_packed422_to_yuv444p(fmt, T.ptr(src), src.strides[0], wm, h, T.planes_arg(*ep), T.strides_arg(*ep), aa)
+            lay = packed_layer(eng, ipal, w, h, src, yuv_subspace=0)
+            assert lb.convert_layer_palette(lay, opal, 0)
+            got = lay.to_host()
+            assert len(got) == 3 + aa
+            for k, g in enumerate(got):
+                assert (g[:, :w] == ep[k][:, :w]).all(), ("444p", w, h, ipal, opal, k)
+        for opal in (588, 589):
+            aa = int(opal == 589)
+            ps = 4 if aa else 3
+            exp = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+            o.pe_or_packed422_to_yuv888(fmt, T.ptr(src), src.strides[0], wm, h, T.ptr(exp), exp.strides[0], aa)
+            lay = packed_layer(eng, ipal, w, h, src, yuv_subspace=0)
+            assert lb.convert_layer_palette(lay, opal, 0)
+            assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), ("888", w, h, ipal, opal)
+        exp = src.copy()
+        o.pe_or_swab(T.ptr(exp), exp.strides[0], wm, h)
+        lay = packed_layer(eng, ipal, w, h, src, yuv_subspace=0)
+        before = eng.launch_count
+        assert lb.convert_layer_palette(lay, 565 if ipal == 564 else 564, 0)
+        assert eng.launch_count - before == 1
+        assert lay.palette == (565 if ipal == 564 else 564)
+        assert (payload(lay.to_host()[0], wm, 4) == payload(exp, wm, 4)).all(), ("swab", w, h, ipal)
+
+
+def test_yuv_clamping_switch(eng):
+    """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
+    every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""
+    o = T.oracle()
+    rng = np.random.default_rng(110)
+    w, h = 66, 10
+    ty = [np.zeros(256, np.uint8) for _ in range(4)]
+    for k in range(4):
+        o.pe_or_yy_table(k, T.ptr(ty[k]))
+    for icl in (0, 1):
+        ocl = 1 - icl
+        tY, tC = (ty[0], ty[1]) if icl == 0 else (ty[2], ty[3])
+        # planar
+        for pal, is422 in ((512, False), (522, True)):
+            y, u, v = T.make_yuv_planar(rng, w, h, is422, False)
+            lay = lb.Layer.from_host(eng, pal, w, h, [y, u, v], yuv_clamping=icl, yuv_subspace=1)
+            assert lb.convert_layer_palette_full(lay, pal, ocl, 0, 1, 0)
+            assert (lay.palette, lay.yuv_clamping) == (pal, ocl)
+            got = lay.to_host()
+            assert (got[0][:, :w] == tY[y[:, :w]]).all() and (got[1][:, :w >> 1] == tC[u[:, :w >> 1]]).all()
+            assert (got[2][:, :w >> 1] == tC[v[:, :w >> 1]]).all()
+        pl = _planes444(rng, w, h, 4)
+        lay = lb.Layer.from_host(eng, 545, w, h, pl, yuv_clamping=icl, yuv_subspace=1)
+        assert lb.convert_layer_palette_full(lay, 545, ocl, 0, 1, 0)
+        got = lay.to_host()
+        assert (got[0][:, :w] == tY[pl[0][:, :w]]).all() and (got[1][:, :w] == tC[pl[1][:, :w]]).all()
+        assert (got[2][:, :w] == tC[pl[2][:, :w]]).all() and (got[3][:, :w] == pl[3][:, :w]).all()
+        # packed: the oracle walks the plane densely, the same way the kernel does
+        for pal, ps, kind in ((588, 3, 2), (589, 4, 3), (564, 2, 4), (565, 2, 5)):
+            src = T.make_packed(rng, w if ps != 2 else w // 2, h, ps if ps != 2 else 4)
+            exp = src.copy()
+            o.pe_or_switch_clamping_plane(T.ptr(exp), exp.size, kind, int(icl == 0))
+            lay = packed_layer(eng, pal, w, h, src, yuv_clamping=icl, yuv_subspace=1)
+            assert lb.convert_layer_palette_full(lay, pal, ocl, 0, 1, 0)
+            assert lay.yuv_clamping == ocl
+            nb = w * ps
+            assert (lay.to_host()[0][:, :nb] == exp[:, :nb]).all(), (pal, icl)
+        # clamping switch + palette change in one call: YUV888 clamped -> YUV444P unclamped
+        # (the reference walks a YUV888 plane densely, Y U V Y U V ... across the row padding: with a rowstride that is not a
+        # multiple of 3 the tables are misapplied from row 1 on -- replicated under ref_quirks, per-row phase without)
+        src = T.make_packed(rng, w, h, 3)
+        sw = src.copy()
+        o.pe_or_switch_clamping_plane(T.ptr(sw), sw.size, 2, int(icl == 0))
+        lay = packed_layer(eng, 588, w, h, src, yuv_clamping=icl, yuv_subspace=1)
+        assert lb.convert_layer_palette_full(lay, 544, ocl, 0, 1, 0)
+        assert (lay.palette, lay.yuv_clamping) == (544, ocl)
+        got = lay.to_host()
+        px = sw[:, :w * 3].reshape(h, w, 3)
+        for k in range(3):
+            assert (got[k][:, :w] == px[:, :, k]).all(), k
+        e_nq = lb.Engine(ref_quirks=False)
+        lay = packed_layer(e_nq, 588, w, h, src, yuv_clamping=icl, yuv_subspace=1)
+        assert lb.convert_layer_palette_full(lay, 588, ocl, 0, 1, 0)
+        px, got = src[:, :w * 3].reshape(h, w, 3), lay.to_host()[0][:, :w * 3].reshape(h, w, 3)
+        assert (got[:, :, 0] == tY[px[:, :, 0]]).all() and (got[:, :, 1] == tC[px[:, :, 1]]).all() and (got[:, :, 2] == tC[px[:, :, 2]]).all()
+        e_nq.close()
+
+
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
     src = T.make_packed(rng, 32, 8, 4)

@@ -494,3 +494,161 @@ def test_avg_tables_and_rgb_to_planar420_422_match_reference():
         r.ref_rgb_to_yuv420(T.ptr(src), w, h, src.strides[0], strides, T.planes_arg(*pb), order, is422, in_alpha, sub, cl)
         for k in range(3):
             assert (pa[k] == pb[k]).all(), ("yuv420p", w, h, order, in_alpha, is422, cl, sub, k)
+
+
+# ---- YUV <-> YUV family ------------------------------------------------------------------------------
+
+def _planes444(rng, w, h, n, stride=None):
+    stride = stride or T.rowstride(w, 1)
+    out = []
+    for _ in range(n):
+        a = np.zeros((h, stride), np.uint8)
+        a[:, :w] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out.append(a)
+    return out
+
+
+def test_yuv444p_to_rgb_matches_reference():
+    """convert_yuv_planar_to_{rgb,bgr}_frame: orders x alpha in / out x clamping.  Excluded (X): BGR24 -- the reference walks
+    4 bytes per BGR24 pixel (colourspace.c:7313) and runs past its buffer; ARGB32 -- the row advance subtracts the width from
+    the OUTPUT stride twice and never from the input stride (:7471-7472), rows after the first are read and written askew"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(70)
+    for (w, h), order, in_alpha, out_alpha, cl in itertools.product(((64, 6), (37, 5)), (0, 1, 2), (0, 1), (0, 1), (0, 1)):
+        if order == 2 or (order == 1 and not out_alpha):
+            continue  # X (see docstring)
+        pl = _planes444(rng, w, h, 4)
+        ps = 4 if out_alpha else 3
+        ors = T.rowstride(w, ps)
+        a, b = np.zeros((h, ors), np.uint8), np.zeros((h, ors), np.uint8)
+        o.pe_or_yuv444p_to_rgb(T.planes_arg(*pl), pl[0].strides[0], w, h, T.ptr(a), ors, order, in_alpha, out_alpha, cl, T.Q_HIGH)
+        r.ref_yuv444p_to_rgb(T.planes_arg(*pl), w, h, pl[0].strides[0], ors, T.ptr(b), order, in_alpha, out_alpha, cl)
+        assert (a == b).all(), (w, h, order, in_alpha, out_alpha, cl)
+
+
+def test_combine_and_split_planes_match_reference():
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(71)
+    for (w, h, padded), ia, oa in itertools.product(((64, 5, False), (37, 4, True), (33, 3, False)), (0, 1), (0, 1)):
+        pl = _planes444(rng, w, h, 4, stride=None if padded else w)
+        ops = 4 if oa else 3
+        ors = T.rowstride(w, ops) if padded else w * ops
+        a, b = np.zeros((h, ors), np.uint8), np.zeros((h, ors), np.uint8)
+        o.pe_or_combine_planes(T.planes_arg(*pl), pl[0].strides[0], w, h, T.ptr(a), ors, ia, oa)
+        if padded and ia and oa:
+            # X: on padded planes the reference never advances its alpha pointer by the row padding (colourspace.c:7625-7637)
+            for k in range(4):
+                assert (a[:, :w * 4].reshape(h, w, 4)[:, :, k] == pl[k][:, :w]).all()
+        else:
+            r.ref_combineplanes(T.planes_arg(*pl), w, h, pl[0].strides[0], ors, T.ptr(b), ia, oa)
+            assert (a == b).all(), ("combine", w, h, padded, ia, oa)
+        # and back: packed (ia = source alpha) -> planes (oa = destination alpha)
+        ips = 4 if ia else 3
+        irs = T.rowstride(w, ips) if padded else w * ips
+        src = T.make_packed(rng, w, h, ips, stride=irs)
+        st = T.rowstride(w, 1) if padded else w
+        pa = [np.zeros((h, st), np.uint8) for _ in range(4)]
+        pb = [np.zeros((h, st), np.uint8) for _ in range(4)]
+        o.pe_or_split_planes(T.ptr(src), irs, w, h, T.planes_arg(*pa), T.strides_arg(*pa), ia, oa)
+        if oa or ia:
+            # X: with a destination alpha plane the reference advances that plane by (stride - width * ipsize) per row
+            # (colourspace.c:9233-9236: the width has already been multiplied) and writes before the buffer; with a source
+            # alpha and no destination alpha it never skips the source's 4th byte (:9238-9246).  The restatement is the
+            # evident intent, checked against numpy here
+            px = src[:, :w * ips].reshape(h, w, ips)
+            for k in range(3):
+                assert (pa[k][:, :w] == px[:, :, k]).all()
+            if oa:
+                assert (pa[3][:, :w] == (px[:, :, 3] if ia else 255)).all()
+            continue
+        r.ref_splitplanes(T.ptr(src), w, h, irs, T.strides_arg(*pb), T.planes_arg(*pb), ia, oa)
+        for k in range(3):
+            assert (pa[k] == pb[k]).all(), ("split", w, h, padded, ia, oa, k)
+
+
+def test_halve_and_double_chroma_match_reference():
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(72)
+    for (cw, ch), cl in itertools.product(((32, 8), (33, 7), (5, 2), (16, 1)), (0, 1)):
+        st = T.align_ceil(cw, 16)
+        src = [np.zeros((ch, st), np.uint8) for _ in range(3)]
+        for p in src[1:]:
+            p[:, :cw] = rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+        # halve: (ch + 1) // 2 rows out
+        da = [np.zeros(((ch + 1) // 2, st), np.uint8) for _ in range(3)]
+        db = [np.zeros(((ch + 1) // 2, st), np.uint8) for _ in range(3)]
+        o.pe_or_halve_chroma(T.planes_arg(*src), T.strides_arg(*src), cw, ch, T.planes_arg(*da), T.strides_arg(*da), cl)
+        r.ref_halve_chroma(T.planes_arg(*src), cw, ch, T.strides_arg(*src), T.strides_arg(*db), T.planes_arg(*db), cl)
+        for k in (1, 2):
+            assert (da[k] == db[k]).all(), ("halve", cw, ch, cl, k)
+        # double: 2 ch rows out
+        da = [np.zeros((2 * ch, st), np.uint8) for _ in range(3)]
+        db = [np.zeros((2 * ch, st), np.uint8) for _ in range(3)]
+        o.pe_or_double_chroma(T.planes_arg(*src), T.strides_arg(*src), cw, ch, T.planes_arg(*da), T.strides_arg(*da), cl)
+        r.ref_double_chroma(T.planes_arg(*src), cw, ch, T.strides_arg(*src), T.strides_arg(*db), T.planes_arg(*db), cl)
+        for k in (1, 2):
+            assert (da[k] == db[k]).all(), ("double", cw, ch, cl, k)
+
+
+def test_packed422_to_yuv_planar_and_yuv888_match_reference():
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(73)
+    for (wm, h), fmt in itertools.product(((32, 4), (17, 3)), (0, 1)):
+        irs = T.rowstride(wm, 4)
+        src = T.make_packed(rng, wm, h, 4, stride=irs)
+        # -> planar 4:2:2: the reference walks everything densely, so compare on unpadded buffers; its source pointer never
+        # advances (colourspace.c:8103): every sample is the first macropixel's -- quirks = 1
+        dense = np.ascontiguousarray(src[:, :wm * 4])
+        pa = [np.zeros((h, 2 * wm), np.uint8), np.zeros((h, wm), np.uint8), np.zeros((h, wm), np.uint8)]
+        pb = [np.zeros_like(p) for p in pa]
+        o.pe_or_packed422_to_yuv422p(fmt, T.ptr(dense), wm * 4, wm, h, T.planes_arg(*pa), T.strides_arg(*pa), 1)
+        r.ref_packed422_to_yuv422p(fmt, T.ptr(dense), wm, h, T.planes_arg(*pb))
+        for k in range(3):
+            assert (pa[k] == pb[k]).all(), ("422p", wm, h, fmt, k)
+        # quirks = 0: the intended per-macropixel split
+        o.pe_or_packed422_to_yuv422p(fmt, T.ptr(dense), wm * 4, wm, h, T.planes_arg(*pa), T.strides_arg(*pa), 0)
+        yo, uo = (1, 0) if fmt == 0 else (0, 1)
+        assert (pa[0] == dense[:, yo::2]).all() and (pa[1] == dense[:, uo::4]).all() and (pa[2] == dense[:, uo + 2::4]).all()
+        # -> planar 4:4:4 (+ alpha)
+        for aa in (0, 1):
+            st = T.rowstride(2 * wm, 1)
+            pa = [np.zeros((h, st), np.uint8) for _ in range(4)]
+            pb = [np.zeros((h, st), np.uint8) for _ in range(4)]
+            o.pe_or_packed422_to_yuv444p(fmt, T.ptr(src), irs, wm, h, T.planes_arg(*pa), T.strides_arg(*pa), aa)
+            r.ref_packed422_to_yuv444p(fmt, T.ptr(src), wm, h, irs, T.strides_arg(*pb), T.planes_arg(*pb), aa)
+            for k in range(4):
+                assert (pa[k] == pb[k]).all(), ("444p", wm, h, fmt, aa, k)
+            ors = T.rowstride(2 * wm, 4 if aa else 3)
+            a, b = np.zeros((h, ors), np.uint8), np.zeros((h, ors), np.uint8)
+            o.pe_or_packed422_to_yuv888(fmt, T.ptr(src), irs, wm, h, T.ptr(a), ors, aa)
+            r.ref_packed422_to_yuv888(fmt, T.ptr(src), wm, h, irs, ors, T.ptr(b), aa)
+            assert (a == b).all(), ("888", wm, h, fmt, aa)
+        # UYVY <-> YUYV
+        a, b = src.copy(), src.copy()
+        o.pe_or_swab(T.ptr(a), irs, wm, h)
+        r.ref_swab(T.ptr(b), wm, h, irs)
+        assert (a == b).all(), ("swab", wm, h)
+
+
+def test_clamping_tables_match_reference():
+    """init_YUV_to_YUV_tables; the frame walk of switch_yuv_clamping_and_subspace is a LUT over every byte and is restated from
+    the source (it needs a weed_layer_t, which the slices do not build)"""
+    o, r = T.oracle(), T.ref()
+    for w in range(4):
+        a, b = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+        o.pe_or_yy_table(w, T.ptr(a))
+        assert r.ref_get_yy_table(w, T.ptr(b)) == 0
+        assert (a == b).all(), w
+    rng = np.random.default_rng(74)
+    ty, tc = np.zeros(256, np.uint8), np.zeros(256, np.uint8)
+    o.pe_or_yy_table(0, T.ptr(ty)); o.pe_or_yy_table(1, T.ptr(tc))
+    buf = rng.integers(0, 256, 96, dtype=np.uint8)
+    for kind, luma_mask in ((0, np.ones(96, bool)), (1, np.zeros(96, bool)), (2, np.arange(96) % 3 == 0), (4, np.arange(96) % 2 == 1),
+                            (5, np.arange(96) % 2 == 0)):
+        x = buf.copy()
+        o.pe_or_switch_clamping_plane(T.ptr(x), 96, kind, 1)
+        assert (x == np.where(luma_mask, ty[buf], tc[buf])).all(), kind
+    x = buf.copy()
+    o.pe_or_switch_clamping_plane(T.ptr(x), 96, 3, 1)
+    i = np.arange(96)
+    assert (x == np.where(i % 4 == 3, buf, np.where(i % 4 == 0, ty[buf], tc[buf]))).all()
