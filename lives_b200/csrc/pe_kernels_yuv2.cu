@@ -354,7 +354,7 @@ struct YuvFrameList {
 };
 
 struct MarchPre {
-  uint32_t yA, yB, u0, u1, v0, v1, u2, u3, v2, v3, vf;   // 4:2:0: chroma row k in u0 u1 v0 v1; 4:2:2: rows 2k-1 / 2k in (u0 u1 v0 v1) / (u2 u3 v2 v3)
+  uint32_t yA, yB, u0, u1, v0, v1, u2, u3, v2, v3, vf, sd;   // 4:2:0: chroma row k in u0 u1 v0 v1; 4:2:2: rows 2k-1 / 2k in (u0 u1 v0 v1) / (u2 u3 v2 v3)
 };
 struct MarchCarry {
   uint32_t DUr, MUr, DVr, MVr, DUl, MUl, DVl, MVl, QUL, aV;
@@ -475,6 +475,9 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
         const uint8_t *ur = up + (size_t)rs_u * (uint32_t)(2 * k - 1), *vr = vp + (size_t)rs_v * (uint32_t)(2 * k - 1);
         p.u0 = ld_u32nc(ur); p.u1 = ld_u32nc(ur + 4); p.u2 = ld_u32nc(ur + rs_u); p.u3 = ld_u32nc(ur + rs_u + 4);
         p.v0 = ld_u32nc(vr); p.v1 = ld_u32nc(vr + 4); p.v2 = ld_u32nc(vr + rs_v); p.v3 = ld_u32nc(vr + rs_v + 4);
+        if (seed_lane)  // the seed slip (:3600): columns <= 0 of row i are column 0 of chroma row (i >> 1) = k - 1 / k
+          p.sd = ld_u8nc(Fu + (size_t)rs_u * (uint32_t)(k - 1)) | (ld_u8nc(Fv + (size_t)rs_v * (uint32_t)(k - 1)) << 8) |
+                 (ld_u8nc(Fu + (size_t)rs_u * (uint32_t)k) << 16) | (ld_u8nc(Fv + (size_t)rs_v * (uint32_t)k) << 24);
       } else {
         const uint8_t *ur = up + (size_t)rs_u * (uint32_t)k, *vr = vp + (size_t)rs_v * (uint32_t)k;
         p.u0 = ld_u32nc(ur); p.u1 = ld_u32nc(ur + 4);
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
     const int k_first = (ra + 1) >> 1, k_last = rb >> 1;
     MarchPre pre;
     MarchCarry C;
-    pre.yA = pre.yB = pre.u0 = pre.u1 = pre.v0 = pre.v1 = pre.u2 = pre.u3 = pre.v2 = pre.v3 = pre.vf = 0u;
+    pre.yA = pre.yB = pre.u0 = pre.u1 = pre.v0 = pre.v1 = pre.u2 = pre.u3 = pre.v2 = pre.v3 = pre.vf = pre.sd = 0u;
     C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
     bool carry_ok = false;
     auto is_fast = [&](int k) { return k >= 1 && k <= k_fast_max; };
@@ -515,12 +518,16 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
         if (stB) load_op(rowB, opB);
         uint32_t pa[4], pb[4];
         if (IS422) {
-          if (seed_lane) {
-            single(rowA, rowA, rowA >> 1, pa);
-            single(rowB, rowB, rowB >> 1, pb);
-          } else {
-            const RowC UA = unpack_row(pre.u0, pre.u1, sel), VA = unpack_row(pre.v0, pre.v1, sel);
-            const RowC UB = unpack_row(pre.u2, pre.u3, sel), VB = unpack_row(pre.v2, pre.v3, sel);
+          {
+            // the seed lane (column 0 under the seed slip) stays on the fast path: sample 0 of its chroma words is replaced by the
+            // seed sample, which column -1 then replicates through the lane's PRMT selector like any frame edge
+            uint32_t u0 = pre.u0, v0 = pre.v0, u2 = pre.u2, v2 = pre.v2;
+            if (seed_lane) {
+              u0 = __byte_perm(u0, pre.sd, 0x3214); v0 = __byte_perm(v0, pre.sd, 0x3215);
+              u2 = __byte_perm(u2, pre.sd, 0x3216); v2 = __byte_perm(v2, pre.sd, 0x3217);
+            }
+            const RowC UA = unpack_row(u0, pre.u1, sel), VA = unpack_row(v0, pre.v1, sel);
+            const RowC UB = unpack_row(u2, pre.u3, sel), VB = unpack_row(v2, pre.v3, sel);
             const uint32_t LUA = UA.a + UA.b, RUA = UA.a + UA.c, LVA = VA.a + VA.b, RVA = VA.a + VA.c;
             const uint32_t LUB = UB.a + UB.b, RUB = UB.a + UB.c, LVB = VB.a + VB.b, RVB = VB.a + VB.c;
 #pragma unroll
