@@ -322,13 +322,23 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host buffers through the C-ABI drop-in, H2D + kernel + D2H timed (per rank, frames independent)
     hframes = host_frames(4, seed0=20 + 100 * rank)
     pinned = []
+    def pinned_block(nbytes):
+        p = lb._capi.lib().pe_host_alloc(nbytes)
+        if not p:
+            raise SystemExit("pinned host allocation failed")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
     for (y, u, v, bg) in hframes:
-        bufs = []
-        for a in (y, u, v, bg, np.zeros((FH, FW * 4), np.uint8)):
-            p = lb._capi.lib().pe_host_alloc(a.nbytes)
-            if not p:
-                raise SystemExit("pinned host allocation failed")
-            arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(a.nbytes,)).reshape(a.shape)
+        # the three planes of the planar frame sit back to back in one allocation, the way LiVES allocates planar pixel data
+        # (create_empty_pixel_data, WEED_LEAF_HOST_PIXEL_DATA_CONTIGUOUS): the drop-in then moves them in one copy
+        blk, off, bufs = pinned_block(y.nbytes + u.nbytes + v.nbytes), 0, []
+        for a in (y, u, v):
+            arr = blk[off:off + a.nbytes].reshape(a.shape)
+            arr[...] = a
+            bufs.append(arr)
+            off += a.nbytes
+        for a in (bg, np.zeros((FH, FW * 4), np.uint8)):
+            arr = pinned_block(a.nbytes).reshape(a.shape)
             arr[...] = a
             bufs.append(arr)
         pinned.append(bufs)

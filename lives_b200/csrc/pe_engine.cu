@@ -2092,18 +2092,20 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
     if (!fg[i] || !bg[i] || !out[i] || !fg[i]->planes[0] || !bg[i]->planes[0] || !out[i]->planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
   std::lock_guard<std::mutex> lk(e->mu);
   PE_CUDA(cudaSetDevice(e->device));
-  constexpr int NS = 3;
+  constexpr int NS_MAX = 6;
+  int NS = 3;  // frames in flight: one uploading, one computing, one downloading
+  if (const char *sv = getenv("PE_PIPE_SLOTS")) { NS = atoi(sv); if (NS < 2) NS = 2; if (NS > NS_MAX) NS = NS_MAX; }
   if (!e->h2d_stream) {
     PE_CUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
     PE_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < NS; k++) {
+    for (int k = 0; k < NS_MAX; k++) {
       PE_CUDA(cudaEventCreateWithFlags(&e->pipe_up[k], cudaEventDisableTiming));
       PE_CUDA(cudaEventCreateWithFlags(&e->pipe_comp[k], cudaEventDisableTiming));
       PE_CUDA(cudaEventCreateWithFlags(&e->pipe_free[k], cudaEventDisableTiming));
     }
   }
   // device slots
-  pe_frame slots[NS][3];
+  pe_frame slots[NS_MAX][3];
   const int ns = n < NS ? n : NS;
   int rc = PE_OK;
   auto release = [&]() { for (int k = 0; k < ns; k++) for (int j = 0; j < 3; j++) frame_release_pixels(&slots[k][j]); };
@@ -2124,10 +2126,25 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
     for (int p = 0; p < dev.d.nplanes; p++) {
       const int wbytes = plane_row_bytes(dev.d, p);
       if (host.rowstrides[p] == dev.d.rowstrides[p] && dev.plane_heights[p] > 0 && !copy2d_only) {  // same pitch on both sides: one linear copy
-        const size_t nbytes = (size_t)dev.d.rowstrides[p] * (dev.plane_heights[p] - 1) + wbytes;
+        size_t nbytes = (size_t)dev.d.rowstrides[p] * (dev.plane_heights[p] - 1) + wbytes;
+        // planes that follow each other without a gap on BOTH sides (LiVES allocates planar frames contiguously,
+        // WEED_LEAF_HOST_PIXEL_DATA_CONTIGUOUS; ours are one pool block) travel in the same copy
+        int q = p;
+        while (q + 1 < dev.d.nplanes && host.rowstrides[q + 1] == dev.d.rowstrides[q + 1] && dev.plane_heights[q + 1] > 0) {
+          const size_t span = (size_t)dev.d.rowstrides[q] * dev.plane_heights[q];
+          if ((const uint8_t *)host.planes[q + 1] != (const uint8_t *)host.planes[q] + span ||
+              (const uint8_t *)dev.d.planes[q + 1] != (const uint8_t *)dev.d.planes[q] + span)
+            break;
+          q++;
+        }
+        if (q > p) {
+          nbytes = (size_t)((const uint8_t *)dev.d.planes[q] - (const uint8_t *)dev.d.planes[p]) +
+                   (size_t)dev.d.rowstrides[q] * (dev.plane_heights[q] - 1) + plane_row_bytes(dev.d, q);
+        }
         cudaError_t ce1 = to_device ? cudaMemcpyAsync(dev.d.planes[p], host.planes[p], nbytes, cudaMemcpyHostToDevice, st)
                                     : cudaMemcpyAsync(host.planes[p], dev.d.planes[p], nbytes, cudaMemcpyDeviceToHost, st);
         if (ce1 != cudaSuccess) return ce1;
+        p = q;
         continue;
       }
       cudaError_t ce = to_device ? cudaMemcpy2DAsync(dev.d.planes[p], dev.d.rowstrides[p], host.planes[p], host.rowstrides[p], wbytes,

@@ -73,7 +73,7 @@ struct pe_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t pipe_up[3] = {}, pipe_comp[3] = {}, pipe_free[3] = {};
+  cudaEvent_t pipe_up[6] = {}, pipe_comp[6] = {}, pipe_free[6] = {};
   std::mutex mu;  // the reference calls these entry points from several proc-threads (different layers)
 
   pe::ConvTables conv_host[2][2];    // [clamping][bt709]
