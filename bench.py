@@ -447,11 +447,18 @@ def run_secondary(args):
         fg = [wrap(3, W, H, [rnd(H, W * 4)]) for _ in range(n)]
         out = [wrap(3, W, H, [rnd(H, W * 4)], gamma_type=G_LINEAR) for _ in range(n)]
 
+        per_frame = os.environ.get("PE_CFG3_PER_FRAME") is not None
+
         def step():
             for i in range(n):
                 out[i].gamma_type = G_LINEAR
-                lb.compositor_gamma(out[i], [fg[i], bg[i]], [0.5, 1.0], G_SRGB)
-        frames, algo, name = n, 3 * W * H * 4, "cfg3: %d x 4K RGBA32 alpha-over(0.5) + gamma LUT8 (pe_fx_compositor_gamma, one kernel / frame)" % n
+            if per_frame:
+                for i in range(n):
+                    lb.compositor_gamma(out[i], [fg[i], bg[i]], [0.5, 1.0], G_SRGB)
+            else:
+                assert lb.compositor_gamma_batch(out, [[fg[i], bg[i]] for i in range(n)], [0.5, 1.0], G_SRGB) == n
+        frames, algo, name = n, 3 * W * H * 4, "cfg3: %d x 4K RGBA32 alpha-over(0.5) + gamma LUT8 (%s)" % (
+            n, "pe_fx_compositor_gamma, one kernel / frame" if per_frame else "pe_fx_compositor_gamma_batch, one kernel / %d frames" % n)
     elif wl == "cfg2":  # 1080p YUV420P -> RGBA32 -> 1280x720 (unfused convert + resize)
         W, H, n = 1920, 1080, 16
         src = [(rnd(H, W, 16, 236), rnd(H // 2, W // 2, 16, 241), rnd(H // 2, W // 2, 16, 241)) for _ in range(n)]

@@ -194,6 +194,11 @@ int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *l
  * src/nodemodel.c:1119-1333) with the LUT folded into the last paint: same bytes, one pass less over the frame */
 int pe_fx_compositor_gamma(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
                            int nlayers, const int bgcol[3], int gamma_to);
+/* the same for n independent output frames (render-to-disk, src/events.c:4239-4253): layers[i * nlayers + z] is layer z of frame
+ * i, alpha[z] the per-layer alpha shared by all frames.  Integer paints (alpha = k / 256) of same-shaped frames leave as one
+ * launch per 32 frames and paint pass.  Returns the number of frames composited. */
+int pe_fx_compositor_gamma_batch(pe_engine_t *e, int n, pe_frame_t *const *outs, const pe_frame_t *const *layers,
+                                 const double *alpha, int nlayers, const int bgcol[3], int gamma_to);
 /* batches of independent frames (render-to-disk / multitrack): one launch, frames spread over the SMs */
 int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const pe_frame_t *const *in1,
                              const pe_frame_t *const *in2, pe_frame_t *const *out, int blend_factor);

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "pe_fx_multi_blend": (I, [VP, I, VP, VP, VP, I]),
     "pe_fx_compositor": (I, [VP, VP, PVP, C.POINTER(D), I, PI]),
     "pe_fx_compositor_gamma": (I, [VP, VP, PVP, C.POINTER(D), I, PI, I]),
+    "pe_fx_compositor_gamma_batch": (I, [VP, I, PVP, PVP, C.POINTER(D), I, PI, I]),
     "pe_fx_simple_blend_batch": (I, [VP, I, I, PVP, PVP, PVP, I]),
     "pe_fused_convert_letterbox_over_gamma": (I, [VP, VP, VP, VP, I, I, D, I, I]),
     "pe_fused_convert_letterbox_over_gamma_batch": (I, [VP, I, PVP, PVP, PVP, I, I, D, I, I]),

@@ -1691,6 +1691,37 @@ namespace {
 //   * the background fill is skipped when an opaque (alpha == 1) layer covers it -- the fill is dead;
 //   * painting that opaque layer is not a pass of its own: the next paint reads it as its background;
 //   * alpha = k / 256 uses the integer blend (exact, see k_alpha_over_arith), other alphas the 64 KB [bg][fg] table.
+// launch the integer alpha-over paints a compositor batch has queued.  Jobs are taken in order; a run of jobs with the same shape
+// and parameters leaves as one launch as long as none of them reads what an earlier job of the run writes (the second paint of
+// a frame reads the first one's output: it starts a new run)
+int flush_over_pending(pe_engine *e) {
+  std::vector<pe_engine::OverJob> q;
+  q.swap(e->over_pending);
+  e->over_defer = false;
+  size_t i = 0;
+  while (i < q.size()) {
+    size_t j = i + 1;
+    auto same = [&](const pe_engine::OverJob &a, const pe_engine::OverJob &b) {
+      return a.rs_bg == b.rs_bg && a.rs_fg == b.rs_fg && a.rs_d == b.rs_d && a.w == b.w && a.h == b.h && a.psize == b.psize && a.k256 == b.k256 &&
+             a.lut == b.lut;
+    };
+    auto depends = [&](const pe_engine::OverJob &b) {
+      for (size_t k = i; k < j; k++)
+        if (q[k].dst == b.bg || q[k].dst == b.fg || q[k].dst == b.dst) return true;
+      return false;
+    };
+    while (j < q.size() && same(q[i], q[j]) && !depends(q[j])) j++;
+    std::vector<const uint8_t *> bgs, fgs;
+    std::vector<uint8_t *> dsts;
+    for (size_t k = i; k < j; k++) { bgs.push_back(q[k].bg); fgs.push_back(q[k].fg); dsts.push_back(q[k].dst); }
+    cudaError_t ce = launch_alpha_over_arith_batch(e->L(), bgs.data(), fgs.data(), dsts.data(), (int)(j - i), q[i].rs_bg, q[i].rs_fg, q[i].rs_d,
+                                                   q[i].w, q[i].h, q[i].psize, q[i].k256, q[i].lut, 1);
+    if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "alpha-over launch failed: %s", cudaGetErrorString(ce));
+    i = j;
+  }
+  return PE_OK;
+}
+
 int compositor_locked(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha, int nlayers,
                       const int bgcol[3], int gamma_to) {
   const int pal = out->d.palette;
@@ -1738,7 +1769,10 @@ int compositor_locked(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *
   auto paint = [&](CImg bg, CImg fg, double a, const uint8_t *l8) -> int {
     const double k256 = a * 256.;
     if (k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256) {
-      PE_CUDA(launch_alpha_over_arith(e->L(), bg, fg, dst, w, h, psize, (int)k256, l8, 1));
+      if (e->over_defer)  // batch call: launched by flush_over_pending
+        e->over_pending.push_back(pe_engine::OverJob{bg.p, fg.p, dst.p, bg.rs, fg.rs, dst.rs, w, h, psize, (int)k256, l8});
+      else
+        PE_CUDA(launch_alpha_over_arith(e->L(), bg, fg, dst, w, h, psize, (int)k256, l8, 1));
     } else {
       uint8_t *tab = get_over_table(e, a, l8);
       if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
@@ -1775,6 +1809,41 @@ extern "C" int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_
   std::lock_guard<std::mutex> lk(e->mu);
   PE_CUDA(cudaSetDevice(e->device));
   return compositor_locked(e, out, layers, alpha, nlayers, bgcol, PE_GAMMA_UNKNOWN);
+}
+
+// n independent output frames through compositor_process (+ gamma), each with its own `nlayers` layers (layers[i * nlayers + z])
+// and the same per-layer alphas: the render-to-disk loop issues them one by one.  The integer alpha-over paints (alpha = k / 256)
+// of the batch are queued and leave as one launch per 32 same-shaped frames and paint pass; fills and table paints are ordered
+// before them only when no integer paint is pending, so a batch that mixes the two falls back to frame-by-frame order.
+// Returns the number of frames composited.
+extern "C" int pe_fx_compositor_gamma_batch(pe_engine_t *e, int n, pe_frame_t *const *outs, const pe_frame_t *const *layers,
+                                            const double *alpha, int nlayers, const int bgcol[3], int gamma_to) {
+  if (!e || n <= 0 || !outs || nlayers < 0 || (nlayers > 0 && (!layers || !alpha))) { set_err(PE_ERR_ARG, "NULL / empty argument"); return 0; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
+  // deferral keeps stream order only if every launch of the batch is a deferred one: all alphas k / 256 and an opaque base layer
+  // (no background fill, no table paint, no trailing LUT pass)
+  bool deferrable = nlayers >= 1;
+  bool has_opaque = false;
+  for (int z = 0; z < nlayers; z++) {
+    const double k256 = alpha[z] * 256.;
+    if (alpha[z] > 0. && !(k256 <= 256. && k256 == (double)(int)k256)) deferrable = false;
+    if (alpha[z] >= 1.0) has_opaque = true;
+  }
+  deferrable = deferrable && has_opaque;
+  if (deferrable)
+    for (int i = 0; i < n && deferrable; i++)
+      for (int z = 0; z < nlayers; z++)
+        if (!layers[(size_t)i * nlayers + z] || !layers[(size_t)i * nlayers + z]->d.planes[0]) deferrable = false;
+  int done = 0;
+  e->over_defer = deferrable;
+  for (int i = 0; i < n; i++) {
+    if (!outs[i] || !outs[i]->d.planes[0]) continue;
+    if (compositor_locked(e, outs[i], layers + (size_t)i * nlayers, alpha, nlayers, bgcol, gamma_to) == PE_OK) done++;
+  }
+  if (deferrable && flush_over_pending(e) != PE_OK) return 0;
+  e->over_defer = false;
+  return done;
 }
 
 extern "C" int pe_fx_compositor_gamma(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,

@@ -98,6 +98,9 @@ struct pe_engine {
   bool rgb_defer = false;            // ... and the RGB <-> RGB permutations (flush_rgb_pending)
   std::vector<RgbJob> rgb_pending;
   struct RszJob { const uint8_t *src; int srs, sw, sh; uint8_t *dst; int drs, dw, dh, psize; };
+  struct OverJob { const uint8_t *bg, *fg; uint8_t *dst; int rs_bg, rs_fg, rs_d, w, h, psize, k256; const uint8_t *lut; };
+  bool over_defer = false;           // ... and the integer alpha-over paints of a compositor batch (flush_over_pending)
+  std::vector<OverJob> over_pending;
   bool rsz_defer = false;            // ... and so are the resizes of 4-byte packed frames (flush_rsz_pending)
   std::vector<RszJob> rsz_pending;
   bool yuv_defer = false;

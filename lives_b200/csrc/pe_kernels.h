@@ -135,6 +135,9 @@ cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int wi
 // alpha = k256 / 256 exactly: integer blend, no table; optional gamma LUT applied to the result
 cudaError_t launch_alpha_over_arith(const Launch &L, CImg bg, CImg fg, Img dst, int width, int height, int psize, int k256,
                                     const uint8_t *lut8_dev, int force_opaque);
+cudaError_t launch_alpha_over_arith_batch(const Launch &L, const uint8_t *const *bgs, const uint8_t *const *fgs, uint8_t *const *dsts, int n,
+                                          int rs_bg, int rs_fg, int rs_d, int width, int height, int psize, int k256,
+                                          const uint8_t *lut8_dev, int force_opaque);
 cudaError_t launch_fill(const Launch &L, Img dst, int width, int height, int psize, uint32_t pixel);
 // ---- resize (our contract) + letterbox (colourspace.c:15343) -------------------------------------------
 struct DevFilter {

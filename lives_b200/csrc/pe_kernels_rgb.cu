@@ -671,7 +671,15 @@ __device__ __forceinline__ uint32_t over_px4(uint32_t b, uint32_t f, uint32_t ka
   return o0 | (o1 << 8) | (o2 << 16) | (force_opaque ? 0xFF000000u : (b & 0xFF000000u));
 }
 
-__global__ void __launch_bounds__(kBlock) k_alpha_over_arith(const OverArithParams P) {
+// frames of one batched launch: same geometry, strides, alpha and LUT; blockIdx.y selects the frame
+struct OverFrameList {
+  const uint8_t *bg[32], *fg[32];
+  uint8_t *dst[32];
+};
+
+__global__ void __launch_bounds__(kBlock) k_alpha_over_arith(const OverArithParams P0, const __grid_constant__ OverFrameList FL) {
+  OverArithParams P = P0;
+  P.bg = FL.bg[blockIdx.y]; P.fg = FL.fg[blockIdx.y]; P.dst = FL.dst[blockIdx.y];
   __shared__ uint8_t s_lut[256];
   const bool has_lut = P.lut != nullptr;
   if (has_lut) {
@@ -723,9 +731,35 @@ cudaError_t launch_alpha_over_arith(const Launch &L, CImg bg, CImg fg, Img dst, 
   P.width = width; P.height = height; P.psize = psize; P.ka = (uint32_t)k256; P.kia = 256u - (uint32_t)k256;
   P.lut = lut8_dev; P.force_opaque = force_opaque;
   const long long work = psize == 4 ? (long long)((width + 3) >> 2) * height : (long long)width * 3 * height;
-  k_alpha_over_arith<<<grid_for(L, work, 8), kBlock, 0, L.stream>>>(P);
+  OverFrameList fl;
+  for (int i = 0; i < 32; i++) { fl.bg[i] = bg.p; fl.fg[i] = fg.p; fl.dst[i] = dst.p; }
+  k_alpha_over_arith<<<grid_for(L, work, 8), kBlock, 0, L.stream>>>(P, fl);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
+}
+
+// n frames that share geometry, strides, alpha and LUT: one launch per 32 (blockIdx.y = frame)
+cudaError_t launch_alpha_over_arith_batch(const Launch &L, const uint8_t *const *bgs, const uint8_t *const *fgs, uint8_t *const *dsts, int n,
+                                          int rs_bg, int rs_fg, int rs_d, int width, int height, int psize, int k256,
+                                          const uint8_t *lut8_dev, int force_opaque) {
+  OverArithParams P;
+  P.bg = nullptr; P.fg = nullptr; P.dst = nullptr; P.rs_bg = rs_bg; P.rs_fg = rs_fg; P.rs_d = rs_d;
+  P.width = width; P.height = height; P.psize = psize; P.ka = (uint32_t)k256; P.kia = 256u - (uint32_t)k256;
+  P.lut = lut8_dev; P.force_opaque = force_opaque;
+  const long long work = psize == 4 ? (long long)((width + 3) >> 2) * height : (long long)width * 3 * height;
+  for (int base = 0; base < n; base += 32) {
+    const int m = n - base < 32 ? n - base : 32;
+    OverFrameList fl;
+    for (int i = 0; i < 32; i++) { const int j = base + (i < m ? i : 0); fl.bg[i] = bgs[j]; fl.fg[i] = fgs[j]; fl.dst[i] = dsts[j]; }
+    // the frames share the grid: keep ~8 CTAs per SM in total, at least one column of CTAs per frame
+    int gx = grid_for(L, work, 8) / m;
+    if (gx < 1) gx = 1;
+    k_alpha_over_arith<<<dim3(gx, m), kBlock, 0, L.stream>>>(P, fl);
+    PE_COUNT_LAUNCH(L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev) {

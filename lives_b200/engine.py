@@ -349,6 +349,18 @@ def compositor_gamma(out, layers, alphas, gamma_to, bgcol=(0, 0, 0)):
     capi.check(e._lib.pe_fx_compositor_gamma(e._h, out._h, _arr(layers), al, len(layers), bg, gamma_to))
 
 
+def compositor_gamma_batch(outs, layers_per_frame, alphas, gamma_to, bgcol=(0, 0, 0)):
+    """compositor_gamma() for a batch of independent output frames: layers_per_frame[i] = the layers of frame i (same count and
+    per-layer alphas for every frame); returns how many frames were composited"""
+    e = outs[0].engine
+    nl = len(alphas)
+    flat = [l for ls in layers_per_frame for l in ls]
+    assert len(flat) == nl * len(outs)
+    al = (C.c_double * max(nl, 1))(*alphas)
+    bg = (C.c_int * 3)(*bgcol)
+    return int(e._lib.pe_fx_compositor_gamma_batch(e._h, len(outs), _arr(outs), _arr(flat), al, nl, bg, gamma_to))
+
+
 def fused_convert_letterbox_over_gamma(fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):
     """convert_layer_palette(fg -> RGBA32); letterbox_layer; compositor over bg; gamma_convert_layer -- one kernel"""
     e = fg.engine

@@ -849,6 +849,33 @@ def test_config3_4k_alpha_over_gamma(eng):
     assert (eng.gamma_lut8(1.0, T.G_SRGB, T.G_LINEAR) == np.arange(256)).all()
 
 
+def test_compositor_gamma_batch(eng):
+    """pe_fx_compositor_gamma_batch == pe_fx_compositor_gamma frame by frame == the oracle: two layers (one launch for the batch),
+    three layers (paint passes stay ordered), a non-dyadic alpha (table paint, frame-by-frame order), RGB24"""
+    o = T.oracle()
+    rng = np.random.default_rng(41)
+    lut = np.zeros(256, np.uint8)
+    o.pe_or_gamma_lut8(1.0, T.G_LINEAR, T.G_SRGB, 1.4, T.ptr(lut))
+    for (w, h, pal), alphas, nframes in (((640, 360, 3), [0.5, 1.0], 5), ((130, 34, 3), [0.25, 0.5, 1.0], 4), ((64, 32, 3), [0.3, 1.0], 3),
+                                         ((200, 50, 1), [0.75, 1.0], 3), ((64, 16, 3), [1.0], 2)):
+        ps = T.psize_of(pal)
+        frames = [[T.make_packed(rng, w, h, ps) for _ in alphas] for _ in range(nframes)]
+        exps = []
+        for ls in frames:
+            exp = _oracle_compositor(o, pal, w, h, ls, alphas, (0, 0, 0))
+            o.pe_or_gamma_apply(T.ptr(exp), exp.strides[0], pal, 0, 0, w, h, T.ptr(lut))
+            exps.append(exp)
+        outs = [lb.Layer.create(eng, pal, w, h, gamma_type=T.G_LINEAR) for _ in range(nframes)]
+        lays = [[packed_layer(eng, pal, w, h, a) for a in ls] for ls in frames]
+        before = eng.launch_count
+        assert lb.compositor_gamma_batch(outs, lays, alphas, T.G_SRGB) == nframes
+        if alphas == [0.5, 1.0]:
+            assert eng.launch_count - before == 1
+        for out, exp in zip(outs, exps):
+            assert out.gamma_type == T.G_SRGB
+            assert (payload(out.to_host()[0], w, ps) == payload(exp, w, ps)).all(), (w, h, pal, alphas)
+
+
 # ------------------------------------------------------------------------------------------------ resize / letterbox
 
 @pytest.mark.parametrize("case", [(64, 48, 32, 24, 3), (64, 48, 96, 72, 4), (130, 50, 77, 34, 4), (1920, 1080, 1280, 720, 3),
