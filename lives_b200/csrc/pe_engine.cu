@@ -1088,6 +1088,32 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
       ce = launch_resample_chroma_v(L, dbl ? 1 : 0, (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2], f->d.rowstrides[1],
                                     f->d.rowstrides[2], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1],
                                     n.d.rowstrides[2], n.d.width >> 1, ch, cavg);
+  } else if ((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && (outpl == PE_PALETTE_UYVY || outpl == PE_PALETTE_YUYV)) {
+    // convert_yuv_planar_to_{uyvy,yuyv}_frame (:12984-12997, :13083-13096): chroma = avg_chroma of the pixel pair, an odd last
+    // column is cut (the layer gets width >> 1 macropixels)
+    n.d.width = width & ~1;
+    if (n.d.width < 2) { set_err(PE_ERR_SIZE, "frame too narrow for a 4:2:2 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2]};
+    ce = launch_yuv444p_to_packed422(L, outpl == PE_PALETTE_UYVY ? 0 : 1, pl, f->d.rowstrides[0], Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]},
+                                     width >> 1, height, cavg);
+  } else if ((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P)) {
+    // convert_yuvp_to_yuv420_frame (:13016-13022, :13115-13121): luma copied, chroma averaged over 2 x 2; the planes are written
+    // in layer order (YVU420P receives Cb in plane 1, as the reference's dest[1]); sampling -> DEFAULT
+    n.d.width = width & ~1; n.d.height = height & ~1;
+    if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    ce = launch_copy2d(L, (const uint8_t *)f->d.planes[0], f->d.rowstrides[0], (uint8_t *)n.d.planes[0], n.d.rowstrides[0], n.d.width,
+                       n.d.height, 0, 0);
+    if (ce == cudaSuccess)
+      ce = launch_yuv444p_to_chroma420(L, (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2], f->d.rowstrides[1],
+                                       (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1], n.d.rowstrides[2],
+                                       n.d.width >> 1, n.d.height, cavg);
+    n.d.yuv_sampling = PE_YUV_SAMPLING_DEFAULT;
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

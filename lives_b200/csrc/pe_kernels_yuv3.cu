@@ -6,6 +6,8 @@
 //   k_halve_chroma        convert_halve_chroma                           colourspace.c:10578  (4:2:2 -> 4:2:0 chroma planes)
 //   k_double_chroma       convert_double_chroma                          colourspace.c:10612  (4:2:0 -> 4:2:2 chroma planes)
 //   k_packed422_unpack    convert_{uyvy,yuyv}_to_{yuv422,yuvp,yuv888}_frame  colourspace.c:8093 / 7800 / 7845
+//   k_yuv444p_to_packed422  convert_yuv_planar_to_{uyvy,yuyv}_frame      colourspace.c:7500 / 7548
+//   k_yuv444p_to_chroma420  convert_yuvp_to_yuv420_frame                 colourspace.c:7690
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -220,6 +222,54 @@ __global__ void __launch_bounds__(kBlock) k_packed422_unpack(int fmt, int mode, 
   }
 }
 
+// planar 4:4:4 -> UYVY / YUYV (convert_yuv_planar_to_{uyvy,yuyv}_frame, colourspace.c:7500 / 7548): one thread = 4 pixels = 2
+// macropixels, chroma = avg_chroma(c[2x], c[2x + 1])
+__global__ void __launch_bounds__(kBlock) k_yuv444p_to_packed422(int fmt, Planes4 S, uint8_t *dst, int orow, int width_mpx, int height,
+                                                                const uint8_t *__restrict__ cavg, int vec) {
+  const int groups = (width_mpx + 1) >> 1;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int m = 2 * g, nm = min(2, width_mpx - m);
+    const long long o = (long long)S.rs * row + 2 * m;
+    const uint32_t yw = ld_px4(S.p[0] + o, 2 * nm, vec), uw = ld_px4(S.p[1] + o, 2 * nm, vec), vw = ld_px4(S.p[2] + o, 2 * nm, vec);
+    const uint32_t cu0 = __ldg(cavg + ((byte_of(uw, 0) << 8) | byte_of(uw, 1))), cv0 = __ldg(cavg + ((byte_of(vw, 0) << 8) | byte_of(vw, 1)));
+    const uint32_t cu1 = __ldg(cavg + ((byte_of(uw, 2) << 8) | byte_of(uw, 3))), cv1 = __ldg(cavg + ((byte_of(vw, 2) << 8) | byte_of(vw, 3)));
+    uint32_t m0 = byte_of(yw, 0) | (cu0 << 8) | (byte_of(yw, 1) << 16) | (cv0 << 24);   // YUYV
+    uint32_t m1 = byte_of(yw, 2) | (cu1 << 8) | (byte_of(yw, 3) << 16) | (cv1 << 24);
+    if (fmt == 0) { m0 = __byte_perm(m0, 0u, 0x2301); m1 = __byte_perm(m1, 0u, 0x2301); }  // UYVY
+    uint8_t *d = dst + (long long)orow * row + 4LL * m;
+    if (vec && nm == 2) st_stream_u2(d, make_uint2(m0, m1));
+    else { st_px4(d, m0, 4, false); if (nm == 2) st_px4(d + 4, m1, 4, false); }
+  }
+}
+
+// planar 4:4:4 -> the chroma planes of 4:2:0 (convert_yuvp_to_yuv420_frame, colourspace.c:7690): out[k][j] = avg_chroma(h(2k)[j],
+// h(2k + 1)[j]), h(r)[j] = avg_chroma(c[r][2j], c[r][2j + 1]); a trailing unpaired row leaves h(r).  One thread = 4 output samples;
+// blockIdx.y = plane (U, V)
+__global__ void __launch_bounds__(kBlock) k_yuv444p_to_chroma420(const uint8_t *su, const uint8_t *sv, int irs, uint8_t *du, uint8_t *dv,
+                                                                int ors_u, int ors_v, int cw, int height, const uint8_t *__restrict__ cavg,
+                                                                int vec) {
+  const uint8_t *s = blockIdx.y ? sv : su;
+  uint8_t *d = blockIdx.y ? dv : du;
+  const int ors = blockIdx.y ? ors_v : ors_u;
+  const int groups = (cw + 3) >> 2, orows = (height + 1) >> 1;
+  const long long total = (long long)groups * orows;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, cw - x);
+    auto hrow = [&](int r) -> uint32_t {
+      const uint8_t *q = s + (long long)irs * r + 2 * x;
+      const uint32_t a = ld_px4(q, min(4, 2 * n), vec), b = n > 2 ? ld_px4(q + 4, 2 * n - 4, vec) : 0u;
+      return (uint32_t)__ldg(cavg + ((byte_of(a, 0) << 8) | byte_of(a, 1))) | ((uint32_t)__ldg(cavg + ((byte_of(a, 2) << 8) | byte_of(a, 3))) << 8) |
+             ((uint32_t)__ldg(cavg + ((byte_of(b, 0) << 8) | byte_of(b, 1))) << 16) | ((uint32_t)__ldg(cavg + ((byte_of(b, 2) << 8) | byte_of(b, 3))) << 24);
+    };
+    uint32_t w = hrow(2 * row);
+    if (2 * row + 1 < height) w = avg4(cavg, w, hrow(2 * row + 1));
+    st_px4(d + (long long)ors * row + x, w, n, vec);
+  }
+}
+
 // UYVY <-> YUYV in place: swab() of every row
 __global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
   const long long total = (long long)width_mpx * height;
@@ -334,6 +384,28 @@ cudaError_t launch_packed422_unpack(const Launch &L, int fmt, int mode, CImg src
   }
   k_packed422_unpack<<<grid_for(L, (long long)((width_mpx + 1) / 2) * height), kBlock, 0, L.stream>>>(fmt, mode, src.p, src.rs, D, width_mpx,
                                                                                                       height, add_alpha, first_only, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_yuv444p_to_packed422(const Launch &L, int fmt, const uint8_t *const planes[3], int irow, Img dst, int width_mpx, int height,
+                                        const uint8_t *cavg_dev) {
+  Planes4 S;
+  for (int k = 0; k < 3; k++) S.p[k] = planes[k];
+  S.p[3] = nullptr;
+  S.rs = irow;
+  const bool vec = aligned4(planes[0]) && aligned4(planes[1]) && aligned4(planes[2]) && !(irow & 3) && (((uintptr_t)dst.p | (uint32_t)dst.rs) & 7) == 0;
+  k_yuv444p_to_packed422<<<grid_for(L, (long long)((width_mpx + 1) / 2) * height), kBlock, 0, L.stream>>>(fmt, S, dst.p, dst.rs, width_mpx, height,
+                                                                                                          cavg_dev, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_yuv444p_to_chroma420(const Launch &L, const uint8_t *su, const uint8_t *sv, int irs, uint8_t *du, uint8_t *dv, int ors_u,
+                                        int ors_v, int cw, int height, const uint8_t *cavg_dev) {
+  const bool vec = aligned4(su) && aligned4(sv) && aligned4(du) && aligned4(dv) && !((irs | ors_u | ors_v) & 3);
+  const dim3 grid(grid_for(L, (long long)((cw + 3) / 4) * ((height + 1) / 2)), 2);
+  k_yuv444p_to_chroma420<<<grid, kBlock, 0, L.stream>>>(su, sv, irs, du, dv, ors_u, ors_v, cw, height, cavg_dev, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

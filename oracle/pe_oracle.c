@@ -1061,6 +1061,40 @@ void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_
   }
 }
 
+/* convert_yuv_planar_to_{uyvy,yuyv}_frame :7500-7590: one macropixel per pixel pair, chroma = avg_chroma(c[2x], c[2x+1]) (first
+ * sample = table row).  Only the reference's dense branch (irowstride == width, orowstride == 2 * width) is right: its strided
+ * branch runs `width` macropixels per row (:7527, :7577) -- X; restated per pair with the strides. */
+void pe_or_yuv444p_to_packed422(int fmt, const uint8_t *const src[3], int irow, int width, int height, uint8_t *dest, int orow,
+                                int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  for (int k = 0; k < height; k++) {
+    const uint8_t *y = src[0] + (long)irow * k, *u = src[1] + (long)irow * k, *v = src[2] + (long)irow * k;
+    uint8_t *d = dest + (long)orow * k;
+    for (int x = 0; x < width >> 1; x++, d += 4) {
+      const uint8_t cu = avg[(u[2 * x] << 8) + u[2 * x + 1]], cv = avg[(v[2 * x] << 8) + v[2 * x + 1]];
+      if (fmt == 0) { d[0] = cu; d[1] = y[2 * x]; d[2] = cv; d[3] = y[2 * x + 1]; }
+      else { d[0] = y[2 * x]; d[1] = cu; d[2] = y[2 * x + 1]; d[3] = cv; }
+    }
+  }
+}
+
+/* convert_yuvp_to_yuv420_frame :7690-7752: luma copied; chroma row k = avg_chroma(h(2k), h(2k+1)) with h(r)[j] =
+ * avg_chroma(c[r][2j], c[r][2j+1]); a trailing unpaired row leaves h(r) */
+void pe_or_yuv444p_to_yuv420p(const uint8_t *const src[3], const int irows[3], int width, int height, uint8_t *const dest[3],
+                              const int orows[3], int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  for (int i = 0; i < height; i++) memcpy(dest[0] + (long)orows[0] * i, src[0] + (long)irows[0] * i, (size_t)width);
+  for (int p = 1; p <= 2; p++)
+    for (int i = 0; i < height; i++) {
+      const uint8_t *s = src[p] + (long)irows[p] * i;
+      uint8_t *d = dest[p] + (long)orows[p] * (i >> 1);
+      for (int j = 0; j < width >> 1; j++) {
+        const uint8_t x = avg[(s[2 * j] << 8) + s[2 * j + 1]];
+        d[j] = (i & 1) ? avg[(d[j] << 8) + x] : x;
+      }
+    }
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

@@ -128,6 +128,12 @@ void pe_or_packed422_to_yuv444p(int fmt, const uint8_t *src, int irow, int width
                                 const int orows[4], int add_alpha);
 void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *dest, int orow,
                                int add_alpha);
+/* planar 4:4:4 -> packed 4:2:2 (convert_yuv_planar_to_{uyvy,yuyv}_frame :7500,:7548): chroma = avg_chroma of the pixel pair;
+ * -> planar 4:2:0 (convert_yuvp_to_yuv420_frame :7690): avg_chroma(avg_chroma(row 2k pair), avg_chroma(row 2k+1 pair)) */
+void pe_or_yuv444p_to_packed422(int fmt, const uint8_t *const src[3], int irow, int width, int height, uint8_t *dest, int orow,
+                                int clamping);
+void pe_or_yuv444p_to_yuv420p(const uint8_t *const src[3], const int irows[3], int width, int height, uint8_t *const dest[3],
+                              const int orows[3], int clamping);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

@@ -315,3 +315,15 @@ void ref_packed422_to_yuv888(int fmt, void *src, int width, int height, int irow
 void ref_swab(uint8_t *src, int width, int height, int irow) {
   convert_swab_frame(src, width, height, irow, -USE_THREADS);
 }
+
+/* fmt 0 uyvy 1 yuyv; only the dense branch (irow == width, orow == 2 * width) of the reference is usable */
+void ref_yuv444p_to_packed422(int fmt, uint8_t **src, int width, int height, int irow, int orow, void *dest, int clamping) {
+  ref_init();
+  if (fmt == 0) convert_yuv_planar_to_uyvy_frame(src, width, height, irow, orow, (uyvy_macropixel *)dest, clamping);
+  else convert_yuv_planar_to_yuyv_frame(src, width, height, irow, orow, (yuyv_macropixel *)dest, clamping);
+}
+
+void ref_yuv444p_to_yuv420p(uint8_t **src, int width, int height, int *irows, int *orows, uint8_t **dest, int clamping) {
+  ref_init();
+  convert_yuvp_to_yuv420_frame(src, width, height, irows, orows, dest, clamping);
+}

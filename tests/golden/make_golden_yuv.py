@@ -89,6 +89,16 @@ def main():
             d8 = np.zeros((H, T.rowstride(W, 4 if aa else 3)), np.uint8)
             r.ref_packed422_to_yuv888(fmt, T.ptr(m), wm, H, m.strides[0], d8.strides[0], T.ptr(d8), aa)
             out["%s_to_yuv888_a%d" % (nm, aa)] = d8
+    dense = [np.ascontiguousarray(p[:, :W]) for p in pl[:3]]
+    for cl in (0, 1):
+        for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
+            d = np.zeros((H, 2 * W), np.uint8)
+            r.ref_yuv444p_to_packed422(fmt, T.planes_arg(*dense), W, H, W, 2 * W, T.ptr(d), cl)
+            out["yuv444p_to_%s_cl%d" % (nm, cl)] = d
+        ys = T.rowstride(W, 1)
+        d3 = [np.zeros((H, ys), np.uint8), np.zeros((H // 2, ys // 2), np.uint8), np.zeros((H // 2, ys // 2), np.uint8)]
+        r.ref_yuv444p_to_yuv420p(T.planes_arg(*pl[:3]), W, H, T.strides_arg(*pl[:3]), T.strides_arg(*d3), T.planes_arg(*d3), cl)
+        out["yuv444p_to_yuv420p_cl%d_u" % cl], out["yuv444p_to_yuv420p_cl%d_v" % cl] = d3[1], d3[2]
     sw = m.copy()
     r.ref_swab(T.ptr(sw), wm, H, sw.strides[0])
     out["swab"] = sw

@@ -66,6 +66,16 @@ def test_oracle_yuv_family_matches_golden():
     sw = m.copy()
     o.pe_or_swab(T.ptr(sw), sw.strides[0], WM, H)
     assert (sw == G["swab"]).all()
+    for cl in (0, 1):
+        for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
+            exp = G["yuv444p_to_%s_cl%d" % (nm, cl)]
+            d = np.zeros_like(exp)
+            o.pe_or_yuv444p_to_packed422(fmt, T.planes_arg(*pl[:3]), pl[0].strides[0], W, H, T.ptr(d), d.strides[0], cl)
+            assert (d == exp).all(), (nm, cl)
+        eu, ev = G["yuv444p_to_yuv420p_cl%d_u" % cl], G["yuv444p_to_yuv420p_cl%d_v" % cl]
+        d3 = [np.zeros((H, pl[0].strides[0]), np.uint8), np.zeros_like(eu), np.zeros_like(ev)]
+        o.pe_or_yuv444p_to_yuv420p(T.planes_arg(*pl[:3]), T.strides_arg(*pl[:3]), W, H, T.planes_arg(*d3), T.strides_arg(*d3), cl)
+        assert (d3[1] == eu).all() and (d3[2] == ev).all(), cl
 
 
 @pytest.mark.gpu
@@ -114,6 +124,15 @@ def test_cuda_yuv_family_matches_golden():
             assert lb.convert_layer_palette(lay, opal, 0)
             n = W * (4 if aa else 3)
             assert (lay.to_host()[0][:, :n] == G["%s_to_yuv888_a%d" % (nm, aa)][:, :n]).all(), (nm, aa)
+    for cl in (0, 1):
+        for opal, nm in ((564, "uyvy"), (565, "yuyv")):
+            lay = lb.Layer.from_host(eng, 544, W, H, pl[:3], yuv_clamping=cl)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.to_host()[0][:, :2 * W] == G["yuv444p_to_%s_cl%d" % (nm, cl)]).all(), (nm, cl)
+        lay = lb.Layer.from_host(eng, 544, W, H, pl[:3], yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, 512, cl)
+        got = lay.to_host()
+        assert (got[1][:, :WM] == G["yuv444p_to_yuv420p_cl%d_u" % cl][:, :WM]).all() and (got[2][:, :WM] == G["yuv444p_to_yuv420p_cl%d_v" % cl][:, :WM]).all()
     lay = lb.Layer.from_host(eng, 564, W, H, [m])
     assert lb.convert_layer_palette(lay, 565, 0)
     assert (lay.to_host()[0][:, :WM * 4] == G["swab"][:, :WM * 4]).all()

@@ -611,6 +611,35 @@ def test_packed422_to_planar_packed444_and_swab(eng, size):
         assert (payload(lay.to_host()[0], wm, 4) == payload(exp, wm, 4)).all(), ("swab", w, h, ipal)
 
 
+@pytest.mark.parametrize("size", [(64, 12), (38, 7), (1920, 1080), (2, 2)])
+def test_yuv444p_to_packed422_and_yuv420p(eng, size):
+    """YUV444P / YUVA4444P -> UYVY / YUYV (convert_yuv_planar_to_{uyvy,yuyv}_frame) and -> YUV420P (convert_yuvp_to_yuv420_frame)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(120 + w)
+    for ipal, cl in itertools.product((544, 545), (0, 1)):
+        pl = _planes444(rng, w, h, 4 if ipal == 545 else 3)
+        for opal in (564, 565):
+            wm = w >> 1
+            exp = np.zeros((h, T.rowstride(wm, 4)), np.uint8)
+            o.pe_or_yuv444p_to_packed422(opal - 564, T.planes_arg(*pl[:3]), pl[0].strides[0], w, h, T.ptr(exp), exp.strides[0], cl)
+            lay = lb.Layer.from_host(eng, ipal, w, h, pl, yuv_clamping=cl)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.palette, lay.width, lay.height, lay.yuv_clamping) == (opal, wm * 2, h, cl)
+            assert (payload(lay.to_host()[0], wm, 4) == payload(exp, wm, 4)).all(), (w, h, ipal, cl, opal)
+        he = h & ~1
+        ys = T.rowstride(w & ~1, 1)
+        ep = [np.zeros((he, ys), np.uint8), np.zeros((he >> 1, ys >> 1), np.uint8), np.zeros((he >> 1, ys >> 1), np.uint8)]
+        o.pe_or_yuv444p_to_yuv420p(T.planes_arg(*pl[:3]), T.strides_arg(*pl[:3]), w & ~1, he, T.planes_arg(*ep), T.strides_arg(*ep), cl)
+        lay = lb.Layer.from_host(eng, ipal, w, h, pl, yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, 512, cl)
+        assert (lay.palette, lay.width, lay.height) == (512, w & ~1, he)
+        got = lay.to_host()
+        assert (got[0][:, :w & ~1] == ep[0][:, :w & ~1]).all()
+        for k in (1, 2):
+            assert (got[k][:, :w >> 1] == ep[k][:, :w >> 1]).all(), ("420p", w, h, ipal, cl, k)
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

@@ -652,3 +652,26 @@ def test_clamping_tables_match_reference():
     o.pe_or_switch_clamping_plane(T.ptr(x), 96, 3, 1)
     i = np.arange(96)
     assert (x == np.where(i % 4 == 3, buf, np.where(i % 4 == 0, ty[buf], tc[buf]))).all()
+
+
+def test_yuv444p_to_packed422_and_yuv420p_match_reference():
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(75)
+    for (w, h), cl in itertools.product(((32, 6), (34, 5), (2, 2)), (0, 1)):
+        # packed 4:2:2: the reference is only right on dense buffers (its strided branch runs `width` macropixels per row)
+        pl = _planes444(rng, w, h, 3, stride=w)
+        for fmt in (0, 1):
+            a, b = np.zeros((h, 2 * w), np.uint8), np.zeros((h, 2 * w), np.uint8)
+            o.pe_or_yuv444p_to_packed422(fmt, T.planes_arg(*pl), w, w, h, T.ptr(a), 2 * w, cl)
+            r.ref_yuv444p_to_packed422(fmt, T.planes_arg(*pl), w, h, w, 2 * w, T.ptr(b), cl)
+            assert (a == b).all(), ("packed422", w, h, fmt, cl)
+        # planar 4:2:0, padded planes
+        pl = _planes444(rng, w, h, 3)
+        ys, cs = T.rowstride(w, 1), T.rowstride(w, 1) >> 1
+        ch = (h + 1) >> 1
+        da = [np.zeros((h, ys), np.uint8), np.zeros((ch, cs), np.uint8), np.zeros((ch, cs), np.uint8)]
+        db = [np.zeros_like(p) for p in da]
+        o.pe_or_yuv444p_to_yuv420p(T.planes_arg(*pl), T.strides_arg(*pl), w, h, T.planes_arg(*da), T.strides_arg(*da), cl)
+        r.ref_yuv444p_to_yuv420p(T.planes_arg(*pl), w, h, T.strides_arg(*pl), T.strides_arg(*db), T.planes_arg(*db), cl)
+        for k in range(3):
+            assert (da[k][:, :w >> (k > 0)] == db[k][:, :w >> (k > 0)]).all(), ("420p", w, h, cl, k)
