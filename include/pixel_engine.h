@@ -183,6 +183,10 @@ int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const pe_frame_t *
  * (clips that fail are left untouched, as convert_layer_palette leaves its layer, colourspace.c:13906-13927). */
 int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *operand, int outpl,
                                   int op_clamping, int blend_factor);
+/* ... and with one operand per clip (operands[i] for clips[i]): successive frames of one clip against successive frames of the
+ * other track, e.g. a group of operand frames received in one broadcast */
+int pe_fx_convert_crossfade_batchv(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *const *operands, int outpl,
+                                   int op_clamping, int blend_factor);
 /* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
 int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                       int blend_factor);

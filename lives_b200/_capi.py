@@ -81,6 +81,7 @@ PROTOTYPES = {
     "pe_resize_layer_batch": (I, [VP, I, VP, I, I, I, I, I]),
     "pe_fx_convert_crossfade": (I, [VP, VP, VP, I, I, I]),
     "pe_fx_convert_crossfade_batch": (I, [VP, I, VP, VP, I, I, I]),
+    "pe_fx_convert_crossfade_batchv": (I, [VP, I, VP, VP, I, I, I]),
     "pe_convert_layer_palette_batch": (I, [VP, I, VP, I, I]),
     "pe_letterbox_layer": (I, [VP, VP, I, I, I, I, I, I, I]),
     "pe_gamma_convert_layer": (I, [VP, I, VP]),

@@ -1659,34 +1659,37 @@ extern "C" int pe_fx_convert_crossfade(pe_engine_t *e, pe_frame_t *clip, const p
   return ok == PE_TRUE ? PE_OK : PE_ERR_PALETTE;
 }
 
-extern "C" int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *operand, int outpl,
-                                             int op_clamping, int blend_factor) {
-  if (!e || !clips || n < 0 || !operand || !operand->d.planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return 0; }
-  if ((outpl != PE_PALETTE_RGB24 && outpl != PE_PALETTE_BGR24) || operand->d.palette != outpl) {
+// n clips, clip i against operands[i] (the frames of ONE clip against the successive frames of the other track, or the clips of a
+// stack against one shared operand): the conversions are queued and leave as one k_yuv_march launch per 32 same-shaped clips
+extern "C" int pe_fx_convert_crossfade_batchv(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *const *operands,
+                                              int outpl, int op_clamping, int blend_factor) {
+  if (!e || !clips || !operands || n < 0) { set_err(PE_ERR_ARG, "NULL argument"); return 0; }
+  if (outpl != PE_PALETTE_RGB24 && outpl != PE_PALETTE_BGR24) {
     set_err(PE_ERR_PALETTE, "convert_crossfade: output and operand must both be RGB24 or both BGR24");
     return 0;
   }
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
-  e->fuse_blend2 = (const uint8_t *)operand->d.planes[0];
-  e->fuse_blend2_rs = operand->d.rowstrides[0];
   e->fuse_blend_bf = blend_factor;
-  // the conversions are queued and leave as one k_yuv_march launch per 32 same-shaped clips (flush_yuv_pending)
   e->yuv_defer = true;
   e->pool.defer(true);
   int done = 0;
   for (int i = 0; i < n; i++) {
     pe_frame_t *c = clips[i];
-    if (!c || !c->d.planes[0]) continue;
+    const pe_frame_t *op = operands[i];
+    if (!c || !c->d.planes[0] || !op || !op->d.planes[0]) continue;
     const int ip = c->d.palette;
     if (ip != PE_PALETTE_YUV420P && ip != PE_PALETTE_YVU420P && ip != PE_PALETTE_YUV422P) {
       set_err(PE_ERR_PALETTE, "convert_crossfade: the clip must be YUV420P / YVU420P / YUV422P");
       continue;
     }
-    if (operand->d.width != c->d.width || operand->d.height != c->d.height) {
+    if (op->d.palette != outpl) { set_err(PE_ERR_PALETTE, "convert_crossfade: output and operand must both be RGB24 or both BGR24"); continue; }
+    if (op->d.width != c->d.width || op->d.height != c->d.height) {
       set_err(PE_ERR_SIZE, "convert_crossfade: clip and operand differ in size");
       continue;
     }
+    e->fuse_blend2 = (const uint8_t *)op->d.planes[0];
+    e->fuse_blend2_rs = op->d.rowstrides[0];
     if (convert_locked(e, c, outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
   }
   e->yuv_defer = false;
@@ -1695,6 +1698,13 @@ extern "C" int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *
   e->pool.defer(false);
   e->pool.flush_deferred();
   return frc == PE_OK ? done : 0;
+}
+
+extern "C" int pe_fx_convert_crossfade_batch(pe_engine_t *e, int n, pe_frame_t *const *clips, const pe_frame_t *operand, int outpl,
+                                             int op_clamping, int blend_factor) {
+  if (!e || !clips || n < 0 || !operand || !operand->d.planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return 0; }
+  std::vector<const pe_frame_t *> ops((size_t)n, operand);
+  return pe_fx_convert_crossfade_batchv(e, n, clips, ops.data(), outpl, op_clamping, blend_factor);
 }
 
 extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,

@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_planar_to_rgb_fast(const __gri
 struct YuvFrameList {
   const uint8_t *y[32], *u[32], *v[32];
   uint8_t *dst[32];
+  const uint8_t *blend2[32];   // crossfade operand of each frame (all null or all set: YuvToRgbArgs::blend2 says which)
   int n;
 };
 
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
     const uint8_t *const Fy = FL.y[fidx], *const Fu = FL.u[fidx], *const Fv = FL.v[fidx];
     const uint8_t *yp = Fy + x, *up = Fu + off0, *vp = Fv + off0;
     uint8_t *dp = FL.dst[fidx] + (size_t)x * A.out.psize;
-    const uint8_t *xp = xf ? A.blend2 + (size_t)x * 3 : nullptr;
+    const uint8_t *xp = xf ? FL.blend2[fidx] + (size_t)x * 3 : nullptr;
     const bool seed_lane = IS422 && QUIRKS && x == 0;
 
     auto store_row = [&](uint32_t *p4, int row, const uint32_t *op) {
@@ -670,16 +671,16 @@ static cudaError_t march_attrs() {
 
 // A batch of frames that share everything but their pointers (geometry, strides, palettes, tables, flags) in ONE launch of the
 // marching kernel: the per-launch costs (table fill, first loads, tail) are paid once, and the warps get shares long enough to
-// march.  frames[i] must all pass yuv_planar_fast_ok and compare equal under yuv_planar_same_shape (which admits ONE shared crossfade
-// operand for the whole run: pe_fx_convert_crossfade_batch).
+// march.  frames[i] must all pass yuv_planar_fast_ok and compare equal under yuv_planar_same_shape (which admits a crossfade
+// operand per frame: pe_fx_convert_crossfade_batch / _batchv).
 bool yuv_planar_same_shape(const YuvToRgbArgs &a, const YuvToRgbArgs &b) {
   return a.width == b.width && a.height == b.height && a.is_422 == b.is_422 && a.clamped == b.clamped && a.low_quality == b.low_quality &&
          a.quirks == b.quirks && a.conv.t == b.conv.t && a.lut16 == b.lut16 && a.src.rs_y == b.src.rs_y && a.src.rs_u == b.src.rs_u &&
          a.src.rs_v == b.src.rs_v && a.src.cw == b.src.cw && a.src.ch == b.src.ch && a.dst.rs == b.dst.rs && a.out.r == b.out.r &&
          a.out.g == b.out.g && a.out.b == b.out.b && a.out.a == b.out.a && a.out.psize == b.out.psize &&
-         // a crossfade operand must be the SAME frame for the whole run (the shared transition operand of a multitrack stack), word aligned
-         a.blend2 == b.blend2 && a.blend2_rs == b.blend2_rs && a.blend_bf == b.blend_bf &&
-         (!a.blend2 || ((((uintptr_t)a.blend2) | (uint32_t)a.blend2_rs) & 3) == 0);
+         // crossfade operands: all frames of the run have one or none (each its own, or all the same), word aligned, same stride / factor
+         (a.blend2 != nullptr) == (b.blend2 != nullptr) && a.blend2_rs == b.blend2_rs && a.blend_bf == b.blend_bf &&
+         (!a.blend2 || (((((uintptr_t)a.blend2) | ((uintptr_t)b.blend2)) | (uint32_t)a.blend2_rs) & 3) == 0);
 }
 cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *frames, int n) {
   cudaError_t e = march_attrs();
@@ -693,7 +694,7 @@ cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *
     fl.n = n - base < 32 ? n - base : 32;
     for (int i = 0; i < 32; i++) {
       const YuvToRgbArgs &f = frames[base + (i < fl.n ? i : 0)];
-      fl.y[i] = f.src.y; fl.u[i] = f.src.u; fl.v[i] = f.src.v; fl.dst[i] = f.dst.p;
+      fl.y[i] = f.src.y; fl.u[i] = f.src.u; fl.v[i] = f.src.v; fl.dst[i] = f.dst.p; fl.blend2[i] = f.blend2;
     }
     long long rows_per_warp = (long long)nstrips * a.height * fl.n / ((long long)L.sm_count * (Y2_NT / 32));
     int band_h = (int)(rows_per_warp < 8 ? 8 : rows_per_warp);
@@ -732,8 +733,8 @@ cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a
     if (band_h < 8) band_h = 8;
     if (band_h > a.height) band_h = a.height;
     YuvFrameList fl;
-    fl.n = 1; fl.y[0] = a.src.y; fl.u[0] = a.src.u; fl.v[0] = a.src.v; fl.dst[0] = a.dst.p;
-    for (int i = 1; i < 32; i++) { fl.y[i] = fl.y[0]; fl.u[i] = fl.u[0]; fl.v[i] = fl.v[0]; fl.dst[i] = fl.dst[0]; }
+    fl.n = 1; fl.y[0] = a.src.y; fl.u[0] = a.src.u; fl.v[0] = a.src.v; fl.dst[0] = a.dst.p; fl.blend2[0] = a.blend2;
+    for (int i = 1; i < 32; i++) { fl.y[i] = fl.y[0]; fl.u[i] = fl.u[0]; fl.v[i] = fl.v[0]; fl.dst[i] = fl.dst[0]; fl.blend2[i] = fl.blend2[0]; }
     launch_march(L, a, fl, kmax, band_h);
     PE_COUNT_LAUNCH(L);
     return cudaGetLastError();

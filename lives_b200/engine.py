@@ -381,6 +381,13 @@ def convert_crossfade_batch(clips, operand, outpl, op_clamping, blend_factor):
     return int(e._lib.pe_fx_convert_crossfade_batch(e._h, len(clips), _arr(clips), operand._h, outpl, op_clamping, blend_factor))
 
 
+def convert_crossfade_batchv(clips, operands, outpl, op_clamping, blend_factor):
+    """convert_crossfade with one operand per clip (operands[i] for clips[i]); one kernel launch per 32 same-shaped clips"""
+    e = clips[0].engine
+    assert len(clips) == len(operands)
+    return int(e._lib.pe_fx_convert_crossfade_batchv(e._h, len(clips), _arr(clips), _arr(operands), outpl, op_clamping, blend_factor))
+
+
 def fused_convert_letterbox_over_gamma_batch(fg, bg, out, inner_w, inner_h, alpha, gamma_from, gamma_to):
     e = fg[0].engine
     capi.check(e._lib.pe_fused_convert_letterbox_over_gamma_batch(e._h, len(fg), _arr(fg), _arr(bg), _arr(out), inner_w,

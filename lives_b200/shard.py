@@ -77,3 +77,28 @@ def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blen
     consumed.record(es)
     ts.wait_event(consumed)
     return clip_layer
+
+
+def multitrack_crossfade_group(engine, clip_layers, operand_group, width, height, blend_factor, src_rank=0, out_palette=1):
+    """config 5 for a GROUP of K consecutive output frames of this rank's clip (render-to-disk, not realtime): `operand_group` is a
+    uint8 CUDA tensor of K x height x rowstride bytes holding K consecutive frames of the shared transition operand; it travels in
+    ONE broadcast, and the K conversions + crossfades leave as ONE kernel launch (pe_fx_convert_crossfade_batchv).  The host cost
+    per output frame (a Python call, a collective launch, two event waits: ~100 us, four times the kernel) is paid once per
+    group.  Same stream ordering as multitrack_crossfade."""
+    from . import engine as E
+    k = len(clip_layers)
+    if operand_group.dim() != 3 or operand_group.shape[0] != k or operand_group.shape[1] != height:
+        raise ValueError("operand_group must be K x height x rowstride")
+    es, ts = _engine_stream(engine), torch.cuda.current_stream()
+    broadcast_operand(operand_group, src=src_rank)
+    arrived = torch.cuda.Event()
+    arrived.record(ts)
+    es.wait_event(arrived)
+    rs = operand_group.shape[2]
+    ops = [E.Layer.wrap_device(engine, out_palette, width, height, [operand_group[i].data_ptr()], [rs]) for i in range(k)]
+    if E.convert_crossfade_batchv(clip_layers, ops, out_palette, 0, blend_factor) != k:
+        raise RuntimeError("grouped crossfade failed: " + E.capi.last_error())
+    consumed = torch.cuda.Event()
+    consumed.record(es)
+    ts.wait_event(consumed)
+    return clip_layers

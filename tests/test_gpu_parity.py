@@ -698,6 +698,31 @@ def test_yuv_clamping_switch(eng):
         e_nq.close()
 
 
+def test_convert_crossfade_batchv_operand_per_clip(eng):
+    """pe_fx_convert_crossfade_batchv: clip i against operand i (the frames of one clip against successive frames of the other
+    track) in one launch == the per-clip call == the oracle"""
+    o = T.oracle()
+    rng = np.random.default_rng(34)
+    for (w, h), is422, n in (((256, 64), 1, 4), ((640, 360), 0, 3), ((1920, 1080), 1, 2)):
+        clips, ops, exps = [], [], []
+        for _ in range(n):
+            y, u, v = T.make_yuv_planar(rng, w, h, bool(is422), True)
+            operand = T.make_packed(rng, w, h, 3)
+            exp = np.zeros((h, T.rowstride(w, 3)), np.uint8)
+            o.pe_or_yuv420p_to_rgb(T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(exp), exp.strides[0], 0, 0, is422, 0, 1,
+                                   T.Q_HIGH, 1, None)
+            o.pe_or_simple_blend(0, 1, T.ptr(exp), exp.strides[0], T.ptr(operand), operand.strides[0], T.ptr(exp), exp.strides[0], w, h,
+                                 77, operand.size)
+            clips.append(lb.Layer.from_host(eng, 522 if is422 else 512, w, h, [y, u, v], yuv_subspace=1))
+            ops.append(packed_layer(eng, 1, w, h, operand))
+            exps.append(exp)
+        before = eng.launch_count
+        assert lb.convert_crossfade_batchv(clips, ops, 1, 0, 77) == n
+        assert eng.launch_count - before == 1
+        for c, exp in zip(clips, exps):
+            assert (payload(c.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (w, h, is422)
+
+
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
     src = T.make_packed(rng, 32, 8, 4)

@@ -35,6 +35,11 @@ def _worker(rank, world, port, q):
         ref = torch.from_numpy(np.random.default_rng(99).integers(0, 256, (h, rs), dtype=np.uint8))
         buf = ref.clone() if rank == 0 else torch.zeros((h, rs), dtype=torch.uint8)
         shard.broadcast_operand(buf, src=0)
+        # a group of K = 3 operand frames in one broadcast (shard.multitrack_crossfade_group)
+        gref = torch.from_numpy(np.random.default_rng(100).integers(0, 256, (3, h, rs), dtype=np.uint8))
+        gbuf = gref.clone() if rank == 0 else torch.zeros((3, h, rs), dtype=torch.uint8)
+        shard.broadcast_operand(gbuf, src=0)
+        assert bool((gbuf == gref).all())
         hist = torch.bincount(buf.flatten().long(), minlength=256)
         shard.allreduce_histogram(hist)
         q.put((rank, (lo, hi), bool((buf == ref).all()), int(hist.sum())))

@@ -71,12 +71,49 @@ def main():
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # ---- the same in groups of K output frames: one broadcast of K operand frames, one kernel launch for the K crossfades
+    K = 8
+    groups = [torch.randint(0, 256, (K, H, W * 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    # parity of the grouped path at 256 x 64 against the per-frame result above
+    gop = torch.from_numpy(op_host).to(dev) if rank == 0 else torch.zeros(op_host.shape, dtype=torch.uint8, device=dev)
+    gop = gop.unsqueeze(0).repeat(3, 1, 1).contiguous()
+    gclips = [lb.Layer.from_host(eng, lb.WEED_PALETTE_YUV422P, w, h, [y, u, v], yuv_subspace=1) for _ in range(3)]
+    shard.multitrack_crossfade_group(eng, gclips, gop, w, h, bf)
+    gok = all(bool((c.to_host()[0][:, :w * 3] == exp[:, :w * 3]).all()) for c in gclips)
+    gflag = torch.tensor([int(gok)], device=dev)
+    dist.all_reduce(gflag, op=dist.ReduceOp.MIN)
+    gsteps = 10
+
+    def group():
+        clips = [lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2],
+                                      yuv_subspace=1) for _ in range(K)]
+        shard.multitrack_crossfade_group(eng, clips, groups[it[0] & 1], W, H, 128)
+        it[0] += 1
+        for c in clips:
+            c.free()
+
+    for _ in range(2):
+        group()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(gsteps):
+        group()
+    eng.sync()
+    ev1.record()
+    torch.cuda.synchronize()
+    gms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": "cfg5 grouped: %d clips x 4K YUV422P -> RGB24 + crossfade, %d operand frames per broadcast, one launch per group" % (world, K),
+                          "n_gpus": world, "parity_all_ranks": bool(gflag.item()), "clip_frames_per_s": world * gsteps * K / (gms.item() / 1e3),
+                          "ms_per_output_frame": gms.item() / (gsteps * K), "broadcast_bytes": K * H * W * 3}), flush=True)
     if rank == 0:
         print(json.dumps({"config": "cfg5: %d clips x 4K YUV422P -> RGB24 + crossfade with broadcast operand" % world, "n_gpus": world,
                           "parity_all_ranks": bool(flag.item()), "clip_frames_per_s": world * steps / (ms.item() / 1e3),
                           "ms_per_output_frame": ms.item() / steps, "broadcast_bytes": H * W * 3}), flush=True)
     dist.destroy_process_group()
-    if not flag.item():
+    if not flag.item() or not gflag.item():
         sys.exit(1)
 
 
