@@ -1114,6 +1114,15 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                                        (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1], n.d.rowstrides[2],
                                        n.d.width >> 1, n.d.height, cavg);
     n.d.yuv_sampling = PE_YUV_SAMPLING_DEFAULT;
+  } else if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YUV422P) && (outpl == PE_PALETTE_UYVY || outpl == PE_PALETTE_YUYV)) {
+    // convert_yuv420_to_{uyvy,yuyv}_frame (:13561-13574): chroma row k serves luma rows 2k and 2k + 1 (the averaging never runs);
+    // convert_yuv422p_to_{uyvy,yuyv}_frame (:13686-13699): interleave (the reference's own row advance is wrong beyond row 0, X)
+    n.d.width = width & ~1;
+    if (n.d.width < 2) { set_err(PE_ERR_SIZE, "frame too narrow for a 4:2:2 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2]};
+    ce = launch_planar42x_to_packed422(L, outpl == PE_PALETTE_UYVY ? 0 : 1, inpl == PE_PALETTE_YUV422P, pl, f->d.rowstrides,
+                                       Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width >> 1, height);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;
@@ -1142,6 +1151,10 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
   }
   if (inplace) f->d.palette = outpl;
   else frame_take(f, &n);
+  // the converters that produce 4:2:0 / 4:2:2 planes from full-resolution chroma leave WEED_YUV_SAMPLING_DEFAULT (:12691, :13022)
+  if ((outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P) &&
+      (pal_is_rgb(inpl) || inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P))
+    f->d.yuv_sampling = PE_YUV_SAMPLING_DEFAULT;
 
   // conv_done (:13859-13900)
   if (new_gamma_type != PE_GAMMA_UNKNOWN && can_inline_gamma(inpl, outpl)) {

@@ -8,6 +8,7 @@
 //   k_packed422_unpack    convert_{uyvy,yuyv}_to_{yuv422,yuvp,yuv888}_frame  colourspace.c:8093 / 7800 / 7845
 //   k_yuv444p_to_packed422  convert_yuv_planar_to_{uyvy,yuyv}_frame      colourspace.c:7500 / 7548
 //   k_yuv444p_to_chroma420  convert_yuvp_to_yuv420_frame                 colourspace.c:7690
+//   k_planar42x_to_packed422  convert_yuv420_to_{uyvy,yuyv}_frame / convert_yuv422p_to_{uyvy,yuyv}_frame  colourspace.c:7104 / 6442
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -270,6 +271,28 @@ __global__ void __launch_bounds__(kBlock) k_yuv444p_to_chroma420(const uint8_t *
   }
 }
 
+// planar 4:2:0 / 4:2:2 -> UYVY / YUYV (convert_yuv420_to_{uyvy,yuyv}_frame colourspace.c:7104 / 7152, convert_yuv422p_to_{uyvy,yuyv}_frame
+// :6442 / 6470): pure interleave, 4:2:0 chroma rows used twice (the reference's vertical averaging never runs).  One thread = 4 pixels.
+__global__ void __launch_bounds__(kBlock) k_planar42x_to_packed422(int fmt, int is_422, const uint8_t *__restrict__ py, const uint8_t *__restrict__ pu,
+                                                                  const uint8_t *__restrict__ pv, int rs_y, int rs_u, int rs_v, uint8_t *dst,
+                                                                  int orow, int width_mpx, int height, int vec) {
+  const int groups = (width_mpx + 1) >> 1;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int m = 2 * g, nm = min(2, width_mpx - m), cr = is_422 ? row : row >> 1;
+    const uint32_t yw = ld_px4(py + (long long)rs_y * row + 2 * m, 2 * nm, vec);
+    const uint8_t *qu = pu + (long long)rs_u * cr + m, *qv = pv + (long long)rs_v * cr + m;
+    const uint32_t u0 = __ldg(qu), v0 = __ldg(qv), u1 = nm == 2 ? __ldg(qu + 1) : 0u, v1 = nm == 2 ? __ldg(qv + 1) : 0u;
+    uint32_t m0 = byte_of(yw, 0) | (u0 << 8) | (byte_of(yw, 1) << 16) | (v0 << 24);   // YUYV
+    uint32_t m1 = byte_of(yw, 2) | (u1 << 8) | (byte_of(yw, 3) << 16) | (v1 << 24);
+    if (fmt == 0) { m0 = __byte_perm(m0, 0u, 0x2301); m1 = __byte_perm(m1, 0u, 0x2301); }  // UYVY
+    uint8_t *d = dst + (long long)orow * row + 4LL * m;
+    if (vec && nm == 2) st_stream_u2(d, make_uint2(m0, m1));
+    else { st_px4(d, m0, 4, false); if (nm == 2) st_px4(d + 4, m1, 4, false); }
+  }
+}
+
 // UYVY <-> YUYV in place: swab() of every row
 __global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
   const long long total = (long long)width_mpx * height;
@@ -406,6 +429,15 @@ cudaError_t launch_yuv444p_to_chroma420(const Launch &L, const uint8_t *su, cons
   const bool vec = aligned4(su) && aligned4(sv) && aligned4(du) && aligned4(dv) && !((irs | ors_u | ors_v) & 3);
   const dim3 grid(grid_for(L, (long long)((cw + 3) / 4) * ((height + 1) / 2)), 2);
   k_yuv444p_to_chroma420<<<grid, kBlock, 0, L.stream>>>(su, sv, irs, du, dv, ors_u, ors_v, cw, height, cavg_dev, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_planar42x_to_packed422(const Launch &L, int fmt, int is_422, const uint8_t *const planes[3], const int irows[3], Img dst,
+                                          int width_mpx, int height) {
+  const bool vec = aligned4(planes[0]) && !(irows[0] & 3) && (((uintptr_t)dst.p | (uint32_t)dst.rs) & 7) == 0;
+  k_planar42x_to_packed422<<<grid_for(L, (long long)((width_mpx + 1) / 2) * height), kBlock, 0, L.stream>>>(
+      fmt, is_422, planes[0], planes[1], planes[2], irows[0], irows[1], irows[2], dst.p, dst.rs, width_mpx, height, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

@@ -1095,6 +1095,26 @@ void pe_or_yuv444p_to_yuv420p(const uint8_t *const src[3], const int irows[3], i
     }
 }
 
+/* convert_yuv420_to_{uyvy,yuyv}_frame :7104-7198: rows 2k and 2k+1 take chroma row k as it is -- the averaging of :7132-7135 is
+ * guarded by `i > 0` and i is never incremented, so it never runs (R).  The chroma pointers are rewound by the full rowstride
+ * (:7143-7144), which is only right for unpadded chroma planes, and the YUYV variant never skips the luma row padding (:7181-7195)
+ * (X: strides honoured here, equal there).
+ * convert_yuv422p_to_{uyvy,yuyv}_frame :6442-6494: plain interleave; the reference's row advance is wrong for every argument
+ * (`irows[0] -= width` for 2 * width luma bytes, and the dispatcher passes the pixel width as the macropixel count, :13691), so only
+ * its first row is defined (X beyond). */
+void pe_or_yuv42xp_to_packed422(int fmt, const uint8_t *const src[3], const int irows[3], int width, int height, int is_422,
+                                uint8_t *dest, int orow) {
+  for (int k = 0; k < height; k++) {
+    const int cr = is_422 ? k : k >> 1;
+    const uint8_t *y = src[0] + (long)irows[0] * k, *u = src[1] + (long)irows[1] * cr, *v = src[2] + (long)irows[2] * cr;
+    uint8_t *d = dest + (long)orow * k;
+    for (int x = 0; x < width >> 1; x++, d += 4) {
+      if (fmt == 0) { d[0] = u[x]; d[1] = y[2 * x]; d[2] = v[x]; d[3] = y[2 * x + 1]; }
+      else { d[0] = y[2 * x]; d[1] = u[x]; d[2] = y[2 * x + 1]; d[3] = v[x]; }
+    }
+  }
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

@@ -134,6 +134,10 @@ void pe_or_yuv444p_to_packed422(int fmt, const uint8_t *const src[3], int irow, 
                                 int clamping);
 void pe_or_yuv444p_to_yuv420p(const uint8_t *const src[3], const int irows[3], int width, int height, uint8_t *const dest[3],
                               const int orows[3], int clamping);
+/* planar 4:2:0 / 4:2:2 -> packed 4:2:2 (convert_yuv420_to_{uyvy,yuyv}_frame :7104,:7152; convert_yuv422p_to_{uyvy,yuyv}_frame
+ * :6442,:6470): luma and chroma interleaved, 4:2:0 chroma rows used twice without interpolation */
+void pe_or_yuv42xp_to_packed422(int fmt, const uint8_t *const src[3], const int irows[3], int width, int height, int is_422,
+                                uint8_t *dest, int orow);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

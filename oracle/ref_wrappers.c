@@ -327,3 +327,18 @@ void ref_yuv444p_to_yuv420p(uint8_t **src, int width, int height, int *irows, in
   ref_init();
   convert_yuvp_to_yuv420_frame(src, width, height, irows, orows, dest, clamping);
 }
+
+/* planar 4:2:0 -> packed 4:2:2; width in pixels (what the dispatcher passes, colourspace.c:13566) */
+void ref_yuv420_to_packed422(int fmt, uint8_t **src, int width, int height, int *irows, int orow, void *dest, int clamping) {
+  int ir[3] = {irows[0], irows[1], irows[2]}; /* the reference modifies its argument */
+  ref_init();
+  if (fmt == 0) convert_yuv420_to_uyvy_frame(src, width, height, ir, orow, (uyvy_macropixel *)dest, clamping);
+  else convert_yuv420_to_yuyv_frame(src, width, height, ir, orow, (yuyv_macropixel *)dest, clamping);
+}
+
+/* planar 4:2:2 -> packed 4:2:2; width = macropixels per row as the function's loop counts them */
+void ref_yuv422p_to_packed422(int fmt, uint8_t **src, int width, int height, int *irows, int orow, uint8_t *dest) {
+  int ir[3] = {irows[0], irows[1], irows[2]};
+  if (fmt == 0) convert_yuv422p_to_uyvy_frame(src, width, height, ir, orow, dest);
+  else convert_yuv422p_to_yuyv_frame(src, width, height, ir, orow, dest);
+}

@@ -640,6 +640,23 @@ def test_yuv444p_to_packed422_and_yuv420p(eng, size):
             assert (got[k][:, :w >> 1] == ep[k][:, :w >> 1]).all(), ("420p", w, h, ipal, cl, k)
 
 
+@pytest.mark.parametrize("size", [(64, 12), (38, 6), (1920, 1080), (2, 2)])
+def test_planar42x_to_packed422(eng, size):
+    """YUV420P / YUV422P -> UYVY / YUYV (convert_yuv420_to_{uyvy,yuyv}_frame, convert_yuv422p_to_{uyvy,yuyv}_frame)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(130 + w)
+    for ipal, opal in itertools.product((512, 522), (564, 565)):
+        y, u, v = T.make_yuv_planar(rng, w, h, ipal == 522, True)
+        wm = w >> 1
+        exp = np.zeros((h, T.rowstride(wm, 4)), np.uint8)
+        o.pe_or_yuv42xp_to_packed422(opal - 564, T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, int(ipal == 522), T.ptr(exp), exp.strides[0])
+        lay = lb.Layer.from_host(eng, ipal, w, h, [y, u, v])
+        assert lb.convert_layer_palette(lay, opal, 0)
+        assert (lay.palette, lay.width, lay.height) == (opal, w, h)
+        assert (payload(lay.to_host()[0], wm, 4) == payload(exp, wm, 4)).all(), (w, h, ipal, opal)
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

@@ -675,3 +675,27 @@ def test_yuv444p_to_packed422_and_yuv420p_match_reference():
         r.ref_yuv444p_to_yuv420p(T.planes_arg(*pl), w, h, T.strides_arg(*pl), T.strides_arg(*db), T.planes_arg(*db), cl)
         for k in range(3):
             assert (da[k][:, :w >> (k > 0)] == db[k][:, :w >> (k > 0)]).all(), ("420p", w, h, cl, k)
+
+
+def test_planar42x_to_packed422_matches_reference():
+    """4:2:0 -> UYVY / YUYV on unpadded chroma planes (where the reference's pointer rewind is right); 4:2:2 -> UYVY / YUYV on a
+    one-row frame (the only row the reference gets right)"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(76)
+    for (w, h), fmt in itertools.product(((32, 6), (34, 4), (2, 2)), (0, 1)):
+        # (the YUYV variant never skips the luma row padding, colourspace.c:7181-7195: unpadded luma for it)
+        ys = T.rowstride(w, 1) if fmt == 0 else w
+        y = np.zeros((h, ys), np.uint8); y[:, :w] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+        v = rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)
+        ors = T.rowstride(w // 2, 4)
+        a, b = np.zeros((h, ors), np.uint8), np.zeros((h, ors), np.uint8)
+        o.pe_or_yuv42xp_to_packed422(fmt, T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, 0, T.ptr(a), ors)
+        r.ref_yuv420_to_packed422(fmt, T.planes_arg(y, u, v), w, h, T.strides_arg(y, u, v), ors, T.ptr(b), 0)
+        assert (a == b).all(), ("420", w, h, fmt)
+        y1 = rng.integers(0, 256, (1, w), dtype=np.uint8)
+        u1, v1 = rng.integers(0, 256, (1, w // 2), dtype=np.uint8), rng.integers(0, 256, (1, w // 2), dtype=np.uint8)
+        a, b = np.zeros((1, 2 * w), np.uint8), np.zeros((1, 2 * w), np.uint8)
+        o.pe_or_yuv42xp_to_packed422(fmt, T.planes_arg(y1, u1, v1), T.strides_arg(y1, u1, v1), w, 1, 1, T.ptr(a), 2 * w)
+        r.ref_yuv422p_to_packed422(fmt, T.planes_arg(y1, u1, v1), w // 2, 1, T.strides_arg(y1, u1, v1), 2 * w, T.ptr(b))
+        assert (a == b).all(), ("422", w, fmt)
