@@ -1364,7 +1364,7 @@ int flush_yuv_pending(pe_engine *e) {
   return PE_OK;
 }
 
-// launch the RGB <-> RGB permutations a batch call has queued: runs of same-shaped frames leave as one launch per 64
+// launch the RGB <-> RGB permutations a batch call has queued: runs of same-shaped frames leave as one launch per 128
 int flush_rgb_pending(pe_engine *e) {
   std::vector<pe_engine::RgbJob> q;
   q.swap(e->rgb_pending);
@@ -1544,7 +1544,7 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
   bool all_rgb = pal_is_rgb(outpl);
   for (int i = 0; i < n && all_rgb; i++) all_rgb = layers[i] && pal_is_rgb(layers[i]->d.palette);
   if (all_rgb) {
-    // RGB <-> RGB: the permutations are queued and leave as one launch per 64 same-shaped frames
+    // RGB <-> RGB: the permutations are queued and leave as one launch per 128 same-shaped frames
     e->rgb_defer = true;
     e->pool.defer(true);
     for (int i = 0; i < n; i++)

@@ -4,6 +4,8 @@
 // All of these are HBM-bound byte streams (<= ~20 integer ops per byte): the design rules are
 // 128-bit coalesced accesses, L1-bypassing streaming loads/stores, grids sized as a multiple of the
 // SM count with grid-stride loops, and look-up tables staged in shared memory.
+#include <cstdlib>
+
 #include "pe_device.cuh"
 #include "pe_kernels.h"
 
@@ -38,6 +40,7 @@ struct PermuteParams {
   uint32_t sel;                    // PRMT selector building an output pixel from (in_pixel, 0xFFFFFFFF)
   const uint8_t *lut;              // device LUT or nullptr
   int vec_ok;                      // rows are 4-byte (3 bpp) / 16-byte (4 bpp) aligned on both sides
+  int vec16_ok;                    // 3 bpp -> 3 bpp: rows 16-byte aligned on both sides, width a multiple of 16
 };
 
 template <bool HAS_LUT>
@@ -50,9 +53,10 @@ __device__ __forceinline__ uint32_t permute_pixel(uint32_t pix, const PermutePar
 }
 
 // frames of one batched launch (same geometry, strides and palettes): blockIdx.y selects the frame
+constexpr int kRgbBatch = 128;  // frames per launch: 2 KB of the 4 KB kernel parameter space
 struct RgbFrameList {
-  const uint8_t *src[64];
-  uint8_t *dst[64];
+  const uint8_t *src[kRgbBatch];
+  uint8_t *dst[kRgbBatch];
 };
 
 template <int IPS, int OPS, bool HAS_LUT>
@@ -63,6 +67,30 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P, co
   if (HAS_LUT) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = P.lut[i];
     __syncthreads();
+  }
+  if (IPS == 3 && OPS == 3 && P.vec16_ok) {
+    // 3-byte pixels with 16-byte aligned rows of whole 16-pixel groups: a thread moves 48 bytes as 3 x 128 bits (a warp's 32-bit
+    // accesses at a 12-byte stride cost three times the LSU wavefronts of the same bytes moved as 128-bit vectors)
+    const int groups16 = P.width >> 4;
+    const long long total16 = (long long)groups16 * P.height;
+    for (long long it = global_tid(); it < total16; it += global_threads()) {
+      const int row = (int)(it / groups16), g = (int)(it - (long long)row * groups16);
+      const uint8_t *s = f_src + (long long)row * P.irow + (long long)g * 48;
+      uint8_t *d = f_dst + (long long)row * P.orow + (long long)g * 48;
+      const uint4 a = ld_u4(s), b = ld_u4(s + 16), c = ld_u4(s + 32);  // may be in place: plain loads
+      uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+        const uint32_t p0 = permute_pixel<HAS_LUT>(w0, P, s_lut), p1 = permute_pixel<HAS_LUT>(__byte_perm(w0, w1, 0x0543), P, s_lut);
+        const uint32_t p2 = permute_pixel<HAS_LUT>(__byte_perm(w1, w2, 0x0432), P, s_lut), p3 = permute_pixel<HAS_LUT>(w2 >> 8, P, s_lut);
+        w[3 * q] = __byte_perm(p0, p1, 0x4210); w[3 * q + 1] = __byte_perm(p1, p2, 0x5421); w[3 * q + 2] = __byte_perm(p2, p3, 0x6542);
+      }
+      *(uint4 *)d = make_uint4(w[0], w[1], w[2], w[3]);
+      *(uint4 *)(d + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      *(uint4 *)(d + 32) = make_uint4(w[8], w[9], w[10], w[11]);
+    }
+    return;
   }
   const int groups = (P.width + 3) >> 2;
   const long long total = (long long)groups * P.height;
@@ -106,7 +134,7 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P, co
 
 }  // namespace
 
-// n frames of the same geometry, strides and palettes in one launch per 64 (srcs[i] may equal dsts[i]: in place)
+// n frames of the same geometry, strides and palettes in one launch per 128 (srcs[i] may equal dsts[i]: in place)
 cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs, int irow, uint8_t *const *dsts, int orow, int n, int width,
                                     int height, RgbLayout in, RgbLayout out, const uint8_t *lut8_dev) {
   PermuteParams P;
@@ -123,11 +151,14 @@ cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs,
   bool vec = (irow % ia == 0) && (orow % oa == 0);
   for (int i = 0; i < n && vec; i++) vec = ((uintptr_t)srcs[i] % ia == 0) && ((uintptr_t)dsts[i] % oa == 0);
   P.vec_ok = vec;
-  const long long work = (long long)((width + 3) >> 2) * height;
-  for (int base = 0; base < n; base += 64) {
+  bool vec16 = in.psize == 3 && out.psize == 3 && !(width & 15) && !(irow & 15) && !(orow & 15) && getenv("PE_RGB_NO_VEC16") == nullptr;
+  for (int i = 0; i < n && vec16; i++) vec16 = ((uintptr_t)srcs[i] % 16 == 0) && ((uintptr_t)dsts[i] % 16 == 0);
+  P.vec16_ok = vec16;
+  const long long work = vec16 ? (long long)(width >> 4) * height : (long long)((width + 3) >> 2) * height;
+  for (int base = 0; base < n; base += kRgbBatch) {
     RgbFrameList fl;
-    const int cnt = n - base < 64 ? n - base : 64;
-    for (int i = 0; i < 64; i++) { fl.src[i] = srcs[base + (i < cnt ? i : 0)]; fl.dst[i] = dsts[base + (i < cnt ? i : 0)]; }
+    const int cnt = n - base < kRgbBatch ? n - base : kRgbBatch;
+    for (int i = 0; i < kRgbBatch; i++) { fl.src[i] = srcs[base + (i < cnt ? i : 0)]; fl.dst[i] = dsts[base + (i < cnt ? i : 0)]; }
     // the frames of a launch share the grid: about 8 CTAs per SM over all of them
     int gx = grid_for(L, work);
     const int cap = (L.sm_count * 8 + cnt - 1) / cnt;
