@@ -1123,6 +1123,19 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2]};
     ce = launch_planar42x_to_packed422(L, outpl == PE_PALETTE_UYVY ? 0 : 1, inpl == PE_PALETTE_YUV422P, pl, f->d.rowstrides,
                                        Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width >> 1, height);
+  } else if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P) && (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P)) {
+    // luma copied, convert_quad_chroma on planes 1 and 2 (:13598-13617; YVU420P with its chroma planes swapped first, :12354), the alpha
+    // plane of YUVA4444P = 255 (the reference also asks for it on YUV444P, whose 4th plane pointer is not valid: X)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const Planes S = planes_of(f, inpl == PE_PALETTE_YVU420P);
+    ce = launch_copy2d(L, S.y, S.rs_y, (uint8_t *)n.d.planes[0], n.d.rowstrides[0], width, height, 0, 0);
+    if (ce == cudaSuccess)
+      ce = launch_quad_chroma(L, S.u, S.v, S.rs_u, S.rs_v, S.ch, (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1], width,
+                              height, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+    if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)
+      ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

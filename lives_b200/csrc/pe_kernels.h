@@ -117,6 +117,8 @@ cudaError_t launch_yuv444p_to_chroma420(const Launch &L, const uint8_t *su, cons
                                         int ors_v, int cw, int height, const uint8_t *cavg_dev);
 cudaError_t launch_planar42x_to_packed422(const Launch &L, int fmt, int is_422, const uint8_t *const planes[3], const int irows[3], Img dst,
                                           int width_mpx, int height);
+cudaError_t launch_quad_chroma(const Launch &L, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, int ch, uint8_t *du, uint8_t *dv,
+                               int ors, int width, int height, int jpeg, const uint8_t *cavg_dev);
 cudaError_t launch_swab(const Launch &L, Img img, int width_mpx, int height);
 // kind 0 luma plane, 1 chroma plane, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; row_phase_stride (YUV888): 0 = the reference's dense
 // walk across the row padding, else the rowstride (the Y U V phase restarts with every row)

@@ -9,6 +9,7 @@
 //   k_yuv444p_to_packed422  convert_yuv_planar_to_{uyvy,yuyv}_frame      colourspace.c:7500 / 7548
 //   k_yuv444p_to_chroma420  convert_yuvp_to_yuv420_frame                 colourspace.c:7690
 //   k_planar42x_to_packed422  convert_yuv420_to_{uyvy,yuyv}_frame / convert_yuv422p_to_{uyvy,yuyv}_frame  colourspace.c:7104 / 6442
+//   k_quad_chroma         convert_quad_chroma                            colourspace.c:10642  (4:2:0 -> 4:4:4 chroma planes)
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -293,6 +294,63 @@ __global__ void __launch_bounds__(kBlock) k_planar42x_to_packed422(int fmt, int 
   }
 }
 
+// 4:2:0 -> 4:4:4 chroma planes (convert_quad_chroma, colourspace.c:10642).  Even destination row 2k from chroma row k: column 0 =
+// s[0], column 2m = f(s[m-1], s[m]), column 2m+1 = g(s[m], s[m+1]) (JPEG sampling: f = g = avg_chroma; otherwise U: f = 3:1, g = 1:3,
+// V mirrored); odd row r = avg_chroma(row r+1, row r-1), the last odd row of an odd-height frame with the operands swapped, the last
+// row of an even-height frame a copy of the row above.  One thread = 4 destination samples; blockIdx.y = plane (U, V).
+struct QuadChromaParams {
+  const uint8_t *su, *sv;
+  uint8_t *du, *dv;
+  int irs_u, irs_v, ors, w2, height, cw, ch, jpeg;
+  const uint8_t *cavg;
+};
+
+__device__ __forceinline__ uint32_t quad_even4(const uint8_t *__restrict__ s, int irs, int k, int m, int cw, int ch, bool is_u, bool jpeg,
+                                               const uint8_t *__restrict__ cavg, int n) {
+  // 4 destination samples 2m .. 2m+3 of even row 2k (n of them valid) from s[m-1 .. m+2]
+  const uint8_t *r = s + (long long)irs * k;
+  auto at = [&](int c) -> uint32_t {
+    if (c < 0) c = 0;
+    if (c >= cw) c = (cw < irs || k + 1 < ch) ? cw : cw - 1;
+    return r[c];
+  };
+  auto av = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
+  auto f = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : (is_u ? av(x, av(x, y)) : av(av(x, y), y)); };   // even column
+  auto g = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : (is_u ? av(av(x, y), y) : av(x, av(x, y))); };   // odd column
+  const uint32_t a = at(m), b = n > 2 ? at(m + 1) : a;
+  const uint32_t v0 = m == 0 ? a : f(at(m - 1), a);
+  const uint32_t v1 = n > 1 ? g(a, n > 2 ? b : at(m + 1)) : 0u;
+  const uint32_t v2 = n > 2 ? f(a, b) : 0u;
+  const uint32_t v3 = n > 3 ? g(b, at(m + 2)) : 0u;
+  return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+}
+
+__global__ void __launch_bounds__(kBlock) k_quad_chroma(const QuadChromaParams P, int vec) {
+  const bool is_u = blockIdx.y == 0;
+  const uint8_t *s = is_u ? P.su : P.sv;
+  uint8_t *d = is_u ? P.du : P.dv;
+  const int irs = is_u ? P.irs_u : P.irs_v;
+  const int groups = (P.w2 + 3) >> 2;
+  const long long total = (long long)groups * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, P.w2 - x), m = x >> 1;
+    uint32_t w;
+    if (!(row & 1)) {
+      w = quad_even4(s, irs, row >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
+    } else {
+      const uint32_t up = quad_even4(s, irs, (row - 1) >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
+      if (row + 1 > P.height - 1) {
+        w = up;
+      } else {
+        const uint32_t dn = quad_even4(s, irs, (row + 1) >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
+        w = ((P.height & 1) && row == P.height - 2) ? avg4(P.cavg, up, dn) : avg4(P.cavg, dn, up);
+      }
+    }
+    st_px4(d + (long long)P.ors * row + x, w, n, vec);
+  }
+}
+
 // UYVY <-> YUYV in place: swab() of every row
 __global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
   const long long total = (long long)width_mpx * height;
@@ -438,6 +496,19 @@ cudaError_t launch_planar42x_to_packed422(const Launch &L, int fmt, int is_422, 
   const bool vec = aligned4(planes[0]) && !(irows[0] & 3) && (((uintptr_t)dst.p | (uint32_t)dst.rs) & 7) == 0;
   k_planar42x_to_packed422<<<grid_for(L, (long long)((width_mpx + 1) / 2) * height), kBlock, 0, L.stream>>>(
       fmt, is_422, planes[0], planes[1], planes[2], irows[0], irows[1], irows[2], dst.p, dst.rs, width_mpx, height, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quad_chroma(const Launch &L, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, int ch, uint8_t *du, uint8_t *dv,
+                               int ors, int width, int height, int jpeg, const uint8_t *cavg_dev) {
+  QuadChromaParams P;
+  P.su = su; P.sv = sv; P.du = du; P.dv = dv; P.irs_u = irs_u; P.irs_v = irs_v; P.ors = ors;
+  P.w2 = (width >> 1) << 1; P.height = height; P.cw = P.w2 >> 1; P.ch = ch; P.jpeg = jpeg; P.cavg = cavg_dev;
+  if (P.w2 < 2 || height < 1) return cudaSuccess;
+  const int vec = aligned4(du) && aligned4(dv) && !(ors & 3);
+  const dim3 grid(grid_for(L, (long long)((P.w2 + 3) / 4) * height), 2);
+  k_quad_chroma<<<grid, kBlock, 0, L.stream>>>(P, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

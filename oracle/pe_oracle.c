@@ -1115,6 +1115,47 @@ void pe_or_yuv42xp_to_packed422(int fmt, const uint8_t *const src[3], const int 
   }
 }
 
+/* convert_quad_chroma :10642-10712.  Even destination row 2k, from chroma row k (s): column 0 = s[0]; column 2m (m > 0) =
+ * f(s[m-1], s[m]); column 2m+1 = g(s[m], s[m+1]) -- s[cw] is the byte behind the row (padding / next row's first sample; on the
+ * last row of an unpadded plane: the edge sample, X) -- with, for JPEG sampling, f = g = avg_chroma; otherwise U: f = avg_3_1
+ * (= avg(x, avg(x, y))), g = avg_1_3 (= avg(avg(x, y), y)) and V the other way round (:10669-10685).  Odd row r is written two
+ * rows later as avg_chroma(row r+1, row r-1) (:10688-10694: the LOWER row is the table row); for an odd height the last odd row is
+ * fixed up after the loop with the operands the other way round (:10707-10708).
+ * X: for an EVEN height the last row is never written by the reference (left as allocated) -- defined here as a copy of the row
+ * above; the odd-row pass writes one sample past `width` (:10692-10694), harmless on padded planes, not restated; the
+ * dispatcher passes add_alpha = TRUE for YUV444P, whose 4th plane pointer is not valid (:13606). */
+void pe_or_quad_chroma(const uint8_t *const src[3], const int istrides[3], int width, int height, uint8_t *const dest[4], int ostride,
+                       int add_alpha, int sampling_jpeg, int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+#define OR_AV(x_, y_) avg[((int)(x_) << 8) + (int)(y_)]
+  const int w2 = (width >> 1) << 1, cw = w2 >> 1, ch = (height + 1) >> 1;
+  for (int p = 1; p <= 2; p++) {
+    for (int i = 0; i < height; i += 2) {
+      const int k = i >> 1;
+      const uint8_t *s = src[p] + (long)istrides[p] * k;
+      uint8_t *d = dest[p] + (long)ostride * i;
+      for (int m = 0; m < cw; m++) {
+        const uint8_t a = s[m], nx = (m + 1 < cw || cw < istrides[p] || k + 1 < ch) ? s[m + 1] : s[m];
+        if (m == 0) d[0] = a;
+        else {
+          const uint8_t pv = s[m - 1];
+          d[2 * m] = sampling_jpeg ? OR_AV(pv, a) : (p == 1 ? OR_AV(pv, OR_AV(pv, a)) : OR_AV(OR_AV(pv, a), a));
+        }
+        d[2 * m + 1] = sampling_jpeg ? OR_AV(a, nx) : (p == 1 ? OR_AV(OR_AV(a, nx), nx) : OR_AV(a, OR_AV(a, nx)));
+      }
+    }
+    for (int r = 1; r < height; r += 2) {
+      uint8_t *d = dest[p] + (long)ostride * r;
+      const uint8_t *up = d - ostride, *dn = d + ostride;
+      if (r + 1 > height - 1) memcpy(d, up, (size_t)w2);                                         /* X */
+      else if ((height & 1) && r == height - 2) for (int j = 0; j < w2; j++) d[j] = OR_AV(up[j], dn[j]);  /* post-loop fix-up */
+      else for (int j = 0; j < w2; j++) d[j] = OR_AV(dn[j], up[j]);
+    }
+  }
+#undef OR_AV
+  if (add_alpha) memset(dest[3], 255, (size_t)ostride * height);
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

@@ -138,6 +138,11 @@ void pe_or_yuv444p_to_yuv420p(const uint8_t *const src[3], const int irows[3], i
  * :6442,:6470): luma and chroma interleaved, 4:2:0 chroma rows used twice without interpolation */
 void pe_or_yuv42xp_to_packed422(int fmt, const uint8_t *const src[3], const int irows[3], int width, int height, int is_422,
                                 uint8_t *dest, int orow);
+/* convert_quad_chroma :10642 (4:2:0 -> 4:4:4 chroma planes 1 and 2, + alpha plane = 255): even rows interpolated horizontally
+ * from chroma row i / 2 (plain average for JPEG sampling, 3:1 / 1:3 weights otherwise, U and V mirrored), odd rows = avg_chroma of
+ * the rows below and above; width x height = the destination plane */
+void pe_or_quad_chroma(const uint8_t *const src[3], const int istrides[3], int width, int height, uint8_t *const dest[4], int ostride,
+                       int add_alpha, int sampling_jpeg, int clamping);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

@@ -342,3 +342,10 @@ void ref_yuv422p_to_packed422(int fmt, uint8_t **src, int width, int height, int
   if (fmt == 0) convert_yuv422p_to_uyvy_frame(src, width, height, ir, orow, dest);
   else convert_yuv422p_to_yuyv_frame(src, width, height, ir, orow, dest);
 }
+
+/* width x height = the destination (4:4:4) plane */
+void ref_quad_chroma(uint8_t **src, int width, int height, int *istrides, int ostride, uint8_t **dest, int add_alpha, int sampling,
+                     int clamping) {
+  ref_init();
+  convert_quad_chroma(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
+}

@@ -99,6 +99,17 @@ def main():
         d3 = [np.zeros((H, ys), np.uint8), np.zeros((H // 2, ys // 2), np.uint8), np.zeros((H // 2, ys // 2), np.uint8)]
         r.ref_yuv444p_to_yuv420p(T.planes_arg(*pl[:3]), W, H, T.strides_arg(*pl[:3]), T.strides_arg(*d3), T.planes_arg(*d3), cl)
         out["yuv444p_to_yuv420p_cl%d_u" % cl], out["yuv444p_to_yuv420p_cl%d_v" % cl] = d3[1], d3[2]
+    # 4:2:0 -> 4:4:4 chroma (convert_quad_chroma): odd height 9 (every row defined), padded planes
+    qh, qch = 9, 5
+    qs = [np.zeros((qch, T.align_ceil(cw + 1, 16)), np.uint8) for _ in range(3)]
+    for p in qs[1:]:
+        p[:, :cw] = rng.integers(0, 256, (qch, cw), dtype=np.uint8)
+    out["quad_src_u"], out["quad_src_v"] = qs[1], qs[2]
+    for samp in (0, 1):
+        for cl in (0, 1):
+            d = [np.zeros((qh + 2, T.align_ceil(W + 1, 32)), np.uint8) for _ in range(4)]
+            r.ref_quad_chroma(T.planes_arg(*qs), W, qh, T.strides_arg(*qs), d[0].strides[0], T.planes_arg(*d), 0, samp, cl)
+            out["quad_s%d_cl%d_u" % (samp, cl)], out["quad_s%d_cl%d_v" % (samp, cl)] = d[1][:qh, :W].copy(), d[2][:qh, :W].copy()
     sw = m.copy()
     r.ref_swab(T.ptr(sw), wm, H, sw.strides[0])
     out["swab"] = sw

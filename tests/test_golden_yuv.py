@@ -66,6 +66,12 @@ def test_oracle_yuv_family_matches_golden():
     sw = m.copy()
     o.pe_or_swab(T.ptr(sw), sw.strides[0], WM, H)
     assert (sw == G["swab"]).all()
+    qs = [np.zeros_like(G["quad_src_u"]), _c("quad_src_u"), _c("quad_src_v")]
+    for samp in (0, 1):
+        for cl in (0, 1):
+            d = [np.zeros((9, T.align_ceil(W + 1, 32)), np.uint8) for _ in range(4)]
+            o.pe_or_quad_chroma(T.planes_arg(*qs), T.strides_arg(*qs), W, 9, T.planes_arg(*d), d[0].strides[0], 0, int(samp == 0), cl)
+            assert (d[1][:, :W] == G["quad_s%d_cl%d_u" % (samp, cl)]).all() and (d[2][:, :W] == G["quad_s%d_cl%d_v" % (samp, cl)]).all(), (samp, cl)
     for cl in (0, 1):
         for fmt, nm in ((0, "uyvy"), (1, "yuyv")):
             exp = G["yuv444p_to_%s_cl%d" % (nm, cl)]

@@ -657,6 +657,30 @@ def test_planar42x_to_packed422(eng, size):
         assert (payload(lay.to_host()[0], wm, 4) == payload(exp, wm, 4)).all(), (w, h, ipal, opal)
 
 
+@pytest.mark.parametrize("size", [(64, 12), (38, 6), (1920, 1080), (2, 2), (6, 4)])
+def test_yuv420p_to_yuv444p_quad_chroma(eng, size):
+    """YUV420P / YVU420P -> YUV444P / YUVA4444P (luma copy + convert_quad_chroma), JPEG and MPEG sampling, both clampings"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(140 + w)
+    for ipal, opal, samp, cl in itertools.product((512, 513), (544, 545), (0, 1), (0, 1)):
+        y, u, v = T.make_yuv_planar(rng, w, h, False, cl == 0)
+        su, sv = (u, v) if ipal == 512 else (v, u)  # YVU420P: plane 1 holds V
+        st = T.rowstride(w, 1)
+        ep = [np.zeros((h, st), np.uint8) for _ in range(4)]
+        o.pe_or_quad_chroma(T.planes_arg(y, su, sv), T.strides_arg(y, su, sv), w, h, T.planes_arg(*ep), st, int(opal == 545), int(samp == 0), cl)
+        lay = lb.Layer.from_host(eng, ipal, w, h, [y, u, v], yuv_clamping=cl, yuv_sampling=samp)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        assert (lay.palette, lay.width, lay.height) == (opal, w, h)
+        got = lay.to_host()
+        assert len(got) == (4 if opal == 545 else 3)
+        assert (got[0][:, :w] == y[:, :w]).all()
+        for k in (1, 2):
+            assert (got[k][:, :w] == ep[k][:, :w]).all(), ("quad", w, h, ipal, opal, samp, cl, k)
+        if opal == 545:
+            assert (got[3][:, :w] == 255).all()
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

@@ -699,3 +699,25 @@ def test_planar42x_to_packed422_matches_reference():
         o.pe_or_yuv42xp_to_packed422(fmt, T.planes_arg(y1, u1, v1), T.strides_arg(y1, u1, v1), w, 1, 1, T.ptr(a), 2 * w)
         r.ref_yuv422p_to_packed422(fmt, T.planes_arg(y1, u1, v1), w // 2, 1, T.strides_arg(y1, u1, v1), 2 * w, T.ptr(b))
         assert (a == b).all(), ("422", w, fmt)
+
+
+def test_quad_chroma_matches_reference():
+    """4:2:0 -> 4:4:4 chroma (convert_quad_chroma) on padded planes, JPEG and MPEG sampling, even and odd heights; for an even
+    height the reference never writes the last row (X: not compared)"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(77)
+    for (w, h), samp, cl, aa in itertools.product(((32, 8), (34, 7), (6, 2), (36, 9)), (0, 1), (0, 1), (0, 1)):
+        cw, ch = w >> 1, (h + 1) >> 1
+        cs, os_ = T.align_ceil(cw + 1, 16), T.align_ceil(w + 1, 32)
+        src = [np.zeros((ch, cs), np.uint8) for _ in range(3)]
+        for p in src[1:]:
+            p[:, :cw] = rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+        da = [np.zeros((h, os_), np.uint8) for _ in range(4)]
+        db = [np.zeros((h + 2, os_), np.uint8) for _ in range(4)]  # (slack rows: the reference's odd-row pass writes past `width`)
+        o.pe_or_quad_chroma(T.planes_arg(*src), T.strides_arg(*src), w, h, T.planes_arg(*da), os_, aa, int(samp == 0), cl)
+        r.ref_quad_chroma(T.planes_arg(*src), w, h, T.strides_arg(*src), os_, T.planes_arg(*db), aa, samp, cl)
+        rows = h if (h & 1) else h - 1
+        for k in (1, 2):
+            assert (da[k][:rows, :w] == db[k][:rows, :w]).all(), ("quad", w, h, samp, cl, k)
+        if aa:
+            assert (da[3] == 255).all() and (db[3][:h] == 255).all()
