@@ -1136,6 +1136,28 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                               height, isampling == PE_YUV_SAMPLING_JPEG, cavg);
     if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)
       ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
+  } else if ((inpl == PE_PALETTE_YUV888 || inpl == PE_PALETTE_YUVA8888) &&
+             (outpl == PE_PALETTE_UYVY || outpl == PE_PALETTE_YUYV || outpl == PE_PALETTE_YUV422P || outpl == PE_PALETTE_YUV420P ||
+              outpl == PE_PALETTE_YVU420P)) {
+    // convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame (:13387-13415, :13479-13507): chroma of a pixel pair = avg_chroma(first,
+    // second), 4:2:0 also over the row pair; planes written in layer order; odd last column / row cut
+    const bool to420 = outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P;
+    n.d.width = width & ~1;
+    if (to420) n.d.height = height & ~1;
+    if (n.d.width < 2 || n.d.height < (to420 ? 2 : 1)) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    uint8_t *pl[3] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2]};
+    const int mode = outpl == PE_PALETTE_UYVY ? 0 : outpl == PE_PALETTE_YUYV ? 1 : outpl == PE_PALETTE_YUV422P ? 2 : 3;
+    ce = launch_yuv888_subsample(L, mode, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, inpl == PE_PALETTE_YUVA8888, pl,
+                                 n.d.rowstrides, n.d.width, n.d.height, cavg);
+  } else if ((inpl == PE_PALETTE_YUV888 && outpl == PE_PALETTE_YUVA8888) || (inpl == PE_PALETTE_YUVA8888 && outpl == PE_PALETTE_YUV888)) {
+    // convert_addpost_frame / convert_delpost_frame on the packed YUV bytes (:13337-13342, :13430-13435): the RGB24 <-> RGBA32 kernel
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    ce = launch_rgb_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width,
+                           height, rgb_layout(inpl == PE_PALETTE_YUV888 ? PE_PALETTE_RGB24 : PE_PALETTE_RGBA32),
+                           rgb_layout(outpl == PE_PALETTE_YUV888 ? PE_PALETTE_RGB24 : PE_PALETTE_RGBA32), nullptr);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

@@ -10,6 +10,7 @@
 //   k_yuv444p_to_chroma420  convert_yuvp_to_yuv420_frame                 colourspace.c:7690
 //   k_planar42x_to_packed422  convert_yuv420_to_{uyvy,yuyv}_frame / convert_yuv422p_to_{uyvy,yuyv}_frame  colourspace.c:7104 / 6442
 //   k_quad_chroma         convert_quad_chroma                            colourspace.c:10642  (4:2:0 -> 4:4:4 chroma planes)
+//   k_yuv888_subsample    convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame  colourspace.c:8184 / 8228 / 8129 / 8035
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -351,6 +352,58 @@ __global__ void __launch_bounds__(kBlock) k_quad_chroma(const QuadChromaParams P
   }
 }
 
+// YUV888 / YUVA8888 -> UYVY (mode 0) / YUYV (1) / planar 4:2:2 (2) / planar 4:2:0 (3): convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame
+// (colourspace.c:8184 / 8228 / 8129 / 8035).  One thread = 4 pixels = 2 pairs (mode 3: of two rows); chroma of a pair =
+// avg_chroma(first, second), 4:2:0 row k = avg_chroma(row 2k pairs, row 2k + 1 pairs).
+__global__ void __launch_bounds__(kBlock) k_yuv888_subsample(int mode, const uint8_t *__restrict__ src, int irow, int src_alpha, OutPlanes4 D,
+                                                            int width, int height, const uint8_t *__restrict__ cavg, int vec) {
+  const int hw = width >> 1, groups = (hw + 1) >> 1, ips = src_alpha ? 4 : 3;
+  const int rows = mode == 3 ? (height + 1) >> 1 : height;
+  const long long total = (long long)groups * rows;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int rr = (int)(it / groups), g = (int)(it - (long long)rr * groups);
+    const int m = 2 * g, nm = min(2, hw - m);  // pairs m, m + 1
+    // one source row -> luma word, (cu0, cu1), (cv0, cv1)
+    auto pairs = [&](int row, uint32_t &yw, uint32_t &cu, uint32_t &cv) {
+      uint32_t px[4];
+      ld_packed4(src + (long long)irow * row + (long long)(2 * m) * ips, px, ips, 2 * nm, vec);
+      const uint32_t a01 = __byte_perm(px[0], px[1], 0x5140), b01 = __byte_perm(px[0], px[1], 0x7362);
+      const uint32_t a23 = __byte_perm(px[2], px[3], 0x5140), b23 = __byte_perm(px[2], px[3], 0x7362);
+      yw = __byte_perm(a01, a23, 0x5410);
+      const uint32_t uw = __byte_perm(a01, a23, 0x7632), vw = __byte_perm(b01, b23, 0x5410);
+      cu = (uint32_t)__ldg(cavg + ((byte_of(uw, 0) << 8) | byte_of(uw, 1))) | ((uint32_t)__ldg(cavg + ((byte_of(uw, 2) << 8) | byte_of(uw, 3))) << 8);
+      cv = (uint32_t)__ldg(cavg + ((byte_of(vw, 0) << 8) | byte_of(vw, 1))) | ((uint32_t)__ldg(cavg + ((byte_of(vw, 2) << 8) | byte_of(vw, 3))) << 8);
+    };
+    uint32_t yw, cu, cv;
+    if (mode <= 1) {
+      pairs(rr, yw, cu, cv);
+      uint32_t m0 = byte_of(yw, 0) | (byte_of(cu, 0) << 8) | (byte_of(yw, 1) << 16) | (byte_of(cv, 0) << 24);   // YUYV
+      uint32_t m1 = byte_of(yw, 2) | (byte_of(cu, 1) << 8) | (byte_of(yw, 3) << 16) | (byte_of(cv, 1) << 24);
+      if (mode == 0) { m0 = __byte_perm(m0, 0u, 0x2301); m1 = __byte_perm(m1, 0u, 0x2301); }
+      uint8_t *d = D.p[0] + (long long)D.rs[0] * rr + 4LL * m;
+      if (vec && nm == 2 && ((D.rs[0] | (int)(uintptr_t)D.p[0]) & 7) == 0) st_stream_u2(d, make_uint2(m0, m1));
+      else { st_px4(d, m0, 4, false); if (nm == 2) st_px4(d + 4, m1, 4, false); }
+    } else if (mode == 2) {
+      pairs(rr, yw, cu, cv);
+      st_px4(D.p[0] + (long long)D.rs[0] * rr + 2 * m, yw, 2 * nm, vec);
+      st_px4(D.p[1] + (long long)D.rs[1] * rr + m, cu, nm, false);
+      st_px4(D.p[2] + (long long)D.rs[2] * rr + m, cv, nm, false);
+    } else {
+      const int r0 = 2 * rr;
+      pairs(r0, yw, cu, cv);
+      st_px4(D.p[0] + (long long)D.rs[0] * r0 + 2 * m, yw, 2 * nm, vec);
+      if (r0 + 1 < height) {
+        uint32_t yw1, cu1, cv1;
+        pairs(r0 + 1, yw1, cu1, cv1);
+        st_px4(D.p[0] + (long long)D.rs[0] * (r0 + 1) + 2 * m, yw1, 2 * nm, vec);
+        cu = avg4(cavg, cu, cu1) & 0xFFFFu; cv = avg4(cavg, cv, cv1) & 0xFFFFu;
+      }
+      st_px4(D.p[1] + (long long)D.rs[1] * rr + m, cu, nm, false);
+      st_px4(D.p[2] + (long long)D.rs[2] * rr + m, cv, nm, false);
+    }
+  }
+}
+
 // UYVY <-> YUYV in place: swab() of every row
 __global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
   const long long total = (long long)width_mpx * height;
@@ -509,6 +562,21 @@ cudaError_t launch_quad_chroma(const Launch &L, const uint8_t *su, const uint8_t
   const int vec = aligned4(du) && aligned4(dv) && !(ors & 3);
   const dim3 grid(grid_for(L, (long long)((P.w2 + 3) / 4) * height), 2);
   k_quad_chroma<<<grid, kBlock, 0, L.stream>>>(P, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_yuv888_subsample(const Launch &L, int mode, CImg src, int src_alpha, uint8_t *const planes[3], const int orows[3], int width,
+                                    int height, const uint8_t *cavg_dev) {
+  OutPlanes4 D;
+  const int np = mode <= 1 ? 1 : 3;
+  bool vec = src_alpha ? aligned16(src.p) && !(src.rs & 15) : aligned4(src.p) && !(src.rs & 3);
+  for (int k = 0; k < 4; k++) { D.p[k] = k < np ? planes[k] : nullptr; D.rs[k] = k < np ? orows[k] : 0; }
+  vec = vec && aligned4(planes[0]) && !(orows[0] & 3);
+  const int hw = width >> 1, rows = mode == 3 ? (height + 1) / 2 : height;
+  if (hw < 1 || rows < 1) return cudaSuccess;
+  k_yuv888_subsample<<<grid_for(L, (long long)((hw + 1) / 2) * rows), kBlock, 0, L.stream>>>(mode, src.p, src.rs, src_alpha, D, width, height,
+                                                                                           cavg_dev, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

@@ -1156,6 +1156,37 @@ void pe_or_quad_chroma(const uint8_t *const src[3], const int istrides[3], int w
   if (add_alpha) memset(dest[3], 255, (size_t)ostride * height);
 }
 
+/* convert_yuv888_to_{uyvy,yuyv}_frame :8184-8270, convert_yuv888_to_yuv422_frame :8129-8182, convert_yuv888_to_yuv420_frame
+ * :8035-8090.  Per pixel pair: both lumas, chroma = avg_chroma(c of the first pixel, c of the second); 4:2:0 row k =
+ * avg_chroma(pair averages of row 2k, pair averages of row 2k+1) (a trailing unpaired row leaves its pair averages).
+ * X: the strided branches of the packed targets advance the macropixel pointer by a BYTE count (:8215), the strided 4:2:2 branch
+ * subtracts a quarter width from the chroma strides (:8163-8164), the 4:2:0 loop walks luma densely and rewinds chroma by the full
+ * rowstride (:8046,:8084) -- all equal to this restatement on unpadded buffers, where they are compared. */
+void pe_or_yuv888_subsample(int mode, const uint8_t *src, int irow, int width, int height, int src_alpha, uint8_t *const dest[3],
+                            const int orows[3], int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  const int ips = src_alpha ? 4 : 3, hw = width >> 1;
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    for (int j = 0; j < hw; j++, s += 2 * ips) {
+      const uint8_t y0 = s[0], y1 = s[ips], cu = avg[(s[1] << 8) + s[1 + ips]], cv = avg[(s[2] << 8) + s[2 + ips]];
+      if (mode <= 1) {
+        uint8_t *d = dest[0] + (long)orows[0] * i + 4L * j;
+        if (mode == 0) { d[0] = cu; d[1] = y0; d[2] = cv; d[3] = y1; }
+        else { d[0] = y0; d[1] = cu; d[2] = y1; d[3] = cv; }
+        continue;
+      }
+      dest[0][(long)orows[0] * i + 2 * j] = y0; dest[0][(long)orows[0] * i + 2 * j + 1] = y1;
+      if (mode == 2) { dest[1][(long)orows[1] * i + j] = cu; dest[2][(long)orows[2] * i + j] = cv; }
+      else {
+        uint8_t *du = dest[1] + (long)orows[1] * (i >> 1) + j, *dv = dest[2] + (long)orows[2] * (i >> 1) + j;
+        *du = (i & 1) ? avg[(*du << 8) + cu] : cu;
+        *dv = (i & 1) ? avg[(*dv << 8) + cv] : cv;
+      }
+    }
+  }
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

@@ -143,6 +143,11 @@ void pe_or_yuv42xp_to_packed422(int fmt, const uint8_t *const src[3], const int 
  * the rows below and above; width x height = the destination plane */
 void pe_or_quad_chroma(const uint8_t *const src[3], const int istrides[3], int width, int height, uint8_t *const dest[4], int ostride,
                        int add_alpha, int sampling_jpeg, int clamping);
+/* YUV888 / YUVA8888 -> UYVY (mode 0) / YUYV (1) / planar 4:2:2 (2) / planar 4:2:0 (3): convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame
+ * :8184,:8228,:8129,:8035.  Chroma of a pixel pair = avg_chroma(first, second); 4:2:0 additionally avg_chroma(row 2k, row 2k+1).
+ * dest[0] is the packed frame for modes 0 / 1 */
+void pe_or_yuv888_subsample(int mode, const uint8_t *src, int irow, int width, int height, int src_alpha, uint8_t *const dest[3],
+                            const int orows[3], int clamping);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

@@ -349,3 +349,13 @@ void ref_quad_chroma(uint8_t **src, int width, int height, int *istrides, int os
   ref_init();
   convert_quad_chroma(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
 }
+
+/* mode 0 uyvy 1 yuyv 2 planar 4:2:2 3 planar 4:2:0; width in pixels */
+void ref_yuv888_subsample(int mode, uint8_t *src, int width, int height, int irow, int *orows, uint8_t **dest, int src_alpha, int clamping) {
+  int o[3] = {orows[0], orows[1], orows[2]};
+  ref_init();
+  if (mode == 0) convert_yuv888_to_uyvy_frame(src, width, height, irow, o[0], (uyvy_macropixel *)dest[0], src_alpha, clamping);
+  else if (mode == 1) convert_yuv888_to_yuyv_frame(src, width, height, irow, o[0], (yuyv_macropixel *)dest[0], src_alpha, clamping);
+  else if (mode == 2) convert_yuv888_to_yuv422_frame(src, width, height, irow, o, dest, src_alpha, clamping);
+  else convert_yuv888_to_yuv420_frame(src, width, height, irow, o, dest, src_alpha, clamping);
+}

@@ -110,6 +110,20 @@ def main():
             d = [np.zeros((qh + 2, T.align_ceil(W + 1, 32)), np.uint8) for _ in range(4)]
             r.ref_quad_chroma(T.planes_arg(*qs), W, qh, T.strides_arg(*qs), d[0].strides[0], T.planes_arg(*d), 0, samp, cl)
             out["quad_s%d_cl%d_u" % (samp, cl)], out["quad_s%d_cl%d_v" % (samp, cl)] = d[1][:qh, :W].copy(), d[2][:qh, :W].copy()
+    # YUV888 -> UYVY / YUYV / YUV422P / YUV420P on dense buffers
+    s888 = np.ascontiguousarray(src[:, :W * 3])
+    out["yuv888_dense"] = s888
+    for cl in (0, 1):
+        for mode in range(4):
+            if mode <= 1:
+                d = [np.zeros((H, 2 * W), np.uint8)]
+            else:
+                chh = H if mode == 2 else H // 2
+                d = [np.zeros((H, W), np.uint8), np.zeros((chh, W // 2), np.uint8), np.zeros((chh, W // 2), np.uint8)]
+            pa = d + [d[0]] * (3 - len(d))
+            r.ref_yuv888_subsample(mode, T.ptr(s888), W, H, s888.strides[0], T.strides_arg(*pa), T.planes_arg(*pa), 0, cl)
+            for k, a in enumerate(d):
+                out["yuv888_sub_m%d_cl%d_%d" % (mode, cl, k)] = a
     sw = m.copy()
     r.ref_swab(T.ptr(sw), wm, H, sw.strides[0])
     out["swab"] = sw

@@ -66,6 +66,15 @@ def test_oracle_yuv_family_matches_golden():
     sw = m.copy()
     o.pe_or_swab(T.ptr(sw), sw.strides[0], WM, H)
     assert (sw == G["swab"]).all()
+    s888 = _c("yuv888_dense")
+    for cl in (0, 1):
+        for mode in range(4):
+            exp = [G["yuv888_sub_m%d_cl%d_%d" % (mode, cl, k)] for k in range(1 if mode <= 1 else 3)]
+            d = [np.zeros_like(e) for e in exp]
+            pa = d + [d[0]] * (3 - len(d))
+            o.pe_or_yuv888_subsample(mode, T.ptr(s888), s888.strides[0], W, H, 0, T.planes_arg(*pa), T.strides_arg(*pa), cl)
+            for k in range(len(d)):
+                assert (d[k] == exp[k]).all(), (mode, cl, k)
     qs = [np.zeros_like(G["quad_src_u"]), _c("quad_src_u"), _c("quad_src_v")]
     for samp in (0, 1):
         for cl in (0, 1):

@@ -681,6 +681,49 @@ def test_yuv420p_to_yuv444p_quad_chroma(eng, size):
             assert (got[3][:, :w] == 255).all()
 
 
+@pytest.mark.parametrize("size", [(64, 12), (38, 6), (1920, 1080), (2, 2), (6, 3)])
+def test_yuv888_subsample_and_alpha(eng, size):
+    """YUV888 / YUVA8888 -> UYVY / YUYV / YUV422P / YUV420P (convert_yuv888_to_*_frame) and YUV888 <-> YUVA8888 (addpost / delpost)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(150 + w)
+    for ipal, cl in itertools.product((588, 589), (0, 1)):
+        ips = 4 if ipal == 589 else 3
+        src = T.make_packed(rng, w, h, ips)
+        we = w & ~1
+        for opal, mode in ((564, 0), (565, 1), (522, 2), (512, 3)):
+            he = h & ~1 if mode == 3 else h
+            if he < 1:
+                continue
+            if mode <= 1:
+                ep = [np.zeros((he, T.rowstride(we // 2, 4)), np.uint8)]
+            else:
+                ys = T.rowstride(we, 1)
+                chh = he if mode == 2 else he >> 1
+                ep = [np.zeros((he, ys), np.uint8), np.zeros((chh, ys >> 1), np.uint8), np.zeros((chh, ys >> 1), np.uint8)]
+            pa = ep + [ep[0]] * (3 - len(ep))
+            o.pe_or_yuv888_subsample(mode, T.ptr(src), src.strides[0], we, he, int(ipal == 589), T.planes_arg(*pa), T.strides_arg(*pa), cl)
+            lay = packed_layer(eng, ipal, w, h, src, yuv_clamping=cl)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.palette, lay.width, lay.height) == (opal, we, he)
+            got = lay.to_host()
+            assert len(got) == len(ep)
+            for k, (g, e_) in enumerate(zip(got, ep)):
+                nb = (we * 2 if mode <= 1 else (we if k == 0 else we >> 1))
+                assert (g[:, :nb] == e_[:, :nb]).all(), ("subsample", w, h, ipal, cl, opal, k)
+        # alpha add / drop on the packed YUV bytes
+        opal = 589 if ipal == 588 else 588
+        lay = packed_layer(eng, ipal, w, h, src, yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        got = lay.to_host()[0]
+        px = src[:, :w * ips].reshape(h, w, ips)
+        ops = 7 - ips
+        gp = got[:, :w * ops].reshape(h, w, ops)
+        assert (gp[:, :, :3] == px[:, :, :3]).all()
+        if ops == 4:
+            assert (gp[:, :, 3] == 255).all()
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

@@ -721,3 +721,23 @@ def test_quad_chroma_matches_reference():
             assert (da[k][:rows, :w] == db[k][:rows, :w]).all(), ("quad", w, h, samp, cl, k)
         if aa:
             assert (da[3] == 255).all() and (db[3][:h] == 255).all()
+
+
+def test_yuv888_subsample_matches_reference():
+    """YUV888 / YUVA8888 -> UYVY / YUYV / YUV422P / YUV420P on unpadded buffers (the reference's strided branches are broken)"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(78)
+    for (w, h), sa, cl, mode in itertools.product(((32, 6), (34, 4), (2, 2)), (0, 1), (0, 1), (0, 1, 2, 3)):
+        ips = 4 if sa else 3
+        src = rng.integers(0, 256, (h, w * ips), dtype=np.uint8)
+        if mode <= 1:
+            da, db = [np.zeros((h, 2 * w), np.uint8)], [np.zeros((h, 2 * w), np.uint8)]
+        else:
+            ch = h if mode == 2 else h // 2
+            da = [np.zeros((h, w), np.uint8), np.zeros((ch, w // 2), np.uint8), np.zeros((ch, w // 2), np.uint8)]
+            db = [np.zeros_like(p) for p in da]
+        pa, pb = da + [da[0]] * (3 - len(da)), db + [db[0]] * (3 - len(db))
+        o.pe_or_yuv888_subsample(mode, T.ptr(src), src.strides[0], w, h, sa, T.planes_arg(*pa), T.strides_arg(*pa), cl)
+        r.ref_yuv888_subsample(mode, T.ptr(src), w, h, src.strides[0], T.strides_arg(*pb), T.planes_arg(*pb), sa, cl)
+        for k in range(len(da)):
+            assert (da[k] == db[k]).all(), ("yuv888 subsample", w, h, sa, cl, mode, k)
