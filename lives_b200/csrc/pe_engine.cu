@@ -1158,6 +1158,17 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     ce = launch_rgb_to_rgb(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width,
                            height, rgb_layout(inpl == PE_PALETTE_YUV888 ? PE_PALETTE_RGB24 : PE_PALETTE_RGBA32),
                            rgb_layout(outpl == PE_PALETTE_YUV888 ? PE_PALETTE_RGB24 : PE_PALETTE_RGBA32), nullptr);
+  } else if ((inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV) && (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P)) {
+    // convert_{uyvy,yuyv}_to_yuv420_frame (:13215-13221, :13315-13321): luma split, chroma averaged over the row pair; planes in
+    // layer order; an odd last row is cut
+    n.d.height = height & ~1;
+    if (n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:0 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    uint8_t *pl[3] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2]};
+    ce = launch_packed422_to_yuv420p(L, inpl == PE_PALETTE_UYVY ? 0 : 1, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl,
+                                     n.d.rowstrides, width >> 1, n.d.height, cavg);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

@@ -11,6 +11,7 @@
 //   k_planar42x_to_packed422  convert_yuv420_to_{uyvy,yuyv}_frame / convert_yuv422p_to_{uyvy,yuyv}_frame  colourspace.c:7104 / 6442
 //   k_quad_chroma         convert_quad_chroma                            colourspace.c:10642  (4:2:0 -> 4:4:4 chroma planes)
 //   k_yuv888_subsample    convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame  colourspace.c:8184 / 8228 / 8129 / 8035
+//   k_packed422_to_yuv420p  convert_{uyvy,yuyv}_to_yuv420_frame          colourspace.c:7887 / 7930
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -404,6 +405,36 @@ __global__ void __launch_bounds__(kBlock) k_yuv888_subsample(int mode, const uin
   }
 }
 
+// UYVY / YUYV -> planar 4:2:0 (convert_{uyvy,yuyv}_to_yuv420_frame, colourspace.c:7887 / 7930): luma split, chroma row k =
+// avg_chroma(row 2k, row 2k + 1).  One thread = 2 macropixels of a row pair.
+__global__ void __launch_bounds__(kBlock) k_packed422_to_yuv420p(int fmt, const uint8_t *__restrict__ src, int irow, OutPlanes4 D, int width_mpx,
+                                                                int height, const uint8_t *__restrict__ cavg, int vec) {
+  const int groups = (width_mpx + 1) >> 1, rows = (height + 1) >> 1;
+  const long long total = (long long)groups * rows;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int rr = (int)(it / groups), g = (int)(it - (long long)rr * groups);
+    const int m = 2 * g, nm = min(2, width_mpx - m);
+    auto row2 = [&](int row, uint32_t &yw, uint32_t &cu, uint32_t &cv) {
+      const uint8_t *q = src + (long long)irow * row + 4LL * m;
+      uint32_t m0 = ld_px4(q, 4, vec), m1 = nm == 2 ? ld_px4(q + 4, 4, vec) : 0u;
+      if (fmt == 0) { m0 = __byte_perm(m0, 0u, 0x2301); m1 = __byte_perm(m1, 0u, 0x2301); }  // -> y0 u y1 v
+      yw = __byte_perm(m0, m1, 0x6420);
+      cu = __byte_perm(m0, m1, 0x4451);   // u, u' in bytes 0, 1 (bytes 2, 3 are not stored)
+      cv = __byte_perm(m0, m1, 0x4473);
+      st_px4(D.p[0] + (long long)D.rs[0] * row + 2 * m, yw, 2 * nm, vec);
+    };
+    uint32_t yw, cu, cv;
+    row2(2 * rr, yw, cu, cv);
+    if (2 * rr + 1 < height) {
+      uint32_t yw1, cu1, cv1;
+      row2(2 * rr + 1, yw1, cu1, cv1);
+      cu = avg4(cavg, cu, cu1); cv = avg4(cavg, cv, cv1);
+    }
+    st_px4(D.p[1] + (long long)D.rs[1] * rr + m, cu, nm, false);
+    st_px4(D.p[2] + (long long)D.rs[2] * rr + m, cv, nm, false);
+  }
+}
+
 // UYVY <-> YUYV in place: swab() of every row
 __global__ void __launch_bounds__(kBlock) k_swab(uint8_t *pix, int rs, int width_mpx, int height, int vec) {
   const long long total = (long long)width_mpx * height;
@@ -577,6 +608,18 @@ cudaError_t launch_yuv888_subsample(const Launch &L, int mode, CImg src, int src
   if (hw < 1 || rows < 1) return cudaSuccess;
   k_yuv888_subsample<<<grid_for(L, (long long)((hw + 1) / 2) * rows), kBlock, 0, L.stream>>>(mode, src.p, src.rs, src_alpha, D, width, height,
                                                                                            cavg_dev, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_packed422_to_yuv420p(const Launch &L, int fmt, CImg src, uint8_t *const planes[3], const int orows[3], int width_mpx,
+                                        int height, const uint8_t *cavg_dev) {
+  OutPlanes4 D;
+  for (int k = 0; k < 4; k++) { D.p[k] = k < 3 ? planes[k] : nullptr; D.rs[k] = k < 3 ? orows[k] : 0; }
+  const bool vec = aligned4(src.p) && !(src.rs & 3) && aligned4(planes[0]) && !(orows[0] & 3);
+  if (width_mpx < 1 || height < 1) return cudaSuccess;
+  k_packed422_to_yuv420p<<<grid_for(L, (long long)((width_mpx + 1) / 2) * ((height + 1) / 2)), kBlock, 0, L.stream>>>(fmt, src.p, src.rs, D, width_mpx,
+                                                                                                                    height, cavg_dev, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

@@ -1187,6 +1187,23 @@ void pe_or_yuv888_subsample(int mode, const uint8_t *src, int irow, int width, i
   }
 }
 
+/* convert_{uyvy,yuyv}_to_yuv420_frame :7887-7970: even source rows write their chroma, odd rows fold theirs in with
+ * avg_chroma(stored, new) (the EVEN row is the table row); a trailing unpaired row leaves its own chroma.  The reference walks
+ * source and planes densely (X: strides honoured here, equal on unpadded buffers). */
+void pe_or_packed422_to_yuv420p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[3],
+                                const int orows[3], int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  for (int k = 0; k < height; k++)
+    for (int x = 0; x < width_mpx; x++) {
+      uint8_t y0, u, y1, v;
+      or_mpx(fmt, src + (long)irow * k + 4L * x, &y0, &u, &y1, &v);
+      dest[0][(long)orows[0] * k + 2 * x] = y0; dest[0][(long)orows[0] * k + 2 * x + 1] = y1;
+      uint8_t *du = dest[1] + (long)orows[1] * (k >> 1) + x, *dv = dest[2] + (long)orows[2] * (k >> 1) + x;
+      *du = (k & 1) ? avg[(*du << 8) + u] : u;
+      *dv = (k & 1) ? avg[(*dv << 8) + v] : v;
+    }
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

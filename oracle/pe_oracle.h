@@ -148,6 +148,10 @@ void pe_or_quad_chroma(const uint8_t *const src[3], const int istrides[3], int w
  * dest[0] is the packed frame for modes 0 / 1 */
 void pe_or_yuv888_subsample(int mode, const uint8_t *src, int irow, int width, int height, int src_alpha, uint8_t *const dest[3],
                             const int orows[3], int clamping);
+/* packed 4:2:2 -> planar 4:2:0 (convert_{uyvy,yuyv}_to_yuv420_frame :7887,:7930): luma split, chroma row k = avg_chroma(row 2k,
+ * row 2k+1) */
+void pe_or_packed422_to_yuv420p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[3],
+                                const int orows[3], int clamping);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

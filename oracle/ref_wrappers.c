@@ -359,3 +359,10 @@ void ref_yuv888_subsample(int mode, uint8_t *src, int width, int height, int iro
   else if (mode == 2) convert_yuv888_to_yuv422_frame(src, width, height, irow, o, dest, src_alpha, clamping);
   else convert_yuv888_to_yuv420_frame(src, width, height, irow, o, dest, src_alpha, clamping);
 }
+
+/* fmt 0 uyvy 1 yuyv; width in macropixels; dense buffers */
+void ref_packed422_to_yuv420p(int fmt, void *src, int width, int height, uint8_t **dest, int clamping) {
+  ref_init();
+  if (fmt == 0) convert_uyvy_to_yuv420_frame((uyvy_macropixel *)src, width, height, dest, clamping);
+  else convert_yuyv_to_yuv420_frame((yuyv_macropixel *)src, width, height, dest, clamping);
+}

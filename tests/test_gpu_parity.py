@@ -724,6 +724,27 @@ def test_yuv888_subsample_and_alpha(eng, size):
             assert (gp[:, :, 3] == 255).all()
 
 
+@pytest.mark.parametrize("size", [(64, 12), (34, 6), (1920, 1080), (2, 2)])
+def test_packed422_to_yuv420p(eng, size):
+    """UYVY / YUYV -> YUV420P (convert_{uyvy,yuyv}_to_yuv420_frame)"""
+    o = T.oracle()
+    w, h = size
+    wm = w >> 1
+    rng = np.random.default_rng(160 + w)
+    for ipal, cl in itertools.product((564, 565), (0, 1)):
+        src = T.make_packed(rng, wm, h, 4)
+        ys = T.rowstride(w, 1)
+        ep = [np.zeros((h, ys), np.uint8), np.zeros((h >> 1, ys >> 1), np.uint8), np.zeros((h >> 1, ys >> 1), np.uint8)]
+        o.pe_or_packed422_to_yuv420p(ipal - 564, T.ptr(src), src.strides[0], wm, h, T.planes_arg(*ep), T.strides_arg(*ep), cl)
+        lay = packed_layer(eng, ipal, w, h, src, yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, 512, cl)
+        assert (lay.palette, lay.width, lay.height) == (512, w, h)
+        got = lay.to_host()
+        assert (got[0][:, :w] == ep[0][:, :w]).all()
+        for k in (1, 2):
+            assert (got[k][:, :wm] == ep[k][:, :wm]).all(), ("packed422 -> 420p", w, h, ipal, cl, k)
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

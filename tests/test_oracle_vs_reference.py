@@ -741,3 +741,16 @@ def test_yuv888_subsample_matches_reference():
         r.ref_yuv888_subsample(mode, T.ptr(src), w, h, src.strides[0], T.strides_arg(*pb), T.planes_arg(*pb), sa, cl)
         for k in range(len(da)):
             assert (da[k] == db[k]).all(), ("yuv888 subsample", w, h, sa, cl, mode, k)
+
+
+def test_packed422_to_yuv420p_matches_reference():
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(79)
+    for (wm, h), fmt, cl in itertools.product(((16, 6), (17, 4), (1, 2)), (0, 1), (0, 1)):
+        src = rng.integers(0, 256, (h, wm * 4), dtype=np.uint8)
+        da = [np.zeros((h, 2 * wm), np.uint8), np.zeros((h // 2, wm), np.uint8), np.zeros((h // 2, wm), np.uint8)]
+        db = [np.zeros_like(p) for p in da]
+        o.pe_or_packed422_to_yuv420p(fmt, T.ptr(src), src.strides[0], wm, h, T.planes_arg(*da), T.strides_arg(*da), cl)
+        r.ref_packed422_to_yuv420p(fmt, T.ptr(src), wm, h, T.planes_arg(*db), cl)
+        for k in range(3):
+            assert (da[k] == db[k]).all(), ("packed422 -> 420p", wm, h, fmt, cl, k)
