@@ -79,6 +79,62 @@ def test_window_push_and_tap_order():
         assert win == [f + 3, f + 2, f + 1, f]
 
 
+def _prmt(x, y, sel):
+    """__byte_perm(x, y, sel) on uint32 (selector nibbles 0-7 only: no sign replication)"""
+    b = [(x >> (8 * k)) & 0xFF for k in range(4)] + [(y >> (8 * k)) & 0xFF for k in range(4)]
+    return sum(b[(sel >> (4 * i)) & 0x7] << (8 * i) for i in range(4))
+
+
+def test_byte_permutation_selectors_of_the_yuv_family_kernels():
+    """pe_kernels_yuv3.cu: the PRMT selector constants do what their comments say (4 x 4 byte transposes of combine / split
+    planes, 3-byte pixel packing / unpacking, macropixel shuffles), on words with all-distinct bytes"""
+    yw, uw, vw, aw = 0x03020100, 0x13121110, 0x23222120, 0x33323130          # byte k of plane p = 0x(p)(k)
+    # k_combine_planes: px[k] = y_k | u_k << 8 | v_k << 16 | a_k << 24
+    yu_lo, yu_hi = _prmt(yw, uw, 0x5140), _prmt(yw, uw, 0x7362)
+    va_lo, va_hi = _prmt(vw, aw, 0x5140), _prmt(vw, aw, 0x7362)
+    px = [_prmt(yu_lo, va_lo, 0x5410), _prmt(yu_lo, va_lo, 0x7632), _prmt(yu_hi, va_hi, 0x5410), _prmt(yu_hi, va_hi, 0x7632)]
+    assert px == [0x30201000 + 0x01010101 * k for k in range(4)]
+    # k_split_planes: the inverse transpose
+    a01, b01 = _prmt(px[0], px[1], 0x5140), _prmt(px[0], px[1], 0x7362)
+    a23, b23 = _prmt(px[2], px[3], 0x5140), _prmt(px[2], px[3], 0x7362)
+    assert (_prmt(a01, a23, 0x5410), _prmt(a01, a23, 0x7632), _prmt(b01, b23, 0x5410), _prmt(b01, b23, 0x7632)) == (yw, uw, vw, aw)
+    # st_packed4 / ld_packed4: four 3-byte pixels <-> three words
+    p = [0x00A2A1A0, 0x00B2B1B0, 0x00C2C1C0, 0x00D2D1D0]
+    w = [_prmt(p[0], p[1], 0x4210), _prmt(p[1], p[2], 0x5421), _prmt(p[2], p[3], 0x6542)]
+    stream = b"".join(int(x).to_bytes(4, "little") for x in w)
+    assert stream == bytes([0xA0, 0xA1, 0xA2, 0xB0, 0xB1, 0xB2, 0xC0, 0xC1, 0xC2, 0xD0, 0xD1, 0xD2])
+    back = [w[0], _prmt(w[0], w[1], 0x0543), _prmt(w[1], w[2], 0x0432), w[2] >> 8]
+    assert [x & 0xFFFFFF for x in back] == p
+    # macropixels: UYVY -> YUYV byte order, luma word of two macropixels, duplicated chroma, YUV(A)888 pixels
+    uyvy0, uyvy1 = 0xB1C0B0A0, 0xB3C1B2A1          # u y0 v y1 (u = A*, y = B*, v = C*)
+    m0, m1 = _prmt(uyvy0, 0, 0x2301), _prmt(uyvy1, 0, 0x2301)
+    assert (m0, m1) == (0xC0B1A0B0, 0xC1B3A1B2)     # y0 u y1 v
+    assert _prmt(m0, m1, 0x6420) == 0xB3B2B1B0      # y0 y1 y0' y1'
+    assert _prmt(m0, m1, 0x5511) == 0xA1A1A0A0 and _prmt(m0, m1, 0x7733) == 0xC1C1C0C0
+    ff = 0xFF000000
+    assert _prmt(m0, ff, 0x7310) == 0xFFC0A0B0 and _prmt(m0, ff, 0x7312) == 0xFFC0A0B1
+    assert _prmt(m0, m1, 0x4451) & 0xFFFF == 0xA1A0 and _prmt(m0, m1, 0x4473) & 0xFFFF == 0xC1C0
+    # k_yuv_march seed lane: byte 0 of a chroma word replaced by byte k of the seed word
+    sd, cw = 0x44332211, 0xDDCCBBAA
+    assert [_prmt(cw, sd, 0x3214 + k) for k in range(4)] == [0xDDCCBB11, 0xDDCCBB22, 0xDDCCBB33, 0xDDCCBB44]
+    # k_alpha_over / clamp LUT: (x >> 3) & 0x1FE0 == 32 * ((x >> 8) & 0xFF)
+    x = np.arange(0, 1 << 16, dtype=np.int64)
+    assert (((x >> 3) & 0x1FE0) == 32 * ((x >> 8) & 0xFF)).all()
+
+
+def test_clamp_walk_phase():
+    """k_clamp_lut on YUV888: byte i of a densely walked plane is luma iff i % 3 == 0; a 4-byte word starting at i0 sees phases
+    (i0 % 3 + k) % 3; with a rowstride that is not a multiple of 3 the dense phase drifts from the per-row phase (the reference's
+    behaviour, replicated under ref_quirks)"""
+    for rs, rows in ((160, 4), (96, 3), (224, 5)):
+        dense = np.arange(rs * rows) % 3 == 0
+        per_row = (np.arange(rs * rows) % rs) % 3 == 0
+        for i0 in range(0, rs * rows, 4):
+            assert [((i0 % 3) + k) % 3 == 0 for k in range(4)] == list(dense[i0:i0 + 4])
+            assert [(((i0 % rs) % 3) + k) % 3 == 0 for k in range(4)] == list(per_row[i0:i0 + 4])
+        assert (dense == per_row).all() == (rs % 3 == 0)
+
+
 def test_resize_contract_tracks_independent_resamplers():
     """The resize filter is OUR contract (the reference calls libswscale, which is neither in its tree nor in this image:
     parity unpinned).  Sanity against an independent implementation (OpenCV): a smooth image resized by the
