@@ -1169,6 +1169,18 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     uint8_t *pl[3] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2]};
     ce = launch_packed422_to_yuv420p(L, inpl == PE_PALETTE_UYVY ? 0 : 1, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl,
                                      n.d.rowstrides, width >> 1, n.d.height, cavg);
+  } else if ((inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P || inpl == PE_PALETTE_YUV422P) &&
+             (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888)) {
+    // convert_quad_chroma_packed (:13624-13635) / convert_double_chroma_packed (:13730-13742): chroma up-sampled on the fly, alpha 255
+    // on EVERY pixel (the reference skips the alpha of odd rows / second pixels: X)
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const Planes S = planes_of(f, inpl == PE_PALETTE_YVU420P);
+    const uint8_t *pl[3] = {S.y, S.u, S.v};
+    const int irs[3] = {S.rs_y, S.rs_u, S.rs_v};
+    ce = launch_chroma_upsample_packed(L, inpl != PE_PALETTE_YUV422P, pl, irs, S.ch, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height,
+                                       outpl == PE_PALETTE_YUVA8888, isampling == PE_YUV_SAMPLING_JPEG, cavg);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

@@ -124,6 +124,8 @@ cudaError_t launch_yuv888_subsample(const Launch &L, int mode, CImg src, int src
                                     int height, const uint8_t *cavg_dev);
 cudaError_t launch_packed422_to_yuv420p(const Launch &L, int fmt, CImg src, uint8_t *const planes[3], const int orows[3], int width_mpx,
                                         int height, const uint8_t *cavg_dev);
+cudaError_t launch_chroma_upsample_packed(const Launch &L, int is_420, const uint8_t *const planes[3], const int irows[3], int ch, Img dst,
+                                          int width, int height, int add_alpha, int jpeg, const uint8_t *cavg_dev);
 cudaError_t launch_swab(const Launch &L, Img img, int width_mpx, int height);
 // kind 0 luma plane, 1 chroma plane, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; row_phase_stride (YUV888): 0 = the reference's dense
 // walk across the row padding, else the rowstride (the Y U V phase restarts with every row)

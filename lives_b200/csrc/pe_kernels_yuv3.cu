@@ -12,6 +12,7 @@
 //   k_quad_chroma         convert_quad_chroma                            colourspace.c:10642  (4:2:0 -> 4:4:4 chroma planes)
 //   k_yuv888_subsample    convert_yuv888_to_{uyvy,yuyv,yuv422,yuv420}_frame  colourspace.c:8184 / 8228 / 8129 / 8035
 //   k_packed422_to_yuv420p  convert_{uyvy,yuyv}_to_yuv420_frame          colourspace.c:7887 / 7930
+//   k_chroma_upsample_packed  convert_quad_chroma_packed / convert_double_chroma_packed  colourspace.c:10715 / 10811
 //   k_swab                convert_swab_frame                             colourspace.c:10517  (UYVY <-> YUYV in place)
 //   k_clamp_lut           switch_yuv_clamping_and_subspace               colourspace.c:10929  (every byte through Y_to_Y / U_to_U)
 //
@@ -308,7 +309,7 @@ struct QuadChromaParams {
 };
 
 __device__ __forceinline__ uint32_t quad_even4(const uint8_t *__restrict__ s, int irs, int k, int m, int cw, int ch, bool is_u, bool jpeg,
-                                               const uint8_t *__restrict__ cavg, int n) {
+                                               const uint8_t *__restrict__ cavg, int n, bool g_is_f = false) {
   // 4 destination samples 2m .. 2m+3 of even row 2k (n of them valid) from s[m-1 .. m+2]
   const uint8_t *r = s + (long long)irs * k;
   auto at = [&](int c) -> uint32_t {
@@ -318,7 +319,8 @@ __device__ __forceinline__ uint32_t quad_even4(const uint8_t *__restrict__ s, in
   };
   auto av = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
   auto f = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : (is_u ? av(x, av(x, y)) : av(av(x, y), y)); };   // even column
-  auto g = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : (is_u ? av(av(x, y), y) : av(x, av(x, y))); };   // odd column
+  // odd column (convert_double_chroma_packed uses the even column's weights there too, colourspace.c:10853-10858: g_is_f)
+  auto g = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : ((is_u != g_is_f) ? av(av(x, y), y) : av(x, av(x, y))); };
   const uint32_t a = at(m), b = n > 2 ? at(m + 1) : a;
   const uint32_t v0 = m == 0 ? a : f(at(m - 1), a);
   const uint32_t v1 = n > 1 ? g(a, n > 2 ? b : at(m + 1)) : 0u;
@@ -432,6 +434,51 @@ __global__ void __launch_bounds__(kBlock) k_packed422_to_yuv420p(int fmt, const 
     }
     st_px4(D.p[1] + (long long)D.rs[1] * rr + m, cu, nm, false);
     st_px4(D.p[2] + (long long)D.rs[2] * rr + m, cv, nm, false);
+  }
+}
+
+// planar 4:2:0 / 4:2:2 -> YUV888 / YUVA8888 with the chroma up-sampled on the fly (convert_quad_chroma_packed colourspace.c:10715,
+// convert_double_chroma_packed :10811): the chroma of k_quad_chroma (4:2:0) or its even-row rule on every row with f on both
+// columns (4:2:2), interleaved with the luma.  One thread = 4 pixels.
+struct UpsamplePackedParams {
+  const uint8_t *y, *u, *v;
+  uint8_t *dst;
+  int rs_y, rs_u, rs_v, orow, w2, height, cw, ch, jpeg, is_420, add_alpha;
+  const uint8_t *cavg;
+};
+
+__global__ void __launch_bounds__(kBlock) k_chroma_upsample_packed(const UpsamplePackedParams P, int vec) {
+  const int groups = (P.w2 + 3) >> 2, ps = P.add_alpha ? 4 : 3;
+  const long long total = (long long)groups * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int x = 4 * g, n = min(4, P.w2 - x), m = x >> 1;
+    const uint32_t yw = ld_px4(P.y + (long long)P.rs_y * row + x, n, vec);
+    uint32_t uw, vw;
+    if (!P.is_420) {
+      uw = quad_even4(P.u, P.rs_u, row, m, P.cw, P.ch, true, P.jpeg, P.cavg, n, true);
+      vw = quad_even4(P.v, P.rs_v, row, m, P.cw, P.ch, false, P.jpeg, P.cavg, n, true);
+    } else if (!(row & 1)) {
+      uw = quad_even4(P.u, P.rs_u, row >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
+      vw = quad_even4(P.v, P.rs_v, row >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
+    } else {
+      const uint32_t uu = quad_even4(P.u, P.rs_u, (row - 1) >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
+      const uint32_t vu = quad_even4(P.v, P.rs_v, (row - 1) >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
+      if (row + 1 > P.height - 1) { uw = uu; vw = vu; }
+      else {
+        const uint32_t ud = quad_even4(P.u, P.rs_u, (row + 1) >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
+        const uint32_t vd = quad_even4(P.v, P.rs_v, (row + 1) >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
+        const bool swapped = (P.height & 1) && row == P.height - 2;
+        uw = swapped ? avg4(P.cavg, uu, ud) : avg4(P.cavg, ud, uu);
+        vw = swapped ? avg4(P.cavg, vu, vd) : avg4(P.cavg, vd, vu);
+      }
+    }
+    const uint32_t aw = 0xFFFFFFFFu;
+    const uint32_t yu_lo = __byte_perm(yw, uw, 0x5140), yu_hi = __byte_perm(yw, uw, 0x7362);
+    const uint32_t va_lo = __byte_perm(vw, aw, 0x5140), va_hi = __byte_perm(vw, aw, 0x7362);
+    const uint32_t px[4] = {__byte_perm(yu_lo, va_lo, 0x5410), __byte_perm(yu_lo, va_lo, 0x7632), __byte_perm(yu_hi, va_hi, 0x5410),
+                            __byte_perm(yu_hi, va_hi, 0x7632)};
+    st_packed4(P.dst + (long long)P.orow * row + (long long)x * ps, px, ps, n, vec);
   }
 }
 
@@ -620,6 +667,19 @@ cudaError_t launch_packed422_to_yuv420p(const Launch &L, int fmt, CImg src, uint
   if (width_mpx < 1 || height < 1) return cudaSuccess;
   k_packed422_to_yuv420p<<<grid_for(L, (long long)((width_mpx + 1) / 2) * ((height + 1) / 2)), kBlock, 0, L.stream>>>(fmt, src.p, src.rs, D, width_mpx,
                                                                                                                     height, cavg_dev, vec);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chroma_upsample_packed(const Launch &L, int is_420, const uint8_t *const planes[3], const int irows[3], int ch, Img dst,
+                                          int width, int height, int add_alpha, int jpeg, const uint8_t *cavg_dev) {
+  UpsamplePackedParams P;
+  P.y = planes[0]; P.u = planes[1]; P.v = planes[2]; P.dst = dst.p; P.rs_y = irows[0]; P.rs_u = irows[1]; P.rs_v = irows[2]; P.orow = dst.rs;
+  P.w2 = (width >> 1) << 1; P.height = height; P.cw = P.w2 >> 1; P.ch = ch; P.jpeg = jpeg; P.is_420 = is_420; P.add_alpha = add_alpha;
+  P.cavg = cavg_dev;
+  if (P.w2 < 2 || height < 1) return cudaSuccess;
+  const int vec = aligned4(planes[0]) && !(irows[0] & 3) && (add_alpha ? aligned16(dst.p) && !(dst.rs & 15) : aligned4(dst.p) && !(dst.rs & 3));
+  k_chroma_upsample_packed<<<grid_for(L, (long long)((P.w2 + 3) / 4) * height), kBlock, 0, L.stream>>>(P, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

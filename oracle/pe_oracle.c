@@ -1204,6 +1204,61 @@ void pe_or_packed422_to_yuv420p(int fmt, const uint8_t *src, int irow, int width
     }
 }
 
+/* convert_quad_chroma_packed :10715-10808 (4:2:0) and convert_double_chroma_packed :10811-10873 (4:2:2) -> packed Y U V (A = 255).
+ * 4:2:2: row i from chroma row i; column 0 = s[0], every other column c = f(s[(c-1)/2 .. ]) -- precisely: column 2m (m > 0) =
+ * f(s[m-1], s[m]) and column 2m+1 = f(s[m], s[m+1]) with the SAME f on both (JPEG: avg_chroma; else U: avg_3_1, V: avg_1_3;
+ * :10843-10862), s[cw] being the byte behind the row.
+ * 4:2:0: even rows exactly as convert_quad_chroma (f on even columns, g on odd ones), odd row r = avg_chroma(row r+1, row r-1)
+ * written two rows later (:10771-10780).
+ * X (4:2:2): with add_alpha the alpha byte of the second pixel of every pair is never written (:10848-10863) -- 255 here.
+ * X (4:2:0): with add_alpha the odd rows get no alpha byte (:10768-10784) -- 255 here;
+ *   the last row of an even-height frame never gets its chroma, and for an odd height the post-loop fix-up addresses the
+ * wrong rows (`jj = j - ostride`, :10801-10805: it reads one row past the frame and overwrites the last even row, the odd row
+ * above stays unwritten) -- defined here as in convert_quad_chroma: last row of an even height = the row above, last odd row of an
+ * odd height = avg_chroma(row above, row below). */
+void pe_or_chroma_upsample_packed(int is_420, const uint8_t *const src[3], const int istrides[3], int width, int height, uint8_t *dest,
+                                  int orow, int add_alpha, int sampling_jpeg, int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+#define OR_AV(x_, y_) avg[((int)(x_) << 8) + (int)(y_)]
+  const int ps = add_alpha ? 4 : 3, w2 = (width >> 1) << 1, cw = w2 >> 1, ch = is_420 ? (height + 1) >> 1 : height;
+  for (int i = 0; i < height; i++) {
+    uint8_t *d = dest + (long)orow * i;
+    const uint8_t *y = src[0] + (long)istrides[0] * i;
+    for (int j = 0; j < w2; j++) { d[j * ps] = y[j]; if (add_alpha) d[j * ps + 3] = 255; }
+    if (is_420 && (i & 1)) continue;
+    const int k = is_420 ? i >> 1 : i;
+    for (int p = 1; p <= 2; p++) {
+      const uint8_t *s = src[p] + (long)istrides[p] * k;
+      for (int m = 0; m < cw; m++) {
+        const uint8_t a = s[m], nx = (m + 1 < cw || cw < istrides[p] || k + 1 < ch) ? s[m + 1] : s[m];
+        uint8_t e, o2;
+        if (m == 0) e = a;
+        else {
+          const uint8_t pv = s[m - 1];
+          e = sampling_jpeg ? OR_AV(pv, a) : (p == 1 ? OR_AV(pv, OR_AV(pv, a)) : OR_AV(OR_AV(pv, a), a));
+        }
+        if (is_420) o2 = sampling_jpeg ? OR_AV(a, nx) : (p == 1 ? OR_AV(OR_AV(a, nx), nx) : OR_AV(a, OR_AV(a, nx)));
+        else o2 = sampling_jpeg ? OR_AV(a, nx) : (p == 1 ? OR_AV(a, OR_AV(a, nx)) : OR_AV(OR_AV(a, nx), nx));
+        d[(2 * m) * ps + p] = e;
+        d[(2 * m + 1) * ps + p] = o2;
+      }
+    }
+  }
+  if (is_420)
+    for (int r = 1; r < height; r += 2) {
+      uint8_t *d = dest + (long)orow * r;
+      const uint8_t *up = d - orow, *dn = d + orow;
+      for (int j = 0; j < w2; j++)
+        for (int p = 1; p <= 2; p++) {
+          const int q = j * ps + p;
+          if (r + 1 > height - 1) d[q] = up[q];
+          else if ((height & 1) && r == height - 2) d[q] = OR_AV(up[q], dn[q]);
+          else d[q] = OR_AV(dn[q], up[q]);
+        }
+    }
+#undef OR_AV
+}
+
 /* convert_swab_frame :10517-10566: swab() of width * 4 bytes per row */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height) {
   for (int k = 0; k < height; k++) {

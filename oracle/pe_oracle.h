@@ -152,6 +152,10 @@ void pe_or_yuv888_subsample(int mode, const uint8_t *src, int irow, int width, i
  * row 2k+1) */
 void pe_or_packed422_to_yuv420p(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[3],
                                 const int orows[3], int clamping);
+/* planar 4:2:0 / 4:2:2 -> YUV888 / YUVA8888 with the chroma up-sampled on the fly: convert_quad_chroma_packed :10715 (is_420 = 1)
+ * and convert_double_chroma_packed :10811 (is_420 = 0) */
+void pe_or_chroma_upsample_packed(int is_420, const uint8_t *const src[3], const int istrides[3], int width, int height, uint8_t *dest,
+                                  int orow, int add_alpha, int sampling_jpeg, int clamping);
 /* convert_swab_frame :10517 (UYVY <-> YUYV in place) */
 void pe_or_swab(uint8_t *pixels, int irow, int width_mpx, int height);
 /* init_YUV_to_YUV_tables :1108; which 0 Yc->Yu 1 UVc->UVu 2 Yu->Yc 3 UVu->UVc */

@@ -366,3 +366,11 @@ void ref_packed422_to_yuv420p(int fmt, void *src, int width, int height, uint8_t
   if (fmt == 0) convert_uyvy_to_yuv420_frame((uyvy_macropixel *)src, width, height, dest, clamping);
   else convert_yuyv_to_yuv420_frame((yuyv_macropixel *)src, width, height, dest, clamping);
 }
+
+/* is_420 1: convert_quad_chroma_packed, 0: convert_double_chroma_packed; width x height = the destination frame in pixels */
+void ref_chroma_upsample_packed(int is_420, uint8_t **src, int width, int height, int *istrides, int ostride, uint8_t *dest, int add_alpha,
+                                int sampling, int clamping) {
+  ref_init();
+  if (is_420) convert_quad_chroma_packed(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
+  else convert_double_chroma_packed(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
+}

@@ -77,6 +77,7 @@ _ORACLE_PROTOS = {
     "pe_or_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv888": [I, VP, I, I, I, VP, I, I],
     "pe_or_swab": [VP, I, I, I],
+    "pe_or_chroma_upsample_packed": [I, VP, VP, I, I, VP, I, I, I, I],
     "pe_or_packed422_to_yuv420p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_yuv888_subsample": [I, VP, I, I, I, I, VP, VP, I],
     "pe_or_quad_chroma": [VP, VP, I, I, VP, I, I, I, I],
@@ -118,6 +119,7 @@ _REF_PROTOS = {
     "ref_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "ref_packed422_to_yuv888": [I, VP, I, I, I, I, VP, I],
     "ref_swab": [VP, I, I, I],
+    "ref_chroma_upsample_packed": [I, VP, I, I, VP, I, VP, I, I, I],
     "ref_packed422_to_yuv420p": [I, VP, I, I, VP, I],
     "ref_yuv888_subsample": [I, VP, I, I, I, VP, VP, I, I],
     "ref_quad_chroma": [VP, I, I, VP, I, VP, I, I, I],

@@ -745,6 +745,25 @@ def test_packed422_to_yuv420p(eng, size):
             assert (got[k][:, :wm] == ep[k][:, :wm]).all(), ("packed422 -> 420p", w, h, ipal, cl, k)
 
 
+@pytest.mark.parametrize("size", [(64, 12), (38, 6), (1920, 1080), (2, 2), (6, 4)])
+def test_planar42x_to_packed_yuv888(eng, size):
+    """YUV420P / YVU420P / YUV422P -> YUV888 / YUVA8888 (convert_quad_chroma_packed / convert_double_chroma_packed)"""
+    o = T.oracle()
+    w, h = size
+    rng = np.random.default_rng(170 + w)
+    for ipal, opal, samp, cl in itertools.product((512, 513, 522), (588, 589), (0, 1), (0, 1)):
+        y, u, v = T.make_yuv_planar(rng, w, h, ipal == 522, cl == 0)
+        su, sv = (v, u) if ipal == 513 else (u, v)
+        ps = 4 if opal == 589 else 3
+        exp = np.zeros((h, T.rowstride(w, ps)), np.uint8)
+        o.pe_or_chroma_upsample_packed(int(ipal != 522), T.planes_arg(y, su, sv), T.strides_arg(y, su, sv), w, h, T.ptr(exp), exp.strides[0],
+                                       int(opal == 589), int(samp == 0), cl)
+        lay = lb.Layer.from_host(eng, ipal, w, h, [y, u, v], yuv_clamping=cl, yuv_sampling=samp)
+        assert lb.convert_layer_palette(lay, opal, cl)
+        assert (lay.palette, lay.width, lay.height) == (opal, w, h)
+        assert (payload(lay.to_host()[0], w, ps) == payload(exp, w, ps)).all(), ("upsample packed", w, h, ipal, opal, samp, cl)
+
+
 def test_yuv_clamping_switch(eng):
     """switch_yuv_clamping_and_subspace: convert_layer_palette_full with the same palette / subspace and the other clamping runs
     every sample through the clamped <-> unclamped tables in place; a palette change on top converts afterwards"""

@@ -754,3 +754,34 @@ def test_packed422_to_yuv420p_matches_reference():
         r.ref_packed422_to_yuv420p(fmt, T.ptr(src), wm, h, T.planes_arg(*db), cl)
         for k in range(3):
             assert (da[k] == db[k]).all(), ("packed422 -> 420p", wm, h, fmt, cl, k)
+
+
+def test_chroma_upsample_packed_matches_reference():
+    """4:2:2 / 4:2:0 planar -> YUV888 / YUVA8888 (convert_double_chroma_packed / convert_quad_chroma_packed) on padded planes; for
+    4:2:0 the rows the reference leaves undefined (last row of an even height, last two of an odd height) are not compared"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(80)
+    for (w, h), is420, samp, cl, aa in itertools.product(((32, 8), (34, 7), (6, 2), (36, 9)), (0, 1), (0, 1), (0, 1), (0, 1)):
+        cw, ch = w >> 1, ((h + 1) >> 1) if is420 else h
+        ys, cs = T.align_ceil(w + 1, 32), T.align_ceil(cw + 1, 16)
+        y = np.zeros((h, ys), np.uint8); y[:, :w] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u, v = np.zeros((ch, cs), np.uint8), np.zeros((ch, cs), np.uint8)
+        u[:, :cw] = rng.integers(0, 256, (ch, cw), dtype=np.uint8); v[:, :cw] = rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+        ps = 4 if aa else 3
+        ors = T.align_ceil(w * ps + 8, 32)
+        a = np.zeros((h, ors), np.uint8)
+        b = np.zeros((h + 2, ors), np.uint8)  # slack rows: the reference's post-loop touches the row past the frame
+        o.pe_or_chroma_upsample_packed(is420, T.planes_arg(y, u, v), T.strides_arg(y, u, v), w, h, T.ptr(a), ors, aa, int(samp == 0), cl)
+        r.ref_chroma_upsample_packed(is420, T.planes_arg(y, u, v), w, h, T.strides_arg(y, u, v), ors, T.ptr(b), aa, samp, cl)
+        rows = h if not is420 else (h - 2 if (h & 1) else h - 1)
+        if aa and not is420:
+            # X: convert_double_chroma_packed never writes the alpha byte of the second pixel of a pair (colourspace.c:10848-10863)
+            assert (a[:, 3:w * 4:4] == 255).all()
+            b[:h, 7:w * 4:8] = 255
+        if aa and is420:
+            # X: convert_quad_chroma_packed writes no alpha on odd rows (colourspace.c:10768-10784)
+            assert (a[:, 3:w * 4:4] == 255).all()
+            b[1:h:2, 3:w * 4:4] = 255
+        assert (a[:rows, :w * ps] == b[:rows, :w * ps]).all(), ("upsample packed", w, h, is420, samp, cl, aa)
+        # luma (and alpha) of every row
+        assert (a[:, 0:w * ps:ps] == b[:h, 0:w * ps:ps]).all()
