@@ -4,7 +4,8 @@ built by oracle/build_ref.py from /root/reference).  Run in the build container 
 
 Only reference behaviour that is defined goes in (see the X rows of DESIGN.md's quirk table): planar 4:4:4 -> RGB24 / RGBA32 /
 BGRA32, combineplanes without source alpha on padded planes, splitplanes 3 -> 3 planes, halve / double chroma, packed 4:2:2 ->
-planar 4:2:2 (dense buffers; the never-advanced source pointer included) / 4:4:4 / YUV888, swab, the four clamping tables.
+planar 4:2:2 (dense buffers; the never-advanced source pointer included) / 4:4:4 / YUV888, swab, the four clamping tables, the packed
+chroma up-samplers (planar 4:2:x -> YUV888 / YUVA8888).
 """
 import os
 import sys
@@ -127,6 +128,29 @@ def main():
     sw = m.copy()
     r.ref_swab(T.ptr(sw), wm, H, sw.strides[0])
     out["swab"] = sw
+    # planar 4:2:2 / 4:2:0 -> YUV888 / YUVA8888 with the chroma up-sampled on the fly (convert_double_chroma_packed /
+    # convert_quad_chroma_packed) on padded planes.  4:2:0: height 9, rows 0 .. 6 (the reference's defined part).  The alpha bytes the
+    # reference never writes (second pixel of a pair / odd rows: X) are set to 255 before freezing.
+    rg2 = np.random.default_rng(2027)
+    uy = np.zeros((H, T.rowstride(W, 1)), np.uint8)  # the engine's own strides: whole rows travel to the device, padding included
+    uy[:, :W] = rg2.integers(0, 256, (H, W), dtype=np.uint8)
+    out["up_y"] = uy
+    for is420, nm, hh, chh in ((0, "422", H, H), (1, "420", 9, 5)):
+        cs = [np.zeros((chh, T.rowstride(W, 1) >> 1), np.uint8) for _ in range(2)]
+        for p_ in cs:
+            p_[:, :cw] = rg2.integers(0, 256, (chh, cw), dtype=np.uint8)
+        out["up%s_u" % nm], out["up%s_v" % nm] = cs
+        rows = hh if not is420 else hh - 2
+        for samp in (0, 1):
+            for cl in (0, 1):
+                for aa in (0, 1):
+                    ps = 4 if aa else 3
+                    ors = T.align_ceil(W * ps + 8, 32)
+                    d = np.zeros((hh + 2, ors), np.uint8)
+                    r.ref_chroma_upsample_packed(is420, T.planes_arg(uy, *cs), W, hh, T.strides_arg(uy, *cs), ors, T.ptr(d), aa, samp, cl)
+                    if aa:
+                        d[:hh, 3:W * 4:4] = 255
+                    out["up%s_s%d_cl%d_a%d" % (nm, samp, cl, aa)] = d[:rows, :W * ps].copy()
     np.savez_compressed(os.path.join(HERE, "ref_vectors_yuv.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_vectors_yuv.npz"), len(out), "arrays")
 

@@ -1,5 +1,6 @@
 """Golden vectors of the YUV <-> YUV family, frozen from the compiled reference (tests/golden/make_golden_yuv.py ->
 ref_vectors_yuv.npz).  CPU: the oracle reproduces every vector; GPU: the CUDA path reproduces them through the C ABI."""
+import itertools
 import os
 
 import numpy as np
@@ -91,6 +92,15 @@ def test_oracle_yuv_family_matches_golden():
         d3 = [np.zeros((H, pl[0].strides[0]), np.uint8), np.zeros_like(eu), np.zeros_like(ev)]
         o.pe_or_yuv444p_to_yuv420p(T.planes_arg(*pl[:3]), T.strides_arg(*pl[:3]), W, H, T.planes_arg(*d3), T.strides_arg(*d3), cl)
         assert (d3[1] == eu).all() and (d3[2] == ev).all(), cl
+    uy = _c("up_y")
+    for is420, nm, hh in ((0, "422", H), (1, "420", 9)):
+        cs = [_c("up%s_u" % nm), _c("up%s_v" % nm)]
+        for samp, cl, aa in itertools.product((0, 1), (0, 1), (0, 1)):
+            exp = G["up%s_s%d_cl%d_a%d" % (nm, samp, cl, aa)]
+            d = np.zeros((hh, T.align_ceil(W * (4 if aa else 3) + 8, 32)), np.uint8)
+            o.pe_or_chroma_upsample_packed(is420, T.planes_arg(uy, *cs), T.strides_arg(uy, *cs), W, hh, T.ptr(d), d.strides[0], aa,
+                                           int(samp == 0), cl)
+            assert (d[:exp.shape[0], :exp.shape[1]] == exp).all(), (nm, samp, cl, aa)
 
 
 @pytest.mark.gpu
@@ -156,4 +166,12 @@ def test_cuda_yuv_family_matches_golden():
     assert lb.convert_layer_palette_full(lay, 564, 1, 0, 1, 0)
     got, px = lay.to_host()[0][:, :WM * 4], m[:, :WM * 4]
     assert (got[:, 1::2] == yy[0][px[:, 1::2]]).all() and (got[:, 0::2] == yy[1][px[:, 0::2]]).all()
+    uy = _c("up_y")
+    for ipal, nm, hh in ((522, "422", H), (512, "420", 9)):
+        cs = [_c("up%s_u" % nm), _c("up%s_v" % nm)]
+        for samp, cl, (aa, opal) in itertools.product((0, 1), (0, 1), ((0, 588), (1, 589))):
+            exp = G["up%s_s%d_cl%d_a%d" % (nm, samp, cl, aa)]
+            lay = lb.Layer.from_host(eng, ipal, W, hh, [np.ascontiguousarray(uy[:hh]), *cs], yuv_clamping=cl, yuv_sampling=samp)
+            assert lb.convert_layer_palette(lay, opal, cl)
+            assert (lay.to_host()[0][:exp.shape[0], :exp.shape[1]] == exp).all(), (nm, samp, cl, aa)
     eng.close()
