@@ -190,6 +190,15 @@ int pe_fx_convert_crossfade_batchv(pe_engine_t *e, int n, pe_frame_t *const *cli
 /* multi_blends.c common_process :26.  type 0 multiply .. 6 burn; RGB24 / BGR24 only */
 int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                       int blend_factor);
+/* slide_over.c sover_process :55 (the "slide over" transition): out = in1 ("upper") on one side of a dividing line, in2 ("lower") on
+ * the other; the line moves with transval 0 .. 255.  direction = the plugin's "plugin_direction" 1 .. 4 as sover_init :38-52 derives
+ * it from the radio parameters (1 / 2: the line runs along x, 3 / 4: along y; the caller resolves "random"); mvlower / mvupper = the
+ * "Slide lower / upper clip" switches.  Every packed palette (ALL_PACKED_PALETTES_PLUS :158); not in-place.
+ * pe_fx_slide_over_bound: the dividing line in rows / macropixels exactly as the reference's -ffast-math build computes it
+ * (host arithmetic, no GPU needed). */
+int pe_fx_slide_over(pe_engine_t *e, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, int transval, int direction,
+                     int mvlower, int mvupper);
+int pe_fx_slide_over_bound(int direction, int transval, int width, int height);
 /* gdk/compositor.c compositor_process :127 at scale 1 / offset 0: out = bgcol, then paint_pixel(:120) of every
  * layer, last first (revz == WEED_FALSE, :189-197); alpha[i] is the scalar per-layer alpha */
 int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,

@@ -90,6 +90,8 @@ PROTOTYPES = {
     "pe_gamma_lut8": (I, [VP, D, I, I, VP]),
     "pe_fx_simple_blend": (I, [VP, I, VP, VP, VP, I]),
     "pe_fx_multi_blend": (I, [VP, I, VP, VP, VP, I]),
+    "pe_fx_slide_over": (I, [VP, VP, VP, VP, I, I, I, I]),
+    "pe_fx_slide_over_bound": (I, [I, I, I, I]),
     "pe_fx_compositor": (I, [VP, VP, PVP, C.POINTER(D), I, PI]),
     "pe_fx_compositor_gamma": (I, [VP, VP, PVP, C.POINTER(D), I, PI, I]),
     "pe_fx_compositor_gamma_batch": (I, [VP, I, PVP, PVP, C.POINTER(D), I, PI, I]),

@@ -1791,6 +1791,49 @@ extern "C" int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1
   return PE_OK;
 }
 
+// slide_over.c:94,109,124,135 as the reference's build computes it: -ffast-math (lives-plugins/weed-plugins/Makefile.am:49) turns
+// `/ 255.` into `* (1 / 255.)` and regroups `(float)dim * (transval / 255.)` as (dim * (1 / 255.)) * transval.  Host arithmetic
+// (this file is compiled without fast-math: the grouping below is what runs); checked on the CPU against the compiled plugin.
+extern "C" int pe_fx_slide_over_bound(int direction, int transval, int width, int height) {
+  const double r255 = 1. / 255.;
+  const double dim = (double)(float)(direction <= 2 ? width : height);
+  if (direction == 1 || direction == 3) return (int)((1. - (double)transval * r255) * dim);
+  if (direction == 2 || direction == 4) return (int)((dim * r255) * (double)transval);
+  return 0;
+}
+
+extern "C" int pe_fx_slide_over(pe_engine_t *e, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, int transval,
+                                int direction, int mvlower, int mvupper) {
+  if (!e) return set_err(PE_ERR_ARG, "NULL engine");
+  if (!in1 || !in2 || !out || !in1->d.planes[0] || !in2->d.planes[0] || !out->d.planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
+  const int pal = in1->d.palette;
+  if (pal_is_planar(pal)) return set_err(PE_ERR_PALETTE, "palette %d is not in this filter's palette list", pal);  // ALL_PACKED_PALETTES_PLUS :158
+  if (in2->d.palette != pal || out->d.palette != pal) return set_err(PE_ERR_PALETTE, "channel palettes differ");
+  if (in2->d.width != in1->d.width || in2->d.height != in1->d.height || out->d.width != in1->d.width || out->d.height != in1->d.height)
+    return set_err(PE_ERR_SIZE, "channel sizes differ");
+  if (out->d.planes[0] == in1->d.planes[0] || out->d.planes[0] == in2->d.planes[0])
+    return set_err(PE_ERR_ARG, "slide over is not an in-place filter (out channel flags 0, slide_over.c:162)");
+  if (direction < 1 || direction > 4) return set_err(PE_ERR_ARG, "direction %d: 1 .. 4 (plugin_direction, slide_over.c:38-52)", direction);
+  if (transval < 0 || transval > 255) return set_err(PE_ERR_ARG, "transition value %d out of 0 .. 255", transval);
+  const int ps = pal_psize(pal), width = in1->d.width / pal_ppmp(pal), height = in1->d.height;  // width in macropixels, as the plugin sees it
+  const int bound = pe_fx_slide_over_bound(direction, transval, width, height);
+  const bool swapped = direction == 2 || direction == 4, along_y = direction >= 3;
+  const pe_frame_t *fa = swapped ? in2 : in1, *fb = swapped ? in1 : in2;
+  const bool mv_a = swapped ? mvlower : mvupper, mv_b = swapped ? mvupper : mvlower;
+  SlideArgs a;
+  a.first = (const uint8_t *)fa->d.planes[0]; a.second = (const uint8_t *)fb->d.planes[0]; a.d = (uint8_t *)out->d.planes[0];
+  a.rs_first = fa->d.rowstrides[0]; a.rs_second = fb->d.rowstrides[0]; a.rsd = out->d.rowstrides[0];
+  a.row_bytes = width * ps; a.height = height; a.along_y = along_y;
+  a.bound = along_y ? bound : bound * ps;
+  // a moving clip is read shifted: its far edge sits on the line (:95-97, :110-112, :126-127, :137-138)
+  a.off_first = !mv_a ? 0 : along_y ? (long long)a.rs_first * (height - bound) : (long long)(width - bound) * ps;
+  a.off_second = !mv_b ? 0 : along_y ? -(long long)a.rs_second * bound : -(long long)bound * ps;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  PE_CUDA(launch_slide_over(e->L(), a));
+  return PE_OK;
+}
+
 namespace {
 
 // compositor_process (gdk/compositor.c:127) at scale 1 / offset 0, optionally followed by gamma_convert_layer(gamma_to, out)

@@ -142,6 +142,15 @@ cudaError_t launch_simple_blend(const Launch &L, int type, const BlendFrame *fra
                                 int height, RgbLayout lay, int bf, const int32_t *luma_tabs_dev);
 cudaError_t launch_multi_blend(const Launch &L, int type, BlendFrame f, int width, int height, int bgr, int bf,
                                const int32_t *luma_tabs_dev);
+// slide_over.c:55: dst byte (j, x) = first[rs_first * j + off_first + x] before the line (j < bound when along_y, else x < bound,
+// bound in rows / bytes), second[rs_second * j + off_second + x] behind it
+struct SlideArgs {
+  const uint8_t *first, *second;
+  uint8_t *d;
+  long long off_first, off_second;
+  int rs_first, rs_second, rsd, row_bytes, height, along_y, bound;
+};
+cudaError_t launch_slide_over(const Launch &L, const SlideArgs &a);
 // dst = trunc(bg * (1 - alpha) + fg * alpha) in double (compositor.c:120), optional lut8 afterwards:
 // launch_over_table builds the 64 KB [bg][fg] result table for one (alpha, lut8), launch_alpha_over applies it
 cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev);

@@ -603,6 +603,43 @@ cudaError_t launch_multi_blend(const Launch &L, int type, BlendFrame f, int widt
 }
 
 // =====================================================================================================
+// slide over (slide_over.c sover_process :55-145): every destination byte is a copy of one byte of in1 or in2 -- the side of the
+// dividing line picks the clip, a "moving" clip is read with a constant offset.  Pure copy, 1 load + 1 store per byte: one thread
+// moves 16 bytes, as one 128-bit access when both ends of the chunk lie on the same side and source and destination are aligned.
+// =====================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(kBlock) k_slide_over(const SlideArgs P) {
+  const int chunks = (P.row_bytes + 15) >> 4;
+  const long long total = (long long)chunks * P.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int j = (int)(it / chunks), x0 = (int)(it - (long long)j * chunks) << 4;
+    const int n = min(16, P.row_bytes - x0);
+    uint8_t *d = P.d + (long long)P.rsd * j + x0;
+    auto is_first = [&](int x) -> bool { return P.along_y ? j < P.bound : x < P.bound; };
+    auto src_of = [&](int x, bool f) -> const uint8_t * {
+      return f ? P.first + (long long)P.rs_first * j + P.off_first + x : P.second + (long long)P.rs_second * j + P.off_second + x;
+    };
+    const bool f0 = is_first(x0), f1 = is_first(x0 + n - 1);
+    const uint8_t *s = src_of(x0, f0);
+    if (n == 16 && f0 == f1 && !((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15)) {
+      *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s);
+    } else {
+      for (int k = 0; k < n; k++) d[k] = *src_of(x0 + k, is_first(x0 + k));
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_slide_over(const Launch &L, const SlideArgs &a) {
+  if (a.row_bytes <= 0 || a.height <= 0) return cudaSuccess;
+  k_slide_over<<<grid_for(L, (long long)((a.row_bytes + 15) >> 4) * a.height), kBlock, 0, L.stream>>>(a);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
 // alpha-over: dst = (u8)(bg * (1 - alpha) + fg * alpha) in double, truncating store
 // (gdk/compositor.c paint_pixel :120-125), optionally followed by the 8-bit gamma LUT in the same pass.
 //

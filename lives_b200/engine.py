@@ -333,6 +333,22 @@ def multi_blend(filter_type, in1, in2, out, blend_factor):
     capi.check(e._lib.pe_fx_multi_blend(e._h, t, in1._h, in2._h, out._h, blend_factor))
 
 
+SLIDE_DIRECTIONS = {"dir_r2l": 1, "dir_l2r": 2, "dir_b2t": 3, "dir_t2b": 4}  # parameter name -> plugin_direction (sover_init :38-52)
+
+
+def slide_over(in1, in2, out, transval, direction, mvlower=True, mvupper=False):
+    """slide_over.c sover_process :55; direction 1 .. 4 or the name of the radio parameter that selects it; the defaults of
+    mvlower / mvupper are the plugin's (:170-171)"""
+    d = SLIDE_DIRECTIONS.get(direction, direction)
+    e = in1.engine
+    capi.check(e._lib.pe_fx_slide_over(e._h, in1._h, in2._h, out._h, transval, d, int(bool(mvlower)), int(bool(mvupper))))
+
+
+def slide_over_bound(direction, transval, width, height):
+    """the dividing line (rows / macropixels) as the reference's build computes it; host arithmetic only"""
+    return capi.lib().pe_fx_slide_over_bound(SLIDE_DIRECTIONS.get(direction, direction), transval, width, height)
+
+
 def compositor(out, layers, alphas, bgcol=(0, 0, 0)):
     """gdk/compositor.c compositor_process :127 at scale 1 / offset 0"""
     e = out.engine

@@ -1310,3 +1310,43 @@ void pe_or_switch_clamping_plane(uint8_t *plane, long nbytes, int kind, int to_u
     plane[i] = luma ? ty[plane[i]] : tc[plane[i]];
   }
 }
+
+/* slide_over.c:94,109,124,135: the dividing line, `(float)dim * (1. - transval / 255.)` resp. `(float)dim * (transval / 255.)`,
+ * truncated -- AS THE REFERENCE BUILDS IT: the weed plugins are compiled with -ffast-math (lives-plugins/weed-plugins/Makefile.am:49),
+ * under which gcc turns the division into a multiplication by the rounded reciprocal of 255 and regroups the second form as
+ * (dim * (1 / 255.)) * transval (read off the compiled plugin; pinned against it for all 256 values in
+ * tests/test_oracle_vs_reference.py).  E.g. a 37 pixel wide frame keeps one column of the old clip at transval 255. */
+int pe_or_slide_over_bound(int direction, int transval, int width, int height) {
+  const double r255 = 1. / 255.;
+  const double dim = (double)(float)(direction <= 2 ? width : height);
+  switch (direction) {
+  case 1: case 3: return (int)((1. - (double)transval * r255) * dim);
+  case 2: case 4: return (int)((dim * r255) * (double)transval);
+  }
+  return 0;
+}
+
+/* slide_over.c sover_process :55-145, restated per destination byte.  Directions 1 and 3 show in1 before the line and in2
+ * behind it, 2 and 4 the other way round; a clip that "moves" is read shifted so that its far edge sits on the line
+ * (:95-97, :110-112, :126-127, :137-138), otherwise it is read in place */
+void pe_or_slide_over(int direction, int transval, int mvlower, int mvupper, const uint8_t *src1, int irow1, const uint8_t *src2,
+                      int irow2, uint8_t *dest, int orow, int width, int height, int psize) {
+  const int bound = pe_or_slide_over_bound(direction, transval, width, height);
+  const int along_y = direction >= 3, swapped = direction == 2 || direction == 4;
+  const uint8_t *first = swapped ? src2 : src1, *second = swapped ? src1 : src2;
+  const int rs_f = swapped ? irow2 : irow1, rs_s = swapped ? irow1 : irow2;
+  const int mv_f = swapped ? mvlower : mvupper, mv_s = swapped ? mvupper : mvlower;
+  const int row_bytes = width * psize;
+  if (direction < 1 || direction > 4) return;
+  for (int j = 0; j < height; j++)
+    for (int x = 0; x < row_bytes; x++) {
+      int sj = j, sx = x;
+      if (along_y ? j < bound : x < bound * psize) {
+        if (mv_f) { if (along_y) sj = j + (height - bound); else sx = x + (width - bound) * psize; }
+        dest[(long)orow * j + x] = first[(long)rs_f * sj + sx];
+      } else {
+        if (mv_s) { if (along_y) sj = j - bound; else sx = x - bound * psize; }
+        dest[(long)orow * j + x] = second[(long)rs_s * sj + sx];
+      }
+    }
+}

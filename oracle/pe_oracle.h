@@ -163,6 +163,13 @@ void pe_or_yy_table(int which, uint8_t out[256]);
 /* switch_yuv_clamping_and_subspace :10929 on one plane walked densely (padding included, as the reference walks it):
  * kind 0 all luma, 1 all chroma, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; to_unclamped selects the table pair */
 void pe_or_switch_clamping_plane(uint8_t *plane, long nbytes, int kind, int to_unclamped);
+/* slide_over.c sover_process :55-145: a straight cut between in1 ("upper") and in2 ("lower") whose dividing line moves with
+ * transval 0 .. 255.  direction 1 .. 4 = the plugin's "plugin_direction" (sover_init :38-52): 1 / 2 the line runs along x, 3 / 4
+ * along y; mvlower / mvupper: the clip slides with the line instead of being uncovered in place.  width in macropixels of psize
+ * bytes.  pe_or_slide_over_bound: the dividing line (rows or macropixels) */
+int pe_or_slide_over_bound(int direction, int transval, int width, int height);
+void pe_or_slide_over(int direction, int transval, int mvlower, int mvupper, const uint8_t *src1, int irow1, const uint8_t *src2,
+                      int irow2, uint8_t *dest, int orow, int width, int height, int psize);
 
 #ifdef __cplusplus
 }

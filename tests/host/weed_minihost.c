@@ -22,6 +22,9 @@
  *        two in channels, one out channel, one integer in-parameter; dst may
  *        equal src1 (in-place, as LiVES does for CAN_DO_INPLACE channels);
  *        calls init once, process nframes times, deinit once.
+ *   int  mh_run2v(... as mh_run2 up to rsd ..., int nparams, const int *vals, int nframes);
+ *        the same with one in-parameter per template of the filter: vals[k] is stored as an int or a boolean,
+ *        whichever seed type the template's default has (radio / switch parameters are booleans).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -137,6 +140,55 @@ int mh_run2(int h, int fidx, int palette, int width, int height, void *src1, int
   if (deinit_fn) (*deinit_fn)(inst);
 
   weed_plant_free(inst); weed_plant_free(param);
+  weed_plant_free(in_ch[0]); weed_plant_free(in_ch[1]); weed_plant_free(out_ch);
+  free(ictm); free(octm); free(iptm);
+  return (int)err;
+}
+
+int mh_run2v(int h, int fidx, int palette, int width, int height, void *src1, int rs1, void *src2, int rs2,
+             void *dst, int rsd, int nparams, const int *vals, int nframes) {
+  weed_plant_t *filter, *inst, *in_ch[2], *out_ch, *params[32];
+  weed_plant_t **ictm, **octm, **iptm;
+  weed_init_f init_fn;
+  weed_process_f process_fn;
+  weed_deinit_f deinit_fn;
+  weed_error_t err = WEED_SUCCESS;
+  int n, np;
+  if (mh_num_filters(h) <= fidx || fidx < 0) return -1;
+  filter = mh_tab[h].filters[fidx];
+  ictm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_CHANNEL_TEMPLATES, &n);
+  if (n < 2) return -2;
+  octm = weed_get_plantptr_array_counted(filter, WEED_LEAF_OUT_CHANNEL_TEMPLATES, &n);
+  if (n < 1) return -3;
+  iptm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_PARAMETER_TEMPLATES, &np);
+  if (np < 1 || np > 32 || np != nparams) return -4;
+
+  in_ch[0] = mh_channel(ictm[0], palette, width, height, src1, rs1);
+  in_ch[1] = mh_channel(ictm[1], palette, width, height, src2, rs2);
+  out_ch = mh_channel(octm[0], palette, width, height, dst, rsd);
+  for (int k = 0; k < np; k++) {
+    params[k] = weed_plant_new(WEED_PLANT_PARAMETER);
+    weed_set_plantptr_value(params[k], WEED_LEAF_TEMPLATE, iptm[k]);
+    if (weed_leaf_seed_type(iptm[k], WEED_LEAF_DEFAULT) == WEED_SEED_BOOLEAN) weed_set_boolean_value(params[k], WEED_LEAF_VALUE, vals[k]);
+    else weed_set_int_value(params[k], WEED_LEAF_VALUE, vals[k]);
+  }
+
+  inst = weed_plant_new(WEED_PLANT_FILTER_INSTANCE);
+  weed_set_plantptr_value(inst, WEED_LEAF_FILTER_CLASS, filter);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_CHANNELS, 2, in_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_OUT_CHANNELS, 1, &out_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_PARAMETERS, np, params);
+
+  init_fn = (weed_init_f)weed_get_funcptr_value(filter, WEED_LEAF_INIT_FUNC, NULL);
+  process_fn = (weed_process_f)weed_get_funcptr_value(filter, WEED_LEAF_PROCESS_FUNC, NULL);
+  deinit_fn = (weed_deinit_f)weed_get_funcptr_value(filter, WEED_LEAF_DEINIT_FUNC, NULL);
+  if (!process_fn) return -5;
+  if (init_fn) err = (*init_fn)(inst);
+  for (int f = 0; f < nframes && err == WEED_SUCCESS; f++) err = (*process_fn)(inst, (weed_timecode_t)f);
+  if (deinit_fn) (*deinit_fn)(inst);
+
+  weed_plant_free(inst);
+  for (int k = 0; k < np; k++) weed_plant_free(params[k]);
   weed_plant_free(in_ch[0]); weed_plant_free(in_ch[1]); weed_plant_free(out_ch);
   free(ictm); free(octm); free(iptm);
   return (int)err;

@@ -77,6 +77,8 @@ _ORACLE_PROTOS = {
     "pe_or_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv888": [I, VP, I, I, I, VP, I, I],
     "pe_or_swab": [VP, I, I, I],
+    "pe_or_slide_over_bound": [I, I, I, I],
+    "pe_or_slide_over": [I, I, I, I, VP, I, VP, I, VP, I, I, I, I],
     "pe_or_chroma_upsample_packed": [I, VP, VP, I, I, VP, I, I, I, I],
     "pe_or_packed422_to_yuv420p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_yuv888_subsample": [I, VP, I, I, I, I, VP, VP, I],

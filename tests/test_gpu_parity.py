@@ -973,6 +973,33 @@ def test_multi_blends(eng):
         assert (payload(lo.to_host()[0], w, 3) == payload(exp, w, 3)).all(), (pal, bf, typ)
 
 
+@pytest.mark.parametrize("size", [(64, 32), (61, 7), (1920, 1080), (2, 2)])
+def test_slide_over(eng, size):
+    """slide_over.c: every direction x moving / fixed clips over the transition range, 3- and 4-byte and macropixel palettes"""
+    o = T.oracle()
+    rng = np.random.default_rng(14)
+    w, h = size
+    big = w > 1000
+    for pal in ((1, 3) if big else (1, 2, 3, 5, 588, 589, 564, 565)):
+        ps = T.psize_of(pal)
+        wm = w // 2 if pal in (564, 565) else w  # the plugin's width: macropixels
+        s1, s2 = T.make_packed(rng, wm, h, ps, stride=T.rowstride(wm, ps)), T.make_packed(rng, wm, h, ps, stride=T.rowstride(wm, ps))
+        l1, l2 = packed_layer(eng, pal, w, h, s1), packed_layer(eng, pal, w, h, s2)
+        lo = packed_layer(eng, pal, w, h, np.full_like(s1, 9))
+        assert lo.desc.rowstrides[0] == s1.strides[0]
+        tvs = (100,) if big else (0, 1, 64, 127, 128, 200, 254, 255)
+        for direction, mvl, mvu, tv in itertools.product((1, 2, 3, 4), (0, 1), (0, 1), tvs):
+            exp = np.full_like(s1, 9)
+            o.pe_or_slide_over(direction, tv, mvl, mvu, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(exp), exp.strides[0],
+                               wm, h, ps)
+            lb.slide_over(l1, l2, lo, tv, direction, mvl, mvu)
+            assert (payload(lo.to_host()[0], wm, ps) == payload(exp, wm, ps)).all(), (pal, direction, mvl, mvu, tv)
+        with pytest.raises(lb.PixelEngineError):
+            lb.slide_over(l1, l2, l1, 10, 1)  # not an in-place filter
+        for l in (l1, l2, lo):
+            l.free()
+
+
 def _oracle_compositor(o, pal, w, h, layers, alphas, bg):
     ps = T.psize_of(pal)
     out = np.zeros((h, T.rowstride(w, ps)), np.uint8)

@@ -155,3 +155,19 @@ def test_resize_contract_tracks_independent_resamplers():
         ref = cv2.resize(src, (dw, dh), interpolation=interp).reshape(dh, dw * 4)
         d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         assert d.mean() < tol_mean and d.max() <= tol_max, (dw, dh, float(d.mean()), int(d.max()))
+
+
+def test_slide_over_dividing_line_of_the_shipped_library():
+    """pe_fx_slide_over_bound (host arithmetic inside libpe_b200.so, no GPU involved) == the oracle's line for every transition
+    value, direction and a spread of sizes; the oracle's line is pinned against the compiled plugin in test_oracle_vs_reference.py"""
+    import lives_b200 as lb
+    import pe_testlib as T
+    o = T.oracle()
+    for dim in list(range(1, 70)) + [255, 256, 333, 510, 720, 765, 1080, 1280, 1920, 2160, 3840, 4096, 7680]:
+        for direction in (1, 2, 3, 4):
+            w, h = (dim, 7) if direction <= 2 else (7, dim)
+            for tv in range(256):
+                got = lb.slide_over_bound(direction, tv, w, h)
+                assert got == o.pe_or_slide_over_bound(direction, tv, w, h), (direction, tv, w, h)
+                assert 0 <= got <= dim
+    assert lb.slide_over_bound("dir_r2l", 255, 37, 1) == 0 and lb.slide_over_bound("dir_l2r", 255, 37, 1) == 36  # the fast-math build

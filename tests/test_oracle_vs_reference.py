@@ -340,7 +340,14 @@ def _minihost():
     mh = C.CDLL(os.path.join(T.REF_DIR, "libweed_minihost.so"))
     mh.mh_open.argtypes = [C.c_char_p]
     mh.mh_run2.argtypes = [T.I, T.I, T.I, T.I, T.I, T.VP, T.I, T.VP, T.I, T.VP, T.I, T.I, T.I]
+    mh.mh_run2v.argtypes = [T.I, T.I, T.I, T.I, T.I, T.VP, T.I, T.VP, T.I, T.VP, T.I, T.I, T.VP, T.I]
     return mh
+
+
+def slide_over_params(transval, direction, mvlower, mvupper):
+    """the 8 in-parameters of slide_over.c:164-172 that make sover_init :38-52 pick `direction` (1 .. 4)"""
+    vals = [transval, 0, int(direction == 1), int(direction == 2), int(direction == 3), 0, mvlower, mvupper]
+    return (C.c_int * 8)(*vals)
 
 
 def test_simple_blend_matches_real_plugin():
@@ -785,3 +792,33 @@ def test_chroma_upsample_packed_matches_reference():
         assert (a[:rows, :w * ps] == b[:rows, :w * ps]).all(), ("upsample packed", w, h, is420, samp, cl, aa)
         # luma (and alpha) of every row
         assert (a[:, 0:w * ps:ps] == b[:h, 0:w * ps:ps]).all()
+
+
+def test_slide_over_matches_real_plugin():
+    """slide_over.c through the real bootstrap: every direction x moving clips, every transition value on small frames, all the
+    packed pixel sizes; the dividing line for all 256 values at the benchmark sizes"""
+    o, mh = T.oracle(), _minihost()
+    h = mh.mh_open(os.path.join(T.REF_DIR, "slide_over.so").encode())
+    assert h >= 0 and mh.mh_num_filters(h) == 1
+    rng = np.random.default_rng(90)
+    for (pal, ps), (w, ht) in itertools.product(((1, 3), (3, 4), (564, 4)), ((37, 19), (64, 32))):
+        s1, s2 = T.make_packed(rng, w, ht, ps), T.make_packed(rng, w, ht, ps)
+        for direction, mvl, mvu in itertools.product((1, 2, 3, 4), (0, 1), (0, 1)):
+            for tv in (list(range(0, 256, 5)) + [1, 127, 128, 254, 255]):
+                a, b = np.zeros_like(s1), np.zeros_like(s1)
+                o.pe_or_slide_over(direction, tv, mvl, mvu, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(a), a.strides[0],
+                                   w, ht, ps)
+                assert mh.mh_run2v(h, 0, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(b), b.strides[0], 8,
+                                   slide_over_params(tv, direction, mvl, mvu), 1) == 0
+                assert (a == b).all(), ("slide over", pal, w, ht, direction, mvl, mvu, tv)
+    # the line itself at large sizes: rows / columns of the result that come from in1 (constant 1) and in2 (constant 2)
+    for w, ht in ((3840, 2), (2, 2160), (1920, 1), (1, 1080), (1280, 1), (1, 720), (255, 1), (1, 255), (765, 1), (1, 510), (37, 1), (1, 333)):
+        s1, s2 = np.full((ht, T.rowstride(w, 3)), 1, np.uint8), np.full((ht, T.rowstride(w, 3)), 2, np.uint8)
+        for direction in ((1, 2) if ht <= 2 else (3, 4)):
+            for tv in range(256):
+                b = np.zeros_like(s1)
+                assert mh.mh_run2v(h, 0, 1, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(b), b.strides[0], 8,
+                                   slide_over_params(tv, direction, 0, 0), 1) == 0
+                line = b[0, 0:w * 3:3] if ht <= 2 else b[:, 0]
+                first = 1 if direction in (1, 3) else 2
+                assert int((line == first).sum()) == o.pe_or_slide_over_bound(direction, tv, w, ht), (w, ht, direction, tv)
