@@ -66,6 +66,8 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 
 /* flags (weed-effects.h:73,107-125) */
 #define PE_WEED_PARAM_INTEGER 1
+#define PE_WEED_PARAM_SWITCH 4
+#define PE_WEED_PARAMETER_REINIT_ON_VALUE_CHANGE (1 << 0)
 #define PE_WEED_FILTER_HINT_STATEFUL (1 << 2)
 #define PE_WEED_FILTER_PREF_LINEAR_GAMMA (1 << 3)
 #define PE_WEED_FILTER_HINT_MAY_THREAD (1 << 6)
@@ -113,6 +115,7 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 #define PE_LEAF_MAX "max"
 #define PE_LEAF_PARAM_TYPE "param_type"
 #define PE_LEAF_IS_TRANSITION "is_transition"
+#define PE_LEAF_GROUP "group"
 #define PE_LEAF_ALIGNMENT_HINT "alignment_hint" /* weed-effects.h:265, honoured at src/effects-weed.c:2319-2324 */
 
 #ifdef __cplusplus

@@ -260,6 +260,9 @@ int pe_host_simple_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, c
                          pe_frame_desc_t *out, int blend_factor);
 int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2,
                         pe_frame_desc_t *out, int blend_factor);
+/* slide_over.c:55 on host frames (H2D of both clips, k_slide_over, D2H of the result) */
+int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, int transval,
+                       int direction, int mvlower, int mvupper);
 int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_desc_t *fg, const pe_frame_desc_t *bg,
                                                pe_frame_desc_t *out, int inner_w, int inner_h, double alpha,
                                                int gamma_from, int gamma_to);

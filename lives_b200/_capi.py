@@ -105,6 +105,7 @@ PROTOTYPES = {
     "pe_host_gamma_convert_layer": (I, [VP, I, PDESC]),
     "pe_host_simple_blend": (I, [VP, I, PDESC, PDESC, PDESC, I]),
     "pe_host_multi_blend": (I, [VP, I, PDESC, PDESC, PDESC, I]),
+    "pe_host_slide_over": (I, [VP, PDESC, PDESC, PDESC, I, I, I, I]),
     "pe_host_fused_convert_letterbox_over_gamma": (I, [VP, PDESC, PDESC, PDESC, I, I, D, I, I]),
     "pe_host_fused_convert_letterbox_over_gamma_batch": (I, [VP, I, C.POINTER(PDESC), C.POINTER(PDESC), C.POINTER(PDESC), I, I, D, I, I]),
 }

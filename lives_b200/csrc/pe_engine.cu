@@ -2298,6 +2298,16 @@ extern "C" int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc
   return host_blend(e, 1, type, in1, in2, out, blend_factor);
 }
 
+extern "C" int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out,
+                                  int transval, int direction, int mvlower, int mvupper) {
+  if (!e || !in1 || !in2 || !out || !in1->planes[0] || !in2->planes[0] || !out->planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  HostFrame a(e), b(e), o(e);
+  int rc;
+  if ((rc = a.upload(in1)) != PE_OK || (rc = b.upload(in2)) != PE_OK || (rc = o.create_like(out)) != PE_OK) return rc;
+  if ((rc = pe_fx_slide_over(e, a.f, b.f, o.f, transval, direction, mvlower, mvupper)) != PE_OK) return rc;
+  return pe_frame_download(e, o.f, out->planes, out->rowstrides);
+}
+
 // A batch of host frames through the fused chain with the PCIe copies overlapped: three device slots rotate through
 // upload (h2d stream) -> kernel (engine stream) -> download (d2h stream), chained by events, so that frame i+1 travels to the
 // device and frame i-1 travels back while frame i is computed.  Host buffers should be pinned (pe_host_alloc) for the copies to

@@ -4,6 +4,7 @@
  * (src/effects-weed.c:4468-4568).  It registers, under the SAME filter names, the filters of
  *     lives-plugins/weed-plugins/simple_blend.c   "chroma blend", "luma overlay", "luma underlay", "negative luma overlay"
  *     lives-plugins/weed-plugins/multi_blends.c   "blend_multiply" ... "blend_burn"
+ *     lives-plugins/weed-plugins/slide_over.c     "slide over"
  * with the same channel / parameter templates, so weed_apply_instance() (src/effects-weed.c:1850) drives it unchanged.
  * Differences from the originals, on purpose:
  *   - WEED_FILTER_HINT_MAY_THREAD is NOT set: the host must call process_func once per frame, not once per row band
@@ -57,6 +58,7 @@ static void channel_desc(pe_weed_plant_t *ch, pe_frame_desc_t *d) {
   memset(d, 0, sizeof(*d));
   d->palette = get_int(ch, PE_LEAF_CURRENT_PALETTE);
   d->width = get_int(ch, PE_LEAF_WIDTH);
+  if (d->palette == PE_PALETTE_UYVY || d->palette == PE_PALETTE_YUYV) d->width *= 2; /* weed counts macropixels, pixel_engine.h pixels */
   d->height = get_int(ch, PE_LEAF_HEIGHT);
   d->nplanes = 1;
   d->rowstrides[0] = get_int(ch, PE_LEAF_ROWSTRIDES);
@@ -99,6 +101,41 @@ static pe_weed_error_t common_init(pe_weed_plant_t *inst) {
   return engine() ? PE_WEED_SUCCESS : PE_WEED_ERROR_PLUGIN_INVALID;
 }
 
+/* slide_over.c sover_init :38-52: the radio parameters pick "plugin_direction" (0 = random, resolved at the first process call) */
+static pe_weed_error_t sover_init(pe_weed_plant_t *inst) {
+  int dirpref = 4, k;
+  if (!engine()) return PE_WEED_ERROR_PLUGIN_INVALID;
+  for (k = 1; k <= 4; k++)
+    if (get_int(get_plant(inst, PE_LEAF_IN_PARAMETERS, k), PE_LEAF_VALUE) == 1) { dirpref = k - 1; break; }
+  set_int(inst, "plugin_direction", dirpref);
+  return PE_WEED_SUCCESS;
+}
+
+/* slide_over.c sover_process :55-145 */
+static pe_weed_error_t sover_process(pe_weed_plant_t *inst, pe_weed_timecode_t tc) {
+  static unsigned int seed = 0x2545F491u;
+  pe_frame_desc_t in1, in2, out;
+  pe_engine_t *e = engine();
+  int transval, dirn, mvlower, mvupper, rc;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 0), &in1);
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 1), &in2);
+  channel_desc(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  transval = get_int(get_plant(inst, PE_LEAF_IN_PARAMETERS, 0), PE_LEAF_VALUE);
+  mvlower = get_int(get_plant(inst, PE_LEAF_IN_PARAMETERS, 6), PE_LEAF_VALUE);
+  mvupper = get_int(get_plant(inst, PE_LEAF_IN_PARAMETERS, 7), PE_LEAF_VALUE);
+  dirn = get_int(inst, "plugin_direction");
+  if (dirn == 0) { /* random, kept for the life of the instance (:79-82) */
+    seed = seed * 1664525u + 1013904223u + (unsigned int)tc;
+    dirn = (int)((seed >> 24) & 3u) + 1;
+    set_int(inst, "plugin_direction", dirn);
+  }
+  rc = pe_host_slide_over(e, &in1, &in2, &out, transval, dirn, mvlower, mvupper);
+  if (rc == PE_OK) return PE_WEED_SUCCESS;
+  fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+  return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
+}
+
 /* ---- plant construction (what weed_channel_template_init / weed_integer_init / weed_filter_class_init of
  *      libweed/weed-plugin-utils.c:247-336 produce) ----------------------------------------------------------------- */
 
@@ -131,12 +168,82 @@ static pe_weed_plant_t *int_param(const char *name, const char *label, int def, 
   return p;
 }
 
+/* weed_switch_init / weed_radio_init (weed-plugin-utils.c:350-367); group < 0: a plain switch */
+static pe_weed_plant_t *switch_param(const char *name, const char *label, int def, int group, int flags) {
+  pe_weed_plant_t *p = w_plant_new(PE_WEED_PLANT_PARAMETER_TEMPLATE), *gui;
+  int32_t one = 1, d = def;
+  if (!p) return NULL;
+  set_str(p, PE_LEAF_NAME, name);
+  set_int(p, PE_LEAF_PARAM_TYPE, PE_WEED_PARAM_SWITCH);
+  w_leaf_set(p, PE_LEAF_DEFAULT, PE_WEED_SEED_BOOLEAN, 1, &d);
+  gui = w_plant_new(PE_WEED_PLANT_GUI);
+  if (gui) {
+    w_leaf_set(p, PE_LEAF_GUI, PE_WEED_SEED_PLANTPTR, 1, &gui);
+    set_str(gui, PE_LEAF_LABEL, label);
+    w_leaf_set(gui, PE_LEAF_USE_MNEMONIC, PE_WEED_SEED_BOOLEAN, 1, &one);
+  }
+  if (group >= 0) set_int(p, PE_LEAF_GROUP, group);
+  if (flags) set_int(p, PE_LEAF_FLAGS, flags);
+  return p;
+}
+
+/* weed_plugin_info_add_filter_class (weed-plugin-utils.c:308-320) */
+static int register_filter(pe_weed_plant_t *plugin_info, pe_weed_plant_t *fc) {
+  pe_weed_size_t n = w_num_elements(plugin_info, PE_LEAF_FILTERS), i;
+  pe_weed_plant_t **filters = (pe_weed_plant_t **)w_malloc((n + 1) * sizeof(pe_weed_plant_t *));
+  if (!filters) return -1;
+  for (i = 0; i < n; i++) w_leaf_get(plugin_info, PE_LEAF_FILTERS, i, &filters[i]);
+  filters[n] = fc;
+  w_leaf_set(plugin_info, PE_LEAF_FILTERS, PE_WEED_SEED_PLANTPTR, n + 1, filters);
+  w_leaf_set(fc, PE_LEAF_PLUGIN_INFO, PE_WEED_SEED_PLANTPTR, 1, &plugin_info);
+  w_free(filters);
+  return 0;
+}
+
+/* slide_over.c:157-196: two in channels, one out channel (not in-place), the transition value, five direction radios (a change
+ * re-inits the instance), two switches */
+static int add_slide_over(pe_weed_plant_t *plugin_info) {
+  int palettes[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24, PE_PALETTE_RGBA32, PE_PALETTE_BGRA32, PE_PALETTE_ARGB32, PE_PALETTE_YUV888,
+                    PE_PALETTE_YUVA8888, PE_PALETTE_UYVY, PE_PALETTE_YUYV}; /* ALL_PACKED_PALETTES_PLUS */
+  pe_weed_plant_t *fc = w_plant_new(PE_WEED_PLANT_FILTER_CLASS);
+  pe_weed_plant_t *in_ct[2], *out_ct[1], *in_pt[8];
+  pe_weed_init_f init_fn = sover_init;
+  pe_weed_process_f process_fn = sover_process;
+  const char *author = "lives_b200";
+  const int re = PE_WEED_PARAMETER_REINIT_ON_VALUE_CHANGE;
+  int k;
+  if (!fc) return -1;
+  in_ct[0] = chantmpl("in channel 0", 0);
+  in_ct[1] = chantmpl("in channel 1", 0);
+  out_ct[0] = chantmpl("out channel 0", 0);
+  in_pt[0] = int_param("amount", "Transition _value", 0, 0, 255);
+  in_pt[1] = switch_param("dir_rand", "_Random", 1, 1, re);
+  in_pt[2] = switch_param("dir_r2l", "_Right to left", 0, 1, re);
+  in_pt[3] = switch_param("dir_l2r", "_Left to right", 0, 1, re);
+  in_pt[4] = switch_param("dir_b2t", "_Bottom to top", 0, 1, re);
+  in_pt[5] = switch_param("dir_t2b", "_Top to bottom", 0, 1, re);
+  in_pt[6] = switch_param("mlower", "_Slide lower clip", 1, -1, 0);
+  in_pt[7] = switch_param("mupper", "_Slide upper clip", 0, -1, 0);
+  if (!in_ct[0] || !in_ct[1] || !out_ct[0]) return -1;
+  for (k = 0; k < 8; k++) if (!in_pt[k]) return -1;
+  set_str(fc, PE_LEAF_NAME, "slide over");
+  w_leaf_set(fc, PE_LEAF_AUTHOR, PE_WEED_SEED_STRING, 1, &author);
+  set_int(fc, PE_LEAF_VERSION, 1);
+  set_int(fc, PE_LEAF_FLAGS, 0);
+  w_leaf_set(fc, PE_LEAF_INIT_FUNC, PE_WEED_SEED_FUNCPTR, 1, &init_fn);
+  w_leaf_set(fc, PE_LEAF_PROCESS_FUNC, PE_WEED_SEED_FUNCPTR, 1, &process_fn);
+  w_leaf_set(fc, PE_LEAF_IN_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 2, in_ct);
+  w_leaf_set(fc, PE_LEAF_OUT_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, out_ct);
+  w_leaf_set(fc, PE_LEAF_IN_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 8, in_pt);
+  w_leaf_set(fc, PE_LEAF_OUT_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 0, NULL);
+  w_leaf_set(fc, PE_LEAF_PALETTE_LIST, PE_WEED_SEED_INT, 9, palettes);
+  return register_filter(plugin_info, fc);
+}
+
 static int add_filter(pe_weed_plant_t *plugin_info, const char *name, int flags, int *palettes, int npal, pe_weed_init_f init_fn,
                       pe_weed_process_f process_fn, const char *pname, const char *plabel, int pdef) {
   pe_weed_plant_t *fc = w_plant_new(PE_WEED_PLANT_FILTER_CLASS);
   pe_weed_plant_t *in_ct[2], *out_ct[1], *in_pt[1];
-  pe_weed_plant_t **filters;
-  pe_weed_size_t n = 0, i;
   const char *author = "lives_b200";
   int32_t version = 1;
   if (!fc) return -1;
@@ -156,16 +263,7 @@ static int add_filter(pe_weed_plant_t *plugin_info, const char *name, int flags,
   w_leaf_set(fc, PE_LEAF_IN_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, in_pt);
   w_leaf_set(fc, PE_LEAF_OUT_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 0, NULL);
   w_leaf_set(fc, PE_LEAF_PALETTE_LIST, PE_WEED_SEED_INT, (pe_weed_size_t)npal, palettes);
-  /* weed_plugin_info_add_filter_class (weed-plugin-utils.c:308-320) */
-  n = w_num_elements(plugin_info, PE_LEAF_FILTERS);
-  filters = (pe_weed_plant_t **)w_malloc((n + 1) * sizeof(pe_weed_plant_t *));
-  if (!filters) return -1;
-  for (i = 0; i < n; i++) w_leaf_get(plugin_info, PE_LEAF_FILTERS, i, &filters[i]);
-  filters[n] = fc;
-  w_leaf_set(plugin_info, PE_LEAF_FILTERS, PE_WEED_SEED_PLANTPTR, n + 1, filters);
-  w_leaf_set(fc, PE_LEAF_PLUGIN_INFO, PE_WEED_SEED_PLANTPTR, 1, &plugin_info);
-  w_free(filters);
-  return 0;
+  return register_filter(plugin_info, fc);
 }
 
 /* ---- entry points --------------------------------------------------------------------------------------------------- */
@@ -220,6 +318,7 @@ pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
       add_filter(plugin_info, "blend_burn", PE_WEED_FILTER_PREF_LINEAR_GAMMA, rgb24, 2, common_init, burn_process, "amount",
                  "Blend _amount", 128))
     return NULL;
+  if (add_slide_over(plugin_info)) return NULL;
   set_int(plugin_info, PE_LEAF_VERSION, package_version);
   return plugin_info;
 }

@@ -18,14 +18,20 @@ pytestmark = pytest.mark.skipif(not T.have_ref() or not os.path.exists(os.path.j
                                 reason="oracle/_ref (reference libweed + minihost) not built")
 
 NAMES = ["chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "blend_multiply", "blend_screen",
-         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn"]
+         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over"]
 
 
 def _minihost():
     mh = C.CDLL(os.path.join(T.REF_DIR, "libweed_minihost.so"))
     mh.mh_open.argtypes = [C.c_char_p]
     mh.mh_run2.argtypes = [T.I, T.I, T.I, T.I, T.I, T.VP, T.I, T.VP, T.I, T.VP, T.I, T.I, T.I]
+    mh.mh_run2v.argtypes = [T.I, T.I, T.I, T.I, T.I, T.VP, T.I, T.VP, T.I, T.VP, T.I, T.I, T.VP, T.I]
     return mh
+
+
+def _sover_params(transval, direction, mvlower, mvupper):
+    """the 8 in-parameters of slide_over.c:164-172 that make sover_init :38-52 pick `direction` (1 .. 4)"""
+    return (C.c_int * 8)(transval, 0, int(direction == 1), int(direction == 2), int(direction == 3), 0, mvlower, mvupper)
 
 
 def _open_ours(mh):
@@ -55,6 +61,14 @@ def test_plugin_bootstraps_through_the_reference_libweed():
     for i in range(7):
         mh.mh_filter_name(ref, i, buf, 64)
         assert buf.value.decode() == NAMES[4 + i]
+    ref = mh.mh_open(os.path.join(T.REF_DIR, "slide_over.so").encode())
+    mh.mh_filter_name(ref, 0, buf, 64)
+    assert buf.value.decode() == NAMES[11]
+    # the 8 parameter templates of "slide over" are accepted with the reference's seed types (a wrong count / type is rc -4 / garbage)
+    s = np.zeros((8, 32), np.uint8)
+    import torch
+    if not torch.cuda.is_available():
+        assert mh.mh_run2v(h, 11, 1, 8, 8, T.ptr(s), 32, T.ptr(s), 32, T.ptr(s.copy()), 32, 8, _sover_params(10, 1, 1, 0), 1) == 64
 
 
 def test_plugin_fails_loudly_without_gpu():
@@ -103,3 +117,20 @@ def test_plugin_matches_reference_plugins_bit_for_bit():
         assert mh.mh_run2(ref_m, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], bf, 1) == 0
         assert mh.mh_run2(ours, 4 + typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], bf, 1) == 0
         assert (d_ref[:, :w * 3] == d_our[:, :w * 3]).all(), (pal, bf, typ)
+
+
+@pytest.mark.gpu
+def test_slide_over_plugin_matches_reference_plugin():
+    """"slide over" of libpe_weed_plugin.so against slide_over.so, both run by the minihost with the same 8 parameters"""
+    mh = _minihost()
+    ours = _open_ours(mh)
+    ref = mh.mh_open(os.path.join(T.REF_DIR, "slide_over.so").encode())
+    rng = np.random.default_rng(32)
+    for (pal, ps), (w, ht) in itertools.product(((1, 3), (4, 4), (589, 4), (565, 4)), ((64, 32), (61, 7))):
+        s1, s2 = T.make_packed(rng, w, ht, ps), T.make_packed(rng, w, ht, ps)
+        for direction, mvl, mvu, tv in itertools.product((1, 2, 3, 4), (0, 1), (0, 1), (0, 77, 128, 255)):
+            d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
+            pr = _sover_params(tv, direction, mvl, mvu)
+            assert mh.mh_run2v(ref, 0, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], 8, pr, 1) == 0
+            assert mh.mh_run2v(ours, 11, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], 8, pr, 1) == 0
+            assert (d_ref == d_our).all(), (pal, w, ht, direction, mvl, mvu, tv)
