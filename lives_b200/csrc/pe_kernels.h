@@ -149,6 +149,7 @@ struct SlideArgs {
   uint8_t *d;
   long long off_first, off_second;
   int rs_first, rs_second, rsd, row_bytes, height, along_y, bound;
+  int word_safe;  // set by launch_slide_over: source strides and bases are multiples of 4 (aligned word loads stay inside the rows)
 };
 cudaError_t launch_slide_over(const Launch &L, const SlideArgs &a);
 // dst = trunc(bg * (1 - alpha) + fg * alpha) in double (compositor.c:120), optional lut8 afterwards:

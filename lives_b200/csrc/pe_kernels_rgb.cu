@@ -622,11 +622,30 @@ __global__ void __launch_bounds__(kBlock) k_slide_over(const SlideArgs P) {
     };
     const bool f0 = is_first(x0), f1 = is_first(x0 + n - 1);
     const uint8_t *s = src_of(x0, f0);
-    if (n == 16 && f0 == f1 && !((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15)) {
-      *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s);
-    } else {
-      for (int k = 0; k < n; k++) d[k] = *src_of(x0 + k, is_first(x0 + k));
+    if (n == 16 && f0 == f1 && !(reinterpret_cast<uintptr_t>(d) & 15)) {
+      const uintptr_t sa = reinterpret_cast<uintptr_t>(s);
+      if (!(sa & 15)) {
+        *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(s);
+        continue;
+      }
+      if (P.word_safe) {
+        // a moving clip is read at an offset of (width - bound) * psize bytes: any alignment.  Aligned 32-bit loads of the 4 or 5
+        // words that hold the 16 bytes, re-aligned with funnel shifts, one 128-bit store (the 5th word stays inside the row
+        // stride: word_safe = every source stride is a multiple of 4)
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(sa & ~uintptr_t(3));
+        const uint32_t sh = (uint32_t)(sa & 3) * 8u;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        uint4 v;
+        if (!sh) v = make_uint4(w0, w1, w2, w3);
+        else {
+          const uint32_t w4 = w[4];
+          v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+        *reinterpret_cast<uint4 *>(d) = v;
+        continue;
+      }
     }
+    for (int k = 0; k < n; k++) d[k] = *src_of(x0 + k, is_first(x0 + k));
   }
 }
 
@@ -634,7 +653,9 @@ __global__ void __launch_bounds__(kBlock) k_slide_over(const SlideArgs P) {
 
 cudaError_t launch_slide_over(const Launch &L, const SlideArgs &a) {
   if (a.row_bytes <= 0 || a.height <= 0) return cudaSuccess;
-  k_slide_over<<<grid_for(L, (long long)((a.row_bytes + 15) >> 4) * a.height), kBlock, 0, L.stream>>>(a);
+  SlideArgs b = a;
+  b.word_safe = !((a.rs_first | a.rs_second) & 3) && !((reinterpret_cast<uintptr_t>(a.first) | reinterpret_cast<uintptr_t>(a.second)) & 3);
+  k_slide_over<<<grid_for(L, (long long)((a.row_bytes + 15) >> 4) * a.height), kBlock, 0, L.stream>>>(b);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }
