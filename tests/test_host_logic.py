@@ -171,3 +171,26 @@ def test_slide_over_dividing_line_of_the_shipped_library():
                 assert got == o.pe_or_slide_over_bound(direction, tv, w, h), (direction, tv, w, h)
                 assert 0 <= got <= dim
     assert lb.slide_over_bound("dir_r2l", 255, 37, 1) == 0 and lb.slide_over_bound("dir_l2r", 255, 37, 1) == 36  # the fast-math build
+
+
+def test_slide_over_realigning_loads():
+    """k_slide_over (pe_kernels_rgb.cu): 16 bytes at ANY source address = the 4 or 5 aligned 32-bit words that hold them, re-aligned
+    with __funnelshift_r(w[i], w[i + 1], 8 * (addr & 3)) = low 32 bits of ((w[i + 1] << 32 | w[i]) >> shift); and the words touched
+    never leave the row: with a 4-byte aligned row start and a stride that is a multiple of 4 they end at round_up4(payload) <= stride"""
+    rng = np.random.default_rng(7)
+    buf = rng.integers(0, 256, 64, dtype=np.uint8)
+    words = buf.view("<u4").astype(np.uint64)
+    for addr in range(0, 40):
+        w0, sh = addr >> 2, 8 * (addr & 3)
+        n = 4 if sh == 0 else 5
+        w = words[w0:w0 + n]
+        if sh == 0:
+            out = w.astype("<u4")
+        else:
+            out = np.array([((int(w[i + 1]) << 32 | int(w[i])) >> sh) & 0xFFFFFFFF for i in range(4)], dtype="<u4")
+        assert (out.view(np.uint8) == buf[addr:addr + 16]).all(), addr
+        assert 4 * (w0 + n) <= ((addr + 16 + 3) // 4) * 4  # last word touched = the word of the last byte needed
+    for payload in range(1, 200):
+        for align in (4, 32):
+            stride = (payload + align - 1) // align * align
+            assert (payload + 3) // 4 * 4 <= stride
