@@ -39,8 +39,7 @@ def init_filter_bilinear(src, dst, one, cutoff=0.002):
     xdst = ((128 * xinc) >> 7) - ((128 * 0x10000) >> 7)
     for i in range(dst):
         num = xdst - (fs - 2) * (1 << 16)
-        xx = int(num / (1 << 17)) if num >= 0 else -int((-num) / (1 << 17))  # C division truncates
-        xx = (abs(num) // (1 << 17)) * (1 if num >= 0 else -1)
+        xx = (abs(num) // (1 << 17)) * (1 if num >= 0 else -1)  # C division truncates towards zero
         pos[i] = xx
         for j in range(fs):
             d = abs(xx * (1 << 17) - xdst) << 13
