@@ -864,12 +864,101 @@ int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, in
   return taps;
 }
 
+/* The bilinear coefficient recipe of libswscale (third-party, not in the reference tree and not pinned by it: configure.ac:562;
+ * restated from the published algorithm of libswscale/utils.c initFilter and checked against libswscale 9.1.100 in
+ * tests/test_resize_vs_swscale.py): triangle taps at 2^-30 precision around a centre-aligned position, near-zero taps (cumulated
+ * weight below 0.002) dropped from either end, taps past the frame folded onto the edge sample, then normalised to 1 << shift_bits
+ * with the rounding error carried from tap to tap.  OPT-IN second recipe beside pe_or_resize_filter. */
+static int64_t or_rounded_div(int64_t a, int64_t b) { return a >= 0 ? (a + (b >> 1)) / b : (a - (b >> 1)) / b; }
+
+int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+  const int64_t xinc = (((int64_t)src_n << 16) + (dst_n >> 1)) / dst_n, one = (int64_t)1 << shift_bits;
+  int fs = xinc <= (1 << 16) ? 3 : 1 + (2 * src_n + dst_n - 1) / dst_n, lg = 0, min_fs = 0;
+  int64_t *f, fone, xdst;
+  if (fs > src_n - 2) fs = src_n - 2;
+  if (fs < 1) fs = 1;
+  if (fs > 64) return -1;
+  for (int r = src_n / dst_n; r > 1; r >>= 1) lg++;
+  fone = (int64_t)1 << (54 - (lg < 8 ? lg : 8));
+  f = (int64_t *)calloc((size_t)dst_n * fs, sizeof(int64_t));
+  xdst = xinc - 65536; /* ((128 * xinc) >> 7) - ((128 * 65536) >> 7): both grids sampled at pixel centres */
+  for (int i = 0; i < dst_n; i++, xdst += 2 * xinc) {
+    int xx = (int)((xdst - (int64_t)(fs - 2) * 65536) / (1 << 17)); /* C division: towards zero */
+    first[i] = xx;
+    for (int j = 0; j < fs; j++, xx++) {
+      int64_t d = llabs((int64_t)xx * (1 << 17) - xdst) << 13, c;
+      if (xinc > (1 << 16)) d = d * dst_n / src_n;
+      c = ((int64_t)1 << 30) - d;
+      f[(long)i * fs + j] = c < 0 ? 0 : c * (fone >> 30);
+    }
+  }
+  for (int i = dst_n - 1; i >= 0; i--) { /* shrink: drop near-zero taps on the left (shifting), count them on the right */
+    int64_t *r = f + (long)i * fs, cut = 0;
+    int mn = fs;
+    for (int j = 0; j < fs; j++) {
+      cut += llabs(r[0]);
+      if ((double)cut > 0.002 * (double)fone) break;
+      if (i < dst_n - 1 && first[i] >= first[i + 1]) break; /* positions stay monotonic */
+      memmove(r, r + 1, sizeof(int64_t) * (fs - 1));
+      r[fs - 1] = 0;
+      first[i]++;
+    }
+    cut = 0;
+    for (int j = fs - 1; j > 0; j--) {
+      cut += llabs(r[j]);
+      if ((double)cut > 0.002 * (double)fone) break;
+      mn--;
+    }
+    if (mn > min_fs) min_fs = mn;
+  }
+  if (min_fs > max_taps) { free(f); return -1; }
+  for (int i = 0; i < dst_n; i++) {
+    int64_t t[64], sum = 0, err = 0;
+    for (int j = 0; j < min_fs; j++) t[j] = f[(long)i * fs + j];
+    if (first[i] < 0) { /* taps left of the frame land on sample 0 */
+      for (int j = 1; j < min_fs; j++) {
+        const int left = j + first[i] > 0 ? j + first[i] : 0;
+        t[left] += t[j];
+        t[j] = 0;
+      }
+      first[i] = 0;
+    }
+    if (first[i] + min_fs > src_n) { /* taps right of the frame land on the last sample, the window moves back inside */
+      const int shift = first[i] + (min_fs - src_n < 0 ? min_fs - src_n : 0);
+      int64_t acc = 0;
+      for (int j = min_fs - 1; j >= 0; j--)
+        if (first[i] + j >= src_n) { acc += t[j]; t[j] = 0; }
+      for (int j = min_fs - 1; j >= 0; j--) t[j] = j < shift ? 0 : t[j - shift];
+      first[i] -= shift;
+      t[src_n - 1 - first[i]] += acc;
+    }
+    for (int j = 0; j < min_fs; j++) sum += t[j];
+    sum = (sum + one / 2) / one;
+    if (!sum) sum = 1;
+    for (int j = 0; j < min_fs; j++) {
+      const int64_t v = t[j] + err, q = or_rounded_div(v, sum);
+      coefs[(long)i * max_taps + j] = (int16_t)q;
+      err = v - q * sum;
+    }
+    for (int j = min_fs; j < max_taps; j++) coefs[(long)i * max_taps + j] = 0;
+  }
+  free(f);
+  return min_fs;
+}
+
+static int or_resize_recipe = 0; /* 0: the published contract (default, what the product ships), 1: the libswscale recipe */
+void pe_or_set_resize_recipe(int recipe) { or_resize_recipe = recipe; }
+static int or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+  return or_resize_recipe ? pe_or_resize_filter_sws(src_n, dst_n, shift_bits, first, coefs, max_taps)
+                          : pe_or_resize_filter(src_n, dst_n, shift_bits, first, coefs, max_taps);
+}
+
 void pe_or_resize_packed(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh,
                          int psize) {
   enum { MT = 64 };
   int32_t *fx = (int32_t *)malloc(sizeof(int32_t) * dw), *fy = (int32_t *)malloc(sizeof(int32_t) * dh);
   int16_t *cx = (int16_t *)malloc(sizeof(int16_t) * MT * dw), *cy = (int16_t *)malloc(sizeof(int16_t) * MT * dh);
-  int tx = pe_or_resize_filter(sw, dw, 14, fx, cx, MT), ty = pe_or_resize_filter(sh, dh, 12, fy, cy, MT);
+  int tx = or_resize_filter(sw, dw, 14, fx, cx, MT), ty = or_resize_filter(sh, dh, 12, fy, cy, MT);
   int16_t *tmp = (int16_t *)malloc(sizeof(int16_t) * (size_t)sh * dw * psize);
   if (tx > 0 && ty > 0) {
     for (int y = 0; y < sh; y++) {

@@ -99,6 +99,10 @@ void pe_or_fill(uint8_t *dst, int orow, int palette, int width, int height, int 
 void pe_or_resize_packed(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh,
                          int psize);
 int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
+/* the same interface with libswscale's bilinear coefficient recipe (opt-in; pe_or_set_resize_recipe(1) makes pe_or_resize_packed use
+ * it; 0 = the published contract the product ships, the default) */
+int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
+void pe_or_set_resize_recipe(int recipe);
 /* letterbox_layer colourspace.c:15343: centre an inner packed frame in a black outer one */
 void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint8_t *outer, int orow, int ow, int oh,
                             int palette);

@@ -67,6 +67,8 @@ _ORACLE_PROTOS = {
     "pe_or_fill": [VP, I, I, I, I, I, I, I],
     "pe_or_resize_packed": [VP, I, I, I, VP, I, I, I, I],
     "pe_or_resize_filter": [I, I, I, VP, VP, I],
+    "pe_or_resize_filter_sws": [I, I, I, VP, VP, I],
+    "pe_or_set_resize_recipe": [I],
     "pe_or_letterbox_packed": [VP, I, I, I, VP, I, I, I, I],
     "pe_or_yuv444p_to_rgb": [VP, I, I, I, VP, I, I, I, I, I, I],
     "pe_or_combine_planes": [VP, I, I, I, VP, I, I, I],

@@ -3,8 +3,9 @@ the reference actually calls?  Measured against a real libswscale when one is lo
 not the reference's to pin (configure.ac:562), so these are DISTANCE bounds, not parity: resize stays "parity unpinned".
 
 Findings the bounds encode (libswscale 9.1.100, SWS_BILINEAR, whole-frame call):
-  * RGBA -> RGBA at horizontal ratios below 2 (config 2's 1.5, the headline's vertical-only squeeze, upscales): ~86 % of the
-    samples equal, > 99.9 % within +-1;
+  * RGBA -> RGBA at horizontal ratios below 2: colour samples 97-98 % equal at config 2's 1.5 and on upscales, 75 % on the
+    headline's vertical 2160 -> 1608 squeeze (the tap cut-off of swscale's coefficient recipe matters there), > 99.9 % within +-1
+    everywhere; a NOISY alpha channel is only ~50 % equal (within 1): swscale scales alpha less precisely (opaque alpha: exact);
   * at a horizontal downscale of 2 or more swscale computes chroma from every other source pixel (its RGB input goes through
     YUV; chrSrcHSubSample is set when dstW <= srcW / 2 unless SWS_FULL_CHR_H_INP): grey images still match, coloured detail does not
     -- a documented divergence;
@@ -40,11 +41,15 @@ def test_rgba_resize_distance_to_swscale_below_2x(geom):
     src[:, :w * 4] = _textured(rng, w, h, 4, 25).reshape(h, w * 4)
     ref = S.scale([src], "rgba", w, h, "rgba", dw, dh, T.rowstride(dw, 4))
     d = np.abs(ref[:, :dw * 4].astype(int) - _oracle_resize(src, w, h, dw, dh)[:, :dw * 4].astype(int))
-    print(geom, "max %d mean %.4f exact %.2f%% within1 %.3f%%" % (d.max(), d.mean(), 100 * (d == 0).mean(), 100 * (d <= 1).mean()))
+    col = np.ones(dw * 4, bool)
+    col[3::4] = False  # a noisy alpha channel takes a less precise scaler inside swscale (~50 % equal, within 1): reported apart
+    c, a = d[:, col], d[:, ~col]
+    print(geom, "colour: max %d mean %.4f equal %.2f%% within1 %.3f%% | alpha: max %d equal %.2f%%"
+          % (c.max(), c.mean(), 100 * (c == 0).mean(), 100 * (c <= 1).mean(), a.max(), 100 * (a == 0).mean()))
     if (w, h) == (dw, dh):
         assert d.max() == 0
     else:
-        assert (d == 0).mean() > 0.75 and (d <= 1).mean() > 0.999 and d.max() <= 12 and d.mean() < 0.25
+        assert (c == 0).mean() > 0.70 and (c <= 1).mean() > 0.999 and c.max() <= 12 and c.mean() < 0.3 and a.max() <= 12
 
 
 def test_grey_2x_downscale_matches_and_colour_does_not():
@@ -85,3 +90,30 @@ def test_config2_one_call_swscale_distance():
     d = np.abs(a - b)
     print("config 2: max %d mean %.3f within2 %.1f%% within4 %.1f%%" % (d.max(), d.mean(), 100 * (d <= 2).mean(), 100 * (d <= 4).mean()))
     assert d.mean() < 3 and (d <= 4).mean() > 0.9 and d.max() <= 24
+
+
+@pytest.mark.parametrize("geom", [(1920, 1080, 1280, 720), (960, 2160, 960, 1608), (320, 240, 640, 480), (300, 200, 160, 120)])
+def test_libswscale_coefficient_recipe_is_closer(geom):
+    """the opt-in second recipe of the oracle (pe_or_resize_filter_sws: libswscale's own way of cutting, folding and normalising
+    the bilinear taps; same two integer passes): on per-channel uniform noise at least 97.5 % (upscale: 93 %) of the colour samples equal
+    the library's and no sample, alpha included, is further than 1 away -- the default contract leaves outliers of 6-8 on downscales.  Not the default
+    because the CUDA side has not been run with it yet."""
+    w, h, dw, dh = geom
+    o = T.oracle()
+    rng = np.random.default_rng(dw)
+    src = np.zeros((h, T.rowstride(w, 4)), np.uint8)
+    src[:, :w * 4] = rng.integers(0, 256, (h, w * 4), dtype=np.uint8)
+    ref = S.scale([src], "rgba", w, h, "rgba", dw, dh, T.rowstride(dw, 4))[:, :dw * 4].astype(int)
+    d0 = np.abs(ref - _oracle_resize(src, w, h, dw, dh)[:, :dw * 4].astype(int))
+    o.pe_or_set_resize_recipe(1)
+    try:
+        d1 = np.abs(ref - _oracle_resize(src, w, h, dw, dh)[:, :dw * 4].astype(int))
+    finally:
+        o.pe_or_set_resize_recipe(0)
+    col = np.ones(dw * 4, bool)
+    col[3::4] = False  # the alpha channel goes through a different (less precise) scaler inside swscale: only ~50 % equal on noise
+    print(geom, "contract: colour %.2f%% equal, max %d | libswscale recipe: colour %.2f%% equal, max %d; alpha %.2f%% equal, max %d"
+          % (100 * (d0[:, col] == 0).mean(), d0[:, col].max(), 100 * (d1[:, col] == 0).mean(), d1[:, col].max(),
+             100 * (d1[:, ~col] == 0).mean(), d1[:, ~col].max()))
+    assert d1.max() <= 1 and (d1[:, col] == 0).mean() > (0.93 if dw > w else 0.975)
+    assert (d1[:, col] == 0).mean() >= (d0[:, col] == 0).mean() - 1e-3 and d1.max() <= d0.max()
