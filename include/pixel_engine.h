@@ -104,6 +104,11 @@ long pe_engine_launch_count(pe_engine_t *e);
 int pe_timer_start(pe_engine_t *e);
 int pe_timer_stop_ms(pe_engine_t *e, float *ms); /* synchronises on the stop event */
 int pe_sm_count(pe_engine_t *e);
+/* resize coefficients (the reference delegates resizing to an unpinned libswscale, src/colourspace.c:15059-15228): recipe 0 = the
+ * published contract of DESIGN.md section 5 (default), 1 = libswscale's own bilinear coefficient recipe (opt-in).
+ * pe_resize_filter_host returns the bank a recipe produces (host arithmetic, no GPU): tap count, or -1 */
+int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe);
+int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
 
 /* ---- frames (create_empty_pixel_data colourspace.c:11434, weed_layer_* src/layers.c) ------- */
 

@@ -62,6 +62,8 @@ PROTOTYPES = {
     "pe_timer_start": (I, [VP]),
     "pe_timer_stop_ms": (I, [VP, C.POINTER(C.c_float)]),
     "pe_sm_count": (I, [VP]),
+    "pe_engine_set_resize_recipe": (I, [VP, I]),
+    "pe_resize_filter_host": (I, [I, I, I, I, VP, VP, I]),
     "pe_frame_layout": (SZ, [I, I, I, PI, PI, PI]),
     "pe_frame_create": (I, [VP, I, I, I, I, I, I, I, I, PVP]),
     "pe_frame_wrap": (I, [VP, PDESC, PVP]),

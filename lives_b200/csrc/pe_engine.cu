@@ -289,6 +289,29 @@ extern "C" void *pe_engine_stream(pe_engine_t *e) { return e ? (void *)e->stream
 extern "C" long pe_engine_launch_count(pe_engine_t *e) { return e ? e->launches : 0; }
 extern "C" int pe_sm_count(pe_engine_t *e) { return e ? e->sm_count : 0; }
 
+// which coefficients the resize / letterbox / fused calls of this engine use from now on: 0 the published contract (default),
+// 1 libswscale's recipe (pe_tables.cpp build_resize_filter_sws; opt-in until it has had its GPU pass)
+extern "C" int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe) {
+  if (!e || recipe < 0 || recipe > 1) return set_err(PE_ERR_ARG, "resize recipe: 0 or 1");
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->resize_recipe = recipe;
+  return PE_OK;
+}
+
+// the coefficient bank the engine would build, on the host (no GPU involved): first[dst_n], coefs[dst_n * max_taps]; returns the
+// tap count or -1
+extern "C" int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+  ResizeFilter f;
+  if (!first || !coefs) return -1;
+  if (!(recipe ? build_resize_filter_sws(src_n, dst_n, shift_bits, &f) : build_resize_filter(src_n, dst_n, shift_bits, &f))) return -1;
+  if (f.taps > max_taps) return -1;
+  for (int i = 0; i < dst_n; i++) {
+    first[i] = f.first[i];
+    for (int k = 0; k < max_taps; k++) coefs[(size_t)i * max_taps + k] = k < f.taps ? f.coef[(size_t)i * f.taps + k] : 0;
+  }
+  return f.taps;
+}
+
 extern "C" int pe_timer_start(pe_engine_t *e) {
   if (!e) return set_err(PE_ERR_ARG, "engine is NULL");
   PE_CUDA(cudaEventRecord(e->ev0, e->stream));
@@ -396,11 +419,12 @@ uint8_t *get_over_table(pe_engine *e, double alpha, const uint8_t *lut_dev) {
 }
 
 DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
-  FilterKey k{src_n, dst_n, bits};
+  FilterKey k{src_n, dst_n, bits | (e->resize_recipe << 8)};
   auto it = e->filters.find(k);
   if (it != e->filters.end()) return &it->second;
   DevFilterEntry ent;
-  if (!build_resize_filter(src_n, dst_n, bits, &ent.host)) return nullptr;
+  if (!(e->resize_recipe ? build_resize_filter_sws(src_n, dst_n, bits, &ent.host) : build_resize_filter(src_n, dst_n, bits, &ent.host)))
+    return nullptr;
   int32_t *first = nullptr;
   int16_t *coef = nullptr;
   if (cudaMalloc(&first, sizeof(int32_t) * dst_n) != cudaSuccess) return nullptr;

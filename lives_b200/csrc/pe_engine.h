@@ -69,6 +69,7 @@ struct pe_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
+  int resize_recipe = 0;  // 0 the published contract (default), 1 libswscale's coefficient recipe (pe_engine_set_resize_recipe)
   long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels

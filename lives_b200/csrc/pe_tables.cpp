@@ -10,7 +10,9 @@
 //    gamma_from (colourspace.c:701): after the first entry the source is treated as linear.
 #include "pe_tables.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/pixel_engine.h"
@@ -294,6 +296,92 @@ bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out
     }
     out->coef[(size_t)i * taps + big] += (int16_t)(one - acc);
     out->first[i] = left;
+  }
+  return true;
+}
+
+// libswscale's bilinear coefficient recipe (third-party library the reference calls, src/colourspace.c:15059; not in the reference
+// tree, version not pinned by it).  Restated from the published algorithm (libswscale/utils.c initFilter): triangle taps at 2^-30
+// precision, near-zero taps (cumulated weight < 0.002) dropped from either end, taps outside the frame folded onto the edge
+// sample, normalised to 1 << shift_bits with the rounding error carried from tap to tap.  OPT-IN (pe_engine_set_resize_recipe):
+// its banks are checked on the CPU (tests/test_host_logic.py, tests/test_resize_vs_swscale.py); not yet run on a GPU.
+bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out) {
+  if (src_n <= 0 || dst_n <= 0) return false;
+  const int64_t xinc = (((int64_t)src_n << 16) + (dst_n >> 1)) / dst_n, one = (int64_t)1 << shift_bits;
+  int fs = xinc <= (1 << 16) ? 3 : 1 + (2 * src_n + dst_n - 1) / dst_n;
+  fs = std::max(std::min(fs, src_n - 2), 1);
+  if (fs > 64) return false;
+  int lg = 0;
+  for (int r = src_n / dst_n; r > 1; r >>= 1) lg++;
+  const int64_t fone = (int64_t)1 << (54 - std::min(lg, 8));
+  const double cutoff = 0.002 * (double)fone;
+  std::vector<int64_t> f((size_t)dst_n * fs, 0);
+  std::vector<int32_t> pos(dst_n, 0);
+  int64_t xdst = xinc - 65536;  // both grids sampled at pixel centres
+  for (int i = 0; i < dst_n; i++, xdst += 2 * xinc) {
+    int xx = (int)((xdst - (int64_t)(fs - 2) * 65536) / (1 << 17));  // towards zero
+    pos[i] = xx;
+    for (int j = 0; j < fs; j++, xx++) {
+      int64_t d = std::llabs((int64_t)xx * (1 << 17) - xdst) << 13;
+      if (xinc > (1 << 16)) d = d * dst_n / src_n;
+      const int64_t c = ((int64_t)1 << 30) - d;
+      f[(size_t)i * fs + j] = c < 0 ? 0 : c * (fone >> 30);
+    }
+  }
+  int min_fs = 0;
+  for (int i = dst_n - 1; i >= 0; i--) {
+    int64_t *r = &f[(size_t)i * fs], cut = 0;
+    int mn = fs;
+    for (int j = 0; j < fs; j++) {
+      cut += std::llabs(r[0]);
+      if ((double)cut > cutoff) break;
+      if (i < dst_n - 1 && pos[i] >= pos[i + 1]) break;  // positions stay monotonic
+      for (int k = 1; k < fs; k++) r[k - 1] = r[k];
+      r[fs - 1] = 0;
+      pos[i]++;
+    }
+    cut = 0;
+    for (int j = fs - 1; j > 0; j--) {
+      cut += std::llabs(r[j]);
+      if ((double)cut > cutoff) break;
+      mn--;
+    }
+    min_fs = std::max(min_fs, mn);
+  }
+  out->taps = min_fs;
+  out->first.assign(dst_n, 0);
+  out->coef.assign((size_t)dst_n * min_fs, 0);
+  std::vector<int64_t> t(min_fs);
+  for (int i = 0; i < dst_n; i++) {
+    for (int j = 0; j < min_fs; j++) t[j] = f[(size_t)i * fs + j];
+    if (pos[i] < 0) {
+      for (int j = 1; j < min_fs; j++) {
+        const int left = std::max(j + pos[i], 0);
+        t[left] += t[j];
+        t[j] = 0;
+      }
+      pos[i] = 0;
+    }
+    if (pos[i] + min_fs > src_n) {
+      const int shift = pos[i] + std::min(min_fs - src_n, 0);
+      int64_t acc = 0;
+      for (int j = min_fs - 1; j >= 0; j--)
+        if (pos[i] + j >= src_n) { acc += t[j]; t[j] = 0; }
+      for (int j = min_fs - 1; j >= 0; j--) t[j] = j < shift ? 0 : t[j - shift];
+      pos[i] -= shift;
+      t[src_n - 1 - pos[i]] += acc;
+    }
+    int64_t sum = 0, err = 0;
+    for (int j = 0; j < min_fs; j++) sum += t[j];
+    sum = (sum + one / 2) / one;
+    if (!sum) sum = 1;
+    for (int j = 0; j < min_fs; j++) {
+      const int64_t v = t[j] + err;
+      const int64_t q = v >= 0 ? (v + (sum >> 1)) / sum : (v - (sum >> 1)) / sum;
+      out->coef[(size_t)i * min_fs + j] = (int16_t)q;
+      err = v - q * sum;
+    }
+    out->first[i] = pos[i];
   }
   return true;
 }

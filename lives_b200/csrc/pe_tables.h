@@ -43,5 +43,7 @@ struct ResizeFilter {
   std::vector<int16_t> coef;   // [dst_n * taps]
 };
 bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out);
+// libswscale's coefficient recipe for the same two passes (opt-in, pe_engine_set_resize_recipe)
+bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out);
 
 }  // namespace pe

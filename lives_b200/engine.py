@@ -95,6 +95,10 @@ class Engine:
     def sm_count(self):
         return self._lib.pe_sm_count(self._h)
 
+    def set_resize_recipe(self, recipe):
+        """0: the published resize contract (default); 1: libswscale's bilinear coefficient recipe (opt-in)"""
+        capi.check(self._lib.pe_engine_set_resize_recipe(self._h, recipe))
+
     def timer_start(self):
         capi.check(self._lib.pe_timer_start(self._h))
 

@@ -194,3 +194,27 @@ def test_slide_over_realigning_loads():
         for align in (4, 32):
             stride = (payload + align - 1) // align * align
             assert (payload + 3) // 4 * 4 <= stride
+
+
+def test_resize_coefficient_banks_of_the_shipped_library():
+    """pe_resize_filter_host (the bank libpe_b200.so builds on the host; no GPU involved) == the oracle's, for the published
+    contract (recipe 0, the default) and for libswscale's coefficient recipe (recipe 1, opt-in), over the BASELINE geometries, odd
+    sizes, extreme ratios; every bank sums to 1 << bits per output sample and keeps its taps inside the frame (recipe 1)"""
+    import ctypes as C
+    import lives_b200  # noqa: F401
+    import pe_testlib as T
+    from lives_b200 import _capi
+    lib, o = _capi.lib(), T.oracle()
+    geoms = [(1080, 720), (1920, 1280), (2160, 1608), (3840, 3840), (720, 1080), (640, 320), (300, 75), (37, 37), (5, 3), (3, 7),
+             (4, 4), (1000, 33), (61, 64), (64, 61), (1081, 719), (2, 2)]
+    for recipe, oracle_fn in ((0, o.pe_or_resize_filter), (1, o.pe_or_resize_filter_sws)):
+        for (s, d), bits in [(g, b) for g in geoms for b in (12, 14)]:
+            fa, ca = np.zeros(d, np.int32), np.zeros((d, 64), np.int16)
+            fb, cb = np.zeros(d, np.int32), np.zeros((d, 64), np.int16)
+            ta = oracle_fn(s, d, bits, T.ptr(fa), T.ptr(ca), 64)
+            tb = lib.pe_resize_filter_host(recipe, s, d, bits, C.c_void_p(fb.ctypes.data), C.c_void_p(cb.ctypes.data), 64)
+            assert ta == tb and ta > 0, (recipe, s, d, bits, ta, tb)
+            assert (fa == fb).all() and (ca == cb).all(), (recipe, s, d, bits)
+            assert (cb.astype(np.int64).sum(axis=1) == (1 << bits)).all(), (recipe, s, d, bits)
+            if recipe == 1:
+                assert fb.min() >= 0 and (fb + tb).max() <= max(s, tb) and (np.diff(fb) >= 0).all()
