@@ -141,6 +141,12 @@ void *DevPool::get(size_t bytes, size_t *granted) {
   return p;
 }
 
+bool DevPool::undefer(void *p) {
+  for (size_t i = 0; i < deferred_.size(); i++)
+    if (deferred_[i].first == p) { deferred_.erase(deferred_.begin() + (long)i); return true; }
+  return false;
+}
+
 void DevPool::flush_deferred() {
   std::vector<std::pair<void *, size_t>> d;
   d.swap(deferred_);
@@ -181,6 +187,8 @@ extern "C" void pe_config_default(pe_config_t *cfg) {
   cfg->stream = nullptr;
 }
 
+static int engine_init(pe_engine *e);
+
 extern "C" int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out) {
   if (!out) return set_err(PE_ERR_ARG, "pe_engine_create: out is NULL");
   *out = nullptr;
@@ -198,6 +206,17 @@ extern "C" int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out) {
   pe_engine *e = new pe_engine();
   e->cfg = c;
   e->device = c.device;
+  const int rc = engine_init(e);
+  if (rc != PE_OK) {  // stream, events and tables created so far go the way of a finished engine
+    pe_engine_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return PE_OK;
+}
+
+static int engine_init(pe_engine *e) {
+  const pe_config_t &c = e->cfg;
   cudaDeviceProp prop;
   PE_CUDA(cudaGetDeviceProperties(&prop, c.device));
   e->sm_count = prop.multiProcessorCount;
@@ -242,14 +261,13 @@ extern "C" int pe_engine_create(const pe_config_t *cfg, pe_engine_t **out) {
     PE_CUDA(cudaStreamSynchronize(e->stream));  // `luma` is a stack buffer
   }
   PE_CUDA(cudaMalloc(&e->stats_dev, sizeof(DevStats)));
-  *out = e;
   return PE_OK;
 }
 
 extern "C" void pe_engine_destroy(pe_engine_t *e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  if (e->stream || !e->own_stream) cudaStreamSynchronize(e->stream);
   for (int cl = 0; cl < 2; cl++)
     for (int hd = 0; hd < 2; hd++) cudaFree(e->conv_dev[cl][hd]);
   for (int k = 0; k < 6; k++) cudaFree(e->premult_dev[k]);
@@ -258,7 +276,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   cudaFree(e->luma_dev);
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
-  for (auto &kv : e->over) cudaFree(kv.second);
+  for (auto &kv : e->over) cudaFree(kv.second.dev);
   for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); cudaFree(kv.second.rows4); }
   e->pool.release_all();
   cudaFree(e->stats_dev);
@@ -267,15 +285,17 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   for (int k = 0; k < 4; k++) { if (e->fan_stream[k]) cudaStreamDestroy(e->fan_stream[k]); if (e->fan_join[k]) cudaEventDestroy(e->fan_join[k]); }
   if (e->fan_fork) cudaEventDestroy(e->fan_fork);
   if (e->args_pinned) cudaFreeHost(e->args_pinned);
-  cudaEventDestroy(e->ev0);
-  cudaEventDestroy(e->ev1);
-  cudaEventDestroy(e->args_ev);
-  if (e->h2d_stream) {
-    cudaStreamDestroy(e->h2d_stream);
-    cudaStreamDestroy(e->d2h_stream);
-    for (int k = 0; k < 3; k++) { cudaEventDestroy(e->pipe_up[k]); cudaEventDestroy(e->pipe_comp[k]); cudaEventDestroy(e->pipe_free[k]); }
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->args_ev) cudaEventDestroy(e->args_ev);
+  if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+  if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
+  for (int k = 0; k < 6; k++) {
+    if (e->pipe_up[k]) cudaEventDestroy(e->pipe_up[k]);
+    if (e->pipe_comp[k]) cudaEventDestroy(e->pipe_comp[k]);
+    if (e->pipe_free[k]) cudaEventDestroy(e->pipe_free[k]);
   }
-  if (e->own_stream) cudaStreamDestroy(e->stream);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
 
@@ -407,22 +427,43 @@ uint8_t *get_cavg(pe_engine *e, bool clamped) {
 uint8_t *get_over_table(pe_engine *e, double alpha, const uint8_t *lut_dev) {
   OverKey k{alpha, lut_dev};
   auto it = e->over.find(k);
-  if (it != e->over.end()) return it->second;
+  if (it != e->over.end()) { it->second.tick = ++e->cache_tick; return it->second.dev; }
   uint8_t *dev = nullptr;
-  if (cudaMalloc(&dev, 65536) != cudaSuccess) return nullptr;
+  // bounded (an animated non-dyadic alpha would otherwise grow HBM without end): past kMaxOver entries the least recently used
+  // table is rebuilt in place for the new key -- stream ordered behind the paints that read it, no cudaMalloc / cudaFree
+  const size_t kMaxOver = 64;
+  if (e->over.size() >= kMaxOver) {
+    auto lru = e->over.begin();
+    for (auto j = e->over.begin(); j != e->over.end(); ++j)
+      if (j->second.tick < lru->second.tick) lru = j;
+    dev = lru->second.dev;
+    e->over.erase(lru);
+  } else if (cudaMalloc(&dev, 65536) != cudaSuccess) {
+    return nullptr;
+  }
   if (launch_over_table(e->L(), alpha, lut_dev, dev) != cudaSuccess) {
     cudaFree(dev);
     return nullptr;
   }
-  e->over.emplace(k, dev);
+  e->over.emplace(k, pe::OverEntry{dev, ++e->cache_tick});
   return dev;
 }
 
 DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
   FilterKey k{src_n, dst_n, bits | (e->resize_recipe << 8)};
   auto it = e->filters.find(k);
-  if (it != e->filters.end()) return &it->second;
+  if (it != e->filters.end()) { it->second.tick = ++e->cache_tick; return &it->second; }
+  const size_t kMaxFilters = 256;  // bounded: a zoom animates through many geometries; callers hold at most a handful of entries at once
+  if (e->filters.size() >= kMaxFilters) {
+    auto lru = e->filters.begin();
+    for (auto j = e->filters.begin(); j != e->filters.end(); ++j)
+      if (j->second.tick < lru->second.tick) lru = j;
+    cudaStreamSynchronize(e->stream);  // kernels that read the bank have finished
+    cudaFree((void *)lru->second.dev.first); cudaFree((void *)lru->second.dev.coef); cudaFree(lru->second.rows4);
+    e->filters.erase(lru);
+  }
   DevFilterEntry ent;
+  ent.tick = ++e->cache_tick;
   if (!(e->resize_recipe ? build_resize_filter_sws(src_n, dst_n, bits, &ent.host) : build_resize_filter(src_n, dst_n, bits, &ent.host)))
     return nullptr;
   int32_t *first = nullptr;
@@ -434,8 +475,12 @@ DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
   r.dev = DevFilter{first, coef, r.host.taps};
   if (cudaMemcpyAsync(first, r.host.first.data(), sizeof(int32_t) * dst_n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
       cudaMemcpyAsync(coef, r.host.coef.data(), sizeof(int16_t) * (size_t)dst_n * r.host.taps, cudaMemcpyHostToDevice,
-                      e->stream) != cudaSuccess)
+                      e->stream) != cudaSuccess) {
+    cudaStreamSynchronize(e->stream);  // no entry with unwritten device data stays behind
+    cudaFree(first); cudaFree(coef);
+    e->filters.erase(ins);
     return nullptr;
+  }
   return &r;
 }
 
@@ -1052,7 +1097,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
              (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P)) {
     // convert_{rgb,bgr}_to_yuv420_frame (:12681-12690, :12754-12763, :12600-12609, :12828-12837): width and height cut to even;
     // 4:2:0 takes the tables of osubspace, 4:2:2 gets WEED_YUV_SAMPLING_DEFAULT in that slot (= YCbCr); the planes are
-    // written in layer order (YVU420P receives Cb in plane 1 exactly as the reference's dest[1]).  ARGB32 (:6323) reads
+    // written Cb to plane 1, Cr to plane 2 (the reference's dest[1] / dest[2]; a YVU420P layer gets them swapped at conv_done, :13895).  ARGB32 (:6323) reads
     // past its pixels (:6357) and is not built.
     n.d.width = width & ~1; n.d.height = height & ~1;
     if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
@@ -1125,7 +1170,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                                      width >> 1, height, cavg);
   } else if ((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P)) {
     // convert_yuvp_to_yuv420_frame (:13016-13022, :13115-13121): luma copied, chroma averaged over 2 x 2; the planes are written
-    // in layer order (YVU420P receives Cb in plane 1, as the reference's dest[1]); sampling -> DEFAULT
+    // Cb to plane 1, Cr to plane 2 (YVU420P: swapped at conv_done, :13895); sampling -> DEFAULT
     n.d.width = width & ~1; n.d.height = height & ~1;
     if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
     if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
@@ -1205,6 +1250,11 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     const int irs[3] = {S.rs_y, S.rs_u, S.rs_v};
     ce = launch_chroma_upsample_packed(L, inpl != PE_PALETTE_YUV422P, pl, irs, S.ch, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height,
                                        outpl == PE_PALETTE_YUVA8888, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+  } else if ((inpl == PE_PALETTE_YUV420P && outpl == PE_PALETTE_YVU420P) || (inpl == PE_PALETTE_YVU420P && outpl == PE_PALETTE_YUV420P)) {
+    // pconv_can_inplace (:12152-12155): no pixel work (:13618-13623) -- the chroma plane pointers and rowstrides change places, on the
+    // way in for a V-first source (:12354), on the way out for a V-first target (:13895, below)
+    inplace = true;
+    if (inpl == PE_PALETTE_YVU420P) { std::swap(f->d.planes[1], f->d.planes[2]); std::swap(f->d.rowstrides[1], f->d.rowstrides[2]); }
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;
@@ -1233,6 +1283,9 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
   }
   if (inplace) f->d.palette = outpl;
   else frame_take(f, &n);
+  // "if V plane is before U, swap the pointers" (:13895): every converter above wrote Cb to plane 1 and Cr to plane 2 (the reference's
+  // dest[1] / dest[2]); a V-first palette has them the other way round in the finished layer
+  if (outpl == PE_PALETTE_YVU420P) { std::swap(f->d.planes[1], f->d.planes[2]); std::swap(f->d.rowstrides[1], f->d.rowstrides[2]); }
   // the converters that produce 4:2:0 / 4:2:2 planes from full-resolution chroma leave WEED_YUV_SAMPLING_DEFAULT (:12691, :13022)
   if ((outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P) &&
       (pal_is_rgb(inpl) || inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P))
@@ -1541,6 +1594,29 @@ struct FanOut {
   }
 };
 
+// "Left untouched on failure" (colourspace.c:13906-13927) for the batch calls whose kernels leave after the layers have been given
+// their new pixel blocks: the old blocks are parked in the pool until the flush (DevPool::defer), so a failed flush can hand them back.
+// (An in-place conversion has no old block: its descriptor is restored, its bytes are whatever the failed launch left.)
+struct BatchSnapshot {
+  std::vector<pe_frame> before;
+  BatchSnapshot(int n, pe_frame_t *const *layers) : before((size_t)n) {
+    for (int i = 0; i < n; i++)
+      if (layers[i]) before[(size_t)i] = *layers[i];
+  }
+  void restore(pe_engine *e, int n, pe_frame_t *const *layers) {
+    for (int i = 0; i < n; i++) {
+      pe_frame *f = layers[i];
+      if (!f) continue;
+      const pe_frame &b = before[(size_t)i];
+      if (f->base == b.base) { *f = b; continue; }      // untouched or in place
+      if (b.base && !e->pool.undefer(b.base)) continue;  // the old block is gone: keep the new state
+      pe_frame cur = *f;
+      *f = b;
+      frame_release_pixels(&cur);
+    }
+  }
+};
+
 inline bool same_geometry(const pe_frame *a, const pe_frame *b) {
   return a->d.palette == b->d.palette && a->d.width == b->d.width && a->d.height == b->d.height &&
          a->d.yuv_clamping == b->d.yuv_clamping && a->d.yuv_subspace == b->d.yuv_subspace && a->d.gamma_type == b->d.gamma_type;
@@ -1559,6 +1635,7 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
   // phase 1: planar YUV layers with an RGB target are converted first (resize_layer_full converts before it scales, :14601);
   // the conversions of the whole batch are queued and leave as one launch per 32 same-shaped frames
   if (pal_is_rgb(opal_hint)) {
+    BatchSnapshot snap(n, layers);
     e->yuv_defer = true;
     e->pool.defer(true);
     for (int i = 0; i < n; i++) {
@@ -1576,6 +1653,7 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
     }
     e->yuv_defer = false;
     const int frc = flush_yuv_pending(e);
+    if (frc != PE_OK) snap.restore(e, n, layers);
     e->pool.defer(false);
     e->pool.flush_deferred();
     if (frc != PE_OK) return 0;
@@ -1588,6 +1666,7 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
       uniform = layers[i] && layers[i]->d.planes[0] && pal_psize(layers[i]->d.palette) == 4 && !pal_is_planar(layers[i]->d.palette) &&
                 same_geometry(layers[0], layers[i]) && (opal_hint == PE_PALETTE_NONE || opal_hint == layers[i]->d.palette);
     if (uniform) {
+      BatchSnapshot snap(n, layers);
       e->rsz_defer = true;
       e->pool.defer(true);
       for (int i = 0; i < n; i++)
@@ -1595,6 +1674,7 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
                           PE_GAMMA_UNKNOWN) == PE_TRUE)
           done++;
       const int frc = flush_rsz_pending(e);
+      if (frc != PE_OK) snap.restore(e, n, layers);
       e->pool.defer(false);
       e->pool.flush_deferred();
       return frc == PE_OK ? done : 0;
@@ -1627,23 +1707,27 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
   for (int i = 0; i < n && all_rgb; i++) all_rgb = layers[i] && pal_is_rgb(layers[i]->d.palette);
   if (all_rgb) {
     // RGB <-> RGB: the permutations are queued and leave as one launch per 128 same-shaped frames
+    BatchSnapshot snap(n, layers);
     e->rgb_defer = true;
     e->pool.defer(true);
     for (int i = 0; i < n; i++)
       if (convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
     const int frc = flush_rgb_pending(e);
+    if (frc != PE_OK) snap.restore(e, n, layers);
     e->pool.defer(false);
     e->pool.flush_deferred();
     return frc == PE_OK ? done : 0;
   }
   if (all_planar) {
     // planar YUV -> RGB: the conversions are queued and leave as one launch per 32 same-shaped frames
+    BatchSnapshot snap(n, layers);
     e->yuv_defer = true;
     e->pool.defer(true);
     for (int i = 0; i < n; i++)
       if (convert_locked(e, layers[i], outpl, op_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN) == PE_TRUE) done++;
     e->yuv_defer = false;
     const int frc = flush_yuv_pending(e);
+    if (frc != PE_OK) snap.restore(e, n, layers);
     e->pool.defer(false);
     e->pool.flush_deferred();
     return frc == PE_OK ? done : 0;
@@ -1766,6 +1850,7 @@ extern "C" int pe_fx_convert_crossfade_batchv(pe_engine_t *e, int n, pe_frame_t 
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   e->fuse_blend_bf = blend_factor;
+  BatchSnapshot snap(n, clips);
   e->yuv_defer = true;
   e->pool.defer(true);
   int done = 0;
@@ -1790,6 +1875,7 @@ extern "C" int pe_fx_convert_crossfade_batchv(pe_engine_t *e, int n, pe_frame_t 
   e->yuv_defer = false;
   e->fuse_blend2 = nullptr;
   const int frc = flush_yuv_pending(e);
+  if (frc != PE_OK) snap.restore(e, n, clips);
   e->pool.defer(false);
   e->pool.flush_deferred();
   return frc == PE_OK ? done : 0;
@@ -1881,7 +1967,9 @@ int flush_over_pending(pe_engine *e) {
     };
     auto depends = [&](const pe_engine::OverJob &b) {
       for (size_t k = i; k < j; k++)
-        if (q[k].dst == b.bg || q[k].dst == b.fg || q[k].dst == b.dst) return true;
+        if (q[k].dst == b.bg || q[k].dst == b.fg || q[k].dst == b.dst ||  // reads / rewrites what an earlier job of the run writes
+            b.dst == q[k].bg || (b.dst == q[k].fg))                        // ... or writes what an earlier job of the run still reads
+          return true;
       return false;
     };
     while (j < q.size() && same(q[i], q[j]) && !depends(q[j])) j++;

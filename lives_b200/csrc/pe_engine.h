@@ -28,6 +28,7 @@ class DevPool {
   // have joined: put() parks them, flush_deferred() returns them to the free lists.
   void defer(bool on) { defer_ = on; }
   void flush_deferred();
+  bool undefer(void *p);  // take a parked block back (a failed batch restores its layers)
 
  private:
   std::multimap<size_t, void *> free_;
@@ -55,6 +56,11 @@ struct DevFilterEntry {
   ResizeFilter host;
   void *rows4 = nullptr;  // int4 per output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}: k_fused3's view of a <= 4-tap bank
   int rows4_x16 = 0;      // its coefficients are scaled by 16 (no tap of the bank is 4096)
+  unsigned long tick = 0; // last use (LRU bound of the cache)
+};
+struct OverEntry {
+  uint8_t *dev;
+  unsigned long tick;
 };
 struct Lut8Entry {
   uint8_t host[256];
@@ -85,7 +91,8 @@ struct pe_engine {
   int32_t *luma_dev = nullptr;       // plugin-side calc_luma tables [3][256]
   std::map<pe::GammaKey, pe::Lut8Entry> lut8;
   std::map<pe::GammaKey, uint16_t *> lut16;
-  std::map<pe::OverKey, uint8_t *> over;
+  std::map<pe::OverKey, pe::OverEntry> over;
+  unsigned long cache_tick = 0;
   std::map<pe::FilterKey, pe::DevFilterEntry> filters;
   pe::DevPool pool;
   pe::DevStats *stats_dev = nullptr;

@@ -12,6 +12,13 @@ struct Launch {
   long *launch_counter;  // host counter, incremented once per kernel launch
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: the launchers keep their opt-in state per CUDA ordinal (the ABI
+// allows one engine per GPU in one process), never in a process-global flag
+struct PerDevice {
+  size_t v[64] = {};
+  size_t &cur() { int d = 0; cudaGetDevice(&d); return v[d & 63]; }
+};
+
 // packed image view
 struct Img {
   uint8_t *p;

@@ -576,14 +576,14 @@ static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, in
   }
   if (!ok) return cudaErrorInvalidConfiguration;
   const int tiles = ((dw + P.tw - 1) / P.tw) * ((dh + P.th - 1) / P.th);
-  static size_t attr[5] = {0, 0, 0, 0, 0};
+  static PerDevice attr[5];
   cudaError_t e = cudaSuccess;
-  if (smem > attr[psize]) {
+  if (smem > attr[psize].cur()) {
     if (psize == 4) e = cudaFuncSetAttribute(k_resize_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     else if (psize == 3) e = cudaFuncSetAttribute(k_resize_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     else e = cudaFuncSetAttribute(k_resize_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr[psize] = 96 * 1024;
+    attr[psize].cur() = 96 * 1024;
   }
   if (psize == 4 && fx.taps <= 4 && fy.taps <= 4 && ((((uintptr_t)dst.p | (uintptr_t)src.p) | (uint32_t)dst.rs | (uint32_t)src.rs) & 3) == 0 &&
       getenv("PE_RESIZE_GENERIC") == nullptr) {
@@ -592,11 +592,11 @@ static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, in
     P.vec_src = ((uint32_t)src.rs & 15) == 0 && getenv("PE_RESIZE_NOVEC") == nullptr;
     for (int i = 0; i < (nbatch > 0 ? nbatch : 1) && P.vec_src; i++) P.vec_src = (((uintptr_t)(nbatch > 0 ? srcs[i] : src.p)) & 15) == 0;
     const size_t smem4 = raw4 + (size_t)(P.max_rows + 3) * P.tw * 8 + (size_t)P.tw * 8 + (size_t)P.th * 16 + (size_t)(P.tw + P.th) * 4;
-    static bool attr4 = false;
+    static PerDevice attr4;
     if (smem4 <= 96 * 1024) {
-      if (!attr4) {
+      if (!attr4.cur()) {
         if ((e = cudaFuncSetAttribute(k_resize_tile4, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
-        attr4 = true;
+        attr4.cur() = 1;
       }
       const int nf = nbatch > 0 ? nbatch : 1;
       for (int base = 0; base < nf; base += 32) {
@@ -629,11 +629,11 @@ cudaError_t launch_fused_dev(const Launch &L, const FusedArgs *frames_dev, int n
   const int tiles_x = (ow + kTileW - 1) / kTileW, tiles_y = (oh + kTileH - 1) / kTileH;
   const size_t smem = 65536 + 5 * 1024 + (((size_t)max_src_rows * max_src_cols * 4 + 15) & ~(size_t)15) + (size_t)max_src_rows * kTileW * 8;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
+  static PerDevice attr_set;
+  if (smem > attr_set.cur()) {
     cudaError_t e = cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = smem;
+    attr_set.cur() = smem;
   }
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   long long total = (long long)tiles_x * tiles_y * nframes;

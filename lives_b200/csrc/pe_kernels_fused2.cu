@@ -643,14 +643,14 @@ int fused2_max_tile_h() { return F2_MAXTH; }
 // blend_a < 0: table blend (FusedArgs::over_table, gamma folded in); else arithmetic blend with weights blend_a / 256 - blend_a
 cudaError_t launch_fused2(const Launch &L, const FusedArgs *frames_host, int nframes, int ow, int oh, int tile_h, int blend_a,
                           const uint8_t *lut8_dev) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_fused2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_ARITH)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_fused2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_ARITH)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_fused2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_TABLE)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_fused2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_TABLE)) != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.cur() = 1;
   }
   for (int base = 0; base < nframes; base += F2_MAXF) {
     Fused2Params P;

@@ -697,8 +697,8 @@ bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
 // rows4_dev: int4 per inner output row {first, c3 | c2 << 16, c1 | c0 << 16, 0} (built by the engine from the filter bank)
 cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nframes, int blend_a, const uint8_t *lut8_dev,
                           const void *rows4_dev, int coef16, unsigned int *sched_dev) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
     cudaError_t e;
     const int mx = S3_BYTES + 16 * F3_MAX_IH;
     const void *fns[8] = {(const void *)k_fused3<true, true, true>,   (const void *)k_fused3<true, true, false>,
@@ -707,7 +707,7 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
                           (const void *)k_fused3<false, false, true>, (const void *)k_fused3<false, false, false>};
     for (int i = 0; i < 8; i++)
       if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.cur() = 1;
   }
   static int cost_b = 0, cost_i = 0, static_pct = 92, chunk_rows = 24;
   if (!cost_b) {

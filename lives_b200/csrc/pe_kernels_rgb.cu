@@ -863,11 +863,11 @@ cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int wi
   P.bg = bg.p; P.fg = fg.p; P.dst = dst.p; P.rs_bg = bg.rs; P.rs_fg = fg.rs; P.rs_d = dst.rs;
   P.width = width; P.height = height; P.psize = psize; P.tab = over_table_dev;
   P.force_opaque = force_opaque; P.a_off = 3;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
     cudaError_t e = cudaFuncSetAttribute(k_alpha_over, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.cur() = 1;
   }
   k_alpha_over<<<L.sm_count, 1024, 65536, L.stream>>>(P);  // persistent: one CTA per SM (64 KB table each)
   PE_COUNT_LAUNCH(L);

@@ -657,14 +657,14 @@ static void launch_march(const Launch &L, const YuvToRgbArgs &a, const YuvFrameL
 }
 
 static cudaError_t march_attrs() {
-  static bool march_attr = false;
-  if (!march_attr) {
+  static PerDevice march_attr;
+  if (!march_attr.cur()) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_yuv_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_yuv_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_yuv_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_yuv_march<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_RING)) != cudaSuccess) return e;
-    march_attr = true;
+    march_attr.cur() = 1;
   }
   return cudaSuccess;
 }
@@ -707,12 +707,12 @@ cudaError_t launch_yuv_planar_to_rgb_batch(const Launch &L, const YuvToRgbArgs *
 }
 
 cudaError_t launch_yuv_planar_to_rgb_fast(const Launch &L, const YuvToRgbArgs &a) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_yuv_planar_to_rgb_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_yuv_planar_to_rgb_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_BYTES)) != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.cur() = 1;
   }
   // the fast paths read whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
   const bool last_row_unsafe = a.src.rs_u < a.src.cw + 4 || a.src.rs_v < a.src.cw + 4;
