@@ -105,23 +105,38 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU reference chain
 
 class CpuChain:
-    """The reference's CPU implementation of the workload, one frame per call (test infrastructure: oracle/).
+    """The reference's CPU implementation of the workload, one frame per call (test infrastructure: oracle/, tests/swscale_ref.py).
 
-    convert   compiled reference convert_yuv420p_to_rgb_frame (oracle/_ref/libref_oracle.so), pb_quality HIGH
-    resize    oracle port of our published filter (the reference calls libswscale, absent from its tree and this image)
-    letterbox oracle port of letterbox_layer's centred row copies
-    over      compiled reference compositor.c paint_pixel (oracle/_ref/ref_paint_pixel.so)
-    gamma     compiled reference gamma_convert_layer_thread with the LUT of create_gamma_lut8
-    Falls back to the oracle port for every stage (kind "port") when oracle/_ref is absent.
-    """
+    The stock path for this chain (letterbox_layer -> resize_layer(tpal = RGBA32) -> resize_layer_full, src/colourspace.c:15343,
+    :14759): a YUV420P layer with an RGBA32 target is converted AND scaled by ONE sws_scale call (get_resizable :14601-14620,
+    flags SWS_BILINEAR :14997, sws_setColorspaceDetails :15079) -- convert_yuv420p_to_rgb_frame is not on this path.
+    convert + resize  libswscale's sws_scale, YUV420P 3840x2160 -> RGBA 3840x1608 in one call (the library the reference links; the
+                      one loadable here is the opencv wheel's, version in `sws_version`); context cached per thread as the reference
+                      caches its own (sws_getCachedContext :15059)
+    letterbox         the centred row copies of letterbox_layer (:15522-15549) into a black frame (oracle port of a memcpy loop)
+    over              compiled reference compositor.c paint_pixel (oracle/_ref/ref_paint_pixel.so)
+    gamma             compiled reference gamma_convert_layer_thread with the LUT of create_gamma_lut8
+    stages = "sws":     the above (kind "reference")
+    stages = "loops":   convert = compiled reference convert_yuv420p_to_rgb_frame, resize = oracle port (round 1's arm; what the
+                        reference would run with libswscale compiled out; kind "reference" / "port")
+    Without oracle/_ref every compiled stage falls back to the oracle port (kind "port")."""
 
-    def __init__(self):
+    def __init__(self, stages="auto"):
         sys.path.insert(0, os.path.join(REPO, "tests"))
         import pe_testlib as T
-        self.T = T
+        import swscale_ref as S
+        self.T, self.S = T, S
         self.o = T.oracle()
-        self.kind = "reference" if T.have_ref() else "port"
-        if self.kind == "reference":
+        self.have_ref = T.have_ref()
+        sws, ver = S.load()
+        self.sws_version = ver if sws is not None else None
+        if stages == "auto":
+            stages = "sws" if sws is not None else "loops"
+        if stages == "sws" and sws is None:
+            raise SystemExit("bench.py: no loadable libswscale (%s)" % ver)
+        self.stages = stages
+        self.kind = "reference" if self.have_ref else "port"
+        if self.have_ref:
             self.r = T.ref()
             self.r.ref_set_prefs(1, T.Q_HIGH, 1.4)  # frames are spread over the cores, one band per frame
             self.p = T.ref_paint()
@@ -129,33 +144,79 @@ class CpuChain:
         assert self.o.pe_or_gamma_lut8(1.0, G_LINEAR, G_SRGB, 1.4, T.ptr(self.lut)) == 0
         self.tls = threading.local()
 
+    def describe(self):
+        if self.stages == "sws":
+            return ("convert + resize = ONE sws_scale call YUV420P 3840x2160 -> RGBA 3840x1608 (libswscale %s, SWS_BILINEAR, as "
+                    "resize_layer_full issues it, colourspace.c:14601-14620); letterbox = row copies; alpha-over / gamma = %s"
+                    % (self.sws_version, "compiled reference loops" if self.have_ref else "oracle port"))
+        return ("convert / alpha-over / gamma = %s, resize + letterbox = oracle port (the reference's path with libswscale compiled out)"
+                % ("compiled reference loops" if self.have_ref else "oracle port"))
+
     def _bufs(self):
         t = self.tls
-        if not hasattr(t, "rgba"):
-            t.rgba_full = np.zeros((FH + 16, FW * 4), np.uint8)  # slack rows: the reference has stray writes (:3584)
-            t.rgba = t.rgba_full[8:8 + FH]
+        if not hasattr(t, "inner"):
             t.inner = np.zeros((IH, IW * 4), np.uint8)
             t.boxed = np.zeros((FH, FW * 4), np.uint8)
+            if self.stages == "sws":
+                t.scaler = self.S.Scaler("yuv420p", FW, FH, "rgba", IW, IH, self.S.SWS_BILINEAR, yuv=(False, False, False))
+            else:
+                t.rgba_full = np.zeros((FH + 16, FW * 4), np.uint8)  # slack rows: the reference has stray writes (:3584)
+                t.rgba = t.rgba_full[8:8 + FH]
         return t
 
-    def frame(self, y, u, v, bg, out):
+    def stage_times(self, y, u, v, bg, out):
+        """one frame, per-stage wall clock (single thread)"""
         T, t = self.T, self._bufs()
+        times = {}
+        t0 = time.perf_counter()
+        self._convert_resize(t, y, u, v)
+        times["convert+resize"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.o.pe_or_letterbox_packed(T.ptr(t.inner), IW * 4, IW, IH, T.ptr(t.boxed), FW * 4, FW, FH, 3)
+        times["letterbox"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        np.copyto(out, bg)
+        self._over(t, out)
+        times["alpha-over"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self._gamma(out)
+        times["gamma"] = time.perf_counter() - t0
+        return times
+
+    def _convert_resize(self, t, y, u, v):
+        T = self.T
+        if self.stages == "sws":
+            t.scaler.run([y, u, v], t.inner)
+            return
         pl, st = T.planes_arg(y, u, v), T.strides_arg(y, u, v)
-        if self.kind == "reference":
+        if self.have_ref:
             self.r.ref_yuv420p_to_rgb(pl, FW, FH, st, FW * 4, T.ptr(t.rgba), 0, 1, 0, 0, 0, 1, 0, 0)
         else:
             self.o.pe_or_yuv420p_to_rgb(pl, st, FW, FH, T.ptr(t.rgba), FW * 4, 0, 1, 0, 0, 1, T.Q_HIGH, 1, None)
         self.o.pe_or_resize_packed(T.ptr(t.rgba), FW * 4, FW, FH, T.ptr(t.inner), IW * 4, IW, IH, 4)
-        self.o.pe_or_letterbox_packed(T.ptr(t.inner), IW * 4, IW, IH, T.ptr(t.boxed), FW * 4, FW, FH, 3)
-        np.copyto(out, bg)
-        if self.kind == "reference":
+
+    def _over(self, t, out):
+        T = self.T
+        if self.have_ref:
             self.p.ref_paint_rows(T.ptr(out), T.ptr(t.boxed), FW * FH, 4, ALPHA)
-            out[:, 3::4] = 255
-            self.r.ref_gamma_apply(T.ptr(out), FW * 4, 4, 0, FW, FH, 0, T.ptr(self.lut))
         else:
             self.o.pe_or_alpha_over(T.ptr(out), FW * 4, T.ptr(t.boxed), FW * 4, 3, FW, FH, ALPHA)
-            out[:, 3::4] = 255
+        out[:, 3::4] = 255
+
+    def _gamma(self, out):
+        T = self.T
+        if self.have_ref:
+            self.r.ref_gamma_apply(T.ptr(out), FW * 4, 4, 0, FW, FH, 0, T.ptr(self.lut))
+        else:
             self.o.pe_or_gamma_apply(T.ptr(out), FW * 4, 3, 0, 0, FW, FH, T.ptr(self.lut))
+
+    def frame(self, y, u, v, bg, out):
+        T, t = self.T, self._bufs()
+        self._convert_resize(t, y, u, v)
+        self.o.pe_or_letterbox_packed(T.ptr(t.inner), IW * 4, IW, IH, T.ptr(t.boxed), FW * 4, FW, FH, 3)
+        np.copyto(out, bg)
+        self._over(t, out)
+        self._gamma(out)
 
 
 def host_frames(n, seed0=20):
@@ -183,9 +244,9 @@ def host_frames(n, seed0=20):
 class CpuBench:
     """n_frames independent frames of the CPU chain spread over `cores` threads (ctypes drops the GIL)"""
 
-    def __init__(self, n_frames, cores):
+    def __init__(self, n_frames, cores, stages="auto"):
         from concurrent.futures import ThreadPoolExecutor
-        self.chain = CpuChain()
+        self.chain = CpuChain(stages)
         self.n, self.cores = n_frames, cores
         self.distinct = host_frames(2)
         self.outs = [np.zeros((FH, FW * 4), np.uint8) for _ in range(min(cores, n_frames))]

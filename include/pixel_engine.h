@@ -4,8 +4,8 @@
  *     palette conversion -> resize / letterbox -> effect blend / composite -> gamma
  * Plain C: opaque handles, raw pointers, ints and doubles only.  Every entry point cites the
  * reference interface it replaces (file:line in the LiVES tree).  INTEGRATION.md shows the
- * reference-side bindings (the weed_layer_t shim of include/pe_weed.h and the dlopen'd effect
- * plugin libpe_weed_plugin.so).
+ * reference-side bindings (the weed_layer_t drop-ins of include/pe_weed_layer.h = libpe_weed_layer.so, and the dlopen'd
+ * effect plugin libpe_weed_plugin.so).
  *
  * Conventions (same as the reference):
  *   - "boolean" results are int PE_TRUE / PE_FALSE; a frame is MUTATED IN PLACE by the layer ops
@@ -104,9 +104,13 @@ long pe_engine_launch_count(pe_engine_t *e);
 int pe_timer_start(pe_engine_t *e);
 int pe_timer_stop_ms(pe_engine_t *e, float *ms); /* synchronises on the stop event */
 int pe_sm_count(pe_engine_t *e);
-/* resize coefficients (the reference delegates resizing to an unpinned libswscale, src/colourspace.c:15059-15228): recipe 0 = the
- * published contract of DESIGN.md section 5 (default), 1 = libswscale's own bilinear coefficient recipe (opt-in).
- * pe_resize_filter_host returns the bank a recipe produces (host arithmetic, no GPU): tap count, or -1 */
+/* resize coefficients.  The reference delegates resizing to libswscale (src/colourspace.c:15059-15228; version unpinned,
+ * configure.ac:562) with one flag per LiVESInterpType (:14991-14997).  recipe 1 (default) = libswscale's own coefficient recipes:
+ * PE_INTERP_NORMAL SWS_BILINEAR, PE_INTERP_BEST SWS_LANCZOS when the frame grows / SWS_BICUBIC when it shrinks, PE_INTERP_FAST
+ * SWS_FAST_BILINEAR (DESIGN.md section 5 states the measured distance to a real libswscale).  recipe 0 = the round-1 triangle
+ * contract for every interpolation type.
+ * pe_resize_filter_host returns the bank a recipe produces (host arithmetic, no GPU): kind 0 triangle, 1 bilinear, 2 bicubic,
+ * 3 Lanczos, 4 / 5 fast bilinear vertical / horizontal; tap count, or -1 */
 int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe);
 int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
 

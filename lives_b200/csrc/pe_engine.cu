@@ -309,8 +309,8 @@ extern "C" void *pe_engine_stream(pe_engine_t *e) { return e ? (void *)e->stream
 extern "C" long pe_engine_launch_count(pe_engine_t *e) { return e ? e->launches : 0; }
 extern "C" int pe_sm_count(pe_engine_t *e) { return e ? e->sm_count : 0; }
 
-// which coefficients the resize / letterbox / fused calls of this engine use from now on: 0 the published contract (default),
-// 1 libswscale's recipe (pe_tables.cpp build_resize_filter_sws; opt-in until it has had its GPU pass)
+// which coefficients the resize / letterbox / fused calls of this engine use from now on: 1 libswscale's recipes (default; one bank
+// per LiVESInterpType, pe_tables.cpp build_resize_filter_sws), 0 the round-1 triangle contract (every interpolation type)
 extern "C" int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe) {
   if (!e || recipe < 0 || recipe > 1) return set_err(PE_ERR_ARG, "resize recipe: 0 or 1");
   std::lock_guard<std::mutex> lk(e->mu);
@@ -323,7 +323,8 @@ extern "C" int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe) {
 extern "C" int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
   ResizeFilter f;
   if (!first || !coefs) return -1;
-  if (!(recipe ? build_resize_filter_sws(src_n, dst_n, shift_bits, &f) : build_resize_filter(src_n, dst_n, shift_bits, &f))) return -1;
+  if (recipe < 0 || recipe > 5) return -1;  // 0 triangle, 1 .. 5 = pe::SwsKind (bilinear, bicubic, Lanczos, fast vertical / horizontal)
+  if (!(recipe ? build_resize_filter_sws(src_n, dst_n, shift_bits, &f, (SwsKind)recipe) : build_resize_filter(src_n, dst_n, shift_bits, &f))) return -1;
   if (f.taps > max_taps) return -1;
   for (int i = 0; i < dst_n; i++) {
     first[i] = f.first[i];
@@ -449,8 +450,23 @@ uint8_t *get_over_table(pe_engine *e, double alpha, const uint8_t *lut_dev) {
   return dev;
 }
 
-DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
-  FilterKey k{src_n, dst_n, bits | (e->resize_recipe << 8)};
+// kind: 0 the round-1 triangle bank, else a pe::SwsKind
+struct AxisKinds { int x, y; };
+// the bank each axis of a resize takes: recipe 0 -> the round-1 triangle whatever the interpolation; recipe 1 (default) -> the
+// flag resize_layer_full hands libswscale (:14991-14997): NORMAL SWS_BILINEAR, BEST SWS_LANCZOS when the frame grows in either
+// direction else SWS_BICUBIC, FAST SWS_FAST_BILINEAR (a position walk horizontally, a two-tap bank vertically)
+AxisKinds filter_kinds(const pe_engine *e, int interp, int sw, int sh, int dw, int dh) {
+  if (!e->resize_recipe) return AxisKinds{0, 0};
+  int kx = SWS_KIND_BILINEAR, ky = SWS_KIND_BILINEAR;
+  if (interp == PE_INTERP_BEST) kx = ky = (dw > sw || dh > sh) ? SWS_KIND_LANCZOS : SWS_KIND_BICUBIC;
+  else if (interp == PE_INTERP_FAST) { kx = SWS_KIND_FAST_H; ky = SWS_KIND_FAST_V; }
+  if (sw == dw) kx = SWS_KIND_BILINEAR;  // an unscaled axis is the identity under every flag
+  if (sh == dh) ky = SWS_KIND_BILINEAR;
+  return AxisKinds{kx, ky};
+}
+
+DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits, int kind) {
+  FilterKey k{src_n, dst_n, bits | (kind << 8)};
   auto it = e->filters.find(k);
   if (it != e->filters.end()) { it->second.tick = ++e->cache_tick; return &it->second; }
   const size_t kMaxFilters = 256;  // bounded: a zoom animates through many geometries; callers hold at most a handful of entries at once
@@ -464,7 +480,7 @@ DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
   }
   DevFilterEntry ent;
   ent.tick = ++e->cache_tick;
-  if (!(e->resize_recipe ? build_resize_filter_sws(src_n, dst_n, bits, &ent.host) : build_resize_filter(src_n, dst_n, bits, &ent.host)))
+  if (!(kind ? build_resize_filter_sws(src_n, dst_n, bits, &ent.host, (SwsKind)kind) : build_resize_filter(src_n, dst_n, bits, &ent.host)))
     return nullptr;
   int32_t *first = nullptr;
   int16_t *coef = nullptr;
@@ -472,7 +488,7 @@ DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits) {
   if (cudaMalloc(&coef, sizeof(int16_t) * (size_t)dst_n * ent.host.taps) != cudaSuccess) { cudaFree(first); return nullptr; }
   auto ins = e->filters.emplace(k, std::move(ent)).first;
   DevFilterEntry &r = ins->second;
-  r.dev = DevFilter{first, coef, r.host.taps};
+  r.dev = DevFilter{first, coef, r.host.taps, r.host.nonneg() ? 1 : 0};
   if (cudaMemcpyAsync(first, r.host.first.data(), sizeof(int32_t) * dst_n, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
       cudaMemcpyAsync(coef, r.host.coef.data(), sizeof(int16_t) * (size_t)dst_n * r.host.taps, cudaMemcpyHostToDevice,
                       e->stream) != cudaSuccess) {
@@ -1327,11 +1343,11 @@ extern "C" int pe_convert_layer_palette(pe_engine_t *e, pe_frame_t *layer, int o
 namespace {
 
 // one plane (or packed image) src -> dst through the separable filter bank
-int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint8_t *dst, int drs, int dw, int dh, int psize) {
-  DevFilterEntry *fx = get_filter(e, sw, dw, 14), *fy = get_filter(e, sh, dh, 12);
+int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint8_t *dst, int drs, int dw, int dh, int psize, AxisKinds kinds) {
+  DevFilterEntry *fx = get_filter(e, sw, dw, 14, kinds.x), *fy = get_filter(e, sh, dh, 12, kinds.y);
   if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range (%dx%d -> %dx%d; at most 31x down)", sw, sh, dw, dh);
-  if (e->rsz_defer && psize == 4 && fx->host.taps <= 4 && fy->host.taps <= 4) {  // batch call: launched by flush_rsz_pending
-    e->rsz_pending.push_back(pe_engine::RszJob{src, srs, sw, sh, dst, drs, dw, dh, psize});
+  if (e->rsz_defer && psize == 4 && fx->host.fast_taps() <= 4 && fy->host.fast_taps() <= 4) {  // batch call: launched by flush_rsz_pending
+    e->rsz_pending.push_back(pe_engine::RszJob{src, srs, sw, sh, dst, drs, dw, dh, psize, kinds.x, kinds.y});
     return PE_OK;
   }
   // one tiled kernel (15-bit intermediate stays in shared memory) ...
@@ -1353,7 +1369,6 @@ int resize_plane(pe_engine *e, const uint8_t *src, int srs, int sw, int sh, uint
 
 int resize_locked(pe_engine *e, pe_frame *f, int width, int height, int interp, int opal_hint, int oclamp_hint, int osamp_hint,
                   int osubs_hint, int tgt_gamma) {
-  (void)interp;  // NORMAL / FAST / BEST all map to the one published filter of this build (DESIGN.md "resize")
   int palette = f->d.palette;
   if (opal_hint == PE_PALETTE_NONE) opal_hint = palette;  // WEED_PALETTE_ANY: keep
   if (!f->d.planes[0]) {  // :14820-14832
@@ -1393,15 +1408,16 @@ int resize_locked(pe_engine *e, pe_frame *f, int width, int height, int interp, 
   n.d.palette = palette; n.d.width = width; n.d.height = height;
   if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
   int rc = PE_OK;
+  const AxisKinds kinds = filter_kinds(e, interp, iwidth, iheight, width, height);  // one flag per call (:14991-14997), every plane
   if (!pal_is_planar(palette)) {
     rc = resize_plane(e, (const uint8_t *)f->d.planes[0], f->d.rowstrides[0], f->d.width, f->d.height, (uint8_t *)n.d.planes[0],
-                      n.d.rowstrides[0], width, height, pal_psize(palette));
+                      n.d.rowstrides[0], width, height, pal_psize(palette), kinds);
   } else {
     for (int p = 0; p < n.d.nplanes && rc == PE_OK; p++) {
       const bool sub_h = p > 0 && p < 3 && palette != PE_PALETTE_YUV444P && palette != PE_PALETTE_YUVA4444P;
       const int sw = sub_h ? f->d.width >> 1 : f->d.width, dw = sub_h ? width >> 1 : width;
       rc = resize_plane(e, (const uint8_t *)f->d.planes[p], f->d.rowstrides[p], sw, f->plane_heights[p], (uint8_t *)n.d.planes[p],
-                        n.d.rowstrides[p], dw, n.plane_heights[p], 1);
+                        n.d.rowstrides[p], dw, n.plane_heights[p], 1, kinds);
     }
   }
   if (rc != PE_OK) { frame_release_pixels(&n); return PE_FALSE; }
@@ -1532,12 +1548,12 @@ int flush_rsz_pending(pe_engine *e) {
   while (i < q.size() && rc == PE_OK) {
     size_t j = i + 1;
     auto same = [&](const pe_engine::RszJob &a, const pe_engine::RszJob &b) {
-      return a.srs == b.srs && a.sw == b.sw && a.sh == b.sh && a.drs == b.drs && a.dw == b.dw && a.dh == b.dh && a.psize == b.psize;
+      return a.srs == b.srs && a.sw == b.sw && a.sh == b.sh && a.drs == b.drs && a.dw == b.dw && a.dh == b.dh && a.psize == b.psize && a.kx == b.kx && a.ky == b.ky;
     };
     while (j < q.size() && same(q[i], q[j])) j++;
     bool done = false;
     if (j - i > 1) {
-      DevFilterEntry *fx = get_filter(e, q[i].sw, q[i].dw, 14), *fy = get_filter(e, q[i].sh, q[i].dh, 12);
+      DevFilterEntry *fx = get_filter(e, q[i].sw, q[i].dw, 14, q[i].kx), *fy = get_filter(e, q[i].sh, q[i].dh, 12, q[i].ky);
       if (fx && fy) {
         std::vector<const uint8_t *> srcs;
         std::vector<uint8_t *> dsts;
@@ -1550,7 +1566,7 @@ int flush_rsz_pending(pe_engine *e) {
     }
     if (!done && rc == PE_OK)
       for (size_t k = i; k < j && rc == PE_OK; k++)
-        rc = resize_plane(e, q[k].src, q[k].srs, q[k].sw, q[k].sh, q[k].dst, q[k].drs, q[k].dw, q[k].dh, q[k].psize);
+        rc = resize_plane(e, q[k].src, q[k].srs, q[k].sw, q[k].sh, q[k].dst, q[k].drs, q[k].dw, q[k].dh, q[k].psize, AxisKinds{q[k].kx, q[k].ky});
     i = j;
   }
   return rc;
@@ -2135,7 +2151,8 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
   }
   uint8_t *tab = get_over_table(e, alpha, lut);
   if (!tab) return set_err(PE_ERR_MEMORY, "alpha-over table could not be built");
-  DevFilterEntry *fx = get_filter(e, f0->d.width, inner_w, 14), *fy = get_filter(e, f0->d.height, inner_h, 12);
+  const AxisKinds kinds = filter_kinds(e, PE_INTERP_NORMAL, f0->d.width, f0->d.height, inner_w, inner_h);
+  DevFilterEntry *fx = get_filter(e, f0->d.width, inner_w, 14, kinds.x), *fy = get_filter(e, f0->d.height, inner_h, 12, kinds.y);
   if (!fx || !fy) return set_err(PE_ERR_SIZE, "scale factor out of range");
   // source extent one output tile can touch
   const int tw = fused_tile_w(), th = fused_tile_h();
@@ -2179,7 +2196,7 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
   }
   // fast path: no horizontal scaling, <= 4 vertical taps, aligned planes (pe_kernels_fused2.cu)
   bool fast = getenv("PE_FUSED_GENERIC") == nullptr;
-  for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.taps, 0) && args[i].is_422 == args[0].is_422;
+  for (int i = 0; i < n && fast; i++) fast = fused2_supported(args[i], fy->host.fast_taps(), 0) && args[i].is_422 == args[0].is_422;
   int tile_h = 0;
   if (fast) {
     // tallest tile whose virtual source rows (first .. first + 3 of its last row) fit the shared-memory tile
@@ -2199,7 +2216,7 @@ static int fused_locked(pe_engine_t *e, int n, const pe_frame_t *const *fg, cons
   const bool dyadic = k256 >= 0. && k256 <= 256. && k256 == (double)(int)k256;
   // register-resident path (pe_kernels_fused3.cu): 4:2:0, full-width letterbox, alpha = k / 256, one conversion variant
   const bool regs = dyadic && getenv("PE_FUSED_GENERIC") == nullptr && getenv("PE_FUSED3_OFF") == nullptr &&
-                    fused3_supported(args.data(), n, fy->host.taps) &&
+                    fused3_supported(args.data(), n, fy->host.fast_taps()) &&
                     fused3_tables_ok(conv_host(e, f0->d.yuv_clamping, f0->d.yuv_subspace));
   if (regs) {
     if (!fy->rows4) {

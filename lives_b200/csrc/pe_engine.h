@@ -75,7 +75,7 @@ struct pe_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
-  int resize_recipe = 0;  // 0 the published contract (default), 1 libswscale's coefficient recipe (pe_engine_set_resize_recipe)
+  int resize_recipe = 1;  // 1 libswscale's coefficient recipes (default), 0 the round-1 triangle contract (pe_engine_set_resize_recipe)
   long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels
@@ -105,7 +105,7 @@ struct pe_engine {
   struct RgbJob { const uint8_t *src; int irow; uint8_t *dst; int orow, width, height; pe::RgbLayout in, out; const uint8_t *lut; };
   bool rgb_defer = false;            // ... and the RGB <-> RGB permutations (flush_rgb_pending)
   std::vector<RgbJob> rgb_pending;
-  struct RszJob { const uint8_t *src; int srs, sw, sh; uint8_t *dst; int drs, dw, dh, psize; };
+  struct RszJob { const uint8_t *src; int srs, sw, sh; uint8_t *dst; int drs, dw, dh, psize, kx, ky; };
   struct OverJob { const uint8_t *bg, *fg; uint8_t *dst; int rs_bg, rs_fg, rs_d, w, h, psize, k256; const uint8_t *lut; };
   bool over_defer = false;           // ... and the integer alpha-over paints of a compositor batch (flush_over_pending)
   std::vector<OverJob> over_pending;

@@ -176,6 +176,7 @@ struct DevFilter {
   const int32_t *first;
   const int16_t *coef;
   int taps;
+  int nonneg;  // no negative coefficient (bilinear banks): the <= 4-tap kernels (unsigned DP2A / packed halves) may take it
 };
 cudaError_t launch_resize_h(const Launch &L, CImg src, int sw, int sh, int16_t *tmp, int dw, int psize, DevFilter fx);
 cudaError_t launch_resize_v(const Launch &L, const int16_t *tmp, int sh, Img dst, int dw, int dh, int psize, DevFilter fy);

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile(const ResizeTileParams P
         }
       }
       a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
-      s_tmp[r * P.tw + xo] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
+      s_tmp[r * P.tw + xo] = make_uint2(((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16), ((uint32_t)a2 & 0xFFFFu) | ((uint32_t)a3 << 16))  /* signed 16-bit halves: bicubic / Lanczos lobes go negative */;
     }
   }
   __syncthreads();
@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(kBlock) k_resize_tile(const ResizeTileParams P
       for (int k = 0; k < ty_taps; k++) {
         const int c = cf[k];
         const uint2 hv = s_tmp[(f0 + k) * P.tw + xo];
-        a0 += c * (int)(hv.x & 0xFFFF);
-        if (PS > 1) { a1 += c * (int)(hv.x >> 16); a2 += c * (int)(hv.y & 0xFFFF); }
-        if (PS == 4) a3 += c * (int)(hv.y >> 16);
+        a0 += c * (int)(short)hv.x;
+        if (PS > 1) { a1 += c * ((int)hv.x >> 16); a2 += c * (int)(short)hv.y; }
+        if (PS == 4) a3 += c * ((int)hv.y >> 16);
       }
       const uint32_t o0 = (uint32_t)min(max(a0 >> 19, 0), 255), o1 = (uint32_t)min(max(a1 >> 19, 0), 255),
                      o2 = (uint32_t)min(max(a2 >> 19, 0), 255), o3 = (uint32_t)min(max(a3 >> 19, 0), 255);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const FusedArgs *__restrict__ 
         a0 += c * (int)(p & 0xFF); a1 += c * (int)((p >> 8) & 0xFF); a2 += c * (int)((p >> 16) & 0xFF); a3 += c * (int)(p >> 24);
       }
       a0 = min(a0 >> 7, 32767); a1 = min(a1 >> 7, 32767); a2 = min(a2 >> 7, 32767); a3 = min(a3 >> 7, 32767);
-      sm.hs[r * kTileW + (xi - ix0)] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2 | ((uint32_t)a3 << 16));
+      sm.hs[r * kTileW + (xi - ix0)] = make_uint2(((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16), ((uint32_t)a2 & 0xFFFFu) | ((uint32_t)a3 << 16))  /* signed 16-bit halves: bicubic / Lanczos lobes go negative */;
     }
     __syncthreads();
     // ---- stage 3: vertical scale, letterbox, alpha-over (+ gamma) and store; one thread = 4 output pixels
@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(kBlock) k_fused(const FusedArgs *__restrict__ 
             const int sy = min(max(vfirst + t2, 0), A.fh - 1) - sr0;
             const int c = A.fy.coef[(long long)iy * A.fy.taps + t2];
             const uint2 hv = sm.hs[sy * kTileW + (ix - ix0)];
-            a0 += c * (int)(hv.x & 0xFFFF); a1 += c * (int)(hv.x >> 16);
-            a2 += c * (int)(hv.y & 0xFFFF); a3 += c * (int)(hv.y >> 16);
+            a0 += c * (int)(short)hv.x; a1 += c * ((int)hv.x >> 16);
+            a2 += c * (int)(short)hv.y; a3 += c * ((int)hv.y >> 16);
           }
           fgp = (uint32_t)sat8(a0 >> 19) | ((uint32_t)sat8(a1 >> 19) << 8) | ((uint32_t)sat8(a2 >> 19) << 16) |
                 ((uint32_t)sat8(a3 >> 19) << 24);
@@ -585,7 +585,7 @@ static cudaError_t launch_resize_tile_impl(const Launch &L, CImg src, int sw, in
     if (e != cudaSuccess) return e;
     attr[psize].cur() = 96 * 1024;
   }
-  if (psize == 4 && fx.taps <= 4 && fy.taps <= 4 && ((((uintptr_t)dst.p | (uintptr_t)src.p) | (uint32_t)dst.rs | (uint32_t)src.rs) & 3) == 0 &&
+  if (psize == 4 && fx.taps <= 4 && fy.taps <= 4 && fx.nonneg && fy.nonneg && ((((uintptr_t)dst.p | (uintptr_t)src.p) | (uint32_t)dst.rs | (uint32_t)src.rs) & 3) == 0 &&
       getenv("PE_RESIZE_GENERIC") == nullptr) {
     // the specialised kernel has its own (slightly larger) shared-memory layout
     const size_t raw4 = (size_t)P.max_rows * ((((size_t)P.max_cols + 10) * 4 + 15) & ~(size_t)15);

@@ -300,34 +300,106 @@ bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out
   return true;
 }
 
-// libswscale's bilinear coefficient recipe (third-party library the reference calls, src/colourspace.c:15059; not in the reference
-// tree, version not pinned by it).  Restated from the published algorithm (libswscale/utils.c initFilter): triangle taps at 2^-30
-// precision, near-zero taps (cumulated weight < 0.002) dropped from either end, taps outside the frame folded onto the edge
-// sample, normalised to 1 << shift_bits with the rounding error carried from tap to tap.  OPT-IN (pe_engine_set_resize_recipe):
-// its banks are checked on the CPU (tests/test_host_logic.py, tests/test_resize_vs_swscale.py); not yet run on a GPU.
-bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out) {
+// libswscale's coefficient recipes (third-party library the reference calls, src/colourspace.c:15059; not in the reference tree,
+// version not pinned by it; flags per LiVESInterpType at :14991-14997).  Restated from the published algorithm (libswscale/utils.c
+// initFilter) and checked against libswscale 9.1.100 (tests/test_resize_vs_swscale.py): tap weights at 2^-30 distance precision --
+// triangle (SWS_BILINEAR), the (B, C) = (0, 0.6) cubic in 24-bit fixed point (SWS_BICUBIC), 3-lobe Lanczos in double (SWS_LANCZOS),
+// or the two-tap bank SWS_FAST_BILINEAR uses vertically --, near-zero taps (cumulated weight < 0.002) dropped from either end, taps
+// outside the frame folded onto the edge sample, normalised to 1 << shift_bits with the rounding error carried from tap to tap.
+namespace {
+
+struct SwsTaps {              // raw 64-bit weights before shrinking
+  int fs = 0;                 // taps per output sample
+  int64_t fone = 0;
+  std::vector<int64_t> w;     // [dst_n * fs]
+  std::vector<int32_t> pos;   // [dst_n]
+};
+
+int64_t sws_weight(SwsKind kind, int64_t d, int64_t fone) {
+  switch (kind) {
+  case SWS_KIND_BICUBIC: {
+    const int64_t B = 0, Cq = (int64_t)(0.6 * (1 << 24)), unit = (int64_t)1 << 30;
+    int64_t c = 0;
+    if (d < 2 * unit) {
+      const int64_t dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+      c = d < unit ? (12 * (1 << 24) - 9 * B - 6 * Cq) * ddd + (-18 * (1 << 24) + 12 * B + 6 * Cq) * dd + (6 * (1 << 24) - 2 * B) * unit
+                   : (-B - 6 * Cq) * ddd + (6 * B + 30 * Cq) * dd + (-12 * B - 48 * Cq) * d + (8 * B + 24 * Cq) * unit;
+    }
+    return c / (((int64_t)1 << 54) / fone);
+  }
+  case SWS_KIND_LANCZOS: {
+    const double fd = (double)d * (1.0 / (1 << 30)), lobes = 3.0;
+    double v = fd == 0.0 ? 1.0 : std::sin(fd * M_PI) * std::sin(fd * M_PI / lobes) / (fd * fd * M_PI * M_PI / lobes);
+    if (fd > lobes) v = 0;
+    return (int64_t)(v * (double)fone);
+  }
+  default: {
+    const int64_t c = ((int64_t)1 << 30) - d;
+    return c < 0 ? 0 : c * (fone >> 30);
+  }
+  }
+}
+
+}  // namespace
+
+bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out, SwsKind kind) {
   if (src_n <= 0 || dst_n <= 0) return false;
   const int64_t xinc = (((int64_t)src_n << 16) + (dst_n >> 1)) / dst_n, one = (int64_t)1 << shift_bits;
-  int fs = xinc <= (1 << 16) ? 3 : 1 + (2 * src_n + dst_n - 1) / dst_n;
-  fs = std::max(std::min(fs, src_n - 2), 1);
-  if (fs > 64) return false;
+  if (kind == SWS_KIND_FAST_H) {
+    // SWS_FAST_BILINEAR's horizontal pass is a 16.16 position walk from the left edge (hyscale_fast): (s[xx] << 7) + (s[xx + 1] -
+    // s[xx]) * xalpha with a 7-bit xalpha -- as 14-bit taps {(128 - xalpha) << 7, xalpha << 7}; the tail holds the last sample
+    out->taps = 2;
+    out->first.assign(dst_n, 0);
+    out->coef.assign((size_t)dst_n * 2, 0);
+    uint32_t xpos = 0;
+    for (int i = 0; i < dst_n; i++, xpos += (uint32_t)xinc) {
+      int xx = (int)(xpos >> 16), xalpha = (int)((xpos & 0xFFFF) >> 9);
+      if (xx >= src_n - 1) { xx = src_n - 2; xalpha = 128; }
+      if (xx < 0) { xx = 0; xalpha = 0; }
+      out->first[i] = xx;
+      out->coef[(size_t)i * 2] = (int16_t)((128 - xalpha) << 7);
+      out->coef[(size_t)i * 2 + 1] = (int16_t)(xalpha << 7);
+    }
+    return true;
+  }
+  SwsTaps T;
   int lg = 0;
   for (int r = src_n / dst_n; r > 1; r >>= 1) lg++;
-  const int64_t fone = (int64_t)1 << (54 - std::min(lg, 8));
-  const double cutoff = 0.002 * (double)fone;
-  std::vector<int64_t> f((size_t)dst_n * fs, 0);
-  std::vector<int32_t> pos(dst_n, 0);
-  int64_t xdst = xinc - 65536;  // both grids sampled at pixel centres
-  for (int i = 0; i < dst_n; i++, xdst += 2 * xinc) {
-    int xx = (int)((xdst - (int64_t)(fs - 2) * 65536) / (1 << 17));  // towards zero
-    pos[i] = xx;
-    for (int j = 0; j < fs; j++, xx++) {
-      int64_t d = std::llabs((int64_t)xx * (1 << 17) - xdst) << 13;
-      if (xinc > (1 << 16)) d = d * dst_n / src_n;
-      const int64_t c = ((int64_t)1 << 30) - d;
-      f[(size_t)i * fs + j] = c < 0 ? 0 : c * (fone >> 30);
+  T.fone = (int64_t)1 << (54 - std::min(lg, 8));
+  T.pos.assign(dst_n, 0);
+  if (kind == SWS_KIND_FAST_V) {  // two taps around a top-left aligned position, whatever the scale factor
+    T.fs = 2;
+    T.w.assign((size_t)dst_n * 2, 0);
+    int64_t at = (xinc >> 1) - 0x8000;
+    for (int i = 0; i < dst_n; i++, at += xinc) {
+      const int xx = (int)(at >> 16);
+      T.pos[i] = xx;
+      for (int j = 0; j < 2; j++) {
+        const int64_t c = T.fone - std::llabs(((int64_t)(xx + j) << 16) - at) * (T.fone >> 16);
+        T.w[(size_t)i * 2 + j] = c < 0 ? 0 : c;
+      }
+    }
+  } else {
+    const int size_factor = kind == SWS_KIND_BICUBIC ? 4 : kind == SWS_KIND_LANCZOS ? 6 : 2;
+    T.fs = xinc <= (1 << 16) ? 1 + size_factor : 1 + (size_factor * src_n + dst_n - 1) / dst_n;
+    T.fs = std::max(std::min(T.fs, src_n - 2), 1);
+    if (T.fs > 64) return false;
+    T.w.assign((size_t)dst_n * T.fs, 0);
+    int64_t at = xinc - 65536;  // both grids sampled at pixel centres
+    for (int i = 0; i < dst_n; i++, at += 2 * xinc) {
+      int xx = (int)((at - (int64_t)(T.fs - 2) * 65536) / (1 << 17));  // towards zero
+      T.pos[i] = xx;
+      for (int j = 0; j < T.fs; j++, xx++) {
+        int64_t d = std::llabs((int64_t)xx * (1 << 17) - at) << 13;
+        if (xinc > (1 << 16)) d = d * dst_n / src_n;
+        T.w[(size_t)i * T.fs + j] = sws_weight(kind, d, T.fone);
+      }
     }
   }
+  const int fs = T.fs;
+  std::vector<int64_t> &f = T.w;
+  std::vector<int32_t> &pos = T.pos;
+  const double cutoff = 0.002 * (double)T.fone;
   int min_fs = 0;
   for (int i = dst_n - 1; i >= 0; i--) {
     int64_t *r = &f[(size_t)i * fs], cut = 0;

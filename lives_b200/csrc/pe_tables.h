@@ -41,9 +41,13 @@ struct ResizeFilter {
   int taps = 0;
   std::vector<int32_t> first;  // [dst_n]
   std::vector<int16_t> coef;   // [dst_n * taps]
+  bool nonneg() const { for (int16_t c : coef) if (c < 0) return false; return true; }
+  int fast_taps() const { return nonneg() ? taps : 1 << 20; }  // what the <= 4-tap kernels may be asked about
 };
 bool build_resize_filter(int src_n, int dst_n, int shift_bits, ResizeFilter *out);
-// libswscale's coefficient recipe for the same two passes (opt-in, pe_engine_set_resize_recipe)
-bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out);
+// libswscale's coefficient recipes for the same two passes (the default, pe_engine_set_resize_recipe): one per flag
+// resize_layer_full passes (src/colourspace.c:14991-14997)
+enum SwsKind { SWS_KIND_BILINEAR = 1, SWS_KIND_BICUBIC = 2, SWS_KIND_LANCZOS = 3, SWS_KIND_FAST_V = 4, SWS_KIND_FAST_H = 5 };
+bool build_resize_filter_sws(int src_n, int dst_n, int shift_bits, ResizeFilter *out, SwsKind kind = SWS_KIND_BILINEAR);
 
 }  // namespace pe

@@ -96,7 +96,7 @@ class Engine:
         return self._lib.pe_sm_count(self._h)
 
     def set_resize_recipe(self, recipe):
-        """0: the published resize contract (default); 1: libswscale's bilinear coefficient recipe (opt-in)"""
+        """1: libswscale's coefficient recipes, one bank per LiVESInterpType (default); 0: the round-1 triangle contract"""
         capi.check(self._lib.pe_engine_set_resize_recipe(self._h, recipe))
 
     def timer_start(self):

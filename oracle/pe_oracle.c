@@ -871,25 +871,77 @@ int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, in
  * with the rounding error carried from tap to tap.  OPT-IN second recipe beside pe_or_resize_filter. */
 static int64_t or_rounded_div(int64_t a, int64_t b) { return a >= 0 ? (a + (b >> 1)) / b : (a - (b >> 1)) / b; }
 
-int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+/* kind: 1 SWS_BILINEAR (LIVES_INTERP_NORMAL), 2 SWS_BICUBIC (BEST, shrinking), 3 SWS_LANCZOS (BEST, growing),
+ * 4 SWS_FAST_BILINEAR as a filter bank (its vertical pass: two taps whatever the scale factor), 5 SWS_FAST_BILINEAR's horizontal pass
+ * (not a bank in libswscale but a 16.16 position walk from the left edge, `(s[xx] << 7) + (s[xx + 1] - s[xx]) * xalpha` with a 7-bit
+ * xalpha: the same numbers as two 14-bit taps) -- the flags resize_layer_full picks, src/colourspace.c:14991-14997 */
+int pe_or_resize_filter_kind(int kind, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
   const int64_t xinc = (((int64_t)src_n << 16) + (dst_n >> 1)) / dst_n, one = (int64_t)1 << shift_bits;
-  int fs = xinc <= (1 << 16) ? 3 : 1 + (2 * src_n + dst_n - 1) / dst_n, lg = 0, min_fs = 0;
+  const int size_factor = kind == 2 ? 4 : kind == 3 ? 6 : 2;
+  int fs = kind == 4 ? 2 : xinc <= (1 << 16) ? 1 + size_factor : 1 + (size_factor * src_n + dst_n - 1) / dst_n, lg = 0, min_fs = 0;
   int64_t *f, fone, xdst;
-  if (fs > src_n - 2) fs = src_n - 2;
-  if (fs < 1) fs = 1;
+  if (kind < 1 || kind > 5 || src_n < 1 || dst_n < 1 || max_taps < 2) return -1;
+  if (kind == 5) { /* the position walk */
+    uint32_t xpos = 0;
+    for (int i = 0; i < dst_n; i++, xpos += (uint32_t)xinc) {
+      int xx = (int)(xpos >> 16), xalpha = (int)((xpos & 0xFFFF) >> 9);
+      if (xx >= src_n - 1) { xx = src_n - 2; xalpha = 128; } /* "dst[i] = src[srcW - 1] * 128" for the tail */
+      if (xx < 0) { xx = 0; xalpha = 0; }                    /* one-sample-wide source */
+      first[i] = xx;
+      coefs[(long)i * max_taps] = (int16_t)((128 - xalpha) << 7);
+      coefs[(long)i * max_taps + 1] = (int16_t)(xalpha << 7);
+      for (int j = 2; j < max_taps; j++) coefs[(long)i * max_taps + j] = 0;
+    }
+    return 2;
+  }
+  if (kind != 4) {
+    if (fs > src_n - 2) fs = src_n - 2;
+    if (fs < 1) fs = 1;
+  }
   if (fs > 64) return -1;
   for (int r = src_n / dst_n; r > 1; r >>= 1) lg++;
   fone = (int64_t)1 << (54 - (lg < 8 ? lg : 8));
   f = (int64_t *)calloc((size_t)dst_n * fs, sizeof(int64_t));
-  xdst = xinc - 65536; /* ((128 * xinc) >> 7) - ((128 * 65536) >> 7): both grids sampled at pixel centres */
-  for (int i = 0; i < dst_n; i++, xdst += 2 * xinc) {
-    int xx = (int)((xdst - (int64_t)(fs - 2) * 65536) / (1 << 17)); /* C division: towards zero */
-    first[i] = xx;
-    for (int j = 0; j < fs; j++, xx++) {
-      int64_t d = llabs((int64_t)xx * (1 << 17) - xdst) << 13, c;
-      if (xinc > (1 << 16)) d = d * dst_n / src_n;
-      c = ((int64_t)1 << 30) - d;
-      f[(long)i * fs + j] = c < 0 ? 0 : c * (fone >> 30);
+  if (kind == 4) {
+    xdst = (xinc >> 1) - 0x8000; /* ((128 * xinc) >> 8) - ((128 * 0x8000) >> 7) */
+    for (int i = 0; i < dst_n; i++, xdst += xinc) {
+      int xx = (int)(xdst >> 16); /* arithmetic shift: floor */
+      first[i] = xx;
+      for (int j = 0; j < 2; j++, xx++) {
+        const int64_t c = fone - llabs(((int64_t)xx << 16) - xdst) * (fone >> 16);
+        f[(long)i * fs + j] = c < 0 ? 0 : c;
+      }
+    }
+  } else {
+    xdst = xinc - 65536; /* ((128 * xinc) >> 7) - ((128 * 65536) >> 7): both grids sampled at pixel centres */
+    for (int i = 0; i < dst_n; i++, xdst += 2 * xinc) {
+      int xx = (int)((xdst - (int64_t)(fs - 2) * 65536) / (1 << 17)); /* C division: towards zero */
+      first[i] = xx;
+      for (int j = 0; j < fs; j++, xx++) {
+        int64_t d = llabs((int64_t)xx * (1 << 17) - xdst) << 13, c;
+        if (xinc > (1 << 16)) d = d * dst_n / src_n;
+        if (kind == 2) { /* Mitchell-Netravali family with libswscale's defaults B = 0, C = 0.6, in 24-bit fixed point */
+          const int64_t B = 0, Cc = (int64_t)(0.6 * (1 << 24));
+          if (d >= (int64_t)1 << 31) c = 0;
+          else {
+            const int64_t dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+            if (d < (int64_t)1 << 30)
+              c = (12 * (1 << 24) - 9 * B - 6 * Cc) * ddd + (-18 * (1 << 24) + 12 * B + 6 * Cc) * dd + (6 * (1 << 24) - 2 * B) * ((int64_t)1 << 30);
+            else
+              c = (-B - 6 * Cc) * ddd + (6 * B + 30 * Cc) * dd + (-12 * B - 48 * Cc) * d + (8 * B + 24 * Cc) * ((int64_t)1 << 30);
+          }
+          c /= ((int64_t)1 << 54) / fone;
+        } else if (kind == 3) { /* Lanczos, 3 lobes, in double */
+          const double fd = (double)d * (1.0 / (1 << 30)), p = 3.0;
+          double v = fd == 0.0 ? 1.0 : sin(fd * M_PI) * sin(fd * M_PI / p) / (fd * fd * M_PI * M_PI / p);
+          if (fd > p) v = 0;
+          c = (int64_t)(v * (double)fone);
+        } else {
+          c = ((int64_t)1 << 30) - d;
+          c = c < 0 ? 0 : c * (fone >> 30);
+        }
+        f[(long)i * fs + j] = c;
+      }
     }
   }
   for (int i = dst_n - 1; i >= 0; i--) { /* shrink: drop near-zero taps on the left (shifting), count them on the right */
@@ -946,19 +998,37 @@ int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first
   return min_fs;
 }
 
-static int or_resize_recipe = 0; /* 0: the published contract (default, what the product ships), 1: the libswscale recipe */
-void pe_or_set_resize_recipe(int recipe) { or_resize_recipe = recipe; }
-static int or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
-  return or_resize_recipe ? pe_or_resize_filter_sws(src_n, dst_n, shift_bits, first, coefs, max_taps)
-                          : pe_or_resize_filter(src_n, dst_n, shift_bits, first, coefs, max_taps);
+int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
+  return pe_or_resize_filter_kind(1, src_n, dst_n, shift_bits, first, coefs, max_taps);
 }
 
+static int or_resize_recipe = 1; /* 1: libswscale's recipes (default, what the product ships), 0: the round-1 triangle contract */
+void pe_or_set_resize_recipe(int recipe) { or_resize_recipe = recipe; }
+/* which bank an axis takes: interp 0 FAST, 1 NORMAL, 2 BEST (LiVESInterpType); `up` = the frame grows in either direction (:14991) */
+static int or_resize_filter(int interp, int up, int horizontal, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs,
+                            int max_taps) {
+  int kind = 1;
+  if (!or_resize_recipe) return pe_or_resize_filter(src_n, dst_n, shift_bits, first, coefs, max_taps);
+  if (interp == 2) kind = up ? 3 : 2;
+  else if (interp == 0) kind = horizontal ? 5 : 4;
+  if (src_n == dst_n) kind = 1; /* an unscaled axis is the identity under every flag */
+  return pe_or_resize_filter_kind(kind, src_n, dst_n, shift_bits, first, coefs, max_taps);
+}
+
+void pe_or_resize_packed_interp(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh, int psize,
+                                int interp);
 void pe_or_resize_packed(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh,
                          int psize) {
+  pe_or_resize_packed_interp(src, irow, sw, sh, dst, orow, dw, dh, psize, 1);
+}
+
+void pe_or_resize_packed_interp(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh, int psize,
+                                int interp) {
   enum { MT = 64 };
+  const int up = dw > sw || dh > sh;
   int32_t *fx = (int32_t *)malloc(sizeof(int32_t) * dw), *fy = (int32_t *)malloc(sizeof(int32_t) * dh);
   int16_t *cx = (int16_t *)malloc(sizeof(int16_t) * MT * dw), *cy = (int16_t *)malloc(sizeof(int16_t) * MT * dh);
-  int tx = or_resize_filter(sw, dw, 14, fx, cx, MT), ty = or_resize_filter(sh, dh, 12, fy, cy, MT);
+  int tx = or_resize_filter(interp, up, 1, sw, dw, 14, fx, cx, MT), ty = or_resize_filter(interp, up, 0, sh, dh, 12, fy, cy, MT);
   int16_t *tmp = (int16_t *)malloc(sizeof(int16_t) * (size_t)sh * dw * psize);
   if (tx > 0 && ty > 0) {
     for (int y = 0; y < sh; y++) {

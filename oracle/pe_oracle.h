@@ -103,6 +103,11 @@ int pe_or_resize_filter(int src_n, int dst_n, int shift_bits, int32_t *first, in
  * it; 0 = the published contract the product ships, the default) */
 int pe_or_resize_filter_sws(int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
 void pe_or_set_resize_recipe(int recipe);
+/* libswscale's recipe per flag (kind 1 bilinear, 2 bicubic, 3 Lanczos, 4 / 5 fast bilinear vertical / horizontal) and the resize with
+ * a LiVESInterpType (0 FAST, 1 NORMAL, 2 BEST: flags of src/colourspace.c:14991-14997) */
+int pe_or_resize_filter_kind(int kind, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
+void pe_or_resize_packed_interp(const uint8_t *src, int irow, int sw, int sh, uint8_t *dst, int orow, int dw, int dh, int psize,
+                                int interp);
 /* letterbox_layer colourspace.c:15343: centre an inner packed frame in a black outer one */
 void pe_or_letterbox_packed(const uint8_t *inner, int irow, int iw, int ih, uint8_t *outer, int orow, int ow, int oh,
                             int palette);

@@ -66,3 +66,30 @@ def scale(planes, src_fmt, w, h, dst_fmt, dw, dh, dst_rowbytes, flags=SWS_BILINE
     sw.sws_freeContext(ctx)
     assert rows == dh, rows
     return dst
+
+
+class Scaler:
+    """a cached SwsContext (the reference keeps its contexts too: sws_getCachedContext, colourspace.c:15059) for repeated calls on
+    frames of one geometry -- what bench.py's CPU arm times"""
+
+    def __init__(self, src_fmt, w, h, dst_fmt, dw, dh, flags=SWS_BILINEAR, yuv=None):
+        sw, _ = load()
+        self.sw, self.h, self.dh = sw, h, dh
+        self.ctx = sw.sws_getContext(w, h, PIX_FMT[src_fmt], dw, dh, PIX_FMT[dst_fmt], flags, None, None, None)
+        assert self.ctx, "sws_getContext failed"
+        if yuv is not None:
+            co = sw.sws_getCoefficients(SWS_CS_ITU709 if yuv[0] else SWS_CS_ITU601)
+            sw.sws_setColorspaceDetails(self.ctx, co, int(yuv[1]), co, int(yuv[2]), 0, 65536, 65536)
+
+    def run(self, planes, dst):
+        sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [0] * (4 - len(planes))))
+        ss = (C.c_int * 4)(*([p.strides[0] for p in planes] + [0] * (4 - len(planes))))
+        dp = (C.c_void_p * 4)(dst.ctypes.data, 0, 0, 0)
+        ds = (C.c_int * 4)(dst.strides[0], 0, 0, 0)
+        rows = self.sw.sws_scale(self.ctx, sp, ss, 0, self.h, dp, ds)
+        assert rows == self.dh, rows
+
+    def close(self):
+        if self.ctx:
+            self.sw.sws_freeContext(self.ctx)
+            self.ctx = None

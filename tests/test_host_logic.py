@@ -197,24 +197,40 @@ def test_slide_over_realigning_loads():
 
 
 def test_resize_coefficient_banks_of_the_shipped_library():
-    """pe_resize_filter_host (the bank libpe_b200.so builds on the host; no GPU involved) == the oracle's, for the published
-    contract (recipe 0, the default) and for libswscale's coefficient recipe (recipe 1, opt-in), over the BASELINE geometries, odd
-    sizes, extreme ratios; every bank sums to 1 << bits per output sample and keeps its taps inside the frame (recipe 1)"""
+    """pe_resize_filter_host (the bank libpe_b200.so builds on the host; no GPU involved) == the oracle's, for the round-1 triangle
+    contract (0) and for each of libswscale's recipes (1 bilinear -- the default --, 2 bicubic, 3 Lanczos, 4 / 5 fast bilinear vertical
+    / horizontal), over the BASELINE geometries, odd sizes, extreme ratios; every bank sums to 1 << bits per output sample and the
+    libswscale banks keep their taps inside the frame with monotonic positions"""
     import ctypes as C
     import lives_b200  # noqa: F401
     import pe_testlib as T
     from lives_b200 import _capi
     lib, o = _capi.lib(), T.oracle()
     geoms = [(1080, 720), (1920, 1280), (2160, 1608), (3840, 3840), (720, 1080), (640, 320), (300, 75), (37, 37), (5, 3), (3, 7),
-             (4, 4), (1000, 33), (61, 64), (64, 61), (1081, 719), (2, 2)]
-    for recipe, oracle_fn in ((0, o.pe_or_resize_filter), (1, o.pe_or_resize_filter_sws)):
+             (4, 4), (1000, 33), (61, 64), (64, 61), (1081, 719), (2, 2), (360, 720), (240, 300)]
+    o.pe_or_resize_filter_kind.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    for recipe in range(6):
         for (s, d), bits in [(g, b) for g in geoms for b in (12, 14)]:
             fa, ca = np.zeros(d, np.int32), np.zeros((d, 64), np.int16)
             fb, cb = np.zeros(d, np.int32), np.zeros((d, 64), np.int16)
-            ta = oracle_fn(s, d, bits, T.ptr(fa), T.ptr(ca), 64)
+            if recipe == 0:
+                ta = o.pe_or_resize_filter(s, d, bits, T.ptr(fa), T.ptr(ca), 64)
+            else:
+                ta = o.pe_or_resize_filter_kind(recipe, s, d, bits, fa.ctypes.data, ca.ctypes.data, 64)
             tb = lib.pe_resize_filter_host(recipe, s, d, bits, C.c_void_p(fb.ctypes.data), C.c_void_p(cb.ctypes.data), 64)
+            if recipe == 5 and bits != 14:
+                continue  # the position walk only exists as the (14-bit) horizontal pass
+            if ta == -1 and tb == -1 and recipe in (2, 3) and s > 15 * d:
+                continue  # more than 64 taps: both refuse (the engine fails the call loudly)
             assert ta == tb and ta > 0, (recipe, s, d, bits, ta, tb)
             assert (fa == fb).all() and (ca == cb).all(), (recipe, s, d, bits)
             assert (cb.astype(np.int64).sum(axis=1) == (1 << bits)).all(), (recipe, s, d, bits)
-            if recipe == 1:
-                assert fb.min() >= 0 and (fb + tb).max() <= max(s, tb) and (np.diff(fb) >= 0).all()
+            if recipe >= 1:
+                assert fb.min() >= 0 and (fb + tb).max() <= max(s, tb) and (np.diff(fb) >= 0).all(), (recipe, s, d)
+            if recipe in (2, 3) and s > 8 and d > 8 and s != d:
+                assert cb.min() < 0, "bicubic / Lanczos banks have negative lobes"
+    # the default recipe is libswscale's bilinear
+    fa, ca = np.zeros(720, np.int32), np.zeros((720, 64), np.int16)
+    fb, cb = np.zeros(720, np.int32), np.zeros((720, 64), np.int16)
+    assert o.pe_or_resize_filter_sws(1080, 720, 12, T.ptr(fa), T.ptr(ca), 64) == o.pe_or_resize_filter_kind(1, 1080, 720, 12, fb.ctypes.data, cb.ctypes.data, 64)
+    assert (fa == fb).all() and (ca == cb).all()
