@@ -42,6 +42,12 @@ ALGO_BYTES_PER_FRAME = FG_BYTES + 2 * RGBA_BYTES    # 78 796 800 (SURVEY.md 8d r
 WORKLOAD = "headline: 3840x2160 YUV420P fg -> RGBA32 + letterbox(3840x1608 in 3840x2160, bilinear) + alpha-over(0.5) RGBA32 bg + gamma LUT8, fused"
 
 
+def config_dict(batch):
+    """the same dict on both arms (the driver compares them): the CPU arm's own step size is in its cpu_baseline.sample"""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": batch, "parallelism": "frames sharded, no collective",
+            "l2": "inputs larger than L2: %.0f MB touched per step vs 126 MB L2" % (ALGO_BYTES_PER_FRAME * batch / 1e6)}
+
+
 def measured_peak():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -275,30 +281,44 @@ def host_cores():
 
 # ------------------------------------------------------------------------------------------------ arms
 
+def cpu_single_thread(chain):
+    """nfx_threads = 1: one frame at a time on one host thread, per-stage wall clock (median of 3 frames after one warm-up)"""
+    fr = host_frames(2)
+    out = np.zeros((FH, FW * 4), np.uint8)
+    runs = []
+    for i in range(4):
+        y, u, v, bg = fr[i % 2]
+        runs.append(chain.stage_times(y, u, v, bg, out))
+    stages = {k: float(np.median([r[k] for r in runs[1:]])) * 1e3 for k in runs[0]}
+    total = sum(stages.values())
+    return {"fps": 1000.0 / total, "ms_per_frame": total, "stage_ms": stages}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = host_cores()
-    n_frames = cores  # one frame per host thread and step: about one chain latency (~1 s) per step
-    cb = CpuBench(n_frames, cores)
-    kind = cb.chain.kind
+    n_frames = cores  # one frame per host thread and step
+    cb = CpuBench(n_frames, cores, args.cpu_stages)
+    chain = cb.chain
     fps_steps = []
     for s in range(args.warmup + args.steps):
         dt = cb.step()
         if s >= args.warmup:
             fps_steps.append((n_frames / dt, dt))
+    single = cpu_single_thread(chain)
     cb.close()
     total_frames = n_frames * len(fps_steps)
     total_t = sum(dt for _, dt in fps_steps)
     value = total_frames / total_t
-    sample = ("%d frames/step of the headline workload over %d host threads (one frame per thread); convert / alpha-over / gamma = "
-              "compiled reference loops, resize + letterbox = oracle port (libswscale absent)" % (n_frames, cores)) if kind == "reference" \
-        else "%d frames/step over %d host threads, oracle port for every stage" % (n_frames, cores)
+    sample = "%d frames/step of the headline workload over %d host threads (one frame per thread); %s" % (n_frames, cores, chain.describe())
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * total_t / max(len(fps_steps), 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": n_frames},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": config_dict(args.batch),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": chain.kind, "sample": sample,
+                             "stages": chain.stages, "libswscale": chain.sws_version,
+                             "nfx_threads_1": single, "nfx_threads_nproc": {"fps": value, "threads": cores}},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -432,23 +452,23 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        cb = CpuBench(cores, cores)
-        kind, n, dt = cb.chain.kind, 0, 0.0
+        cb = CpuBench(cores, cores, args.cpu_stages)
+        chain, n, dt = cb.chain, 0, 0.0
         while dt < 10.0 and n < 64 * cores:  # bounded sample: >= 10 s of wall clock over all host threads
             dt += cb.step()
             n += cores
+        single = cpu_single_thread(chain)
         cb.close()
         fps = n / dt
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": "%d frames of the same workload over %d host threads in %.1f s; convert / alpha-over / gamma = compiled "
-                         "reference loops, resize + letterbox = oracle port (libswscale absent)" % (n, cores, dt)}
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": chain.kind, "stages": chain.stages, "libswscale": chain.sws_version,
+               "sample": "%d frames of the same workload over %d host threads in %.1f s; %s" % (n, cores, dt, chain.describe()),
+               "nfx_threads_1": single, "nfx_threads_nproc": {"fps": fps, "threads": cores}}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": "frames sharded, no collective",
-                           "l2": "inputs larger than L2: %.0f MB touched per step vs 126 MB L2" % (ALGO_BYTES_PER_FRAME * B / 1e6)},
+                "config": config_dict(B),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "k_fused3", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "single_frame_launch_us": single_frame_us},
@@ -598,6 +618,9 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=48, help="host frames per e2e step (one batch call)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-stages", default="auto", choices=["auto", "sws", "loops"],
+                    help="CPU arm: sws = convert + resize as the ONE sws_scale call the reference issues (needs a loadable libswscale; auto picks "
+                         "it when there is one), loops = the reference's own converter loop + the oracle's resize")
     ap.add_argument("--workload", default="headline", help="headline (the driver's line) | cfg1 | cfg2 | cfg3 | cfg4 | cfg5: kernel-level "
                     "numbers of the other BASELINE configs, N = 1 only")
     args = ap.parse_args()
