@@ -72,7 +72,11 @@ constexpr int S3_RING = 131072;           // per warp: F3_RING bg rows of 512 by
 #endif
 constexpr int F3_RING = PE_F3_RING;      // power of two
 constexpr int S3_BYTES = S3_RING + F3_NW * F3_RING * 512;   // + 16 bytes per inner output row (filter rows)
-constexpr int F3_MAX_IH = 3200;
+constexpr int F3_SMEM_MAX = 227 * 1024;   // opt-in limit of dynamic shared memory per CTA on sm_100
+constexpr int F3_MAX_IH = (F3_SMEM_MAX - S3_BYTES - 8 * F3_NW * F3_RING) / 16 < 3200 ? (F3_SMEM_MAX - S3_BYTES - 8 * F3_NW * F3_RING) / 16 : 3200;
+#ifndef PE_F3_TMA_DEFAULT
+#define PE_F3_TMA_DEFAULT 0
+#endif
 
 struct Fused3Frame {
   const uint8_t *y, *u, *v, *bg;
@@ -129,6 +133,28 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: the PE_F3_TMA variant of the bg ring
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PE_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PE_MBAR_DONE;\n"
+      "bra PE_MBAR_WAIT;\n"
+      "PE_MBAR_DONE:\n"
+      "}" :: "r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
@@ -283,7 +309,9 @@ __device__ __noinline__ SlowRows slow_rows(const uint8_t *smem, const uint8_t *p
 
 // C16: the filter coefficients arrive scaled by 16 (sum 65536; only banks without a 4096 tap): the filtered value is byte 2 of
 // the accumulator (byte 3 is zero), so R | B pack with one PRMT and two of the three shifts per pixel disappear
-template <bool QUIRKS, bool HAS_LUT, bool C16>
+// TMA: the bg ring is filled by ONE elected lane per row with a 512-byte cp.async.bulk (UBLKCP) that completes on the slot's
+// mbarrier, instead of 32 per-lane 16-byte cp.async (LDGSTS) + commit / wait groups (full-width strips only: ow % 128 == 0, ox == 0)
+template <bool QUIRKS, bool HAS_LUT, bool C16, bool TMA>
 __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -291,6 +319,25 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 
   // ---- replicated tables
   {
+#ifdef PE_F3_INTERLEAVE
+    // 16 consecutive lanes write the 16 x 16-byte chunks of one 256-byte {LUT | RGB_Y} entry, 8 lanes the chunks of a 128-byte
+    // chroma entry: a warp's 128-bit store covers 512 contiguous bytes = 4 wavefronts, the minimum.  (A thread per entry writing
+    // its 128 bytes alone is a 32-way bank conflict per store: 4.4 us per launch, profiles/r02c_k_fused3_single_frame_ncu.txt.)
+    for (int i = tid; i < 256 * 16; i += F3_NT) {
+      const int m = i >> 4, j = i & 15;
+      uint32_t e;
+      if (j < 8) e = HAS_LUT ? ((uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u) : 0u;
+      else e = (uint32_t)P.conv[9 * 256 + m];
+      reinterpret_cast<uint4 *>(smem + S3_LUT + 256 * m)[j] = make_uint4(e, e, e, e);
+    }
+    for (int i = tid; i < 256 * 8; i += F3_NT) {
+      const int m = i >> 3, j = i & 7;
+      const uint32_t rcr = (uint32_t)P.conv[10 * 256 + m], gcb = (uint32_t)P.conv[11 * 256 + m], gcr = (uint32_t)P.conv[12 * 256 + m],
+                     bcb = (uint32_t)P.conv[13 * 256 + m];
+      reinterpret_cast<uint4 *>(smem + S3_TV + 128 * m)[j] = make_uint4(rcr, gcr, rcr, gcr);
+      reinterpret_cast<uint4 *>(smem + S3_TU + 128 * m)[j] = make_uint4(gcb, bcb, gcb, bcb);
+    }
+#else
     uint32_t *tl = reinterpret_cast<uint32_t *>(smem + S3_LUT);
     fill_replicated_yuv_tables(smem + S3_TY, smem + S3_TV, smem + S3_TU, P.conv, tid, F3_NT, S3_TYSTRIDE);
     if (HAS_LUT)
@@ -299,8 +346,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 #pragma unroll
         for (int j = 0; j < 8; j++) reinterpret_cast<uint4 *>(tl + (S3_TYSTRIDE / 4) * m)[j] = make_uint4(e, e, e, e);
       }
+#endif
     int4 *sr = reinterpret_cast<int4 *>(smem + S3_BYTES);
     for (int i = tid; i < P.ih; i += F3_NT) sr[i] = P.rows4[i];
+    if (TMA) {  // one mbarrier per (warp, ring slot), behind the filter rows
+      if (tid < F3_NW * F3_RING) mbar_init(sbase + S3_BYTES + 16u * (uint32_t)P.ih + 8u * (uint32_t)tid, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
   }
   const int4 *s_rows = reinterpret_cast<const int4 *>(smem + S3_BYTES);  // per inner output row: first, c3 | c2 << 16, c1 | c0 << 16
   __syncthreads();  // the only barrier of the kernel
@@ -388,6 +441,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   // static part: [0, static_cost) in equal shares; the rest is handed out in small chunks as warps run dry (P.sched: the
   // chunk counter and the count of finished warps; the last warp to finish zeroes both for the next launch)
   const long long gw = (long long)blockIdx.x * F3_NW + warp, nwarps = (long long)gridDim.x * F3_NW;
+  uint32_t bg_push_seq = 0u, bg_pop_seq = 0u;  // TMA variant: rows pushed into / popped from the warp's bg ring so far
   long long pos = P.static_cost * gw / nwarps;
   long long pos_end = P.static_cost * (gw + 1) / nwarps;
 
@@ -395,17 +449,25 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   while (pos < pos_end) {
     // ---- locate the unit (frame, band, strip) that holds `pos` and the rows of it that belong to this warp
     const int f = (int)(pos / P.frame_cost);
-    long long rem = pos - (long long)f * P.frame_cost;
-    int b = 0, bc = 0, base = 0;
-    for (;; b++) {
+    int rem = (int)(pos - (long long)f * P.frame_cost);  // (a frame's cost fits 31 bits: checked by the launcher)
+    // the band that holds `rem`, without walking the bands (a single-frame launch has ~80 of them per frame and every warp looked its
+    // two or three units up by linear search: a quarter of that launch's instructions): cost_upto is strictly increasing, so the row
+    // rq with cost_upto(rq) <= rem / nstrips < cost_upto(rq + 1) lies in the band
+    int base, bc;
+    {
+      const int q = rem / nstrips;
+      int rq;
+      if (q < cb * oy) rq = q / cb;
+      else if (q < cb * oy + ci * ih) rq = oy + (q - cb * oy) / ci;
+      else rq = oy + ih + (q - cb * oy - ci * ih) / cb;
+      const int b = rq / Hb;
       const int r0 = b * Hb, r1 = min(oh, r0 + Hb);
       base = cost_upto(r0);
       bc = cost_upto(r1) - base;
-      if (rem < (long long)bc * nstrips) break;
-      rem -= (long long)bc * nstrips;
+      rem -= base * nstrips;
     }
-    const int s = (int)(rem / bc);
-    const int within = (int)(rem - (long long)s * bc);
+    const int s = rem / bc;
+    const int within = rem - s * bc;
     const long long unit0 = pos - within;
     const int hi = (int)min((long long)bc, pos_end - unit0);
     const int ra = row_at(base + within), rb = row_at(base + hi);
@@ -503,11 +565,30 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       }
       // bg rows travel through the warp's cp.async ring, F3_RING - 1 rows ahead of the emit: no registers are tied up and the
       // emit never waits on a load it has just issued.  A lane only ever reads the 16 bytes it copied itself.
-      const uint32_t ring = sbase + S3_RING + (uint32_t)warp * (F3_RING * 512) + 16u * (uint32_t)lane;
+      const uint32_t ring_w = sbase + S3_RING + (uint32_t)warp * (F3_RING * 512);
+      const uint32_t ring = ring_w + 16u * (uint32_t)lane;
+      // TMA variant: rows enter the ring in the order they are emitted; bg_seq counts the rows this warp has pushed / popped since the
+      // kernel started (slot = seq % F3_RING, the slot's mbarrier phase = seq / F3_RING); every pushed row is popped before the
+      // segment ends
+      const uint32_t mbar_w = sbase + S3_BYTES + 16u * (uint32_t)ih + 8u * (uint32_t)(warp * F3_RING);
+      const uint8_t *bg_strip = F.bg + 512u * (size_t)s + (size_t)rs_bg * (uint32_t)oy;   // row 0 of the inner rectangle, this strip
+      auto bg_push = [&](int row) {   // all lanes call it; lane 0 issues
+        if (lane == 0) {
+          const uint32_t slot = bg_push_seq & (F3_RING - 1);
+          mbar_expect_tx(mbar_w + 8u * slot, 512u);
+          bulk_g2s(ring_w + 512u * slot, bg_strip + (size_t)rs_bg * (uint32_t)row, 512u, mbar_w + 8u * slot);
+        }
+        bg_push_seq++;
+      };
+      if (TMA) {
+        __syncwarp();
+        for (int j = 0; j < F3_RING - 1 && iy + j < ib; j++) bg_push(iy + j);
+      } else {
 #pragma unroll
-      for (int j = 0; j < F3_RING - 1; j++) {
-        cp_async16(ring + (uint32_t)((iy + j) & (F3_RING - 1)) * 512u, bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + j, ib - 1)));
-        cp_async_commit();
+        for (int j = 0; j < F3_RING - 1; j++) {
+          cp_async16(ring + (uint32_t)((iy + j) & (F3_RING - 1)) * 512u, bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + j, ib - 1)));
+          cp_async_commit();
+        }
       }
 
       auto step = [&](int k, uint32_t(&Wc)[12], const uint32_t(&Wp)[12]) {
@@ -584,11 +665,21 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           const int j0 = 2 * k - ri.x - 3;  // 0: the window is Wc; 1: one row older
           const uint32_t CA = (uint32_t)ri.y, CB = (uint32_t)ri.z;
           const int iyn = min(iy + 1, ib - 1);
-          cp_async16(ring + (uint32_t)((iy + F3_RING - 1) & (F3_RING - 1)) * 512u,
-                     bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_RING - 1, ib - 1)));
-          cp_async_commit();
-          cp_async_wait<F3_RING - 1>();  // all but the newest F3_RING - 1 groups have landed: row iy is in its slot
-          const uint4 bgw = lds128(ring + (uint32_t)(iy & (F3_RING - 1)) * 512u);
+          uint4 bgw;
+          if (TMA) {
+            __syncwarp();  // every lane has read the slot that is refilled now (row iy - 1's)
+            if (iy + F3_RING - 1 < ib) bg_push(iy + F3_RING - 1);
+            const uint32_t slot = bg_pop_seq & (F3_RING - 1);
+            mbar_wait(mbar_w + 8u * slot, (bg_pop_seq / F3_RING) & 1u);
+            bgw = lds128(ring + 512u * slot);
+            bg_pop_seq++;
+          } else {
+            cp_async16(ring + (uint32_t)((iy + F3_RING - 1) & (F3_RING - 1)) * 512u,
+                       bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_RING - 1, ib - 1)));
+            cp_async_commit();
+            cp_async_wait<F3_RING - 1>();  // all but the newest F3_RING - 1 groups have landed: row iy is in its slot
+            bgw = lds128(ring + (uint32_t)(iy & (F3_RING - 1)) * 512u);
+          }
           const int4 rin = s_rows[iyn];
           const uint32_t bgv[4] = {bgw.x, bgw.y, bgw.z, bgw.w};
           uint32_t ov[4];
@@ -636,7 +727,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         if (iy >= ib) break;
         k++;
       }
-      cp_async_wait<0>();  // the ring is reused by the warp's next segment
+      if (!TMA) cp_async_wait<0>();  // the ring is reused by the warp's next segment
     }
     border_rows(max(ra, oy + ih), rb);
   }
@@ -700,12 +791,16 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
   static PerDevice attr_set;
   if (!attr_set.cur()) {
     cudaError_t e;
-    const int mx = S3_BYTES + 16 * F3_MAX_IH;
-    const void *fns[8] = {(const void *)k_fused3<true, true, true>,   (const void *)k_fused3<true, true, false>,
-                          (const void *)k_fused3<true, false, true>,  (const void *)k_fused3<true, false, false>,
-                          (const void *)k_fused3<false, true, true>,  (const void *)k_fused3<false, true, false>,
-                          (const void *)k_fused3<false, false, true>, (const void *)k_fused3<false, false, false>};
-    for (int i = 0; i < 8; i++)
+    const int mx = S3_BYTES + 16 * F3_MAX_IH + 8 * F3_NW * F3_RING;
+    const void *fns[16] = {(const void *)k_fused3<true, true, true, false>,   (const void *)k_fused3<true, true, false, false>,
+                           (const void *)k_fused3<true, false, true, false>,  (const void *)k_fused3<true, false, false, false>,
+                           (const void *)k_fused3<false, true, true, false>,  (const void *)k_fused3<false, true, false, false>,
+                           (const void *)k_fused3<false, false, true, false>, (const void *)k_fused3<false, false, false, false>,
+                           (const void *)k_fused3<true, true, true, true>,    (const void *)k_fused3<true, true, false, true>,
+                           (const void *)k_fused3<true, false, true, true>,   (const void *)k_fused3<true, false, false, true>,
+                           (const void *)k_fused3<false, true, true, true>,   (const void *)k_fused3<false, true, false, true>,
+                           (const void *)k_fused3<false, false, true, true>,  (const void *)k_fused3<false, false, false, true>};
+    for (int i = 0; i < 16; i++)
       if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
     attr_set.cur() = 1;
   }
@@ -759,9 +854,16 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     P.rows4 = reinterpret_cast<const int4 *>(rows4_dev);
     P.conv = a0.conv.t;
     P.lut8 = lut8_dev;
-    const int smem_bytes = S3_BYTES + 16 * a0.ih;
+    if (P.frame_cost >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+    const int smem_bytes = S3_BYTES + 16 * a0.ih + 8 * F3_NW * F3_RING;
+    // the TMA variant of the bg ring takes whole 128-column strips of rows that start 16-byte aligned (PE_F3_TMA=0 / 1 overrides the
+    // default, which is what measured faster: profiles/r02_k_fused3_tma_vs_ldgsts.txt)
+    static int tma_pref = -1;
+    if (tma_pref < 0) tma_pref = getenv("PE_F3_TMA") ? atoi(getenv("PE_F3_TMA")) != 0 : PE_F3_TMA_DEFAULT;
+    const bool tma = tma_pref && a0.ox == 0 && a0.ow == a0.fw && (a0.ow & 127) == 0;
     auto go = [&](auto q, auto l, auto c) {
-      k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      if (tma) k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      else k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
     };
     auto pick_c = [&](auto q, auto l) { if (coef16) go(q, l, std::true_type()); else go(q, l, std::false_type()); };
     auto pick_l = [&](auto q) { if (lut8_dev) pick_c(q, std::true_type()); else pick_c(q, std::false_type()); };
