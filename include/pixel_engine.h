@@ -114,6 +114,15 @@ int pe_sm_count(pe_engine_t *e);
 int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe);
 int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
 
+/* one engine per process and GPU, shared by the weed_layer_t drop-ins (libpe_weed_layer.so) and the effect plugin
+ * (libpe_weed_plugin.so): created on first use with the configuration given to pe_engine_shared_configure (default:
+ * pe_config_default, device = $PE_DEVICE or 0); NULL + pe_last_error when no CUDA device is usable */
+int pe_engine_shared_configure(const pe_config_t *cfg);
+pe_engine_t *pe_engine_shared(void);
+/* the host's prefs as they change at run time (prefs->pb_quality, screen_gamma, apply_gamma, alpha_post; src/preferences.h) */
+int pe_engine_set_prefs(pe_engine_t *e, int pb_quality, double screen_gamma, int apply_gamma, int alpha_post);
+int pe_engine_get_config(pe_engine_t *e, pe_config_t *out);
+
 /* ---- frames (create_empty_pixel_data colourspace.c:11434, weed_layer_* src/layers.c) ------- */
 
 /* plane geometry for a palette: fills nplanes / rowstrides / plane heights; returns total bytes when the
@@ -138,6 +147,9 @@ int pe_frame_copy(pe_engine_t *e, const pe_frame_t *src, pe_frame_t **out);
 /* pinned host buffers for callers without their own allocator */
 void *pe_host_alloc(size_t bytes);
 void pe_host_free(void *p);
+/* page-lock caller-owned host memory in place (LiVES recycles its big pixel buffers, src/memory.c:37-47: register once) */
+int pe_host_register(void *p, size_t bytes);
+int pe_host_unregister(void *p);
 
 /* ---- boundary B2: frame ops (same argument meaning as the reference functions) -------------- */
 

@@ -59,6 +59,12 @@ PROTOTYPES = {
     "pe_engine_stream": (VP, [VP]),
     "pe_last_error": (C.c_char_p, []),
     "pe_engine_launch_count": (L, [VP]),
+    "pe_engine_shared_configure": (I, [C.c_void_p]),
+    "pe_engine_shared": (VP, []),
+    "pe_engine_set_prefs": (I, [VP, I, C.c_double, I, I]),
+    "pe_engine_get_config": (I, [VP, C.c_void_p]),
+    "pe_host_register": (I, [VP, SZ]),
+    "pe_host_unregister": (I, [VP]),
     "pe_timer_start": (I, [VP]),
     "pe_timer_stop_ms": (I, [VP, C.POINTER(C.c_float)]),
     "pe_sm_count": (I, [VP]),

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpe_b200.so")
 PLUGIN = os.path.join(HERE, "libpe_weed_plugin.so")
+LAYERLIB = os.path.join(HERE, "libpe_weed_layer.so")
 
 SOURCES = ["pe_engine.cu", "pe_kernels_rgb.cu", "pe_kernels_yuv.cu", "pe_kernels_yuv2.cu", "pe_kernels_yuv3.cu", "pe_kernels_fused.cu", "pe_kernels_fused2.cu", "pe_kernels_fused3.cu", "pe_tables.cpp"]
 OBJ = os.path.join(HERE, "build")
@@ -69,6 +70,13 @@ def build(force=False, verbose=False):
     if os.path.exists(plugin_src) and (force or _stale(PLUGIN, [plugin_src, LIB] + deps)):
         cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-I", os.path.join(HERE, "..", "include"),
                "-o", PLUGIN, plugin_src, "-L", HERE, "-lpe_b200", "-Wl,-rpath,$ORIGIN", "-ldl"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, cwd=CSRC)
+    layer_src = os.path.join(CSRC, "pe_weed_layer.c")
+    if os.path.exists(layer_src) and (force or _stale(LAYERLIB, [layer_src, LIB] + deps)):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-I", os.path.join(HERE, "..", "include"),
+               "-o", LAYERLIB, layer_src, "-L", HERE, "-lpe_b200", "-Wl,-rpath,$ORIGIN", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd, cwd=CSRC)

@@ -791,6 +791,79 @@ extern "C" int pe_frame_copy(pe_engine_t *e, const pe_frame_t *src, pe_frame_t *
   return PE_OK;
 }
 
+// ---- process-wide engine + host prefs + host-buffer registration (what the weed_layer_t drop-ins and the effect plugin share) ----
+
+namespace {
+std::mutex g_shared_mu;
+pe_engine_t *g_shared = nullptr;
+pe_config_t g_shared_cfg;
+bool g_shared_cfg_set = false;
+}  // namespace
+
+// the configuration the shared engine is created with on first use (device, prefs); PE_DEVICE in the environment picks the GPU when
+// the host never calls this (a plugin has no other channel)
+extern "C" int pe_engine_shared_configure(const pe_config_t *cfg) {
+  std::lock_guard<std::mutex> lk(g_shared_mu);
+  if (g_shared) return set_err(PE_ERR_ARG, "the shared engine already exists: use pe_engine_set_prefs");
+  if (!cfg) return set_err(PE_ERR_ARG, "NULL config");
+  g_shared_cfg = *cfg;
+  g_shared_cfg_set = true;
+  return PE_OK;
+}
+
+extern "C" pe_engine_t *pe_engine_shared(void) {
+  std::lock_guard<std::mutex> lk(g_shared_mu);
+  if (!g_shared) {
+    if (!g_shared_cfg_set) {
+      pe_config_default(&g_shared_cfg);
+      if (const char *d = getenv("PE_DEVICE")) g_shared_cfg.device = atoi(d);
+    }
+    if (pe_engine_create(&g_shared_cfg, &g_shared) != PE_OK) g_shared = nullptr;  // reason in pe_last_error()
+  }
+  return g_shared;
+}
+
+// prefs->pb_quality / screen_gamma / apply_gamma / alpha_post of the host (src/preferences.h) as they change at run time.  The gamma
+// LUT caches depend on screen_gamma (colourspace.c:677): they are dropped when it changes.
+extern "C" int pe_engine_set_prefs(pe_engine_t *e, int pb_quality, double screen_gamma, int apply_gamma, int alpha_post) {
+  if (!e) return set_err(PE_ERR_ARG, "engine is NULL");
+  if (pb_quality < PE_QUALITY_LOW || pb_quality > PE_QUALITY_HIGH) return set_err(PE_ERR_ARG, "pb_quality %d out of range", pb_quality);
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  if (screen_gamma != e->cfg.screen_gamma) {
+    PE_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto &kv : e->lut8) cudaFree(kv.second.dev);
+    for (auto &kv : e->lut16) cudaFree(kv.second);
+    for (auto &kv : e->over) cudaFree(kv.second.dev);  // keyed by LUT pointers
+    e->lut8.clear(); e->lut16.clear(); e->over.clear();
+  }
+  e->cfg.pb_quality = pb_quality; e->cfg.screen_gamma = screen_gamma; e->cfg.apply_gamma = apply_gamma; e->cfg.alpha_post = alpha_post;
+  return PE_OK;
+}
+
+extern "C" int pe_engine_get_config(pe_engine_t *e, pe_config_t *out) {
+  if (!e || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = e->cfg;
+  return PE_OK;
+}
+
+// page-lock caller-owned host memory in place (cudaHostRegister): LiVES recycles a fixed set of big pixel buffers (bigblocks,
+// src/memory.c:37-47), so a buffer registered once serves every later frame at pinned-copy speed.  Idempotent per range.
+extern "C" int pe_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return set_err(PE_ERR_ARG, "NULL / empty range");
+  cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (ce == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return PE_OK; }
+  if (ce != cudaSuccess) { cudaGetLastError(); return set_err(PE_ERR_CUDA, "cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(ce)); }
+  return PE_OK;
+}
+extern "C" int pe_host_unregister(void *p) {
+  if (!p) return PE_OK;
+  cudaError_t ce = cudaHostUnregister(p);
+  if (ce != cudaSuccess) { cudaGetLastError(); return set_err(PE_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(ce)); }
+  return PE_OK;
+}
+
 extern "C" void *pe_host_alloc(size_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }

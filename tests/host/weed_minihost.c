@@ -193,3 +193,65 @@ int mh_run2v(int h, int fidx, int palette, int width, int height, void *src1, in
   free(ictm); free(octm); free(iptm);
   return (int)err;
 }
+
+/* ---- layers: a weed_layer_t built the way src/layers.c builds one (WEED_PLANT_LAYER = 128, src/layers.h:14; leaves of
+ *      libweed/weed-effects.h:269-277,350-375), for the weed_layer_t drop-ins of lives_b200/libpe_weed_layer.so.  Pixel planes are
+ *      COPIED into malloc'ed (64-byte aligned) buffers the layer then owns: the drop-ins release / replace them with free(). */
+#define MH_PLANT_LAYER 128
+
+void *mh_layer_new(int palette, int width_macropixels, int height, int nplanes, void **planes, int *rowstrides, int *plane_rows,
+                   int clamping, int sampling, int subspace, int gamma_type, int with_yuv_leaves) {
+  weed_plant_t *l;
+  void *pd[4] = {NULL, NULL, NULL, NULL};
+  int i;
+  mh_init_once();
+  l = weed_plant_new(MH_PLANT_LAYER);
+  weed_set_int_value(l, WEED_LEAF_CURRENT_PALETTE, palette);
+  weed_set_int_value(l, WEED_LEAF_WIDTH, width_macropixels);
+  weed_set_int_value(l, WEED_LEAF_HEIGHT, height);
+  if (nplanes > 0 && planes) {
+    for (i = 0; i < nplanes; i++) {
+      size_t n = (size_t)rowstrides[i] * (size_t)plane_rows[i];
+      if (posix_memalign(&pd[i], 64, n + 64)) return NULL;
+      memcpy(pd[i], planes[i], n);
+      memset((char *)pd[i] + n, 0, 64);
+    }
+    weed_set_voidptr_array(l, WEED_LEAF_PIXEL_DATA, nplanes, pd);
+    weed_set_int_array(l, WEED_LEAF_ROWSTRIDES, nplanes, rowstrides);
+  }
+  if (with_yuv_leaves) {
+    weed_set_int_value(l, WEED_LEAF_YUV_CLAMPING, clamping);
+    weed_set_int_value(l, WEED_LEAF_YUV_SAMPLING, sampling);
+    weed_set_int_value(l, WEED_LEAF_YUV_SUBSPACE, subspace);
+  }
+  if (gamma_type) weed_set_int_value(l, WEED_LEAF_GAMMA_TYPE, gamma_type);
+  return l;
+}
+
+int mh_layer_has(void *layer, const char *key) { return weed_plant_has_leaf((weed_plant_t *)layer, key) ? 1 : 0; }
+int mh_layer_int(void *layer, const char *key, int dflt) {
+  return weed_plant_has_leaf((weed_plant_t *)layer, key) ? weed_get_int_value((weed_plant_t *)layer, key, NULL) : dflt;
+}
+void mh_layer_set_int(void *layer, const char *key, int v) { weed_set_int_value((weed_plant_t *)layer, key, v); }
+int mh_layer_nplanes(void *layer) { return weed_leaf_num_elements((weed_plant_t *)layer, WEED_LEAF_PIXEL_DATA); }
+void *mh_layer_plane(void *layer, int p) {
+  int n = 0;
+  void **pd = weed_get_voidptr_array_counted((weed_plant_t *)layer, WEED_LEAF_PIXEL_DATA, &n);
+  void *r = (pd && p < n) ? pd[p] : NULL;
+  if (pd) free(pd);
+  return r;
+}
+int mh_layer_rowstride(void *layer, int p) {
+  int n = 0, r;
+  int *rs = weed_get_int_array_counted((weed_plant_t *)layer, WEED_LEAF_ROWSTRIDES, &n);
+  r = (rs && p < n) ? rs[p] : 0;
+  if (rs) free(rs);
+  return r;
+}
+void mh_layer_free(void *layer) {
+  int n = 0, i;
+  void **pd = weed_get_voidptr_array_counted((weed_plant_t *)layer, WEED_LEAF_PIXEL_DATA, &n);
+  for (i = 0; pd && i < n; i++) free(pd[i]);
+  if (pd) free(pd);
+  weed_plant_free((weed_plant_t *)layer);
+}

@@ -35,6 +35,20 @@ def test_header_symbols_exported_and_bound():
     _capi.lib()  # binds every prototype
 
 
+def test_weed_layer_and_plugin_libraries_export_what_their_headers_declare():
+    """include/pe_weed_layer.h (the weed_layer_t drop-ins, src/colourspace.h:387-415) and include/pe_weed_abi.h (weed_setup)"""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(T.REPO, "include", "pe_weed_layer.h")).read(), flags=re.S)
+    names = set(re.findall(r"\b([a-z][a-z0-9_]+)\s*\(", src)) - {"defined"}
+    names = {n for n in names if not n.endswith("_f") and not n.endswith("_t")}  # typedefs
+    assert {"convert_layer_palette_full", "convert_layer_palette", "resize_layer_full", "resize_layer", "letterbox_layer",
+            "gamma_convert_layer", "gamma_convert_sub_layer", "alpha_premult", "pe_weed_layer_bind"} <= names
+    handle = C.CDLL(os.path.join(T.REPO, "lives_b200", "libpe_weed_layer.so"))
+    for n in sorted(names):
+        assert hasattr(handle, n), "libpe_weed_layer.so does not export %s" % n
+    plug = C.CDLL(os.path.join(T.REPO, "lives_b200", "libpe_weed_plugin.so"))
+    assert hasattr(plug, "weed_setup") and hasattr(plug, "weed_desetup")
+
+
 def test_every_entry_point_cites_the_reference():
     src = open(HEADER).read()
     for fn in ("pe_convert_layer_palette_full", "pe_resize_layer_full", "pe_letterbox_layer", "pe_gamma_convert_layer",
