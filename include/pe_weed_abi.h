@@ -66,6 +66,10 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 
 /* flags (weed-effects.h:73,107-125) */
 #define PE_WEED_PARAM_INTEGER 1
+#define PE_WEED_PARAM_FLOAT 2
+#define PE_WEED_PARAM_COLOR 5
+#define PE_WEED_COLORSPACE_RGB 1                       /* weed-effects.h:96 */
+#define PE_WEED_FILTER_CHANNEL_SIZES_MAY_VARY (1 << 8) /* weed-effects.h:113 */
 #define PE_WEED_PARAM_SWITCH 4
 #define PE_WEED_PARAMETER_REINIT_ON_VALUE_CHANGE (1 << 0)
 #define PE_WEED_FILTER_HINT_STATEFUL (1 << 2)
@@ -116,6 +120,8 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 #define PE_LEAF_PARAM_TYPE "param_type"
 #define PE_LEAF_IS_TRANSITION "is_transition"
 #define PE_LEAF_GROUP "group"
+#define PE_LEAF_MAX_REPEATS "max_repeats" /* weed-effects.h:339 */
+#define PE_LEAF_COLORSPACE "colorspace"   /* weed-effects.h:392 */
 #define PE_LEAF_ALIGNMENT_HINT "alignment_hint" /* weed-effects.h:265, honoured at src/effects-weed.c:2319-2324 */
 
 #ifdef __cplusplus

@@ -284,6 +284,9 @@ int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, co
 /* slide_over.c:55 on host frames (H2D of both clips, k_slide_over, D2H of the result) */
 int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, int transval,
                        int direction, int mvlower, int mvupper);
+/* gdk/compositor.c compositor_process :127 on host channels (layers[z] NULL = a channel the host disabled, :195-199) */
+int pe_host_compositor(pe_engine_t *e, pe_frame_desc_t *out, const pe_frame_desc_t *const *layers, const double *alpha, int nlayers,
+                       const int bgcol[3]);
 int pe_host_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_frame_desc_t *fg, const pe_frame_desc_t *bg,
                                                pe_frame_desc_t *out, int inner_w, int inner_h, double alpha,
                                                int gamma_from, int gamma_to);

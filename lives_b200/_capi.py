@@ -64,6 +64,7 @@ PROTOTYPES = {
     "pe_engine_set_prefs": (I, [VP, I, C.c_double, I, I]),
     "pe_engine_get_config": (I, [VP, C.c_void_p]),
     "pe_host_register": (I, [VP, SZ]),
+    "pe_host_compositor": (I, [VP, C.c_void_p, C.c_void_p, C.c_void_p, I, C.c_void_p]),
     "pe_host_unregister": (I, [VP]),
     "pe_timer_start": (I, [VP]),
     "pe_timer_stop_ms": (I, [VP, C.POINTER(C.c_float)]),

@@ -2510,6 +2510,27 @@ extern "C" int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, co
   return pe_frame_download(e, o.f, out->planes, out->rowstrides);
 }
 
+// gdk/compositor.c compositor_process :127 on host channels: every enabled in channel travels up once, the paints run on the device,
+// the out channel travels back.  layers[z] == NULL (or without pixel data): the host disabled that channel (:195-199).
+extern "C" int pe_host_compositor(pe_engine_t *e, pe_frame_desc_t *out, const pe_frame_desc_t *const *layers, const double *alpha,
+                                  int nlayers, const int bgcol[3]) {
+  if (!e || !out || !out->planes[0] || nlayers < 0 || (nlayers && (!layers || !alpha))) return set_err(PE_ERR_ARG, "NULL argument");
+  std::vector<HostFrame> up;
+  up.reserve((size_t)nlayers);
+  std::vector<const pe_frame_t *> dev((size_t)nlayers, nullptr);
+  int rc;
+  for (int z = 0; z < nlayers; z++) {
+    up.emplace_back(e);
+    if (!layers[z] || !layers[z]->planes[0] || alpha[z] <= 0.) continue;
+    if ((rc = up.back().upload(layers[z])) != PE_OK) return rc;
+    dev[(size_t)z] = up.back().f;
+  }
+  HostFrame o(e);
+  if ((rc = o.create_like(out)) != PE_OK) return rc;
+  if ((rc = pe_fx_compositor(e, o.f, dev.data(), alpha, nlayers, bgcol)) != PE_OK) return rc;
+  return pe_frame_download(e, o.f, out->planes, out->rowstrides);
+}
+
 // A batch of host frames through the fused chain with the PCIe copies overlapped: three device slots rotate through
 // upload (h2d stream) -> kernel (engine stream) -> download (d2h stream), chained by events, so that frame i+1 travels to the
 // device and frame i-1 travels back while frame i is computed.  Host buffers should be pinned (pe_host_alloc) for the copies to

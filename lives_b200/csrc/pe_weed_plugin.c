@@ -5,6 +5,7 @@
  *     lives-plugins/weed-plugins/simple_blend.c   "chroma blend", "luma overlay", "luma underlay", "negative luma overlay"
  *     lives-plugins/weed-plugins/multi_blends.c   "blend_multiply" ... "blend_burn"
  *     lives-plugins/weed-plugins/slide_over.c     "slide over"
+ *     lives-plugins/weed-plugins/gdk/compositor.c "compositor" (layers at scale 1 / offset 0: BASELINE config 3 through weed_apply_instance)
  * with the same channel / parameter templates, so weed_apply_instance() (src/effects-weed.c:1850) drives it unchanged.
  * Differences from the originals, on purpose:
  *   - WEED_FILTER_HINT_MAY_THREAD is NOT set: the host must call process_func once per frame, not once per row band
@@ -27,18 +28,12 @@ static pe_weed_leaf_num_elements_f w_num_elements;
 static pe_weed_malloc_f w_malloc;
 static pe_weed_free_f w_free;
 
-static pe_engine_t *g_engine;
-
+/* the process-wide engine of libpe_b200.so, shared with the weed_layer_t drop-ins (libpe_weed_layer.so): the host's prefs reach it
+ * through pe_engine_set_prefs(pe_engine_shared(), prefs->pb_quality, ...), the GPU is picked by pe_engine_shared_configure / $PE_DEVICE */
 static pe_engine_t *engine(void) {
-  if (!g_engine) {
-    pe_config_t cfg;
-    pe_config_default(&cfg);
-    if (pe_engine_create(&cfg, &g_engine) != PE_OK) {
-      fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
-      g_engine = NULL;
-    }
-  }
-  return g_engine;
+  pe_engine_t *e = pe_engine_shared();
+  if (!e) fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+  return e;
 }
 
 /* ---- leaf helpers ---------------------------------------------------------------------------------------------- */
@@ -136,6 +131,55 @@ static pe_weed_error_t sover_process(pe_weed_plant_t *inst, pe_weed_timecode_t t
   return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
 }
 
+/* gdk/compositor.c compositor_process :127-297: N repeating in channels painted onto the background colour, last first (or first
+ * to last with "revz").  Offsets / scales other than 0 / 1 need gdk_pixbuf_scale_simple (absent from this image, nothing to pin
+ * against): such an instance fails loudly.  A disabled channel (WEED_LEAF_DISABLED, :195) is skipped. */
+#define PE_MAX_COMP_LAYERS 64
+static double get_dbl(pe_weed_plant_t *p, const char *key, int idx, double dflt) {
+  double v = dflt;
+  if ((int)w_num_elements(p, key) > idx) w_leaf_get(p, key, (pe_weed_size_t)idx, &v);
+  return v;
+}
+static pe_weed_error_t compositor_process(pe_weed_plant_t *inst, pe_weed_timecode_t tc) {
+  pe_frame_desc_t out, in[PE_MAX_COMP_LAYERS];
+  const pe_frame_desc_t *layers[PE_MAX_COMP_LAYERS];
+  double alpha[PE_MAX_COMP_LAYERS];
+  pe_weed_plant_t *par[7], *ch;
+  pe_engine_t *e = engine();
+  int n, z, k, bgcol[3] = {0, 0, 0}, revz = 0, rc;
+  (void)tc;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  n = (int)w_num_elements(inst, PE_LEAF_IN_CHANNELS);
+  if (n > PE_MAX_COMP_LAYERS) n = PE_MAX_COMP_LAYERS;
+  for (k = 0; k < 7; k++) par[k] = get_plant(inst, PE_LEAF_IN_PARAMETERS, k);
+  channel_desc(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  for (k = 0; k < 3; k++) { int32_t c = 0; if ((int)w_num_elements(par[5], PE_LEAF_VALUE) > k) w_leaf_get(par[5], PE_LEAF_VALUE, (pe_weed_size_t)k, &c); bgcol[k] = c; }
+  { int32_t b = 0; w_leaf_get(par[6], PE_LEAF_VALUE, 0, &b); revz = b; }
+  for (z = 0; z < n; z++) {
+    /* pe_fx_compositor paints the LAST layer first (revz == WEED_FALSE, :189-192): with revz the order of the list is reversed */
+    const int src = revz ? n - 1 - z : z;
+    int32_t disabled = 0;
+    ch = get_plant(inst, PE_LEAF_IN_CHANNELS, src);
+    layers[z] = NULL;
+    alpha[z] = get_dbl(par[4], PE_LEAF_VALUE, src, 1.);
+    if (!ch) continue;
+    if (w_num_elements(ch, "disabled") > 0) w_leaf_get(ch, "disabled", 0, &disabled);
+    if (disabled) continue;
+    channel_desc(ch, &in[z]);
+    if (!in[z].planes[0]) continue;
+    if (get_dbl(par[0], PE_LEAF_VALUE, src, 0.) != 0. || get_dbl(par[1], PE_LEAF_VALUE, src, 0.) != 0. ||
+        get_dbl(par[2], PE_LEAF_VALUE, src, 1.) != 1. || get_dbl(par[3], PE_LEAF_VALUE, src, 1.) != 1.) {
+      fprintf(stderr, "pe_weed_plugin: compositor layer %d: offsets / scales other than 0 / 1 are not handled by this build\n", src);
+      return PE_WEED_ERROR_FILTER_INVALID;
+    }
+    layers[z] = &in[z];
+  }
+  rc = pe_host_compositor(e, &out, layers, alpha, n, bgcol);
+  if (rc == PE_OK) return PE_WEED_SUCCESS;
+  fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+  return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
+}
+
 /* ---- plant construction (what weed_channel_template_init / weed_integer_init / weed_filter_class_init of
  *      libweed/weed-plugin-utils.c:247-336 produce) ----------------------------------------------------------------- */
 
@@ -185,6 +229,81 @@ static pe_weed_plant_t *switch_param(const char *name, const char *label, int de
   if (group >= 0) set_int(p, PE_LEAF_GROUP, group);
   if (flags) set_int(p, PE_LEAF_FLAGS, flags);
   return p;
+}
+
+static int register_filter(pe_weed_plant_t *plugin_info, pe_weed_plant_t *fc);
+
+/* weed_float_init / weed_colRGBi_init (weed-plugin-utils.c:369-382, :397-413) */
+static pe_weed_plant_t *param_gui(pe_weed_plant_t *p, const char *label) {
+  pe_weed_plant_t *gui = w_plant_new(PE_WEED_PLANT_GUI);
+  int32_t one = 1;
+  if (gui) {
+    w_leaf_set(p, PE_LEAF_GUI, PE_WEED_SEED_PLANTPTR, 1, &gui);
+    set_str(gui, PE_LEAF_LABEL, label);
+    w_leaf_set(gui, PE_LEAF_USE_MNEMONIC, PE_WEED_SEED_BOOLEAN, 1, &one);
+  }
+  return gui;
+}
+static pe_weed_plant_t *float_param(const char *name, const char *label, double def, double min, double max) {
+  pe_weed_plant_t *p = w_plant_new(PE_WEED_PLANT_PARAMETER_TEMPLATE);
+  if (!p) return NULL;
+  set_str(p, PE_LEAF_NAME, name);
+  set_int(p, PE_LEAF_PARAM_TYPE, PE_WEED_PARAM_FLOAT);
+  w_leaf_set(p, PE_LEAF_DEFAULT, PE_WEED_SEED_DOUBLE, 1, &def);
+  w_leaf_set(p, PE_LEAF_MIN, PE_WEED_SEED_DOUBLE, 1, &min);
+  w_leaf_set(p, PE_LEAF_MAX, PE_WEED_SEED_DOUBLE, 1, &max);
+  param_gui(p, label);
+  return p;
+}
+static pe_weed_plant_t *rgb_param(const char *name, const char *label, int r, int g, int b) {
+  pe_weed_plant_t *p = w_plant_new(PE_WEED_PLANT_PARAMETER_TEMPLATE);
+  int32_t def[3] = {r, g, b};
+  if (!p) return NULL;
+  set_str(p, PE_LEAF_NAME, name);
+  set_int(p, PE_LEAF_PARAM_TYPE, PE_WEED_PARAM_COLOR);
+  set_int(p, PE_LEAF_COLORSPACE, PE_WEED_COLORSPACE_RGB);
+  w_leaf_set(p, PE_LEAF_DEFAULT, PE_WEED_SEED_INT, 3, def);
+  set_int(p, PE_LEAF_MIN, 0);
+  set_int(p, PE_LEAF_MAX, 255);
+  param_gui(p, label);
+  return p;
+}
+
+/* gdk/compositor.c:300-340: ONE repeating in channel template (max_repeats 0 = any number), one out channel, seven parameters, channel
+ * sizes may vary.  (The RFX layout strings of the original only arrange its parameter window; they are not reproduced.) */
+static int add_compositor(pe_weed_plant_t *plugin_info) {
+  int palettes[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24, PE_PALETTE_RGBA32, PE_PALETTE_BGRA32};
+  pe_weed_plant_t *fc = w_plant_new(PE_WEED_PLANT_FILTER_CLASS);
+  pe_weed_plant_t *in_ct[1], *out_ct[1], *in_pt[7];
+  pe_weed_process_f process_fn = compositor_process;
+  pe_weed_init_f init_fn = common_init;
+  const char *author = "lives_b200";
+  int k;
+  if (!fc) return -1;
+  in_ct[0] = chantmpl("in channel 0", 0);
+  out_ct[0] = chantmpl("out channel 0", 0);
+  in_pt[0] = float_param("xoffs", "_X offset", 0., 0., 1.);
+  in_pt[1] = float_param("yoffs", "_Y offset", 0., 0., 1.);
+  in_pt[2] = float_param("scalex", "Scale _width", 1., 0., 1.);
+  in_pt[3] = float_param("scaley", "Scale _height", 1., 0., 1.);
+  in_pt[4] = float_param("alpha", "_Alpha", 1., 0., 1.);
+  in_pt[5] = rgb_param("bgcol", "_Background color", 0, 0, 0);
+  in_pt[6] = switch_param("revz", "Invert _Z Index", 0, -1, 0);
+  if (!in_ct[0] || !out_ct[0]) return -1;
+  for (k = 0; k < 7; k++) if (!in_pt[k]) return -1;
+  set_int(in_ct[0], PE_LEAF_MAX_REPEATS, 0);
+  set_str(fc, PE_LEAF_NAME, "compositor");
+  w_leaf_set(fc, PE_LEAF_AUTHOR, PE_WEED_SEED_STRING, 1, &author);
+  set_int(fc, PE_LEAF_VERSION, 1);
+  set_int(fc, PE_LEAF_FLAGS, PE_WEED_FILTER_CHANNEL_SIZES_MAY_VARY);
+  w_leaf_set(fc, PE_LEAF_INIT_FUNC, PE_WEED_SEED_FUNCPTR, 1, &init_fn);
+  w_leaf_set(fc, PE_LEAF_PROCESS_FUNC, PE_WEED_SEED_FUNCPTR, 1, &process_fn);
+  w_leaf_set(fc, PE_LEAF_IN_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, in_ct);
+  w_leaf_set(fc, PE_LEAF_OUT_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, out_ct);
+  w_leaf_set(fc, PE_LEAF_IN_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 7, in_pt);
+  w_leaf_set(fc, PE_LEAF_OUT_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 0, NULL);
+  w_leaf_set(fc, PE_LEAF_PALETTE_LIST, PE_WEED_SEED_INT, 4, palettes);
+  return register_filter(plugin_info, fc);
 }
 
 /* weed_plugin_info_add_filter_class (weed-plugin-utils.c:308-320) */
@@ -319,13 +438,11 @@ pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
                  "Blend _amount", 128))
     return NULL;
   if (add_slide_over(plugin_info)) return NULL;
+  if (add_compositor(plugin_info)) return NULL;
   set_int(plugin_info, PE_LEAF_VERSION, package_version);
   return plugin_info;
 }
 
 void weed_desetup(void) {
-  if (g_engine) {
-    pe_engine_destroy(g_engine);
-    g_engine = NULL;
-  }
+  /* the engine is the process-wide one (pe_engine_shared): it outlives this plugin */
 }

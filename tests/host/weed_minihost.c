@@ -255,3 +255,60 @@ void mh_layer_free(void *layer) {
   if (pd) free(pd);
   weed_plant_free((weed_plant_t *)layer);
 }
+
+/* ---- "compositor" (gdk/compositor.c:300-340): nlayers repeats of the one in-channel template, the seven parameters with per-layer
+ *      double arrays, as weed_apply_instance hands them over.  srcs[z] == NULL: a disabled channel. */
+int mh_run_compositor(int h, int fidx, int palette, int width, int height, int nlayers, void **srcs, int *rss, void *dst, int rsd,
+                      const double *offsx, const double *offsy, const double *scalex, const double *scaley, const double *alpha,
+                      const int *bgcol, int revz) {
+  weed_plant_t *filter, *inst, *in_ch[64], *out_ch, *params[7];
+  weed_plant_t **ictm, **octm, **iptm;
+  weed_init_f init_fn;
+  weed_process_f process_fn;
+  weed_deinit_f deinit_fn;
+  weed_error_t err = WEED_SUCCESS;
+  int n, z;
+  if (mh_num_filters(h) <= fidx || fidx < 0 || nlayers > 64) return -1;
+  filter = mh_tab[h].filters[fidx];
+  ictm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_CHANNEL_TEMPLATES, &n);
+  if (n < 1) return -2;
+  octm = weed_get_plantptr_array_counted(filter, WEED_LEAF_OUT_CHANNEL_TEMPLATES, &n);
+  if (n < 1) return -3;
+  iptm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_PARAMETER_TEMPLATES, &n);
+  if (n != 7) return -4;
+  if (!weed_plant_has_leaf(ictm[0], WEED_LEAF_MAX_REPEATS)) return -5;
+  for (z = 0; z < nlayers; z++) {
+    in_ch[z] = mh_channel(ictm[0], palette, width, height, srcs[z], rss[z]);
+    if (!srcs[z]) weed_set_boolean_value(in_ch[z], WEED_LEAF_DISABLED, WEED_TRUE);
+  }
+  out_ch = mh_channel(octm[0], palette, width, height, dst, rsd);
+  for (z = 0; z < 7; z++) {
+    params[z] = weed_plant_new(WEED_PLANT_PARAMETER);
+    weed_set_plantptr_value(params[z], WEED_LEAF_TEMPLATE, iptm[z]);
+  }
+  weed_set_double_array(params[0], WEED_LEAF_VALUE, nlayers, (double *)offsx);
+  weed_set_double_array(params[1], WEED_LEAF_VALUE, nlayers, (double *)offsy);
+  weed_set_double_array(params[2], WEED_LEAF_VALUE, nlayers, (double *)scalex);
+  weed_set_double_array(params[3], WEED_LEAF_VALUE, nlayers, (double *)scaley);
+  weed_set_double_array(params[4], WEED_LEAF_VALUE, nlayers, (double *)alpha);
+  weed_set_int_array(params[5], WEED_LEAF_VALUE, 3, (int *)bgcol);
+  weed_set_boolean_value(params[6], WEED_LEAF_VALUE, revz ? WEED_TRUE : WEED_FALSE);
+  inst = weed_plant_new(WEED_PLANT_FILTER_INSTANCE);
+  weed_set_plantptr_value(inst, WEED_LEAF_FILTER_CLASS, filter);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_CHANNELS, nlayers, in_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_OUT_CHANNELS, 1, &out_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_PARAMETERS, 7, params);
+  init_fn = (weed_init_f)weed_get_funcptr_value(filter, WEED_LEAF_INIT_FUNC, NULL);
+  process_fn = (weed_process_f)weed_get_funcptr_value(filter, WEED_LEAF_PROCESS_FUNC, NULL);
+  deinit_fn = (weed_deinit_f)weed_get_funcptr_value(filter, WEED_LEAF_DEINIT_FUNC, NULL);
+  if (!process_fn) return -6;
+  if (init_fn) err = (*init_fn)(inst);
+  if (err == WEED_SUCCESS) err = (*process_fn)(inst, 0);
+  if (deinit_fn) (*deinit_fn)(inst);
+  for (z = 0; z < nlayers; z++) weed_plant_free(in_ch[z]);
+  for (z = 0; z < 7; z++) weed_plant_free(params[z]);
+  weed_plant_free(out_ch);
+  weed_plant_free(inst);
+  free(ictm); free(octm); free(iptm);
+  return (int)err;
+}

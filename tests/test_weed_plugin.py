@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not T.have_ref() or not os.path.exists(os.path.j
                                 reason="oracle/_ref (reference libweed + minihost) not built")
 
 NAMES = ["chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "blend_multiply", "blend_screen",
-         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over"]
+         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over", "compositor"]
 
 
 def _minihost():
@@ -134,3 +134,47 @@ def test_slide_over_plugin_matches_reference_plugin():
             assert mh.mh_run2v(ref, 0, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], 8, pr, 1) == 0
             assert mh.mh_run2v(ours, 11, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], 8, pr, 1) == 0
             assert (d_ref == d_our).all(), (pal, w, ht, direction, mvl, mvu, tv)
+
+
+@pytest.mark.gpu
+def test_compositor_filter_config3_through_the_plugin_boundary():
+    """BASELINE config 3 reached the way weed_apply_instance reaches it: the "compositor" filter of libpe_weed_plugin.so (templates of
+    gdk/compositor.c:300-340: one repeating in channel, per-layer double arrays) run by the minihost through the reference's libweed,
+    against bgcol fill + paint_pixel (:120, :172-197) of the oracle (pinned to the compiled paint_pixel).  Layers are painted last
+    first; "revz" reverses; a disabled channel is skipped; offsets / scales other than 0 / 1 fail loudly."""
+    mh = _minihost()
+    mh.mh_run_compositor.argtypes = [T.I] * 6 + [T.VP, T.VP, T.VP, T.I] + [T.VP] * 6 + [T.I]
+    ours = _open_ours(mh)
+    o = T.oracle()
+    rng = np.random.default_rng(33)
+    fidx = NAMES.index("compositor")
+    D = C.c_double
+    for (pal, ps), (w, ht), revz in itertools.product(((3, 4), (1, 3), (2, 3)), ((3840, 2160), (61, 7)), (0, 1)):
+        if (w, ht) == (3840, 2160) and (pal != 3 or revz):
+            continue
+        layers = [T.make_packed(rng, w, ht, ps) for _ in range(3)]
+        alphas = [0.5, 0.3, 1.0] if (w, ht) != (3840, 2160) else [0.5, 1.0, 1.0]
+        enabled = [True, (w, ht) != (61, 7) or revz == 0, True]
+        bg = (10, 200, 77)
+        exp = np.zeros_like(layers[0])
+        o.pe_or_fill(T.ptr(exp), exp.strides[0], pal, w, ht, bg[0], bg[1], bg[2])
+        order = range(3) if revz else range(2, -1, -1)
+        for z in order:
+            if enabled[z]:
+                o.pe_or_alpha_over(T.ptr(exp), exp.strides[0], T.ptr(layers[z]), layers[z].strides[0], pal, w, ht, alphas[z])
+        if ps == 4:
+            exp[:, 3:w * 4:4] = 255
+        srcs = (C.c_void_p * 3)(*[layers[z].ctypes.data if enabled[z] else None for z in range(3)])
+        rss = (C.c_int * 3)(*[a.strides[0] for a in layers])
+        zero, one = (D * 3)(0, 0, 0), (D * 3)(1, 1, 1)
+        got = np.full_like(layers[0], 9)
+        rc = mh.mh_run_compositor(ours, fidx, pal, w, ht, 3, srcs, rss, T.ptr(got), got.strides[0], zero, zero, one, one, (D * 3)(*alphas),
+                                  (C.c_int * 3)(*bg), revz)
+        assert rc == 0, rc
+        assert (got[:, :w * ps] == exp[:, :w * ps]).all(), (pal, w, ht, revz)
+    # a scaled layer is refused, the out channel keeps its bytes
+    got = np.full_like(layers[0], 9)
+    half = (D * 3)(1, 0.5, 1)
+    rc = mh.mh_run_compositor(ours, fidx, pal, w, ht, 3, srcs, rss, T.ptr(got), got.strides[0], zero, zero, half, one, (D * 3)(*alphas),
+                              (C.c_int * 3)(*bg), 0)
+    assert rc == 65 and (got == 9).all()  # WEED_ERROR_FILTER_INVALID
