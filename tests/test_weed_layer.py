@@ -205,7 +205,7 @@ def test_letterbox_gamma_premult_on_a_real_layer(host):
     assert (s["planes"][0][:, :w * 4] == exp[:, :w * 4]).all()
     # alpha_premult forward: flags leaf gets WEED_LAYER_ALPHA_PREMULT
     pm = exp.copy()
-    o.pe_or_alpha_premult(T.ptr(pm), w, h, pm.strides[0], 3, 0, 1)
+    o.pe_or_alpha_premult(T.ptr(pm), pm.strides[0], 3, 0, w, h, 1)
     host.lib.alpha_premult(lay, 1)
     s = host.snapshot(lay)
     assert (s["planes"][0][:, :w * 4] == pm[:, :w * 4]).all() and s["leaves"][b"flags"][1] & 1

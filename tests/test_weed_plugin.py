@@ -174,7 +174,7 @@ def test_compositor_filter_config3_through_the_plugin_boundary():
         assert (got[:, :w * ps] == exp[:, :w * ps]).all(), (pal, w, ht, revz)
     # a scaled layer is refused, the out channel keeps its bytes
     got = np.full_like(layers[0], 9)
-    half = (D * 3)(1, 0.5, 1)
+    half = (D * 3)(0.5, 1, 1)
     rc = mh.mh_run_compositor(ours, fidx, pal, w, ht, 3, srcs, rss, T.ptr(got), got.strides[0], zero, zero, half, one, (D * 3)(*alphas),
                               (C.c_int * 3)(*bg), 0)
     assert rc == 65 and (got == 9).all()  # WEED_ERROR_FILTER_INVALID
