@@ -449,12 +449,24 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = e2e_frames * args.e2e_steps * world / e2e_s
     checksum = int(pinned[0][4][::97, ::101].astype(np.uint64).sum())  # the D2H result is really read
 
+    # ---- the link alone, all ranks copying at once (what the e2e figure is bounded by on this box)
+    probe = pcie_probe(dev)
+    if dist is not None:
+        t = torch.tensor([probe["frames_per_s"]], dtype=torch.float64, device=dev)
+        tmin, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        probe = {"frames_per_s_all_ranks": float(tsum.item()), "frames_per_s_slowest_rank": float(tmin.item()), "rank0": probe}
+    else:
+        probe = {"frames_per_s_all_ranks": probe["frames_per_s"], "frames_per_s_slowest_rank": probe["frames_per_s"], "rank0": probe}
+    subs = None if args.no_sub_records else sub_records(args, eng, dist, rank, world, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         cb = CpuBench(cores, cores, args.cpu_stages)
         chain, n, dt = cb.chain, 0, 0.0
-        while dt < 10.0 and n < 64 * cores:  # bounded sample: >= 10 s of wall clock over all host threads
+        while dt < 10.0 and n < 4096 * cores:  # bounded sample: >= 10 s of wall clock over all host threads
             dt += cb.step()
             n += cores
         single = cpu_single_thread(chain)
@@ -477,7 +489,7 @@ def run_ours(args, rank, world, local_rank):
                         "d2h_bytes_per_step": RGBA_BYTES * e2e_frames, "frames_per_step": e2e_frames, "steps": args.e2e_steps,
                         "api": "pe_host_fused_convert_letterbox_over_gamma_batch (pinned host frames in / out; H2D, kernel, D2H "
                                "of consecutive frames overlapped on three streams)", "checksum": checksum},
-                "gpu_launches": int(launches), "clocks": clk}
+                "gpu_launches": int(launches), "clocks": clk, "configs": subs, "pcie_ceiling": probe}
         prof = os.path.join(REPO, "profiles", "traffic_r01.json")
         if os.path.exists(prof):
             try:
@@ -492,6 +504,139 @@ def run_ours(args, rank, world, local_rank):
             lb._capi.lib().pe_host_free(a.ctypes.data)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sub_records(args, eng, dist, rank, world, dev):
+    """BASELINE configs 4 and 5 at N GPUs, inside the driver's line (the one collective of the path had no driver-side
+    measurement).  Device-resident, CUDA-event timed on the engine stream, max over ranks; weak scaling.
+      cfg4  32 x 1080p RGB24 'chroma blend' bf = 100 per GPU and step (256 frames over 8 GPUs), one launch, no collective
+      cfg5  one clip per GPU: K = 8 consecutive 4K YUV422P frames -> RGB24 + crossfade (chroma blend bf = 128) with K frames of the
+            shared operand, which rank 0 owns and every step BROADCASTS over NCCL (199 MB per step); three operand group buffers so
+            that two broadcasts can run ahead of the kernel.  parity_all_ranks: every rank also crossfades against a locally generated
+            copy of the operand (same seed everywhere) and compares the results bit for bit."""
+    import torch
+    import lives_b200 as lb
+    from lives_b200 import shard
+    out = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+
+    def timed(step, steps, warm=3):
+        for _ in range(warm):
+            step()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+        l0 = eng.launch_count
+        eng.timer_start()
+        for _ in range(steps):
+            step()
+        ms = eng.timer_stop_ms()
+        torch.cuda.synchronize()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, eng.launch_count - l0
+
+    peak, _ = measured_peak()
+    # ---- cfg4
+    W, H, n = 1920, 1080, 32
+    keep = [torch.randint(0, 256, (3, n, H, W * 3), dtype=torch.uint8, device=dev, generator=g)]
+    a = [lb.Layer.wrap_device(eng, 1, W, H, [keep[0][0, i].data_ptr()], [W * 3]) for i in range(n)]
+    b = [lb.Layer.wrap_device(eng, 1, W, H, [keep[0][1, i].data_ptr()], [W * 3]) for i in range(n)]
+    o = [lb.Layer.wrap_device(eng, 1, W, H, [keep[0][2, i].data_ptr()], [W * 3]) for i in range(n)]
+    steps4 = 20
+    ms, launches = timed(lambda: lb.simple_blend_batch("chroma blend", a, b, o, 100), steps4)
+    fps = world * n * steps4 / (ms / 1e3)
+    algo4 = 3 * W * H * 3
+    out["cfg4"] = {"workload": "256 x 1080p RGB24 'chroma blend' bf=100 over 8 GPUs = 32 frames per GPU and step, one launch, no collective",
+                   "value": fps, "unit": "frames/s", "ms_per_step": ms / steps4, "gpu_launches": int(launches),
+                   "roofline_frac_per_gpu": algo4 * n * steps4 / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_frame": algo4}
+    del a, b, o, keep
+    # ---- cfg5
+    W, H, K = 3840, 2160, 8
+    yy = torch.randint(16, 236, (H, W), dtype=torch.uint8, device=dev, generator=g)
+    uu = torch.randint(16, 241, (H, W // 2), dtype=torch.uint8, device=dev, generator=g)
+    vv = torch.randint(16, 241, (H, W // 2), dtype=torch.uint8, device=dev, generator=g)
+    og = torch.Generator(device=dev)
+    og.manual_seed(99)  # the SAME operand frames on every rank: rank 0's copy travels, the others are the parity reference
+    local_ops = torch.randint(0, 256, (K, H, W * 3), dtype=torch.uint8, device=dev, generator=og)
+    groups = [local_ops.clone() if rank == 0 else torch.zeros_like(local_ops) for _ in range(3)]
+    it = [0]
+
+    def clips():
+        return [lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2],
+                                     yuv_subspace=1) for _ in range(K)]
+
+    def step5(keep_result=False):
+        cl = clips()
+        shard.multitrack_crossfade_group(eng, cl, groups[it[0] % 3], W, H, 128)
+        it[0] += 1
+        if keep_result:
+            return cl
+        for c in cl:
+            c.free()
+
+    # parity: broadcast path vs the local copy of the operand
+    got = step5(keep_result=True)
+    ref = clips()
+    ops = [lb.Layer.wrap_device(eng, 1, W, H, [local_ops[i].data_ptr()], [W * 3]) for i in range(K)]
+    assert lb.convert_crossfade_batchv(ref, ops, 1, 0, 128) == K
+    eng.sync()
+    torch.cuda.synchronize()
+    same = True
+    for x, y_ in zip(got, ref):
+        dx, dy = x.desc, y_.desc
+        hx, hy = x.to_host()[0], y_.to_host()[0]
+        same = same and bool((hx == hy).all()) and dx.palette == 1 and dy.palette == 1
+    for c in got + ref:
+        c.free()
+    flag = torch.tensor([int(same)], device=dev)
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    steps5 = 10
+    ms, launches = timed(step5, steps5, warm=2)
+    cps = world * K * steps5 / (ms / 1e3)
+    algo5 = W * H * 2 + 2 * W * H * 3
+    out["cfg5"] = {"workload": "multitrack: one clip per GPU, %d x 4K YUV422P -> RGB24 + crossfade bf=128 per step against %d frames of the shared "
+                               "operand, %s" % (K, K, "broadcast from rank 0 over NCCL once per step (3 group buffers)" if world > 1 else "no broadcast at N = 1"),
+                   "value": cps, "unit": "clip frames/s", "ms_per_output_frame": ms / (steps5 * K), "gpu_launches": int(launches),
+                   "parity_all_ranks": bool(flag.item()), "broadcast_bytes_per_step": (K * H * W * 3) if world > 1 else 0,
+                   "broadcast_gbs": (K * H * W * 3 * steps5 / (ms / 1e3) / 1e9) if world > 1 else None,
+                   "roofline_frac_per_gpu": algo5 * K * steps5 / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_frame": algo5}
+    return out
+
+
+def pcie_probe(dev):
+    """this rank's pinned-copy ceiling for the e2e path (45.6 MB up + 33.2 MB down per frame, both directions busy), so that an e2e
+    figure that does not scale can be told apart from the box: frames/s the link alone would allow"""
+    import torch
+    UP, DOWN, N = FG_BYTES + RGBA_BYTES, RGBA_BYTES, 12
+    hu, hd = torch.empty(UP, dtype=torch.uint8).pin_memory(), torch.empty(DOWN, dtype=torch.uint8).pin_memory()
+    du, dd = torch.empty(UP, dtype=torch.uint8, device=dev), torch.empty(DOWN, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s_up.wait_stream(torch.cuda.current_stream())
+        s_dn.wait_stream(torch.cuda.current_stream())
+        for _ in range(N):
+            with torch.cuda.stream(s_up):
+                du.copy_(hu, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hd.copy_(dd, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s_up)
+        torch.cuda.current_stream().wait_stream(s_dn)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3
+    run()
+    t = min(run() for _ in range(2))
+    return {"frames_per_s": N / t, "h2d_gbs": UP * N / t / 1e9, "d2h_gbs": DOWN * N / t / 1e9}
 
 
 def run_secondary(args):
@@ -618,6 +763,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=48, help="host frames per e2e step (one batch call)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the cfg4 / cfg5 sub-records of the line")
     ap.add_argument("--cpu-stages", default="auto", choices=["auto", "sws", "loops"],
                     help="CPU arm: sws = convert + resize as the ONE sws_scale call the reference issues (needs a loadable libswscale; auto picks "
                          "it when there is one), loops = the reference's own converter loop + the oracle's resize")

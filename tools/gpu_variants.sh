@@ -7,7 +7,7 @@ for LIB in /tmp/libpe_b200_base.so tmp_variants/libpe_b200_*.so; do
   cp $LIB lives_b200/libpe_b200.so
   for T in ${TMA_LIST:-0 1}; do
     for B in ${BATCH_LIST:-32 1}; do
-      PE_F3_TMA=$T timeout 300 python bench.py --batch $B --steps 100 --no-cpu-baseline --e2e-frames 4 --e2e-steps 1 2>&1 | tail -1 | python -c "
+      PE_F3_TMA=$T timeout 300 python bench.py --batch $B --steps 100 --no-cpu-baseline --no-sub-records --e2e-frames 4 --e2e-steps 1 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('$LIB TMA=$T batch %d: %.0f fps, kernel %.4f ms, frac %.4f' % (d['config']['frames_per_step_per_gpu'], d['value'], r['kernel_ms'], r['frac']))" >> gpurun_out/variants_$TAG.log 2>&1
