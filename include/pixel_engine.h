@@ -249,6 +249,41 @@ int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_
                                                 const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
                                                 int inner_h, double alpha, int gamma_from, int gamma_to);
 
+/* ---- frame ingest / egress in device memory -------------------------------------------------------------- */
+
+/* boolean get_frame(const lives_clip_data_t *, int64_t frame, int *rowstrides, int height, void **pixel_data)
+ *                                                  src/plugins.h:442, lives-plugins/plugins/decoders/decplugin.h:280
+ * with pixel_data in DEVICE memory: a device decoder (NVDEC / nvJPEG) writes the planes of frame `frame` on `cuda_stream` and returns
+ * TRUE; nothing crosses PCIe.  rowstrides / height are the device frame's (rowstride rule of colourspace.c:11299-11357). */
+typedef int (*pe_device_get_frame_f)(void *clip_data, int64_t frame, const int *rowstrides, int height, void *const *pixel_data_dev,
+                                     void *cuda_stream);
+typedef struct pe_clip_source {
+  void *clip_data;                 /* lives_clip_data_t of the decoder */
+  pe_device_get_frame_f get_frame;
+  int palette, width, height;      /* cdata->current_palette, width, height (pixels) */
+  int yuv_clamping, yuv_sampling, yuv_subspace, gamma_type;
+} pe_clip_source_t;
+/* pull_frame (src/frameloader.c:1494,1841) on the device: a new layer filled by the source */
+int pe_ingest_frame(pe_engine_t *e, const pe_clip_source_t *src, int64_t frame, pe_frame_t **out);
+
+/* the built-in source: a clip that already sits in HBM (decoded once, or written there by a device decoder) */
+typedef struct pe_clip_cache pe_clip_cache_t;
+int pe_clip_cache_create(pe_engine_t *e, int palette, int width, int height, int nframes, int yuv_clamping, int yuv_sampling,
+                         int yuv_subspace, int gamma_type, pe_clip_cache_t **out);
+void pe_clip_cache_destroy(pe_clip_cache_t *c);
+int pe_clip_cache_load(pe_clip_cache_t *c, int64_t frame, const void *const host_planes[PE_MAXPLANES],
+                       const int host_rowstrides[PE_MAXPLANES]);                 /* the one-time fill from host memory */
+int pe_clip_cache_frame_desc(pe_clip_cache_t *c, int64_t frame, pe_frame_desc_t *out); /* device pointers of a cached frame */
+int pe_clip_cache_source(pe_clip_cache_t *c, pe_clip_source_t *out);            /* get_frame = device-to-device plane copies */
+int pe_clip_cache_borrow(pe_clip_cache_t *c, int64_t frame, pe_frame_t **out);  /* zero copy: the cached frame as a read-only layer */
+
+/* the render-to-disk tail (src/events.c:4247-4263: convert to the clip's palette, layer_to_pixbuf): convert_layer_palette(layer,
+ * out_palette) when needed, then ONLY that packed frame is copied to (pinned) host memory, on its own stream.  _begin returns at once;
+ * slot 0 .. 3 names the copy for _wait; the layer stays alive and unwritten until then. */
+int pe_render_out_begin(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride, int slot);
+int pe_render_out_wait(pe_engine_t *e, int slot);
+int pe_render_out(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride);
+
 /* ---- per-frame diagnostics (is_all_black_ish colourspace.c:2554, hash_cmp_layer :16044) ------ */
 
 typedef struct pe_frame_stats {

@@ -64,6 +64,16 @@ PROTOTYPES = {
     "pe_engine_set_prefs": (I, [VP, I, C.c_double, I, I]),
     "pe_engine_get_config": (I, [VP, C.c_void_p]),
     "pe_host_register": (I, [VP, SZ]),
+    "pe_ingest_frame": (I, [VP, C.c_void_p, C.c_int64, PVP]),
+    "pe_clip_cache_create": (I, [VP, I, I, I, I, I, I, I, I, PVP]),
+    "pe_clip_cache_destroy": (None, [VP]),
+    "pe_clip_cache_load": (I, [VP, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pe_clip_cache_frame_desc": (I, [VP, C.c_int64, PDESC]),
+    "pe_clip_cache_source": (I, [VP, C.c_void_p]),
+    "pe_clip_cache_borrow": (I, [VP, C.c_int64, PVP]),
+    "pe_render_out_begin": (I, [VP, VP, I, VP, I, I]),
+    "pe_render_out_wait": (I, [VP, I]),
+    "pe_render_out": (I, [VP, VP, I, VP, I]),
     "pe_host_compositor": (I, [VP, C.c_void_p, C.c_void_p, C.c_void_p, I, C.c_void_p]),
     "pe_host_unregister": (I, [VP]),
     "pe_timer_start": (I, [VP]),

@@ -295,6 +295,8 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
     if (e->pipe_comp[k]) cudaEventDestroy(e->pipe_comp[k]);
     if (e->pipe_free[k]) cudaEventDestroy(e->pipe_free[k]);
   }
+  if (e->egress_stream) cudaStreamDestroy(e->egress_stream);
+  for (int k = 0; k < 4; k++) { if (e->egress_ready[k]) cudaEventDestroy(e->egress_ready[k]); if (e->egress_done[k]) cudaEventDestroy(e->egress_done[k]); }
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -789,6 +791,192 @@ extern "C" int pe_frame_copy(pe_engine_t *e, const pe_frame_t *src, pe_frame_t *
   }
   *out = f;
   return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// frame ingest / egress in device memory.
+//   ingest: the decoder plugin's get_frame (src/plugins.h:442, decplugin.h:280: "fill these planes with frame N") with the planes in
+//           HBM -- a device decoder (NVDEC / nvJPEG writing YUV420P / NV12) implements pe_device_get_frame_f; pe_clip_cache is the
+//           built-in source: a clip that already sits in HBM
+//   egress: the render-to-disk tail (src/events.c:4247-4263: convert to the clip's palette, layer_to_pixbuf) -- only the final packed
+//           frame crosses PCIe, on its own stream, while the next frame is computed
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osampling, int osubspace, int tgt_gamma);  // below
+}
+
+extern "C" int pe_ingest_frame(pe_engine_t *e, const pe_clip_source_t *src, int64_t frame, pe_frame_t **out) {
+  if (!e || !src || !src->get_frame || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  pe_frame_t *f = nullptr;
+  int rc = frame_create_impl(e, src->palette, src->width, src->height, src->yuv_clamping, src->yuv_sampling, src->yuv_subspace,
+                             src->gamma_type, 0, &f);
+  if (rc != PE_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (cudaSetDevice(e->device) != cudaSuccess) rc = set_err(PE_ERR_CUDA, "cudaSetDevice failed");
+    // boolean get_frame(cdata, frame, rowstrides, height, pixel_data): FALSE = the frame could not be produced
+    else if (!src->get_frame(src->clip_data, frame, f->d.rowstrides, f->d.height, f->d.planes, (void *)e->stream))
+      rc = set_err(PE_ERR_ARG, "the clip source could not produce frame %lld", (long long)frame);
+  }
+  if (rc != PE_OK) { pe_frame_destroy(f); return rc; }
+  *out = f;
+  return PE_OK;
+}
+
+struct pe_clip_cache {
+  pe_engine *e = nullptr;
+  pe_frame_desc_t d{};          // geometry of one frame; planes unused
+  int plane_heights[PE_MAXPLANES] = {};
+  size_t plane_off[PE_MAXPLANES] = {};
+  size_t frame_bytes = 0;
+  int nframes = 0;
+  uint8_t *base = nullptr;      // nframes * frame_bytes of HBM
+};
+
+extern "C" int pe_clip_cache_create(pe_engine_t *e, int palette, int width, int height, int nframes, int yuv_clamping, int yuv_sampling,
+                                    int yuv_subspace, int gamma_type, pe_clip_cache_t **out) {
+  if (!e || !out || nframes <= 0) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  *out = nullptr;
+  if (!pal_known(palette)) return set_err(PE_ERR_PALETTE, "palette %d is not handled by this build", palette);
+  if (palette == PE_PALETTE_YUV420P || palette == PE_PALETTE_YVU420P) { width &= ~1; height &= ~1; }
+  pe_clip_cache *c = new pe_clip_cache();
+  c->e = e;
+  c->d.palette = palette; c->d.width = width; c->d.height = height;
+  c->d.yuv_clamping = yuv_clamping; c->d.yuv_sampling = yuv_sampling; c->d.yuv_subspace = yuv_subspace; c->d.gamma_type = gamma_type;
+  const size_t bytes = pe_frame_layout(palette, width, height, &c->d.nplanes, c->d.rowstrides, c->plane_heights);
+  if (!bytes) { delete c; return set_err(PE_ERR_ARG, "bad frame geometry"); }
+  size_t off = 0;
+  for (int p = 0; p < c->d.nplanes; p++) { c->plane_off[p] = off; off += ((size_t)c->d.rowstrides[p] * c->plane_heights[p] + 255) / 256 * 256; }
+  c->frame_bytes = off + 256;  // slack: the 4:2:x converters read a few bytes past the last chroma row (colourspace.c:3508)
+  c->nframes = nframes;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaMalloc(&c->base, c->frame_bytes * (size_t)nframes) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return set_err(PE_ERR_MEMORY, "device allocation of %zu bytes failed", c->frame_bytes * (size_t)nframes);
+  }
+  cudaMemsetAsync(c->base, 0, c->frame_bytes * (size_t)nframes, e->stream);
+  *out = c;
+  return PE_OK;
+}
+
+extern "C" void pe_clip_cache_destroy(pe_clip_cache_t *c) {
+  if (!c) return;
+  {
+    std::lock_guard<std::mutex> lk(c->e->mu);
+    cudaSetDevice(c->e->device);
+    cudaStreamSynchronize(c->e->stream);
+    cudaFree(c->base);
+  }
+  delete c;
+}
+
+// the one-time fill (what a device decoder would have written): host planes of frame `frame` -> HBM
+extern "C" int pe_clip_cache_load(pe_clip_cache_t *c, int64_t frame, const void *const host_planes[PE_MAXPLANES],
+                                  const int host_rowstrides[PE_MAXPLANES]) {
+  if (!c || !host_planes || frame < 0 || frame >= c->nframes) return set_err(PE_ERR_ARG, "bad clip cache argument");
+  pe_engine *e = c->e;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  for (int p = 0; p < c->d.nplanes; p++) {
+    if (!host_planes[p]) return set_err(PE_ERR_ARG, "host plane %d is NULL", p);
+    const int hrs = host_rowstrides ? host_rowstrides[p] : c->d.rowstrides[p];
+    const int wbytes = hrs < c->d.rowstrides[p] ? hrs : c->d.rowstrides[p];
+    PE_CUDA(cudaMemcpy2DAsync(c->base + c->frame_bytes * (size_t)frame + c->plane_off[p], c->d.rowstrides[p], host_planes[p], hrs, wbytes,
+                              c->plane_heights[p], cudaMemcpyHostToDevice, e->stream));
+  }
+  PE_CUDA(cudaStreamSynchronize(e->stream));
+  return PE_OK;
+}
+
+// device pointers of a cached frame (a device decoder / another kernel may write them directly)
+extern "C" int pe_clip_cache_frame_desc(pe_clip_cache_t *c, int64_t frame, pe_frame_desc_t *out) {
+  if (!c || !out || frame < 0 || frame >= c->nframes) return set_err(PE_ERR_ARG, "bad clip cache argument");
+  *out = c->d;
+  for (int p = 0; p < c->d.nplanes; p++) out->planes[p] = c->base + c->frame_bytes * (size_t)frame + c->plane_off[p];
+  return PE_OK;
+}
+
+namespace {
+// pe_device_get_frame_f of the cache: device-to-device copies of the planes on the engine stream (frame numbers wrap around)
+int clip_cache_get_frame(void *clip_data, int64_t frame, const int *rowstrides, int height, void *const *pixel_data, void *stream) {
+  pe_clip_cache *c = (pe_clip_cache *)clip_data;
+  if (!c || height != c->d.height) return 0;
+  const int64_t k = ((frame % c->nframes) + c->nframes) % c->nframes;
+  for (int p = 0; p < c->d.nplanes; p++) {
+    const int rb = rowstrides[p] < c->d.rowstrides[p] ? rowstrides[p] : c->d.rowstrides[p];
+    if (cudaMemcpy2DAsync(pixel_data[p], (size_t)rowstrides[p], c->base + c->frame_bytes * (size_t)k + c->plane_off[p], (size_t)c->d.rowstrides[p],
+                          (size_t)rb, (size_t)c->plane_heights[p], cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+  }
+  return 1;
+}
+}  // namespace
+
+extern "C" int pe_clip_cache_source(pe_clip_cache_t *c, pe_clip_source_t *out) {
+  if (!c || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  out->clip_data = c;
+  out->get_frame = clip_cache_get_frame;
+  out->palette = c->d.palette; out->width = c->d.width; out->height = c->d.height;
+  out->yuv_clamping = c->d.yuv_clamping; out->yuv_sampling = c->d.yuv_sampling; out->yuv_subspace = c->d.yuv_subspace;
+  out->gamma_type = c->d.gamma_type;
+  return PE_OK;
+}
+
+// zero-copy ingest: the cached frame itself as a (borrowed) layer -- for chains that only read it (the fused kernel's fg / bg)
+extern "C" int pe_clip_cache_borrow(pe_clip_cache_t *c, int64_t frame, pe_frame_t **out) {
+  pe_frame_desc_t d;
+  if (!c || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  const int64_t k = ((frame % c->nframes) + c->nframes) % c->nframes;
+  int rc = pe_clip_cache_frame_desc(c, k, &d);
+  if (rc != PE_OK) return rc;
+  return pe_frame_wrap(c->e, &d, out);
+}
+
+// egress, asynchronous: convert_layer_palette(layer, out_palette) when needed (the render tail converts to the clip's palette,
+// src/events.c:4250), then ONLY that packed frame travels to host memory on the download stream; slot 0 .. 3 names the copy for
+// pe_render_out_wait.  The layer must stay alive (and unwritten) until the wait.
+extern "C" int pe_render_out_begin(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride, int slot) {
+  if (!e || !layer || !host_dst || slot < 0 || slot >= 4) return set_err(PE_ERR_ARG, "bad render-out argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  if (out_palette != PE_PALETTE_NONE && layer->d.palette != out_palette) {
+    if (!convert_locked(e, layer, out_palette, layer->d.yuv_clamping, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YUV, PE_GAMMA_UNKNOWN))
+      return PE_ERR_PALETTE;
+  }
+  if (pal_is_planar(layer->d.palette)) return set_err(PE_ERR_PALETTE, "render-out takes a packed frame (RGB24 / RGBA32 / ...)");
+  if (!e->egress_stream) {
+    PE_CUDA(cudaStreamCreateWithFlags(&e->egress_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) {
+      PE_CUDA(cudaEventCreateWithFlags(&e->egress_ready[k], cudaEventDisableTiming));
+      PE_CUDA(cudaEventCreateWithFlags(&e->egress_done[k], cudaEventDisableTiming));
+    }
+  }
+  const int hrs = host_rowstride > 0 ? host_rowstride : layer->d.rowstrides[0];
+  PE_CUDA(cudaEventRecord(e->egress_ready[slot], e->stream));
+  PE_CUDA(cudaStreamWaitEvent(e->egress_stream, e->egress_ready[slot], 0));
+  PE_CUDA(cudaMemcpy2DAsync(host_dst, (size_t)hrs, layer->d.planes[0], (size_t)layer->d.rowstrides[0], (size_t)plane_row_bytes(layer->d, 0),
+                            (size_t)layer->d.height, cudaMemcpyDeviceToHost, e->egress_stream));
+  PE_CUDA(cudaEventRecord(e->egress_done[slot], e->egress_stream));
+  e->egress_busy[slot] = true;
+  return PE_OK;
+}
+
+extern "C" int pe_render_out_wait(pe_engine_t *e, int slot) {
+  if (!e || slot < 0 || slot >= 4) return set_err(PE_ERR_ARG, "bad render-out slot");
+  if (!e->egress_busy[slot]) return PE_OK;
+  PE_CUDA(cudaEventSynchronize(e->egress_done[slot]));
+  e->egress_busy[slot] = false;
+  return PE_OK;
+}
+
+extern "C" int pe_render_out(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride) {
+  int rc = pe_render_out_begin(e, layer, out_palette, host_dst, host_rowstride, 0);
+  return rc == PE_OK ? pe_render_out_wait(e, 0) : rc;
 }
 
 // ---- process-wide engine + host prefs + host-buffer registration (what the weed_layer_t drop-ins and the effect plugin share) ----

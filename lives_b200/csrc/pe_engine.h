@@ -81,6 +81,9 @@ struct pe_engine {
   // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t pipe_up[6] = {}, pipe_comp[6] = {}, pipe_free[6] = {};
+  cudaStream_t egress_stream = nullptr;  // pe_render_out_*: the final packed frame travels on its own stream
+  cudaEvent_t egress_ready[4] = {}, egress_done[4] = {};
+  bool egress_busy[4] = {};
   std::mutex mu;  // the reference calls these entry points from several proc-threads (different layers)
 
   pe::ConvTables conv_host[2][2];    // [clamping][bt709]

@@ -528,3 +528,63 @@ def host_fused_convert_letterbox_over_gamma_batch(engine, fgs, bgs, outs, inner_
         return a
     capi.check(engine._lib.pe_host_fused_convert_letterbox_over_gamma_batch(engine._h, n, arr(fgs), arr(bgs), arr(outs), inner_w,
                                                                             inner_h, alpha, gamma_from, gamma_to))
+
+
+# ---- ingest / egress in device memory ------------------------------------------------------------------
+
+class pe_clip_source_t(C.Structure):
+    _fields_ = [("clip_data", C.c_void_p), ("get_frame", C.c_void_p), ("palette", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("yuv_clamping", C.c_int), ("yuv_sampling", C.c_int), ("yuv_subspace", C.c_int), ("gamma_type", C.c_int)]
+
+
+class ClipCache:
+    """A clip resident in HBM (pe_clip_cache_t): the built-in device source behind the decoder plugin's get_frame shape
+    (src/plugins.h:442).  load() is the one-time fill; frame() / borrow() never touch host memory."""
+
+    def __init__(self, engine, palette, width, height, nframes, yuv_clamping=0, yuv_sampling=0, yuv_subspace=0, gamma_type=0):
+        self.engine = engine
+        h = C.c_void_p()
+        capi.check(engine._lib.pe_clip_cache_create(engine._h, palette, width, height, nframes, yuv_clamping, yuv_sampling, yuv_subspace,
+                                                    gamma_type, C.byref(h)))
+        self._h = h
+        self.nframes = nframes
+        self._src = pe_clip_source_t()
+        capi.check(engine._lib.pe_clip_cache_source(self._h, C.byref(self._src)))
+
+    def load(self, frame, planes):
+        ptrs, rs = (C.c_void_p * 4)(), (C.c_int * 4)()
+        for i, p in enumerate(planes):
+            ptrs[i], rs[i] = p.ctypes.data, p.strides[0]
+        capi.check(self.engine._lib.pe_clip_cache_load(self._h, frame, ptrs, rs))
+
+    def frame(self, n):
+        """pull_frame on the device: a new Layer filled by the source's get_frame (device-to-device)"""
+        h = C.c_void_p()
+        capi.check(self.engine._lib.pe_ingest_frame(self.engine._h, C.byref(self._src), n, C.byref(h)))
+        return Layer(self.engine, h)
+
+    def borrow(self, n):
+        """zero copy: the cached frame itself as a read-only Layer"""
+        h = C.c_void_p()
+        capi.check(self.engine._lib.pe_clip_cache_borrow(self._h, n, C.byref(h)))
+        return Layer(self.engine, h)
+
+    def close(self):
+        if self._h:
+            self.engine._lib.pe_clip_cache_destroy(self._h)
+            self._h = None
+
+
+def render_out(layer, out_palette, host_array):
+    """the render tail (src/events.c:4247-4263): convert to out_palette, download only that packed frame"""
+    e = layer.engine
+    capi.check(e._lib.pe_render_out(e._h, layer._h, out_palette, host_array.ctypes.data, host_array.strides[0]))
+
+
+def render_out_begin(layer, out_palette, host_array, slot):
+    e = layer.engine
+    capi.check(e._lib.pe_render_out_begin(e._h, layer._h, out_palette, host_array.ctypes.data, host_array.strides[0], slot))
+
+
+def render_out_wait(engine, slot):
+    capi.check(engine._lib.pe_render_out_wait(engine._h, slot))
