@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 1
+#define PE_ABI_VERSION 2
 #define PE_TRUE 1
 #define PE_FALSE 0
 #define PE_MAXPLANES 4 /* WEED_MAXPPLANES */
@@ -249,6 +249,29 @@ int pe_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, int n, const pe_
                                                 const pe_frame_t *const *bg, pe_frame_t *const *out, int inner_w,
                                                 int inner_h, double alpha, int gamma_from, int gamma_to);
 
+/* ---- the node model's CONVERT step as one descriptor ----------------------------------------------------- */
+
+/* What get_op_order (src/nodemodel.c:161, called :1981) decides per layer -- which of resize / palette conversion / gamma / letterbox
+ * are needed and in which order (equal numbers = one operation does both) -- with their arguments: the binding hands the whole
+ * chain over in one call instead of issuing res -> pconv -> lbox -> gamma substeps (:1065-1282). */
+enum { PE_OP_RESIZE = 0, PE_OP_PCONV = 1, PE_OP_GAMMA = 2, PE_OP_LETTERBOX = 3, PE_N_OP_TYPES = 6 }; /* src/nodemodel.h:717-722 */
+typedef struct pe_convert_plan {
+  int op_order[PE_N_OP_TYPES]; /* get_op_order's output: 0 not needed, 1 .. the substep an op runs in */
+  int width, height;           /* OP_RESIZE target = the inner rectangle when letterboxing (pixels) */
+  int lb_width, lb_height;     /* OP_LETTERBOX outer size */
+  int interp;                  /* LiVESInterpType */
+  int out_palette, out_clamping, out_sampling, out_subspace; /* OP_PCONV */
+  int out_gamma;               /* OP_GAMMA */
+  int no_fuse;                 /* 1: never take the fused kernel (tests) */
+} pe_convert_plan_t;
+/* the substeps, one reference op at a time, in the plan's order; boolean */
+int pe_run_convert_plan(pe_engine_t *e, pe_frame_t *layer, const pe_convert_plan_t *plan);
+/* CONVERT + the compositor APPLY_INST over one background layer + gamma (:1119-1333): ONE fused launch when the plan is planar YUV ->
+ * RGBA32 + letterbox (bilinear), the op-by-op sequence otherwise; same bytes.  pe_last_plan_path(): 1 fused, 0 op by op */
+int pe_run_convert_plan_over(pe_engine_t *e, const pe_frame_t *fg, const pe_convert_plan_t *plan, const pe_frame_t *bg, pe_frame_t *out,
+                             double alpha, int gamma_to);
+int pe_last_plan_path(void);
+
 /* ---- frame ingest / egress in device memory -------------------------------------------------------------- */
 
 /* boolean get_frame(const lives_clip_data_t *, int64_t frame, int *rowstrides, int height, void **pixel_data)
@@ -288,11 +311,16 @@ int pe_render_out(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host
 
 typedef struct pe_frame_stats {
   uint8_t min[4], max[4]; /* per byte position of a packed pixel (plane 0 for planar) */
-  uint32_t hist[256];     /* histogram of byte position 0..2 (colour bytes) of plane 0 */
+  uint32_t hist[256];     /* histogram of the colour bytes (the alpha byte excluded) of plane 0 */
   uint64_t sum;           /* sum of all payload bytes of plane 0 */
-  int all_black_ish;      /* every colour byte < 20 (colourspace.c:2554-2594, exact == 0 mode) */
+  int all_black_ish;      /* is_all_black_ish(..., exact = FALSE): the reference's bit expression on bytes 0 .. 2 of every pixel
+                             (colourspace.c:2583-2587); -1 when the palette is not packed RGB */
+  int all_black;          /* is_all_black_ish(..., exact = TRUE): bytes 0 .. 2 of every pixel are 0 (:2589); -1 as above */
 } pe_frame_stats_t;
 int pe_frame_stats(pe_engine_t *e, const pe_frame_t *f, pe_frame_stats_t *out);
+/* hash_cmp_layer (colourspace.c:16044-16075): minimd5 (src/maths.c:575, the reference's own MD5 variant) of the first nbytes bytes of
+ * every row of plane 0 (nbytes <= 0: the reference's `width` bytes, width in macropixels) + their XOR (the "parity", :16068) */
+int pe_frame_row_hashes(pe_engine_t *e, const pe_frame_t *f, int nbytes, uint64_t *hashes, uint64_t *parity);
 
 /* ---- host-frame drop-ins: H2D -> device op -> D2H around the calls above --------------------- */
 

@@ -38,7 +38,7 @@ class pe_frame_desc_t(C.Structure):
 
 class pe_frame_stats_t(C.Structure):
     _fields_ = [("min", C.c_uint8 * 4), ("max", C.c_uint8 * 4), ("hist", C.c_uint32 * 256), ("sum", C.c_uint64),
-                ("all_black_ish", C.c_int)]
+                ("all_black_ish", C.c_int), ("all_black", C.c_int)]
 
 
 class pe_host_allocator_t(C.Structure):
@@ -64,6 +64,9 @@ PROTOTYPES = {
     "pe_engine_set_prefs": (I, [VP, I, C.c_double, I, I]),
     "pe_engine_get_config": (I, [VP, C.c_void_p]),
     "pe_host_register": (I, [VP, SZ]),
+    "pe_run_convert_plan": (I, [VP, VP, C.c_void_p]),
+    "pe_run_convert_plan_over": (I, [VP, VP, C.c_void_p, VP, VP, C.c_double, I]),
+    "pe_last_plan_path": (I, []),
     "pe_ingest_frame": (I, [VP, C.c_void_p, C.c_int64, PVP]),
     "pe_clip_cache_create": (I, [VP, I, I, I, I, I, I, I, I, PVP]),
     "pe_clip_cache_destroy": (None, [VP]),
@@ -118,6 +121,7 @@ PROTOTYPES = {
     "pe_fused_convert_letterbox_over_gamma": (I, [VP, VP, VP, VP, I, I, D, I, I]),
     "pe_fused_convert_letterbox_over_gamma_batch": (I, [VP, I, PVP, PVP, PVP, I, I, D, I, I]),
     "pe_frame_stats": (I, [VP, VP, C.POINTER(pe_frame_stats_t)]),
+    "pe_frame_row_hashes": (I, [VP, VP, I, C.c_void_p, C.c_void_p]),
     "pe_host_convert_layer_palette_full": (I, [VP, PDESC, I, I, I, I, I, VP]),
     "pe_host_resize_layer": (I, [VP, PDESC, I, I, I, I, I, VP]),
     "pe_host_letterbox_layer": (I, [VP, PDESC, I, I, I, I, I, I, I, VP]),

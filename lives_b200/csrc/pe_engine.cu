@@ -2538,6 +2538,89 @@ extern "C" int pe_fused_convert_letterbox_over_gamma(pe_engine_t *e, const pe_fr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// the CONVERT step of the node model as one descriptor (src/nodemodel.c:161 get_op_order -> :1065-1282)
+// ---------------------------------------------------------------------------------------------------------
+
+static thread_local int g_last_plan_path = -1;
+extern "C" int pe_last_plan_path(void) { return g_last_plan_path; }
+
+// the substeps in get_op_order's order, one op at a time: what run_plan's CONVERT step does with the reference's own functions
+extern "C" int pe_run_convert_plan(pe_engine_t *e, pe_frame_t *layer, const pe_convert_plan_t *plan) {
+  if (!e || !layer || !plan) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  int maxord = 0;
+  for (int i = 0; i < PE_N_OP_TYPES; i++) maxord = plan->op_order[i] > maxord ? plan->op_order[i] : maxord;
+  const int lbox = plan->op_order[PE_OP_LETTERBOX];
+  for (int ord = 1; ord <= maxord; ord++) {
+    const bool rsz = plan->op_order[PE_OP_RESIZE] == ord, pcv = plan->op_order[PE_OP_PCONV] == ord, gam = plan->op_order[PE_OP_GAMMA] == ord;
+    if (lbox == ord) {
+      // letterbox_layer resizes the image to the inner rectangle itself (:15388-15393); a plan that also names OP_RESIZE earlier has
+      // already brought the layer to that size
+      if (!pe_letterbox_layer(e, layer, plan->lb_width, plan->lb_height, plan->width, plan->height, plan->interp,
+                              pcv ? plan->out_palette : PE_PALETTE_NONE, plan->out_clamping))
+        return PE_FALSE;
+      continue;
+    }
+    if (rsz) {
+      // "resize can do resize OR resize + palconv OR resize + gamma OR resize + palconv + gamma" (:167-169)
+      if (lbox == ord + 1 && !pcv && !gam) continue;  // the letterbox that follows does this resize
+      if (!pe_resize_layer_full(e, layer, plan->width, plan->height, plan->interp, pcv ? plan->out_palette : PE_PALETTE_NONE,
+                                plan->out_clamping, plan->out_sampling, plan->out_subspace, gam ? plan->out_gamma : PE_GAMMA_UNKNOWN))
+        return PE_FALSE;
+      if (pcv && layer->d.palette != plan->out_palette &&
+          !pe_convert_layer_palette_full(e, layer, plan->out_palette, plan->out_clamping, plan->out_sampling, plan->out_subspace,
+                                         gam ? plan->out_gamma : PE_GAMMA_UNKNOWN))
+        return PE_FALSE;
+      if (gam && layer->d.gamma_type != plan->out_gamma && !pe_gamma_convert_layer(e, plan->out_gamma, layer)) return PE_FALSE;
+    } else if (pcv) {
+      if (!pe_convert_layer_palette_full(e, layer, plan->out_palette, plan->out_clamping, plan->out_sampling, plan->out_subspace,
+                                         gam ? plan->out_gamma : PE_GAMMA_UNKNOWN))
+        return PE_FALSE;
+      if (gam && layer->d.gamma_type != plan->out_gamma && !pe_gamma_convert_layer(e, plan->out_gamma, layer)) return PE_FALSE;
+    } else if (gam) {
+      if (!pe_gamma_convert_layer(e, plan->out_gamma, layer)) return PE_FALSE;
+    }
+  }
+  return PE_TRUE;
+}
+
+// CONVERT (the plan) followed by the APPLY_INST + gamma substeps (:1119-1333) when the instance is the compositor painting the converted
+// layer over ONE background layer: the whole chain is one fused kernel launch when the plan is "planar YUV -> RGBA32, letterboxed,
+// bilinear" -- which is what the fused kernels cover -- and the reference's op-by-op sequence otherwise.  Same bytes either way.
+// plan->no_fuse forces the op-by-op path (tests); pe_last_plan_path(): 1 fused, 0 op by op.
+extern "C" int pe_run_convert_plan_over(pe_engine_t *e, const pe_frame_t *fg, const pe_convert_plan_t *plan, const pe_frame_t *bg,
+                                        pe_frame_t *out, double alpha, int gamma_to) {
+  if (!e || !fg || !plan || !bg || !out) return set_err(PE_ERR_ARG, "NULL argument");
+  const int ip = fg->d.palette;
+  const bool planar_src = ip == PE_PALETTE_YUV420P || ip == PE_PALETTE_YVU420P || ip == PE_PALETTE_YUV422P;
+  const bool wants_gamma_before = plan->op_order[PE_OP_GAMMA] != 0;
+  const bool fusable = !plan->no_fuse && planar_src && plan->op_order[PE_OP_PCONV] != 0 && plan->out_palette == PE_PALETTE_RGBA32 &&
+                       plan->op_order[PE_OP_LETTERBOX] != 0 && !wants_gamma_before && plan->interp == PE_INTERP_NORMAL &&
+                       bg->d.palette == PE_PALETTE_RGBA32 && out->d.palette == PE_PALETTE_RGBA32 && bg->d.width == plan->lb_width &&
+                       bg->d.height == plan->lb_height && out->d.width == plan->lb_width && out->d.height == plan->lb_height &&
+                       plan->width <= plan->lb_width && plan->height <= plan->lb_height;
+  if (fusable) {
+    g_last_plan_path = 1;
+    return pe_fused_convert_letterbox_over_gamma(e, fg, bg, out, plan->width, plan->height, alpha, bg->d.gamma_type, gamma_to);
+  }
+  g_last_plan_path = 0;
+  pe_frame_t *work = nullptr;
+  int rc = pe_frame_copy(e, fg, &work);
+  if (rc != PE_OK) return rc;
+  if (!pe_run_convert_plan(e, work, plan)) { pe_frame_destroy(work); return PE_ERR_PALETTE; }
+  if (work->d.palette != out->d.palette || work->d.width != out->d.width || work->d.height != out->d.height) {
+    pe_frame_destroy(work);
+    return set_err(PE_ERR_SIZE, "the plan does not end in the out layer's palette / size");
+  }
+  // compositor: bg opaque underneath, the converted layer over it with `alpha`; then gamma
+  const pe_frame_t *layers[2] = {work, bg};
+  const double alphas[2] = {alpha, 1.0};
+  out->d.gamma_type = bg->d.gamma_type;
+  rc = pe_fx_compositor_gamma(e, out, layers, alphas, 2, nullptr, gamma_to);
+  pe_frame_destroy(work);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------------------------------------
 
@@ -2562,7 +2645,32 @@ extern "C" int pe_frame_stats(pe_engine_t *e, const pe_frame_t *f, pe_frame_stat
   for (int k = 0; k < 4; k++) { out->min[k] = (uint8_t)res.minv[k]; out->max[k] = (uint8_t)res.maxv[k]; }
   memcpy(out->hist, res.hist, sizeof(out->hist));
   out->sum = res.sum;
-  out->all_black_ish = res.not_black ? 0 : 1;
+  // is_all_black_ish is defined on packed RGB pixels (bytes 0 .. 2 of every pixel, :2575-2577); elsewhere: -1
+  const bool rgbish = !pal_is_planar(pal) && (psize == 3 || psize == 4);
+  out->all_black = rgbish ? (res.not_black ? 0 : 1) : -1;
+  out->all_black_ish = rgbish ? (res.not_black_ish ? 0 : 1) : -1;
+  return PE_OK;
+}
+
+// hash_cmp_layer (colourspace.c:16044-16075): one 64-bit hash per row of plane 0 (minimd5 of the row's first `nbytes` bytes; nbytes
+// <= 0: what the reference hashes -- `width` bytes with width the layer's width leaf in MACROpixels, i.e. the first third / quarter of
+// a packed RGB row) and their XOR ("parity", :16068).  hashes: host array of `height` entries.
+extern "C" int pe_frame_row_hashes(pe_engine_t *e, const pe_frame_t *f, int nbytes, uint64_t *hashes, uint64_t *parity) {
+  if (!e || !f || !hashes || !f->d.planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  const int pal = f->d.palette, h = f->d.height;
+  if (nbytes <= 0) nbytes = f->d.width / pal_ppmp(pal);
+  if (nbytes > f->d.rowstrides[0]) return set_err(PE_ERR_ARG, "row hash: %d bytes asked of a %d-byte row", nbytes, f->d.rowstrides[0]);
+  size_t granted = 0;
+  unsigned long long *dev = (unsigned long long *)e->pool.get(sizeof(unsigned long long) * (size_t)h, &granted);
+  if (!dev) return set_err(PE_ERR_MEMORY, "device allocation failed");
+  cudaError_t ce = launch_row_hash(e->L(), CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, nbytes, h, dev);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(hashes, dev, sizeof(uint64_t) * (size_t)h, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  e->pool.put(dev, granted);
+  if (ce != cudaSuccess) return set_err(PE_ERR_CUDA, "row hash failed: %s", cudaGetErrorString(ce));
+  if (parity) { uint64_t x = 0; for (int i = 0; i < h; i++) x ^= hashes[i]; *parity = x; }
   return PE_OK;
 }
 

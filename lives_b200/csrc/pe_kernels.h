@@ -229,8 +229,11 @@ struct DevStats {
   unsigned int minv[4], maxv[4];
   unsigned int hist[256];
   unsigned long long sum;
-  unsigned int not_black;
+  unsigned int not_black;      // some colour byte of bytes 0..2 is non-zero (is_all_black_ish exact branch fails)
+  unsigned int not_black_ish;  // the reference's "ish" expression is non-zero for some pixel (:2583-2587)
 };
 cudaError_t launch_stats(const Launch &L, CImg img, int width, int height, int psize, int a_off, DevStats *out_dev);
+// minimd5 (src/maths.c:575) of the first nbytes bytes of every row: the row hashes of hash_cmp_layer (colourspace.c:16044)
+cudaError_t launch_row_hash(const Launch &L, CImg img, int nbytes, int height, unsigned long long *out_dev);
 
 }  // namespace pe

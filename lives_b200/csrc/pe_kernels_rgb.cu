@@ -881,21 +881,78 @@ cudaError_t launch_alpha_over(const Launch &L, CImg bg, CImg fg, Img dst, int wi
 
 namespace {
 
-__global__ void __launch_bounds__(kBlock) k_stats(const uint8_t *__restrict__ p, int rs, int width, int height, int psize,
-                                                  int a_off, DevStats *out) {
-  __shared__ unsigned int s_hist[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
-  unsigned int mn[4] = {255, 255, 255, 255}, mx[4] = {0, 0, 0, 0}, notblack = 0;
+// k_stats: min / max / sum per byte position, histogram of the colour bytes, and both branches of is_all_black_ish
+// (colourspace.c:2554-2594) in one pass.  A CTA stages a chunk of a row in shared memory with 128-bit streaming loads (every byte
+// crosses HBM once, as whole sectors); a thread then owns whole pixels of the chunk, so its channel indices are static; the histogram
+// goes to a per-WARP private copy in shared memory (no contention between warps), everything else is reduced with warp shuffles and
+// leaves the CTA as one atomic per quantity.
+constexpr int ST_CHUNK3 = 4080, ST_CHUNK4 = 4096;   // bytes of a row per step: whole pixels and whole 16-byte vectors
+
+// the reference's "ish" test on the first three bytes a, b, c of a pixel, bit for bit (:2583-2587): nonzero = not black-ish
+__device__ __forceinline__ unsigned int ish_expr(unsigned int a, unsigned int b, unsigned int c) {
+  const unsigned int na = (a & 0x1Fu) ^ a, nc = (c & 0x1Fu) ^ c, nb = (b & 0x1Fu) ^ b;
+  const unsigned int t1 = ((b << 1) & 0x1Fu) ^ (b << 1), t2 = (((b & 0x0Fu) << 2) & 0x1Fu) ^ ((b & 0x0Fu) << 2);
+  return na & nc & (nb | (t1 & t2));
+}
+
+template <int PS>
+__global__ void __launch_bounds__(kBlock) k_stats(const uint8_t *__restrict__ p, int rs, int width, int height, int a_off, DevStats *out) {
+  constexpr int CHUNK = PS == 3 ? ST_CHUNK3 : ST_CHUNK4;
+  __shared__ __align__(16) uint8_t s_buf[ST_CHUNK4];
+  __shared__ unsigned int s_hist[kBlock / 32][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (kBlock / 32) * 256; i += kBlock) (&s_hist[0][0])[i] = 0u;
+  unsigned int mn[4] = {255, 255, 255, 255}, mx[4] = {0, 0, 0, 0}, notblack = 0, notish = 0;
   unsigned long long sum = 0;
-  const long long total = (long long)width * height;
-  for (long long it = global_tid(); it < total; it += global_threads()) {
-    const int row = (int)(it / width), x = (int)(it - (long long)row * width);
-    const uint8_t *q = p + (long long)row * rs + (long long)x * psize;
-    for (int k = 0; k < psize; k++) {
-      const unsigned int v = q[k];
-      mn[k] = min(mn[k], v); mx[k] = max(mx[k], v); sum += v;
-      if (k != a_off) { atomicAdd(&s_hist[v], 1u); notblack |= (v != 0); }
+  const int row_bytes = width * PS;
+  const int chunks_per_row = (row_bytes + CHUNK - 1) / CHUNK;
+  const long long units = (long long)chunks_per_row * height;
+  unsigned int *hist = s_hist[warp];
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const int row = (int)(u / chunks_per_row), c0 = (int)(u - (long long)row * chunks_per_row) * CHUNK;
+    const int nb = min(CHUNK, row_bytes - c0);
+    const uint8_t *src = p + (long long)rs * row + c0;
+    __syncthreads();  // the previous chunk has been consumed
+    if ((((uintptr_t)src) & 15) == 0) {
+      for (int i = threadIdx.x; i * 16 < nb; i += kBlock) {
+        if (i * 16 + 16 <= nb) reinterpret_cast<uint4 *>(s_buf)[i] = ld_stream_u4(src + 16 * i);
+        else for (int k = i * 16; k < nb; k++) s_buf[k] = src[k];
+      }
+    } else {
+      for (int k = threadIdx.x; k < nb; k += kBlock) s_buf[k] = src[k];
+    }
+    __syncthreads();
+    if (PS == 1) {  // planar: one byte per sample, 4 at a time
+      for (int i = threadIdx.x * 4; i < nb; i += kBlock * 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (i + k < nb) {
+            const unsigned int v = s_buf[i + k];
+            mn[0] = min(mn[0], v); mx[0] = max(mx[0], v); sum += v;
+            atomicAdd(&hist[v], 1u);
+            notblack |= v;
+          }
+        }
+      }
+    } else {
+      const int npx = nb / PS;
+      for (int i = threadIdx.x; i < npx; i += kBlock) {
+        unsigned int v[4];
+        if (PS == 4) {
+          const unsigned int w = reinterpret_cast<const unsigned int *>(s_buf)[i];
+          v[0] = w & 255u; v[1] = (w >> 8) & 255u; v[2] = (w >> 16) & 255u; v[3] = w >> 24;
+        } else {
+          v[0] = s_buf[3 * i]; v[1] = s_buf[3 * i + 1]; v[2] = s_buf[3 * i + 2]; v[3] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < PS; k++) {
+          mn[k] = min(mn[k], v[k]); mx[k] = max(mx[k], v[k]); sum += v[k];
+          if (k != a_off) atomicAdd(&hist[v[k]], 1u);
+        }
+        // is_all_black_ish looks at bytes 0, 1, 2 of the pixel whatever the palette (:2575-2577; its caller passes offs = 0)
+        notblack |= v[0] | v[1] | v[2];
+        notish |= ish_expr(v[0], v[1], v[2]);
+      }
     }
   }
 #pragma unroll
@@ -907,20 +964,141 @@ __global__ void __launch_bounds__(kBlock) k_stats(const uint8_t *__restrict__ p,
     }
     sum += __shfl_xor_sync(0xffffffffu, sum, off);
     notblack |= __shfl_xor_sync(0xffffffffu, notblack, off);
+    notish |= __shfl_xor_sync(0xffffffffu, notish, off);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     for (int k = 0; k < 4; k++) { atomicMin(&out->minv[k], mn[k]); atomicMax(&out->maxv[k], mx[k]); }
     atomicAdd(&out->sum, sum);
     if (notblack) atomicOr(&out->not_black, 1u);
+    if (notish) atomicOr(&out->not_black_ish, 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (s_hist[i]) atomicAdd(&out->hist[i], s_hist[i]);
+  for (int i = threadIdx.x; i < 256; i += kBlock) {
+    unsigned int t = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) t += s_hist[w][i];
+    if (t) atomicAdd(&out->hist[i], t);
+  }
+}
+
+// k_row_hash: the row hashes of hash_cmp_layer (colourspace.c:16044-16075): minimd5 (src/maths.c:575) of the first `nbytes` bytes of
+// every row.  minimd5 is the reference's OWN MD5 variant (src/maths.h:42-56): rounds 2 - 4 are RFC 1321's, round 1 is not -- its BX
+// macro runs the four state words in the order A B C D with the rotations 7 22 17 12, and its fourth step mixes the step-2 CONSTANT
+// where RFC 1321 has the state word C (a macro parameter named X shadows nothing but reads as the constant).  Restated as written.
+// One warp per row: the lanes load the row 128 bytes at a time (coalesced), the 16 words of each 64-byte block are broadcast with
+// shuffles and every lane runs the same 64 steps (no divergence); the tail block(s) with the padding and the bit count are built in
+// registers.
+__device__ __forceinline__ uint32_t md5_rotl(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
+__device__ __forceinline__ uint32_t md5_f(uint32_t b, uint32_t c, uint32_t d) { return d ^ (b & (c ^ d)); }
+
+__device__ __forceinline__ void lives_md5_block(const uint32_t (&X)[16], uint32_t &A, uint32_t &B, uint32_t &C, uint32_t &D) {
+  const uint32_t T1[16] = {0xd76aa478u, 0xe8c7b756u, 0x242070dbu, 0xc1bdceeeu, 0xf57c0fafu, 0x4787c62au, 0xa8304613u, 0xfd469501u,
+                           0x698098d8u, 0x8b44f7afu, 0xffff5bb1u, 0x895cd7beu, 0x6b901122u, 0xfd987193u, 0xa679438eu, 0x49b40821u};
+  const uint32_t a0 = A, b0 = B, c0 = C, d0 = D;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {  // BX(W, X, Y, Z), src/maths.h:48
+    A += md5_f(B, C, D) + X[4 * q] + T1[4 * q]; A = md5_rotl(A, 7) + B;
+    B += md5_f(C, D, A) + X[4 * q + 1] + T1[4 * q + 1]; B = md5_rotl(B, 22) + C;
+    C += md5_f(D, A, B) + X[4 * q + 2] + T1[4 * q + 2]; C = md5_rotl(C, 17) + D;
+    D += md5_f(A, B, T1[4 * q + 1]) + X[4 * q + 3] + T1[4 * q + 3]; D = md5_rotl(D, 12) + A;
+  }
+#define PE_MD5_STEP(fn, a, b, c, d, k, s, t) a += fn(b, c, d) + X[k] + t; a = md5_rotl(a, s) + b;
+#define PE_MD5_G(b, c, d) md5_f(d, b, c)
+#define PE_MD5_H(b, c, d) ((b) ^ (c) ^ (d))
+#define PE_MD5_I(b, c, d) ((c) ^ ((b) | ~(d)))
+  PE_MD5_STEP(PE_MD5_G, A, B, C, D, 1, 5, 0xf61e2562u) PE_MD5_STEP(PE_MD5_G, D, A, B, C, 6, 9, 0xc040b340u)
+  PE_MD5_STEP(PE_MD5_G, C, D, A, B, 11, 14, 0x265e5a51u) PE_MD5_STEP(PE_MD5_G, B, C, D, A, 0, 20, 0xe9b6c7aau)
+  PE_MD5_STEP(PE_MD5_G, A, B, C, D, 5, 5, 0xd62f105du) PE_MD5_STEP(PE_MD5_G, D, A, B, C, 10, 9, 0x02441453u)
+  PE_MD5_STEP(PE_MD5_G, C, D, A, B, 15, 14, 0xd8a1e681u) PE_MD5_STEP(PE_MD5_G, B, C, D, A, 4, 20, 0xe7d3fbc8u)
+  PE_MD5_STEP(PE_MD5_G, A, B, C, D, 9, 5, 0x21e1cde6u) PE_MD5_STEP(PE_MD5_G, D, A, B, C, 14, 9, 0xc33707d6u)
+  PE_MD5_STEP(PE_MD5_G, C, D, A, B, 3, 14, 0xf4d50d87u) PE_MD5_STEP(PE_MD5_G, B, C, D, A, 8, 20, 0x455a14edu)
+  PE_MD5_STEP(PE_MD5_G, A, B, C, D, 13, 5, 0xa9e3e905u) PE_MD5_STEP(PE_MD5_G, D, A, B, C, 2, 9, 0xfcefa3f8u)
+  PE_MD5_STEP(PE_MD5_G, C, D, A, B, 7, 14, 0x676f02d9u) PE_MD5_STEP(PE_MD5_G, B, C, D, A, 12, 20, 0x8d2a4c8au)
+  PE_MD5_STEP(PE_MD5_H, A, B, C, D, 5, 4, 0xfffa3942u) PE_MD5_STEP(PE_MD5_H, D, A, B, C, 8, 11, 0x8771f681u)
+  PE_MD5_STEP(PE_MD5_H, C, D, A, B, 11, 16, 0x6d9d6122u) PE_MD5_STEP(PE_MD5_H, B, C, D, A, 14, 23, 0xfde5380cu)
+  PE_MD5_STEP(PE_MD5_H, A, B, C, D, 1, 4, 0xa4beea44u) PE_MD5_STEP(PE_MD5_H, D, A, B, C, 4, 11, 0x4bdecfa9u)
+  PE_MD5_STEP(PE_MD5_H, C, D, A, B, 7, 16, 0xf6bb4b60u) PE_MD5_STEP(PE_MD5_H, B, C, D, A, 10, 23, 0xbebfbc70u)
+  PE_MD5_STEP(PE_MD5_H, A, B, C, D, 13, 4, 0x289b7ec6u) PE_MD5_STEP(PE_MD5_H, D, A, B, C, 0, 11, 0xeaa127fau)
+  PE_MD5_STEP(PE_MD5_H, C, D, A, B, 3, 16, 0xd4ef3085u) PE_MD5_STEP(PE_MD5_H, B, C, D, A, 6, 23, 0x04881d05u)
+  PE_MD5_STEP(PE_MD5_H, A, B, C, D, 9, 4, 0xd9d4d039u) PE_MD5_STEP(PE_MD5_H, D, A, B, C, 12, 11, 0xe6db99e5u)
+  PE_MD5_STEP(PE_MD5_H, C, D, A, B, 15, 16, 0x1fa27cf8u) PE_MD5_STEP(PE_MD5_H, B, C, D, A, 2, 23, 0xc4ac5665u)
+  PE_MD5_STEP(PE_MD5_I, A, B, C, D, 0, 6, 0xf4292244u) PE_MD5_STEP(PE_MD5_I, D, A, B, C, 7, 10, 0x432aff97u)
+  PE_MD5_STEP(PE_MD5_I, C, D, A, B, 14, 15, 0xab9423a7u) PE_MD5_STEP(PE_MD5_I, B, C, D, A, 5, 21, 0xfc93a039u)
+  PE_MD5_STEP(PE_MD5_I, A, B, C, D, 12, 6, 0x655b59c3u) PE_MD5_STEP(PE_MD5_I, D, A, B, C, 3, 10, 0x8f0ccc92u)
+  PE_MD5_STEP(PE_MD5_I, C, D, A, B, 10, 15, 0xffeff47du) PE_MD5_STEP(PE_MD5_I, B, C, D, A, 1, 21, 0x85845dd1u)
+  PE_MD5_STEP(PE_MD5_I, A, B, C, D, 8, 6, 0x6fa87e4fu) PE_MD5_STEP(PE_MD5_I, D, A, B, C, 15, 10, 0xfe2ce6e0u)
+  PE_MD5_STEP(PE_MD5_I, C, D, A, B, 6, 15, 0xa3014314u) PE_MD5_STEP(PE_MD5_I, B, C, D, A, 13, 21, 0x4e0811a1u)
+  PE_MD5_STEP(PE_MD5_I, A, B, C, D, 4, 6, 0xf7537e82u) PE_MD5_STEP(PE_MD5_I, D, A, B, C, 11, 10, 0xbd3af235u)
+  PE_MD5_STEP(PE_MD5_I, C, D, A, B, 2, 15, 0x2ad7d2bbu) PE_MD5_STEP(PE_MD5_I, B, C, D, A, 9, 21, 0xeb86d391u)
+#undef PE_MD5_STEP
+#undef PE_MD5_G
+#undef PE_MD5_H
+#undef PE_MD5_I
+  A += a0; B += b0; C += c0; D += d0;
+}
+
+// word `wi` of the padded message of a row of n bytes: data, then 0x80, zeros, the bit count in the last two words of the last block
+__device__ __forceinline__ uint32_t md5_msg_word(const uint8_t *__restrict__ row, int n, int wi, int total_words) {
+  const int o = 4 * wi;
+  if (o + 4 <= n) {
+    if ((((uintptr_t)row) & 3) == 0) return *reinterpret_cast<const uint32_t *>(row + o);
+    return (uint32_t)row[o] | ((uint32_t)row[o + 1] << 8) | ((uint32_t)row[o + 2] << 16) | ((uint32_t)row[o + 3] << 24);
+  }
+  if (wi == total_words - 2) return (uint32_t)n << 3;
+  if (wi == total_words - 1) return (uint32_t)n >> 29;
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int b = o + k;
+    const uint32_t v = b < n ? row[b] : (b == n ? 0x80u : 0u);
+    w |= v << (8 * k);
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(kBlock) k_row_hash(const uint8_t *__restrict__ p, int rs, int nbytes, int height, unsigned long long *out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (row >= height) return;
+  const uint8_t *r = p + (long long)rs * row;
+  const int nblocks = (nbytes + 8) / 64 + 1;       // 0x80 and the 8 length bytes must fit
+  const int total_words = nblocks * 16;
+  uint32_t A = 0x67452301u, B = 0xefcdab89u, C = 0x98badcfeu, D = 0x10325476u;
+  for (int blk = 0; blk < nblocks; blk += 2) {     // the warp fetches two blocks (32 words) at a time
+    const int wi = blk * 16 + lane;
+    const uint32_t mine = wi < total_words ? md5_msg_word(r, nbytes, wi, total_words) : 0u;
+    uint32_t X[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) X[k] = __shfl_sync(0xffffffffu, mine, k);
+    lives_md5_block(X, A, B, C, D);
+    if (blk + 1 < nblocks) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) X[k] = __shfl_sync(0xffffffffu, mine, 16 + k);
+      lives_md5_block(X, A, B, C, D);
+    }
+  }
+  // minimd5: U[0] ^ U[1] of the 16 digest bytes (little endian)
+  if (lane == 0) out[row] = ((unsigned long long)A | ((unsigned long long)B << 32)) ^ ((unsigned long long)C | ((unsigned long long)D << 32));
 }
 
 }  // namespace
 
 cudaError_t launch_stats(const Launch &L, CImg img, int width, int height, int psize, int a_off, DevStats *out_dev) {
-  k_stats<<<grid_for(L, (long long)width * height, 4), kBlock, 0, L.stream>>>(img.p, img.rs, width, height, psize, a_off, out_dev);
+  const int row_bytes = width * psize, chunk = psize == 3 ? ST_CHUNK3 : ST_CHUNK4;
+  const long long units = (long long)((row_bytes + chunk - 1) / chunk) * height;
+  long long g = (long long)L.sm_count * 6;
+  if (g > units) g = units;
+  if (g < 1) g = 1;
+  if (psize == 4) k_stats<4><<<(int)g, kBlock, 0, L.stream>>>(img.p, img.rs, width, height, a_off, out_dev);
+  else if (psize == 3) k_stats<3><<<(int)g, kBlock, 0, L.stream>>>(img.p, img.rs, width, height, a_off, out_dev);
+  else if (psize == 1) k_stats<1><<<(int)g, kBlock, 0, L.stream>>>(img.p, img.rs, width, height, a_off, out_dev);
+  else return cudaErrorInvalidValue;
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_hash(const Launch &L, CImg img, int nbytes, int height, unsigned long long *out_dev) {
+  k_row_hash<<<(height + kBlock / 32 - 1) / (kBlock / 32), kBlock, 0, L.stream>>>(img.p, img.rs, nbytes, height, out_dev);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

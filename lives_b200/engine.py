@@ -235,7 +235,14 @@ class Layer:
         s = capi.pe_frame_stats_t()
         capi.check(self.engine._lib.pe_frame_stats(self.engine._h, self._h, C.byref(s)))
         return dict(min=list(s.min), max=list(s.max), hist=np.array(list(s.hist), np.uint32), sum=int(s.sum),
-                    all_black_ish=bool(s.all_black_ish))
+                    all_black_ish=s.all_black_ish, all_black=s.all_black)
+
+    def row_hashes(self, nbytes=0):
+        """hash_cmp_layer (colourspace.c:16044): (per-row minimd5 hashes as uint64 array, parity)"""
+        h = np.zeros(self.height, np.uint64)
+        par = C.c_uint64(0)
+        capi.check(self.engine._lib.pe_frame_row_hashes(self.engine._h, self._h, nbytes, h.ctypes.data, C.byref(par)))
+        return h, int(par.value)
 
 
 # ---- boundary B2: the reference's frame ops --------------------------------------------------------------------
@@ -588,3 +595,37 @@ def render_out_begin(layer, out_palette, host_array, slot):
 
 def render_out_wait(engine, slot):
     capi.check(engine._lib.pe_render_out_wait(engine._h, slot))
+
+
+# ---- the node model's CONVERT step as one descriptor -------------------------------------------------------
+
+OP_RESIZE, OP_PCONV, OP_GAMMA, OP_LETTERBOX, N_OP_TYPES = 0, 1, 2, 3, 6  # src/nodemodel.h:717-722
+
+
+class pe_convert_plan_t(C.Structure):
+    _fields_ = [("op_order", C.c_int * 6), ("width", C.c_int), ("height", C.c_int), ("lb_width", C.c_int), ("lb_height", C.c_int),
+                ("interp", C.c_int), ("out_palette", C.c_int), ("out_clamping", C.c_int), ("out_sampling", C.c_int),
+                ("out_subspace", C.c_int), ("out_gamma", C.c_int), ("no_fuse", C.c_int)]
+
+
+def convert_plan(op_order, width=0, height=0, lb_width=0, lb_height=0, interp=LIVES_INTERP_NORMAL, out_palette=0, out_clamping=0,
+                 out_sampling=0, out_subspace=0, out_gamma=0, no_fuse=False):
+    """op_order: dict {OP_*: substep} as get_op_order (src/nodemodel.c:161) fills its array"""
+    p = pe_convert_plan_t()
+    for k, v in op_order.items():
+        p.op_order[k] = v
+    p.width, p.height, p.lb_width, p.lb_height, p.interp = width, height, lb_width, lb_height, interp
+    p.out_palette, p.out_clamping, p.out_sampling, p.out_subspace, p.out_gamma, p.no_fuse = (out_palette, out_clamping, out_sampling,
+                                                                                             out_subspace, out_gamma, int(no_fuse))
+    return p
+
+
+def run_convert_plan(layer, plan):
+    return bool(layer.engine._lib.pe_run_convert_plan(layer.engine._h, layer._h, C.byref(plan)))
+
+
+def run_convert_plan_over(fg, plan, bg, out, alpha, gamma_to):
+    """returns 1 when the chain left as one fused launch, 0 when it ran op by op"""
+    e = fg.engine
+    capi.check(e._lib.pe_run_convert_plan_over(e._h, fg._h, C.byref(plan), bg._h, out._h, alpha, gamma_to))
+    return e._lib.pe_last_plan_path()

@@ -135,6 +135,24 @@ def build_plugins(inc):
         os.path.join(SRC, "ref_paint_pixel_tu.c"), "-o", os.path.join(OUT, "ref_paint_pixel.so")])
 
 
+def build_diag():
+    """per-frame diagnostics: is_all_black_ish (colourspace.c:2554-2594, both branches) and the row hash of hash_cmp_layer (:16044:
+    minimd5 of src/maths.c:473-585 -- an MD5 variant of the reference's own, see its BX macro, src/maths.h:42-57)"""
+    cs_c = os.path.join(REF, "src", "colourspace.c")
+    mc, mh = os.path.join(REF, "src", "maths.c"), os.path.join(REF, "src", "maths.h")
+    tu = ["#include <stdint.h>\n#include <stddef.h>\n#include <string.h>\n#include <stdlib.h>\n",
+          "typedef int boolean;\n#define TRUE 1\n#define FALSE 0\n#define LIVES_LOCAL_INLINE static inline\n#define LIVES_HOT\n"
+          "#define lives_memcpy memcpy\n#define lives_calloc calloc\n",
+          slice_file(mh, [(42, 57)]), slice_file(mc, [(473, 546), (575, 585)]), slice_file(cs_c, [(2554, 2594)]),
+          "int ref_is_all_black_ish(int width, int height, int rstride, int has_alpha, const uint8_t *pdata, int exact)"
+          " { return is_all_black_ish(width, height, rstride, has_alpha, pdata, exact); }\n"
+          "void ref_row_hashes(const uint8_t *pd, int nbytes, int height, int rowstride, uint64_t *out)"
+          " { for (int i = 0; i < height; i++) out[i] = minimd5((void *)&pd[(size_t)rowstride * i], nbytes); }\n"]
+    with open(os.path.join(SRC, "ref_diag_tu.c"), "w") as f:
+        f.write("".join(tu))
+    sh(["gcc", "-O2", "-fPIC", "-shared", "-w", os.path.join(SRC, "ref_diag_tu.c"), "-o", os.path.join(OUT, "ref_diag.so")])
+
+
 def build_minihost(inc):
     host = os.path.join(REPO, "tests", "host", "weed_minihost.c")
     if not os.path.exists(host):
@@ -152,6 +170,7 @@ def main():
     build_colourspace()
     inc = build_libweed()
     build_plugins(inc)
+    build_diag()
     build_minihost(inc)
     print("oracle/_ref built")
     return 0

@@ -1509,3 +1509,94 @@ void pe_or_slide_over(int direction, int transval, int mvlower, int mvupper, con
       }
     }
 }
+
+/* ==== per-frame diagnostics ===================================================================================== */
+
+/* is_all_black_ish src/colourspace.c:2554-2594.  The non-exact branch is a chain of BITWISE ands (not logical ones): with
+ * hi(x) = x & 0xE0 it reads  hi(a) & hi(c) & (hi(b) | (b has bits 4 and 3 ? 0x20 : 0)), so "not black" also needs the three
+ * bytes to share a set bit among bits 5 .. 7 -- replicated as written. */
+int pe_or_is_all_black_ish(int width, int height, int rowstride, int has_alpha, const uint8_t *pixels, int exact) {
+  const int psize = has_alpha ? 4 : 3;
+  for (int y = 0; y < height; y++) {
+    const uint8_t *q = pixels + (long)rowstride * y;
+    for (int x = 0; x < width; x++, q += psize) {
+      const unsigned a = q[0], b = q[1], c = q[2];
+      if (exact) {
+        if (a | b | c) return 0;
+      } else {
+        const unsigned na = (a & 0x1F) ^ a, nc = (c & 0x1F) ^ c, nb = (b & 0x1F) ^ b;
+        const unsigned t1 = ((b << 1) & 0x1F) ^ (b << 1), t2 = (((b & 0x0F) << 2) & 0x1F) ^ ((b & 0x0F) << 2);
+        if (na & nc & (nb | (t1 & t2))) return 0;
+      }
+    }
+  }
+  return 1;
+}
+
+/* The reference's MD5 variant (src/maths.c:473-546, macros src/maths.h:42-56).  Padding, length and rounds 2 - 4 are RFC 1321's;
+ * round 1 is its BX macro as written: the state words are stepped in the order A B C D with rotations 7, 22, 17, 12, and the
+ * fourth step takes the second step's CONSTANT where the function's third operand would be the state word C. */
+static uint32_t or_rotl(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
+static uint32_t or_ff(uint32_t b, uint32_t c, uint32_t d) { return d ^ (b & (c ^ d)); }
+
+static void or_md5_block(const uint8_t *blk, uint32_t st[4]) {
+  static const uint32_t T[64] = {
+    0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
+    0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
+    0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
+    0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
+    0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
+    0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+  static const int K[48] = {1, 6, 11, 0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 5, 8, 11, 14, 1, 4, 7, 10, 13, 0, 3, 6, 9, 12, 15, 2,
+                            0, 7, 14, 5, 12, 3, 10, 1, 8, 15, 6, 13, 4, 11, 2, 9};
+  static const int S[3][4] = {{5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
+  uint32_t X[16], v[4] = {st[0], st[1], st[2], st[3]};
+  for (int i = 0; i < 16; i++) X[i] = (uint32_t)blk[4 * i] | ((uint32_t)blk[4 * i + 1] << 8) | ((uint32_t)blk[4 * i + 2] << 16) | ((uint32_t)blk[4 * i + 3] << 24);
+  for (int q = 0; q < 4; q++) { /* BX */
+    static const int rot[4] = {7, 22, 17, 12};
+    for (int j = 0; j < 4; j++) {
+      /* step j updates word j (A, B, C, D in turn) from the next three words in A B C D order ... */
+      uint32_t h = v[(j + 1) & 3], i2 = v[(j + 2) & 3], jj = v[(j + 3) & 3];
+      if (j == 3) jj = T[4 * q + 1]; /* ... except that the last step's third operand is the second step's constant */
+      v[j] += or_ff(h, i2, jj) + X[4 * q + j] + T[4 * q + j];
+      v[j] = or_rotl(v[j], rot[j]) + h;
+    }
+  }
+  for (int r = 0; r < 3; r++)
+    for (int i = 0; i < 16; i++) {
+      /* RFC 1321 order: A D C B, each from (next, next + 1, next + 2) in A B C D order */
+      const int g = (4 - (i & 3)) & 3; /* 0, 3, 2, 1 */
+      const uint32_t b = v[(g + 1) & 3], c = v[(g + 2) & 3], d = v[(g + 3) & 3];
+      const uint32_t f = r == 0 ? or_ff(d, b, c) : r == 1 ? (b ^ c ^ d) : (c ^ (b | ~d));
+      v[g] += f + X[K[16 * r + i]] + T[16 + 16 * r + i];
+      v[g] = or_rotl(v[g], S[r][i & 3]) + b;
+    }
+  for (int i = 0; i < 4; i++) st[i] += v[i];
+}
+
+uint64_t pe_or_minimd5(const uint8_t *data, size_t n) {
+  uint32_t st[4] = {0x67452301, 0xefcdab89, 0x98badcfe, 0x10325476};
+  uint8_t tail[128];
+  size_t full = n / 64, rem = n - full * 64, tl;
+  for (size_t i = 0; i < full; i++) or_md5_block(data + 64 * i, st);
+  memset(tail, 0, sizeof(tail));
+  memcpy(tail, data + 64 * full, rem);
+  tail[rem] = 0x80;
+  tl = rem >= 56 ? 128 : 64;
+  {
+    const uint64_t bits = (uint64_t)n << 3;
+    for (int i = 0; i < 8; i++) tail[tl - 8 + i] = (uint8_t)(bits >> (8 * i));
+  }
+  or_md5_block(tail, st);
+  if (tl == 128) or_md5_block(tail + 64, st);
+  return ((uint64_t)st[0] | ((uint64_t)st[1] << 32)) ^ ((uint64_t)st[2] | ((uint64_t)st[3] << 32));
+}
+
+uint64_t pe_or_row_hashes(const uint8_t *pixels, int nbytes, int height, int rowstride, uint64_t *out) {
+  uint64_t parity = 0;
+  for (int y = 0; y < height; y++) {
+    out[y] = pe_or_minimd5(pixels + (long)rowstride * y, (size_t)nbytes);
+    parity ^= out[y];
+  }
+  return parity;
+}

@@ -17,6 +17,7 @@
  */
 #ifndef PE_ORACLE_H
 #define PE_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -179,6 +180,14 @@ void pe_or_switch_clamping_plane(uint8_t *plane, long nbytes, int kind, int to_u
 int pe_or_slide_over_bound(int direction, int transval, int width, int height);
 void pe_or_slide_over(int direction, int transval, int mvlower, int mvupper, const uint8_t *src1, int irow1, const uint8_t *src2,
                       int irow2, uint8_t *dest, int orow, int width, int height, int psize);
+
+/* ---- per-frame diagnostics ------------------------------------------------------------------------------------------- */
+/* is_all_black_ish src/colourspace.c:2554-2594, both branches (exact = 0: the bit expression of :2583-2587) */
+int pe_or_is_all_black_ish(int width, int height, int rowstride, int has_alpha, const uint8_t *pixels, int exact);
+/* minimd5 src/maths.c:575 = U[0] ^ U[1] of the reference's own MD5 variant (src/maths.h:42-56: RFC 1321 except round 1) */
+uint64_t pe_or_minimd5(const uint8_t *data, size_t n);
+/* hash_cmp_layer src/colourspace.c:16044-16075: per-row hashes of the first nbytes bytes + their XOR */
+uint64_t pe_or_row_hashes(const uint8_t *pixels, int nbytes, int height, int rowstride, uint64_t *out);
 
 #ifdef __cplusplus
 }

@@ -72,3 +72,36 @@ def test_render_out_downloads_only_the_final_rgb24(eng):
     with pytest.raises(lb.PixelEngineError):
         lb.render_out(pl, 0, np.zeros((48, 64 * 3), np.uint8))
     lb.render_out(pl, 1, np.zeros((48, 64 * 3), np.uint8))
+
+
+@pytest.mark.parametrize("geom", [(1280, 720, 536), (640, 360, 300)])
+def test_convert_plan_descriptor_fused_equals_op_by_op(eng, geom):
+    """get_op_order's result handed over as one descriptor (src/nodemodel.c:161, :1065-1282): the chain leaves as one
+    fused launch, and the same descriptor run op by op (the reference's substeps) gives the same bytes"""
+    rng = np.random.default_rng(9)
+    w, h, ih = geom
+    y, u, v = T.make_yuv_planar(rng, w, h, False, True)
+    bg = T.make_packed(rng, w, h, 4)
+    res = []
+    for no_fuse in (False, True):
+        # YUV420P -> RGBA32 (substep 1, done by the resize), letterbox to w x ih inside w x h (substep 2), no gamma before the effect
+        plan = lb.convert_plan({lb.OP_RESIZE: 1, lb.OP_PCONV: 1, lb.OP_LETTERBOX: 2}, width=w, height=ih, lb_width=w, lb_height=h,
+                               out_palette=3, no_fuse=no_fuse)
+        fg_l = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_subspace=1)
+        bg_l = lb.Layer.from_host(eng, 3, w, h, [bg], gamma_type=T.G_LINEAR)
+        out_l = lb.Layer.create(eng, 3, w, h)
+        n0 = eng.launch_count
+        path = lb.run_convert_plan_over(fg_l, plan, bg_l, out_l, 0.5, T.G_SRGB)
+        assert path == (0 if no_fuse else 1)
+        if not no_fuse:
+            assert eng.launch_count - n0 == 1, "the whole chain is one kernel launch"
+        res.append(out_l.to_host()[0])
+    assert (res[0] == res[1]).all()
+    # the plain CONVERT step on its own layer: pconv then resize then gamma, in the plan's order
+    src = T.make_packed(rng, 320, 240, 3)
+    lay = lb.Layer.from_host(eng, 1, 320, 240, [src], gamma_type=T.G_SRGB)
+    plan = lb.convert_plan({lb.OP_PCONV: 1, lb.OP_RESIZE: 2, lb.OP_GAMMA: 3}, width=160, height=120, out_palette=3, out_gamma=T.G_LINEAR)
+    assert lb.run_convert_plan(lay, plan)
+    ref = lb.Layer.from_host(eng, 1, 320, 240, [src], gamma_type=T.G_SRGB)
+    assert lb.convert_layer_palette(ref, 3, 0) and lb.resize_layer(ref, 160, 120, 1, 3, 0) and lb.gamma_convert_layer(T.G_LINEAR, ref)
+    assert lay.palette == 3 and (lay.width, lay.height) == (160, 120) and (lay.to_host()[0] == ref.to_host()[0]).all()

@@ -1334,9 +1334,9 @@ def test_frame_stats(eng):
         col = [k for k in range(ps) if k != a_off]
         assert (st["hist"] == np.bincount(px[..., col].reshape(-1), minlength=256)).all()
         assert st["sum"] == int(px.astype(np.uint64).sum())
-        assert not st["all_black_ish"]
+        assert not st["all_black_ish"] and not st["all_black"]
     blk = lb.Layer.create(eng, 3, 64, 64, black_fill=True)
-    assert blk.stats()["all_black_ish"]
+    assert blk.stats()["all_black_ish"] == 1 and blk.stats()["all_black"] == 1
 
 
 def test_host_dropins(eng):
