@@ -62,8 +62,9 @@ typedef struct pe_weed_host_funcs {
 int pe_weed_layer_bind(const pe_weed_host_funcs_t *funcs);
 /* where new pixel buffers come from / old ones go (LiVES: lives_calloc_safety / lives_free_maybe_big); NULL = malloc / free */
 void pe_weed_layer_set_allocator(const pe_host_allocator_t *alloc);
-/* 1: page-lock every plane the ops touch with pe_host_register before copying (buffers that LiVES recycles are registered once and
- * stay registered); 0 (default): copy from / to pageable memory as it is */
+/* 1: page-lock the planes around each transfer (pe_host_register ... pe_host_unregister inside the call: the buffers are the host's,
+ * it frees them without telling this library, so no registration outlives a call); 0 (default): copy from / to pageable memory as it
+ * is.  A host that owns its pixel allocator does better: register its big blocks once (pe_host_register) and leave this off. */
 void pe_weed_layer_set_pinning(int on);
 /* the engine the drop-ins run on (pe_engine_shared()); NULL + pe_last_error when no CUDA device is usable */
 pe_engine_t *pe_weed_layer_engine(void);

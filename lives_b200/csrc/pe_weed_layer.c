@@ -103,9 +103,17 @@ static pe_frame_t *to_device(pe_engine_t *e, const layer_view *v) {
                       &f) != PE_OK)
     return NULL;
   pe_frame_set_flags(f, v->d.flags);
+  /* page-locking is TRANSIENT: the buffers belong to the host, which frees them without telling us -- a registration left behind
+   * would poison whatever malloc() later places at the same address */
   if (pinning)
     for (p = 0; p < np; p++) pe_host_register(v->d.planes[p], (size_t)v->d.rowstrides[p] * (size_t)ph[p]);
-  if (pe_frame_upload(e, f, (const void *const *)v->d.planes, v->d.rowstrides) != PE_OK) { pe_frame_destroy(f); return NULL; }
+  p = pe_frame_upload(e, f, (const void *const *)v->d.planes, v->d.rowstrides);
+  if (pinning) {
+    int q;
+    pe_engine_sync(e);
+    for (q = 0; q < np; q++) pe_host_unregister(v->d.planes[q]);
+  }
+  if (p != PE_OK) { pe_frame_destroy(f); return NULL; }
   return f;
 }
 
@@ -130,17 +138,23 @@ static int from_device(pe_engine_t *e, pe_frame_t *f, weed_layer_t *l, const lay
     for (p = 0; p < np; p++) {
       planes[p] = A.alloc((size_t)rs[p] * (size_t)ph[p] + 64, A.user); /* + slack: the reference's converters read a byte past a chroma row */
       if (!planes[p]) { while (p--) A.free(planes[p], A.user); return 0; }
-      if (pinning) pe_host_register(planes[p], (size_t)rs[p] * (size_t)ph[p] + 64);
     }
   }
-  if (pe_frame_download(e, f, planes, rs) != PE_OK) {
-    if (!same) for (p = 0; p < np; p++) { if (pinning) pe_host_unregister(planes[p]); A.free(planes[p], A.user); }
+  if (pinning)
+    for (p = 0; p < np; p++) pe_host_register(planes[p], (size_t)rs[p] * (size_t)ph[p]);
+  p = pe_frame_download(e, f, planes, rs); /* synchronises */
+  if (pinning) {
+    int q;
+    for (q = 0; q < np; q++) pe_host_unregister(planes[q]);
+  }
+  if (p != PE_OK) {
+    if (!same) for (p = 0; p < np; p++) A.free(planes[p], A.user);
     return 0;
   }
   /* ---- the layer changes from here on */
   if (!same) {
     for (p = 0; p < old->d.nplanes; p++)
-      if (old->d.planes[p]) { if (pinning) pe_host_unregister(old->d.planes[p]); A.free(old->d.planes[p], A.user); }
+      if (old->d.planes[p]) A.free(old->d.planes[p], A.user);
     H.leaf_set(l, PE_LEAF_PIXEL_DATA, PE_WEED_SEED_VOIDPTR, (pe_weed_size_t)np, planes);
   }
   for (p = 0; p < np; p++) rs32[p] = rs[p];
