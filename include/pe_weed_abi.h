@@ -53,6 +53,7 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 #define PE_WEED_SEED_DOUBLE 2
 #define PE_WEED_SEED_BOOLEAN 3
 #define PE_WEED_SEED_STRING 4
+#define PE_WEED_SEED_INT64 5
 #define PE_WEED_SEED_FUNCPTR 64
 #define PE_WEED_SEED_VOIDPTR 65
 #define PE_WEED_SEED_PLANTPTR 66
@@ -76,6 +77,7 @@ typedef pe_weed_error_t (*pe_weed_deinit_f)(pe_weed_plant_t *filter_instance);
 #define PE_WEED_FILTER_PREF_LINEAR_GAMMA (1 << 3)
 #define PE_WEED_FILTER_HINT_MAY_THREAD (1 << 6)
 #define PE_WEED_CHANNEL_CAN_DO_INPLACE (1 << 4)
+#define PE_WEED_CHANNEL_REINIT_ON_SIZE_CHANGE (1 << 0) /* weed-effects.h:121 */
 
 /* leaf names (weed.h:493-496, weed-effects.h:195-424) */
 #define PE_LEAF_TYPE "type"

@@ -220,6 +220,27 @@ int pe_fx_multi_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_
 int pe_fx_slide_over(pe_engine_t *e, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, int transval, int direction,
                      int mvlower, int mvupper);
 int pe_fx_slide_over_bound(int direction, int transval, int width, int height);
+/* softlight.c softlight_process :62: an edge-magnitude "soft light" on the luma plane of a planar YUV frame (YUV444P, YUVA4444P,
+ * YUV422P, YUV420P, YVU420P :169); chroma (and alpha) planes are copied.  in's yuv_clamping picks the luma range (:100-106). */
+int pe_fx_softlight(pe_engine_t *e, const pe_frame_t *in, pe_frame_t *out);
+/* layout_blends.c common_process :19, the "triple split" filter (RGB24 / BGR24): in1 inside a band, in2 outside, a border of
+ * borderw in bordercol (RGB order) between them.  Parameters as the plugin's templates :137-144: start, sym ("make symmetrical"),
+ * end, vert ("split horizontally"), borderw, bordercol.  out may be in1 (CAN_DO_INPLACE :135). */
+int pe_fx_triple_split(pe_engine_t *e, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, double start, int sym, double end,
+                       int vert, double borderw, const int bordercol[3]);
+/* the column / row tests of layout_blends.c:92-99 as the reference evaluates them (bit 0 "outside", bit 1 "inside"; host arithmetic) */
+void pe_fx_triple_split_classes(int width, int height, double start, int sym, double end, int vert, double borderw, uint8_t *colclass,
+                                uint8_t *rowclass);
+/* multi_transitions.c common_process :85.  type 0 "iris rectangle", 1 "iris circle", 2 "4 way split", 3 "dissolve"; amount = the
+ * transition parameter 0 .. 1; every packed palette (ALL_PACKED_PALETTES :232).  out may be in1 except for type 2 (:268).  The float
+ * geometry is evaluated in the form the plugins' -ffast-math build (lives-plugins/weed-plugins/Makefile.am:49) compiles to.
+ * "dissolve" needs the per-instance mask dissolve_init :42 draws from the host's random seed (WEED_LEAF_RANDOM_SEED); type 4 ("rand
+ * replace") is a whole-frame choice made by the plugin's host-side random stream: no pixel arithmetic, handled by the caller. */
+typedef struct pe_dissolve_mask pe_dissolve_mask_t;
+int pe_fx_dissolve_mask_create(pe_engine_t *e, int width, int height, int64_t random_seed, pe_dissolve_mask_t **out);
+void pe_fx_dissolve_mask_destroy(pe_dissolve_mask_t *m);
+int pe_fx_multi_transition(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, double amount,
+                           const pe_dissolve_mask_t *mask);
 /* gdk/compositor.c compositor_process :127 at scale 1 / offset 0: out = bgcol, then paint_pixel(:120) of every
  * layer, last first (revz == WEED_FALSE, :189-197); alpha[i] is the scalar per-layer alpha */
 int pe_fx_compositor(pe_engine_t *e, pe_frame_t *out, const pe_frame_t *const *layers, const double *alpha,
@@ -347,6 +368,12 @@ int pe_host_multi_blend(pe_engine_t *e, int type, const pe_frame_desc_t *in1, co
 /* slide_over.c:55 on host frames (H2D of both clips, k_slide_over, D2H of the result) */
 int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, int transval,
                        int direction, int mvlower, int mvupper);
+/* softlight.c:62 / layout_blends.c:19 / multi_transitions.c:85 on host channels */
+int pe_host_softlight(pe_engine_t *e, const pe_frame_desc_t *in, pe_frame_desc_t *out);
+int pe_host_triple_split(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, double start, int sym,
+                         double end, int vert, double borderw, const int bordercol[3]);
+int pe_host_multi_transition(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out,
+                             double amount, const pe_dissolve_mask_t *mask);
 /* gdk/compositor.c compositor_process :127 on host channels (layers[z] NULL = a channel the host disabled, :195-199) */
 int pe_host_compositor(pe_engine_t *e, pe_frame_desc_t *out, const pe_frame_desc_t *const *layers, const double *alpha, int nlayers,
                        const int bgcol[3]);

@@ -114,6 +114,15 @@ PROTOTYPES = {
     "pe_fx_multi_blend": (I, [VP, I, VP, VP, VP, I]),
     "pe_fx_slide_over": (I, [VP, VP, VP, VP, I, I, I, I]),
     "pe_fx_slide_over_bound": (I, [I, I, I, I]),
+    "pe_fx_softlight": (I, [VP, VP, VP]),
+    "pe_fx_triple_split": (I, [VP, VP, VP, VP, D, I, D, I, D, PI]),
+    "pe_fx_triple_split_classes": (None, [I, I, D, I, D, I, D, VP, VP]),
+    "pe_fx_dissolve_mask_create": (I, [VP, I, I, C.c_int64, C.POINTER(VP)]),
+    "pe_fx_dissolve_mask_destroy": (None, [VP]),
+    "pe_fx_multi_transition": (I, [VP, I, VP, VP, VP, D, VP]),
+    "pe_host_softlight": (I, [VP, PDESC, PDESC]),
+    "pe_host_triple_split": (I, [VP, PDESC, PDESC, PDESC, D, I, D, I, D, PI]),
+    "pe_host_multi_transition": (I, [VP, I, PDESC, PDESC, PDESC, D, VP]),
     "pe_fx_compositor": (I, [VP, VP, PVP, C.POINTER(D), I, PI]),
     "pe_fx_compositor_gamma": (I, [VP, VP, PVP, C.POINTER(D), I, PI, I]),
     "pe_fx_compositor_gamma_batch": (I, [VP, I, PVP, PVP, C.POINTER(D), I, PI, I]),

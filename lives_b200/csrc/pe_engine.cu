@@ -2221,6 +2221,170 @@ extern "C" int pe_fx_slide_over(pe_engine_t *e, const pe_frame_t *in1, const pe_
   return PE_OK;
 }
 
+// ---- softlight.c / layout_blends.c / multi_transitions.c ---------------------------------------------------
+
+extern "C" int pe_fx_softlight(pe_engine_t *e, const pe_frame_t *in, pe_frame_t *out) {
+  if (!e) return set_err(PE_ERR_ARG, "NULL engine");
+  if (!in || !out || !in->d.planes[0] || !out->d.planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
+  const int pal = in->d.palette;
+  if (pal != PE_PALETTE_YUV444P && pal != PE_PALETTE_YUVA4444P && pal != PE_PALETTE_YUV422P && pal != PE_PALETTE_YUV420P &&
+      pal != PE_PALETTE_YVU420P)
+    return set_err(PE_ERR_PALETTE, "palette %d is not in this filter's palette list (softlight.c:169)", pal);
+  if (out->d.palette != pal) return set_err(PE_ERR_PALETTE, "channel palettes differ");
+  if (out->d.width != in->d.width || out->d.height != in->d.height) return set_err(PE_ERR_SIZE, "channel sizes differ");
+  if (out->d.planes[0] == in->d.planes[0]) return set_err(PE_ERR_ARG, "softlight is not an in-place filter (out channel flags 0, softlight.c:173)");
+  const bool unclamped = in->d.yuv_clamping == PE_YUV_CLAMPING_UNCLAMPED;  // :100-106
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  PE_CUDA(launch_softlight(e->L(), CImg{(const uint8_t *)in->d.planes[0], in->d.rowstrides[0]}, Img{(uint8_t *)out->d.planes[0], out->d.rowstrides[0]},
+                           in->d.width, in->d.height, unclamped ? 0 : 16, unclamped ? 255 : 235));
+  // the other planes are copied (:144-154: chroma width / height by palette, alpha plane at full size)
+  for (int p = 1; p < in->d.nplanes; p++) {
+    const bool sub = p < 3 && pal != PE_PALETTE_YUV444P && pal != PE_PALETTE_YUVA4444P;
+    const int w = sub ? in->d.width >> 1 : in->d.width;
+    const int h = (p < 3 && (pal == PE_PALETTE_YUV420P || pal == PE_PALETTE_YVU420P)) ? in->d.height >> 1 : in->d.height;
+    PE_CUDA(launch_copy2d(e->L(), (const uint8_t *)in->d.planes[p], in->d.rowstrides[p], (uint8_t *)out->d.planes[p], out->d.rowstrides[p], w, h, 0, 0));
+  }
+  return PE_OK;
+}
+
+namespace {
+// the channel checks the selector filters share: packed palettes of 3 / 4 bytes per (macro)pixel, equal sizes, out may be in1 only
+int check_select_frames(const pe_frame *in1, const pe_frame *in2, const pe_frame *out, bool rgb24_only, bool inplace_ok, SelectArgs *a) {
+  if (!in1 || !in2 || !out || !in1->d.planes[0] || !in2->d.planes[0] || !out->d.planes[0]) return set_err(PE_ERR_ARG, "NULL frame");
+  const int pal = in1->d.palette;
+  if (pal_is_planar(pal) || !pal_known(pal) || (rgb24_only && pal != PE_PALETTE_RGB24 && pal != PE_PALETTE_BGR24))
+    return set_err(PE_ERR_PALETTE, "palette %d is not in this filter's palette list", pal);
+  if (in2->d.palette != pal || out->d.palette != pal) return set_err(PE_ERR_PALETTE, "channel palettes differ");
+  if (in2->d.width != in1->d.width || in2->d.height != in1->d.height || out->d.width != in1->d.width || out->d.height != in1->d.height)
+    return set_err(PE_ERR_SIZE, "channel sizes differ");
+  if (out->d.planes[0] == in2->d.planes[0] || (!inplace_ok && out->d.planes[0] == in1->d.planes[0]))
+    return set_err(PE_ERR_ARG, "the out channel may only share pixels with in channel 0 of a CAN_DO_INPLACE filter");
+  memset(a, 0, sizeof(*a));
+  a->s1 = (const uint8_t *)in1->d.planes[0]; a->s2 = (const uint8_t *)in2->d.planes[0]; a->d = (uint8_t *)out->d.planes[0];
+  a->rs1 = in1->d.rowstrides[0]; a->rs2 = in2->d.rowstrides[0]; a->rsd = out->d.rowstrides[0];
+  a->psize = pal_psize(pal);
+  a->width = in1->d.width / pal_ppmp(pal);  // macropixels, as the plugins see the channel
+  a->height = in1->d.height;
+  return PE_OK;
+}
+}  // namespace
+
+// layout_blends.c:43-99: the two double comparisons per column and per row, evaluated once per column / row on the host exactly as
+// the reference writes them (bit 0 "outside", bit 1 "inside")
+extern "C" void pe_fx_triple_split_classes(int width, int height, double xstart, int sym, double xend, int vert, double bw, uint8_t *colclass,
+                                           uint8_t *rowclass) {
+  const int wb = width * 3;
+  int tbs = height, tbe = height, bbs = height, bbe = height;  // tbs = tbe = bbs = bbe = end (:72)
+  if (sym) { xstart /= 2.; xend = 1. - xstart; }
+  if (xstart > xend) { const double t = xend; xend = xstart; xstart = t; }
+  if (vert) {  // :74-80
+    tbs = (int)(height * (xstart - bw) + .5); tbe = (int)(height * (xstart + bw) + .5);
+    bbs = (int)(height * (xend - bw) + .5); bbe = (int)(height * (xend + bw) + .5);
+    xstart = xend = -bw;
+  }
+  const double lo_out = wb * (xstart - bw), hi_out = wb * (xend + bw), lo_in = wb * (xstart + bw), hi_in = wb * (xend - bw);
+  for (int x = 0; x < width; x++) {
+    const int j = 3 * x;
+    colclass[x] = (uint8_t)(((j < lo_out || j >= hi_out) ? 1 : 0) | ((j > lo_in && j < hi_in) ? 2 : 0));
+  }
+  for (int y = 0; y < height; y++) rowclass[y] = (uint8_t)(((y <= tbs || y >= bbe) ? 1 : 0) | ((y > tbe && y < bbs) ? 2 : 0));
+}
+
+extern "C" int pe_fx_triple_split(pe_engine_t *e, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, double start, int sym,
+                                  double end, int vert, double borderw, const int bordercol[3]) {
+  if (!e) return set_err(PE_ERR_ARG, "NULL engine");
+  if (!bordercol) return set_err(PE_ERR_ARG, "NULL border colour");
+  SelectArgs a;
+  int rc = check_select_frames(in1, in2, out, true, true, &a);
+  if (rc != PE_OK) return rc;
+  std::vector<uint8_t> cls((size_t)a.width + (size_t)a.height);
+  pe_fx_triple_split_classes(a.width, a.height, start, sym, end, vert, borderw, cls.data(), cls.data() + a.width);
+  const bool bgr = in1->d.palette == PE_PALETTE_BGR24;  // :66-70
+  a.colour[0] = bordercol[bgr ? 2 : 0]; a.colour[1] = bordercol[1]; a.colour[2] = bordercol[bgr ? 0 : 2];
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  const uint8_t *dev = (const uint8_t *)upload_args(e, cls.data(), cls.size());
+  if (!dev) return PE_ERR_CUDA;
+  a.colclass = dev; a.rowclass = dev + a.width;
+  PE_CUDA(launch_select(e->L(), 0, a));
+  return PE_OK;
+}
+
+struct pe_dissolve_mask {
+  pe_engine *e;
+  float *dev;
+  int width, height;
+};
+
+// multi_transitions.c dissolve_init :42-70: width x height floats from the xorshift64 stream of the host's random seed
+// (libweed/weed-plugin-utils.c:666,686-704; `val / divd / divd * 1.` is ONE multiplication in the plugins' -ffast-math build)
+extern "C" int pe_fx_dissolve_mask_create(pe_engine_t *e, int width, int height, int64_t random_seed, pe_dissolve_mask_t **out) {
+  if (!e || !out || width <= 0 || height <= 0) return set_err(PE_ERR_ARG, "NULL / empty argument");
+  const size_t n = (size_t)width * (size_t)height;
+  std::vector<float> host(n);
+  uint64_t x = (uint64_t)random_seed;
+  union { uint64_t u; double d; } k;
+  k.u = 0x3BF0000000200000ull;  // 1 / (double)0xFFFFFFFF squared, as the compiled plugin holds it
+  for (size_t i = 0; i < n; i++) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    host[i] = (float)((double)x * k.d);
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  float *dev = nullptr;
+  PE_CUDA(cudaMalloc(&dev, n * sizeof(float)));
+  cudaError_t ce = cudaMemcpy(dev, host.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(dev); return set_err(PE_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(ce)); }
+  *out = new pe_dissolve_mask{e, dev, width, height};
+  return PE_OK;
+}
+
+extern "C" void pe_fx_dissolve_mask_destroy(pe_dissolve_mask_t *m) {
+  if (!m) return;
+  {
+    std::lock_guard<std::mutex> lk(m->e->mu);
+    cudaSetDevice(m->e->device);
+    cudaStreamSynchronize(m->e->stream);
+    cudaFree(m->dev);
+  }
+  delete m;
+}
+
+extern "C" int pe_fx_multi_transition(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out, double amount,
+                                      const pe_dissolve_mask_t *mask) {
+  if (!e) return set_err(PE_ERR_ARG, "NULL engine");
+  if (type < 0 || type > 3) return set_err(PE_ERR_ARG, "transition type %d: 0 iris rectangle, 1 iris circle, 2 4 way split, 3 dissolve", type);
+  SelectArgs a;
+  int rc = check_select_frames(in1, in2, out, false, type != 2, &a);
+  if (rc != PE_OK) return rc;
+  if (type == 3 && (!mask || mask->width != a.width || mask->height != a.height))
+    return set_err(PE_ERR_ARG, "dissolve needs the mask of this channel size (REINIT_ON_SIZE_CHANGE, multi_transitions.c:281)");
+  // the per-frame constants of :118-143, in float as the plugin computes them (no -ffast-math here: every step is written out in the
+  // form the reference's build evaluates)
+  const int psize = a.psize, wb = a.width * psize;
+  const float bf = (float)amount, bfneg = 1.f - bf;
+  const float hheight = (float)a.height * 0.5f, hwidth_px = (float)a.width * 0.5f, hwidth = (float)wb * 0.5f;
+  a.bf = bf;
+  a.ihwidth = wb >> 1; a.ihheight = a.height >> 1;
+  a.hheight = hheight; a.hwidth = hwidth;
+  a.inv_psize = 1.f / (float)psize;
+  a.inv_maxradsq = 1.f / (hheight * hheight + hwidth_px * hwidth_px);
+  a.inv_hh = 1.f / hheight; a.inv_hw = 1.f / hwidth;
+  if (type == 0) {
+    a.xx = (int)((double)((float)(int)hwidth * bfneg) + .5);
+    a.yy = (int)((double)((float)(int)hheight * bfneg) + .5);
+  } else if (type == 2) {
+    a.xx = (int)((double)(hheight * bf) + .5);  // rows
+    a.yy = (int)((double)((bf * (psize == 3 ? 0.333333343267440796f : 0.25f)) * hwidth) + .5) * psize;  // bytes
+  }
+  a.mask = mask ? mask->dev : nullptr;
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  PE_CUDA(launch_select(e->L(), type + 1, a));
+  return PE_OK;
+}
+
 namespace {
 
 // compositor_process (gdk/compositor.c:127) at scale 1 / offset 0, optionally followed by gamma_convert_layer(gamma_to, out)
@@ -2804,6 +2968,43 @@ extern "C" int pe_host_slide_over(pe_engine_t *e, const pe_frame_desc_t *in1, co
   if ((rc = a.upload(in1)) != PE_OK || (rc = b.upload(in2)) != PE_OK || (rc = o.create_like(out)) != PE_OK) return rc;
   if ((rc = pe_fx_slide_over(e, a.f, b.f, o.f, transval, direction, mvlower, mvupper)) != PE_OK) return rc;
   return pe_frame_download(e, o.f, out->planes, out->rowstrides);
+}
+
+extern "C" int pe_host_softlight(pe_engine_t *e, const pe_frame_desc_t *in, pe_frame_desc_t *out) {
+  if (!e || !in || !out || !in->planes[0] || !out->planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  HostFrame a(e), o(e);
+  int rc;
+  if ((rc = a.upload(in)) != PE_OK || (rc = o.create_like(out)) != PE_OK) return rc;
+  if ((rc = pe_fx_softlight(e, a.f, o.f)) != PE_OK) return rc;
+  return pe_frame_download(e, o.f, out->planes, out->rowstrides);
+}
+
+namespace {
+// two host in channels, one host out channel that may be in channel 0 (CAN_DO_INPLACE, effects-weed.c:2304-2314)
+template <class F>
+int host_select(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, F run) {
+  if (!e || !in1 || !in2 || !out || !in1->planes[0] || !in2->planes[0] || !out->planes[0]) return set_err(PE_ERR_ARG, "NULL argument");
+  HostFrame a(e), b(e), o(e);
+  int rc;
+  if ((rc = a.upload(in1)) != PE_OK || (rc = b.upload(in2)) != PE_OK) return rc;
+  const bool inplace = out->planes[0] == in1->planes[0];
+  if (!inplace && (rc = o.create_like(out)) != PE_OK) return rc;
+  pe_frame *of = inplace ? a.f : o.f;
+  if ((rc = run(a.f, b.f, of)) != PE_OK) return rc;
+  return pe_frame_download(e, of, out->planes, out->rowstrides);
+}
+}  // namespace
+
+extern "C" int pe_host_triple_split(pe_engine_t *e, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out, double start,
+                                    int sym, double end, int vert, double borderw, const int bordercol[3]) {
+  return host_select(e, in1, in2, out, [&](pe_frame *a, pe_frame *b, pe_frame *o) {
+    return pe_fx_triple_split(e, a, b, o, start, sym, end, vert, borderw, bordercol);
+  });
+}
+
+extern "C" int pe_host_multi_transition(pe_engine_t *e, int type, const pe_frame_desc_t *in1, const pe_frame_desc_t *in2, pe_frame_desc_t *out,
+                                        double amount, const pe_dissolve_mask_t *mask) {
+  return host_select(e, in1, in2, out, [&](pe_frame *a, pe_frame *b, pe_frame *o) { return pe_fx_multi_transition(e, type, a, b, o, amount, mask); });
 }
 
 // gdk/compositor.c compositor_process :127 on host channels: every enabled in channel travels up once, the paints run on the device,

@@ -159,6 +159,25 @@ struct SlideArgs {
   int word_safe;  // set by launch_slide_over: source strides and bases are multiples of 4 (aligned word loads stay inside the rows)
 };
 cudaError_t launch_slide_over(const Launch &L, const SlideArgs &a);
+// softlight.c softlight_process :62 on one luma plane (rows / columns at the frame edge are copied)
+cudaError_t launch_softlight(const Launch &L, CImg src, Img dst, int width, int height, int ymin, int ymax);
+// the per-pixel selectors of layout_blends.c ("triple split", mode 0) and multi_transitions.c ("iris rectangle" 1, "iris circle" 2,
+// "4 way split" 3, "dissolve" 4): dst pixel = in1 pixel, in2 pixel or the constant colour.  The host fills the fields its mode reads
+// (the float fields hold the values the reference's -ffast-math build computes once per frame; pe_engine.cu pe_fx_multi_transition).
+struct SelectArgs {
+  const uint8_t *s1, *s2;
+  uint8_t *d;
+  int rs1, rs2, rsd, width, height, psize;
+  int row_bytes;                        // set by launch_select
+  const uint8_t *colclass, *rowclass;   // mode 0: bit 0 = "outside" test, bit 1 = "inside" test of the column / row (device memory)
+  int colour[3];                        // mode 0: the border colour in the frame's byte order
+  uint32_t colour_words[3];             // set by launch_select
+  int xx, yy;                           // mode 1: inset in bytes / rows; mode 3: displacement in rows / bytes
+  int ihwidth, ihheight;                // (width * psize) >> 1, height >> 1
+  float bf, inv_psize, inv_maxradsq, hheight, hwidth, inv_hh, inv_hw;
+  const float *mask;                    // mode 4: [height][width] (device memory)
+};
+cudaError_t launch_select(const Launch &L, int mode, const SelectArgs &a);
 // dst = trunc(bg * (1 - alpha) + fg * alpha) in double (compositor.c:120), optional lut8 afterwards:
 // launch_over_table builds the 64 KB [bg][fg] result table for one (alpha, lut8), launch_alpha_over applies it
 cudaError_t launch_over_table(const Launch &L, double alpha, const uint8_t *lut8_dev, uint8_t *table_dev);

@@ -6,6 +6,9 @@
  *     lives-plugins/weed-plugins/multi_blends.c   "blend_multiply" ... "blend_burn"
  *     lives-plugins/weed-plugins/slide_over.c     "slide over"
  *     lives-plugins/weed-plugins/gdk/compositor.c "compositor" (layers at scale 1 / offset 0: BASELINE config 3 through weed_apply_instance)
+ *     lives-plugins/weed-plugins/softlight.c      "softlight"
+ *     lives-plugins/weed-plugins/layout_blends.c  "triple split"
+ *     lives-plugins/weed-plugins/multi_transitions.c "iris rectangle", "iris circle", "4 way split", "dissolve", "rand replace"
  * with the same channel / parameter templates, so weed_apply_instance() (src/effects-weed.c:1850) drives it unchanged.
  * Differences from the originals, on purpose:
  *   - WEED_FILTER_HINT_MAY_THREAD is NOT set: the host must call process_func once per frame, not once per row band
@@ -179,6 +182,125 @@ static pe_weed_error_t compositor_process(pe_weed_plant_t *inst, pe_weed_timecod
   fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
   return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
 }
+
+/* a planar channel: pixel_data / rowstrides are arrays (softlight.c:66-73) */
+static void channel_desc_planar(pe_weed_plant_t *ch, pe_frame_desc_t *d) {
+  int np, k;
+  channel_desc(ch, d);
+  np = (int)w_num_elements(ch, PE_LEAF_PIXEL_DATA);
+  if (np > PE_MAXPLANES) np = PE_MAXPLANES;
+  d->nplanes = np;
+  for (k = 0; k < np; k++) {
+    int32_t rs = 0;
+    void *pp = NULL;
+    w_leaf_get(ch, PE_LEAF_PIXEL_DATA, (pe_weed_size_t)k, &pp);
+    w_leaf_get(ch, PE_LEAF_ROWSTRIDES, (pe_weed_size_t)k, &rs);
+    d->planes[k] = pp;
+    d->rowstrides[k] = rs;
+  }
+  d->yuv_clamping = PE_YUV_CLAMPING_CLAMPED;
+  if (w_num_elements(ch, "YUV_clamping") > 0) d->yuv_clamping = get_int(ch, "YUV_clamping");
+}
+
+static pe_weed_error_t rc_to_weed(int rc) {
+  if (rc == PE_OK) return PE_WEED_SUCCESS;
+  fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+  return rc == PE_ERR_MEMORY ? PE_WEED_ERROR_MEMORY_ALLOCATION : PE_WEED_ERROR_PLUGIN_INVALID;
+}
+
+/* softlight.c softlight_process :62 */
+static pe_weed_error_t softlight_process(pe_weed_plant_t *inst, pe_weed_timecode_t tc) {
+  pe_frame_desc_t in, out;
+  pe_engine_t *e = engine();
+  (void)tc;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  channel_desc_planar(get_plant(inst, PE_LEAF_IN_CHANNELS, 0), &in);
+  channel_desc_planar(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  return rc_to_weed(pe_host_softlight(e, &in, &out));
+}
+
+/* layout_blends.c tsplit_process :122 */
+static pe_weed_error_t tsplit_process(pe_weed_plant_t *inst, pe_weed_timecode_t tc) {
+  pe_frame_desc_t in1, in2, out;
+  pe_engine_t *e = engine();
+  pe_weed_plant_t *par[7];
+  double xstart = 0., xend = 0., bw = 0.;
+  int32_t sym = 0, vert = 0, bc[3] = {0, 0, 0};
+  int k, col[3];
+  (void)tc;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 0), &in1);
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 1), &in2);
+  channel_desc(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  for (k = 0; k < 7; k++) par[k] = get_plant(inst, PE_LEAF_IN_PARAMETERS, k);
+  w_leaf_get(par[0], PE_LEAF_VALUE, 0, &xstart);
+  w_leaf_get(par[1], PE_LEAF_VALUE, 0, &sym);
+  w_leaf_get(par[3], PE_LEAF_VALUE, 0, &xend);
+  w_leaf_get(par[4], PE_LEAF_VALUE, 0, &vert);
+  w_leaf_get(par[5], PE_LEAF_VALUE, 0, &bw);
+  for (k = 0; k < 3 && k < (int)w_num_elements(par[6], PE_LEAF_VALUE); k++) w_leaf_get(par[6], PE_LEAF_VALUE, (pe_weed_size_t)k, &bc[k]);
+  for (k = 0; k < 3; k++) col[k] = bc[k];
+  return rc_to_weed(pe_host_triple_split(e, &in1, &in2, &out, xstart, sym, xend, vert, bw, col));
+}
+
+/* multi_transitions.c: dissolve_init :42 (the mask drawn from the host's random seed), common_deinit :75, common_process :85 */
+static pe_weed_error_t dissolve_init(pe_weed_plant_t *inst) {
+  pe_engine_t *e = engine();
+  pe_weed_plant_t *ch = get_plant(inst, PE_LEAF_IN_CHANNELS, 0);
+  pe_dissolve_mask_t *m = NULL;
+  int64_t seed = 0;
+  void *vp;
+  if (!e || !ch) return PE_WEED_ERROR_PLUGIN_INVALID;
+  if (w_num_elements(inst, "random_seed") > 0) w_leaf_get(inst, "random_seed", 0, &seed);
+  if (pe_fx_dissolve_mask_create(e, get_int(ch, PE_LEAF_WIDTH), get_int(ch, PE_LEAF_HEIGHT), seed, &m) != PE_OK) {
+    fprintf(stderr, "pe_weed_plugin: %s\n", pe_last_error());
+    return PE_WEED_ERROR_MEMORY_ALLOCATION;
+  }
+  vp = m;
+  w_leaf_set(inst, "plugin_internal", PE_WEED_SEED_VOIDPTR, 1, &vp);
+  return PE_WEED_SUCCESS;
+}
+
+static pe_weed_error_t dissolve_deinit(pe_weed_plant_t *inst) {
+  void *vp = get_ptr(inst, "plugin_internal");
+  if (vp) {
+    pe_fx_dissolve_mask_destroy((pe_dissolve_mask_t *)vp);
+    vp = NULL;
+    w_leaf_set(inst, "plugin_internal", PE_WEED_SEED_VOIDPTR, 1, &vp);
+  }
+  return PE_WEED_SUCCESS;
+}
+
+static pe_weed_error_t run_transition(int type, pe_weed_plant_t *inst, pe_weed_timecode_t tc) {
+  static uint64_t rnd = 0;
+  pe_frame_desc_t in1, in2, out;
+  pe_engine_t *e = engine();
+  const pe_dissolve_mask_t *mask = NULL;
+  double bfd = 0.;
+  if (!e) return PE_WEED_ERROR_PLUGIN_INVALID;
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 0), &in1);
+  channel_desc(get_plant(inst, PE_LEAF_IN_CHANNELS, 1), &in2);
+  channel_desc(get_plant(inst, PE_LEAF_OUT_CHANNELS, 0), &out);
+  w_leaf_get(get_plant(inst, PE_LEAF_IN_PARAMETERS, 0), PE_LEAF_VALUE, 0, &bfd);
+  if (type == 3) mask = (const pe_dissolve_mask_t *)get_ptr(inst, "plugin_internal");
+  if (type == 4) {
+    /* "rand replace" :102-119: the whole frame is in2 with probability `amount`, else in1 -- host logic (the plugin's own random
+     * stream); the copy itself runs on the device as the degenerate iris rectangle (amount 1: all in2, amount 0: all in1) */
+    if (!rnd) rnd = 0x9E3779B97F4A7C15ull ^ (uint64_t)tc ^ (uint64_t)(uintptr_t)inst;
+    rnd ^= rnd << 13; rnd ^= rnd >> 7; rnd ^= rnd << 17;
+    bfd = ((double)rnd * (1. / 18446744073709551616.) >= bfd) ? 0. : 1.;
+    if (bfd == 0. && out.planes[0] == in1.planes[0]) return PE_WEED_SUCCESS;
+    type = 0;
+  }
+  return rc_to_weed(pe_host_multi_transition(e, type, &in1, &in2, &out, bfd, mask));
+}
+#define PE_TRANSITION(name, type) \
+  static pe_weed_error_t name(pe_weed_plant_t *inst, pe_weed_timecode_t tc) { return run_transition(type, inst, tc); }
+PE_TRANSITION(irisr_process, 0)
+PE_TRANSITION(irisc_process, 1)
+PE_TRANSITION(fourw_process, 2)
+PE_TRANSITION(dissolve_process, 3)
+PE_TRANSITION(rreplace_process, 4)
 
 /* ---- plant construction (what weed_channel_template_init / weed_integer_init / weed_filter_class_init of
  *      libweed/weed-plugin-utils.c:247-336 produce) ----------------------------------------------------------------- */
@@ -385,6 +507,74 @@ static int add_filter(pe_weed_plant_t *plugin_info, const char *name, int flags,
   return register_filter(plugin_info, fc);
 }
 
+/* a filter class from ready-made templates (weed_filter_class_init, weed-plugin-utils.c:258-305) */
+static int add_class(pe_weed_plant_t *plugin_info, const char *name, int flags, const int *palettes, int npal, pe_weed_init_f init_fn,
+                     pe_weed_process_f process_fn, pe_weed_init_f deinit_fn, pe_weed_plant_t **in_ct, int nin, pe_weed_plant_t **out_ct,
+                     pe_weed_plant_t **in_pt, int npar) {
+  pe_weed_plant_t *fc = w_plant_new(PE_WEED_PLANT_FILTER_CLASS);
+  const char *author = "lives_b200";
+  int k;
+  if (!fc) return -1;
+  for (k = 0; k < nin; k++) if (!in_ct[k]) return -1;
+  for (k = 0; k < npar; k++) if (!in_pt[k]) return -1;
+  if (!out_ct[0]) return -1;
+  set_str(fc, PE_LEAF_NAME, name);
+  w_leaf_set(fc, PE_LEAF_AUTHOR, PE_WEED_SEED_STRING, 1, &author);
+  set_int(fc, PE_LEAF_VERSION, 1);
+  set_int(fc, PE_LEAF_FLAGS, flags);
+  if (init_fn) w_leaf_set(fc, PE_LEAF_INIT_FUNC, PE_WEED_SEED_FUNCPTR, 1, &init_fn);
+  if (deinit_fn) w_leaf_set(fc, PE_LEAF_DEINIT_FUNC, PE_WEED_SEED_FUNCPTR, 1, &deinit_fn);
+  w_leaf_set(fc, PE_LEAF_PROCESS_FUNC, PE_WEED_SEED_FUNCPTR, 1, &process_fn);
+  w_leaf_set(fc, PE_LEAF_IN_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, (pe_weed_size_t)nin, in_ct);
+  w_leaf_set(fc, PE_LEAF_OUT_CHANNEL_TEMPLATES, PE_WEED_SEED_PLANTPTR, 1, out_ct);
+  w_leaf_set(fc, PE_LEAF_IN_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, (pe_weed_size_t)npar, npar ? in_pt : NULL);
+  w_leaf_set(fc, PE_LEAF_OUT_PARAMETER_TEMPLATES, PE_WEED_SEED_PLANTPTR, 0, NULL);
+  w_leaf_set(fc, PE_LEAF_PALETTE_LIST, PE_WEED_SEED_INT, (pe_weed_size_t)npal, (void *)palettes);
+  return register_filter(plugin_info, fc);
+}
+
+/* softlight.c:168-183: one in, one out channel, no parameters; the in channel template prefers unclamped YUV */
+static int add_softlight(pe_weed_plant_t *plugin_info) {
+  const int palettes[] = {PE_PALETTE_YUV444P, PE_PALETTE_YUVA4444P, PE_PALETTE_YUV422P, PE_PALETTE_YUV420P, PE_PALETTE_YVU420P};
+  pe_weed_plant_t *in_ct[1], *out_ct[1];
+  in_ct[0] = chantmpl("in channel 0", 0);
+  out_ct[0] = chantmpl("out channel 0", 0);
+  if (in_ct[0]) set_int(in_ct[0], "YUV_clamping", PE_YUV_CLAMPING_UNCLAMPED);
+  return add_class(plugin_info, "softlight", 0, palettes, 5, common_init, softlight_process, NULL, in_ct, 1, out_ct, NULL, 0);
+}
+
+/* layout_blends.c:127-158 */
+static int add_triple_split(pe_weed_plant_t *plugin_info) {
+  const int palettes[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24};
+  pe_weed_plant_t *in_ct[2], *out_ct[1], *in_pt[7];
+  in_ct[0] = chantmpl("in channel 0", 0);
+  in_ct[1] = chantmpl("in channel 1", 0);
+  out_ct[0] = chantmpl("out channel 0", PE_WEED_CHANNEL_CAN_DO_INPLACE);
+  in_pt[0] = float_param("start", "_Start", 0.666667, 0., 1.);
+  in_pt[1] = switch_param("sym", "Make s_ymmetrical", 1, 1, 0);
+  in_pt[2] = switch_param("usend", "Use _end value", 0, 1, 0);
+  in_pt[3] = float_param("end", "_End", 0.333333, 0., 1.);
+  in_pt[4] = switch_param("vert", "Split _horizontally", 0, -1, 0);
+  in_pt[5] = float_param("borderw", "Border _width", 0., 0., 0.5);
+  in_pt[6] = rgb_param("borderc", "Border _colour", 0, 0, 0);
+  return add_class(plugin_info, "triple split", 0, palettes, 2, common_init, tsplit_process, NULL, in_ct, 2, out_ct, in_pt, 7);
+}
+
+/* multi_transitions.c:229-330: five filters over every packed palette, one transition parameter each */
+static int add_transition(pe_weed_plant_t *plugin_info, const char *name, int flags, int out_flags, pe_weed_init_f init_fn,
+                          pe_weed_process_f process_fn, pe_weed_init_f deinit_fn) {
+  const int palettes[] = {PE_PALETTE_RGB24, PE_PALETTE_BGR24, PE_PALETTE_RGBA32, PE_PALETTE_BGRA32, PE_PALETTE_ARGB32, PE_PALETTE_UYVY,
+                          PE_PALETTE_YUYV, PE_PALETTE_YUV888, PE_PALETTE_YUVA8888}; /* ALL_PACKED_PALETTES */
+  pe_weed_plant_t *in_ct[2], *out_ct[1], *in_pt[1];
+  int32_t one = 1;
+  in_ct[0] = chantmpl("in channel 0", 0);
+  in_ct[1] = chantmpl("in channel 1", 0);
+  out_ct[0] = chantmpl("out channel 0", out_flags);
+  in_pt[0] = float_param("amount", "_Transition", 0., 0., 1.);
+  if (in_pt[0]) w_leaf_set(in_pt[0], PE_LEAF_IS_TRANSITION, PE_WEED_SEED_BOOLEAN, 1, &one);
+  return add_class(plugin_info, name, flags, palettes, 9, init_fn, process_fn, deinit_fn, in_ct, 2, out_ct, in_pt, 1);
+}
+
 /* ---- entry points --------------------------------------------------------------------------------------------------- */
 
 pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
@@ -439,6 +629,15 @@ pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
     return NULL;
   if (add_slide_over(plugin_info)) return NULL;
   if (add_compositor(plugin_info)) return NULL;
+  if (add_softlight(plugin_info) || add_triple_split(plugin_info)) return NULL;
+  /* multi_transitions.c:242-326 (filter order kept; "4 way split" is not in-place :268, "dissolve" re-inits when the size changes :281) */
+  if (add_transition(plugin_info, "iris rectangle", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE, common_init, irisr_process, NULL) ||
+      add_transition(plugin_info, "iris circle", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE, common_init, irisc_process, NULL) ||
+      add_transition(plugin_info, "4 way split", 0, 0, common_init, fourw_process, NULL) ||
+      add_transition(plugin_info, "dissolve", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE | PE_WEED_CHANNEL_REINIT_ON_SIZE_CHANGE, dissolve_init,
+                     dissolve_process, dissolve_deinit) ||
+      add_transition(plugin_info, "rand replace", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE, common_init, rreplace_process, NULL))
+    return NULL;
   set_int(plugin_info, PE_LEAF_VERSION, package_version);
   return plugin_info;
 }

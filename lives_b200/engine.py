@@ -360,6 +360,49 @@ def slide_over_bound(direction, transval, width, height):
     return capi.lib().pe_fx_slide_over_bound(SLIDE_DIRECTIONS.get(direction, direction), transval, width, height)
 
 
+def softlight(in_layer, out):
+    """softlight.c softlight_process :62 (planar YUV: the luma plane is filtered, the other planes are copied)"""
+    e = in_layer.engine
+    capi.check(e._lib.pe_fx_softlight(e._h, in_layer._h, out._h))
+
+
+def triple_split(in1, in2, out, start=0.666667, sym=True, end=0.333333, vert=False, borderw=0., bordercol=(0, 0, 0)):
+    """layout_blends.c common_process :19 ("triple split"); the defaults are the plugin's parameter templates :137-144"""
+    e = in1.engine
+    capi.check(e._lib.pe_fx_triple_split(e._h, in1._h, in2._h, out._h, start, int(bool(sym)), end, int(bool(vert)), borderw,
+                                         (C.c_int * 3)(*bordercol)))
+
+
+MULTI_TRANSITION_TYPES = {"iris rectangle": 0, "iris circle": 1, "4 way split": 2, "dissolve": 3}
+
+
+class DissolveMask:
+    """the per-instance mask of multi_transitions.c dissolve_init :42, drawn from the host's random seed"""
+
+    def __init__(self, engine, width, height, random_seed):
+        self.engine = engine
+        self._h = C.c_void_p()
+        capi.check(engine._lib.pe_fx_dissolve_mask_create(engine._h, width, height, random_seed, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self.engine._lib.pe_fx_dissolve_mask_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def multi_transition(filter_type, in1, in2, out, amount, mask=None):
+    """multi_transitions.c common_process :85: "iris rectangle", "iris circle", "4 way split", "dissolve" (needs a DissolveMask)"""
+    t = MULTI_TRANSITION_TYPES.get(filter_type, filter_type)
+    e = in1.engine
+    capi.check(e._lib.pe_fx_multi_transition(e._h, t, in1._h, in2._h, out._h, amount, mask._h if mask is not None else None))
+
+
 def compositor(out, layers, alphas, bgcol=(0, 0, 0)):
     """gdk/compositor.c compositor_process :127 at scale 1 / offset 0"""
     e = out.engine

@@ -17,7 +17,7 @@ with the repo snapshot and this script is a no-op):
      ever copied into tracked files.
   2. libweed.so / libweed-utils.so / libweed-host-utils.so -- the reference's
      libweed/*.c compiled unchanged.
-  3. simple_blend.so / multi_blends.so / slide_over.so -- the reference's effect plugins
+  3. simple_blend.so / multi_blends.so / slide_over.so / softlight.so / layout_blends.so / multi_transitions.so -- the reference's effect plugins
      compiled unchanged against those libs (flags per
      lives-plugins/weed-plugins/Makefile.am).
   4. ref_paint_pixel.so -- compositor.c's paint_pixel() (gdk is not available,
@@ -118,7 +118,7 @@ def build_libweed():
 
 def build_plugins(inc):
     pdir = os.path.join(REF, "lives-plugins", "weed-plugins")
-    for name in ("simple_blend", "multi_blends", "slide_over"):
+    for name in ("simple_blend", "multi_blends", "slide_over", "softlight", "layout_blends", "multi_transitions"):
         sh(["gcc", "-O3", "-fPIC", "-shared", "-w", "-ffast-math", "-fno-math-errno",
             "-I", inc, os.path.join(pdir, name + ".c"),
             "-o", os.path.join(OUT, name + ".so"),

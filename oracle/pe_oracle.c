@@ -1600,3 +1600,144 @@ uint64_t pe_or_row_hashes(const uint8_t *pixels, int nbytes, int height, int row
   }
   return parity;
 }
+
+/* ---- SURVEY 8f rank 3, second batch: softlight.c, layout_blends.c ("triple split"), multi_transitions.c ------------------------ */
+
+/* softlight.c sqrti :33-47: digit-by-digit integer square root = floor(sqrt(n)) */
+static uint32_t or_sqrti(uint32_t n) {
+  uint32_t root = 0, rem = n, place = 0x40000000u;
+  while (place > rem) place >>= 2;
+  while (place) {
+    const uint32_t t = root + place;
+    if (rem >= t) { rem -= t; root += place << 1; }
+    root >>= 1;
+    place >>= 2;
+  }
+  return root;
+}
+
+/* softlight.c softlight_process :62-162 on the luma plane (the chroma planes are copied, :150-154): rows 0 and height - 1 and columns
+ * 0 and width - 1 are copied; elsewhere an edge magnitude (two 3 x 3 differences exactly as written at :114-118 -- the last term of
+ * row0 subtracts the lower-LEFT sample from the lower-right one, the last term of row1 ADDS the two lower corners) is scaled, clamped
+ * to the luma range and mixed 64 : 192 with the source sample. */
+void pe_or_softlight(const uint8_t *src, int irow, uint8_t *dst, int orow, int width, int height, int clamped) {
+  const int ymin = clamped ? 16 : 0, ymax = clamped ? 235 : 255, scale = 384, mix = 192;
+  memcpy(dst, src, (size_t)width);
+  for (int y = 1; y < height - 1; y++) {
+    const uint8_t *s = src + (long)irow * y;
+    uint8_t *d = dst + (long)orow * y;
+    d[0] = s[0];
+    for (int x = 1; x < width - 1; x++) {
+      const uint8_t *p = s + x;
+      const int row0 = (p[irow - 1] - p[-irow - 1]) + ((p[irow] - p[-irow]) << 1) + (p[irow + 1] - p[irow - 1]);
+      const int row1 = (p[-irow + 1] - p[-irow - 1]) + ((p[1] - p[-1]) << 1) + (p[irow + 1] + p[irow - 1]);
+      int sum = (int)(((3 * or_sqrti((uint32_t)(row0 * row0 + row1 * row1)) / 2) * scale) >> 8);
+      sum = sum < ymin ? ymin : sum > ymax ? ymax : sum;
+      sum = ((256 - mix) * sum + mix * p[0]) >> 8;
+      d[x] = (uint8_t)(sum < ymin ? ymin : sum > ymax ? ymax : sum);
+    }
+    if (width > 1) d[width - 1] = s[width - 1];
+  }
+  if (height > 1) memcpy(dst + (long)orow * (height - 1), src + (long)irow * (height - 1), (size_t)width);
+}
+
+/* layout_blends.c common_process :19-119 ("triple split", RGB24 / BGR24): per pixel one of src2 (outside the band), src1 (inside)
+ * or the border colour, decided by the double comparisons of :92-99 on the byte offset j and the row.  colclass[x] / rowclass[y]:
+ * bit 0 = "outside" test, bit 1 = "inside" test of that column / row, exactly as the reference evaluates them (the same function
+ * serves the product's host code: the comparisons are per column and per row, never per pixel).  bordercol is in RGB order; a
+ * BGR24 frame swaps it (:66-70). */
+void pe_or_triple_split_classes(int width, int height, double xstart, int sym, double xend, int vert, double bw, uint8_t *colclass,
+                                uint8_t *rowclass) {
+  const int wb = width * 3;
+  int tbs = height, tbe = height, bbs = height, bbe = height; /* rows; "end" = row `height` */
+  if (sym) { xstart /= 2.; xend = 1. - xstart; }
+  if (xstart > xend) { const double t = xend; xend = xstart; xstart = t; }
+  if (vert) {
+    tbs = (int)(height * (xstart - bw) + .5); tbe = (int)(height * (xstart + bw) + .5);
+    bbs = (int)(height * (xend - bw) + .5); bbe = (int)(height * (xend + bw) + .5);
+    xstart = xend = -bw;
+  }
+  for (int x = 0; x < width; x++) {
+    const int j = 3 * x;
+    const int out = (j < wb * (xstart - bw) || j >= wb * (xend + bw)) ? 1 : 0;
+    const int in = (j > wb * (xstart + bw) && j < wb * (xend - bw)) ? 2 : 0;
+    colclass[x] = (uint8_t)(out | in);
+  }
+  for (int y = 0; y < height; y++) rowclass[y] = (uint8_t)(((y <= tbs || y >= bbe) ? 1 : 0) | ((y > tbe && y < bbs) ? 2 : 0));
+}
+
+void pe_or_triple_split(const uint8_t *src1, int irow1, const uint8_t *src2, int irow2, uint8_t *dst, int orow, int width, int height,
+                        int bgr, double xstart, int sym, double xend, int vert, double bw, const int bordercol[3]) {
+  uint8_t *cc = (uint8_t *)malloc((size_t)width), *rc = (uint8_t *)malloc((size_t)height);
+  const int c0 = bgr ? bordercol[2] : bordercol[0], c1 = bordercol[1], c2 = bgr ? bordercol[0] : bordercol[2];
+  pe_or_triple_split_classes(width, height, xstart, sym, xend, vert, bw, cc, rc);
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      uint8_t *d = dst + (long)orow * y + 3 * x;
+      if ((cc[x] & 1) && (rc[y] & 1)) memcpy(d, src2 + (long)irow2 * y + 3 * x, 3);
+      else if ((cc[x] & 2) || (rc[y] & 2)) { if (d != src1 + (long)irow1 * y + 3 * x) memcpy(d, src1 + (long)irow1 * y + 3 * x, 3); }
+      else { d[0] = (uint8_t)c0; d[1] = (uint8_t)c1; d[2] = (uint8_t)c2; }
+    }
+  free(cc); free(rc);
+}
+
+/* multi_transitions.c dissolve_init :42-70: mask[i] = (float)fastrand_dbl_re(1., ...) -- xorshift64 (13, 7, 17) of the host's random
+ * seed (libweed/weed-plugin-utils.c:666,686-704), `val / divd / divd * range` with divd = (double)0xFFFFFFFF, which the plugins'
+ * -ffast-math build (Makefile.am:49) folds into ONE multiplication by 1 / divd^2 (the constant 0x3BF0000000200000, read off the
+ * compiled plugin) */
+void pe_or_dissolve_mask(int64_t seed, long n, float *mask) {
+  uint64_t x = (uint64_t)seed;
+  union { uint64_t u; double d; } k;
+  k.u = 0x3BF0000000200000ull;
+  for (long i = 0; i < n; i++) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    mask[i] = (float)((double)x * k.d);
+  }
+}
+
+/* multi_transitions.c common_process :85-225, types 0 "iris rectangle", 1 "iris circle", 2 "4 way split", 3 "dissolve" (type 4, "rand
+ * replace", is a whole-frame copy of src1 or src2 decided by the plugin's own random stream: host logic, no pixel arithmetic).
+ * Float expressions in the form the plugins' -ffast-math build evaluates them (divisions by loop invariants become multiplications by
+ * a reciprocal computed once; read off the compiled plugin, checked against it in tests/test_oracle_vs_reference.py):
+ *   0: xx = (int)((double)((float)(int)hwidth_bytes * bfneg) + .5), yy likewise with hheight; src2 inside [xx, wb - xx) x [yy, h - yy)
+ *   1: t = (yyf * yyf + xxf * xxf) * (1.f / maxradsq), yyf = (float)(j - ihwidth) * (1.f / (float)psize); src1 when sqrt((double)t) > bf
+ *   2: src2 when |i - hheight| * (1.f / hheight) < bf or |j - hwidth| * (1.f / hwidth) < bf or bf == 1; else src1 displaced by
+ *      (+-yy bytes, +-xx rows), xx = (int)((double)(hheight * bf) + .5), yy = (int)((double)((bf * (1.f / psize)) * hwidth) + .5) * psize
+ *   3: src2 where mask[pixel] < bf
+ * dst may alias src1 for types 0, 1, 3 (pixels that keep src1 are not written). */
+void pe_or_multi_transition(int type, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2, uint8_t *dst, int orow, int width,
+                            int height, int psize, double bfd, const float *mask) {
+  const float bf = (float)bfd, bfneg = 1.f - bf;
+  const float hheight = (float)height * 0.5f;
+  const int wb = width * psize, ihwidth = wb >> 1, ihheight = height >> 1;
+  const float hwidth_px = (float)width * 0.5f, hwidth = (float)wb * 0.5f;
+  const float maxradsq = hheight * hheight + hwidth_px * hwidth_px;
+  const float inv_maxradsq = 1.f / maxradsq, inv_psize = 1.f / (float)psize, inv_hh = 1.f / hheight, inv_hw = 1.f / hwidth;
+  int xx = 0, yy = 0;
+  if (type == 0) {
+    xx = (int)((double)((float)(int)hwidth * bfneg) + .5);
+    yy = (int)((double)((float)(int)hheight * bfneg) + .5);
+  } else if (type == 2) {
+    xx = (int)((double)(hheight * bf) + .5);
+    yy = (int)((double)((bf * (psize == 3 ? 0.333333343267440796f : psize == 4 ? 0.25f : inv_psize)) * hwidth) + .5) * psize;
+  }
+  for (int i = 0; i < height; i++)
+    for (int j = 0; j < wb; j += psize) {
+      const uint8_t *s1 = src1 + (long)irow1 * i + j, *s2 = src2 + (long)irow2 * i + j;
+      uint8_t *d = dst + (long)orow * i + j;
+      const uint8_t *from = s1;
+      if (type == 0) {
+        if (!(j < xx || j >= wb - xx || i < yy || i >= height - yy)) from = s2;
+      } else if (type == 1) {
+        const float xxf = (float)(i - ihheight), yyf = (float)(j - ihwidth) * inv_psize;
+        const float t = (yyf * yyf + xxf * xxf) * inv_maxradsq;
+        if (!(sqrt((double)t) > (double)bf)) from = s2;
+      } else if (type == 2) {
+        if (fabsf((float)i - hheight) * inv_hh < bf || fabsf((float)j - hwidth) * inv_hw < bf || bf == 1.f) from = s2;
+        else from = s1 + (j > ihwidth ? -yy : yy) + (long)(i > ihheight ? -xx : xx) * irow1;
+      } else {
+        if (mask[(long)i * width + j / psize] < bf) from = s2;
+      }
+      if (from != d) memmove(d, from, (size_t)psize);
+    }
+}

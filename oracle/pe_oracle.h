@@ -193,3 +193,13 @@ uint64_t pe_or_row_hashes(const uint8_t *pixels, int nbytes, int height, int row
 }
 #endif
 #endif
+
+/* ---- SURVEY 8f rank 3, second batch (lives-plugins/weed-plugins/softlight.c, layout_blends.c, multi_transitions.c) ---- */
+void pe_or_softlight(const uint8_t *src, int irow, uint8_t *dst, int orow, int width, int height, int clamped);
+void pe_or_triple_split_classes(int width, int height, double xstart, int sym, double xend, int vert, double bw, uint8_t *colclass,
+                                uint8_t *rowclass);
+void pe_or_triple_split(const uint8_t *src1, int irow1, const uint8_t *src2, int irow2, uint8_t *dst, int orow, int width, int height,
+                        int bgr, double xstart, int sym, double xend, int vert, double bw, const int bordercol[3]);
+void pe_or_dissolve_mask(int64_t seed, long n, float *mask);
+void pe_or_multi_transition(int type, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2, uint8_t *dst, int orow, int width,
+                            int height, int psize, double bfd, const float *mask);

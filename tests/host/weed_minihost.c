@@ -312,3 +312,79 @@ int mh_run_compositor(int h, int fidx, int palette, int width, int height, int n
   free(ictm); free(octm); free(iptm);
   return (int)err;
 }
+
+/* ---- generic runner: any number of in channels (planar or packed), one out channel, one in-parameter per template of the filter.
+ *      vals holds the parameter values back to back, counts[k] of them for parameter k; each is stored with the seed type of the
+ *      template's default (boolean / int / double; a colour is three ints).  `seed` becomes the instance's WEED_LEAF_RANDOM_SEED
+ *      (what the host hands "dissolve", multi_transitions.c:55).  init once, process nframes times, deinit once. */
+typedef struct {
+  int palette, width, height, nplanes, yuv_clamping;
+  void *planes[4];
+  int rowstrides[4];
+} mh_chan_desc;
+
+static weed_plant_t *mh_channel_n(weed_plant_t *tmpl, const mh_chan_desc *d) {
+  weed_plant_t *ch = weed_plant_new(WEED_PLANT_CHANNEL);
+  weed_set_plantptr_value(ch, WEED_LEAF_TEMPLATE, tmpl);
+  weed_set_int_value(ch, WEED_LEAF_WIDTH, d->width);
+  weed_set_int_value(ch, WEED_LEAF_HEIGHT, d->height);
+  weed_set_int_value(ch, WEED_LEAF_CURRENT_PALETTE, d->palette);
+  weed_set_int_array(ch, WEED_LEAF_ROWSTRIDES, d->nplanes, (int *)d->rowstrides);
+  weed_set_voidptr_array(ch, WEED_LEAF_PIXEL_DATA, d->nplanes, (void **)d->planes);
+  if (d->yuv_clamping >= 0) weed_set_int_value(ch, WEED_LEAF_YUV_CLAMPING, d->yuv_clamping);
+  return ch;
+}
+
+int mh_run_generic(int h, int fidx, int nin, const mh_chan_desc *in, const mh_chan_desc *out, int nparams, const double *vals,
+                   const int *counts, long long seed, int nframes) {
+  weed_plant_t *filter, *inst, *in_ch[8], *out_ch, *params[32];
+  weed_plant_t **ictm, **octm, **iptm = NULL;
+  weed_init_f init_fn;
+  weed_process_f process_fn;
+  weed_deinit_f deinit_fn;
+  weed_error_t err = WEED_SUCCESS;
+  int n, np = 0, k, j, pos = 0;
+  if (mh_num_filters(h) <= fidx || fidx < 0 || nin < 1 || nin > 8) return -1;
+  filter = mh_tab[h].filters[fidx];
+  ictm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_CHANNEL_TEMPLATES, &n);
+  if (n < nin) return -2;
+  octm = weed_get_plantptr_array_counted(filter, WEED_LEAF_OUT_CHANNEL_TEMPLATES, &n);
+  if (n < 1) return -3;
+  if (weed_plant_has_leaf(filter, WEED_LEAF_IN_PARAMETER_TEMPLATES))
+    iptm = weed_get_plantptr_array_counted(filter, WEED_LEAF_IN_PARAMETER_TEMPLATES, &np);
+  if (np > 32 || np != nparams) return -4;
+  for (k = 0; k < nin; k++) in_ch[k] = mh_channel_n(ictm[k], &in[k]);
+  out_ch = mh_channel_n(octm[0], out);
+  for (k = 0; k < np; k++) {
+    const uint32_t st = weed_leaf_seed_type(iptm[k], WEED_LEAF_DEFAULT);
+    params[k] = weed_plant_new(WEED_PLANT_PARAMETER);
+    weed_set_plantptr_value(params[k], WEED_LEAF_TEMPLATE, iptm[k]);
+    if (st == WEED_SEED_DOUBLE) weed_set_double_array(params[k], WEED_LEAF_VALUE, counts[k], (double *)(vals + pos));
+    else {
+      int iv[8];
+      for (j = 0; j < counts[k] && j < 8; j++) iv[j] = (int)vals[pos + j];
+      if (st == WEED_SEED_BOOLEAN) weed_set_boolean_array(params[k], WEED_LEAF_VALUE, counts[k], iv);
+      else weed_set_int_array(params[k], WEED_LEAF_VALUE, counts[k], iv);
+    }
+    pos += counts[k];
+  }
+  inst = weed_plant_new(WEED_PLANT_FILTER_INSTANCE);
+  weed_set_plantptr_value(inst, WEED_LEAF_FILTER_CLASS, filter);
+  weed_set_plantptr_array(inst, WEED_LEAF_IN_CHANNELS, nin, in_ch);
+  weed_set_plantptr_array(inst, WEED_LEAF_OUT_CHANNELS, 1, &out_ch);
+  if (np > 0) weed_set_plantptr_array(inst, WEED_LEAF_IN_PARAMETERS, np, params);
+  weed_set_int64_value(inst, WEED_LEAF_RANDOM_SEED, (int64_t)seed);
+  init_fn = weed_plant_has_leaf(filter, WEED_LEAF_INIT_FUNC) ? (weed_init_f)weed_get_funcptr_value(filter, WEED_LEAF_INIT_FUNC, NULL) : NULL;
+  process_fn = (weed_process_f)weed_get_funcptr_value(filter, WEED_LEAF_PROCESS_FUNC, NULL);
+  deinit_fn = weed_plant_has_leaf(filter, WEED_LEAF_DEINIT_FUNC) ? (weed_deinit_f)weed_get_funcptr_value(filter, WEED_LEAF_DEINIT_FUNC, NULL) : NULL;
+  if (!process_fn) return -5;
+  if (init_fn) err = (*init_fn)(inst);
+  for (k = 0; k < nframes && err == WEED_SUCCESS; k++) err = (*process_fn)(inst, (weed_timecode_t)k);
+  if (deinit_fn) (*deinit_fn)(inst);
+  weed_plant_free(inst);
+  for (k = 0; k < np; k++) weed_plant_free(params[k]);
+  for (k = 0; k < nin; k++) weed_plant_free(in_ch[k]);
+  weed_plant_free(out_ch);
+  free(ictm); free(octm); if (iptm) free(iptm);
+  return (int)err;
+}

@@ -241,3 +241,40 @@ def planes_arg(*planes):
 
 def strides_arg(*planes):
     return (C.c_int * len(planes))(*[p.strides[0] for p in planes])
+
+
+# ---------------------------------------------------------------- the mini weed host (tests/host/weed_minihost.c)
+
+class ChanDesc(C.Structure):
+    """mh_chan_desc: one channel of mh_run_generic"""
+    _fields_ = [("palette", I), ("width", I), ("height", I), ("nplanes", I), ("yuv_clamping", I), ("planes", VP * 4), ("rowstrides", I * 4)]
+
+
+def chan(palette, width, height, planes, clamping=-1):
+    d = ChanDesc()
+    d.palette, d.width, d.height, d.nplanes, d.yuv_clamping = palette, width, height, len(planes), clamping
+    for i, p in enumerate(planes):
+        d.planes[i] = p.ctypes.data
+        d.rowstrides[i] = p.strides[0]
+    return d
+
+
+_mh = None
+
+
+def minihost():
+    global _mh
+    if _mh is None:
+        _mh = C.CDLL(os.path.join(REF_DIR, "libweed_minihost.so"))
+        _mh.mh_open.argtypes = [C.c_char_p]
+        _mh.mh_run_generic.argtypes = [I, I, I, C.POINTER(ChanDesc), C.POINTER(ChanDesc), I, C.POINTER(D), C.POINTER(I), C.c_longlong, I]
+    return _mh
+
+
+def mh_run(h, fidx, ins, out, params=(), seed=1, nframes=1):
+    """run filter fidx of plugin handle h: ins / out = ChanDesc, params = one list of numbers per in-parameter template"""
+    mh = minihost()
+    flat = [float(v) for p in params for v in p]
+    counts = [len(p) for p in params]
+    return mh.mh_run_generic(h, fidx, len(ins), (ChanDesc * len(ins))(*ins), C.byref(out), len(params), (D * max(1, len(flat)))(*flat),
+                             (I * max(1, len(counts)))(*counts), seed, nframes)

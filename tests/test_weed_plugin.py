@@ -18,7 +18,8 @@ pytestmark = pytest.mark.skipif(not T.have_ref() or not os.path.exists(os.path.j
                                 reason="oracle/_ref (reference libweed + minihost) not built")
 
 NAMES = ["chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "blend_multiply", "blend_screen",
-         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over", "compositor"]
+         "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over", "compositor", "softlight",
+         "triple split", "iris rectangle", "iris circle", "4 way split", "dissolve", "rand replace"]
 
 
 def _minihost():
@@ -64,6 +65,12 @@ def test_plugin_bootstraps_through_the_reference_libweed():
     ref = mh.mh_open(os.path.join(T.REF_DIR, "slide_over.so").encode())
     mh.mh_filter_name(ref, 0, buf, 64)
     assert buf.value.decode() == NAMES[11]
+    for so, first, cnt in (("softlight", 13, 1), ("layout_blends", 14, 1), ("multi_transitions", 15, 5)):
+        ref = mh.mh_open(os.path.join(T.REF_DIR, so + ".so").encode())
+        assert mh.mh_num_filters(ref) == cnt
+        for i in range(cnt):
+            mh.mh_filter_name(ref, i, buf, 64)
+            assert buf.value.decode() == NAMES[first + i]
     # the 8 parameter templates of "slide over" are accepted with the reference's seed types (a wrong count / type is rc -4 / garbage)
     s = np.zeros((8, 32), np.uint8)
     import torch
@@ -178,3 +185,68 @@ def test_compositor_filter_config3_through_the_plugin_boundary():
     rc = mh.mh_run_compositor(ours, fidx, pal, w, ht, 3, srcs, rss, T.ptr(got), got.strides[0], zero, zero, half, one, (D * 3)(*alphas),
                               (C.c_int * 3)(*bg), 0)
     assert rc == 65 and (got == 9).all()  # WEED_ERROR_FILTER_INVALID
+
+
+@pytest.mark.gpu
+def test_softlight_triple_split_multi_transitions_match_the_reference_plugins():
+    """"softlight", "triple split" and the five multi_transitions filters of libpe_weed_plugin.so against the
+    reference's softlight.so / layout_blends.so / multi_transitions.so, both run by the minihost with the same channels and parameters"""
+    mh = _minihost()
+    ours = _open_ours(mh)
+    T.minihost()  # binds mh_run_generic on the same library object
+    ref_sl = mh.mh_open(os.path.join(T.REF_DIR, "softlight.so").encode())
+    ref_ts = mh.mh_open(os.path.join(T.REF_DIR, "layout_blends.so").encode())
+    ref_mt = mh.mh_open(os.path.join(T.REF_DIR, "multi_transitions.so").encode())
+    rng = np.random.default_rng(34)
+    # ---- softlight
+    for pal, clamp, (w, ht) in itertools.product((512, 513, 522, 544, 545), (0, 1), ((64, 16), (70, 9), (1920, 1080))):
+        if (w, ht) == (1920, 1080) and pal != 512:
+            continue
+        ys = T.rowstride(w, 1)
+        cw = w if pal in (544, 545) else w >> 1
+        chh = ht >> 1 if pal in (512, 513) else ht
+        cs = ys if pal in (544, 545) else ys >> 1
+        planes = [T.make_packed(rng, w, ht, 1, ys)] + [T.make_packed(rng, cw, chh, 1, cs) for _ in range(3 if pal == 545 else 2)]
+        o_ref, o_our = [np.full_like(p, 7) for p in planes], [np.full_like(p, 7) for p in planes]
+        assert T.mh_run(ref_sl, 0, [T.chan(pal, w, ht, planes, clamp)], T.chan(pal, w, ht, o_ref, clamp)) == 0
+        assert T.mh_run(ours, NAMES.index("softlight"), [T.chan(pal, w, ht, planes, clamp)], T.chan(pal, w, ht, o_our, clamp)) == 0
+        assert (o_ref[0][:, :w] == o_our[0][:, :w]).all(), (pal, clamp, w, ht)
+        for a, b in zip(o_ref[1:], o_our[1:]):
+            assert (a[:, :cw] == b[:, :cw]).all(), (pal, "chroma")
+    # ---- triple split
+    cases = [(0.666667, 1, 0.333333, 0, 0.0), (0.666667, 1, 0.333333, 0, 0.05), (0.2, 0, 0.7, 0, 0.03), (0.5, 1, 0.5, 1, 0.0),
+             (0.3, 0, 0.9, 1, 0.07), (1.0, 1, 0.0, 1, 0.2)]
+    for (w, ht), pal, (xs, sym, xe, vert, bw) in itertools.product(((64, 32), (61, 17), (1920, 1080)), (1, 2), cases):
+        s1, s2 = T.make_packed(rng, w, ht, 3), T.make_packed(rng, w, ht, 3)
+        params = [[xs], [sym], [1 - sym], [xe], [vert], [bw], [200, 100, 50]]
+        d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
+        assert T.mh_run(ref_ts, 0, [T.chan(pal, w, ht, [s1]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [d_ref]), params) == 0
+        assert T.mh_run(ours, NAMES.index("triple split"), [T.chan(pal, w, ht, [s1]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [d_our]), params) == 0
+        assert (d_ref[:, :w * 3] == d_our[:, :w * 3]).all(), (w, ht, pal, xs, sym, xe, vert, bw)
+        a, b = s1.copy(), s1.copy()  # in place
+        T.mh_run(ref_ts, 0, [T.chan(pal, w, ht, [a]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [a]), params)
+        T.mh_run(ours, NAMES.index("triple split"), [T.chan(pal, w, ht, [b]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [b]), params)
+        assert (a[:, :w * 3] == b[:, :w * 3]).all()
+    # ---- multi_transitions
+    first = NAMES.index("iris rectangle")
+    for ftype, (pal, ps), (w, ht) in itertools.product(range(4), ((1, 3), (3, 4), (565, 4), (588, 3)), ((64, 32), (61, 17), (37, 50), (1280, 720))):
+        if (w, ht) == (1280, 720) and pal not in (1, 3):
+            continue
+        s1, s2 = T.make_packed(rng, w, ht, ps), T.make_packed(rng, w, ht, ps)
+        seed = int(rng.integers(1, 2 ** 62))
+        for bf in [0.0, 1.0, 0.5, 1 / 3, 0.013, 0.999] + [float(x) for x in rng.random(3)]:
+            d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
+            assert T.mh_run(ref_mt, ftype, [T.chan(pal, w, ht, [s1]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [d_ref]), [[bf]], seed=seed) == 0
+            assert T.mh_run(ours, first + ftype, [T.chan(pal, w, ht, [s1]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [d_our]), [[bf]], seed=seed) == 0
+            assert (d_ref[:, :w * ps] == d_our[:, :w * ps]).all(), (ftype, pal, w, ht, bf)
+            if ftype != 2:
+                a, b = s1.copy(), s1.copy()
+                T.mh_run(ref_mt, ftype, [T.chan(pal, w, ht, [a]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [a]), [[bf]], seed=seed)
+                T.mh_run(ours, first + ftype, [T.chan(pal, w, ht, [b]), T.chan(pal, w, ht, [s2])], T.chan(pal, w, ht, [b]), [[bf]], seed=seed)
+                assert (a[:, :w * ps] == b[:, :w * ps]).all(), (ftype, "inplace", pal, w, ht, bf)
+    # ---- rand replace: a whole-frame choice
+    s1, s2 = T.make_packed(rng, 64, 8, 3), T.make_packed(rng, 64, 8, 3)
+    for bf, want in ((0.0, s1), (1.0, s2)):
+        d = np.full_like(s1, 9)
+        assert T.mh_run(ours, NAMES.index("rand replace"), [T.chan(1, 64, 8, [s1]), T.chan(1, 64, 8, [s2])], T.chan(1, 64, 8, [d]), [[bf]]) == 0
+        assert (d[:, :192] == want[:, :192]).all()
