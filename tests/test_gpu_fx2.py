@@ -36,6 +36,8 @@ def _o():
 def test_softlight_device_frames(eng, size, pal, clamped):
     o = _o()
     w, ht = size
+    if pal == 512:
+        ht &= ~1  # 4:2:0 frames are created with even sizes (colourspace.c:11603-11604)
     rng = np.random.default_rng(w + pal)
     ys = T.rowstride(w, 1)
     cw = w if pal == 545 else w >> 1

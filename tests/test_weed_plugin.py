@@ -202,6 +202,8 @@ def test_softlight_triple_split_multi_transitions_match_the_reference_plugins():
     for pal, clamp, (w, ht) in itertools.product((512, 513, 522, 544, 545), (0, 1), ((64, 16), (70, 9), (1920, 1080))):
         if (w, ht) == (1920, 1080) and pal != 512:
             continue
+        if pal in (512, 513):
+            ht &= ~1  # the host creates 4:2:0 layers with even sizes (colourspace.c:11603-11604)
         ys = T.rowstride(w, 1)
         cw = w if pal in (544, 545) else w >> 1
         chh = ht >> 1 if pal in (512, 513) else ht
