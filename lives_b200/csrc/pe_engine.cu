@@ -1549,6 +1549,36 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                                  mode == 0 && e->cfg.ref_quirks);
     if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)  // lives_memset(dest[3], 255, orow[3] * height): padding included
       ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
+  } else if (((inpl == PE_PALETTE_YUV444P || inpl == PE_PALETTE_YUVA4444P) && outpl == PE_PALETTE_YUV422P) ||
+             (inpl == PE_PALETTE_YUV422P && (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P))) {
+    // 4:4:4 planar <-> 4:2:2 planar.  The reference's dispatcher hands these to the VERTICAL convert_halve_chroma / convert_double_chroma
+    // (:12948, :13719: full-width rows written into half-width planes, half of the target never written) -- nothing defined to
+    // replicate (X).  Defined here through the reference's own HORIZONTAL converters of the same two samplings, composed:
+    //   4:4:4 planar -> (convert_combineplanes_frame) YUV888 -> (convert_yuv888_to_yuv422_frame: avg_chroma of the pixel pair) 4:2:2 planar
+    //   4:2:2 planar -> (convert_double_chroma_packed) YUV888 -> (convert_splitplanes_frame) 4:4:4 planar, alpha plane 255
+    const bool down = outpl == PE_PALETTE_YUV422P;
+    if (down) n.d.width = width & ~1;
+    if (n.d.width < 2) { set_err(PE_ERR_SIZE, "frame too narrow for a 4:2:2 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const int trs = align_ceil(width * 3, 32);
+    size_t granted = 0;
+    uint8_t *tmp = (uint8_t *)e->pool.get((size_t)trs * height, &granted);
+    if (!tmp) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "device allocation of %zu bytes failed", (size_t)trs * height); return PE_FALSE; }
+    if (down) {
+      const uint8_t *pl[4] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2], nullptr};
+      ce = launch_combine_planes(L, pl, f->d.rowstrides[0], Img{tmp, trs}, width, height, 0, 0);
+      uint8_t *opl[3] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2]};
+      if (ce == cudaSuccess) ce = launch_yuv888_subsample(L, 2, CImg{tmp, trs}, 0, opl, n.d.rowstrides, n.d.width, height, cavg);
+    } else {
+      const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2]};
+      ce = launch_chroma_upsample_packed(L, 0, pl, f->d.rowstrides, height, Img{tmp, trs}, width, height, 0, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+      uint8_t *opl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], nullptr};
+      if (ce == cudaSuccess) ce = launch_split_planes(L, CImg{tmp, trs}, opl, n.d.rowstrides, width, height, 0, 0);
+      if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P) ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
+    }
+    e->pool.put(tmp, granted);  // stream ordered: the next user is enqueued behind the two kernels
   } else {
     set_err(PE_ERR_PALETTE, "palette conversion %d -> %d is not handled by this build", inpl, outpl);
     return PE_FALSE;  // memfail: the layer is left as it was

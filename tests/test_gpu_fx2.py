@@ -107,3 +107,43 @@ def test_multi_transition_device_frames(eng, ftype, size):
     if ftype == 3:
         with pytest.raises(lb.PixelEngineError):
             lb.multi_transition(3, a, b, d, 0.5, None)
+
+
+@pytest.mark.parametrize("size", [(64, 16), (70, 9), (1920, 1080)])
+@pytest.mark.parametrize("clamping", [0, 1])
+def test_yuv444p_yuv422p_planar_both_ways(eng, size, clamping):
+    """4:4:4 planar <-> 4:2:2 planar (X row of the quirk table: the reference's dispatcher calls its VERTICAL resamplers there,
+    colourspace.c:12948,13719).  Contract = the reference's own horizontal converters composed: combineplanes + yuv888_to_yuv422 one way,
+    double_chroma_packed + splitplanes the other."""
+    o = T.oracle()
+    w, ht = size
+    rng = np.random.default_rng(w + clamping)
+    rs = T.rowstride(w, 1)
+    p444 = [T.make_packed(rng, w, ht, 1, rs) for _ in range(3)]
+    # ---- 4:4:4 -> 4:2:2
+    lay = lb.Layer.from_host(eng, 544, w, ht, p444, yuv_clamping=clamping)
+    assert lb.convert_layer_palette(lay, 522, clamping)
+    assert lay.palette == 522 and lay.width == (w & ~1)
+    got = lay.to_host()
+    t888 = np.zeros((ht, T.rowstride(w, 3)), np.uint8)
+    o.pe_or_combine_planes(T.planes_arg(*p444, p444[0]), rs, w, ht, T.ptr(t888), t888.strides[0], 0, 0)
+    exp = [np.zeros_like(g) for g in got]
+    o.pe_or_yuv888_subsample(2, T.ptr(t888), t888.strides[0], w & ~1, ht, 0, T.planes_arg(*exp), T.strides_arg(*exp), clamping)
+    cw = (w & ~1) >> 1
+    assert (got[0][:, :w & ~1] == exp[0][:, :w & ~1]).all()
+    assert (got[1][:, :cw] == exp[1][:, :cw]).all() and (got[2][:, :cw] == exp[2][:, :cw]).all()
+    # ---- 4:2:2 -> 4:4:4 (+ alpha)
+    w2 = w & ~1
+    y, u, v = T.make_yuv_planar(rng, w2, ht, True, clamping == 0)
+    for outpl in (544, 545):
+        lay = lb.Layer.from_host(eng, 522, w2, ht, [y, u, v], yuv_clamping=clamping)
+        assert lb.convert_layer_palette(lay, outpl, clamping)
+        got = lay.to_host()
+        t888 = np.zeros((ht, T.rowstride(w2, 3)), np.uint8)
+        o.pe_or_chroma_upsample_packed(0, T.planes_arg(y, u, v), T.strides_arg(y, u, v), w2, ht, T.ptr(t888), t888.strides[0], 0, 1, clamping)
+        exp = [np.zeros_like(got[0]) for _ in range(4)]
+        o.pe_or_split_planes(T.ptr(t888), t888.strides[0], w2, ht, T.planes_arg(*exp), T.strides_arg(*exp), 0, 0)
+        for k in range(3):
+            assert (got[k][:, :w2] == exp[k][:, :w2]).all(), (outpl, k)
+        if outpl == 545:
+            assert (got[3][:, :w2] == 255).all()
