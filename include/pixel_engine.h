@@ -188,6 +188,17 @@ void pe_alpha_premult(pe_engine_t *e, pe_frame_t *layer, int direction);
 /* uint8_t *create_gamma_lut8(double fileg, int gamma_from, int gamma_to)      colourspace.c:655 (host copy) */
 int pe_gamma_lut8(pe_engine_t *e, double fileg, int gamma_from, int gamma_to, uint8_t out[256]);
 
+/* The reference's float ("experimental") YUV -> RGB arithmetic: float tables colourspace.c:101-172 (filled :1040-1104, BT.709 only),
+ * clamp0255f :592, yuv2rgb_float :2367 (the reference compiles it but routes yuv2rgb to yuv2rgb_int, :2374-2375).  layer: YUV888 /
+ * YUVA8888 with the BT.709 subspace -> outpl (an RGB palette), converted in place like convert_layer_palette.
+ *   mode 0: yuv2rgb_float exactly as written (`int yy = RGB_Y[y]`, the 16.16 integer table, plus the float chroma tables);
+ *   mode 1: the form of the commented-out variant at :2398-2400 (RGBf_Y[y] + Rf_Cr[v], ...).
+ * sums_host (optional): width * height * 3 floats, the sums before clamp0255f -- equal to the compiled reference's bit for bit
+ * (0 ULP; every addition is an IEEE single-precision add in the source's order).
+ * pe_float_yuv_table: the float tables on the host (which 0 RGBf_Y 1 Rf_Cr 2 Gf_Cb 3 Gf_Cr 4 Bf_Cb). */
+int pe_convert_yuv888_to_rgb_float(pe_engine_t *e, pe_frame_t *layer, int outpl, int mode, float *sums_host);
+int pe_float_yuv_table(int clamping, int which, float out[256]);
+
 /* ---- boundary B1 arithmetic: effect process functions on device frames ---------------------- */
 
 /* simple_blend.c common_process :58.  type 0 "chroma blend", 1 "luma overlay", 2 "luma underlay",

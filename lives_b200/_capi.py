@@ -114,6 +114,8 @@ PROTOTYPES = {
     "pe_fx_multi_blend": (I, [VP, I, VP, VP, VP, I]),
     "pe_fx_slide_over": (I, [VP, VP, VP, VP, I, I, I, I]),
     "pe_fx_slide_over_bound": (I, [I, I, I, I]),
+    "pe_convert_yuv888_to_rgb_float": (I, [VP, VP, I, I, VP]),
+    "pe_float_yuv_table": (I, [I, I, VP]),
     "pe_fx_softlight": (I, [VP, VP, VP]),
     "pe_fx_triple_split": (I, [VP, VP, VP, VP, D, I, D, I, D, PI]),
     "pe_fx_triple_split_classes": (None, [I, I, D, I, D, I, D, VP, VP]),

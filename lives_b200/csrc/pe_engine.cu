@@ -273,6 +273,8 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   for (int k = 0; k < 6; k++) cudaFree(e->premult_dev[k]);
   for (int k = 0; k < 2; k++) cudaFree(e->cavg_dev[k]);
   cudaFree(e->yy_dev);
+  cudaFree(e->ftab_dev[0]);
+  cudaFree(e->ftab_dev[1]);
   cudaFree(e->luma_dev);
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
@@ -1613,6 +1615,74 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
 }
 
 }  // namespace
+
+// ---- the reference's float ("experimental") YUV -> RGB path (colourspace.c:101-172, :592, :2367) ---------------------------------
+extern "C" int pe_float_yuv_table(int clamping, int which, float out[256]) {
+  if (which < 0 || which > 4 || !out) return set_err(PE_ERR_ARG, "table 0 .. 4 (RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr, Bf_Cb)");
+  float t[5][256];
+  build_float_yuv_tables(clamping, t);
+  memcpy(out, t[which], sizeof(t[which]));
+  return PE_OK;
+}
+
+extern "C" int pe_convert_yuv888_to_rgb_float(pe_engine_t *e, pe_frame_t *f, int outpl, int mode, float *sums_host) {
+  if (!e || !f || !f->d.planes[0]) { set_err(PE_ERR_ARG, "NULL argument"); return PE_FALSE; }
+  const int inpl = f->d.palette;
+  if ((inpl != PE_PALETTE_YUV888 && inpl != PE_PALETTE_YUVA8888) || !pal_is_rgb(outpl)) {
+    set_err(PE_ERR_PALETTE, "float path: YUV888 / YUVA8888 -> an RGB palette (%d -> %d asked)", inpl, outpl);
+    return PE_FALSE;
+  }
+  if (f->d.yuv_subspace != PE_YUV_SUBSPACE_BT709) {
+    set_err(PE_ERR_PALETTE, "float path: the reference only has float tables for the BT.709 subspace (colourspace.c:279-310, :316-355)");
+    return PE_FALSE;
+  }
+  if (mode != 0 && mode != 1) { set_err(PE_ERR_ARG, "mode 0 (yuv2rgb_float as written) or 1 (RGBf_Y form)"); return PE_FALSE; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return PE_FALSE; }
+  const int ci = f->d.yuv_clamping == PE_YUV_CLAMPING_UNCLAMPED ? 1 : 0;
+  if (!e->ftab_dev[ci]) {
+    float t[5][256];
+    build_float_yuv_tables(ci ? PE_YUV_CLAMPING_UNCLAMPED : PE_YUV_CLAMPING_CLAMPED, t);
+    float *d = nullptr;
+    if (cudaMalloc(&d, sizeof(t)) != cudaSuccess || cudaMemcpy(d, t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (d) cudaFree(d);
+      set_err(PE_ERR_CUDA, "float table upload failed");
+      return PE_FALSE;
+    }
+    e->ftab_dev[ci] = d;
+  }
+  const DevConv conv = dev_conv(e, f->d.yuv_clamping, PE_YUV_SUBSPACE_BT709);
+  pe_frame n;
+  n.e = e;
+  n.d = f->d;
+  n.d.palette = outpl;
+  if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+  const int width = f->d.width, height = f->d.height;
+  float *sums_dev = nullptr;
+  size_t granted = 0;
+  const size_t sums_bytes = sizeof(float) * 3 * (size_t)width * height;
+  if (sums_host && !(sums_dev = (float *)e->pool.get(sums_bytes, &granted))) {
+    frame_release_pixels(&n);
+    set_err(PE_ERR_MEMORY, "device allocation of %zu bytes failed", sums_bytes);
+    return PE_FALSE;
+  }
+  cudaError_t ce = launch_yuv888_to_rgb_float(e->L(), mode, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]},
+                                              Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height, inpl == PE_PALETTE_YUVA8888,
+                                              rgb_layout(outpl), e->ftab_dev[ci], conv.t + 9 * 256, sums_dev);
+  if (ce == cudaSuccess && sums_dev) {
+    ce = cudaMemcpyAsync(sums_host, sums_dev, sums_bytes, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  }
+  if (sums_dev) e->pool.put(sums_dev, granted);
+  if (ce != cudaSuccess) {
+    frame_release_pixels(&n);
+    set_err(PE_ERR_CUDA, "float conversion failed: %s", cudaGetErrorString(ce));
+    return PE_FALSE;
+  }
+  frame_take(f, &n);
+  f->d.yuv_clamping = 0; f->d.yuv_subspace = 0; f->d.yuv_sampling = 0;  // conv_done (:13859-13900): the YUV leaves are deleted
+  return PE_TRUE;
+}
 
 extern "C" int pe_convert_layer_palette_full(pe_engine_t *e, pe_frame_t *layer, int outpl, int oclamping, int osampling,
                                              int osubspace, int tgt_gamma) {

@@ -89,6 +89,7 @@ struct pe_engine {
   pe::ConvTables conv_host[2][2];    // [clamping][bt709]
   int32_t *conv_dev[2][2] = {};      // 14 x 256 int32 each, followed by the extended planar tables (DevConv::ext)
   uint8_t *cavg_dev[2] = {};         // chroma averaging tables (init_average :190): [0] clamped, [1] unclamped
+  float *ftab_dev[2] = {};           // the BT.709 float tables of the reference's experimental float path (pe_convert_yuv888_to_rgb_float)
   uint8_t *yy_dev = nullptr;         // the four 256-byte clamped <-> unclamped tables (init_YUV_to_YUV_tables :1108)
   uint8_t *premult_dev[6] = {};      // built on first use (init_unal is lazy in the reference too, :11985)
   int32_t *luma_dev = nullptr;       // plugin-side calc_luma tables [3][256]

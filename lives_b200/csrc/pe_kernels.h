@@ -104,6 +104,10 @@ cudaError_t launch_rgb_to_yuv444p(const Launch &L, CImg src, uint8_t *const plan
 // RGB(A) -> YUV420P / YUV422P (colourspace.c:6250 / :6385); cavg_dev: the 64 KB averaging table of the output clamping
 cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const planes[3], const int rowstrides[3], int width, int height,
                                   RgbLayout in, int is_422, DevConv conv, const uint8_t *cavg_dev);
+// the reference's float ("experimental") YUV -> RGB arithmetic (colourspace.c:2367 yuv2rgb_float; pe_kernels_float.cu): ftab_dev = the five
+// float tables [RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr, Bf_Cb][256], rgb_y_dev = the integer RGB_Y table mode 0 adds them to; sums_dev optional
+cudaError_t launch_yuv888_to_rgb_float(const Launch &L, int mode, CImg src, Img dst, int width, int height, int in_alpha, RgbLayout out,
+                                       const float *ftab_dev, const int32_t *rgb_y_dev, float *sums_dev);
 // ---- effects ---------------------------------------------------------------------------------------
 // ---- YUV <-> YUV family + planar 4:4:4 -> RGB (pe_kernels_yuv3.cu) ---------------------------------------
 cudaError_t launch_yuv444p_to_rgb(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,

@@ -105,6 +105,24 @@ void build_conv_tables(int clamping, int subspace, ConvTables *out) {
   }
 }
 
+// ---- float YUV -> RGB tables (colourspace.c:1040-1104, BT.709 only) ------------------------------------------------------------
+// Kept as the reference leaves them: the clamped RGBf_Y holds 0 from 235 up (the loop at :1051 starts where the integer loop of :1050
+// ended and never runs -- the statics stay zero); the clamped chroma tables saturate at 254 - 128 above 240 (:1083-1086) where the
+// integer tables use 255 - 128.
+void build_float_yuv_tables(int clamping, float out[5][256]) {
+  const double kr = 0.2126, kb = 0.0722;
+  const double c[5] = {1., 2. * (1. - kr), -.5 / (1. + kb + kb), -.5 / (1. - kr), 2. * (1. - kb)};
+  const bool clamped = clamping == PE_YUV_CLAMPING_CLAMPED;
+  for (int w = 0; w < 5; w++)
+    for (int i = 0; i < 256; i++) {
+      double v;
+      if (!clamped) v = w == 0 ? (double)i : c[w] * ((double)i - 128.);
+      else if (w == 0) v = i <= 16 ? 0. : i < 235 ? ((double)i - 16.) / (235. - 16.) * 255. : 0.;
+      else v = i <= 16 ? 0. : i < 240 ? c[w] * ((((double)i - 16.) / (240. - 16.) * 255.) - 128.) : c[w] * (254. - 128.);
+      out[w][i] = (float)v;
+    }
+}
+
 // ---- gamma ------------------------------------------------------------------------------------
 
 namespace {

@@ -18,6 +18,10 @@ struct ConvTables {
 
 void build_conv_tables(int clamping, int subspace, ConvTables *out);
 
+// the "float - experimental" BT.709 tables of init_YUV_to_RGB_tables (colourspace.c:1040-1104): out[0..4] = RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr,
+// Bf_Cb, evaluated in double and stored as float32 like the reference's assignments (quirks kept: see pe_tables.cpp)
+void build_float_yuv_tables(int clamping, float out[5][256]);
+
 // create_gamma_lut8 / create_gamma_lut (colourspace.c:655 / :738); return false when the reference returns NULL
 bool build_gamma_lut8(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint8_t out[256]);
 bool build_gamma_lut16(double fileg, int gamma_from, int gamma_to, double screen_gamma, uint16_t *out /*65536*/);

@@ -285,6 +285,21 @@ def convert_layer_palette_batch(layers, outpl, op_clamping):
     return int(e._lib.pe_convert_layer_palette_batch(e._h, len(layers), _arr(layers), outpl, op_clamping))
 
 
+def convert_yuv888_to_rgb_float(layer, outpl, mode=1, want_sums=False):
+    """the reference's float ("experimental") YUV -> RGB path (colourspace.c:2367 yuv2rgb_float; BT.709 only).  mode 0: as written,
+    1: the RGBf_Y form.  Returns TRUE / FALSE, or (ok, sums[h, w, 3] float32) with want_sums"""
+    e = layer.engine
+    sums = np.zeros((layer.height, layer.width, 3), np.float32) if want_sums else None
+    ok = bool(e._lib.pe_convert_yuv888_to_rgb_float(e._h, layer._h, outpl, mode, sums.ctypes.data if want_sums else None))
+    return (ok, sums) if want_sums else ok
+
+
+def float_yuv_table(clamping, which):
+    t = np.zeros(256, np.float32)
+    capi.check(capi.lib().pe_float_yuv_table(clamping, which, t.ctypes.data))
+    return t
+
+
 def letterbox_layer(layer, nwidth, nheight, width, height, interp, tpal, tclamp):
     """colourspace.h:415 / colourspace.c:15343"""
     e = layer.engine

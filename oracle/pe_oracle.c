@@ -1741,3 +1741,48 @@ void pe_or_multi_transition(int type, const uint8_t *src1, int irow1, const uint
       if (from != d) memmove(d, from, (size_t)psize);
     }
 }
+
+/* ---- the reference's float ("experimental") YUV -> RGB path: tables colourspace.c:1040-1104 (BT.709 only), clamp0255f :592,
+ *      yuv2rgb_float :2367 ------------------------------------------------------------------------------------------------------- */
+/* which: 0 RGBf_Y 1 Rf_Cr 2 Gf_Cb 3 Gf_Cr 4 Bf_Cb; clamping 0 clamped, 1 unclamped.  Evaluated in double and stored as float32, as
+ * the reference's assignments do.  Quirks replicated: the clamped RGBf_Y keeps 0 from 235 up (the loop at :1051 starts where the
+ * integer loop of :1050 ended, so it never runs); the clamped chroma tables saturate at 254 - 128 above 240 (:1083-1086) where the
+ * integer ones use 255 - 128. */
+void pe_or_float_table(int clamping, int which, float out[256]) {
+  const double kr = 0.2126, kb = 0.0722;
+  const double c[5] = {1., 2. * (1. - kr), -.5 / (1. + kb + kb), -.5 / (1. - kr), 2. * (1. - kb)};
+  for (int i = 0; i < 256; i++) {
+    double v;
+    if (clamping == 1) v = which == 0 ? (double)i : c[which] * ((double)i - 128.);
+    else if (which == 0) v = i <= 16 ? 0. : i < 235 ? ((double)i - 16.) / (235. - 16.) * 255. : 0.;
+    else v = i <= 16 ? 0. : i < 240 ? c[which] * ((((double)i - 16.) / (240. - 16.) * 255.) - 128.) : c[which] * (254. - 128.);
+    out[i] = (float)v;
+  }
+}
+
+static uint8_t or_clampf_lc(float f) { /* clamp0255f, the lower-case inline function of colourspace.c:592-596 */
+  if (f > 255.) f = 255.;
+  if (f < 0.) f = 0;
+  return (uint8_t)f;
+}
+
+/* mode 0: yuv2rgb_float as written (:2367-2372: `int yy = RGB_Y[y]`, the 16.16 INTEGER table, added to the float chroma tables);
+ * mode 1: the form of the commented-out variant at :2398-2400 (RGBf_Y[y] + ...).  rgb_y_int: the BT.709 RGB_Y table of `clamping`
+ * (pe_or_conv_table which 9); sums (optional): the float sums before the clamp */
+void pe_or_yuv2rgb_float(int mode, int clamping, const int32_t *rgb_y_int, const uint8_t *yuv, uint8_t *rgb, float *sums, long n) {
+  float ty[256], rcr[256], gcb[256], gcr[256], bcb[256];
+  pe_or_float_table(clamping, 0, ty); pe_or_float_table(clamping, 1, rcr); pe_or_float_table(clamping, 2, gcb);
+  pe_or_float_table(clamping, 3, gcr); pe_or_float_table(clamping, 4, bcb);
+  for (long i = 0; i < n; i++) {
+    const uint8_t y = yuv[i * 3], u = yuv[i * 3 + 1], v = yuv[i * 3 + 2];
+    float r, g, b;
+    if (mode == 0) {
+      const int yy = rgb_y_int[y];
+      r = yy + rcr[v]; g = yy + gcb[u] + gcr[v]; b = yy + bcb[u];
+    } else {
+      r = ty[y] + rcr[v]; g = ty[y] + gcb[u] + gcr[v]; b = ty[y] + bcb[u];
+    }
+    rgb[i * 3] = or_clampf_lc(r); rgb[i * 3 + 1] = or_clampf_lc(g); rgb[i * 3 + 2] = or_clampf_lc(b);
+    if (sums) { sums[i * 3] = r; sums[i * 3 + 1] = g; sums[i * 3 + 2] = b; }
+  }
+}

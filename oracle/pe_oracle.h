@@ -203,3 +203,7 @@ void pe_or_triple_split(const uint8_t *src1, int irow1, const uint8_t *src2, int
 void pe_or_dissolve_mask(int64_t seed, long n, float *mask);
 void pe_or_multi_transition(int type, const uint8_t *src1, int irow1, const uint8_t *src2, int irow2, uint8_t *dst, int orow, int width,
                             int height, int psize, double bfd, const float *mask);
+
+/* ---- the reference's float YUV -> RGB path (colourspace.c:101-172, :592, :1040-1104, :2367) ---- */
+void pe_or_float_table(int clamping, int which, float out[256]);
+void pe_or_yuv2rgb_float(int mode, int clamping, const int32_t *rgb_y_int, const uint8_t *yuv, uint8_t *rgb, float *sums, long n);

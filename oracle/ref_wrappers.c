@@ -374,3 +374,35 @@ void ref_chroma_upsample_packed(int is_420, uint8_t **src, int width, int height
   if (is_420) convert_quad_chroma_packed(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
   else convert_double_chroma_packed(src, width, height, istrides, ostride, dest, add_alpha, sampling, clamping);
 }
+
+/* ---- the reference's "float - experimental" YUV -> RGB path (colourspace.c:101-172 tables, :592 clamp0255f, :2367 yuv2rgb_float);
+ *      float tables exist for the BT.709 subspace only (:279-310, :316-355) ---- */
+/* which: 0 RGBf_Y 1 Rf_Cr 2 Gf_Cb 3 Gf_Cr 4 Bf_Cb */
+int ref_get_float_table(int clamping, int which, float *out) {
+  ref_init();
+  set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_BT709);
+  float *t[5] = {RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr, Bf_Cb}; /* the reference's own accessor macros (:411-415) */
+  if (which < 0 || which > 4 || !t[which]) return -1;
+  memcpy(out, t[which], 256 * sizeof(float));
+  return 0;
+}
+
+/* yuv2rgb_float exactly as the reference writes it (:2367-2372: the INTEGER RGB_Y table plus the float chroma tables) */
+void ref_yuv2rgb_float_bulk(int clamping, const uint8_t *yuv, uint8_t *rgb, long n) {
+  ref_init();
+  set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_BT709);
+  for (long i = 0; i < n; i++) yuv2rgb_float(yuv[i * 3], yuv[i * 3 + 1], yuv[i * 3 + 2], &rgb[i * 3], &rgb[i * 3 + 1], &rgb[i * 3 + 2]);
+}
+
+/* the form the commented-out variant at :2398-2400 spells (RGBf_Y[y] + ...): the reference's float tables and clamp0255f, our loop;
+ * sums (optional): the three float sums per pixel before the clamp */
+void ref_yuv2rgb_floaty_bulk(int clamping, const uint8_t *yuv, uint8_t *rgb, float *sums, long n) {
+  ref_init();
+  set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_BT709);
+  for (long i = 0; i < n; i++) {
+    const uint8_t y = yuv[i * 3], u = yuv[i * 3 + 1], v = yuv[i * 3 + 2];
+    const float r = RGBf_Y[y] + Rf_Cr[v], g = RGBf_Y[y] + Gf_Cb[u] + Gf_Cr[v], b = RGBf_Y[y] + Bf_Cb[u];
+    rgb[i * 3] = clamp0255f(r); rgb[i * 3 + 1] = clamp0255f(g); rgb[i * 3 + 2] = clamp0255f(b);
+    if (sums) { sums[i * 3] = r; sums[i * 3 + 1] = g; sums[i * 3 + 2] = b; }
+  }
+}
