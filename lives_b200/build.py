@@ -12,6 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpe_b200.so")
 PLUGIN = os.path.join(HERE, "libpe_weed_plugin.so")
 LAYERLIB = os.path.join(HERE, "libpe_weed_layer.so")
+VPPLIB = os.path.join(HERE, "libpe_vpp.so")
 
 SOURCES = ["pe_engine.cu", "pe_kernels_rgb.cu", "pe_kernels_yuv.cu", "pe_kernels_yuv2.cu", "pe_kernels_yuv3.cu", "pe_kernels_fused.cu", "pe_kernels_fused2.cu", "pe_kernels_fused3.cu", "pe_kernels_fx2.cu", "pe_kernels_float.cu", "pe_tables.cpp"]
 OBJ = os.path.join(HERE, "build")
@@ -77,6 +78,13 @@ def build(force=False, verbose=False):
     if os.path.exists(layer_src) and (force or _stale(LAYERLIB, [layer_src, LIB] + deps)):
         cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-I", os.path.join(HERE, "..", "include"),
                "-o", LAYERLIB, layer_src, "-L", HERE, "-lpe_b200", "-Wl,-rpath,$ORIGIN", "-ldl"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, cwd=CSRC)
+    vpp_src = os.path.join(CSRC, "pe_vpp.c")
+    if os.path.exists(vpp_src) and (force or _stale(VPPLIB, [vpp_src, LIB] + deps)):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-I", os.path.join(HERE, "..", "include"),
+               "-o", VPPLIB, vpp_src, "-L", HERE, "-lpe_b200", "-Wl,-rpath,$ORIGIN", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd, cwd=CSRC)

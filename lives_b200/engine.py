@@ -69,10 +69,22 @@ class Engine:
         self._h = h
         self._lib = lib
 
+    @classmethod
+    def shared(cls):
+        """the process-wide engine the weed plugin, the weed_layer_t drop-ins and the playback plugin run on (pe_engine_shared); never
+        destroyed by this handle"""
+        lib = capi.lib()
+        h = lib.pe_engine_shared()
+        if not h:
+            raise capi.PixelEngineError(lib.pe_last_error().decode())
+        self = cls.__new__(cls)
+        self._h, self._lib, self._borrowed = C.c_void_p(h), lib, True
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             self._lib.pe_engine_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
