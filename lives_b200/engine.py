@@ -76,7 +76,7 @@ class Engine:
         lib = capi.lib()
         h = lib.pe_engine_shared()
         if not h:
-            raise capi.PixelEngineError(lib.pe_last_error().decode())
+            raise capi.PixelEngineError(-1, lib.pe_last_error().decode())
         self = cls.__new__(cls)
         self._h, self._lib, self._borrowed = C.c_void_p(h), lib, True
         return self
