@@ -1933,6 +1933,43 @@ int flush_rsz_pending(pe_engine *e) {
   return rc;
 }
 
+// A batch call queued both the planar -> RGB conversions (yuv_pending) and the resizes of their results (rsz_pending).  When every
+// pair (conversion i, resize i) meets through an intermediate frame that nothing else reads, the pairs leave as ONE k_cvt_resize
+// launch per 32 (pe_kernels_fused4.cu) and the intermediate frames are never written; otherwise the queues are flushed in order.
+int flush_cvt_rsz_pending(pe_engine *e) {
+  std::vector<YuvToRgbArgs> &Y = e->yuv_pending;
+  std::vector<pe_engine::RszJob> &R = e->rsz_pending;
+  bool fuse = getenv("PE_NO_CVT_RESIZE") == nullptr && !Y.empty() && Y.size() == R.size();
+  for (size_t i = 0; i < Y.size() && fuse; i++)
+    fuse = R[i].src == Y[i].dst.p && R[i].srs == Y[i].dst.rs && R[i].sw == Y[i].width && R[i].sh == Y[i].height && R[i].psize == 4 &&
+           yuv_planar_same_shape(Y[0], Y[i]) && R[i].drs == R[0].drs && R[i].dw == R[0].dw && R[i].dh == R[0].dh && R[i].kx == R[0].kx &&
+           R[i].ky == R[0].ky;
+  if (fuse) {
+    DevFilterEntry *fx = get_filter(e, R[0].sw, R[0].dw, 14, R[0].kx), *fy = get_filter(e, R[0].sh, R[0].dh, 12, R[0].ky);
+    fuse = fx && fy;
+    for (size_t i = 0; i < Y.size() && fuse; i++) fuse = cvt_resize_supported(Y[i], R[0].dw, R[0].dh, R[0].drs, R[i].dst, fx->host, fy->host);
+    if (fuse) {
+      std::vector<uint8_t *> dsts;
+      for (size_t i = 0; i < R.size(); i++) dsts.push_back(R[i].dst);
+      cudaError_t ce = launch_cvt_resize(e->L(), Y.data(), dsts.data(), (int)Y.size(), R[0].dw, R[0].dh, R[0].drs, fx->dev, fy->dev, fx->host, fy->host);
+      if (ce == cudaSuccess) {
+        Y.clear(); R.clear();
+        e->rsz_defer = false;
+        return PE_OK;
+      }
+      if (ce != cudaErrorInvalidConfiguration) {
+        Y.clear(); R.clear();
+        e->rsz_defer = false;
+        return set_err(PE_ERR_CUDA, "conversion + resize launch failed: %s", cudaGetErrorString(ce));
+      }
+    }
+  }
+  int rc = flush_yuv_pending(e);
+  if (rc == PE_OK) rc = flush_rsz_pending(e);
+  else { R.clear(); e->rsz_defer = false; }
+  return rc;
+}
+
 // Fan a batch of independent per-layer calls out over four side streams.  Layer 0 runs on the engine stream first (it
 // creates whatever cached tables the batch needs: filter banks, LUTs -- their uploads are ordered before the fork); the other
 // layers of the same geometry run on the side streams, so that the small kernels of different layers overlap instead of
@@ -2009,6 +2046,43 @@ extern "C" int pe_resize_layer_batch(pe_engine_t *e, int n, pe_frame_t *const *l
   std::lock_guard<std::mutex> lk(e->mu);
   if (cudaSetDevice(e->device) != cudaSuccess) { set_err(PE_ERR_CUDA, "cudaSetDevice failed"); return 0; }
   int done = 0;
+  // BASELINE config 2 as a batch (and as a single layer): same-shaped 4:2:0 layers with a 4-byte RGB target whose resize takes the
+  // <= 4-tap kernels.  Conversion and resize of every layer are queued by the ordinary resize_locked (all metadata rules stay its own)
+  // and leave together as one fused launch per 32 frames -- the converted frame never exists in HBM.
+  if ((opal_hint == PE_PALETTE_RGBA32 || opal_hint == PE_PALETTE_BGRA32) && width > 0 && height > 0 && layers[0] && layers[0]->d.planes[0]) {
+    bool ok = true;
+    for (int i = 0; i < n && ok; i++)
+      ok = layers[i] && layers[i]->d.planes[0] && (layers[i]->d.palette == PE_PALETTE_YUV420P || layers[i]->d.palette == PE_PALETTE_YVU420P) &&
+           same_geometry(layers[0], layers[i]);
+    if (ok) {  // the resize must be one flush_rsz_pending would batch (else it would launch ahead of the queued conversions)
+      const int iw = (layers[0]->d.width >> 1) << 1, ih = (layers[0]->d.height >> 1) << 1, w2 = width < 4 ? 4 : width;
+      int h2 = height < 4 ? 4 : height;
+      if (iw != w2 || ih != h2) h2 = (h2 >> 1) << 1;
+      ok = !(iw == w2 && ih == h2);
+      if (ok) {
+        const AxisKinds kinds = filter_kinds(e, interp, iw, ih, w2, h2);
+        DevFilterEntry *fx = get_filter(e, layers[0]->d.width, w2, 14, kinds.x), *fy = get_filter(e, layers[0]->d.height, h2, 12, kinds.y);
+        ok = fx && fy && fx->host.fast_taps() <= 4 && fy->host.fast_taps() <= 4;
+      }
+    }
+    if (ok) {
+      BatchSnapshot snap(n, layers);
+      e->yuv_defer = true;
+      e->rsz_defer = true;
+      e->pool.defer(true);
+      for (int i = 0; i < n; i++)
+        if (resize_locked(e, layers[i], width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT, PE_YUV_SUBSPACE_YCBCR,
+                          PE_GAMMA_UNKNOWN) == PE_TRUE)
+          done++;
+      e->yuv_defer = false;
+      const int frc = flush_cvt_rsz_pending(e);
+      e->rsz_defer = false;
+      if (frc != PE_OK) snap.restore(e, n, layers);
+      e->pool.defer(false);
+      e->pool.flush_deferred();
+      return frc == PE_OK ? done : 0;
+    }
+  }
   // phase 1: planar YUV layers with an RGB target are converted first (resize_layer_full converts before it scales, :14601);
   // the conversions of the whole batch are queued and leave as one launch per 32 same-shaped frames
   if (pal_is_rgb(opal_hint)) {
@@ -2123,6 +2197,14 @@ extern "C" int pe_convert_layer_palette_batch(pe_engine_t *e, int n, pe_frame_t 
 
 extern "C" int pe_resize_layer(pe_engine_t *e, pe_frame_t *layer, int width, int height, int interp, int opal_hint,
                                int oclamp_hint) {  // :15331
+  // a 4:2:0 layer with a 4-byte RGB target: conversion + resize as one kernel (the batch call with one layer)
+  if (e && layer && layer->d.planes[0] && (opal_hint == PE_PALETTE_RGBA32 || opal_hint == PE_PALETTE_BGRA32) &&
+      (layer->d.palette == PE_PALETTE_YUV420P || layer->d.palette == PE_PALETTE_YVU420P)) {
+    const pe_frame before = *layer;
+    pe_frame_t *one[1] = {layer};
+    if (pe_resize_layer_batch(e, 1, one, width, height, interp, opal_hint, oclamp_hint) == 1) return PE_TRUE;
+    if (layer->base != before.base || layer->d.palette != before.d.palette) return PE_FALSE;  // changed and failed: nothing to retry
+  }
   return pe_resize_layer_full(e, layer, width, height, interp, opal_hint, oclamp_hint, PE_YUV_SAMPLING_DEFAULT,
                               PE_YUV_SUBSPACE_YCBCR, PE_GAMMA_UNKNOWN);
 }

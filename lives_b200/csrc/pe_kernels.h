@@ -214,6 +214,13 @@ cudaError_t launch_letterbox(const Launch &L, CImg inner, int iw, int ih, Img ou
                              uint32_t black_pixel);
 cudaError_t launch_copy2d(const Launch &L, const uint8_t *src, int srs, uint8_t *dst, int drs, int row_bytes, int rows,
                           int fill, uint8_t fill_value);
+// ---- conversion + resize in one kernel (pe_kernels_fused4.cu): planar 4:2:0 -> RGBA32 / BGRA32 scaled on both axes, <= 4 non-negative taps
+struct ResizeFilter;
+bool cvt_resize_supported(const YuvToRgbArgs &a, int dw, int dh, int drs, const uint8_t *dst, const ResizeFilter &hx, const ResizeFilter &hy);
+// frames: n same-shaped conversions (yuv_planar_same_shape); dsts[i]: the dw x dh destination of frames[i] (rowstride drs);
+// cudaErrorInvalidConfiguration when a tile's source rectangle does not fit shared memory (the caller runs the unfused pair)
+cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, DevFilter fx,
+                              DevFilter fy, const ResizeFilter &hx, const ResizeFilter &hy);
 // ---- fused chain -----------------------------------------------------------------------------------------
 struct FusedArgs {
   Planes fg;

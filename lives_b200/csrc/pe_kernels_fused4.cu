@@ -1,0 +1,480 @@
+// pe_kernels_fused4.cu -- k_cvt_resize: planar 4:2:0 -> RGBA32 / BGRA32 AND the separable resize (both axes scaled, <= 4 non-negative
+// taps per axis: the bilinear banks) in ONE kernel.  BASELINE config 2 (1080p YUV420P -> RGBA32 -> 1280 x 720) as resize_layer_full
+// runs it (convert, then scale: colourspace.c:14601-14620 / our contract DESIGN.md section 5), without the 8.3 MB RGBA intermediate
+// ever reaching HBM: the unfused pair k_yuv_march + k_resize_tile4 moved 2.5 x the algorithmic bytes (profiles/r01s_*, r01t_*).
+// Same arithmetic, bit for bit, as the two unfused ops (tests/test_gpu_parity.py::test_cvt_resize_*).
+//
+// One 512-thread CTA per SM walks output tiles of 128 x 32 pixels (persistent, tile = blockIdx.x + i * gridDim.x); per tile
+//   0. (issued one tile ahead with cp.async, landing while the previous tile's passes 2 and 3 run) the raw source words the tile
+//      needs: luma rows [2 k0 - 1, 2 k1], chroma rows [k0 - 1, k1] -- whole reference row pairs (colourspace.c:3440-3549);
+//   1. conversion, one thread = 4 columns x one row pair, with k_fused3's arithmetic (bank-replicated tables, packed chroma sums,
+//      third_round as one multiply-high) but BOTH chroma rows summed locally; the result goes to three byte planes in shared memory
+//      (R, G, B: the alpha of every source pixel is 255 and is carried as two per-column / per-row factors instead);
+//   2. horizontal pass: the four taps of a column are four consecutive bytes of a plane row = two aligned words + one funnel shift,
+//      two DP2A, >> 7, min 32767 -> a 16-bit intermediate row in shared memory (one warp = one source row, a lane = 4 output columns
+//      32 apart: every access of the warp is one contiguous wavefront, the coefficients stay in registers across the warp's rows);
+//   3. vertical pass: 4 taps x 3 channels of 16-bit loads and multiply-adds, + 2^18 >> 19, saturating pack, one 32-bit store per pixel
+//      (a warp = one output row: 128-byte contiguous stores).
+// Rows the fast step cannot take (row 0, the last row of an even frame, the last chroma row of a plane without padding) go through
+// slow_unit(): scalar code with the reference's edge rules, a few units per frame.
+#include <cstdlib>
+
+#include "pe_device.cuh"
+#include "pe_kernels.h"
+#include "pe_tables.h"
+
+namespace pe {
+
+namespace {
+
+#define PE_COUNT_LAUNCH(L) do { if ((L).launch_counter) ++*(L).launch_counter; } while (0)
+
+constexpr int F4_NT = 512, F4_NW = F4_NT / 32;
+constexpr int F4_TW = 128, F4_TH = 32;
+constexpr int F4_TY = 0, F4_TV = 32768, F4_TU = 65536, F4_DYN = 98304;  // u32 [256][32] | uint2 [256][16] | uint2 [256][16] | per-tile part
+constexpr int F4_MAXF = 32;
+constexpr int F4_SMEM_MAX = 227 * 1024;
+
+struct CvtRszParams {
+  const uint8_t *y[F4_MAXF], *u[F4_MAXF], *v[F4_MAXF];
+  uint8_t *dst[F4_MAXF];
+  int nframes;
+  int fw, fh, cw, ch, rs_y, rs_u, rs_v;   // source (shared by all frames of the launch)
+  int dw, dh, drs;                        // destination
+  int tiles_x, tiles_y;
+  int GW, PR, CWW, TR;                    // per-tile maxima: 4-column groups, row pairs, chroma words per staged row, needed source rows
+  int k_fast_max;
+  int swap_rb;                            // BGRA32
+  const int32_t *fx_first, *fy_first;
+  const int16_t *fx_coef, *fy_coef;
+  int fx_taps, fy_taps;
+  const int32_t *conv;                    // [14][256]
+  // byte offsets of the per-tile arrays behind the tables
+  int o_rawy, o_rawu, o_rawv, o_vf, o_pl, o_tmp, o_cx, o_fx, o_ax, o_cy, o_fy, o_sy;
+  int pl_stride, pl_plane, tmp_plane;     // plane row stride (bytes), plane size (bytes), intermediate plane size (16-bit samples)
+};
+
+__device__ __forceinline__ uint32_t f4_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t f4_dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t f4_pack_sat(int a, int b, uint32_t c) {  // (c[15:0] << 16) | (sat_u8(a) << 8) | sat_u8(b)
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void f4_cp_async4(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void f4_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void f4_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr uint32_t F4_MSK = 0xFFFEFFFEu, F4_K3 = 0x00030003u;
+// third_round of the HIGH / LOW half of a packed Q = 2 n + 3, as the byte offset 128 * m of the chroma table entry (k_fused3: idx_hi / idx_lo)
+__device__ __forceinline__ uint32_t f4_idx_hi(uint32_t q) { return __umulhi(q, 10923u * 128u) & 0x7F80u; }
+__device__ __forceinline__ uint32_t f4_idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u * 128u) & 0x7F80u; }
+
+struct F4Row {
+  uint32_t a, b, c;  // a = [c(jc0), c(jc0+1)], b = [c(jc0-1), c(jc0)], c = [c(jc0+1), c(jc0+2)] as 16-bit halves
+};
+__device__ __forceinline__ F4Row f4_unpack(uint32_t w0, uint32_t w1, uint32_t sel) {
+  const uint32_t cw4 = __byte_perm(w0, w1, sel);
+  F4Row r;
+  r.a = __byte_perm(cw4, 0u, 0x4241u);
+  r.b = __byte_perm(cw4, 0u, 0x4140u);
+  r.c = __byte_perm(cw4, 0u, 0x4342u);
+  return r;
+}
+
+__device__ __forceinline__ int f4_chroma_at(const uint8_t *__restrict__ p, int stride, int r, int c, int cw, int ch) {
+  if (c >= cw) c = (cw < stride || r + 1 < ch) ? cw : cw - 1;
+  return __ldg(p + (long long)stride * r + c);
+}
+
+// (u, v) of source pixel (sx, sy) of a 4:2:0 frame with the reference's edge rules: the per-pixel form of colourspace.c:3391-3642
+// (identical to chroma_for_pixel of pe_kernels_fused.cu / k_yuv_planar_to_rgb)
+template <bool QUIRKS>
+__device__ void f4_chroma_px(const uint8_t *pu, const uint8_t *pv, int rs_u, int rs_v, int cw, int ch, int h, int sx, int sy, int &u, int &v) {
+  const int jc = sx >> 1, right = sx & 1;
+  if (sy == 0 || (!(h & 1) && sy == h - 1)) {
+    const int cr = sy == 0 ? 0 : ch - 1;
+    const int ca = jc, cb = right ? jc + 1 : jc - 1;
+    const int ua = ca <= 0 ? __ldg(pu + (long long)rs_u * cr) : f4_chroma_at(pu, rs_u, cr, ca, cw, ch);
+    const int va = ca <= 0 ? __ldg(pv + (long long)rs_v * cr) : f4_chroma_at(pv, rs_v, cr, ca, cw, ch);
+    const int ub = cb <= 0 ? __ldg(pu + (long long)rs_u * cr) : f4_chroma_at(pu, rs_u, cr, cb, cw, ch);
+    const int vb = cb <= 0 ? __ldg(pv + (long long)rs_v * cr) : f4_chroma_at(pv, rs_v, cr, cb, cw, ch);
+    u = (ua + ub) >> 1;
+    v = (va + vb) >> 1;
+    return;
+  }
+  const int k = (sy + 1) >> 1, cr_a = k - 1, cr_b = k, upper = sy & 1;
+  const int cn = right ? jc + 1 : max(jc - 1, 0);
+  const int u1t = f4_chroma_at(pu, rs_u, cr_a, jc, cw, ch), u1n = f4_chroma_at(pu, rs_u, cr_a, cn, cw, ch);
+  const int u2t = f4_chroma_at(pu, rs_u, cr_b, jc, cw, ch), u2n = f4_chroma_at(pu, rs_u, cr_b, cn, cw, ch);
+  const int v1t = f4_chroma_at(pv, rs_v, cr_a, jc, cw, ch), v1n = f4_chroma_at(pv, rs_v, cr_a, cn, cw, ch);
+  const int v2t = f4_chroma_at(pv, rs_v, cr_b, jc, cw, ch), v2n = f4_chroma_at(pv, rs_v, cr_b, cn, cw, ch);
+  int u1 = u1t + u1n, u2 = u2t + u2n, v1 = v1t + v1n, v2 = v2t + v2n;
+  if (QUIRKS && !right) {
+    u2 = u1;                                             // colourspace.c:3461
+    if (jc > 0) v1 = v1t + v2n;                          // :3544
+    v2 = v2t + __ldg(pv + (long long)rs_v * cr_b);       // last_v2 never advanced
+  }
+  u = upper ? third_round(u1 + (u2 >> 1)) : third_round((u1 >> 1) + u2);
+  v = upper ? third_round(v1 + (v2 >> 1)) : third_round((v1 >> 1) + v2);
+}
+
+template <bool QUIRKS>
+__global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__ CvtRszParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  fill_replicated_yuv_tables(smem + F4_TY, smem + F4_TV, smem + F4_TU, P.conv, tid, F4_NT);
+
+  uint8_t *const s_rawy = smem + P.o_rawy, *const s_rawu = smem + P.o_rawu, *const s_rawv = smem + P.o_rawv;
+  uint32_t *const s_vf = reinterpret_cast<uint32_t *>(smem + P.o_vf);
+  uint8_t *const s_pl = smem + P.o_pl;
+  uint16_t *const s_tmp = reinterpret_cast<uint16_t *>(smem + P.o_tmp);
+  uint2 *const s_cx = reinterpret_cast<uint2 *>(smem + P.o_cx);
+  int *const s_fx = reinterpret_cast<int *>(smem + P.o_fx), *const s_ax = reinterpret_cast<int *>(smem + P.o_ax);
+  int4 *const s_cy = reinterpret_cast<int4 *>(smem + P.o_cy);
+  int *const s_fy = reinterpret_cast<int *>(smem + P.o_fy), *const s_sy = reinterpret_cast<int *>(smem + P.o_sy);
+
+  const int GW = P.GW, CWB = P.CWW * 4;
+  const int tiles_per_frame = P.tiles_x * P.tiles_y;
+  const long long total = (long long)tiles_per_frame * P.nframes;
+  const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
+
+  struct Geo {
+    int f, x0, y0, ncol, nrow, vr0, nvr, cb, ng, k0, np, ubase;
+  };
+  auto geometry = [&](long long t) -> Geo {
+    Geo g;
+    g.f = (int)(t / tiles_per_frame);
+    const int r = (int)(t - (long long)g.f * tiles_per_frame);
+    const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+    g.x0 = tx * F4_TW; g.y0 = ty * F4_TH;
+    const int x1 = min(g.x0 + F4_TW, P.dw), y1 = min(g.y0 + F4_TH, P.dh);
+    g.ncol = x1 - g.x0; g.nrow = y1 - g.y0;
+    const int vc0 = __ldg(P.fx_first + g.x0), vc1 = __ldg(P.fx_first + x1 - 1) + P.fx_taps - 1;
+    g.vr0 = __ldg(P.fy_first + g.y0);
+    const int vr1 = __ldg(P.fy_first + y1 - 1) + P.fy_taps - 1;
+    g.nvr = vr1 - g.vr0 + 1;
+    g.cb = vc0 & ~3;
+    g.ng = (((vc1 | 3) + 1) - g.cb) >> 2;
+    g.k0 = (g.vr0 + 1) >> 1;
+    g.np = ((vr1 + 1) >> 1) - g.k0 + 1;
+    g.ubase = g.cb == 0 ? 0 : (((g.cb >> 1) - 1) & ~3);
+    return g;
+  };
+  // cp.async of the raw words of tile t: luma rows 2 k0 - 1 .. 2 k1 (clamped to the frame), chroma rows k0 - 1 .. k1, the first V
+  // sample of every chroma row (the reference's never-advanced last_v2, colourspace.c:3544)
+  auto stage = [&](const Geo &g) {
+    const uint8_t *Fy = P.y[g.f], *Fu = P.u[g.f], *Fv = P.v[g.f];
+    const int rowbase = 2 * g.k0 - 1;
+    for (int i = tid; i < 2 * g.np * g.ng; i += F4_NT) {
+      const int ri = i / g.ng, w = i - ri * g.ng;
+      const int sr = min(max(rowbase + ri, 0), P.fh - 1);
+      f4_cp_async4(sbase + P.o_rawy + ri * (GW * 4) + 4 * w, Fy + (size_t)P.rs_y * sr + g.cb + 4 * w);
+    }
+    const long long ulim = (long long)P.rs_u * P.ch - 4, vlim = (long long)P.rs_v * P.ch - 4;
+    for (int i = tid; i < (g.np + 1) * P.CWW; i += F4_NT) {
+      const int ri = i / P.CWW, w = i - ri * P.CWW;
+      const int cr = min(max(g.k0 - 1 + ri, 0), P.ch - 1);
+      const long long ou = min((long long)P.rs_u * cr + g.ubase + 4 * w, ulim), ov = min((long long)P.rs_v * cr + g.ubase + 4 * w, vlim);
+      f4_cp_async4(sbase + P.o_rawu + ri * CWB + 4 * w, Fu + ou);
+      f4_cp_async4(sbase + P.o_rawv + ri * CWB + 4 * w, Fv + ov);
+    }
+    for (int i = tid; i <= g.np; i += F4_NT) {
+      const int cr = min(max(g.k0 - 1 + i, 0), P.ch - 1);
+      f4_cp_async4(sbase + P.o_vf + 4 * i, Fv + (size_t)P.rs_v * cr);
+    }
+    f4_cp_async_commit();
+  };
+
+  // yuv2rgb_int through the replicated tables, UNSATURATED (ou, ov = 128 * m)
+  auto rgb = [&](uint32_t y, uint32_t ou, uint32_t ov, int &r, int &g, int &b) {
+    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + F4_TY + (y * 128u + lane4));
+    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + F4_TV + (ov | lane8));
+    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + F4_TU + (ou | lane8));
+    r = (yy + (int)tv.x) >> 16;
+    g = (yy + (int)tu.x + (int)tv.y) >> 16;
+    b = (yy + (int)tu.y) >> 16;
+  };
+
+  long long t = blockIdx.x;
+  if (t >= total) return;
+  Geo G = geometry(t);
+  stage(G);
+  for (; t < total; t += gridDim.x) {
+    f4_cp_async_wait_all();
+    __syncthreads();  // raw words of this tile have landed; the previous tile's passes are done with the planes, the intermediate and the filter rows
+    const Geo g = G;
+    const int rowbase = 2 * g.k0 - 1;
+    // ---- filter data of the tile (read by passes 2 and 3, behind the next barrier)
+    for (int i = tid; i < g.ncol; i += F4_NT) {
+      uint32_t c[4] = {0, 0, 0, 0};
+      int sum = 0;
+      for (int k = 0; k < P.fx_taps; k++) {
+        const int cf = P.fx_coef[(size_t)(g.x0 + i) * P.fx_taps + k];
+        c[k] = (uint16_t)cf;
+        sum += cf;
+      }
+      s_cx[i] = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
+      s_fx[i] = __ldg(P.fx_first + g.x0 + i) - g.cb;
+      s_ax[i] = min((sum * 255) >> 7, 32767);  // the horizontal pass on an all-255 alpha row
+    }
+    for (int i = tid; i < g.nrow; i += F4_NT) {
+      int c[4] = {0, 0, 0, 0}, sum = 0;
+      for (int k = 0; k < P.fy_taps; k++) { c[k] = P.fy_coef[(size_t)(g.y0 + i) * P.fy_taps + k]; sum += c[k]; }
+      s_cy[i] = make_int4(c[0], c[1], c[2], c[3]);
+      s_fy[i] = __ldg(P.fy_first + g.y0 + i) - g.vr0;
+      s_sy[i] = sum;
+    }
+    // ---- 1. conversion: unit = (row pair p, 4-column group gi) -> rows 2p, 2p + 1 of the three planes
+    for (int i = tid; i < g.np * g.ng; i += F4_NT) {
+      const int p = i / g.ng, gi = i - p * g.ng;
+      const int k = g.k0 + p, x = g.cb + 4 * gi;
+      uint32_t oA[3], oB[3];
+      if (k >= 1 && k <= P.k_fast_max) {
+        const uint32_t yA = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p) * (GW * 4) + 4 * gi);
+        const uint32_t yB = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p + 1) * (GW * 4) + 4 * gi);
+        const int jc0 = x >> 1, o = jc0 - 1;
+        const int off0 = x == 0 ? 0 : (o & ~3);
+        const uint32_t sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
+        const uint32_t selB = x == 0 ? 0x3254u : 0x3210u;
+        const int wo = off0 - g.ubase;
+        const uint32_t *up = reinterpret_cast<const uint32_t *>(s_rawu + p * CWB + wo), *uc = reinterpret_cast<const uint32_t *>(s_rawu + (p + 1) * CWB + wo);
+        const uint32_t *vp = reinterpret_cast<const uint32_t *>(s_rawv + p * CWB + wo), *vc = reinterpret_cast<const uint32_t *>(s_rawv + (p + 1) * CWB + wo);
+        const F4Row Up = f4_unpack(up[0], up[1], sel), Uc = f4_unpack(uc[0], uc[1], sel);
+        const F4Row Vp = f4_unpack(vp[0], vp[1], sel), Vc = f4_unpack(vc[0], vc[1], sel);
+        // right pixel of both chroma columns: this + next; rows 2k-1 ("up") / 2k ("lo") weigh the chroma rows k-1 / k 2 : 1 and 1 : 2
+        const uint32_t RUp = Up.a + Up.c, RUc = Uc.a + Uc.c, RVp = Vp.a + Vp.c, RVc = Vc.a + Vc.c;
+        const uint32_t QUR_up = RUp * 2u + (RUc & F4_MSK) + F4_K3, QUR_lo = (RUp & F4_MSK) + RUc * 2u + F4_K3;
+        const uint32_t QVR_up = RVp * 2u + (RVc & F4_MSK) + F4_K3, QVR_lo = (RVp & F4_MSK) + RVc * 2u + F4_K3;
+        // left pixel: this + last
+        uint32_t QUL_up, QUL_lo, QVL_up, QVL_lo;
+        const uint32_t LUp = Up.a + Up.b;
+        if (QUIRKS) {
+          QUL_up = QUL_lo = LUp * 2u + (LUp & F4_MSK) + F4_K3;          // u2 = this_u1 + last_u1 (colourspace.c:3461)
+          const uint32_t bq = __byte_perm(Vc.b, Vp.a, selB);           // last_v1 = this_v2 (:3544), except at column 0
+          const uint32_t v1 = Vp.a + bq;
+          const uint32_t v2 = Vc.a + (s_vf[p + 1] & 0xFFu) * 0x10001u;  // last_v2 is never advanced: the row's first V sample
+          QVL_up = v1 * 2u + (v2 & F4_MSK) + F4_K3;
+          QVL_lo = (v1 & F4_MSK) + v2 * 2u + F4_K3;
+        } else {
+          const uint32_t LUc = Uc.a + Uc.b, LVp = Vp.a + Vp.b, LVc = Vc.a + Vc.b;
+          QUL_up = LUp * 2u + (LUc & F4_MSK) + F4_K3; QUL_lo = (LUp & F4_MSK) + LUc * 2u + F4_K3;
+          QVL_up = LVp * 2u + (LVc & F4_MSK) + F4_K3; QVL_lo = (LVp & F4_MSK) + LVc * 2u + F4_K3;
+        }
+        int rA[12], rB[12];
+#pragma unroll
+        for (int col = 0; col < 4; col++) {
+          const bool hi_half = col >> 1, right = col & 1;
+          const uint32_t qu_up = right ? QUR_up : QUL_up, qu_lo = right ? QUR_lo : QUL_lo;
+          const uint32_t qv_up = right ? QVR_up : QVL_up, qv_lo = right ? QVR_lo : QVL_lo;
+          const uint32_t mu_up = hi_half ? f4_idx_hi(qu_up) : f4_idx_lo(qu_up), mv_up = hi_half ? f4_idx_hi(qv_up) : f4_idx_lo(qv_up);
+          const uint32_t mv_lo = hi_half ? f4_idx_hi(qv_lo) : f4_idx_lo(qv_lo);
+          const uint32_t mu_lo = (QUIRKS && !right) ? mu_up : (hi_half ? f4_idx_hi(qu_lo) : f4_idx_lo(qu_lo));
+          rgb(byte_of(yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+          rgb(byte_of(yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {  // bytes = columns 0 .. 3 of channel c
+          oA[c] = f4_pack_sat(rA[3 + c], rA[c], f4_pack_sat(rA[9 + c], rA[6 + c], 0u));
+          oB[c] = f4_pack_sat(rB[3 + c], rB[c], f4_pack_sat(rB[9 + c], rB[6 + c], 0u));
+        }
+      } else {
+        // ---- slow unit (frame edges): per pixel with the reference's edge rules, straight from global memory
+        oA[0] = oA[1] = oA[2] = oB[0] = oB[1] = oB[2] = 0u;
+        const uint8_t *Fy = P.y[g.f], *Fu = P.u[g.f], *Fv = P.v[g.f];
+#pragma unroll 1
+        for (int rr = 0; rr < 2; rr++) {
+          const int sy = 2 * k - 1 + rr;
+          if (sy < 0 || sy >= P.fh) continue;
+          uint32_t o3[3] = {0u, 0u, 0u};
+#pragma unroll 1
+          for (int col = 0; col < 4; col++) {
+            int u, v, r, gg, b;
+            f4_chroma_px<QUIRKS>(Fu, Fv, P.rs_u, P.rs_v, P.cw, P.ch, P.fh, x + col, sy, u, v);
+            rgb(__ldg(Fy + (size_t)P.rs_y * sy + x + col), (uint32_t)u * 128u, (uint32_t)v * 128u, r, gg, b);
+            o3[0] |= (uint32_t)min(max(r, 0), 255) << (8 * col);
+            o3[1] |= (uint32_t)min(max(gg, 0), 255) << (8 * col);
+            o3[2] |= (uint32_t)min(max(b, 0), 255) << (8 * col);
+          }
+          if (rr == 0) { oA[0] = o3[0]; oA[1] = o3[1]; oA[2] = o3[2]; }
+          else { oB[0] = o3[0]; oB[1] = o3[1]; oB[2] = o3[2]; }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        uint8_t *pl = s_pl + c * P.pl_plane + 4 * gi;
+        *reinterpret_cast<uint32_t *>(pl + (2 * p) * P.pl_stride) = oA[c];
+        *reinterpret_cast<uint32_t *>(pl + (2 * p + 1) * P.pl_stride) = oB[c];
+      }
+    }
+    __syncthreads();
+    // the raw buffers are free again: bring in the next tile's words while passes 2 and 3 run
+    const long long tn = t + gridDim.x;
+    if (tn < total) {
+      G = geometry(tn);
+      stage(G);
+    }
+    // ---- 2. horizontal pass: warp = one source row at a time, lane = output columns lane, lane + 32, lane + 64, lane + 96
+    {
+      uint2 cf[4];
+      int fo[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int xo = lane + 32 * j;
+        const bool ok = xo < g.ncol;
+        cf[j] = ok ? s_cx[xo] : make_uint2(0u, 0u);
+        fo[j] = ok ? s_fx[xo] : 0;
+      }
+      for (int tr = warp; tr < g.nvr; tr += F4_NW) {
+        const int pr = g.vr0 + tr - rowbase;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint8_t *row = s_pl + c * P.pl_plane + pr * P.pl_stride;
+          uint16_t *trow = s_tmp + c * P.tmp_plane + tr * F4_TW;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(row) + (fo[j] >> 2);
+            const uint32_t win = __funnelshift_r(q[0], q[1], 8u * (uint32_t)(fo[j] & 3));
+            const uint32_t v = min(f4_dp2a_hi(cf[j].y, win, f4_dp2a_lo(cf[j].x, win, 0u)) >> 7, 32767u);
+            trow[lane + 32 * j] = (uint16_t)v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 3. vertical pass: warp = one output row at a time
+    for (int yo = warp; yo < g.nrow; yo += F4_NW) {
+      const int4 cy = s_cy[yo];
+      const int tr0 = s_fy[yo], sy = s_sy[yo];
+      uint8_t *drow = P.dst[g.f] + (size_t)P.drs * (g.y0 + yo) + (size_t)g.x0 * 4;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int xo = lane + 32 * j;
+        if (xo >= g.ncol) continue;
+        int acc[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint16_t *tp = s_tmp + c * P.tmp_plane + tr0 * F4_TW + xo;
+          acc[c] = ((1 << 18) + cy.x * (int)tp[0] + cy.y * (int)tp[F4_TW] + cy.z * (int)tp[2 * F4_TW] + cy.w * (int)tp[3 * F4_TW]) >> 19;
+        }
+        const int al = ((1 << 18) + sy * s_ax[xo]) >> 19;
+        const int c0 = P.swap_rb ? acc[2] : acc[0], c2 = P.swap_rb ? acc[0] : acc[2];
+        // bytes c0, G, c2, A
+        const uint32_t px = f4_pack_sat(acc[1], c0, 0u) | (f4_pack_sat(al, c2, 0u) << 16);
+        st_stream_u32(drow + 4 * xo, px);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// Can k_cvt_resize take this (conversion, resize) pair?  a: the queued planar -> RGB conversion (already yuv_planar_fast_ok), its
+// destination the 4-byte packed frame the resize reads.
+bool cvt_resize_supported(const YuvToRgbArgs &a, int dw, int dh, int drs, const uint8_t *dst, const ResizeFilter &hx, const ResizeFilter &hy) {
+  if (a.is_422 || a.low_quality || a.lut16 || a.blend2) return false;
+  if (a.out.psize != 4 || a.out.a != 3 || a.out.g != 1) return false;   // RGBA32 / BGRA32
+  if ((a.width & 3) || a.width < 8 || a.height < 4 || (a.height & 1)) return false;
+  if (hx.taps > 4 || hy.taps > 4 || !hx.nonneg() || !hy.nonneg()) return false;
+  if ((drs & 3) || (reinterpret_cast<uintptr_t>(dst) & 3) || dw < 1 || dh < 1) return false;
+  // every tap inside the frame (the libswscale recipes fold the border taps in; the round-1 triangle contract clamps instead)
+  for (int i = 0; i < dw; i++)
+    if (hx.first[i] < 0 || hx.first[i] + hx.taps > a.width) return false;
+  for (int i = 0; i < dh; i++)
+    if (hy.first[i] < 0 || hy.first[i] + hy.taps > a.height) return false;
+  for (int i = 1; i < dw; i++)
+    if (hx.first[i] < hx.first[i - 1]) return false;
+  for (int i = 1; i < dh; i++)
+    if (hy.first[i] < hy.first[i - 1]) return false;
+  return true;
+}
+
+// frames: n conversions of the same shape (yuv_planar_same_shape), dsts[i] the resized destination of frames[i]
+cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, DevFilter fx,
+                              DevFilter fy, const ResizeFilter &hx, const ResizeFilter &hy) {
+  const YuvToRgbArgs &a0 = frames[0];
+  CvtRszParams P;
+  memset(&P, 0, sizeof(P));
+  P.fw = a0.width; P.fh = a0.height; P.cw = a0.src.cw; P.ch = a0.src.ch;
+  P.rs_y = a0.src.rs_y; P.rs_u = a0.src.rs_u; P.rs_v = a0.src.rs_v;
+  P.dw = dw; P.dh = dh; P.drs = drs;
+  P.tiles_x = (dw + F4_TW - 1) / F4_TW; P.tiles_y = (dh + F4_TH - 1) / F4_TH;
+  P.fx_first = fx.first; P.fx_coef = fx.coef; P.fx_taps = fx.taps;
+  P.fy_first = fy.first; P.fy_coef = fy.coef; P.fy_taps = fy.taps;
+  P.conv = a0.conv.t;
+  P.swap_rb = a0.out.r == 2;
+  const bool last_row_unsafe = a0.src.rs_u < a0.src.cw + 4 || a0.src.rs_v < a0.src.cw + 4;
+  P.k_fast_max = a0.src.ch - 1 - (last_row_unsafe ? 1 : 0);
+  // per-tile maxima
+  int GW = 1, PR = 1, TR = 1;
+  for (int x0 = 0; x0 < dw; x0 += F4_TW) {
+    const int x1 = (x0 + F4_TW < dw ? x0 + F4_TW : dw) - 1;
+    const int vc0 = hx.first[x0], vc1 = hx.first[x1] + hx.taps - 1;
+    const int ng = (((vc1 | 3) + 1) - (vc0 & ~3)) >> 2;
+    if (ng > GW) GW = ng;
+  }
+  for (int y0 = 0; y0 < dh; y0 += F4_TH) {
+    const int y1 = (y0 + F4_TH < dh ? y0 + F4_TH : dh) - 1;
+    const int vr0 = hy.first[y0], vr1 = hy.first[y1] + hy.taps - 1;
+    const int np = ((vr1 + 1) >> 1) - ((vr0 + 1) >> 1) + 1;
+    if (np > PR) PR = np;
+    if (vr1 - vr0 + 1 > TR) TR = vr1 - vr0 + 1;
+  }
+  P.GW = GW; P.PR = PR; P.TR = TR;
+  P.CWW = GW / 2 + 3;
+  auto al16 = [](int v) { return (v + 15) & ~15; };
+  int off = F4_DYN;
+  P.o_rawy = off; off = al16(off + 2 * PR * GW * 4);
+  P.o_rawu = off; off = al16(off + (PR + 1) * P.CWW * 4);
+  P.o_rawv = off; off = al16(off + (PR + 1) * P.CWW * 4);
+  P.o_vf = off; off = al16(off + (PR + 1) * 4);
+  P.pl_stride = (GW + 1) * 4;
+  P.pl_plane = al16(2 * PR * P.pl_stride);
+  P.o_pl = off; off += 3 * P.pl_plane;
+  P.tmp_plane = (TR + 3) * F4_TW;
+  P.o_tmp = off; off = al16(off + 3 * P.tmp_plane * 2);
+  P.o_cx = off; off += F4_TW * 8;
+  P.o_fx = off; off += F4_TW * 4;
+  P.o_ax = off; off += F4_TW * 4;
+  P.o_cy = off; off += F4_TH * 16;
+  P.o_fy = off; off += F4_TH * 4;
+  P.o_sy = off; off += F4_TH * 4;
+  const int smem_bytes = off;
+  if (smem_bytes > F4_SMEM_MAX) return cudaErrorInvalidConfiguration;  // scale factor too large for one tile: the caller runs the unfused pair
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_cvt_resize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_MAX)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_cvt_resize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_MAX)) != cudaSuccess) return e;
+    attr_set.cur() = 1;
+  }
+  for (int base = 0; base < n; base += F4_MAXF) {
+    P.nframes = n - base < F4_MAXF ? n - base : F4_MAXF;
+    for (int i = 0; i < F4_MAXF; i++) {
+      const int k = base + (i < P.nframes ? i : 0);
+      P.y[i] = frames[k].src.y; P.u[i] = frames[k].src.u; P.v[i] = frames[k].src.v;
+      P.dst[i] = dsts[k];
+    }
+    const long long total = (long long)P.tiles_x * P.tiles_y * P.nframes;
+    const int grid = (int)(total < L.sm_count ? total : L.sm_count);
+    if (a0.quirks) k_cvt_resize<true><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
+    else k_cvt_resize<false><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
+    PE_COUNT_LAUNCH(L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace pe
