@@ -279,7 +279,7 @@ extern "C" void pe_engine_destroy(pe_engine_t *e) {
   for (auto &kv : e->lut8) cudaFree(kv.second.dev);
   for (auto &kv : e->lut16) cudaFree(kv.second);
   for (auto &kv : e->over) cudaFree(kv.second.dev);
-  for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); cudaFree(kv.second.rows4); }
+  for (auto &kv : e->filters) { cudaFree((void *)kv.second.dev.first); cudaFree((void *)kv.second.dev.coef); cudaFree(kv.second.rows4); cudaFree(kv.second.pack4); }
   e->pool.release_all();
   cudaFree(e->stats_dev);
   cudaFree(e->args_dev);
@@ -479,7 +479,7 @@ DevFilterEntry *get_filter(pe_engine *e, int src_n, int dst_n, int bits, int kin
     for (auto j = e->filters.begin(); j != e->filters.end(); ++j)
       if (j->second.tick < lru->second.tick) lru = j;
     cudaStreamSynchronize(e->stream);  // kernels that read the bank have finished
-    cudaFree((void *)lru->second.dev.first); cudaFree((void *)lru->second.dev.coef); cudaFree(lru->second.rows4);
+    cudaFree((void *)lru->second.dev.first); cudaFree((void *)lru->second.dev.coef); cudaFree(lru->second.rows4); cudaFree(lru->second.pack4);
     e->filters.erase(lru);
   }
   DevFilterEntry ent;
@@ -1936,6 +1936,34 @@ int flush_rsz_pending(pe_engine *e) {
 // A batch call queued both the planar -> RGB conversions (yuv_pending) and the resizes of their results (rsz_pending).  When every
 // pair (conversion i, resize i) meets through an intermediate frame that nothing else reads, the pairs leave as ONE k_cvt_resize
 // launch per 32 (pe_kernels_fused4.cu) and the intermediate frames are never written; otherwise the queues are flushed in order.
+// k_cvt_resize's view of a <= 4-tap non-negative bank, built once per cached bank: per output sample the four coefficients as 16-bit
+// pairs, the first source index, and what the pass does to an all-255 alpha channel -- horizontal (14 bit): min((sum c * 255) >> 7,
+// 32767), the 15-bit intermediate of alpha; vertical (12 bit): sum c, its multiplier
+const void *get_pack4(pe_engine *e, DevFilterEntry *f, int bits) {
+  if (f->pack4) return f->pack4;
+  const int n = (int)f->host.first.size(), taps = f->host.taps;
+  if (taps > 4) return nullptr;
+  std::vector<int32_t> h((size_t)n * 4);
+  for (int i = 0; i < n; i++) {
+    uint32_t c[4] = {0, 0, 0, 0};
+    int sum = 0;
+    for (int k = 0; k < taps; k++) { c[k] = (uint16_t)f->host.coef[(size_t)i * taps + k]; sum += f->host.coef[(size_t)i * taps + k]; }
+    h[4 * (size_t)i] = (int32_t)(c[0] | (c[1] << 16));
+    h[4 * (size_t)i + 1] = (int32_t)(c[2] | (c[3] << 16));
+    h[4 * (size_t)i + 2] = f->host.first[(size_t)i];
+    h[4 * (size_t)i + 3] = bits == 14 ? std::min((sum * 255) >> 7, 32767) : sum;
+  }
+  void *d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(int32_t)) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {  // (h is pageable and dies with this call)
+    cudaFree(d);
+    return nullptr;
+  }
+  f->pack4 = d;
+  return d;
+}
+
 int flush_cvt_rsz_pending(pe_engine *e) {
   std::vector<YuvToRgbArgs> &Y = e->yuv_pending;
   std::vector<pe_engine::RszJob> &R = e->rsz_pending;
@@ -1948,10 +1976,12 @@ int flush_cvt_rsz_pending(pe_engine *e) {
     DevFilterEntry *fx = get_filter(e, R[0].sw, R[0].dw, 14, R[0].kx), *fy = get_filter(e, R[0].sh, R[0].dh, 12, R[0].ky);
     fuse = fx && fy;
     for (size_t i = 0; i < Y.size() && fuse; i++) fuse = cvt_resize_supported(Y[i], R[0].dw, R[0].dh, R[0].drs, R[i].dst, fx->host, fy->host);
+    const void *px = fuse ? get_pack4(e, fx, 14) : nullptr, *py = fuse ? get_pack4(e, fy, 12) : nullptr;
+    fuse = fuse && px && py;
     if (fuse) {
       std::vector<uint8_t *> dsts;
       for (size_t i = 0; i < R.size(); i++) dsts.push_back(R[i].dst);
-      cudaError_t ce = launch_cvt_resize(e->L(), Y.data(), dsts.data(), (int)Y.size(), R[0].dw, R[0].dh, R[0].drs, fx->dev, fy->dev, fx->host, fy->host);
+      cudaError_t ce = launch_cvt_resize(e->L(), Y.data(), dsts.data(), (int)Y.size(), R[0].dw, R[0].dh, R[0].drs, px, py, fx->host, fy->host);
       if (ce == cudaSuccess) {
         Y.clear(); R.clear();
         e->rsz_defer = false;

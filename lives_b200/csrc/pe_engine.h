@@ -56,6 +56,7 @@ struct DevFilterEntry {
   ResizeFilter host;
   void *rows4 = nullptr;  // int4 per output row {first, c3 | c2 << 16, c1 | c0 << 16, 0}: k_fused3's view of a <= 4-tap bank
   int rows4_x16 = 0;      // its coefficients are scaled by 16 (no tap of the bank is 4096)
+  void *pack4 = nullptr;  // int4 per output sample {c0 | c1 << 16, c2 | c3 << 16, first, aux}: k_cvt_resize's view of a <= 4-tap non-negative bank
   unsigned long tick = 0; // last use (LRU bound of the cache)
 };
 struct OverEntry {

@@ -219,8 +219,9 @@ struct ResizeFilter;
 bool cvt_resize_supported(const YuvToRgbArgs &a, int dw, int dh, int drs, const uint8_t *dst, const ResizeFilter &hx, const ResizeFilter &hy);
 // frames: n same-shaped conversions (yuv_planar_same_shape); dsts[i]: the dw x dh destination of frames[i] (rowstride drs);
 // cudaErrorInvalidConfiguration when a tile's source rectangle does not fit shared memory (the caller runs the unfused pair)
-cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, DevFilter fx,
-                              DevFilter fy, const ResizeFilter &hx, const ResizeFilter &hy);
+// px_dev / py_dev: the banks as int4 per output sample {c0 | c1 << 16, c2 | c3 << 16, first, aux} (pe_engine.cu get_pack4)
+cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, const void *px_dev,
+                              const void *py_dev, const ResizeFilter &hx, const ResizeFilter &hy);
 // ---- fused chain -----------------------------------------------------------------------------------------
 struct FusedArgs {
   Planes fg;

@@ -34,6 +34,25 @@ constexpr int F4_TW = 128, F4_TH = 32;
 constexpr int F4_TY = 0, F4_TV = 32768, F4_TU = 65536, F4_DYN = 98304;  // u32 [256][32] | uint2 [256][16] | uint2 [256][16] | per-tile part
 constexpr int F4_MAXF = 32;
 constexpr int F4_SMEM_MAX = 227 * 1024;
+// Per-tile maxima, COMPILE-TIME so that every shared-memory address in the three passes is a register plus an immediate: a 128 x 32 tile
+// of a <= 4-tap bank (scale factors down to 1 : 1.5 per axis) needs at most 4-column groups / row pairs / source rows as below; a
+// geometry that asks for more takes the unfused kernels (launch_cvt_resize returns cudaErrorInvalidConfiguration).
+constexpr int F4_GW = 56;                   // words per staged luma row (224 bytes = 14 x 16: 51 groups + 12 bytes of alignment slack)
+constexpr int F4_NG = 51;                   // 4-column groups a tile may convert per row pair
+constexpr int F4_PR = 28;                   // row pairs
+constexpr int F4_TR = 54;                   // source rows the vertical pass reads
+constexpr int F4_CWB = 128;                 // bytes per staged chroma row (8 x 16)
+constexpr int F4_PLS = (F4_NG + 1) * 4;     // plane row stride
+constexpr int F4_PLP = 2 * F4_PR * F4_PLS;  // plane size
+constexpr int F4_TMP = (F4_TR + 3) * F4_TW; // 16-bit samples per intermediate plane
+constexpr int O_RAWY = F4_DYN, O_RAWU = O_RAWY + 2 * F4_PR * F4_GW * 4, O_RAWV = O_RAWU + (F4_PR + 1) * F4_CWB, O_VF = O_RAWV + (F4_PR + 1) * F4_CWB;
+constexpr int O_PL = (O_VF + (F4_PR + 1) * 4 + 15) & ~15, O_TMP = (O_PL + 3 * F4_PLP + 15) & ~15, O_CX = (O_TMP + 3 * F4_TMP * 2 + 15) & ~15;
+// filter rows of the tile, double buffered (tile parity): int4 per output column / row {c0 | c1 << 16, c2 | c3 << 16, first, aux};
+// tile tables: the tap range [first, last] of every tile column / tile row, read once per launch
+constexpr int F4_MAXTX = 128, F4_MAXTY = 160;
+constexpr int O_PY = O_CX + 2 * F4_TW * 16, O_TCOL = O_PY + 2 * F4_TH * 16, O_TROW = O_TCOL + F4_MAXTX * 8;
+constexpr int F4_SMEM = O_TROW + F4_MAXTY * 8;
+static_assert(F4_SMEM <= F4_SMEM_MAX, "k_cvt_resize: shared memory budget");
 
 struct CvtRszParams {
   const uint8_t *y[F4_MAXF], *u[F4_MAXF], *v[F4_MAXF];
@@ -42,16 +61,12 @@ struct CvtRszParams {
   int fw, fh, cw, ch, rs_y, rs_u, rs_v;   // source (shared by all frames of the launch)
   int dw, dh, drs;                        // destination
   int tiles_x, tiles_y;
-  int GW, PR, CWW, TR;                    // per-tile maxima: 4-column groups, row pairs, chroma words per staged row, needed source rows
+  int vec16;                              // planes and strides 16-byte aligned: the raw words travel as 16-byte cp.async
   int k_fast_max;
   int swap_rb;                            // BGRA32
-  const int32_t *fx_first, *fy_first;
-  const int16_t *fx_coef, *fy_coef;
+  const int4 *px, *py;                    // [dw] / [dh]: {c0 | c1 << 16, c2 | c3 << 16, first, aux}; aux = alpha's 15-bit intermediate / the sum of the row's taps
   int fx_taps, fy_taps;
   const int32_t *conv;                    // [14][256]
-  // byte offsets of the per-tile arrays behind the tables
-  int o_rawy, o_rawu, o_rawv, o_vf, o_pl, o_tmp, o_cx, o_fx, o_ax, o_cy, o_fy, o_sy;
-  int pl_stride, pl_plane, tmp_plane;     // plane row stride (bytes), plane size (bytes), intermediate plane size (16-bit samples)
 };
 
 __device__ __forceinline__ uint32_t f4_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
@@ -71,6 +86,9 @@ __device__ __forceinline__ uint32_t f4_pack_sat(int a, int b, uint32_t c) {  // 
 }
 __device__ __forceinline__ void f4_cp_async4(uint32_t smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void f4_cp_async16(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void f4_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void f4_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -136,64 +154,93 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   fill_replicated_yuv_tables(smem + F4_TY, smem + F4_TV, smem + F4_TU, P.conv, tid, F4_NT);
 
-  uint8_t *const s_rawy = smem + P.o_rawy, *const s_rawu = smem + P.o_rawu, *const s_rawv = smem + P.o_rawv;
-  uint32_t *const s_vf = reinterpret_cast<uint32_t *>(smem + P.o_vf);
-  uint8_t *const s_pl = smem + P.o_pl;
-  uint16_t *const s_tmp = reinterpret_cast<uint16_t *>(smem + P.o_tmp);
-  uint2 *const s_cx = reinterpret_cast<uint2 *>(smem + P.o_cx);
-  int *const s_fx = reinterpret_cast<int *>(smem + P.o_fx), *const s_ax = reinterpret_cast<int *>(smem + P.o_ax);
-  int4 *const s_cy = reinterpret_cast<int4 *>(smem + P.o_cy);
-  int *const s_fy = reinterpret_cast<int *>(smem + P.o_fy), *const s_sy = reinterpret_cast<int *>(smem + P.o_sy);
+  uint8_t *const s_rawy = smem + O_RAWY, *const s_rawu = smem + O_RAWU, *const s_rawv = smem + O_RAWV;
+  uint32_t *const s_vf = reinterpret_cast<uint32_t *>(smem + O_VF);
+  uint8_t *const s_pl = smem + O_PL;
+  uint16_t *const s_tmp = reinterpret_cast<uint16_t *>(smem + O_TMP);
+  int2 *const s_tcol = reinterpret_cast<int2 *>(smem + O_TCOL), *const s_trow = reinterpret_cast<int2 *>(smem + O_TROW);
+  for (int i = tid; i < P.tiles_x; i += F4_NT)
+    s_tcol[i] = make_int2(__ldg(&P.px[i * F4_TW].z), __ldg(&P.px[min(i * F4_TW + F4_TW, P.dw) - 1].z) + P.fx_taps - 1);
+  for (int i = tid; i < P.tiles_y; i += F4_NT)
+    s_trow[i] = make_int2(__ldg(&P.py[i * F4_TH].z), __ldg(&P.py[min(i * F4_TH + F4_TH, P.dh) - 1].z) + P.fy_taps - 1);
+  __syncthreads();
 
-  const int GW = P.GW, CWB = P.CWW * 4;
+  constexpr int GW = F4_GW, CWB = F4_CWB;
   const int tiles_per_frame = P.tiles_x * P.tiles_y;
-  const long long total = (long long)tiles_per_frame * P.nframes;
+  const int total = tiles_per_frame * P.nframes;  // (fits 31 bits: checked by the launcher)
   const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
 
   struct Geo {
-    int f, x0, y0, ncol, nrow, vr0, nvr, cb, ng, k0, np, ubase;
+    int f, x0, y0, ncol, nrow, vr0, nvr, cb, ng, k0, np, ybase, ubase;  // cb: first converted column; ybase / ubase: first staged luma column / chroma byte
+    uint32_t ng_magic;  // ceil(2^32 / ng): i / ng = umulhi(i, magic) for the unit indices of a tile (i < 2^16)
   };
-  auto geometry = [&](long long t) -> Geo {
+  auto geometry = [&](int t) -> Geo {
     Geo g;
-    g.f = (int)(t / tiles_per_frame);
-    const int r = (int)(t - (long long)g.f * tiles_per_frame);
+    g.f = t / tiles_per_frame;
+    const int r = t - g.f * tiles_per_frame;
     const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
     g.x0 = tx * F4_TW; g.y0 = ty * F4_TH;
     const int x1 = min(g.x0 + F4_TW, P.dw), y1 = min(g.y0 + F4_TH, P.dh);
     g.ncol = x1 - g.x0; g.nrow = y1 - g.y0;
-    const int vc0 = __ldg(P.fx_first + g.x0), vc1 = __ldg(P.fx_first + x1 - 1) + P.fx_taps - 1;
-    g.vr0 = __ldg(P.fy_first + g.y0);
-    const int vr1 = __ldg(P.fy_first + y1 - 1) + P.fy_taps - 1;
+    const int2 tc = s_tcol[tx], trw = s_trow[ty];
+    const int vc0 = tc.x, vc1 = tc.y, vr1 = trw.y;
+    g.vr0 = trw.x;
     g.nvr = vr1 - g.vr0 + 1;
     g.cb = vc0 & ~3;
     g.ng = (((vc1 | 3) + 1) - g.cb) >> 2;
     g.k0 = (g.vr0 + 1) >> 1;
     g.np = ((vr1 + 1) >> 1) - g.k0 + 1;
     g.ubase = g.cb == 0 ? 0 : (((g.cb >> 1) - 1) & ~3);
+    g.ybase = g.cb;
+    if (P.vec16) { g.ybase &= ~15; g.ubase &= ~15; }  // the staged rectangle starts on a 16-byte boundary of the planes
+    g.ng_magic = 0xFFFFFFFFu / (uint32_t)g.ng + 1u;  // = ceil(2^32 / ng) for ng > 1
     return g;
   };
   // cp.async of the raw words of tile t: luma rows 2 k0 - 1 .. 2 k1 (clamped to the frame), chroma rows k0 - 1 .. k1, the first V
   // sample of every chroma row (the reference's never-advanced last_v2, colourspace.c:3544)
-  auto stage = [&](const Geo &g) {
+  auto stage = [&](const Geo &g, int buf) {
     const uint8_t *Fy = P.y[g.f], *Fu = P.u[g.f], *Fv = P.v[g.f];
     const int rowbase = 2 * g.k0 - 1;
-    for (int i = tid; i < 2 * g.np * g.ng; i += F4_NT) {
-      const int ri = i / g.ng, w = i - ri * g.ng;
-      const int sr = min(max(rowbase + ri, 0), P.fh - 1);
-      f4_cp_async4(sbase + P.o_rawy + ri * (GW * 4) + 4 * w, Fy + (size_t)P.rs_y * sr + g.cb + 4 * w);
+    const long long ulim = (long long)P.rs_u * P.ch, vlim = (long long)P.rs_v * P.ch;
+    if (P.vec16) {
+      // a warp = one row at a time, a lane = one 16-byte chunk of it (rows are <= 13 / 8 chunks: few lanes, but no index arithmetic)
+      const int nchy = (g.cb - g.ybase + 4 * g.ng + 15) >> 4;
+      for (int ri = warp; ri < 2 * g.np; ri += F4_NW) {
+        const int sr = min(max(rowbase + ri, 0), P.fh - 1);
+        if (lane < nchy) f4_cp_async16(sbase + O_RAWY + ri * (GW * 4) + 16 * lane, Fy + (size_t)P.rs_y * sr + g.ybase + 16 * lane);
+      }
+      for (int ri = warp; ri <= g.np; ri += F4_NW) {
+        const int cr = min(max(g.k0 - 1 + ri, 0), P.ch - 1);
+        const int w = lane & 7;
+        if (lane < 16 && 16 * w < 2 * g.ng + 21) {  // lanes 0 .. 7: U, 8 .. 15: V (a row pair's last unit reads up to byte 2 ng + 20 of the staged row)
+          const bool isv = lane >= 8;
+          const long long o = min((long long)(isv ? P.rs_v : P.rs_u) * cr + g.ubase + 16 * w, (isv ? vlim : ulim) - 16);
+          f4_cp_async16(sbase + (isv ? O_RAWV : O_RAWU) + ri * CWB + 16 * w, (isv ? Fv : Fu) + o);
+        }
+        if (lane == 16) f4_cp_async4(sbase + O_VF + 4 * ri, Fv + (size_t)P.rs_v * cr);
+      }
+    } else {
+      for (int i = tid; i < 2 * g.np * g.ng; i += F4_NT) {
+        const int ri = g.ng == 1 ? i : (int)__umulhi((uint32_t)i, g.ng_magic), w = i - ri * g.ng;
+        const int sr = min(max(rowbase + ri, 0), P.fh - 1);
+        f4_cp_async4(sbase + O_RAWY + ri * (GW * 4) + 4 * w, Fy + (size_t)P.rs_y * sr + g.ybase + 4 * w);
+      }
+      const int cww = g.ng / 2 + 3;
+      for (int i = tid; i < (g.np + 1) * cww; i += F4_NT) {
+        const int ri = i / cww, w = i - ri * cww;
+        const int cr = min(max(g.k0 - 1 + ri, 0), P.ch - 1);
+        const long long ou = min((long long)P.rs_u * cr + g.ubase + 4 * w, ulim - 4), ov = min((long long)P.rs_v * cr + g.ubase + 4 * w, vlim - 4);
+        f4_cp_async4(sbase + O_RAWU + ri * CWB + 4 * w, Fu + ou);
+        f4_cp_async4(sbase + O_RAWV + ri * CWB + 4 * w, Fv + ov);
+      }
+      for (int i = tid; i <= g.np; i += F4_NT) {
+        const int cr = min(max(g.k0 - 1 + i, 0), P.ch - 1);
+        f4_cp_async4(sbase + O_VF + 4 * i, Fv + (size_t)P.rs_v * cr);
+      }
     }
-    const long long ulim = (long long)P.rs_u * P.ch - 4, vlim = (long long)P.rs_v * P.ch - 4;
-    for (int i = tid; i < (g.np + 1) * P.CWW; i += F4_NT) {
-      const int ri = i / P.CWW, w = i - ri * P.CWW;
-      const int cr = min(max(g.k0 - 1 + ri, 0), P.ch - 1);
-      const long long ou = min((long long)P.rs_u * cr + g.ubase + 4 * w, ulim), ov = min((long long)P.rs_v * cr + g.ubase + 4 * w, vlim);
-      f4_cp_async4(sbase + P.o_rawu + ri * CWB + 4 * w, Fu + ou);
-      f4_cp_async4(sbase + P.o_rawv + ri * CWB + 4 * w, Fv + ov);
-    }
-    for (int i = tid; i <= g.np; i += F4_NT) {
-      const int cr = min(max(g.k0 - 1 + i, 0), P.ch - 1);
-      f4_cp_async4(sbase + P.o_vf + 4 * i, Fv + (size_t)P.rs_v * cr);
-    }
+    // the filter rows of the tile (their 16-byte entries are aligned: cudaMalloc'ed arrays, x0 / y0 multiples of the tile size)
+    if (tid < g.ncol) f4_cp_async16(sbase + O_CX + (buf * F4_TW + tid) * 16, P.px + g.x0 + tid);
+    else if (tid >= 256 && tid - 256 < g.nrow) f4_cp_async16(sbase + O_PY + (buf * F4_TH + tid - 256) * 16, P.py + g.y0 + tid - 256);
     f4_cp_async_commit();
   };
 
@@ -207,43 +254,25 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     b = (yy + (int)tu.y) >> 16;
   };
 
-  long long t = blockIdx.x;
+  int t = blockIdx.x;
   if (t >= total) return;
   Geo G = geometry(t);
-  stage(G);
-  for (; t < total; t += gridDim.x) {
+  int buf = 0;
+  stage(G, buf);
+  for (; t < total; t += gridDim.x, buf ^= 1) {
     f4_cp_async_wait_all();
     __syncthreads();  // raw words of this tile have landed; the previous tile's passes are done with the planes, the intermediate and the filter rows
     const Geo g = G;
     const int rowbase = 2 * g.k0 - 1;
-    // ---- filter data of the tile (read by passes 2 and 3, behind the next barrier)
-    for (int i = tid; i < g.ncol; i += F4_NT) {
-      uint32_t c[4] = {0, 0, 0, 0};
-      int sum = 0;
-      for (int k = 0; k < P.fx_taps; k++) {
-        const int cf = P.fx_coef[(size_t)(g.x0 + i) * P.fx_taps + k];
-        c[k] = (uint16_t)cf;
-        sum += cf;
-      }
-      s_cx[i] = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
-      s_fx[i] = __ldg(P.fx_first + g.x0 + i) - g.cb;
-      s_ax[i] = min((sum * 255) >> 7, 32767);  // the horizontal pass on an all-255 alpha row
-    }
-    for (int i = tid; i < g.nrow; i += F4_NT) {
-      int c[4] = {0, 0, 0, 0}, sum = 0;
-      for (int k = 0; k < P.fy_taps; k++) { c[k] = P.fy_coef[(size_t)(g.y0 + i) * P.fy_taps + k]; sum += c[k]; }
-      s_cy[i] = make_int4(c[0], c[1], c[2], c[3]);
-      s_fy[i] = __ldg(P.fy_first + g.y0 + i) - g.vr0;
-      s_sy[i] = sum;
-    }
+    const int4 *const s_px = reinterpret_cast<const int4 *>(smem + O_CX) + buf * F4_TW, *const s_py = reinterpret_cast<const int4 *>(smem + O_PY) + buf * F4_TH;
     // ---- 1. conversion: unit = (row pair p, 4-column group gi) -> rows 2p, 2p + 1 of the three planes
     for (int i = tid; i < g.np * g.ng; i += F4_NT) {
-      const int p = i / g.ng, gi = i - p * g.ng;
+      const int p = g.ng == 1 ? i : (int)__umulhi((uint32_t)i, g.ng_magic), gi = i - p * g.ng;  // (ceil(2^32 / 1) does not fit the magic)
       const int k = g.k0 + p, x = g.cb + 4 * gi;
       uint32_t oA[3], oB[3];
       if (k >= 1 && k <= P.k_fast_max) {
-        const uint32_t yA = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p) * (GW * 4) + 4 * gi);
-        const uint32_t yB = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p + 1) * (GW * 4) + 4 * gi);
+        const uint32_t yA = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p) * (GW * 4) + (x - g.ybase));
+        const uint32_t yB = *reinterpret_cast<const uint32_t *>(s_rawy + (2 * p + 1) * (GW * 4) + (x - g.ybase));
         const int jc0 = x >> 1, o = jc0 - 1;
         const int off0 = x == 0 ? 0 : (o & ~3);
         const uint32_t sel = x == 0 ? 0x2100u : ((o & 3) == 3 ? 0x6543u : 0x4321u);
@@ -313,17 +342,17 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        uint8_t *pl = s_pl + c * P.pl_plane + 4 * gi;
-        *reinterpret_cast<uint32_t *>(pl + (2 * p) * P.pl_stride) = oA[c];
-        *reinterpret_cast<uint32_t *>(pl + (2 * p + 1) * P.pl_stride) = oB[c];
+        uint8_t *pl = s_pl + c * F4_PLP + 4 * gi;
+        *reinterpret_cast<uint32_t *>(pl + (2 * p) * F4_PLS) = oA[c];
+        *reinterpret_cast<uint32_t *>(pl + (2 * p + 1) * F4_PLS) = oB[c];
       }
     }
     __syncthreads();
     // the raw buffers are free again: bring in the next tile's words while passes 2 and 3 run
-    const long long tn = t + gridDim.x;
+    const int tn = t + (int)gridDim.x;
     if (tn < total) {
       G = geometry(tn);
-      stage(G);
+      stage(G, buf ^ 1);
     }
     // ---- 2. horizontal pass: warp = one source row at a time, lane = output columns lane, lane + 32, lane + 64, lane + 96
     {
@@ -333,15 +362,16 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
       for (int j = 0; j < 4; j++) {
         const int xo = lane + 32 * j;
         const bool ok = xo < g.ncol;
-        cf[j] = ok ? s_cx[xo] : make_uint2(0u, 0u);
-        fo[j] = ok ? s_fx[xo] : 0;
+        const int4 e = ok ? s_px[xo] : make_int4(0, 0, g.cb, 0);
+        cf[j] = make_uint2((uint32_t)e.x, (uint32_t)e.y);
+        fo[j] = e.z - g.cb;
       }
       for (int tr = warp; tr < g.nvr; tr += F4_NW) {
         const int pr = g.vr0 + tr - rowbase;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const uint8_t *row = s_pl + c * P.pl_plane + pr * P.pl_stride;
-          uint16_t *trow = s_tmp + c * P.tmp_plane + tr * F4_TW;
+          const uint8_t *row = s_pl + c * F4_PLP + pr * F4_PLS;
+          uint16_t *trow = s_tmp + c * F4_TMP + tr * F4_TW;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const uint32_t *q = reinterpret_cast<const uint32_t *>(row) + (fo[j] >> 2);
@@ -355,8 +385,9 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     __syncthreads();
     // ---- 3. vertical pass: warp = one output row at a time
     for (int yo = warp; yo < g.nrow; yo += F4_NW) {
-      const int4 cy = s_cy[yo];
-      const int tr0 = s_fy[yo], sy = s_sy[yo];
+      const int4 ey = s_py[yo];
+      const int4 cy = make_int4(ey.x & 0xFFFF, (int)((uint32_t)ey.x >> 16), ey.y & 0xFFFF, (int)((uint32_t)ey.y >> 16));
+      const int tr0 = ey.z - g.vr0, sy = ey.w;
       uint8_t *drow = P.dst[g.f] + (size_t)P.drs * (g.y0 + yo) + (size_t)g.x0 * 4;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -365,10 +396,10 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
         int acc[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const uint16_t *tp = s_tmp + c * P.tmp_plane + tr0 * F4_TW + xo;
+          const uint16_t *tp = s_tmp + c * F4_TMP + tr0 * F4_TW + xo;
           acc[c] = ((1 << 18) + cy.x * (int)tp[0] + cy.y * (int)tp[F4_TW] + cy.z * (int)tp[2 * F4_TW] + cy.w * (int)tp[3 * F4_TW]) >> 19;
         }
-        const int al = ((1 << 18) + sy * s_ax[xo]) >> 19;
+        const int al = ((1 << 18) + sy * s_px[xo].w) >> 19;
         const int c0 = P.swap_rb ? acc[2] : acc[0], c2 = P.swap_rb ? acc[0] : acc[2];
         // bytes c0, G, c2, A
         const uint32_t px = f4_pack_sat(acc[1], c0, 0u) | (f4_pack_sat(al, c2, 0u) << 16);
@@ -401,8 +432,8 @@ bool cvt_resize_supported(const YuvToRgbArgs &a, int dw, int dh, int drs, const 
 }
 
 // frames: n conversions of the same shape (yuv_planar_same_shape), dsts[i] the resized destination of frames[i]
-cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, DevFilter fx,
-                              DevFilter fy, const ResizeFilter &hx, const ResizeFilter &hy) {
+cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8_t *const *dsts, int n, int dw, int dh, int drs, const void *px_dev,
+                              const void *py_dev, const ResizeFilter &hx, const ResizeFilter &hy) {
   const YuvToRgbArgs &a0 = frames[0];
   CvtRszParams P;
   memset(&P, 0, sizeof(P));
@@ -410,48 +441,30 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
   P.rs_y = a0.src.rs_y; P.rs_u = a0.src.rs_u; P.rs_v = a0.src.rs_v;
   P.dw = dw; P.dh = dh; P.drs = drs;
   P.tiles_x = (dw + F4_TW - 1) / F4_TW; P.tiles_y = (dh + F4_TH - 1) / F4_TH;
-  P.fx_first = fx.first; P.fx_coef = fx.coef; P.fx_taps = fx.taps;
-  P.fy_first = fy.first; P.fy_coef = fy.coef; P.fy_taps = fy.taps;
+  P.px = reinterpret_cast<const int4 *>(px_dev); P.py = reinterpret_cast<const int4 *>(py_dev);
+  P.fx_taps = hx.taps; P.fy_taps = hy.taps;
+  if (P.tiles_x > F4_MAXTX || P.tiles_y > F4_MAXTY) return cudaErrorInvalidConfiguration;
   P.conv = a0.conv.t;
   P.swap_rb = a0.out.r == 2;
   const bool last_row_unsafe = a0.src.rs_u < a0.src.cw + 4 || a0.src.rs_v < a0.src.cw + 4;
   P.k_fast_max = a0.src.ch - 1 - (last_row_unsafe ? 1 : 0);
-  // per-tile maxima
-  int GW = 1, PR = 1, TR = 1;
+  // per-tile maxima against the kernel's compile-time buffers
   for (int x0 = 0; x0 < dw; x0 += F4_TW) {
     const int x1 = (x0 + F4_TW < dw ? x0 + F4_TW : dw) - 1;
     const int vc0 = hx.first[x0], vc1 = hx.first[x1] + hx.taps - 1;
-    const int ng = (((vc1 | 3) + 1) - (vc0 & ~3)) >> 2;
-    if (ng > GW) GW = ng;
+    if (((((vc1 | 3) + 1) - (vc0 & ~3)) >> 2) > F4_NG) return cudaErrorInvalidConfiguration;  // the caller runs the unfused pair
   }
   for (int y0 = 0; y0 < dh; y0 += F4_TH) {
     const int y1 = (y0 + F4_TH < dh ? y0 + F4_TH : dh) - 1;
     const int vr0 = hy.first[y0], vr1 = hy.first[y1] + hy.taps - 1;
-    const int np = ((vr1 + 1) >> 1) - ((vr0 + 1) >> 1) + 1;
-    if (np > PR) PR = np;
-    if (vr1 - vr0 + 1 > TR) TR = vr1 - vr0 + 1;
+    if (((vr1 + 1) >> 1) - ((vr0 + 1) >> 1) + 1 > F4_PR || vr1 - vr0 + 1 > F4_TR) return cudaErrorInvalidConfiguration;
   }
-  P.GW = GW; P.PR = PR; P.TR = TR;
-  P.CWW = GW / 2 + 3;
-  auto al16 = [](int v) { return (v + 15) & ~15; };
-  int off = F4_DYN;
-  P.o_rawy = off; off = al16(off + 2 * PR * GW * 4);
-  P.o_rawu = off; off = al16(off + (PR + 1) * P.CWW * 4);
-  P.o_rawv = off; off = al16(off + (PR + 1) * P.CWW * 4);
-  P.o_vf = off; off = al16(off + (PR + 1) * 4);
-  P.pl_stride = (GW + 1) * 4;
-  P.pl_plane = al16(2 * PR * P.pl_stride);
-  P.o_pl = off; off += 3 * P.pl_plane;
-  P.tmp_plane = (TR + 3) * F4_TW;
-  P.o_tmp = off; off = al16(off + 3 * P.tmp_plane * 2);
-  P.o_cx = off; off += F4_TW * 8;
-  P.o_fx = off; off += F4_TW * 4;
-  P.o_ax = off; off += F4_TW * 4;
-  P.o_cy = off; off += F4_TH * 16;
-  P.o_fy = off; off += F4_TH * 4;
-  P.o_sy = off; off += F4_TH * 4;
-  const int smem_bytes = off;
-  if (smem_bytes > F4_SMEM_MAX) return cudaErrorInvalidConfiguration;  // scale factor too large for one tile: the caller runs the unfused pair
+  if ((long long)P.tiles_x * P.tiles_y * F4_MAXF >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+  P.vec16 = !((a0.src.rs_y | a0.src.rs_u | a0.src.rs_v) & 15);
+  for (int i = 0; i < n && P.vec16; i++)
+    P.vec16 = !((reinterpret_cast<uintptr_t>(frames[i].src.y) | reinterpret_cast<uintptr_t>(frames[i].src.u) | reinterpret_cast<uintptr_t>(frames[i].src.v)) & 15);
+  if (getenv("PE_F4_NOVEC")) P.vec16 = 0;
+  const int smem_bytes = F4_SMEM;
   static PerDevice attr_set;
   if (!attr_set.cur()) {
     cudaError_t e;
