@@ -38,10 +38,11 @@
 #include <weed/weed-utils.h>
 #include <weed/weed-host-utils.h>
 
-#define MH_MAX 16
+#define MH_MAX 64
 
 typedef struct {
   void *dl;
+  char path[512];
   weed_plant_t *plugin_info;
   weed_plant_t **filters;
   int nfilters;
@@ -60,6 +61,8 @@ int mh_open(const char *path) {
   int h;
   weed_setup_f setup_fn;
   mh_init_once();
+  /* a plugin is set up once per process: opening the same path again returns its handle */
+  for (h = 0; h < MH_MAX; h++) if (mh_tab[h].dl && !strcmp(mh_tab[h].path, path)) return h;
   for (h = 0; h < MH_MAX; h++) if (!mh_tab[h].dl) break;
   if (h == MH_MAX) return -1;
   mh_tab[h].dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -69,6 +72,7 @@ int mh_open(const char *path) {
   mh_tab[h].plugin_info = (*setup_fn)(weed_bootstrap);
   if (!mh_tab[h].plugin_info) { dlclose(mh_tab[h].dl); mh_tab[h].dl = NULL; return -4; }
   mh_tab[h].filters = weed_get_plantptr_array_counted(mh_tab[h].plugin_info, WEED_LEAF_FILTERS, &mh_tab[h].nfilters);
+  strncpy(mh_tab[h].path, path, sizeof(mh_tab[h].path) - 1);
   return h;
 }
 
