@@ -250,7 +250,10 @@ static int engine_init(pe_engine *e) {
         ext[256 + 3 * kExtN + n] = ct.t[B_CB][c];
       }
       PE_CUDA(cudaMalloc(&e->conv_dev[cl][hd], sizeof(int32_t) * host.size()));
-      PE_CUDA(cudaMemcpy(e->conv_dev[cl][hd], host.data(), sizeof(int32_t) * host.size(), cudaMemcpyHostToDevice));
+      // (on the engine stream: a synchronous cudaMemcpy from pageable memory returns once the bytes are staged, the DMA itself is
+      // ordered on the legacy stream only, and the engine's stream is non-blocking -- a kernel could read the table before it lands)
+      PE_CUDA(cudaMemcpyAsync(e->conv_dev[cl][hd], host.data(), sizeof(int32_t) * host.size(), cudaMemcpyHostToDevice, e->stream));
+      PE_CUDA(cudaStreamSynchronize(e->stream));
     }
   }
   {
@@ -1644,7 +1647,9 @@ extern "C" int pe_convert_yuv888_to_rgb_float(pe_engine_t *e, pe_frame_t *f, int
     float t[5][256];
     build_float_yuv_tables(ci ? PE_YUV_CLAMPING_UNCLAMPED : PE_YUV_CLAMPING_CLAMPED, t);
     float *d = nullptr;
-    if (cudaMalloc(&d, sizeof(t)) != cudaSuccess || cudaMemcpy(d, t, sizeof(t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    // stream-ordered upload (see conv_dev in pe_engine_create: a synchronous copy from the stack is not ordered with e->stream)
+    if (cudaMalloc(&d, sizeof(t)) != cudaSuccess || cudaMemcpyAsync(d, t, sizeof(t), cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaStreamSynchronize(e->stream) != cudaSuccess) {
       if (d) cudaFree(d);
       set_err(PE_ERR_CUDA, "float table upload failed");
       return PE_FALSE;
@@ -2546,7 +2551,8 @@ extern "C" int pe_fx_dissolve_mask_create(pe_engine_t *e, int width, int height,
   PE_CUDA(cudaSetDevice(e->device));
   float *dev = nullptr;
   PE_CUDA(cudaMalloc(&dev, n * sizeof(float)));
-  cudaError_t ce = cudaMemcpy(dev, host.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+  cudaError_t ce = cudaMemcpyAsync(dev, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   if (ce != cudaSuccess) { cudaFree(dev); return set_err(PE_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(ce)); }
   *out = new pe_dissolve_mask{e, dev, width, height};
   return PE_OK;

@@ -92,7 +92,8 @@ def test_cuda_float_path_is_bit_exact_every_triple(mode, cl):
     got = lay.to_host()[0][:, :w * 3].reshape(-1, 3)
     exp, se = np.zeros_like(yuv), np.zeros((len(yuv), 3), np.float32)
     o.pe_or_yuv2rgb_float(mode, cl, T.ptr(_rgb_y(o, cl)), T.ptr(yuv), T.ptr(exp), T.ptr(se), len(yuv))
-    assert (got == exp).all()
+    bad = np.flatnonzero((got != exp).any(axis=1))
+    assert bad.size == 0, "%d triples differ, first (Y, U, V) = %s: got %s, oracle %s" % (bad.size, yuv[bad[0]], got[bad[0]], exp[bad[0]])
     ulp = np.abs(sums.reshape(-1, 3).view(np.int32).astype(np.int64) - se.view(np.int32).astype(np.int64))
     assert ulp.max() == 0, "float sums differ by up to %d ULP" % ulp.max()
     eng.close()
