@@ -47,33 +47,31 @@ namespace {
 constexpr int F3_NT = PE_F3_NT;         // threads per CTA (one CTA per SM).  Measured: 512 (128 regs) 46.6k fps, 640 (96 regs) 42.7k, 768 (80 regs) 36.8k
 constexpr int F3_NW = F3_NT / 32;
 constexpr int F3_MAXF = 32;               // frames per launch (their pointers travel as kernel parameters)
-// RGB_Y and the gamma LUT share one [256][2][32] region (entry stride 256 bytes), so that a lookup offset is
-// (value << 8) | lane * 4 -- one LOP3 on the word that already holds the byte at bits 8..15, no PRMT + IMAD
-// (measured: 49.7k vs 49.0k fps with separate 128-byte-stride tables, -DPE_F3_SEPARATE_TABLES)
-#ifndef PE_F3_SEPARATE_TABLES
-#define PE_F3_INTERLEAVE 1
-#endif
-#ifdef PE_F3_INTERLEAVE
-constexpr int S3_TV = 0;                  // uint2 [256][16]: {R_Cr, G_Cr}
-constexpr int S3_TU = 32768;              // uint2 [256][16]: {G_Cb, B_Cb}
-constexpr int S3_LUT = 65536;             // u32 [256][64]: words 0..31 of an entry = the gamma LUT copies ...
-constexpr int S3_TY = 65536 + 128;        //                words 32..63 = the RGB_Y copies
-constexpr int S3_TYSTRIDE = 256;
-#else
-constexpr int S3_TY = 0;                  // u32 [256][32]
-constexpr int S3_TYSTRIDE = 128;
-constexpr int S3_TV = 32768;              // uint2 [256][16]: {R_Cr, G_Cr}
-constexpr int S3_TU = 65536;              // uint2 [256][16]: {G_Cb, B_Cb}
-constexpr int S3_LUT = 98304;             // u32 [256][32]
-#endif
-constexpr int S3_RING = 131072;           // per warp: F3_RING bg rows of 512 bytes, filled by cp.async ahead of the emit
+// Shared-memory layout, as ABSOLUTE addresses of the CTA's shared window (dynamic shared memory starts at 0x400 on sm_100: the
+// first KB is the system's; the kernel traps if it does not).  Every table region starts at a multiple of its own size, so a
+// lookup address is ONE LOP3 / PRMT -- (index bits) | (region base | the lane's bank offset) -- with no add and no base register:
+//   0x08000  uint2 [256][16]  {R_Cr, G_Cr}                 entry stride 128: index bits 7..14
+//   0x10000  u32   [256][64]  words 0..31 of an entry = the gamma LUT copies, words 32..63 = the RGB_Y copies
+//                             (entry stride 256: the index is byte 1 of the address -- RGB_Y straight from the luma word with one
+//                             PRMT, the LUT from the blended 16-bit value with one LOP3)
+//   0x20000  uint2 [256][16]  {G_Cb, B_Cb}
+//   0x28000  per warp: F3_RING bg rows of 512 bytes, filled by cp.async ahead of the emit (2 KB-aligned per warp: slot | base)
+//   then     int4 per inner output row (+ 1): first source row, c3 | c2 << 16, c1 | c0 << 16, 0; then the TMA variant's mbarriers
+// (measured with separate, 128-byte-stride RGB_Y / LUT tables: 49.0k vs 49.7k fps)
+constexpr uint32_t A_DYN = 0x400u;        // where dynamic shared memory starts
+constexpr uint32_t A_TV = 0x8000u;
+constexpr uint32_t A_LUT = 0x10000u;
+constexpr uint32_t A_TY = 0x10080u;
+constexpr uint32_t A_TU = 0x20000u;
+constexpr uint32_t A_RING = 0x28000u;
 #ifndef PE_F3_RING
 #define PE_F3_RING 4
 #endif
 constexpr int F3_RING = PE_F3_RING;      // power of two
-constexpr int S3_BYTES = S3_RING + F3_NW * F3_RING * 512;   // + 16 bytes per inner output row (filter rows)
+constexpr uint32_t A_ROWS = A_RING + F3_NW * F3_RING * 512;
 constexpr int F3_SMEM_MAX = 227 * 1024;   // opt-in limit of dynamic shared memory per CTA on sm_100
-constexpr int F3_MAX_IH = (F3_SMEM_MAX - S3_BYTES - 8 * F3_NW * F3_RING) / 16 < 3200 ? (F3_SMEM_MAX - S3_BYTES - 8 * F3_NW * F3_RING) / 16 : 3200;
+constexpr int F3_MAX_IH = ((int)A_DYN + F3_SMEM_MAX - (int)A_ROWS - 8 * F3_NW * F3_RING) / 16 - 1;
+__host__ __device__ constexpr int f3_smem_bytes(int ih) { return (int)(A_ROWS - A_DYN) + 16 * (ih + 1) + 8 * F3_NW * F3_RING; }
 #ifndef PE_F3_TMA_DEFAULT
 #define PE_F3_TMA_DEFAULT 0
 #endif
@@ -96,6 +94,8 @@ struct Fused3Params {
   long long frame_cost, total_cost, static_cost, chunk_cost;
   unsigned int *sched;                     // [2] device counters, zero between launches
   uint32_t ka, kia;                        // blend weights of fg / bg, sum 256
+  int spread;                              // share numbering, see the kernel
+  uint32_t zero;                           // 0 (orders the loads of the marching loop, see step())
   const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0 (coefficients x 16 under C16)
   const int32_t *conv;                     // [14][256] (ConvTab order)
   const uint8_t *lut8;                     // optional
@@ -160,6 +160,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ int4 lds128_ro(uint32_t a) {   // read-only after the kernel's barrier (filter rows)
+  int4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 // chroma words are read by the lanes of two neighbouring strips (one sector of overlap on each side): plain read-only loads,
 // so that L2 keeps the shared sectors until the neighbour has asked for them (the streaming hint marks them evict-first)
 __device__ __forceinline__ uint32_t ld_keep_u32(const void *p) {
@@ -173,14 +178,8 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
   return r;
 }
 
-// luma byte `col` of a word as the RGB_Y table index: the byte value, or (PE_F3_INTERLEAVE) the value already shifted to bits 8..15
-__device__ __forceinline__ uint32_t ysel(uint32_t w, int col) {
-#ifdef PE_F3_INTERLEAVE
-  return col == 0 ? (w << 8) & 0xFF00u : col == 1 ? w & 0xFF00u : col == 2 ? (w >> 8) & 0xFF00u : (w >> 16) & 0xFF00u;
-#else
-  return byte_of(w, col);
-#endif
-}
+// address of the lane's RGB_Y copy for luma byte `col` of word w: the byte becomes byte 1 of tyl = A_TY | 4 * lane (one PRMT)
+__device__ __forceinline__ uint32_t yaddr(uint32_t w, int col, uint32_t tyl) { return __byte_perm(w, tyl, 0x7604u | ((uint32_t)col << 4)); }
 
 // acc >> 12 of the vertical filter.  PE_F3_SHR12_IMAD: as a multiply-high on the FMA-heavy pipe instead of a shift on the ALU pipe
 __device__ __forceinline__ uint32_t shr12(uint32_t x) {
@@ -201,13 +200,21 @@ constexpr uint32_t K3 = 0x00030003u;    // + 3 in both halves (Q = 2 n + 3)
 // and (2 n + 3) / 6 is never closer than 1 / 6 to an integer, so the floor is exact.
 // The kernel wants the table offset 128 * m: with the multiplier scaled by 128 the product is floor(128 * m_real), whose bits
 // 7.. are 128 * floor(m_real) (the bits below are masked off together with the OR of the lane's column offset).
-__device__ __forceinline__ uint32_t idx_hi(uint32_t q) { return __umulhi(q, 10923u * 128u) & 0x7F80u; }
-__device__ __forceinline__ uint32_t idx_lo(uint32_t q) { return __umulhi(q << 16, 10923u * 128u) & 0x7F80u; }
+// (tl = region base | 8 * (lane & 15): the OR with the lane's bank pair and the mask are one LOP3)
+__device__ __forceinline__ uint32_t idx_hi(uint32_t q, uint32_t tl) { return (__umulhi(q, 10923u * 128u) & 0x7F80u) | tl; }
+__device__ __forceinline__ uint32_t idx_lo(uint32_t q, uint32_t tl) { return (__umulhi(q << 16, 10923u * 128u) & 0x7F80u) | tl; }
 
 // the three 'this / last / next' views of one chroma row for the lane's two chroma columns jc0, jc0 + 1, as 16-bit halves
 struct RowC {
   uint32_t a, b, c;  // a = [c(jc0), c(jc0+1)], b = [c(jc0-1), c(jc0)], c = [c(jc0+1), c(jc0+2)]
 };
+__device__ __forceinline__ RowC unpack_cw4(uint32_t cw4) {   // cw4 bytes: columns jc0-1, jc0, jc0+1, jc0+2
+  RowC r;
+  r.a = __byte_perm(cw4, 0u, 0x4241u);
+  r.b = __byte_perm(cw4, 0u, 0x4140u);
+  r.c = __byte_perm(cw4, 0u, 0x4342u);
+  return r;
+}
 __device__ __forceinline__ RowC unpack_row(uint32_t w0, uint32_t w1, uint32_t sel) {
   const uint32_t cw4 = __byte_perm(w0, w1, sel);  // bytes: columns jc0-1, jc0, jc0+1, jc0+2
   RowC r;
@@ -233,7 +240,6 @@ struct Lane {
   // per-lane constants of the current segment
   const uint8_t *yp, *up0, *vp0, *vfp;
   uint32_t sel, selB;
-  uint32_t tyl, tul, tvl, lutl;
   int x;
 };
 
@@ -253,14 +259,14 @@ struct SlowRows {
   uint32_t ab[12];
 };
 template <bool QUIRKS>
-__device__ __noinline__ SlowRows slow_rows(const uint8_t *smem, const uint8_t *py, const uint8_t *pu, const uint8_t *pv, uint32_t rs_y,
+__device__ __noinline__ SlowRows slow_rows(const uint8_t *py, const uint8_t *pu, const uint8_t *pv, uint32_t rs_y,
                                            uint32_t rs_u, uint32_t rs_v, int x0, int k, int fh, int cw, int ch, int lane) {
   const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
   int rA[12], rB[12];
   auto rgb = [&](uint32_t y, uint32_t mu, uint32_t mv, int &r, int &g, int &b) {   // y: byte value, mu / mv: table indices
-    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S3_TY + (y * (uint32_t)S3_TYSTRIDE + lane4));
-    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (mv * 128u + lane8));
-    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (mu * 128u + lane8));
+    const int yy = (int)lds32(A_TY + (y * 256u + lane4));
+    const uint2 tv = lds64(A_TV + (mv * 128u + lane8));
+    const uint2 tu = lds64(A_TU + (mu * 128u + lane8));
     r = (yy + (int)tv.x) >> 16; g = (yy + (int)tu.x + (int)tv.y) >> 16; b = (yy + (int)tu.y) >> 16;
   };
   auto single = [&](int row, int cr) {
@@ -315,11 +321,11 @@ template <bool QUIRKS, bool HAS_LUT, bool C16, bool TMA>
 __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  if ((uint32_t)__cvta_generic_to_shared(smem) != A_DYN) __trap();   // the absolute layout above assumes it
+  uint8_t *const sm0 = smem - A_DYN;   // sm0 + absolute address = generic pointer (table fill only)
 
   // ---- replicated tables
   {
-#ifdef PE_F3_INTERLEAVE
     // 16 consecutive lanes write the 16 x 16-byte chunks of one 256-byte {LUT | RGB_Y} entry, 8 lanes the chunks of a 128-byte
     // chroma entry: a warp's 128-bit store covers 512 contiguous bytes = 4 wavefronts, the minimum.  (A thread per entry writing
     // its 128 bytes alone is a 32-way bank conflict per store: 4.4 us per launch, profiles/r02c_k_fused3_single_frame_ncu.txt.)
@@ -328,58 +334,42 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       uint32_t e;
       if (j < 8) e = HAS_LUT ? ((uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u) : 0u;
       else e = (uint32_t)P.conv[9 * 256 + m];
-      reinterpret_cast<uint4 *>(smem + S3_LUT + 256 * m)[j] = make_uint4(e, e, e, e);
+      reinterpret_cast<uint4 *>(sm0 + A_LUT + 256 * m)[j] = make_uint4(e, e, e, e);
     }
     for (int i = tid; i < 256 * 8; i += F3_NT) {
       const int m = i >> 3, j = i & 7;
       const uint32_t rcr = (uint32_t)P.conv[10 * 256 + m], gcb = (uint32_t)P.conv[11 * 256 + m], gcr = (uint32_t)P.conv[12 * 256 + m],
                      bcb = (uint32_t)P.conv[13 * 256 + m];
-      reinterpret_cast<uint4 *>(smem + S3_TV + 128 * m)[j] = make_uint4(rcr, gcr, rcr, gcr);
-      reinterpret_cast<uint4 *>(smem + S3_TU + 128 * m)[j] = make_uint4(gcb, bcb, gcb, bcb);
+      reinterpret_cast<uint4 *>(sm0 + A_TV + 128 * m)[j] = make_uint4(rcr, gcr, rcr, gcr);
+      reinterpret_cast<uint4 *>(sm0 + A_TU + 128 * m)[j] = make_uint4(gcb, bcb, gcb, bcb);
     }
-#else
-    uint32_t *tl = reinterpret_cast<uint32_t *>(smem + S3_LUT);
-    fill_replicated_yuv_tables(smem + S3_TY, smem + S3_TV, smem + S3_TU, P.conv, tid, F3_NT, S3_TYSTRIDE);
-    if (HAS_LUT)
-      for (int m = tid; m < 256; m += F3_NT) {
-        const uint32_t e = (uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) reinterpret_cast<uint4 *>(tl + (S3_TYSTRIDE / 4) * m)[j] = make_uint4(e, e, e, e);
-      }
-#endif
-    int4 *sr = reinterpret_cast<int4 *>(smem + S3_BYTES);
-    for (int i = tid; i < P.ih; i += F3_NT) sr[i] = P.rows4[i];
+    int4 *sr = reinterpret_cast<int4 *>(sm0 + A_ROWS);
+    for (int i = tid; i <= P.ih; i += F3_NT) sr[i] = P.rows4[min(i, P.ih - 1)];   // (one entry past the end: the emit reads one row ahead)
     if (TMA) {  // one mbarrier per (warp, ring slot), behind the filter rows
-      if (tid < F3_NW * F3_RING) mbar_init(sbase + S3_BYTES + 16u * (uint32_t)P.ih + 8u * (uint32_t)tid, 1u);
+      if (tid < F3_NW * F3_RING) mbar_init(A_ROWS + 16u * (uint32_t)(P.ih + 1) + 8u * (uint32_t)tid, 1u);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
-  const int4 *s_rows = reinterpret_cast<const int4 *>(smem + S3_BYTES);  // per inner output row: first, c3 | c2 << 16, c1 | c0 << 16
   __syncthreads();  // the only barrier of the kernel
 
   Lane L;
-  L.tyl = sbase + S3_TY + 4 * lane;
-  L.tul = sbase + S3_TU + 8 * (lane & 15);
-  L.tvl = sbase + S3_TV + 8 * (lane & 15);
-  L.lutl = sbase + S3_LUT + 4 * lane;
+  // region base | the lane's bank offset: OR-ed into every lookup address
+  const uint32_t tyl = A_TY | (4u * (uint32_t)lane), lutl = A_LUT | (4u * (uint32_t)lane);
+  const uint32_t tul = A_TU | (8u * (uint32_t)(lane & 15)), tvl = A_TV | (8u * (uint32_t)(lane & 15));
 
   const int fw = P.fw, fh = P.fh, cw = P.cw, ch = P.ch;
   const int oy = P.oy, ih = P.ih, oh = P.oh;
   const uint32_t ka = P.ka, kia = P.kia;
+  const uint32_t kk = kia | (ka << 16);   // both blend weights as the 16-bit halves of a DP2A operand
+  const uint32_t zero = P.zero;
 
   // yuv2rgb_int (colourspace.c:2345-2356) through the replicated tables; results UNSATURATED (saturated by pack_sat)
-  // (ou, ov = 128 * m: byte offsets of the chroma entries; plain shared-memory loads so that the table bases fold into the
-  // instructions' address immediates)
-  const uint32_t lane8 = 8u * (uint32_t)(lane & 15), lane4 = 4u * (uint32_t)lane;
-  auto rgb = [&](uint32_t y, uint32_t ou, uint32_t ov, int &r, int &g, int &b) {
-#ifdef PE_F3_INTERLEAVE
-    const int yy = (int)*reinterpret_cast<const uint32_t *>(smem + S3_TY + (y | lane4));   // y = value << 8
-#else
-    const int yy = (int)lds32(L.tyl + y * 128u);
-#endif
-    const uint2 tv = *reinterpret_cast<const uint2 *>(smem + S3_TV + (ov | lane8));
-    const uint2 tu = *reinterpret_cast<const uint2 *>(smem + S3_TU + (ou | lane8));
+  // (ya, ou, ov: complete shared-memory addresses, see yaddr / idx_hi / idx_lo)
+  auto rgb = [&](uint32_t ya, uint32_t ou, uint32_t ov, int &r, int &g, int &b) {
+    const int yy = (int)lds32(ya);
+    const uint2 tv = lds64(ov);
+    const uint2 tu = lds64(ou);
     r = (yy + (int)tv.x) >> 16;
 #ifdef PE_F3_SAR16_G_IMAD
     asm("mul.hi.s32 %0, %1, 65536;" : "=r"(g) : "r"(yy + (int)tu.x + (int)tv.y));   // one of the three shifts on the FMA-heavy pipe
@@ -389,40 +379,34 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     b = (yy + (int)tu.y) >> 16;
   };
 
-  // alpha-over (integer form of compositor.c:120 for alpha = ka / 256) + gamma LUT of one pixel
+  // gamma LUT of the three blended channels (16-bit values, the byte to look up is byte 1) -> RGBA word
+  auto lut_pack = [&](uint32_t vr, uint32_t vg, uint32_t vb) -> uint32_t {
+    if (HAS_LUT) {
+      const uint32_t e0 = lds32((vr & 0xFF00u) | lutl);
+      const uint32_t e1 = lds32((vg & 0xFF00u) | lutl);
+      const uint32_t e2 = lds32((vb & 0xFF00u) | lutl);
+      return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
+    }
+    return __byte_perm(__byte_perm(vr, vg, 0x0051u), vb, 0x0510u) | 0xFF000000u;
+  };
+  // alpha-over (integer form of compositor.c:120 for alpha = ka / 256) + gamma LUT of one pixel.
+  // C16: the filtered channel is byte 2 of its accumulator (byte 3 is zero): one PRMT puts it next to the bg byte and ONE DP2A
+  // forms bg * kia + f * ka (no extraction of the filtered bytes, no 16-bit-pair multiplies)
+  auto blend_acc = [&](uint32_t bg, uint32_t a0, uint32_t a1, uint32_t a2) -> uint32_t {
+    const uint32_t vr = dp2a_hi(kk, __byte_perm(bg, a0, 0x6000u), 0u);
+    const uint32_t vg = dp2a_hi(kk, __byte_perm(bg, a1, 0x6100u), 0u);
+    const uint32_t vb = dp2a_hi(kk, __byte_perm(bg, a2, 0x6200u), 0u);
+    return lut_pack(vr, vg, vb);
+  };
   auto blend = [&](uint32_t bg, uint32_t frb, uint32_t fg_) -> uint32_t {   // frb = filtered R | B << 16
     const uint32_t rb = (bg & 0x00FF00FFu) * kia + frb * ka;   // R | B in the 16-bit halves
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia + fg_ * ka;
-    if (HAS_LUT) {
-#ifdef PE_F3_INTERLEAVE
-      const uint32_t e0 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((rb & 0xFF00u) | lane4));
-      const uint32_t e1 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((gg & 0xFF00u) | lane4));
-      const uint32_t e2 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + (((rb >> 16) & 0xFF00u) | lane4));
-#else
-      const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
-      const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
-      const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
-#endif
-      return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
-    }
-    return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
+    return lut_pack(rb, gg, rb >> 16);
   };
   auto blend_border = [&](uint32_t bg) -> uint32_t {  // letterbox border: fg = black (blank_pixel, colourspace.c:11169)
     const uint32_t rb = (bg & 0x00FF00FFu) * kia;
     const uint32_t gg = __byte_perm(bg, 0u, 0x4441u) * kia;
-    if (HAS_LUT) {
-#ifdef PE_F3_INTERLEAVE
-      const uint32_t e0 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((rb & 0xFF00u) | lane4));
-      const uint32_t e1 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + ((gg & 0xFF00u) | lane4));
-      const uint32_t e2 = *reinterpret_cast<const uint32_t *>(smem + S3_LUT + (((rb >> 16) & 0xFF00u) | lane4));
-#else
-      const uint32_t e0 = lds32(L.lutl + __byte_perm(rb, 0u, 0x4441u) * 128u);
-      const uint32_t e1 = lds32(L.lutl + __byte_perm(gg, 0u, 0x4441u) * 128u);
-      const uint32_t e2 = lds32(L.lutl + (rb >> 24) * 128u);
-#endif
-      return __byte_perm(__byte_perm(e0, e1, 0x0040u), e2, 0x7410u);
-    }
-    return __byte_perm(rb, gg, 0x0351u) | 0xFF000000u;
+    return lut_pack(rb, gg, rb >> 16);
   };
 
   // ---- the warp's share of the cost sequence (frame, band, strip, row)
@@ -440,7 +424,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   };
   // static part: [0, static_cost) in equal shares; the rest is handed out in small chunks as warps run dry (P.sched: the
   // chunk counter and the count of finished warps; the last warp to finish zeroes both for the next launch)
-  const long long gw = (long long)blockIdx.x * F3_NW + warp, nwarps = (long long)gridDim.x * F3_NW;
+  // share number of this warp: consecutive shares to the warps of one CTA (neighbouring strips of a band: the chroma sectors two
+  // strips share are fetched once per SM), or (P.spread) shares gridDim.x apart, so that the warps of an SM are in different
+  // phases of a frame -- border rows are pure memory traffic, inner rows mostly arithmetic
+  const long long nwarps = (long long)gridDim.x * F3_NW;
+  const long long gw = P.spread ? (long long)warp * gridDim.x + blockIdx.x : (long long)blockIdx.x * F3_NW + warp;
   uint32_t bg_push_seq = 0u, bg_pop_seq = 0u;  // TMA variant: rows pushed into / popped from the warp's bg ring so far
   long long pos = P.static_cost * gw / nwarps;
   long long pos_end = P.static_cost * (gw + 1) / nwarps;
@@ -524,8 +512,10 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       const uint32_t rs_y = (uint32_t)P.rs_y, rs_u = (uint32_t)P.rs_u, rs_v = (uint32_t)P.rs_v;
       const int k_fast_max = P.k_fast_max;
 
-      auto load_pre = [&](int k, Pre &p) {  // raw words of the fast step k: luma rows 2k-1, 2k, chroma row k
-        const uint8_t *yr = L.yp + (size_t)rs_y * (uint32_t)(2 * k - 1);
+      // raw words of a fast step: luma rows 2k-1, 2k, chroma row k.  The step loads the words of step k + 1 through RUNNING
+      // pointers (yq, uq, vq, vfq: advanced once per step, whatever kind of step it is) -- per step 4 64-bit additions instead of
+      // 7 address computations from the row number (profiles/r02k: a tenth of the step's instructions were address arithmetic)
+      auto load_at = [&](const uint8_t *yr, const uint8_t *ur, const uint8_t *vr, const uint8_t *vfr, Pre &p) {
 #ifdef PE_F3_LUMA_NC
         p.yA = ld_keep_u32(yr);
         p.yB = ld_keep_u32(yr + rs_y);
@@ -533,10 +523,9 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         p.yA = ld_stream_u32(yr);
         p.yB = ld_stream_u32(yr + rs_y);
 #endif
-        const uint32_t uo = rs_u * (uint32_t)k, vo = rs_v * (uint32_t)k;
-        p.u0 = ld_keep_u32(L.up0 + uo); p.u1 = ld_keep_u32(L.up0 + uo + 4);
-        p.v0 = ld_keep_u32(L.vp0 + vo); p.v1 = ld_keep_u32(L.vp0 + vo + 4);
-        p.vf = ldg_u8(L.vfp + vo);
+        p.u0 = ld_keep_u32(ur); p.u1 = ld_keep_u32(ur + 4);
+        p.v0 = ld_keep_u32(vr); p.v1 = ld_keep_u32(vr + 4);
+        p.vf = ldg_u8(vfr);
       };
       auto init_carry = [&](int r, Carry &c) {  // sums of chroma row r (0 <= r <= ch - 2), as a fast step leaves them
         const uint32_t uo = rs_u * (uint32_t)r, vo = rs_v * (uint32_t)r;
@@ -551,26 +540,33 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 
       // ---- one step: rows A = 2k-1, B = 2k of the lane's 4 columns -> Wc = [B, A, Wp.byte0, Wp.byte1]
       int iy = ia;
-      int4 ri = s_rows[iy];
+      int4 ri = lds128_ro(A_ROWS + 16u * (uint32_t)iy);
       int k = ((ri.x + 4) >> 1) - 2;
       bool carry_ok = false;
       Carry C;
-      Pre pre;
+      Pre preA, preB;
       C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
-      pre.yA = pre.yB = pre.u0 = pre.u1 = pre.v0 = pre.v1 = pre.vf = 0u;
+      preA.yA = preA.yB = preA.u0 = preA.u1 = preA.v0 = preA.v1 = preA.vf = 0u;
+      preB = preA;
+      // rows of step k (k may be <= 0 here: the pointers are only dereferenced for fast steps)
+      const uint8_t *yq = L.yp + (long long)rs_y * (2 * k - 1);
+      const uint8_t *uq = L.up0 + (long long)rs_u * k;
+      const uint8_t *vq = L.vp0 + (long long)rs_v * k;
+      const uint8_t *vfq = L.vfp + (long long)rs_v * k;
       if (k >= 1 && k <= k_fast_max) {
-        load_pre(k, pre);
+        load_at(yq, uq, vq, vfq, preA);
         init_carry(k - 1, C);
         carry_ok = true;
       }
       // bg rows travel through the warp's cp.async ring, F3_RING - 1 rows ahead of the emit: no registers are tied up and the
       // emit never waits on a load it has just issued.  A lane only ever reads the 16 bytes it copied itself.
-      const uint32_t ring_w = sbase + S3_RING + (uint32_t)warp * (F3_RING * 512);
+      const uint32_t ring_w = A_RING + (uint32_t)warp * (F3_RING * 512);
       const uint32_t ring = ring_w + 16u * (uint32_t)lane;
+      constexpr uint32_t RMASK = (uint32_t)(F3_RING - 1) * 512u;   // the slot bits of a ring address (the warp's ring is aligned to its size)
       // TMA variant: rows enter the ring in the order they are emitted; bg_seq counts the rows this warp has pushed / popped since the
       // kernel started (slot = seq % F3_RING, the slot's mbarrier phase = seq / F3_RING); every pushed row is popped before the
       // segment ends
-      const uint32_t mbar_w = sbase + S3_BYTES + 16u * (uint32_t)ih + 8u * (uint32_t)(warp * F3_RING);
+      const uint32_t mbar_w = A_ROWS + 16u * (uint32_t)(ih + 1) + 8u * (uint32_t)(warp * F3_RING);
       const uint8_t *bg_strip = F.bg + 512u * (size_t)s + (size_t)rs_bg * (uint32_t)oy;   // row 0 of the inner rectangle, this strip
       auto bg_push = [&](int row) {   // all lanes call it; lane 0 issues
         if (lane == 0) {
@@ -580,25 +576,37 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         }
         bg_push_seq++;
       };
+      // running state of the emit: the bg row the ring is refilled with when row iy leaves, the output row, the ring slot of row
+      // iy and of row iy - 1 (== the slot of row iy + F3_RING - 1), the filter row of iy + 1
+      const uint8_t *bg_fill = bgp + (size_t)rs_bg * (uint32_t)(oy + iy + F3_RING - 1);
+      uint8_t *out_row = outp + (size_t)rs_out * (uint32_t)(oy + iy);
+      uint32_t rd = ring | (((uint32_t)iy * 512u) & RMASK);
+      uint32_t rows_sa = A_ROWS + 16u * (uint32_t)(iy + 1);
       if (TMA) {
         __syncwarp();
         for (int j = 0; j < F3_RING - 1 && iy + j < ib; j++) bg_push(iy + j);
       } else {
 #pragma unroll
         for (int j = 0; j < F3_RING - 1; j++) {
-          cp_async16(ring + (uint32_t)((iy + j) & (F3_RING - 1)) * 512u, bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + j, ib - 1)));
+          if (iy + j < ib) cp_async16(ring | (((uint32_t)(iy + j) * 512u) & RMASK), bgp + (size_t)rs_bg * (uint32_t)(oy + iy + j));
           cp_async_commit();
         }
       }
 
-      auto step = [&](int k, uint32_t(&Wc)[12], const uint32_t(&Wp)[12]) {
+      // pre: the words of step k (loaded one step ago); nxt: where the words of step k + 1 go.  The two buffers swap roles from
+      // step to step (the marching loop is unrolled by two), so nothing is copied.
+      // Order matters: the step first WAITS for its own words, then issues the loads of step k + 1 -- those have the whole step and
+      // the emit behind it to land.  Issued the other way round, the first use of `pre` sits right behind the new loads and ptxas
+      // waits on a scoreboard they share (long-scoreboard stalls per issue 0.41 -> 1.90, 50.3k -> 47.9k fps: profiles/r02l).
+      // Nothing in CUDA C orders independent loads behind a use, so the order is a data dependency: the row pointers advance by
+      // stride + dep, dep = (words of this step) & P.zero -- a kernel parameter that is 0, which the compiler cannot know.
+      auto step = [&](int k, uint32_t(&Wc)[12], const uint32_t(&Wp)[12], const Pre &pre, Pre &nxt) {
         int rA[12], rB[12];
         const bool fast = k >= 1 && k <= k_fast_max;
         const bool next_fast = k + 1 >= 1 && k + 1 <= k_fast_max;
-        // (the copy keeps the consumer of these loads at the END of the step: ptxas then waits for them there, one step after
-        // they were issued, instead of tying the next step's first instructions to the scoreboard of the loads just issued)
-        Pre nxt = pre;
-        if (next_fast) load_pre(k + 1, nxt);
+        const uint32_t dep = ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.vf) & zero;
+        yq += 2 * (size_t)rs_y + dep; uq += rs_u + dep; vq += rs_v + dep; vfq += rs_v + dep;
+        if (next_fast) load_at(yq, uq, vq, vfq, nxt);
         if (fast) {
           const RowC U = unpack_row(pre.u0, pre.u1, L.sel), V = unpack_row(pre.v0, pre.v1, L.sel);
           // right pixel of both chroma columns: this + next
@@ -631,11 +639,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
             const bool hi_half = col >> 1, right = col & 1;
             const uint32_t qu_up = right ? QUR_up : QUL_up, qu_lo = right ? QUR_lo : QUL_lo;
             const uint32_t qv_up = right ? QVR_up : QVL_up, qv_lo = right ? QVR_lo : QVL_lo;
-            const uint32_t mu_up = hi_half ? idx_hi(qu_up) : idx_lo(qu_up), mv_up = hi_half ? idx_hi(qv_up) : idx_lo(qv_up);
-            const uint32_t mv_lo = hi_half ? idx_hi(qv_lo) : idx_lo(qv_lo);
-            const uint32_t mu_lo = (QUIRKS && !right) ? mu_up : (hi_half ? idx_hi(qu_lo) : idx_lo(qu_lo));
-            rgb(ysel(pre.yA, col), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
-            rgb(ysel(pre.yB, col), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+            const uint32_t mu_up = hi_half ? idx_hi(qu_up, tul) : idx_lo(qu_up, tul), mv_up = hi_half ? idx_hi(qv_up, tvl) : idx_lo(qv_up, tvl);
+            const uint32_t mv_lo = hi_half ? idx_hi(qv_lo, tvl) : idx_lo(qv_lo, tvl);
+            const uint32_t mu_lo = (QUIRKS && !right) ? mu_up : (hi_half ? idx_hi(qu_lo, tul) : idx_lo(qu_lo, tul));
+            rgb(yaddr(pre.yA, col, tyl), mu_up, mv_up, rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+            rgb(yaddr(pre.yB, col, tyl), mu_lo, mv_lo, rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
           }
 #pragma unroll
           for (int i = 0; i < 12; i++) Wc[i] = pack_sat(rA[i], rB[i], Wp[i]);
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           // ---- slow step (frame edges): out of line; rows beyond the frame replicate the last row (the filter clamps its
           //      source indices)
           if (k <= 0 || 2 * k - 1 <= fh - 1) {
-            const SlowRows sr = slow_rows<QUIRKS>(smem, F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane);
+            const SlowRows sr = slow_rows<QUIRKS>(F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane);
 #pragma unroll
             for (int i = 0; i < 12; i++) Wc[i] = __byte_perm(sr.ab[i], Wp[i], 0x5410u);
           } else {
@@ -656,7 +664,6 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           init_carry(k, C);
           carry_ok = true;
         }
-        pre = nxt;
       };
 
       // ---- emit every output row whose window [first, first + 3] is complete after step k
@@ -664,7 +671,6 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         while (iy < ib && ri.x + 3 <= 2 * k) {
           const int j0 = 2 * k - ri.x - 3;  // 0: the window is Wc; 1: one row older
           const uint32_t CA = (uint32_t)ri.y, CB = (uint32_t)ri.z;
-          const int iyn = min(iy + 1, ib - 1);
           uint4 bgw;
           if (TMA) {
             __syncwarp();  // every lane has read the slot that is refilled now (row iy - 1's)
@@ -674,13 +680,12 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
             bgw = lds128(ring + 512u * slot);
             bg_pop_seq++;
           } else {
-            cp_async16(ring + (uint32_t)((iy + F3_RING - 1) & (F3_RING - 1)) * 512u,
-                       bgp + (size_t)rs_bg * (uint32_t)(oy + min(iy + F3_RING - 1, ib - 1)));
+            if (iy + F3_RING - 1 < ib) cp_async16(ring | ((rd - 512u) & RMASK), bg_fill);   // the slot row iy - 1 has left
             cp_async_commit();
             cp_async_wait<F3_RING - 1>();  // all but the newest F3_RING - 1 groups have landed: row iy is in its slot
-            bgw = lds128(ring + (uint32_t)(iy & (F3_RING - 1)) * 512u);
+            bgw = lds128(rd);
           }
-          const int4 rin = s_rows[iyn];
+          const int4 rin = lds128_ro(rows_sa);
           const uint32_t bgv[4] = {bgw.x, bgw.y, bgw.z, bgw.w};
           uint32_t ov[4];
           if (j0 == 0) {
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
                 const uint32_t win = Wc[3 * col + c];
                 acc[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, C16 ? 32768u : 2048u));
               }
-              ov[col] = C16 ? blend(bgv[col], __byte_perm(acc[0], acc[2], 0x7632u), acc[1] >> 16)
+              ov[col] = C16 ? blend_acc(bgv[col], acc[0], acc[1], acc[2])
                             : blend(bgv[col], __byte_perm(shr12(acc[0]), shr12(acc[2]), 0x5410u), shr12(acc[1]));
             }
           } else {
@@ -704,11 +709,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
                 const uint32_t win = __byte_perm(Wc[3 * col + c], Wp[3 * col + c], 0x6321u);
                 acc[c] = dp2a_hi(CB, win, dp2a_lo(CA, win, C16 ? 32768u : 2048u));
               }
-              ov[col] = C16 ? blend(bgv[col], __byte_perm(acc[0], acc[2], 0x7632u), acc[1] >> 16)
+              ov[col] = C16 ? blend_acc(bgv[col], acc[0], acc[1], acc[2])
                             : blend(bgv[col], __byte_perm(shr12(acc[0]), shr12(acc[2]), 0x5410u), shr12(acc[1]));
             }
           }
-          st_stream_u4(outp + (size_t)rs_out * (uint32_t)(oy + iy), make_uint4(ov[0], ov[1], ov[2], ov[3]));
+          st_stream_u4(out_row, make_uint4(ov[0], ov[1], ov[2], ov[3]));
+          bg_fill += rs_bg; out_row += rs_out;
+          rd = ring | ((rd + 512u) & RMASK);
+          rows_sa += 16u;
           ri = rin;
           iy++;
         }
@@ -718,11 +726,11 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 #pragma unroll
       for (int i = 0; i < 12; i++) W0[i] = W1[i] = 0u;
       for (;;) {
-        step(k, W0, W1);
+        step(k, W0, W1, preA, preB);
         emit(k, W0, W1);
         if (iy >= ib) break;
         k++;
-        step(k, W1, W0);
+        step(k, W1, W0, preB, preA);
         emit(k, W1, W0);
         if (iy >= ib) break;
         k++;
@@ -791,7 +799,7 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
   static PerDevice attr_set;
   if (!attr_set.cur()) {
     cudaError_t e;
-    const int mx = S3_BYTES + 16 * F3_MAX_IH + 8 * F3_NW * F3_RING;
+    const int mx = f3_smem_bytes(F3_MAX_IH);
     const void *fns[16] = {(const void *)k_fused3<true, true, true, false>,   (const void *)k_fused3<true, true, false, false>,
                            (const void *)k_fused3<true, false, true, false>,  (const void *)k_fused3<true, false, false, false>,
                            (const void *)k_fused3<false, true, true, false>,  (const void *)k_fused3<false, true, false, false>,
@@ -851,11 +859,15 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (P.total_cost - P.static_cost < P.chunk_cost * grid) P.static_cost = P.total_cost;  // small jobs: all static
     P.sched = sched_dev;
     P.ka = (uint32_t)blend_a; P.kia = (uint32_t)(256 - blend_a);
+    P.zero = 0u;
+    static int spread_pref = -1;
+    if (spread_pref < 0) spread_pref = getenv("PE_F3_SPREAD") ? atoi(getenv("PE_F3_SPREAD")) != 0 : 0;
+    P.spread = spread_pref;
     P.rows4 = reinterpret_cast<const int4 *>(rows4_dev);
     P.conv = a0.conv.t;
     P.lut8 = lut8_dev;
     if (P.frame_cost >= (1ll << 31)) return cudaErrorInvalidConfiguration;
-    const int smem_bytes = S3_BYTES + 16 * a0.ih + 8 * F3_NW * F3_RING;
+    const int smem_bytes = f3_smem_bytes(a0.ih);
     // the TMA variant of the bg ring takes whole 128-column strips of rows that start 16-byte aligned (PE_F3_TMA=0 / 1 overrides the
     // default, which is what measured faster: profiles/r02_k_fused3_tma_vs_ldgsts.txt)
     static int tma_pref = -1;
