@@ -607,8 +607,33 @@ def sub_records(args, eng, dist, rank, world, dev):
     og = torch.Generator(device=dev)
     og.manual_seed(99)  # the SAME operand frames on every rank: rank 0's copy travels, the others are the parity reference
     local_ops = torch.randint(0, 256, (K, H, W * 3), dtype=torch.uint8, device=dev, generator=og)
-    groups = [local_ops.clone() if rank == 0 else torch.zeros_like(local_ops) for _ in range(3)]
+    # transport of the operand: an NVSwitch multicast ring (shard.OperandMulticast: the owner's pe_mc_publish kernel stores each group
+    # into every rank's buffer at once) when the group has multicast support, NCCL broadcast into three group buffers otherwise
+    ring, transport = None, "none (N = 1)"
+    if world > 1:
+        ok = 1
+        try:
+            if os.environ.get("PE_CFG5_TRANSPORT", "nccl") != "multicast":
+                raise RuntimeError("not selected (PE_CFG5_TRANSPORT=multicast selects it; NCCL measured faster, profiles/r02t_cfg5_transports.log)")
+            ring = shard.OperandMulticast(eng, (K, H, W * 3), nslots=3)
+        except Exception as ex:  # noqa: BLE001
+            ok, why = 0, str(ex).splitlines()[0][:80]
+        okt = torch.tensor([ok], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()):
+            transport = "NVSwitch multicast: one pe_mc_publish kernel on rank 0 stores each group into all ranks' symmetric buffers (3 slots, 2 groups ahead)"
+        else:
+            ring = None
+            transport = "broadcast from rank 0 over NCCL once per step (3 group buffers, per-buffer ordering)" + ("" if ok else "; multicast: " + why)
+    # the collective's CTAs need somewhere to run: the marching kernel is persistent (one CTA per SM), so it leaves some SMs free
+    sm_reserve = int(os.environ.get("PE_CFG5_SM_RESERVE", "8")) if world > 1 else 0
+    if sm_reserve > 0:
+        eng.set_sm_limit(eng.sm_count - sm_reserve)
+    groups = [local_ops.clone() if rank == 0 else torch.zeros_like(local_ops) for _ in range(3)] if ring is None else []
     it = [0]
+    if ring is not None:
+        ring.publish(local_ops)
+        ring.publish(local_ops)
 
     def clips():
         return [lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2],
@@ -616,7 +641,11 @@ def sub_records(args, eng, dist, rank, world, dev):
 
     def step5(keep_result=False):
         cl = clips()
-        shard.multitrack_crossfade_group(eng, cl, groups[it[0] % 3], W, H, 128)
+        if ring is not None:
+            shard.multitrack_crossfade_group_mc(eng, cl, ring, W, H, 128)
+            ring.publish(local_ops)   # group t + 2, behind barrier t: it travels while the kernels of groups t and t + 1 run
+        else:
+            shard.multitrack_crossfade_group(eng, cl, groups[it[0] % 3], W, H, 128)
         it[0] += 1
         if keep_result:
             return cl
@@ -644,8 +673,9 @@ def sub_records(args, eng, dist, rank, world, dev):
     ms, launches = timed(step5, steps5, warm=2)
     cps = world * K * steps5 / (ms / 1e3)
     algo5 = W * H * 2 + 2 * W * H * 3
+    eng.set_sm_limit(0)
     out["cfg5"] = {"workload": "multitrack: one clip per GPU, %d x 4K YUV422P -> RGB24 + crossfade bf=128 per step against %d frames of the shared "
-                               "operand, %s" % (K, K, "broadcast from rank 0 over NCCL once per step (3 group buffers)" if world > 1 else "no broadcast at N = 1"),
+                               "operand, %s" % (K, K, (transport + "; %d SMs left to the transfer" % sm_reserve) if world > 1 else "no broadcast at N = 1"),
                    "value": cps, "unit": "clip frames/s", "ms_per_output_frame": ms / (steps5 * K), "gpu_launches": int(launches),
                    "parity_all_ranks": bool(flag.item()), "broadcast_bytes_per_step": (K * H * W * 3) if world > 1 else 0,
                    "broadcast_gbs": (K * H * W * 3 * steps5 / (ms / 1e3) / 1e9) if world > 1 else None,

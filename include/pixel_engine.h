@@ -104,6 +104,10 @@ long pe_engine_launch_count(pe_engine_t *e);
 int pe_timer_start(pe_engine_t *e);
 int pe_timer_stop_ms(pe_engine_t *e, float *ms); /* synchronises on the stop event */
 int pe_sm_count(pe_engine_t *e);
+/* The persistent kernels (one CTA per SM: the fused chain, the marching converters) size their grids by the SM count.  n > 0 caps that
+ * at n SMs, 0 lifts the cap: a host that runs a collective (the operand broadcast of a multitrack crossfade) beside the
+ * engine leaves the collective's CTAs somewhere to run, instead of having them time-sliced against 148 resident CTAs. */
+int pe_engine_set_sm_limit(pe_engine_t *e, int n);
 /* resize coefficients.  The reference delegates resizing to libswscale (src/colourspace.c:15059-15228; version unpinned,
  * configure.ac:562) with one flag per LiVESInterpType (:14991-14997).  recipe 1 (default) = libswscale's own coefficient recipes:
  * PE_INTERP_NORMAL SWS_BILINEAR, PE_INTERP_BEST SWS_LANCZOS when the frame grows / SWS_BICUBIC when it shrinks, PE_INTERP_FAST
@@ -338,6 +342,16 @@ int pe_clip_cache_borrow(pe_clip_cache_t *c, int64_t frame, pe_frame_t **out);  
 int pe_render_out_begin(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride, int slot);
 int pe_render_out_wait(pe_engine_t *e, int slot);
 int pe_render_out(pe_engine_t *e, pe_frame_t *layer, int out_palette, void *host_dst, int host_rowstride);
+
+/* ---- the one exchange step of the path (BASELINE config 5) ---------------------------------------------------------
+ * The shared transition operand of a multitrack crossfade (src/multitrack.h:84: every track's clip fades against the same frame)
+ * lives on ONE rank; with one clip per GPU every rank needs it for every output frame.  pe_mc_publish is the owner's side as ONE
+ * kernel: `bytes` bytes (a multiple of 16; 16-byte aligned addresses) are read from `src` in the owner's memory and stored through
+ * `mc_dst`, an NVSwitch multicast address that maps a buffer on every GPU of the group (cuMulticast* / symmetric memory: the host's
+ * plumbing, lives_b200/shard.py), so the operand leaves the owner's NVLink once whatever the number of receivers.  Asynchronous on
+ * `cuda_stream` (NULL: the engine's stream); max_ctas <= 0: one CTA per SM (the kernel is small enough to share the SMs with the
+ * conversion kernels).  Completion is ordered like any kernel's: an event on the stream, then the group's barrier. */
+int pe_mc_publish(pe_engine_t *e, void *mc_dst, const void *src, size_t bytes, void *cuda_stream, int max_ctas);
 
 /* ---- per-frame diagnostics (is_all_black_ish colourspace.c:2554, hash_cmp_layer :16044) ------ */
 

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "pe_timer_start": (I, [VP]),
     "pe_timer_stop_ms": (I, [VP, C.POINTER(C.c_float)]),
     "pe_sm_count": (I, [VP]),
+    "pe_engine_set_sm_limit": (I, [VP, I]),
     "pe_engine_set_resize_recipe": (I, [VP, I]),
     "pe_resize_filter_host": (I, [I, I, I, I, VP, VP, I]),
     "pe_frame_layout": (SZ, [I, I, I, PI, PI, PI]),
@@ -104,6 +105,7 @@ PROTOTYPES = {
     "pe_fx_convert_crossfade": (I, [VP, VP, VP, I, I, I]),
     "pe_fx_convert_crossfade_batch": (I, [VP, I, VP, VP, I, I, I]),
     "pe_fx_convert_crossfade_batchv": (I, [VP, I, VP, VP, I, I, I]),
+    "pe_mc_publish": (I, [VP, VP, VP, C.c_size_t, VP, I]),
     "pe_convert_layer_palette_batch": (I, [VP, I, VP, I, I]),
     "pe_letterbox_layer": (I, [VP, VP, I, I, I, I, I, I, I]),
     "pe_gamma_convert_layer": (I, [VP, I, VP]),

@@ -315,6 +315,12 @@ extern "C" int pe_engine_sync(pe_engine_t *e) {
 extern "C" void *pe_engine_stream(pe_engine_t *e) { return e ? (void *)e->stream : nullptr; }
 extern "C" long pe_engine_launch_count(pe_engine_t *e) { return e ? e->launches : 0; }
 extern "C" int pe_sm_count(pe_engine_t *e) { return e ? e->sm_count : 0; }
+extern "C" int pe_engine_set_sm_limit(pe_engine_t *e, int n) {
+  if (!e || n < 0) return set_err(PE_ERR_ARG, "pe_engine_set_sm_limit: engine and n >= 0");
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->sm_limit = n;
+  return PE_OK;
+}
 
 // which coefficients the resize / letterbox / fused calls of this engine use from now on: 1 libswscale's recipes (default; one bank
 // per LiVESInterpType, pe_tables.cpp build_resize_filter_sws), 0 the round-1 triangle contract (every interpolation type)
@@ -1687,6 +1693,17 @@ extern "C" int pe_convert_yuv888_to_rgb_float(pe_engine_t *e, pe_frame_t *f, int
   frame_take(f, &n);
   f->d.yuv_clamping = 0; f->d.yuv_subspace = 0; f->d.yuv_sampling = 0;  // conv_done (:13859-13900): the YUV leaves are deleted
   return PE_TRUE;
+}
+
+extern "C" int pe_mc_publish(pe_engine_t *e, void *mc_dst, const void *src, size_t bytes, void *cuda_stream, int max_ctas) {
+  if (!e || !mc_dst || !src) return set_err(PE_ERR_ARG, "NULL argument");
+  if ((bytes & 15) || ((uintptr_t)mc_dst & 15) || ((uintptr_t)src & 15)) return set_err(PE_ERR_ARG, "pe_mc_publish: 16-byte granularity");
+  std::lock_guard<std::mutex> lk(e->mu);
+  PE_CUDA(cudaSetDevice(e->device));
+  pe::Launch L = e->L();
+  if (cuda_stream) L.stream = (cudaStream_t)cuda_stream;
+  PE_CUDA(launch_mc_publish(L, src, mc_dst, bytes, max_ctas));
+  return PE_OK;
 }
 
 extern "C" int pe_convert_layer_palette_full(pe_engine_t *e, pe_frame_t *layer, int outpl, int oclamping, int osampling,

@@ -76,6 +76,7 @@ struct pe_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
+  int sm_limit = 0;   // > 0: persistent kernels use at most this many SMs (pe_engine_set_sm_limit)
   int resize_recipe = 1;  // 1 libswscale's coefficient recipes (default), 0 the round-1 triangle contract (pe_engine_set_resize_recipe)
   long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -127,7 +128,7 @@ struct pe_engine {
   size_t args_pinned_cap = 0;
   cudaEvent_t args_ev = nullptr;  // args_pinned may be rewritten once the previous upload has completed
 
-  pe::Launch L() { return pe::Launch{stream, sm_count, &launches}; }
+  pe::Launch L() { return pe::Launch{stream, sm_limit > 0 && sm_limit < sm_count ? sm_limit : sm_count, &launches}; }
 };
 
 struct pe_frame {

@@ -108,6 +108,8 @@ cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const plan
 // float tables [RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr, Bf_Cb][256], rgb_y_dev = the integer RGB_Y table mode 0 adds them to; sums_dev optional
 cudaError_t launch_yuv888_to_rgb_float(const Launch &L, int mode, CImg src, Img dst, int width, int height, int in_alpha, RgbLayout out,
                                        const float *ftab_dev, const int32_t *rgb_y_dev, float *sums_dev);
+// the owner's side of the multitrack operand exchange (pe_kernels_mc.cu): bytes from local memory through an NVSwitch multicast address
+cudaError_t launch_mc_publish(const Launch &L, const void *src, void *mc_dst, size_t bytes, int max_ctas);
 // ---- effects ---------------------------------------------------------------------------------------
 // ---- YUV <-> YUV family + planar 4:4:4 -> RGB (pe_kernels_yuv3.cu) ---------------------------------------
 cudaError_t launch_yuv444p_to_rgb(const Launch &L, const uint8_t *const planes[4], int irow, Img dst, int width, int height, int in_alpha,

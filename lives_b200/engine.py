@@ -111,6 +111,14 @@ class Engine:
         """1: libswscale's coefficient recipes, one bank per LiVESInterpType (default); 0: the round-1 triangle contract"""
         capi.check(self._lib.pe_engine_set_resize_recipe(self._h, recipe))
 
+    def set_sm_limit(self, n):
+        """persistent kernels use at most n SMs (0: all) -- leaves room for a collective that runs beside the engine"""
+        capi.check(self._lib.pe_engine_set_sm_limit(self._h, int(n)))
+
+    def mc_publish(self, mc_dst, src, nbytes, cuda_stream=None, max_ctas=0):
+        """pe_mc_publish: `nbytes` from device address `src` through the multicast address `mc_dst` (see lives_b200/shard.py)"""
+        capi.check(self._lib.pe_mc_publish(self._h, C.c_void_p(mc_dst), C.c_void_p(src), nbytes, C.c_void_p(cuda_stream or 0), max_ctas))
+
     def timer_start(self):
         capi.check(self._lib.pe_timer_start(self._h))
 

@@ -42,6 +42,23 @@ def allreduce_histogram(hist, group=None):
 
 
 _ENGINE_STREAMS = {}
+_CONSUMED = {}   # (engine id, data_ptr) -> event of the last kernel that read that operand buffer
+
+
+def _await_buffer(engine, tensor, stream):
+    """a transfer into `tensor` may only start once the last kernel that read it has finished -- that buffer's kernel, not the stream's
+    latest one: with several operand buffers the transfer of group t + 1 then really overlaps the kernel of group t (waiting on the
+    newest kernel, as this module did before, serialised them: 0.48 ms per group = 0.31 ms broadcast + 0.17 ms kernel on 2 GPUs)"""
+    ev = _CONSUMED.get((id(engine), tensor.data_ptr()))
+    if ev is not None:
+        stream.wait_event(ev)
+
+
+def _mark_consumed(engine, tensor, es):
+    ev = torch.cuda.Event()
+    ev.record(es)
+    _CONSUMED[(id(engine), tensor.data_ptr())] = ev
+    return ev
 
 
 def _engine_stream(engine):
@@ -57,10 +74,11 @@ def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blen
     then 'chroma blend' (the crossfade / auto-transition of src/multitrack.h:84) of the clip with the operand, in place.
     `operand_tensor`: uint8 CUDA tensor of height x rowstride bytes on every rank.
     Stream ordered, no host synchronisation: the fused convert + crossfade kernel (engine stream) waits for the broadcast
-    (torch's current stream), and the next broadcast into the same tensor waits for that kernel; with two operand buffers
+    (torch's current stream), and the next broadcast into the SAME tensor waits for that kernel; with two or more operand buffers
     the broadcast of output frame t + 1 overlaps the kernel of frame t."""
     from . import engine as E
     es, ts = _engine_stream(engine), torch.cuda.current_stream()
+    _await_buffer(engine, operand_tensor, ts)
     broadcast_operand(operand_tensor, src=src_rank)
     arrived = torch.cuda.Event()
     arrived.record(ts)
@@ -73,9 +91,7 @@ def multitrack_crossfade(engine, clip_layer, operand_tensor, width, height, blen
         if not E.convert_layer_palette(clip_layer, out_palette, 0):
             raise RuntimeError("clip conversion failed: " + E.capi.last_error())
         E.simple_blend("chroma blend", clip_layer, operand, clip_layer, blend_factor)
-    consumed = torch.cuda.Event()
-    consumed.record(es)
-    ts.wait_event(consumed)
+    _mark_consumed(engine, operand_tensor, es)
     return clip_layer
 
 
@@ -90,6 +106,7 @@ def multitrack_crossfade_group(engine, clip_layers, operand_group, width, height
     if operand_group.dim() != 3 or operand_group.shape[0] != k or operand_group.shape[1] != height:
         raise ValueError("operand_group must be K x height x rowstride")
     es, ts = _engine_stream(engine), torch.cuda.current_stream()
+    _await_buffer(engine, operand_group, ts)
     broadcast_operand(operand_group, src=src_rank)
     arrived = torch.cuda.Event()
     arrived.record(ts)
@@ -98,7 +115,103 @@ def multitrack_crossfade_group(engine, clip_layers, operand_group, width, height
     ops = [E.Layer.wrap_device(engine, out_palette, width, height, [operand_group[i].data_ptr()], [rs]) for i in range(k)]
     if E.convert_crossfade_batchv(clip_layers, ops, out_palette, 0, blend_factor) != k:
         raise RuntimeError("grouped crossfade failed: " + E.capi.last_error())
-    consumed = torch.cuda.Event()
-    consumed.record(es)
-    ts.wait_event(consumed)
+    _mark_consumed(engine, operand_group, es)
+    return clip_layers
+
+
+class OperandMulticast:
+    """The shared operand of config 5 without a collective library on the data path: `nslots` group buffers in SYMMETRIC memory (the
+    same allocation mapped on every rank, torch.distributed._symmetric_memory) behind an NVSwitch multicast address.  The owner
+    publishes a group with ONE kernel (pe_mc_publish: ld.global -> multimem.st, lives_b200/csrc/pe_kernels_mc.cu) that reads its frames
+    once and lands them in every rank's buffer -- the owner's NVLink egress carries the operand once whatever the number of
+    receivers, nothing is staged, no receiver runs a copy kernel.  Groups are handed over with the symmetric-memory stream barrier.
+
+    Protocol, step t (slot t % nslots), everything stream ordered, no host synchronisation:
+      owner      publish(src)   on its own stream, up to nslots - 1 groups ahead: waits until the slot's previous group (t - nslots) has
+                                been consumed everywhere, i.e. until the owner has passed barrier t - nslots + 1
+      every rank acquire()      waits for this rank's previous crossfade kernel and (owner) for the publish of group t, then the barrier:
+                                behind it group t is in every buffer and every kernel <= t - 1 of every rank has finished
+                 consumed(ev)   after launching the kernel that reads the slot
+    Raises RuntimeError when the group has no multicast support (the caller keeps the NCCL broadcast)."""
+
+    def __init__(self, engine, slot_shape, nslots=3, src_rank=0, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.engine, self.nslots, self.src = engine, nslots, src_rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty((nslots,) + tuple(slot_shape), dtype=torch.uint8, device=dev)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        if not self.hdl.multicast_ptr:
+            raise RuntimeError("no multicast address for this group")
+        self.slot_bytes = self.buf[0].numel()
+        if self.slot_bytes % 16:
+            raise ValueError("a slot must be a multiple of 16 bytes")
+        self.pub_stream = torch.cuda.Stream(device=dev)
+        self.pub_ev = [None] * nslots      # owner: the publish of the group in the slot
+        self.free_ev = {}                  # owner: step -> event behind that step's barrier
+        self.kernel_ev = None              # this rank's latest crossfade kernel
+        self.t_pub = self.t_acq = 0
+
+    def publish(self, src_tensor, ready_event=None):
+        """owner only: group number t_pub from `src_tensor` (contiguous uint8, slot_bytes) into every rank's slot"""
+        if self.rank != self.src:
+            self.t_pub += 1
+            return
+        if src_tensor.numel() != self.slot_bytes or not src_tensor.is_contiguous():
+            raise ValueError("operand group must be %d contiguous bytes" % self.slot_bytes)
+        t, slot = self.t_pub, self.t_pub % self.nslots
+        need = t - self.nslots + 1          # the barrier that proves the slot free
+        if need >= 0:
+            if need not in self.free_ev:
+                raise RuntimeError("publish runs more than nslots - 1 groups ahead of acquire")
+            self.pub_stream.wait_event(self.free_ev[need])
+        if ready_event is not None:
+            self.pub_stream.wait_event(ready_event)
+        self.engine.mc_publish(self.hdl.multicast_ptr + slot * self.slot_bytes, src_tensor.data_ptr(), self.slot_bytes,
+                               self.pub_stream.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(self.pub_stream)
+        self.pub_ev[slot] = ev
+        self.t_pub += 1
+
+    def acquire(self):
+        """every rank: the local buffer of group t_acq, valid behind the returned event (record it -- the caller's kernel stream waits)"""
+        t, slot = self.t_acq, self.t_acq % self.nslots
+        ts = torch.cuda.current_stream()
+        if self.rank == self.src:
+            if self.pub_ev[slot] is None or self.t_pub <= t:
+                raise RuntimeError("acquire before publish")
+            ts.wait_event(self.pub_ev[slot])
+        if self.kernel_ev is not None:
+            ts.wait_event(self.kernel_ev)
+        self.hdl.barrier(channel=0)
+        ev = torch.cuda.Event()
+        ev.record(ts)
+        if self.rank == self.src:
+            self.free_ev[t] = ev
+            self.free_ev.pop(t - self.nslots - 1, None)
+        self.t_acq += 1
+        return self.buf[slot], ev
+
+    def consumed(self, es):
+        self.kernel_ev = torch.cuda.Event()
+        self.kernel_ev.record(es)
+
+
+def multitrack_crossfade_group_mc(engine, clip_layers, ring, width, height, blend_factor, out_palette=1):
+    """multitrack_crossfade_group with the operand group taken from an OperandMulticast ring (the owner has published it): barrier,
+    then ONE kernel launch for the K conversions + crossfades of this rank's clip."""
+    from . import engine as E
+    k = len(clip_layers)
+    es = _engine_stream(engine)
+    group, ready = ring.acquire()
+    if group.dim() != 3 or group.shape[0] != k or group.shape[1] != height:
+        raise ValueError("ring slots must be K x height x rowstride")
+    es.wait_event(ready)
+    rs = group.shape[2]
+    ops = [E.Layer.wrap_device(engine, out_palette, width, height, [group[i].data_ptr()], [rs]) for i in range(k)]
+    if E.convert_crossfade_batchv(clip_layers, ops, out_palette, 0, blend_factor) != k:
+        raise RuntimeError("grouped crossfade failed: " + E.capi.last_error())
+    ring.consumed(es)
     return clip_layers
