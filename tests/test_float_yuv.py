@@ -91,7 +91,8 @@ def test_cuda_float_path_is_bit_exact_every_triple(mode, cl):
     assert ok and lay.palette == T.PAL["RGB24"]
     got = lay.to_host()[0][:, :w * 3].reshape(-1, 3)
     exp, se = np.zeros_like(yuv), np.zeros((len(yuv), 3), np.float32)
-    o.pe_or_yuv2rgb_float(mode, cl, T.ptr(_rgb_y(o, cl)), T.ptr(yuv), T.ptr(exp), T.ptr(se), len(yuv))
+    ty = _rgb_y(o, cl)   # (kept alive across the call: T.ptr() of a temporary is a dangling pointer once the array is collected)
+    o.pe_or_yuv2rgb_float(mode, cl, T.ptr(ty), T.ptr(yuv), T.ptr(exp), T.ptr(se), len(yuv))
     bad = np.flatnonzero((got != exp).any(axis=1))
     assert bad.size == 0, "%d triples differ, first (Y, U, V) = %s: got %s, oracle %s" % (bad.size, yuv[bad[0]], got[bad[0]], exp[bad[0]])
     ulp = np.abs(sums.reshape(-1, 3).view(np.int32).astype(np.int64) - se.view(np.int32).astype(np.int64))
@@ -109,7 +110,8 @@ def test_cuda_float_path_layouts_alpha_and_refusals():
     src = T.make_packed(rng, w, h, 4)
     yuv = np.ascontiguousarray(src[:, :w * 4].reshape(-1, 4)[:, :3])
     exp = np.zeros_like(yuv)
-    o.pe_or_yuv2rgb_float(1, T.UNCLAMPED, T.ptr(_rgb_y(o, T.UNCLAMPED)), T.ptr(yuv), T.ptr(exp), None, len(yuv))
+    ty = _rgb_y(o, T.UNCLAMPED)
+    o.pe_or_yuv2rgb_float(1, T.UNCLAMPED, T.ptr(ty), T.ptr(yuv), T.ptr(exp), None, len(yuv))
     for pal, order in ((T.PAL["RGBA32"], (0, 1, 2, 3)), (T.PAL["BGRA32"], (2, 1, 0, 3)), (T.PAL["ARGB32"], (1, 2, 3, 0)), (T.PAL["BGR24"], (2, 1, 0))):
         lay = lb.Layer.from_host(eng, T.PAL["YUVA8888"], w, h, [src], yuv_clamping=T.UNCLAMPED, yuv_subspace=T.SUB_BT709)
         assert lb.convert_yuv888_to_rgb_float(lay, pal, 1)

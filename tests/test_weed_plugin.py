@@ -75,7 +75,8 @@ def test_plugin_bootstraps_through_the_reference_libweed():
     s = np.zeros((8, 32), np.uint8)
     import torch
     if not torch.cuda.is_available():
-        assert mh.mh_run2v(h, 11, 1, 8, 8, T.ptr(s), 32, T.ptr(s), 32, T.ptr(s.copy()), 32, 8, _sover_params(10, 1, 1, 0), 1) == 64
+        d = s.copy()
+        assert mh.mh_run2v(h, 11, 1, 8, 8, T.ptr(s), 32, T.ptr(s), 32, T.ptr(d), 32, 8, _sover_params(10, 1, 1, 0), 1) == 64
 
 
 def test_plugin_fails_loudly_without_gpu():
