@@ -50,7 +50,8 @@ enum {
   PE_PALETTE_RGB24 = 1, PE_PALETTE_BGR24 = 2, PE_PALETTE_RGBA32 = 3, PE_PALETTE_BGRA32 = 4, PE_PALETTE_ARGB32 = 5,
   PE_PALETTE_YUV420P = 512, PE_PALETTE_YVU420P = 513, PE_PALETTE_YUV422P = 522, PE_PALETTE_YUV444P = 544,
   PE_PALETTE_YUVA4444P = 545, PE_PALETTE_UYVY = 564, PE_PALETTE_YUYV = 565, PE_PALETTE_YUV888 = 588,
-  PE_PALETTE_YUVA8888 = 589
+  PE_PALETTE_YUVA8888 = 589,
+  PE_PALETTE_YUV411 = 595 /* IYU1: {u2, y0, y1, v2, y2, y3} per 4 pixels; as a conversion SOURCE only (what the dv decoder delivers) */
 };
 enum { PE_YUV_CLAMPING_CLAMPED = 0, PE_YUV_CLAMPING_UNCLAMPED = 1 };
 enum { PE_YUV_SAMPLING_DEFAULT = 0, PE_YUV_SAMPLING_JPEG = 0, PE_YUV_SAMPLING_MPEG = 1 };

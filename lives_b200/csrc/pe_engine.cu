@@ -63,6 +63,7 @@ inline bool pal_known(int p) {
   case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_ARGB32:
   case PE_PALETTE_YUV420P: case PE_PALETTE_YVU420P: case PE_PALETTE_YUV422P: case PE_PALETTE_YUV444P:
   case PE_PALETTE_YUVA4444P: case PE_PALETTE_UYVY: case PE_PALETTE_YUYV: case PE_PALETTE_YUV888: case PE_PALETTE_YUVA8888:
+  case PE_PALETTE_YUV411:
     return true;
   }
   return false;
@@ -81,10 +82,11 @@ inline int pal_psize(int p) {
   case PE_PALETTE_RGB24: case PE_PALETTE_BGR24: case PE_PALETTE_YUV888: return 3;
   case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_ARGB32: case PE_PALETTE_YUVA8888:
   case PE_PALETTE_UYVY: case PE_PALETTE_YUYV: return 4;
+  case PE_PALETTE_YUV411: return 6;
   default: return 1;
   }
 }
-inline int pal_ppmp(int p) { return (p == PE_PALETTE_UYVY || p == PE_PALETTE_YUYV) ? 2 : 1; }
+inline int pal_ppmp(int p) { return (p == PE_PALETTE_UYVY || p == PE_PALETTE_YUYV) ? 2 : p == PE_PALETTE_YUV411 ? 4 : 1; }
 
 inline RgbLayout rgb_layout(int p) {
   switch (p) {
@@ -1543,6 +1545,23 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     // way in for a V-first source (:12354), on the way out for a V-first target (:13895, below)
     inplace = true;
     if (inpl == PE_PALETTE_YVU420P) { std::swap(f->d.planes[1], f->d.planes[2]); std::swap(f->d.rowstrides[1], f->d.rowstrides[2]); }
+  } else if (inpl == PE_PALETTE_YUV411 && (pal_is_rgb(outpl) || outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888 ||
+                                           outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P || outpl == PE_PALETTE_UYVY ||
+                                           outpl == PE_PALETTE_YUYV)) {
+    // convert_yuv411_to_{rgb,bgr,argb,yuv888,yuvp,uyvy,yuyv}_frame (:13755-13826): every variant selects the YCbCr tables of the
+    // layer's clamping itself (set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_YCBCR)); the layer's width in macropixels is a
+    // quarter of the pixel width.  (The reference walks source and most destinations densely; strides are honoured here, X.)
+    if (width & 3) { set_err(PE_ERR_SIZE, "a YUV411 frame is a whole number of 4-pixel macropixels wide"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const int target = pal_is_rgb(outpl) ? 0 : (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888) ? 1
+                       : (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P) ? 2 : outpl == PE_PALETTE_UYVY ? 3 : 4;
+    uint8_t *pl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], (uint8_t *)n.d.planes[3]};
+    ce = launch_yuv411_to(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, width >> 2, height, pl, n.d.rowstrides, target,
+                          pal_has_alpha(outpl), pal_is_rgb(outpl) ? rgb_layout(outpl) : RgbLayout{0, 1, 2, -1, 3},
+                          e->cfg.ref_quirks && (outpl == PE_PALETTE_BGR24 || outpl == PE_PALETTE_BGRA32),
+                          dev_conv(e, iclamping, PE_YUV_SUBSPACE_YCBCR), cavg);
   } else if ((inpl == PE_PALETTE_UYVY && outpl == PE_PALETTE_YUYV) || (inpl == PE_PALETTE_YUYV && outpl == PE_PALETTE_UYVY)) {
     // convert_swab_frame in place (:13138-13140, :13238-13240)
     inplace = true;

@@ -108,6 +108,10 @@ cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const plan
 // float tables [RGBf_Y, Rf_Cr, Gf_Cb, Gf_Cr, Bf_Cb][256], rgb_y_dev = the integer RGB_Y table mode 0 adds them to; sums_dev optional
 cudaError_t launch_yuv888_to_rgb_float(const Launch &L, int mode, CImg src, Img dst, int width, int height, int in_alpha, RgbLayout out,
                                        const float *ftab_dev, const int32_t *rgb_y_dev, float *sums_dev);
+// YUV411 (IYU1) -> RGB(A) / packed 4:4:4 / planar 4:4:4 / UYVY / YUYV (convert_yuv411_to_*_frame, colourspace.c:8305-8910); target: 0 RGB,
+// 1 YUV888 / YUVA8888, 2 YUV444P / YUVA4444P, 3 UYVY, 4 YUYV; cavg_dev: the 64 KB averaging table of the frame's clamping
+cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,
+                             int alpha, RgbLayout out, int bgr_quirk, DevConv conv, const uint8_t *cavg_dev);
 // the owner's side of the multitrack operand exchange (pe_kernels_mc.cu): bytes from local memory through an NVSwitch multicast address
 cudaError_t launch_mc_publish(const Launch &L, const void *src, void *mc_dst, size_t bytes, int max_ctas);
 // ---- effects ---------------------------------------------------------------------------------------

@@ -401,6 +401,100 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_yuv444p(const uint8_t *__rest
   }
 }
 
+// YUV411 (IYU1, weed-palettes.h:96: macropixel {u2, y0, y1, v2, y2, y3} = 4 pixels sharing one chroma sample) -> RGB(A) / packed
+// 4:4:4 / planar 4:4:4 / UYVY / YUYV: convert_yuv411_to_{rgb,bgr,argb,yuv888,yuvp,uyvy,yuyv}_frame colourspace.c:8305-8910.
+// A row of w macropixels is w + 1 UNITS: unit 0 = the first two pixels with macropixel 0's chroma, unit w = the last two with
+// macropixel w-1's, unit j in between = four pixels (y2, y3 of macropixel j-1, then y0, y1 of macropixel j) whose chroma climbs a
+// ladder of averages between p = chroma(j-1) and c = chroma(j), each step one lookup in the reference's 64 KB averaging table
+// (avg_chroma(x, y) = cavg[x][y], the table of the frame's clamping):  h = avg(p, c);  qp = avg(h, p);  qc = avg(h, c);
+//   pixel 0: avg(qp, p)   pixel 1: avg(qp, c)   pixel 2: avg(qc, p)   pixel 3: avg(qc, c)          (RGB, packed / planar 4:4:4)
+//   first macropixel: avg(h, p)   second: avg(h, c)                                                  (UYVY / YUYV)
+// Replicated: the planar 4:4:4 and the packed 4:2:2 converters write the FIRST luma of each pair twice (`y0` for both samples,
+// :8745-8822, :8867-8893); the planar one also in unit 0.  One thread = one unit.
+struct Yuv411Args {
+  const uint8_t *src;
+  int irow, wmp, height;
+  uint8_t *dst[4];
+  int orow[4];
+  int target;   // 0 RGB (layout `out`), 1 packed 4:4:4 (alpha: 4 bytes), 2 planar 4:4:4 (alpha: plane 3), 3 UYVY, 4 YUYV
+  int alpha;
+  int bgr_quirk;   // BGR / BGRA: the row's first pixel and its last two in R, G, B order (convert_yuv411_to_bgr_frame :8445, :8514)
+  RgbLayout out;
+};
+
+__global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv, const uint8_t *__restrict__ cavg) {
+  __shared__ SmemYuvTabs s;
+  if (A.target == 0) {
+    load_yuv_tabs(s, conv.t);
+    __syncthreads();
+  }
+  auto avg = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
+  const int units = A.wmp + 1;
+  const long long total = (long long)units * A.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / units), j = (int)(it - (long long)row * units);
+    const uint8_t *r0 = A.src + (long long)A.irow * row;
+    uint32_t ys[4], us[4], vs[4];
+    int npx, px0;
+    if (j == 0 || j == A.wmp) {
+      const uint8_t *m = r0 + 6LL * (j == 0 ? 0 : A.wmp - 1);
+      npx = 2; px0 = j == 0 ? 0 : 4 * A.wmp - 2;
+      ys[0] = j == 0 ? m[1] : m[4];
+      ys[1] = j == 0 ? m[2] : m[5];
+      if (A.target == 2 && j == 0) ys[1] = ys[0];   // convert_yuv411_to_yuvp_frame writes y0 twice at the row start (:8726-8734)
+      us[0] = us[1] = m[0]; vs[0] = vs[1] = m[3];
+    } else {
+      const uint8_t *mp = r0 + 6LL * (j - 1), *mc = mp + 6;
+      npx = 4; px0 = 4 * j - 2;
+      const uint32_t pu = mp[0], pv = mp[3], cu = mc[0], cv = mc[3];
+      ys[0] = mp[4]; ys[1] = mp[5]; ys[2] = mc[1]; ys[3] = mc[2];
+      const uint32_t hu = avg(pu, cu), hv = avg(pv, cv);
+      if (A.target >= 3) {       // two 4:2:2 macropixels: one ladder step, first luma twice
+        us[0] = us[1] = avg(hu, pu); vs[0] = vs[1] = avg(hv, pv);
+        us[2] = us[3] = avg(hu, cu); vs[2] = vs[3] = avg(hv, cv);
+        ys[1] = ys[0]; ys[3] = ys[2];
+      } else {
+        const uint32_t qpu = avg(hu, pu), qpv = avg(hv, pv), qcu = avg(hu, cu), qcv = avg(hv, cv);
+        us[0] = avg(qpu, pu); vs[0] = avg(qpv, pv);
+        us[1] = avg(qpu, cu); vs[1] = avg(qpv, cv);
+        us[2] = avg(qcu, pu); vs[2] = avg(qcv, pv);
+        us[3] = avg(qcu, cu); vs[3] = avg(qcv, cv);
+        if (A.target == 2) { ys[1] = ys[0]; ys[3] = ys[2]; }
+      }
+    }
+    if (A.target == 0) {
+      uint8_t *d = A.dst[0] + (long long)A.orow[0] * row + (long long)px0 * A.out.psize;
+      for (int k = 0; k < npx; k++, d += A.out.psize) {
+        int r, g, b;
+        yuv_px(s, nullptr, (int)ys[k], (int)us[k], (int)vs[k], r, g, b);
+        const bool swap = A.bgr_quirk && (px0 + k == 0 || px0 + k >= 4 * A.wmp - 2);
+        d[swap ? A.out.b : A.out.r] = (uint8_t)r; d[A.out.g] = (uint8_t)g; d[swap ? A.out.r : A.out.b] = (uint8_t)b;
+        if (A.out.a >= 0) d[A.out.a] = 255;
+      }
+    } else if (A.target == 1) {
+      const int ps = A.alpha ? 4 : 3;
+      uint8_t *d = A.dst[0] + (long long)A.orow[0] * row + (long long)px0 * ps;
+      for (int k = 0; k < npx; k++, d += ps) {
+        d[0] = (uint8_t)ys[k]; d[1] = (uint8_t)us[k]; d[2] = (uint8_t)vs[k];
+        if (A.alpha) d[3] = 255;
+      }
+    } else if (A.target == 2) {
+      for (int k = 0; k < npx; k++) {
+        A.dst[0][(long long)A.orow[0] * row + px0 + k] = (uint8_t)ys[k];
+        A.dst[1][(long long)A.orow[1] * row + px0 + k] = (uint8_t)us[k];
+        A.dst[2][(long long)A.orow[2] * row + px0 + k] = (uint8_t)vs[k];
+        if (A.alpha) A.dst[3][(long long)A.orow[3] * row + px0 + k] = 255;
+      }
+    } else {
+      uint8_t *d = A.dst[0] + (long long)A.orow[0] * row + (long long)(px0 >> 1) * 4;
+      for (int k = 0; k < npx; k += 2, d += 4) {
+        if (A.target == 3) { d[0] = (uint8_t)us[k]; d[1] = (uint8_t)ys[k]; d[2] = (uint8_t)vs[k]; d[3] = (uint8_t)ys[k + 1]; }
+        else { d[0] = (uint8_t)ys[k]; d[1] = (uint8_t)us[k]; d[2] = (uint8_t)ys[k + 1]; d[3] = (uint8_t)vs[k]; }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_yuv_planar_to_rgb(const Launch &L, const YuvToRgbArgs &a) {
@@ -538,3 +632,18 @@ cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const plan
 
 }  // namespace pe
 
+
+namespace pe {
+cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,
+                             int alpha, RgbLayout out, int bgr_quirk, DevConv conv, const uint8_t *cavg_dev) {
+  if (width_mpx <= 0 || height <= 0) return cudaSuccess;
+  Yuv411Args A;
+  A.bgr_quirk = bgr_quirk;
+  A.src = src.p; A.irow = src.rs; A.wmp = width_mpx; A.height = height;
+  for (int i = 0; i < 4; i++) { A.dst[i] = dst[i]; A.orow[i] = orow[i]; }
+  A.target = target; A.alpha = alpha; A.out = out;
+  k_yuv411_to<<<grid_for(L, (long long)(width_mpx + 1) * height), kBlock, 0, L.stream>>>(A, conv, cavg_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+}  // namespace pe

@@ -69,7 +69,7 @@ typedef struct {
   int plane_bytes_known;  /* rowstrides and planes present */
 } layer_view;
 
-static int ppmp(int pal) { return (pal == PE_PALETTE_UYVY || pal == PE_PALETTE_YUYV) ? 2 : 1; }
+static int ppmp(int pal) { return (pal == PE_PALETTE_UYVY || pal == PE_PALETTE_YUYV) ? 2 : pal == PE_PALETTE_YUV411 ? 4 : 1; }
 
 static int read_layer(weed_layer_t *l, layer_view *v) {
   int np, nrs, i;

@@ -21,6 +21,7 @@ WEED_PALETTE_NONE = 0
 WEED_PALETTE_RGB24, WEED_PALETTE_BGR24, WEED_PALETTE_RGBA32, WEED_PALETTE_BGRA32, WEED_PALETTE_ARGB32 = 1, 2, 3, 4, 5
 WEED_PALETTE_YUV420P, WEED_PALETTE_YVU420P, WEED_PALETTE_YUV422P, WEED_PALETTE_YUV444P = 512, 513, 522, 544
 WEED_PALETTE_YUVA4444P, WEED_PALETTE_UYVY, WEED_PALETTE_YUYV, WEED_PALETTE_YUV888, WEED_PALETTE_YUVA8888 = 545, 564, 565, 588, 589
+WEED_PALETTE_YUV411 = 595
 WEED_YUV_CLAMPING_CLAMPED, WEED_YUV_CLAMPING_UNCLAMPED = 0, 1
 WEED_YUV_SAMPLING_DEFAULT, WEED_YUV_SAMPLING_MPEG = 0, 1
 WEED_YUV_SUBSPACE_YUV, WEED_YUV_SUBSPACE_YCBCR, WEED_YUV_SUBSPACE_BT709 = 0, 1, 2
@@ -49,6 +50,8 @@ def plane_row_bytes(palette, width, plane):
     if plane == 0:
         if palette in (WEED_PALETTE_UYVY, WEED_PALETTE_YUYV):
             return (width // 2) * 4
+        if palette == WEED_PALETTE_YUV411:
+            return (width // 4) * 6
         return width * {1: 3, 2: 3, 588: 3, 3: 4, 4: 4, 5: 4, 589: 4}.get(palette, 1)
     return width >> 1 if palette in (512, 513, 522) else width
 

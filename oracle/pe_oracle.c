@@ -1786,3 +1786,76 @@ void pe_or_yuv2rgb_float(int mode, int clamping, const int32_t *rgb_y_int, const
     if (sums) { sums[i * 3] = r; sums[i * 3 + 1] = g; sums[i * 3 + 2] = b; }
   }
 }
+
+/* ---- YUV411 (IYU1) as a conversion source: convert_yuv411_to_{rgb,bgr,argb,yuv888,yuvp,uyvy,yuyv}_frame  colourspace.c:8305-8910 ----
+ * macropixel {u2, y0, y1, v2, y2, y3} (colourspace.h:203-210) = 4 pixels.  Per row of w macropixels the reference writes: 2 pixels
+ * with macropixel 0's chroma; for j = 1 .. w-1 the 4 pixels (y2, y3 of j-1; y0, y1 of j) with the chroma ladder
+ *   h = avg(p, c); qp = avg(h, p); qc = avg(h, c);  u = avg(qp, p), avg(qp, c), avg(qc, p), avg(qc, c)      (p = chroma j-1, c = chroma j)
+ * (UYVY / YUYV: one step, avg(h, p) / avg(h, c)); 2 pixels with macropixel w-1's chroma.  avg = avg_chromaf = the cavg table of the
+ * frame's clamping (:2100-2104); RGB through yuv2rgb with the YCbCr tables of that clamping.  Replicated: the planar 4:4:4 and packed
+ * 4:2:2 variants write the first luma of a pair twice (:8745-8822, :8867-8893; planar also in the first pair :8726-8734).
+ * Replicated under `quirks`: the BGR / BGRA variant writes the first pixel of a row and its last two in R, G, B order (:8445, :8514).
+ * X (defined here): the RGBA / BGRA variants never write the alpha bytes of the first pixel pair of a loop iteration (:8338-8370):
+ * 255; source and (except RGB) destination rows are walked densely: strides honoured.
+ * target: 0 RGB (order, add_alpha), 1 packed 4:4:4, 2 planar 4:4:4 (dest[3] = alpha plane when add_alpha), 3 UYVY, 4 YUYV */
+void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[4], const int orow[4],
+                     int order, int add_alpha, int clamping, int quality, int quirks) {
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  const uint8_t *avg = or_avg(clamping);
+  int ro = 0, go = 1, bo = 2, ao = -1, ps = 3;
+  if (target == 0) or_order_offsets(order, add_alpha, &ro, &go, &bo, &ao, &ps);
+  else if (target == 1) ps = add_alpha ? 4 : 3;
+#define OR_AVG(x, y) (avg[((int)(x) << 8) + (int)(y)])
+  for (int i = 0; i < height; i++) {
+    const uint8_t *m = src + (long)irow * i;
+    for (int j = 0; j <= width_mpx; j++) {
+      uint8_t ys[4], us[4], vs[4];
+      int npx, px0;
+      if (j == 0 || j == width_mpx) {
+        const uint8_t *q = m + 6L * (j == 0 ? 0 : width_mpx - 1);
+        npx = 2; px0 = j == 0 ? 0 : 4 * width_mpx - 2;
+        ys[0] = j == 0 ? q[1] : q[4]; ys[1] = j == 0 ? q[2] : q[5];
+        if (target == 2 && j == 0) ys[1] = ys[0];
+        us[0] = us[1] = q[0]; vs[0] = vs[1] = q[3];
+      } else {
+        const uint8_t *p = m + 6L * (j - 1), *q = p + 6;
+        const uint8_t pu = p[0], pv = p[3], cu = q[0], cv = q[3];
+        const uint8_t hu = OR_AVG(pu, cu), hv = OR_AVG(pv, cv);
+        npx = 4; px0 = 4 * j - 2;
+        ys[0] = p[4]; ys[1] = p[5]; ys[2] = q[1]; ys[3] = q[2];
+        if (target >= 3) {
+          us[0] = us[1] = OR_AVG(hu, pu); vs[0] = vs[1] = OR_AVG(hv, pv);
+          us[2] = us[3] = OR_AVG(hu, cu); vs[2] = vs[3] = OR_AVG(hv, cv);
+          ys[1] = ys[0]; ys[3] = ys[2];
+        } else {
+          const uint8_t qpu = OR_AVG(hu, pu), qpv = OR_AVG(hv, pv), qcu = OR_AVG(hu, cu), qcv = OR_AVG(hv, cv);
+          us[0] = OR_AVG(qpu, pu); vs[0] = OR_AVG(qpv, pv); us[1] = OR_AVG(qpu, cu); vs[1] = OR_AVG(qpv, cv);
+          us[2] = OR_AVG(qcu, pu); vs[2] = OR_AVG(qcv, pv); us[3] = OR_AVG(qcu, cu); vs[3] = OR_AVG(qcv, cv);
+          if (target == 2) { ys[1] = ys[0]; ys[3] = ys[2]; }
+        }
+      }
+      for (int k = 0; k < npx; k++) {
+        const long x = px0 + k;
+        if (target == 0) {
+          uint8_t *d = dest[0] + (long)orow[0] * i + x * ps;
+          /* convert_yuv411_to_bgr_frame hands the row's first pixel and its last two to uyvy2rgb in R, G, B order (:8445, :8514) */
+          const int swap = quirks && order == OR_ORDER_BGR && (x == 0 || x >= 4L * width_mpx - 2);
+          or_px_yuv2rgb(c, quality, NULL, ys[k], us[k], vs[k], &d[swap ? bo : ro], &d[go], &d[swap ? ro : bo]);
+          if (ao >= 0) d[ao] = 255;
+        } else if (target == 1) {
+          uint8_t *d = dest[0] + (long)orow[0] * i + x * ps;
+          d[0] = ys[k]; d[1] = us[k]; d[2] = vs[k];
+          if (add_alpha) d[3] = 255;
+        } else if (target == 2) {
+          dest[0][(long)orow[0] * i + x] = ys[k]; dest[1][(long)orow[1] * i + x] = us[k]; dest[2][(long)orow[2] * i + x] = vs[k];
+          if (add_alpha) dest[3][(long)orow[3] * i + x] = 255;
+        } else if (!(k & 1)) {
+          uint8_t *d = dest[0] + (long)orow[0] * i + (x >> 1) * 4;
+          if (target == 3) { d[0] = us[k]; d[1] = ys[k]; d[2] = vs[k]; d[3] = ys[k + 1]; }
+          else { d[0] = ys[k]; d[1] = us[k]; d[2] = ys[k + 1]; d[3] = vs[k]; }
+        }
+      }
+    }
+  }
+#undef OR_AVG
+}

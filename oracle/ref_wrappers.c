@@ -378,6 +378,21 @@ void ref_chroma_upsample_packed(int is_420, uint8_t **src, int width, int height
 /* ---- the reference's "float - experimental" YUV -> RGB path (colourspace.c:101-172 tables, :592 clamp0255f, :2367 yuv2rgb_float);
  *      float tables exist for the BT.709 subspace only (:279-310, :316-355) ---- */
 /* which: 0 RGBf_Y 1 Rf_Cr 2 Gf_Cb 3 Gf_Cr 4 Bf_Cb */
+/* YUV411 as a source; target as pe_or_yuv411_to; width in macropixels.  Only convert_yuv411_to_{rgb,bgr,argb}_frame take an output
+ * rowstride; the others write densely */
+void ref_yuv411_to(int target, void *src, int width, int height, int orow, uint8_t **dest, int order, int add_alpha, int clamping) {
+  ref_init();
+  yuv411_macropixel *s = (yuv411_macropixel *)src;
+  if (target == 0) {
+    if (order == 0) convert_yuv411_to_rgb_frame(s, width, height, orow, dest[0], add_alpha, clamping);
+    else if (order == 1) convert_yuv411_to_bgr_frame(s, width, height, orow, dest[0], add_alpha, clamping);
+    else convert_yuv411_to_argb_frame(s, width, height, orow, dest[0], clamping);
+  } else if (target == 1) convert_yuv411_to_yuv888_frame(s, width, height, dest[0], add_alpha, clamping);
+  else if (target == 2) convert_yuv411_to_yuvp_frame(s, width, height, dest, add_alpha, clamping);
+  else if (target == 3) convert_yuv411_to_uyvy_frame(s, width, height, (uyvy_macropixel *)dest[0], clamping);
+  else convert_yuv411_to_yuyv_frame(s, width, height, (yuyv_macropixel *)dest[0], clamping);
+}
+
 int ref_get_float_table(int clamping, int which, float *out) {
   ref_init();
   set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_BT709);

@@ -15,7 +15,7 @@ REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
 PAL = dict(RGB24=1, BGR24=2, RGBA32=3, BGRA32=4, ARGB32=5, YUV420P=512, YVU420P=513, YUV422P=522,
-           YUV444P=544, YUVA4444P=545, UYVY=564, YUYV=565, YUV888=588, YUVA8888=589)
+           YUV444P=544, YUVA4444P=545, UYVY=564, YUYV=565, YUV888=588, YUVA8888=589, YUV411=595)
 CLAMPED, UNCLAMPED = 0, 1
 SUB_YUV, SUB_YCBCR, SUB_BT709 = 0, 1, 2
 G_UNKNOWN, G_LINEAR, G_SRGB, G_BT709, G_MONITOR = 0, -1, 1, 2, 1024
@@ -38,7 +38,7 @@ def rowstride(width, psize):
 
 
 def psize_of(pal):
-    return {1: 3, 2: 3, 3: 4, 4: 4, 5: 4, 588: 3, 589: 4, 564: 4, 565: 4}.get(pal, 1)
+    return {1: 3, 2: 3, 3: 4, 4: 4, 5: 4, 588: 3, 589: 4, 564: 4, 565: 4, 595: 6}.get(pal, 1)
 
 
 I, L, D, VP = C.c_int, C.c_long, C.c_double, C.c_void_p
@@ -78,6 +78,7 @@ _ORACLE_PROTOS = {
     "pe_or_packed422_to_yuv422p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv888": [I, VP, I, I, I, VP, I, I],
+    "pe_or_yuv411_to": [I, VP, I, I, I, VP, VP, I, I, I, I, I],
     "pe_or_swab": [VP, I, I, I],
     "pe_or_slide_over_bound": [I, I, I, I],
     "pe_or_slide_over": [I, I, I, I, VP, I, VP, I, VP, I, I, I, I],
@@ -122,6 +123,7 @@ _REF_PROTOS = {
     "ref_packed422_to_yuv422p": [I, VP, I, I, VP],
     "ref_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "ref_packed422_to_yuv888": [I, VP, I, I, I, I, VP, I],
+    "ref_yuv411_to": [I, VP, I, I, I, VP, I, I, I],
     "ref_swab": [VP, I, I, I],
     "ref_chroma_upsample_packed": [I, VP, I, I, VP, I, VP, I, I, I],
     "ref_packed422_to_yuv420p": [I, VP, I, I, VP, I],

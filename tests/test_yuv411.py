@@ -1,0 +1,165 @@
+"""YUV411 (IYU1) as a conversion source -- convert_yuv411_to_{rgb,bgr,argb,yuv888,yuvp,uyvy,yuyv}_frame, src/colourspace.c:8305-8910.
+
+CPU: the oracle against the compiled reference on the buffers the reference defines (dense rows; for RGBA / BGRA the destination is
+prefilled with 255, because the reference never writes the alpha bytes of the first pixel pair of a loop iteration, :8338-8370).
+GPU: the CUDA converter (pe_convert_layer_palette on a YUV411 layer) against the oracle, padded rowstrides included."""
+import itertools
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import pe_testlib as T  # noqa: E402
+
+# (target, order, add_alpha, palette): target 0 RGB, 1 packed 4:4:4, 2 planar 4:4:4, 3 UYVY, 4 YUYV
+CASES = [(0, 0, 0, "RGB24"), (0, 0, 1, "RGBA32"), (0, 1, 0, "BGR24"), (0, 1, 1, "BGRA32"), (0, 2, 1, "ARGB32"),
+         (1, 0, 0, "YUV888"), (1, 0, 1, "YUVA8888"), (2, 0, 0, "YUV444P"), (2, 0, 1, "YUVA4444P"), (3, 0, 0, "UYVY"), (4, 0, 0, "YUYV")]
+
+
+def _src(rng, wm, h, clamped, stride=None):
+    """wm macropixels {u2, y0, y1, v2, y2, y3} per row"""
+    stride = stride or wm * 6
+    a = np.zeros((h, stride), np.uint8)
+    lo, hy, hc = (16, 236, 241) if clamped else (0, 256, 256)
+    m = rng.integers(lo, hy, (h, wm, 6), dtype=np.uint8)
+    m[:, :, 0] = rng.integers(lo, hc, (h, wm), dtype=np.uint8)
+    m[:, :, 3] = rng.integers(lo, hc, (h, wm), dtype=np.uint8)
+    a[:, :wm * 6] = m.reshape(h, wm * 6)
+    return a
+
+
+def _out_planes(target, add_alpha, wm, h, dense):
+    w = 4 * wm
+    if target == 2:
+        st = w if dense else T.rowstride(w, 1)
+        return [np.zeros((h, st), np.uint8) for _ in range(4 if add_alpha else 3)]
+    ps = (4 if add_alpha else 3) if target < 3 else 2
+    st = w * ps if dense else T.rowstride(w, ps)
+    return [np.zeros((h, st), np.uint8)]
+
+
+def _oracle(target, order, add_alpha, src, wm, h, cl, planes, quirks=1):
+    o = T.oracle()
+    pl = list(planes) + [planes[0]] * (4 - len(planes))
+    o.pe_or_yuv411_to(target, T.ptr(src), src.strides[0], wm, h, T.planes_arg(*pl), T.strides_arg(*pl), order, add_alpha, cl, T.Q_HIGH, quirks)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", CASES, ids=[c[3] for c in CASES])
+def test_oracle_equals_compiled_reference(case):
+    target, order, add_alpha, _ = case
+    r = T.ref()
+    rng = np.random.default_rng(411 + target * 7 + order)
+    for (wm, h), cl in itertools.product(((1, 2), (2, 3), (9, 4), (40, 5)), (T.CLAMPED, T.UNCLAMPED)):
+        src = _src(rng, wm, h, cl == T.CLAMPED)
+        exp = _out_planes(target, add_alpha, wm, h, dense=True)
+        got = [np.zeros_like(p) for p in exp]
+        if target == 0 and add_alpha:
+            for p in exp:
+                p[:] = 255   # the alpha bytes the reference leaves unwritten
+        pl = exp + [exp[0]] * (4 - len(exp))
+        r.ref_yuv411_to(target, T.ptr(src), wm, h, exp[0].strides[0], T.planes_arg(*pl), order, add_alpha, cl)
+        _oracle(target, order, add_alpha, src, wm, h, cl, got)
+        for k in range(len(exp)):
+            assert (got[k] == exp[k]).all(), (case, wm, h, cl, k)
+
+
+def test_known_answers():
+    """a flat frame stays flat, and the ladder is monotone between two macropixels"""
+    o = T.oracle()
+    wm, h = 3, 1
+    src = np.zeros((h, wm * 6), np.uint8)
+    src[0] = [100, 50, 60, 200, 70, 80, 140, 90, 100, 160, 110, 120, 140, 130, 140, 160, 150, 160]
+    out = _out_planes(1, 0, wm, h, dense=True)
+    _oracle(1, 0, 0, src, wm, h, T.UNCLAMPED, out)
+    px = out[0].reshape(12, 3)
+    assert list(px[:, 0]) == [50, 60, 70, 80, 90, 100, 110, 120, 130, 140, 150, 160]
+    assert list(px[:2, 1]) == [100, 100] and list(px[-2:, 1]) == [140, 140]
+    # the ladder as the reference climbs it (its comments promise 1/8, 3/8, 5/8, 7/8): p = 100, c = 140 -> h 120, qp 110, qc 130
+    assert list(px[2:6, 1]) == [105, 125, 115, 135] and list(px[2:6, 2]) == [195, 175, 185, 165]
+    assert list(px[6:10, 1]) == [140] * 4
+
+
+def test_bgr_quirk_and_intended_order():
+    """convert_yuv411_to_bgr_frame writes the first pixel of a row and its last two in R, G, B order (:8445, :8514)"""
+    rng = np.random.default_rng(5)
+    wm, h = 5, 2
+    src = _src(rng, wm, h, True)
+    rgb, bq, bi = (_out_planes(0, 0, wm, h, dense=True) for _ in range(3))
+    _oracle(0, 0, 0, src, wm, h, T.CLAMPED, rgb)
+    _oracle(0, 1, 0, src, wm, h, T.CLAMPED, bq, quirks=1)
+    _oracle(0, 1, 0, src, wm, h, T.CLAMPED, bi, quirks=0)
+    r, q, i = (a[0].reshape(h, 4 * wm, 3) for a in (rgb, bq, bi))
+    assert (i == r[:, :, ::-1]).all()
+    assert (q[:, 1:-2] == i[:, 1:-2]).all() and (q[:, 0] == r[:, 0]).all() and (q[:, -2:] == r[:, -2:]).all()
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors_yuv411.npz")
+
+
+def test_oracle_equals_golden_vectors():
+    """the outputs of the compiled reference, frozen by tests/golden/make_golden_yuv411.py (for boxes without /root/reference)"""
+    g = np.load(GOLDEN)
+    wm, h = 12, 6
+    for cl in (T.CLAMPED, T.UNCLAMPED):
+        src = g["src_cl%d" % cl]
+        for target, order, add_alpha, pal in CASES:
+            got = _out_planes(target, add_alpha, wm, h, dense=True)
+            _oracle(target, order, add_alpha, src, wm, h, cl, got)
+            for k, p in enumerate(got):
+                assert (p == g["%s_cl%d_p%d" % (pal, cl, k)]).all(), (pal, cl, k)
+
+
+@pytest.mark.gpu
+def test_cuda_equals_golden_vectors():
+    lb = pytest.importorskip("lives_b200")
+    g = np.load(GOLDEN)
+    eng = lb.Engine()
+    wm, h = 12, 6
+    for cl in (T.CLAMPED, T.UNCLAMPED):
+        src = g["src_cl%d" % cl]
+        for target, order, add_alpha, pal in CASES:
+            lay = lb.Layer.from_host(eng, T.PAL["YUV411"], 4 * wm, h, [src], yuv_clamping=cl)
+            assert lb.convert_layer_palette(lay, T.PAL[pal], cl)
+            got = lay.to_host()
+            for k, p in enumerate(got):
+                e = g["%s_cl%d_p%d" % (pal, cl, k)]
+                assert (p[:, :e.shape[1]] == e).all(), (pal, cl, k)
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[3] for c in CASES])
+def test_cuda_equals_oracle(case):
+    lb = pytest.importorskip("lives_b200")
+    target, order, add_alpha, pal = case
+    eng = lb.Engine()
+    rng = np.random.default_rng(595 + target)
+    for (wm, h), cl in itertools.product(((1, 1), (2, 3), (9, 4), (40, 17), (480, 270)), (T.CLAMPED, T.UNCLAMPED)):
+        w = 4 * wm
+        src = _src(rng, wm, h, cl == T.CLAMPED, stride=T.align_ceil(wm * 6, 32))
+        lay = lb.Layer.from_host(eng, T.PAL["YUV411"], w, h, [src], yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, T.PAL[pal], cl), (case, lb.capi.last_error())
+        got = lay.to_host()
+        assert lay.palette == T.PAL[pal] and lay.width == w and lay.height == h
+        exp = [np.zeros_like(p) for p in got]
+        _oracle(target, order, add_alpha, src, wm, h, cl, exp)
+        rb = [lb.plane_row_bytes(T.PAL[pal], w, k) for k in range(len(got))]
+        for k in range(len(got)):
+            assert (got[k][:, :rb[k]] == exp[k][:, :rb[k]]).all(), (case, wm, h, cl, k)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_cuda_refuses_what_is_not_built():
+    lb = pytest.importorskip("lives_b200")
+    eng = lb.Engine()
+    src = _src(np.random.default_rng(1), 4, 2, True, stride=32)
+    lay = lb.Layer.from_host(eng, T.PAL["YUV411"], 16, 2, [src], yuv_clamping=T.CLAMPED)
+    assert not lb.convert_layer_palette(lay, T.PAL["YUV420P"], T.CLAMPED)     # 4:1:1 -> 4:2:0 / 4:2:2 planar: not built, loud
+    assert lay.palette == T.PAL["YUV411"] and (lay.to_host()[0] == src).all()  # and the layer is untouched
+    rgb = lb.Layer.from_host(eng, T.PAL["RGB24"], 16, 2, [T.make_packed(np.random.default_rng(2), 16, 2, 3)])
+    assert not lb.convert_layer_palette(rgb, T.PAL["YUV411"], T.CLAMPED)      # -> YUV411: not built
+    eng.close()
