@@ -1545,6 +1545,14 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     // way in for a V-first source (:12354), on the way out for a V-first target (:13895, below)
     inplace = true;
     if (inpl == PE_PALETTE_YVU420P) { std::swap(f->d.planes[1], f->d.planes[2]); std::swap(f->d.rowstrides[1], f->d.rowstrides[2]); }
+  } else if (pal_is_rgb(inpl) && outpl == PE_PALETTE_YUV411) {
+    // convert_{rgb,bgr,argb}_to_yuv411_frame (:12627, :12705, :12779, :12852, :12925): YCbCr tables of oclamping, whole macropixels
+    // ("cut the rightmost one, two or three pixels": the layer becomes width >> 2 macropixels wide)
+    n.d.width = width & ~3;
+    if (n.d.width < 4) { set_err(PE_ERR_SIZE, "frame too narrow for a YUV411 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    ce = launch_rgb_to_yuv411(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]},
+                              width >> 2, height, rgb_layout(inpl), dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
   } else if (inpl == PE_PALETTE_YUV411 && (pal_is_rgb(outpl) || outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888 ||
                                            outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P || outpl == PE_PALETTE_UYVY ||
                                            outpl == PE_PALETTE_YUYV)) {

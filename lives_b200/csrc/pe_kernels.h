@@ -110,6 +110,8 @@ cudaError_t launch_yuv888_to_rgb_float(const Launch &L, int mode, CImg src, Img 
                                        const float *ftab_dev, const int32_t *rgb_y_dev, float *sums_dev);
 // YUV411 (IYU1) -> RGB(A) / packed 4:4:4 / planar 4:4:4 / UYVY / YUYV (convert_yuv411_to_*_frame, colourspace.c:8305-8910); target: 0 RGB,
 // 1 YUV888 / YUVA8888, 2 YUV444P / YUVA4444P, 3 UYVY, 4 YUYV; cavg_dev: the 64 KB averaging table of the frame's clamping
+// RGB(A) / BGR(A) / ARGB -> YUV411 (colourspace.c:6499-6614): whole macropixels
+cudaError_t launch_rgb_to_yuv411(const Launch &L, CImg src, Img dst, int width_mpx, int height, RgbLayout in, DevConv conv);
 cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,
                              int alpha, RgbLayout out, int bgr_quirk, DevConv conv, const uint8_t *cavg_dev);
 // the owner's side of the multitrack operand exchange (pe_kernels_mc.cu): bytes from local memory through an NVSwitch multicast address

@@ -634,6 +634,42 @@ cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const plan
 
 
 namespace pe {
+namespace {
+// RGB(A) / BGR(A) / ARGB -> YUV411: convert_{rgb,bgr,argb}_to_yuv411_frame colourspace.c:6499-6614, rgb2_411 :2323.  One thread = one
+// macropixel = 4 pixels: luma per pixel, chroma = (sum of the four pixels' >> 16 terms) >> 2, clamped.
+__global__ void __launch_bounds__(kBlock) k_rgb_to_yuv411(const uint8_t *__restrict__ src, int irow, uint8_t *dst, int orow, int wmp, int height,
+                                                          RgbLayout in, DevConv conv) {
+  __shared__ int32_t t[9][256];
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) t[i >> 8][i & 255] = conv.t[i];
+  __syncthreads();
+  const long long total = (long long)wmp * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / wmp), j = (int)(it - (long long)row * wmp);
+    const uint8_t *q = src + (long long)irow * row + (long long)j * 4 * in.psize;
+    int su = 0, sv = 0, yy[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int r = q[k * in.psize + in.r], g = q[k * in.psize + in.g], b = q[k * in.psize + in.b];
+      yy[k] = min(max((t[0][r] + t[1][g] + t[2][b]) >> 16, conv.min_y), conv.max_y);
+      su += (t[3][r] + t[4][g] + t[5][b]) >> 16;
+      sv += (t[6][r] + t[7][g] + t[8][b]) >> 16;
+    }
+    uint8_t *d = dst + (long long)orow * row + 6LL * j;
+    d[0] = (uint8_t)min(max(su >> 2, conv.min_uv), conv.max_uv);
+    d[1] = (uint8_t)yy[0]; d[2] = (uint8_t)yy[1];
+    d[3] = (uint8_t)min(max(sv >> 2, conv.min_uv), conv.max_uv);
+    d[4] = (uint8_t)yy[2]; d[5] = (uint8_t)yy[3];
+  }
+}
+}  // namespace
+
+cudaError_t launch_rgb_to_yuv411(const Launch &L, CImg src, Img dst, int width_mpx, int height, RgbLayout in, DevConv conv) {
+  if (width_mpx <= 0 || height <= 0) return cudaSuccess;
+  k_rgb_to_yuv411<<<grid_for(L, (long long)width_mpx * height), kBlock, 0, L.stream>>>(src.p, src.rs, dst.p, dst.rs, width_mpx, height, in, conv);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,
                              int alpha, RgbLayout out, int bgr_quirk, DevConv conv, const uint8_t *cavg_dev) {
   if (width_mpx <= 0 || height <= 0) return cudaSuccess;

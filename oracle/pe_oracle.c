@@ -1859,3 +1859,34 @@ void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, in
   }
 #undef OR_AVG
 }
+
+/* ---- RGB(A) / BGR(A) / ARGB -> YUV411: convert_{rgb,bgr,argb}_to_yuv411_frame :6499-6614, rgb2_411 :2323-2343.  Whole macropixels
+ * only (the rightmost width % 4 pixels are cut); always the YCbCr tables; luma per pixel `(Y_R + Y_G + Y_B) >> 16` clamped, chroma = the
+ * sum of the four pixels' `>> 16` terms, `>> 2`, clamped (plain shifts: rgb2_411 does not go through spc_rnd).  The reference writes
+ * the macropixels densely (`u++`); the output rowstride is honoured here (X). */
+void pe_or_rgb_to_yuv411(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order, int in_alpha,
+                         int clamping) {
+  const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
+  int ro, go, bo, ao, ips;
+  or_order_offsets(order, in_alpha, &ro, &go, &bo, &ao, &ips);
+  for (int i = 0; i < height; i++) {
+    const uint8_t *s = src + (long)irow * i;
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < width >> 2; j++, s += 4 * ips, d += 6) {
+      int su = 0, sv = 0;
+      uint8_t yy[4];
+      for (int k = 0; k < 4; k++) {
+        const uint8_t r = s[k * ips + ro], g = s[k * ips + go], b = s[k * ips + bo];
+        int a = (c->t[0][r] + c->t[1][g] + c->t[2][b]) >> 16;
+        yy[k] = a > c->max_y ? c->max_y : a < c->min_y ? c->min_y : a;
+        su += (c->t[3][r] + c->t[4][g] + c->t[5][b]) >> 16;
+        sv += (c->t[6][r] + c->t[7][g] + c->t[8][b]) >> 16;
+      }
+      su >>= 2; sv >>= 2;
+      d[0] = su > c->max_uv ? c->max_uv : su < c->min_uv ? c->min_uv : su;
+      d[1] = yy[0]; d[2] = yy[1];
+      d[3] = sv > c->max_uv ? c->max_uv : sv < c->min_uv ? c->min_uv : sv;
+      d[4] = yy[2]; d[5] = yy[3];
+    }
+  }
+}

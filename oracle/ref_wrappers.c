@@ -393,6 +393,14 @@ void ref_yuv411_to(int target, void *src, int width, int height, int orow, uint8
   else convert_yuv411_to_yuyv_frame(s, width, height, (yuyv_macropixel *)dest[0], clamping);
 }
 
+/* order 0 RGB(A), 1 BGR(A), 2 ARGB; width in pixels; dense output */
+void ref_rgb_to_yuv411(uint8_t *src, int width, int height, int irow, void *dest, int order, int has_alpha, int clamping) {
+  ref_init();
+  if (order == 0) convert_rgb_to_yuv411_frame(src, width, height, irow, (yuv411_macropixel *)dest, has_alpha, clamping);
+  else if (order == 1) convert_bgr_to_yuv411_frame(src, width, height, irow, (yuv411_macropixel *)dest, has_alpha, clamping);
+  else convert_argb_to_yuv411_frame(src, width, height, irow, (yuv411_macropixel *)dest, clamping);
+}
+
 int ref_get_float_table(int clamping, int which, float *out) {
   ref_init();
   set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_BT709);

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 import pe_testlib as T  # noqa: E402
-from test_yuv411 import CASES, _src, _out_planes  # noqa: E402
+from test_yuv411 import CASES, RGB_SOURCES, _src, _out_planes  # noqa: E402
 
 WM, H = 12, 6
 
@@ -32,6 +32,13 @@ def main():
             r.ref_yuv411_to(target, T.ptr(src), WM, H, exp[0].strides[0], T.planes_arg(*pl), order, add_alpha, cl)
             for k, p in enumerate(exp):
                 out["%s_cl%d_p%d" % (pal, cl, k)] = p
+    for order, has_alpha, pal in RGB_SOURCES:   # RGB sources -> YUV411 (convert_{rgb,bgr,argb}_to_yuv411_frame), 24 x 6 pixels
+        rgb = T.make_packed(rng, 24, H, 4 if has_alpha else 3)
+        out["rgbsrc_%s" % pal] = rgb
+        for cl in (T.CLAMPED, T.UNCLAMPED):
+            d = np.zeros((H, 6 * 6), np.uint8)
+            r.ref_rgb_to_yuv411(T.ptr(rgb), 24, H, rgb.strides[0], T.ptr(d), order, has_alpha, cl)
+            out["from_%s_cl%d" % (pal, cl)] = d
     np.savez_compressed(os.path.join(HERE, "ref_vectors_yuv411.npz"), **out)
     print("wrote %d arrays" % len(out))
 

@@ -96,6 +96,50 @@ def test_bgr_quirk_and_intended_order():
     assert (q[:, 1:-2] == i[:, 1:-2]).all() and (q[:, 0] == r[:, 0]).all() and (q[:, -2:] == r[:, -2:]).all()
 
 
+# (order, has_alpha, palette) of the RGB sources of convert_{rgb,bgr,argb}_to_yuv411_frame (:6499-6614)
+RGB_SOURCES = [(0, 0, "RGB24"), (0, 1, "RGBA32"), (1, 0, "BGR24"), (1, 1, "BGRA32"), (2, 1, "ARGB32")]
+
+
+def _oracle_from_rgb(order, has_alpha, src, w, h, cl, dest):
+    T.oracle().pe_or_rgb_to_yuv411(T.ptr(src), src.strides[0], w, h, T.ptr(dest), dest.strides[0], order, has_alpha, cl)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", RGB_SOURCES, ids=[c[2] for c in RGB_SOURCES])
+def test_rgb_to_yuv411_oracle_equals_compiled_reference(case):
+    order, has_alpha, _ = case
+    r = T.ref()
+    rng = np.random.default_rng(4110 + order)
+    for (w, h), cl in itertools.product(((4, 1), (8, 3), (23, 4), (64, 5)), (T.CLAMPED, T.UNCLAMPED)):
+        src = T.make_packed(rng, w, h, 4 if has_alpha else 3)
+        wm = w >> 2
+        exp, got = np.zeros((h, wm * 6), np.uint8), np.zeros((h, wm * 6), np.uint8)
+        r.ref_rgb_to_yuv411(T.ptr(src), w, h, src.strides[0], T.ptr(exp), order, has_alpha, cl)
+        _oracle_from_rgb(order, has_alpha, src, w, h, cl, got)
+        assert (got == exp).all(), (case, w, h, cl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RGB_SOURCES, ids=[c[2] for c in RGB_SOURCES])
+def test_rgb_to_yuv411_cuda_equals_oracle_and_round_trip_geometry(case):
+    lb = pytest.importorskip("lives_b200")
+    order, has_alpha, pal = case
+    eng = lb.Engine()
+    rng = np.random.default_rng(5950 + order)
+    for (w, h), cl in itertools.product(((4, 1), (23, 4), (64, 5), (1920, 270)), (T.CLAMPED, T.UNCLAMPED)):
+        src = T.make_packed(rng, w, h, 4 if has_alpha else 3)
+        lay = lb.Layer.from_host(eng, T.PAL[pal], w, h, [src])
+        assert lb.convert_layer_palette(lay, T.PAL["YUV411"], cl), lb.capi.last_error()
+        wm = w >> 2
+        assert lay.palette == T.PAL["YUV411"] and lay.width == 4 * wm and lay.height == h and lay.desc.yuv_clamping == cl
+        got = lay.to_host()[0]
+        exp = np.zeros_like(got)
+        _oracle_from_rgb(order, has_alpha, src, w, h, cl, exp)
+        assert (got[:, :wm * 6] == exp[:, :wm * 6]).all(), (case, w, h, cl)
+        assert lb.convert_layer_palette(lay, T.PAL[pal], cl) and lay.palette == T.PAL[pal] and lay.width == 4 * wm   # and back
+    eng.close()
+
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors_yuv411.npz")
 
 
@@ -110,6 +154,11 @@ def test_oracle_equals_golden_vectors():
             _oracle(target, order, add_alpha, src, wm, h, cl, got)
             for k, p in enumerate(got):
                 assert (p == g["%s_cl%d_p%d" % (pal, cl, k)]).all(), (pal, cl, k)
+        for order, has_alpha, pal in RGB_SOURCES:
+            rgb = g["rgbsrc_%s" % pal]
+            got = np.zeros((rgb.shape[0], 6 * 6), np.uint8)
+            _oracle_from_rgb(order, has_alpha, rgb, 24, rgb.shape[0], cl, got)
+            assert (got == g["from_%s_cl%d" % (pal, cl)]).all(), (pal, cl)
 
 
 @pytest.mark.gpu
@@ -160,6 +209,6 @@ def test_cuda_refuses_what_is_not_built():
     lay = lb.Layer.from_host(eng, T.PAL["YUV411"], 16, 2, [src], yuv_clamping=T.CLAMPED)
     assert not lb.convert_layer_palette(lay, T.PAL["YUV420P"], T.CLAMPED)     # 4:1:1 -> 4:2:0 / 4:2:2 planar: not built, loud
     assert lay.palette == T.PAL["YUV411"] and (lay.to_host()[0] == src).all()  # and the layer is untouched
-    rgb = lb.Layer.from_host(eng, T.PAL["RGB24"], 16, 2, [T.make_packed(np.random.default_rng(2), 16, 2, 3)])
-    assert not lb.convert_layer_palette(rgb, T.PAL["YUV411"], T.CLAMPED)      # -> YUV411: not built
+    uy = lb.Layer.from_host(eng, T.PAL["UYVY"], 16, 2, [T.make_packed(np.random.default_rng(2), 8, 2, 4)])
+    assert not lb.convert_layer_palette(uy, T.PAL["YUV411"], T.CLAMPED)       # YUV -> YUV411: not built (the reference stops early)
     eng.close()
