@@ -1545,6 +1545,24 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     // way in for a V-first source (:12354), on the way out for a V-first target (:13895, below)
     inplace = true;
     if (inpl == PE_PALETTE_YVU420P) { std::swap(f->d.planes[1], f->d.planes[2]); std::swap(f->d.rowstrides[1], f->d.rowstrides[2]); }
+  } else if (outpl == PE_PALETTE_YUV411 &&
+             (inpl == PE_PALETTE_UYVY || inpl == PE_PALETTE_YUYV || inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P ||
+              inpl == PE_PALETTE_YUV422P || inpl == PE_PALETTE_YUV888 || inpl == PE_PALETTE_YUVA8888 || inpl == PE_PALETTE_YUV444P ||
+              inpl == PE_PALETTE_YUVA4444P)) {
+    // convert_{uyvy,yuyv}_to_yuv411_frame (:13227, :13327), convert_yuv420_to_yuv411_frame (:13640, :13747),
+    // convert_yuv888_to_yuv411_frame (:13420, :13512; every row here, the reference stops after a third / a quarter of them, X),
+    // convert_yuvp_to_yuv411_frame (:13028, :13127; per macropixel, the reference never advances its output pointer, X)
+    n.d.width = width & ~3;
+    if (n.d.width < 4) { set_err(PE_ERR_SIZE, "frame too narrow for a YUV411 macropixel"); return PE_FALSE; }
+    if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;
+    const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
+    if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
+    const int mode = inpl == PE_PALETTE_UYVY ? 0 : inpl == PE_PALETTE_YUYV ? 1 : (inpl == PE_PALETTE_YUV420P || inpl == PE_PALETTE_YVU420P) ? 2
+                     : inpl == PE_PALETTE_YUV422P ? 3 : inpl == PE_PALETTE_YUV888 ? 4 : inpl == PE_PALETTE_YUVA8888 ? 5 : 6;
+    const bool swap = inpl == PE_PALETTE_YVU420P;
+    const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[swap ? 2 : 1], (const uint8_t *)f->d.planes[swap ? 1 : 2]};
+    const int rs[3] = {f->d.rowstrides[0], f->d.rowstrides[swap ? 2 : 1], f->d.rowstrides[swap ? 1 : 2]};
+    ce = launch_to_yuv411(L, mode, pl, rs, width >> 2, height, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, cavg);
   } else if (pal_is_rgb(inpl) && outpl == PE_PALETTE_YUV411) {
     // convert_{rgb,bgr,argb}_to_yuv411_frame (:12627, :12705, :12779, :12852, :12925): YCbCr tables of oclamping, whole macropixels
     // ("cut the rightmost one, two or three pixels": the layer becomes width >> 2 macropixels wide)
@@ -1555,7 +1573,8 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                               width >> 2, height, rgb_layout(inpl), dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
   } else if (inpl == PE_PALETTE_YUV411 && (pal_is_rgb(outpl) || outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888 ||
                                            outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P || outpl == PE_PALETTE_UYVY ||
-                                           outpl == PE_PALETTE_YUYV)) {
+                                           outpl == PE_PALETTE_YUYV || outpl == PE_PALETTE_YUV422P || outpl == PE_PALETTE_YUV420P ||
+                                           outpl == PE_PALETTE_YVU420P)) {
     // convert_yuv411_to_{rgb,bgr,argb,yuv888,yuvp,uyvy,yuyv}_frame (:13755-13826): every variant selects the YCbCr tables of the
     // layer's clamping itself (set_conversion_arrays(clamping, WEED_YUV_SUBSPACE_YCBCR)); the layer's width in macropixels is a
     // quarter of the pixel width.  (The reference walks source and most destinations densely; strides are honoured here, X.)
@@ -1564,7 +1583,8 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     const uint8_t *cavg = get_cavg(e, iclamping == PE_YUV_CLAMPING_CLAMPED);
     if (!cavg) { frame_release_pixels(&n); set_err(PE_ERR_MEMORY, "averaging table could not be built"); return PE_FALSE; }
     const int target = pal_is_rgb(outpl) ? 0 : (outpl == PE_PALETTE_YUV888 || outpl == PE_PALETTE_YUVA8888) ? 1
-                       : (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P) ? 2 : outpl == PE_PALETTE_UYVY ? 3 : 4;
+                       : (outpl == PE_PALETTE_YUV444P || outpl == PE_PALETTE_YUVA4444P) ? 2 : outpl == PE_PALETTE_UYVY ? 3
+                       : outpl == PE_PALETTE_YUYV ? 4 : outpl == PE_PALETTE_YUV422P ? 5 : 6;   // (4:2:0: Cb to plane 1, swapped below for YVU)
     uint8_t *pl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], (uint8_t *)n.d.planes[3]};
     ce = launch_yuv411_to(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, width >> 2, height, pl, n.d.rowstrides, target,
                           pal_has_alpha(outpl), pal_is_rgb(outpl) ? rgb_layout(outpl) : RgbLayout{0, 1, 2, -1, 3},

@@ -109,7 +109,10 @@ cudaError_t launch_rgb_to_yuv420p(const Launch &L, CImg src, uint8_t *const plan
 cudaError_t launch_yuv888_to_rgb_float(const Launch &L, int mode, CImg src, Img dst, int width, int height, int in_alpha, RgbLayout out,
                                        const float *ftab_dev, const int32_t *rgb_y_dev, float *sums_dev);
 // YUV411 (IYU1) -> RGB(A) / packed 4:4:4 / planar 4:4:4 / UYVY / YUYV (convert_yuv411_to_*_frame, colourspace.c:8305-8910); target: 0 RGB,
-// 1 YUV888 / YUVA8888, 2 YUV444P / YUVA4444P, 3 UYVY, 4 YUYV; cavg_dev: the 64 KB averaging table of the frame's clamping
+// 1 YUV888 / YUVA8888, 2 YUV444P / YUVA4444P, 3 UYVY, 4 YUYV, 5 YUV422P, 6 YUV420P; cavg_dev: the 64 KB averaging table of the frame's clamping
+// YUV -> YUV411: mode 0 UYVY, 1 YUYV, 2 YUV420P, 3 YUV422P, 4 YUV888, 5 YUVA8888, 6 planar 4:4:4 (colourspace.c:7755-8302, :9148)
+cudaError_t launch_to_yuv411(const Launch &L, int mode, const uint8_t *const src[3], const int irow[3], int width_mpx, int height, Img dst,
+                             const uint8_t *cavg_dev);
 // RGB(A) / BGR(A) / ARGB -> YUV411 (colourspace.c:6499-6614): whole macropixels
 cudaError_t launch_rgb_to_yuv411(const Launch &L, CImg src, Img dst, int width_mpx, int height, RgbLayout in, DevConv conv);
 cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,

@@ -416,7 +416,8 @@ struct Yuv411Args {
   int irow, wmp, height;
   uint8_t *dst[4];
   int orow[4];
-  int target;   // 0 RGB (layout `out`), 1 packed 4:4:4 (alpha: 4 bytes), 2 planar 4:4:4 (alpha: plane 3), 3 UYVY, 4 YUYV
+  int target;   // 0 RGB (layout `out`), 1 packed 4:4:4 (alpha: 4 bytes), 2 planar 4:4:4 (alpha: plane 3), 3 UYVY, 4 YUYV, 5 planar 4:2:2,
+                // 6 planar 4:2:0 (convert_yuv411_to_yuv422_frame :8976 / _to_yuv420_frame :9037, the latter by its intent)
   int alpha;
   int bgr_quirk;   // BGR / BGRA: the row's first pixel and its last two in R, G, B order (convert_yuv411_to_bgr_frame :8445, :8514)
   RgbLayout out;
@@ -429,13 +430,9 @@ __global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv
     __syncthreads();
   }
   auto avg = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
-  const int units = A.wmp + 1;
-  const long long total = (long long)units * A.height;
-  for (long long it = global_tid(); it < total; it += global_threads()) {
-    const int row = (int)(it / units), j = (int)(it - (long long)row * units);
+  // the pixels of unit j of a row: lumas, chromas, how many, the first pixel's index
+  auto unit = [&](int row, int j, uint32_t (&ys)[4], uint32_t (&us)[4], uint32_t (&vs)[4], int &npx, int &px0) {
     const uint8_t *r0 = A.src + (long long)A.irow * row;
-    uint32_t ys[4], us[4], vs[4];
-    int npx, px0;
     if (j == 0 || j == A.wmp) {
       const uint8_t *m = r0 + 6LL * (j == 0 ? 0 : A.wmp - 1);
       npx = 2; px0 = j == 0 ? 0 : 4 * A.wmp - 2;
@@ -449,10 +446,10 @@ __global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv
       const uint32_t pu = mp[0], pv = mp[3], cu = mc[0], cv = mc[3];
       ys[0] = mp[4]; ys[1] = mp[5]; ys[2] = mc[1]; ys[3] = mc[2];
       const uint32_t hu = avg(pu, cu), hv = avg(pv, cv);
-      if (A.target >= 3) {       // two 4:2:2 macropixels: one ladder step, first luma twice
+      if (A.target >= 3) {       // 4:2:2 chroma: one ladder step per pixel pair; the packed variants write the first luma twice
         us[0] = us[1] = avg(hu, pu); vs[0] = vs[1] = avg(hv, pv);
         us[2] = us[3] = avg(hu, cu); vs[2] = vs[3] = avg(hv, cv);
-        ys[1] = ys[0]; ys[3] = ys[2];
+        if (A.target < 5) { ys[1] = ys[0]; ys[3] = ys[2]; }
       } else {
         const uint32_t qpu = avg(hu, pu), qpv = avg(hv, pv), qcu = avg(hu, cu), qcv = avg(hv, cv);
         us[0] = avg(qpu, pu); vs[0] = avg(qpv, pv);
@@ -462,6 +459,17 @@ __global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv
         if (A.target == 2) { ys[1] = ys[0]; ys[3] = ys[2]; }
       }
     }
+  };
+  const int units = A.wmp + 1;
+  // planar 4:2:0: one thread = one unit of a ROW PAIR (chroma row k = avg_chroma(4:2:2 row 2k, 4:2:2 row 2k + 1), the even row as the table row)
+  const int vrows = A.target == 6 ? (A.height + 1) >> 1 : A.height;
+  const long long total = (long long)units * vrows;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int vrow = (int)(it / units), j = (int)(it - (long long)vrow * units);
+    const int row = A.target == 6 ? 2 * vrow : vrow;
+    uint32_t ys[4], us[4], vs[4];
+    int npx, px0;
+    unit(row, j, ys, us, vs, npx, px0);
     if (A.target == 0) {
       uint8_t *d = A.dst[0] + (long long)A.orow[0] * row + (long long)px0 * A.out.psize;
       for (int k = 0; k < npx; k++, d += A.out.psize) {
@@ -485,6 +493,21 @@ __global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv
         A.dst[2][(long long)A.orow[2] * row + px0 + k] = (uint8_t)vs[k];
         if (A.alpha) A.dst[3][(long long)A.orow[3] * row + px0 + k] = 255;
       }
+    } else if (A.target >= 5) {
+      for (int k = 0; k < npx; k++) A.dst[0][(long long)A.orow[0] * row + px0 + k] = (uint8_t)ys[k];
+      uint32_t cu[2] = {us[0], us[2]}, cv[2] = {vs[0], vs[2]};
+      if (A.target == 6 && row + 1 < A.height) {
+        uint32_t yb[4], ub[4], vb[4];
+        int nb, pb;
+        unit(row + 1, j, yb, ub, vb, nb, pb);
+        for (int k = 0; k < nb; k++) A.dst[0][(long long)A.orow[0] * (row + 1) + pb + k] = (uint8_t)yb[k];
+        cu[0] = avg(cu[0], ub[0]); cv[0] = avg(cv[0], vb[0]);
+        if (npx == 4) { cu[1] = avg(cu[1], ub[2]); cv[1] = avg(cv[1], vb[2]); }
+      }
+      for (int k = 0; k < npx >> 1; k++) {
+        A.dst[1][(long long)A.orow[1] * vrow + (px0 >> 1) + k] = (uint8_t)cu[k];
+        A.dst[2][(long long)A.orow[2] * vrow + (px0 >> 1) + k] = (uint8_t)cv[k];
+      }
     } else {
       uint8_t *d = A.dst[0] + (long long)A.orow[0] * row + (long long)(px0 >> 1) * 4;
       for (int k = 0; k < npx; k += 2, d += 4) {
@@ -492,6 +515,60 @@ __global__ void __launch_bounds__(kBlock) k_yuv411_to(Yuv411Args A, DevConv conv
         else { d[0] = (uint8_t)ys[k]; d[1] = (uint8_t)us[k]; d[2] = (uint8_t)ys[k + 1]; d[3] = (uint8_t)vs[k]; }
       }
     }
+  }
+}
+
+// YUV -> YUV411, one thread = one output macropixel.  mode 0 UYVY / 1 YUYV (convert_{uyvy,yuyv}_to_yuv411_frame :7973-8032), 2 YUV420P /
+// 3 YUV422P (convert_yuv420_to_yuv411_frame :9148: 4:2:0 folds every even row r >= 2 into the chroma of row r - 1), 4 YUV888 / 5 YUVA8888
+// (convert_yuv888_to_yuv411_frame :8272: plain (sum of four) >> 2), 6 planar 4:4:4 (convert_yuvp_to_yuv411_frame :7755)
+struct ToYuv411Args {
+  const uint8_t *src[3];
+  int irow[3];
+  int wmp, height, mode;
+  uint8_t *dst;
+  int orow;
+};
+
+__global__ void __launch_bounds__(kBlock) k_to_yuv411(ToYuv411Args A, const uint8_t *__restrict__ cavg) {
+  auto avg = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
+  auto chroma_42x = [&](int row, int j, uint32_t &u, uint32_t &v) {   // modes 2 / 3: the macropixel's own chroma
+    const long long cr = A.mode == 2 ? row >> 1 : row;
+    const uint8_t *pu = A.src[1] + A.irow[1] * cr + 2LL * j, *pv = A.src[2] + A.irow[2] * cr + 2LL * j;
+    u = avg(pu[0], pu[1]); v = avg(pv[0], pv[1]);
+  };
+  const long long total = (long long)A.wmp * A.height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / A.wmp), j = (int)(it - (long long)row * A.wmp);
+    uint32_t u, v, y[4];
+    if (A.mode <= 1) {
+      const uint8_t *m = A.src[0] + (long long)A.irow[0] * row + 8LL * j;
+      const int yo = A.mode == 0 ? 1 : 0, uo = A.mode == 0 ? 0 : 1;
+      y[0] = m[yo]; y[1] = m[yo + 2]; y[2] = m[4 + yo]; y[3] = m[6 + yo];
+      u = avg(m[uo], m[4 + uo]); v = avg(m[uo + 2], m[6 + uo]);
+    } else if (A.mode <= 3) {
+      const uint8_t *py = A.src[0] + (long long)A.irow[0] * row + 4LL * j;
+      y[0] = py[0]; y[1] = py[1]; y[2] = py[2]; y[3] = py[3];
+      chroma_42x(row, j, u, v);
+      if (A.mode == 2 && (row & 1) && row + 1 < A.height) {   // the fold of row + 1 (even, >= 2) into this row (:9176-9179)
+        uint32_t u2, v2;
+        chroma_42x(row + 1, j, u2, v2);
+        u = avg(u, u2); v = avg(v, v2);
+      }
+    } else if (A.mode <= 5) {
+      const int ps = A.mode == 4 ? 3 : 4;
+      const uint8_t *q = A.src[0] + (long long)A.irow[0] * row + 4LL * ps * j;
+      y[0] = q[0]; y[1] = q[ps]; y[2] = q[2 * ps]; y[3] = q[3 * ps];
+      u = ((uint32_t)q[1] + q[ps + 1] + q[2 * ps + 1] + q[3 * ps + 1]) >> 2;
+      v = ((uint32_t)q[2] + q[ps + 2] + q[2 * ps + 2] + q[3 * ps + 2]) >> 2;
+    } else {
+      const long long o = 4LL * j;
+      const uint8_t *py = A.src[0] + (long long)A.irow[0] * row + o, *pu = A.src[1] + (long long)A.irow[1] * row + o,
+                    *pv = A.src[2] + (long long)A.irow[2] * row + o;
+      y[0] = py[0]; y[1] = py[1]; y[2] = py[2]; y[3] = py[3];
+      u = avg(avg(pu[0], pu[1]), avg(pu[2], pu[3])); v = avg(avg(pv[0], pv[1]), avg(pv[2], pv[3]));
+    }
+    uint8_t *d = A.dst + (long long)A.orow * row + 6LL * j;
+    d[0] = (uint8_t)u; d[1] = (uint8_t)y[0]; d[2] = (uint8_t)y[1]; d[3] = (uint8_t)v; d[4] = (uint8_t)y[2]; d[5] = (uint8_t)y[3];
   }
 }
 
@@ -670,6 +747,17 @@ cudaError_t launch_rgb_to_yuv411(const Launch &L, CImg src, Img dst, int width_m
   return cudaGetLastError();
 }
 
+cudaError_t launch_to_yuv411(const Launch &L, int mode, const uint8_t *const src[3], const int irow[3], int width_mpx, int height, Img dst,
+                             const uint8_t *cavg_dev) {
+  if (width_mpx <= 0 || height <= 0) return cudaSuccess;
+  ToYuv411Args A;
+  for (int i = 0; i < 3; i++) { A.src[i] = src[i]; A.irow[i] = irow[i]; }
+  A.wmp = width_mpx; A.height = height; A.mode = mode; A.dst = dst.p; A.orow = dst.rs;
+  k_to_yuv411<<<grid_for(L, (long long)width_mpx * height), kBlock, 0, L.stream>>>(A, cavg_dev);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int height, uint8_t *const dst[4], const int orow[4], int target,
                              int alpha, RgbLayout out, int bgr_quirk, DevConv conv, const uint8_t *cavg_dev) {
   if (width_mpx <= 0 || height <= 0) return cudaSuccess;
@@ -678,7 +766,7 @@ cudaError_t launch_yuv411_to(const Launch &L, CImg src, int width_mpx, int heigh
   A.src = src.p; A.irow = src.rs; A.wmp = width_mpx; A.height = height;
   for (int i = 0; i < 4; i++) { A.dst[i] = dst[i]; A.orow[i] = orow[i]; }
   A.target = target; A.alpha = alpha; A.out = out;
-  k_yuv411_to<<<grid_for(L, (long long)(width_mpx + 1) * height), kBlock, 0, L.stream>>>(A, conv, cavg_dev);
+  k_yuv411_to<<<grid_for(L, (long long)(width_mpx + 1) * (target == 6 ? (height + 1) / 2 : height)), kBlock, 0, L.stream>>>(A, conv, cavg_dev);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

@@ -1797,7 +1797,8 @@ void pe_or_yuv2rgb_float(int mode, int clamping, const int32_t *rgb_y_int, const
  * Replicated under `quirks`: the BGR / BGRA variant writes the first pixel of a row and its last two in R, G, B order (:8445, :8514).
  * X (defined here): the RGBA / BGRA variants never write the alpha bytes of the first pixel pair of a loop iteration (:8338-8370):
  * 255; source and (except RGB) destination rows are walked densely: strides honoured.
- * target: 0 RGB (order, add_alpha), 1 packed 4:4:4, 2 planar 4:4:4 (dest[3] = alpha plane when add_alpha), 3 UYVY, 4 YUYV */
+ * target: 0 RGB (order, add_alpha), 1 packed 4:4:4, 2 planar 4:4:4 (dest[3] = alpha plane when add_alpha), 3 UYVY, 4 YUYV,
+ * 5 planar 4:2:2, 6 planar 4:2:0 (dest[1] = Cb, dest[2] = Cr) */
 void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[4], const int orow[4],
                      int order, int add_alpha, int clamping, int quality, int quirks) {
   const or_conv_t *c = or_conv(clamping, OR_SUBSPACE_YCBCR);
@@ -1826,7 +1827,7 @@ void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, in
         if (target >= 3) {
           us[0] = us[1] = OR_AVG(hu, pu); vs[0] = vs[1] = OR_AVG(hv, pv);
           us[2] = us[3] = OR_AVG(hu, cu); vs[2] = vs[3] = OR_AVG(hv, cv);
-          ys[1] = ys[0]; ys[3] = ys[2];
+          if (target < 5) { ys[1] = ys[0]; ys[3] = ys[2]; }
         } else {
           const uint8_t qpu = OR_AVG(hu, pu), qpv = OR_AVG(hv, pv), qcu = OR_AVG(hu, cu), qcv = OR_AVG(hv, cv);
           us[0] = OR_AVG(qpu, pu); vs[0] = OR_AVG(qpv, pv); us[1] = OR_AVG(qpu, cu); vs[1] = OR_AVG(qpv, cv);
@@ -1849,6 +1850,17 @@ void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, in
         } else if (target == 2) {
           dest[0][(long)orow[0] * i + x] = ys[k]; dest[1][(long)orow[1] * i + x] = us[k]; dest[2][(long)orow[2] * i + x] = vs[k];
           if (add_alpha) dest[3][(long)orow[3] * i + x] = 255;
+        } else if (target >= 5) {
+          /* planar 4:2:2 (:8976-9032, every luma kept) / 4:2:0: chroma row k = avg(4:2:2 row 2k, 4:2:2 row 2k+1), the even row as the
+           * table row; a trailing unpaired row keeps its own (the reference's 4:2:0 loop never advances its chroma pointers on odd
+           * rows and rewinds them on even ones, :9060-9140: only chroma row 0 is ever written -- X, defined by its evident intent) */
+          dest[0][(long)orow[0] * i + x] = ys[k];
+          if (!(k & 1)) {
+            const long cr = target == 5 ? i : i >> 1;
+            uint8_t *du = dest[1] + (long)orow[1] * cr + (x >> 1), *dv = dest[2] + (long)orow[2] * cr + (x >> 1);
+            if (target == 5 || !(i & 1)) { *du = us[k]; *dv = vs[k]; }
+            else { *du = OR_AVG(*du, us[k]); *dv = OR_AVG(*dv, vs[k]); }
+          }
         } else if (!(k & 1)) {
           uint8_t *d = dest[0] + (long)orow[0] * i + (x >> 1) * 4;
           if (target == 3) { d[0] = us[k]; d[1] = ys[k]; d[2] = vs[k]; d[3] = ys[k + 1]; }
@@ -1889,4 +1901,51 @@ void pe_or_rgb_to_yuv411(const uint8_t *src, int irow, int width, int height, ui
       d[4] = yy[2]; d[5] = yy[3];
     }
   }
+}
+
+/* ---- YUV -> YUV411.  mode 0 UYVY / 1 YUYV (convert_{uyvy,yuyv}_to_yuv411_frame :7973-8032): one macropixel from two, chroma =
+ * avg_chroma(first, second).  mode 2 YUV420P / 3 YUV422P (convert_yuv420_to_yuv411_frame :9148-9195): chroma = avg_chroma of the two
+ * samples under the four pixels; 4:2:0 reads chroma row r >> 1 for luma row r and then folds every EVEN row r >= 2 into the macropixels
+ * of row r - 1: u2(r-1) = avg_chroma(u2(r-1), u2(r)) (:9176-9179) -- replicated.  mode 4 YUV888 / 5 YUVA8888
+ * (convert_yuv888_to_yuv411_frame :8272-8302): chroma = (sum of the four samples) >> 2, no table; the reference stops after
+ * width * height BYTES, a third / a quarter of the frame (:8278) -- X, every row here, pinned on the rows it reaches.  mode 6 planar
+ * 4:4:4 (convert_yuvp_to_yuv411_frame :7755-7797): chroma = avg_chroma(avg_chroma(c0, c1), avg_chroma(c2, c3)); the reference never
+ * advances its output pointer (every macropixel lands on the first one) nor its luma rows by the padding -- X, pinned macropixel by
+ * macropixel.  All walk densely; strides honoured (X).  width in pixels; whole macropixels only. */
+void pe_or_to_yuv411(int mode, const uint8_t *const src[3], const int irow[3], int width, int height, uint8_t *dest, int orow,
+                     int clamping) {
+  const uint8_t *avg = or_avg(clamping);
+  const int wm = width >> 2;
+#define OR_AVG(x, y) (avg[((int)(x) << 8) + (int)(y)])
+  for (int i = 0; i < height; i++) {
+    uint8_t *d = dest + (long)orow * i;
+    for (int j = 0; j < wm; j++, d += 6) {
+      if (mode <= 1) {
+        uint8_t y0, u0, y1, v0, y2, u1, y3, v1;
+        or_mpx(mode, src[0] + (long)irow[0] * i + 8L * j, &y0, &u0, &y1, &v0);
+        or_mpx(mode, src[0] + (long)irow[0] * i + 8L * j + 4, &y2, &u1, &y3, &v1);
+        d[0] = OR_AVG(u0, u1); d[1] = y0; d[2] = y1; d[3] = OR_AVG(v0, v1); d[4] = y2; d[5] = y3;
+      } else if (mode <= 3) {
+        const long cr = mode == 2 ? i >> 1 : i;
+        const uint8_t *y = src[0] + (long)irow[0] * i + 4L * j, *u = src[1] + (long)irow[1] * cr + 2L * j, *v = src[2] + (long)irow[2] * cr + 2L * j;
+        d[0] = OR_AVG(u[0], u[1]); d[1] = y[0]; d[2] = y[1]; d[3] = OR_AVG(v[0], v[1]); d[4] = y[2]; d[5] = y[3];
+        if (mode == 2 && i >= 2 && !(i & 1)) {
+          uint8_t *p = d - orow;
+          p[0] = OR_AVG(p[0], d[0]); p[3] = OR_AVG(p[3], d[3]);
+        }
+      } else if (mode <= 5) {
+        const int ps = mode == 4 ? 3 : 4;
+        const uint8_t *q = src[0] + (long)irow[0] * i + 4L * ps * j;
+        d[0] = (uint8_t)((q[1] + q[ps + 1] + q[2 * ps + 1] + q[3 * ps + 1]) >> 2);
+        d[1] = q[0]; d[2] = q[ps];
+        d[3] = (uint8_t)((q[2] + q[ps + 2] + q[2 * ps + 2] + q[3 * ps + 2]) >> 2);
+        d[4] = q[2 * ps]; d[5] = q[3 * ps];
+      } else {
+        const uint8_t *y = src[0] + (long)irow[0] * i + 4L * j, *u = src[1] + (long)irow[1] * i + 4L * j, *v = src[2] + (long)irow[2] * i + 4L * j;
+        d[0] = OR_AVG(OR_AVG(u[0], u[1]), OR_AVG(u[2], u[3])); d[1] = y[0]; d[2] = y[1];
+        d[3] = OR_AVG(OR_AVG(v[0], v[1]), OR_AVG(v[2], v[3])); d[4] = y[2]; d[5] = y[3];
+      }
+    }
+  }
+#undef OR_AVG
 }

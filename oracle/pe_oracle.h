@@ -139,6 +139,8 @@ void pe_or_packed422_to_yuv444p(int fmt, const uint8_t *src, int irow, int width
 /* YUV411 (IYU1) -> RGB(A) / YUV888 / YUVA8888 / YUV444P / YUVA4444P / UYVY / YUYV, colourspace.c:8305-8910 (see pe_oracle.c) */
 void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *const dest[4], const int orow[4],
                      int order, int add_alpha, int clamping, int quality, int quirks);
+void pe_or_to_yuv411(int mode, const uint8_t *const src[3], const int irow[3], int width, int height, uint8_t *dest, int orow,
+                     int clamping);
 void pe_or_rgb_to_yuv411(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order, int in_alpha,
                          int clamping);
 void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *dest, int orow,

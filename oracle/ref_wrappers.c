@@ -390,7 +390,20 @@ void ref_yuv411_to(int target, void *src, int width, int height, int orow, uint8
   } else if (target == 1) convert_yuv411_to_yuv888_frame(s, width, height, dest[0], add_alpha, clamping);
   else if (target == 2) convert_yuv411_to_yuvp_frame(s, width, height, dest, add_alpha, clamping);
   else if (target == 3) convert_yuv411_to_uyvy_frame(s, width, height, (uyvy_macropixel *)dest[0], clamping);
-  else convert_yuv411_to_yuyv_frame(s, width, height, (yuyv_macropixel *)dest[0], clamping);
+  else if (target == 4) convert_yuv411_to_yuyv_frame(s, width, height, (yuyv_macropixel *)dest[0], clamping);
+  else if (target == 5) convert_yuv411_to_yuv422_frame(s, width, height, dest, clamping);
+  else convert_yuv411_to_yuv420_frame(s, width, height, dest, FALSE, clamping);
+}
+
+/* mode as pe_or_to_yuv411; width as the reference's dispatcher passes it (UYVY / YUYV: macropixels; otherwise pixels); dense walks */
+void ref_to_yuv411(int mode, uint8_t **src, int width, int height, int irow, void *dest, int clamping) {
+  ref_init();
+  yuv411_macropixel *d = (yuv411_macropixel *)dest;
+  if (mode == 0) convert_uyvy_to_yuv411_frame((uyvy_macropixel *)src[0], width, height, d, clamping);
+  else if (mode == 1) convert_yuyv_to_yuv411_frame((yuyv_macropixel *)src[0], width, height, d, clamping);
+  else if (mode <= 3) convert_yuv420_to_yuv411_frame(src, width, height, d, mode == 3, clamping);
+  else if (mode <= 5) convert_yuv888_to_yuv411_frame(src[0], width, height, irow, d, mode == 5);
+  else convert_yuvp_to_yuv411_frame(src, width, height, irow, d, clamping);
 }
 
 /* order 0 RGB(A), 1 BGR(A), 2 ARGB; width in pixels; dense output */

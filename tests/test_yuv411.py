@@ -140,6 +140,156 @@ def test_rgb_to_yuv411_cuda_equals_oracle_and_round_trip_geometry(case):
     eng.close()
 
 
+# ---- the remaining converters: YUV411 -> planar 4:2:2 / 4:2:0, and UYVY / YUYV / YUV420P / YUV422P / YUV888 / YUVA8888 / YUV444P -> YUV411
+TO_411 = [(0, "UYVY"), (1, "YUYV"), (2, "YUV420P"), (3, "YUV422P"), (4, "YUV888"), (5, "YUVA8888"), (6, "YUV444P")]
+
+
+def _yuv_source(rng, mode, w, h, dense):
+    """planes of a w x h frame of the source palette of `mode` (see pe_or_to_yuv411)"""
+    def plane(cols, rows):
+        st = cols if dense else T.rowstride(cols, 1)
+        a = np.zeros((rows, st), np.uint8)
+        a[:, :cols] = rng.integers(16, 236, (rows, cols), dtype=np.uint8)
+        return a
+    if mode <= 1:
+        return [plane(2 * w, h)]
+    if mode == 2:
+        return [plane(w, h), plane(w // 2, (h + 1) // 2), plane(w // 2, (h + 1) // 2)]
+    if mode == 3:
+        return [plane(w, h), plane(w // 2, h), plane(w // 2, h)]
+    if mode <= 5:
+        return [plane(w * (3 if mode == 4 else 4), h)]
+    return [plane(w, h), plane(w, h), plane(w, h)]
+
+
+def _oracle_to_411(mode, planes, w, h, cl, dest):
+    pl = list(planes) + [planes[0]] * (3 - len(planes))
+    T.oracle().pe_or_to_yuv411(mode, T.planes_arg(*pl), T.strides_arg(*pl), w, h, T.ptr(dest), dest.strides[0], cl)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", TO_411, ids=[c[1] for c in TO_411])
+def test_to_yuv411_oracle_equals_compiled_reference(case):
+    mode, _ = case
+    r = T.ref()
+    rng = np.random.default_rng(4200 + mode)
+    for (w, h), cl in itertools.product(((4, 1), (8, 2), (24, 6), (64, 9)), (T.CLAMPED, T.UNCLAMPED)):
+        if mode == 2 and h & 1 and h > 1:
+            h += 1   # 4:2:0 frames are even (colourspace.c:11603)
+        if mode == 6:
+            # convert_yuvp_to_yuv411_frame never advances its output pointer (:7755-7797): pinned macropixel by macropixel
+            for _ in range(64):
+                pl = _yuv_source(rng, 6, 4, 1, dense=True)
+                exp, got = np.zeros((1, 6), np.uint8), np.zeros((1, 6), np.uint8)
+                r.ref_to_yuv411(6, T.planes_arg(*pl), 4, 1, 4, T.ptr(exp), cl)
+                _oracle_to_411(6, pl, 4, 1, cl, got)
+                assert (got == exp).all(), (cl, pl)
+            continue
+        pl = _yuv_source(rng, mode, w, h, dense=True)
+        wm = w >> 2
+        exp, got = np.zeros((h, wm * 6), np.uint8), np.zeros((h, wm * 6), np.uint8)
+        r.ref_to_yuv411(mode, T.planes_arg(*(pl + [pl[0]] * (3 - len(pl)))), (w // 2) if mode <= 1 else w, h, pl[0].strides[0], T.ptr(exp), cl)
+        _oracle_to_411(mode, pl, w, h, cl, got)
+        rows = h
+        if mode in (4, 5):   # the reference stops after width * height BYTES of its 3- / 4-byte pixels (:8278)
+            ips = 3 if mode == 4 else 4
+            rows = -(-h // ips)
+            assert (exp[rows:] == 0).all()
+        assert (got[:rows] == exp[:rows]).all(), (case, w, h, cl)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_yuv411_to_planar_422_and_420_oracle_equals_compiled_reference():
+    r = T.ref()
+    rng = np.random.default_rng(4222)
+    for (wm, h), cl in itertools.product(((1, 1), (2, 3), (9, 4), (40, 5)), (T.CLAMPED, T.UNCLAMPED)):
+        src = _src(rng, wm, h, cl == T.CLAMPED)
+        w = 4 * wm
+        exp = [np.zeros((h, w), np.uint8), np.zeros((h, w // 2), np.uint8), np.zeros((h, w // 2), np.uint8)]
+        got = [np.zeros_like(p) for p in exp]
+        r.ref_yuv411_to(5, T.ptr(src), wm, h, 0, T.planes_arg(*(exp + [exp[0]])), 0, 0, cl)
+        _oracle(5, 0, 0, src, wm, h, cl, got)
+        for k in range(3):
+            assert (got[k] == exp[k]).all(), ("422P", wm, h, cl, k)
+    # 4:2:0: the reference only ever writes chroma row 0 (:9060-9140); a one-row frame is the case it defines
+    for wm, cl in itertools.product((1, 2, 9, 40), (T.CLAMPED, T.UNCLAMPED)):
+        src = _src(rng, wm, 1, cl == T.CLAMPED)
+        w = 4 * wm
+        exp = [np.zeros((1, w), np.uint8), np.zeros((1, w // 2), np.uint8), np.zeros((1, w // 2), np.uint8)]
+        got = [np.zeros_like(p) for p in exp]
+        r.ref_yuv411_to(6, T.ptr(src), wm, 1, 0, T.planes_arg(*(exp + [exp[0]])), 0, 0, cl)
+        _oracle(6, 0, 0, src, wm, 1, cl, got)
+        for k in range(3):
+            assert (got[k] == exp[k]).all(), ("420P", wm, cl, k)
+
+
+def test_yuv411_to_420_is_the_vertical_average_of_its_422():
+    rng = np.random.default_rng(4201)
+    wm, h = 7, 5
+    src = _src(rng, wm, h, True)
+    w = 4 * wm
+    p422 = [np.zeros((h, w), np.uint8), np.zeros((h, w // 2), np.uint8), np.zeros((h, w // 2), np.uint8)]
+    p420 = [np.zeros((h, w), np.uint8), np.zeros(((h + 1) // 2, w // 2), np.uint8), np.zeros(((h + 1) // 2, w // 2), np.uint8)]
+    _oracle(5, 0, 0, src, wm, h, T.CLAMPED, p422)
+    _oracle(6, 0, 0, src, wm, h, T.CLAMPED, p420)
+    avg = np.zeros(65536, np.uint8)
+    T.oracle().pe_or_avg_table(0, T.ptr(avg))
+    assert (p420[0] == p422[0]).all()
+    for k in (1, 2):
+        for r_ in range((h + 1) // 2):
+            a = p422[k][2 * r_]
+            e = a if 2 * r_ + 1 >= h else avg[(a.astype(int) << 8) + p422[k][2 * r_ + 1]]
+            assert (p420[k][r_] == e).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TO_411 + [(2, "YVU420P"), (6, "YUVA4444P")], ids=[c[1] for c in TO_411] + ["YVU420P", "YUVA4444P"])
+def test_to_yuv411_cuda_equals_oracle(case):
+    lb = pytest.importorskip("lives_b200")
+    mode, pal = case
+    eng = lb.Engine()
+    rng = np.random.default_rng(5960 + mode)
+    for (w, h), cl in itertools.product(((4, 2), (24, 6), (64, 10), (1920, 270)), (T.CLAMPED, T.UNCLAMPED)):
+        pl = _yuv_source(rng, mode, w, h, dense=False)
+        if pal == "YUVA4444P":
+            pl = pl + [np.full_like(pl[0], 200)]
+        up = [pl[0], pl[2], pl[1]] if pal == "YVU420P" else pl     # a YVU layer holds Cr in plane 1
+        lay = lb.Layer.from_host(eng, T.PAL[pal], w, h, up, yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, T.PAL["YUV411"], cl), lb.capi.last_error()
+        assert lay.palette == T.PAL["YUV411"] and lay.width == w and lay.height == h
+        got = lay.to_host()[0]
+        exp = np.zeros_like(got)
+        _oracle_to_411(mode, pl[:3], w, h, cl, exp)
+        assert (got[:, :(w >> 2) * 6] == exp[:, :(w >> 2) * 6]).all(), (case, w, h, cl)
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pal", ["YUV422P", "YUV420P", "YVU420P"])
+def test_yuv411_to_planar_42x_cuda_equals_oracle(pal):
+    lb = pytest.importorskip("lives_b200")
+    eng = lb.Engine()
+    rng = np.random.default_rng(5970)
+    target = 5 if pal == "YUV422P" else 6
+    for (wm, h), cl in itertools.product(((1, 2), (9, 4), (40, 18), (480, 270)), (T.CLAMPED, T.UNCLAMPED)):
+        w = 4 * wm
+        src = _src(rng, wm, h, cl == T.CLAMPED, stride=T.align_ceil(wm * 6, 32))
+        lay = lb.Layer.from_host(eng, T.PAL["YUV411"], w, h, [src], yuv_clamping=cl)
+        assert lb.convert_layer_palette(lay, T.PAL[pal], cl), lb.capi.last_error()
+        got = lay.to_host()
+        assert lay.palette == T.PAL[pal] and lay.width == w and lay.height == h
+        exp = [np.zeros_like(p) for p in got]
+        if pal == "YVU420P":
+            exp = [exp[0], exp[2], exp[1]]       # the oracle writes Cb to dest[1]; the finished YVU layer holds it in plane 2
+        _oracle(target, 0, 0, src, wm, h, cl, exp)
+        if pal == "YVU420P":
+            exp = [exp[0], exp[2], exp[1]]
+        for k in range(3):
+            cols = w if k == 0 else w // 2
+            assert (got[k][:, :cols] == exp[k][:, :cols]).all(), (pal, wm, h, cl, k)
+    eng.close()
+
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors_yuv411.npz")
 
 
@@ -202,13 +352,11 @@ def test_cuda_equals_oracle(case):
 
 
 @pytest.mark.gpu
-def test_cuda_refuses_what_is_not_built():
+def test_cuda_refuses_bad_geometry_and_leaves_the_layer_untouched():
     lb = pytest.importorskip("lives_b200")
     eng = lb.Engine()
-    src = _src(np.random.default_rng(1), 4, 2, True, stride=32)
-    lay = lb.Layer.from_host(eng, T.PAL["YUV411"], 16, 2, [src], yuv_clamping=T.CLAMPED)
-    assert not lb.convert_layer_palette(lay, T.PAL["YUV420P"], T.CLAMPED)     # 4:1:1 -> 4:2:0 / 4:2:2 planar: not built, loud
-    assert lay.palette == T.PAL["YUV411"] and (lay.to_host()[0] == src).all()  # and the layer is untouched
-    uy = lb.Layer.from_host(eng, T.PAL["UYVY"], 16, 2, [T.make_packed(np.random.default_rng(2), 8, 2, 4)])
-    assert not lb.convert_layer_palette(uy, T.PAL["YUV411"], T.CLAMPED)       # YUV -> YUV411: not built (the reference stops early)
+    rgb_src = T.make_packed(np.random.default_rng(2), 3, 2, 3)
+    rgb = lb.Layer.from_host(eng, T.PAL["RGB24"], 3, 2, [rgb_src])
+    assert not lb.convert_layer_palette(rgb, T.PAL["YUV411"], T.CLAMPED)      # narrower than one macropixel
+    assert rgb.palette == T.PAL["RGB24"] and (rgb.to_host()[0][:, :9] == rgb_src[:, :9]).all()
     eng.close()
