@@ -1135,10 +1135,20 @@ namespace {
 void alpha_premult_locked(pe_engine *e, pe_frame *f, int direction) {
   const int pal = f->d.palette;
   int coffs, aoffs;
+  if (pal == PE_PALETTE_YUVA4444P) {  // "special case - planar with alpha" (:12001-12049)
+    const bool clamped = f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED;
+    const bool rev = direction == PE_DIRECTION_REVERSE;
+    const uint8_t *ty = get_premult(e, clamped ? (rev ? 2 : 3) : (rev ? 0 : 1)), *tc = get_premult(e, clamped ? (rev ? 4 : 5) : (rev ? 0 : 1));
+    if (!ty || !tc) { set_err(PE_ERR_MEMORY, "premultiply tables could not be built"); return; }
+    uint8_t *pl[4] = {(uint8_t *)f->d.planes[0], (uint8_t *)f->d.planes[1], (uint8_t *)f->d.planes[2], (uint8_t *)f->d.planes[3]};
+    cudaError_t ce = launch_premult_planar(e->L(), pl, f->d.rowstrides, f->d.width, f->d.height, ty, tc);
+    if (ce != cudaSuccess) { set_err(PE_ERR_CUDA, "premult launch failed: %s", cudaGetErrorString(ce)); return; }
+    return;  // (the planar branch returns before the flag update of :12100-12104, as the reference does)
+  }
   switch (pal) {
   case PE_PALETTE_RGBA32: case PE_PALETTE_BGRA32: case PE_PALETTE_YUVA8888: coffs = 0; aoffs = 3; break;
   case PE_PALETTE_ARGB32: coffs = 1; aoffs = 0; break;
-  default: return;  // YUVA4444P: not handled by this build (planar alpha); other palettes: no-op as in the reference
+  default: return;  // other palettes: no-op as in the reference
   }
   const bool clamped_yuva = (pal == PE_PALETTE_YUVA8888 && f->d.yuv_clamping == PE_YUV_CLAMPING_CLAMPED);
   const uint8_t *t0, *t1, *t2;
@@ -1383,12 +1393,12 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
                       outpl == PE_PALETTE_YUVA4444P ? (uint8_t *)n.d.planes[3] : nullptr};
     ce = launch_rgb_to_yuv444p(L, CImg{(const uint8_t *)f->d.planes[0], f->d.rowstrides[0]}, pl, n.d.rowstrides[0], width, height,
                                rgb_layout(inpl), dev_conv(e, oclamping, PE_YUV_SUBSPACE_YCBCR));
-  } else if (pal_is_rgb(inpl) && inpl != PE_PALETTE_ARGB32 &&
-             (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P)) {
+  } else if (pal_is_rgb(inpl) && (outpl == PE_PALETTE_YUV420P || outpl == PE_PALETTE_YVU420P || outpl == PE_PALETTE_YUV422P)) {
     // convert_{rgb,bgr}_to_yuv420_frame (:12681-12690, :12754-12763, :12600-12609, :12828-12837): width and height cut to even;
     // 4:2:0 takes the tables of osubspace, 4:2:2 gets WEED_YUV_SAMPLING_DEFAULT in that slot (= YCbCr); the planes are
-    // written Cb to plane 1, Cr to plane 2 (the reference's dest[1] / dest[2]; a YVU420P layer gets them swapped at conv_done, :13895).  ARGB32 (:6323) reads
-    // past its pixels (:6357) and is not built.
+    // written Cb to plane 1, Cr to plane 2 (the reference's dest[1] / dest[2]; a YVU420P layer gets them swapped at conv_done, :13895).  convert_argb_to_yuv420_frame
+    // (:6323) takes G1 / B1 one / two bytes too far (:6357: the next pixel's bytes, past the buffer on the last pair of the frame): ARGB32 is
+    // converted like the other orders, each pixel's own R, G, B (X).
     n.d.width = width & ~1; n.d.height = height & ~1;
     if (n.d.width < 2 || n.d.height < 2) { set_err(PE_ERR_SIZE, "frame too small for a 4:2:x macropixel"); return PE_FALSE; }
     if (frame_alloc(e, &n) != PE_OK) return PE_FALSE;

@@ -61,6 +61,8 @@ cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs,
 cudaError_t launch_lut8_rect(const Launch &L, Img img, RgbLayout lay, int x, int y, int width, int height,
                              const uint8_t *lut8_dev);
 // ---- premultiply (colourspace.c:11968) ------------------------------------------------------------
+cudaError_t launch_premult_planar(const Launch &L, uint8_t *const planes[4], const int rowstrides[4], int width, int height,
+                                  const uint8_t *tab_y, const uint8_t *tab_c);   // YUVA4444P, colourspace.c:12001-12049
 cudaError_t launch_premult(const Launch &L, Img img, int width, int height, int coffs, int ncol, int aoffs,
                            const uint8_t *tab0, const uint8_t *tab1, const uint8_t *tab2, int yuva_fwd_quirk);
 // ---- planar 4:2:0 / 4:2:2 -> RGB (colourspace.c:3260-5127) -----------------------------------------

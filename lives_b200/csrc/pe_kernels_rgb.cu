@@ -287,6 +287,34 @@ __global__ void __launch_bounds__(kBlock) k_premult(uint8_t *p, int rs, int widt
 
 }  // namespace
 
+namespace {
+// YUVA4444P (colourspace.c:12001-12049): 4 samples of each plane per thread, every plane through its own table with the sample's alpha
+__global__ void __launch_bounds__(kBlock) k_premult_planar(uint8_t *py, uint8_t *pu, uint8_t *pv, const uint8_t *__restrict__ pa, int rs_y,
+                                                           int rs_u, int rs_v, int rs_a, int width, int height,
+                                                           const uint8_t *__restrict__ ty, const uint8_t *__restrict__ tc) {
+  const int groups = (width + 3) >> 2;
+  const long long total = (long long)groups * height;
+  for (long long it = global_tid(); it < total; it += global_threads()) {
+    const int row = (int)(it / groups), x0 = 4 * (int)(it - (long long)row * groups);
+    const int n = min(4, width - x0);
+    for (int k = 0; k < n; k++) {
+      const uint32_t a = pa[(long long)rs_a * row + x0 + k] * 256u;
+      uint8_t *y = py + (long long)rs_y * row + x0 + k, *u = pu + (long long)rs_u * row + x0 + k, *v = pv + (long long)rs_v * row + x0 + k;
+      *y = __ldg(ty + a + *y); *u = __ldg(tc + a + *u); *v = __ldg(tc + a + *v);
+    }
+  }
+}
+}  // namespace
+
+cudaError_t launch_premult_planar(const Launch &L, uint8_t *const planes[4], const int rowstrides[4], int width, int height,
+                                  const uint8_t *tab_y, const uint8_t *tab_c) {
+  if (width <= 0 || height <= 0) return cudaSuccess;
+  k_premult_planar<<<grid_for(L, (long long)((width + 3) >> 2) * height), kBlock, 0, L.stream>>>(
+      planes[0], planes[1], planes[2], planes[3], rowstrides[0], rowstrides[1], rowstrides[2], rowstrides[3], width, height, tab_y, tab_c);
+  PE_COUNT_LAUNCH(L);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_premult(const Launch &L, Img img, int width, int height, int coffs, int ncol, int aoffs,
                            const uint8_t *tab0, const uint8_t *tab1, const uint8_t *tab2, int yuva_fwd_quirk) {
   (void)ncol;

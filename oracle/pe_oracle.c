@@ -671,6 +671,23 @@ void pe_or_alpha_premult(uint8_t *pixels, int rowstride, int palette, int clampi
   }
 }
 
+/* YUVA4444P (:12001-12049): every plane through its own table with the sample's alpha -- unal / al when unclamped, (un)alcy for the
+ * luma plane and (un)alcuv for both chroma planes when clamped; each plane reads its ORIGINAL value (no rewritten-Y slip here) */
+void pe_or_alpha_premult_planar(uint8_t *const planes[4], const int rows[4], int clamping, int width, int height, int direction) {
+  static int32_t *tabs[6];
+  if (!tabs[0]) for (int k = 0; k < 6; k++) { tabs[k] = (int32_t *)malloc(65536 * sizeof(int32_t)); pe_or_premult_table(k, tabs[k]); }
+  const int32_t *ty, *tc;
+  if (clamping != OR_CLAMPED) ty = tc = direction < 0 ? tabs[0] : tabs[1];
+  else if (direction < 0) { ty = tabs[2]; tc = tabs[4]; }
+  else { ty = tabs[3]; tc = tabs[5]; }
+  for (int i = 0; i < height; i++)
+    for (int j = 0; j < width; j++) {
+      const int alpha = planes[3][(long)rows[3] * i + j];
+      uint8_t *y = planes[0] + (long)rows[0] * i + j, *u = planes[1] + (long)rows[1] * i + j, *v = planes[2] + (long)rows[2] * i + j;
+      *y = (uint8_t)ty[alpha * 256 + *y]; *u = (uint8_t)tc[alpha * 256 + *u]; *v = (uint8_t)tc[alpha * 256 + *v];
+    }
+}
+
 /* ---- effects --------------------------------------------------------------- */
 
 /* calc_luma libweed/weed-plugin-utils.c:924-934 with its own 16.16 tables (:881-886, SCALE_FACTOR 65536) */

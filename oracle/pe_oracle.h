@@ -141,6 +141,7 @@ void pe_or_yuv411_to(int target, const uint8_t *src, int irow, int width_mpx, in
                      int order, int add_alpha, int clamping, int quality, int quirks);
 void pe_or_to_yuv411(int mode, const uint8_t *const src[3], const int irow[3], int width, int height, uint8_t *dest, int orow,
                      int clamping);
+void pe_or_alpha_premult_planar(uint8_t *const planes[4], const int rows[4], int clamping, int width, int height, int direction);
 void pe_or_rgb_to_yuv411(const uint8_t *src, int irow, int width, int height, uint8_t *dest, int orow, int order, int in_alpha,
                          int clamping);
 void pe_or_packed422_to_yuv888(int fmt, const uint8_t *src, int irow, int width_mpx, int height, uint8_t *dest, int orow,

@@ -262,6 +262,18 @@ void ref_alpha_premult(uint8_t *pixels, int width, int height, int rowstride, in
   if (flags_inout) *flags_inout = l.flags;
 }
 
+void ref_alpha_premult_planar(uint8_t **planes, int *rowstrides, int width, int height, int clamping, int direction, int *flags_inout) {
+  ref_init();
+  weed_layer_t l;
+  memset(&l, 0, sizeof(l));
+  l.width = width; l.height = height; l.palette = WEED_PALETTE_YUVA4444P; l.clamping = clamping;
+  l.nplanes = 4;
+  for (int p = 0; p < 4; p++) { l.rowstrides[p] = rowstrides[p]; l.pixel_data[p] = planes[p]; }
+  l.flags = flags_inout ? *flags_inout : 0;
+  alpha_premult(&l, direction);
+  if (flags_inout) *flags_inout = l.flags;
+}
+
 /* the per-band worker of gamma_convert_sub_layer (colourspace.c:14034) on an
  * explicit rectangle; the banding arithmetic of the caller (:14096-14110) is
  * thread-count dependent and is not part of the contract */

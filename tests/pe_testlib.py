@@ -78,6 +78,7 @@ _ORACLE_PROTOS = {
     "pe_or_packed422_to_yuv422p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "pe_or_packed422_to_yuv888": [I, VP, I, I, I, VP, I, I],
+    "pe_or_alpha_premult_planar": [VP, VP, I, I, I, I],
     "pe_or_to_yuv411": [I, VP, VP, I, I, VP, I, I],
     "pe_or_rgb_to_yuv411": [VP, I, I, I, VP, I, I, I, I],
     "pe_or_yuv411_to": [I, VP, I, I, I, VP, VP, I, I, I, I, I],
@@ -125,6 +126,7 @@ _REF_PROTOS = {
     "ref_packed422_to_yuv422p": [I, VP, I, I, VP],
     "ref_packed422_to_yuv444p": [I, VP, I, I, I, VP, VP, I],
     "ref_packed422_to_yuv888": [I, VP, I, I, I, I, VP, I],
+    "ref_alpha_premult_planar": [VP, VP, I, I, I, I, VP],
     "ref_to_yuv411": [I, VP, I, I, I, VP, I],
     "ref_rgb_to_yuv411": [VP, I, I, I, VP, I, I, I],
     "ref_yuv411_to": [I, VP, I, I, I, VP, I, I, I],

@@ -310,6 +310,25 @@ def test_swap3_single_thread_width_bug_documented():
     assert (ww[:, npx:] == sw[:, npx:]).all()
 
 
+def test_premult_planar_yuva4444p_matches_reference():
+    """alpha_premult on YUVA4444P ("special case - planar with alpha", colourspace.c:12001-12049): padded planes, both clampings and
+    directions; the planar branch returns before the flag update of :12100-12104"""
+    o, r = T.oracle(), T.ref()
+    rng = np.random.default_rng(4444)
+    for (w, h), cl, direction in itertools.product(((45, 9), (64, 3)), (T.CLAMPED, T.UNCLAMPED), (1, -1)):
+        st = T.rowstride(w, 1)
+        a = [np.zeros((h, st), np.uint8) for _ in range(4)]
+        for p in a:
+            p[:, :w] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        b = [p.copy() for p in a]
+        flags = C.c_int(0)
+        o.pe_or_alpha_premult_planar(T.planes_arg(*a), T.strides_arg(*a), cl, w, h, direction)
+        r.ref_alpha_premult_planar(T.planes_arg(*b), T.strides_arg(*b), w, h, cl, direction, C.byref(flags))
+        for k in range(4):
+            assert (a[k] == b[k]).all(), (w, h, cl, direction, k)
+        assert flags.value == 0
+
+
 def test_gamma_apply_and_premult_match_reference():
     o, r = T.oracle(), T.ref()
     rng = np.random.default_rng(8)
