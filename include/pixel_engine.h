@@ -207,7 +207,8 @@ int pe_float_yuv_table(int clamping, int which, float out[256]);
 /* ---- boundary B1 arithmetic: effect process functions on device frames ---------------------- */
 
 /* simple_blend.c common_process :58.  type 0 "chroma blend", 1 "luma overlay", 2 "luma underlay",
- * 3 "negative luma overlay".  out may be in1 (in-place, effects-weed.c:2304-2314). */
+ * 3 "negative luma overlay", 4 "averaged luma overlay" (its averaging branch is unreachable in the reference, :153-169: == type 1).
+ * out may be in1 (in-place, effects-weed.c:2304-2314). */
 int pe_fx_simple_blend(pe_engine_t *e, int type, const pe_frame_t *in1, const pe_frame_t *in2, pe_frame_t *out,
                        int blend_factor);
 /* convert_layer_palette(clip, outpl) (colourspace.c:13521-13685) + the 'chroma blend' of simple_blend.c:58 with in1 = the

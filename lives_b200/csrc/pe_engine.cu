@@ -2358,7 +2358,11 @@ inline BlendFrame blend_frame(const pe_frame *in1, const pe_frame *in2, const pe
 extern "C" int pe_fx_simple_blend_batch(pe_engine_t *e, int type, int n, const pe_frame_t *const *in1,
                                         const pe_frame_t *const *in2, pe_frame_t *const *out, int blend_factor) {
   if (!e || n <= 0 || !in1 || !in2 || !out) return set_err(PE_ERR_ARG, "NULL / empty argument");
-  if (type < 0 || type > 3) return set_err(PE_ERR_ARG, "simple_blend type %d out of range", type);
+  if (type < 0 || type > 4) return set_err(PE_ERR_ARG, "simple_blend type %d out of range", type);
+  // "averaged luma overlay" (type 4, simple_blend.c:153-169): its 3 x 3 average is guarded by `row > 0`, and `row` is only advanced
+  // inside that guard -- it stays 0, every pixel falls through to `case 1`: the filter IS the luma overlay (checked against the
+  // compiled plugin, tests/test_weed_plugin.py)
+  if (type == 4) type = 1;
   std::lock_guard<std::mutex> lk(e->mu);
   PE_CUDA(cudaSetDevice(e->device));
   std::vector<BlendFrame> frames(n);

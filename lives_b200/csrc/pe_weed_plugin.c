@@ -2,7 +2,7 @@
  *
  * Loaded exactly like the reference's plugins: dlopen + dlsym("weed_setup") + setup(weed_bootstrap)
  * (src/effects-weed.c:4468-4568).  It registers, under the SAME filter names, the filters of
- *     lives-plugins/weed-plugins/simple_blend.c   "chroma blend", "luma overlay", "luma underlay", "negative luma overlay"
+ *     lives-plugins/weed-plugins/simple_blend.c   "chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "averaged luma overlay"
  *     lives-plugins/weed-plugins/multi_blends.c   "blend_multiply" ... "blend_burn"
  *     lives-plugins/weed-plugins/slide_over.c     "slide over"
  *     lives-plugins/weed-plugins/gdk/compositor.c "compositor" (layers at scale 1 / offset 0: BASELINE config 3 through weed_apply_instance)
@@ -86,6 +86,7 @@ PE_PROCESS(chroma_process, 0, 0)
 PE_PROCESS(lumo_process, 0, 1)
 PE_PROCESS(lumu_process, 0, 2)
 PE_PROCESS(nlumo_process, 0, 3)
+PE_PROCESS(avlumo_process, 0, 4)
 PE_PROCESS(mpy_process, 1, 0)
 PE_PROCESS(screen_process, 1, 1)
 PE_PROCESS(darken_process, 1, 2)
@@ -637,6 +638,10 @@ pe_weed_plant_t *weed_setup(pe_weed_bootstrap_f weed_boot) {
       add_transition(plugin_info, "dissolve", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE | PE_WEED_CHANNEL_REINIT_ON_SIZE_CHANGE, dissolve_init,
                      dissolve_process, dissolve_deinit) ||
       add_transition(plugin_info, "rand replace", 0, PE_WEED_CHANNEL_CAN_DO_INPLACE, common_init, rreplace_process, NULL))
+    return NULL;
+  /* simple_blend.c:281-287, the file's fifth filter (registered last here so that the filter indices of the earlier rounds stay) */
+  if (add_filter(plugin_info, "averaged luma overlay", PE_WEED_FILTER_PREF_LINEAR_GAMMA, all_rgb, 5, common_init, avlumo_process,
+                 "threshold", "luma _threshold", 64))
     return NULL;
   set_int(plugin_info, PE_LEAF_VERSION, package_version);
   return plugin_info;

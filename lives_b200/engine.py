@@ -349,7 +349,7 @@ def alpha_premult(layer, direction):
 
 # ---- boundary B1 arithmetic: effect process functions -------------------------------------------------------------
 
-SIMPLE_BLEND_TYPES = {"chroma blend": 0, "luma overlay": 1, "luma underlay": 2, "negative luma overlay": 3}
+SIMPLE_BLEND_TYPES = {"chroma blend": 0, "luma overlay": 1, "luma underlay": 2, "negative luma overlay": 3, "averaged luma overlay": 4}
 MULTI_BLEND_TYPES = {"blend_multiply": 0, "blend_screen": 1, "blend_darken": 2, "blend_lighten": 3, "blend_overlay": 4,
                      "blend_dodge": 5, "blend_burn": 6}
 

@@ -742,7 +742,10 @@ void pe_or_simple_blend(int type, int palette, const uint8_t *src1, int irow1, c
 #undef OR_BL
     return;
   }
-  /* luma overlay / underlay / negative overlay :153-197 (type 4 "averaged" not restated).
+  /* luma overlay / underlay / negative overlay / averaged luma overlay :150-197.
+   * Type 4 ("averaged luma overlay" :153-169): the 3 x 3 luma average runs only `if (j > start && j < width - 1 && row > 0 &&
+   * row < height - 1)`; `row` starts at 0 (:73) and its only `row++` (:167) sits INSIDE that guard, so the guard never holds and
+   * every pixel falls through into `case 1`: type 4 computes exactly the luma overlay (== the compiled plugin, tests).
    * ARGB (start == 1): calc_luma is handed the pixel pointer + 1, so it weighs G, B and the NEXT pixel's alpha byte
    * (libweed/weed-plugin-utils.c:924-934 reads px[1..3]) -- replicated.  For the last pixel of the buffer that byte
    * lies outside it (the reference reads out of bounds); there we take 255, as for the chroma blend above.  Both
@@ -755,7 +758,7 @@ void pe_or_simple_blend(int type, int palette, const uint8_t *src1, int irow1, c
       memcpy(p1, &src1[r1 + j], 3); memcpy(p2, &src2[r2 + j], 3);
       p1[3] = (psize == 4 && r1 + j + 3 < src2_bytes) ? src1[r1 + j + 3] : 255;
       p2[3] = (psize == 4 && r2 + j + 3 < src2_bytes) ? src2[r2 + j + 3] : 255;
-      if (type == 1) take2 = or_calc_luma(p1, palette) < blend_factor;
+      if (type == 1 || type == 4) take2 = or_calc_luma(p1, palette) < blend_factor;
       else if (type == 2) take2 = or_calc_luma(p2, palette) > blendneg;
       else take2 = or_calc_luma(p1, palette) > blendneg;
       if (take2) memcpy(&dst[o + j], &src2[r2 + j], 3);

@@ -385,7 +385,7 @@ def test_simple_blend_matches_real_plugin():
         if ps == 4:
             al = s2[:, 3::4]
             al[rng.random(al.shape) < 0.4] = 255
-        for typ in (0, 1, 2, 3):
+        for typ in (0, 1, 2, 3, 4):   # 4 "averaged luma overlay": its averaging branch is dead code (:153-169), == type 1
             d_ref = np.full_like(s1, 9)
             d_or = np.full_like(s1, 9)
             assert mh.mh_run2(h, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref),

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not T.have_ref() or not os.path.exists(os.path.j
 
 NAMES = ["chroma blend", "luma overlay", "luma underlay", "negative luma overlay", "blend_multiply", "blend_screen",
          "blend_darken", "blend_lighten", "blend_overlay", "blend_dodge", "blend_burn", "slide over", "compositor", "softlight",
-         "triple split", "iris rectangle", "iris circle", "4 way split", "dissolve", "rand replace"]
+         "triple split", "iris rectangle", "iris circle", "4 way split", "dissolve", "rand replace", "averaged luma overlay"]
 
 
 def _minihost():
@@ -58,6 +58,8 @@ def test_plugin_bootstraps_through_the_reference_libweed():
     for i in range(4):
         mh.mh_filter_name(ref, i, buf, 64)
         assert buf.value.decode() == NAMES[i]
+    mh.mh_filter_name(ref, 4, buf, 64)
+    assert buf.value.decode() == NAMES[20]   # the file's fifth filter is registered last in ours (earlier indices kept)
     ref = mh.mh_open(os.path.join(T.REF_DIR, "multi_blends.so").encode())
     for i in range(7):
         mh.mh_filter_name(ref, i, buf, 64)
@@ -104,10 +106,10 @@ def test_plugin_matches_reference_plugins_bit_for_bit():
         if ps == 4:
             al = s2[:, 3::4] if pal != 5 else s2[:, 0::4]
             al[rng.random(al.shape) < 0.4] = 255
-        for typ in range(4):
+        for typ in range(5):
             d_ref, d_our = np.full_like(s1, 9), np.full_like(s1, 9)
             assert mh.mh_run2(ref_s, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_ref), d_ref.strides[0], bf, 1) == 0
-            assert mh.mh_run2(ours, typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], bf, 1) == 0
+            assert mh.mh_run2(ours, 20 if typ == 4 else typ, pal, w, ht, T.ptr(s1), s1.strides[0], T.ptr(s2), s2.strides[0], T.ptr(d_our), d_our.strides[0], bf, 1) == 0
             if pal == 5 and s2.strides[0] == w * 4:
                 d_ref[-1, w * 4 - 3:] = d_our[-1, w * 4 - 3:]  # the reference reads one byte past the frame there (UB)
             assert (d_ref == d_our).all(), (pal, bf, typ, w, ht)
