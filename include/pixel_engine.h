@@ -118,6 +118,10 @@ int pe_engine_set_sm_limit(pe_engine_t *e, int n);
  * 3 Lanczos, 4 / 5 fast bilinear vertical / horizontal; tap count, or -1 */
 int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe);
 int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps);
+/* avg_chroma (colourspace.c:2079, the tables of init_average :190-217) in the closed form the chroma up-sampling kernels compute:
+ * table[x][y] = clamp((((x + y) * A + B) * M) >> 32, lo, hi); out = {A, B, M, lo, hi}.  Returns 1 when the form equals the table the
+ * library builds for this clamping, entry by entry (host arithmetic, no GPU). */
+int pe_avg_closed_form(int clamped, uint32_t out[5]);
 
 /* one engine per process and GPU, shared by the weed_layer_t drop-ins (libpe_weed_layer.so) and the effect plugin
  * (libpe_weed_plugin.so): created on first use with the configuration given to pe_engine_shared_configure (default:

@@ -335,6 +335,14 @@ extern "C" int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe) {
 
 // the coefficient bank the engine would build, on the host (no GPU involved): first[dst_n], coefs[dst_n * max_taps]; returns the
 // tap count or -1
+extern "C" int pe_avg_closed_form(int clamped, uint32_t out[5]) {
+  const AvgForm F = avg_form(clamped != 0);
+  if (out) { out[0] = F.A; out[1] = F.B; out[2] = F.M; out[3] = (uint32_t)F.lo; out[4] = (uint32_t)F.hi; }
+  std::vector<uint8_t> t(65536);
+  build_avg_table(clamped != 0, t.data());
+  return avg_form_matches(clamped != 0, t.data()) ? 1 : 0;
+}
+
 extern "C" int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int32_t *first, int16_t *coefs, int max_taps) {
   ResizeFilter f;
   if (!first || !coefs) return -1;
@@ -428,6 +436,10 @@ uint8_t *get_cavg(pe_engine *e, bool clamped) {
   if (e->cavg_dev[which]) return e->cavg_dev[which];
   std::vector<uint8_t> host(65536);
   build_avg_table(clamped, host.data());
+  if (!avg_form_matches(clamped, host.data())) {   // k_quad_chroma / k_chroma_upsample_packed compute avg_chroma in closed form
+    set_err(PE_ERR_ARG, "the averaging table left its closed form");
+    return nullptr;
+  }
   uint8_t *dev = nullptr;
   if (cudaMalloc(&dev, 65536) != cudaSuccess) return nullptr;
   if (cudaMemcpyAsync(dev, host.data(), 65536, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
@@ -1502,7 +1514,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     ce = launch_copy2d(L, S.y, S.rs_y, (uint8_t *)n.d.planes[0], n.d.rowstrides[0], width, height, 0, 0);
     if (ce == cudaSuccess)
       ce = launch_quad_chroma(L, S.u, S.v, S.rs_u, S.rs_v, S.ch, (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], n.d.rowstrides[1], width,
-                              height, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+                              height, isampling == PE_YUV_SAMPLING_JPEG, iclamping == PE_YUV_CLAMPING_CLAMPED);
     if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P)
       ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);
   } else if ((inpl == PE_PALETTE_YUV888 || inpl == PE_PALETTE_YUVA8888) &&
@@ -1549,7 +1561,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
     const uint8_t *pl[3] = {S.y, S.u, S.v};
     const int irs[3] = {S.rs_y, S.rs_u, S.rs_v};
     ce = launch_chroma_upsample_packed(L, inpl != PE_PALETTE_YUV422P, pl, irs, S.ch, Img{(uint8_t *)n.d.planes[0], n.d.rowstrides[0]}, width, height,
-                                       outpl == PE_PALETTE_YUVA8888, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+                                       outpl == PE_PALETTE_YUVA8888, isampling == PE_YUV_SAMPLING_JPEG, iclamping == PE_YUV_CLAMPING_CLAMPED);
   } else if ((inpl == PE_PALETTE_YUV420P && outpl == PE_PALETTE_YVU420P) || (inpl == PE_PALETTE_YVU420P && outpl == PE_PALETTE_YUV420P)) {
     // pconv_can_inplace (:12152-12155): no pixel work (:13618-13623) -- the chroma plane pointers and rowstrides change places, on the
     // way in for a V-first source (:12354), on the way out for a V-first target (:13895, below)
@@ -1641,7 +1653,7 @@ int convert_locked(pe_engine *e, pe_frame *f, int outpl, int oclamping, int osam
       if (ce == cudaSuccess) ce = launch_yuv888_subsample(L, 2, CImg{tmp, trs}, 0, opl, n.d.rowstrides, n.d.width, height, cavg);
     } else {
       const uint8_t *pl[3] = {(const uint8_t *)f->d.planes[0], (const uint8_t *)f->d.planes[1], (const uint8_t *)f->d.planes[2]};
-      ce = launch_chroma_upsample_packed(L, 0, pl, f->d.rowstrides, height, Img{tmp, trs}, width, height, 0, isampling == PE_YUV_SAMPLING_JPEG, cavg);
+      ce = launch_chroma_upsample_packed(L, 0, pl, f->d.rowstrides, height, Img{tmp, trs}, width, height, 0, isampling == PE_YUV_SAMPLING_JPEG, iclamping == PE_YUV_CLAMPING_CLAMPED);
       uint8_t *opl[4] = {(uint8_t *)n.d.planes[0], (uint8_t *)n.d.planes[1], (uint8_t *)n.d.planes[2], nullptr};
       if (ce == cudaSuccess) ce = launch_split_planes(L, CImg{tmp, trs}, opl, n.d.rowstrides, width, height, 0, 0);
       if (ce == cudaSuccess && outpl == PE_PALETTE_YUVA4444P) ce = cudaMemsetAsync(n.d.planes[3], 255, (size_t)n.d.rowstrides[3] * height, e->stream);

@@ -142,14 +142,14 @@ cudaError_t launch_yuv444p_to_chroma420(const Launch &L, const uint8_t *su, cons
 cudaError_t launch_planar42x_to_packed422(const Launch &L, int fmt, int is_422, const uint8_t *const planes[3], const int irows[3], Img dst,
                                           int width_mpx, int height);
 cudaError_t launch_quad_chroma(const Launch &L, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, int ch, uint8_t *du, uint8_t *dv,
-                               int ors, int width, int height, int jpeg, const uint8_t *cavg_dev);
+                               int ors, int width, int height, int jpeg, int clamped /* which avg_chroma table: closed form, pe_tables.h AvgForm */);
 // mode 0 UYVY 1 YUYV (planes[0] = the packed frame) 2 planar 4:2:2 3 planar 4:2:0
 cudaError_t launch_yuv888_subsample(const Launch &L, int mode, CImg src, int src_alpha, uint8_t *const planes[3], const int orows[3], int width,
                                     int height, const uint8_t *cavg_dev);
 cudaError_t launch_packed422_to_yuv420p(const Launch &L, int fmt, CImg src, uint8_t *const planes[3], const int orows[3], int width_mpx,
                                         int height, const uint8_t *cavg_dev);
 cudaError_t launch_chroma_upsample_packed(const Launch &L, int is_420, const uint8_t *const planes[3], const int irows[3], int ch, Img dst,
-                                          int width, int height, int add_alpha, int jpeg, const uint8_t *cavg_dev);
+                                          int width, int height, int add_alpha, int jpeg, int clamped);
 cudaError_t launch_swab(const Launch &L, Img img, int width_mpx, int height);
 // kind 0 luma plane, 1 chroma plane, 2 YUV888, 3 YUVA8888, 4 UYVY, 5 YUYV; row_phase_stride (YUV888): 0 = the reference's dense
 // walk across the row padding, else the rowstride (the Y U V phase restarts with every row)

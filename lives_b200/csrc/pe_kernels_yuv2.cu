@@ -423,23 +423,28 @@ __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ 
     const bool seed_lane = IS422 && QUIRKS && x == 0;
 
     auto store_row = [&](uint32_t *p4, int row, const uint32_t *op) {
-      if (xf) {  // dst = (bf * in2 + (255 - bf) * converted) >> 8 per byte (make_blend_table, simple_blend.c:31-35)
-        const uint32_t o4[4] = {op[0], __byte_perm(op[0], op[1], 0x0543), __byte_perm(op[1], op[2], 0x0432), op[2] >> 8};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t even = (((p4[k] & 0x00FF00FFu) * nb + (o4[k] & 0x00FF00FFu) * bf) >> 8) & 0x00FF00FFu;
-          const uint32_t mid = (((p4[k] >> 8) & 0xFFu) * nb + ((o4[k] >> 8) & 0xFFu) * bf) & 0xFF00u;
-          p4[k] = even | mid;
-        }
-      }
       uint8_t *d = dp + (size_t)rs_d * (uint32_t)row;
       if (A.out.psize == 4) {
         st_stream_u4(d, make_uint4(p4[0], p4[1], p4[2], p4[3]));
-      } else {
-        st_stream_u32(d, __byte_perm(p4[0], p4[1], 0x4210));
-        st_stream_u32(d + 4, __byte_perm(p4[1], p4[2], 0x5421));
-        st_stream_u32(d + 8, __byte_perm(p4[2], p4[3], 0x6542));
+        return;
       }
+      uint32_t w3[3] = {__byte_perm(p4[0], p4[1], 0x4210), __byte_perm(p4[1], p4[2], 0x5421), __byte_perm(p4[2], p4[3], 0x6542)};
+      if (xf) {
+        // dst = (bf * in2 + (255 - bf) * converted) >> 8 per byte (make_blend_table, simple_blend.c:31-35), on the 12 PACKED bytes:
+        // even / odd bytes of a word as 16-bit pairs (one PRMT each), two multiply-adds per pair (<= 255 * 255: no carry between
+        // the halves), and ONE PRMT that picks byte 1 of every product.  5 ALU-pipe + 4 FMA-pipe instructions per 4 bytes; the
+        // per-pixel mask / shift form this replaces cost 10 + 4 per 3 bytes, and the kernel is bound by the ALU pipe
+        // (profiles/r01u_k_yuv_march_cfg5_ncu_full.txt: 72 %)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const uint32_t E = __byte_perm(w3[k], 0u, 0x4240) * nb + __byte_perm(op[k], 0u, 0x4240) * bf;
+          const uint32_t O = __byte_perm(w3[k], 0u, 0x4341) * nb + __byte_perm(op[k], 0u, 0x4341) * bf;
+          w3[k] = __byte_perm(E, O, 0x7351);
+        }
+      }
+      st_stream_u32(d, w3[0]);
+      st_stream_u32(d + 4, w3[1]);
+      st_stream_u32(d + 8, w3[2]);
     };
     auto load_op = [&](int row, uint32_t *op) {   // crossfade operand: the 12 bytes under the lane's 4 pixels
       if (!xf) return;

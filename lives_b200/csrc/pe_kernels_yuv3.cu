@@ -21,6 +21,7 @@
 // ragged last group of a row, go byte by byte through the same code.
 #include "pe_device.cuh"
 #include "pe_kernels.h"
+#include "pe_tables.h"
 
 namespace pe {
 
@@ -297,27 +298,47 @@ __global__ void __launch_bounds__(kBlock) k_planar42x_to_packed422(int fmt, int 
   }
 }
 
+// avg_chroma in closed form (pe_tables.h AvgForm: both tables of init_average are functions of x + y; checked against the table when
+// the engine builds it): two multiplies and a clamp instead of a gather from the 64 KB table.  k_quad_chroma / k_chroma_upsample_packed
+// do 3 - 7 of these per output pixel: as 32-address gathers they ran at 5 - 9 % of the HBM roofline (round 1: 79 us per 4K frame).
+__device__ __forceinline__ uint32_t avg1(const AvgForm &F, uint32_t x, uint32_t y) {
+  const int f = (int)__umulhi((x + y) * F.A + F.B, F.M);
+  return (uint32_t)min(max(f, F.lo), F.hi);
+}
+__device__ __forceinline__ uint32_t avg4(const AvgForm &F, uint32_t a, uint32_t b) {
+  // the four byte sums as two 16-bit pairs (no carry between the halves: <= 510)
+  const uint32_t se = __byte_perm(a, 0u, 0x4240) + __byte_perm(b, 0u, 0x4240), so = __byte_perm(a, 0u, 0x4341) + __byte_perm(b, 0u, 0x4341);
+  auto one = [&](uint32_t s) -> uint32_t {
+    const int f = (int)__umulhi(s * F.A + F.B, F.M);
+    return (uint32_t)min(max(f, F.lo), F.hi);
+  };
+  const uint32_t r0 = one(se & 0xFFFFu), r2 = one(se >> 16), r1 = one(so & 0xFFFFu), r3 = one(so >> 16);
+  return __byte_perm(r0 | (r1 << 8), r2 | (r3 << 8), 0x5410);
+}
+
 // 4:2:0 -> 4:4:4 chroma planes (convert_quad_chroma, colourspace.c:10642).  Even destination row 2k from chroma row k: column 0 =
 // s[0], column 2m = f(s[m-1], s[m]), column 2m+1 = g(s[m], s[m+1]) (JPEG sampling: f = g = avg_chroma; otherwise U: f = 3:1, g = 1:3,
 // V mirrored); odd row r = avg_chroma(row r+1, row r-1), the last odd row of an odd-height frame with the operands swapped, the last
-// row of an even-height frame a copy of the row above.  One thread = 4 destination samples; blockIdx.y = plane (U, V).
+// row of an even-height frame a copy of the row above.  One thread = 4 destination columns of QC_PAIRS consecutive row pairs: the even
+// row of chroma row k + 1 is computed once and serves rows 2k + 1 and 2k + 2; blockIdx.y = plane (U, V).
+constexpr int QC_PAIRS = 4;
 struct QuadChromaParams {
   const uint8_t *su, *sv;
   uint8_t *du, *dv;
   int irs_u, irs_v, ors, w2, height, cw, ch, jpeg;
-  const uint8_t *cavg;
+  AvgForm avg;
 };
 
 __device__ __forceinline__ uint32_t quad_even4(const uint8_t *__restrict__ s, int irs, int k, int m, int cw, int ch, bool is_u, bool jpeg,
-                                               const uint8_t *__restrict__ cavg, int n, bool g_is_f = false) {
+                                               const AvgForm &F, int n, bool g_is_f = false) {
   // 4 destination samples 2m .. 2m+3 of even row 2k (n of them valid) from s[m-1 .. m+2]
   const uint8_t *r = s + (long long)irs * k;
   auto at = [&](int c) -> uint32_t {
     if (c < 0) c = 0;
     if (c >= cw) c = (cw < irs || k + 1 < ch) ? cw : cw - 1;
-    return r[c];
+    return __ldg(r + c);
   };
-  auto av = [&](uint32_t x, uint32_t y) -> uint32_t { return __ldg(cavg + ((x << 8) | y)); };
+  auto av = [&](uint32_t x, uint32_t y) -> uint32_t { return avg1(F, x, y); };
   auto f = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : (is_u ? av(x, av(x, y)) : av(av(x, y), y)); };   // even column
   // odd column (convert_double_chroma_packed uses the even column's weights there too, colourspace.c:10853-10858: g_is_f)
   auto g = [&](uint32_t x, uint32_t y) -> uint32_t { return jpeg ? av(x, y) : ((is_u != g_is_f) ? av(av(x, y), y) : av(x, av(x, y))); };
@@ -334,24 +355,25 @@ __global__ void __launch_bounds__(kBlock) k_quad_chroma(const QuadChromaParams P
   const uint8_t *s = is_u ? P.su : P.sv;
   uint8_t *d = is_u ? P.du : P.dv;
   const int irs = is_u ? P.irs_u : P.irs_v;
-  const int groups = (P.w2 + 3) >> 2;
-  const long long total = (long long)groups * P.height;
+  const int groups = (P.w2 + 3) >> 2, npairs = (P.height + 1) >> 1, nchunks = (npairs + QC_PAIRS - 1) / QC_PAIRS;
+  const long long total = (long long)groups * nchunks;
   for (long long it = global_tid(); it < total; it += global_threads()) {
-    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int chunk = (int)(it / groups), g = (int)(it - (long long)chunk * groups);
     const int x = 4 * g, n = min(4, P.w2 - x), m = x >> 1;
-    uint32_t w;
-    if (!(row & 1)) {
-      w = quad_even4(s, irs, row >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
-    } else {
-      const uint32_t up = quad_even4(s, irs, (row - 1) >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
-      if (row + 1 > P.height - 1) {
-        w = up;
-      } else {
-        const uint32_t dn = quad_even4(s, irs, (row + 1) >> 1, m, P.cw, P.ch, is_u, P.jpeg, P.cavg, n);
-        w = ((P.height & 1) && row == P.height - 2) ? avg4(P.cavg, up, dn) : avg4(P.cavg, dn, up);
+    const int k0 = chunk * QC_PAIRS, k1 = min(k0 + QC_PAIRS, npairs);
+    uint32_t E = quad_even4(s, irs, k0, m, P.cw, P.ch, is_u, P.jpeg, P.avg, n);
+    for (int k = k0; k < k1; k++) {
+      st_px4(d + (long long)P.ors * (2 * k) + x, E, n, vec);
+      const int row = 2 * k + 1;
+      if (row >= P.height) break;
+      uint32_t w = E;   // the last row of an even-height frame copies the row above
+      if (row + 1 <= P.height - 1) {
+        const uint32_t En = quad_even4(s, irs, k + 1, m, P.cw, P.ch, is_u, P.jpeg, P.avg, n);
+        w = ((P.height & 1) && row == P.height - 2) ? avg4(P.avg, E, En) : avg4(P.avg, En, E);
+        E = En;
       }
+      st_px4(d + (long long)P.ors * row + x, w, n, vec);
     }
-    st_px4(d + (long long)P.ors * row + x, w, n, vec);
   }
 }
 
@@ -439,46 +461,55 @@ __global__ void __launch_bounds__(kBlock) k_packed422_to_yuv420p(int fmt, const 
 
 // planar 4:2:0 / 4:2:2 -> YUV888 / YUVA8888 with the chroma up-sampled on the fly (convert_quad_chroma_packed colourspace.c:10715,
 // convert_double_chroma_packed :10811): the chroma of k_quad_chroma (4:2:0) or its even-row rule on every row with f on both
-// columns (4:2:2), interleaved with the luma.  One thread = 4 pixels.
+// columns (4:2:2), interleaved with the luma.  One thread = 4 pixels of QC_PAIRS consecutive row pairs (4:2:0: the even-row chroma of
+// chroma row k + 1 is computed once for rows 2k + 1 and 2k + 2).
 struct UpsamplePackedParams {
   const uint8_t *y, *u, *v;
   uint8_t *dst;
   int rs_y, rs_u, rs_v, orow, w2, height, cw, ch, jpeg, is_420, add_alpha;
-  const uint8_t *cavg;
+  AvgForm avg;
 };
 
 __global__ void __launch_bounds__(kBlock) k_chroma_upsample_packed(const UpsamplePackedParams P, int vec) {
   const int groups = (P.w2 + 3) >> 2, ps = P.add_alpha ? 4 : 3;
-  const long long total = (long long)groups * P.height;
+  const int npairs = (P.height + 1) >> 1, nchunks = (npairs + QC_PAIRS - 1) / QC_PAIRS;
+  const long long total = (long long)groups * nchunks;
   for (long long it = global_tid(); it < total; it += global_threads()) {
-    const int row = (int)(it / groups), g = (int)(it - (long long)row * groups);
+    const int chunk = (int)(it / groups), g = (int)(it - (long long)chunk * groups);
     const int x = 4 * g, n = min(4, P.w2 - x), m = x >> 1;
-    const uint32_t yw = ld_px4(P.y + (long long)P.rs_y * row + x, n, vec);
-    uint32_t uw, vw;
+    const int k0 = chunk * QC_PAIRS, k1 = min(k0 + QC_PAIRS, npairs);
+    auto put = [&](int row, uint32_t uw, uint32_t vw) {
+      const uint32_t yw = ld_px4(P.y + (long long)P.rs_y * row + x, n, vec);
+      const uint32_t aw = 0xFFFFFFFFu;
+      const uint32_t yu_lo = __byte_perm(yw, uw, 0x5140), yu_hi = __byte_perm(yw, uw, 0x7362);
+      const uint32_t va_lo = __byte_perm(vw, aw, 0x5140), va_hi = __byte_perm(vw, aw, 0x7362);
+      const uint32_t px[4] = {__byte_perm(yu_lo, va_lo, 0x5410), __byte_perm(yu_lo, va_lo, 0x7632), __byte_perm(yu_hi, va_hi, 0x5410),
+                              __byte_perm(yu_hi, va_hi, 0x7632)};
+      st_packed4(P.dst + (long long)P.orow * row + (long long)x * ps, px, ps, n, vec);
+    };
     if (!P.is_420) {
-      uw = quad_even4(P.u, P.rs_u, row, m, P.cw, P.ch, true, P.jpeg, P.cavg, n, true);
-      vw = quad_even4(P.v, P.rs_v, row, m, P.cw, P.ch, false, P.jpeg, P.cavg, n, true);
-    } else if (!(row & 1)) {
-      uw = quad_even4(P.u, P.rs_u, row >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
-      vw = quad_even4(P.v, P.rs_v, row >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
-    } else {
-      const uint32_t uu = quad_even4(P.u, P.rs_u, (row - 1) >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
-      const uint32_t vu = quad_even4(P.v, P.rs_v, (row - 1) >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
-      if (row + 1 > P.height - 1) { uw = uu; vw = vu; }
-      else {
-        const uint32_t ud = quad_even4(P.u, P.rs_u, (row + 1) >> 1, m, P.cw, P.ch, true, P.jpeg, P.cavg, n);
-        const uint32_t vd = quad_even4(P.v, P.rs_v, (row + 1) >> 1, m, P.cw, P.ch, false, P.jpeg, P.cavg, n);
-        const bool swapped = (P.height & 1) && row == P.height - 2;
-        uw = swapped ? avg4(P.cavg, uu, ud) : avg4(P.cavg, ud, uu);
-        vw = swapped ? avg4(P.cavg, vu, vd) : avg4(P.cavg, vd, vu);
-      }
+      for (int row = 2 * k0; row < min(2 * k1, P.height); row++)
+        put(row, quad_even4(P.u, P.rs_u, row, m, P.cw, P.ch, true, P.jpeg, P.avg, n, true),
+            quad_even4(P.v, P.rs_v, row, m, P.cw, P.ch, false, P.jpeg, P.avg, n, true));
+      continue;
     }
-    const uint32_t aw = 0xFFFFFFFFu;
-    const uint32_t yu_lo = __byte_perm(yw, uw, 0x5140), yu_hi = __byte_perm(yw, uw, 0x7362);
-    const uint32_t va_lo = __byte_perm(vw, aw, 0x5140), va_hi = __byte_perm(vw, aw, 0x7362);
-    const uint32_t px[4] = {__byte_perm(yu_lo, va_lo, 0x5410), __byte_perm(yu_lo, va_lo, 0x7632), __byte_perm(yu_hi, va_hi, 0x5410),
-                            __byte_perm(yu_hi, va_hi, 0x7632)};
-    st_packed4(P.dst + (long long)P.orow * row + (long long)x * ps, px, ps, n, vec);
+    uint32_t EU = quad_even4(P.u, P.rs_u, k0, m, P.cw, P.ch, true, P.jpeg, P.avg, n);
+    uint32_t EV = quad_even4(P.v, P.rs_v, k0, m, P.cw, P.ch, false, P.jpeg, P.avg, n);
+    for (int k = k0; k < k1; k++) {
+      put(2 * k, EU, EV);
+      const int row = 2 * k + 1;
+      if (row >= P.height) break;
+      uint32_t uw = EU, vw = EV;
+      if (row + 1 <= P.height - 1) {
+        const uint32_t nu = quad_even4(P.u, P.rs_u, k + 1, m, P.cw, P.ch, true, P.jpeg, P.avg, n);
+        const uint32_t nv = quad_even4(P.v, P.rs_v, k + 1, m, P.cw, P.ch, false, P.jpeg, P.avg, n);
+        const bool swapped = (P.height & 1) && row == P.height - 2;
+        uw = swapped ? avg4(P.avg, EU, nu) : avg4(P.avg, nu, EU);
+        vw = swapped ? avg4(P.avg, EV, nv) : avg4(P.avg, nv, EV);
+        EU = nu; EV = nv;
+      }
+      put(row, uw, vw);
+    }
   }
 }
 
@@ -632,13 +663,14 @@ cudaError_t launch_planar42x_to_packed422(const Launch &L, int fmt, int is_422, 
 }
 
 cudaError_t launch_quad_chroma(const Launch &L, const uint8_t *su, const uint8_t *sv, int irs_u, int irs_v, int ch, uint8_t *du, uint8_t *dv,
-                               int ors, int width, int height, int jpeg, const uint8_t *cavg_dev) {
+                               int ors, int width, int height, int jpeg, int clamped) {
   QuadChromaParams P;
   P.su = su; P.sv = sv; P.du = du; P.dv = dv; P.irs_u = irs_u; P.irs_v = irs_v; P.ors = ors;
-  P.w2 = (width >> 1) << 1; P.height = height; P.cw = P.w2 >> 1; P.ch = ch; P.jpeg = jpeg; P.cavg = cavg_dev;
+  P.w2 = (width >> 1) << 1; P.height = height; P.cw = P.w2 >> 1; P.ch = ch; P.jpeg = jpeg;
+  P.avg = avg_form(clamped != 0);
   if (P.w2 < 2 || height < 1) return cudaSuccess;
   const int vec = aligned4(du) && aligned4(dv) && !(ors & 3);
-  const dim3 grid(grid_for(L, (long long)((P.w2 + 3) / 4) * height), 2);
+  const dim3 grid(grid_for(L, (long long)((P.w2 + 3) / 4) * ((height + 2 * QC_PAIRS - 1) / (2 * QC_PAIRS))), 2);
   k_quad_chroma<<<grid, kBlock, 0, L.stream>>>(P, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
@@ -672,14 +704,14 @@ cudaError_t launch_packed422_to_yuv420p(const Launch &L, int fmt, CImg src, uint
 }
 
 cudaError_t launch_chroma_upsample_packed(const Launch &L, int is_420, const uint8_t *const planes[3], const int irows[3], int ch, Img dst,
-                                          int width, int height, int add_alpha, int jpeg, const uint8_t *cavg_dev) {
+                                          int width, int height, int add_alpha, int jpeg, int clamped) {
   UpsamplePackedParams P;
   P.y = planes[0]; P.u = planes[1]; P.v = planes[2]; P.dst = dst.p; P.rs_y = irows[0]; P.rs_u = irows[1]; P.rs_v = irows[2]; P.orow = dst.rs;
   P.w2 = (width >> 1) << 1; P.height = height; P.cw = P.w2 >> 1; P.ch = ch; P.jpeg = jpeg; P.is_420 = is_420; P.add_alpha = add_alpha;
-  P.cavg = cavg_dev;
+  P.avg = avg_form(clamped != 0);
   if (P.w2 < 2 || height < 1) return cudaSuccess;
   const int vec = aligned4(planes[0]) && !(irows[0] & 3) && (add_alpha ? aligned16(dst.p) && !(dst.rs & 15) : aligned4(dst.p) && !(dst.rs & 3));
-  k_chroma_upsample_packed<<<grid_for(L, (long long)((P.w2 + 3) / 4) * height), kBlock, 0, L.stream>>>(P, vec);
+  k_chroma_upsample_packed<<<grid_for(L, (long long)((P.w2 + 3) / 4) * ((height + 2 * QC_PAIRS - 1) / (2 * QC_PAIRS))), kBlock, 0, L.stream>>>(P, vec);
   PE_COUNT_LAUNCH(L);
   return cudaGetLastError();
 }

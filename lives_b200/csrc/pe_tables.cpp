@@ -248,6 +248,18 @@ void build_avg_table(bool clamped, uint8_t *out) {
   }
 }
 
+bool avg_form_matches(bool clamped, const uint8_t *table) {
+  const AvgForm F = avg_form(clamped);
+  for (int x = 0; x < 256; x++)
+    for (int y = 0; y < 256; y++) {
+      const uint32_t n = (uint32_t)(x + y) * F.A + F.B;
+      int f = (int)(((unsigned long long)n * F.M) >> 32);
+      f = f < F.lo ? F.lo : f > F.hi ? F.hi : f;
+      if (table[x * 256 + y] != f) return false;
+    }
+  return true;
+}
+
 // init_YUV_to_YUV_tables (colourspace.c:1108-1138): clamped <-> unclamped, same subspace.  Limits 16 / 235 / 240
 // (colourspace.h:96-109); the first luma loop runs to i <= 16, the first chroma loop to i < 16; rounding is myround
 // (maths.h:118: half away from zero, in double)

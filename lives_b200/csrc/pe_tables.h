@@ -31,6 +31,19 @@ void build_premult_table(int which, uint8_t *out /*65536*/);
 
 // init_average (colourspace.c:190): cavgc (clamped) / cavgu, [x][y] as uint8
 void build_avg_table(bool clamped, uint8_t *out /*65536*/);
+// avg_chroma(x, y) in closed form: both tables of init_average depend on s = x + y only,
+//   table[x][y] = clamp(((s * A + B) * M) >> 32, lo, hi)
+// clamped: floor((1785 (s - 256) + 128 * 3904) / 3904) (the float expression of colourspace.c:208 is never closer than 1 / 3904 to an
+// integer except at s = 256, where it is exact), limits 16 / 240; unclamped: s >> 1.  avg_form_matches() compares the form with the
+// table entry by entry (the engine refuses to use it otherwise).
+struct AvgForm {
+  uint32_t A, B, M;
+  int lo, hi;
+};
+inline AvgForm avg_form(bool clamped) {
+  return clamped ? AvgForm{1785u, 42752u, 1100154u, 16, 240} : AvgForm{1u, 0u, 0x80000000u, 0, 255};
+}
+bool avg_form_matches(bool clamped, const uint8_t *table);
 
 // init_YUV_to_YUV_tables (colourspace.c:1108): which = 0 Yclamped_to_Yunclamped 1 UVclamped_to_UVunclamped 2 Yunclamped_to_Yclamped
 // 3 UVunclamped_to_UVclamped

@@ -846,8 +846,8 @@ def test_convert_crossfade_batchv_operand_per_clip(eng):
 def test_unhandled_conversion_fails_and_leaves_layer(eng):
     rng = np.random.default_rng(9)
     src = T.make_packed(rng, 32, 8, 4)
-    lay = packed_layer(eng, 5, 32, 8, src)  # ARGB32 -> YUV420P: the reference loop reads past its pixels (:6357); not built
-    assert not lb.convert_layer_palette(lay, lb.WEED_PALETTE_YUV420P, 0)
+    lay = packed_layer(eng, 5, 32, 8, src)  # ARGB32 -> WEED_PALETTE_RGBFLOAT (64, libweed/weed-palettes.h:59): the reference has no converter for it either
+    assert not lb.convert_layer_palette(lay, 64, 0)
     assert "not handled" in lb._capi.last_error()
     assert lay.palette == 5
     assert (lay.to_host()[0] == src).all()

@@ -234,3 +234,26 @@ def test_resize_coefficient_banks_of_the_shipped_library():
     fb, cb = np.zeros(720, np.int32), np.zeros((720, 64), np.int16)
     assert o.pe_or_resize_filter_sws(1080, 720, 12, T.ptr(fa), T.ptr(ca), 64) == o.pe_or_resize_filter_kind(1, 1080, 720, 12, fb.ctypes.data, cb.ctypes.data, 64)
     assert (fa == fb).all() and (ca == cb).all()
+
+
+def test_avg_chroma_closed_form_equals_the_reference_tables():
+    """the chroma up-sampling kernels compute avg_chroma(x, y) as clamp((((x + y) * A + B) * M) >> 32, lo, hi) instead of gathering
+    from the 64 KB tables of init_average (colourspace.c:190-217): the constants the library ships reproduce the oracle's tables
+    (which tests/test_oracle_vs_reference.py pins to the compiled reference) entry by entry, for both clampings"""
+    import ctypes as C
+    import lives_b200  # noqa: F401
+    import pe_testlib as T
+    from lives_b200 import _capi
+    lib, o = _capi.lib(), T.oracle()
+    o.pe_or_avg_table.argtypes = [C.c_int, C.c_void_p]
+    for clamped in (1, 0):
+        k = np.zeros(5, np.uint32)
+        assert lib.pe_avg_closed_form(clamped, C.c_void_p(k.ctypes.data)) == 1
+        A, B, M, lo, hi = (int(v) for v in k)
+        tab = np.zeros(65536, np.uint8)
+        o.pe_or_avg_table(0 if clamped else 1, C.c_void_p(tab.ctypes.data))
+        s = np.add.outer(np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64))
+        n = s * A + B
+        assert n.max() < 2 ** 32
+        f = np.clip((n * M) >> 32, lo, hi).astype(np.uint8)
+        assert (f.reshape(-1) == tab).all(), clamped

@@ -214,12 +214,13 @@ def test_letterbox_gamma_premult_on_a_real_layer(host):
 
 @pytest.mark.gpu
 def test_failed_op_leaves_the_layer_untouched(host):
-    """a palette pair this build refuses (ARGB32 -> YUV420P reads past its pixels in the reference, :6357): FALSE, nothing changed"""
+    """a target this build refuses (WEED_PALETTE_RGBFLOAT = 64, libweed/weed-palettes.h:59: no converter in the reference either):
+    FALSE, nothing changed"""
     rng = np.random.default_rng(4)
     src = T.make_packed(rng, 64, 48, 4)
     lay = host.layer(5, 64, 48, [src])
     before = host.snapshot(lay)
-    assert host.lib.convert_layer_palette(lay, 512, 0) == 0
+    assert host.lib.convert_layer_palette(lay, 64, 0) == 0
     after = host.snapshot(lay)
     assert before["leaves"] == after["leaves"] and before["ptrs"] == after["ptrs"] and (before["planes"][0] == after["planes"][0]).all()
     # a layer without pixel data: resize_layer_full records the target and returns FALSE (:14820-14832)

@@ -1,6 +1,7 @@
 #!/bin/bash
-# quick GPU iteration: a pytest selection (-k "$2") and, optionally, bench workloads ("$3")
+# iteration pass: GPU tests, the secondary-kernel timings, config 5 kernel rate
 TAG=${1:-it}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "$2" > gpurun_out/pytest_$TAG.log 2>&1; grep -E "^E  |passed|failed|Error" gpurun_out/pytest_$TAG.log | head -30
-for w in $3; do timeout 120 python bench.py --workload $w --steps 20 2>&1 | tail -1 | grep -o '"value": [0-9.]*\|"frac": [0-9.]*' | paste - - ; done | tee gpurun_out/bench_$TAG.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -3 gpurun_out/pytest_gpu_$TAG.log
+timeout 200 python tools/time_new_kernels.py > gpurun_out/new_kernels_$TAG.jsonl 2>&1; cat gpurun_out/new_kernels_$TAG.jsonl | cut -c1-250
+for w in cfg5 cfg2; do timeout 120 python bench.py --workload $w --steps 20 >> gpurun_out/bench_cfgs_$TAG.log 2>&1; done; cut -c1-400 gpurun_out/bench_cfgs_$TAG.log
