@@ -350,6 +350,37 @@ __device__ __forceinline__ uint32_t quad_even4(const uint8_t *__restrict__ s, in
   return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
 }
 
+// The same four samples for an interior group (m >= 2, all of s[m-1 .. m+2] inside the row, 4-byte aligned plane): the four bytes come
+// from two aligned words, av(c1, c2) is shared between the two middle samples (7 table values instead of 8), no edge tests.
+// toward_x: A(x, y) = av(x, av(x, y));  toward_y: B(x, y) = av(av(x, y), y).  U: f = A, g = B; V: f = B, g = A; g_is_f: g = f.
+__device__ __forceinline__ bool quad_fast_ok(const uint8_t *s, int irs, int m, int cw, int n) {
+  return n == 4 && m >= 2 && (((m - 1) & ~3) + 8) <= cw && (((uintptr_t)s | (uint32_t)irs) & 3) == 0;
+}
+__device__ __forceinline__ uint32_t quad_load4(const uint8_t *__restrict__ s, int irs, int k, int m) {   // bytes m-1 .. m+2 of chroma row k
+  const uint8_t *r = s + (long long)irs * k + ((m - 1) & ~3);
+  const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(r)), w1 = __ldg(reinterpret_cast<const uint32_t *>(r + 4));
+  return __byte_perm(w0, w1, (m & 2) ? 0x4321u : 0x6543u);
+}
+__device__ __forceinline__ uint32_t quad_even4_from(uint32_t c, bool is_u, bool jpeg, const AvgForm &F, bool g_is_f = false) {
+  const uint32_t c0 = byte_of(c, 0), c1 = byte_of(c, 1), c2 = byte_of(c, 2), c3 = byte_of(c, 3);
+  const uint32_t t01 = avg1(F, c0, c1), t12 = avg1(F, c1, c2), t23 = avg1(F, c2, c3);
+  uint32_t v0, v1, v2, v3;
+  if (jpeg) {
+    v0 = t01; v1 = t12; v2 = t12; v3 = t23;
+  } else {
+    const bool f_x = is_u, g_x = is_u == g_is_f;   // f / g lean toward their first operand
+    v0 = f_x ? avg1(F, c0, t01) : avg1(F, t01, c1);
+    v2 = f_x ? avg1(F, c1, t12) : avg1(F, t12, c2);
+    v1 = g_x ? avg1(F, c1, t12) : avg1(F, t12, c2);
+    v3 = g_x ? avg1(F, c2, t23) : avg1(F, t23, c3);
+  }
+  return __byte_perm(v0 | (v1 << 8), v2 | (v3 << 8), 0x5410);
+}
+__device__ __forceinline__ uint32_t quad_even4_fast(const uint8_t *__restrict__ s, int irs, int k, int m, bool is_u, bool jpeg, const AvgForm &F,
+                                                    bool g_is_f = false) {
+  return quad_even4_from(quad_load4(s, irs, k, m), is_u, jpeg, F, g_is_f);
+}
+
 __global__ void __launch_bounds__(kBlock) k_quad_chroma(const QuadChromaParams P, int vec) {
   const bool is_u = blockIdx.y == 0;
   const uint8_t *s = is_u ? P.su : P.sv;
@@ -361,14 +392,35 @@ __global__ void __launch_bounds__(kBlock) k_quad_chroma(const QuadChromaParams P
     const int chunk = (int)(it / groups), g = (int)(it - (long long)chunk * groups);
     const int x = 4 * g, n = min(4, P.w2 - x), m = x >> 1;
     const int k0 = chunk * QC_PAIRS, k1 = min(k0 + QC_PAIRS, npairs);
-    uint32_t E = quad_even4(s, irs, k0, m, P.cw, P.ch, is_u, P.jpeg, P.avg, n);
+    const bool fast = quad_fast_ok(s, irs, m, P.cw, n);
+    auto even = [&](int k) -> uint32_t {
+      return fast ? quad_even4_fast(s, irs, k, m, is_u, P.jpeg, P.avg) : quad_even4(s, irs, k, m, P.cw, P.ch, is_u, P.jpeg, P.avg, n);
+    };
+    if (fast && vec && 2 * k0 + 2 * QC_PAIRS <= P.height - 2) {
+      // a whole chunk away from the frame's edges: every load is issued before the first use (5 chroma rows in flight per thread)
+      uint32_t c[QC_PAIRS + 1];
+#pragma unroll
+      for (int j = 0; j <= QC_PAIRS; j++) c[j] = quad_load4(s, irs, k0 + j, m);
+      uint32_t E = quad_even4_from(c[0], is_u, P.jpeg, P.avg);
+      uint8_t *dr = d + (long long)P.ors * (2 * k0) + x;
+#pragma unroll
+      for (int j = 0; j < QC_PAIRS; j++) {
+        const uint32_t En = quad_even4_from(c[j + 1], is_u, P.jpeg, P.avg);
+        st_stream_u32(dr, E);
+        st_stream_u32(dr + P.ors, avg4(P.avg, En, E));
+        dr += 2 * (long long)P.ors;
+        E = En;
+      }
+      continue;
+    }
+    uint32_t E = even(k0);
     for (int k = k0; k < k1; k++) {
       st_px4(d + (long long)P.ors * (2 * k) + x, E, n, vec);
       const int row = 2 * k + 1;
       if (row >= P.height) break;
       uint32_t w = E;   // the last row of an even-height frame copies the row above
       if (row + 1 <= P.height - 1) {
-        const uint32_t En = quad_even4(s, irs, k + 1, m, P.cw, P.ch, is_u, P.jpeg, P.avg, n);
+        const uint32_t En = even(k + 1);
         w = ((P.height & 1) && row == P.height - 2) ? avg4(P.avg, E, En) : avg4(P.avg, En, E);
         E = En;
       }
@@ -485,24 +537,79 @@ __global__ void __launch_bounds__(kBlock) k_chroma_upsample_packed(const Upsampl
       const uint32_t va_lo = __byte_perm(vw, aw, 0x5140), va_hi = __byte_perm(vw, aw, 0x7362);
       const uint32_t px[4] = {__byte_perm(yu_lo, va_lo, 0x5410), __byte_perm(yu_lo, va_lo, 0x7632), __byte_perm(yu_hi, va_hi, 0x5410),
                               __byte_perm(yu_hi, va_hi, 0x7632)};
-      st_packed4(P.dst + (long long)P.orow * row + (long long)x * ps, px, ps, n, vec);
+      uint8_t *d = P.dst + (long long)P.orow * row + (long long)x * ps;
+      if (vec && n == 4 && ps == 4) st_stream_u4(d, make_uint4(px[0], px[1], px[2], px[3]));
+      else st_packed4(d, px, ps, n, vec);
     };
-    if (!P.is_420) {
-      for (int row = 2 * k0; row < min(2 * k1, P.height); row++)
-        put(row, quad_even4(P.u, P.rs_u, row, m, P.cw, P.ch, true, P.jpeg, P.avg, n, true),
-            quad_even4(P.v, P.rs_v, row, m, P.cw, P.ch, false, P.jpeg, P.avg, n, true));
+    const bool fast = quad_fast_ok(P.u, P.rs_u, m, P.cw, n) && quad_fast_ok(P.v, P.rs_v, m, P.cw, n);
+    const bool g_is_f = !P.is_420;
+    auto even_u = [&](int k) -> uint32_t {
+      return fast ? quad_even4_fast(P.u, P.rs_u, k, m, true, P.jpeg, P.avg, g_is_f) : quad_even4(P.u, P.rs_u, k, m, P.cw, P.ch, true, P.jpeg, P.avg, n, g_is_f);
+    };
+    auto even_v = [&](int k) -> uint32_t {
+      return fast ? quad_even4_fast(P.v, P.rs_v, k, m, false, P.jpeg, P.avg, g_is_f) : quad_even4(P.v, P.rs_v, k, m, P.cw, P.ch, false, P.jpeg, P.avg, n, g_is_f);
+    };
+    auto put_y = [&](uint8_t *d, uint32_t yw, uint32_t uw, uint32_t vw) {   // vec && n == 4
+      const uint32_t yu_lo = __byte_perm(yw, uw, 0x5140), yu_hi = __byte_perm(yw, uw, 0x7362);
+      const uint32_t va_lo = __byte_perm(vw, 0xFFFFFFFFu, 0x5140), va_hi = __byte_perm(vw, 0xFFFFFFFFu, 0x7362);
+      const uint32_t p0 = __byte_perm(yu_lo, va_lo, 0x5410), p1 = __byte_perm(yu_lo, va_lo, 0x7632), p2 = __byte_perm(yu_hi, va_hi, 0x5410),
+                     p3 = __byte_perm(yu_hi, va_hi, 0x7632);
+      if (ps == 4) {
+        st_stream_u4(d, make_uint4(p0, p1, p2, p3));
+      } else {
+        st_stream_u32(d, __byte_perm(p0, p1, 0x4210));
+        st_stream_u32(d + 4, __byte_perm(p1, p2, 0x5421));
+        st_stream_u32(d + 8, __byte_perm(p2, p3, 0x6542));
+      }
+    };
+    if (fast && vec && P.is_420 && 2 * k0 + 2 * QC_PAIRS <= P.height - 2) {
+      // a whole chunk away from the frame's edges: every load is issued before the first use
+      uint32_t cu[QC_PAIRS + 1], cv[QC_PAIRS + 1], yw[2 * QC_PAIRS];
+#pragma unroll
+      for (int j = 0; j <= QC_PAIRS; j++) { cu[j] = quad_load4(P.u, P.rs_u, k0 + j, m); cv[j] = quad_load4(P.v, P.rs_v, k0 + j, m); }
+#pragma unroll
+      for (int j = 0; j < 2 * QC_PAIRS; j++) yw[j] = ld_stream_u32(P.y + (long long)P.rs_y * (2 * k0 + j) + x);
+      uint32_t EU = quad_even4_from(cu[0], true, P.jpeg, P.avg), EV = quad_even4_from(cv[0], false, P.jpeg, P.avg);
+      uint8_t *d = P.dst + (long long)P.orow * (2 * k0) + (long long)x * ps;
+#pragma unroll
+      for (int j = 0; j < QC_PAIRS; j++) {
+        const uint32_t nu = quad_even4_from(cu[j + 1], true, P.jpeg, P.avg), nv = quad_even4_from(cv[j + 1], false, P.jpeg, P.avg);
+        put_y(d, yw[2 * j], EU, EV);
+        put_y(d + P.orow, yw[2 * j + 1], avg4(P.avg, nu, EU), avg4(P.avg, nv, EV));
+        d += 2 * (long long)P.orow;
+        EU = nu; EV = nv;
+      }
       continue;
     }
-    uint32_t EU = quad_even4(P.u, P.rs_u, k0, m, P.cw, P.ch, true, P.jpeg, P.avg, n);
-    uint32_t EV = quad_even4(P.v, P.rs_v, k0, m, P.cw, P.ch, false, P.jpeg, P.avg, n);
+    if (fast && vec && !P.is_420 && 2 * k0 + 2 * QC_PAIRS <= P.height) {
+      uint32_t cu[2 * QC_PAIRS], cv[2 * QC_PAIRS], yw[2 * QC_PAIRS];
+#pragma unroll
+      for (int j = 0; j < 2 * QC_PAIRS; j++) {
+        cu[j] = quad_load4(P.u, P.rs_u, 2 * k0 + j, m); cv[j] = quad_load4(P.v, P.rs_v, 2 * k0 + j, m);
+        yw[j] = ld_stream_u32(P.y + (long long)P.rs_y * (2 * k0 + j) + x);
+      }
+      uint8_t *d = P.dst + (long long)P.orow * (2 * k0) + (long long)x * ps;
+#pragma unroll
+      for (int j = 0; j < 2 * QC_PAIRS; j++) {
+        put_y(d, yw[j], quad_even4_from(cu[j], true, P.jpeg, P.avg, true), quad_even4_from(cv[j], false, P.jpeg, P.avg, true));
+        d += P.orow;
+      }
+      continue;
+    }
+    if (!P.is_420) {
+      for (int row = 2 * k0; row < min(2 * k1, P.height); row++) put(row, even_u(row), even_v(row));
+      continue;
+    }
+    uint32_t EU = even_u(k0);
+    uint32_t EV = even_v(k0);
     for (int k = k0; k < k1; k++) {
       put(2 * k, EU, EV);
       const int row = 2 * k + 1;
       if (row >= P.height) break;
       uint32_t uw = EU, vw = EV;
       if (row + 1 <= P.height - 1) {
-        const uint32_t nu = quad_even4(P.u, P.rs_u, k + 1, m, P.cw, P.ch, true, P.jpeg, P.avg, n);
-        const uint32_t nv = quad_even4(P.v, P.rs_v, k + 1, m, P.cw, P.ch, false, P.jpeg, P.avg, n);
+        const uint32_t nu = even_u(k + 1);
+        const uint32_t nv = even_v(k + 1);
         const bool swapped = (P.height & 1) && row == P.height - 2;
         uw = swapped ? avg4(P.avg, EU, nu) : avg4(P.avg, nu, EU);
         vw = swapped ? avg4(P.avg, EV, nv) : avg4(P.avg, nv, EV);
