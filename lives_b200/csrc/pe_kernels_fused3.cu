@@ -234,6 +234,7 @@ struct Carry {
 // raw words of one step, loaded one step ahead
 struct Pre {
   uint32_t yA, yB, u0, u1, v0, v1, vf;
+  uint32_t u2, u3, v2, v3, sd;   // 4:2:2 only: the chroma words of row 2k (u0 .. v1 are row 2k - 1's), the seed samples of the lane of column 0
 };
 
 struct Lane {
@@ -313,11 +314,56 @@ __device__ __noinline__ SlowRows slow_rows(const uint8_t *py, const uint8_t *pu,
   return out;
 }
 
+// the 4:2:2 form (convert_yuv420p_to_rgb_frame with is_422, colourspace.c:3598-3642): every luma row has its own chroma row, the only
+// averaging is horizontal.  QUIRKS: the seed slip (:3600) -- columns <= 0 of row i take column 0 of chroma row i >> 1.
+template <bool QUIRKS>
+__device__ __noinline__ SlowRows slow_rows422(const uint8_t *py, const uint8_t *pu, const uint8_t *pv, uint32_t rs_y, uint32_t rs_u,
+                                              uint32_t rs_v, int x0, int k, int fh, int cw, int ch, int lane) {
+  const uint32_t lane4 = 4u * (uint32_t)lane, lane8 = 8u * (uint32_t)(lane & 15);
+  int rA[12], rB[12];
+  auto single = [&](int row, int *out) {
+    const int seed_row = QUIRKS ? row >> 1 : row;
+    const uint32_t yw = *reinterpret_cast<const uint32_t *>(py + (size_t)rs_y * row + x0);
+#pragma unroll
+    for (int col = 0; col < 4; col++) {
+      const int jc = (x0 >> 1) + (col >> 1), jo = (col & 1) ? jc + 1 : jc - 1;
+      uint32_t ua = chroma_at(pu, rs_u, row, jc, cw, ch), ub = chroma_at(pu, rs_u, row, jo, cw, ch);
+      uint32_t va = chroma_at(pv, rs_v, row, jc, cw, ch), vb = chroma_at(pv, rs_v, row, jo, cw, ch);
+      if (x0 == 0 && seed_row != row) {
+        const uint32_t su = pu[(size_t)rs_u * seed_row], sv = pv[(size_t)rs_v * seed_row];
+        if (jc == 0) { ua = su; va = sv; }
+        if (jo <= 0) { ub = su; vb = sv; }
+      }
+      const int yy = (int)lds32(A_TY + (byte_of(yw, col) * 256u + lane4));
+      const uint2 tv = lds64(A_TV + (((va + vb) >> 1) * 128u + lane8));
+      const uint2 tu = lds64(A_TU + (((ua + ub) >> 1) * 128u + lane8));
+      out[3 * col] = (yy + (int)tv.x) >> 16; out[3 * col + 1] = (yy + (int)tu.x + (int)tv.y) >> 16; out[3 * col + 2] = (yy + (int)tu.y) >> 16;
+    }
+  };
+  if (k <= 0) {
+    single(0, rA);
+#pragma unroll
+    for (int i = 0; i < 12; i++) rB[i] = rA[i];
+  } else if (2 * k <= fh - 1) {
+    single(2 * k - 1, rA);
+    single(2 * k, rB);
+  } else {
+    single(fh - 1, rA);
+#pragma unroll
+    for (int i = 0; i < 12; i++) rB[i] = rA[i];
+  }
+  SlowRows out;
+#pragma unroll
+  for (int i = 0; i < 12; i++) out.ab[i] = pack_sat(rA[i], rB[i], 0u);
+  return out;
+}
+
 // C16: the filter coefficients arrive scaled by 16 (sum 65536; only banks without a 4096 tap): the filtered value is byte 2 of
 // the accumulator (byte 3 is zero), so R | B pack with one PRMT and two of the three shifts per pixel disappear
 // TMA: the bg ring is filled by ONE elected lane per row with a 512-byte cp.async.bulk (UBLKCP) that completes on the slot's
 // mbarrier, instead of 32 per-lane 16-byte cp.async (LDGSTS) + commit / wait groups (full-width strips only: ow % 128 == 0, ox == 0)
-template <bool QUIRKS, bool HAS_LUT, bool C16, bool TMA>
+// IS422: a planar 4:2:2 fg (a step = two luma rows with their own chroma rows; no carried sums)
+template <bool QUIRKS, bool HAS_LUT, bool C16, bool TMA, bool IS422 = false>
 __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -515,7 +561,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       // raw words of a fast step: luma rows 2k-1, 2k, chroma row k.  The step loads the words of step k + 1 through RUNNING
       // pointers (yq, uq, vq, vfq: advanced once per step, whatever kind of step it is) -- per step 4 64-bit additions instead of
       // 7 address computations from the row number (profiles/r02k: a tenth of the step's instructions were address arithmetic)
-      auto load_at = [&](const uint8_t *yr, const uint8_t *ur, const uint8_t *vr, const uint8_t *vfr, Pre &p) {
+      auto load_at = [&](const uint8_t *yr, const uint8_t *ur, const uint8_t *vr, const uint8_t *vfr, const uint8_t *ufr, Pre &p) {
 #ifdef PE_F3_LUMA_NC
         p.yA = ld_keep_u32(yr);
         p.yB = ld_keep_u32(yr + rs_y);
@@ -525,7 +571,14 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 #endif
         p.u0 = ld_keep_u32(ur); p.u1 = ld_keep_u32(ur + 4);
         p.v0 = ld_keep_u32(vr); p.v1 = ld_keep_u32(vr + 4);
-        p.vf = ldg_u8(vfr);
+        if (IS422) {   // ur / vr: chroma row 2k - 1; ufr / vfr: column 0 of chroma row k - 1 (the seed slip, colourspace.c:3600: columns
+                       // <= 0 of rows 2k - 1 / 2k take column 0 of chroma rows k - 1 / k; read by the lane of column 0 only)
+          p.u2 = ld_keep_u32(ur + rs_u); p.u3 = ld_keep_u32(ur + rs_u + 4);
+          p.v2 = ld_keep_u32(vr + rs_v); p.v3 = ld_keep_u32(vr + rs_v + 4);
+          if (QUIRKS && L.x == 0) p.sd = ldg_u8(ufr) | (ldg_u8(vfr) << 8) | (ldg_u8(ufr + rs_u) << 16) | (ldg_u8(vfr + rs_v) << 24);
+        } else {
+          p.vf = ldg_u8(vfr);
+        }
       };
       auto init_carry = [&](int r, Carry &c) {  // sums of chroma row r (0 <= r <= ch - 2), as a fast step leaves them
         const uint32_t uo = rs_u * (uint32_t)r, vo = rs_v * (uint32_t)r;
@@ -546,17 +599,21 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       Carry C;
       Pre preA, preB;
       C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
-      preA.yA = preA.yB = preA.u0 = preA.u1 = preA.v0 = preA.v1 = preA.vf = 0u;
+      preA.yA = preA.yB = preA.u0 = preA.u1 = preA.v0 = preA.v1 = preA.vf = preA.u2 = preA.u3 = preA.v2 = preA.v3 = preA.sd = 0u;
       preB = preA;
       // rows of step k (k may be <= 0 here: the pointers are only dereferenced for fast steps)
       const uint8_t *yq = L.yp + (long long)rs_y * (2 * k - 1);
-      const uint8_t *uq = L.up0 + (long long)rs_u * k;
-      const uint8_t *vq = L.vp0 + (long long)rs_v * k;
-      const uint8_t *vfq = L.vfp + (long long)rs_v * k;
+      // 4:2:0: chroma row k, its first V sample.  4:2:2: chroma row 2k - 1, column 0 of chroma row k - 1 of V and U (the seed samples)
+      const uint8_t *uq = L.up0 + (long long)rs_u * (IS422 ? 2 * k - 1 : k);
+      const uint8_t *vq = L.vp0 + (long long)rs_v * (IS422 ? 2 * k - 1 : k);
+      const uint8_t *vfq = L.vfp + (long long)rs_v * (IS422 ? k - 1 : k);
+      const uint8_t *ufq = F.u + (long long)rs_u * (k - 1);
       if (k >= 1 && k <= k_fast_max) {
-        load_at(yq, uq, vq, vfq, preA);
-        init_carry(k - 1, C);
-        carry_ok = true;
+        load_at(yq, uq, vq, vfq, ufq, preA);
+        if (!IS422) {
+          init_carry(k - 1, C);
+          carry_ok = true;
+        }
       }
       // bg rows travel through the warp's cp.async ring, F3_RING - 1 rows ahead of the emit: no registers are tied up and the
       // emit never waits on a load it has just issued.  A lane only ever reads the 16 bytes it copied itself.
@@ -604,10 +661,34 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         int rA[12], rB[12];
         const bool fast = k >= 1 && k <= k_fast_max;
         const bool next_fast = k + 1 >= 1 && k + 1 <= k_fast_max;
-        const uint32_t dep = ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.vf) & zero;
-        yq += 2 * (size_t)rs_y + dep; uq += rs_u + dep; vq += rs_v + dep; vfq += rs_v + dep;
-        if (next_fast) load_at(yq, uq, vq, vfq, nxt);
-        if (fast) {
+        const uint32_t dep = (IS422 ? ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.u2 | pre.v2) : ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.vf)) & zero;
+        yq += 2 * (size_t)rs_y + dep; uq += (IS422 ? 2u : 1u) * rs_u + dep; vq += (IS422 ? 2u : 1u) * rs_v + dep; vfq += rs_v + dep;
+        if (IS422) ufq += rs_u;
+        if (next_fast) load_at(yq, uq, vq, vfq, ufq, nxt);
+        if (fast && IS422) {
+          // the lane of column 0 under the seed slip stays on the fast path: sample 0 of its chroma words is replaced by the seed sample,
+          // which column -1 then replicates through the lane's PRMT selector like any frame edge
+          uint32_t u0 = pre.u0, v0 = pre.v0, u2 = pre.u2, v2 = pre.v2;
+          if (QUIRKS && L.x == 0) {
+            u0 = __byte_perm(u0, pre.sd, 0x3214); v0 = __byte_perm(v0, pre.sd, 0x3215);
+            u2 = __byte_perm(u2, pre.sd, 0x3216); v2 = __byte_perm(v2, pre.sd, 0x3217);
+          }
+          const RowC UA = unpack_row(u0, pre.u1, L.sel), VA = unpack_row(v0, pre.v1, L.sel);
+          const RowC UB = unpack_row(u2, pre.u3, L.sel), VB = unpack_row(v2, pre.v3, L.sel);
+          const uint32_t LUA = UA.a + UA.b, RUA = UA.a + UA.c, LVA = VA.a + VA.b, RVA = VA.a + VA.c;
+          const uint32_t LUB = UB.a + UB.b, RUB = UB.a + UB.c, LVB = VB.a + VB.b, RVB = VB.a + VB.c;
+#pragma unroll
+          for (int col = 0; col < 4; col++) {
+            const bool hi_half = col >> 1, right = col & 1;
+            const uint32_t sua = right ? RUA : LUA, sva = right ? RVA : LVA, sub = right ? RUB : LUB, svb = right ? RVB : LVB;
+            // table offset 128 * (s >> 1) = (s & ~1) << 6, OR-ed with the region base and the lane's bank pair in the same LOP3
+            auto off = [&](uint32_t sm, uint32_t tl) -> uint32_t { return ((hi_half ? (sm >> 10) : (sm << 6)) & 0x7F80u) | tl; };
+            rgb(yaddr(pre.yA, col, tyl), off(sua, tul), off(sva, tvl), rA[3 * col], rA[3 * col + 1], rA[3 * col + 2]);
+            rgb(yaddr(pre.yB, col, tyl), off(sub, tul), off(svb, tvl), rB[3 * col], rB[3 * col + 1], rB[3 * col + 2]);
+          }
+#pragma unroll
+          for (int i = 0; i < 12; i++) Wc[i] = pack_sat(rA[i], rB[i], Wp[i]);
+        } else if (fast) {
           const RowC U = unpack_row(pre.u0, pre.u1, L.sel), V = unpack_row(pre.v0, pre.v1, L.sel);
           // right pixel of both chroma columns: this + next
           const uint32_t RU = U.a + U.c, RV = V.a + V.c;
@@ -651,7 +732,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           // ---- slow step (frame edges): out of line; rows beyond the frame replicate the last row (the filter clamps its
           //      source indices)
           if (k <= 0 || 2 * k - 1 <= fh - 1) {
-            const SlowRows sr = slow_rows<QUIRKS>(F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane);
+            const SlowRows sr = IS422 ? slow_rows422<QUIRKS>(F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane)
+                                      : slow_rows<QUIRKS>(F.y, F.u, F.v, rs_y, rs_u, rs_v, L.x, k, fh, cw, ch, lane);
 #pragma unroll
             for (int i = 0; i < 12; i++) Wc[i] = __byte_perm(sr.ab[i], Wp[i], 0x5410u);
           } else {
@@ -660,7 +742,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
           }
           carry_ok = false;
         }
-        if (next_fast && !carry_ok) {
+        if (!IS422 && next_fast && !carry_ok) {
           init_carry(k, C);
           carry_ok = true;
         }
@@ -775,10 +857,11 @@ bool fused3_tables_ok(const ConvTables &t) {
 bool fused3_supported(const FusedArgs *a, int n, int fy_taps) {
   if (n <= 0 || fy_taps > 4) return false;
   const FusedArgs &f0 = a[0];
-  if (f0.is_422 || f0.low_quality) return false;
+  if (f0.low_quality) return false;
+  if (f0.is_422 && getenv("PE_F3_NO_422")) return false;   // measurement switch: 4:2:2 back to k_fused2
   if (f0.iw != f0.fw || (f0.ox & 3) || (f0.ow & 3) || f0.ox + f0.iw > f0.ow) return false;   // no horizontal scaling; lanes = 4 px
   if ((f0.fw & 3) || f0.fw < 4 || f0.fh < 4 || f0.ih > F3_MAX_IH) return false;
-  if (f0.fg.cw != f0.fw / 2 || f0.fg.ch != (f0.fh + 1) / 2) return false;
+  if (f0.fg.cw != f0.fw / 2 || f0.fg.ch != (f0.is_422 ? f0.fh : (f0.fh + 1) / 2)) return false;
   for (int i = 0; i < n; i++) {
     const FusedArgs &f = a[i];
     if (f.is_422 != f0.is_422 || f.low_quality != f0.low_quality || f.quirks != f0.quirks || f.conv.t != f0.conv.t) return false;
@@ -810,6 +893,12 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
                            (const void *)k_fused3<false, false, true, true>,  (const void *)k_fused3<false, false, false, true>};
     for (int i = 0; i < 16; i++)
       if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+    const void *fns422[8] = {(const void *)k_fused3<true, true, true, false, true>,   (const void *)k_fused3<true, true, false, false, true>,
+                             (const void *)k_fused3<true, false, true, false, true>,  (const void *)k_fused3<true, false, false, false, true>,
+                             (const void *)k_fused3<false, true, true, false, true>,  (const void *)k_fused3<false, true, false, false, true>,
+                             (const void *)k_fused3<false, false, true, false, true>, (const void *)k_fused3<false, false, false, false, true>};
+    for (int i = 0; i < 8; i++)
+      if ((e = cudaFuncSetAttribute(fns422[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
     attr_set.cur() = 1;
   }
   static int cost_b = 0, cost_i = 0, static_pct = 92, chunk_rows = 24;
@@ -838,7 +927,8 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     P.nstrips = (a0.ow + 127) / 128;
     // the fast step reads whole words behind chroma column cw: on the last chroma row that needs 4 bytes of row padding
     const bool last_row_unsafe = a0.fg.rs_u < a0.fg.cw + 4 || a0.fg.rs_v < a0.fg.cw + 4;
-    P.k_fast_max = a0.fg.ch - 1 - (last_row_unsafe ? 1 : 0);
+    // (4:2:2: a fast step reads luma and chroma rows 2k - 1 and 2k)
+    P.k_fast_max = a0.is_422 ? (a0.fh - 1 - (last_row_unsafe ? 1 : 0)) / 2 : a0.fg.ch - 1 - (last_row_unsafe ? 1 : 0);
     P.cost_b = cost_b; P.cost_i = cost_i;
     const long long strip_cost = (long long)cost_b * (a0.oh - a0.ih) + (long long)cost_i * a0.ih;
     P.frame_cost = strip_cost * P.nstrips;
@@ -874,7 +964,8 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (tma_pref < 0) tma_pref = getenv("PE_F3_TMA") ? atoi(getenv("PE_F3_TMA")) != 0 : PE_F3_TMA_DEFAULT;
     const bool tma = tma_pref && a0.ox == 0 && a0.ow == a0.fw && (a0.ow & 127) == 0;
     auto go = [&](auto q, auto l, auto c) {
-      if (tma) k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      if (a0.is_422) k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, false, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
+      else if (tma) k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, true><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
       else k_fused3<decltype(q)::value, decltype(l)::value, decltype(c)::value, false><<<grid, F3_NT, smem_bytes, L.stream>>>(P);
     };
     auto pick_c = [&](auto q, auto l) { if (coef16) go(q, l, std::true_type()); else go(q, l, std::false_type()); };

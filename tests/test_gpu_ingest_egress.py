@@ -90,6 +90,9 @@ def test_convert_plan_descriptor_fused_equals_op_by_op(eng, geom):
         fg_l = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_subspace=1)
         bg_l = lb.Layer.from_host(eng, 3, w, h, [bg], gamma_type=T.G_LINEAR)
         out_l = lb.Layer.create(eng, 3, w, h)
+        if not no_fuse:  # once untimed: a cold engine builds its gamma / filter tables with a kernel of its own on first use
+            warm = lb.Layer.from_host(eng, 512, w, h, [y, u, v], yuv_subspace=1)
+            lb.run_convert_plan_over(warm, plan, bg_l, lb.Layer.create(eng, 3, w, h), 0.5, T.G_SRGB)
         n0 = eng.launch_count
         path = lb.run_convert_plan_over(fg_l, plan, bg_l, out_l, 0.5, T.G_SRGB)
         assert path == (0 if no_fuse else 1)

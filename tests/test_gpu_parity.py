@@ -1237,6 +1237,17 @@ def test_fused_chain_equals_unfused_oracle(eng, case):
     (4, 4, 0, 4, 4, 4, 0.5, (-1, 1)),               # one lane, identity
     (128, 64, 0, 160, 100, 100, 0.5, (-1, 1)),      # pillarbox + letterbox: inner offset 16, border lanes inside inner rows
     (640, 360, 0, 1000, 360, 360, 0.25, (-1, 1)),   # pure pillarbox (offset 180), strips left and right without inner lanes
+    # ... and its 4:2:2 instantiation (a step = two luma rows with their own chroma rows; the seed slip :3600 on the lane of column 0)
+    (132, 50, 1, 132, 60, 45, 0.5, (-1, 1)),        # partial strip, padded chroma rows
+    (64, 30, 1, 64, 80, 72, 0.5, (-1, 1)),          # vertical stretch 2.4x
+    (644, 362, 1, 644, 400, 300, 0.5, (-1, 1)),     # six strips, squeeze 1.207
+    (1920, 1080, 1, 1920, 1080, 804, 0.5, (-1, 1)), # the headline's ratio at 1080p; chroma stride == chroma width (last rows: slow steps)
+    (256, 96, 1, 256, 96, 64, 0.375, None),         # ratio 1.5, alpha 3/8, no gamma
+    (8, 6, 1, 8, 9, 7, 0.5, (-1, 1)),               # tiny frame
+    (4, 4, 1, 4, 4, 4, 0.5, (-1, 1)),               # one lane, identity
+    (128, 64, 1, 160, 100, 100, 0.5, (-1, 1)),      # pillarbox + letterbox: the seed lane is not lane 0 of the strip
+    (128, 33, 1, 128, 33, 33, 0.5, (-1, 1)),        # odd height (4:2:2 frames may be odd), identity
+    (128, 35, 1, 128, 60, 52, 0.75, (-1, 1)),       # odd height, stretch
 ])
 @pytest.mark.parametrize("variant", ["clamped", "unclamped_noquirks"])
 def test_fused_fast_path_cases(case, variant):
@@ -1289,14 +1300,16 @@ def test_fused_random_geometries_equal_unfused_ops(eng):
         ow = fw + 8 * int(rng.integers(0, 12)) if it % 3 else fw     # pillarbox offsets: multiples of 4
         alpha = float(rng.choice([0.0, 0.25, 0.5, 0.75, 1.0, 37 / 256]))
         cl = int(rng.integers(0, 2))
-        y, u, v = T.make_yuv_planar(rng, fw, fh, False, cl == 0)
+        is422 = it % 4 == 1
+        ipal = 522 if is422 else 512
+        y, u, v = T.make_yuv_planar(rng, fw, fh, is422, cl == 0)
         bg = T.make_packed(rng, ow, oh, 4)
-        fg_l = lb.Layer.from_host(eng, 512, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
+        fg_l = lb.Layer.from_host(eng, ipal, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
         bg_l = packed_layer(eng, 3, ow, oh, bg, gamma_type=T.G_LINEAR)
         out_l = lb.Layer.create(eng, 3, ow, oh)
         lb.fused_convert_letterbox_over_gamma(fg_l, bg_l, out_l, fw, ih, alpha, T.G_LINEAR, T.G_SRGB)
         got = out_l.to_host()[0]
-        lay = lb.Layer.from_host(eng, 512, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
+        lay = lb.Layer.from_host(eng, ipal, fw, fh, [y, u, v], yuv_clamping=cl, yuv_subspace=1)
         assert lb.convert_layer_palette(lay, 3, 0)
         assert lb.letterbox_layer(lay, ow, oh, fw, ih, 1, 3, 0)
         out2 = lb.Layer.create(eng, 3, ow, oh, gamma_type=T.G_LINEAR)
@@ -1304,7 +1317,7 @@ def test_fused_random_geometries_equal_unfused_ops(eng):
         assert lb.gamma_convert_layer(T.G_SRGB, out2)
         exp = out2.to_host()[0]
         bad = np.argwhere(payload(got, ow, 4) != payload(exp, ow, 4))
-        assert len(bad) == 0, (it, fw, fh, ih, ow, oh, alpha, cl, len(bad), bad[:4])
+        assert len(bad) == 0, (it, fw, fh, is422, ih, ow, oh, alpha, cl, len(bad), bad[:4])
         for l in (fg_l, bg_l, out_l, lay, out2):
             l.free()
 
