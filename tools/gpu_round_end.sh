@@ -16,3 +16,9 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytes
 timeout 600 python tools/cpu_baselines.py --out gpurun_out/cpu_baselines_$TAG.json --seconds 2 > gpurun_out/cpu_baselines_$TAG.log 2>&1; tail -8 gpurun_out/cpu_baselines_$TAG.log
 timeout 300 python tools/measure_layer_dropin.py > gpurun_out/layer_dropin_$TAG.json 2>&1; tail -2 gpurun_out/layer_dropin_$TAG.json | cut -c1-600
 ls gpurun_out | tail -20
+# one ncu --set full capture of the dominant kernel of the headline, of config 5 and of config 2
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_fused3 -s 3 -c 1 -o gpurun_out/prof_f3_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sub-records --e2e-frames 2 --e2e-steps 1 > gpurun_out/ncu_full_f3_$TAG.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_yuv_march -s 2 -c 1 -o gpurun_out/prof_cfg5_$TAG python bench.py --workload cfg5 --steps 2 --warmup 3 > gpurun_out/ncu_full_cfg5_$TAG.log 2>&1
+timeout 200 python tools/time_new_kernels.py > gpurun_out/new_kernels_$TAG.jsonl 2>&1
+timeout 200 python tools/f3_422_probe.py > gpurun_out/f3_422_$TAG.jsonl 2>&1
+ls -la gpurun_out | tail -30
