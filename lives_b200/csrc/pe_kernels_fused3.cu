@@ -30,6 +30,9 @@
 // row of a plane without padding) go through slow_step(): scalar code with the reference's edge rules, a few steps per strip.
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
+#include <algorithm>
+#include <cstdio>
 
 #include "pe_device.cuh"
 #include "pe_kernels.h"
@@ -99,6 +102,9 @@ struct Fused3Params {
   const int4 *rows4;                       // [ih]: first source row, c3 | c2 << 16, c1 | c0 << 16, 0 (coefficients x 16 under C16)
   const int32_t *conv;                     // [14][256] (ConvTab order)
   const uint8_t *lut8;                     // optional
+#ifdef PE_F3_TIMELINE
+  unsigned long long *tl;                  // [grid][2 + F3_NW] globaltimer stamps: CTA start, tables filled, every warp's end (tools/f3_timeline.py)
+#endif
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -367,6 +373,14 @@ template <bool QUIRKS, bool HAS_LUT, bool C16, bool TMA, bool IS422 = false>
 __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fused3Params P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef PE_F3_TIMELINE
+  auto stamp = [&](int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.tl[(size_t)blockIdx.x * (2 + F3_NW) + slot] = t;
+  };
+  if (tid == 0) stamp(0);
+#endif
   if ((uint32_t)__cvta_generic_to_shared(smem) != A_DYN) __trap();   // the absolute layout above assumes it
   uint8_t *const sm0 = smem - A_DYN;   // sm0 + absolute address = generic pointer (table fill only)
 
@@ -375,19 +389,34 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     // 16 consecutive lanes write the 16 x 16-byte chunks of one 256-byte {LUT | RGB_Y} entry, 8 lanes the chunks of a 128-byte
     // chroma entry: a warp's 128-bit store covers 512 contiguous bytes = 4 wavefronts, the minimum.  (A thread per entry writing
     // its 128 bytes alone is a 32-way bank conflict per store: 4.4 us per launch, profiles/r02c_k_fused3_single_frame_ncu.txt.)
-    for (int i = tid; i < 256 * 16; i += F3_NT) {
-      const int m = i >> 4, j = i & 15;
-      uint32_t e;
-      if (j < 8) e = HAS_LUT ? ((uint32_t)P.lut8[m] * 0x010101u | 0xFF000000u) : 0u;
-      else e = (uint32_t)P.conv[9 * 256 + m];
-      reinterpret_cast<uint4 *>(sm0 + A_LUT + 256 * m)[j] = make_uint4(e, e, e, e);
+    // every global load of the fill is issued before the first shared-memory store: the stores go through a generic pointer, and
+    // the compiler keeps a load behind a store it cannot prove disjoint -- the fill was eight dependent L2 round trips, 7.4 us of a
+    // single-frame launch (tools/f3_timeline.sh)
+    static_assert(256 * 16 % F3_NT == 0 && 256 * 8 % F3_NT == 0, "table fill: whole rounds");
+    constexpr int R1 = 256 * 16 / F3_NT, R2 = 256 * 8 / F3_NT;
+    uint32_t e1[R1], rcr[R2], gcb[R2], gcr[R2], bcb[R2];
+#pragma unroll
+    for (int q = 0; q < R1; q++) {
+      const int i = tid + q * F3_NT, m = i >> 4, j = i & 15;
+      if (j < 8) e1[q] = HAS_LUT ? ((uint32_t)__ldg(P.lut8 + m) * 0x010101u | 0xFF000000u) : 0u;
+      else e1[q] = (uint32_t)__ldg(P.conv + 9 * 256 + m);
     }
-    for (int i = tid; i < 256 * 8; i += F3_NT) {
-      const int m = i >> 3, j = i & 7;
-      const uint32_t rcr = (uint32_t)P.conv[10 * 256 + m], gcb = (uint32_t)P.conv[11 * 256 + m], gcr = (uint32_t)P.conv[12 * 256 + m],
-                     bcb = (uint32_t)P.conv[13 * 256 + m];
-      reinterpret_cast<uint4 *>(sm0 + A_TV + 128 * m)[j] = make_uint4(rcr, gcr, rcr, gcr);
-      reinterpret_cast<uint4 *>(sm0 + A_TU + 128 * m)[j] = make_uint4(gcb, bcb, gcb, bcb);
+#pragma unroll
+    for (int q = 0; q < R2; q++) {
+      const int m = (tid + q * F3_NT) >> 3;
+      rcr[q] = (uint32_t)__ldg(P.conv + 10 * 256 + m); gcb[q] = (uint32_t)__ldg(P.conv + 11 * 256 + m);
+      gcr[q] = (uint32_t)__ldg(P.conv + 12 * 256 + m); bcb[q] = (uint32_t)__ldg(P.conv + 13 * 256 + m);
+    }
+#pragma unroll
+    for (int q = 0; q < R1; q++) {
+      const int i = tid + q * F3_NT, m = i >> 4, j = i & 15;
+      reinterpret_cast<uint4 *>(sm0 + A_LUT + 256 * m)[j] = make_uint4(e1[q], e1[q], e1[q], e1[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < R2; q++) {
+      const int i = tid + q * F3_NT, m = i >> 3, j = i & 7;
+      reinterpret_cast<uint4 *>(sm0 + A_TV + 128 * m)[j] = make_uint4(rcr[q], gcr[q], rcr[q], gcr[q]);
+      reinterpret_cast<uint4 *>(sm0 + A_TU + 128 * m)[j] = make_uint4(gcb[q], bcb[q], gcb[q], bcb[q]);
     }
     int4 *sr = reinterpret_cast<int4 *>(sm0 + A_ROWS);
     for (int i = tid; i <= P.ih; i += F3_NT) sr[i] = P.rows4[min(i, P.ih - 1)];   // (one entry past the end: the emit reads one row ahead)
@@ -398,6 +427,9 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     }
   }
   __syncthreads();  // the only barrier of the kernel
+#ifdef PE_F3_TIMELINE
+  if (tid == 0) stamp(1);
+#endif
 
   Lane L;
   // region base | the lane's bank offset: OR-ed into every lookup address
@@ -479,6 +511,9 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   long long pos = P.static_cost * gw / nwarps;
   long long pos_end = P.static_cost * (gw + 1) / nwarps;
 
+#ifdef PE_F3_TIMELINE
+  int tl_nseg = 0, tl_rows = 0, tl_inner = 0;
+#endif
   for (;;) {
   while (pos < pos_end) {
     // ---- locate the unit (frame, band, strip) that holds `pos` and the rows of it that belong to this warp
@@ -509,6 +544,9 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
 
     const int x = 128 * s + 4 * lane;  // the lane's first output column
     if (x >= P.ow || ra >= rb) continue;
+#ifdef PE_F3_TIMELINE
+    tl_nseg++; tl_rows += rb - ra; tl_inner += max(0, min(rb, oy + ih) - max(ra, oy));
+#endif
     const int xs = x - P.ox;           // ... and its first source column (pillarbox: the inner rectangle starts at ox)
     const Fused3Frame &F = P.fr[f];
     const uint8_t *bgp = F.bg + 4 * (size_t)x;
@@ -596,6 +634,7 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
       int4 ri = lds128_ro(A_ROWS + 16u * (uint32_t)iy);
       int k = ((ri.x + 4) >> 1) - 2;
       bool carry_ok = false;
+      uint32_t order_mask = 0u;   // 0 for the segment's first step: its words were only just requested, the loads of step k + 1 go out with them
       Carry C;
       Pre preA, preB;
       C.DUr = C.MUr = C.DVr = C.MVr = C.DUl = C.MUl = C.DVl = C.MVl = C.QUL = C.aV = 0u;
@@ -661,7 +700,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
         int rA[12], rB[12];
         const bool fast = k >= 1 && k <= k_fast_max;
         const bool next_fast = k + 1 >= 1 && k + 1 <= k_fast_max;
-        const uint32_t dep = (IS422 ? ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.u2 | pre.v2) : ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.vf)) & zero;
+        const uint32_t dep = (IS422 ? ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.u2 | pre.v2) : ((pre.u0 | pre.v0 | pre.yA) | pre.yB | pre.vf)) & zero & order_mask;
+        order_mask = 0xFFFFFFFFu;
         yq += 2 * (size_t)rs_y + dep; uq += (IS422 ? 2u : 1u) * rs_u + dep; vq += (IS422 ? 2u : 1u) * rs_v + dep; vfq += rs_v + dep;
         if (IS422) ufq += rs_u;
         if (next_fast) load_at(yq, uq, vq, vfq, ufq, nxt);
@@ -830,6 +870,13 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
     if (pos >= P.total_cost) break;
     pos_end = min(pos + P.chunk_cost, P.total_cost);
   }
+#ifdef PE_F3_TIMELINE
+  if (lane == 0) {
+    stamp(2 + warp);
+    P.tl[(size_t)gridDim.x * (2 + F3_NW) + (size_t)blockIdx.x * F3_NW + warp] =
+        (unsigned long long)tl_nseg | ((unsigned long long)tl_rows << 16) | ((unsigned long long)tl_inner << 40);
+  }
+#endif
   if (lane == 0) {
     const unsigned int done = atomicAdd(P.sched + 1, 1u);
     if (done == (unsigned int)nwarps - 1u) {  // every warp has drawn its last (out of range) chunk: reset for the next launch
@@ -901,7 +948,10 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
       if ((e = cudaFuncSetAttribute(fns422[i], cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
     attr_set.cur() = 1;
   }
-  static int cost_b = 0, cost_i = 0, static_pct = 92, chunk_rows = 24;
+  // Defaults measured on B200 (tools/f3_single_variants.sh, profiles/r02zc_f3_split_variants.log): the whole sequence in static shares
+  // with border : inner rows costed 2 : 5.  Round 1's split (92 % static + a dynamic tail of 24-row chunks, 2 : 7) is as fast at 32
+  // frames per launch (51.3 k fps either way) but every chunk is a segment start-up of ~3 us: a single-frame launch 41 -> 34 us
+  static int cost_b = 0, cost_i = 0, static_pct = 100, chunk_rows = 24;
   if (!cost_b) {
     if (getenv("PE_F3_STATIC_PCT")) static_pct = atoi(getenv("PE_F3_STATIC_PCT"));
     if (getenv("PE_F3_CHUNK_ROWS")) chunk_rows = atoi(getenv("PE_F3_CHUNK_ROWS"));
@@ -909,7 +959,7 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (chunk_rows < 4) chunk_rows = 4;
     const char *eb = getenv("PE_F3_COST_B"), *ei = getenv("PE_F3_COST_I");
     cost_b = eb ? atoi(eb) : 2;
-    cost_i = ei ? atoi(ei) : 7;
+    cost_i = ei ? atoi(ei) : 5;
     if (cost_b < 1) cost_b = 1;
     if (cost_i < 1) cost_i = 1;
   }
@@ -957,6 +1007,13 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     P.conv = a0.conv.t;
     P.lut8 = lut8_dev;
     if (P.frame_cost >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+#ifdef PE_F3_TIMELINE
+    static unsigned long long *tl_dev = nullptr;
+    const size_t tl_n = (size_t)grid * (2 + F3_NW) + (size_t)grid * F3_NW;
+    if (!tl_dev) cudaMalloc(&tl_dev, tl_n * 8);
+    cudaMemsetAsync(tl_dev, 0, tl_n * 8, L.stream);
+    P.tl = tl_dev;
+#endif
     const int smem_bytes = f3_smem_bytes(a0.ih);
     // the TMA variant of the bg ring takes whole 128-column strips of rows that start 16-byte aligned (PE_F3_TMA=0 / 1 overrides the
     // default, which is what measured faster: profiles/r02_k_fused3_tma_vs_ldgsts.txt)
@@ -974,6 +1031,69 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     PE_COUNT_LAUNCH(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+#ifdef PE_F3_TIMELINE
+    if (getenv("PE_F3_TIMELINE_DUMP")) {   // one line per launch: stamps relative to the earliest CTA start, in ns
+      std::vector<unsigned long long> h(tl_n);
+      cudaStreamSynchronize(L.stream);
+      cudaMemcpy(h.data(), tl_dev, tl_n * 8, cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull, s_max = 0, f_max = 0, e_min = ~0ull, e_max = 0;
+      double e_sum = 0;
+      for (int b = 0; b < grid; b++) t0 = h[(size_t)b * (2 + F3_NW)] < t0 ? h[(size_t)b * (2 + F3_NW)] : t0;
+      for (int b = 0; b < grid; b++) {
+        const unsigned long long *r = &h[(size_t)b * (2 + F3_NW)];
+        if (r[0] - t0 > s_max) s_max = r[0] - t0;
+        if (r[1] - t0 > f_max) f_max = r[1] - t0;
+        for (int w = 0; w < F3_NW; w++) {
+          const unsigned long long x = r[2 + w] - t0;
+          if (x < e_min) e_min = x;
+          if (x > e_max) e_max = x;
+          e_sum += (double)x;
+        }
+      }
+      fprintf(stderr, "f3 timeline (ns after the first CTA start): last CTA start %llu, last table fill done %llu, warp ends min %llu mean %.0f max %llu, frames %d\n",
+              s_max, f_max, e_min, e_sum / ((double)grid * F3_NW), e_max, P.nframes);
+      // mean / max end per 5 % bucket of the share number (shares follow the frame from its top border band to its bottom one)
+      fprintf(stderr, "f3 timeline buckets (mean/max us):");
+      for (int q = 0; q < 20; q++) {
+        double sum = 0; unsigned long long mx = 0; int cnt = 0;
+        for (int b = 0; b < grid; b++)
+          for (int w = 0; w < F3_NW; w++) {
+            const long long gw = (long long)b * F3_NW + w;
+            if (gw * 20 / ((long long)grid * F3_NW) != q) continue;
+            const unsigned long long x = h[(size_t)b * (2 + F3_NW) + 2 + w] - t0;
+            sum += (double)x; if (x > mx) mx = x; cnt++;
+          }
+        fprintf(stderr, " %.1f/%.1f", sum / (cnt ? cnt : 1) / 1e3, (double)mx / 1e3);
+      }
+      fprintf(stderr, "\n");
+      if (P.nframes == 1) {   // end time (us) by number of segments, and the slowest warps
+        double sum[8] = {0}; int cnt[8] = {0};
+        std::vector<std::pair<unsigned long long, int>> all;
+        for (int b = 0; b < grid; b++)
+          for (int w = 0; w < F3_NW; w++) {
+            const unsigned long long x = h[(size_t)b * (2 + F3_NW) + 2 + w] - t0, info = h[(size_t)grid * (2 + F3_NW) + (size_t)b * F3_NW + w];
+            const int ns = (int)(info & 0xFFFF) < 7 ? (int)(info & 0xFFFF) : 7;
+            sum[ns] += (double)x; cnt[ns]++;
+            all.push_back({x, b * F3_NW + w});
+          }
+        fprintf(stderr, "f3 timeline by segments:");
+        for (int i = 0; i < 8; i++) if (cnt[i]) fprintf(stderr, " nseg %d: %d warps mean %.1f us;", i, cnt[i], sum[i] / cnt[i] / 1e3);
+        fprintf(stderr, "\n");
+        std::sort(all.begin(), all.end());
+        for (int i = 0; i < 6; i++) {
+          const auto &a = all[all.size() - 1 - i];
+          const unsigned long long info = h[(size_t)grid * (2 + F3_NW) + a.second];
+          fprintf(stderr, "  slow warp gw %d (sm %d warp %d): %.1f us, nseg %llu rows %llu inner %llu\n", a.second, a.second / F3_NW, a.second % F3_NW, a.first / 1e3,
+                  info & 0xFFFF, (info >> 16) & 0xFFFFFF, info >> 40);
+        }
+        for (int i = 0; i < 3; i++) {
+          const auto &a = all[i];
+          const unsigned long long info = h[(size_t)grid * (2 + F3_NW) + a.second];
+          fprintf(stderr, "  fast warp gw %d: %.1f us, nseg %llu rows %llu inner %llu\n", a.second, a.first / 1e3, info & 0xFFFF, (info >> 16) & 0xFFFFFF, info >> 40);
+        }
+      }
+    }
+#endif
   }
   return cudaSuccess;
 }
