@@ -92,6 +92,7 @@ struct Fused3Params {
   int oh, oy, ih;                          // outer height, first inner row, inner height
   int ow, ox;                              // outer width, first inner column (inner width == fw)
   int nstrips, band_h;
+  long long nshares;                       // static shares (<= warps of the grid; the warps beyond it only take part in the dynamic tail)
   int k_fast_max;                          // steps 1 .. k_fast_max take the fast path
   int cost_b, cost_i;                      // cost of a border / an inner output row
   long long frame_cost, total_cost, static_cost, chunk_cost;
@@ -508,8 +509,8 @@ __global__ void __launch_bounds__(F3_NT, 1) k_fused3(const __grid_constant__ Fus
   const long long nwarps = (long long)gridDim.x * F3_NW;
   const long long gw = P.spread ? (long long)warp * gridDim.x + blockIdx.x : (long long)blockIdx.x * F3_NW + warp;
   uint32_t bg_push_seq = 0u, bg_pop_seq = 0u;  // TMA variant: rows pushed into / popped from the warp's bg ring so far
-  long long pos = P.static_cost * gw / nwarps;
-  long long pos_end = P.static_cost * (gw + 1) / nwarps;
+  long long pos = P.static_cost * min(gw, P.nshares) / P.nshares;
+  long long pos_end = P.static_cost * min(gw + 1, P.nshares) / P.nshares;
 
 #ifdef PE_F3_TIMELINE
   int tl_nseg = 0, tl_rows = 0, tl_inner = 0;
@@ -990,6 +991,20 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     if (bh < 16) bh = 16;
     if (bh > a0.oh) bh = a0.oh;
     P.band_h = (int)bh;
+    P.nshares = (long long)grid * F3_NW;
+    // Few frames per launch (the realtime path issues ONE): a share is a few dozen rows, and every unit a share straddles is another
+    // segment start-up (~3 us: unit lookup, carried sums, ring prefetch, two steps before the first row leaves --
+    // profiles/r02zc_f3_split_variants.log: warps with one segment end at 26 us, with two at 30).  So when the warps divide among the
+    // strips almost evenly, the bands become the whole strip and the share count a multiple of the strip count: every share lies inside
+    // one strip = one segment per warp; the few warps beyond the share count idle (<= 5 %).
+    {
+      const long long strips_total = (long long)P.nstrips * P.nframes;
+      const long long per_strip = P.nshares / strips_total;
+      if (getenv("PE_F3_NO_STRIP_SHARES") == nullptr && per_strip >= 1 && per_strip * strips_total * 100 >= P.nshares * 95) {
+        P.nshares = per_strip * strips_total;
+        P.band_h = a0.oh;
+      }
+    }
     // the last part of the sequence is handed out dynamically, in chunks of about F3_CHUNK_ROWS inner rows
     // (a chunk is at most a third of a warp's static share, so that a single-frame launch is not stretched by its last chunks)
     P.chunk_cost = (long long)cost_i * chunk_rows;
