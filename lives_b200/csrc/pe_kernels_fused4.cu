@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-  fill_replicated_yuv_tables(smem + F4_TY, smem + F4_TV, smem + F4_TU, P.conv, tid, F4_NT);
+  fill_replicated_yuv_tables<F4_NT>(smem + F4_TY, smem + F4_TV, smem + F4_TU, P.conv, tid);
 
   uint8_t *const s_rawy = smem + O_RAWY, *const s_rawu = smem + O_RAWU, *const s_rawv = smem + O_RAWV;
   uint32_t *const s_vf = reinterpret_cast<uint32_t *>(smem + O_VF);

@@ -89,7 +89,7 @@ template <bool QUIRKS>
 __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_planar_to_rgb_fast(const __grid_constant__ YuvToRgbArgs A, int k_fast_max) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31;
-  fill_replicated_yuv_tables(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid, Y2_NT);
+  fill_replicated_yuv_tables<Y2_NT>(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid);
   __syncthreads();
 
   const Planes &S = A.src;
@@ -365,7 +365,7 @@ template <bool QUIRKS, bool IS422>
 __global__ void __launch_bounds__(Y2_NT, 1) k_yuv_march(const __grid_constant__ YuvToRgbArgs A, const __grid_constant__ YuvFrameList FL, int k_fast_max, int band_h) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  fill_replicated_yuv_tables(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid, Y2_NT);
+  fill_replicated_yuv_tables<Y2_NT>(smem + S2_TY, smem + S2_TV, smem + S2_TU, A.conv.t, tid);
   __syncthreads();
 
   const Planes &S = A.src;

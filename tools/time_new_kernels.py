@@ -38,7 +38,7 @@ def main():
         l.free()
     # YUV420P -> YUVA8888: 1.5 bytes read + 4 written per pixel
     y, u, v = T.make_yuv_planar(rng, W, H, False, True)
-    for opal, ps in ((589, 4), (588, 3), (544, 3)):
+    for opal, ps in ((589, 4), (588, 3), (544, 3), (3, 4), (1, 3)):
         tot = 0.0
         warm = [lb.Layer.from_host(eng, 512, W, H, [y, u, v]) for _ in range(N)]   # one untimed round: the pool owns blocks of the
         for l in warm:                                                              # destination size afterwards (no cudaMalloc below)
@@ -56,7 +56,7 @@ def main():
             for l in ls:
                 l.free()
         ms = tot / (REPS * N)
-        out.append({"kernel": "k_quad_chroma (+ luma copy)" if opal == 544 else "k_chroma_upsample_packed", "case": "YUV420P -> %d 4K (pool warm; the call includes taking the destination block from the pool)" % opal,
+        out.append({"kernel": "k_yuv_planar_to_rgb_fast (single frame)" if opal < 512 else "k_quad_chroma (+ luma copy)" if opal == 544 else "k_chroma_upsample_packed", "case": "YUV420P -> %d 4K (pool warm; the call includes taking the destination block from the pool)" % opal,
                     "us": ms * 1e3, "GB/s": W * H * (1.5 + ps) / ms / 1e6})
     for r in out:
         print(json.dumps(r))
