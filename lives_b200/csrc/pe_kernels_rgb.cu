@@ -440,6 +440,48 @@ __global__ void __launch_bounds__(kBlock) k_chroma_blend3(const BlendParams P) {
   if (vec) {
     const int chunks = (row_bytes + 15) >> 4;
     const long long total = (long long)chunks * P.height;
+    if (total < (1ll << 31) && F.d != F.s2 && (long long)P.height * max(max(F.rs1, F.rs2), F.rsd) < (1ll << 32)) {
+      // the streaming form: 32-bit index arithmetic (the 64-bit division per 16-byte chunk was a third of the kernel's instructions),
+      // four independent chunks in flight per thread, L1-bypassing loads and stores.  Every byte is read before the same thread
+      // writes it, so the in-place call (d == s1, effects-weed.c:2304-2314) keeps plain loads for s1 and is otherwise identical.
+      const bool inplace = F.d == F.s1;
+      const uint32_t T = (uint32_t)gridDim.x * blockDim.x, tot = (uint32_t)total, uch = (uint32_t)chunks;
+      for (uint32_t it0 = (uint32_t)blockIdx.x * blockDim.x + threadIdx.x; it0 < tot; it0 += 4u * T) {
+        uint4 a[4], b[4];
+        uint32_t od[4];
+        bool full[4], ok[4];
+        uint32_t o1s[4], o2s[4], rem[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t it = it0 + (uint32_t)j * T;
+          ok[j] = it < tot;
+          const uint32_t row = ok[j] ? it / uch : 0u, c = ok[j] ? it - row * uch : 0u;
+          o1s[j] = row * (uint32_t)F.rs1 + c * 16u; o2s[j] = row * (uint32_t)F.rs2 + c * 16u; od[j] = row * (uint32_t)F.rsd + c * 16u;
+          rem[j] = (uint32_t)row_bytes - c * 16u;
+          full[j] = ok[j] && rem[j] >= 16u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (full[j]) {
+            a[j] = ld_stream_u4(F.s2 + o2s[j]);
+            b[j] = inplace ? ld_u4(F.s1 + o1s[j]) : ld_stream_u4(F.s1 + o1s[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (full[j]) {
+            uint4 r;
+            r.x = blend4(a[j].x, b[j].x, bf, bfn); r.y = blend4(a[j].y, b[j].y, bf, bfn);
+            r.z = blend4(a[j].z, b[j].z, bf, bfn); r.w = blend4(a[j].w, b[j].w, bf, bfn);
+            st_stream_u4(F.d + od[j], r);
+          } else if (ok[j]) {
+            for (uint32_t k = 0; k < rem[j]; k++)
+              F.d[od[j] + k] = (uint8_t)((bf * F.s2[o2s[j] + k] + bfn * F.s1[o1s[j] + k]) >> 8);
+          }
+        }
+      }
+      return;
+    }
     for (long long it = global_tid(); it < total; it += global_threads()) {
       const int row = (int)(it / chunks), c = (int)(it - (long long)row * chunks);
       const long long o1 = (long long)row * F.rs1 + c * 16, o2 = (long long)row * F.rs2 + c * 16,
