@@ -609,31 +609,42 @@ def sub_records(args, eng, dist, rank, world, dev):
     local_ops = torch.randint(0, 256, (K, H, W * 3), dtype=torch.uint8, device=dev, generator=og)
     # transport of the operand: an NVSwitch multicast ring (shard.OperandMulticast: the owner's pe_mc_publish kernel stores each group
     # into every rank's buffer at once) when the group has multicast support, NCCL broadcast into three group buffers otherwise
-    ring, transport = None, "none (N = 1)"
+    ring, chain, transport = None, None, "none (N = 1)"
+    sel = os.environ.get("PE_CFG5_TRANSPORT", "chain")
     if world > 1:
-        ok = 1
+        ok, why = 1, ""
         try:
-            if os.environ.get("PE_CFG5_TRANSPORT", "nccl") != "multicast":
-                raise RuntimeError("not selected (PE_CFG5_TRANSPORT=multicast selects it; NCCL measured faster, profiles/r02t_cfg5_transports.log)")
-            ring = shard.OperandMulticast(eng, (K, H, W * 3), nslots=3)
+            if sel == "multicast":
+                ring = shard.OperandMulticast(eng, (K, H, W * 3), nslots=3)
+            elif sel == "chain":
+                lag = int(os.environ.get("PE_CFG5_CHAIN_LAG", "2"))
+                chain = shard.OperandChain(eng, (K, H, W * 3), nslots=max(4, lag + 2), lag=lag)
+            else:
+                raise RuntimeError("PE_CFG5_TRANSPORT=%s" % sel)
         except Exception as ex:  # noqa: BLE001
             ok, why = 0, str(ex).splitlines()[0][:80]
         okt = torch.tensor([ok], device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        if int(okt.item()):
+        if int(okt.item()) and ring is not None:
             transport = "NVSwitch multicast: one pe_mc_publish kernel on rank 0 stores each group into all ranks' symmetric buffers (3 slots, 2 groups ahead)"
+        elif int(okt.item()) and chain is not None:
+            transport = ("systolic chain on the copy engines: rank r pulls each group from rank r - 1's symmetric buffer (peer-to-peer cudaMemcpyAsync, one hop "
+                         "per step, all hops at once, %d slots; rank r runs %d r groups behind rank 0); no collective library and no SM on the data path" % (chain.nslots, chain.lag))
         else:
-            ring = None
-            transport = "broadcast from rank 0 over NCCL once per step (3 group buffers, per-buffer ordering)" + ("" if ok else "; multicast: " + why)
+            ring = chain = None
+            transport = "broadcast from rank 0 over NCCL once per step (3 group buffers, per-buffer ordering)" + ("" if ok else "; " + sel + ": " + why)
     # the collective's CTAs need somewhere to run: the marching kernel is persistent (one CTA per SM), so it leaves some SMs free
-    sm_reserve = int(os.environ.get("PE_CFG5_SM_RESERVE", "8")) if world > 1 else 0
+    # (the chain moves the operand with copy engines: nothing to reserve)
+    sm_reserve = int(os.environ.get("PE_CFG5_SM_RESERVE", "0" if chain is not None else "8")) if world > 1 else 0
     if sm_reserve > 0:
         eng.set_sm_limit(eng.sm_count - sm_reserve)
-    groups = [local_ops.clone() if rank == 0 else torch.zeros_like(local_ops) for _ in range(3)] if ring is None else []
+    groups = [local_ops.clone() if rank == 0 else torch.zeros_like(local_ops) for _ in range(3)] if ring is None and chain is None else []
     it = [0]
     if ring is not None:
         ring.publish(local_ops)
         ring.publish(local_ops)
+    if chain is not None:
+        chain.prime(local_ops if rank == 0 else None)   # world - 1 transfer-only steps: from here on every step hands every rank a group
 
     def clips():
         return [lb.Layer.wrap_device(eng, lb.WEED_PALETTE_YUV422P, W, H, [yy.data_ptr(), uu.data_ptr(), vv.data_ptr()], [W, W // 2, W // 2],
@@ -644,6 +655,8 @@ def sub_records(args, eng, dist, rank, world, dev):
         if ring is not None:
             shard.multitrack_crossfade_group_mc(eng, cl, ring, W, H, 128)
             ring.publish(local_ops)   # group t + 2, behind barrier t: it travels while the kernels of groups t and t + 1 run
+        elif chain is not None:
+            shard.multitrack_crossfade_group_chain(eng, cl, chain, local_ops if rank == 0 else None, W, H, 128)
         else:
             shard.multitrack_crossfade_group(eng, cl, groups[it[0] % 3], W, H, 128)
         it[0] += 1

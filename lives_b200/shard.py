@@ -215,3 +215,113 @@ def multitrack_crossfade_group_mc(engine, clip_layers, ring, width, height, blen
         raise RuntimeError("grouped crossfade failed: " + E.capi.last_error())
     ring.consumed(es)
     return clip_layers
+
+
+def chain_schedule(step, rank, nslots, lag=1):
+    """OperandChain's lockstep schedule (pure; tests/test_shard_cpu.py simulates it): at global step `step`, rank 0 stages group `step`
+    into its slot, rank r >= 1 pulls group `step - lag * r` from rank r - 1 (which obtained it `lag` steps earlier); the group a rank
+    obtains in a step is the group it consumes in that step.  Returns (group, slot) or (None, None) while the pipeline fills.
+    A slot is rewritten nslots steps after it was filled and read by the successor `lag` steps after: nslots >= lag + 2 keeps a whole
+    step (and its barrier) between the successor's read and the rewrite."""
+    g = step - lag * rank
+    if g < 0:
+        return None, None
+    return g, g % nslots
+
+
+class OperandChain:
+    """The shared operand of config 5 as a SYSTOLIC CHAIN on the copy engines: rank r pulls each operand group from rank r - 1's
+    symmetric buffer with a peer-to-peer cudaMemcpyAsync (no SM runs a copy, the marching kernel keeps every SM), one hop per step,
+    all hops at once -- every NVLink carries one group per step in one direction, so every GPU takes the operand in at the
+    point-to-point rate (803 GB/s measured between two B200s, profiles/r02t_cfg5_transports.log) instead of the 530 - 640 GB/s of
+    ncclBroadcast or the 119 GB/s per receiver of seven pulls from one owner.  Rank r runs lag * r groups behind rank 0: a render of G
+    groups takes G + lag * (world - 1) steps; prime() runs the fill steps.
+
+    Step T on every rank (stream ordered, no host synchronisation; chain_schedule() is the same rule as a pure function):
+      copy stream    wait for this rank's kernel that read the slot's previous group (nslots steps ago) and for barrier T - lag
+                     rank 0: stage group T from `src` into its slot; rank r: pull group T - lag * r from rank r - 1's slot into its own
+                     record `arrived`
+      barrier stream wait `arrived`, symmetric-memory barrier T (behind it every rank's step-T copy has landed)
+      engine stream  wait `arrived`, ONE kernel for the K conversions + crossfades, record `consumed`.
+    With lag = 1 the barrier of step T sits between the copies of steps T and T + 1 (every step pays it and the slowest rank's skew);
+    with lag = 2 (the default) a copy waits for the barrier of TWO steps ago, which has long passed: the copies of consecutive steps
+    run back to back."""
+
+    def __init__(self, engine, slot_shape, nslots=4, lag=2, group=None):
+        import torch.distributed._symmetric_memory as symm
+        if lag < 1 or nslots < lag + 2:
+            raise ValueError("the chain needs lag >= 1 and at least lag + 2 slots")
+        self.engine, self.nslots, self.lag = engine, nslots, lag
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.shape = (nslots,) + tuple(slot_shape)
+        self.buf = symm.empty(self.shape, dtype=torch.uint8, device=dev)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.prev = self.hdl.get_buffer(self.rank - 1, self.shape, torch.uint8) if self.rank > 0 else None
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.barrier_stream = torch.cuda.Stream(device=dev)
+        self.kernel_ev = [None] * nslots   # this rank's kernel that read the slot last
+        self.barrier_ev = {}               # step -> event behind that step's barrier
+        self.t = 0
+        self.pending_slot = None
+
+    def step(self, src=None):
+        """one lockstep step; returns (buffer of the group this rank consumes now, event behind which it is valid) or (None, None)
+        while the pipeline fills.  `src`: on rank 0 the next group (contiguous uint8 of one slot's size)."""
+        g, slot = chain_schedule(self.t, self.rank, self.nslots, self.lag)
+        ev = None
+        with torch.cuda.stream(self.copy_stream):
+            need = self.barrier_ev.pop(self.t - self.lag, None)
+            if need is not None:
+                self.copy_stream.wait_event(need)
+            if g is not None:
+                if self.kernel_ev[slot] is not None:
+                    self.copy_stream.wait_event(self.kernel_ev[slot])
+                if self.rank == 0:
+                    if src is None or src.numel() != self.buf[slot].numel():
+                        raise ValueError("rank 0 stages one slot-sized group per step")
+                    self.buf[slot].copy_(src.view(self.buf[slot].shape), non_blocking=True)
+                else:
+                    self.buf[slot].copy_(self.prev[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        with torch.cuda.stream(self.barrier_stream):
+            self.barrier_stream.wait_event(ev)
+            self.hdl.barrier(channel=0)
+            bev = torch.cuda.Event()
+            bev.record(self.barrier_stream)
+            self.barrier_ev[self.t] = bev
+        self.t += 1
+        self.pending_slot = slot
+        return (self.buf[slot], ev) if g is not None else (None, None)
+
+    def prime(self, src=None):
+        """the lag * (world - 1) steps that fill the pipeline: afterwards every step() hands every rank a group"""
+        for _ in range(self.lag * (self.world - 1)):
+            self.step(src)
+
+    def consumed(self, es):
+        ev = torch.cuda.Event()
+        ev.record(es)
+        self.kernel_ev[self.pending_slot] = ev
+
+
+def multitrack_crossfade_group_chain(engine, clip_layers, chain, src, width, height, blend_factor, out_palette=1):
+    """multitrack_crossfade_group with the operand group taken from an OperandChain (primed): one chain step, then ONE kernel launch for
+    the K conversions + crossfades of this rank's clip.  `src`: rank 0's next operand group (ignored elsewhere)."""
+    from . import engine as E
+    k = len(clip_layers)
+    es = _engine_stream(engine)
+    group, ready = chain.step(src)
+    if group is None:
+        raise RuntimeError("the chain is not primed")
+    if group.dim() != 3 or group.shape[0] != k or group.shape[1] != height:
+        raise ValueError("chain slots must be K x height x rowstride")
+    es.wait_event(ready)
+    rs = group.shape[2]
+    ops = [E.Layer.wrap_device(engine, out_palette, width, height, [group[i].data_ptr()], [rs]) for i in range(k)]
+    if E.convert_crossfade_batchv(clip_layers, ops, out_palette, 0, blend_factor) != k:
+        raise RuntimeError("grouped crossfade failed: " + E.capi.last_error())
+    chain.consumed(es)
+    return clip_layers

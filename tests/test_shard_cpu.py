@@ -64,3 +64,41 @@ def test_operand_broadcast_and_partition_world_size_2():
     assert res[0][1] == (0, 5) and res[1][1] == (5, 10)
     assert res[0][2] and res[1][2]
     assert res[0][3] == res[1][3] == 2 * 36 * 192
+
+
+def test_operand_chain_schedule_is_safe():
+    """shard.chain_schedule (OperandChain's lockstep rule), simulated for 2 .. 8 ranks, lag 1 / 2 and lag + 2 .. lag + 3 slots: every rank
+    consumes group step - lag * rank, a pull always finds that group in its predecessor's slot -- copied there `lag` steps earlier, so
+    the barrier that ended THAT step is the only one the pull depends on --, and a slot is only rewritten a whole step after this rank
+    consumed its previous group and the successor pulled it"""
+    from lives_b200 import shard
+    for world in (2, 3, 4, 8):
+        for lag in (1, 2):
+            for nslots in (lag + 2, lag + 3):
+                slots = [[None] * nslots for _ in range(world)]       # (group, step it was written) held by rank r, slot s
+                pulled_at = [dict() for _ in range(world)]            # rank r: group -> step rank r + 1 pulled it
+                consumed = [set() for _ in range(world)]
+                for step in range(60):
+                    moves = []
+                    for r in range(world):
+                        g, s = shard.chain_schedule(step, r, nslots, lag)
+                        if g is None:
+                            assert step < lag * r
+                            continue
+                        assert g == step - lag * r and s == g % nslots
+                        if r > 0:
+                            held = slots[r - 1][s]
+                            assert held is not None and held[0] == g and held[1] <= step - lag, (world, lag, nslots, step, r)
+                        old = slots[r][s]
+                        if old is not None:
+                            assert old[0] == g - nslots and old[0] in consumed[r]
+                            # the successor's pull of the old group ended at least one whole step (one barrier) before `step - lag`'s barrier
+                            assert r == world - 1 or pulled_at[r][old[0]] <= step - lag, (world, lag, nslots, step, r)
+                        moves.append((r, s, g))
+                    for r, s, g in moves:   # all copies of a step run at once
+                        slots[r][s] = (g, step)
+                        consumed[r].add(g)
+                        if r > 0:
+                            pulled_at[r - 1][g] = step
+                for r in range(world):
+                    assert consumed[r] == set(range(60 - lag * r))
