@@ -53,7 +53,7 @@ __device__ __forceinline__ uint32_t permute_pixel(uint32_t pix, const PermutePar
 }
 
 // frames of one batched launch (same geometry, strides and palettes): blockIdx.y selects the frame
-constexpr int kRgbBatch = 128;  // frames per launch: 2 KB of the 4 KB kernel parameter space
+constexpr int kRgbBatch = 256;  // frames per launch: 4 KB of kernel parameters (CUDA 12.1+ takes up to 32 764 bytes on sm_70+)
 struct RgbFrameList {
   const uint8_t *src[kRgbBatch];
   uint8_t *dst[kRgbBatch];
@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(kBlock) k_rgb_to_rgb(const PermuteParams P, co
     // accesses at a 12-byte stride cost three times the LSU wavefronts of the same bytes moved as 128-bit vectors)
     const int groups16 = P.width >> 4;
     const long long total16 = (long long)groups16 * P.height;
-    for (long long it = global_tid(); it < total16; it += global_threads()) {
-      const int row = (int)(it / groups16), g = (int)(it - (long long)row * groups16);
+    // (32-bit index arithmetic: a 64-bit division per 48 bytes was a third of this loop's instructions; frames are far below 2^31 groups)
+    const uint32_t tot = (uint32_t)total16, ug = (uint32_t)groups16, T = (uint32_t)gridDim.x * blockDim.x;
+    for (uint32_t it = (uint32_t)blockIdx.x * blockDim.x + threadIdx.x; it < tot; it += T) {
+      const uint32_t row = it / ug, g = it - row * ug;
       const uint8_t *s = f_src + (long long)row * P.irow + (long long)g * 48;
       uint8_t *d = f_dst + (long long)row * P.orow + (long long)g * 48;
       const uint4 a = ld_u4(s), b = ld_u4(s + 16), c = ld_u4(s + 32);  // may be in place: plain loads
@@ -151,7 +153,8 @@ cudaError_t launch_rgb_to_rgb_batch(const Launch &L, const uint8_t *const *srcs,
   bool vec = (irow % ia == 0) && (orow % oa == 0);
   for (int i = 0; i < n && vec; i++) vec = ((uintptr_t)srcs[i] % ia == 0) && ((uintptr_t)dsts[i] % oa == 0);
   P.vec_ok = vec;
-  bool vec16 = in.psize == 3 && out.psize == 3 && !(width & 15) && !(irow & 15) && !(orow & 15) && getenv("PE_RGB_NO_VEC16") == nullptr;
+  bool vec16 = in.psize == 3 && out.psize == 3 && !(width & 15) && !(irow & 15) && !(orow & 15) && getenv("PE_RGB_NO_VEC16") == nullptr &&
+               (long long)(width >> 4) * height < (1ll << 31);   // (the kernel's 32-bit group index)
   for (int i = 0; i < n && vec16; i++) vec16 = ((uintptr_t)srcs[i] % 16 == 0) && ((uintptr_t)dsts[i] % 16 == 0);
   P.vec16_ok = vec16;
   const long long work = vec16 ? (long long)(width >> 4) * height : (long long)((width + 3) >> 2) * height;
