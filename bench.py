@@ -534,7 +534,7 @@ def run_ours(args, rank, world, local_rank):
                                "of consecutive frames overlapped on three streams)", "checksum": checksum},
                 "e2e_device_ingest": e2e_ingest,
                 "gpu_launches": int(launches), "clocks": clk, "configs": subs, "pcie_ceiling": probe}
-        prof = os.path.join(REPO, "profiles", "traffic_r01.json")
+        prof = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
                 # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per frame

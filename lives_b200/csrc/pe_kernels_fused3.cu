@@ -985,9 +985,18 @@ cudaError_t launch_fused3(const Launch &L, const FusedArgs *frames_host, int nfr
     P.frame_cost = strip_cost * P.nstrips;
     P.total_cost = P.frame_cost * P.nframes;
     const int grid = L.sm_count;
-    // band height: about one warp share of rows, so that consecutive warps work on neighbouring strips of the same band
+    // band height: the rows of an ALL-INNER share, so that inside the inner rectangle a warp owns about one (band, strip) unit and
+    // consecutive warps march down neighbouring strips of the same band in step: the chroma sectors two strips share are then still
+    // in L2 when the neighbour asks for them.  Measured at 32 frames per launch (tools/f3_band_variants.sh,
+    // profiles/r02zf_f3_band_variants.log): 602 us and 1.69 GB of DRAM reads per launch, against 610 us / 1.81 GB with the average
+    // rows of a share (border rows included) and 623 - 628 us / 1.88 GB with heights in between
     const long long share = P.total_cost / ((long long)grid * F3_NW);
-    long long bh = share * a0.oh / (strip_cost > 0 ? strip_cost : 1);
+    long long bh = share / cost_i;
+    if (getenv("PE_F3_BAND_MODE")) {   // experiments: 1 = the average rows of a share, >= 16 = that many rows
+      const int m = atoi(getenv("PE_F3_BAND_MODE"));
+      if (m == 1) bh = share * a0.oh / (strip_cost > 0 ? strip_cost : 1);
+      else if (m >= 16) bh = m;
+    }
     if (bh < 16) bh = 16;
     if (bh > a0.oh) bh = a0.oh;
     P.band_h = (int)bh;
