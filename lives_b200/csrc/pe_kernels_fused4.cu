@@ -18,6 +18,7 @@
 // Rows the fast step cannot take (row 0, the last row of an even frame, the last chroma row of a plane without padding) go through
 // slow_unit(): scalar code with the reference's edge rules, a few units per frame.
 #include <cstdlib>
+#include <cstdio>
 
 #include "pe_device.cuh"
 #include "pe_kernels.h"
@@ -51,7 +52,8 @@ constexpr int O_PL = (O_VF + (F4_PR + 1) * 4 + 15) & ~15, O_TMP = (O_PL + 3 * F4
 // tile tables: the tap range [first, last] of every tile column / tile row, read once per launch
 constexpr int F4_MAXTX = 128, F4_MAXTY = 160;
 constexpr int O_PY = O_CX + 2 * F4_TW * 16, O_TCOL = O_PY + 2 * F4_TH * 16, O_TROW = O_TCOL + F4_MAXTX * 8;
-constexpr int F4_SMEM = O_TROW + F4_MAXTY * 8;
+constexpr int O_MBAR = O_TROW + F4_MAXTY * 8;   // one mbarrier: the bulk copies of a tile's raw rows complete on it
+constexpr int F4_SMEM = O_MBAR + 16;
 static_assert(F4_SMEM <= F4_SMEM_MAX, "k_cvt_resize: shared memory budget");
 
 struct CvtRszParams {
@@ -62,11 +64,15 @@ struct CvtRszParams {
   int dw, dh, drs;                        // destination
   int tiles_x, tiles_y;
   int vec16;                              // planes and strides 16-byte aligned: the raw words travel as 16-byte cp.async
+  int tma;                                // ... or (PE_F4_TMA=1, needs vec16) as one cp.async.bulk per row, see stage()
   int k_fast_max;
   int swap_rb;                            // BGRA32
   const int4 *px, *py;                    // [dw] / [dh]: {c0 | c1 << 16, c2 | c3 << 16, first, aux}; aux = alpha's 15-bit intermediate / the sum of the row's taps
   int fx_taps, fy_taps;
   const int32_t *conv;                    // [14][256]
+#ifdef PE_F4_TIMELINE
+  unsigned long long *tl;                 // [grid][6]: cycles of CTA thread 0 in: wait for the raw words, conversion, staging the next tile, horizontal, vertical, total
+#endif
 };
 
 __device__ __forceinline__ uint32_t f4_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
@@ -92,6 +98,31 @@ __device__ __forceinline__ void f4_cp_async16(uint32_t smem_dst, const void *gsr
 }
 __device__ __forceinline__ void f4_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void f4_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: the raw rows of a tile.  One instruction moves a whole
+// row (<= 224 bytes); as 16-byte cp.async (LDGSTS) the staging of a tile was ~1200 instructions with their 64-bit addresses spread over
+// all 16 warps and took 19 % of the kernel (-DPE_F4_TIMELINE); as bulk copies it is ~4 instructions per lane of ONE warp.
+__device__ __forceinline__ void f4_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void f4_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f4_bulk_g2s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void f4_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PE_F4_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PE_F4_MBAR_DONE;\n"
+      "bra PE_F4_MBAR_WAIT;\n"
+      "PE_F4_MBAR_DONE:\n"
+      "}" :: "r"(bar), "r"(parity) : "memory");
+}
 
 constexpr uint32_t F4_MSK = 0xFFFEFFFEu, F4_K3 = 0x00030003u;
 // third_round of the HIGH / LOW half of a packed Q = 2 n + 3, as the byte offset 128 * m of the chroma table entry (k_fused3: idx_hi / idx_lo)
@@ -163,6 +194,10 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     s_tcol[i] = make_int2(__ldg(&P.px[i * F4_TW].z), __ldg(&P.px[min(i * F4_TW + F4_TW, P.dw) - 1].z) + P.fx_taps - 1);
   for (int i = tid; i < P.tiles_y; i += F4_NT)
     s_trow[i] = make_int2(__ldg(&P.py[i * F4_TH].z), __ldg(&P.py[min(i * F4_TH + F4_TH, P.dh) - 1].z) + P.fy_taps - 1);
+  if (tid == 0) {
+    f4_mbar_init(sbase + O_MBAR, 32u);   // the 32 lanes of warp 0 arrive once per tile, each with the bytes it has asked for
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   constexpr int GW = F4_GW, CWB = F4_CWB;
@@ -202,6 +237,53 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     const uint8_t *Fy = P.y[g.f], *Fu = P.u[g.f], *Fv = P.v[g.f];
     const int rowbase = 2 * g.k0 - 1;
     const long long ulim = (long long)P.rs_u * P.ch, vlim = (long long)P.rs_v * P.ch;
+    if (P.tma) {
+      // warp 0: lane l asks for rows l, l + 32, ... of the tile's 2 np luma + 2 (np + 1) chroma rows with one bulk copy each (a row:
+      // <= 224 / 128 bytes, 16-byte aligned at both ends), lanes 0 / 1 for the tile's filter rows as well; every lane arrives on the
+      // mbarrier with the byte count it is about to request.  The other warps go straight on to the horizontal pass.
+      if (warp == 0) {
+        const uint32_t bar = sbase + O_MBAR;
+        const int ny = 2 * g.np, nc = g.np + 1, nrows = ny + 2 * nc;
+        const uint32_t ybytes = (uint32_t)((g.cb - g.ybase + 4 * g.ng + 15) >> 4) * 16u;
+        const uint32_t cbytes = (uint32_t)((2 * g.ng + 21 + 15) >> 4) * 16u;   // (a row pair's last unit reads up to byte 2 ng + 20 of the staged row)
+        auto row_copy = [&](int r, const uint8_t *&src, uint32_t &dst, uint32_t &bytes) {
+          if (r < ny) {
+            const int sr = min(max(rowbase + r, 0), P.fh - 1);
+            src = Fy + (size_t)P.rs_y * sr + g.ybase; dst = sbase + O_RAWY + r * (GW * 4); bytes = ybytes;
+          } else {
+            const bool isv = r - ny >= nc;
+            const int ri = r - ny - (isv ? nc : 0);
+            const int cr = min(max(g.k0 - 1 + ri, 0), P.ch - 1);
+            const long long o = (long long)(isv ? P.rs_v : P.rs_u) * cr + g.ubase, lim = isv ? vlim : ulim;
+            src = (isv ? Fv : Fu) + o; dst = sbase + (isv ? O_RAWV : O_RAWU) + ri * CWB;
+            bytes = (uint32_t)min((long long)cbytes, lim - o);   // never past the end of the plane (planes are whole 16-byte chunks here)
+          }
+        };
+        uint32_t mine = 0;
+        for (int r = lane; r < nrows; r += 32) {
+          const uint8_t *src; uint32_t dst, bytes;
+          row_copy(r, src, dst, bytes);
+          mine += bytes;
+        }
+        if (lane == 0) mine += (uint32_t)g.ncol * 16u;
+        if (lane == 1) mine += (uint32_t)g.nrow * 16u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffers were read through the generic proxy until the barrier before
+        f4_mbar_expect_tx(bar, mine);
+        for (int r = lane; r < nrows; r += 32) {
+          const uint8_t *src; uint32_t dst, bytes;
+          row_copy(r, src, dst, bytes);
+          f4_bulk_g2s(dst, src, bytes, bar);
+        }
+        // the filter rows of the tile (16-byte entries of cudaMalloc'ed arrays; x0 / y0 are multiples of the tile size)
+        if (lane == 0) f4_bulk_g2s(sbase + O_CX + (buf * F4_TW) * 16, P.px + g.x0, (uint32_t)g.ncol * 16u, bar);
+        if (lane == 1) f4_bulk_g2s(sbase + O_PY + (buf * F4_TH) * 16, P.py + g.y0, (uint32_t)g.nrow * 16u, bar);
+      } else if (warp == 1 && lane <= g.np) {
+        const int cr = min(max(g.k0 - 1 + lane, 0), P.ch - 1);
+        f4_cp_async4(sbase + O_VF + 4 * lane, Fv + (size_t)P.rs_v * cr);
+      }
+      f4_cp_async_commit();
+      return;
+    }
     if (P.vec16) {
       // a warp = one row at a time, a lane = one 16-byte chunk of it (rows are <= 13 / 8 chunks: few lanes, but no index arithmetic)
       const int nchy = (g.cb - g.ybase + 4 * g.ng + 15) >> 4;
@@ -254,14 +336,26 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     b = (yy + (int)tu.y) >> 16;
   };
 
+#ifdef PE_F4_TIMELINE
+  long long tl_acc[5] = {0, 0, 0, 0, 0};
+  const long long tl_begin = clock64();
+  long long tl_mark = tl_begin;
+  auto tl_lap = [&](int k) { const long long now = clock64(); tl_acc[k] += now - tl_mark; tl_mark = now; };
+#endif
   int t = blockIdx.x;
   if (t >= total) return;
   Geo G = geometry(t);
   int buf = 0;
+  uint32_t tile_phase = 0u;   // tiles this CTA has staged so far: the mbarrier's phase
   stage(G, buf);
   for (; t < total; t += gridDim.x, buf ^= 1) {
     f4_cp_async_wait_all();
+    if (P.tma) f4_mbar_wait(sbase + O_MBAR, tile_phase & 1u);
+    tile_phase++;
     __syncthreads();  // raw words of this tile have landed; the previous tile's passes are done with the planes, the intermediate and the filter rows
+#ifdef PE_F4_TIMELINE
+    tl_lap(0);
+#endif
     const Geo g = G;
     const int rowbase = 2 * g.k0 - 1;
     const int4 *const s_px = reinterpret_cast<const int4 *>(smem + O_CX) + buf * F4_TW, *const s_py = reinterpret_cast<const int4 *>(smem + O_PY) + buf * F4_TH;
@@ -348,12 +442,18 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
       }
     }
     __syncthreads();
+#ifdef PE_F4_TIMELINE
+    tl_lap(1);
+#endif
     // the raw buffers are free again: bring in the next tile's words while passes 2 and 3 run
     const int tn = t + (int)gridDim.x;
     if (tn < total) {
       G = geometry(tn);
       stage(G, buf ^ 1);
     }
+#ifdef PE_F4_TIMELINE
+    tl_lap(2);
+#endif
     // ---- 2. horizontal pass: warp = one source row at a time, lane = output columns lane, lane + 32, lane + 64, lane + 96
     {
       uint2 cf[4];
@@ -383,6 +483,9 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
       }
     }
     __syncthreads();
+#ifdef PE_F4_TIMELINE
+    tl_lap(3);
+#endif
     // ---- 3. vertical pass: warp = one output row at a time
     for (int yo = warp; yo < g.nrow; yo += F4_NW) {
       const int4 ey = s_py[yo];
@@ -406,7 +509,16 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
         st_stream_u32(drow + 4 * xo, px);
       }
     }
+#ifdef PE_F4_TIMELINE
+    tl_lap(4);   // (thread 0's own share of the vertical pass; the barrier wait of the next tile lands in lap 0)
+#endif
   }
+#ifdef PE_F4_TIMELINE
+  if (tid == 0) {
+    for (int k = 0; k < 5; k++) P.tl[(size_t)blockIdx.x * 6 + k] = (unsigned long long)tl_acc[k];
+    P.tl[(size_t)blockIdx.x * 6 + 5] = (unsigned long long)(clock64() - tl_begin);
+  }
+#endif
 }
 
 }  // namespace
@@ -464,6 +576,9 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
   for (int i = 0; i < n && P.vec16; i++)
     P.vec16 = !((reinterpret_cast<uintptr_t>(frames[i].src.y) | reinterpret_cast<uintptr_t>(frames[i].src.u) | reinterpret_cast<uintptr_t>(frames[i].src.v)) & 15);
   if (getenv("PE_F4_NOVEC")) P.vec16 = 0;
+  // the bulk-copy (TMA) staging is kept as a measured variant: 67.0 k frames/s against 99.7 k with 16-byte cp.async on config 2
+  // (profiles/r02zg_k_cvt_resize_staging.txt) -- a tile's rows are <= 224 bytes, far below the size a bulk copy needs to pay off
+  P.tma = P.vec16 && getenv("PE_F4_TMA") && atoi(getenv("PE_F4_TMA")) != 0;
   const int smem_bytes = F4_SMEM;
   static PerDevice attr_set;
   if (!attr_set.cur()) {
@@ -481,8 +596,25 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
     }
     const long long total = (long long)P.tiles_x * P.tiles_y * P.nframes;
     const int grid = (int)(total < L.sm_count ? total : L.sm_count);
+#ifdef PE_F4_TIMELINE
+    static unsigned long long *tl_dev = nullptr;
+    if (!tl_dev) cudaMalloc(&tl_dev, sizeof(unsigned long long) * 6 * 1024);
+    cudaMemsetAsync(tl_dev, 0, sizeof(unsigned long long) * 6 * 1024, L.stream);
+    P.tl = tl_dev;
+#endif
     if (a0.quirks) k_cvt_resize<true><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
     else k_cvt_resize<false><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
+#ifdef PE_F4_TIMELINE
+    if (getenv("PE_F4_TIMELINE_DUMP")) {   // where the tiles' time goes (thread 0 of every CTA: its waits at the barriers land in the lap before them)
+      static unsigned long long h[6 * 1024];
+      cudaStreamSynchronize(L.stream);
+      cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost);
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      for (int b = 0; b < grid; b++) for (int k = 0; k < 6; k++) acc[k] += (double)h[b * 6 + k];
+      fprintf(stderr, "f4 timeline (thread 0 of %d CTAs, cycles per CTA): wait %.0f conversion %.0f staging %.0f horizontal %.0f vertical %.0f total %.0f | tiles %lld\n",
+              grid, acc[0] / grid, acc[1] / grid, acc[2] / grid, acc[3] / grid, acc[4] / grid, acc[5] / grid, total);
+    }
+#endif
     PE_COUNT_LAUNCH(L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
