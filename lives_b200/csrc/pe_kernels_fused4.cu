@@ -51,7 +51,7 @@ constexpr int O_PL = (O_VF + (F4_PR + 1) * 4 + 15) & ~15, O_TMP = (O_PL + 3 * F4
 // filter rows of the tile, double buffered (tile parity): int4 per output column / row {c0 | c1 << 16, c2 | c3 << 16, first, aux};
 // tile tables: the tap range [first, last] of every tile column / tile row, read once per launch
 constexpr int F4_MAXTX = 128, F4_MAXTY = 160;
-constexpr int O_PY = O_CX + 2 * F4_TW * 16, O_TCOL = O_PY + 2 * F4_TH * 16, O_TROW = O_TCOL + F4_MAXTX * 8;
+constexpr int O_PY = O_CX + 2 * F4_TW * 16, O_TCOL = O_PY + 2 * F4_TH * 16, O_TROW = O_TCOL + F4_MAXTX * 16;
 constexpr int O_MBAR = O_TROW + F4_MAXTY * 8;   // one mbarrier: the bulk copies of a tile's raw rows complete on it
 constexpr int F4_SMEM = O_MBAR + 16;
 static_assert(F4_SMEM <= F4_SMEM_MAX, "k_cvt_resize: shared memory budget");
@@ -69,6 +69,7 @@ struct CvtRszParams {
   int swap_rb;                            // BGRA32
   const int4 *px, *py;                    // [dw] / [dh]: {c0 | c1 << 16, c2 | c3 << 16, first, aux}; aux = alpha's 15-bit intermediate / the sum of the row's taps
   int fx_taps, fy_taps;
+  uint32_t magic_tpf, magic_tx;           // ceil(2^32 / tiles per frame), ceil(2^32 / tiles_x): tile index -> (frame, ty, tx) without a division (0: divide)
   const int32_t *conv;                    // [14][256]
 #ifdef PE_F4_TIMELINE
   unsigned long long *tl;                 // [grid][6]: cycles of CTA thread 0 in: wait for the raw words, conversion, staging the next tile, horizontal, vertical, total
@@ -189,9 +190,13 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   uint32_t *const s_vf = reinterpret_cast<uint32_t *>(smem + O_VF);
   uint8_t *const s_pl = smem + O_PL;
   uint16_t *const s_tmp = reinterpret_cast<uint16_t *>(smem + O_TMP);
-  int2 *const s_tcol = reinterpret_cast<int2 *>(smem + O_TCOL), *const s_trow = reinterpret_cast<int2 *>(smem + O_TROW);
-  for (int i = tid; i < P.tiles_x; i += F4_NT)
-    s_tcol[i] = make_int2(__ldg(&P.px[i * F4_TW].z), __ldg(&P.px[min(i * F4_TW + F4_TW, P.dw) - 1].z) + P.fx_taps - 1);
+  int4 *const s_tcol = reinterpret_cast<int4 *>(smem + O_TCOL);   // per tile column: first / last tap column, ceil(2^32 / groups) of the column
+  int2 *const s_trow = reinterpret_cast<int2 *>(smem + O_TROW);
+  for (int i = tid; i < P.tiles_x; i += F4_NT) {
+    const int vc0 = __ldg(&P.px[i * F4_TW].z), vc1 = __ldg(&P.px[min(i * F4_TW + F4_TW, P.dw) - 1].z) + P.fx_taps - 1;
+    const int ng = (((vc1 | 3) + 1) - (vc0 & ~3)) >> 2;
+    s_tcol[i] = make_int4(vc0, vc1, (int)(0xFFFFFFFFu / (uint32_t)ng + 1u), 0);   // (the third word: ceil(2^32 / ng) for ng > 1)
+  }
   for (int i = tid; i < P.tiles_y; i += F4_NT)
     s_trow[i] = make_int2(__ldg(&P.py[i * F4_TH].z), __ldg(&P.py[min(i * F4_TH + F4_TH, P.dh) - 1].z) + P.fy_taps - 1);
   if (tid == 0) {
@@ -211,13 +216,16 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   };
   auto geometry = [&](int t) -> Geo {
     Geo g;
-    g.f = t / tiles_per_frame;
+    // (the divisions of the tile index were a visible part of the 19 % of the kernel spent between the conversion and the horizontal
+    // pass -- every thread computes the next tile's geometry: multiply-high by constants of the launch instead)
+    g.f = P.magic_tpf ? (int)__umulhi((uint32_t)t, P.magic_tpf) : t / tiles_per_frame;
     const int r = t - g.f * tiles_per_frame;
-    const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+    const int ty = P.magic_tx ? (int)__umulhi((uint32_t)r, P.magic_tx) : r / P.tiles_x, tx = r - ty * P.tiles_x;
     g.x0 = tx * F4_TW; g.y0 = ty * F4_TH;
     const int x1 = min(g.x0 + F4_TW, P.dw), y1 = min(g.y0 + F4_TH, P.dh);
     g.ncol = x1 - g.x0; g.nrow = y1 - g.y0;
-    const int2 tc = s_tcol[tx], trw = s_trow[ty];
+    const int4 tc = s_tcol[tx];
+    const int2 trw = s_trow[ty];
     const int vc0 = tc.x, vc1 = tc.y, vr1 = trw.y;
     g.vr0 = trw.x;
     g.nvr = vr1 - g.vr0 + 1;
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
     g.ubase = g.cb == 0 ? 0 : (((g.cb >> 1) - 1) & ~3);
     g.ybase = g.cb;
     if (P.vec16) { g.ybase &= ~15; g.ubase &= ~15; }  // the staged rectangle starts on a 16-byte boundary of the planes
-    g.ng_magic = 0xFFFFFFFFu / (uint32_t)g.ng + 1u;  // = ceil(2^32 / ng) for ng > 1
+    g.ng_magic = (uint32_t)tc.z;  // = ceil(2^32 / ng) for ng > 1
     return g;
   };
   // cp.async of the raw words of tile t: luma rows 2 k0 - 1 .. 2 k1 (clamped to the frame), chroma rows k0 - 1 .. k1, the first V
@@ -572,6 +580,12 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
     if (((vr1 + 1) >> 1) - ((vr0 + 1) >> 1) + 1 > F4_PR || vr1 - vr0 + 1 > F4_TR) return cudaErrorInvalidConfiguration;
   }
   if ((long long)P.tiles_x * P.tiles_y * F4_MAXF >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+  {
+    // t / d == umulhi(t, ceil(2^32 / d)) for every t with t * d < 2^32 (d > 1): true for every tile index of the launch or not used
+    const long long tpf = (long long)P.tiles_x * P.tiles_y, tmax = tpf * F4_MAXF;
+    P.magic_tpf = (tpf > 1 && tmax * tpf < (1ll << 32)) ? (uint32_t)(0xFFFFFFFFu / (uint32_t)tpf + 1u) : 0u;
+    P.magic_tx = (P.tiles_x > 1 && tpf * P.tiles_x < (1ll << 32)) ? (uint32_t)(0xFFFFFFFFu / (uint32_t)P.tiles_x + 1u) : 0u;
+  }
   P.vec16 = !((a0.src.rs_y | a0.src.rs_u | a0.src.rs_v) & 15);
   for (int i = 0; i < n && P.vec16; i++)
     P.vec16 = !((reinterpret_cast<uintptr_t>(frames[i].src.y) | reinterpret_cast<uintptr_t>(frames[i].src.u) | reinterpret_cast<uintptr_t>(frames[i].src.v)) & 15);
