@@ -449,6 +449,26 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = e2e_frames * args.e2e_steps * world / e2e_s
     checksum = int(pinned[0][4][::97, ::101].astype(np.uint64).sum())  # the D2H result is really read
 
+    # ---- the same call on PAGEABLE host buffers (what LiVES' lives_calloc_safety hands out; the `e2e` above is the case of a host
+    #      that page-locked its pixel blocks once, pe_host_register): plain numpy allocations, never registered, a few frames
+    e2e_pageable = None
+    if rank == 0 or dist is not None:
+        try:
+            pg = [(lb.HostLayer(lb.WEED_PALETTE_YUV420P, FW, FH, [y, u, v], yuv_subspace=1),
+                   lb.HostLayer(lb.WEED_PALETTE_RGBA32, FW, FH, [bg], gamma_type=G_LINEAR),
+                   lb.HostLayer(lb.WEED_PALETTE_RGBA32, FW, FH, [np.full((FH, FW * 4), 1, np.uint8)])) for (y, u, v, bg) in hframes]   # (np.full: pages touched)
+            npg = min(8, max(4, e2e_frames // 4))
+            pf, pb, po = [pg[i % 4][0] for i in range(npg)], [pg[i % 4][1] for i in range(npg)], [pg[i % 4][2] for i in range(npg)]
+            lb.host_fused_convert_letterbox_over_gamma_batch(eng, pf[:4], pb[:4], po[:4], IW, IH, ALPHA, G_LINEAR, G_SRGB)
+            eng.sync()
+            t0 = time.perf_counter()
+            lb.host_fused_convert_letterbox_over_gamma_batch(eng, pf, pb, po, IW, IH, ALPHA, G_LINEAR, G_SRGB)
+            eng.sync()
+            e2e_pageable = {"value": npg / (time.perf_counter() - t0), "unit": "frames/s per GPU", "frames": npg,
+                            "note": "pe_host_fused_convert_letterbox_over_gamma_batch on pageable (never registered) host buffers, this rank alone"}
+        except Exception as ex:  # noqa: BLE001
+            e2e_pageable = {"value": None, "note": "failed: %s" % str(ex).splitlines()[0][:100]}
+
     # ---- e2e with device-resident ingest: fg and bg frames come from clips that already sit in HBM (the decoder
     #      plugin's get_frame shape over a device clip: zero H2D), the chain runs fused, and ONLY the final RGB24 frame (the render
     #      tail's layer_to_pixbuf, src/events.c:4263) crosses PCIe, on its own stream, four frames in flight
@@ -532,7 +552,7 @@ def run_ours(args, rank, world, local_rank):
                         "d2h_bytes_per_step": RGBA_BYTES * e2e_frames, "frames_per_step": e2e_frames, "steps": args.e2e_steps,
                         "api": "pe_host_fused_convert_letterbox_over_gamma_batch (pinned host frames in / out; H2D, kernel, D2H "
                                "of consecutive frames overlapped on three streams)", "checksum": checksum},
-                "e2e_device_ingest": e2e_ingest,
+                "e2e_device_ingest": e2e_ingest, "e2e_pageable": e2e_pageable,
                 "gpu_launches": int(launches), "clocks": clk, "configs": subs, "pcie_ceiling": probe}
         prof = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(prof):

@@ -122,6 +122,12 @@ int pe_resize_filter_host(int recipe, int src_n, int dst_n, int shift_bits, int3
  * table[x][y] = clamp((((x + y) * A + B) * M) >> 32, lo, hi); out = {A, B, M, lo, hi}.  Returns 1 when the form equals the table the
  * library builds for this clamping, entry by entry (host arithmetic, no GPU). */
 int pe_avg_closed_form(int clamped, uint32_t out[5]);
+/* Pageable host planes (what lives_calloc_safety hands out) of 1 MB and more do not go to cudaMemcpyAsync as they are -- the driver
+ * would stage them with one thread, ~10 GB/s -- but through page-locked ring buffers filled / drained by a small pool of copy threads
+ * (PE_HOST_COPY_THREADS, default min(8, cores / 2); PE_HOST_NO_STAGING=1 switches it off).  Page-locked planes (pe_host_alloc,
+ * pe_host_register) are never staged.  This is the pool's copy on its own: rows of row_bytes bytes at the given strides, `threads`
+ * workers (host arithmetic, no GPU). */
+int pe_host_parallel_copy2d(void *dst, size_t dst_stride, const void *src, size_t src_stride, size_t row_bytes, size_t rows, int threads);
 
 /* one engine per process and GPU, shared by the weed_layer_t drop-ins (libpe_weed_layer.so) and the effect plugin
  * (libpe_weed_plugin.so): created on first use with the configuration given to pe_engine_shared_configure (default:

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "pe_engine_set_resize_recipe": (I, [VP, I]),
     "pe_resize_filter_host": (I, [I, I, I, I, VP, VP, I]),
     "pe_avg_closed_form": (I, [I, VP]),
+    "pe_host_parallel_copy2d": (I, [VP, C.c_size_t, VP, C.c_size_t, C.c_size_t, C.c_size_t, I]),
     "pe_frame_layout": (SZ, [I, I, I, PI, PI, PI]),
     "pe_frame_create": (I, [VP, I, I, I, I, I, I, I, I, PVP]),
     "pe_frame_wrap": (I, [VP, PDESC, PVP]),

@@ -14,7 +14,7 @@ PLUGIN = os.path.join(HERE, "libpe_weed_plugin.so")
 LAYERLIB = os.path.join(HERE, "libpe_weed_layer.so")
 VPPLIB = os.path.join(HERE, "libpe_vpp.so")
 
-SOURCES = ["pe_engine.cu", "pe_kernels_rgb.cu", "pe_kernels_yuv.cu", "pe_kernels_yuv2.cu", "pe_kernels_yuv3.cu", "pe_kernels_fused.cu", "pe_kernels_fused2.cu", "pe_kernels_fused3.cu", "pe_kernels_fused4.cu", "pe_kernels_fx2.cu", "pe_kernels_float.cu", "pe_kernels_mc.cu", "pe_tables.cpp"]
+SOURCES = ["pe_engine.cu", "pe_kernels_rgb.cu", "pe_kernels_yuv.cu", "pe_kernels_yuv2.cu", "pe_kernels_yuv3.cu", "pe_kernels_fused.cu", "pe_kernels_fused2.cu", "pe_kernels_fused3.cu", "pe_kernels_fused4.cu", "pe_kernels_fx2.cu", "pe_kernels_float.cu", "pe_kernels_mc.cu", "pe_tables.cpp", "pe_hoststage.cpp"]
 OBJ = os.path.join(HERE, "build")
 NVCC_COMPILE = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared"]

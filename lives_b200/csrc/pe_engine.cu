@@ -222,6 +222,7 @@ static int engine_init(pe_engine *e) {
   cudaDeviceProp prop;
   PE_CUDA(cudaGetDeviceProperties(&prop, c.device));
   e->sm_count = prop.multiProcessorCount;
+  e->no_host_staging = getenv("PE_HOST_NO_STAGING") != nullptr;
   if (c.stream) {
     e->stream = (cudaStream_t)c.stream;
   } else {
@@ -335,6 +336,13 @@ extern "C" int pe_engine_set_resize_recipe(pe_engine_t *e, int recipe) {
 
 // the coefficient bank the engine would build, on the host (no GPU involved): first[dst_n], coefs[dst_n * max_taps]; returns the
 // tap count or -1
+extern "C" int pe_host_parallel_copy2d(void *dst, size_t dst_stride, const void *src, size_t src_stride, size_t row_bytes, size_t rows, int threads) {
+  if (!dst || !src || threads < 1 || threads > 64) return set_err(PE_ERR_ARG, "bad argument");
+  pe::CopyPool pool(threads);
+  pool.copy2d(dst, dst_stride, src, src_stride, row_bytes, rows);
+  return PE_OK;
+}
+
 extern "C" int pe_avg_closed_form(int clamped, uint32_t out[5]) {
   const AvgForm F = avg_form(clamped != 0);
   if (out) { out[0] = F.A; out[1] = F.B; out[2] = F.M; out[3] = (uint32_t)F.lo; out[4] = (uint32_t)F.hi; }
@@ -777,6 +785,13 @@ extern "C" int pe_frame_upload(pe_engine_t *e, pe_frame_t *f, const void *const 
     // past the chroma row, colourspace.c:3508), else the payload bytes
     int wbytes = plane_row_bytes(f->d, p);
     if (hrs == f->d.rowstrides[p]) wbytes = hrs;
+    // a big pageable plane: copy threads fill a page-locked ring buffer, the DMA runs from there (pe_hoststage.h); anything else -- and
+    // any failure of the staged path -- is the plain copy, which the driver stages itself
+    if ((size_t)f->d.rowstrides[p] * f->plane_heights[p] >= pe::HostStager::kMinBytes && !e->no_host_staging && pe::HostStager::pageable(host_planes[p]) &&
+        e->stager.upload(e->stream, f->d.planes[p], (size_t)f->d.rowstrides[p], host_planes[p], (size_t)hrs, (size_t)wbytes,
+                         (size_t)f->plane_heights[p]) == cudaSuccess)
+      continue;
+    cudaGetLastError();
     PE_CUDA(cudaMemcpy2DAsync(f->d.planes[p], f->d.rowstrides[p], host_planes[p], hrs, wbytes, f->plane_heights[p],
                               cudaMemcpyHostToDevice, e->stream));
   }
@@ -788,12 +803,25 @@ extern "C" int pe_frame_download(pe_engine_t *e, const pe_frame_t *f, void *cons
   if (!e || !f || !host_planes) return set_err(PE_ERR_ARG, "NULL argument");
   std::lock_guard<std::mutex> lk(e->mu);
   PE_CUDA(cudaSetDevice(e->device));
+  std::vector<pe::PendingOut> pending;
   for (int p = 0; p < f->d.nplanes; p++) {
     if (!host_planes[p]) return set_err(PE_ERR_ARG, "host plane %d is NULL", p);
     const int hrs = host_rowstrides ? host_rowstrides[p] : f->d.rowstrides[p];
+    if ((size_t)f->d.rowstrides[p] * f->plane_heights[p] >= pe::HostStager::kMinBytes && !e->no_host_staging && pe::HostStager::pageable(host_planes[p])) {
+      pe::PendingOut po;
+      if (e->stager.download_begin(e->stream, f->d.planes[p], (size_t)f->d.rowstrides[p], host_planes[p], (size_t)hrs,
+                                   (size_t)plane_row_bytes(f->d, p), (size_t)f->plane_heights[p], &po) == cudaSuccess) {
+        pending.push_back(po);   // (plane p is copied out by the threads while plane p + 1 travels)
+        continue;
+      }
+      cudaGetLastError();
+    }
     PE_CUDA(cudaMemcpy2DAsync(host_planes[p], hrs, f->d.planes[p], f->d.rowstrides[p], plane_row_bytes(f->d, p),
                               f->plane_heights[p], cudaMemcpyDeviceToHost, e->stream));
   }
+  cudaError_t pend_err = cudaSuccess;
+  for (auto &po : pending) { const cudaError_t ce = e->stager.finish(po); if (ce != cudaSuccess) pend_err = ce; }
+  PE_CUDA(pend_err);
   PE_CUDA(cudaStreamSynchronize(e->stream));
   return PE_OK;
 }
@@ -3379,9 +3407,34 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
   PE_CUDA(cudaEventRecord(e->pipe_free[0], e->stream));
   PE_CUDA(cudaStreamWaitEvent(e->h2d_stream, e->pipe_free[0], 0));
   const bool copy2d_only = getenv("PE_HOST_COPY2D") != nullptr;  // A/B switch for the measurement only
-  auto copy_planes = [&](cudaStream_t st, pe_frame &dev, const pe_frame_desc_t &host, bool to_device) -> cudaError_t {
+  // pageable host planes go through the stager (pe_hoststage.h): uploads are staged by the copy threads before their DMA is queued,
+  // downloads land in a ring buffer and are copied out when the slot comes round again (pend[k]) or at the end
+  std::vector<pe::PendingOut> pend[NS_MAX];
+  auto flush_pending = [&](int k) -> cudaError_t {
+    cudaError_t r = cudaSuccess;
+    for (auto &po : pend[k]) { const cudaError_t c = e->stager.finish(po); if (c != cudaSuccess) r = c; }
+    pend[k].clear();
+    return r;
+  };
+  auto copy_planes = [&](cudaStream_t st, pe_frame &dev, const pe_frame_desc_t &host, bool to_device, int slot) -> cudaError_t {
     for (int p = 0; p < dev.d.nplanes; p++) {
       const int wbytes = plane_row_bytes(dev.d, p);
+      if ((size_t)dev.d.rowstrides[p] * dev.plane_heights[p] >= pe::HostStager::kMinBytes && !e->no_host_staging && pe::HostStager::pageable(host.planes[p])) {
+        if (to_device) {
+          const size_t wb = host.rowstrides[p] == dev.d.rowstrides[p] ? (size_t)dev.d.rowstrides[p] : (size_t)wbytes;
+          if (e->stager.upload(st, dev.d.planes[p], (size_t)dev.d.rowstrides[p], host.planes[p], (size_t)host.rowstrides[p], wb,
+                               (size_t)dev.plane_heights[p]) == cudaSuccess)
+            continue;
+        } else {
+          pe::PendingOut po;
+          if (e->stager.download_begin(st, dev.d.planes[p], (size_t)dev.d.rowstrides[p], host.planes[p], (size_t)host.rowstrides[p], (size_t)wbytes,
+                                       (size_t)dev.plane_heights[p], &po) == cudaSuccess) {
+            pend[slot].push_back(po);
+            continue;
+          }
+        }
+        cudaGetLastError();   // the staged path could not take it: the plain copy below
+      }
       if (host.rowstrides[p] == dev.d.rowstrides[p] && dev.plane_heights[p] > 0 && !copy2d_only) {  // same pitch on both sides: one linear copy
         size_t nbytes = (size_t)dev.d.rowstrides[p] * (dev.plane_heights[p] - 1) + wbytes;
         // planes that follow each other without a gap on BOTH sides (LiVES allocates planar frames contiguously,
@@ -3421,12 +3474,13 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
       break;
     }
     cudaError_t ce = cudaSuccess;
-    // upload into slot k once its previous occupant has been downloaded
+    // upload into slot k once its previous occupant has been downloaded (and, from a ring buffer, copied out to its pageable owner)
     if (i >= NS) ce = cudaStreamWaitEvent(e->h2d_stream, e->pipe_free[k], 0);
+    if (ce == cudaSuccess && !pend[k].empty()) ce = flush_pending(k);
     slots[k][0].d.yuv_clamping = fg[i]->yuv_clamping; slots[k][0].d.yuv_subspace = fg[i]->yuv_subspace;
     slots[k][1].d.gamma_type = bg[i]->gamma_type; slots[k][1].d.flags = bg[i]->flags;
-    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][0], *fg[i], true);
-    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][1], *bg[i], true);
+    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][0], *fg[i], true, k);
+    if (ce == cudaSuccess) ce = copy_planes(e->h2d_stream, slots[k][1], *bg[i], true, k);
     if (ce == cudaSuccess) ce = cudaEventRecord(e->pipe_up[k], e->h2d_stream);
     // compute
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->pipe_up[k], 0);
@@ -3438,13 +3492,15 @@ extern "C" int pe_host_fused_convert_letterbox_over_gamma_batch(pe_engine_t *e, 
     ce = cudaEventRecord(e->pipe_comp[k], e->stream);
     // download
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->d2h_stream, e->pipe_comp[k], 0);
-    if (ce == cudaSuccess) ce = copy_planes(e->d2h_stream, slots[k][2], *out[i], false);
+    if (ce == cudaSuccess) ce = copy_planes(e->d2h_stream, slots[k][2], *out[i], false, k);
     if (ce == cudaSuccess) ce = cudaEventRecord(e->pipe_free[k], e->d2h_stream);
     if (ce != cudaSuccess) { rc = set_err(PE_ERR_CUDA, "pipeline download failed: %s", cudaGetErrorString(ce)); break; }
     out[i]->gamma_type = slots[k][2].d.gamma_type;
     out[i]->flags = slots[k][2].d.flags;
   }
-  cudaError_t ce = cudaStreamSynchronize(e->d2h_stream);
+  cudaError_t ce = cudaSuccess;
+  for (int k = 0; k < NS_MAX; k++) { const cudaError_t c = flush_pending(k); if (c != cudaSuccess) ce = c; }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->d2h_stream);
   cudaError_t ce2 = cudaStreamSynchronize(e->h2d_stream);
   cudaError_t ce3 = cudaStreamSynchronize(e->stream);
   release();

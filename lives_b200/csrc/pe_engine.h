@@ -1,5 +1,6 @@
 // pe_engine.h -- internal state behind the opaque handles of include/pixel_engine.h.
 #pragma once
+#include "pe_hoststage.h"
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -82,6 +83,8 @@ struct pe_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-frame batch pipeline (pe_host_*_batch): copies run on their own streams, overlapped with the kernels
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  bool no_host_staging = false;      // PE_HOST_NO_STAGING=1: measurement switch (every host copy is the plain cudaMemcpy*Async)
+  pe::HostStager stager;             // pageable host planes travel through page-locked ring buffers filled / drained by copy threads
   cudaEvent_t pipe_up[6] = {}, pipe_comp[6] = {}, pipe_free[6] = {};
   cudaStream_t egress_stream = nullptr;  // pe_render_out_*: the final packed frame travels on its own stream
   cudaEvent_t egress_ready[4] = {}, egress_done[4] = {};

@@ -257,3 +257,22 @@ def test_avg_chroma_closed_form_equals_the_reference_tables():
         assert n.max() < 2 ** 32
         f = np.clip((n * M) >> 32, lo, hi).astype(np.uint8)
         assert (f.reshape(-1) == tab).all(), clamped
+
+
+def test_parallel_host_copy_pool():
+    """pe_host_parallel_copy2d = the copy-thread pool behind the staging of pageable host planes (pe_hoststage.h): dense blocks cut into
+    page-sized pieces per thread, strided rows cut by rows; every byte of the payload arrives, nothing outside it is written"""
+    import ctypes as C
+    import lives_b200  # noqa: F401
+    from lives_b200 import _capi
+    lib = _capi.lib()
+    rng = np.random.default_rng(5)
+    for threads in (1, 3, 8):
+        for (rows, wbytes, ss, ds) in ((1, 5_000_003, 5_000_003, 5_000_003), (1080, 1920, 1920, 1920), (270, 1921, 2048, 1984), (7, 13, 64, 32),
+                                      (1, 1, 1, 1), (2160, 3840 * 4, 3840 * 4, 3840 * 4 + 64)):
+            src = rng.integers(0, 256, rows * ss, dtype=np.uint8)
+            dst = np.full(rows * ds, 7, np.uint8)
+            assert lib.pe_host_parallel_copy2d(C.c_void_p(dst.ctypes.data), ds, C.c_void_p(src.ctypes.data), ss, wbytes, rows, threads) == 0
+            s2, d2 = src.reshape(rows, ss), dst.reshape(rows, ds)
+            assert (d2[:, :wbytes] == s2[:, :wbytes]).all(), (threads, rows, wbytes)
+            assert (d2[:, wbytes:] == 7).all(), (threads, rows, wbytes)
