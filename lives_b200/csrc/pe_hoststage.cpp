@@ -3,8 +3,40 @@
 
 #include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace pe {
+
+// A staging copy writes a buffer it will not read again (the DMA or the caller does): non-temporal stores skip the read-for-ownership
+// of the destination lines, a third of the memory traffic of a plain memcpy -- and host memory bandwidth is what bounds the pageable
+// path (profiles/r02zj_pageable.log).  glibc's memcpy only switches to them far above the piece a copy thread gets.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t *dst, const uint8_t *src, size_t n) {
+  size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+  if (head > n) head = n;
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64)), d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+    _mm256_stream_si256((__m256i *)(dst + i), a); _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+    _mm256_stream_si256((__m256i *)(dst + i + 64), c); _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+  }
+  _mm_sfence();
+  memcpy(dst + i, src + i, n - i);
+}
+#endif
+
+static void copy_bytes(uint8_t *dst, const uint8_t *src, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("PE_HOST_COPY_STREAM") != nullptr;   // opt-in, see profiles/r02zj_pageable.log
+  if (avx2 && n >= 4096) { copy_stream_avx2(dst, src, n); return; }
+#endif
+  memcpy(dst, src, n);
+}
 
 CopyPool::CopyPool(int nthreads) : n_(nthreads < 1 ? 1 : nthreads) {
   for (int i = 0; i < n_; i++) th_.emplace_back([this, i] { worker(i); });
@@ -36,11 +68,11 @@ void CopyPool::worker(int idx) {
       size_t piece = (total / (size_t)n_ + 4095) & ~(size_t)4095;
       if (piece == 0) piece = 4096;
       const size_t a = piece * (size_t)idx, b = a + piece < total ? a + piece : total;
-      if (a < total) memcpy(j.dst + a, j.src + a, b - a);
+      if (a < total) copy_bytes(j.dst + a, j.src + a, b - a);
     } else {
       const size_t per = (j.rows + (size_t)n_ - 1) / (size_t)n_;
       const size_t r0 = per * (size_t)idx, r1 = r0 + per < j.rows ? r0 + per : j.rows;
-      for (size_t r = r0; r < r1; r++) memcpy(j.dst + r * j.ds, j.src + r * j.ss, j.wbytes);
+      for (size_t r = r0; r < r1; r++) copy_bytes(j.dst + r * j.ds, j.src + r * j.ss, j.wbytes);
     }
     {
       std::lock_guard<std::mutex> lk(m_);
