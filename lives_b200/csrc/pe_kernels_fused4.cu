@@ -17,6 +17,8 @@
 //      (a warp = one output row: 128-byte contiguous stores).
 // Rows the fast step cannot take (row 0, the last row of an even frame, the last chroma row of a plane without padding) go through
 // slow_unit(): scalar code with the reference's edge rules, a few units per frame.
+#include <cuda.h>   // CUtensorMap (the 2-D TMA staging variant); the encoder is fetched through cudaGetDriverEntryPoint: no -lcuda
+
 #include <cstdlib>
 #include <cstdio>
 
@@ -75,6 +77,17 @@ struct CvtRszParams {
   unsigned long long *tl;                 // [grid][6]: cycles of CTA thread 0 in: wait for the raw words, conversion, staging the next tile, horizontal, vertical, total
 #endif
 };
+
+// 2-D tensor maps of the launch's planes (PE_F4_TMA=2): box = the largest staged rectangle of a tile, so ONE cp.async.bulk.tensor per plane
+// stages a tile (rows outside the plane arrive as zeros: only the slow units, which read global memory themselves, would look at them)
+struct alignas(64) CvtRszMaps {
+  CUtensorMap y[F4_MAXF], u[F4_MAXF], v[F4_MAXF];
+};
+
+__device__ __forceinline__ void f4_tensor_g2s_2d(uint32_t smem_dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
 
 __device__ __forceinline__ uint32_t f4_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -180,7 +193,7 @@ __device__ void f4_chroma_px(const uint8_t *pu, const uint8_t *pv, int rs_u, int
 }
 
 template <bool QUIRKS>
-__global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__ CvtRszParams P) {
+__global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__ CvtRszParams P, const __grid_constant__ CvtRszMaps M) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
@@ -241,11 +254,36 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   };
   // cp.async of the raw words of tile t: luma rows 2 k0 - 1 .. 2 k1 (clamped to the frame), chroma rows k0 - 1 .. k1, the first V
   // sample of every chroma row (the reference's never-advanced last_v2, colourspace.c:3544)
+  auto box_staged = [&](const Geo &g) -> bool { return P.tma == 2 && g.ubase + 2 * g.ng + 21 <= min(P.rs_u, P.rs_v); };
+  auto mbar_staged = [&](const Geo &g) -> bool { return P.tma == 1 || box_staged(g); };   // which completion the tile's raw words signal
   auto stage = [&](const Geo &g, int buf) {
     const uint8_t *Fy = P.y[g.f], *Fu = P.u[g.f], *Fv = P.v[g.f];
     const int rowbase = 2 * g.k0 - 1;
     const long long ulim = (long long)P.rs_u * P.ch, vlim = (long long)P.rs_v * P.ch;
-    if (P.tma) {
+    // A tile whose chroma bytes run past the end of the plane's rows (the reference's one-past-row read, colourspace.c:3508: with a
+    // stride equal to the width those bytes are the NEXT row's first samples) cannot come through a 2-D box -- the box would deliver
+    // zeros there -- and takes the 16-byte cp.async path (box_staged() below: its completion is the cp.async group, not the mbarrier).
+    if (box_staged(g)) {
+      // three tensor copies (luma, U, V rectangles of the compile-time box sizes) + two bulk copies (filter rows), all from lane 0 of warp 0
+      if (warp == 0) {
+        const uint32_t bar = sbase + O_MBAR;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        f4_mbar_expect_tx(bar, lane == 0 ? (uint32_t)(2 * F4_PR * GW * 4 + 2 * (F4_PR + 1) * CWB) + (uint32_t)(g.ncol + g.nrow) * 16u : 0u);
+        if (lane == 0) {
+          f4_tensor_g2s_2d(sbase + O_RAWY, &M.y[g.f], g.ybase, rowbase, bar);
+          f4_tensor_g2s_2d(sbase + O_RAWU, &M.u[g.f], g.ubase, g.k0 - 1, bar);
+          f4_tensor_g2s_2d(sbase + O_RAWV, &M.v[g.f], g.ubase, g.k0 - 1, bar);
+          f4_bulk_g2s(sbase + O_CX + (buf * F4_TW) * 16, P.px + g.x0, (uint32_t)g.ncol * 16u, bar);
+          f4_bulk_g2s(sbase + O_PY + (buf * F4_TH) * 16, P.py + g.y0, (uint32_t)g.nrow * 16u, bar);
+        }
+      } else if (warp == 1 && lane <= g.np) {
+        const int cr = min(max(g.k0 - 1 + lane, 0), P.ch - 1);
+        f4_cp_async4(sbase + O_VF + 4 * lane, Fv + (size_t)P.rs_v * cr);
+      }
+      f4_cp_async_commit();
+      return;
+    }
+    if (P.tma == 1) {
       // warp 0: lane l asks for rows l, l + 32, ... of the tile's 2 np luma + 2 (np + 1) chroma rows with one bulk copy each (a row:
       // <= 224 / 128 bytes, 16-byte aligned at both ends), lanes 0 / 1 for the tile's filter rows as well; every lane arrives on the
       // mbarrier with the byte count it is about to request.  The other warps go straight on to the horizontal pass.
@@ -354,12 +392,11 @@ __global__ void __launch_bounds__(F4_NT, 1) k_cvt_resize(const __grid_constant__
   if (t >= total) return;
   Geo G = geometry(t);
   int buf = 0;
-  uint32_t tile_phase = 0u;   // tiles this CTA has staged so far: the mbarrier's phase
+  uint32_t tile_phase = 0u;   // tiles this CTA has staged through the mbarrier so far: its phase
   stage(G, buf);
   for (; t < total; t += gridDim.x, buf ^= 1) {
     f4_cp_async_wait_all();
-    if (P.tma) f4_mbar_wait(sbase + O_MBAR, tile_phase & 1u);
-    tile_phase++;
+    if (mbar_staged(G)) { f4_mbar_wait(sbase + O_MBAR, tile_phase & 1u); tile_phase++; }
     __syncthreads();  // raw words of this tile have landed; the previous tile's passes are done with the planes, the intermediate and the filter rows
 #ifdef PE_F4_TIMELINE
     tl_lap(0);
@@ -590,9 +627,34 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
   for (int i = 0; i < n && P.vec16; i++)
     P.vec16 = !((reinterpret_cast<uintptr_t>(frames[i].src.y) | reinterpret_cast<uintptr_t>(frames[i].src.u) | reinterpret_cast<uintptr_t>(frames[i].src.v)) & 15);
   if (getenv("PE_F4_NOVEC")) P.vec16 = 0;
-  // the bulk-copy (TMA) staging is kept as a measured variant: 67.0 k frames/s against 99.7 k with 16-byte cp.async on config 2
-  // (profiles/r02zg_k_cvt_resize_staging.txt) -- a tile's rows are <= 224 bytes, far below the size a bulk copy needs to pay off
-  P.tma = P.vec16 && getenv("PE_F4_TMA") && atoi(getenv("PE_F4_TMA")) != 0;
+  // How a tile's raw rows reach shared memory (PE_F4_TMA; profiles/r02zg_k_cvt_resize_staging.txt, config 2):
+  //   2 (default)  three cp.async.bulk.tensor.2d (TMA, one per plane, from 2-D tensor maps of the launch's planes) + two bulk copies
+  //                of the filter rows, issued by ONE lane: 105.4 k frames/s.  Tiles at the right edge of a plane whose stride equals
+  //                its width keep the cp.async path (box_staged()).
+  //   0            16-byte cp.async (LDGSTS) from all warps: 100.2 k
+  //   1            one cp.async.bulk per row (<= 224 bytes) from one warp: 67 - 69 k -- far below the size a bulk copy needs to pay off
+  P.tma = P.vec16 ? (getenv("PE_F4_TMA") ? atoi(getenv("PE_F4_TMA")) : 2) : 0;
+  if (P.tma < 0 || P.tma > 2) P.tma = 0;
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool encode_tried = false;
+  if (P.tma == 2 && !encode_tried) {
+    encode_tried = true;
+    void *fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (EncodeFn)fp;
+  }
+  // (the boxes are the kernel's compile-time maxima: they must fit the planes' rows)
+  if (P.tma == 2 && (!encode || a0.src.rs_y < F4_GW * 4 || a0.src.rs_u < F4_CWB || a0.src.rs_v < F4_CWB)) P.tma = 0;   // (narrow planes: the cp.async path)
+  CvtRszMaps maps;   // (12 KB of kernel parameters, copied at launch)
+  memset(&maps, 0, sizeof(maps));
+  auto make_map = [&](CUtensorMap *m, const uint8_t *base, int rs, int rows, int box_w, int box_h) -> bool {
+    const cuuint64_t gdim[2] = {(cuuint64_t)rs, (cuuint64_t)rows}, gstr[1] = {(cuuint64_t)rs};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1u, 1u};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
   const int smem_bytes = F4_SMEM;
   static PerDevice attr_set;
   if (!attr_set.cur()) {
@@ -608,6 +670,13 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
       P.y[i] = frames[k].src.y; P.u[i] = frames[k].src.u; P.v[i] = frames[k].src.v;
       P.dst[i] = dsts[k];
     }
+    if (P.tma == 2) {
+      bool ok = true;
+      for (int i = 0; i < P.nframes && ok; i++)
+        ok = make_map(&maps.y[i], P.y[i], P.rs_y, P.fh, F4_GW * 4, 2 * F4_PR) && make_map(&maps.u[i], P.u[i], P.rs_u, P.ch, F4_CWB, F4_PR + 1) &&
+             make_map(&maps.v[i], P.v[i], P.rs_v, P.ch, F4_CWB, F4_PR + 1);
+      if (!ok) P.tma = 0;
+    }
     const long long total = (long long)P.tiles_x * P.tiles_y * P.nframes;
     const int grid = (int)(total < L.sm_count ? total : L.sm_count);
 #ifdef PE_F4_TIMELINE
@@ -616,8 +685,8 @@ cudaError_t launch_cvt_resize(const Launch &L, const YuvToRgbArgs *frames, uint8
     cudaMemsetAsync(tl_dev, 0, sizeof(unsigned long long) * 6 * 1024, L.stream);
     P.tl = tl_dev;
 #endif
-    if (a0.quirks) k_cvt_resize<true><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
-    else k_cvt_resize<false><<<grid, F4_NT, smem_bytes, L.stream>>>(P);
+    if (a0.quirks) k_cvt_resize<true><<<grid, F4_NT, smem_bytes, L.stream>>>(P, maps);
+    else k_cvt_resize<false><<<grid, F4_NT, smem_bytes, L.stream>>>(P, maps);
 #ifdef PE_F4_TIMELINE
     if (getenv("PE_F4_TIMELINE_DUMP")) {   // where the tiles' time goes (thread 0 of every CTA: its waits at the barriers land in the lap before them)
       static unsigned long long h[6 * 1024];
